@@ -1,0 +1,106 @@
+"""ctypes binding of libctgan_sm100.so (include/ctgan_sm100.h).
+
+There is NO fallback: if the shared library is missing this module raises at import,
+and every entry point raises RuntimeError with `ctgan_last_error()` on a non-zero
+return code.
+"""
+import ctypes
+import os
+from ctypes import c_int, c_int32, c_int64, c_uint64, c_float, c_void_p, c_char_p, POINTER, Structure
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libctgan_sm100.so')
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        "ctgan_b200: %s not found. Build it with `python -m ctgan_b200.build` "
+        "(nvcc, sm_100a). There is no CPU or PyTorch fallback." % LIB_PATH)
+
+lib = ctypes.CDLL(LIB_PATH)
+
+F32, BF16 = 0, 1
+EPI_RELU = 1
+
+
+class ConvDesc(Structure):
+    _fields_ = [(n, c_int32) for n in (
+        'N', 'H', 'W', 'Cin', 'Ho', 'Wo', 'Cout', 'kh', 'kw', 'stride', 'pad_t', 'pad_l', 'x_dtype', 'y_dtype')]
+
+
+class LossDesc(Structure):
+    _fields_ = [('B', c_int32), ('NF', c_int32), ('F', c_int32), ('P', c_int32), ('n_classes', c_int32),
+                ('feat_dtype', c_int32), ('lambda_gp', c_float), ('lambda2', c_float), ('factor_m', c_float),
+                ('acgan_scale', c_float)]
+
+
+P = c_void_p
+_PROTOS = {
+    'ctgan_version': (c_int, []),
+    'ctgan_last_error': (c_char_p, []),
+    'ctgan_tc_available': (c_int, []),
+    'ctgan_conv_fprop': (c_int, [POINTER(ConvDesc), P, P, P, P, c_int, P]),
+    'ctgan_conv_dgrad': (c_int, [POINTER(ConvDesc), P, P, P, P]),
+    'ctgan_conv_wgrad': (c_int, [POINTER(ConvDesc), P, P, P, c_int, P]),
+    'ctgan_conv_fprop_tc': (c_int, [POINTER(ConvDesc), P, P, P, P, P, c_int, P]),
+    'ctgan_conv_wgrad_tc': (c_int, [POINTER(ConvDesc), P, P, P, P]),
+    'ctgan_pack_filter_bf16': (c_int, [P, P, c_int, c_int, c_int, c_int, P]),
+    'ctgan_bias_grad': (c_int, [P, P, c_int64, c_int, c_int, c_int, P]),
+    'ctgan_cast': (c_int, [P, c_int, P, c_int, c_int64, P]),
+    'ctgan_add': (c_int, [P, P, P, c_int64, c_int, P]),
+    'ctgan_mul': (c_int, [P, P, P, c_int64, c_int, P]),
+    'ctgan_scale': (c_int, [P, c_float, P, c_int64, c_int, P]),
+    'ctgan_act_dropout_fwd': (c_int, [P, P, P, P, c_int64, c_int, c_float, c_float, c_uint64, c_uint64, P]),
+    'ctgan_unary_fwd': (c_int, [P, P, c_int64, c_int, c_int, P]),
+    'ctgan_unary_bwd': (c_int, [P, P, P, c_int64, c_int, c_int, P]),
+    'ctgan_pool2x2': (c_int, [P, P, c_int, c_int, c_int, c_int, c_float, c_int, P]),
+    'ctgan_upsample2x': (c_int, [P, P, c_int, c_int, c_int, c_int, c_float, c_int, P]),
+    'ctgan_spatial_sum': (c_int, [P, P, c_int, c_int, c_int, c_float, c_int, P]),
+    'ctgan_spatial_bcast': (c_int, [P, P, c_int, c_int, c_int, c_float, c_int, P]),
+    'ctgan_nchw_to_nhwc': (c_int, [P, c_int, P, c_int, c_int, c_int, c_int, c_int, P]),
+    'ctgan_nhwc_to_nchw': (c_int, [P, c_int, P, c_int, c_int, c_int, c_int, c_int, P]),
+    'ctgan_crop': (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
+    'ctgan_crop_bwd': (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
+    'ctgan_prep_real': (c_int, [P, P, c_int64, c_float, c_float, c_uint64, c_uint64, P]),
+    'ctgan_interpolate': (c_int, [P, P, P, P, c_int, c_int, P]),
+    'ctgan_bn_workspace_floats': (c_int64, [c_int, c_int, c_int]),
+    'ctgan_bn_fwd': (c_int, [P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_float, c_int, c_int, P]),
+    'ctgan_bn_bwd': (c_int, [P, P, P, P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
+    'ctgan_ct_gp_loss_fwd': (c_int, [POINTER(LossDesc), P, P, P, P, P, P, P, P, P, P, P]),
+    'ctgan_ct_gp_loss_bwd': (c_int, [POINTER(LossDesc), P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P]),
+    'ctgan_mean_fwd': (c_int, [P, P, c_int, c_float, P]),
+    'ctgan_mean_bwd': (c_int, [P, P, c_int, c_float, P]),
+    'ctgan_softmax_ce_fwd': (c_int, [P, P, P, c_int, c_int, P]),
+    'ctgan_softmax_ce_bwd': (c_int, [P, P, P, c_float, P, c_int, c_int, P]),
+    'ctgan_adam_step': (c_int, [P, P, P, P, c_int64, c_float, c_float, c_float, c_float, c_float, P]),
+    'ctgan_philox_uniform': (c_int, [P, c_int64, c_float, c_float, c_uint64, c_uint64, P]),
+    'ctgan_philox_normal': (c_int, [P, c_int64, c_uint64, c_uint64, P]),
+    'ctgan_philox_labels': (c_int, [P, c_int64, c_int, c_uint64, c_uint64, P]),
+}
+
+EXPORTS = sorted(_PROTOS)
+
+for _name, (_res, _args) in _PROTOS.items():
+    _fn = getattr(lib, _name)            # AttributeError here == header/library mismatch: fail loudly
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+
+class CtganError(RuntimeError):
+    pass
+
+
+def check(rc, what=''):
+    if rc != 0:
+        msg = lib.ctgan_last_error()
+        raise CtganError('%s failed (rc=%d): %s' % (what or 'libctgan_sm100 call', rc,
+                                                   msg.decode('utf-8', 'replace') if msg else ''))
+
+
+# Count of kernel-launching C-ABI calls made by this process (bench.py reports it).
+launch_calls = 0
+
+
+def call(name, *args):
+    global launch_calls
+    launch_calls += 1
+    check(getattr(lib, name)(*args), name)

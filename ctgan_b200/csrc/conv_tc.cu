@@ -1,0 +1,589 @@
+// conv_tc.cu -- implicit-GEMM convolution on the 5th-gen tensor cores (tcgen05 + TMEM),
+// operands staged by TMA, BF16 inputs, FP32 accumulation.  sm_100a only.
+//
+//   fprop_tc:  Y[n,h,w,co] = sum_{r,s,ci} X[n,h+r-pt,w+s-pl,ci] * Wp[(r,s)][co][ci]   (+bias,+residual,ReLU)
+//              GEMM view: M = pixels (128 per CTA: a BN x BH x BW box of the NHWC tensor),
+//              N = Cout tile, K = taps x Cin in blocks of 64.  The A operand of tap (r,s) is ONE
+//              4-D TMA box load at coordinates shifted by (r-pt, s-pl): TMA's out-of-bounds
+//              zero fill IS the SAME padding, so no im2col buffer and no bounds code exist.
+//              Both operands are K-major, 128B-swizzled: the box [pixels][64 ch] lands in smem
+//              exactly in the canonical UMMA layout (8-row x 128 B atoms, SBO = 1024 B).
+//              Also serves stride-1 dgrad (flipped/transposed filter pack) and Linear (H=W=1).
+//   wgrad_tc:  dW[(r,s)][ci][co] += sum_{pixels} X[pixel+(r,s)-pad][ci] * dY[pixel][co]
+//              GEMM view: M = Cin tile (128), N = Cout tile (128), K = pixels in blocks of 64.
+//              The same TMA boxes are consumed as MN-major operands (a_major=b_major=1), so
+//              no transposed copy of the activations is ever made.  Up to 4 taps accumulate in
+//              4 x 128 TMEM columns per CTA; the pixel range is split across CTAs and reduced
+//              with vector fp32 reductions (red.global.add.v4.f32).
+//
+// Pipeline per CTA (128 threads): warp 0 = TMA producer (one elected lane), warp 1 = MMA
+// issuer (one elected lane), warp 2 = TMEM allocator; all four warps run the epilogue
+// (tcgen05.ld 32x32b: warp w owns TMEM lanes 32w..32w+31 = tile rows).  smem full/empty
+// mbarrier ring between TMA and MMA, tcgen05.commit releases slots and publishes the
+// accumulator.  fprop uses 3 x 32 KB stages so two CTAs co-reside per SM and one CTA's
+// epilogue overlaps the other's main loop.
+//
+// Replaces (BF16 path) tf.nn.conv2d / conv2d_transpose / matmul and their gradients:
+// TG/tflib/ops/conv2d.py:106-112, deconv2d.py:97-103, linear.py:132-136.
+#include <cuda.h>
+#include "common.cuh"
+
+namespace ctgan {
+namespace tc {
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// Bounded wait: a descriptor/programming error must surface as a trap (-> cudaErrorLaunchFailure),
+// never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000ll) { __trap(); }
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
+                                            int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
+                                            int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "n"(COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after()  { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// D[tmem] (+)= A[smem] * B[smem], BF16 x BF16 -> FP32
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (thread = TMEM lane)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ------------------------------------------------------------------ descriptors
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+//   [0,14) start address >> 4   [16,30) leading byte offset >> 4   [32,46) stride byte offset >> 4
+//   [46,48) version = 1 (Blackwell)   [49,52) base offset = 0   [61,64) layout type (2 = SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (1) @4, a/b format BF16 (1) @7/@10,
+// a_major @15, b_major @16 (0 = K-major, 1 = MN-major), N>>3 @17, M>>4 @24.
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+constexpr int BLOCK_M = 128;       // tile rows = TMEM lanes
+constexpr int BLOCK_K = 64;        // bf16 elements per 128-byte swizzle row
+constexpr int UMMA_K  = 16;
+
+struct FpropParams {
+    int N, H, W, Cin, Cout;
+    int kh, kw, pad_t, pad_l;
+    int BW, BH, BN;                // pixel box of one M tile: BN*BH*BW == 128
+    int tilesW, tilesH, tilesN;
+    int flags;
+    __nv_bfloat16* y;
+    const float* bias;
+    const __nv_bfloat16* residual;
+};
+
+// ------------------------------------------------------------------ fprop kernel
+template <int BLOCK_N, int STAGES>
+__global__ void __launch_bounds__(128)
+conv_fprop_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+                     const FpropParams p)
+{
+    constexpr uint32_t A_BYTES = BLOCK_M * BLOCK_K * 2;       // 16 KB
+    constexpr uint32_t B_BYTES = BLOCK_N * BLOCK_K * 2;
+    constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+    constexpr int TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
+
+    extern __shared__ uint8_t smem_raw[];
+    // SWIZZLE_128B atoms need 1024-byte alignment
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+    float* s_bias = reinterpret_cast<float*>(tmem_slot + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES), accum_bar = smem_u32(bars + 2 * STAGES);
+
+    // ---- tile coordinates
+    int mt = blockIdx.x;
+    const int tw = mt % p.tilesW; mt /= p.tilesW;
+    const int th = mt % p.tilesH; const int tn = mt / p.tilesH;
+    const int w0 = tw * p.BW, h0 = th * p.BH, n0 = tn * p.BN;
+    const int co0 = blockIdx.y * BLOCK_N;
+
+    const int cin_blocks = p.Cin / BLOCK_K;
+    const int num_kb = p.kh * p.kw * cin_blocks;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmap_x);
+        prefetch_tmap(&tmap_w);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        mbar_init(accum_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc<TMEM_COLS>(smem_u32(tmem_slot));
+    if (threadIdx.x < BLOCK_N) s_bias[threadIdx.x] = p.bias ? p.bias[co0 + threadIdx.x] : 0.f;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0 && lane == 0) {
+        // ================= TMA producer =================
+        int stage = 0; uint32_t phase = 0;
+        for (int kb = 0; kb < num_kb; ++kb) {
+            const int tap = kb / cin_blocks, cb = kb - tap * cin_blocks;
+            const int r = tap / p.kw, s = tap - r * p.kw;
+            mbar_wait(empty0 + 8 * stage, phase ^ 1);
+            const uint32_t a_dst = smem_base + stage * STAGE_BYTES, b_dst = a_dst + A_BYTES;
+            const uint32_t fb = full0 + 8 * stage;
+            mbar_expect_tx(fb, STAGE_BYTES);
+            tma_load_4d(a_dst, &tmap_x, fb, cb * BLOCK_K, w0 + s - p.pad_l, h0 + r - p.pad_t, n0);
+            tma_load_3d(b_dst, &tmap_w, fb, cb * BLOCK_K, co0, tap);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ================= MMA issuer =================
+        constexpr uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N, 0, 0);
+        int stage = 0; uint32_t phase = 0;
+        for (int kb = 0; kb < num_kb; ++kb) {
+            mbar_wait(full0 + 8 * stage, phase);
+            tc_fence_after();
+            const uint32_t a_src = smem_base + stage * STAGE_BYTES, b_src = a_src + A_BYTES;
+            const uint64_t a_desc = make_smem_desc(a_src, 16, 1024);
+            const uint64_t b_desc = make_smem_desc(b_src, 16, 1024);
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                // advance 32 bytes (16 bf16) along K inside the 128-byte swizzle row: +2 in 16-byte units
+                umma_bf16(tmem_base, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+            }
+            umma_commit(empty0 + 8 * stage);                   // frees this smem slot when the MMAs retire
+            if (kb == num_kb - 1) umma_commit(accum_bar);      // accumulator complete
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+    }
+    __syncwarp();
+
+    // ================= epilogue: TMEM -> registers -> global =================
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+    const int row = warp * 32 + lane;                          // tile row == TMEM lane
+    int t = row;
+    const int bw = t % p.BW; t /= p.BW;
+    const int bh = t % p.BH; const int bn = t / p.BH;
+    const int n = n0 + bn, h = h0 + bh, w = w0 + bw;
+    const bool valid = (n < p.N) && (h < p.H) && (w < p.W);
+    const int64_t pix = ((int64_t)n * p.H + h) * p.W + w;
+    __nv_bfloat16* yrow = p.y + pix * p.Cout + co0;
+    const __nv_bfloat16* rrow = p.residual ? p.residual + pix * p.Cout + co0 : nullptr;
+    const bool relu = (p.flags & CTGAN_EPI_RELU) != 0;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        uint32_t acc[32];
+        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, acc);   // warp-collective
+        if (valid) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+                float v[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(acc[j + e]) + s_bias[c0 + j + e];
+                if (rrow) {
+                    uint4 rv = *reinterpret_cast<const uint4*>(rrow + c0 + j);
+                    const __nv_bfloat162* rp = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) { v[2 * e] += __bfloat162float(rp[e].x); v[2 * e + 1] += __bfloat162float(rp[e].y); }
+                }
+                if (relu) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
+                }
+                uint4 ov;
+                __nv_bfloat162* op = reinterpret_cast<__nv_bfloat162*>(&ov);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) op[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+                *reinterpret_cast<uint4*>(yrow + c0 + j) = ov;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
+// ------------------------------------------------------------------ wgrad kernel
+struct WgradParams {
+    int N, H, W, Cin, Cout;
+    int kh, kw, pad_t, pad_l;
+    int BW, BH, BN;                // pixel box of one K chunk: BN*BH*BW == 64
+    int chunksW, chunksH, chunksN; // pixel chunks per dimension
+    int taps_per_cta;
+    int chunks_per_split;
+    float* dw;
+};
+
+template <int STAGES>
+__global__ void __launch_bounds__(128)
+conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_dy,
+                     const WgradParams p)
+{
+    constexpr int BLOCK_N = 128;
+    constexpr uint32_t HALF_BYTES = 64 * 64 * 2;              // [64 px][64 ch] bf16 = 8 KB
+    constexpr uint32_t A_BYTES = 2 * HALF_BYTES, B_BYTES = 2 * HALF_BYTES;
+    constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;       // 32 KB
+    constexpr int TMEM_COLS = 512;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES), accum_bar = smem_u32(bars + 2 * STAGES);
+
+    const int co_blocks = p.Cout / 128;
+    const int ci0 = (blockIdx.x / co_blocks) * 128, co0 = (blockIdx.x % co_blocks) * 128;
+    const int taps = p.kh * p.kw;
+    const int tap0 = blockIdx.y * p.taps_per_cta;
+    const int ntaps = min(p.taps_per_cta, taps - tap0);
+    const int total_chunks = p.chunksN * p.chunksH * p.chunksW;
+    const int chunk0 = blockIdx.z * p.chunks_per_split;
+    const int nchunks = min(p.chunks_per_split, total_chunks - chunk0);
+    const int num_kb = nchunks * ntaps;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmap_x);
+        prefetch_tmap(&tmap_dy);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        mbar_init(accum_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc<TMEM_COLS>(smem_u32(tmem_slot));
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0 && lane == 0) {
+        // ================= TMA producer =================
+        int stage = 0; uint32_t phase = 0;
+        for (int c = 0; c < nchunks; ++c) {
+            int ch = chunk0 + c;
+            const int cw = ch % p.chunksW; ch /= p.chunksW;
+            const int chh = ch % p.chunksH; const int cn = ch / p.chunksH;
+            const int w0 = cw * p.BW, h0 = chh * p.BH, n0 = cn * p.BN;
+            for (int tl = 0; tl < ntaps; ++tl) {
+                const int tap = tap0 + tl;
+                const int r = tap / p.kw, s = tap - r * p.kw;
+                mbar_wait(empty0 + 8 * stage, phase ^ 1);
+                const uint32_t a_dst = smem_base + stage * STAGE_BYTES, b_dst = a_dst + A_BYTES;
+                const uint32_t fb = full0 + 8 * stage;
+                mbar_expect_tx(fb, STAGE_BYTES);
+                tma_load_4d(a_dst,              &tmap_x,  fb, ci0,      w0 + s - p.pad_l, h0 + r - p.pad_t, n0);
+                tma_load_4d(a_dst + HALF_BYTES, &tmap_x,  fb, ci0 + 64, w0 + s - p.pad_l, h0 + r - p.pad_t, n0);
+                tma_load_4d(b_dst,              &tmap_dy, fb, co0,      w0, h0, n0);
+                tma_load_4d(b_dst + HALF_BYTES, &tmap_dy, fb, co0 + 64, w0, h0, n0);
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ================= MMA issuer =================
+        // both operands MN-major: rows of the smem tile are K (pixels), 64 channels = 128 B contiguous
+        constexpr uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N, 1, 1);
+        int stage = 0; uint32_t phase = 0;
+        for (int c = 0; c < nchunks; ++c) {
+            for (int tl = 0; tl < ntaps; ++tl) {
+                mbar_wait(full0 + 8 * stage, phase);
+                tc_fence_after();
+                const uint32_t a_src = smem_base + stage * STAGE_BYTES, b_src = a_src + A_BYTES;
+                // LBO = byte distance between the two 64-channel halves, SBO = 8 pixel rows x 128 B
+                const uint64_t a_desc = make_smem_desc(a_src, HALF_BYTES, 1024);
+                const uint64_t b_desc = make_smem_desc(b_src, HALF_BYTES, 1024);
+#pragma unroll
+                for (int k = 0; k < 64 / UMMA_K; ++k) {
+                    // advance 16 pixel rows = 2048 bytes along K: +128 in 16-byte units
+                    umma_bf16(tmem_base + (uint32_t)(tl * BLOCK_N), a_desc + (uint64_t)(128 * k), b_desc + (uint64_t)(128 * k),
+                              idesc, (c | k) != 0);
+                }
+                umma_commit(empty0 + 8 * stage);
+                if (c == nchunks - 1 && tl == ntaps - 1) umma_commit(accum_bar);
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    }
+    __syncwarp();
+
+    // ================= epilogue: TMEM -> vector reductions into dW (float, HWIO) =================
+    if (num_kb > 0) {
+        mbar_wait(accum_bar, 0);
+        tc_fence_after();
+        const int ci = ci0 + warp * 32 + lane;
+        for (int tl = 0; tl < ntaps; ++tl) {
+            float* dst = p.dw + ((int64_t)(tap0 + tl) * p.Cin + ci) * p.Cout + co0;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+                uint32_t acc[32];
+                tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(tl * BLOCK_N + c0), acc);
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};"
+                                 ::"l"(dst + c0 + j), "f"(__uint_as_float(acc[j])), "f"(__uint_as_float(acc[j + 1])),
+                                   "f"(__uint_as_float(acc[j + 2])), "f"(__uint_as_float(acc[j + 3])) : "memory");
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
+// ------------------------------------------------------------------ filter packing
+// transpose_flip == 0: wp[t][o][c] = w[t][c][o];  == 1: wp[t][c][o] = w[taps-1-t][c][o]
+__global__ void pack_filter_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wp,
+                                   int taps, int Cin, int Cout, int transpose_flip) {
+    int64_t total = (int64_t)taps * Cin * Cout;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        if (transpose_flip) {
+            int64_t t = i / ((int64_t)Cin * Cout), rem = i - t * (int64_t)Cin * Cout;
+            wp[i] = __float2bfloat16_rn(w[(int64_t)(taps - 1 - t) * Cin * Cout + rem]);
+        } else {
+            int c = i % Cin; int64_t q = i / Cin;
+            int o = q % Cout; int t = q / Cout;
+            wp[i] = __float2bfloat16_rn(w[((int64_t)t * Cin + c) * Cout + o]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
+        if (e == cudaSuccess && qres == cudaDriverEntryPointSuccess) fn = reinterpret_cast<EncodeTiledFn>(ptr);
+        else (void)cudaGetLastError();
+    }
+    return fn;
+}
+
+static int pow2ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+// 4-D map over an NHWC bf16 tensor: dims (C, W, H, N), box (64, BW, BH, BN), 128B swizzle, zero OOB fill
+static int make_act_map(CUtensorMap* map, const void* base, int N, int H, int W, int C, int BW, int BH, int BN) {
+    EncodeTiledFn enc = get_encode_fn();
+    CTGAN_REQUIRE(enc != nullptr, CTGAN_ERR_DRIVER, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)BW, (cuuint32_t)BH, (cuuint32_t)BN};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CTGAN_REQUIRE(r == CUDA_SUCCESS, CTGAN_ERR_DRIVER, "cuTensorMapEncodeTiled(activation) failed: CUresult %d", (int)r);
+    return 0;
+}
+// 3-D map over a packed filter [taps][rows][K] bf16: dims (K, rows, taps), box (64, box_rows, 1)
+static int make_filter_map(CUtensorMap* map, const void* base, int taps, int rows, int K, int box_rows) {
+    EncodeTiledFn enc = get_encode_fn();
+    CTGAN_REQUIRE(enc != nullptr, CTGAN_ERR_DRIVER, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)taps};
+    cuuint64_t strides[2] = {(cuuint64_t)K * 2, (cuuint64_t)rows * K * 2};
+    cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CTGAN_REQUIRE(r == CUDA_SUCCESS, CTGAN_ERR_DRIVER, "cuTensorMapEncodeTiled(filter) failed: CUresult %d", (int)r);
+    return 0;
+}
+
+static void pixel_box(int H, int W, int pixels, int* BW, int* BH, int* BN) {
+    int bw = pow2ceil(W); if (bw > pixels) bw = pixels;
+    int bh = pow2ceil(H); if (bh > pixels / bw) bh = pixels / bw;
+    *BW = bw; *BH = bh; *BN = pixels / (bw * bh);
+}
+
+static int check_tc_desc(const ctgan_conv_desc* d, const char* who) {
+    CTGAN_REQUIRE(d != nullptr, CTGAN_ERR_BAD_DESC, "%s: null descriptor", who);
+    CTGAN_REQUIRE(d->x_dtype == CTGAN_BF16 && d->y_dtype == CTGAN_BF16, CTGAN_ERR_UNSUPPORTED, "%s: tensor-core path needs BF16 activations", who);
+    CTGAN_REQUIRE(d->stride == 1 && d->Ho == d->H && d->Wo == d->W, CTGAN_ERR_UNSUPPORTED, "%s: tensor-core path needs stride 1 and Ho==H, Wo==W", who);
+    CTGAN_REQUIRE(d->N > 0 && d->H > 0 && d->W > 0 && d->kh > 0 && d->kw > 0 && d->pad_t >= 0 && d->pad_l >= 0 &&
+                  d->pad_t < d->kh && d->pad_l < d->kw, CTGAN_ERR_BAD_DESC, "%s: bad geometry", who);
+    CTGAN_REQUIRE(d->Cin % 64 == 0 && d->Cout % 64 == 0 && d->Cin > 0 && d->Cout > 0, CTGAN_ERR_UNSUPPORTED, "%s: Cin and Cout must be multiples of 64", who);
+    CTGAN_REQUIRE(ctgan_tc_available(), CTGAN_ERR_UNSUPPORTED, "%s: device is not sm_100", who);
+    return 0;
+}
+
+template <int BLOCK_N, int STAGES>
+static int launch_fprop(const CUtensorMap& mx, const CUtensorMap& mw, const FpropParams& p, cudaStream_t st) {
+    constexpr size_t smem = (size_t)STAGES * (BLOCK_M * BLOCK_K * 2 + BLOCK_N * BLOCK_K * 2) + 1024 /*align slack*/ +
+                            (2 * STAGES + 1) * 8 + 16 + BLOCK_N * 4;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(conv_fprop_tc_kernel<BLOCK_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return cuda_status(e, "fprop_tc smem attribute");
+        attr_set = true;
+    }
+    dim3 grid(p.tilesW * p.tilesH * p.tilesN, p.Cout / BLOCK_N);
+    conv_fprop_tc_kernel<BLOCK_N, STAGES><<<grid, 128, smem, st>>>(mx, mw, p);
+    CTGAN_CHECK_LAUNCH("conv_fprop_tc");
+    return 0;
+}
+
+}  // namespace tc
+}  // namespace ctgan
+
+using namespace ctgan;
+using namespace ctgan::tc;
+
+extern "C" int ctgan_conv_fprop_tc(const ctgan_conv_desc* d, const void* x, const void* wp,
+                                   const float* bias, const void* residual, void* y, int flags, void* stream) {
+    if (int r = check_tc_desc(d, "conv_fprop_tc")) return r;
+    CTGAN_REQUIRE(x && wp && y, CTGAN_ERR_BAD_DESC, "conv_fprop_tc: null pointer");
+    CTGAN_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(wp) & 15) == 0 &&
+                  (reinterpret_cast<uintptr_t>(y) & 15) == 0 && (reinterpret_cast<uintptr_t>(residual) & 15) == 0,
+                  CTGAN_ERR_BAD_DESC, "conv_fprop_tc: pointers must be 16-byte aligned");
+    FpropParams p;
+    p.N = d->N; p.H = d->H; p.W = d->W; p.Cin = d->Cin; p.Cout = d->Cout;
+    p.kh = d->kh; p.kw = d->kw; p.pad_t = d->pad_t; p.pad_l = d->pad_l;
+    pixel_box(d->H, d->W, BLOCK_M, &p.BW, &p.BH, &p.BN);
+    p.tilesW = ceil_div(d->W, p.BW); p.tilesH = ceil_div(d->H, p.BH); p.tilesN = ceil_div(d->N, p.BN);
+    p.flags = flags;
+    p.y = reinterpret_cast<__nv_bfloat16*>(y);
+    p.bias = bias;
+    p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
+    const int block_n = (d->Cout % 128 == 0) ? 128 : 64;
+    CUtensorMap mx, mw;
+    if (int r = make_act_map(&mx, x, d->N, d->H, d->W, d->Cin, p.BW, p.BH, p.BN)) return r;
+    if (int r = make_filter_map(&mw, wp, d->kh * d->kw, d->Cout, d->Cin, block_n)) return r;
+    cudaStream_t st = as_stream(stream);
+    if (block_n == 128) return launch_fprop<128, 3>(mx, mw, p, st);
+    return launch_fprop<64, 4>(mx, mw, p, st);
+}
+
+extern "C" int ctgan_conv_wgrad_tc(const ctgan_conv_desc* d, const void* x, const void* dy, float* dw, void* stream) {
+    if (int r = check_tc_desc(d, "conv_wgrad_tc")) return r;
+    CTGAN_REQUIRE(d->Cin % 128 == 0 && d->Cout % 128 == 0, CTGAN_ERR_UNSUPPORTED, "conv_wgrad_tc: Cin and Cout must be multiples of 128");
+    CTGAN_REQUIRE(x && dy && dw, CTGAN_ERR_BAD_DESC, "conv_wgrad_tc: null pointer");
+    CTGAN_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(dy) & 15) == 0 &&
+                  (reinterpret_cast<uintptr_t>(dw) & 15) == 0, CTGAN_ERR_BAD_DESC, "conv_wgrad_tc: pointers must be 16-byte aligned");
+    constexpr int STAGES = 4;
+    WgradParams p;
+    p.N = d->N; p.H = d->H; p.W = d->W; p.Cin = d->Cin; p.Cout = d->Cout;
+    p.kh = d->kh; p.kw = d->kw; p.pad_t = d->pad_t; p.pad_l = d->pad_l;
+    pixel_box(d->H, d->W, 64, &p.BW, &p.BH, &p.BN);
+    p.chunksW = ceil_div(d->W, p.BW); p.chunksH = ceil_div(d->H, p.BH); p.chunksN = ceil_div(d->N, p.BN);
+    const int taps = d->kh * d->kw;
+    p.taps_per_cta = (taps % 3 == 0) ? 3 : (taps < 4 ? taps : 4);
+    const int tap_groups = ceil_div(taps, p.taps_per_cta);
+    const int tiles = (d->Cin / 128) * (d->Cout / 128);
+    const int total_chunks = p.chunksN * p.chunksH * p.chunksW;
+    // about one wave of CTAs (TMEM: 512 columns => one CTA per SM), at least 16 pixel chunks each
+    int splits = sm_count() / (tiles * tap_groups);
+    if (splits < 1) splits = 1;
+    int max_splits = total_chunks / 16; if (max_splits < 1) max_splits = 1;
+    if (splits > max_splits) splits = max_splits;
+    p.chunks_per_split = ceil_div(total_chunks, splits);
+    splits = ceil_div(total_chunks, p.chunks_per_split);
+    p.dw = dw;
+    CUtensorMap mx, mdy;
+    if (int r = make_act_map(&mx, x, d->N, d->H, d->W, d->Cin, p.BW, p.BH, p.BN)) return r;
+    if (int r = make_act_map(&mdy, dy, d->N, d->H, d->W, d->Cout, p.BW, p.BH, p.BN)) return r;
+    constexpr size_t smem = (size_t)STAGES * 32768 + 1024 + (2 * STAGES + 1) * 8 + 16;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(conv_wgrad_tc_kernel<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return cuda_status(e, "wgrad_tc smem attribute");
+        attr_set = true;
+    }
+    dim3 grid(tiles, tap_groups, splits);
+    conv_wgrad_tc_kernel<STAGES><<<grid, 128, smem, as_stream(stream)>>>(mx, mdy, p);
+    CTGAN_CHECK_LAUNCH("conv_wgrad_tc");
+    return 0;
+}
+
+extern "C" int ctgan_pack_filter_bf16(const float* w, void* wp, int taps, int Cin, int Cout, int transpose_flip, void* stream) {
+    CTGAN_REQUIRE(w && wp && taps > 0 && Cin > 0 && Cout > 0, CTGAN_ERR_BAD_DESC, "pack_filter_bf16: bad args");
+    int64_t total = (int64_t)taps * Cin * Cout;
+    pack_filter_kernel<<<elementwise_grid(total, 256), 256, 0, as_stream(stream)>>>(w, reinterpret_cast<__nv_bfloat16*>(wp), taps, Cin, Cout, transpose_flip);
+    CTGAN_CHECK_LAUNCH("pack_filter_bf16");
+    return 0;
+}

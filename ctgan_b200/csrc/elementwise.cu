@@ -1,0 +1,429 @@
+// elementwise.cu -- HBM-bound element-wise, data-movement and RNG kernels.
+//
+// All are grid-stride kernels moving 16 bytes per thread per access when the buffers
+// allow it (8 x bf16 / 4 x float), falling back to scalar accesses otherwise.  Grids are
+// capped at 8 CTAs per SM (common.cuh: elementwise_grid).
+#include "common.cuh"
+
+namespace ctgan {
+
+template <typename T, int V> struct alignas(sizeof(T) * V) Pack { T v[V]; };
+
+template <typename T> constexpr int vec_width() { return 16 / sizeof(T); }
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// ---- generic map kernels: out[i] = f(a[i]) / f(a[i], b[i]) -----------------
+template <typename T, int V, typename F>
+__global__ void map1_kernel(const T* __restrict__ a, T* __restrict__ out, int64_t nvec, F f) {
+    using P = Pack<T, V>;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+        P pa = reinterpret_cast<const P*>(a)[i], po;
+#pragma unroll
+        for (int j = 0; j < V; ++j) po.v[j] = from_f<T>(f(to_f<T>(pa.v[j])));
+        reinterpret_cast<P*>(out)[i] = po;
+    }
+}
+template <typename T, int V, typename F>
+__global__ void map2_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ out, int64_t nvec, F f) {
+    using P = Pack<T, V>;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+        P pa = reinterpret_cast<const P*>(a)[i], pb = reinterpret_cast<const P*>(b)[i], po;
+#pragma unroll
+        for (int j = 0; j < V; ++j) po.v[j] = from_f<T>(f(to_f<T>(pa.v[j]), to_f<T>(pb.v[j])));
+        reinterpret_cast<P*>(out)[i] = po;
+    }
+}
+
+template <typename T, typename F>
+static int launch_map1(const void* a, void* out, int64_t n, F f, cudaStream_t st, const char* what) {
+    if (n <= 0) return 0;
+    constexpr int V = vec_width<T>();
+    if (aligned16(a) && aligned16(out) && n % V == 0) {
+        int64_t nv = n / V;
+        map1_kernel<T, V, F><<<elementwise_grid(nv, 256), 256, 0, st>>>((const T*)a, (T*)out, nv, f);
+    } else {
+        map1_kernel<T, 1, F><<<elementwise_grid(n, 256), 256, 0, st>>>((const T*)a, (T*)out, n, f);
+    }
+    CTGAN_CHECK_LAUNCH(what);
+    return 0;
+}
+template <typename T, typename F>
+static int launch_map2(const void* a, const void* b, void* out, int64_t n, F f, cudaStream_t st, const char* what) {
+    if (n <= 0) return 0;
+    constexpr int V = vec_width<T>();
+    if (aligned16(a) && aligned16(b) && aligned16(out) && n % V == 0) {
+        int64_t nv = n / V;
+        map2_kernel<T, V, F><<<elementwise_grid(nv, 256), 256, 0, st>>>((const T*)a, (const T*)b, (T*)out, nv, f);
+    } else {
+        map2_kernel<T, 1, F><<<elementwise_grid(n, 256), 256, 0, st>>>((const T*)a, (const T*)b, (T*)out, n, f);
+    }
+    CTGAN_CHECK_LAUNCH(what);
+    return 0;
+}
+
+struct AddOp  { __device__ float operator()(float a, float b) const { return a + b; } };
+struct MulOp  { __device__ float operator()(float a, float b) const { return a * b; } };
+struct ScaleOp { float s; __device__ float operator()(float a) const { return a * s; } };
+struct TanhOp { __device__ float operator()(float a) const { return tanhf(a); } };
+struct SigmOp { __device__ float operator()(float a) const { return 1.f / (1.f + __expf(-a)); } };
+// backward given forward OUTPUT y and upstream dy
+struct TanhBwd { __device__ float operator()(float y, float dy) const { return dy * (1.f - y * y); } };
+struct SigmBwd { __device__ float operator()(float y, float dy) const { return dy * y * (1.f - y); } };
+
+// ---- cast --------------------------------------------------------------------
+template <typename TI, typename TO>
+__global__ void cast_kernel(const TI* __restrict__ x, TO* __restrict__ y, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        y[i] = from_f<TO>(to_f<TI>(x[i]));
+}
+
+// ---- fused activation + dropout ---------------------------------------------
+template <typename T, int V>
+__global__ void act_dropout_kernel(const T* __restrict__ x, const float* __restrict__ u, T* __restrict__ y,
+                                   T* __restrict__ m, int64_t nvec, float slope, float keep,
+                                   uint64_t seed, uint64_t offset) {
+    using P = Pack<T, V>;
+    const bool drop = keep < 1.f;
+    const float inv_keep = 1.f / keep;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+        P px = reinterpret_cast<const P*>(x)[i], py, pm;
+        uint32_t r[4];
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            float xv = to_f<T>(px.v[j]);
+            float mult = xv > 0.f ? 1.f : slope;
+            if (drop) {
+                int64_t e = i * V + j;
+                float uu;
+                if (u) {
+                    uu = u[e];
+                } else {
+                    uint64_t se = offset + (uint64_t)e;
+                    // offset is required to be a multiple of 4 when V > 1, so lanes j&3 share a block
+                    if (V == 1 || (j & 3) == 0) Philox::block(seed, se >> 2, r);
+                    uu = Philox::to_uniform(r[se & 3]);
+                }
+                mult *= floorf(keep + uu) * inv_keep;
+            }
+            pm.v[j] = from_f<T>(mult);
+            // multiply by the ROUNDED multiplier so that y == x * m holds exactly for the saved m
+            py.v[j] = from_f<T>(xv * to_f<T>(pm.v[j]));
+        }
+        reinterpret_cast<P*>(y)[i] = py;
+        if (m) reinterpret_cast<P*>(m)[i] = pm;
+    }
+}
+
+// ---- pooling / upsampling on NHWC --------------------------------------------
+template <typename T>
+__global__ void pool2x2_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H, int W, int C, float scale) {
+    const int Ho = H / 2, Wo = W / 2;
+    int64_t total = (int64_t)N * Ho * Wo * C;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int c = i % C; int64_t t = i / C;
+        int wo = t % Wo; t /= Wo;
+        int ho = t % Ho; int n = t / Ho;
+        const T* p = x + (((int64_t)n * H + 2 * ho) * W + 2 * wo) * C + c;
+        float s = to_f<T>(p[0]) + to_f<T>(p[(int64_t)W * C]) + to_f<T>(p[C]) + to_f<T>(p[(int64_t)W * C + C]);
+        y[i] = from_f<T>(s * scale);
+    }
+}
+template <typename T>
+__global__ void upsample2x_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H, int W, int C, float scale) {
+    const int Ho = 2 * H, Wo = 2 * W;
+    int64_t total = (int64_t)N * Ho * Wo * C;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int c = i % C; int64_t t = i / C;
+        int wo = t % Wo; t /= Wo;
+        int ho = t % Ho; int n = t / Ho;
+        float v = to_f<T>(x[(((int64_t)n * H + ho / 2) * W + wo / 2) * C + c]);
+        y[i] = from_f<T>(v * scale);
+    }
+}
+template <typename T>
+__global__ void spatial_sum_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int HW, int C, float scale) {
+    int64_t total = (int64_t)N * C;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int c = i % C; int n = i / C;
+        const T* p = x + (int64_t)n * HW * C + c;
+        float s = 0.f;
+        for (int j = 0; j < HW; ++j) s += to_f<T>(p[(int64_t)j * C]);
+        y[i] = from_f<T>(s * scale);
+    }
+}
+template <typename T>
+__global__ void spatial_bcast_kernel(const T* __restrict__ y, T* __restrict__ x, int N, int HW, int C, float scale) {
+    int64_t total = (int64_t)N * HW * C;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int c = i % C; int n = i / ((int64_t)HW * C);
+        x[i] = from_f<T>(to_f<T>(y[(int64_t)n * C + c]) * scale);
+    }
+}
+
+// ---- layout ----------------------------------------------------------------
+// Both directions index by the OUTPUT element; the 1/3-channel image tensors they are
+// used on are tiny, so no smem transpose.
+__global__ void nchw_to_nhwc_kernel(const void* __restrict__ x, int xdt, void* __restrict__ y, int ydt,
+                                    int N, int C, int H, int W) {
+    int64_t total = (int64_t)N * C * H * W;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int c = i % C; int64_t t = i / C;
+        int w = t % W; t /= W;
+        int h = t % H; int n = t / H;
+        st_act(y, i, ydt, ld_act(x, (((int64_t)n * C + c) * H + h) * W + w, xdt));
+    }
+}
+__global__ void nhwc_to_nchw_kernel(const void* __restrict__ x, int xdt, void* __restrict__ y, int ydt,
+                                    int N, int C, int H, int W) {
+    int64_t total = (int64_t)N * C * H * W;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int w = i % W; int64_t t = i / W;
+        int h = t % H; t /= H;
+        int c = t % C; int n = t / C;
+        st_act(y, i, ydt, ld_act(x, (((int64_t)n * H + h) * W + w) * C + c, xdt));
+    }
+}
+template <typename T>
+__global__ void crop_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H, int W, int C, int h, int w, int fwd) {
+    // fwd: y[N,h,w,C] = x[N,:h,:w,C];  !fwd: y is [N,H,W,C] zero-padded copy of x[N,h,w,C]
+    int64_t total = fwd ? (int64_t)N * h * w * C : (int64_t)N * H * W * C;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int c = i % C; int64_t t = i / C;
+        if (fwd) {
+            int ww = t % w; t /= w;
+            int hh = t % h; int n = t / h;
+            y[i] = x[(((int64_t)n * H + hh) * W + ww) * C + c];
+        } else {
+            int ww = t % W; t /= W;
+            int hh = t % H; int n = t / H;
+            y[i] = (hh < h && ww < w) ? x[(((int64_t)n * h + hh) * w + ww) * C + c] : from_f<T>(0.f);
+        }
+    }
+}
+
+__global__ void prep_real_kernel(const int32_t* __restrict__ x, float* __restrict__ y, int64_t n, float inv_denom,
+                                 float noise_hi, uint64_t seed, uint64_t offset) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        float v = 2.f * ((float)x[i] * inv_denom - 0.5f);
+        if (noise_hi > 0.f) v += noise_hi * Philox::uniform_at(seed, offset + (uint64_t)i);
+        y[i] = v;
+    }
+}
+__global__ void prep_real_div_kernel(const int32_t* __restrict__ x, float* __restrict__ y, int64_t n, float denom,
+                                     float noise_hi, uint64_t seed, uint64_t offset) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        float v = 2.f * (__fdiv_rn((float)x[i], denom) - 0.5f);       // true division: /255 is not exact as a multiply
+        if (noise_hi > 0.f) v += noise_hi * Philox::uniform_at(seed, offset + (uint64_t)i);
+        y[i] = v;
+    }
+}
+__global__ void interpolate_kernel(const float* __restrict__ real, const float* __restrict__ fake,
+                                   const float* __restrict__ alpha, float* __restrict__ out, int B, int P) {
+    int64_t total = (int64_t)B * P;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int b = i / P;
+        float r = real[i];
+        out[i] = r + alpha[b] * (fake[i] - r);
+    }
+}
+
+// ---- RNG ---------------------------------------------------------------------
+__global__ void philox_uniform_kernel(float* __restrict__ out, int64_t n, float lo, float hi, uint64_t seed, uint64_t offset) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = lo + (hi - lo) * Philox::uniform_at(seed, offset + (uint64_t)i);
+}
+__global__ void philox_normal_kernel(float* __restrict__ out, int64_t n, uint64_t seed, uint64_t offset) {
+    // element i uses stream elements (2i, 2i+1): Box-Muller, cosine branch only
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        uint64_t e = offset + 2ull * (uint64_t)i;
+        float u1 = Philox::uniform_at(seed, e), u2 = Philox::uniform_at(seed, e + 1);
+        u1 = fmaxf(u1, 5.9604645e-8f);                                   // avoid log(0)
+        out[i] = sqrtf(-2.f * logf(u1)) * cospif(2.f * u2);
+    }
+}
+__global__ void philox_labels_kernel(int32_t* __restrict__ out, int64_t n, int n_labels, uint64_t seed, uint64_t offset) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = (int32_t)(Philox::uniform_at(seed, offset + (uint64_t)i) * (float)n_labels);
+}
+
+}  // namespace ctgan
+
+using namespace ctgan;
+
+#define DISPATCH_T(dtype, CALL_F32, CALL_BF16)                                  \
+    do {                                                                        \
+        if ((dtype) == CTGAN_F32) { CALL_F32; }                                 \
+        else if ((dtype) == CTGAN_BF16) { CALL_BF16; }                          \
+        else { set_error("bad dtype %d", (int)(dtype)); return CTGAN_ERR_BAD_DESC; } \
+    } while (0)
+
+extern "C" int ctgan_add(const void* a, const void* b, void* out, int64_t n, int dtype, void* stream) {
+    DISPATCH_T(dtype, return launch_map2<float>(a, b, out, n, AddOp{}, as_stream(stream), "add"),
+                      return launch_map2<__nv_bfloat16>(a, b, out, n, AddOp{}, as_stream(stream), "add"));
+}
+extern "C" int ctgan_mul(const void* a, const void* b, void* out, int64_t n, int dtype, void* stream) {
+    DISPATCH_T(dtype, return launch_map2<float>(a, b, out, n, MulOp{}, as_stream(stream), "mul"),
+                      return launch_map2<__nv_bfloat16>(a, b, out, n, MulOp{}, as_stream(stream), "mul"));
+}
+extern "C" int ctgan_scale(const void* a, float s, void* out, int64_t n, int dtype, void* stream) {
+    DISPATCH_T(dtype, return launch_map1<float>(a, out, n, ScaleOp{s}, as_stream(stream), "scale"),
+                      return launch_map1<__nv_bfloat16>(a, out, n, ScaleOp{s}, as_stream(stream), "scale"));
+}
+extern "C" int ctgan_unary_fwd(const void* x, void* y, int64_t n, int dtype, int kind, void* stream) {
+    CTGAN_REQUIRE(kind == 0 || kind == 1, CTGAN_ERR_BAD_DESC, "unary_fwd: kind must be 0 (tanh) or 1 (sigmoid)");
+    cudaStream_t st = as_stream(stream);
+    if (kind == 0)
+        DISPATCH_T(dtype, return launch_map1<float>(x, y, n, TanhOp{}, st, "tanh"),
+                          return launch_map1<__nv_bfloat16>(x, y, n, TanhOp{}, st, "tanh"));
+    DISPATCH_T(dtype, return launch_map1<float>(x, y, n, SigmOp{}, st, "sigmoid"),
+                      return launch_map1<__nv_bfloat16>(x, y, n, SigmOp{}, st, "sigmoid"));
+}
+extern "C" int ctgan_unary_bwd(const void* y, const void* dy, void* dx, int64_t n, int dtype, int kind, void* stream) {
+    CTGAN_REQUIRE(kind == 0 || kind == 1, CTGAN_ERR_BAD_DESC, "unary_bwd: kind must be 0 (tanh) or 1 (sigmoid)");
+    cudaStream_t st = as_stream(stream);
+    if (kind == 0)
+        DISPATCH_T(dtype, return launch_map2<float>(y, dy, dx, n, TanhBwd{}, st, "tanh_bwd"),
+                          return launch_map2<__nv_bfloat16>(y, dy, dx, n, TanhBwd{}, st, "tanh_bwd"));
+    DISPATCH_T(dtype, return launch_map2<float>(y, dy, dx, n, SigmBwd{}, st, "sigmoid_bwd"),
+                      return launch_map2<__nv_bfloat16>(y, dy, dx, n, SigmBwd{}, st, "sigmoid_bwd"));
+}
+
+extern "C" int ctgan_cast(const void* x, int xdt, void* y, int ydt, int64_t n, void* stream) {
+    CTGAN_REQUIRE(dtype_ok(xdt) && dtype_ok(ydt), CTGAN_ERR_BAD_DESC, "cast: bad dtype");
+    if (n <= 0) return 0;
+    cudaStream_t st = as_stream(stream);
+    int grid = elementwise_grid(n, 256);
+    if (xdt == CTGAN_F32 && ydt == CTGAN_BF16) cast_kernel<float, __nv_bfloat16><<<grid, 256, 0, st>>>((const float*)x, (__nv_bfloat16*)y, n);
+    else if (xdt == CTGAN_BF16 && ydt == CTGAN_F32) cast_kernel<__nv_bfloat16, float><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, (float*)y, n);
+    else if (xdt == CTGAN_F32) cast_kernel<float, float><<<grid, 256, 0, st>>>((const float*)x, (float*)y, n);
+    else cast_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, n);
+    CTGAN_CHECK_LAUNCH("cast");
+    return 0;
+}
+
+template <typename T>
+static int launch_act_dropout(const void* x, const float* u, void* y, void* m, int64_t n, float slope, float keep,
+                              uint64_t seed, uint64_t offset, cudaStream_t st) {
+    constexpr int V = vec_width<T>();
+    bool vec = aligned16(x) && aligned16(y) && (m == nullptr || aligned16(m)) && n % V == 0 && (offset & 3) == 0;
+    if (vec) {
+        int64_t nv = n / V;
+        act_dropout_kernel<T, V><<<elementwise_grid(nv, 256), 256, 0, st>>>((const T*)x, u, (T*)y, (T*)m, nv, slope, keep, seed, offset);
+    } else {
+        act_dropout_kernel<T, 1><<<elementwise_grid(n, 256), 256, 0, st>>>((const T*)x, u, (T*)y, (T*)m, n, slope, keep, seed, offset);
+    }
+    CTGAN_CHECK_LAUNCH("act_dropout_fwd");
+    return 0;
+}
+extern "C" int ctgan_act_dropout_fwd(const void* x, const float* u, void* y, void* m, int64_t n, int dtype,
+                                     float slope, float keep, uint64_t seed, uint64_t offset, void* stream) {
+    CTGAN_REQUIRE(keep > 0.f && keep <= 1.f, CTGAN_ERR_BAD_DESC, "act_dropout_fwd: keep must be in (0,1]");
+    if (n <= 0) return 0;
+    DISPATCH_T(dtype, return launch_act_dropout<float>(x, u, y, m, n, slope, keep, seed, offset, as_stream(stream)),
+                      return launch_act_dropout<__nv_bfloat16>(x, u, y, m, n, slope, keep, seed, offset, as_stream(stream)));
+}
+
+extern "C" int ctgan_pool2x2(const void* x, void* y, int N, int H, int W, int C, float scale, int dtype, void* stream) {
+    CTGAN_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && H % 2 == 0 && W % 2 == 0, CTGAN_ERR_BAD_DESC, "pool2x2: H and W must be even and positive");
+    int64_t total = (int64_t)N * (H / 2) * (W / 2) * C;
+    int grid = elementwise_grid(total, 256);
+    cudaStream_t st = as_stream(stream);
+    DISPATCH_T(dtype, (pool2x2_kernel<float><<<grid, 256, 0, st>>>((const float*)x, (float*)y, N, H, W, C, scale)),
+                      (pool2x2_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, N, H, W, C, scale)));
+    CTGAN_CHECK_LAUNCH("pool2x2");
+    return 0;
+}
+extern "C" int ctgan_upsample2x(const void* x, void* y, int N, int H, int W, int C, float scale, int dtype, void* stream) {
+    CTGAN_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0, CTGAN_ERR_BAD_DESC, "upsample2x: bad shape");
+    int64_t total = (int64_t)N * H * W * C * 4;
+    int grid = elementwise_grid(total, 256);
+    cudaStream_t st = as_stream(stream);
+    DISPATCH_T(dtype, (upsample2x_kernel<float><<<grid, 256, 0, st>>>((const float*)x, (float*)y, N, H, W, C, scale)),
+                      (upsample2x_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, N, H, W, C, scale)));
+    CTGAN_CHECK_LAUNCH("upsample2x");
+    return 0;
+}
+extern "C" int ctgan_spatial_sum(const void* x, void* y, int N, int HW, int C, float scale, int dtype, void* stream) {
+    CTGAN_REQUIRE(N > 0 && HW > 0 && C > 0, CTGAN_ERR_BAD_DESC, "spatial_sum: bad shape");
+    int grid = elementwise_grid((int64_t)N * C, 128);
+    cudaStream_t st = as_stream(stream);
+    DISPATCH_T(dtype, (spatial_sum_kernel<float><<<grid, 128, 0, st>>>((const float*)x, (float*)y, N, HW, C, scale)),
+                      (spatial_sum_kernel<__nv_bfloat16><<<grid, 128, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, N, HW, C, scale)));
+    CTGAN_CHECK_LAUNCH("spatial_sum");
+    return 0;
+}
+extern "C" int ctgan_spatial_bcast(const void* y, void* x, int N, int HW, int C, float scale, int dtype, void* stream) {
+    CTGAN_REQUIRE(N > 0 && HW > 0 && C > 0, CTGAN_ERR_BAD_DESC, "spatial_bcast: bad shape");
+    int grid = elementwise_grid((int64_t)N * HW * C, 256);
+    cudaStream_t st = as_stream(stream);
+    DISPATCH_T(dtype, (spatial_bcast_kernel<float><<<grid, 256, 0, st>>>((const float*)y, (float*)x, N, HW, C, scale)),
+                      (spatial_bcast_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)y, (__nv_bfloat16*)x, N, HW, C, scale)));
+    CTGAN_CHECK_LAUNCH("spatial_bcast");
+    return 0;
+}
+
+extern "C" int ctgan_nchw_to_nhwc(const void* x, int xdt, void* y, int ydt, int N, int C, int H, int W, void* stream) {
+    CTGAN_REQUIRE(dtype_ok(xdt) && dtype_ok(ydt) && N > 0 && C > 0 && H > 0 && W > 0, CTGAN_ERR_BAD_DESC, "nchw_to_nhwc: bad args");
+    nchw_to_nhwc_kernel<<<elementwise_grid((int64_t)N * C * H * W, 256), 256, 0, as_stream(stream)>>>(x, xdt, y, ydt, N, C, H, W);
+    CTGAN_CHECK_LAUNCH("nchw_to_nhwc");
+    return 0;
+}
+extern "C" int ctgan_nhwc_to_nchw(const void* x, int xdt, void* y, int ydt, int N, int C, int H, int W, void* stream) {
+    CTGAN_REQUIRE(dtype_ok(xdt) && dtype_ok(ydt) && N > 0 && C > 0 && H > 0 && W > 0, CTGAN_ERR_BAD_DESC, "nhwc_to_nchw: bad args");
+    nhwc_to_nchw_kernel<<<elementwise_grid((int64_t)N * C * H * W, 256), 256, 0, as_stream(stream)>>>(x, xdt, y, ydt, N, C, H, W);
+    CTGAN_CHECK_LAUNCH("nhwc_to_nchw");
+    return 0;
+}
+static int crop_impl(const void* x, void* y, int N, int H, int W, int C, int h, int w, int dtype, int fwd, void* stream) {
+    CTGAN_REQUIRE(N > 0 && C > 0 && h > 0 && w > 0 && h <= H && w <= W, CTGAN_ERR_BAD_DESC, "crop: bad shape");
+    int64_t total = fwd ? (int64_t)N * h * w * C : (int64_t)N * H * W * C;
+    int grid = elementwise_grid(total, 256);
+    cudaStream_t st = as_stream(stream);
+    DISPATCH_T(dtype, (crop_kernel<float><<<grid, 256, 0, st>>>((const float*)x, (float*)y, N, H, W, C, h, w, fwd)),
+                      (crop_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, N, H, W, C, h, w, fwd)));
+    CTGAN_CHECK_LAUNCH("crop");
+    return 0;
+}
+extern "C" int ctgan_crop(const void* x, void* y, int N, int H, int W, int C, int h, int w, int dtype, void* stream) {
+    return crop_impl(x, y, N, H, W, C, h, w, dtype, 1, stream);
+}
+extern "C" int ctgan_crop_bwd(const void* dy, void* dx, int N, int H, int W, int C, int h, int w, int dtype, void* stream) {
+    return crop_impl(dy, dx, N, H, W, C, h, w, dtype, 0, stream);
+}
+
+extern "C" int ctgan_prep_real(const int32_t* x, float* y, int64_t n, float denom, float noise_hi,
+                               uint64_t seed, uint64_t offset, void* stream) {
+    CTGAN_REQUIRE(denom > 0.f, CTGAN_ERR_BAD_DESC, "prep_real: denom must be positive");
+    if (n <= 0) return 0;
+    prep_real_div_kernel<<<elementwise_grid(n, 256), 256, 0, as_stream(stream)>>>(x, y, n, denom, noise_hi, seed, offset);
+    CTGAN_CHECK_LAUNCH("prep_real");
+    return 0;
+}
+extern "C" int ctgan_interpolate(const float* real, const float* fake, const float* alpha, float* out,
+                                 int B, int P, void* stream) {
+    CTGAN_REQUIRE(B > 0 && P > 0, CTGAN_ERR_BAD_DESC, "interpolate: bad shape");
+    interpolate_kernel<<<elementwise_grid((int64_t)B * P, 256), 256, 0, as_stream(stream)>>>(real, fake, alpha, out, B, P);
+    CTGAN_CHECK_LAUNCH("interpolate");
+    return 0;
+}
+
+extern "C" int ctgan_philox_uniform(float* out, int64_t n, float lo, float hi, uint64_t seed, uint64_t offset, void* stream) {
+    if (n <= 0) return 0;
+    philox_uniform_kernel<<<elementwise_grid(n, 256), 256, 0, as_stream(stream)>>>(out, n, lo, hi, seed, offset);
+    CTGAN_CHECK_LAUNCH("philox_uniform");
+    return 0;
+}
+extern "C" int ctgan_philox_normal(float* out, int64_t n, uint64_t seed, uint64_t offset, void* stream) {
+    if (n <= 0) return 0;
+    philox_normal_kernel<<<elementwise_grid(n, 256), 256, 0, as_stream(stream)>>>(out, n, seed, offset);
+    CTGAN_CHECK_LAUNCH("philox_normal");
+    return 0;
+}
+extern "C" int ctgan_philox_labels(int32_t* out, int64_t n, int n_labels, uint64_t seed, uint64_t offset, void* stream) {
+    CTGAN_REQUIRE(n_labels > 0, CTGAN_ERR_BAD_DESC, "philox_labels: n_labels must be positive");
+    if (n <= 0) return 0;
+    philox_labels_kernel<<<elementwise_grid(n, 256), 256, 0, as_stream(stream)>>>(out, n, n_labels, seed, offset);
+    CTGAN_CHECK_LAUNCH("philox_labels");
+    return 0;
+}

@@ -1,0 +1,362 @@
+// norm.cu -- training-mode batch norm (+ per-label gamma/beta gather, + fused ReLU) and
+// the bias-gradient column reduction.  HBM-bound: forward reads x twice (stats, apply) and
+// writes y once; backward reads dy,x(,y) twice and writes dx once.
+//
+// Replaces tf.nn.fused_batch_norm (TG/tflib/ops/batchnorm.py:29-30), tf.nn.moments +
+// tf.nn.batch_normalization (batchnorm.py:77-84, cond_batchnorm.py:10-16) and the
+// following tf.nn.relu (TG/CT_gan_cifar_resnet.py:135,138,164; TG/CT_gan_cifar.py:64,69,73).
+#include "common.cuh"
+
+namespace ctgan {
+
+constexpr int BN_LANES = 32;   // threads along channels, each owning 4 consecutive channels
+constexpr int BN_ROWS  = 8;    // threads along rows
+constexpr int BN_CCH   = BN_LANES * 4;   // channels per CTA
+
+static inline int bn_fwd_rowblocks(int64_t R) {
+    int64_t nb = (R + 63) / 64;
+    if (nb > 512) nb = 512;
+    if (nb < 1) nb = 1;
+    return (int)nb;
+}
+static inline int bn_bwd_splits(int HW) {
+    int s = HW / 64;
+    if (s < 1) s = 1;
+    if (s > 16) s = 16;
+    return s;
+}
+
+template <typename T>
+__device__ __forceinline__ void load4(const T* p, float (&v)[4]);
+template <> __device__ __forceinline__ void load4<float>(const float* p, float (&v)[4]) {
+    float4 t = *reinterpret_cast<const float4*>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+template <> __device__ __forceinline__ void load4<__nv_bfloat16>(const __nv_bfloat16* p, float (&v)[4]) {
+    uint2 t = *reinterpret_cast<const uint2*>(p);
+    __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&t.x), b = *reinterpret_cast<__nv_bfloat162*>(&t.y);
+    v[0] = __bfloat162float(a.x); v[1] = __bfloat162float(a.y); v[2] = __bfloat162float(b.x); v[3] = __bfloat162float(b.y);
+}
+template <typename T>
+__device__ __forceinline__ void store4(T* p, const float (&v)[4]);
+template <> __device__ __forceinline__ void store4<float>(float* p, const float (&v)[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+template <> __device__ __forceinline__ void store4<__nv_bfloat16>(__nv_bfloat16* p, const float (&v)[4]) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+    uint2 t;
+    t.x = *reinterpret_cast<uint32_t*>(&a); t.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(p) = t;
+}
+
+// ---- forward stage 1: per-(row block, channel) Welford partials ----------------
+// ws[(rb*C + c)*2 + {0,1}] = {mean, M2} over the rows of row block rb.
+template <typename T>
+__global__ void __launch_bounds__(BN_LANES * BN_ROWS)
+bn_stats_kernel(const T* __restrict__ x, float* __restrict__ ws, int64_t R, int C, int rows_per_block) {
+    const int lane = threadIdx.x, ry = threadIdx.y;
+    const int c = blockIdx.y * BN_CCH + lane * 4;
+    const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+    const int64_t r1 = min(R, r0 + rows_per_block);
+    float cnt = 0.f, mean[4] = {0, 0, 0, 0}, m2[4] = {0, 0, 0, 0};
+    if (c < C) {
+        for (int64_t r = r0 + ry; r < r1; r += BN_ROWS) {
+            float v[4];
+            load4<T>(x + r * C + c, v);
+            cnt += 1.f;
+            float inv = 1.f / cnt;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float d = v[j] - mean[j];
+                mean[j] += d * inv;
+                m2[j] += d * (v[j] - mean[j]);
+            }
+        }
+    }
+    __shared__ float s_cnt[BN_ROWS][BN_LANES];
+    __shared__ float s_mean[BN_ROWS][BN_LANES][4];
+    __shared__ float s_m2[BN_ROWS][BN_LANES][4];
+    s_cnt[ry][lane] = cnt;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { s_mean[ry][lane][j] = mean[j]; s_m2[ry][lane][j] = m2[j]; }
+    __syncthreads();
+    if (ry == 0 && c < C) {
+        for (int k = 1; k < BN_ROWS; ++k) {
+            float nb = s_cnt[k][lane];
+            if (nb == 0.f) continue;
+            float n = cnt + nb;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float d = s_mean[k][lane][j] - mean[j];
+                mean[j] += d * (nb / n);
+                m2[j] += s_m2[k][lane][j] + d * d * (cnt * nb / n);
+            }
+            cnt = n;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            ws[((int64_t)blockIdx.x * C + c + j) * 2 + 0] = mean[j];
+            ws[((int64_t)blockIdx.x * C + c + j) * 2 + 1] = m2[j];
+        }
+    }
+}
+
+// ---- forward stage 2: merge the row-block partials (Chan), biased variance --------
+__global__ void bn_finalize_kernel(const float* __restrict__ ws, float* __restrict__ save_mean,
+                                   float* __restrict__ save_invstd, int64_t R, int C, int nb,
+                                   int rows_per_block, float eps) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float cnt = 0.f, mean = 0.f, m2 = 0.f;
+    for (int b = 0; b < nb; ++b) {
+        int64_t r0 = (int64_t)b * rows_per_block;
+        float nbc = (float)(min(R, r0 + rows_per_block) - r0);
+        if (nbc <= 0.f) break;
+        float mb = ws[((int64_t)b * C + c) * 2], m2b = ws[((int64_t)b * C + c) * 2 + 1];
+        float n = cnt + nbc;
+        float d = mb - mean;
+        mean += d * (nbc / n);
+        m2 += m2b + d * d * (cnt * nbc / n);
+        cnt = n;
+    }
+    save_mean[c] = mean;
+    save_invstd[c] = rsqrtf(m2 / (float)R + eps);
+}
+
+// ---- forward stage 3: normalise, affine (per-label rows), optional ReLU -------------
+template <typename T>
+__global__ void bn_apply_kernel(const T* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                const int32_t* __restrict__ labels, const float* __restrict__ mean,
+                                const float* __restrict__ invstd, T* __restrict__ y,
+                                int64_t R, int HW, int C, int relu) {
+    const int C4 = C / 4;
+    int64_t total = R * C4;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int c = (int)(i % C4) * 4;
+        int64_t r = i / C4;
+        int n = (int)(r / HW);
+        int l = labels ? labels[n] : 0;
+        float v[4], o[4];
+        load4<T>(x + r * C + c, v);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float xh = (v[j] - mean[c + j]) * invstd[c + j];
+            float t = xh * gamma[(int64_t)l * C + c + j] + beta[(int64_t)l * C + c + j];
+            o[j] = relu ? fmaxf(t, 0.f) : t;
+        }
+        store4<T>(y + r * C + c, o);
+    }
+}
+
+// ---- backward stage 1: per-(sample, hw split, channel) sums of dy and dy*xhat ---------
+// ws[((n*S + s)*C + c)*2 + {0,1}]
+template <typename T>
+__global__ void __launch_bounds__(BN_LANES * BN_ROWS)
+bn_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ y,
+                     const float* __restrict__ mean, const float* __restrict__ invstd, float* __restrict__ ws,
+                     int HW, int C, int S, int relu) {
+    const int lane = threadIdx.x, ry = threadIdx.y;
+    const int c = blockIdx.y * BN_CCH + lane * 4;
+    const int n = blockIdx.x / S, s = blockIdx.x % S;
+    const int per = (HW + S - 1) / S;
+    const int h0 = s * per, h1 = min(HW, h0 + per);
+    float s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+    if (c < C) {
+        float mu[4], is[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { mu[j] = mean[c + j]; is[j] = invstd[c + j]; }
+        for (int h = h0 + ry; h < h1; h += BN_ROWS) {
+            int64_t off = ((int64_t)n * HW + h) * C + c;
+            float g[4], v[4];
+            load4<T>(dy + off, g);
+            load4<T>(x + off, v);
+            if (relu) {
+                float o[4];
+                load4<T>(y + off, o);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) g[j] = o[j] > 0.f ? g[j] : 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { s1[j] += g[j]; s2[j] += g[j] * (v[j] - mu[j]) * is[j]; }
+        }
+    }
+    __shared__ float sh1[BN_ROWS][BN_LANES][4];
+    __shared__ float sh2[BN_ROWS][BN_LANES][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { sh1[ry][lane][j] = s1[j]; sh2[ry][lane][j] = s2[j]; }
+    __syncthreads();
+    if (ry == 0 && c < C) {
+        for (int k = 1; k < BN_ROWS; ++k)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { s1[j] += sh1[k][lane][j]; s2[j] += sh2[k][lane][j]; }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            ws[((int64_t)blockIdx.x * C + c + j) * 2 + 0] = s1[j];
+            ws[((int64_t)blockIdx.x * C + c + j) * 2 + 1] = s2[j];
+        }
+    }
+}
+
+// ---- backward stage 2: per channel: table gradients + the two means BN needs ----------
+// coef[c] = mean_R(gamma_l * dy), coef[C + c] = mean_R(gamma_l * dy * xhat)
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ ws, const float* __restrict__ gamma,
+                                       const int32_t* __restrict__ labels, float* __restrict__ dgamma,
+                                       float* __restrict__ dbeta, float* __restrict__ coef,
+                                       int N, int S, int C, int n_labels, float inv_R) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    for (int l = 0; l < n_labels; ++l) { dgamma[(int64_t)l * C + c] = 0.f; dbeta[(int64_t)l * C + c] = 0.f; }
+    float a1 = 0.f, a2 = 0.f;
+    for (int n = 0; n < N; ++n) {
+        int l = labels ? labels[n] : 0;
+        float t1 = 0.f, t2 = 0.f;
+        for (int s = 0; s < S; ++s) {
+            t1 += ws[(((int64_t)n * S + s) * C + c) * 2];
+            t2 += ws[(((int64_t)n * S + s) * C + c) * 2 + 1];
+        }
+        float g = gamma[(int64_t)l * C + c];
+        a1 += g * t1; a2 += g * t2;
+        dbeta[(int64_t)l * C + c] += t1;
+        dgamma[(int64_t)l * C + c] += t2;
+    }
+    coef[c] = a1 * inv_R;
+    coef[C + c] = a2 * inv_R;
+}
+
+// ---- backward stage 3: dx = invstd * (gamma_l*dy - mean(.) - xhat*mean(. xhat)) ----------
+template <typename T>
+__global__ void bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ y,
+                                    const float* __restrict__ gamma, const int32_t* __restrict__ labels,
+                                    const float* __restrict__ mean, const float* __restrict__ invstd,
+                                    const float* __restrict__ coef, T* __restrict__ dx,
+                                    int64_t R, int HW, int C, int relu) {
+    const int C4 = C / 4;
+    int64_t total = R * C4;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int c = (int)(i % C4) * 4;
+        int64_t r = i / C4;
+        int n = (int)(r / HW);
+        int l = labels ? labels[n] : 0;
+        float g[4], v[4], o[4];
+        load4<T>(dy + r * C + c, g);
+        load4<T>(x + r * C + c, v);
+        if (relu) {
+            float yo[4];
+            load4<T>(y + r * C + c, yo);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) g[j] = yo[j] > 0.f ? g[j] : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float is = invstd[c + j];
+            float xh = (v[j] - mean[c + j]) * is;
+            o[j] = is * (gamma[(int64_t)l * C + c + j] * g[j] - coef[c + j] - xh * coef[C + c + j]);
+        }
+        store4<T>(dx + r * C + c, o);
+    }
+}
+
+// ---- bias gradient: column sums -------------------------------------------------
+__global__ void __launch_bounds__(256)
+bias_grad_kernel(const void* __restrict__ dy, float* __restrict__ db, int64_t rows, int C, int dt, int rows_per_block) {
+    // blockDim = (32 channel lanes, 8 row lanes); one channel per lane
+    const int lane = threadIdx.x, ry = threadIdx.y;
+    const int c = blockIdx.y * 32 + lane;
+    const int64_t r0 = (int64_t)blockIdx.x * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+    float s = 0.f;
+    if (c < C)
+        for (int64_t r = r0 + ry; r < r1; r += 8) s += ld_act(dy, r * C + c, dt);
+    __shared__ float sh[8][33];
+    sh[ry][lane] = s;
+    __syncthreads();
+    if (ry == 0 && c < C) {
+        for (int k = 1; k < 8; ++k) s += sh[k][lane];
+        atomicAdd(db + c, s);
+    }
+}
+
+}  // namespace ctgan
+
+using namespace ctgan;
+
+extern "C" int64_t ctgan_bn_workspace_floats(int N, int HW, int C) {
+    int64_t R = (int64_t)N * HW;
+    int64_t fwd = (int64_t)bn_fwd_rowblocks(R) * C * 2;
+    int64_t bwd = (int64_t)N * bn_bwd_splits(HW) * C * 2 + 2 * (int64_t)C;
+    return fwd > bwd ? fwd : bwd;
+}
+
+extern "C" int ctgan_bn_fwd(const void* x, const float* gamma, const float* beta, const int32_t* labels,
+                            void* y, float* save_mean, float* save_invstd, float* ws,
+                            int N, int HW, int C, float eps, int relu, int dtype, void* stream) {
+    CTGAN_REQUIRE(N > 0 && HW > 0 && C > 0 && C % 4 == 0, CTGAN_ERR_UNSUPPORTED, "bn_fwd: C must be a positive multiple of 4");
+    CTGAN_REQUIRE(x && gamma && beta && y && save_mean && save_invstd && ws, CTGAN_ERR_BAD_DESC, "bn_fwd: null pointer");
+    CTGAN_REQUIRE(dtype_ok(dtype), CTGAN_ERR_BAD_DESC, "bn_fwd: bad dtype");
+    cudaStream_t st = as_stream(stream);
+    int64_t R = (int64_t)N * HW;
+    int nb = bn_fwd_rowblocks(R);
+    int rpb = (int)((R + nb - 1) / nb);
+    nb = (int)((R + rpb - 1) / rpb);
+    dim3 blk(BN_LANES, BN_ROWS), grid(nb, ceil_div(C, BN_CCH));
+    if (dtype == CTGAN_F32) bn_stats_kernel<float><<<grid, blk, 0, st>>>((const float*)x, ws, R, C, rpb);
+    else bn_stats_kernel<__nv_bfloat16><<<grid, blk, 0, st>>>((const __nv_bfloat16*)x, ws, R, C, rpb);
+    CTGAN_CHECK_LAUNCH("bn_stats");
+    bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, st>>>(ws, save_mean, save_invstd, R, C, nb, rpb, eps);
+    CTGAN_CHECK_LAUNCH("bn_finalize");
+    int g2 = elementwise_grid(R * (C / 4), 256);
+    if (dtype == CTGAN_F32)
+        bn_apply_kernel<float><<<g2, 256, 0, st>>>((const float*)x, gamma, beta, labels, save_mean, save_invstd, (float*)y, R, HW, C, relu);
+    else
+        bn_apply_kernel<__nv_bfloat16><<<g2, 256, 0, st>>>((const __nv_bfloat16*)x, gamma, beta, labels, save_mean, save_invstd, (__nv_bfloat16*)y, R, HW, C, relu);
+    CTGAN_CHECK_LAUNCH("bn_apply");
+    return 0;
+}
+
+extern "C" int ctgan_bn_bwd(const void* dy, const void* x, const void* y, const float* gamma,
+                            const int32_t* labels, const float* save_mean, const float* save_invstd,
+                            void* dx, float* dgamma, float* dbeta, float* ws,
+                            int N, int HW, int C, int n_labels, int relu, int dtype, void* stream) {
+    CTGAN_REQUIRE(N > 0 && HW > 0 && C > 0 && C % 4 == 0 && n_labels > 0, CTGAN_ERR_UNSUPPORTED, "bn_bwd: C must be a positive multiple of 4");
+    CTGAN_REQUIRE(dy && x && gamma && save_mean && save_invstd && dx && dgamma && dbeta && ws && (!relu || y),
+                  CTGAN_ERR_BAD_DESC, "bn_bwd: null pointer");
+    CTGAN_REQUIRE(dtype_ok(dtype), CTGAN_ERR_BAD_DESC, "bn_bwd: bad dtype");
+    cudaStream_t st = as_stream(stream);
+    int64_t R = (int64_t)N * HW;
+    int S = bn_bwd_splits(HW);
+    float* coef = ws + (int64_t)N * S * C * 2;
+    dim3 blk(BN_LANES, BN_ROWS), grid(N * S, ceil_div(C, BN_CCH));
+    if (dtype == CTGAN_F32)
+        bn_bwd_reduce_kernel<float><<<grid, blk, 0, st>>>((const float*)dy, (const float*)x, (const float*)y, save_mean, save_invstd, ws, HW, C, S, relu);
+    else
+        bn_bwd_reduce_kernel<__nv_bfloat16><<<grid, blk, 0, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (const __nv_bfloat16*)y, save_mean, save_invstd, ws, HW, C, S, relu);
+    CTGAN_CHECK_LAUNCH("bn_bwd_reduce");
+    bn_bwd_finalize_kernel<<<ceil_div(C, 128), 128, 0, st>>>(ws, gamma, labels, dgamma, dbeta, coef, N, S, C, n_labels, 1.f / (float)R);
+    CTGAN_CHECK_LAUNCH("bn_bwd_finalize");
+    int g2 = elementwise_grid(R * (C / 4), 256);
+    if (dtype == CTGAN_F32)
+        bn_bwd_apply_kernel<float><<<g2, 256, 0, st>>>((const float*)dy, (const float*)x, (const float*)y, gamma, labels, save_mean, save_invstd, coef, (float*)dx, R, HW, C, relu);
+    else
+        bn_bwd_apply_kernel<__nv_bfloat16><<<g2, 256, 0, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (const __nv_bfloat16*)y, gamma, labels, save_mean, save_invstd, coef, (__nv_bfloat16*)dx, R, HW, C, relu);
+    CTGAN_CHECK_LAUNCH("bn_bwd_apply");
+    return 0;
+}
+
+extern "C" int ctgan_bias_grad(const void* dy, float* db, int64_t rows, int C, int dtype, int accumulate, void* stream) {
+    CTGAN_REQUIRE(rows > 0 && C > 0 && dtype_ok(dtype) && dy && db, CTGAN_ERR_BAD_DESC, "bias_grad: bad args");
+    cudaStream_t st = as_stream(stream);
+    if (!accumulate) {
+        cudaError_t e = cudaMemsetAsync(db, 0, sizeof(float) * (size_t)C, st);
+        if (e != cudaSuccess) return cuda_status(e, "bias_grad memset");
+    }
+    int cblocks = ceil_div(C, 32);
+    int64_t want = (2 * (int64_t)sm_count() + cblocks - 1) / cblocks;
+    int64_t maxb = (rows + 63) / 64;
+    int64_t nb = want < maxb ? want : maxb;
+    if (nb < 1) nb = 1;
+    int rpb = (int)((rows + nb - 1) / nb);
+    nb = (rows + rpb - 1) / rpb;
+    dim3 blk(32, 8), grid((unsigned)nb, cblocks);
+    bias_grad_kernel<<<grid, blk, 0, st>>>(dy, db, rows, C, dtype, rpb);
+    CTGAN_CHECK_LAUNCH("bias_grad");
+    return 0;
+}

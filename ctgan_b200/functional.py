@@ -1,0 +1,454 @@
+"""Autograd shell over the CUDA kernels: twice-differentiable primitives.
+
+The gradient penalty differentiates THROUGH `tf.gradients(D(x^), x^)`
+(TG/CT_gan_cifar.py:144-154), so every op on the critic path must have a backward that
+is itself built from differentiable ops.  The conv family is closed under
+differentiation:
+    F(x, w)  = fprop            dF/dx -> D(gy, w)      dF/dw -> G(x, gy)
+    D(gy, w) = dgrad            dD/dgy -> F(c, w)      dD/dw -> G(c, gy)
+    G(x, gy) = wgrad            dG/dx -> D(gy, c)      dG/dgy -> F(x, c)
+and all critic non-linearities are multiplications by a constant 0/alpha/(1/keep) mask
+(ReLU, LeakyReLU, dropout), whose backward is the same multiplication; pooling /
+upsampling / layout changes are linear maps paired with their adjoints.  Backward
+functions return None (not zeros) for paths that carry no gradient, so the second-order
+pass costs exactly one fprop-shaped and one wgrad-shaped GEMM per layer.
+
+Generator-only ops (batch norm, tanh, sigmoid) and the loss heads are once-differentiable.
+"""
+import torch
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from . import kernels as K
+from ._lib import LossDesc, F32, BF16
+
+CL = torch.channels_last
+
+_param_ptrs = set()
+
+
+def register_param(t):
+    _param_ptrs.add(t.data_ptr())
+
+
+def _is_param(w):
+    return w.data_ptr() in _param_ptrs
+
+
+def _dense_like(g, ref_dim4):
+    """Make an incoming gradient dense in the layout the kernels use."""
+    if g is None:
+        return None
+    if g.dim() == 4:
+        if not g.is_contiguous(memory_format=CL):
+            g = g.contiguous(memory_format=CL)
+    elif not g.is_contiguous():
+        g = g.contiguous()
+    return g
+
+
+# ------------------------------------------------------------------------- conv family
+class ConvF(Function):
+    @staticmethod
+    def forward(ctx, x, w, b, g, out_dtype):
+        ctx.g = g
+        ctx.save_for_backward(x, w)
+        ctx.has_bias = b is not None
+        return K.conv_fprop(x, w, b, g, out_dtype=out_dtype, w_is_param=_is_param(w))
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w = ctx.saved_tensors
+        gy = _dense_like(gy, True)
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = ConvD.apply(gy, w, ctx.g, x.dtype)
+        if ctx.needs_input_grad[1]:
+            gw = ConvG.apply(x, gy, ctx.g, tuple(w.shape))
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = K.bias_grad(gy.detach())
+        return gx, gw, gb, None, None
+
+
+class ConvD(Function):
+    """dx = conv^T(gy, w) for the forward geometry g (== Deconv2D forward)."""
+
+    @staticmethod
+    def forward(ctx, gy, w, g, out_dtype):
+        ctx.g = g
+        ctx.save_for_backward(gy, w)
+        return K.conv_dgrad(gy, w, g, out_dtype=out_dtype, w_is_param=_is_param(w))
+
+    @staticmethod
+    def backward(ctx, c):
+        gy, w = ctx.saved_tensors
+        c = _dense_like(c, True)
+        ggy = gw = None
+        if ctx.needs_input_grad[0]:
+            ggy = ConvF.apply(c, w, None, ctx.g, gy.dtype)
+        if ctx.needs_input_grad[1]:
+            gw = ConvG.apply(c, gy, ctx.g, tuple(w.shape))
+        return ggy, gw, None, None
+
+
+class ConvG(Function):
+    """dw = wgrad(x, gy) (float HWIO)."""
+
+    @staticmethod
+    def forward(ctx, x, gy, g, w_shape):
+        ctx.g = g
+        ctx.save_for_backward(x, gy)
+        return K.conv_wgrad(x, gy, g, w_shape)
+
+    @staticmethod
+    def backward(ctx, c):
+        x, gy = ctx.saved_tensors
+        c = c.contiguous()
+        gx = ggy = None
+        if ctx.needs_input_grad[0]:
+            gx = ConvD.apply(gy, c, ctx.g, x.dtype)
+        if ctx.needs_input_grad[1]:
+            ggy = ConvF.apply(x, c, None, ctx.g, gy.dtype)
+        return gx, ggy, None, None
+
+
+def conv2d(x, w, b, k, stride, out_dtype=None):
+    """tf.nn.conv2d(SAME) + bias_add on a logical-NCHW activation."""
+    N, H, W, Cin = K.nhwc_dims(x)
+    g = K.same_geom(N, H, W, Cin, w.shape[-1], k, stride)
+    return ConvF.apply(x, w, b, g, out_dtype or x.dtype)
+
+
+def conv2d_transpose2(x, w, b):
+    """tf.nn.conv2d_transpose(SAME, stride 2), filter [k,k,out,in]: the dgrad of the stride-2
+    SAME conv that maps [N,2H,2W,out] -> [N,H,W,in]; bias added by a 1x1 'fprop' of nothing --
+    here simply the bias_add kernel through Add of a broadcast is avoided: see BiasAdd."""
+    N, H, W, Cin = K.nhwc_dims(x)
+    k, Cout = w.shape[0], w.shape[2]
+    g = K.same_geom(N, 2 * H, 2 * W, Cout, Cin, k, 2)
+    y = ConvD.apply(x, w, g, x.dtype)
+    if b is not None:
+        y = BiasAdd.apply(y, b)
+    return y
+
+
+def linear(x, w, b, out_dtype=None):
+    """tf.matmul + bias_add on [batch, in] (TG/tflib/ops/linear.py:132-146)."""
+    g = K.ConvGeom(x.shape[0], 1, 1, w.shape[0], 1, 1, w.shape[1], 1, 1, 1, 0, 0)
+    return ConvF.apply(x, w, b, g, out_dtype or x.dtype)
+
+
+class BiasAdd(Function):
+    """y = x + b[c]; implemented as a 1-tap identity-free kernel pair: scale-free add of a
+    broadcast bias via the conv epilogue is not available for dgrad outputs, so this uses
+    the dedicated bias path of the fprop kernel with a unit 1x1 filter avoided: we use
+    spatial_bcast of the bias row followed by add."""
+
+    @staticmethod
+    def forward(ctx, x, b):
+        N, H, W, C = K.nhwc_dims(x)
+        row = K.cast(b.detach().reshape(1, C).expand(N, C).contiguous(), x.dtype)
+        bb = K.spatial_bcast(row, H, W, 1.0) if x.dim() == 4 else row
+        return K.add(x, bb)
+
+    @staticmethod
+    def backward(ctx, gy):
+        gy = _dense_like(gy, True)
+        gb = K.bias_grad(gy.detach()) if ctx.needs_input_grad[1] else None
+        return gy, gb
+
+
+# ------------------------------------------------------------------------- masks / element-wise
+class MulConst(Function):
+    """y = x * m with m a constant (no gradient).  Its own backward."""
+
+    @staticmethod
+    def forward(ctx, x, m):
+        ctx.save_for_backward(m)
+        return K.mul(x, m)
+
+    @staticmethod
+    def backward(ctx, gy):
+        (m,) = ctx.saved_tensors
+        return MulConst.apply(_dense_like(gy, True), m), None
+
+
+class ActDropout(Function):
+    """y = act(x) then tf.nn.dropout: one fused kernel producing y and the multiplier m."""
+
+    @staticmethod
+    def forward(ctx, x, slope, keep, u, seed, offset):
+        y, m = K.act_dropout(x, slope, keep, u=u, seed=seed, offset=offset)
+        ctx.save_for_backward(m)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        (m,) = ctx.saved_tensors
+        return MulConst.apply(_dense_like(gy, True), m), None, None, None, None, None
+
+
+def relu(x):
+    return ActDropout.apply(x, 0.0, 1.0, None, 0, 0)
+
+
+def leaky_relu_dropout(x, slope, keep, u=None, seed=0, offset=0):
+    return ActDropout.apply(x, slope, keep, u, seed, offset)
+
+
+def dropout(x, keep, u=None, seed=0, offset=0):
+    if keep == 1.0:
+        return x
+    return ActDropout.apply(x, 1.0, keep, u, seed, offset)
+
+
+class Add(Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        return K.add(a, b)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, g
+
+
+def add(a, b):
+    return Add.apply(a, b)
+
+
+class Pool(Function):
+    @staticmethod
+    def forward(ctx, x, scale):
+        ctx.scale = scale
+        return K.pool2x2(x, scale)
+
+    @staticmethod
+    def backward(ctx, g):
+        return Upsample.apply(_dense_like(g, True), ctx.scale), None
+
+
+class Upsample(Function):
+    @staticmethod
+    def forward(ctx, x, scale):
+        ctx.scale = scale
+        return K.upsample2x(x, scale)
+
+    @staticmethod
+    def backward(ctx, g):
+        return Pool.apply(_dense_like(g, True), ctx.scale), None
+
+
+def mean_pool_2x2(x):
+    return Pool.apply(x, 0.25)
+
+
+def upsample_2x(x):
+    return Upsample.apply(x, 1.0)
+
+
+class SpatialSum(Function):
+    @staticmethod
+    def forward(ctx, x, scale):
+        ctx.scale, ctx.hw = scale, (x.shape[2], x.shape[3])
+        return K.spatial_sum(x, scale)
+
+    @staticmethod
+    def backward(ctx, g):
+        return SpatialBcast.apply(_dense_like(g, False), ctx.hw[0], ctx.hw[1], ctx.scale), None
+
+
+class SpatialBcast(Function):
+    @staticmethod
+    def forward(ctx, y, H, W, scale):
+        ctx.scale = scale
+        return K.spatial_bcast(y, H, W, scale)
+
+    @staticmethod
+    def backward(ctx, g):
+        return SpatialSum.apply(_dense_like(g, True), ctx.scale), None, None, None
+
+
+def spatial_mean(x):
+    return SpatialSum.apply(x, 1.0 / (x.shape[2] * x.shape[3]))
+
+
+class ToNHWC(Function):
+    """[N, C*H*W] (NCHW element order, the reference's flat tensors) -> logical [N,C,H,W] NHWC."""
+
+    @staticmethod
+    def forward(ctx, x, C, H, W, out_dtype):
+        ctx.in_dtype, ctx.in_shape = x.dtype, tuple(x.shape)
+        return K.nchw_to_nhwc(x.contiguous(), x.shape[0], C, H, W, out_dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return ToNCHW.apply(_dense_like(g, True), ctx.in_dtype, ctx.in_shape), None, None, None, None
+
+
+class ToNCHW(Function):
+    """logical [N,C,H,W] NHWC -> contiguous `out_shape` in NCHW element order."""
+
+    @staticmethod
+    def forward(ctx, x, out_dtype, out_shape):
+        ctx.in_dtype, ctx.chw = x.dtype, tuple(x.shape[1:])
+        return K.nhwc_to_nchw(x, out_dtype, out_shape)
+
+    @staticmethod
+    def backward(ctx, g):
+        C, H, W = ctx.chw
+        return ToNHWC.apply(g.contiguous(), C, H, W, ctx.in_dtype), None, None
+
+
+def to_nhwc(x_flat, C, H, W, dtype):
+    return ToNHWC.apply(x_flat, C, H, W, dtype)
+
+
+def to_flat_nchw(x, dtype=None):
+    N, C, H, W = x.shape
+    return ToNCHW.apply(x, dtype or x.dtype, (N, C * H * W))
+
+
+class Crop(Function):
+    @staticmethod
+    def forward(ctx, x, h, w):
+        ctx.hw = (x.shape[2], x.shape[3])
+        return K.crop(x, h, w)
+
+    @staticmethod
+    def backward(ctx, g):
+        return CropBwd.apply(_dense_like(g, True), ctx.hw[0], ctx.hw[1]), None, None
+
+
+class CropBwd(Function):
+    @staticmethod
+    def forward(ctx, g, H, W):
+        ctx.hw = (g.shape[2], g.shape[3])
+        return K.crop_bwd(g, H, W)
+
+    @staticmethod
+    def backward(ctx, c):
+        return Crop.apply(_dense_like(c, True), ctx.hw[0], ctx.hw[1]), None, None
+
+
+def crop(x, h, w):
+    return Crop.apply(x, h, w)
+
+
+class Cast(Function):
+    @staticmethod
+    def forward(ctx, x, dtype):
+        ctx.in_dtype = x.dtype
+        return K.cast(x, dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return Cast.apply(_dense_like(g, True), ctx.in_dtype), None
+
+
+def cast(x, dtype):
+    return x if x.dtype == dtype else Cast.apply(x, dtype)
+
+
+# ------------------------------------------------------------------------- generator-only ops
+class BatchNormReLU(Function):
+    """Training-mode BN (biased var, eps) with optional per-label gamma/beta and fused ReLU."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, labels, eps, relu):
+        y, mean, invstd = K.bn_fwd(x, gamma, beta, labels, eps, relu)
+        ctx.relu = relu
+        ctx.labels = labels
+        ctx.save_for_backward(x, y, gamma, mean, invstd)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy):
+        x, y, gamma, mean, invstd = ctx.saved_tensors
+        gy = _dense_like(gy, True)
+        dx, dgamma, dbeta = K.bn_bwd(gy, x, y, gamma, ctx.labels, mean, invstd, ctx.relu)
+        return dx, dgamma, dbeta, None, None, None
+
+
+def batch_norm(x, gamma, beta, labels=None, eps=1e-5, relu=False):
+    return BatchNormReLU.apply(x, gamma, beta, labels, eps, relu)
+
+
+class Unary(Function):
+    @staticmethod
+    def forward(ctx, x, kind):
+        y = K.unary_fwd(x, kind)
+        ctx.kind = kind
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy):
+        (y,) = ctx.saved_tensors
+        return K.unary_bwd(y, _dense_like(gy, True), ctx.kind), None
+
+
+def tanh(x):
+    return Unary.apply(x, 0)
+
+
+def sigmoid(x):
+    return Unary.apply(x, 1)
+
+
+# ------------------------------------------------------------------------- losses
+class CTGPLoss(Function):
+    """Fused critic loss (TG/CT_gan_cifar.py:123-151, TG/CT_gan_cifar_resnet.py:244-300).
+    Returns a float[8] tensor {cost, wgan, ct, gp, acgan, ...}; only element 0 is differentiable."""
+
+    @staticmethod
+    def forward(ctx, d_real, d_real2, d_fake, f1, f2, grad, logits, labels, hp):
+        B, F_ = f1.shape
+        desc = LossDesc(B, d_fake.shape[0], F_, grad.shape[1], 0 if logits is None else logits.shape[1],
+                        BF16 if f1.dtype == torch.bfloat16 else F32,
+                        hp['lambda_gp'], hp['lambda2'], hp['factor_m'], hp.get('acgan_scale', 0.0))
+        tensors = [t.contiguous() for t in (d_real, d_real2, d_fake, f1, f2, grad)]
+        lg = logits.contiguous() if logits is not None else None
+        out, per_sample = K.ct_gp_loss_fwd(desc, *tensors, lg, labels)
+        ctx.desc, ctx.labels, ctx.has_logits = desc, labels, logits is not None
+        ctx.save_for_backward(*tensors, per_sample, *([lg] if lg is not None else []))
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gout):
+        saved = ctx.saved_tensors
+        d_real, d_real2, d_fake, f1, f2, grad, per_sample = saved[:7]
+        lg = saved[7] if ctx.has_logits else None
+        gcost = gout[0:1].contiguous()
+        g = K.ct_gp_loss_bwd(ctx.desc, gcost, d_real, d_real2, f1, f2, grad, lg, ctx.labels, per_sample)
+        g_real, g_real2, g_fake, g_f1, g_f2, g_grad, g_logits = g
+        return g_real, g_real2, g_fake, g_f1, g_f2, g_grad, g_logits, None, None
+
+
+class MeanLoss(Function):
+    @staticmethod
+    def forward(ctx, d, sign):
+        ctx.n, ctx.sign = d.numel(), sign
+        return K.mean_fwd(d.contiguous(), sign)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        return K.mean_bwd(g.contiguous(), ctx.n, ctx.sign), None
+
+
+class SoftmaxCE(Function):
+    @staticmethod
+    def forward(ctx, logits, labels):
+        logits = logits.contiguous()
+        ctx.labels = labels
+        ctx.save_for_backward(logits)
+        return K.softmax_ce_fwd(logits, labels)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        (logits,) = ctx.saved_tensors
+        return K.softmax_ce_bwd(logits, ctx.labels, g.contiguous(), 1.0), None

@@ -1,0 +1,480 @@
+"""Tensor-level launchers over the C ABI (no autograd here; see functional.py).
+
+PyTorch supplies device memory (caching allocator) and the current CUDA stream; every
+arithmetic op is a kernel of libctgan_sm100.so.  Activations are torch tensors that are
+*logically* NCHW (the reference's convention, TG/tflib/ops/conv2d.py:22-26) and
+*physically* NHWC (torch.channels_last), dtype float32 ("fp32 path") or bfloat16
+("BF16 path").  2-D tensors [batch, features] are the H=W=1 case.
+"""
+import collections
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import F32, BF16, ConvDesc, LossDesc, call
+
+CL = torch.channels_last
+
+
+class Config:
+    use_tc = True            # use the tcgen05 kernels when a call is eligible
+    tc_min_rows = 1          # (tunable) minimum GEMM rows to prefer the tensor-core path
+
+
+config = Config()
+
+_tc_avail = None
+
+
+def tc_available():
+    global _tc_avail
+    if _tc_avail is None:
+        _tc_avail = bool(_lib.lib.ctgan_tc_available())
+    return _tc_avail
+
+
+def _dt(t):
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise TypeError('ctgan_b200: unsupported dtype %s' % t.dtype)
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _chk(t, name='tensor'):
+    if not t.is_cuda:
+        raise RuntimeError('ctgan_b200: %s must be a CUDA tensor (there is no CPU path)' % name)
+
+
+def is_nhwc(x):
+    return x.dim() != 4 or x.is_contiguous(memory_format=CL)
+
+
+def require_nhwc(x, name='activation'):
+    _chk(x, name)
+    if x.dim() == 4:
+        if not x.is_contiguous(memory_format=CL):
+            raise RuntimeError('ctgan_b200: %s must be channels_last (NHWC) contiguous' % name)
+    elif not x.is_contiguous():
+        raise RuntimeError('ctgan_b200: %s must be contiguous' % name)
+    return x
+
+
+def empty_act(shape, dtype, device):
+    if len(shape) == 4:
+        return torch.empty(shape, dtype=dtype, device=device, memory_format=CL)
+    return torch.empty(shape, dtype=dtype, device=device)
+
+
+def nhwc_dims(x):
+    """(N, H, W, C) of a logical-NCHW / 2-D activation."""
+    if x.dim() == 4:
+        N, C, H, W = x.shape
+        return N, H, W, C
+    if x.dim() == 2:
+        return x.shape[0], 1, 1, x.shape[1]
+    raise RuntimeError('ctgan_b200: activations must be 2-D or 4-D')
+
+
+# --------------------------------------------------------------------------- conv family
+ConvGeom = collections.namedtuple('ConvGeom', 'N H W Cin Ho Wo Cout kh kw stride pad_t pad_l')
+
+
+def same_geom(N, H, W, Cin, Cout, k, stride):
+    """TF 'SAME' geometry (SURVEY.md 8(c) rule 1)."""
+    Ho, Wo = -(-H // stride), -(-W // stride)
+    pt = max((Ho - 1) * stride + k - H, 0) // 2
+    pl = max((Wo - 1) * stride + k - W, 0) // 2
+    return ConvGeom(N, H, W, Cin, Ho, Wo, Cout, k, k, stride, pt, pl)
+
+
+def _desc(g, xdt, ydt):
+    return ConvDesc(g.N, g.H, g.W, g.Cin, g.Ho, g.Wo, g.Cout, g.kh, g.kw, g.stride, g.pad_t, g.pad_l, xdt, ydt)
+
+
+def _x_shape(g, two_d):
+    return (g.N, g.Cin) if two_d else (g.N, g.Cin, g.H, g.W)
+
+
+def _y_shape(g, two_d):
+    return (g.N, g.Cout) if two_d else (g.N, g.Cout, g.Ho, g.Wo)
+
+
+def _tc_geom_ok(g):
+    return (config.use_tc and tc_available() and g.stride == 1 and g.Ho == g.H and g.Wo == g.W
+            and g.Cin % 64 == 0 and g.Cout % 64 == 0 and 0 <= g.pad_t < g.kh and 0 <= g.pad_l < g.kw)
+
+
+# packed-filter cache for PARAMETERS only (keyed by storage address + optimizer epoch)
+_pack_cache = {}
+_epoch = 0
+
+
+def invalidate_weight_cache():
+    """Called by the optimizer after parameters change in place."""
+    global _epoch
+    _epoch += 1
+    _pack_cache.clear()
+
+
+def pack_filter(w, transpose_flip, cacheable=False):
+    """float HWIO [kh,kw,Cin,Cout] (or [in,out]) -> bf16 operand of the tcgen05 kernels."""
+    key = (w.data_ptr(), tuple(w.shape), transpose_flip, _epoch) if cacheable else None
+    if key is not None and key in _pack_cache:
+        return _pack_cache[key]
+    if w.dim() == 4:
+        taps, cin, cout = w.shape[0] * w.shape[1], w.shape[2], w.shape[3]
+    else:
+        taps, cin, cout = 1, w.shape[0], w.shape[1]
+    if w.dtype != torch.float32 or not w.is_contiguous():
+        raise RuntimeError('ctgan_b200: filters must be contiguous float32 HWIO')
+    wp = torch.empty(taps * cin * cout, dtype=torch.bfloat16, device=w.device)
+    call('ctgan_pack_filter_bf16', _p(w), _p(wp), taps, cin, cout, int(transpose_flip), _stream())
+    if key is not None:
+        _pack_cache[key] = wp
+    return wp
+
+
+def conv_fprop(x, w, bias, g, relu=False, residual=None, out_dtype=None, w_is_param=False):
+    """y = conv(x, w) [+ bias] [+ residual] [relu].  x NHWC/2-D act, w float HWIO."""
+    require_nhwc(x, 'x')
+    two_d = x.dim() == 2
+    out_dtype = out_dtype or x.dtype
+    y = empty_act(_y_shape(g, two_d), out_dtype, x.device)
+    xdt, ydt = _dt(x), _dt(y)
+    flags = _lib.EPI_RELU if relu else 0
+    if xdt == BF16 and ydt == BF16 and _tc_geom_ok(g):
+        wp = pack_filter(w, 0, cacheable=w_is_param)
+        if residual is not None:
+            require_nhwc(residual, 'residual')
+        d = _desc(g, xdt, ydt)
+        call('ctgan_conv_fprop_tc', ctypes.byref(d), _p(x), _p(wp), _p(bias), _p(residual), _p(y), flags, _stream())
+        return y
+    d = _desc(g, xdt, ydt)
+    call('ctgan_conv_fprop', ctypes.byref(d), _p(x), _p(w), _p(bias), _p(y), flags, _stream())
+    if residual is not None:
+        if relu:
+            raise RuntimeError('ctgan_b200: residual+relu fusion needs the tensor-core path')
+        call('ctgan_add', _p(y), _p(residual), _p(y), y.numel(), ydt, _stream())
+    return y
+
+
+def conv_dgrad(dy, w, g, out_dtype=None, w_is_param=False):
+    """dx = conv^T(dy, w) with the geometry of the FORWARD conv g.  Also Deconv2D forward."""
+    require_nhwc(dy, 'dy')
+    two_d = dy.dim() == 2
+    out_dtype = out_dtype or dy.dtype
+    dx = empty_act(_x_shape(g, two_d), out_dtype, dy.device)
+    xdt, ydt = _dt(dx), _dt(dy)
+    if xdt == BF16 and ydt == BF16 and _tc_geom_ok(g):
+        # stride-1 dgrad == fprop of dy with the tap-flipped filter, Cin<->Cout, pad -> k-1-pad
+        gt = ConvGeom(g.N, g.H, g.W, g.Cout, g.H, g.W, g.Cin, g.kh, g.kw, 1, g.kh - 1 - g.pad_t, g.kw - 1 - g.pad_l)
+        wp = pack_filter(w, 1, cacheable=w_is_param)
+        d = _desc(gt, BF16, BF16)
+        call('ctgan_conv_fprop_tc', ctypes.byref(d), _p(dy), _p(wp), None, None, _p(dx), 0, _stream())
+        return dx
+    d = _desc(g, xdt, ydt)
+    call('ctgan_conv_dgrad', ctypes.byref(d), _p(dy), _p(w), _p(dx), _stream())
+    return dx
+
+
+def conv_wgrad(x, dy, g, w_shape):
+    """dw (float HWIO, shape w_shape) = sum over pixels of x (shifted) * dy."""
+    require_nhwc(x, 'x')
+    require_nhwc(dy, 'dy')
+    xdt, ydt = _dt(x), _dt(dy)
+    d = _desc(g, xdt, ydt)
+    if xdt == BF16 and ydt == BF16 and _tc_geom_ok(g) and g.Cin % 128 == 0 and g.Cout % 128 == 0:
+        dw = torch.zeros(w_shape, dtype=torch.float32, device=x.device)
+        call('ctgan_conv_wgrad_tc', ctypes.byref(d), _p(x), _p(dy), _p(dw), _stream())
+        return dw
+    dw = torch.empty(w_shape, dtype=torch.float32, device=x.device)
+    call('ctgan_conv_wgrad', ctypes.byref(d), _p(x), _p(dy), _p(dw), 0, _stream())
+    return dw
+
+
+def bias_grad(dy):
+    require_nhwc(dy, 'dy')
+    N, H, W, C = nhwc_dims(dy)
+    db = torch.empty(C, dtype=torch.float32, device=dy.device)
+    call('ctgan_bias_grad', _p(dy), _p(db), N * H * W, C, _dt(dy), 0, _stream())
+    return db
+
+
+# --------------------------------------------------------------------------- element-wise
+def _same_layout(a, b):
+    if a.shape != b.shape or a.dtype != b.dtype or a.stride() != b.stride():
+        raise RuntimeError('ctgan_b200: element-wise operands must share shape, dtype and layout')
+
+
+def _dense(x, name='tensor'):
+    _chk(x, name)
+    if not (x.is_contiguous() or (x.dim() == 4 and x.is_contiguous(memory_format=CL))):
+        raise RuntimeError('ctgan_b200: %s must be dense' % name)
+    return x
+
+
+def add(a, b):
+    _dense(a); _dense(b); _same_layout(a, b)
+    out = torch.empty_like(a)
+    call('ctgan_add', _p(a), _p(b), _p(out), a.numel(), _dt(a), _stream())
+    return out
+
+
+def mul(a, b):
+    _dense(a); _dense(b); _same_layout(a, b)
+    out = torch.empty_like(a)
+    call('ctgan_mul', _p(a), _p(b), _p(out), a.numel(), _dt(a), _stream())
+    return out
+
+
+def scale(a, s):
+    _dense(a)
+    out = torch.empty_like(a)
+    call('ctgan_scale', _p(a), float(s), _p(out), a.numel(), _dt(a), _stream())
+    return out
+
+
+def cast(x, dtype):
+    _dense(x)
+    if x.dtype == dtype:
+        return x
+    out = torch.empty_like(x, dtype=dtype)
+    call('ctgan_cast', _p(x), _dt(x), _p(out), _dt(out), x.numel(), _stream())
+    return out
+
+
+def act_dropout(x, slope, keep, u=None, seed=0, offset=0, want_mask=True):
+    """y = x * m,  m = (x>0 ? 1 : slope) * (keep<1 ? floor(keep+u)/keep : 1).
+    `u` (float32, same logical shape/layout as x) overrides the Philox stream (seed, offset)."""
+    _dense(x)
+    y = torch.empty_like(x)
+    m = torch.empty_like(x) if want_mask else None
+    if u is not None:
+        _dense(u)
+        if u.dtype != torch.float32 or u.shape != x.shape or u.stride() != x.stride():
+            raise RuntimeError('ctgan_b200: explicit dropout noise must be float32 with the layout of x')
+    call('ctgan_act_dropout_fwd', _p(x), _p(u), _p(y), _p(m), x.numel(), _dt(x), float(slope), float(keep),
+         int(seed), int(offset), _stream())
+    return y, m
+
+
+def unary_fwd(x, kind):
+    _dense(x)
+    y = torch.empty_like(x)
+    call('ctgan_unary_fwd', _p(x), _p(y), x.numel(), _dt(x), kind, _stream())
+    return y
+
+
+def unary_bwd(y, dy, kind):
+    _dense(y); _dense(dy); _same_layout(y, dy)
+    dx = torch.empty_like(y)
+    call('ctgan_unary_bwd', _p(y), _p(dy), _p(dx), y.numel(), _dt(y), kind, _stream())
+    return dx
+
+
+def pool2x2(x, scale_):
+    require_nhwc(x)
+    N, C, H, W = x.shape
+    y = empty_act((N, C, H // 2, W // 2), x.dtype, x.device)
+    call('ctgan_pool2x2', _p(x), _p(y), N, H, W, C, float(scale_), _dt(x), _stream())
+    return y
+
+
+def upsample2x(x, scale_):
+    require_nhwc(x)
+    N, C, H, W = x.shape
+    y = empty_act((N, C, 2 * H, 2 * W), x.dtype, x.device)
+    call('ctgan_upsample2x', _p(x), _p(y), N, H, W, C, float(scale_), _dt(x), _stream())
+    return y
+
+
+def spatial_sum(x, scale_):
+    require_nhwc(x)
+    N, C, H, W = x.shape
+    y = torch.empty((N, C), dtype=x.dtype, device=x.device)
+    call('ctgan_spatial_sum', _p(x), _p(y), N, H * W, C, float(scale_), _dt(x), _stream())
+    return y
+
+
+def spatial_bcast(y, H, W, scale_):
+    _dense(y)
+    N, C = y.shape
+    x = empty_act((N, C, H, W), y.dtype, y.device)
+    call('ctgan_spatial_bcast', _p(y), _p(x), N, H * W, C, float(scale_), _dt(y), _stream())
+    return x
+
+
+def nchw_to_nhwc(x, N, C, H, W, out_dtype):
+    """x: any dense tensor holding N*C*H*W elements in NCHW order -> logical [N,C,H,W] channels_last."""
+    _chk(x)
+    if not x.is_contiguous():
+        raise RuntimeError('ctgan_b200: nchw_to_nhwc input must be contiguous')
+    y = empty_act((N, C, H, W), out_dtype, x.device)
+    call('ctgan_nchw_to_nhwc', _p(x), _dt(x), _p(y), _dt(y), N, C, H, W, _stream())
+    return y
+
+
+def nhwc_to_nchw(x, out_dtype, out_shape):
+    """x: logical [N,C,H,W] channels_last -> contiguous tensor of `out_shape` in NCHW element order."""
+    require_nhwc(x)
+    N, C, H, W = x.shape
+    y = torch.empty(out_shape, dtype=out_dtype, device=x.device)
+    call('ctgan_nhwc_to_nchw', _p(x), _dt(x), _p(y), _dt(y), N, C, H, W, _stream())
+    return y
+
+
+def crop(x, h, w):
+    require_nhwc(x)
+    N, C, H, W = x.shape
+    y = empty_act((N, C, h, w), x.dtype, x.device)
+    call('ctgan_crop', _p(x), _p(y), N, H, W, C, h, w, _dt(x), _stream())
+    return y
+
+
+def crop_bwd(dy, H, W):
+    require_nhwc(dy)
+    N, C, h, w = dy.shape
+    dx = empty_act((N, C, H, W), dy.dtype, dy.device)
+    call('ctgan_crop_bwd', _p(dy), _p(dx), N, H, W, C, h, w, _dt(dy), _stream())
+    return dx
+
+
+def prep_real(x_int, denom, noise_hi=0., seed=0, offset=0):
+    _chk(x_int)
+    if x_int.dtype != torch.int32 or not x_int.is_contiguous():
+        raise RuntimeError('ctgan_b200: real data must be contiguous int32')
+    y = torch.empty(x_int.shape, dtype=torch.float32, device=x_int.device)
+    call('ctgan_prep_real', _p(x_int), _p(y), x_int.numel(), float(denom), float(noise_hi), int(seed), int(offset), _stream())
+    return y
+
+
+def interpolate(real, fake, alpha):
+    for t in (real, fake, alpha):
+        _chk(t)
+        if t.dtype != torch.float32 or not t.is_contiguous():
+            raise RuntimeError('ctgan_b200: interpolate operands must be contiguous float32')
+    B, P_ = real.shape
+    out = torch.empty_like(real)
+    call('ctgan_interpolate', _p(real), _p(fake), _p(alpha), _p(out), B, P_, _stream())
+    return out
+
+
+# --------------------------------------------------------------------------- batch norm
+def bn_fwd(x, gamma, beta, labels, eps, relu):
+    require_nhwc(x)
+    N, H, W, C = nhwc_dims(x)
+    y = torch.empty_like(x)
+    mean = torch.empty(C, dtype=torch.float32, device=x.device)
+    invstd = torch.empty(C, dtype=torch.float32, device=x.device)
+    ws = torch.empty(_lib.lib.ctgan_bn_workspace_floats(N, H * W, C), dtype=torch.float32, device=x.device)
+    call('ctgan_bn_fwd', _p(x), _p(gamma), _p(beta), _p(labels), _p(y), _p(mean), _p(invstd), _p(ws),
+         N, H * W, C, float(eps), int(relu), _dt(x), _stream())
+    return y, mean, invstd
+
+
+def bn_bwd(dy, x, y, gamma, labels, mean, invstd, relu):
+    require_nhwc(dy); require_nhwc(x)
+    N, H, W, C = nhwc_dims(x)
+    n_labels = gamma.numel() // C
+    dx = torch.empty_like(x)
+    dgamma = torch.empty_like(gamma)
+    dbeta = torch.empty_like(gamma)
+    ws = torch.empty(_lib.lib.ctgan_bn_workspace_floats(N, H * W, C), dtype=torch.float32, device=x.device)
+    call('ctgan_bn_bwd', _p(dy), _p(x), _p(y), _p(gamma), _p(labels), _p(mean), _p(invstd), _p(dx), _p(dgamma),
+         _p(dbeta), _p(ws), N, H * W, C, n_labels, int(relu), _dt(x), _stream())
+    return dx, dgamma, dbeta
+
+
+# --------------------------------------------------------------------------- losses
+def _f32c(t, name):
+    _chk(t, name)
+    if t.dtype != torch.float32 or not t.is_contiguous():
+        raise RuntimeError('ctgan_b200: %s must be contiguous float32' % name)
+    return t
+
+
+def ct_gp_loss_fwd(desc, d_real, d_real2, d_fake, f1, f2, grad, logits, labels):
+    out = torch.empty(8, dtype=torch.float32, device=d_real.device)
+    per_sample = torch.empty(4 * desc.B, dtype=torch.float32, device=d_real.device)
+    call('ctgan_ct_gp_loss_fwd', ctypes.byref(desc), _p(d_real), _p(d_real2), _p(d_fake), _p(f1), _p(f2), _p(grad),
+         _p(logits), _p(labels), _p(out), _p(per_sample), _stream())
+    return out, per_sample
+
+
+def ct_gp_loss_bwd(desc, gcost, d_real, d_real2, f1, f2, grad, logits, labels, per_sample):
+    dev = d_real.device
+    g_real = torch.empty(desc.B, dtype=torch.float32, device=dev)
+    g_real2 = torch.empty(desc.B, dtype=torch.float32, device=dev)
+    g_fake = torch.empty(desc.NF, dtype=torch.float32, device=dev)
+    g_f1 = torch.empty_like(f1)
+    g_f2 = torch.empty_like(f2)
+    g_grad = torch.empty_like(grad)
+    g_logits = torch.empty_like(logits) if logits is not None else None
+    call('ctgan_ct_gp_loss_bwd', ctypes.byref(desc), _p(gcost), _p(d_real), _p(d_real2), _p(f1), _p(f2), _p(grad),
+         _p(logits), _p(labels), _p(per_sample), _p(g_real), _p(g_real2), _p(g_fake), _p(g_f1), _p(g_f2),
+         _p(g_grad), _p(g_logits), _stream())
+    return g_real, g_real2, g_fake, g_f1, g_f2, g_grad, g_logits
+
+
+def mean_fwd(d, sign):
+    _f32c(d, 'd')
+    out = torch.empty(1, dtype=torch.float32, device=d.device)
+    call('ctgan_mean_fwd', _p(d), _p(out), d.numel(), float(sign), _stream())
+    return out
+
+
+def mean_bwd(gcost, n, sign):
+    g = torch.empty(n, dtype=torch.float32, device=gcost.device)
+    call('ctgan_mean_bwd', _p(gcost), _p(g), n, float(sign), _stream())
+    return g
+
+
+def softmax_ce_fwd(logits, labels):
+    _f32c(logits, 'logits')
+    out = torch.empty(1, dtype=torch.float32, device=logits.device)
+    call('ctgan_softmax_ce_fwd', _p(logits), _p(labels), _p(out), logits.shape[0], logits.shape[1], _stream())
+    return out
+
+
+def softmax_ce_bwd(logits, labels, gcost, scale_):
+    g = torch.empty_like(logits)
+    call('ctgan_softmax_ce_bwd', _p(logits), _p(labels), _p(gcost), float(scale_), _p(g), logits.shape[0],
+         logits.shape[1], _stream())
+    return g
+
+
+# --------------------------------------------------------------------------- optimizer / rng
+def adam_step(p, g, m, v, lr_t, beta1, beta2, eps, grad_scale=1.0):
+    for t in (p, g, m, v):
+        _f32c(t, 'adam buffer')
+    call('ctgan_adam_step', _p(p), _p(g), _p(m), _p(v), p.numel(), float(lr_t), float(beta1), float(beta2),
+         float(eps), float(grad_scale), _stream())
+
+
+def philox_uniform(shape, device, seed, offset, lo=0., hi=1., memory_format=None):
+    out = (torch.empty(shape, dtype=torch.float32, device=device, memory_format=memory_format)
+           if memory_format is not None else torch.empty(shape, dtype=torch.float32, device=device))
+    call('ctgan_philox_uniform', _p(out), out.numel(), float(lo), float(hi), int(seed), int(offset), _stream())
+    return out
+
+
+def philox_normal(shape, device, seed, offset):
+    out = torch.empty(shape, dtype=torch.float32, device=device)
+    call('ctgan_philox_normal', _p(out), out.numel(), int(seed), int(offset), _stream())
+    return out
+
+
+def philox_labels(n, device, n_labels, seed, offset):
+    out = torch.empty(n, dtype=torch.int32, device=device)
+    call('ctgan_philox_labels', _p(out), n, int(n_labels), int(seed), int(offset), _stream())
+    return out

@@ -1,0 +1,69 @@
+"""lib.ops.deconv2d.Deconv2D -- drop-in for TG/tflib/ops/deconv2d.py:20-115.
+
+Stride-2 SAME transposed convolution H -> 2H with filter `<name>.Filters` [k,k,out,in].
+It is the dgrad kernel of the stride-2 SAME conv run as a forward op; the reference's two
+NCHW<->NHWC transposes (deconv2d.py:89,112) vanish because activations are NHWC inside.
+"""
+import numpy as np
+
+from ... import tflib as lib
+from ... import functional as F
+
+_default_weightnorm = False
+
+
+def enable_default_weightnorm():
+    global _default_weightnorm
+    _default_weightnorm = True
+
+
+_weights_stdev = None
+
+
+def set_weights_stdev(weights_stdev):
+    global _weights_stdev
+    _weights_stdev = weights_stdev
+
+
+def unset_weights_stdev():
+    global _weights_stdev
+    _weights_stdev = None
+
+
+def _uniform(stdev, size):
+    return np.random.uniform(low=-stdev * np.sqrt(3), high=stdev * np.sqrt(3), size=size).astype('float32')
+
+
+def Deconv2D(name, input_dim, output_dim, filter_size, inputs, he_init=True, weightnorm=None, biases=True,
+             gain=1., mask_type=None):
+    """
+    inputs: tensor of shape (batch size, input_dim, height, width)
+    returns: tensor of shape (batch size, output_dim, 2*height, 2*width)
+    """
+    if mask_type is not None:
+        raise Exception('Unsupported configuration')
+    if weightnorm is None:
+        weightnorm = _default_weightnorm
+    if weightnorm:
+        raise Exception('Unsupported configuration')
+
+    if not lib.has_param(name + '.Filters'):
+        stride = 2
+        fan_in = input_dim * filter_size ** 2 / (stride ** 2)
+        fan_out = output_dim * filter_size ** 2
+        if he_init:
+            filters_stdev = np.sqrt(4. / (fan_in + fan_out))
+        else:  # Normalized init (Glorot & Bengio)
+            filters_stdev = np.sqrt(2. / (fan_in + fan_out))
+        stdev = _weights_stdev if _weights_stdev is not None else filters_stdev
+        filter_values = _uniform(stdev, (filter_size, filter_size, output_dim, input_dim))
+        filter_values *= gain
+    else:
+        filter_values = None
+    filters = lib.param(name + '.Filters', filter_values)
+    _biases = lib.param(name + '.Biases', np.zeros(output_dim, dtype='float32')) if biases else None
+
+    inputs = F.ensure_nhwc(inputs)
+    if inputs.shape[1] != input_dim:
+        raise Exception('Deconv2D %s: expected %d input channels, got %d' % (name, input_dim, inputs.shape[1]))
+    return F.conv2d_transpose2(inputs, filters, _biases)

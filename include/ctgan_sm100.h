@@ -1,0 +1,223 @@
+/* ctgan_sm100.h -- C ABI of libctgan_sm100.so: hand-written sm_100a kernels for the
+ * CT-GAN critic/generator training step.
+ *
+ * The reference (biuyq/CT-GAN) has no FFI: its boundary is the python op surface
+ * tflib.ops.* which hands every tensor op to TensorFlow 1.2.1.  Each entry point
+ * below replaces the TF call(s) a reference file makes (cited as TG/<file>:<line>,
+ * TG = CT-GANs/tensorflow_generative_model) and is what a `ctypes` binding in the
+ * reference's tflib would bind.
+ *
+ * Conventions
+ *  - plain pointers + sizes; no torch types.  All pointers are DEVICE pointers
+ *    unless a parameter is documented as host.  The caller owns every buffer
+ *    (including workspaces); the library allocates nothing persistent.
+ *  - activations are NHWC ("channels last"), element type `dtype`:
+ *      CTGAN_F32 = 0 (float), CTGAN_BF16 = 1 (__nv_bfloat16).
+ *    parameters, gradients of parameters and optimizer state are always float.
+ *  - conv filters are HWIO [kh][kw][Cin][Cout] float, exactly the reference's
+ *    `<name>.Filters` layout (TG/tflib/ops/conv2d.py:70-88).
+ *  - every call is asynchronous on `stream` (a cudaStream_t passed as void*), is
+ *    CUDA-graph capturable (no sync, no allocation) and returns 0 on success,
+ *    <0 for a bad/unsupported descriptor, >0 for a cudaError_t.  The message of
+ *    the last failure on the calling thread is returned by ctgan_last_error().
+ *  - sm_100a only.  There is no CPU fallback.
+ */
+#ifndef CTGAN_SM100_H
+#define CTGAN_SM100_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CTGAN_F32  0
+#define CTGAN_BF16 1
+
+#define CTGAN_ERR_BAD_DESC    (-1)
+#define CTGAN_ERR_UNSUPPORTED (-2)
+#define CTGAN_ERR_DRIVER      (-3)
+
+/* ---- library ------------------------------------------------------------- */
+int         ctgan_version(void);              /* 100*major + minor */
+const char* ctgan_last_error(void);
+/* 1 when the tcgen05/TMA path is usable on the current device (cc 10.x), else 0 */
+int         ctgan_tc_available(void);
+
+/* ---- convolution family --------------------------------------------------
+ * One descriptor describes the FORWARD correlation
+ *   y[n,p,q,o] = sum_{r,s,c} x[n, p*stride + r - pad_t, q*stride + s - pad_l, c] * w[r,s,c,o]
+ * with x [N,H,W,Cin], y [N,Ho,Wo,Cout].  TF 'SAME' padding is
+ * pad_t = pad_l = max((Ho-1)*stride + k - H, 0) / 2  (asymmetric: the remainder
+ * goes after), see oracle/tf_ops.py:same_pad.
+ *   fprop  replaces tf.nn.conv2d            TG/tflib/ops/conv2d.py:106-112 (+bias_add :120)
+ *   dgrad  replaces Conv2DBackpropInput and IS tf.nn.conv2d_transpose
+ *                                           TG/tflib/ops/deconv2d.py:97-103
+ *   wgrad  replaces Conv2DBackpropFilter    (tf.gradients, TG/CT_gan_cifar.py:153-154)
+ * tf.matmul in TG/tflib/ops/linear.py:132-136 is the H=W=k=1 case.
+ * The GP double-backward (TG/CT_gan_cifar.py:144-154) composes these three.
+ */
+typedef struct {
+    int32_t N, H, W, Cin;          /* input  x  [N,H,W,Cin]   */
+    int32_t Ho, Wo, Cout;          /* output y  [N,Ho,Wo,Cout] */
+    int32_t kh, kw, stride;
+    int32_t pad_t, pad_l;
+    int32_t x_dtype;               /* dtype of x / dx */
+    int32_t y_dtype;               /* dtype of y / dy */
+} ctgan_conv_desc;
+
+#define CTGAN_EPI_RELU 1           /* y = max(y, 0) after bias (+residual) */
+
+/* generic SIMT implicit-GEMM kernels: any shape, fp32 FMA, float accumulate */
+int ctgan_conv_fprop(const ctgan_conv_desc* d, const void* x, const float* w_hwio,
+                     const float* bias /*nullable*/, void* y, int flags, void* stream);
+int ctgan_conv_dgrad(const ctgan_conv_desc* d, const void* dy, const float* w_hwio,
+                     void* dx, void* stream);
+/* dw (float, HWIO) is OVERWRITTEN when accumulate==0, else added to. */
+int ctgan_conv_wgrad(const ctgan_conv_desc* d, const void* x, const void* dy,
+                     float* dw, int accumulate, void* stream);
+
+/* tcgen05/TMEM/TMA implicit-GEMM kernels (BF16 operands, fp32 accumulate in TMEM).
+ * Eligibility: x/y BF16, stride 1, Ho==H, Wo==W, Cin % 64 == 0, Cout % 64 == 0.
+ * `wp` is a packed BF16 filter [kh*kw][Cout][Cin] made by ctgan_pack_filter_bf16.
+ * fprop_tc also serves dgrad of a stride-1 conv: pack with transpose_flip=1 and
+ * swap Cin/Cout, pad = k-1-pad in the descriptor.
+ * residual (nullable, BF16, same shape as y) is added before the optional ReLU. */
+int ctgan_conv_fprop_tc(const ctgan_conv_desc* d, const void* x, const void* wp,
+                        const float* bias /*nullable*/, const void* residual /*nullable*/,
+                        void* y, int flags, void* stream);
+/* dw[r,s,c,o] (float HWIO) = sum_pixels x[.., c] * dy[.., o]; split over pixels with
+ * fp32 atomics, so dw must hold the value to accumulate onto (zeros for a plain wgrad). */
+int ctgan_conv_wgrad_tc(const ctgan_conv_desc* d, const void* x, const void* dy,
+                        float* dw, void* stream);
+/* w_hwio float [taps][Cin][Cout] ->
+ *   transpose_flip==0: wp[t][o][c] = w[t][c][o]                (fprop operand)
+ *   transpose_flip==1: wp[t][c][o] = w[taps-1-t][c][o]         (dgrad operand)  */
+int ctgan_pack_filter_bf16(const float* w_hwio, void* wp, int taps, int Cin, int Cout,
+                           int transpose_flip, void* stream);
+
+/* db[c] (float) = sum over rows of dy[rows][C]   (gradient of tf.nn.bias_add) */
+int ctgan_bias_grad(const void* dy, float* db, int64_t rows, int C, int dtype,
+                    int accumulate, void* stream);
+
+/* ---- element-wise / data movement --------------------------------------- */
+int ctgan_cast(const void* x, int x_dtype, void* y, int y_dtype, int64_t n, void* stream);
+int ctgan_add(const void* a, const void* b, void* out, int64_t n, int dtype, void* stream);
+int ctgan_mul(const void* a, const void* b, void* out, int64_t n, int dtype, void* stream);
+int ctgan_scale(const void* a, float s, void* out, int64_t n, int dtype, void* stream);
+
+/* Fused activation + dropout multiplier (TG/CT_gan_cifar.py:47-48,86 ; tf.nn.dropout):
+ *   m = (x > 0 ? 1 : slope) * (keep < 1 ? floor(keep + u) / keep : 1);   y = x * m
+ * slope = 0 -> ReLU, 0.2 -> LeakyReLU, 1 -> dropout only.  u is read from `u`
+ * (float, nullable) or, when u == NULL and keep < 1, generated as
+ * philox_uniform(seed, offset + i) for element i -- identical to what
+ * ctgan_philox_uniform(seed, offset) materialises.  m (nullable) gets the multiplier. */
+int ctgan_act_dropout_fwd(const void* x, const float* u, void* y, void* m, int64_t n, int dtype,
+                          float slope, float keep, uint64_t seed, uint64_t offset, void* stream);
+
+/* unary: kind 0 = tanh, 1 = sigmoid (TG/CT_gan_cifar.py:77, TG/CT_gan_mnist.py:85) */
+int ctgan_unary_fwd(const void* x, void* y, int64_t n, int dtype, int kind, void* stream);
+int ctgan_unary_bwd(const void* y, const void* dy, void* dx, int64_t n, int dtype, int kind, void* stream);
+
+/* 2x2 mean pool / nearest 2x upsample on NHWC (TG/CT_gan_cifar_resnet.py:91,96,102-105).
+ * pool:     y[N,H/2,W/2,C] = scale * (sum of the 2x2 block)      (scale .25 = mean pool)
+ * upsample: y[N,2H,2W,C]   = scale * x[n,h/2,w/2,c]
+ * Each is the other's adjoint, so they also serve as backward kernels. */
+int ctgan_pool2x2(const void* x, void* y, int N, int H, int W, int C, float scale, int dtype, void* stream);
+int ctgan_upsample2x(const void* x, void* y, int N, int H, int W, int C, float scale, int dtype, void* stream);
+/* y[N,C] = scale * sum_hw x[N,HW,C]  and its adjoint x[N,HW,C] = scale * y[N,C]
+ * (tf.reduce_mean(output, axis=[2,3]), TG/CT_gan_cifar_resnet.py:179) */
+int ctgan_spatial_sum(const void* x, void* y, int N, int HW, int C, float scale, int dtype, void* stream);
+int ctgan_spatial_bcast(const void* y, void* x, int N, int HW, int C, float scale, int dtype, void* stream);
+
+/* NCHW float <-> NHWC dtype (the reference's NCHW<->NHWC transposes, TG/tflib/ops/deconv2d.py:89,112) */
+int ctgan_nchw_to_nhwc(const void* x, int x_dtype, void* y, int y_dtype, int N, int C, int H, int W, void* stream);
+int ctgan_nhwc_to_nchw(const void* x, int x_dtype, void* y, int y_dtype, int N, int C, int H, int W, void* stream);
+/* crop the top-left h x w window of NHWC x[N,H,W,C] (TG/CT_gan_mnist.py:77) and its adjoint (zero pad) */
+int ctgan_crop(const void* x, void* y, int N, int H, int W, int C, int h, int w, int dtype, void* stream);
+int ctgan_crop_bwd(const void* dy, void* dx, int N, int H, int W, int C, int h, int w, int dtype, void* stream);
+
+/* real-data preparation (TG/CT_gan_cifar.py:102-103, TG/CT_gan_cifar_resnet.py:201-202):
+ *   y = 2 * (x_int / denom - 0.5) + noise,  noise = noise_hi * philox_uniform(seed, offset+i)
+ * when noise_hi > 0.  y is float [n]. */
+int ctgan_prep_real(const int32_t* x_int, float* y, int64_t n, float denom, float noise_hi,
+                    uint64_t seed, uint64_t offset, void* stream);
+/* out[b,p] = real[b,p] + alpha[b] * (fake[b,p] - real[b,p])   (TG/CT_gan_cifar.py:142-143) */
+int ctgan_interpolate(const float* real, const float* fake, const float* alpha, float* out,
+                      int B, int P, void* stream);
+
+/* ---- batch norm (+ conditional gamma/beta gather, + fused ReLU) ----------
+ * Training-mode BN over rows = N*HW per channel, biased variance, eps
+ * (tf.nn.fused_batch_norm TG/tflib/ops/batchnorm.py:29-30; moments+batch_normalization
+ * batchnorm.py:77-84 and cond_batchnorm.py:10-16).  x is [N,HW,C].  gamma/beta are
+ * float [n_labels][C]; labels (int32 [N], nullable) picks the row per sample
+ * (labels == NULL -> row 0).  relu != 0 fuses tf.nn.relu on the output.
+ * ws: float workspace of ctgan_bn_workspace_floats(N, HW, C) floats.
+ * save_mean / save_invstd: float [C], consumed by the backward. */
+int64_t ctgan_bn_workspace_floats(int N, int HW, int C);
+int ctgan_bn_fwd(const void* x, const float* gamma, const float* beta, const int32_t* labels,
+                 void* y, float* save_mean, float* save_invstd, float* ws,
+                 int N, int HW, int C, float eps, int relu, int dtype, void* stream);
+/* y is the forward OUTPUT (used for the ReLU mask when relu != 0).  dgamma/dbeta are
+ * float [n_labels][C], overwritten. */
+int ctgan_bn_bwd(const void* dy, const void* x, const void* y, const float* gamma,
+                 const int32_t* labels, const float* save_mean, const float* save_invstd,
+                 void* dx, float* dgamma, float* dbeta, float* ws,
+                 int N, int HW, int C, int n_labels, int relu, int dtype, void* stream);
+
+/* ---- fused CT + GP + WGAN (+ACGAN) loss -----------------------------------
+ * TG/CT_gan_cifar.py:123-151, TG/CT_gan_mnist.py:146-167, TG/CT_gan_cifar_resnet.py:244-300.
+ *   wgan  = mean(d_fake[0..NF)) - mean(d_real[0..B))
+ *   CT_i  = lambda2*(d_real-d_real2)^2 + 0.1*lambda2*mean_f((f1-f2)^2); ct = mean(max(CT_i - M, 0))
+ *   s_i   = ||grad[i,:]||_2 ;  gp = mean((s_i-1)^2)
+ *   acgan = mean(logsumexp(logits_i) - logits_i[label_i])      (logits nullable)
+ *   cost  = wgan + ct + lambda*gp + acgan_scale*acgan
+ * d_* are float; f1,f2 [B,F] have `feat_dtype`; grad [B,P] float; logits [B,10] float.
+ * out (float[8]) = {cost, wgan, ct, gp, acgan, 0,0,0}.  per_sample (float [4*B]) keeps
+ * {CT_i - M, s_i, 0, 0} for the backward.  One warp-shuffle reduction kernel. */
+typedef struct {
+    int32_t B, NF, F, P, n_classes, feat_dtype;
+    float lambda_gp, lambda2, factor_m, acgan_scale;
+} ctgan_loss_desc;
+int ctgan_ct_gp_loss_fwd(const ctgan_loss_desc* d, const float* d_real, const float* d_real2,
+                         const float* d_fake, const void* f1, const void* f2, const float* grad,
+                         const float* logits, const int32_t* labels,
+                         float* out, float* per_sample, void* stream);
+/* cotangents of `cost` scaled by *gcost (device float): g_d_real [B], g_d_real2 [B],
+ * g_d_fake [NF], g_f1/g_f2 [B,F] (feat_dtype), g_grad [B,P] float, g_logits [B,n_classes] float. */
+int ctgan_ct_gp_loss_bwd(const ctgan_loss_desc* d, const float* gcost,
+                         const float* d_real, const float* d_real2, const void* f1, const void* f2,
+                         const float* grad, const float* logits, const int32_t* labels,
+                         const float* per_sample,
+                         float* g_d_real, float* g_d_real2, float* g_d_fake, void* g_f1, void* g_f2,
+                         float* g_grad, float* g_logits, void* stream);
+/* generator loss pieces: out[0] = sign * mean(d[0..n)); g[i] = sign * (*gcost) / n */
+int ctgan_mean_fwd(const float* d, float* out, int n, float sign, void* stream);
+int ctgan_mean_bwd(const float* gcost, float* g, int n, float sign, void* stream);
+/* softmax cross-entropy: out[0] = mean_i CE_i ; g_logits = (*gcost) * scale * (softmax - onehot) / B */
+int ctgan_softmax_ce_fwd(const float* logits, const int32_t* labels, float* out, int B, int n_classes, void* stream);
+int ctgan_softmax_ce_bwd(const float* logits, const int32_t* labels, const float* gcost, float scale,
+                         float* g_logits, int B, int n_classes, void* stream);
+
+/* ---- optimizer -------------------------------------------------------------
+ * tf.train.AdamOptimizer on one flat float buffer (TG/CT_gan_cifar_resnet.py:333-338):
+ *   m = b1*m + (1-b1)*g ; v = b2*v + (1-b2)*g*g ; p -= lr_t * m / (sqrt(v) + eps)
+ * lr_t = lr*sqrt(1-b2^t)/(1-b1^t) is computed by the host and passed in.
+ * grad_scale multiplies g first (1/world_size after a sum all-reduce). */
+int ctgan_adam_step(float* p, const float* g, float* m, float* v, int64_t n,
+                    float lr_t, float beta1, float beta2, float eps, float grad_scale, void* stream);
+
+/* ---- Philox4x32-10 random numbers -------------------------------------------
+ * Element i of a stream (seed, offset) is lane (offset+i)&3 of
+ * philox4x32_10(counter = (offset+i)>>2, key = seed); u = (bits >> 8) * 2^-24 in [0,1).
+ * uniform:  out = lo + (hi-lo)*u           (tf.random_uniform, TG/CT_gan_cifar.py:138)
+ * normal:   Box-Muller on elements (2i,2i+1) of the stream   (tf.random_normal, :60)
+ * labels:   (int32)(u * n_labels)          (TG/CT_gan_cifar_resnet.py:319) */
+int ctgan_philox_uniform(float* out, int64_t n, float lo, float hi, uint64_t seed, uint64_t offset, void* stream);
+int ctgan_philox_normal(float* out, int64_t n, uint64_t seed, uint64_t offset, void* stream);
+int ctgan_philox_labels(int32_t* out, int64_t n, int n_labels, uint64_t seed, uint64_t offset, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CTGAN_SM100_H */
