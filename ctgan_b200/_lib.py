@@ -45,11 +45,12 @@ _PROTOS = {
     'ctgan_conv_wgrad_tc': (c_int, [POINTER(ConvDesc), P, P, P, P]),
     'ctgan_pack_filter_bf16': (c_int, [P, P, c_int, c_int, c_int, c_int, P]),
     'ctgan_bias_grad': (c_int, [P, P, c_int64, c_int, c_int, c_int, P]),
+    'ctgan_bias_add': (c_int, [P, P, P, c_int64, c_int, c_int, P]),
     'ctgan_cast': (c_int, [P, c_int, P, c_int, c_int64, P]),
     'ctgan_add': (c_int, [P, P, P, c_int64, c_int, P]),
     'ctgan_mul': (c_int, [P, P, P, c_int64, c_int, P]),
     'ctgan_scale': (c_int, [P, c_float, P, c_int64, c_int, P]),
-    'ctgan_act_dropout_fwd': (c_int, [P, P, P, P, c_int64, c_int, c_float, c_float, c_uint64, c_uint64, P]),
+    'ctgan_act_dropout_fwd': (c_int, [P, P, P, P, c_int64, c_int, c_float, c_float, c_uint64, c_uint64, P, P]),
     'ctgan_unary_fwd': (c_int, [P, P, c_int64, c_int, c_int, P]),
     'ctgan_unary_bwd': (c_int, [P, P, P, c_int64, c_int, c_int, P]),
     'ctgan_pool2x2': (c_int, [P, P, c_int, c_int, c_int, c_int, c_float, c_int, P]),
@@ -60,7 +61,7 @@ _PROTOS = {
     'ctgan_nhwc_to_nchw': (c_int, [P, c_int, P, c_int, c_int, c_int, c_int, c_int, P]),
     'ctgan_crop': (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     'ctgan_crop_bwd': (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
-    'ctgan_prep_real': (c_int, [P, P, c_int64, c_float, c_float, c_uint64, c_uint64, P]),
+    'ctgan_prep_real': (c_int, [P, P, c_int64, c_float, c_float, c_uint64, c_uint64, P, P]),
     'ctgan_interpolate': (c_int, [P, P, P, P, c_int, c_int, P]),
     'ctgan_bn_workspace_floats': (c_int64, [c_int, c_int, c_int]),
     'ctgan_bn_fwd': (c_int, [P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_float, c_int, c_int, P]),
@@ -71,10 +72,11 @@ _PROTOS = {
     'ctgan_mean_bwd': (c_int, [P, P, c_int, c_float, P]),
     'ctgan_softmax_ce_fwd': (c_int, [P, P, P, c_int, c_int, P]),
     'ctgan_softmax_ce_bwd': (c_int, [P, P, P, c_float, P, c_int, c_int, P]),
-    'ctgan_adam_step': (c_int, [P, P, P, P, c_int64, c_float, c_float, c_float, c_float, c_float, P]),
-    'ctgan_philox_uniform': (c_int, [P, c_int64, c_float, c_float, c_uint64, c_uint64, P]),
-    'ctgan_philox_normal': (c_int, [P, c_int64, c_uint64, c_uint64, P]),
-    'ctgan_philox_labels': (c_int, [P, c_int64, c_int, c_uint64, c_uint64, P]),
+    'ctgan_adam_step': (c_int, [P, P, P, P, c_int64, c_float, c_float, c_float, c_float, c_float, P, P]),
+    'ctgan_philox_uniform': (c_int, [P, c_int64, c_float, c_float, c_uint64, c_uint64, P, P]),
+    'ctgan_counter_add': (c_int, [P, c_uint64, P]),
+    'ctgan_philox_normal': (c_int, [P, c_int64, c_uint64, c_uint64, P, P]),
+    'ctgan_philox_labels': (c_int, [P, c_int64, c_int, c_uint64, c_uint64, P, P]),
 }
 
 EXPORTS = sorted(_PROTOS)

@@ -82,8 +82,9 @@ __global__ void cast_kernel(const TI* __restrict__ x, TO* __restrict__ y, int64_
 template <typename T, int V>
 __global__ void act_dropout_kernel(const T* __restrict__ x, const float* __restrict__ u, T* __restrict__ y,
                                    T* __restrict__ m, int64_t nvec, float slope, float keep,
-                                   uint64_t seed, uint64_t offset) {
+                                   uint64_t seed, uint64_t offset, const uint64_t* __restrict__ dyn) {
     using P = Pack<T, V>;
+    if (dyn) offset += dyn[0];
     const bool drop = keep < 1.f;
     const float inv_keep = 1.f / keep;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
@@ -113,6 +114,12 @@ __global__ void act_dropout_kernel(const T* __restrict__ x, const float* __restr
         reinterpret_cast<P*>(y)[i] = py;
         if (m) reinterpret_cast<P*>(m)[i] = pm;
     }
+}
+
+template <typename T>
+__global__ void bias_add_kernel(const T* __restrict__ x, const float* __restrict__ b, T* __restrict__ y, int64_t total, int C) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+        y[i] = from_f<T>(to_f<T>(x[i]) + b[i % C]);
 }
 
 // ---- pooling / upsampling on NHWC --------------------------------------------
@@ -202,16 +209,9 @@ __global__ void crop_kernel(const T* __restrict__ x, T* __restrict__ y, int N, i
     }
 }
 
-__global__ void prep_real_kernel(const int32_t* __restrict__ x, float* __restrict__ y, int64_t n, float inv_denom,
-                                 float noise_hi, uint64_t seed, uint64_t offset) {
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        float v = 2.f * ((float)x[i] * inv_denom - 0.5f);
-        if (noise_hi > 0.f) v += noise_hi * Philox::uniform_at(seed, offset + (uint64_t)i);
-        y[i] = v;
-    }
-}
 __global__ void prep_real_div_kernel(const int32_t* __restrict__ x, float* __restrict__ y, int64_t n, float denom,
-                                     float noise_hi, uint64_t seed, uint64_t offset) {
+                                     float noise_hi, uint64_t seed, uint64_t offset, const uint64_t* __restrict__ dyn) {
+    if (dyn) offset += dyn[0];
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         float v = 2.f * (__fdiv_rn((float)x[i], denom) - 0.5f);       // true division: /255 is not exact as a multiply
         if (noise_hi > 0.f) v += noise_hi * Philox::uniform_at(seed, offset + (uint64_t)i);
@@ -229,11 +229,15 @@ __global__ void interpolate_kernel(const float* __restrict__ real, const float* 
 }
 
 // ---- RNG ---------------------------------------------------------------------
-__global__ void philox_uniform_kernel(float* __restrict__ out, int64_t n, float lo, float hi, uint64_t seed, uint64_t offset) {
+__global__ void philox_uniform_kernel(float* __restrict__ out, int64_t n, float lo, float hi, uint64_t seed, uint64_t offset,
+                                      const uint64_t* __restrict__ dyn) {
+    if (dyn) offset += dyn[0];
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         out[i] = lo + (hi - lo) * Philox::uniform_at(seed, offset + (uint64_t)i);
 }
-__global__ void philox_normal_kernel(float* __restrict__ out, int64_t n, uint64_t seed, uint64_t offset) {
+__global__ void philox_normal_kernel(float* __restrict__ out, int64_t n, uint64_t seed, uint64_t offset,
+                                     const uint64_t* __restrict__ dyn) {
+    if (dyn) offset += dyn[0];
     // element i uses stream elements (2i, 2i+1): Box-Muller, cosine branch only
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         uint64_t e = offset + 2ull * (uint64_t)i;
@@ -242,10 +246,14 @@ __global__ void philox_normal_kernel(float* __restrict__ out, int64_t n, uint64_
         out[i] = sqrtf(-2.f * logf(u1)) * cospif(2.f * u2);
     }
 }
-__global__ void philox_labels_kernel(int32_t* __restrict__ out, int64_t n, int n_labels, uint64_t seed, uint64_t offset) {
+__global__ void philox_labels_kernel(int32_t* __restrict__ out, int64_t n, int n_labels, uint64_t seed, uint64_t offset,
+                                     const uint64_t* __restrict__ dyn) {
+    if (dyn) offset += dyn[0];
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         out[i] = (int32_t)(Philox::uniform_at(seed, offset + (uint64_t)i) * (float)n_labels);
 }
+
+__global__ void counter_add_kernel(uint64_t* ctr, uint64_t delta) { ctr[0] += delta; }
 
 }  // namespace ctgan
 
@@ -304,26 +312,37 @@ extern "C" int ctgan_cast(const void* x, int xdt, void* y, int ydt, int64_t n, v
 
 template <typename T>
 static int launch_act_dropout(const void* x, const float* u, void* y, void* m, int64_t n, float slope, float keep,
-                              uint64_t seed, uint64_t offset, cudaStream_t st) {
+                              uint64_t seed, uint64_t offset, const uint64_t* dyn, cudaStream_t st) {
     constexpr int V = vec_width<T>();
     bool vec = aligned16(x) && aligned16(y) && (m == nullptr || aligned16(m)) && n % V == 0 && (offset & 3) == 0;
     if (vec) {
         int64_t nv = n / V;
-        act_dropout_kernel<T, V><<<elementwise_grid(nv, 256), 256, 0, st>>>((const T*)x, u, (T*)y, (T*)m, nv, slope, keep, seed, offset);
+        act_dropout_kernel<T, V><<<elementwise_grid(nv, 256), 256, 0, st>>>((const T*)x, u, (T*)y, (T*)m, nv, slope, keep, seed, offset, dyn);
     } else {
-        act_dropout_kernel<T, 1><<<elementwise_grid(n, 256), 256, 0, st>>>((const T*)x, u, (T*)y, (T*)m, n, slope, keep, seed, offset);
+        act_dropout_kernel<T, 1><<<elementwise_grid(n, 256), 256, 0, st>>>((const T*)x, u, (T*)y, (T*)m, n, slope, keep, seed, offset, dyn);
     }
     CTGAN_CHECK_LAUNCH("act_dropout_fwd");
     return 0;
 }
 extern "C" int ctgan_act_dropout_fwd(const void* x, const float* u, void* y, void* m, int64_t n, int dtype,
-                                     float slope, float keep, uint64_t seed, uint64_t offset, void* stream) {
+                                     float slope, float keep, uint64_t seed, uint64_t offset,
+                                     const uint64_t* dyn_offset, void* stream) {
     CTGAN_REQUIRE(keep > 0.f && keep <= 1.f, CTGAN_ERR_BAD_DESC, "act_dropout_fwd: keep must be in (0,1]");
     if (n <= 0) return 0;
-    DISPATCH_T(dtype, return launch_act_dropout<float>(x, u, y, m, n, slope, keep, seed, offset, as_stream(stream)),
-                      return launch_act_dropout<__nv_bfloat16>(x, u, y, m, n, slope, keep, seed, offset, as_stream(stream)));
+    DISPATCH_T(dtype, return launch_act_dropout<float>(x, u, y, m, n, slope, keep, seed, offset, dyn_offset, as_stream(stream)),
+                      return launch_act_dropout<__nv_bfloat16>(x, u, y, m, n, slope, keep, seed, offset, dyn_offset, as_stream(stream)));
 }
 
+extern "C" int ctgan_bias_add(const void* x, const float* b, void* y, int64_t rows, int C, int dtype, void* stream) {
+    CTGAN_REQUIRE(x && b && y && rows > 0 && C > 0, CTGAN_ERR_BAD_DESC, "bias_add: bad args");
+    int64_t total = rows * C;
+    int grid = elementwise_grid(total, 256);
+    cudaStream_t st = as_stream(stream);
+    DISPATCH_T(dtype, (bias_add_kernel<float><<<grid, 256, 0, st>>>((const float*)x, b, (float*)y, total, C)),
+                      (bias_add_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, b, (__nv_bfloat16*)y, total, C)));
+    CTGAN_CHECK_LAUNCH("bias_add");
+    return 0;
+}
 extern "C" int ctgan_pool2x2(const void* x, void* y, int N, int H, int W, int C, float scale, int dtype, void* stream) {
     CTGAN_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && H % 2 == 0 && W % 2 == 0, CTGAN_ERR_BAD_DESC, "pool2x2: H and W must be even and positive");
     int64_t total = (int64_t)N * (H / 2) * (W / 2) * C;
@@ -393,10 +412,10 @@ extern "C" int ctgan_crop_bwd(const void* dy, void* dx, int N, int H, int W, int
 }
 
 extern "C" int ctgan_prep_real(const int32_t* x, float* y, int64_t n, float denom, float noise_hi,
-                               uint64_t seed, uint64_t offset, void* stream) {
+                               uint64_t seed, uint64_t offset, const uint64_t* dyn_offset, void* stream) {
     CTGAN_REQUIRE(denom > 0.f, CTGAN_ERR_BAD_DESC, "prep_real: denom must be positive");
     if (n <= 0) return 0;
-    prep_real_div_kernel<<<elementwise_grid(n, 256), 256, 0, as_stream(stream)>>>(x, y, n, denom, noise_hi, seed, offset);
+    prep_real_div_kernel<<<elementwise_grid(n, 256), 256, 0, as_stream(stream)>>>(x, y, n, denom, noise_hi, seed, offset, dyn_offset);
     CTGAN_CHECK_LAUNCH("prep_real");
     return 0;
 }
@@ -408,22 +427,30 @@ extern "C" int ctgan_interpolate(const float* real, const float* fake, const flo
     return 0;
 }
 
-extern "C" int ctgan_philox_uniform(float* out, int64_t n, float lo, float hi, uint64_t seed, uint64_t offset, void* stream) {
+extern "C" int ctgan_counter_add(uint64_t* counter, uint64_t delta, void* stream) {
+    CTGAN_REQUIRE(counter != nullptr, CTGAN_ERR_BAD_DESC, "counter_add: null pointer");
+    counter_add_kernel<<<1, 1, 0, as_stream(stream)>>>(counter, delta);
+    CTGAN_CHECK_LAUNCH("counter_add");
+    return 0;
+}
+extern "C" int ctgan_philox_uniform(float* out, int64_t n, float lo, float hi, uint64_t seed, uint64_t offset,
+                                    const uint64_t* dyn_offset, void* stream) {
     if (n <= 0) return 0;
-    philox_uniform_kernel<<<elementwise_grid(n, 256), 256, 0, as_stream(stream)>>>(out, n, lo, hi, seed, offset);
+    philox_uniform_kernel<<<elementwise_grid(n, 256), 256, 0, as_stream(stream)>>>(out, n, lo, hi, seed, offset, dyn_offset);
     CTGAN_CHECK_LAUNCH("philox_uniform");
     return 0;
 }
-extern "C" int ctgan_philox_normal(float* out, int64_t n, uint64_t seed, uint64_t offset, void* stream) {
+extern "C" int ctgan_philox_normal(float* out, int64_t n, uint64_t seed, uint64_t offset, const uint64_t* dyn_offset, void* stream) {
     if (n <= 0) return 0;
-    philox_normal_kernel<<<elementwise_grid(n, 256), 256, 0, as_stream(stream)>>>(out, n, seed, offset);
+    philox_normal_kernel<<<elementwise_grid(n, 256), 256, 0, as_stream(stream)>>>(out, n, seed, offset, dyn_offset);
     CTGAN_CHECK_LAUNCH("philox_normal");
     return 0;
 }
-extern "C" int ctgan_philox_labels(int32_t* out, int64_t n, int n_labels, uint64_t seed, uint64_t offset, void* stream) {
+extern "C" int ctgan_philox_labels(int32_t* out, int64_t n, int n_labels, uint64_t seed, uint64_t offset,
+                                   const uint64_t* dyn_offset, void* stream) {
     CTGAN_REQUIRE(n_labels > 0, CTGAN_ERR_BAD_DESC, "philox_labels: n_labels must be positive");
     if (n <= 0) return 0;
-    philox_labels_kernel<<<elementwise_grid(n, 256), 256, 0, as_stream(stream)>>>(out, n, n_labels, seed, offset);
+    philox_labels_kernel<<<elementwise_grid(n, 256), 256, 0, as_stream(stream)>>>(out, n, n_labels, seed, offset, dyn_offset);
     CTGAN_CHECK_LAUNCH("philox_labels");
     return 0;
 }

@@ -112,6 +112,14 @@ class ConvG(Function):
         return gx, ggy, None, None
 
 
+def ensure_nhwc(x):
+    """Accept an NCHW-contiguous 4-D activation at the op boundary and re-lay it out as NHWC."""
+    if x.dim() == 4 and not x.is_contiguous(memory_format=CL):
+        N, C, H, W = x.shape
+        return ToNHWC.apply(x.reshape(N, C * H * W), C, H, W, x.dtype)
+    return x
+
+
 def conv2d(x, w, b, k, stride, out_dtype=None):
     """tf.nn.conv2d(SAME) + bias_add on a logical-NCHW activation."""
     N, H, W, Cin = K.nhwc_dims(x)
@@ -121,8 +129,7 @@ def conv2d(x, w, b, k, stride, out_dtype=None):
 
 def conv2d_transpose2(x, w, b):
     """tf.nn.conv2d_transpose(SAME, stride 2), filter [k,k,out,in]: the dgrad of the stride-2
-    SAME conv that maps [N,2H,2W,out] -> [N,H,W,in]; bias added by a 1x1 'fprop' of nothing --
-    here simply the bias_add kernel through Add of a broadcast is avoided: see BiasAdd."""
+    SAME conv that maps [N,2H,2W,out] -> [N,H,W,in], then bias_add."""
     N, H, W, Cin = K.nhwc_dims(x)
     k, Cout = w.shape[0], w.shape[2]
     g = K.same_geom(N, 2 * H, 2 * W, Cout, Cin, k, 2)
@@ -139,17 +146,11 @@ def linear(x, w, b, out_dtype=None):
 
 
 class BiasAdd(Function):
-    """y = x + b[c]; implemented as a 1-tap identity-free kernel pair: scale-free add of a
-    broadcast bias via the conv epilogue is not available for dgrad outputs, so this uses
-    the dedicated bias path of the fprop kernel with a unit 1x1 filter avoided: we use
-    spatial_bcast of the bias row followed by add."""
+    """y = x + b[c] (tf.nn.bias_add after conv2d_transpose, TG/tflib/ops/deconv2d.py:105-110)."""
 
     @staticmethod
     def forward(ctx, x, b):
-        N, H, W, C = K.nhwc_dims(x)
-        row = K.cast(b.detach().reshape(1, C).expand(N, C).contiguous(), x.dtype)
-        bb = K.spatial_bcast(row, H, W, 1.0) if x.dim() == 4 else row
-        return K.add(x, bb)
+        return K.bias_add(x, b)
 
     @staticmethod
     def backward(ctx, gy):
@@ -177,29 +178,29 @@ class ActDropout(Function):
     """y = act(x) then tf.nn.dropout: one fused kernel producing y and the multiplier m."""
 
     @staticmethod
-    def forward(ctx, x, slope, keep, u, seed, offset):
-        y, m = K.act_dropout(x, slope, keep, u=u, seed=seed, offset=offset)
+    def forward(ctx, x, slope, keep, u, seed, offset, dyn=None):
+        y, m = K.act_dropout(x, slope, keep, u=u, seed=seed, offset=offset, dyn=dyn)
         ctx.save_for_backward(m)
         return y
 
     @staticmethod
     def backward(ctx, gy):
         (m,) = ctx.saved_tensors
-        return MulConst.apply(_dense_like(gy, True), m), None, None, None, None, None
+        return MulConst.apply(_dense_like(gy, True), m), None, None, None, None, None, None
 
 
 def relu(x):
     return ActDropout.apply(x, 0.0, 1.0, None, 0, 0)
 
 
-def leaky_relu_dropout(x, slope, keep, u=None, seed=0, offset=0):
-    return ActDropout.apply(x, slope, keep, u, seed, offset)
+def leaky_relu_dropout(x, slope, keep, u=None, seed=0, offset=0, dyn=None):
+    return ActDropout.apply(x, slope, keep, u, seed, offset, dyn)
 
 
-def dropout(x, keep, u=None, seed=0, offset=0):
+def dropout(x, keep, u=None, seed=0, offset=0, dyn=None):
     if keep == 1.0:
         return x
-    return ActDropout.apply(x, 1.0, keep, u, seed, offset)
+    return ActDropout.apply(x, 1.0, keep, u, seed, offset, dyn)
 
 
 class Add(Function):

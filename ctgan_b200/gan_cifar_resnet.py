@@ -1,0 +1,290 @@
+"""CT-GAN ResNet for CIFAR-10: the training step of TG/CT_gan_cifar_resnet.py on B200.
+
+Same hyper-parameters (:33-56), the same builder functions with the same signatures
+(Normalize :70-87, ConvMeanPool :89-92, MeanPoolConv :94-98, UpsampleConv :100-107,
+ResidualBlock :109-141, OptimizedResBlockDisc1 :143-153, Generator :155-167,
+Discriminator :169-186), the same loss graph (:190-330) and Adam settings (:333-338),
+restated as two eager functions `critic_step` / `gen_step` (the reference's
+`disc_train_op` / `gen_train_op`).  All arithmetic runs in libctgan_sm100 kernels.
+
+Deliberate, result-preserving departures from the reference graph:
+  * the second stochastic critic pass runs on the REAL half only -- the fake half of that
+    pass feeds nothing (`disc_fake_`, `disc_fake_2_` are never used, :238-242);
+  * the metrics-only clean pass (:228) runs only when `with_metrics=True`.
+"""
+import functools
+
+import torch
+
+from . import tflib as lib
+from . import functional as F
+from . import kernels as K
+from .tflib.ops import linear as _linear, conv2d as _conv2d, batchnorm as _batchnorm, cond_batchnorm as _cond_batchnorm
+from .runtime import DeviceRandom, FlatAdam
+
+lib.ops.linear, lib.ops.conv2d, lib.ops.batchnorm, lib.ops.cond_batchnorm = _linear, _conv2d, _batchnorm, _cond_batchnorm
+
+N_GPUS = 1
+LAMBDA_2 = 2.0  # parameter LAMBDA2
+n_examples = 50000  # Number of examples
+Factor_M = 0.0  # factor M
+BATCH_SIZE = 64  # Critic batch size
+GEN_BS_MULTIPLE = 2  # Generator batch size, as a multiple of BATCH_SIZE
+ITERS = 100000  # How many iterations to train for
+DIM_G = 128  # Generator dimensionality
+DIM_D = 128  # Critic dimensionality
+NORMALIZATION_G = True  # Use batchnorm in generator?
+NORMALIZATION_D = False  # Use batchnorm (or layernorm) in critic?
+OUTPUT_DIM = 3072  # Number of pixels in CIFAR10 (32*32*3)
+LR = 2e-4  # Initial learning rate
+DECAY = True  # Whether to decay LR over learning
+N_CRITIC = 5  # Critic steps per generator steps
+CONDITIONAL = True  # Whether to train a conditional or unconditional model
+ACGAN = True  # If CONDITIONAL, whether to use ACGAN or "vanilla" conditioning
+ACGAN_SCALE = 1.  # How to scale the critic's ACGAN loss relative to WGAN loss
+ACGAN_SCALE_G = 0.1  # How to scale generator's ACGAN loss relative to WGAN loss
+LAMBDA = 10.0  # gradient penalty weight (literal 10.0 at :286)
+N_DEVICES = 2  # len(DEVICES): the reference always builds two sub-graphs (:61-63)
+
+ACT_DTYPE = torch.bfloat16   # activation storage: bfloat16 ("BF16 path") or float32 ("fp32 path")
+RNG = None                   # DeviceRandom, set by Trainer
+
+
+def nonlinearity(x):
+    return F.relu(x)
+
+
+def Normalize(name, inputs, labels=None, relu=False):
+    """:70-87.  `relu=True` fuses the nonlinearity() that follows every Normalize call."""
+    if not CONDITIONAL:
+        labels = None
+    if CONDITIONAL and ACGAN and ('Discriminator' in name):
+        labels = None
+    if ('Discriminator' in name) and NORMALIZATION_D:
+        raise Exception('Unsupported configuration')      # layernorm call is dead/broken in the reference
+    elif ('Generator' in name) and NORMALIZATION_G:
+        if labels is not None:
+            return lib.ops.cond_batchnorm.Batchnorm(name, [0, 2, 3], inputs, labels=labels, n_labels=10, relu=relu)
+        else:
+            return lib.ops.batchnorm.Batchnorm(name, [0, 2, 3], inputs, fused=True, relu=relu)
+    else:
+        return nonlinearity(inputs) if relu else inputs
+
+
+def ConvMeanPool(name, input_dim, output_dim, filter_size, inputs, he_init=True, biases=True):
+    output = lib.ops.conv2d.Conv2D(name, input_dim, output_dim, filter_size, inputs, he_init=he_init, biases=biases)
+    return F.mean_pool_2x2(output)
+
+
+def MeanPoolConv(name, input_dim, output_dim, filter_size, inputs, he_init=True, biases=True):
+    output = F.mean_pool_2x2(inputs)
+    return lib.ops.conv2d.Conv2D(name, input_dim, output_dim, filter_size, output, he_init=he_init, biases=biases)
+
+
+def UpsampleConv(name, input_dim, output_dim, filter_size, inputs, he_init=True, biases=True):
+    output = F.upsample_2x(inputs)
+    return lib.ops.conv2d.Conv2D(name, input_dim, output_dim, filter_size, output, he_init=he_init, biases=biases)
+
+
+def ResidualBlock(name, input_dim, output_dim, filter_size, inputs, resample=None, no_dropout=False, labels=None):
+    """
+    resample: None, 'down', or 'up'
+    """
+    if resample == 'down':
+        conv_1 = functools.partial(lib.ops.conv2d.Conv2D, input_dim=input_dim, output_dim=input_dim)
+        conv_2 = functools.partial(ConvMeanPool, input_dim=input_dim, output_dim=output_dim)
+        conv_shortcut = ConvMeanPool
+    elif resample == 'up':
+        conv_1 = functools.partial(UpsampleConv, input_dim=input_dim, output_dim=output_dim)
+        conv_shortcut = UpsampleConv
+        conv_2 = functools.partial(lib.ops.conv2d.Conv2D, input_dim=output_dim, output_dim=output_dim)
+    elif resample is None:
+        conv_shortcut = lib.ops.conv2d.Conv2D
+        conv_1 = functools.partial(lib.ops.conv2d.Conv2D, input_dim=input_dim, output_dim=output_dim)
+        conv_2 = functools.partial(lib.ops.conv2d.Conv2D, input_dim=output_dim, output_dim=output_dim)
+    else:
+        raise Exception('invalid resample value')
+
+    if output_dim == input_dim and resample is None:
+        shortcut = inputs  # Identity skip-connection
+    else:
+        shortcut = conv_shortcut(name + '.Shortcut', input_dim=input_dim, output_dim=output_dim, filter_size=1,
+                                 he_init=False, biases=True, inputs=inputs)
+
+    output = inputs
+    output = Normalize(name + '.N1', output, labels=labels, relu=True)
+    output = conv_1(name + '.Conv1', filter_size=filter_size, inputs=output)
+    output = Normalize(name + '.N2', output, labels=labels, relu=True)
+    output = conv_2(name + '.Conv2', filter_size=filter_size, inputs=output)
+
+    return F.add(shortcut, output)
+
+
+def OptimizedResBlockDisc1(inputs):
+    conv_1 = functools.partial(lib.ops.conv2d.Conv2D, input_dim=3, output_dim=DIM_D)
+    conv_2 = functools.partial(ConvMeanPool, input_dim=DIM_D, output_dim=DIM_D)
+    conv_shortcut = MeanPoolConv
+    shortcut = conv_shortcut('Discriminator.1.Shortcut', input_dim=3, output_dim=DIM_D, filter_size=1, he_init=False,
+                             biases=True, inputs=inputs)
+
+    output = inputs
+    output = conv_1('Discriminator.1.Conv1', filter_size=3, inputs=output)
+    output = nonlinearity(output)
+    output = conv_2('Discriminator.1.Conv2', filter_size=3, inputs=output)
+    return F.add(shortcut, output)
+
+
+def Generator(n_samples, labels, noise=None):
+    if noise is None:
+        noise = RNG.normal(RNG._scope + '.z', (n_samples, 128))
+    noise = F.cast(noise, ACT_DTYPE)
+    output = lib.ops.linear.Linear('Generator.Input', 128, 4 * 4 * DIM_G, noise)
+    output = F.to_nhwc(output, DIM_G, 4, 4, ACT_DTYPE)           # tf.reshape(output, [-1, DIM_G, 4, 4])
+    output = ResidualBlock('Generator.1', DIM_G, DIM_G, 3, output, resample='up', labels=labels)
+    output = ResidualBlock('Generator.2', DIM_G, DIM_G, 3, output, resample='up', labels=labels)
+    output = ResidualBlock('Generator.3', DIM_G, DIM_G, 3, output, resample='up', labels=labels)
+    output = Normalize('Generator.OutputN', output, relu=True)
+    output = lib.ops.conv2d.Conv2D('Generator.Output', DIM_G, 3, 3, output, he_init=False)
+    output = F.tanh(output)
+    return F.to_flat_nchw(output, torch.float32)                  # tf.reshape(output, [-1, OUTPUT_DIM])
+
+
+def _dropout(output, keep):
+    if keep == 1.0:
+        return output
+    tag = RNG.next_dropout_tag()
+    seed, off, dyn = RNG.stream(tag, output)
+    return F.dropout(output, keep, seed=seed, offset=off, dyn=dyn)
+
+
+def Discriminator(inputs, labels, kp1, kp2, kp3):  # three more parameters of keep rate
+    output = F.to_nhwc(inputs, 3, 32, 32, ACT_DTYPE)              # tf.reshape(inputs, [-1, 3, 32, 32])
+    output = OptimizedResBlockDisc1(output)
+    output = ResidualBlock('Discriminator.2', DIM_D, DIM_D, 3, output, resample='down', labels=labels)
+    output = _dropout(output, kp1)  # dropout after activator
+    output = ResidualBlock('Discriminator.3', DIM_D, DIM_D, 3, output, resample=None, labels=labels)
+    output = _dropout(output, kp2)  # dropout after activator
+    output = ResidualBlock('Discriminator.4', DIM_D, DIM_D, 3, output, resample=None, labels=labels)
+    output = _dropout(output, kp3)  # dropout after activator
+    output = nonlinearity(output)
+    output2 = F.spatial_mean(output)  # corresponding to D_
+    output_wgan = lib.ops.linear.Linear('Discriminator.Output', DIM_D, 1, output2, out_dtype=torch.float32)
+    output_wgan = output_wgan.reshape(-1)  # conrresponding to D
+    if CONDITIONAL and ACGAN:
+        output_acgan = lib.ops.linear.Linear('Discriminator.ACGANOutput', DIM_D, 10, output2, out_dtype=torch.float32)
+        return output_wgan, output2, output_acgan
+    else:
+        return output_wgan, output2, None  # two layers' of output
+
+
+class Trainer:
+    """Owns the parameters, both optimizers and the random stream of one training process."""
+
+    def __init__(self, device='cuda', seed=1234, act_dtype=torch.bfloat16, batch_size=BATCH_SIZE, record=False,
+                 graph_safe_rng=False):
+        global ACT_DTYPE, RNG
+        ACT_DTYPE = act_dtype
+        self.device = torch.device(device)
+        self.B = batch_size
+        lib.delete_all_params()           # one model per process, like the reference's module-level dict
+        lib.set_device(self.device)
+        self.rng = RNG = DeviceRandom(seed, self.device, record=record, graph_safe=graph_safe_rng)
+        # build every parameter in the reference's graph-construction order (G first, then D)
+        with torch.no_grad():
+            RNG.scope('build')
+            labels = torch.zeros(2, dtype=torch.int32, device=self.device)
+            fake = Generator(2, labels)
+            Discriminator(fake, labels, 1.0, 1.0, 1.0)
+        self.rng.offset = 0
+        self.gen_opt = FlatAdam('Generator', LR, 0.0, 0.9)          # :333, var_list :336
+        self.disc_opt = FlatAdam('Discriminator.', LR, 0.0, 0.9)    # :334, var_list :302
+        self.hp = dict(lambda_gp=LAMBDA, lambda2=LAMBDA_2, factor_m=Factor_M,
+                       acgan_scale=ACGAN_SCALE if (CONDITIONAL and ACGAN) else 0.0)
+
+    def activate(self):
+        global ACT_DTYPE, RNG
+        RNG = self.rng
+
+    @staticmethod
+    def lr(iteration):
+        decay = max(0., 1. - (float(iteration) / ITERS)) if DECAY else 1.
+        return LR * decay
+
+    # ---------------------------------------------------------------- critic (disc_train_op, :190-300,336-338)
+    def critic_forward_backward(self, all_real_data_int, all_real_labels, with_metrics=False):
+        RNG = self.rng
+        B = all_real_data_int.shape[0]
+        h = B // N_DEVICES
+        labels_splits = [all_real_labels[:h].contiguous(), all_real_labels[h:].contiguous()]
+        with torch.no_grad():
+            fakes = []
+            for i in range(N_DEVICES):
+                RNG.scope('z.%d' % i)
+                noise = RNG.normal('z.%d' % i, (h, 128))
+                fakes.append(Generator(h, labels_splits[i], noise=noise))
+        seed, off, dyn = RNG.stream('dequant', all_real_data_int)
+        all_real_data = K.prep_real(all_real_data_int, 256., 1. / 128, seed, off, dyn=dyn)     # :201-202
+        real_and_fake_data = torch.cat([all_real_data] + fakes, dim=0)
+        real_and_fake_labels = torch.cat([all_real_labels, all_real_labels], dim=0)
+        RNG.scope('drop.p1')
+        disc_all, disc_all_2, disc_all_acgan = Discriminator(real_and_fake_data, real_and_fake_labels, 0.8, 0.5, 0.5)
+        RNG.scope('drop.p2')
+        disc_real_, disc_real_2_, _ = Discriminator(all_real_data, all_real_labels, 0.8, 0.5, 0.5)
+        metrics = {}
+        if with_metrics and CONDITIONAL and ACGAN:
+            with torch.no_grad():
+                _, _, clean = Discriminator(real_and_fake_data, real_and_fake_labels, 1.0, 1.0, 1.0)
+                pred = clean.argmax(dim=1).to(torch.int32)
+                metrics['acgan_acc'] = (pred[:B] == real_and_fake_labels[:B]).float().mean()
+                metrics['acgan_fake_acc'] = (pred[B:] == real_and_fake_labels[B:]).float().mean()
+        disc_real, disc_fake = disc_all[:B], disc_all[B:]
+        disc_real_2 = disc_all_2[:B]
+        fake_data = torch.cat(fakes, dim=0)
+        alpha = RNG.uniform('alpha', (B, 1))
+        interpolates = K.interpolate(all_real_data, fake_data, alpha).requires_grad_(True)     # :277-283
+        RNG.scope('drop.gp')
+        d_interp = Discriminator(interpolates, all_real_labels, 0.8, 0.5, 0.5)[0]
+        gradients = torch.autograd.grad(d_interp, interpolates, grad_outputs=torch.ones_like(d_interp),
+                                        create_graph=True)[0]                                   # :284
+        logits = disc_all_acgan[:B] if (CONDITIONAL and ACGAN) else None
+        out = F.CTGPLoss.apply(disc_real, disc_real_, disc_fake, disc_real_2, disc_real_2_, gradients, logits,
+                               all_real_labels if logits is not None else None, self.hp)
+        out[0].backward(inputs=self.disc_opt.param_list())
+        res = dict(out=out.detach(), gradients=gradients.detach(), fake_data=fake_data, real_data=all_real_data)
+        res.update(metrics)
+        return res
+
+    def critic_step(self, all_real_data_int, all_real_labels, iteration=0, with_metrics=False, use_device_lr=False):
+        self.disc_opt.zero_grad()
+        res = self.critic_forward_backward(all_real_data_int, all_real_labels, with_metrics)
+        world = self.disc_opt.all_reduce()
+        self.disc_opt.step(self.lr(iteration), world, use_device_lr=use_device_lr)
+        self.rng.end_step()
+        return res
+
+    # ---------------------------------------------------------------- generator (gen_train_op, :314-330,335,337)
+    def gen_forward_backward(self):
+        RNG = self.rng
+        n_samples = GEN_BS_MULTIPLE * self.B // N_DEVICES
+        costs = []
+        for i in range(N_DEVICES):
+            fake_labels = RNG.labels('labels.%d' % i, n_samples)
+            noise = RNG.normal('z.%d' % i, (n_samples, 128))
+            fake = Generator(n_samples, fake_labels, noise=noise)
+            RNG.scope('drop.%d' % i)
+            disc_fake, _, disc_fake_acgan = Discriminator(fake, fake_labels, 0.8, 0.5, 0.5)
+            c = F.MeanLoss.apply(disc_fake, -1.0)
+            if CONDITIONAL and ACGAN:
+                c = c + ACGAN_SCALE_G * F.SoftmaxCE.apply(disc_fake_acgan, fake_labels)
+            costs.append(c)
+        gen_cost = (costs[0] + costs[1]) / N_DEVICES
+        gen_cost.backward(inputs=self.gen_opt.param_list())
+        return dict(cost=gen_cost.detach())
+
+    def gen_step(self, iteration=0, use_device_lr=False):
+        self.gen_opt.zero_grad()
+        res = self.gen_forward_backward()
+        world = self.gen_opt.all_reduce()
+        self.gen_opt.step(self.lr(iteration), world, use_device_lr=use_device_lr)
+        self.rng.end_step()
+        return res

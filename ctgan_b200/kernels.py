@@ -210,6 +210,14 @@ def bias_grad(dy):
     return db
 
 
+def bias_add(x, b):
+    require_nhwc(x, 'x')
+    N, H, W, C = nhwc_dims(x)
+    y = torch.empty_like(x)
+    call('ctgan_bias_add', _p(x), _p(b), _p(y), N * H * W, C, _dt(x), _stream())
+    return y
+
+
 # --------------------------------------------------------------------------- element-wise
 def _same_layout(a, b):
     if a.shape != b.shape or a.dtype != b.dtype or a.stride() != b.stride():
@@ -253,7 +261,7 @@ def cast(x, dtype):
     return out
 
 
-def act_dropout(x, slope, keep, u=None, seed=0, offset=0, want_mask=True):
+def act_dropout(x, slope, keep, u=None, seed=0, offset=0, want_mask=True, dyn=None):
     """y = x * m,  m = (x>0 ? 1 : slope) * (keep<1 ? floor(keep+u)/keep : 1).
     `u` (float32, same logical shape/layout as x) overrides the Philox stream (seed, offset)."""
     _dense(x)
@@ -264,7 +272,7 @@ def act_dropout(x, slope, keep, u=None, seed=0, offset=0, want_mask=True):
         if u.dtype != torch.float32 or u.shape != x.shape or u.stride() != x.stride():
             raise RuntimeError('ctgan_b200: explicit dropout noise must be float32 with the layout of x')
     call('ctgan_act_dropout_fwd', _p(x), _p(u), _p(y), _p(m), x.numel(), _dt(x), float(slope), float(keep),
-         int(seed), int(offset), _stream())
+         int(seed), int(offset), _p(dyn), _stream())
     return y, m
 
 
@@ -349,12 +357,12 @@ def crop_bwd(dy, H, W):
     return dx
 
 
-def prep_real(x_int, denom, noise_hi=0., seed=0, offset=0):
+def prep_real(x_int, denom, noise_hi=0., seed=0, offset=0, dyn=None):
     _chk(x_int)
     if x_int.dtype != torch.int32 or not x_int.is_contiguous():
         raise RuntimeError('ctgan_b200: real data must be contiguous int32')
     y = torch.empty(x_int.shape, dtype=torch.float32, device=x_int.device)
-    call('ctgan_prep_real', _p(x_int), _p(y), x_int.numel(), float(denom), float(noise_hi), int(seed), int(offset), _stream())
+    call('ctgan_prep_real', _p(x_int), _p(y), x_int.numel(), float(denom), float(noise_hi), int(seed), int(offset), _p(dyn), _stream())
     return y
 
 
@@ -454,27 +462,31 @@ def softmax_ce_bwd(logits, labels, gcost, scale_):
 
 
 # --------------------------------------------------------------------------- optimizer / rng
-def adam_step(p, g, m, v, lr_t, beta1, beta2, eps, grad_scale=1.0):
+def adam_step(p, g, m, v, lr_t, beta1, beta2, eps, grad_scale=1.0, lr_t_dev=None):
     for t in (p, g, m, v):
         _f32c(t, 'adam buffer')
     call('ctgan_adam_step', _p(p), _p(g), _p(m), _p(v), p.numel(), float(lr_t), float(beta1), float(beta2),
-         float(eps), float(grad_scale), _stream())
+         float(eps), float(grad_scale), _p(lr_t_dev), _stream())
 
 
-def philox_uniform(shape, device, seed, offset, lo=0., hi=1., memory_format=None):
+def philox_uniform(shape, device, seed, offset, lo=0., hi=1., memory_format=None, dyn=None):
     out = (torch.empty(shape, dtype=torch.float32, device=device, memory_format=memory_format)
            if memory_format is not None else torch.empty(shape, dtype=torch.float32, device=device))
-    call('ctgan_philox_uniform', _p(out), out.numel(), float(lo), float(hi), int(seed), int(offset), _stream())
+    call('ctgan_philox_uniform', _p(out), out.numel(), float(lo), float(hi), int(seed), int(offset), _p(dyn), _stream())
     return out
 
 
-def philox_normal(shape, device, seed, offset):
+def philox_normal(shape, device, seed, offset, dyn=None):
     out = torch.empty(shape, dtype=torch.float32, device=device)
-    call('ctgan_philox_normal', _p(out), out.numel(), int(seed), int(offset), _stream())
+    call('ctgan_philox_normal', _p(out), out.numel(), int(seed), int(offset), _p(dyn), _stream())
     return out
 
 
-def philox_labels(n, device, n_labels, seed, offset):
+def philox_labels(n, device, n_labels, seed, offset, dyn=None):
     out = torch.empty(n, dtype=torch.int32, device=device)
-    call('ctgan_philox_labels', _p(out), n, int(n_labels), int(seed), int(offset), _stream())
+    call('ctgan_philox_labels', _p(out), n, int(n_labels), int(seed), int(offset), _p(dyn), _stream())
     return out
+
+
+def counter_add(counter, delta):
+    call('ctgan_counter_add', _p(counter), int(delta), _stream())

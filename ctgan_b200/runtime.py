@@ -1,0 +1,175 @@
+"""Step-level runtime: device-side random streams, the flat-buffer Adam optimizer and the
+data-parallel gradient exchange.
+
+  * `DeviceRandom` replaces the TF graph's random ops (tf.random_normal / random_uniform /
+    nn.dropout, TG/CT_gan_cifar_resnet.py:157,202,277-281,319): one Philox4x32-10 stream per
+    training process, every draw takes a disjoint [offset, offset+n) slice.  With
+    `record=True` each draw is also materialised under a tag so that the CPU oracle can
+    replay the very same numbers (parity tests).
+  * `FlatAdam` replaces tf.train.AdamOptimizer(...).minimize(cost, var_list=...)
+    (TG/CT_gan_cifar.py:153-154, TG/CT_gan_cifar_resnet.py:333-338): parameters, gradients
+    and both moments live in four flat float buffers, one fused kernel per update.
+  * Data parallel: one process per GPU, gradients of the flat buffer are
+    summed with one NCCL all-reduce and the 1/world factor is folded into the Adam kernel.
+"""
+import math
+
+import torch
+
+from . import kernels as K
+from . import tflib as lib
+
+CL = torch.channels_last
+
+
+class DeviceRandom:
+    def __init__(self, seed, device, record=False, graph_safe=False):
+        self.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        self.device = torch.device(device)
+        self.offset = 0
+        self.record = record
+        self.tape = {}
+        self._scope = ''
+        self._site = 0
+        # graph_safe: kernels add a device-resident base offset, advanced by a kernel at step end
+        self.dyn = torch.zeros(1, dtype=torch.int64, device=self.device) if graph_safe else None
+
+    # -- stream bookkeeping ---------------------------------------------------
+    def _take(self, n):
+        off = self.offset
+        self.offset += (int(n) + 3) // 4 * 4        # keep every slice 4-aligned (vectorised Philox)
+        return off
+
+    def end_step(self):
+        """Graph-safe mode: fold the offsets consumed by this step into the device counter."""
+        if self.dyn is not None and self.offset:
+            K.counter_add(self.dyn, self.offset)
+            self.offset = 0
+
+    def begin_recording(self):
+        self.record = True
+        self.tape = {}
+
+    def scope(self, name):
+        self._scope, self._site = name, 0
+
+    def _keep(self, tag, t):
+        if self.record:
+            assert tag not in self.tape, 'duplicate random tag %s' % tag
+            self.tape[tag] = t
+
+    # -- draws ------------------------------------------------------------------
+    def normal(self, tag, shape):
+        n = int(math.prod(shape))
+        t = K.philox_normal(tuple(shape), self.device, self.seed, self._take(2 * n), dyn=self.dyn)
+        self._keep(tag, t)
+        return t
+
+    def uniform(self, tag, shape, lo=0., hi=1.):
+        n = int(math.prod(shape))
+        t = K.philox_uniform(tuple(shape), self.device, self.seed, self._take(n), lo, hi, dyn=self.dyn)
+        self._keep(tag, t)
+        return t
+
+    def labels(self, tag, n, n_labels=10):
+        t = K.philox_labels(int(n), self.device, n_labels, self.seed, self._take(n), dyn=self.dyn)
+        self._keep(tag, t)
+        return t
+
+    def stream(self, tag, like):
+        """Reserve a slice for an in-kernel consumer (fused dropout / dequantisation noise) shaped
+        like `like`; returns (seed, offset, dyn).  When recording, the same slice is materialised
+        with the memory layout of `like`, i.e. element i of the buffer == stream element offset+i."""
+        off = self._take(like.numel())
+        if self.record:
+            mf = CL if (like.dim() == 4 and like.is_contiguous(memory_format=CL)) else None
+            u = K.philox_uniform(tuple(like.shape), self.device, self.seed, off, memory_format=mf, dyn=self.dyn)
+            self._keep(tag, u)
+        return self.seed, off, self.dyn
+
+    def next_dropout_tag(self):
+        self._site += 1
+        return '%s.%d' % (self._scope, self._site)
+
+
+class FlatAdam:
+    """TF-semantics Adam over the parameters selected by name (substring), held flat.
+
+    On construction the selected tflib parameters are MOVED into one flat float buffer
+    (each tensor becomes a view, padded to 64 floats), their `.grad`s become views of a
+    flat gradient buffer, and the registry is re-bound to the new Parameter objects."""
+
+    PAD = 64
+
+    def __init__(self, selector, lr, beta1, beta2, eps=1e-8):
+        named = lib.named_params_with_name(selector, trainable_only=True)
+        if not named:
+            raise RuntimeError('FlatAdam: no trainable parameter matches %r' % selector)
+        self.lr, self.beta1, self.beta2, self.eps = lr, beta1, beta2, eps
+        self.t = 0
+        dev = next(iter(named.values())).device
+        sizes = {n: p.numel() for n, p in named.items()}
+        offs, total = {}, 0
+        for n in named:
+            offs[n] = total
+            total += (sizes[n] + self.PAD - 1) // self.PAD * self.PAD
+        self.n = total
+        self.flat_p = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.flat_g = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.flat_m = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.flat_v = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.lr_t_dev = torch.zeros(1, dtype=torch.float32, device=dev)
+        self._lr_t_pinned = torch.zeros(1, dtype=torch.float32).pin_memory() if dev.type == 'cuda' else None
+        self.params = {}
+        new = {}
+        for n, p in named.items():
+            o, sz = offs[n], sizes[n]
+            self.flat_p[o:o + sz].copy_(p.detach().reshape(-1))
+            q = torch.nn.Parameter(self.flat_p[o:o + sz].view(p.shape), requires_grad=True)
+            q.grad = self.flat_g[o:o + sz].view(p.shape)
+            new[n] = q
+            self.params[n] = q
+        lib.rebind_params(new)
+        self.offsets, self.sizes = offs, sizes
+        K.invalidate_weight_cache()
+
+    def param_list(self):
+        return list(self.params.values())
+
+    def zero_grad(self):
+        self.flat_g.zero_()
+        for q in self.params.values():       # keep .grad bound to the flat views
+            if q.grad is None or q.grad.data_ptr() != self.flat_g.data_ptr() + 4 * self.offsets[q.ctgan_name]:
+                q.grad = self.flat_g[self.offsets[q.ctgan_name]:self.offsets[q.ctgan_name] + q.numel()].view(q.shape)
+
+    def lr_t(self, lr=None):
+        lr = self.lr if lr is None else lr
+        t = self.t
+        return lr * math.sqrt(1. - self.beta2 ** t) / (1. - self.beta1 ** t)
+
+    def all_reduce(self):
+        """Sum the flat gradient bucket over ranks (NCCL); the 1/world scale is applied in step()."""
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(self.flat_g)
+            return dist.get_world_size()
+        return 1
+
+    def step(self, lr=None, world=1, use_device_lr=False):
+        """One update.  use_device_lr: read lr_t from self.lr_t_dev (set with set_device_lr) so the
+        launch is replayable inside a CUDA graph."""
+        self.t += 1
+        K.adam_step(self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.lr_t(lr), self.beta1, self.beta2,
+                    self.eps, grad_scale=1.0 / world, lr_t_dev=self.lr_t_dev if use_device_lr else None)
+        K.invalidate_weight_cache()
+
+    def set_device_lr(self, lr=None, advance=True):
+        """Host side of a graph replay: bump t and upload lr_t (async, pinned)."""
+        if advance:
+            self.t += 1
+        self._lr_t_pinned[0] = self.lr_t(lr)
+        self.lr_t_dev.copy_(self._lr_t_pinned, non_blocking=True)
+
+    def state_dict(self):
+        return {'t': self.t, 'p': {n: q.detach().clone() for n, q in self.params.items()},
+                'm': self.flat_m.clone(), 'v': self.flat_v.clone()}

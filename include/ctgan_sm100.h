@@ -100,6 +100,9 @@ int ctgan_pack_filter_bf16(const float* w_hwio, void* wp, int taps, int Cin, int
 int ctgan_bias_grad(const void* dy, float* db, int64_t rows, int C, int dtype,
                     int accumulate, void* stream);
 
+/* y[r,c] = x[r,c] + b[c]  (tf.nn.bias_add after conv2d_transpose, TG/tflib/ops/deconv2d.py:105-110) */
+int ctgan_bias_add(const void* x, const float* b, void* y, int64_t rows, int C, int dtype, void* stream);
+
 /* ---- element-wise / data movement --------------------------------------- */
 int ctgan_cast(const void* x, int x_dtype, void* y, int y_dtype, int64_t n, void* stream);
 int ctgan_add(const void* a, const void* b, void* out, int64_t n, int dtype, void* stream);
@@ -113,7 +116,8 @@ int ctgan_scale(const void* a, float s, void* out, int64_t n, int dtype, void* s
  * philox_uniform(seed, offset + i) for element i -- identical to what
  * ctgan_philox_uniform(seed, offset) materialises.  m (nullable) gets the multiplier. */
 int ctgan_act_dropout_fwd(const void* x, const float* u, void* y, void* m, int64_t n, int dtype,
-                          float slope, float keep, uint64_t seed, uint64_t offset, void* stream);
+                          float slope, float keep, uint64_t seed, uint64_t offset,
+                          const uint64_t* dyn_offset /*nullable*/, void* stream);
 
 /* unary: kind 0 = tanh, 1 = sigmoid (TG/CT_gan_cifar.py:77, TG/CT_gan_mnist.py:85) */
 int ctgan_unary_fwd(const void* x, void* y, int64_t n, int dtype, int kind, void* stream);
@@ -141,7 +145,7 @@ int ctgan_crop_bwd(const void* dy, void* dx, int N, int H, int W, int C, int h, 
  *   y = 2 * (x_int / denom - 0.5) + noise,  noise = noise_hi * philox_uniform(seed, offset+i)
  * when noise_hi > 0.  y is float [n]. */
 int ctgan_prep_real(const int32_t* x_int, float* y, int64_t n, float denom, float noise_hi,
-                    uint64_t seed, uint64_t offset, void* stream);
+                    uint64_t seed, uint64_t offset, const uint64_t* dyn_offset /*nullable*/, void* stream);
 /* out[b,p] = real[b,p] + alpha[b] * (fake[b,p] - real[b,p])   (TG/CT_gan_cifar.py:142-143) */
 int ctgan_interpolate(const float* real, const float* fake, const float* alpha, float* out,
                       int B, int P, void* stream);
@@ -205,7 +209,8 @@ int ctgan_softmax_ce_bwd(const float* logits, const int32_t* labels, const float
  * lr_t = lr*sqrt(1-b2^t)/(1-b1^t) is computed by the host and passed in.
  * grad_scale multiplies g first (1/world_size after a sum all-reduce). */
 int ctgan_adam_step(float* p, const float* g, float* m, float* v, int64_t n,
-                    float lr_t, float beta1, float beta2, float eps, float grad_scale, void* stream);
+                    float lr_t, float beta1, float beta2, float eps, float grad_scale,
+                    const float* lr_t_dev /*nullable: overrides lr_t, for graph replay*/, void* stream);
 
 /* ---- Philox4x32-10 random numbers -------------------------------------------
  * Element i of a stream (seed, offset) is lane (offset+i)&3 of
@@ -213,9 +218,15 @@ int ctgan_adam_step(float* p, const float* g, float* m, float* v, int64_t n,
  * uniform:  out = lo + (hi-lo)*u           (tf.random_uniform, TG/CT_gan_cifar.py:138)
  * normal:   Box-Muller on elements (2i,2i+1) of the stream   (tf.random_normal, :60)
  * labels:   (int32)(u * n_labels)          (TG/CT_gan_cifar_resnet.py:319) */
-int ctgan_philox_uniform(float* out, int64_t n, float lo, float hi, uint64_t seed, uint64_t offset, void* stream);
-int ctgan_philox_normal(float* out, int64_t n, uint64_t seed, uint64_t offset, void* stream);
-int ctgan_philox_labels(int32_t* out, int64_t n, int n_labels, uint64_t seed, uint64_t offset, void* stream);
+int ctgan_philox_uniform(float* out, int64_t n, float lo, float hi, uint64_t seed, uint64_t offset,
+                         const uint64_t* dyn_offset, void* stream);
+int ctgan_philox_normal(float* out, int64_t n, uint64_t seed, uint64_t offset, const uint64_t* dyn_offset, void* stream);
+int ctgan_philox_labels(int32_t* out, int64_t n, int n_labels, uint64_t seed, uint64_t offset,
+                        const uint64_t* dyn_offset, void* stream);
+/* CUDA-graph-safe streams: every RNG consumer adds *dyn_offset (device, nullable, a multiple of 4) to
+ * its `offset`, so a captured step draws fresh numbers on every replay once the counter is advanced
+ * by ctgan_counter_add (itself a kernel, captured at the end of the step). */
+int ctgan_counter_add(uint64_t* counter, uint64_t delta, void* stream);
 
 #ifdef __cplusplus
 }
