@@ -26,6 +26,10 @@ CL = torch.channels_last
 
 _param_ptrs = set()
 
+# Parity-test hook: when set (DeviceRandom.begin_recording), every activation site reports the
+# 0/1 pattern it applied, in call order, so the oracle can be evaluated on the same linear region.
+pattern_recorder = None
+
 
 def register_param(t):
     _param_ptrs.add(t.data_ptr())
@@ -180,6 +184,8 @@ class ActDropout(Function):
     @staticmethod
     def forward(ctx, x, slope, keep, u, seed, offset, dyn=None):
         y, m = K.act_dropout(x, slope, keep, u=u, seed=seed, offset=offset, dyn=dyn)
+        if pattern_recorder is not None and slope != 1.0:
+            pattern_recorder(x.detach() > 0)
         ctx.save_for_backward(m)
         return y
 
@@ -357,6 +363,8 @@ class BatchNormReLU(Function):
     @staticmethod
     def forward(ctx, x, gamma, beta, labels, eps, relu):
         y, mean, invstd = K.bn_fwd(x, gamma, beta, labels, eps, relu)
+        if pattern_recorder is not None and relu:
+            pattern_recorder(y.detach() > 0)
         ctx.relu = relu
         ctx.labels = labels
         ctx.save_for_backward(x, y, gamma, mean, invstd)

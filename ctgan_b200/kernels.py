@@ -144,9 +144,16 @@ def pack_filter(w, transpose_flip, cacheable=False):
     return wp
 
 
+def _check_filter(w, g):
+    _chk(w, 'filter')
+    if w.dtype != torch.float32 or not w.is_contiguous() or w.numel() != g.kh * g.kw * g.Cin * g.Cout:
+        raise RuntimeError('ctgan_b200: filter must be a contiguous float32 HWIO tensor matching the geometry')
+
+
 def conv_fprop(x, w, bias, g, relu=False, residual=None, out_dtype=None, w_is_param=False):
     """y = conv(x, w) [+ bias] [+ residual] [relu].  x NHWC/2-D act, w float HWIO."""
     require_nhwc(x, 'x')
+    _check_filter(w, g)
     two_d = x.dim() == 2
     out_dtype = out_dtype or x.dtype
     y = empty_act(_y_shape(g, two_d), out_dtype, x.device)
@@ -171,6 +178,7 @@ def conv_fprop(x, w, bias, g, relu=False, residual=None, out_dtype=None, w_is_pa
 def conv_dgrad(dy, w, g, out_dtype=None, w_is_param=False):
     """dx = conv^T(dy, w) with the geometry of the FORWARD conv g.  Also Deconv2D forward."""
     require_nhwc(dy, 'dy')
+    _check_filter(w, g)
     two_d = dy.dim() == 2
     out_dtype = out_dtype or dy.dtype
     dx = empty_act(_x_shape(g, two_d), out_dtype, dy.device)

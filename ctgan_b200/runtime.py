@@ -47,8 +47,16 @@ class DeviceRandom:
             self.offset = 0
 
     def begin_recording(self):
+        from . import functional as F
         self.record = True
         self.tape = {}
+        self.patterns = []
+        F.pattern_recorder = self.patterns.append
+
+    def stop_recording(self):
+        from . import functional as F
+        self.record = False
+        F.pattern_recorder = None
 
     def scope(self, name):
         self._scope, self._site = name, 0

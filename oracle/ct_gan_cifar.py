@@ -38,14 +38,14 @@ class Model(StepMixin):
         lib, DIM = self.lib, self.DIM
         output = lib.Linear('Generator.Input', 128, 4 * 4 * 4 * DIM, noise)
         output = lib.Batchnorm('Generator.BN1', [0], output)
-        output = torch.relu(output)
+        output = self._relu(output)
         output = output.reshape(-1, 4 * DIM, 4, 4)
         output = lib.Deconv2D('Generator.2', 4 * DIM, 2 * DIM, 5, output)
         output = lib.Batchnorm('Generator.BN2', [0, 2, 3], output)
-        output = torch.relu(output)
+        output = self._relu(output)
         output = lib.Deconv2D('Generator.3', 2 * DIM, DIM, 5, output)
         output = lib.Batchnorm('Generator.BN3', [0, 2, 3], output)
-        output = torch.relu(output)
+        output = self._relu(output)
         output = lib.Deconv2D('Generator.5', DIM, 3, 5, output)
         output = torch.tanh(output)
         return output.reshape(-1, OUTPUT_DIM)
@@ -54,13 +54,13 @@ class Model(StepMixin):
         lib, DIM = self.lib, self.DIM
         output = inputs.reshape(-1, 3, 32, 32)
         output = lib.Conv2D('Discriminator.1', 3, DIM, 5, output, stride=2)
-        output = tf_ops.leaky_relu(output)
+        output = self._lrelu(output)
         output = tf_ops.dropout(output, 0.5, rnd.uniform(tag + '.1', output.shape))
         output = lib.Conv2D('Discriminator.2', DIM, 2 * DIM, 5, output, stride=2)
-        output = tf_ops.leaky_relu(output)
+        output = self._lrelu(output)
         output = tf_ops.dropout(output, 0.5, rnd.uniform(tag + '.2', output.shape))
         output = lib.Conv2D('Discriminator.3', 2 * DIM, 4 * DIM, 5, output, stride=2)
-        output = tf_ops.leaky_relu(output)
+        output = self._lrelu(output)
         output = tf_ops.dropout(output, 0.5, rnd.uniform(tag + '.3', output.shape))
         output2 = output.reshape(-1, 4 * 4 * 4 * DIM)
         output = lib.Linear('Discriminator.Output', 4 * 4 * 4 * DIM, 1, output2)
@@ -79,6 +79,7 @@ class Model(StepMixin):
         return 2 * ((real_data_int.to(torch.float32) / 255.) - .5)
 
     def disc_cost(self, rnd, real_data_int):               # :123-151
+        self._begin(rnd)
         B = real_data_int.shape[0]
         real_data = self.prep_real(real_data_int).to(self.dtype)
         with torch.no_grad():
@@ -96,6 +97,7 @@ class Model(StepMixin):
                     disc_real=disc_real, disc_fake=disc_fake, fake_data=fake_data)
 
     def gen_cost(self, rnd):                               # :125
+        self._begin(rnd)
         B = self.B
         fake_data = self.Generator(B, rnd.normal('z', (B, 128)).to(self.dtype))
         disc_fake, _ = self.Discriminator(fake_data, rnd, 'drop.fake')

@@ -102,10 +102,10 @@ class Model(StepMixin):
                                      filter_size=1, he_init=False, biases=True, inputs=inputs)
         output = inputs
         output = self.Normalize(name + '.N1', output, labels=labels)
-        output = torch.relu(output)
+        output = self._relu(output)
         output = conv_1(name + '.Conv1', filter_size=filter_size, inputs=output)
         output = self.Normalize(name + '.N2', output, labels=labels)
-        output = torch.relu(output)
+        output = self._relu(output)
         output = conv_2(name + '.Conv2', filter_size=filter_size, inputs=output)
         return shortcut + output
 
@@ -114,7 +114,7 @@ class Model(StepMixin):
         shortcut = self.MeanPoolConv('Discriminator.1.Shortcut', input_dim=3, output_dim=D, filter_size=1,
                                      he_init=False, biases=True, inputs=inputs)
         output = self.lib.Conv2D('Discriminator.1.Conv1', 3, D, 3, inputs)
-        output = torch.relu(output)
+        output = self._relu(output)
         output = self.ConvMeanPool('Discriminator.1.Conv2', D, D, 3, output)
         return shortcut + output
 
@@ -126,7 +126,7 @@ class Model(StepMixin):
         output = self.ResidualBlock('Generator.2', G, G, 3, output, resample='up', labels=labels)
         output = self.ResidualBlock('Generator.3', G, G, 3, output, resample='up', labels=labels)
         output = self.Normalize('Generator.OutputN', output)
-        output = torch.relu(output)
+        output = self._relu(output)
         output = self.lib.Conv2D('Generator.Output', G, 3, 3, output, he_init=False)
         output = torch.tanh(output)
         return output.reshape(-1, OUTPUT_DIM)
@@ -141,7 +141,7 @@ class Model(StepMixin):
         output = tf_ops.dropout(output, kp2, None if kp2 == 1.0 else rnd.uniform(tag + '.2', output.shape))
         output = self.ResidualBlock('Discriminator.4', D, D, 3, output, resample=None, labels=labels)
         output = tf_ops.dropout(output, kp3, None if kp3 == 1.0 else rnd.uniform(tag + '.3', output.shape))
-        output = torch.relu(output)
+        output = self._relu(output)
         output2 = output.mean(dim=[2, 3])
         output_wgan = self.lib.Linear('Discriminator.Output', D, 1, output2).reshape(-1)
         if self.CONDITIONAL and self.ACGAN:
@@ -162,6 +162,7 @@ class Model(StepMixin):
         return x + dequant
 
     def disc_cost(self, rnd, all_real_data_int, all_real_labels, with_clean=True):   # :190-300
+        self._begin(rnd)
         B = all_real_data_int.shape[0]
         h = B // N_DEVICES
         labels_splits = [all_real_labels[:h], all_real_labels[h:]]
@@ -210,6 +211,7 @@ class Model(StepMixin):
         return out
 
     def gen_cost(self, rnd):                               # :314-330
+        self._begin(rnd)
         B = self.B
         n_samples = GEN_BS_MULTIPLE * B // N_DEVICES
         gen_costs, gen_acgan_costs = [], []

@@ -36,6 +36,35 @@ class StepMixin:
     """Needs: self.lib (TFLib), self.disc_cost(real, rnd[, labels]), self.gen_cost(rnd),
     self.gen_name / self.disc_name (substring selectors), self.adam_args, self.lr(iteration)."""
 
+    # Activation sites.  By default the oracle decides the ReLU / LeakyReLU pattern from its own
+    # pre-activation (tf.nn.relu, tf.maximum(alpha*x, x)).  For the "pattern-conditioned" parity
+    # mode the test hands over the 0/1 patterns the device computed (`patterns`: an iterator of
+    # bool tensors in call order): both sides then evaluate the SAME linear region of the
+    # piecewise-linear network, which separates arithmetic error from the activation-pattern
+    # flips that reduced-precision pre-activations cause at near-zero values.
+    _patterns = None
+
+    def _pattern(self, x):
+        if self._patterns is None:
+            return x > 0
+        p = next(self._patterns)
+        if p.shape[0] < x.shape[0]:            # device ran this pass on the leading samples only
+            pad = torch.ones((x.shape[0] - p.shape[0],) + tuple(p.shape[1:]), dtype=torch.bool)
+            p = torch.cat([p, pad], dim=0)
+        assert p.shape == x.shape, (tuple(p.shape), tuple(x.shape))
+        return p
+
+    def _relu(self, x):
+        return x * self._pattern(x).to(x.dtype)
+
+    def _lrelu(self, x, alpha=0.2):
+        p = self._pattern(x)
+        return x * torch.where(p, torch.ones((), dtype=x.dtype), torch.full((), alpha, dtype=x.dtype))
+
+    def _begin(self, rnd):
+        pats = getattr(rnd, 'patterns', None)
+        self._patterns = iter(pats) if pats is not None else None
+
     def _init_opt(self):
         self.gen_opt = TFAdam(*self.adam_args)
         self.disc_opt = TFAdam(*self.adam_args)

@@ -37,13 +37,13 @@ class Model(StepMixin):
     def Generator(self, n_samples, noise):                 # :62-87
         lib, DIM = self.lib, self.DIM
         output = lib.Linear('Generator.Input', 128, 4 * 4 * 4 * DIM, noise)
-        output = torch.relu(output)
+        output = self._relu(output)
         output = output.reshape(-1, 4 * DIM, 4, 4)
         output = lib.Deconv2D('Generator.2', 4 * DIM, 2 * DIM, 5, output)
-        output = torch.relu(output)
+        output = self._relu(output)
         output = output[:, :, :7, :7]
         output = lib.Deconv2D('Generator.3', 2 * DIM, DIM, 5, output)
-        output = torch.relu(output)
+        output = self._relu(output)
         output = lib.Deconv2D('Generator.5', DIM, 1, 5, output)
         output = torch.sigmoid(output)
         return output.reshape(-1, OUTPUT_DIM)
@@ -52,13 +52,13 @@ class Model(StepMixin):
         lib, DIM = self.lib, self.DIM
         output = inputs.reshape(-1, 1, 28, 28)
         output = lib.Conv2D('Discriminator.1', 1, DIM, 5, output, stride=2)
-        output = tf_ops.leaky_relu(output)
+        output = self._lrelu(output)
         output = tf_ops.dropout(output, 0.5, rnd.uniform(tag + '.1', output.shape))
         output = lib.Conv2D('Discriminator.2', DIM, 2 * DIM, 5, output, stride=2)
-        output = tf_ops.leaky_relu(output)
+        output = self._lrelu(output)
         output = tf_ops.dropout(output, 0.5, rnd.uniform(tag + '.2', output.shape))
         output = lib.Conv2D('Discriminator.3', 2 * DIM, 4 * DIM, 5, output, stride=2)
-        output = tf_ops.leaky_relu(output)
+        output = self._lrelu(output)
         output = tf_ops.dropout(output, 0.5, rnd.uniform(tag + '.3', output.shape))
         output2 = output.reshape(-1, 4 * 4 * 4 * DIM)
         output = lib.Linear('Discriminator.Output', 4 * 4 * 4 * DIM, 1, output2)
@@ -75,6 +75,7 @@ class Model(StepMixin):
         return self
 
     def disc_cost(self, rnd, real_data):                   # :146-167
+        self._begin(rnd)
         B = real_data.shape[0]
         real_data = real_data.to(self.dtype)
         with torch.no_grad():
@@ -92,6 +93,7 @@ class Model(StepMixin):
                     disc_real=disc_real, disc_fake=disc_fake, fake_data=fake_data)
 
     def gen_cost(self, rnd):                               # :147
+        self._begin(rnd)
         B = self.B
         fake_data = self.Generator(B, rnd.normal('z', (B, 128)).to(self.dtype))
         disc_fake, _ = self.Discriminator(fake_data, rnd, 'drop.fake')

@@ -38,7 +38,9 @@ class SeededRandom:
 class ReplayRandom:
     """Replays a tape {tag: tensor} recorded elsewhere (e.g. by the CUDA path)."""
 
-    def __init__(self, tape):
+    def __init__(self, tape, patterns=None):
+        # optional activation patterns recorded on the device (see ct_gan_common.StepMixin._pattern)
+        self.patterns = [p.detach().cpu().bool() for p in patterns] if patterns is not None else None
         self.tape = {k: (v.detach().cpu() if isinstance(v, torch.Tensor) else torch.as_tensor(v))
                      for k, v in tape.items()}
         self.used = set()

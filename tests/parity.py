@@ -25,8 +25,8 @@ def rel_err(a, b, floor=1e-30):
     return (a - b).norm().item() / max(den, floor)
 
 
-def _grad_floor(ref_grads):
-    return 1e-4 * max(float(g.detach().double().norm()) for g in ref_grads.values() if g is not None)
+def _grad_floor(ref_grads, frac=1e-4):
+    return frac * max(float(g.detach().double().norm()) for g in ref_grads.values() if g is not None)
 
 
 def make_inputs(script, B, seed):
@@ -88,15 +88,18 @@ def _fix_tape(script, tape, B):
     return tape
 
 
-def critic_parity(script, tr, om, inputs, iteration=0):
+def critic_parity(script, tr, om, inputs, iteration=0, conditioned=False, floor_frac=1e-4):
+    """conditioned=True: the oracle applies the activation patterns the device computed (same linear
+    region), isolating arithmetic error from near-zero ReLU flips; False: fully independent oracle."""
     dev = tr.device
     inputs_dev = tuple(t.to(dev) for t in inputs)
     tr.disc_opt.zero_grad()
     tr.rng.begin_recording()
     res = tr.critic_forward_backward(*inputs_dev)
+    tr.rng.stop_recording()
     tape = _fix_tape(script, tr.rng.tape, inputs[0].shape[0])
     kw = dict(with_clean=False) if script == 'resnet' else {}
-    ref = om.disc_cost(ReplayRandom(tape), *inputs, **kw)
+    ref = om.disc_cost(ReplayRandom(tape, tr.rng.patterns if conditioned else None), *inputs, **kw)
     named = om.lib.named_params_with_name(om.disc_name)
     ref_grads = om._grads(ref['cost'], named)
     out = res['out'].cpu()
@@ -111,7 +114,7 @@ def critic_parity(script, tr, om, inputs, iteration=0):
         report['loss.' + k] = abs(float(a) - float(b)) / max(abs(float(b)), 0.05 * scale)
     report['fake_data'] = rel_err(res['fake_data'], ref['fake_data'])
     report['gp_gradient'] = rel_err(res['gradients'], ref['gradients'])
-    floor = _grad_floor(ref_grads)
+    floor = _grad_floor(ref_grads, floor_frac)
     for n, q in tr.disc_opt.params.items():
         report['grad.' + n] = rel_err(q.grad, ref_grads[n], floor)
     # optimizer: the SAME gradients (the product's) go through both Adam implementations, so this
@@ -127,16 +130,17 @@ def critic_parity(script, tr, om, inputs, iteration=0):
     return report
 
 
-def gen_parity(script, tr, om, iteration=1):
+def gen_parity(script, tr, om, iteration=1, conditioned=False, floor_frac=1e-4):
     tr.gen_opt.zero_grad()
     tr.rng.begin_recording()
     res = tr.gen_forward_backward()
+    tr.rng.stop_recording()
     tape = dict(tr.rng.tape)
-    ref = om.gen_cost(ReplayRandom(tape))
+    ref = om.gen_cost(ReplayRandom(tape, tr.rng.patterns if conditioned else None))
     named = om.lib.named_params_with_name(om.gen_name)
     ref_grads = om._grads(ref['cost'], named)
     report = {'loss.gen_cost': abs(float(res['cost']) - float(ref['cost'])) / max(abs(float(ref['cost'])), 0.05)}
-    floor = _grad_floor(ref_grads)
+    floor = _grad_floor(ref_grads, floor_frac)
     for n, q in tr.gen_opt.params.items():
         report['grad.' + n] = rel_err(q.grad, ref_grads[n], floor)
     before = {n: q.detach().clone() for n, q in tr.gen_opt.params.items()}

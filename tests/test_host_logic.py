@@ -29,6 +29,18 @@ def test_step_parity_fake_kernels_fp32(fake_kernels, script, B):
     assert grads[-1] < 1e-2, 'gen: ' + parity.format_report(rep)
 
 
+@pytest.mark.parametrize('script,B', [('mnist', 4), ('cifar', 4), ('resnet', 4)])
+def test_step_parity_pattern_conditioned(fake_kernels, script, B):
+    """With the device's activation patterns handed to the oracle (same linear region) the ReLU-tie
+    caveat disappears and every gradient agrees to accumulation-order precision."""
+    tr, om = parity.build_pair(script, 'cpu', torch.float32, B)
+    parity.perturb_params(tr, om)
+    rep = parity.critic_parity(script, tr, om, parity.make_inputs(script, B, 11), conditioned=True)
+    assert parity.worst({k: v for k, v in rep.items() if not k.startswith('adam.')})[0] < 5e-4, parity.format_report(rep)
+    rep = parity.gen_parity(script, tr, om, conditioned=True)
+    assert parity.worst({k: v for k, v in rep.items() if not k.startswith('adam.')})[0] < 5e-4, parity.format_report(rep)
+
+
 def test_second_step_uses_updated_weights(fake_kernels):
     """Two consecutive critic steps stay in parity (optimizer state + weight-cache invalidation)."""
     tr, om = parity.build_pair('cifar', 'cpu', torch.float32, 4)

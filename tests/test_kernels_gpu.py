@@ -1,0 +1,297 @@
+"""GPU tests (`-m gpu`): every kernel of libctgan_sm100, called through the C ABI, against an
+independent CPU evaluation of the same contract (tests/fake_backend.py = PyTorch-CPU,
+tests/philox_ref.py = numpy Philox4x32-10).  Tolerances: float path 1e-4 relative
+(accumulation-order only), BF16 path 1e-2 (one bf16 rounding of the output)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+CL = torch.channels_last
+
+
+def _need_gpu():
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+
+
+@pytest.fixture(scope='module')
+def K():
+    _need_gpu()
+    import ctgan_b200.kernels as K
+    return K
+
+
+def FB():
+    from tests import fake_backend
+    return fake_backend
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def act(shape, dtype, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    t = (torch.randn(shape, generator=g) * scale).to(dtype)
+    return t.contiguous(memory_format=CL) if len(shape) == 4 else t.contiguous()
+
+
+def filt(shape, seed, scale=0.05):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).contiguous()      # HWIO, plain contiguous
+
+
+def to_dev(t):
+    if t.dim() == 4:
+        return t.cuda().contiguous(memory_format=CL)
+    return t.cuda()
+
+
+GEOMS = [
+    # N, H, W, Cin, Cout, k, stride
+    (3, 32, 32, 3, 128, 5, 2),     # CIFAR D.1   (pad 1,2)
+    (2, 16, 16, 128, 256, 5, 2),   # CIFAR D.2
+    (3, 28, 28, 1, 64, 5, 2),      # MNIST D.1
+    (2, 7, 7, 128, 256, 5, 2),     # MNIST D.3   (pad 2,2)
+    (2, 32, 32, 3, 128, 3, 1),     # ResNet D.1.Conv1
+    (2, 16, 16, 128, 128, 3, 1),   # ResNet body
+    (3, 8, 8, 128, 128, 1, 1),     # shortcut
+    (2, 32, 32, 128, 3, 3, 1),     # Generator.Output
+    (5, 1, 1, 128, 2048, 1, 1),    # Generator.Input (linear)
+    (7, 1, 1, 4096, 1, 1, 1),      # Discriminator.Output (GEMV)
+]
+
+
+@pytest.mark.parametrize('use_tc', [False, True])
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('geom', GEOMS)
+def test_conv_family(K, geom, dtype, use_tc):
+    N, H, W, Cin, Cout, k, s = geom
+    if use_tc and dtype != torch.bfloat16:
+        pytest.skip('tensor-core path is BF16 only')
+    g = K.same_geom(N, H, W, Cin, Cout, k, s)
+    two_d = (H == 1 and W == 1)
+    x = act((N, Cin) if two_d else (N, Cin, H, W), dtype, 1)
+    dy = act((N, Cout) if two_d else (N, Cout, g.Ho, g.Wo), dtype, 2)
+    w = filt((k, k, Cin, Cout), 3)
+    b = act((Cout,), torch.float32, 4)
+    K.config.use_tc = use_tc
+    try:
+        y = K.conv_fprop(to_dev(x), w.cuda(), b.cuda(), g)
+        dx = K.conv_dgrad(to_dev(dy), w.cuda(), g)
+        dw = K.conv_wgrad(to_dev(x), to_dev(dy), g, tuple(w.shape))
+        db = K.bias_grad(to_dev(dy))
+    finally:
+        K.config.use_tc = True
+    wq = w.to(torch.bfloat16).float() if (use_tc and K._tc_geom_ok(g)) else w     # TC path rounds the filter to bf16
+    fb = FB()
+    tol = 1e-4 if dtype == torch.float32 else 1e-2
+    assert y.shape == ((N, Cout) if two_d else (N, Cout, g.Ho, g.Wo)) and y.dtype == dtype
+    assert rel(y, fb.conv_fprop(x, wq, b, g)) < tol
+    assert rel(dx, fb.conv_dgrad(dy, wq, g)) < tol
+    assert rel(dw, fb.conv_wgrad(x, dy, g, tuple(w.shape))) < 1e-4 + (2e-3 if dtype == torch.bfloat16 else 0)
+    assert rel(db, fb.bias_grad(dy)) < 1e-4
+
+
+def test_conv_mixed_dtype_heads(K):
+    """Critic heads: BF16 features in, float logits out, and the matching backward dtypes."""
+    g = K.ConvGeom(6, 1, 1, 128, 1, 1, 10, 1, 1, 1, 0, 0)
+    x, w, b = act((6, 128), torch.bfloat16, 1), filt((1, 1, 128, 10), 2, 0.1), act((10,), torch.float32, 3)
+    dy = act((6, 10), torch.float32, 4)
+    fb = FB()
+    y = K.conv_fprop(x.cuda(), w.cuda(), b.cuda(), g, out_dtype=torch.float32)
+    assert y.dtype == torch.float32 and rel(y, fb.conv_fprop(x, w, b, g, out_dtype=torch.float32)) < 1e-5
+    dx = K.conv_dgrad(dy.cuda(), w.cuda(), g, out_dtype=torch.bfloat16)
+    assert dx.dtype == torch.bfloat16 and rel(dx, fb.conv_dgrad(dy, w, g, out_dtype=torch.bfloat16)) < 1e-2
+    dw = K.conv_wgrad(x.cuda(), dy.cuda(), g, tuple(w.shape))
+    assert rel(dw, fb.conv_wgrad(x, dy, g, tuple(w.shape))) < 1e-5
+
+
+def test_tc_residual_relu_epilogue(K):
+    g = K.same_geom(3, 8, 8, 128, 128, 3, 1)
+    x, r = act((3, 128, 8, 8), torch.bfloat16, 1), act((3, 128, 8, 8), torch.bfloat16, 2)
+    w, b = filt((3, 3, 128, 128), 3), act((128,), torch.float32, 4)
+    y = K.conv_fprop(to_dev(x), w.cuda(), b.cuda(), g, relu=True, residual=to_dev(r))
+    ref = FB().conv_fprop(x, w.to(torch.bfloat16).float(), b, g, relu=True, residual=r)
+    assert rel(y, ref) < 1e-2
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_elementwise_and_layout(K, dtype):
+    fb = FB()
+    tol = 1e-6 if dtype == torch.float32 else 1e-2
+    a, b = act((3, 16, 6, 6), dtype, 1), act((3, 16, 6, 6), dtype, 2)
+    A, B = to_dev(a), to_dev(b)
+    assert rel(K.add(A, B), fb.add(a, b)) < tol
+    assert rel(K.mul(A, B), fb.mul(a, b)) < tol
+    assert rel(K.scale(A, 0.37), fb.scale(a, 0.37)) < tol
+    bias = act((16,), torch.float32, 3)
+    assert rel(K.bias_add(A, bias.cuda()), fb.bias_add(a, bias)) < tol
+    assert rel(K.pool2x2(A, 0.25), fb.pool2x2(a, 0.25)) < tol
+    assert rel(K.upsample2x(A, 1.0), fb.upsample2x(a, 1.0)) < tol
+    assert rel(K.spatial_sum(A, 1 / 36.), fb.spatial_sum(a, 1 / 36.)) < tol
+    y2 = act((3, 16), dtype, 4)
+    assert rel(K.spatial_bcast(y2.cuda(), 6, 6, 0.5), fb.spatial_bcast(y2, 6, 6, 0.5)) < tol
+    assert rel(K.crop(A, 5, 4), fb.crop(a, 5, 4)) < tol
+    c = act((3, 16, 5, 4), dtype, 5)
+    assert rel(K.crop_bwd(to_dev(c), 6, 6), fb.crop_bwd(c, 6, 6)) < tol
+    for kind in (0, 1):
+        yk = K.unary_fwd(A, kind)
+        assert rel(yk, fb.unary_fwd(a, kind)) < max(tol, 1e-5)
+        assert rel(K.unary_bwd(yk, B, kind), fb.unary_bwd(yk.cpu(), b, kind)) < max(tol, 1e-5)
+    flat = act((3, 16 * 36), torch.float32, 6)
+    nh = K.nchw_to_nhwc(flat.cuda(), 3, 16, 6, 6, dtype)
+    assert nh.is_contiguous(memory_format=CL) and rel(nh, fb.nchw_to_nhwc(flat, 3, 16, 6, 6, dtype)) < tol
+    back = K.nhwc_to_nchw(nh, torch.float32, (3, 16 * 36))
+    assert rel(back, flat.to(dtype).float()) < 1e-7
+    assert rel(K.cast(A, torch.float32), a.float()) == 0.0
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('slope,keep', [(0.0, 1.0), (0.2, 0.5), (1.0, 0.8)])
+def test_act_dropout_matches_philox_reference(K, dtype, slope, keep):
+    """The in-kernel Philox stream == ctgan_philox_uniform's materialisation == the numpy reference."""
+    fb = FB()
+    x = act((4, 8, 5, 5), dtype, 1)
+    seed, off = 0x1234ABCD5678, 4096
+    y, m = K.act_dropout(to_dev(x), slope, keep, seed=seed, offset=off)
+    yr, mr = fb.act_dropout(x, slope, keep, seed=seed, offset=off)
+    assert torch.equal(m.cpu().float(), mr.float())
+    assert rel(y, yr) < (1e-6 if dtype == torch.float32 else 1e-2)
+    u = K.philox_uniform((4, 8, 5, 5), 'cuda', seed, off, memory_format=CL)
+    y2, m2 = K.act_dropout(to_dev(x), slope, keep, u=u)
+    assert torch.equal(m2, m) and torch.equal(y2, y)
+    dyn = torch.tensor([off], dtype=torch.int64, device='cuda')
+    y3, _ = K.act_dropout(to_dev(x), slope, keep, seed=seed, offset=0, dyn=dyn)
+    assert torch.equal(y3, y)
+
+
+def test_philox_streams_match_reference(K):
+    from tests import philox_ref
+    seed = 987654321987
+    u = K.philox_uniform((1000,), 'cuda', seed, 12, lo=-1.0, hi=3.0).cpu().numpy()
+    np.testing.assert_allclose(u, -1.0 + 4.0 * philox_ref.uniform(seed, 12, 1000), rtol=0, atol=1e-6)
+    z = K.philox_normal((501,), 'cuda', seed, 40).cpu().numpy()
+    np.testing.assert_allclose(z, philox_ref.normal(seed, 40, 501), rtol=1e-4, atol=1e-5)
+    assert abs(float(z.mean())) < 0.2 and 0.8 < float(z.std()) < 1.2
+    lab = K.philox_labels(777, 'cuda', 10, seed, 8).cpu().numpy()
+    np.testing.assert_array_equal(lab, (philox_ref.uniform(seed, 8, 777) * np.float32(10)).astype('int32'))
+    ctr = torch.zeros(1, dtype=torch.int64, device='cuda')
+    K.counter_add(ctr, 12)
+    u2 = K.philox_uniform((1000,), 'cuda', seed, 0, lo=-1.0, hi=3.0, dyn=ctr).cpu().numpy()
+    np.testing.assert_array_equal(u, u2)
+
+
+def test_prep_real_and_interpolate(K):
+    fb = FB()
+    xi = torch.randint(0, 256, (5, 3072), dtype=torch.int32)
+    np.testing.assert_allclose(K.prep_real(xi.cuda(), 255.).cpu().numpy(), fb.prep_real(xi, 255.).numpy(), atol=1e-7)
+    got = K.prep_real(xi.cuda(), 256., 1. / 128, seed=5, offset=16).cpu()
+    ref = fb.prep_real(xi, 256., 1. / 128, seed=5, offset=16)
+    np.testing.assert_allclose(got.numpy(), ref.numpy(), atol=1e-7)
+    assert float(got.min()) >= -1.0 and float(got.max()) < 1.0
+    r, f, a = torch.randn(5, 64), torch.randn(5, 64), torch.rand(5, 1)
+    np.testing.assert_allclose(K.interpolate(r.cuda(), f.cuda(), a.cuda()).cpu().numpy(),
+                               fb.interpolate(r, f, a).numpy(), atol=1e-6)
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('shape,cond', [((32, 128, 8, 8), True), ((6, 128, 32, 32), False), ((64, 8192), False),
+                                        ((5, 256, 8, 8), False)])
+@pytest.mark.parametrize('relu', [False, True])
+def test_batch_norm(K, dtype, shape, cond, relu):
+    fb = FB()
+    C = shape[1]
+    x = act(shape, dtype, 1, 2.0) + 0.5
+    x = x.contiguous(memory_format=CL) if len(shape) == 4 else x
+    nl = 10 if cond else 1
+    gamma, beta = act((nl, C), torch.float32, 2) + 1.0, act((nl, C), torch.float32, 3)
+    labels = torch.randint(0, 10, (shape[0],), dtype=torch.int32) if cond else None
+    dy = act(shape, dtype, 4)
+    y, mean, invstd = K.bn_fwd(to_dev(x), gamma.cuda(), beta.cuda(), labels.cuda() if cond else None, 1e-5, relu)
+    yr, mr, ir = fb.bn_fwd(x, gamma, beta, labels, 1e-5, relu)
+    tol = 2e-5 if dtype == torch.float32 else 1e-2
+    assert rel(mean, mr) < 1e-5 and rel(invstd, ir) < 1e-5 and rel(y, yr) < tol
+    dx, dg, db = K.bn_bwd(to_dev(dy), to_dev(x), y, gamma.cuda(), labels.cuda() if cond else None, mean, invstd, relu)
+    dxr, dgr, dbr = fb.bn_bwd(dy, x, y.cpu(), gamma, labels, mean.cpu(), invstd.cpu(), relu)
+    assert rel(dx, dxr) < (1e-4 if dtype == torch.float32 else 2e-2)
+    assert rel(dg, dgr) < 1e-4 and rel(db, dbr) < 1e-4
+
+
+@pytest.mark.parametrize('feat_dtype', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('with_logits', [False, True])
+def test_ct_gp_loss(K, feat_dtype, with_logits):
+    from ctgan_b200._lib import LossDesc, F32, BF16
+    fb = FB()
+    B, NF, Fd, Pd = 16, 16, 640, 3072
+    g = torch.Generator().manual_seed(0)
+    d_real, d_real2, d_fake = torch.randn(B, generator=g), torch.randn(B, generator=g), torch.randn(NF, generator=g)
+    f1, f2 = act((B, Fd), feat_dtype, 1), act((B, Fd), feat_dtype, 2)
+    grad = torch.randn(B, Pd, generator=g) * 0.02
+    logits = torch.randn(B, 10, generator=g) if with_logits else None
+    labels = torch.randint(0, 10, (B,), dtype=torch.int32) if with_logits else None
+    desc = LossDesc(B, NF, Fd, Pd, 10 if with_logits else 0, BF16 if feat_dtype == torch.bfloat16 else F32,
+                    10.0, 2.0, 0.05, 1.0 if with_logits else 0.0)
+    c = lambda t: t.cuda() if t is not None else None
+    out, per = K.ct_gp_loss_fwd(desc, c(d_real), c(d_real2), c(d_fake), c(f1), c(f2), c(grad), c(logits), c(labels))
+    outr, perr = fb.ct_gp_loss_fwd(desc, d_real, d_real2, d_fake, f1, f2, grad, logits, labels)
+    np.testing.assert_allclose(out.cpu().numpy()[:5], outr.numpy()[:5], rtol=2e-5, atol=1e-6)
+    gcost = torch.tensor([0.7])
+    gs = K.ct_gp_loss_bwd(desc, c(gcost), c(d_real), c(d_real2), c(f1), c(f2), c(grad), c(logits), c(labels), per)
+    gr = fb.ct_gp_loss_bwd(desc, gcost, d_real, d_real2, f1, f2, grad, logits, labels, perr)
+    for a, b in zip(gs, gr):
+        if b is None:
+            assert a is None
+        else:
+            assert rel(a, b) < (1e-2 if b.dtype == torch.bfloat16 else 2e-5)
+
+
+def test_generator_loss_pieces(K):
+    fb = FB()
+    d = torch.randn(64)
+    lg, lab = torch.randn(64, 10), torch.randint(0, 10, (64,), dtype=torch.int32)
+    gc = torch.tensor([1.3])
+    np.testing.assert_allclose(K.mean_fwd(d.cuda(), -1.0).cpu().numpy(), fb.mean_fwd(d, -1.0).numpy(), rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(K.mean_bwd(gc.cuda(), 64, -1.0).cpu().numpy(), fb.mean_bwd(gc, 64, -1.0).numpy(), rtol=1e-6)
+    np.testing.assert_allclose(K.softmax_ce_fwd(lg.cuda(), lab.cuda()).cpu().numpy(), fb.softmax_ce_fwd(lg, lab).numpy(), rtol=1e-5)
+    assert rel(K.softmax_ce_bwd(lg.cuda(), lab.cuda(), gc.cuda(), 0.1), fb.softmax_ce_bwd(lg, lab, gc, 0.1)) < 1e-5
+
+
+def test_adam_tf_semantics(K):
+    from oracle.tf_ops import TFAdam
+    n = 100003
+    g0 = torch.Generator().manual_seed(0)
+    p = torch.randn(n, generator=g0)
+    ref_p = {'w': p.clone().double()}
+    opt = TFAdam(0.5, 0.9)
+    P, M, V = p.cuda(), torch.zeros(n, device='cuda'), torch.zeros(n, device='cuda')
+    lr = 1e-4
+    for t in range(1, 4):
+        g = torch.randn(n, generator=g0) * 10 ** float(-t)
+        opt.apply(ref_p, {'w': g.double()}, lr)
+        lr_t = lr * np.sqrt(1 - 0.9 ** t) / (1 - 0.5 ** t)
+        K.adam_step(P, g.cuda(), M, V, lr_t, 0.5, 0.9, 1e-8)
+    assert rel(P.cpu() - p, ref_p['w'] - p.double()) < 1e-3     # update recovered from fp32 params
+    assert rel(M, opt.m['w']) < 1e-6 and rel(V, opt.v['w']) < 1e-6
+    # device-resident lr and gradient pre-scale
+    P2, M2, V2 = p.cuda(), torch.zeros(n, device='cuda'), torch.zeros(n, device='cuda')
+    g = torch.randn(n, generator=g0)
+    K.adam_step(P2, (2 * g).cuda(), M2, V2, 123.0, 0.0, 0.9, 1e-8, grad_scale=0.5, lr_t_dev=torch.tensor([1e-3], device='cuda'))
+    P3, M3, V3 = p.cuda(), torch.zeros(n, device='cuda'), torch.zeros(n, device='cuda')
+    K.adam_step(P3, g.cuda(), M3, V3, 1e-3, 0.0, 0.9, 1e-8)
+    assert torch.equal(P2, P3)
+
+
+def test_bad_descriptors_fail_loudly(K):
+    from ctgan_b200._lib import CtganError
+    g = K.ConvGeom(1, 4, 4, 8, 4, 4, 8, 3, 3, 1, 1, 1)
+    x = act((1, 8, 4, 4), torch.float32).cuda().contiguous(memory_format=CL)
+    with pytest.raises(CtganError):
+        K.conv_fprop(x, torch.zeros(3, 3, 8, 8, device='cuda'), None, g._replace(stride=0))
+    with pytest.raises(RuntimeError):
+        K.conv_fprop(x.cpu(), torch.zeros(3, 3, 8, 8), None, g)           # no CPU path
+    with pytest.raises(CtganError):
+        K.act_dropout(x, 0.2, 0.0)
