@@ -1,0 +1,337 @@
+"""bench.py -- CT-GAN training throughput on B200 (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--no-graph]
+  torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+A "step" is ONE training iteration of CT_gan_cifar_resnet.py -- 1 generator step + 5 critic
+steps (TG/CT_gan_cifar_resnet.py:393-404) -- at batch 64 per GPU, DIM 128, BF16 tensor-core
+path, synthetic CIFAR-shaped data, random-init weights.  One JSON line is printed by rank 0.
+
+  value     iterations/s with the real batches already resident in HBM
+  e2e       the same loop through the public API with HOST batches: every critic step copies
+            its int32 [64,3072] batch + labels from pinned host memory and reads the 8 loss
+            scalars back; every generator step reads its loss back
+  roofline  the dominant kernel (tcgen05 implicit-GEMM conv, 3x3 128->128 @32x32, 128 images),
+            timed alone with CUDA events over buffers that exceed L2
+  cpu_baseline / --impl reference
+            the CPU transcription of the reference graph (oracle/, PyTorch-CPU fp32, all host
+            threads) -- TF 1.2.1 cannot be installed here
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = 'CT-GAN train iters/sec (CIFAR ResNet)'
+UNIT = 'iterations/s (1 gen + 5 critic steps of batch 64 per GPU; aggregate over GPUs)'
+BATCH = 64
+N_CRITIC = 5
+ITER_GFLOP = 2990.34          # algorithmic FLOPs of one iteration
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            p = json.load(f)
+        return dict(hbm=p['hbm_gbs'], burst=p['bf16_tflops'], sustained=p['bf16_tflops_sustained'], src='measured')
+    except Exception:
+        return dict(hbm=6650.0, burst=1590.0, sustained=1400.0, src='fallback')
+
+
+# ----------------------------------------------------------------------------- CPU reference arm
+def time_cpu_reference(max_seconds=150.0, want_steps=1):
+    """Times the oracle (CPU transcription of CT_gan_cifar_resnet.py, fp32, all host threads) on a
+    bounded sample: n critic steps + n generator steps at batch 64; an iteration = 5 critic + 1 gen."""
+    import numpy as np
+    import torch
+    from oracle import ct_gan_cifar_resnet as R
+    from oracle.rand import SeededRandom
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    np.random.seed(1234)
+    m = R.Model(dtype=torch.float32, batch_size=BATCH).build()
+    rs = np.random.RandomState(1234)
+    x = torch.from_numpy(rs.randint(0, 256, (BATCH, 3072)).astype('int32'))
+    y = torch.from_numpy(rs.randint(0, 10, (BATCH,)).astype('int32'))
+    t0 = time.time()
+    m.critic_step(SeededRandom(1), x, y, iteration=0)            # warm-up (also sizes the sample)
+    t_warm = time.time() - t0
+    n = max(1, min(want_steps, int(max_seconds / max(2.2 * t_warm, 1e-3))))
+    tc = tg = 0.0
+    for i in range(n):
+        t0 = time.time(); m.critic_step(SeededRandom(10 + i), x, y, iteration=i); tc += time.time() - t0
+        t0 = time.time(); m.gen_step(SeededRandom(100 + i), iteration=i); tg += time.time() - t0
+    tc, tg = tc / n, tg / n
+    it_s = 1.0 / (N_CRITIC * tc + tg)
+    return dict(value=it_s, unit=UNIT, cores=torch.get_num_threads(), kind='port',
+                sample='%d critic + %d generator steps at batch 64 (fp32 oracle, PyTorch-CPU); iteration = 5*critic + 1*gen '
+                       '= %.2f s' % (n, n, N_CRITIC * tc + tg)), (N_CRITIC * tc + tg)
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    cb, sec = time_cpu_reference(max_seconds=150.0, want_steps=max(1, args.steps))
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': cb['value'], 'unit': UNIT, 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': sec * 1e3, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': 'CT_gan_cifar_resnet.py critic+generator iteration, batch 64, DIM 128 (BASELINE configs[2]); '
+                               'CPU transcription of the reference graph on host cores'},
+        'cpu_baseline': cb,
+        'e2e': {'value': cb['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '--query-gpu=' + self.Q, '--format=csv,noheader,nounits', '-lms', '100',
+                                          '-i', str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[5:9]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        sm.sort()
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+# ----------------------------------------------------------------------------- our arm
+def roofline_dominant_kernel(torch, peaks):
+    """tcgen05 implicit-GEMM conv of Discriminator.1.Conv2's shape on the stacked real+fake pass:
+    128 images, 32x32, 3x3, 128->128 (55 % of the critic's forward FLOPs).  Timed alone with CUDA
+    events on the launching stream; 6 rotating buffer sets (6 x 67 MB) exceed the 126 MB L2."""
+    import ctgan_b200.kernels as K
+    N, H, W, C = 128, 32, 32, 128
+    g = K.same_geom(N, H, W, C, C, 3, 1)
+    sets = []
+    for i in range(6):
+        x = torch.randn(N, C, H, W, device='cuda').to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        sets.append(x)
+    w = (torch.randn(3, 3, C, C, device='cuda') * 0.03).contiguous()
+    b = torch.zeros(C, device='cuda')
+    for i in range(6):
+        K.conv_fprop(sets[i], w, b, g, w_is_param=False)
+    torch.cuda.synchronize()
+    reps = 30
+    wp = K.pack_filter(w, 0)
+    import ctypes
+    from ctgan_b200 import _lib
+    d = K._desc(g, _lib.BF16, _lib.BF16)
+    ys = [torch.empty_like(sets[0]) for _ in range(6)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(reps):
+        _lib.call('ctgan_conv_fprop_tc', ctypes.byref(d), K._p(sets[i % 6]), K._p(wp), K._p(b), None, K._p(ys[i % 6]), 0, K._stream())
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    flops = 2.0 * N * H * W * C * C * 9
+    achieved = flops / (ms * 1e-3) / 1e12
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'roofline_traffic.json')) as f:
+            traffic = json.load(f).get('conv_fprop_tc_128x32x32x128_bytes')
+    except Exception:
+        pass
+    return {'bound': 'tensor', 'kernel': 'conv_fprop_tc_kernel<128,3> (3x3, 128->128, 128x32x32)', 'achieved': achieved,
+            'peak': peaks['burst'], 'peak_source': 'MEASURED_PEAKS.json bf16_tflops (burst; kernel timed alone)'
+            if peaks['src'] == 'measured' else 'fallback 1590', 'unit': 'TFLOP/s', 'frac': achieved / peaks['burst'],
+            'traffic': traffic, 'flops_per_launch': flops, 'us_per_launch': ms * 1e3}
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device (the product has no CPU path; use --impl reference for the CPU arm)')
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    dev = torch.device('cuda', local_rank)
+
+    import ctgan_b200.gan_cifar_resnet as R
+    from ctgan_b200 import _lib
+    from ctgan_b200.graphs import GraphedTrainer
+    np.random.seed(1234)                      # identical initial weights on every rank (reference init formulas)
+    tr = R.Trainer(device=dev, seed=1234 + rank, act_dtype=torch.bfloat16, batch_size=BATCH,
+                   graph_safe_rng=not args.no_graph)
+
+    # synthetic data: a pool of batches, pinned on the host (e2e) and resident on the device (value)
+    pool = 8
+    rs = np.random.RandomState(1234 + rank)
+    host_x = torch.from_numpy(rs.randint(0, 256, (pool, BATCH, 3072)).astype('int32')).pin_memory()
+    host_y = torch.from_numpy(rs.randint(0, 10, (pool, BATCH)).astype('int32')).pin_memory()
+    dev_x, dev_y = host_x.to(dev), host_y.to(dev)
+    host_out = torch.zeros(N_CRITIC + 1, 8, dtype=torch.float32).pin_memory()
+
+    if args.no_graph:
+        gt = None
+    else:
+        gt = GraphedTrainer(tr, (dev_x[0], dev_y[0]))
+    state = {'it': 0, 'b': 0}
+
+    def iteration(e2e):
+        it = state['it']
+        src_x, src_y = (host_x, host_y) if e2e else (dev_x, dev_y)
+        if gt is not None:
+            gt.iteration = it
+            if it > 0 or True:                # the reference skips the very first generator step (:396); timed loops never hit it==0
+                g = gt.gen_step()
+                if e2e:
+                    host_out[N_CRITIC, 0:1].copy_(g.reshape(-1)[:1], non_blocking=True)
+            for i in range(N_CRITIC):
+                b = state['b'] = (state['b'] + 1) % pool
+                out = gt.critic_step(src_x[b], src_y[b])
+                if e2e:
+                    host_out[i].copy_(out, non_blocking=True)
+        else:
+            res = tr.gen_step(iteration=it)
+            if e2e:
+                host_out[N_CRITIC, 0:1].copy_(res['cost'].reshape(-1)[:1], non_blocking=True)
+            for i in range(N_CRITIC):
+                b = state['b'] = (state['b'] + 1) % pool
+                x = src_x[b].to(dev, non_blocking=True) if e2e else src_x[b]
+                y = src_y[b].to(dev, non_blocking=True) if e2e else src_y[b]
+                res = tr.critic_step(x, y, iteration=it)
+                if e2e:
+                    host_out[i].copy_(res['out'], non_blocking=True)
+        state['it'] = it + 1
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(e2e, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            iteration(e2e)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    for _ in range(max(3, args.warmup)):
+        iteration(False)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    k0 = _lib.lib.ctgan_kernel_launches()
+    ms = timed(False, args.steps)
+    eager_launches = _lib.lib.ctgan_kernel_launches() - k0
+    clocks = sampler.stop() if sampler else None
+    for _ in range(2):
+        iteration(True)
+    ms_e2e = timed(True, args.steps)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = load_peaks()
+    it_s = world * args.steps / (ms * 1e-3)
+    it_s_e2e = world * args.steps / (ms_e2e * 1e-3)
+    if gt is not None:
+        launches = args.steps * (gt.gen_kernels + N_CRITIC * gt.critic_kernels)
+    else:
+        launches = eager_launches
+    roof = roofline_dominant_kernel(torch, peaks)
+    step_tflops = ITER_GFLOP * 1e-3 * (args.steps / (ms * 1e-3))            # per GPU
+    line = {
+        'metric': METRIC, 'value': it_s, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': max(3, args.warmup),
+        'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'bf16', 'data': 'synthetic',
+        'config': {
+            'workload': 'CT_gan_cifar_resnet.py iteration = 1 generator step (2x64 fakes) + 5 critic steps (64 real + 64 fake, '
+                        '2 stochastic passes + GP double-backward), batch 64 per GPU, DIM_G=DIM_D=128, conditional+ACGAN '
+                        '(BASELINE configs[2]; configs[3] when n_gpus>1: batch-sharded data parallel, NCCL all-reduce of flat grads)',
+            'per_gpu_batch': BATCH, 'critic_iters': N_CRITIC, 'cuda_graphs': gt is not None,
+            'l2_policy': 'working set per iteration (~1.5 GB of activations, 8 rotating input batches) exceeds the 126 MB L2; no explicit flush',
+            'precision': 'BF16 operands / fp32 accumulate (tcgen05), fp32 master weights and optimizer',
+        },
+        'clocks': clocks,
+        'e2e': {'value': it_s_e2e, 'unit': UNIT, 'ms_per_step': ms_e2e / args.steps,
+                'h2d_bytes_per_step': N_CRITIC * (BATCH * 3072 * 4 + BATCH * 4 + 4) + 4,
+                'd2h_bytes_per_step': N_CRITIC * 32 + 4},
+        'gpu_launches': int(launches),
+        'roofline': roof,
+        'step_tensor_utilisation': {'algorithmic_gflop_per_iteration': ITER_GFLOP, 'achieved_tflops_per_gpu': step_tflops,
+                                    'frac_of_sustained_peak': step_tflops / peaks['sustained'], 'peak': peaks['sustained']},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        cb, _ = time_cpu_reference(max_seconds=25.0, want_steps=1)
+        line['cpu_baseline'] = cb
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--no-graph', action='store_true', help='launch every kernel eagerly (debug / profiling)')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

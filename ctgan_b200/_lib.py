@@ -36,6 +36,7 @@ class LossDesc(Structure):
 P = c_void_p
 _PROTOS = {
     'ctgan_version': (c_int, []),
+    'ctgan_kernel_launches': (ctypes.c_ulonglong, []),
     'ctgan_last_error': (c_char_p, []),
     'ctgan_tc_available': (c_int, []),
     'ctgan_conv_fprop': (c_int, [POINTER(ConvDesc), P, P, P, P, c_int, P]),

@@ -12,8 +12,11 @@ namespace ctgan {
 void set_error(const char* fmt, ...);
 int  cuda_status(cudaError_t e, const char* what);
 
+extern unsigned long long g_kernel_launches;   // kernels launched by this library (api.cu)
+
 #define CTGAN_CHECK_LAUNCH(what)                                   \
     do {                                                           \
+        ++::ctgan::g_kernel_launches;                              \
         cudaError_t _e = cudaGetLastError();                       \
         if (_e != cudaSuccess) return ::ctgan::cuda_status(_e, what); \
     } while (0)

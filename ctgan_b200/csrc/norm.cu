@@ -102,25 +102,41 @@ bn_stats_kernel(const T* __restrict__ x, float* __restrict__ ws, int64_t R, int 
 }
 
 // ---- forward stage 2: merge the row-block partials (Chan), biased variance --------
-__global__ void bn_finalize_kernel(const float* __restrict__ ws, float* __restrict__ save_mean,
-                                   float* __restrict__ save_invstd, int64_t R, int C, int nb,
-                                   int rows_per_block, float eps) {
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
-    float cnt = 0.f, mean = 0.f, m2 = 0.f;
-    for (int b = 0; b < nb; ++b) {
-        int64_t r0 = (int64_t)b * rows_per_block;
-        float nbc = (float)(min(R, r0 + rows_per_block) - r0);
-        if (nbc <= 0.f) break;
-        float mb = ws[((int64_t)b * C + c) * 2], m2b = ws[((int64_t)b * C + c) * 2 + 1];
-        float n = cnt + nbc;
+// One warp per channel: lane l folds partials l, l+32, ... sequentially, then a 5-step butterfly
+// merges the 32 (count, mean, M2) triples.
+__device__ __forceinline__ void chan_merge(float& cnt, float& mean, float& m2, float cb, float mb, float m2b) {
+    if (cb > 0.f) {
+        float n = cnt + cb;
         float d = mb - mean;
-        mean += d * (nbc / n);
-        m2 += m2b + d * d * (cnt * nbc / n);
+        mean += d * (cb / n);
+        m2 += m2b + d * d * (cnt * cb / n);
         cnt = n;
     }
-    save_mean[c] = mean;
-    save_invstd[c] = rsqrtf(m2 / (float)R + eps);
+}
+__global__ void __launch_bounds__(128)
+bn_finalize_kernel(const float* __restrict__ ws, float* __restrict__ save_mean,
+                   float* __restrict__ save_invstd, int64_t R, int C, int nb,
+                   int rows_per_block, float eps) {
+    const int lane = threadIdx.x & 31;
+    const int c = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (c >= C) return;
+    float cnt = 0.f, mean = 0.f, m2 = 0.f;
+    for (int b = lane; b < nb; b += 32) {
+        int64_t r0 = (int64_t)b * rows_per_block;
+        float nbc = (float)(min(R, r0 + rows_per_block) - r0);
+        chan_merge(cnt, mean, m2, nbc, ws[((int64_t)b * C + c) * 2], ws[((int64_t)b * C + c) * 2 + 1]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        float cb = __shfl_xor_sync(0xffffffffu, cnt, o);
+        float mb = __shfl_xor_sync(0xffffffffu, mean, o);
+        float m2b = __shfl_xor_sync(0xffffffffu, m2, o);
+        chan_merge(cnt, mean, m2, cb, mb, m2b);
+    }
+    if (lane == 0) {
+        save_mean[c] = mean;
+        save_invstd[c] = rsqrtf(m2 / (float)R + eps);
+    }
 }
 
 // ---- forward stage 3: normalise, affine (per-label rows), optional ReLU -------------
@@ -198,29 +214,45 @@ bn_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T*
 }
 
 // ---- backward stage 2: per channel: table gradients + the two means BN needs ----------
-// coef[c] = mean_R(gamma_l * dy), coef[C + c] = mean_R(gamma_l * dy * xhat)
-__global__ void bn_bwd_finalize_kernel(const float* __restrict__ ws, const float* __restrict__ gamma,
-                                       const int32_t* __restrict__ labels, float* __restrict__ dgamma,
-                                       float* __restrict__ dbeta, float* __restrict__ coef,
-                                       int N, int S, int C, int n_labels, float inv_R) {
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
+// coef[c] = mean_R(gamma_l * dy), coef[C + c] = mean_R(gamma_l * dy * xhat).  One warp per channel;
+// the per-label table sums go through shared-memory atomics (n_labels <= 10 in the reference).
+__global__ void __launch_bounds__(128)
+bn_bwd_finalize_kernel(const float* __restrict__ ws, const float* __restrict__ gamma,
+                       const int32_t* __restrict__ labels, float* __restrict__ dgamma,
+                       float* __restrict__ dbeta, float* __restrict__ coef,
+                       int N, int S, int C, int n_labels, float inv_R) {
+    extern __shared__ float tab[];                    // [4 warps][2][n_labels]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c = blockIdx.x * 4 + warp;
+    float* t1 = tab + (size_t)warp * 2 * n_labels;
+    float* t2 = t1 + n_labels;
+    for (int l = lane; l < 2 * n_labels; l += 32) t1[l] = 0.f;
+    __syncwarp();
     if (c >= C) return;
-    for (int l = 0; l < n_labels; ++l) { dgamma[(int64_t)l * C + c] = 0.f; dbeta[(int64_t)l * C + c] = 0.f; }
     float a1 = 0.f, a2 = 0.f;
-    for (int n = 0; n < N; ++n) {
+    for (int n = lane; n < N; n += 32) {
         int l = labels ? labels[n] : 0;
-        float t1 = 0.f, t2 = 0.f;
+        float s1 = 0.f, s2 = 0.f;
         for (int s = 0; s < S; ++s) {
-            t1 += ws[(((int64_t)n * S + s) * C + c) * 2];
-            t2 += ws[(((int64_t)n * S + s) * C + c) * 2 + 1];
+            s1 += ws[(((int64_t)n * S + s) * C + c) * 2];
+            s2 += ws[(((int64_t)n * S + s) * C + c) * 2 + 1];
         }
         float g = gamma[(int64_t)l * C + c];
-        a1 += g * t1; a2 += g * t2;
-        dbeta[(int64_t)l * C + c] += t1;
-        dgamma[(int64_t)l * C + c] += t2;
+        a1 += g * s1; a2 += g * s2;
+        atomicAdd(t1 + l, s1);
+        atomicAdd(t2 + l, s2);
     }
-    coef[c] = a1 * inv_R;
-    coef[C + c] = a2 * inv_R;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+        a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+    }
+    __syncwarp();
+    for (int l = lane; l < n_labels; l += 32) {
+        dbeta[(int64_t)l * C + c] = t1[l];
+        dgamma[(int64_t)l * C + c] = t2[l];
+    }
+    if (lane == 0) { coef[c] = a1 * inv_R; coef[C + c] = a2 * inv_R; }
 }
 
 // ---- backward stage 3: dx = invstd * (gamma_l*dy - mean(.) - xhat*mean(. xhat)) ----------
@@ -301,7 +333,7 @@ extern "C" int ctgan_bn_fwd(const void* x, const float* gamma, const float* beta
     if (dtype == CTGAN_F32) bn_stats_kernel<float><<<grid, blk, 0, st>>>((const float*)x, ws, R, C, rpb);
     else bn_stats_kernel<__nv_bfloat16><<<grid, blk, 0, st>>>((const __nv_bfloat16*)x, ws, R, C, rpb);
     CTGAN_CHECK_LAUNCH("bn_stats");
-    bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, st>>>(ws, save_mean, save_invstd, R, C, nb, rpb, eps);
+    bn_finalize_kernel<<<ceil_div(C, 4), 128, 0, st>>>(ws, save_mean, save_invstd, R, C, nb, rpb, eps);
     CTGAN_CHECK_LAUNCH("bn_finalize");
     int g2 = elementwise_grid(R * (C / 4), 256);
     if (dtype == CTGAN_F32)
@@ -330,7 +362,7 @@ extern "C" int ctgan_bn_bwd(const void* dy, const void* x, const void* y, const 
     else
         bn_bwd_reduce_kernel<__nv_bfloat16><<<grid, blk, 0, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (const __nv_bfloat16*)y, save_mean, save_invstd, ws, HW, C, S, relu);
     CTGAN_CHECK_LAUNCH("bn_bwd_reduce");
-    bn_bwd_finalize_kernel<<<ceil_div(C, 128), 128, 0, st>>>(ws, gamma, labels, dgamma, dbeta, coef, N, S, C, n_labels, 1.f / (float)R);
+    bn_bwd_finalize_kernel<<<ceil_div(C, 4), 128, sizeof(float) * 8 * n_labels, st>>>(ws, gamma, labels, dgamma, dbeta, coef, N, S, C, n_labels, 1.f / (float)R);
     CTGAN_CHECK_LAUNCH("bn_bwd_finalize");
     int g2 = elementwise_grid(R * (C / 4), 256);
     if (dtype == CTGAN_F32)

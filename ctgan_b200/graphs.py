@@ -1,0 +1,126 @@
+"""CUDA-graph capture of the critic step and the generator step.
+
+At batch 64 a CT-GAN iteration is several hundred short kernels (hard part 1):
+launched eagerly through Python/ctypes/autograd it is host-bound.  Both steps are therefore
+captured once (forward, first- and second-order backward, Adam, RNG counter advance) and
+replayed; everything that changes between replays lives in device memory:
+  * the real batch / labels      -> static input buffers (copied into before each replay),
+  * random numbers               -> Philox streams offset by a device counter (runtime.DeviceRandom),
+  * the learning rate lr_t       -> FlatAdam.lr_t_dev, uploaded from pinned memory per replay.
+
+Data parallel (world_size > 1): each step is captured as TWO graphs -- (zero_grad, forward,
+backward) and (Adam, RNG advance) -- with the NCCL all-reduce of the flat gradient bucket
+issued eagerly between them on the same stream.  The collective is one launch per step
+(4.2 MB / 4.9 MB), so keeping it out of the capture costs ~one host launch and avoids
+depending on NCCL-inside-capture behaviour.
+"""
+import torch
+
+from . import kernels as K
+
+
+def _world():
+    import torch.distributed as dist
+    return dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+
+
+class _Step:
+    """One training step (critic or generator) as one graph (single GPU) or two graphs + all-reduce."""
+
+    def __init__(self, opt, fwd_bwd, rng, pool):
+        self.opt, self.rng, self.world = opt, rng, _world()
+        self.kernels = 0
+
+        def whole():
+            opt.zero_grad()
+            out = fwd_bwd()
+            opt.step(None, 1, use_device_lr=True)
+            rng.end_step()
+            return out
+
+        def part_a():
+            opt.zero_grad()
+            return fwd_bwd()
+
+        def part_b():
+            opt.step(None, self.world, use_device_lr=True)
+            rng.end_step()
+
+        k0 = K._lib.lib.ctgan_kernel_launches()
+        K.invalidate_weight_cache()
+        if self.world == 1:
+            self.g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.g, pool=pool):
+                self.out = whole()
+            self.pool = self.g.pool()
+        else:
+            self.ga, self.gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.ga, pool=pool):
+                self.out = part_a()
+            self.pool = self.ga.pool()
+            offset = rng.offset                   # consumed by part A; folded into the device counter by part B
+            with torch.cuda.graph(self.gb, pool=self.pool):
+                rng.offset = offset
+                part_b()
+        self.kernels = K._lib.lib.ctgan_kernel_launches() - k0
+        K.invalidate_weight_cache()
+
+    def replay(self):
+        if self.world == 1:
+            self.g.replay()
+        else:
+            self.ga.replay()
+            self.opt.all_reduce()
+            self.gb.replay()
+        return self.out
+
+
+class GraphedTrainer:
+    """Wraps a Trainer (gan_cifar_resnet / gan_cifar / gan_mnist) built with graph_safe_rng=True."""
+
+    def __init__(self, trainer, example_inputs, warmup=3):
+        self.tr = tr = trainer
+        self.static_inputs = tuple(torch.empty_like(t) for t in example_inputs)
+        for s, t in zip(self.static_inputs, example_inputs):
+            s.copy_(t)
+        self.iteration = 0
+        if tr.rng.dyn is None:
+            raise RuntimeError('GraphedTrainer needs a Trainer created with graph_safe_rng=True')
+        tr.rng.record = False
+
+        def critic_fb():
+            return tr.critic_forward_backward(*self.static_inputs)['out']
+
+        def gen_fb():
+            return tr.gen_forward_backward()['cost']
+
+        # warm-up on a side stream (allocator + lazy init), eager, including the all-reduce
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                tr.disc_opt.set_device_lr(self._lr())
+                tr.critic_step(*self.static_inputs, use_device_lr=True)
+                tr.gen_opt.set_device_lr(self._lr())
+                tr.gen_step(use_device_lr=True)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+
+        self.critic = _Step(tr.disc_opt, critic_fb, tr.rng, None)
+        self.gen = _Step(tr.gen_opt, gen_fb, tr.rng, self.critic.pool)
+        self.critic_kernels, self.gen_kernels = self.critic.kernels, self.gen.kernels
+
+    def _lr(self):
+        return self.tr.lr(self.iteration) if hasattr(self.tr, 'lr') else None
+
+    def critic_step(self, *inputs, non_blocking=True):
+        """inputs: tensors (device or pinned host) copied into the static buffers, then one replay.
+        Returns the static float[8] loss tensor {cost, wgan, ct, gp, acgan, ...} (device)."""
+        for s, t in zip(self.static_inputs, inputs):
+            s.copy_(t, non_blocking=non_blocking)
+        self.tr.disc_opt.set_device_lr(self._lr())
+        return self.critic.replay()
+
+    def gen_step(self):
+        self.tr.gen_opt.set_device_lr(self._lr())
+        return self.gen.replay()

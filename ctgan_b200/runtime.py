@@ -166,9 +166,11 @@ class FlatAdam:
     def step(self, lr=None, world=1, use_device_lr=False):
         """One update.  use_device_lr: read lr_t from self.lr_t_dev (set with set_device_lr) so the
         launch is replayable inside a CUDA graph."""
-        self.t += 1
-        K.adam_step(self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.lr_t(lr), self.beta1, self.beta2,
-                    self.eps, grad_scale=1.0 / world, lr_t_dev=self.lr_t_dev if use_device_lr else None)
+        if not use_device_lr:
+            self.t += 1                      # graph mode: t advances in set_device_lr() at replay time
+        K.adam_step(self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.lr_t(lr) if not use_device_lr else 0.0,
+                    self.beta1, self.beta2, self.eps, grad_scale=1.0 / world,
+                    lr_t_dev=self.lr_t_dev if use_device_lr else None)
         K.invalidate_weight_cache()
 
     def set_device_lr(self, lr=None, advance=True):

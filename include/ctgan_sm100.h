@@ -40,6 +40,8 @@ extern "C" {
 
 /* ---- library ------------------------------------------------------------- */
 int         ctgan_version(void);              /* 100*major + minor */
+/* number of GPU kernels this library has launched (or captured into a CUDA graph) so far */
+unsigned long long ctgan_kernel_launches(void);
 const char* ctgan_last_error(void);
 /* 1 when the tcgen05/TMA path is usable on the current device (cc 10.x), else 0 */
 int         ctgan_tc_available(void);
