@@ -12,6 +12,14 @@
 
 namespace ctgan {
 
+namespace thin {   // conv_thin.cu: warp-per-pixel kernels for <= 4 channels on one side
+int try_fprop(const ctgan_conv_desc* d, const void* x, const float* w, const float* bias, void* y, int flags,
+              cudaStream_t st, int* rc);
+int try_dgrad(const ctgan_conv_desc* d, const void* dy, const float* w, void* dx, cudaStream_t st, int* rc);
+bool wgrad_ok(const ctgan_conv_desc* d, const void* x, const void* dy);
+int try_wgrad(const ctgan_conv_desc* d, const void* x, const void* dy, float* dw, cudaStream_t st, int* rc);
+}
+
 enum { MODE_FPROP = 0, MODE_DGRAD = 1, MODE_WGRAD = 2 };
 
 struct Geom {
@@ -219,6 +227,7 @@ extern "C" int ctgan_conv_fprop(const ctgan_conv_desc* d, const void* x, const f
                                 const float* bias, void* y, int flags, void* stream) {
     if (int r = check_desc(d)) return r;
     CTGAN_REQUIRE(x && w && y, CTGAN_ERR_BAD_DESC, "conv_fprop: null pointer");
+    { int rc = 0; if (thin::try_fprop(d, x, w, bias, y, flags, as_stream(stream), &rc)) return rc; }
     Geom g = make_geom(d);
     int64_t M64 = (int64_t)d->N * d->Ho * d->Wo;
     CTGAN_REQUIRE(M64 < (1ll << 31), CTGAN_ERR_UNSUPPORTED, "conv_fprop: too many output pixels");
@@ -233,6 +242,7 @@ extern "C" int ctgan_conv_dgrad(const ctgan_conv_desc* d, const void* dy, const 
                                 void* dx, void* stream) {
     if (int r = check_desc(d)) return r;
     CTGAN_REQUIRE(dy && w && dx, CTGAN_ERR_BAD_DESC, "conv_dgrad: null pointer");
+    { int rc = 0; if (thin::try_dgrad(d, dy, w, dx, as_stream(stream), &rc)) return rc; }
     Geom g = make_geom(d);
     int64_t M64 = (int64_t)d->N * d->H * d->W;
     CTGAN_REQUIRE(M64 < (1ll << 31), CTGAN_ERR_UNSUPPORTED, "conv_dgrad: too many input pixels");
@@ -247,6 +257,15 @@ extern "C" int ctgan_conv_wgrad(const ctgan_conv_desc* d, const void* x, const v
                                 float* dw, int accumulate, void* stream) {
     if (int r = check_desc(d)) return r;
     CTGAN_REQUIRE(x && dy && dw, CTGAN_ERR_BAD_DESC, "conv_wgrad: null pointer");
+    if (thin::wgrad_ok(d, x, dy)) {
+        cudaStream_t ts = as_stream(stream);
+        if (!accumulate) {
+            cudaError_t e = cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)d->kh * d->kw * d->Cin * d->Cout, ts);
+            if (e != cudaSuccess) return cuda_status(e, "conv_wgrad memset");
+        }
+        int rc = 0;
+        if (thin::try_wgrad(d, x, dy, dw, ts, &rc)) return rc;
+    }
     Geom g = make_geom(d);
     int64_t P64 = (int64_t)d->N * d->Ho * d->Wo;
     CTGAN_REQUIRE(P64 < (1ll << 31), CTGAN_ERR_UNSUPPORTED, "conv_wgrad: too many output pixels");

@@ -535,7 +535,13 @@ extern "C" int ctgan_conv_fprop_tc(const ctgan_conv_desc* d, const void* x, cons
     if (int r = make_act_map(&mx, x, d->N, d->H, d->W, d->Cin, p.BW, p.BH, p.BN)) return r;
     if (int r = make_filter_map(&mw, wp, d->kh * d->kw, d->Cout, d->Cin, block_n)) return r;
     cudaStream_t st = as_stream(stream);
-    if (block_n == 128) return launch_fprop<128, 3>(mx, mw, p, st);
+    if (block_n == 128) {
+        // Few tiles (8x8 / 4x4 layers at batch 64): one CTA per SM at most, so the K loop is latency-bound --
+        // use a 6-deep TMA ring.  Many tiles: 3 stages x 2 co-resident CTAs per SM.
+        const int ctas = p.tilesW * p.tilesH * p.tilesN * (d->Cout / 128);
+        if (ctas <= sm_count()) return launch_fprop<128, 6>(mx, mw, p, st);
+        return launch_fprop<128, 3>(mx, mw, p, st);
+    }
     return launch_fprop<64, 4>(mx, mw, p, st);
 }
 

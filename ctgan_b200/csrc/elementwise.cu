@@ -123,29 +123,37 @@ __global__ void bias_add_kernel(const T* __restrict__ x, const float* __restrict
 }
 
 // ---- pooling / upsampling on NHWC --------------------------------------------
-template <typename T>
+// V channels (16 bytes when the channel count allows) per thread; index math once per vector.
+template <typename T, int V>
 __global__ void pool2x2_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H, int W, int C, float scale) {
-    const int Ho = H / 2, Wo = W / 2;
-    int64_t total = (int64_t)N * Ho * Wo * C;
+    using P = Pack<T, V>;
+    const int Ho = H / 2, Wo = W / 2, CV = C / V;
+    int64_t total = (int64_t)N * Ho * Wo * CV;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        int c = i % C; int64_t t = i / C;
+        int cv = i % CV; int64_t t = i / CV;
         int wo = t % Wo; t /= Wo;
         int ho = t % Ho; int n = t / Ho;
-        const T* p = x + (((int64_t)n * H + 2 * ho) * W + 2 * wo) * C + c;
-        float s = to_f<T>(p[0]) + to_f<T>(p[(int64_t)W * C]) + to_f<T>(p[C]) + to_f<T>(p[(int64_t)W * C + C]);
-        y[i] = from_f<T>(s * scale);
+        const P* p = reinterpret_cast<const P*>(x + (((int64_t)n * H + 2 * ho) * W + 2 * wo) * C) + cv;
+        P a = p[0], b = p[CV], c = p[(int64_t)W * CV], d = p[(int64_t)W * CV + CV], o;
+#pragma unroll
+        for (int k = 0; k < V; ++k)
+            o.v[k] = from_f<T>((to_f<T>(a.v[k]) + to_f<T>(c.v[k]) + to_f<T>(b.v[k]) + to_f<T>(d.v[k])) * scale);
+        reinterpret_cast<P*>(y)[i] = o;
     }
 }
-template <typename T>
+template <typename T, int V>
 __global__ void upsample2x_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H, int W, int C, float scale) {
-    const int Ho = 2 * H, Wo = 2 * W;
-    int64_t total = (int64_t)N * Ho * Wo * C;
+    using P = Pack<T, V>;
+    const int Ho = 2 * H, Wo = 2 * W, CV = C / V;
+    int64_t total = (int64_t)N * Ho * Wo * CV;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        int c = i % C; int64_t t = i / C;
+        int cv = i % CV; int64_t t = i / CV;
         int wo = t % Wo; t /= Wo;
         int ho = t % Ho; int n = t / Ho;
-        float v = to_f<T>(x[(((int64_t)n * H + ho / 2) * W + wo / 2) * C + c]);
-        y[i] = from_f<T>(v * scale);
+        P a = reinterpret_cast<const P*>(x + (((int64_t)n * H + ho / 2) * W + wo / 2) * C)[cv], o;
+#pragma unroll
+        for (int k = 0; k < V; ++k) o.v[k] = from_f<T>(to_f<T>(a.v[k]) * scale);
+        reinterpret_cast<P*>(y)[i] = o;
     }
 }
 template <typename T>
@@ -343,25 +351,31 @@ extern "C" int ctgan_bias_add(const void* x, const float* b, void* y, int64_t ro
     CTGAN_CHECK_LAUNCH("bias_add");
     return 0;
 }
+template <typename T>
+static int launch_resample(bool pool, const void* x, void* y, int N, int H, int W, int C, float scale, cudaStream_t st) {
+    constexpr int V = vec_width<T>();
+    const int64_t out_elems = pool ? (int64_t)N * (H / 2) * (W / 2) * C : (int64_t)N * H * W * C * 4;
+    const bool vec = C % V == 0 && aligned16(x) && aligned16(y);
+    const int grid = elementwise_grid(vec ? out_elems / V : out_elems, 256);
+    if (pool) {
+        if (vec) pool2x2_kernel<T, V><<<grid, 256, 0, st>>>((const T*)x, (T*)y, N, H, W, C, scale);
+        else     pool2x2_kernel<T, 1><<<grid, 256, 0, st>>>((const T*)x, (T*)y, N, H, W, C, scale);
+    } else {
+        if (vec) upsample2x_kernel<T, V><<<grid, 256, 0, st>>>((const T*)x, (T*)y, N, H, W, C, scale);
+        else     upsample2x_kernel<T, 1><<<grid, 256, 0, st>>>((const T*)x, (T*)y, N, H, W, C, scale);
+    }
+    CTGAN_CHECK_LAUNCH(pool ? "pool2x2" : "upsample2x");
+    return 0;
+}
 extern "C" int ctgan_pool2x2(const void* x, void* y, int N, int H, int W, int C, float scale, int dtype, void* stream) {
     CTGAN_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && H % 2 == 0 && W % 2 == 0, CTGAN_ERR_BAD_DESC, "pool2x2: H and W must be even and positive");
-    int64_t total = (int64_t)N * (H / 2) * (W / 2) * C;
-    int grid = elementwise_grid(total, 256);
-    cudaStream_t st = as_stream(stream);
-    DISPATCH_T(dtype, (pool2x2_kernel<float><<<grid, 256, 0, st>>>((const float*)x, (float*)y, N, H, W, C, scale)),
-                      (pool2x2_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, N, H, W, C, scale)));
-    CTGAN_CHECK_LAUNCH("pool2x2");
-    return 0;
+    DISPATCH_T(dtype, return launch_resample<float>(true, x, y, N, H, W, C, scale, as_stream(stream)),
+                      return launch_resample<__nv_bfloat16>(true, x, y, N, H, W, C, scale, as_stream(stream)));
 }
 extern "C" int ctgan_upsample2x(const void* x, void* y, int N, int H, int W, int C, float scale, int dtype, void* stream) {
     CTGAN_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0, CTGAN_ERR_BAD_DESC, "upsample2x: bad shape");
-    int64_t total = (int64_t)N * H * W * C * 4;
-    int grid = elementwise_grid(total, 256);
-    cudaStream_t st = as_stream(stream);
-    DISPATCH_T(dtype, (upsample2x_kernel<float><<<grid, 256, 0, st>>>((const float*)x, (float*)y, N, H, W, C, scale)),
-                      (upsample2x_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, N, H, W, C, scale)));
-    CTGAN_CHECK_LAUNCH("upsample2x");
-    return 0;
+    DISPATCH_T(dtype, return launch_resample<float>(false, x, y, N, H, W, C, scale, as_stream(stream)),
+                      return launch_resample<__nv_bfloat16>(false, x, y, N, H, W, C, scale, as_stream(stream)));
 }
 extern "C" int ctgan_spatial_sum(const void* x, void* y, int N, int HW, int C, float scale, int dtype, void* stream) {
     CTGAN_REQUIRE(N > 0 && HW > 0 && C > 0, CTGAN_ERR_BAD_DESC, "spatial_sum: bad shape");
