@@ -562,10 +562,11 @@ extern "C" int ctgan_conv_wgrad_tc(const ctgan_conv_desc* d, const void* x, cons
     const int tap_groups = ceil_div(taps, p.taps_per_cta);
     const int tiles = (d->Cin / 128) * (d->Cout / 128);
     const int total_chunks = p.chunksN * p.chunksH * p.chunksW;
-    // about one wave of CTAs (TMEM: 512 columns => one CTA per SM), at least 16 pixel chunks each
+    // about one wave of CTAs (TMEM: 512 columns => one CTA per SM), at least 4 pixel chunks each: the small
+    // layers are bound by the latency of the per-CTA K loop, not by the 49 K reductions each CTA adds
     int splits = sm_count() / (tiles * tap_groups);
     if (splits < 1) splits = 1;
-    int max_splits = total_chunks / 16; if (max_splits < 1) max_splits = 1;
+    int max_splits = total_chunks / 4; if (max_splits < 1) max_splits = 1;
     if (splits > max_splits) splits = max_splits;
     p.chunks_per_split = ceil_div(total_chunks, splits);
     splits = ceil_div(total_chunks, p.chunks_per_split);

@@ -39,6 +39,17 @@ def _is_param(w):
     return w.data_ptr() in _param_ptrs
 
 
+# When True, the FINAL (non-differentiable) backward pass adds filter / bias gradients straight into
+# the parameter's `.grad` (a view of FlatAdam's flat bucket) inside the wgrad / bias-grad kernels and
+# returns None to autograd: no temporary, no zero-fill, no AccumulateGrad add per contribution.
+direct_param_grads = True
+
+
+def _direct(p):
+    return (direct_param_grads and not torch.is_grad_enabled() and p.is_leaf and p.grad is not None
+            and p.grad.is_contiguous() and _is_param(p))
+
+
 def _dense_like(g, ref_dim4):
     """Make an incoming gradient dense in the layout the kernels use."""
     if g is None:
@@ -58,6 +69,7 @@ class ConvF(Function):
         ctx.g = g
         ctx.save_for_backward(x, w)
         ctx.has_bias = b is not None
+        ctx.bias = b
         return K.conv_fprop(x, w, b, g, out_dtype=out_dtype, w_is_param=_is_param(w))
 
     @staticmethod
@@ -68,9 +80,16 @@ class ConvF(Function):
         if ctx.needs_input_grad[0]:
             gx = ConvD.apply(gy, w, ctx.g, x.dtype)
         if ctx.needs_input_grad[1]:
-            gw = ConvG.apply(x, gy, ctx.g, tuple(w.shape))
+            if _direct(w):
+                K.conv_wgrad(x, gy, ctx.g, tuple(w.shape), accumulate_into=w.grad)
+            else:
+                gw = ConvG.apply(x, gy, ctx.g, tuple(w.shape))
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            gb = K.bias_grad(gy.detach())
+            b = ctx.bias
+            if _direct(b):
+                K.bias_grad(gy.detach(), accumulate_into=b.grad)
+            else:
+                gb = K.bias_grad(gy.detach())
         return gx, gw, gb, None, None
 
 
@@ -91,7 +110,10 @@ class ConvD(Function):
         if ctx.needs_input_grad[0]:
             ggy = ConvF.apply(c, w, None, ctx.g, gy.dtype)
         if ctx.needs_input_grad[1]:
-            gw = ConvG.apply(c, gy, ctx.g, tuple(w.shape))
+            if _direct(w):
+                K.conv_wgrad(c, gy, ctx.g, tuple(w.shape), accumulate_into=w.grad)
+            else:
+                gw = ConvG.apply(c, gy, ctx.g, tuple(w.shape))
         return ggy, gw, None, None
 
 
@@ -154,12 +176,18 @@ class BiasAdd(Function):
 
     @staticmethod
     def forward(ctx, x, b):
+        ctx.bias = b
         return K.bias_add(x, b)
 
     @staticmethod
     def backward(ctx, gy):
         gy = _dense_like(gy, True)
-        gb = K.bias_grad(gy.detach()) if ctx.needs_input_grad[1] else None
+        gb = None
+        if ctx.needs_input_grad[1]:
+            if _direct(ctx.bias):
+                K.bias_grad(gy.detach(), accumulate_into=ctx.bias.grad)
+            else:
+                gb = K.bias_grad(gy.detach())
         return gy, gb
 
 

@@ -195,26 +195,31 @@ def conv_dgrad(dy, w, g, out_dtype=None, w_is_param=False):
     return dx
 
 
-def conv_wgrad(x, dy, g, w_shape):
-    """dw (float HWIO, shape w_shape) = sum over pixels of x (shifted) * dy."""
+def conv_wgrad(x, dy, g, w_shape, accumulate_into=None):
+    """dw (float HWIO, shape w_shape) = sum over pixels of x (shifted) * dy.
+    accumulate_into: a float tensor of that shape (e.g. the parameter's slice of the flat gradient
+    bucket) to ADD the result to instead of allocating one; returns it."""
     require_nhwc(x, 'x')
     require_nhwc(dy, 'dy')
     xdt, ydt = _dt(x), _dt(dy)
     d = _desc(g, xdt, ydt)
+    acc = accumulate_into
+    if acc is not None and (acc.dtype != torch.float32 or not acc.is_contiguous() or tuple(acc.shape) != tuple(w_shape)):
+        raise RuntimeError('ctgan_b200: accumulate_into must be a contiguous float32 tensor of the filter shape')
     if xdt == BF16 and ydt == BF16 and _tc_geom_ok(g) and g.Cin % 128 == 0 and g.Cout % 128 == 0:
-        dw = torch.zeros(w_shape, dtype=torch.float32, device=x.device)
+        dw = acc if acc is not None else torch.zeros(w_shape, dtype=torch.float32, device=x.device)
         call('ctgan_conv_wgrad_tc', ctypes.byref(d), _p(x), _p(dy), _p(dw), _stream())
         return dw
-    dw = torch.empty(w_shape, dtype=torch.float32, device=x.device)
-    call('ctgan_conv_wgrad', ctypes.byref(d), _p(x), _p(dy), _p(dw), 0, _stream())
+    dw = acc if acc is not None else torch.empty(w_shape, dtype=torch.float32, device=x.device)
+    call('ctgan_conv_wgrad', ctypes.byref(d), _p(x), _p(dy), _p(dw), 1 if acc is not None else 0, _stream())
     return dw
 
 
-def bias_grad(dy):
+def bias_grad(dy, accumulate_into=None):
     require_nhwc(dy, 'dy')
     N, H, W, C = nhwc_dims(dy)
-    db = torch.empty(C, dtype=torch.float32, device=dy.device)
-    call('ctgan_bias_grad', _p(dy), _p(db), N * H * W, C, _dt(dy), 0, _stream())
+    db = accumulate_into if accumulate_into is not None else torch.empty(C, dtype=torch.float32, device=dy.device)
+    call('ctgan_bias_grad', _p(dy), _p(db), N * H * W, C, _dt(dy), 1 if accumulate_into is not None else 0, _stream())
     return db
 
 

@@ -68,20 +68,28 @@ def conv_dgrad(dy, w, g, out_dtype=None, w_is_param=False):
     return _out(dx, out_dtype or dy.dtype)
 
 
-def conv_wgrad(x, dy, g, w_shape):
+def conv_wgrad(x, dy, g, w_shape, accumulate_into=None):
     w = torch.zeros(g.kh, g.kw, g.Cin, g.Cout, requires_grad=True)
     with torch.enable_grad():
         y = _conv(_as4(x, g, 'x'), w, g)
         (dw,) = torch.autograd.grad(y, w, _as4(dy, g, 'y'))
-    return dw.reshape(w_shape).contiguous()
+    dw = dw.reshape(w_shape).contiguous()
+    if accumulate_into is not None:
+        accumulate_into.add_(dw)
+        return accumulate_into
+    return dw
 
 
 def _cols(x):
     return _f(x).reshape(x.shape[0], x.shape[1], -1) if x.dim() == 4 else _f(x).unsqueeze(-1)
 
 
-def bias_grad(dy):
-    return _cols(dy).sum(dim=(0, 2))
+def bias_grad(dy, accumulate_into=None):
+    db = _cols(dy).sum(dim=(0, 2))
+    if accumulate_into is not None:
+        accumulate_into.add_(db.reshape(accumulate_into.shape))
+        return accumulate_into
+    return db
 
 
 def bias_add(x, b):
