@@ -64,9 +64,9 @@ _PROTOS = {
     'ctgan_crop_bwd': (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     'ctgan_prep_real': (c_int, [P, P, c_int64, c_float, c_float, c_uint64, c_uint64, P, P]),
     'ctgan_interpolate': (c_int, [P, P, P, P, c_int, c_int, P]),
-    'ctgan_bn_workspace_floats': (c_int64, [c_int, c_int, c_int]),
-    'ctgan_bn_fwd': (c_int, [P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_float, c_int, c_int, P]),
-    'ctgan_bn_bwd': (c_int, [P, P, P, P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
+    'ctgan_bn_workspace_floats': (c_int64, [c_int, c_int, c_int, c_int]),
+    'ctgan_bn_fwd': (c_int, [P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_float, c_int, c_int, c_int, P]),
+    'ctgan_bn_bwd': (c_int, [P, P, P, P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     'ctgan_ct_gp_loss_fwd': (c_int, [POINTER(LossDesc), P, P, P, P, P, P, P, P, P, P, P]),
     'ctgan_ct_gp_loss_bwd': (c_int, [POINTER(LossDesc), P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P]),
     'ctgan_mean_fwd': (c_int, [P, P, c_int, c_float, P]),

@@ -49,15 +49,21 @@ template <> __device__ __forceinline__ void store4<__nv_bfloat16>(__nv_bfloat16*
     *reinterpret_cast<uint2*>(p) = t;
 }
 
-// ---- forward stage 1: per-(row block, channel) Welford partials ----------------
-// ws[(rb*C + c)*2 + {0,1}] = {mean, M2} over the rows of row block rb.
+// Statistics can be computed per GROUP of samples (groups G >= 1, N % G == 0: group g = samples
+// [g*N/G, (g+1)*N/G)): the reference builds its generator once per device split, so batch-norm
+// statistics are per 32- / 64-sample split (TG/CT_gan_cifar_resnet.py:196-199, 314-321); running
+// the splits as ONE batch with G = 2 halves the launch count and gives identical results.
+
+// ---- forward stage 1: per-(group, row block, channel) Welford partials ----------------
+// blockIdx.x = g * nbg + rb;  ws[(blockIdx.x*C + c)*2 + {0,1}] = {mean, M2} over that block's rows.
 template <typename T>
 __global__ void __launch_bounds__(BN_LANES * BN_ROWS)
-bn_stats_kernel(const T* __restrict__ x, float* __restrict__ ws, int64_t R, int C, int rows_per_block) {
+bn_stats_kernel(const T* __restrict__ x, float* __restrict__ ws, int64_t Rg, int C, int rows_per_block, int nbg) {
     const int lane = threadIdx.x, ry = threadIdx.y;
     const int c = blockIdx.y * BN_CCH + lane * 4;
-    const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
-    const int64_t r1 = min(R, r0 + rows_per_block);
+    const int g = blockIdx.x / nbg, rb = blockIdx.x - g * nbg;
+    const int64_t r0 = (int64_t)g * Rg + (int64_t)rb * rows_per_block;
+    const int64_t r1 = min((int64_t)(g + 1) * Rg, r0 + rows_per_block);
     float cnt = 0.f, mean[4] = {0, 0, 0, 0}, m2[4] = {0, 0, 0, 0};
     if (c < C) {
         for (int64_t r = r0 + ry; r < r1; r += BN_ROWS) {
@@ -102,8 +108,8 @@ bn_stats_kernel(const T* __restrict__ x, float* __restrict__ ws, int64_t R, int 
 }
 
 // ---- forward stage 2: merge the row-block partials (Chan), biased variance --------
-// One warp per channel: lane l folds partials l, l+32, ... sequentially, then a 5-step butterfly
-// merges the 32 (count, mean, M2) triples.
+// One warp per (group, channel): lane l folds partials l, l+32, ... sequentially, then a 5-step
+// butterfly merges the 32 (count, mean, M2) triples.  save_mean / save_invstd are [G][C].
 __device__ __forceinline__ void chan_merge(float& cnt, float& mean, float& m2, float cb, float mb, float m2b) {
     if (cb > 0.f) {
         float n = cnt + cb;
@@ -115,16 +121,18 @@ __device__ __forceinline__ void chan_merge(float& cnt, float& mean, float& m2, f
 }
 __global__ void __launch_bounds__(128)
 bn_finalize_kernel(const float* __restrict__ ws, float* __restrict__ save_mean,
-                   float* __restrict__ save_invstd, int64_t R, int C, int nb,
+                   float* __restrict__ save_invstd, int64_t Rg, int C, int nbg,
                    int rows_per_block, float eps) {
     const int lane = threadIdx.x & 31;
     const int c = blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int g = blockIdx.y;
     if (c >= C) return;
     float cnt = 0.f, mean = 0.f, m2 = 0.f;
-    for (int b = lane; b < nb; b += 32) {
+    for (int b = lane; b < nbg; b += 32) {
         int64_t r0 = (int64_t)b * rows_per_block;
-        float nbc = (float)(min(R, r0 + rows_per_block) - r0);
-        chan_merge(cnt, mean, m2, nbc, ws[((int64_t)b * C + c) * 2], ws[((int64_t)b * C + c) * 2 + 1]);
+        float nbc = (float)(min(Rg, r0 + rows_per_block) - r0);
+        const float* p = ws + ((int64_t)(g * nbg + b) * C + c) * 2;
+        chan_merge(cnt, mean, m2, nbc, p[0], p[1]);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -134,8 +142,8 @@ bn_finalize_kernel(const float* __restrict__ ws, float* __restrict__ save_mean,
         chan_merge(cnt, mean, m2, cb, mb, m2b);
     }
     if (lane == 0) {
-        save_mean[c] = mean;
-        save_invstd[c] = rsqrtf(m2 / (float)R + eps);
+        save_mean[(int64_t)g * C + c] = mean;
+        save_invstd[(int64_t)g * C + c] = rsqrtf(m2 / (float)Rg + eps);
     }
 }
 
@@ -144,7 +152,7 @@ template <typename T>
 __global__ void bn_apply_kernel(const T* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                                 const int32_t* __restrict__ labels, const float* __restrict__ mean,
                                 const float* __restrict__ invstd, T* __restrict__ y,
-                                int64_t R, int HW, int C, int relu) {
+                                int64_t R, int HW, int C, int relu, int n_per_group) {
     const int C4 = C / 4;
     int64_t total = R * C4;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -152,11 +160,13 @@ __global__ void bn_apply_kernel(const T* __restrict__ x, const float* __restrict
         int64_t r = i / C4;
         int n = (int)(r / HW);
         int l = labels ? labels[n] : 0;
+        const float* mu = mean + (int64_t)(n / n_per_group) * C;
+        const float* is = invstd + (int64_t)(n / n_per_group) * C;
         float v[4], o[4];
         load4<T>(x + r * C + c, v);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            float xh = (v[j] - mean[c + j]) * invstd[c + j];
+            float xh = (v[j] - mu[c + j]) * is[c + j];
             float t = xh * gamma[(int64_t)l * C + c + j] + beta[(int64_t)l * C + c + j];
             o[j] = relu ? fmaxf(t, 0.f) : t;
         }
@@ -170,7 +180,7 @@ template <typename T>
 __global__ void __launch_bounds__(BN_LANES * BN_ROWS)
 bn_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ y,
                      const float* __restrict__ mean, const float* __restrict__ invstd, float* __restrict__ ws,
-                     int HW, int C, int S, int relu) {
+                     int HW, int C, int S, int relu, int n_per_group) {
     const int lane = threadIdx.x, ry = threadIdx.y;
     const int c = blockIdx.y * BN_CCH + lane * 4;
     const int n = blockIdx.x / S, s = blockIdx.x % S;
@@ -179,8 +189,9 @@ bn_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T*
     float s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
     if (c < C) {
         float mu[4], is[4];
+        const int64_t go = (int64_t)(n / n_per_group) * C;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { mu[j] = mean[c + j]; is[j] = invstd[c + j]; }
+        for (int j = 0; j < 4; ++j) { mu[j] = mean[go + c + j]; is[j] = invstd[go + c + j]; }
         for (int h = h0 + ry; h < h1; h += BN_ROWS) {
             int64_t off = ((int64_t)n * HW + h) * C + c;
             float g[4], v[4];
@@ -214,13 +225,13 @@ bn_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T*
 }
 
 // ---- backward stage 2: per channel: table gradients + the two means BN needs ----------
-// coef[c] = mean_R(gamma_l * dy), coef[C + c] = mean_R(gamma_l * dy * xhat).  One warp per channel;
-// the per-label table sums go through shared-memory atomics (n_labels <= 10 in the reference).
+// coef[g*C + c] = mean_Rg(gamma_l * dy), coef[G*C + g*C + c] = mean_Rg(gamma_l * dy * xhat).
+// One warp per channel; the per-label table sums (shared by all groups) go through shared-memory atomics.
 __global__ void __launch_bounds__(128)
 bn_bwd_finalize_kernel(const float* __restrict__ ws, const float* __restrict__ gamma,
                        const int32_t* __restrict__ labels, float* __restrict__ dgamma,
                        float* __restrict__ dbeta, float* __restrict__ coef,
-                       int N, int S, int C, int n_labels, float inv_R) {
+                       int N, int S, int C, int n_labels, float inv_Rg, int groups) {
     extern __shared__ float tab[];                    // [4 warps][2][n_labels]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int c = blockIdx.x * 4 + warp;
@@ -229,30 +240,33 @@ bn_bwd_finalize_kernel(const float* __restrict__ ws, const float* __restrict__ g
     for (int l = lane; l < 2 * n_labels; l += 32) t1[l] = 0.f;
     __syncwarp();
     if (c >= C) return;
-    float a1 = 0.f, a2 = 0.f;
-    for (int n = lane; n < N; n += 32) {
-        int l = labels ? labels[n] : 0;
-        float s1 = 0.f, s2 = 0.f;
-        for (int s = 0; s < S; ++s) {
-            s1 += ws[(((int64_t)n * S + s) * C + c) * 2];
-            s2 += ws[(((int64_t)n * S + s) * C + c) * 2 + 1];
+    const int npg = N / groups;
+    for (int g = 0; g < groups; ++g) {
+        float a1 = 0.f, a2 = 0.f;
+        for (int n = g * npg + lane; n < (g + 1) * npg; n += 32) {
+            int l = labels ? labels[n] : 0;
+            float s1 = 0.f, s2 = 0.f;
+            for (int s = 0; s < S; ++s) {
+                s1 += ws[(((int64_t)n * S + s) * C + c) * 2];
+                s2 += ws[(((int64_t)n * S + s) * C + c) * 2 + 1];
+            }
+            float gm = gamma[(int64_t)l * C + c];
+            a1 += gm * s1; a2 += gm * s2;
+            atomicAdd(t1 + l, s1);
+            atomicAdd(t2 + l, s2);
         }
-        float g = gamma[(int64_t)l * C + c];
-        a1 += g * s1; a2 += g * s2;
-        atomicAdd(t1 + l, s1);
-        atomicAdd(t2 + l, s2);
-    }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        a1 += __shfl_xor_sync(0xffffffffu, a1, o);
-        a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+        for (int o = 16; o > 0; o >>= 1) {
+            a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+            a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+        }
+        if (lane == 0) { coef[(int64_t)g * C + c] = a1 * inv_Rg; coef[(int64_t)(groups + g) * C + c] = a2 * inv_Rg; }
     }
     __syncwarp();
     for (int l = lane; l < n_labels; l += 32) {
         dbeta[(int64_t)l * C + c] = t1[l];
         dgamma[(int64_t)l * C + c] = t2[l];
     }
-    if (lane == 0) { coef[c] = a1 * inv_R; coef[C + c] = a2 * inv_R; }
 }
 
 // ---- backward stage 3: dx = invstd * (gamma_l*dy - mean(.) - xhat*mean(. xhat)) ----------
@@ -261,7 +275,7 @@ __global__ void bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restric
                                     const float* __restrict__ gamma, const int32_t* __restrict__ labels,
                                     const float* __restrict__ mean, const float* __restrict__ invstd,
                                     const float* __restrict__ coef, T* __restrict__ dx,
-                                    int64_t R, int HW, int C, int relu) {
+                                    int64_t R, int HW, int C, int relu, int n_per_group, int groups) {
     const int C4 = C / 4;
     int64_t total = R * C4;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -269,6 +283,7 @@ __global__ void bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restric
         int64_t r = i / C4;
         int n = (int)(r / HW);
         int l = labels ? labels[n] : 0;
+        const int64_t go = (int64_t)(n / n_per_group) * C;
         float g[4], v[4], o[4];
         load4<T>(dy + r * C + c, g);
         load4<T>(x + r * C + c, v);
@@ -280,9 +295,9 @@ __global__ void bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restric
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            float is = invstd[c + j];
-            float xh = (v[j] - mean[c + j]) * is;
-            o[j] = is * (gamma[(int64_t)l * C + c + j] * g[j] - coef[c + j] - xh * coef[C + c + j]);
+            float is = invstd[go + c + j];
+            float xh = (v[j] - mean[go + c + j]) * is;
+            o[j] = is * (gamma[(int64_t)l * C + c + j] * g[j] - coef[go + c + j] - xh * coef[(int64_t)groups * C + go + c + j]);
         }
         store4<T>(dx + r * C + c, o);
     }
@@ -311,35 +326,37 @@ bias_grad_kernel(const void* __restrict__ dy, float* __restrict__ db, int64_t ro
 
 using namespace ctgan;
 
-extern "C" int64_t ctgan_bn_workspace_floats(int N, int HW, int C) {
-    int64_t R = (int64_t)N * HW;
-    int64_t fwd = (int64_t)bn_fwd_rowblocks(R) * C * 2;
-    int64_t bwd = (int64_t)N * bn_bwd_splits(HW) * C * 2 + 2 * (int64_t)C;
+extern "C" int64_t ctgan_bn_workspace_floats(int N, int HW, int C, int groups) {
+    if (groups < 1) groups = 1;
+    int64_t Rg = (int64_t)(N / groups) * HW;
+    int64_t fwd = (int64_t)bn_fwd_rowblocks(Rg) * groups * C * 2;
+    int64_t bwd = (int64_t)N * bn_bwd_splits(HW) * C * 2 + 2 * (int64_t)groups * C;
     return fwd > bwd ? fwd : bwd;
 }
 
 extern "C" int ctgan_bn_fwd(const void* x, const float* gamma, const float* beta, const int32_t* labels,
                             void* y, float* save_mean, float* save_invstd, float* ws,
-                            int N, int HW, int C, float eps, int relu, int dtype, void* stream) {
+                            int N, int HW, int C, float eps, int relu, int groups, int dtype, void* stream) {
     CTGAN_REQUIRE(N > 0 && HW > 0 && C > 0 && C % 4 == 0, CTGAN_ERR_UNSUPPORTED, "bn_fwd: C must be a positive multiple of 4");
+    CTGAN_REQUIRE(groups >= 1 && N % groups == 0, CTGAN_ERR_BAD_DESC, "bn_fwd: groups must divide N");
     CTGAN_REQUIRE(x && gamma && beta && y && save_mean && save_invstd && ws, CTGAN_ERR_BAD_DESC, "bn_fwd: null pointer");
     CTGAN_REQUIRE(dtype_ok(dtype), CTGAN_ERR_BAD_DESC, "bn_fwd: bad dtype");
     cudaStream_t st = as_stream(stream);
-    int64_t R = (int64_t)N * HW;
-    int nb = bn_fwd_rowblocks(R);
-    int rpb = (int)((R + nb - 1) / nb);
-    nb = (int)((R + rpb - 1) / rpb);
-    dim3 blk(BN_LANES, BN_ROWS), grid(nb, ceil_div(C, BN_CCH));
-    if (dtype == CTGAN_F32) bn_stats_kernel<float><<<grid, blk, 0, st>>>((const float*)x, ws, R, C, rpb);
-    else bn_stats_kernel<__nv_bfloat16><<<grid, blk, 0, st>>>((const __nv_bfloat16*)x, ws, R, C, rpb);
+    const int64_t R = (int64_t)N * HW, Rg = R / groups;
+    int nbg = bn_fwd_rowblocks(Rg);
+    int rpb = (int)((Rg + nbg - 1) / nbg);
+    nbg = (int)((Rg + rpb - 1) / rpb);
+    dim3 blk(BN_LANES, BN_ROWS), grid(nbg * groups, ceil_div(C, BN_CCH));
+    if (dtype == CTGAN_F32) bn_stats_kernel<float><<<grid, blk, 0, st>>>((const float*)x, ws, Rg, C, rpb, nbg);
+    else bn_stats_kernel<__nv_bfloat16><<<grid, blk, 0, st>>>((const __nv_bfloat16*)x, ws, Rg, C, rpb, nbg);
     CTGAN_CHECK_LAUNCH("bn_stats");
-    bn_finalize_kernel<<<ceil_div(C, 4), 128, 0, st>>>(ws, save_mean, save_invstd, R, C, nb, rpb, eps);
+    bn_finalize_kernel<<<dim3(ceil_div(C, 4), groups), 128, 0, st>>>(ws, save_mean, save_invstd, Rg, C, nbg, rpb, eps);
     CTGAN_CHECK_LAUNCH("bn_finalize");
     int g2 = elementwise_grid(R * (C / 4), 256);
     if (dtype == CTGAN_F32)
-        bn_apply_kernel<float><<<g2, 256, 0, st>>>((const float*)x, gamma, beta, labels, save_mean, save_invstd, (float*)y, R, HW, C, relu);
+        bn_apply_kernel<float><<<g2, 256, 0, st>>>((const float*)x, gamma, beta, labels, save_mean, save_invstd, (float*)y, R, HW, C, relu, N / groups);
     else
-        bn_apply_kernel<__nv_bfloat16><<<g2, 256, 0, st>>>((const __nv_bfloat16*)x, gamma, beta, labels, save_mean, save_invstd, (__nv_bfloat16*)y, R, HW, C, relu);
+        bn_apply_kernel<__nv_bfloat16><<<g2, 256, 0, st>>>((const __nv_bfloat16*)x, gamma, beta, labels, save_mean, save_invstd, (__nv_bfloat16*)y, R, HW, C, relu, N / groups);
     CTGAN_CHECK_LAUNCH("bn_apply");
     return 0;
 }
@@ -347,28 +364,29 @@ extern "C" int ctgan_bn_fwd(const void* x, const float* gamma, const float* beta
 extern "C" int ctgan_bn_bwd(const void* dy, const void* x, const void* y, const float* gamma,
                             const int32_t* labels, const float* save_mean, const float* save_invstd,
                             void* dx, float* dgamma, float* dbeta, float* ws,
-                            int N, int HW, int C, int n_labels, int relu, int dtype, void* stream) {
+                            int N, int HW, int C, int n_labels, int relu, int groups, int dtype, void* stream) {
     CTGAN_REQUIRE(N > 0 && HW > 0 && C > 0 && C % 4 == 0 && n_labels > 0, CTGAN_ERR_UNSUPPORTED, "bn_bwd: C must be a positive multiple of 4");
+    CTGAN_REQUIRE(groups >= 1 && N % groups == 0, CTGAN_ERR_BAD_DESC, "bn_bwd: groups must divide N");
     CTGAN_REQUIRE(dy && x && gamma && save_mean && save_invstd && dx && dgamma && dbeta && ws && (!relu || y),
                   CTGAN_ERR_BAD_DESC, "bn_bwd: null pointer");
     CTGAN_REQUIRE(dtype_ok(dtype), CTGAN_ERR_BAD_DESC, "bn_bwd: bad dtype");
     cudaStream_t st = as_stream(stream);
-    int64_t R = (int64_t)N * HW;
+    const int64_t R = (int64_t)N * HW, Rg = R / groups;
     int S = bn_bwd_splits(HW);
     float* coef = ws + (int64_t)N * S * C * 2;
     dim3 blk(BN_LANES, BN_ROWS), grid(N * S, ceil_div(C, BN_CCH));
     if (dtype == CTGAN_F32)
-        bn_bwd_reduce_kernel<float><<<grid, blk, 0, st>>>((const float*)dy, (const float*)x, (const float*)y, save_mean, save_invstd, ws, HW, C, S, relu);
+        bn_bwd_reduce_kernel<float><<<grid, blk, 0, st>>>((const float*)dy, (const float*)x, (const float*)y, save_mean, save_invstd, ws, HW, C, S, relu, N / groups);
     else
-        bn_bwd_reduce_kernel<__nv_bfloat16><<<grid, blk, 0, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (const __nv_bfloat16*)y, save_mean, save_invstd, ws, HW, C, S, relu);
+        bn_bwd_reduce_kernel<__nv_bfloat16><<<grid, blk, 0, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (const __nv_bfloat16*)y, save_mean, save_invstd, ws, HW, C, S, relu, N / groups);
     CTGAN_CHECK_LAUNCH("bn_bwd_reduce");
-    bn_bwd_finalize_kernel<<<ceil_div(C, 4), 128, sizeof(float) * 8 * n_labels, st>>>(ws, gamma, labels, dgamma, dbeta, coef, N, S, C, n_labels, 1.f / (float)R);
+    bn_bwd_finalize_kernel<<<ceil_div(C, 4), 128, sizeof(float) * 8 * n_labels, st>>>(ws, gamma, labels, dgamma, dbeta, coef, N, S, C, n_labels, 1.f / (float)Rg, groups);
     CTGAN_CHECK_LAUNCH("bn_bwd_finalize");
     int g2 = elementwise_grid(R * (C / 4), 256);
     if (dtype == CTGAN_F32)
-        bn_bwd_apply_kernel<float><<<g2, 256, 0, st>>>((const float*)dy, (const float*)x, (const float*)y, gamma, labels, save_mean, save_invstd, coef, (float*)dx, R, HW, C, relu);
+        bn_bwd_apply_kernel<float><<<g2, 256, 0, st>>>((const float*)dy, (const float*)x, (const float*)y, gamma, labels, save_mean, save_invstd, coef, (float*)dx, R, HW, C, relu, N / groups, groups);
     else
-        bn_bwd_apply_kernel<__nv_bfloat16><<<g2, 256, 0, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (const __nv_bfloat16*)y, gamma, labels, save_mean, save_invstd, coef, (__nv_bfloat16*)dx, R, HW, C, relu);
+        bn_bwd_apply_kernel<__nv_bfloat16><<<g2, 256, 0, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (const __nv_bfloat16*)y, gamma, labels, save_mean, save_invstd, coef, (__nv_bfloat16*)dx, R, HW, C, relu, N / groups, groups);
     CTGAN_CHECK_LAUNCH("bn_bwd_apply");
     return 0;
 }

@@ -389,8 +389,9 @@ class BatchNormReLU(Function):
     """Training-mode BN (biased var, eps) with optional per-label gamma/beta and fused ReLU."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, labels, eps, relu):
-        y, mean, invstd = K.bn_fwd(x, gamma, beta, labels, eps, relu)
+    def forward(ctx, x, gamma, beta, labels, eps, relu, groups=1):
+        y, mean, invstd = K.bn_fwd(x, gamma, beta, labels, eps, relu, groups)
+        ctx.groups = groups
         if pattern_recorder is not None and relu:
             pattern_recorder(y.detach() > 0)
         ctx.relu = relu
@@ -403,12 +404,13 @@ class BatchNormReLU(Function):
     def backward(ctx, gy):
         x, y, gamma, mean, invstd = ctx.saved_tensors
         gy = _dense_like(gy, True)
-        dx, dgamma, dbeta = K.bn_bwd(gy, x, y, gamma, ctx.labels, mean, invstd, ctx.relu)
-        return dx, dgamma, dbeta, None, None, None
+        dx, dgamma, dbeta = K.bn_bwd(gy, x, y, gamma, ctx.labels, mean, invstd, ctx.relu, ctx.groups)
+        return dx, dgamma, dbeta, None, None, None, None
 
 
-def batch_norm(x, gamma, beta, labels=None, eps=1e-5, relu=False):
-    return BatchNormReLU.apply(x, gamma, beta, labels, eps, relu)
+def batch_norm(x, gamma, beta, labels=None, eps=1e-5, relu=False, groups=1):
+    """groups > 1: statistics per block of N/groups consecutive samples (one block per reference device split)."""
+    return BatchNormReLU.apply(x, gamma, beta, labels, eps, relu, groups)
 
 
 class Unary(Function):

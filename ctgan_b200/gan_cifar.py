@@ -35,8 +35,7 @@ def LeakyReLU(x, alpha=0.2):
 
 def _lrelu_dropout(output, keep):
     """LeakyReLU (:47-48) followed by tf.nn.dropout(keep_prob) (:86): one fused kernel."""
-    tag = RNG.next_dropout_tag()
-    seed, off, dyn = RNG.stream(tag, output)
+    seed, off, dyn = RNG.dropout_stream(output)
     return F.leaky_relu_dropout(output, 0.2, keep, seed=seed, offset=off, dyn=dyn)
 
 
@@ -111,12 +110,15 @@ class Trainer:
         B = real_data.shape[0]
         with torch.no_grad():
             fake_data = m.Generator(B, noise=RNG.normal('z', (B, 128)))
-        RNG.scope('drop.real1')
-        disc_real, disc_real_2 = m.Discriminator(real_data)
-        RNG.scope('drop.real2')
-        disc_real_, disc_real_2_ = m.Discriminator(real_data)
-        RNG.scope('drop.fake')
-        disc_fake, _ = m.Discriminator(fake_data)
+        # the three stochastic critic calls of the reference (real', real'', fake) as ONE stacked batch:
+        # shared weights, independent dropout draws per row
+        stacked = torch.cat([real_data, real_data, fake_data], dim=0)
+        RNG.scope_parts([('drop.real1', B), ('drop.real2', B), ('drop.fake', B)])
+        RNG.begin_stack([B, B, B])
+        d_all, f_all = m.Discriminator(stacked)
+        RNG.end_stack()
+        disc_real, disc_real_, disc_fake = d_all[:B], d_all[B:2 * B], d_all[2 * B:]
+        disc_real_2, disc_real_2_ = f_all[:B], f_all[B:2 * B]
         alpha = RNG.uniform('alpha', (B, 1))
         interpolates = K.interpolate(real_data, fake_data, alpha).requires_grad_(True)
         RNG.scope('drop.gp')

@@ -48,6 +48,7 @@ N_DEVICES = 2  # len(DEVICES): the reference always builds two sub-graphs (:61-6
 
 ACT_DTYPE = torch.bfloat16   # activation storage: bfloat16 ("BF16 path") or float32 ("fp32 path")
 RNG = None                   # DeviceRandom, set by Trainer
+BN_GROUPS = 1                # >1 while the per-device-split generator calls of the reference run as ONE batch
 
 
 def nonlinearity(x):
@@ -64,9 +65,10 @@ def Normalize(name, inputs, labels=None, relu=False):
         raise Exception('Unsupported configuration')      # layernorm call is dead/broken in the reference
     elif ('Generator' in name) and NORMALIZATION_G:
         if labels is not None:
-            return lib.ops.cond_batchnorm.Batchnorm(name, [0, 2, 3], inputs, labels=labels, n_labels=10, relu=relu)
+            return lib.ops.cond_batchnorm.Batchnorm(name, [0, 2, 3], inputs, labels=labels, n_labels=10, relu=relu,
+                                                    groups=BN_GROUPS)
         else:
-            return lib.ops.batchnorm.Batchnorm(name, [0, 2, 3], inputs, fused=True, relu=relu)
+            return lib.ops.batchnorm.Batchnorm(name, [0, 2, 3], inputs, fused=True, relu=relu, groups=BN_GROUPS)
     else:
         return nonlinearity(inputs) if relu else inputs
 
@@ -152,8 +154,7 @@ def Generator(n_samples, labels, noise=None):
 def _dropout(output, keep):
     if keep == 1.0:
         return output
-    tag = RNG.next_dropout_tag()
-    seed, off, dyn = RNG.stream(tag, output)
+    seed, off, dyn = RNG.dropout_stream(output)
     return F.dropout(output, keep, seed=seed, offset=off, dyn=dyn)
 
 
@@ -211,35 +212,45 @@ class Trainer:
         return LR * decay
 
     # ---------------------------------------------------------------- critic (disc_train_op, :190-300,336-338)
+    def _generate(self, parts_z, labels, n_total):
+        """The reference calls Generator once per device split (:196-199, :318-321); here the splits run as ONE
+        batch whose batch-norm statistics are computed per split (groups) -- same numbers, half the launches."""
+        global BN_GROUPS
+        RNG = self.rng
+        noise = RNG.normal_parts(parts_z, 128)
+        BN_GROUPS = len(parts_z)
+        try:
+            return Generator(n_total, labels, noise=noise)
+        finally:
+            BN_GROUPS = 1
+
     def critic_forward_backward(self, all_real_data_int, all_real_labels, with_metrics=False):
         RNG = self.rng
         B = all_real_data_int.shape[0]
         h = B // N_DEVICES
-        labels_splits = [all_real_labels[:h].contiguous(), all_real_labels[h:].contiguous()]
         with torch.no_grad():
-            fakes = []
-            for i in range(N_DEVICES):
-                RNG.scope('z.%d' % i)
-                noise = RNG.normal('z.%d' % i, (h, 128))
-                fakes.append(Generator(h, labels_splits[i], noise=noise))
+            RNG.begin_stack([h] * N_DEVICES)
+            fake_data = self._generate([('z.%d' % i, h) for i in range(N_DEVICES)], all_real_labels, B)
+            RNG.end_stack()
         seed, off, dyn = RNG.stream('dequant', all_real_data_int)
         all_real_data = K.prep_real(all_real_data_int, 256., 1. / 128, seed, off, dyn=dyn)     # :201-202
-        real_and_fake_data = torch.cat([all_real_data] + fakes, dim=0)
-        real_and_fake_labels = torch.cat([all_real_labels, all_real_labels], dim=0)
-        RNG.scope('drop.p1')
-        disc_all, disc_all_2, disc_all_acgan = Discriminator(real_and_fake_data, real_and_fake_labels, 0.8, 0.5, 0.5)
-        RNG.scope('drop.p2')
-        disc_real_, disc_real_2_, _ = Discriminator(all_real_data, all_real_labels, 0.8, 0.5, 0.5)
+        # stochastic pass ' on real+fake (2B rows) and pass '' on the real half (B rows) as ONE critic call:
+        # same weights, independent dropout draws per row -- the reference's two calls at :226-227
+        stacked = torch.cat([all_real_data, fake_data, all_real_data], dim=0)
+        stacked_labels = torch.cat([all_real_labels, all_real_labels, all_real_labels], dim=0)
+        RNG.scope_parts([('drop.p1', 2 * B), ('drop.p2', B)])
+        RNG.begin_stack([2 * B, B])
+        disc_all, disc_all_2, disc_all_acgan = Discriminator(stacked, stacked_labels, 0.8, 0.5, 0.5)
+        RNG.end_stack()
         metrics = {}
         if with_metrics and CONDITIONAL and ACGAN:
             with torch.no_grad():
-                _, _, clean = Discriminator(real_and_fake_data, real_and_fake_labels, 1.0, 1.0, 1.0)
+                _, _, clean = Discriminator(stacked[:2 * B], stacked_labels[:2 * B], 1.0, 1.0, 1.0)
                 pred = clean.argmax(dim=1).to(torch.int32)
-                metrics['acgan_acc'] = (pred[:B] == real_and_fake_labels[:B]).float().mean()
-                metrics['acgan_fake_acc'] = (pred[B:] == real_and_fake_labels[B:]).float().mean()
-        disc_real, disc_fake = disc_all[:B], disc_all[B:]
-        disc_real_2 = disc_all_2[:B]
-        fake_data = torch.cat(fakes, dim=0)
+                metrics['acgan_acc'] = (pred[:B] == all_real_labels).float().mean()
+                metrics['acgan_fake_acc'] = (pred[B:] == all_real_labels).float().mean()
+        disc_real, disc_fake, disc_real_ = disc_all[:B], disc_all[B:2 * B], disc_all[2 * B:]
+        disc_real_2, disc_real_2_ = disc_all_2[:B], disc_all_2[2 * B:]
         alpha = RNG.uniform('alpha', (B, 1))
         interpolates = K.interpolate(all_real_data, fake_data, alpha).requires_grad_(True)     # :277-283
         RNG.scope('drop.gp')
@@ -265,19 +276,17 @@ class Trainer:
     # ---------------------------------------------------------------- generator (gen_train_op, :314-330,335,337)
     def gen_forward_backward(self):
         RNG = self.rng
-        n_samples = GEN_BS_MULTIPLE * self.B // N_DEVICES
-        costs = []
-        for i in range(N_DEVICES):
-            fake_labels = RNG.labels('labels.%d' % i, n_samples)
-            noise = RNG.normal('z.%d' % i, (n_samples, 128))
-            fake = Generator(n_samples, fake_labels, noise=noise)
-            RNG.scope('drop.%d' % i)
-            disc_fake, _, disc_fake_acgan = Discriminator(fake, fake_labels, 0.8, 0.5, 0.5)
-            c = F.MeanLoss.apply(disc_fake, -1.0)
-            if CONDITIONAL and ACGAN:
-                c = c + ACGAN_SCALE_G * F.SoftmaxCE.apply(disc_fake_acgan, fake_labels)
-            costs.append(c)
-        gen_cost = (costs[0] + costs[1]) / N_DEVICES
+        n = GEN_BS_MULTIPLE * self.B // N_DEVICES
+        fake_labels = RNG.labels_parts([('labels.%d' % i, n) for i in range(N_DEVICES)])
+        RNG.begin_stack([n] * N_DEVICES)
+        fake = self._generate([('z.%d' % i, n) for i in range(N_DEVICES)], fake_labels, n * N_DEVICES)
+        RNG.scope_parts([('drop.%d' % i, n) for i in range(N_DEVICES)])
+        disc_fake, _, disc_fake_acgan = Discriminator(fake, fake_labels, 0.8, 0.5, 0.5)
+        RNG.end_stack()
+        # mean over the stacked batch == (cost_dev0 + cost_dev1) / len(DEVICES)  (equal split sizes)
+        gen_cost = F.MeanLoss.apply(disc_fake, -1.0)
+        if CONDITIONAL and ACGAN:
+            gen_cost = gen_cost + ACGAN_SCALE_G * F.SoftmaxCE.apply(disc_fake_acgan, fake_labels)
         gen_cost.backward(inputs=self.gen_opt.param_list())
         return dict(cost=gen_cost.detach())
 

@@ -32,8 +32,7 @@ def LeakyReLU(x, alpha=0.2):
 
 
 def _lrelu_dropout(output, keep):
-    tag = RNG.next_dropout_tag()
-    seed, off, dyn = RNG.stream(tag, output)
+    seed, off, dyn = RNG.dropout_stream(output)
     return F.leaky_relu_dropout(output, 0.2, keep, seed=seed, offset=off, dyn=dyn)
 
 

@@ -391,28 +391,28 @@ def interpolate(real, fake, alpha):
 
 
 # --------------------------------------------------------------------------- batch norm
-def bn_fwd(x, gamma, beta, labels, eps, relu):
+def bn_fwd(x, gamma, beta, labels, eps, relu, groups=1):
     require_nhwc(x)
     N, H, W, C = nhwc_dims(x)
     y = torch.empty_like(x)
-    mean = torch.empty(C, dtype=torch.float32, device=x.device)
-    invstd = torch.empty(C, dtype=torch.float32, device=x.device)
-    ws = torch.empty(_lib.lib.ctgan_bn_workspace_floats(N, H * W, C), dtype=torch.float32, device=x.device)
+    mean = torch.empty((groups, C), dtype=torch.float32, device=x.device)
+    invstd = torch.empty((groups, C), dtype=torch.float32, device=x.device)
+    ws = torch.empty(_lib.lib.ctgan_bn_workspace_floats(N, H * W, C, groups), dtype=torch.float32, device=x.device)
     call('ctgan_bn_fwd', _p(x), _p(gamma), _p(beta), _p(labels), _p(y), _p(mean), _p(invstd), _p(ws),
-         N, H * W, C, float(eps), int(relu), _dt(x), _stream())
+         N, H * W, C, float(eps), int(relu), int(groups), _dt(x), _stream())
     return y, mean, invstd
 
 
-def bn_bwd(dy, x, y, gamma, labels, mean, invstd, relu):
+def bn_bwd(dy, x, y, gamma, labels, mean, invstd, relu, groups=1):
     require_nhwc(dy); require_nhwc(x)
     N, H, W, C = nhwc_dims(x)
     n_labels = gamma.numel() // C
     dx = torch.empty_like(x)
     dgamma = torch.empty_like(gamma)
     dbeta = torch.empty_like(gamma)
-    ws = torch.empty(_lib.lib.ctgan_bn_workspace_floats(N, H * W, C), dtype=torch.float32, device=x.device)
+    ws = torch.empty(_lib.lib.ctgan_bn_workspace_floats(N, H * W, C, groups), dtype=torch.float32, device=x.device)
     call('ctgan_bn_bwd', _p(dy), _p(x), _p(y), _p(gamma), _p(labels), _p(mean), _p(invstd), _p(dx), _p(dgamma),
-         _p(dbeta), _p(ws), N, H * W, C, n_labels, int(relu), _dt(x), _stream())
+         _p(dbeta), _p(ws), N, H * W, C, n_labels, int(relu), int(groups), _dt(x), _stream())
     return dx, dgamma, dbeta
 
 

@@ -30,7 +30,10 @@ class DeviceRandom:
         self.record = record
         self.tape = {}
         self._scope = ''
+        self._parts = None           # [(tag prefix, rows)] when several reference passes run as one stacked batch
         self._site = 0
+        self.patterns = []
+        self._stack = None
         # graph_safe: kernels add a device-resident base offset, advanced by a kernel at step end
         self.dyn = torch.zeros(1, dtype=torch.int64, device=self.device) if graph_safe else None
 
@@ -51,6 +54,7 @@ class DeviceRandom:
         self.record = True
         self.tape = {}
         self.patterns = []
+        self._stack = None
         F.pattern_recorder = self.patterns.append
 
     def stop_recording(self):
@@ -59,7 +63,62 @@ class DeviceRandom:
         F.pattern_recorder = None
 
     def scope(self, name):
-        self._scope, self._site = name, 0
+        self._scope, self._parts, self._site = name, None, 0
+
+    def scope_parts(self, parts):
+        """The next dropout sites act on a batch that stacks several reference passes along dim 0:
+        parts = [(tag prefix, rows), ...].  One Philox slice per site; when recording, each part's rows are
+        exported under '<prefix>.<site>' exactly as if the passes had run separately."""
+        self._scope, self._parts, self._site = parts[0][0], list(parts), 0
+
+    def begin_stack(self, rows):
+        """Activation patterns recorded until end_stack() belong to a stacked batch with these row counts."""
+        self._stack = (list(rows), len(self.patterns))
+
+    def end_stack(self):
+        if self._stack is None:
+            return
+        rows, start = self._stack
+        self._stack = None
+        seg = self.patterns[start:]
+        if not seg:
+            return
+        out, r0 = [], 0
+        for n in rows:                       # part-major: every site of part 0, then every site of part 1, ...
+            out += [p[r0:r0 + n] for p in seg]
+            r0 += n
+        self.patterns[start:] = out
+
+    def _split_keep(self, parts, t):
+        if self.record:
+            r0 = 0
+            for tag, n in parts:
+                self._keep(tag, t[r0:r0 + n])
+                r0 += n
+
+    def normal_parts(self, parts, cols):
+        rows = sum(n for _, n in parts)
+        t = K.philox_normal((rows, cols), self.device, self.seed, self._take(2 * rows * cols), dyn=self.dyn)
+        self._split_keep(parts, t)
+        return t
+
+    def labels_parts(self, parts, n_labels=10):
+        rows = sum(n for _, n in parts)
+        t = K.philox_labels(rows, self.device, n_labels, self.seed, self._take(rows), dyn=self.dyn)
+        self._split_keep(parts, t)
+        return t
+
+    def dropout_stream(self, like):
+        """Philox slice for the next dropout site of the current scope; returns (seed, offset, dyn)."""
+        self._site += 1
+        if self._parts is None:
+            return self.stream('%s.%d' % (self._scope, self._site), like)
+        off = self._take(like.numel())
+        if self.record:
+            mf = CL if (like.dim() == 4 and like.is_contiguous(memory_format=CL)) else None
+            u = K.philox_uniform(tuple(like.shape), self.device, self.seed, off, memory_format=mf, dyn=self.dyn)
+            self._split_keep([('%s.%d' % (p, self._site), n) for p, n in self._parts], u)
+        return self.seed, off, self.dyn
 
     def _keep(self, tag, t):
         if self.record:

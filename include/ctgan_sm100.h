@@ -158,18 +158,20 @@ int ctgan_interpolate(const float* real, const float* fake, const float* alpha, 
  * batchnorm.py:77-84 and cond_batchnorm.py:10-16).  x is [N,HW,C].  gamma/beta are
  * float [n_labels][C]; labels (int32 [N], nullable) picks the row per sample
  * (labels == NULL -> row 0).  relu != 0 fuses tf.nn.relu on the output.
- * ws: float workspace of ctgan_bn_workspace_floats(N, HW, C) floats.
- * save_mean / save_invstd: float [C], consumed by the backward. */
-int64_t ctgan_bn_workspace_floats(int N, int HW, int C);
+ * groups >= 1 (N % groups == 0): statistics are computed separately for each block of N/groups
+ * consecutive samples -- the reference normalises per device split (TG/CT_gan_cifar_resnet.py:196-199).
+ * ws: float workspace of ctgan_bn_workspace_floats(N, HW, C, groups) floats.
+ * save_mean / save_invstd: float [groups][C], consumed by the backward. */
+int64_t ctgan_bn_workspace_floats(int N, int HW, int C, int groups);
 int ctgan_bn_fwd(const void* x, const float* gamma, const float* beta, const int32_t* labels,
                  void* y, float* save_mean, float* save_invstd, float* ws,
-                 int N, int HW, int C, float eps, int relu, int dtype, void* stream);
+                 int N, int HW, int C, float eps, int relu, int groups, int dtype, void* stream);
 /* y is the forward OUTPUT (used for the ReLU mask when relu != 0).  dgamma/dbeta are
  * float [n_labels][C], overwritten. */
 int ctgan_bn_bwd(const void* dy, const void* x, const void* y, const float* gamma,
                  const int32_t* labels, const float* save_mean, const float* save_invstd,
                  void* dx, float* dgamma, float* dbeta, float* ws,
-                 int N, int HW, int C, int n_labels, int relu, int dtype, void* stream);
+                 int N, int HW, int C, int n_labels, int relu, int groups, int dtype, void* stream);
 
 /* ---- fused CT + GP + WGAN (+ACGAN) loss -----------------------------------
  * TG/CT_gan_cifar.py:123-151, TG/CT_gan_mnist.py:146-167, TG/CT_gan_cifar_resnet.py:244-300.

@@ -198,7 +198,7 @@ def interpolate(real, fake, alpha):
     return real + alpha * (fake - real)
 
 
-def bn_fwd(x, gamma, beta, labels, eps, relu):
+def _bn_fwd1(x, gamma, beta, labels, eps, relu):
     xf = _f(x)
     dims = (0, 2, 3) if x.dim() == 4 else (0,)
     mean = xf.mean(dim=dims)
@@ -212,10 +212,27 @@ def bn_fwd(x, gamma, beta, labels, eps, relu):
     y = (xf - mean.view(bc)) * invstd.view(bc) * g2[idx].view(sh) + b2[idx].view(sh)
     if relu:
         y = torch.relu(y)
-    return _out(y, x.dtype), mean, invstd
+    return y, mean, invstd
 
 
-def bn_bwd(dy, x, y, gamma, labels, mean, invstd, relu):
+def bn_fwd(x, gamma, beta, labels, eps, relu, groups=1):
+    n = x.shape[0] // groups
+    parts = [_bn_fwd1(x[g * n:(g + 1) * n], gamma, beta, None if labels is None else labels[g * n:(g + 1) * n], eps, relu)
+             for g in range(groups)]
+    y = torch.cat([p[0] for p in parts], 0)
+    return _out(y, x.dtype), torch.stack([p[1] for p in parts]), torch.stack([p[2] for p in parts])
+
+
+def bn_bwd(dy, x, y, gamma, labels, mean, invstd, relu, groups=1):
+    n = x.shape[0] // groups
+    outs = [_bn_bwd1(dy[g * n:(g + 1) * n], x[g * n:(g + 1) * n], y[g * n:(g + 1) * n], gamma,
+                     None if labels is None else labels[g * n:(g + 1) * n], mean.reshape(groups, -1)[g],
+                     invstd.reshape(groups, -1)[g], relu) for g in range(groups)]
+    dx = torch.cat([o[0] for o in outs], 0)
+    return _out(dx, x.dtype), sum(o[1] for o in outs), sum(o[2] for o in outs)
+
+
+def _bn_bwd1(dy, x, y, gamma, labels, mean, invstd, relu):
     xf, g = _f(x), _f(dy)
     C = xf.shape[1]
     if relu:
@@ -235,7 +252,7 @@ def bn_bwd(dy, x, y, gamma, labels, mean, invstd, relu):
     dims = (0,) + red
     R = xf.numel() // C
     dx = invstd.view(bc) * (dxh - dxh.sum(dim=dims).view(bc) / R - xh * (dxh * xh).sum(dim=dims).view(bc) / R)
-    return _out(dx, x.dtype), dgamma.reshape(gamma.shape), dbeta.reshape(gamma.shape)
+    return dx, dgamma.reshape(gamma.shape), dbeta.reshape(gamma.shape)
 
 
 def _loss_terms(desc, d_real, d_real2, d_fake, f1, f2, grad, logits, labels):

@@ -201,9 +201,12 @@ def test_prep_real_and_interpolate(K):
 @pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize('shape,cond', [((32, 128, 8, 8), True), ((6, 128, 32, 32), False), ((64, 8192), False),
                                         ((5, 256, 8, 8), False)])
+@pytest.mark.parametrize('groups', [1, 2])
 @pytest.mark.parametrize('relu', [False, True])
-def test_batch_norm(K, dtype, shape, cond, relu):
+def test_batch_norm(K, dtype, shape, cond, relu, groups):
     fb = FB()
+    if shape[0] % groups:
+        pytest.skip('batch not divisible by groups')
     C = shape[1]
     x = act(shape, dtype, 1, 2.0) + 0.5
     x = x.contiguous(memory_format=CL) if len(shape) == 4 else x
@@ -211,12 +214,12 @@ def test_batch_norm(K, dtype, shape, cond, relu):
     gamma, beta = act((nl, C), torch.float32, 2) + 1.0, act((nl, C), torch.float32, 3)
     labels = torch.randint(0, 10, (shape[0],), dtype=torch.int32) if cond else None
     dy = act(shape, dtype, 4)
-    y, mean, invstd = K.bn_fwd(to_dev(x), gamma.cuda(), beta.cuda(), labels.cuda() if cond else None, 1e-5, relu)
-    yr, mr, ir = fb.bn_fwd(x, gamma, beta, labels, 1e-5, relu)
+    y, mean, invstd = K.bn_fwd(to_dev(x), gamma.cuda(), beta.cuda(), labels.cuda() if cond else None, 1e-5, relu, groups)
+    yr, mr, ir = fb.bn_fwd(x, gamma, beta, labels, 1e-5, relu, groups)
     tol = 2e-5 if dtype == torch.float32 else 1e-2
     assert rel(mean, mr) < 1e-5 and rel(invstd, ir) < 1e-5 and rel(y, yr) < tol
-    dx, dg, db = K.bn_bwd(to_dev(dy), to_dev(x), y, gamma.cuda(), labels.cuda() if cond else None, mean, invstd, relu)
-    dxr, dgr, dbr = fb.bn_bwd(dy, x, y.cpu(), gamma, labels, mean.cpu(), invstd.cpu(), relu)
+    dx, dg, db = K.bn_bwd(to_dev(dy), to_dev(x), y, gamma.cuda(), labels.cuda() if cond else None, mean, invstd, relu, groups)
+    dxr, dgr, dbr = fb.bn_bwd(dy, x, y.cpu(), gamma, labels, mean.cpu(), invstd.cpu(), relu, groups)
     assert rel(dx, dxr) < (1e-4 if dtype == torch.float32 else 2e-2)
     assert rel(dg, dgr) < 1e-4 and rel(db, dbr) < 1e-4
 
