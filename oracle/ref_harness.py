@@ -1,0 +1,179 @@
+"""Runs the reference's OWN source for the hot path in this container -- TEST INFRASTRUCTURE.
+
+The reference is Python 2 + TensorFlow 1.2.1 and cannot be imported here.  This harness
+  1. translates the needed reference files py2->py3 on the fly (print statements, xrange, integer `/` in
+     the few batch-split expressions) -- the translated text is exec'd / written under oracle/_ref/
+     (git-ignored), never committed;
+  2. executes TG/tflib/__init__.py and TG/tflib/ops/{conv2d,deconv2d,linear,batchnorm,cond_batchnorm}.py
+     unmodified otherwise, with `tensorflow` bound to oracle/tf_shim;
+  3. executes the hyper-parameter, model-function and loss-graph SECTIONS of TG/CT_gan_mnist.py,
+     TG/CT_gan_cifar.py, TG/CT_gan_cifar_resnet.py (line ranges below) in that namespace, feeding
+     `tf.placeholder`s with concrete tensors;
+  4. returns the losses, the GP gradient, every parameter and every parameter gradient, plus the random
+     draws in graph order mapped onto the oracle's tags.
+`tests/test_oracle_vs_reference.py` compares the oracle restatement against these runs and
+`tests/golden/make_golden.py` stores them as fixtures.  What this pins: the reference's own graph code, parameter
+naming/layout, init formulas, loss formulas.  What it cannot pin: TensorFlow's internal kernels (absent).
+"""
+import importlib
+import os
+import re
+import sys
+import textwrap
+import types
+
+import numpy as np
+import torch
+
+REF_ROOT = '/root/reference/CT-GANs/tensorflow_generative_model'
+OUT_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), '_ref')
+
+
+def available():
+    return os.path.isdir(REF_ROOT)
+
+
+def py2to3(src):
+    """The py2 idioms that occur in the reference files on the path."""
+    out = []
+    for line in src.splitlines():
+        m = re.match(r'^(\s*)print\s+(?!\()(.*)$', line)
+        if m:
+            line = '%sprint(%s)' % (m.group(1), m.group(2))
+        line = line.replace('xrange(', 'range(').replace('import cPickle as pickle', 'import pickle')
+        # py2 int/int in the batch-split expressions (tensor / int stays a true division)
+        line = line.replace('BATCH_SIZE/len(', 'BATCH_SIZE//len(').replace('BATCH_SIZE / len(', 'BATCH_SIZE // len(')
+        line = line.replace('len(DEVICES)/2', 'len(DEVICES)//2')
+        out.append(line)
+    return '\n'.join(out) + '\n'
+
+
+def _load_ref_tflib(shim):
+    """Import the reference's tflib package (translated) with `tensorflow` -> shim.  Returns the module."""
+    pkg_dir = os.path.join(OUT_DIR, 'tflib')
+    os.makedirs(os.path.join(pkg_dir, 'ops'), exist_ok=True)
+    for rel in ['__init__.py', 'ops/__init__.py', 'ops/conv2d.py', 'ops/deconv2d.py', 'ops/linear.py',
+                'ops/batchnorm.py', 'ops/cond_batchnorm.py']:
+        with open(os.path.join(REF_ROOT, 'tflib', rel)) as f:
+            src = py2to3(f.read())
+        if rel == '__init__.py':
+            src = src.replace("locale.setlocale(locale.LC_ALL, '')", "pass")
+        with open(os.path.join(pkg_dir, rel), 'w') as f:
+            f.write(src)
+    for k in [k for k in sys.modules if k == 'tflib' or k.startswith('tflib.')]:
+        del sys.modules[k]
+    saved_tf = sys.modules.get('tensorflow')
+    sys.modules['tensorflow'] = shim
+    sys.path.insert(0, OUT_DIR)
+    try:
+        lib = importlib.import_module('tflib')
+        for m in ('conv2d', 'deconv2d', 'linear', 'batchnorm', 'cond_batchnorm'):
+            importlib.import_module('tflib.ops.' + m)
+    finally:
+        sys.path.remove(OUT_DIR)
+        if saved_tf is None:
+            del sys.modules['tensorflow']
+        else:
+            sys.modules['tensorflow'] = saved_tf
+    return lib
+
+
+def _section(path, first, last, dedent=False):
+    with open(path) as f:
+        lines = f.read().splitlines()
+    src = '\n'.join(lines[first - 1:last]) + '\n'
+    if dedent:
+        src = textwrap.dedent(src)
+    return py2to3(src)
+
+
+# (constants, functions, graph) line ranges, 1-based inclusive, of the reference scripts
+SECTIONS = {
+    'mnist': dict(file='CT_gan_mnist.py', consts=(26, 35), funcs=(39, 108), graph=(110, 167), dedent=False),
+    'cifar': dict(file='CT_gan_cifar.py', consts=(34, 43), funcs=(47, 100), graph=(102, 151), dedent=False),
+    'resnet': dict(file='CT_gan_cifar_resnet.py', consts=(37, 56), funcs=(67, 186), graph=(190, 330), dedent=True),
+}
+
+# random draws of the reference graph, in graph-construction order, mapped onto the oracle's tags
+# (None = the draw feeds nothing the training step uses)
+def _draw_tags(script):
+    D3 = lambda p: [p + '.1', p + '.2', p + '.3']
+    if script in ('mnist', 'cifar'):
+        tags = ['z']                                   # fake_data = Generator(BATCH_SIZE)
+        if script == 'cifar':
+            tags += [None]                             # fake_data_2 = Generator(BATCH_SIZE)      (:105, unused)
+        tags += D3('drop.real1') + D3('drop.real2') + D3('drop.fake') + [None] * 3     # 4 critic calls, last unused
+        if script == 'cifar':
+            tags += [None]                             # fake_data_2 = Generator(...) again       (:117, unused)
+        tags += ['alpha'] + D3('drop.gp')
+        if script == 'cifar':
+            tags += [None] * 3                         # Discriminator(real_data) for `gradients2` (:145, dev metric)
+        return tags
+    tags = ['z.0', 'z.1', 'dequant'] + D3('drop.p1') + D3('drop.p2')     # clean pass: keep_prob 1 -> no draw
+    tags += ['alpha'] + D3('drop.gp')
+    tags += ['labels.0', 'z.0g', 'drop.0.1', 'drop.0.2', 'drop.0.3', 'labels.1', 'z.1g', 'drop.1.1', 'drop.1.2', 'drop.1.3']
+    return tags
+
+
+def run_reference(script, batch_size, seed, inputs, dim=None):
+    """Execute the reference's own code for one evaluation of disc_cost / gen_cost.
+    inputs: tuple of numpy arrays fed to the script's placeholders (real data[, labels]).
+    Returns dict(params, disc, gen, tape_disc, tape_gen, disc_grads, gen_grads, gp_gradients)."""
+    from . import tf_shim as shim
+    sec = SECTIONS[script]
+    path = os.path.join(REF_ROOT, sec['file'])
+    lib = _load_ref_tflib(shim)
+    lib.delete_all_params()
+    ns = {'tf': shim, 'lib': lib, 'np': np, 'functools': importlib.import_module('functools'), '__name__': 'ref_section'}
+    exec(compile(_section(path, *sec['consts']), sec['file'] + ':consts', 'exec'), ns)
+    ns['BATCH_SIZE'] = batch_size
+    if dim is not None:                                # smaller model for the committed golden fixtures
+        for k in ('DIM', 'DIM_G', 'DIM_D'):
+            if k in ns:
+                ns[k] = dim
+    if script == 'resnet':
+        ns['N_GPUS'] = 1
+        ns['DEVICES'] = ['/gpu:0', '/gpu:0']           # :61-63 with N_GPUS == 1
+    exec(compile(_section(path, *sec['funcs']), sec['file'] + ':funcs', 'exec'), ns)
+    np.random.seed(seed)                               # the reference draws initial weights from numpy's global RNG
+    feeds = [torch.from_numpy(np.asarray(a)) for a in inputs]
+    if script == 'resnet':
+        feeds = [torch.tensor(0, dtype=torch.int32)] + feeds          # _iteration placeholder (:190)
+    shim.reset(seed + 1, feeds)
+    graph_src = _section(path, *sec['graph'], dedent=sec['dedent'])
+    exec(compile(graph_src, sec['file'] + ':graph', 'exec'), ns)
+    draws = list(shim.draws)
+    tags = _draw_tags(script)
+    assert len(draws) == len(tags), (len(draws), len(tags), [k for k, _ in draws])
+    tape_disc, tape_gen = {}, {}
+    for tag, (kind, t) in zip(tags, draws):
+        if tag is None:
+            continue
+        if script == 'resnet' and (tag.endswith('g') or tag.startswith('labels.') or tag.startswith('drop.0') or tag.startswith('drop.1')):
+            t2 = t
+            if tag.startswith('labels.'):
+                t2 = torch.floor(t * np.float32(10)).to(torch.int32)
+            tape_gen[tag[:-1] if tag.endswith('g') else tag] = t2
+        else:
+            tape_disc[tag] = t
+    if script != 'resnet':
+        tape_gen = {k: v for k, v in tape_disc.items() if k == 'z' or k.startswith('drop.fake')}
+    params = {n: p for n, p in lib._params.items()}
+    disc_sel = 'Discriminator.' if script == 'resnet' else 'Discriminator'
+    dnames = [n for n, p in params.items() if disc_sel in n and p.requires_grad]
+    gnames = [n for n, p in params.items() if 'Generator' in n and p.requires_grad]
+    dgr = torch.autograd.grad(ns['disc_cost'], [params[n] for n in dnames], retain_graph=True, allow_unused=True)
+    ggr = torch.autograd.grad(ns['gen_cost'], [params[n] for n in gnames], retain_graph=True, allow_unused=True)
+    out = dict(
+        params={n: p.detach().clone() for n, p in params.items()},
+        trainable={n: bool(p.requires_grad) for n, p in params.items()},
+        disc_cost=ns['disc_cost'].detach(), gen_cost=ns['gen_cost'].detach(),
+        gp_gradients=ns['gradients'].detach(),
+        disc_grads={n: (g.detach() if g is not None else None) for n, g in zip(dnames, dgr)},
+        gen_grads={n: (g.detach() if g is not None else None) for n, g in zip(gnames, ggr)},
+        tape_disc=tape_disc, tape_gen=tape_gen,
+    )
+    for k in ('gradient_penalty', 'CT_', 'disc_wgan', 'disc_acgan'):
+        if k in ns and isinstance(ns[k], torch.Tensor):
+            out[k] = ns[k].detach()
+    return out
