@@ -35,8 +35,7 @@ def LeakyReLU(x, alpha=0.2):
 
 def _lrelu_dropout(output, keep):
     """LeakyReLU (:47-48) followed by tf.nn.dropout(keep_prob) (:86): one fused kernel."""
-    seed, off, dyn = RNG.dropout_stream(output)
-    return F.leaky_relu_dropout(output, 0.2, keep, seed=seed, offset=off, dyn=dyn)
+    return F.leaky_relu_dropout(output, 0.2, keep, **RNG.dropout_args(output))
 
 
 def Generator(n_samples, noise=None):

@@ -154,8 +154,7 @@ def Generator(n_samples, labels, noise=None):
 def _dropout(output, keep):
     if keep == 1.0:
         return output
-    seed, off, dyn = RNG.dropout_stream(output)
-    return F.dropout(output, keep, seed=seed, offset=off, dyn=dyn)
+    return F.dropout(output, keep, **RNG.dropout_args(output))
 
 
 def Discriminator(inputs, labels, kp1, kp2, kp3):  # three more parameters of keep rate
@@ -232,8 +231,11 @@ class Trainer:
             RNG.begin_stack([h] * N_DEVICES)
             fake_data = self._generate([('z.%d' % i, h) for i in range(N_DEVICES)], all_real_labels, B)
             RNG.end_stack()
-        seed, off, dyn = RNG.stream('dequant', all_real_data_int)
-        all_real_data = K.prep_real(all_real_data_int, 256., 1. / 128, seed, off, dyn=dyn)     # :201-202
+        if RNG.replay is not None:                                                              # golden-vector tests
+            all_real_data = K.add(K.prep_real(all_real_data_int, 256., 0.), RNG.uniform('dequant', all_real_data_int.shape))
+        else:
+            seed, off, dyn = RNG.stream('dequant', all_real_data_int)
+            all_real_data = K.prep_real(all_real_data_int, 256., 1. / 128, seed, off, dyn=dyn)  # :201-202
         # stochastic pass ' on real+fake (2B rows) and pass '' on the real half (B rows) as ONE critic call:
         # same weights, independent dropout draws per row -- the reference's two calls at :226-227
         stacked = torch.cat([all_real_data, fake_data, all_real_data], dim=0)

@@ -32,8 +32,7 @@ def LeakyReLU(x, alpha=0.2):
 
 
 def _lrelu_dropout(output, keep):
-    seed, off, dyn = RNG.dropout_stream(output)
-    return F.leaky_relu_dropout(output, 0.2, keep, seed=seed, offset=off, dyn=dyn)
+    return F.leaky_relu_dropout(output, 0.2, keep, **RNG.dropout_args(output))
 
 
 def Generator(n_samples, noise=None):

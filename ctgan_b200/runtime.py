@@ -34,6 +34,9 @@ class DeviceRandom:
         self._site = 0
         self.patterns = []
         self._stack = None
+        # replay: {tag: tensor} of externally supplied draws (golden-vector tests): every draw is taken from here
+        # instead of the Philox stream; dropout sites then receive explicit uniform tensors
+        self.replay = None
         # graph_safe: kernels add a device-resident base offset, advanced by a kernel at step end
         self.dyn = torch.zeros(1, dtype=torch.int64, device=self.device) if graph_safe else None
 
@@ -97,16 +100,33 @@ class DeviceRandom:
                 r0 += n
 
     def normal_parts(self, parts, cols):
+        if self.replay is not None:
+            return torch.cat([self._replayed(tag, n) for tag, n in parts], dim=0)
         rows = sum(n for _, n in parts)
         t = K.philox_normal((rows, cols), self.device, self.seed, self._take(2 * rows * cols), dyn=self.dyn)
         self._split_keep(parts, t)
         return t
 
     def labels_parts(self, parts, n_labels=10):
+        if self.replay is not None:
+            return torch.cat([self._replayed(tag, n, torch.int32) for tag, n in parts], dim=0)
         rows = sum(n for _, n in parts)
         t = K.philox_labels(rows, self.device, n_labels, self.seed, self._take(rows), dyn=self.dyn)
         self._split_keep(parts, t)
         return t
+
+    def dropout_args(self, like):
+        """Keyword arguments for F.dropout / F.leaky_relu_dropout at the next dropout site of the current scope:
+        a Philox slice (seed, offset, dyn) or, in replay mode, the explicit uniform tensor `u`."""
+        if self.replay is not None:
+            self._site += 1
+            parts = self._parts if self._parts is not None else [(self._scope, like.shape[0])]
+            u = torch.cat([self._replayed('%s.%d' % (p, self._site), n) for p, n in parts], dim=0)
+            if like.dim() == 4:
+                u = u.contiguous(memory_format=CL)
+            return dict(u=u)
+        seed, off, dyn = self.dropout_stream(like)
+        return dict(seed=seed, offset=off, dyn=dyn)
 
     def dropout_stream(self, like):
         """Philox slice for the next dropout site of the current scope; returns (seed, offset, dyn)."""
@@ -126,19 +146,31 @@ class DeviceRandom:
             self.tape[tag] = t
 
     # -- draws ------------------------------------------------------------------
+    def _replayed(self, tag, rows=None, dtype=torch.float32):
+        t = torch.as_tensor(self.replay[tag])
+        if rows is not None:
+            t = t[:rows]                     # the reference ran this pass on more rows than the product needs
+        return t.to(self.device).to(dtype).contiguous()
+
     def normal(self, tag, shape):
+        if self.replay is not None:
+            return self._replayed(tag)
         n = int(math.prod(shape))
         t = K.philox_normal(tuple(shape), self.device, self.seed, self._take(2 * n), dyn=self.dyn)
         self._keep(tag, t)
         return t
 
     def uniform(self, tag, shape, lo=0., hi=1.):
+        if self.replay is not None:
+            return self._replayed(tag)
         n = int(math.prod(shape))
         t = K.philox_uniform(tuple(shape), self.device, self.seed, self._take(n), lo, hi, dyn=self.dyn)
         self._keep(tag, t)
         return t
 
     def labels(self, tag, n, n_labels=10):
+        if self.replay is not None:
+            return self._replayed(tag, dtype=torch.int32)
         t = K.philox_labels(int(n), self.device, n_labels, self.seed, self._take(n), dyn=self.dyn)
         self._keep(tag, t)
         return t
