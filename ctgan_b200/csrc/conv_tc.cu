@@ -152,6 +152,51 @@ struct FpropParams {
     const __nv_bfloat16* residual;
 };
 
+// Epilogue shared by the fprop kernels: thread = tile row = TMEM lane; 32 fp32 columns per tcgen05.ld,
+// + bias (+ residual) (ReLU), bf16 pack, 16-byte stores.
+template <int BLOCK_N>
+__device__ __forceinline__ void fprop_epilogue(const FpropParams& p, uint32_t tmem_base, const float* s_bias,
+                                               int warp, int lane, int w0, int h0, int n0, int co0) {
+    const int row = warp * 32 + lane;
+    int t = row;
+    const int bw = t % p.BW; t /= p.BW;
+    const int bh = t % p.BH; const int bn = t / p.BH;
+    const int n = n0 + bn, h = h0 + bh, w = w0 + bw;
+    const bool valid = (n < p.N) && (h < p.H) && (w < p.W);
+    const int64_t pix = ((int64_t)n * p.H + h) * p.W + w;
+    __nv_bfloat16* yrow = p.y + pix * p.Cout + co0;
+    const __nv_bfloat16* rrow = p.residual ? p.residual + pix * p.Cout + co0 : nullptr;
+    const bool relu = (p.flags & CTGAN_EPI_RELU) != 0;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        uint32_t acc[32];
+        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, acc);   // warp-collective
+        if (valid) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+                float v[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(acc[j + e]) + s_bias[c0 + j + e];
+                if (rrow) {
+                    uint4 rv = *reinterpret_cast<const uint4*>(rrow + c0 + j);
+                    const __nv_bfloat162* rp = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) { v[2 * e] += __bfloat162float(rp[e].x); v[2 * e + 1] += __bfloat162float(rp[e].y); }
+                }
+                if (relu) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
+                }
+                uint4 ov;
+                __nv_bfloat162* op = reinterpret_cast<__nv_bfloat162*>(&ov);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) op[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+                *reinterpret_cast<uint4*>(yrow + c0 + j) = ov;
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------ fprop kernel
 template <int BLOCK_N, int STAGES>
 __global__ void __launch_bounds__(128)
@@ -237,47 +282,295 @@ conv_fprop_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
     // ================= epilogue: TMEM -> registers -> global =================
     mbar_wait(accum_bar, 0);
     tc_fence_after();
-    const int row = warp * 32 + lane;                          // tile row == TMEM lane
-    int t = row;
-    const int bw = t % p.BW; t /= p.BW;
-    const int bh = t % p.BH; const int bn = t / p.BH;
-    const int n = n0 + bn, h = h0 + bh, w = w0 + bw;
-    const bool valid = (n < p.N) && (h < p.H) && (w < p.W);
-    const int64_t pix = ((int64_t)n * p.H + h) * p.W + w;
-    __nv_bfloat16* yrow = p.y + pix * p.Cout + co0;
-    const __nv_bfloat16* rrow = p.residual ? p.residual + pix * p.Cout + co0 : nullptr;
-    const bool relu = (p.flags & CTGAN_EPI_RELU) != 0;
+    fprop_epilogue<BLOCK_N>(p, tmem_base, s_bias, warp, lane, w0, h0, n0, co0);
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
+// ------------------------------------------------------------------ fprop kernel, halo reuse (k x k, k > 1)
+// Tiles that cover BH full-width rows of ONE image (BN == 1, BW*128 B a multiple of the 1 KB swizzle atom).
+// For every (cin block, column shift s) ONE box of BH+kh-1 rows is loaded; the kh row taps read it through
+// descriptors advanced by r*BW rows (r*BW*128 bytes: whole swizzle atoms, so the layout stays canonical).
+// L2->SM traffic of the A operand drops by kh/(1+(kh-1)/BH) (2x for 3x3 on 4-row tiles); the filter (B operand)
+// streams through its own, deeper ring.
+template <int BLOCK_N, int SA, int SB>
+__global__ void __launch_bounds__(128)
+conv_fprop_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+                          const FpropParams p, const uint32_t a_slot_bytes)
+{
+    constexpr uint32_t B_BYTES = BLOCK_N * BLOCK_K * 2;
+    constexpr int TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const uint32_t a_base = smem_u32(smem);
+    const uint32_t b_base = a_base + SA * a_slot_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SA * a_slot_bytes + SB * B_BYTES);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * SA + 2 * SB + 1);
+    float* s_bias = reinterpret_cast<float*>(tmem_slot + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t fullA = smem_u32(bars), emptyA = smem_u32(bars + SA);
+    const uint32_t fullB = smem_u32(bars + 2 * SA), emptyB = smem_u32(bars + 2 * SA + SB);
+    const uint32_t accum_bar = smem_u32(bars + 2 * SA + 2 * SB);
+
+    int mt = blockIdx.x;
+    const int tw = mt % p.tilesW; mt /= p.tilesW;
+    const int th = mt % p.tilesH; const int tn = mt / p.tilesH;
+    const int w0 = tw * p.BW, h0 = th * p.BH, n0 = tn;          // BN == 1
+    const int co0 = blockIdx.y * BLOCK_N;
+    const int cin_blocks = p.Cin / BLOCK_K;
+    const uint32_t a_bytes = (uint32_t)(p.BH + p.kh - 1) * p.BW * 128u;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmap_x);
+        prefetch_tmap(&tmap_w);
+        for (int s = 0; s < SA; ++s) { mbar_init(fullA + 8 * s, 1); mbar_init(emptyA + 8 * s, 1); }
+        for (int s = 0; s < SB; ++s) { mbar_init(fullB + 8 * s, 1); mbar_init(emptyB + 8 * s, 1); }
+        mbar_init(accum_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc<TMEM_COLS>(smem_u32(tmem_slot));
+    if (threadIdx.x < BLOCK_N) s_bias[threadIdx.x] = p.bias ? p.bias[co0 + threadIdx.x] : 0.f;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0 && lane == 0) {
+        // ================= TMA producer =================
+        int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
+        for (int cb = 0; cb < cin_blocks; ++cb) {
+            for (int s = 0; s < p.kw; ++s) {
+                mbar_wait(emptyA + 8 * sa, pa ^ 1);
+                mbar_expect_tx(fullA + 8 * sa, a_bytes);
+                tma_load_4d(a_base + sa * a_slot_bytes, &tmap_x, fullA + 8 * sa, cb * BLOCK_K, w0 + s - p.pad_l, h0 - p.pad_t, n0);
+                if (++sa == SA) { sa = 0; pa ^= 1; }
+                for (int r = 0; r < p.kh; ++r) {
+                    mbar_wait(emptyB + 8 * sb, pb ^ 1);
+                    mbar_expect_tx(fullB + 8 * sb, B_BYTES);
+                    tma_load_3d(b_base + sb * B_BYTES, &tmap_w, fullB + 8 * sb, cb * BLOCK_K, co0, r * p.kw + s);
+                    if (++sb == SB) { sb = 0; pb ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ================= MMA issuer =================
+        constexpr uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N, 0, 0);
+        int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
+        uint32_t first = 1;
+        const int last_cb = cin_blocks - 1, last_s = p.kw - 1, last_r = p.kh - 1;
+        for (int cb = 0; cb < cin_blocks; ++cb) {
+            for (int s = 0; s < p.kw; ++s) {
+                mbar_wait(fullA + 8 * sa, pa);
+                tc_fence_after();
+                const uint32_t a_src = a_base + sa * a_slot_bytes;
+                for (int r = 0; r < p.kh; ++r) {
+                    mbar_wait(fullB + 8 * sb, pb);
+                    tc_fence_after();
+                    // row tap r: skip r image rows = r*BW pixel rows of 128 B each
+                    const uint64_t a_desc = make_smem_desc(a_src + (uint32_t)(r * p.BW) * 128u, 16, 1024);
+                    const uint64_t b_desc = make_smem_desc(b_base + sb * B_BYTES, 16, 1024);
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                        umma_bf16(tmem_base, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, first ? 0u : 1u);
+                        first = 0;
+                    }
+                    umma_commit(emptyB + 8 * sb);
+                    if (r == last_r) umma_commit(emptyA + 8 * sa);
+                    if (cb == last_cb && s == last_s && r == last_r) umma_commit(accum_bar);
+                    if (++sb == SB) { sb = 0; pb ^= 1; }
+                }
+                if (++sa == SA) { sa = 0; pa ^= 1; }
+            }
+        }
+    }
+    __syncwarp();
+
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+    fprop_epilogue<BLOCK_N>(p, tmem_base, s_bias, warp, lane, w0, h0, n0, co0);
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
+// ------------------------------------------------------------------ fprop kernel, persistent
+// One CTA per SM loops over output tiles (static round-robin).  Six warps: warp 0 = TMA producer, warp 1 = MMA
+// issuer (+ TMEM allocator), warps 2-5 = epilogue.  Two 128-column TMEM accumulators: the epilogue of tile i
+// overlaps the main loop of tile i+1.  Operands flow through two independent mbarrier rings, SA slots for the
+// activation boxes and SB slots for the 16 KB filter boxes (200 KB of shared memory in flight per SM), deep
+// enough to cover the L2 round trip that bounds the 3-stage kernels above (ncu: 36-38 % tensor-active, far from
+// both the L2 and the tensor ceiling).  HALO = 1: one (BH+kh-1)-row box per (cin block, column shift), row taps
+// through shifted descriptors (see the halo kernel); HALO = 0: one box per (cin block, tap).
+template <int SA, int SB, int A_SLOT, int HALO>
+__global__ void __launch_bounds__(192, 1)
+conv_fprop_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+                                const FpropParams p, const int n_tiles)
+{
+    constexpr int BLOCK_N = 128;
+    constexpr uint32_t B_BYTES = BLOCK_N * BLOCK_K * 2;
+    constexpr int TMEM_COLS = 256;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const uint32_t a_base = smem_u32(smem);
+    const uint32_t b_base = a_base + SA * A_SLOT;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SA * A_SLOT + SB * B_BYTES);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * SA + 2 * SB + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t fullA = smem_u32(bars), emptyA = smem_u32(bars + SA);
+    const uint32_t fullB = smem_u32(bars + 2 * SA), emptyB = smem_u32(bars + 2 * SA + SB);
+    const uint32_t tfull = smem_u32(bars + 2 * SA + 2 * SB), tempty = smem_u32(bars + 2 * SA + 2 * SB + 2);
+
+    const int cin_blocks = p.Cin / BLOCK_K;
+    const int n_blocks = p.Cout / BLOCK_N;
+    const int rtaps = HALO ? p.kh : 1;                              // row taps served by one activation box
+    const int groups = cin_blocks * (HALO ? p.kw : p.kh * p.kw);    // activation boxes per tile
+    const uint32_t a_bytes = (uint32_t)(HALO ? p.BH + p.kh - 1 : p.BH) * p.BW * p.BN * 128u;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmap_x);
+        prefetch_tmap(&tmap_w);
+        for (int s = 0; s < SA; ++s) { mbar_init(fullA + 8 * s, 1); mbar_init(emptyA + 8 * s, 1); }
+        for (int s = 0; s < SB; ++s) { mbar_init(fullB + 8 * s, 1); mbar_init(emptyB + 8 * s, 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(tfull + 8 * s, 1); mbar_init(tempty + 8 * s, 4); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<TMEM_COLS>(smem_u32(tmem_slot));
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0 && lane == 0) {
+        // ================= TMA producer =================
+        int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int nb = tile % n_blocks; int mt = tile / n_blocks;
+            const int tw = mt % p.tilesW; mt /= p.tilesW;
+            const int th = mt % p.tilesH; const int tn = mt / p.tilesH;
+            const int w0 = tw * p.BW, h0 = th * p.BH, n0 = tn * p.BN, co0 = nb * BLOCK_N;
+            for (int gi = 0; gi < groups; ++gi) {
+                int cb, s, r0;
+                if (HALO) { cb = gi / p.kw; s = gi - cb * p.kw; r0 = 0; }
+                else { cb = gi / (p.kh * p.kw); const int tap = gi - cb * p.kh * p.kw; r0 = tap / p.kw; s = tap - r0 * p.kw; }
+                mbar_wait(emptyA + 8 * sa, pa ^ 1);
+                mbar_expect_tx(fullA + 8 * sa, a_bytes);
+                tma_load_4d(a_base + sa * A_SLOT, &tmap_x, fullA + 8 * sa, cb * BLOCK_K, w0 + s - p.pad_l, h0 + r0 - p.pad_t, n0);
+                if (++sa == SA) { sa = 0; pa ^= 1; }
+                for (int r = 0; r < rtaps; ++r) {
+                    mbar_wait(emptyB + 8 * sb, pb ^ 1);
+                    mbar_expect_tx(fullB + 8 * sb, B_BYTES);
+                    tma_load_3d(b_base + sb * B_BYTES, &tmap_w, fullB + 8 * sb, cb * BLOCK_K, co0, (r0 + r) * p.kw + s);
+                    if (++sb == SB) { sb = 0; pb ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ================= MMA issuer =================
+        constexpr uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N, 0, 0);
+        int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            const int acc = it & 1;
+            const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+            mbar_wait(tempty + 8 * acc, acc_phase ^ 1);            // epilogue has drained this accumulator
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
+            uint32_t first = 1;
+            for (int gi = 0; gi < groups; ++gi) {
+                mbar_wait(fullA + 8 * sa, pa);
+                tc_fence_after();
+                const uint32_t a_src = a_base + sa * A_SLOT;
+                for (int r = 0; r < rtaps; ++r) {
+                    mbar_wait(fullB + 8 * sb, pb);
+                    tc_fence_after();
+                    const uint64_t a_desc = make_smem_desc(a_src + (HALO ? (uint32_t)(r * p.BW) * 128u : 0u), 16, 1024);
+                    const uint64_t b_desc = make_smem_desc(b_base + sb * B_BYTES, 16, 1024);
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                        umma_bf16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, first ? 0u : 1u);
+                        first = 0;
+                    }
+                    umma_commit(emptyB + 8 * sb);
+                    if (++sb == SB) { sb = 0; pb ^= 1; }
+                }
+                umma_commit(emptyA + 8 * sa);
+                if (++sa == SA) { sa = 0; pa ^= 1; }
+            }
+            umma_commit(tfull + 8 * acc);
+        }
+    } else if (warp >= 2) {
+        // ================= epilogue warps: TMEM -> registers -> global =================
+        const int q = warp & 3;                                    // TMEM lane quadrant this warp may access
+        const bool relu = (p.flags & CTGAN_EPI_RELU) != 0;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            const int acc = it & 1;
+            const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+            const int nb = tile % n_blocks; int mt = tile / n_blocks;
+            const int tw = mt % p.tilesW; mt /= p.tilesW;
+            const int th = mt % p.tilesH; const int tn = mt / p.tilesH;
+            const int co0 = nb * BLOCK_N;
+            int t = q * 32 + lane;
+            const int bw = t % p.BW; t /= p.BW;
+            const int bh = t % p.BH; const int bn = t / p.BH;
+            const int n = tn * p.BN + bn, h = th * p.BH + bh, w = tw * p.BW + bw;
+            const bool valid = (n < p.N) && (h < p.H) && (w < p.W);
+            const int64_t pix = ((int64_t)n * p.H + h) * p.W + w;
+            __nv_bfloat16* yrow = p.y + pix * p.Cout + co0;
+            const __nv_bfloat16* rrow = p.residual ? p.residual + pix * p.Cout + co0 : nullptr;
+            mbar_wait(tfull + 8 * acc, acc_phase);
+            tc_fence_after();
 #pragma unroll 1
-    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-        uint32_t acc[32];
-        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, acc);   // warp-collective
-        if (valid) {
+            for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+                uint32_t v32[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + c0), v32);
+                if (valid) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-                float v[8];
+                    for (int j = 0; j < 32; j += 8) {
+                        float v[8];
+                        if (p.bias) {
+                            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + co0 + c0 + j));
+                            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + co0 + c0 + j + 4));
+                            v[0] = b0.x; v[1] = b0.y; v[2] = b0.z; v[3] = b0.w; v[4] = b1.x; v[5] = b1.y; v[6] = b1.z; v[7] = b1.w;
+                        } else {
 #pragma unroll
-                for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(acc[j + e]) + s_bias[c0 + j + e];
-                if (rrow) {
-                    uint4 rv = *reinterpret_cast<const uint4*>(rrow + c0 + j);
-                    const __nv_bfloat162* rp = reinterpret_cast<const __nv_bfloat162*>(&rv);
+                            for (int e = 0; e < 8; ++e) v[e] = 0.f;
+                        }
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) { v[2 * e] += __bfloat162float(rp[e].x); v[2 * e + 1] += __bfloat162float(rp[e].y); }
+                        for (int e = 0; e < 8; ++e) v[e] += __uint_as_float(v32[j + e]);
+                        if (rrow) {
+                            uint4 rv = *reinterpret_cast<const uint4*>(rrow + c0 + j);
+                            const __nv_bfloat162* rp = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) { v[2 * e] += __bfloat162float(rp[e].x); v[2 * e + 1] += __bfloat162float(rp[e].y); }
+                        }
+                        if (relu) {
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
+                        }
+                        uint4 ov;
+                        __nv_bfloat162* op = reinterpret_cast<__nv_bfloat162*>(&ov);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) op[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+                        *reinterpret_cast<uint4*>(yrow + c0 + j) = ov;
+                    }
                 }
-                if (relu) {
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
-                }
-                uint4 ov;
-                __nv_bfloat162* op = reinterpret_cast<__nv_bfloat162*>(&ov);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) op[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
-                *reinterpret_cast<uint4*>(yrow + c0 + j) = ov;
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {                                        // this warp has finished reading the accumulator
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty + 8 * acc) : "memory");
             }
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 2) tmem_dealloc<TMEM_COLS>(tmem_base);
+    if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem_base);
 }
 
 // ------------------------------------------------------------------ wgrad kernel
@@ -425,6 +718,27 @@ __global__ void pack_filter_kernel(const float* __restrict__ w, __nv_bfloat16* _
     }
 }
 
+// One launch packs every filter of an optimizer: entry e (blockIdx.y) = {src offset in the flat float parameter
+// buffer, dst offset in the bf16 pack buffer, taps, Cin, Cout, transpose_flip}.
+struct PackEntry { long long src, dst; int taps, cin, cout, flip; };
+__global__ void pack_filters_multi_kernel(const float* __restrict__ flat, __nv_bfloat16* __restrict__ packs,
+                                          const PackEntry* __restrict__ table) {
+    const PackEntry e = table[blockIdx.y];
+    const float* w = flat + e.src;
+    __nv_bfloat16* wp = packs + e.dst;
+    const int64_t total = (int64_t)e.taps * e.cin * e.cout;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        if (e.flip) {
+            int64_t t = i / ((int64_t)e.cin * e.cout), rem = i - t * (int64_t)e.cin * e.cout;
+            wp[i] = __float2bfloat16_rn(w[(int64_t)(e.taps - 1 - t) * e.cin * e.cout + rem]);
+        } else {
+            int c = i % e.cin; int64_t q = i / e.cin;
+            int o = q % e.cout; int t = q / e.cout;
+            wp[i] = __float2bfloat16_rn(w[((int64_t)t * e.cin + c) * e.cout + o]);
+        }
+    }
+}
+
 // ------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -448,6 +762,7 @@ static int pow2ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 
 // 4-D map over an NHWC bf16 tensor: dims (C, W, H, N), box (64, BW, BH, BN), 128B swizzle, zero OOB fill
 static int make_act_map(CUtensorMap* map, const void* base, int N, int H, int W, int C, int BW, int BH, int BN) {
+    CTGAN_REQUIRE(BW <= 256 && BH <= 256 && BN <= 256, CTGAN_ERR_UNSUPPORTED, "activation box dimension exceeds 256");
     EncodeTiledFn enc = get_encode_fn();
     CTGAN_REQUIRE(enc != nullptr, CTGAN_ERR_DRIVER, "cuTensorMapEncodeTiled entry point not available");
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
@@ -508,11 +823,53 @@ static int launch_fprop(const CUtensorMap& mx, const CUtensorMap& mw, const Fpro
     return 0;
 }
 
+template <int BLOCK_N, int SA, int SB>
+static int launch_fprop_halo(const CUtensorMap& mx, const CUtensorMap& mw, const FpropParams& p, cudaStream_t st) {
+    const uint32_t a_bytes = (uint32_t)(p.BH + p.kh - 1) * p.BW * 128u;
+    const uint32_t a_slot = (a_bytes + 1023u) & ~1023u;
+    const size_t smem = (size_t)SA * a_slot + (size_t)SB * BLOCK_N * BLOCK_K * 2 + 1024 + (2 * SA + 2 * SB + 1) * 8 + 16 + BLOCK_N * 4;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(conv_fprop_tc_halo_kernel<BLOCK_N, SA, SB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return cuda_status(e, "fprop_tc_halo smem attribute");
+        attr_set = true;
+    }
+    dim3 grid(p.tilesW * p.tilesH * p.tilesN, p.Cout / BLOCK_N);
+    conv_fprop_tc_halo_kernel<BLOCK_N, SA, SB><<<grid, 128, smem, st>>>(mx, mw, p, a_slot);
+    CTGAN_CHECK_LAUNCH("conv_fprop_tc_halo");
+    return 0;
+}
+
+template <int SA, int SB, int A_SLOT, int HALO>
+static int launch_fprop_persistent(const CUtensorMap& mx, const CUtensorMap& mw, const FpropParams& p, cudaStream_t st) {
+    constexpr size_t smem = (size_t)SA * A_SLOT + (size_t)SB * 16384 + 1024 + (2 * SA + 2 * SB + 4) * 8 + 16;
+    static_assert(smem <= 227 * 1024, "persistent fprop: shared memory budget");
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(conv_fprop_tc_persistent_kernel<SA, SB, A_SLOT, HALO>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return cuda_status(e, "fprop_tc_persistent smem attribute");
+        attr_set = true;
+    }
+    const int n_tiles = p.tilesW * p.tilesH * p.tilesN * (p.Cout / 128);
+    const int grid = n_tiles < sm_count() ? n_tiles : sm_count();
+    conv_fprop_tc_persistent_kernel<SA, SB, A_SLOT, HALO><<<grid, 192, smem, st>>>(mx, mw, p, n_tiles);
+    CTGAN_CHECK_LAUNCH("conv_fprop_tc_persistent");
+    return 0;
+}
+
 }  // namespace tc
 }  // namespace ctgan
 
 using namespace ctgan;
 using namespace ctgan::tc;
+
+static bool g_use_halo = true;
+static int g_fprop_variant = 2;   // 2 = persistent kernel, 1 = one tile per CTA (3/6-stage) kernels
+/* test hook: selects the fprop_tc kernel family (both are compared in tests/) */
+extern "C" void ctgan_set_fprop_variant(int v) { g_fprop_variant = v; }
+/* test hook: 0 disables the halo-reuse fprop variant (both variants are compared in tests/) */
+extern "C" void ctgan_set_fprop_halo(int on) { g_use_halo = on != 0; }
 
 extern "C" int ctgan_conv_fprop_tc(const ctgan_conv_desc* d, const void* x, const void* wp,
                                    const float* bias, const void* residual, void* y, int flags, void* stream) {
@@ -531,14 +888,22 @@ extern "C" int ctgan_conv_fprop_tc(const ctgan_conv_desc* d, const void* x, cons
     p.bias = bias;
     p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
     const int block_n = (d->Cout % 128 == 0) ? 128 : 64;
+    const int ctas = p.tilesW * p.tilesH * p.tilesN * (d->Cout / block_n);
+    // halo-reuse variant: k x k filters (k > 1) on tiles that are whole rows of one image, more than one wave of CTAs
+    const bool halo = g_use_halo && block_n == 128 && d->kh > 1 && d->kh <= 5 && p.BN == 1 && (p.BW % 8) == 0 &&
+                      (uint32_t)(p.BH + d->kh - 1) * p.BW * 128u <= 24576u && (g_fprop_variant == 2 || ctas > sm_count());
     CUtensorMap mx, mw;
-    if (int r = make_act_map(&mx, x, d->N, d->H, d->W, d->Cin, p.BW, p.BH, p.BN)) return r;
+    if (int r = make_act_map(&mx, x, d->N, d->H, d->W, d->Cin, p.BW, halo ? p.BH + d->kh - 1 : p.BH, p.BN)) return r;
     if (int r = make_filter_map(&mw, wp, d->kh * d->kw, d->Cout, d->Cin, block_n)) return r;
     cudaStream_t st = as_stream(stream);
+    if (g_fprop_variant == 2 && block_n == 128) {                    // persistent, deep rings (default)
+        if (halo) return launch_fprop_persistent<3, 8, 24576, 1>(mx, mw, p, st);
+        return launch_fprop_persistent<6, 6, 16384, 0>(mx, mw, p, st);
+    }
+    if (halo) return launch_fprop_halo<128, 2, 3>(mx, mw, p, st);
     if (block_n == 128) {
         // Few tiles (8x8 / 4x4 layers at batch 64): one CTA per SM at most, so the K loop is latency-bound --
         // use a 6-deep TMA ring.  Many tiles: 3 stages x 2 co-resident CTAs per SM.
-        const int ctas = p.tilesW * p.tilesH * p.tilesN * (d->Cout / 128);
         if (ctas <= sm_count()) return launch_fprop<128, 6>(mx, mw, p, st);
         return launch_fprop<128, 3>(mx, mw, p, st);
     }
@@ -584,6 +949,14 @@ extern "C" int ctgan_conv_wgrad_tc(const ctgan_conv_desc* d, const void* x, cons
     dim3 grid(tiles, tap_groups, splits);
     conv_wgrad_tc_kernel<STAGES><<<grid, 128, smem, as_stream(stream)>>>(mx, mdy, p);
     CTGAN_CHECK_LAUNCH("conv_wgrad_tc");
+    return 0;
+}
+
+extern "C" int ctgan_pack_filters_multi(const float* flat, void* packs, const void* table, int n_entries, void* stream) {
+    CTGAN_REQUIRE(flat && packs && table && n_entries > 0 && n_entries <= 65535, CTGAN_ERR_BAD_DESC, "pack_filters_multi: bad args");
+    pack_filters_multi_kernel<<<dim3(64, n_entries), 256, 0, as_stream(stream)>>>(flat, reinterpret_cast<__nv_bfloat16*>(packs),
+                                                                                reinterpret_cast<const PackEntry*>(table));
+    CTGAN_CHECK_LAUNCH("pack_filters_multi");
     return 0;
 }
 

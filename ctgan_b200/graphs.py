@@ -47,7 +47,6 @@ class _Step:
             rng.end_step()
 
         k0 = K._lib.lib.ctgan_kernel_launches()
-        K.invalidate_weight_cache()
         if self.world == 1:
             self.g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.g, pool=pool):
@@ -63,7 +62,6 @@ class _Step:
                 rng.offset = offset
                 part_b()
         self.kernels = K._lib.lib.ctgan_kernel_launches() - k0
-        K.invalidate_weight_cache()
 
     def replay(self):
         if self.world == 1:

@@ -114,21 +114,22 @@ def _tc_geom_ok(g):
             and g.Cin % 64 == 0 and g.Cout % 64 == 0 and 0 <= g.pad_t < g.kh and 0 <= g.pad_l < g.kw)
 
 
-# packed-filter cache for PARAMETERS only (keyed by storage address + optimizer epoch)
+# packed-filter cache for PARAMETERS only (keyed by storage address, shape, layout)
 _pack_cache = {}
-_epoch = 0
 
 
-def invalidate_weight_cache():
-    """Called by the optimizer after parameters change in place."""
-    global _epoch
-    _epoch += 1
-    _pack_cache.clear()
+def invalidate_weight_cache(ptrs=None):
+    """Called by an optimizer after ITS parameters changed in place (ptrs = their data pointers; None = all)."""
+    if ptrs is None:
+        _pack_cache.clear()
+        return
+    for k in [k for k in _pack_cache if k[0] in ptrs]:
+        del _pack_cache[k]
 
 
 def pack_filter(w, transpose_flip, cacheable=False):
     """float HWIO [kh,kw,Cin,Cout] (or [in,out]) -> bf16 operand of the tcgen05 kernels."""
-    key = (w.data_ptr(), tuple(w.shape), transpose_flip, _epoch) if cacheable else None
+    key = (w.data_ptr(), tuple(w.shape), transpose_flip) if cacheable else None
     if key is not None and key in _pack_cache:
         return _pack_cache[key]
     if w.dim() == 4:
@@ -148,6 +149,44 @@ def _check_filter(w, g):
     _chk(w, 'filter')
     if w.dtype != torch.float32 or not w.is_contiguous() or w.numel() != g.kh * g.kw * g.Cin * g.Cout:
         raise RuntimeError('ctgan_b200: filter must be a contiguous float32 HWIO tensor matching the geometry')
+
+
+class FilterPacker:
+    """BF16 operand copies (fprop layout + tap-flipped dgrad layout) of every tensor-core-eligible filter of one
+    flat parameter buffer, refreshed with ONE kernel launch after each optimizer step."""
+
+    def __init__(self, flat_p, params, offsets):
+        import numpy as np
+        self.flat_p = flat_p
+        rows, self.views, dst = [], [], 0
+        for name, p in params.items():
+            if p.dim() == 4:
+                taps, cin, cout = p.shape[0] * p.shape[1], p.shape[2], p.shape[3]
+            elif p.dim() == 2 and name.endswith('.W'):
+                taps, cin, cout = 1, p.shape[0], p.shape[1]
+            else:
+                continue
+            if cin % 64 or cout % 64:
+                continue
+            for flip in (0, 1):
+                rows.append((offsets[name], dst, taps, cin, cout, flip))
+                self.views.append((p, flip, dst, taps * cin * cout))
+                dst += (taps * cin * cout + 63) // 64 * 64
+        self.n = len(rows)
+        if self.n:
+            tab = np.zeros(self.n, dtype=[('src', '<i8'), ('dst', '<i8'), ('taps', '<i4'), ('cin', '<i4'), ('cout', '<i4'), ('flip', '<i4')])
+            for i, r in enumerate(rows):
+                tab[i] = r
+            self.table = torch.from_numpy(tab.view(np.uint8).copy()).to(flat_p.device)
+            self.packs = torch.empty(dst, dtype=torch.bfloat16, device=flat_p.device)
+
+    def refresh(self):
+        """Re-pack everything (one launch) and publish the views in the pack cache of the current epoch."""
+        if not self.n or not (config.use_tc and tc_available()):
+            return
+        call('ctgan_pack_filters_multi', _p(self.flat_p), _p(self.packs), _p(self.table), self.n, _stream())
+        for p, flip, dst, numel in self.views:
+            _pack_cache[(p.data_ptr(), tuple(p.shape), flip)] = self.packs[dst:dst + numel]
 
 
 def conv_fprop(x, w, bias, g, relu=False, residual=None, out_dtype=None, w_is_param=False):

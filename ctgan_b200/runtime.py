@@ -230,7 +230,9 @@ class FlatAdam:
             self.params[n] = q
         lib.rebind_params(new)
         self.offsets, self.sizes = offs, sizes
+        self._ptrs = set(q.data_ptr() for q in self.params.values())
         K.invalidate_weight_cache()
+        self.packer = K.FilterPacker(self.flat_p, self.params, offs) if dev.type == 'cuda' else None
 
     def param_list(self):
         return list(self.params.values())
@@ -262,7 +264,13 @@ class FlatAdam:
         K.adam_step(self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.lr_t(lr) if not use_device_lr else 0.0,
                     self.beta1, self.beta2, self.eps, grad_scale=1.0 / world,
                     lr_t_dev=self.lr_t_dev if use_device_lr else None)
-        K.invalidate_weight_cache()
+        K.invalidate_weight_cache(self._ptrs)
+        self.refresh_packs()
+
+    def refresh_packs(self):
+        """BF16 operand copies of all filters of this optimizer for the new parameter values (one launch)."""
+        if self.packer is not None:
+            self.packer.refresh()
 
     def set_device_lr(self, lr=None, advance=True):
         """Host side of a graph replay: bump t and upload lr_t (async, pinned)."""

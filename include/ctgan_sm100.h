@@ -85,6 +85,10 @@ int ctgan_conv_wgrad(const ctgan_conv_desc* d, const void* x, const void* dy,
  * fprop_tc also serves dgrad of a stride-1 conv: pack with transpose_flip=1 and
  * swap Cin/Cout, pad = k-1-pad in the descriptor.
  * residual (nullable, BF16, same shape as y) is added before the optional ReLU. */
+/* test hook: on == 0 disables the halo-reuse variant of fprop_tc (default on) */
+void ctgan_set_fprop_halo(int on);
+/* test hook: 2 = persistent fprop_tc kernel (default), 1 = one-tile-per-CTA kernels */
+void ctgan_set_fprop_variant(int v);
 int ctgan_conv_fprop_tc(const ctgan_conv_desc* d, const void* x, const void* wp,
                         const float* bias /*nullable*/, const void* residual /*nullable*/,
                         void* y, int flags, void* stream);
@@ -97,6 +101,10 @@ int ctgan_conv_wgrad_tc(const ctgan_conv_desc* d, const void* x, const void* dy,
  *   transpose_flip==1: wp[t][c][o] = w[taps-1-t][c][o]         (dgrad operand)  */
 int ctgan_pack_filter_bf16(const float* w_hwio, void* wp, int taps, int Cin, int Cout,
                            int transpose_flip, void* stream);
+
+/* Packs many filters of one flat float parameter buffer in ONE launch.  table: device array of n_entries records
+ * {int64 src_offset (floats), int64 dst_offset (bf16 elements), int32 taps, Cin, Cout, transpose_flip}. */
+int ctgan_pack_filters_multi(const float* flat_params, void* packs_bf16, const void* table, int n_entries, void* stream);
 
 /* db[c] (float) = sum over rows of dy[rows][C]   (gradient of tf.nn.bias_add) */
 int ctgan_bias_grad(const void* dy, float* db, int64_t rows, int C, int dtype,

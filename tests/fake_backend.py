@@ -353,7 +353,7 @@ def counter_add(counter, delta):
     counter[0] += int(delta)
 
 
-def invalidate_weight_cache():
+def invalidate_weight_cache(ptrs=None):
     pass
 
 

@@ -110,6 +110,34 @@ def test_conv_mixed_dtype_heads(K):
     assert rel(dw, fb.conv_wgrad(x, dy, g, tuple(w.shape))) < 1e-5
 
 
+@pytest.mark.parametrize('shape', [(24, 32, 32, 3), (80, 16, 16, 3), (20, 32, 32, 5), (300, 8, 8, 3), (3, 16, 16, 1),
+                                   (200, 4, 4, 3), (37, 32, 32, 3)])
+def test_tc_fprop_variants_match(K, shape):
+    """The fprop_tc kernel family -- persistent (default) vs one-tile-per-CTA, each with and without the halo-reuse
+    A pipeline -- all compute the same convolution (up to the bf16 rounding of a different accumulation order)
+    and match the CPU reference; also as dgrad (flipped filter pack) and with the residual/ReLU epilogue."""
+    from ctgan_b200 import _lib
+    N, H, W, k = shape
+    g = K.same_geom(N, H, W, 128, 128, k, 1)
+    x, dy, r = act((N, 128, H, W), torch.bfloat16, 1), act((N, 128, H, W), torch.bfloat16, 2), act((N, 128, H, W), torch.bfloat16, 5)
+    w, b = filt((k, k, 128, 128), 3), act((128,), torch.float32, 4)
+    wq = w.to(torch.bfloat16).float()
+    ref_f, ref_d = FB().conv_fprop(x, wq, b, g), FB().conv_dgrad(dy, wq, g)
+    ref_r = FB().conv_fprop(x, wq, b, g, relu=True, residual=r)
+    try:
+        for variant in (2, 1):
+            for halo in (1, 0):
+                _lib.lib.ctgan_set_fprop_variant(variant)
+                _lib.lib.ctgan_set_fprop_halo(halo)
+                yf = K.conv_fprop(to_dev(x), w.cuda(), b.cuda(), g)
+                yd = K.conv_dgrad(to_dev(dy), w.cuda(), g)
+                yr = K.conv_fprop(to_dev(x), w.cuda(), b.cuda(), g, relu=True, residual=to_dev(r))
+                assert rel(yf, ref_f) < 1e-2 and rel(yd, ref_d) < 1e-2 and rel(yr, ref_r) < 1e-2, (variant, halo)
+    finally:
+        _lib.lib.ctgan_set_fprop_variant(2)
+        _lib.lib.ctgan_set_fprop_halo(1)
+
+
 def test_tc_residual_relu_epilogue(K):
     g = K.same_geom(3, 8, 8, 128, 128, 3, 1)
     x, r = act((3, 128, 8, 8), torch.bfloat16, 1), act((3, 128, 8, 8), torch.bfloat16, 2)
