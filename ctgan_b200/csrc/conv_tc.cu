@@ -117,6 +117,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// one elected lane of a converged warp (the surrounding control flow stays warp-uniform, so descriptor and barrier
+// address arithmetic can live in uniform registers)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 // ------------------------------------------------------------------ descriptors
 // Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
 //   [0,14) start address >> 4   [16,30) leading byte offset >> 4   [32,46) stride byte offset >> 4
@@ -573,6 +581,205 @@ conv_fprop_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, cons
     if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem_base);
 }
 
+// ------------------------------------------------------------------ fprop kernel, persistent, grouped stages
+// Same roles as the persistent kernel above, but the MMA-issuing thread is kept as lean as possible: with N = 128 one
+// tcgen05.mma occupies the tensor pipe for only 64 cycles, so every scalar instruction of the issuing thread between two
+// MMAs shows up as idle tensor time (tests/micro/mma_rate.cu: 75 cycles per MMA with a bare loop, 163 with a barrier
+// wait + fence + commit per 4 MMAs).  Here ONE mbarrier wait and ONE commit cover a group of 8-12 MMAs:
+//   HALO = 1 (3x3, tiles = whole rows of one image): stage = one (BH+2)-row activation box + the 3 filter boxes of the
+//            taps (r = 0..2, s) of one 64-channel block                                            -> 12 MMAs, 72 KB
+//   HALO = 0 (1x1, 8x8 / 4x4 tiles, linear): stage = 2 consecutive (activation, filter) box pairs   ->  8 MMAs, 64 KB
+// Three stages in flight; descriptors are pre-built 32-bit words plus immediate offsets.
+__device__ __forceinline__ void umma_bf16_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+    // descriptor = {lo: start address (>>4) | LBO(16 B) << 16,  hi: SBO(1024 B) | version 1 | SWIZZLE_128B}
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %5};\n\t"
+        "mov.b64 db, {%2, %5};\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(0x40004040u) : "memory");
+}
+
+template <int HALO>
+__global__ void __launch_bounds__(192, 1)
+conv_fprop_tc_lean_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+                          const FpropParams p, const int n_tiles)
+{
+    constexpr int BLOCK_N = 128;
+    constexpr int STAGES = 3;
+    constexpr int NB = HALO ? 3 : 2;                                  // filter boxes (k-blocks) per stage
+    constexpr uint32_t A_REGION = HALO ? 24576u : 32768u;             // one halo box | two 16 KB boxes
+    constexpr uint32_t B_BYTES = BLOCK_N * BLOCK_K * 2;               // 16 KB
+    constexpr uint32_t STAGE_BYTES = A_REGION + NB * B_BYTES;         // 72 KB | 64 KB
+    constexpr int TMEM_COLS = 256;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const uint32_t s_base = smem_u32(smem);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES);
+    const uint32_t tfull = smem_u32(bars + 2 * STAGES), tempty = smem_u32(bars + 2 * STAGES + 2);
+
+    const int cin_blocks = p.Cin / BLOCK_K;
+    const int n_blocks = p.Cout / BLOCK_N;
+    const int taps = p.kh * p.kw;
+    const int kblocks = cin_blocks * taps;                            // non-halo: k-block index = tap * cin_blocks + cb
+    const int groups = HALO ? cin_blocks * p.kw : (kblocks + 1) / 2;
+    const uint32_t a_bytes = (uint32_t)(HALO ? p.BH + 2 : p.BH) * p.BW * p.BN * 128u;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmap_x);
+        prefetch_tmap(&tmap_w);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(tfull + 8 * s, 1); mbar_init(tempty + 8 * s, 4); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<TMEM_COLS>(smem_u32(tmem_slot));
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0 && lane == 0) {
+        // ================= TMA producer =================
+        int st = 0; uint32_t ph = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int nb = tile % n_blocks; int mt = tile / n_blocks;
+            const int tw = mt % p.tilesW; mt /= p.tilesW;
+            const int th = mt % p.tilesH; const int tn = mt / p.tilesH;
+            const int w0 = tw * p.BW, h0 = th * p.BH, n0 = tn * p.BN, co0 = nb * BLOCK_N;
+            for (int gi = 0; gi < groups; ++gi) {
+                const uint32_t sb = s_base + st * STAGE_BYTES, fb = full0 + 8 * st;
+                mbar_wait(empty0 + 8 * st, ph ^ 1);
+                if (HALO) {
+                    const int cb = gi / p.kw, s = gi - cb * p.kw;
+                    mbar_expect_tx(fb, a_bytes + NB * B_BYTES);
+                    tma_load_4d(sb, &tmap_x, fb, cb * BLOCK_K, w0 + s - p.pad_l, h0 - p.pad_t, n0);
+#pragma unroll
+                    for (int r = 0; r < NB; ++r)
+                        tma_load_3d(sb + A_REGION + r * B_BYTES, &tmap_w, fb, cb * BLOCK_K, co0, r * p.kw + s);
+                } else {
+                    const int kb0 = gi * 2, nk = min(2, kblocks - kb0);
+                    mbar_expect_tx(fb, (uint32_t)nk * (a_bytes + B_BYTES));
+                    for (int j = 0; j < nk; ++j) {
+                        const int kb = kb0 + j, tap = kb / cin_blocks, cb = kb - tap * cin_blocks;
+                        const int r = tap / p.kw, s = tap - r * p.kw;
+                        tma_load_4d(sb + j * 16384u, &tmap_x, fb, cb * BLOCK_K, w0 + s - p.pad_l, h0 + r - p.pad_t, n0);
+                        tma_load_3d(sb + A_REGION + j * B_BYTES, &tmap_w, fb, cb * BLOCK_K, co0, tap);
+                    }
+                }
+                if (++st == STAGES) { st = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer (whole warp runs the loop; one elected lane issues) =================
+        constexpr uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N, 0, 0);
+        // low descriptor word of byte address a: (a >> 4) | (LBO 16 B >> 4) << 16
+        uint32_t lo[STAGES];
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) lo[s] = (((s_base + s * STAGE_BYTES) & 0x3FFFFu) >> 4) | (1u << 16);
+        const uint32_t row_step = HALO ? ((uint32_t)p.BW * 128u) >> 4 : (16384u >> 4);   // A offset between the NB k-blocks
+        int st = 0; uint32_t ph = 0;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            const int acc = it & 1;
+            mbar_wait(tempty + 8 * acc, ((uint32_t)(it >> 1) & 1u) ^ 1u);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
+            for (int gi = 0; gi < groups; ++gi) {
+                mbar_wait(full0 + 8 * st, ph);
+                tc_fence_after();
+                const uint32_t a_lo = st == 0 ? lo[0] : (st == 1 ? lo[1] : lo[2]);
+                const uint32_t b_lo = a_lo + (A_REGION >> 4);
+                const int nk = HALO ? NB : min(2, kblocks - gi * 2);
+                if (elect_one()) {
+#pragma unroll
+                    for (int j = 0; j < NB; ++j) {
+                        if (j < nk) {
+#pragma unroll
+                            for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+                                umma_bf16_lo(d_tmem, a_lo + j * row_step + 2 * k, b_lo + j * (B_BYTES >> 4) + 2 * k, idesc,
+                                             (j | k) ? 1u : (gi > 0 ? 1u : 0u));
+                        }
+                    }
+                    umma_commit(empty0 + 8 * st);
+                    if (gi == groups - 1) umma_commit(tfull + 8 * acc);
+                }
+                __syncwarp();
+                if (++st == STAGES) { st = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp >= 2) {
+        // ================= epilogue warps: TMEM -> registers -> global =================
+        const int q = warp & 3;
+        const bool relu = (p.flags & CTGAN_EPI_RELU) != 0;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            const int acc = it & 1;
+            const int nb = tile % n_blocks; int mt = tile / n_blocks;
+            const int tw = mt % p.tilesW; mt /= p.tilesW;
+            const int th = mt % p.tilesH; const int tn = mt / p.tilesH;
+            const int co0 = nb * BLOCK_N;
+            int t = q * 32 + lane;
+            const int bw = t % p.BW; t /= p.BW;
+            const int bh = t % p.BH; const int bn = t / p.BH;
+            const int n = tn * p.BN + bn, h = th * p.BH + bh, w = tw * p.BW + bw;
+            const bool valid = (n < p.N) && (h < p.H) && (w < p.W);
+            const int64_t pix = ((int64_t)n * p.H + h) * p.W + w;
+            __nv_bfloat16* yrow = p.y + pix * p.Cout + co0;
+            const __nv_bfloat16* rrow = p.residual ? p.residual + pix * p.Cout + co0 : nullptr;
+            mbar_wait(tfull + 8 * acc, (uint32_t)(it >> 1) & 1u);
+            tc_fence_after();
+#pragma unroll 1
+            for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+                uint32_t v32[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + c0), v32);
+                if (valid) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) {
+                        float v[8];
+                        if (p.bias) {
+                            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + co0 + c0 + j));
+                            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + co0 + c0 + j + 4));
+                            v[0] = b0.x; v[1] = b0.y; v[2] = b0.z; v[3] = b0.w; v[4] = b1.x; v[5] = b1.y; v[6] = b1.z; v[7] = b1.w;
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) v[e] = 0.f;
+                        }
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) v[e] += __uint_as_float(v32[j + e]);
+                        if (rrow) {
+                            uint4 rv = *reinterpret_cast<const uint4*>(rrow + c0 + j);
+                            const __nv_bfloat162* rp = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) { v[2 * e] += __bfloat162float(rp[e].x); v[2 * e + 1] += __bfloat162float(rp[e].y); }
+                        }
+                        if (relu) {
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
+                        }
+                        uint4 ov;
+                        __nv_bfloat162* op = reinterpret_cast<__nv_bfloat162*>(&ov);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) op[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+                        *reinterpret_cast<uint4*>(yrow + c0 + j) = ov;
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty + 8 * acc) : "memory");
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
 // ------------------------------------------------------------------ wgrad kernel
 struct WgradParams {
     int N, H, W, Cin, Cout;
@@ -858,6 +1065,24 @@ static int launch_fprop_persistent(const CUtensorMap& mx, const CUtensorMap& mw,
     return 0;
 }
 
+template <int HALO>
+static int launch_fprop_lean(const CUtensorMap& mx, const CUtensorMap& mw, const FpropParams& p, cudaStream_t st) {
+    constexpr size_t stage = HALO ? (24576 + 3 * 16384) : (32768 + 2 * 16384);
+    constexpr size_t smem = 3 * stage + 1024 + (2 * 3 + 4) * 8 + 16;
+    static_assert(smem <= 227 * 1024, "lean fprop: shared memory budget");
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(conv_fprop_tc_lean_kernel<HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return cuda_status(e, "fprop_tc_lean smem attribute");
+        attr_set = true;
+    }
+    const int n_tiles = p.tilesW * p.tilesH * p.tilesN * (p.Cout / 128);
+    const int grid = n_tiles < sm_count() ? n_tiles : sm_count();
+    conv_fprop_tc_lean_kernel<HALO><<<grid, 192, smem, st>>>(mx, mw, p, n_tiles);
+    CTGAN_CHECK_LAUNCH("conv_fprop_tc_lean");
+    return 0;
+}
+
 }  // namespace tc
 }  // namespace ctgan
 
@@ -865,7 +1090,7 @@ using namespace ctgan;
 using namespace ctgan::tc;
 
 static bool g_use_halo = true;
-static int g_fprop_variant = 2;   // 2 = persistent kernel, 1 = one tile per CTA (3/6-stage) kernels
+static int g_fprop_variant = 3;   // 3 = persistent grouped-stage kernel, 2 = persistent per-k-block rings, 1 = one tile per CTA
 /* test hook: selects the fprop_tc kernel family (both are compared in tests/) */
 extern "C" void ctgan_set_fprop_variant(int v) { g_fprop_variant = v; }
 /* test hook: 0 disables the halo-reuse fprop variant (both variants are compared in tests/) */
@@ -891,12 +1116,16 @@ extern "C" int ctgan_conv_fprop_tc(const ctgan_conv_desc* d, const void* x, cons
     const int ctas = p.tilesW * p.tilesH * p.tilesN * (d->Cout / block_n);
     // halo-reuse variant: k x k filters (k > 1) on tiles that are whole rows of one image, more than one wave of CTAs
     const bool halo = g_use_halo && block_n == 128 && d->kh > 1 && d->kh <= 5 && p.BN == 1 && (p.BW % 8) == 0 &&
-                      (uint32_t)(p.BH + d->kh - 1) * p.BW * 128u <= 24576u && (g_fprop_variant == 2 || ctas > sm_count());
+                      (uint32_t)(p.BH + d->kh - 1) * p.BW * 128u <= 24576u && (g_fprop_variant >= 2 || ctas > sm_count());
     CUtensorMap mx, mw;
     if (int r = make_act_map(&mx, x, d->N, d->H, d->W, d->Cin, p.BW, halo ? p.BH + d->kh - 1 : p.BH, p.BN)) return r;
     if (int r = make_filter_map(&mw, wp, d->kh * d->kw, d->Cout, d->Cin, block_n)) return r;
     cudaStream_t st = as_stream(stream);
-    if (g_fprop_variant == 2 && block_n == 128) {                    // persistent, deep rings (default)
+    if (g_fprop_variant == 3 && block_n == 128) {                    // persistent, grouped stages, lean issue loop (default)
+        if (halo && d->kh == 3) return launch_fprop_lean<1>(mx, mw, p, st);
+        if (!halo) return launch_fprop_lean<0>(mx, mw, p, st);
+    }
+    if (g_fprop_variant >= 2 && block_n == 128) {                    // persistent, per-k-block rings
         if (halo) return launch_fprop_persistent<3, 8, 24576, 1>(mx, mw, p, st);
         return launch_fprop_persistent<6, 6, 16384, 0>(mx, mw, p, st);
     }

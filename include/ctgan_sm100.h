@@ -87,7 +87,7 @@ int ctgan_conv_wgrad(const ctgan_conv_desc* d, const void* x, const void* dy,
  * residual (nullable, BF16, same shape as y) is added before the optional ReLU. */
 /* test hook: on == 0 disables the halo-reuse variant of fprop_tc (default on) */
 void ctgan_set_fprop_halo(int on);
-/* test hook: 2 = persistent fprop_tc kernel (default), 1 = one-tile-per-CTA kernels */
+/* test hook: 3 = persistent grouped-stage fprop_tc kernel (default), 2 = persistent per-k-block rings, 1 = one tile per CTA */
 void ctgan_set_fprop_variant(int v);
 int ctgan_conv_fprop_tc(const ctgan_conv_desc* d, const void* x, const void* wp,
                         const float* bias /*nullable*/, const void* residual /*nullable*/,

@@ -125,7 +125,7 @@ def test_tc_fprop_variants_match(K, shape):
     ref_f, ref_d = FB().conv_fprop(x, wq, b, g), FB().conv_dgrad(dy, wq, g)
     ref_r = FB().conv_fprop(x, wq, b, g, relu=True, residual=r)
     try:
-        for variant in (2, 1):
+        for variant in (3, 2, 1):
             for halo in (1, 0):
                 _lib.lib.ctgan_set_fprop_variant(variant)
                 _lib.lib.ctgan_set_fprop_halo(halo)
@@ -134,7 +134,7 @@ def test_tc_fprop_variants_match(K, shape):
                 yr = K.conv_fprop(to_dev(x), w.cuda(), b.cuda(), g, relu=True, residual=to_dev(r))
                 assert rel(yf, ref_f) < 1e-2 and rel(yd, ref_d) < 1e-2 and rel(yr, ref_r) < 1e-2, (variant, halo)
     finally:
-        _lib.lib.ctgan_set_fprop_variant(2)
+        _lib.lib.ctgan_set_fprop_variant(3)
         _lib.lib.ctgan_set_fprop_halo(1)
 
 
