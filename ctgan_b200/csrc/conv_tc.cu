@@ -908,6 +908,123 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
     if (warp == 2) tmem_dealloc<TMEM_COLS>(tmem_base);
 }
 
+// 3x3 wgrad with the lean issue loop of conv_fprop_tc_lean_kernel.  One CTA owns the three taps (r = 0..2, s) of one
+// filter COLUMN s = blockIdx.y: they read the same (BH+2)-row halo box of x, shifted by r rows, and the same dY chunk.
+//   stage = x halo box, two 64-channel halves (2 x 16 KB slots) + dY chunk, two halves (2 x 8 KB) = 48 KB for 12 MMAs
+// (the per-tap kernel above moves 96 KB for the same 12 MMAs and waits/commits three times).
+template <int STAGES>
+__global__ void __launch_bounds__(128, 1)
+conv_wgrad_tc_lean_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_dy,
+                          const WgradParams p)
+{
+    constexpr int BLOCK_N = 128;
+    constexpr uint32_t A_SLOT = 16384, B_HALF = 8192;
+    constexpr uint32_t STAGE_BYTES = 2 * A_SLOT + 2 * B_HALF;             // 48 KB
+    constexpr int TMEM_COLS = 512;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform
+    const uint32_t s_base = smem_u32(smem);
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES), accum_bar = smem_u32(bars + 2 * STAGES);
+
+    const int co_blocks = p.Cout / 128;
+    const int ci0 = (blockIdx.x / co_blocks) * 128, co0 = (blockIdx.x % co_blocks) * 128;
+    const int s_tap = blockIdx.y;
+    const int total_chunks = p.chunksN * p.chunksH * p.chunksW;
+    const int chunk0 = blockIdx.z * p.chunks_per_split;
+    const int nchunks = min(p.chunks_per_split, total_chunks - chunk0);
+    const uint32_t a_bytes = (uint32_t)(p.BH + 2) * p.BW * 128u;          // one 64-channel half of the halo box
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmap_x);
+        prefetch_tmap(&tmap_dy);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        mbar_init(accum_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc<TMEM_COLS>(smem_u32(tmem_slot));
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ================= TMA producer =================
+            int st = 0; uint32_t ph = 0;
+            for (int c = 0; c < nchunks; ++c) {
+                int ch = chunk0 + c;
+                const int cw = ch % p.chunksW; ch /= p.chunksW;
+                const int chh = ch % p.chunksH; const int cn = ch / p.chunksH;
+                const int w0 = cw * p.BW, h0 = chh * p.BH;
+                const uint32_t sb = s_base + st * STAGE_BYTES, fb = full0 + 8 * st;
+                mbar_wait(empty0 + 8 * st, ph ^ 1);
+                mbar_expect_tx(fb, 2 * a_bytes + 2 * B_HALF);
+                tma_load_4d(sb,                       &tmap_x,  fb, ci0,      w0 + s_tap - p.pad_l, h0 - p.pad_t, cn);
+                tma_load_4d(sb + A_SLOT,              &tmap_x,  fb, ci0 + 64, w0 + s_tap - p.pad_l, h0 - p.pad_t, cn);
+                tma_load_4d(sb + 2 * A_SLOT,          &tmap_dy, fb, co0,      w0, h0, cn);
+                tma_load_4d(sb + 2 * A_SLOT + B_HALF, &tmap_dy, fb, co0 + 64, w0, h0, cn);
+                if (++st == STAGES) { st = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer (whole warp runs the loop; one elected lane issues) =================
+        // both operands MN-major: smem rows are K (pixels); LBO = distance between the two 64-channel halves
+        constexpr uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N, 1, 1);
+        const uint32_t a_lo0 = ((s_base & 0x3FFFFu) >> 4) | ((A_SLOT >> 4) << 16);
+        const uint32_t b_lo0 = (((s_base + 2 * A_SLOT) & 0x3FFFFu) >> 4) | ((B_HALF >> 4) << 16);
+        const uint32_t row_step = ((uint32_t)p.BW * 128u) >> 4;          // one image row down = filter row r + 1
+        int st = 0; uint32_t ph = 0;
+        for (int c = 0; c < nchunks; ++c) {
+            mbar_wait(full0 + 8 * st, ph);
+            tc_fence_after();
+            const uint32_t a_lo = a_lo0 + st * (STAGE_BYTES >> 4), b_lo = b_lo0 + st * (STAGE_BYTES >> 4);
+            if (elect_one()) {
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+#pragma unroll
+                    for (int k = 0; k < 64 / UMMA_K; ++k)     // 16 pixel rows = 2048 bytes along K
+                        umma_bf16_lo(tmem_base + (uint32_t)(r * BLOCK_N), a_lo + r * row_step + 128 * k, b_lo + 128 * k, idesc,
+                                     k ? 1u : (c > 0 ? 1u : 0u));
+                }
+                umma_commit(empty0 + 8 * st);
+                if (c == nchunks - 1) umma_commit(accum_bar);
+            }
+            __syncwarp();
+            if (++st == STAGES) { st = 0; ph ^= 1; }
+        }
+    }
+    __syncwarp();
+
+    // ================= epilogue: TMEM -> vector reductions into dW (float, HWIO) =================
+    if (nchunks > 0) {
+        mbar_wait(accum_bar, 0);
+        tc_fence_after();
+        const int ci = ci0 + warp * 32 + lane;
+        for (int r = 0; r < 3; ++r) {
+            float* dst = p.dw + ((int64_t)(r * p.kw + s_tap) * p.Cin + ci) * p.Cout + co0;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+                uint32_t acc[32];
+                tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(r * BLOCK_N + c0), acc);
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};"
+                                 ::"l"(dst + c0 + j), "f"(__uint_as_float(acc[j])), "f"(__uint_as_float(acc[j + 1])),
+                                   "f"(__uint_as_float(acc[j + 2])), "f"(__uint_as_float(acc[j + 3])) : "memory");
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
 // ------------------------------------------------------------------ filter packing
 // transpose_flip == 0: wp[t][o][c] = w[t][c][o];  == 1: wp[t][c][o] = w[taps-1-t][c][o]
 __global__ void pack_filter_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wp,
@@ -1093,6 +1210,8 @@ static bool g_use_halo = true;
 static int g_fprop_variant = 3;   // 3 = persistent grouped-stage kernel, 2 = persistent per-k-block rings, 1 = one tile per CTA
 /* test hook: selects the fprop_tc kernel family (both are compared in tests/) */
 extern "C" void ctgan_set_fprop_variant(int v) { g_fprop_variant = v; }
+static int g_wgrad_variant = 2;   // 2 = filter-column CTAs sharing one x halo box (3x3), 1 = one (x, dY) box pair per tap
+extern "C" void ctgan_set_wgrad_variant(int v) { g_wgrad_variant = v; }
 /* test hook: 0 disables the halo-reuse fprop variant (both variants are compared in tests/) */
 extern "C" void ctgan_set_fprop_halo(int on) { g_use_halo = on != 0; }
 
@@ -1152,8 +1271,10 @@ extern "C" int ctgan_conv_wgrad_tc(const ctgan_conv_desc* d, const void* x, cons
     pixel_box(d->H, d->W, 64, &p.BW, &p.BH, &p.BN);
     p.chunksW = ceil_div(d->W, p.BW); p.chunksH = ceil_div(d->H, p.BH); p.chunksN = ceil_div(d->N, p.BN);
     const int taps = d->kh * d->kw;
-    p.taps_per_cta = (taps % 3 == 0) ? 3 : (taps < 4 ? taps : 4);
-    const int tap_groups = ceil_div(taps, p.taps_per_cta);
+    const bool lean = g_wgrad_variant == 2 && d->kh == 3 && p.BN == 1 && p.BW % 8 == 0 &&
+                      (uint32_t)(p.BH + 2) * p.BW * 128u <= 16384u;
+    p.taps_per_cta = lean ? 3 : ((taps % 3 == 0) ? 3 : (taps < 4 ? taps : 4));
+    const int tap_groups = lean ? d->kw : ceil_div(taps, p.taps_per_cta);
     const int tiles = (d->Cin / 128) * (d->Cout / 128);
     const int total_chunks = p.chunksN * p.chunksH * p.chunksW;
     // about one wave of CTAs (TMEM: 512 columns => one CTA per SM), at least 4 pixel chunks each: the small
@@ -1166,8 +1287,20 @@ extern "C" int ctgan_conv_wgrad_tc(const ctgan_conv_desc* d, const void* x, cons
     splits = ceil_div(total_chunks, p.chunks_per_split);
     p.dw = dw;
     CUtensorMap mx, mdy;
-    if (int r = make_act_map(&mx, x, d->N, d->H, d->W, d->Cin, p.BW, p.BH, p.BN)) return r;
+    if (int r = make_act_map(&mx, x, d->N, d->H, d->W, d->Cin, p.BW, lean ? p.BH + 2 : p.BH, p.BN)) return r;
     if (int r = make_act_map(&mdy, dy, d->N, d->H, d->W, d->Cout, p.BW, p.BH, p.BN)) return r;
+    if (lean) {
+        constexpr size_t smem_lean = (size_t)STAGES * 49152 + 1024 + (2 * STAGES + 1) * 8 + 16;
+        static bool lean_attr_set = false;
+        if (!lean_attr_set) {
+            cudaError_t e = cudaFuncSetAttribute(conv_wgrad_tc_lean_kernel<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_lean);
+            if (e != cudaSuccess) return cuda_status(e, "wgrad_tc_lean smem attribute");
+            lean_attr_set = true;
+        }
+        conv_wgrad_tc_lean_kernel<STAGES><<<dim3(tiles, tap_groups, splits), 128, smem_lean, as_stream(stream)>>>(mx, mdy, p);
+        CTGAN_CHECK_LAUNCH("conv_wgrad_tc_lean");
+        return 0;
+    }
     constexpr size_t smem = (size_t)STAGES * 32768 + 1024 + (2 * STAGES + 1) * 8 + 16;
     static bool attr_set = false;
     if (!attr_set) {

@@ -89,6 +89,8 @@ int ctgan_conv_wgrad(const ctgan_conv_desc* d, const void* x, const void* dy,
 void ctgan_set_fprop_halo(int on);
 /* test hook: 3 = persistent grouped-stage fprop_tc kernel (default), 2 = persistent per-k-block rings, 1 = one tile per CTA */
 void ctgan_set_fprop_variant(int v);
+/* test/benchmark hook: 2 (default) = 3x3 wgrad CTAs own one filter column and share the x halo box; 1 = per-tap boxes */
+void ctgan_set_wgrad_variant(int v);
 int ctgan_conv_fprop_tc(const ctgan_conv_desc* d, const void* x, const void* wp,
                         const float* bias /*nullable*/, const void* residual /*nullable*/,
                         void* y, int flags, void* stream);

@@ -326,3 +326,25 @@ def test_bad_descriptors_fail_loudly(K):
         K.conv_fprop(x.cpu(), torch.zeros(3, 3, 8, 8), None, g)           # no CPU path
     with pytest.raises(CtganError):
         K.act_dropout(x, 0.2, 0.0)
+
+
+@pytest.mark.parametrize('shape', [(24, 32, 32, 3, 128, 128), (80, 16, 16, 3, 128, 256), (300, 8, 8, 3, 256, 128),
+                                   (37, 32, 32, 3, 128, 128), (200, 4, 4, 3, 128, 128), (9, 16, 16, 1, 128, 128)])
+def test_tc_wgrad_variants_match(K, shape):
+    """wgrad_tc: filter-column CTAs sharing one x halo box (default for 3x3) vs one box pair per tap; both match
+    the CPU reference, also when accumulating into a pre-filled gradient buffer."""
+    from ctgan_b200 import _lib
+    N, H, W, k, Cin, Cout = shape
+    g = K.same_geom(N, H, W, Cin, Cout, k, 1)
+    x, dy = act((N, Cin, H, W), torch.bfloat16, 1), act((N, Cout, H, W), torch.bfloat16, 2)
+    ref = FB().conv_wgrad(x, dy, g, (k, k, Cin, Cout))
+    try:
+        for variant in (2, 1):
+            _lib.lib.ctgan_set_wgrad_variant(variant)
+            dw = K.conv_wgrad(to_dev(x), to_dev(dy), g, (k, k, Cin, Cout))
+            assert rel(dw, ref) < 2e-3, variant
+            acc = torch.full((k, k, Cin, Cout), 0.5, device='cuda')
+            K.conv_wgrad(to_dev(x), to_dev(dy), g, (k, k, Cin, Cout), accumulate_into=acc)
+            assert rel(acc - 0.5, ref) < 2e-3, variant
+    finally:
+        _lib.lib.ctgan_set_wgrad_variant(2)
