@@ -49,6 +49,10 @@ _PROTOS = {
     'ctgan_conv_wgrad_tc': (c_int, [POINTER(ConvDesc), P, P, P, P]),
     'ctgan_pack_filter_bf16': (c_int, [P, P, c_int, c_int, c_int, c_int, P]),
     'ctgan_pack_filters_multi': (c_int, [P, P, P, c_int, P]),
+    'ctgan_im2col_thin': (c_int, [POINTER(ConvDesc), c_int, c_int, P, P, P]),
+    'ctgan_col2im_thin': (c_int, [POINTER(ConvDesc), c_int, c_int, P, P, P, P]),
+    'ctgan_pack_filter_thin': (c_int, [P, P, c_int, c_int, c_int, c_int, P]),
+    'ctgan_wgrad_thin_tc': (c_int, [P, P, c_int64, c_int, c_int, c_int, c_int, P, P]),
     'ctgan_bias_grad': (c_int, [P, P, c_int64, c_int, c_int, c_int, P]),
     'ctgan_bias_add': (c_int, [P, P, P, c_int64, c_int, c_int, P]),
     'ctgan_cast': (c_int, [P, c_int, P, c_int, c_int64, P]),

@@ -1042,6 +1042,31 @@ __global__ void pack_filter_kernel(const float* __restrict__ w, __nv_bfloat16* _
     }
 }
 
+// Thin-channel filters (one side has C <= 8 channels, the other Cw): 64-row / 64-column zero-padded operands of the
+// im2col GEMMs below.  k = tap*C + c indexes the thin side.
+//   kind 0: w [taps][C][Cw] -> wp[Cw][64], wp[j][k] = w[k*Cw + j]            (fprop of a C -> Cw conv)
+//   kind 1: w [taps][Cw][C] -> wp[Cw][64], wp[j][k] = w[(t*Cw + j)*C + o]    (dgrad of a Cw -> C conv)
+//   kind 2: w [taps][Cw][C] -> wp[64][Cw], wp[k][j] = w[(t*Cw + j)*C + o]    (fprop of a Cw -> C conv)
+//   kind 3: w [taps][C][Cw] -> wp[64][Cw], wp[k][j] = w[k*Cw + j]            (dgrad of a C -> Cw conv)
+__device__ __forceinline__ void pack_thin_body(const float* __restrict__ w, __nv_bfloat16* __restrict__ wp,
+                                               int taps, int C, int Cw, int kind, int64_t start, int64_t step) {
+    const int64_t total = (int64_t)64 * Cw;
+    const int kreal = taps * C;
+    for (int64_t i = start; i < total; i += step) {
+        int j, k;
+        if (kind <= 1) { j = (int)(i >> 6); k = (int)(i & 63); } else { k = (int)(i / Cw); j = (int)(i - (int64_t)k * Cw); }
+        float v = 0.f;
+        if (k < kreal) {
+            if (kind == 0 || kind == 3) v = w[(int64_t)k * Cw + j];
+            else { const int t = k / C, o = k - t * C; v = w[((int64_t)t * Cw + j) * C + o]; }
+        }
+        wp[i] = __float2bfloat16_rn(v);
+    }
+}
+__global__ void pack_thin_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wp, int taps, int C, int Cw, int kind) {
+    pack_thin_body(w, wp, taps, C, Cw, kind, blockIdx.x * (int64_t)blockDim.x + threadIdx.x, (int64_t)gridDim.x * blockDim.x);
+}
+
 // One launch packs every filter of an optimizer: entry e (blockIdx.y) = {src offset in the flat float parameter
 // buffer, dst offset in the bf16 pack buffer, taps, Cin, Cout, transpose_flip}.
 struct PackEntry { long long src, dst; int taps, cin, cout, flip; };
@@ -1050,6 +1075,11 @@ __global__ void pack_filters_multi_kernel(const float* __restrict__ flat, __nv_b
     const PackEntry e = table[blockIdx.y];
     const float* w = flat + e.src;
     __nv_bfloat16* wp = packs + e.dst;
+    if (e.flip >= 2) {                                   // thin kinds 0..3 (cin, cout = HWIO dims)
+        pack_thin_body(w, wp, e.taps, min(e.cin, e.cout), max(e.cin, e.cout), e.flip - 2,
+                       blockIdx.x * (int64_t)blockDim.x + threadIdx.x, (int64_t)gridDim.x * blockDim.x);
+        return;
+    }
     const int64_t total = (int64_t)e.taps * e.cin * e.cout;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         if (e.flip) {
@@ -1061,6 +1091,190 @@ __global__ void pack_filters_multi_kernel(const float* __restrict__ flat, __nv_b
             wp[i] = __float2bfloat16_rn(w[((int64_t)t * e.cin + c) * e.cout + o]);
         }
     }
+}
+
+// ------------------------------------------------------------------ thin-channel convolutions (3-channel image side)
+// Discriminator.1.Conv1 / .Shortcut (3 -> DIM_D) and Generator.Output (DIM_G -> 3) have one side with C = 3 channels:
+// K = taps*C = 27 is far below a tensor-core k-block and a SIMT implicit GEMM wastes most of its tile.  The thin side
+// is expanded into col[pixel][64] (k = tap*C + c, zero for k >= taps*C) so that every member of the conv family is a
+// [P x 64] x [64 x Cw] (or [P x Cw] x [Cw x 64]) GEMM on the 1x1 tcgen05 kernels, plus one of these gather kernels.
+//   im2col: col[p][(t,c)] = src[p + sign*off(t)][c]           off(t) = (r - pad_t, s - pad_l)
+//   col2im: dst[p][c]     = bias[c] + sum_t col[p + sign*off(t)][(t,c)]
+__global__ void __launch_bounds__(256)
+im2col_thin_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ col,
+                   int N, int H, int W, int C, int kh, int kw, int pad_t, int pad_l, int sign) {
+    // per column k: (dh, dw, c) packed as bytes (dh+8, dw+8, c, valid); built once per block
+    __shared__ uint32_t tab[64];
+    if (threadIdx.x < 64) {
+        const int k = threadIdx.x;
+        uint32_t e = 0;
+        if (k < kh * kw * C) {
+            const int t = k / C, c = k - t * C;
+            const int r = t / kw, s = t - r * kw;
+            e = (uint32_t)(sign * (r - pad_t) + 8) | ((uint32_t)(sign * (s - pad_l) + 8) << 8) | ((uint32_t)c << 16) | (1u << 24);
+        }
+        tab[k] = e;
+    }
+    __syncthreads();
+    const int64_t total = (int64_t)N * H * W * 8;            // 8 threads per pixel, one 16-byte store each
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t p = i >> 3;
+        const int g = (int)(i & 7);
+        const int w = (int)(p % W); const int64_t q = p / W;
+        const int h = (int)(q % H);
+        const __nv_bfloat16* base = src + p * C;                              // pixel (n, h, w)
+        __align__(16) __nv_bfloat16 v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const uint32_t te = tab[g * 8 + e];
+            const int dh = (int)(te & 0xff) - 8, dw = (int)((te >> 8) & 0xff) - 8, c = (int)((te >> 16) & 0xff);
+            const int hh = h + dh, ww = w + dw;
+            const bool ok = (te >> 24) && hh >= 0 && hh < H && ww >= 0 && ww < W;
+            v[e] = ok ? base[(dh * W + dw) * C + c] : __float2bfloat16_rn(0.f);
+        }
+        *reinterpret_cast<uint4*>(col + p * 64 + g * 8) = *reinterpret_cast<const uint4*>(v);
+    }
+}
+
+__global__ void col2im_thin_kernel(const __nv_bfloat16* __restrict__ col, const float* __restrict__ bias,
+                                   __nv_bfloat16* __restrict__ dst, int N, int H, int W, int C, int kh, int kw,
+                                   int pad_t, int pad_l, int sign) {
+    const int64_t total = (int64_t)N * H * W;
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < total; p += (int64_t)gridDim.x * blockDim.x) {
+        const int w = (int)(p % W); const int64_t q = p / W;
+        const int h = (int)(q % H); const int64_t n = q / H;
+        float acc[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[c] = (bias && c < C) ? bias[c] : 0.f;
+        for (int r = 0; r < kh; ++r) {
+            const int hh = h + sign * (r - pad_t);
+            if (hh < 0 || hh >= H) continue;
+            for (int s = 0; s < kw; ++s) {
+                const int ww = w + sign * (s - pad_l);
+                if (ww < 0 || ww >= W) continue;
+                const __nv_bfloat16* row = col + ((n * H + hh) * W + ww) * 64 + (r * kw + s) * C;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) if (c < C) acc[c] += __bfloat162float(row[c]);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 8; ++c) if (c < C) dst[p * C + c] = __float2bfloat16_rn(acc[c]);
+    }
+}
+
+// dw += wide^T x col over all pixels: M = 128 channels of the wide tensor, N = 64 im2col columns, K = pixels.
+// Both operands MN-major straight out of TMA (rows = pixels).  Stage = 2 chunks of 64 pixels (48 KB, 8 MMAs).
+// The accumulator element (row j, column k = (t, c)) is added to dw[t*sA + c*sB + j*sC].
+struct WgradThinParams {
+    long long total_chunks;
+    int chunks_per_split, C, kreal;
+    long long sA, sB, sC;
+    float* dw;
+};
+
+template <int STAGES>
+__global__ void __launch_bounds__(128, 1)
+wgrad_thin_tc_kernel(const __grid_constant__ CUtensorMap tmap_wide, const __grid_constant__ CUtensorMap tmap_col,
+                     const WgradThinParams p)
+{
+    constexpr uint32_t A_BYTES = 16384, A_HALF = 8192, B_BYTES = 8192;
+    constexpr uint32_t STAGE_BYTES = 2 * (A_BYTES + B_BYTES);             // 48 KB
+    constexpr int TMEM_COLS = 64;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+    const uint32_t s_base = smem_u32(smem);
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES), accum_bar = smem_u32(bars + 2 * STAGES);
+
+    const int cw0 = blockIdx.x * 128;
+    const long long chunk0 = (long long)blockIdx.z * p.chunks_per_split;
+    const int nchunks = (int)min((long long)p.chunks_per_split, p.total_chunks - chunk0);
+    const int groups = (nchunks + 1) / 2;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmap_wide);
+        prefetch_tmap(&tmap_col);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        mbar_init(accum_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc<TMEM_COLS>(smem_u32(tmem_slot));
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int st = 0; uint32_t ph = 0;
+            for (int g = 0; g < groups; ++g) {
+                const uint32_t sb = s_base + st * STAGE_BYTES, fb = full0 + 8 * st;
+                const int nk = min(2, nchunks - 2 * g);
+                mbar_wait(empty0 + 8 * st, ph ^ 1);
+                mbar_expect_tx(fb, (uint32_t)nk * (A_BYTES + B_BYTES));
+                for (int j = 0; j < nk; ++j) {
+                    const int px0 = (int)((chunk0 + 2 * g + j) * 64);
+                    tma_load_4d(sb + j * A_BYTES,          &tmap_wide, fb, cw0,      px0, 0, 0);
+                    tma_load_4d(sb + j * A_BYTES + A_HALF, &tmap_wide, fb, cw0 + 64, px0, 0, 0);
+                    tma_load_4d(sb + 2 * A_BYTES + j * B_BYTES, &tmap_col, fb, 0, px0, 0, 0);
+                }
+                if (++st == STAGES) { st = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        constexpr uint32_t idesc = make_idesc(BLOCK_M, 64, 1, 1);
+        const uint32_t a_lo0 = ((s_base & 0x3FFFFu) >> 4) | ((A_HALF >> 4) << 16);
+        const uint32_t b_lo0 = (((s_base + 2 * A_BYTES) & 0x3FFFFu) >> 4) | ((B_BYTES >> 4) << 16);
+        int st = 0; uint32_t ph = 0;
+        for (int g = 0; g < groups; ++g) {
+            mbar_wait(full0 + 8 * st, ph);
+            tc_fence_after();
+            const uint32_t a_lo = a_lo0 + st * (STAGE_BYTES >> 4), b_lo = b_lo0 + st * (STAGE_BYTES >> 4);
+            const int nk = min(2, nchunks - 2 * g);
+            if (elect_one()) {
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    if (j < nk) {
+#pragma unroll
+                        for (int k = 0; k < 64 / UMMA_K; ++k)
+                            umma_bf16_lo(tmem_base, a_lo + j * (A_BYTES >> 4) + 128 * k, b_lo + j * (B_BYTES >> 4) + 128 * k, idesc,
+                                         (j | k) ? 1u : (g > 0 ? 1u : 0u));
+                    }
+                }
+                umma_commit(empty0 + 8 * st);
+                if (g == groups - 1) umma_commit(accum_bar);
+            }
+            __syncwarp();
+            if (++st == STAGES) { st = 0; ph ^= 1; }
+        }
+    }
+    __syncwarp();
+
+    if (nchunks > 0) {
+        mbar_wait(accum_bar, 0);
+        tc_fence_after();
+        float* dst = p.dw + (long long)(cw0 + warp * 32 + lane) * p.sC;
+        int t = 0, c = 0;
+#pragma unroll 1
+        for (int c0 = 0; c0 < 64 && c0 < p.kreal; c0 += 32) {
+            uint32_t acc[32];
+            tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, acc);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                if (c0 + j < p.kreal) {
+                    atomicAdd(dst + t * p.sA + c * p.sB, __uint_as_float(acc[j]));
+                    if (++c == p.C) { c = 0; ++t; }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc<TMEM_COLS>(tmem_base);
 }
 
 // ------------------------------------------------------------------ host side
@@ -1327,5 +1541,77 @@ extern "C" int ctgan_pack_filter_bf16(const float* w, void* wp, int taps, int Ci
     int64_t total = (int64_t)taps * Cin * Cout;
     pack_filter_kernel<<<elementwise_grid(total, 256), 256, 0, as_stream(stream)>>>(w, reinterpret_cast<__nv_bfloat16*>(wp), taps, Cin, Cout, transpose_flip);
     CTGAN_CHECK_LAUNCH("pack_filter_bf16");
+    return 0;
+}
+
+// ------------------------------------------------------------------ thin-channel entry points
+static int check_thin(const ctgan_conv_desc* d, int C, const char* who) {
+    CTGAN_REQUIRE(d != nullptr, CTGAN_ERR_BAD_DESC, "%s: null descriptor", who);
+    CTGAN_REQUIRE(d->N > 0 && d->H > 0 && d->W > 0 && d->kh > 0 && d->kw > 0 && d->stride == 1 && d->Ho == d->H && d->Wo == d->W &&
+                  d->pad_t >= 0 && d->pad_l >= 0 && d->pad_t < d->kh && d->pad_l < d->kw, CTGAN_ERR_BAD_DESC, "%s: bad geometry", who);
+    CTGAN_REQUIRE(C > 0 && C <= 8 && d->kh * d->kw * C <= 64, CTGAN_ERR_UNSUPPORTED, "%s: needs C <= 8 and taps*C <= 64", who);
+    return 0;
+}
+
+extern "C" int ctgan_im2col_thin(const ctgan_conv_desc* d, int C, int sign, const void* src, void* col, void* stream) {
+    if (int r = check_thin(d, C, "im2col_thin")) return r;
+    CTGAN_REQUIRE(src && col && (sign == 1 || sign == -1) && (reinterpret_cast<uintptr_t>(col) & 15) == 0, CTGAN_ERR_BAD_DESC, "im2col_thin: bad args");
+    const int64_t total = (int64_t)d->N * d->H * d->W * 8;
+    im2col_thin_kernel<<<elementwise_grid(total, 256), 256, 0, as_stream(stream)>>>(
+        reinterpret_cast<const __nv_bfloat16*>(src), reinterpret_cast<__nv_bfloat16*>(col), d->N, d->H, d->W, C, d->kh, d->kw,
+        d->pad_t, d->pad_l, sign);
+    CTGAN_CHECK_LAUNCH("im2col_thin");
+    return 0;
+}
+
+extern "C" int ctgan_col2im_thin(const ctgan_conv_desc* d, int C, int sign, const void* col, const float* bias, void* dst, void* stream) {
+    if (int r = check_thin(d, C, "col2im_thin")) return r;
+    CTGAN_REQUIRE(col && dst && (sign == 1 || sign == -1), CTGAN_ERR_BAD_DESC, "col2im_thin: bad args");
+    const int64_t total = (int64_t)d->N * d->H * d->W;
+    col2im_thin_kernel<<<elementwise_grid(total, 128), 128, 0, as_stream(stream)>>>(
+        reinterpret_cast<const __nv_bfloat16*>(col), bias, reinterpret_cast<__nv_bfloat16*>(dst), d->N, d->H, d->W, C, d->kh, d->kw,
+        d->pad_t, d->pad_l, sign);
+    CTGAN_CHECK_LAUNCH("col2im_thin");
+    return 0;
+}
+
+extern "C" int ctgan_pack_filter_thin(const float* w, void* wp, int taps, int C, int Cw, int kind, void* stream) {
+    CTGAN_REQUIRE(w && wp && taps > 0 && C > 0 && taps * C <= 64 && Cw > 0 && kind >= 0 && kind <= 3, CTGAN_ERR_BAD_DESC, "pack_filter_thin: bad args");
+    pack_thin_kernel<<<elementwise_grid((int64_t)64 * Cw, 256), 256, 0, as_stream(stream)>>>(w, reinterpret_cast<__nv_bfloat16*>(wp), taps, C, Cw, kind);
+    CTGAN_CHECK_LAUNCH("pack_filter_thin");
+    return 0;
+}
+
+extern "C" int ctgan_wgrad_thin_tc(const void* wide, const void* col, long long P, int Cw, int C, int taps, int mode,
+                                   float* dw, void* stream) {
+    CTGAN_REQUIRE(wide && col && dw && P > 0 && P < (1ll << 31) && Cw > 0 && Cw % 128 == 0 && C > 0 && taps > 0 && taps * C <= 64 &&
+                  (mode == 0 || mode == 1), CTGAN_ERR_BAD_DESC, "wgrad_thin_tc: bad args");
+    CTGAN_REQUIRE((reinterpret_cast<uintptr_t>(wide) & 15) == 0 && (reinterpret_cast<uintptr_t>(col) & 15) == 0, CTGAN_ERR_BAD_DESC,
+                  "wgrad_thin_tc: pointers must be 16-byte aligned");
+    CTGAN_REQUIRE(ctgan_tc_available(), CTGAN_ERR_UNSUPPORTED, "wgrad_thin_tc: device is not sm_100");
+    constexpr int STAGES = 4;
+    WgradThinParams p;
+    p.total_chunks = (P + 63) / 64;
+    p.C = C; p.kreal = taps * C; p.dw = dw;
+    if (mode == 0) { p.sA = (long long)C * Cw; p.sB = Cw; p.sC = 1; }          // dw [taps][C][Cw]
+    else           { p.sA = (long long)Cw * C; p.sB = 1;  p.sC = C; }          // dw [taps][Cw][C]
+    const int tiles = Cw / 128;
+    long long splits = sm_count() / tiles; if (splits < 1) splits = 1;
+    long long max_splits = p.total_chunks / 8; if (max_splits < 1) max_splits = 1;
+    if (splits > max_splits) splits = max_splits;
+    p.chunks_per_split = (int)((p.total_chunks + splits - 1) / splits);
+    splits = (p.total_chunks + p.chunks_per_split - 1) / p.chunks_per_split;
+    CUtensorMap mw, mc;
+    if (int r = make_act_map(&mw, wide, 1, 1, (int)P, Cw, 64, 1, 1)) return r;
+    if (int r = make_act_map(&mc, col, 1, 1, (int)P, 64, 64, 1, 1)) return r;
+    constexpr size_t smem = (size_t)STAGES * 49152 + 1024 + (2 * STAGES + 1) * 8 + 16;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(wgrad_thin_tc_kernel<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return cuda_status(e, "wgrad_thin_tc smem attribute");
+        attr_set = true;
+    }
+    wgrad_thin_tc_kernel<STAGES><<<dim3(tiles, 1, (unsigned)splits), 128, smem, as_stream(stream)>>>(mw, mc, p);
+    CTGAN_CHECK_LAUNCH("wgrad_thin_tc");
     return 0;
 }

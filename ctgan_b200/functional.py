@@ -65,23 +65,25 @@ def _dense_like(g, ref_dim4):
 # ------------------------------------------------------------------------- conv family
 class ConvF(Function):
     @staticmethod
-    def forward(ctx, x, w, b, g, out_dtype):
+    def forward(ctx, x, w, b, g, out_dtype, col=None):
         ctx.g = g
         ctx.save_for_backward(x, w)
         ctx.has_bias = b is not None
         ctx.bias = b
-        return K.conv_fprop(x, w, b, g, out_dtype=out_dtype, w_is_param=_is_param(w))
+        ctx.col = col if col is not None else K.thin_col(x, g, 'x')   # im2col of a 3-channel x: built once, reused by wgrad
+        return K.conv_fprop(x, w, b, g, out_dtype=out_dtype, w_is_param=_is_param(w), col=ctx.col)
 
     @staticmethod
     def backward(ctx, gy):
         x, w = ctx.saved_tensors
         gy = _dense_like(gy, True)
         gx = gw = gb = None
+        dycol = K.thin_col(gy, ctx.g, 'dy')          # im2col of a 3-channel gy: shared by dgrad and wgrad
         if ctx.needs_input_grad[0]:
-            gx = ConvD.apply(gy, w, ctx.g, x.dtype)
+            gx = ConvD.apply(gy, w, ctx.g, x.dtype, dycol)
         if ctx.needs_input_grad[1]:
             if _direct(w):
-                K.conv_wgrad(x, gy, ctx.g, tuple(w.shape), accumulate_into=w.grad)
+                K.conv_wgrad(x, gy, ctx.g, tuple(w.shape), accumulate_into=w.grad, col=ctx.col if ctx.col is not None else dycol)
             else:
                 gw = ConvG.apply(x, gy, ctx.g, tuple(w.shape))
         if ctx.has_bias and ctx.needs_input_grad[2]:
@@ -90,31 +92,32 @@ class ConvF(Function):
                 K.bias_grad(gy.detach(), accumulate_into=b.grad)
             else:
                 gb = K.bias_grad(gy.detach())
-        return gx, gw, gb, None, None
+        return gx, gw, gb, None, None, None
 
 
 class ConvD(Function):
     """dx = conv^T(gy, w) for the forward geometry g (== Deconv2D forward)."""
 
     @staticmethod
-    def forward(ctx, gy, w, g, out_dtype):
+    def forward(ctx, gy, w, g, out_dtype, col=None):
         ctx.g = g
         ctx.save_for_backward(gy, w)
-        return K.conv_dgrad(gy, w, g, out_dtype=out_dtype, w_is_param=_is_param(w))
+        return K.conv_dgrad(gy, w, g, out_dtype=out_dtype, w_is_param=_is_param(w), col=col)
 
     @staticmethod
     def backward(ctx, c):
         gy, w = ctx.saved_tensors
         c = _dense_like(c, True)
         ggy = gw = None
+        ccol = K.thin_col(c, ctx.g, 'x')             # im2col of a 3-channel c: shared by fprop and wgrad
         if ctx.needs_input_grad[0]:
-            ggy = ConvF.apply(c, w, None, ctx.g, gy.dtype)
+            ggy = ConvF.apply(c, w, None, ctx.g, gy.dtype, ccol)
         if ctx.needs_input_grad[1]:
             if _direct(w):
-                K.conv_wgrad(c, gy, ctx.g, tuple(w.shape), accumulate_into=w.grad)
+                K.conv_wgrad(c, gy, ctx.g, tuple(w.shape), accumulate_into=w.grad, col=ccol)
             else:
                 gw = ConvG.apply(c, gy, ctx.g, tuple(w.shape))
-        return ggy, gw, None, None
+        return ggy, gw, None, None, None
 
 
 class ConvG(Function):

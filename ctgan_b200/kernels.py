@@ -19,6 +19,7 @@ CL = torch.channels_last
 
 class Config:
     use_tc = True            # use the tcgen05 kernels when a call is eligible
+    use_thin_tc = True       # route 3-channel-side convs through the im2col tensor-core path
     tc_min_rows = 1          # (tunable) minimum GEMM rows to prefer the tensor-core path
 
 
@@ -151,6 +152,68 @@ def _check_filter(w, g):
         raise RuntimeError('ctgan_b200: filter must be a contiguous float32 HWIO tensor matching the geometry')
 
 
+# ---- thin-channel (3-channel image side) convolutions on the tensor cores: see include/ctgan_sm100.h
+def _thin_side(g, t):
+    """'in' / 'out' when the conv has a thin (<= 8 channel) input / output side the im2col GEMM path handles."""
+    if not (config.use_tc and config.use_thin_tc and tc_available()) or t.dim() != 4 or t.dtype != torch.bfloat16:
+        return None
+    if not (g.stride == 1 and g.Ho == g.H and g.Wo == g.W and 0 <= g.pad_t < g.kh and 0 <= g.pad_l < g.kw and g.H * g.W >= 64):
+        return None
+    taps = g.kh * g.kw
+    if g.Cin <= 8 and taps * g.Cin <= 64 and g.Cout % 128 == 0:
+        return 'in'
+    if g.Cout <= 8 and taps * g.Cout <= 64 and g.Cin % 128 == 0:
+        return 'out'
+    return None
+
+
+def pack_filter_thin(w, kind, cacheable=False):
+    """float HWIO filter with one thin side -> zero-padded 64 x Cw bf16 operand (kinds: conv_tc.cu)."""
+    key = (w.data_ptr(), tuple(w.shape), 2 + kind) if cacheable else None
+    if key is not None and key in _pack_cache:
+        return _pack_cache[key]
+    taps, cin, cout = w.shape[0] * w.shape[1], w.shape[2], w.shape[3]
+    wp = torch.empty(64 * max(cin, cout), dtype=torch.bfloat16, device=w.device)
+    call('ctgan_pack_filter_thin', _p(w), _p(wp), taps, min(cin, cout), max(cin, cout), kind, _stream())
+    if key is not None:
+        _pack_cache[key] = wp
+    return wp
+
+
+def thin_col(t, g, role):
+    """The im2col matrix conv_fprop/conv_wgrad (role 'x') or conv_dgrad/conv_wgrad (role 'dy') would build from t, or
+    None when the call does not take the thin path -- lets a caller build it once and pass it to both."""
+    side = _thin_side(g, t)
+    if side == 'in' and role == 'x':
+        return im2col_thin(t, g, g.Cin, 1)
+    if side == 'out' and role == 'dy':
+        return im2col_thin(t, g, g.Cout, -1)
+    return None
+
+
+def im2col_thin(src, g, C, sign):
+    col = empty_act((g.N, 64, g.H, g.W), torch.bfloat16, src.device)
+    d = _desc(g, BF16, BF16)
+    call('ctgan_im2col_thin', ctypes.byref(d), C, sign, _p(src), _p(col), _stream())
+    return col
+
+
+def _gemm1x1_tc(x, wp, bias, g, cin, cout, residual=None, flags=0):
+    """1x1 tensor-core conv over the pixels of g: [P x cin] x packed filter -> [P x cout]."""
+    g1 = ConvGeom(g.N, g.H, g.W, cin, g.H, g.W, cout, 1, 1, 1, 0, 0)
+    y = empty_act((g.N, cout, g.H, g.W), torch.bfloat16, x.device)
+    d = _desc(g1, BF16, BF16)
+    call('ctgan_conv_fprop_tc', ctypes.byref(d), _p(x), _p(wp), _p(bias), _p(residual), _p(y), flags, _stream())
+    return y
+
+
+def _col2im_thin(col, bias, g, C, sign):
+    dst = empty_act((g.N, C, g.H, g.W), torch.bfloat16, col.device)
+    d = _desc(g, BF16, BF16)
+    call('ctgan_col2im_thin', ctypes.byref(d), C, sign, _p(col), _p(bias), _p(dst), _stream())
+    return dst
+
+
 class FilterPacker:
     """BF16 operand copies (fprop layout + tap-flipped dgrad layout) of every tensor-core-eligible filter of one
     flat parameter buffer, refreshed with ONE kernel launch after each optimizer step."""
@@ -165,6 +228,12 @@ class FilterPacker:
             elif p.dim() == 2 and name.endswith('.W'):
                 taps, cin, cout = 1, p.shape[0], p.shape[1]
             else:
+                continue
+            if p.dim() == 4 and taps * min(cin, cout) <= 64 and min(cin, cout) <= 8 and max(cin, cout) % 128 == 0:
+                for kind in ((0, 3) if cin < cout else (2, 1)):       # thin operands: 64 x Cw each
+                    rows.append((offsets[name], dst, taps, cin, cout, 2 + kind))
+                    self.views.append((p, 2 + kind, dst, 64 * max(cin, cout)))
+                    dst += 64 * max(cin, cout)
                 continue
             if cin % 64 or cout % 64:
                 continue
@@ -189,7 +258,7 @@ class FilterPacker:
             _pack_cache[(p.data_ptr(), tuple(p.shape), flip)] = self.packs[dst:dst + numel]
 
 
-def conv_fprop(x, w, bias, g, relu=False, residual=None, out_dtype=None, w_is_param=False):
+def conv_fprop(x, w, bias, g, relu=False, residual=None, out_dtype=None, w_is_param=False, col=None):
     """y = conv(x, w) [+ bias] [+ residual] [relu].  x NHWC/2-D act, w float HWIO."""
     require_nhwc(x, 'x')
     _check_filter(w, g)
@@ -205,6 +274,15 @@ def conv_fprop(x, w, bias, g, relu=False, residual=None, out_dtype=None, w_is_pa
         d = _desc(g, xdt, ydt)
         call('ctgan_conv_fprop_tc', ctypes.byref(d), _p(x), _p(wp), _p(bias), _p(residual), _p(y), flags, _stream())
         return y
+    side = _thin_side(g, x) if (xdt == BF16 and ydt == BF16) else None
+    if side == 'in':                                  # y = im2col(x) x w[(t,c)][Cout]
+        if residual is not None:
+            require_nhwc(residual, 'residual')
+        col = col if col is not None else im2col_thin(x, g, g.Cin, 1)
+        return _gemm1x1_tc(col, pack_filter_thin(w, 0, cacheable=w_is_param), bias, g, 64, g.Cout, residual, flags)
+    if side == 'out' and not relu and residual is None:   # ycol[(t,o)] = x x w, y = col2im(ycol) + bias
+        ycol = _gemm1x1_tc(x, pack_filter_thin(w, 2, cacheable=w_is_param), None, g, g.Cin, 64)
+        return _col2im_thin(ycol, bias, g, g.Cout, 1)
     d = _desc(g, xdt, ydt)
     call('ctgan_conv_fprop', ctypes.byref(d), _p(x), _p(w), _p(bias), _p(y), flags, _stream())
     if residual is not None:
@@ -214,7 +292,7 @@ def conv_fprop(x, w, bias, g, relu=False, residual=None, out_dtype=None, w_is_pa
     return y
 
 
-def conv_dgrad(dy, w, g, out_dtype=None, w_is_param=False):
+def conv_dgrad(dy, w, g, out_dtype=None, w_is_param=False, col=None):
     """dx = conv^T(dy, w) with the geometry of the FORWARD conv g.  Also Deconv2D forward."""
     require_nhwc(dy, 'dy')
     _check_filter(w, g)
@@ -229,12 +307,19 @@ def conv_dgrad(dy, w, g, out_dtype=None, w_is_param=False):
         d = _desc(gt, BF16, BF16)
         call('ctgan_conv_fprop_tc', ctypes.byref(d), _p(dy), _p(wp), None, None, _p(dx), 0, _stream())
         return dx
+    side = _thin_side(g, dy) if (xdt == BF16 and ydt == BF16) else None
+    if side == 'in':                                  # dxcol[(t,ci)] = dy x w^T, dx = col2im(dxcol, -1)
+        dxcol = _gemm1x1_tc(dy, pack_filter_thin(w, 3, cacheable=w_is_param), None, g, g.Cout, 64)
+        return _col2im_thin(dxcol, None, g, g.Cin, -1)
+    if side == 'out':                                 # dx = im2col(dy, -1) x w[(t,o)][Cin]
+        col = col if col is not None else im2col_thin(dy, g, g.Cout, -1)
+        return _gemm1x1_tc(col, pack_filter_thin(w, 1, cacheable=w_is_param), None, g, 64, g.Cin)
     d = _desc(g, xdt, ydt)
     call('ctgan_conv_dgrad', ctypes.byref(d), _p(dy), _p(w), _p(dx), _stream())
     return dx
 
 
-def conv_wgrad(x, dy, g, w_shape, accumulate_into=None):
+def conv_wgrad(x, dy, g, w_shape, accumulate_into=None, col=None):
     """dw (float HWIO, shape w_shape) = sum over pixels of x (shifted) * dy.
     accumulate_into: a float tensor of that shape (e.g. the parameter's slice of the flat gradient
     bucket) to ADD the result to instead of allocating one; returns it."""
@@ -248,6 +333,17 @@ def conv_wgrad(x, dy, g, w_shape, accumulate_into=None):
     if xdt == BF16 and ydt == BF16 and _tc_geom_ok(g) and g.Cin % 128 == 0 and g.Cout % 128 == 0:
         dw = acc if acc is not None else torch.zeros(w_shape, dtype=torch.float32, device=x.device)
         call('ctgan_conv_wgrad_tc', ctypes.byref(d), _p(x), _p(dy), _p(dw), _stream())
+        return dw
+    side = _thin_side(g, x) if (xdt == BF16 and ydt == BF16) else None
+    if side is not None:
+        dw = acc if acc is not None else torch.zeros(w_shape, dtype=torch.float32, device=x.device)
+        P, taps = g.N * g.H * g.W, g.kh * g.kw
+        if side == 'in':
+            col = col if col is not None else im2col_thin(x, g, g.Cin, 1)
+            call('ctgan_wgrad_thin_tc', _p(dy), _p(col), P, g.Cout, g.Cin, taps, 0, _p(dw), _stream())
+        else:
+            col = col if col is not None else im2col_thin(dy, g, g.Cout, -1)
+            call('ctgan_wgrad_thin_tc', _p(x), _p(col), P, g.Cin, g.Cout, taps, 1, _p(dw), _stream())
         return dw
     dw = acc if acc is not None else torch.empty(w_shape, dtype=torch.float32, device=x.device)
     call('ctgan_conv_wgrad', ctypes.byref(d), _p(x), _p(dy), _p(dw), 1 if acc is not None else 0, _stream())

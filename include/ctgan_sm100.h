@@ -106,6 +106,19 @@ int ctgan_pack_filter_bf16(const float* w_hwio, void* wp, int taps, int Cin, int
 
 /* Packs many filters of one flat float parameter buffer in ONE launch.  table: device array of n_entries records
  * {int64 src_offset (floats), int64 dst_offset (bf16 elements), int32 taps, Cin, Cout, transpose_flip}. */
+/* ---- thin-channel convolutions on the tensor cores (the 3-channel image side of the ResNet: Conv2D
+ * 'Discriminator.1.Conv1' / '.Shortcut' 3 -> DIM_D and 'Generator.Output' DIM_G -> 3, CT_gan_cifar_resnet.py:125-136, :148-150;
+ * op = tflib/ops/conv2d.py:106-112).  The thin side (C <= 8 channels, taps*C <= 64) is expanded to
+ * col[pixel][64] bf16, k = tap*C + c, so that fprop / dgrad / wgrad become 1x1 tensor-core GEMMs:
+ *   im2col: col[p][(t,c)] = src[p + sign*off(t)][c],  off(t) = (r - pad_t, s - pad_l), zero outside the image
+ *   col2im: dst[p][c] = bias[c] + sum_t col[p + sign*off(t)][(t,c)]
+ * d gives N,H,W,kh,kw,pads (stride 1).  pack kinds: see conv_tc.cu (0: C->Cw fprop, 1: Cw->C dgrad, 2: Cw->C fprop,
+ * 3: C->Cw dgrad); every pack is 64*Cw bf16.  wgrad_thin_tc ADDS wide^T x col into dw: mode 0 = dw [taps][C][Cw]
+ * (wide = dy, col = im2col(x, +1)), mode 1 = dw [taps][Cw][C] (wide = x, col = im2col(dy, -1)). */
+int ctgan_im2col_thin(const ctgan_conv_desc* d, int C, int sign, const void* src, void* col, void* stream);
+int ctgan_col2im_thin(const ctgan_conv_desc* d, int C, int sign, const void* col, const float* bias, void* dst, void* stream);
+int ctgan_pack_filter_thin(const float* w, void* wp_bf16, int taps, int C, int Cw, int kind, void* stream);
+int ctgan_wgrad_thin_tc(const void* wide, const void* col, long long P, int Cw, int C, int taps, int mode, float* dw, void* stream);
 int ctgan_pack_filters_multi(const float* flat_params, void* packs_bf16, const void* table, int n_entries, void* stream);
 
 /* db[c] (float) = sum over rows of dy[rows][C]   (gradient of tf.nn.bias_add) */

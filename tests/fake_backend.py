@@ -45,7 +45,7 @@ def _conv(x4, w, g):
     return y[:, :, :g.Ho, :g.Wo]
 
 
-def conv_fprop(x, w, bias, g, relu=False, residual=None, out_dtype=None, w_is_param=False):
+def conv_fprop(x, w, bias, g, relu=False, residual=None, out_dtype=None, w_is_param=False, col=None):
     two_d = x.dim() == 2
     y = _conv(_as4(x, g, 'x'), w.detach(), g)
     if bias is not None:
@@ -58,7 +58,7 @@ def conv_fprop(x, w, bias, g, relu=False, residual=None, out_dtype=None, w_is_pa
     return _out(y, out_dtype or x.dtype)
 
 
-def conv_dgrad(dy, w, g, out_dtype=None, w_is_param=False):
+def conv_dgrad(dy, w, g, out_dtype=None, w_is_param=False, col=None):
     two_d = dy.dim() == 2
     x = torch.zeros(g.N, g.Cin, g.H, g.W, requires_grad=True)
     with torch.enable_grad():
@@ -68,7 +68,11 @@ def conv_dgrad(dy, w, g, out_dtype=None, w_is_param=False):
     return _out(dx, out_dtype or dy.dtype)
 
 
-def conv_wgrad(x, dy, g, w_shape, accumulate_into=None):
+def thin_col(t, g, role):
+    return None
+
+
+def conv_wgrad(x, dy, g, w_shape, accumulate_into=None, col=None):
     w = torch.zeros(g.kh, g.kw, g.Cin, g.Cout, requires_grad=True)
     with torch.enable_grad():
         y = _conv(_as4(x, g, 'x'), w, g)

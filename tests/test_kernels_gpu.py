@@ -348,3 +348,36 @@ def test_tc_wgrad_variants_match(K, shape):
             assert rel(acc - 0.5, ref) < 2e-3, variant
     finally:
         _lib.lib.ctgan_set_wgrad_variant(2)
+
+
+@pytest.mark.parametrize('geom', [(5, 32, 32, 3, 128, 3), (3, 16, 16, 3, 128, 1), (4, 32, 32, 128, 3, 3), (70, 8, 8, 3, 256, 3),
+                                  (2, 16, 16, 256, 4, 3), (3, 12, 20, 3, 128, 3)])
+def test_thin_tc_conv_family(K, geom):
+    """3-channel-side convs (Discriminator.1.*, Generator.Output) through the im2col tensor-core path: fprop, dgrad,
+    wgrad (fresh and accumulating) against the CPU reference, and against the SIMT thin kernels."""
+    N, H, W, Cin, Cout, k = geom
+    g = K.same_geom(N, H, W, Cin, Cout, k, 1)
+    x, dy = act((N, Cin, H, W), torch.bfloat16, 1), act((N, Cout, g.Ho, g.Wo), torch.bfloat16, 2)
+    w, b = filt((k, k, Cin, Cout), 3), act((Cout,), torch.float32, 4)
+    wq = w.to(torch.bfloat16).float()
+    fb = FB()
+    assert K._thin_side(g, to_dev(x)) == ('in' if Cin < Cout else 'out')
+    res = {}
+    for thin in (True, False):
+        K.config.use_thin_tc = thin
+        try:
+            y = K.conv_fprop(to_dev(x), w.cuda(), b.cuda(), g)
+            dx = K.conv_dgrad(to_dev(dy), w.cuda(), g)
+            dw = K.conv_wgrad(to_dev(x), to_dev(dy), g, tuple(w.shape))
+            acc = torch.full(tuple(w.shape), 0.25, device='cuda')
+            K.conv_wgrad(to_dev(x), to_dev(dy), g, tuple(w.shape), accumulate_into=acc)
+        finally:
+            K.config.use_thin_tc = True
+        res[thin] = (y, dx, dw)
+        wr = wq if thin else w
+        assert rel(y, fb.conv_fprop(x, wr, b, g)) < 1e-2, thin
+        assert rel(dx, fb.conv_dgrad(dy, wr, g)) < 1e-2, thin
+        assert rel(dw, fb.conv_wgrad(x, dy, g, tuple(w.shape))) < 2e-3, thin
+        assert rel(acc - 0.25, fb.conv_wgrad(x, dy, g, tuple(w.shape))) < 2e-3, thin
+    for a, b_ in zip(res[True], res[False]):
+        assert rel(a, b_.float().cpu()) < 2e-2
