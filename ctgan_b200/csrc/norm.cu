@@ -15,14 +15,14 @@ constexpr int BN_CCH   = BN_LANES * 4;   // channels per CTA
 
 static inline int bn_fwd_rowblocks(int64_t R) {
     int64_t nb = (R + 63) / 64;
-    if (nb > 512) nb = 512;
+    if (nb > 160) nb = 160;
     if (nb < 1) nb = 1;
     return (int)nb;
 }
 static inline int bn_bwd_splits(int HW) {
     int s = HW / 64;
     if (s < 1) s = 1;
-    if (s > 16) s = 16;
+    if (s > 4) s = 4;
     return s;
 }
 
@@ -322,6 +322,45 @@ bias_grad_kernel(const void* __restrict__ dy, float* __restrict__ db, int64_t ro
     }
 }
 
+// BF16, C/8 a power of two <= 256: 16-byte loads, C/8 threads per row, 4 rows in flight per thread
+__global__ void __launch_bounds__(256)
+bias_grad_bf16_kernel(const __nv_bfloat16* __restrict__ dy, float* __restrict__ db, int64_t rows, int C, int rows_per_block) {
+    __shared__ float sh[256 * 8];
+    const int tpr = C >> 3;                                  // threads per row
+    const int cg = threadIdx.x % tpr, rl = threadIdx.x / tpr, rstep = 256 / tpr;
+    const int64_t r0 = (int64_t)blockIdx.x * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+    const __nv_bfloat16* base = dy + cg * 8;
+    int64_t r = r0 + rl;
+    for (; r + 3 * (int64_t)rstep < r1; r += 4 * (int64_t)rstep) {
+        uint4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = __ldg(reinterpret_cast<const uint4*>(base + (r + u * (int64_t)rstep) * C));
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v[u]);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { acc[2 * e] += __bfloat162float(h[e].x); acc[2 * e + 1] += __bfloat162float(h[e].y); }
+        }
+    }
+    for (; r < r1; r += rstep) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(base + r * C));
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { acc[2 * e] += __bfloat162float(h[e].x); acc[2 * e + 1] += __bfloat162float(h[e].y); }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) sh[rl * C + cg * 8 + e] = acc[e];
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += 256) {
+        float s = 0.f;
+        for (int k = 0; k < rstep; ++k) s += sh[k * C + c];
+        atomicAdd(db + c, s);
+    }
+}
+
 }  // namespace ctgan
 
 using namespace ctgan;
@@ -397,6 +436,18 @@ extern "C" int ctgan_bias_grad(const void* dy, float* db, int64_t rows, int C, i
     if (!accumulate) {
         cudaError_t e = cudaMemsetAsync(db, 0, sizeof(float) * (size_t)C, st);
         if (e != cudaSuccess) return cuda_status(e, "bias_grad memset");
+    }
+    const int tpr = C / 8;
+    if (dtype == CTGAN_BF16 && C % 8 == 0 && tpr <= 256 && (tpr & (tpr - 1)) == 0 && (reinterpret_cast<uintptr_t>(dy) & 15) == 0) {
+        const int rstep = 256 / tpr;
+        int64_t nb = (rows + 4 * rstep - 1) / (4 * rstep);              // >= 4 rows per thread
+        const int64_t cap = 4 * (int64_t)sm_count();
+        if (nb > cap) nb = cap;
+        int rpb = (int)((rows + nb - 1) / nb);
+        nb = (rows + rpb - 1) / rpb;
+        bias_grad_bf16_kernel<<<(unsigned)nb, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(dy), db, rows, C, rpb);
+        CTGAN_CHECK_LAUNCH("bias_grad");
+        return 0;
     }
     int cblocks = ceil_div(C, 32);
     int64_t want = (2 * (int64_t)sm_count() + cblocks - 1) / cblocks;
