@@ -83,13 +83,14 @@ class ConvF(Function):
             gx = ConvD.apply(gy, w, ctx.g, x.dtype, dycol)
         if ctx.needs_input_grad[1]:
             if _direct(w):
-                K.conv_wgrad(x, gy, ctx.g, tuple(w.shape), accumulate_into=w.grad, col=ctx.col if ctx.col is not None else dycol)
+                col, g = (ctx.col if ctx.col is not None else dycol), ctx.g
+                K.on_side(lambda: K.conv_wgrad(x, gy, g, tuple(w.shape), accumulate_into=w.grad, col=col), x, gy, col)
             else:
                 gw = ConvG.apply(x, gy, ctx.g, tuple(w.shape))
         if ctx.has_bias and ctx.needs_input_grad[2]:
             b = ctx.bias
             if _direct(b):
-                K.bias_grad(gy.detach(), accumulate_into=b.grad)
+                K.on_side(lambda: K.bias_grad(gy.detach(), accumulate_into=b.grad), gy)
             else:
                 gb = K.bias_grad(gy.detach())
         return gx, gw, gb, None, None, None
@@ -114,7 +115,8 @@ class ConvD(Function):
             ggy = ConvF.apply(c, w, None, ctx.g, gy.dtype, ccol)
         if ctx.needs_input_grad[1]:
             if _direct(w):
-                K.conv_wgrad(c, gy, ctx.g, tuple(w.shape), accumulate_into=w.grad, col=ccol)
+                g = ctx.g
+                K.on_side(lambda: K.conv_wgrad(c, gy, g, tuple(w.shape), accumulate_into=w.grad, col=ccol), c, gy, ccol)
             else:
                 gw = ConvG.apply(c, gy, ctx.g, tuple(w.shape))
         return ggy, gw, None, None, None
@@ -188,7 +190,8 @@ class BiasAdd(Function):
         gb = None
         if ctx.needs_input_grad[1]:
             if _direct(ctx.bias):
-                K.bias_grad(gy.detach(), accumulate_into=ctx.bias.grad)
+                b = ctx.bias
+                K.on_side(lambda: K.bias_grad(gy.detach(), accumulate_into=b.grad), gy)
             else:
                 gb = K.bias_grad(gy.detach())
         return gy, gb

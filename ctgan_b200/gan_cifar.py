@@ -127,6 +127,7 @@ class Trainer:
         out = F.CTGPLoss.apply(disc_real, disc_real_, disc_fake, disc_real_2, disc_real_2_, gradients, None, None,
                                self.hp)
         out[0].backward(inputs=self.disc_opt.param_list())
+        K.join_side()
         return dict(out=out.detach(), gradients=gradients.detach(), fake_data=fake_data, real_data=real_data)
 
     def critic_step(self, real_data_in, iteration=0, use_device_lr=False):
@@ -144,6 +145,7 @@ class Trainer:
         disc_fake, _ = m.Discriminator(fake_data)
         gen_cost = F.MeanLoss.apply(disc_fake, -1.0)
         gen_cost.backward(inputs=self.gen_opt.param_list())
+        K.join_side()
         return dict(cost=gen_cost.detach())
 
     def gen_step(self, iteration=0, use_device_lr=False):

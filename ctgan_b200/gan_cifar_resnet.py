@@ -263,6 +263,7 @@ class Trainer:
         out = F.CTGPLoss.apply(disc_real, disc_real_, disc_fake, disc_real_2, disc_real_2_, gradients, logits,
                                all_real_labels if logits is not None else None, self.hp)
         out[0].backward(inputs=self.disc_opt.param_list())
+        K.join_side()
         res = dict(out=out.detach(), gradients=gradients.detach(), fake_data=fake_data, real_data=all_real_data)
         res.update(metrics)
         return res
@@ -290,6 +291,7 @@ class Trainer:
         if CONDITIONAL and ACGAN:
             gen_cost = gen_cost + ACGAN_SCALE_G * F.SoftmaxCE.apply(disc_fake_acgan, fake_labels)
         gen_cost.backward(inputs=self.gen_opt.param_list())
+        K.join_side()
         return dict(cost=gen_cost.detach())
 
     def gen_step(self, iteration=0, use_device_lr=False):

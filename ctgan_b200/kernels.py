@@ -20,6 +20,7 @@ CL = torch.channels_last
 class Config:
     use_tc = True            # use the tcgen05 kernels when a call is eligible
     use_thin_tc = True       # route 3-channel-side convs through the im2col tensor-core path
+    side_stream = True       # run direct-accumulation wgrad / bias-grad launches on a second stream
     tc_min_rows = 1          # (tunable) minimum GEMM rows to prefer the tensor-core path
 
 
@@ -84,6 +85,39 @@ def nhwc_dims(x):
     if x.dim() == 2:
         return x.shape[0], 1, 1, x.shape[1]
     raise RuntimeError('ctgan_b200: activations must be 2-D or 4-D')
+
+
+# --------------------------------------------------------------------------- side stream
+# Filter / bias gradients are off the critical path of a backward pass: nothing reads them before the optimizer
+# step, while the dgrad chain is a strict sequence of (at batch 64, often under-filled) kernels.  The
+# direct-accumulation wgrad / bias-grad launches therefore go to a second stream and overlap that chain; inside a
+# CUDA-graph capture the fork/join becomes parallel graph branches.
+_side_streams = {}
+_side_pending = []       # tensors the side stream may still be reading (kept alive until the join)
+
+
+def on_side(fn, *keep):
+    """Run fn() (kernel launches only) on the side stream, ordered after everything queued so far on the current
+    stream; `keep` = the tensors those kernels read."""
+    if not (config.side_stream and keep and keep[0].is_cuda):
+        fn()
+        return
+    dev = keep[0].device.index
+    side = _side_streams.get(dev)
+    if side is None:
+        side = _side_streams[dev] = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        fn()
+    _side_pending.append((dev, keep))
+
+
+def join_side():
+    """Make the current stream wait for the side stream's work; release the kept tensors."""
+    if _side_pending:
+        for dev in {d for d, _ in _side_pending}:
+            torch.cuda.current_stream(dev).wait_stream(_side_streams[dev])
+        _side_pending.clear()
 
 
 # --------------------------------------------------------------------------- conv family

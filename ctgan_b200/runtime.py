@@ -251,6 +251,7 @@ class FlatAdam:
     def all_reduce(self):
         """Sum the flat gradient bucket over ranks (NCCL); the 1/world scale is applied in step()."""
         import torch.distributed as dist
+        K.join_side()
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             dist.all_reduce(self.flat_g)
             return dist.get_world_size()
@@ -259,6 +260,7 @@ class FlatAdam:
     def step(self, lr=None, world=1, use_device_lr=False):
         """One update.  use_device_lr: read lr_t from self.lr_t_dev (set with set_device_lr) so the
         launch is replayable inside a CUDA graph."""
+        K.join_side()                        # filter / bias gradients accumulated on the side stream
         if not use_device_lr:
             self.t += 1                      # graph mode: t advances in set_device_lr() at replay time
         K.adam_step(self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.lr_t(lr) if not use_device_lr else 0.0,
