@@ -238,6 +238,7 @@ class Trainer:
             all_real_data = K.prep_real(all_real_data_int, 256., 1. / 128, seed, off, dyn=dyn)  # :201-202
         # stochastic pass ' on real+fake (2B rows) and pass '' on the real half (B rows) as ONE critic call:
         # same weights, independent dropout draws per row -- the reference's two calls at :226-227
+        fork = K.fork_branch(all_real_data)          # the gradient-penalty pass below depends on nothing after this point
         stacked = torch.cat([all_real_data, fake_data, all_real_data], dim=0)
         stacked_labels = torch.cat([all_real_labels, all_real_labels, all_real_labels], dim=0)
         RNG.scope_parts([('drop.p1', 2 * B), ('drop.p2', B)])
@@ -253,16 +254,21 @@ class Trainer:
                 metrics['acgan_fake_acc'] = (pred[B:] == all_real_labels).float().mean()
         disc_real, disc_fake, disc_real_ = disc_all[:B], disc_all[B:2 * B], disc_all[2 * B:]
         disc_real_2, disc_real_2_ = disc_all_2[:B], disc_all_2[2 * B:]
-        alpha = RNG.uniform('alpha', (B, 1))
-        interpolates = K.interpolate(all_real_data, fake_data, alpha).requires_grad_(True)     # :277-283
-        RNG.scope('drop.gp')
-        d_interp = Discriminator(interpolates, all_real_labels, 0.8, 0.5, 0.5)[0]
-        gradients = torch.autograd.grad(d_interp, interpolates, grad_outputs=torch.ones_like(d_interp),
-                                        create_graph=True)[0]                                   # :284
+        # gradient-penalty pass: independent of the stacked pass until the loss, so it runs as a second branch
+        # (stream / CUDA-graph branch); autograd replays each branch's backward on the stream of its forward
+        with K.branch(fork):
+            alpha = RNG.uniform('alpha', (B, 1))
+            interpolates = K.interpolate(all_real_data, fake_data, alpha).requires_grad_(True)     # :277-283
+            RNG.scope('drop.gp')
+            d_interp = Discriminator(interpolates, all_real_labels, 0.8, 0.5, 0.5)[0]
+            gradients = torch.autograd.grad(d_interp, interpolates, grad_outputs=torch.ones_like(d_interp),
+                                            create_graph=True)[0]                                   # :284
+        K.join_branch(fork)
         logits = disc_all_acgan[:B] if (CONDITIONAL and ACGAN) else None
         out = F.CTGPLoss.apply(disc_real, disc_real_, disc_fake, disc_real_2, disc_real_2_, gradients, logits,
                                all_real_labels if logits is not None else None, self.hp)
         out[0].backward(inputs=self.disc_opt.param_list())
+        K.join_branch(fork)
         K.join_side()
         res = dict(out=out.detach(), gradients=gradients.detach(), fake_data=fake_data, real_data=all_real_data)
         res.update(metrics)

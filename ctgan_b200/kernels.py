@@ -21,6 +21,7 @@ class Config:
     use_tc = True            # use the tcgen05 kernels when a call is eligible
     use_thin_tc = True       # route 3-channel-side convs through the im2col tensor-core path
     side_stream = True       # run direct-accumulation wgrad / bias-grad launches on a second stream
+    branch_streams = True    # run independent sub-graphs of a step (GP pass vs stacked pass) as stream branches
     tc_min_rows = 1          # (tunable) minimum GEMM rows to prefer the tensor-core path
 
 
@@ -118,6 +119,48 @@ def join_side():
         for dev in {d for d, _ in _side_pending}:
             torch.cuda.current_stream(dev).wait_stream(_side_streams[dev])
         _side_pending.clear()
+
+
+# Independent sub-graphs of one step (the gradient-penalty pass vs the stacked critic pass) as two stream branches.
+_branch_streams = {}
+
+
+def fork_branch(t):
+    """Mark the point after which a branch may start: returns a handle (None when branching is off / on CPU)."""
+    if not (config.branch_streams and t.is_cuda):
+        return None
+    dev = t.device.index
+    if dev not in _branch_streams:
+        _branch_streams[dev] = torch.cuda.Stream(device=dev)
+    ev = torch.cuda.Event()
+    ev.record(torch.cuda.current_stream(dev))
+    return (dev, ev)
+
+
+class branch:
+    """with branch(fork): launches go to the branch stream, ordered after the fork point only."""
+
+    def __init__(self, fork):
+        self.fork, self.ctx = fork, None
+
+    def __enter__(self):
+        if self.fork is not None:
+            dev, ev = self.fork
+            _branch_streams[dev].wait_event(ev)
+            self.ctx = torch.cuda.stream(_branch_streams[dev])
+            self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            self.ctx.__exit__(*exc)
+        return False
+
+
+def join_branch(fork):
+    """The current stream waits for everything queued on the branch stream."""
+    if fork is not None:
+        torch.cuda.current_stream(fork[0]).wait_stream(_branch_streams[fork[0]])
 
 
 # --------------------------------------------------------------------------- conv family
