@@ -111,6 +111,7 @@ class Trainer:
             fake_data = m.Generator(B, noise=RNG.normal('z', (B, 128)))
         # the three stochastic critic calls of the reference (real', real'', fake) as ONE stacked batch:
         # shared weights, independent dropout draws per row
+        fork = K.fork_branch(real_data)               # the gradient-penalty pass depends on nothing after this point
         stacked = torch.cat([real_data, real_data, fake_data], dim=0)
         RNG.scope_parts([('drop.real1', B), ('drop.real2', B), ('drop.fake', B)])
         RNG.begin_stack([B, B, B])
@@ -118,15 +119,18 @@ class Trainer:
         RNG.end_stack()
         disc_real, disc_real_, disc_fake = d_all[:B], d_all[B:2 * B], d_all[2 * B:]
         disc_real_2, disc_real_2_ = f_all[:B], f_all[B:2 * B]
-        alpha = RNG.uniform('alpha', (B, 1))
-        interpolates = K.interpolate(real_data, fake_data, alpha).requires_grad_(True)
-        RNG.scope('drop.gp')
-        d_interp = m.Discriminator(interpolates)[0]
-        gradients = torch.autograd.grad(d_interp, interpolates, grad_outputs=torch.ones_like(d_interp),
-                                        create_graph=True)[0]
+        with K.branch(fork):                          # second stream / CUDA-graph branch (see gan_cifar_resnet.py)
+            alpha = RNG.uniform('alpha', (B, 1))
+            interpolates = K.interpolate(real_data, fake_data, alpha).requires_grad_(True)
+            RNG.scope('drop.gp')
+            d_interp = m.Discriminator(interpolates)[0]
+            gradients = torch.autograd.grad(d_interp, interpolates, grad_outputs=torch.ones_like(d_interp),
+                                            create_graph=True)[0]
+        K.join_branch(fork)
         out = F.CTGPLoss.apply(disc_real, disc_real_, disc_fake, disc_real_2, disc_real_2_, gradients, None, None,
                                self.hp)
         out[0].backward(inputs=self.disc_opt.param_list())
+        K.join_branch(fork)
         K.join_side()
         return dict(out=out.detach(), gradients=gradients.detach(), fake_data=fake_data, real_data=real_data)
 
