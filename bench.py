@@ -174,7 +174,7 @@ def roofline_dominant_kernel(torch, peaks):
             traffic = json.load(f).get('conv_fprop_tc_128x32x32x128_bytes')
     except Exception:
         pass
-    return {'bound': 'tensor', 'kernel': 'conv_fprop_tc_lean_kernel<1> (3x3, 128->128, 128x32x32)', 'achieved': achieved,
+    return {'bound': 'tensor', 'kernel': 'conv_fprop_tc_pair_kernel (3x3, 128->128, 128x32x32)', 'achieved': achieved,
             'peak': peaks['burst'], 'peak_source': 'MEASURED_PEAKS.json bf16_tflops (burst; kernel timed alone)'
             if peaks['src'] == 'measured' else 'fallback 1590', 'unit': 'TFLOP/s', 'frac': achieved / peaks['burst'],
             'traffic': traffic, 'flops_per_launch': flops, 'us_per_launch': ms * 1e3}

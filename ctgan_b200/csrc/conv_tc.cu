@@ -780,6 +780,204 @@ conv_fprop_tc_lean_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
     if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem_base);
 }
 
+// ------------------------------------------------------------------ fprop, 256-pixel work items ("pair" kernel)
+// The lean kernel at 128x128 tiles is bound by the L2 -> shared-memory fill (ncu: 453 MB at ~80 % of the chip's LTS cap for
+// D.1.Conv2).  Here a work item is TWO vertically adjacent 128-pixel tiles of one image whenever the CTA's tile range
+// allows it: one (2*BH+2)-row halo box of x (40 KB) and the same three filter boxes (48 KB) feed 24 MMAs into two TMEM
+// accumulators -- 44 KB per 12 MMAs instead of 72 KB.  Two stages of 88 KB; TMEM 2 x (2 x 128) columns double-buffered.
+// Tiles are enumerated n-block-major (tile = nb * m_tiles + mt) and split into contiguous per-CTA ranges, so every warp
+// role derives the same item sequence (pair if the next tile is the next row block of the same image, else single).
+__device__ __forceinline__ void lean_epilogue_tile(const FpropParams& p, uint32_t tmem_addr, int q, int lane,
+                                                   int w0, int h0, int n0, int co0, bool relu) {
+    int t = q * 32 + lane;
+    const int bw = t % p.BW; t /= p.BW;
+    const int bh = t % p.BH; const int bn = t / p.BH;
+    const int n = n0 + bn, h = h0 + bh, w = w0 + bw;
+    const bool valid = (n < p.N) && (h < p.H) && (w < p.W);
+    const int64_t pix = ((int64_t)n * p.H + h) * p.W + w;
+    __nv_bfloat16* yrow = p.y + pix * p.Cout + co0;
+    const __nv_bfloat16* rrow = p.residual ? p.residual + pix * p.Cout + co0 : nullptr;
+#pragma unroll 1
+    for (int c0 = 0; c0 < 128; c0 += 32) {
+        uint32_t v32[32];
+        tmem_ld32(tmem_addr + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v32);
+        if (valid) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+                float v[8];
+                if (p.bias) {
+                    const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + co0 + c0 + j));
+                    const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + co0 + c0 + j + 4));
+                    v[0] = b0.x; v[1] = b0.y; v[2] = b0.z; v[3] = b0.w; v[4] = b1.x; v[5] = b1.y; v[6] = b1.z; v[7] = b1.w;
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) v[e] = 0.f;
+                }
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] += __uint_as_float(v32[j + e]);
+                if (rrow) {
+                    uint4 rv = *reinterpret_cast<const uint4*>(rrow + c0 + j);
+                    const __nv_bfloat162* rp = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) { v[2 * e] += __bfloat162float(rp[e].x); v[2 * e + 1] += __bfloat162float(rp[e].y); }
+                }
+                if (relu) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
+                }
+                uint4 ov;
+                __nv_bfloat162* op = reinterpret_cast<__nv_bfloat162*>(&ov);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) op[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+                *reinterpret_cast<uint4*>(yrow + c0 + j) = ov;
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(192, 1)
+conv_fprop_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_x2,
+                          const __grid_constant__ CUtensorMap tmap_w, const FpropParams p, const int m_tiles, const int n_tiles)
+{
+    constexpr int BLOCK_N = 128;
+    constexpr int STAGES = 2;
+    constexpr uint32_t A_REGION = 40960u;                             // (2*BH+2) rows x BW pixels x 128 B <= 40 KB
+    constexpr uint32_t B_BYTES = BLOCK_N * BLOCK_K * 2;               // 16 KB
+    constexpr uint32_t STAGE_BYTES = A_REGION + 3 * B_BYTES;          // 88 KB
+    constexpr int TMEM_COLS = 512;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const uint32_t s_base = smem_u32(smem);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES);
+    const uint32_t tfull = smem_u32(bars + 2 * STAGES), tempty = smem_u32(bars + 2 * STAGES + 2);
+
+    const int cin_blocks = p.Cin / BLOCK_K;
+    const int groups = cin_blocks * p.kw;
+    const uint32_t a1_bytes = (uint32_t)(p.BH + 2) * p.BW * 128u, a2_bytes = (uint32_t)(2 * p.BH + 2) * p.BW * 128u;
+    // contiguous tile range of this CTA
+    const int t_begin = (int)(((long long)n_tiles * blockIdx.x) / gridDim.x);
+    const int t_end = (int)(((long long)n_tiles * (blockIdx.x + 1)) / gridDim.x);
+    // pair(t): tile t+1 is in range, same n-block, and the next row block of the same image (tilesW == 1 here)
+    auto is_pair = [&](int t) -> bool {
+        if (t + 1 >= t_end) return false;
+        const int mt = t % m_tiles;
+        return (mt + 1 < m_tiles) && ((mt % p.tilesH) + 1 < p.tilesH);
+    };
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmap_x);
+        prefetch_tmap(&tmap_x2);
+        prefetch_tmap(&tmap_w);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(tfull + 8 * s, 1); mbar_init(tempty + 8 * s, 4); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<TMEM_COLS>(smem_u32(tmem_slot));
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0 && lane == 0) {
+        // ================= TMA producer =================
+        int st = 0; uint32_t ph = 0;
+        for (int t = t_begin; t < t_end;) {
+            const bool pair = is_pair(t);
+            const int nb = t / m_tiles, mt = t - nb * m_tiles;
+            const int th = mt % p.tilesH, tn = mt / p.tilesH;
+            const int h0 = th * p.BH, n0 = tn * p.BN, co0 = nb * BLOCK_N;
+            for (int gi = 0; gi < groups; ++gi) {
+                const uint32_t sb = s_base + st * STAGE_BYTES, fb = full0 + 8 * st;
+                const int cb = gi / p.kw, s = gi - cb * p.kw;
+                mbar_wait(empty0 + 8 * st, ph ^ 1);
+                mbar_expect_tx(fb, (pair ? a2_bytes : a1_bytes) + 3 * B_BYTES);
+                tma_load_4d(sb, pair ? &tmap_x2 : &tmap_x, fb, cb * BLOCK_K, s - p.pad_l, h0 - p.pad_t, n0);
+#pragma unroll
+                for (int r = 0; r < 3; ++r)
+                    tma_load_3d(sb + A_REGION + r * B_BYTES, &tmap_w, fb, cb * BLOCK_K, co0, r * p.kw + s);
+                if (++st == STAGES) { st = 0; ph ^= 1; }
+            }
+            t += pair ? 2 : 1;
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer (whole warp runs the loop; one elected lane issues) =================
+        constexpr uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N, 0, 0);
+        const uint32_t lo0 = ((s_base & 0x3FFFFu) >> 4) | (1u << 16);
+        const uint32_t row_step = ((uint32_t)p.BW * 128u) >> 4;          // one image row
+        const uint32_t tile1_off = (uint32_t)p.BH * row_step;            // lower tile inside the halo box
+        int st = 0; uint32_t ph = 0;
+        int it = 0;
+        for (int t = t_begin; t < t_end; ++it) {
+            const bool pair = is_pair(t);
+            const int acc = it & 1;
+            mbar_wait(tempty + 8 * acc, ((uint32_t)(it >> 1) & 1u) ^ 1u);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 2 * BLOCK_N);
+            for (int gi = 0; gi < groups; ++gi) {
+                mbar_wait(full0 + 8 * st, ph);
+                tc_fence_after();
+                const uint32_t a_lo = lo0 + st * (STAGE_BYTES >> 4);
+                const uint32_t b_lo = a_lo + (A_REGION >> 4);
+                if (elect_one()) {
+                    if (pair) {
+#pragma unroll
+                        for (int r = 0; r < 3; ++r) {
+#pragma unroll
+                            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                                const uint32_t accf = (r | k) ? 1u : (gi > 0 ? 1u : 0u);
+                                umma_bf16_lo(d_tmem, a_lo + r * row_step + 2 * k, b_lo + r * (B_BYTES >> 4) + 2 * k, idesc, accf);
+                                umma_bf16_lo(d_tmem + BLOCK_N, a_lo + tile1_off + r * row_step + 2 * k, b_lo + r * (B_BYTES >> 4) + 2 * k,
+                                             idesc, accf);
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int r = 0; r < 3; ++r) {
+#pragma unroll
+                            for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+                                umma_bf16_lo(d_tmem, a_lo + r * row_step + 2 * k, b_lo + r * (B_BYTES >> 4) + 2 * k, idesc,
+                                             (r | k) ? 1u : (gi > 0 ? 1u : 0u));
+                        }
+                    }
+                    umma_commit(empty0 + 8 * st);
+                    if (gi == groups - 1) umma_commit(tfull + 8 * acc);
+                }
+                __syncwarp();
+                if (++st == STAGES) { st = 0; ph ^= 1; }
+            }
+            t += pair ? 2 : 1;
+        }
+    } else if (warp >= 2) {
+        // ================= epilogue warps: TMEM -> registers -> global =================
+        const int q = warp & 3;
+        const bool relu = (p.flags & CTGAN_EPI_RELU) != 0;
+        int it = 0;
+        for (int t = t_begin; t < t_end; ++it) {
+            const bool pair = is_pair(t);
+            const int acc = it & 1;
+            const int nb = t / m_tiles, mt = t - nb * m_tiles;
+            const int th = mt % p.tilesH, tn = mt / p.tilesH;
+            const int h0 = th * p.BH, n0 = tn * p.BN, co0 = nb * BLOCK_N;
+            mbar_wait(tfull + 8 * acc, (uint32_t)(it >> 1) & 1u);
+            tc_fence_after();
+            lean_epilogue_tile(p, tmem_base + (uint32_t)(acc * 2 * BLOCK_N), q, lane, 0, h0, n0, co0, relu);
+            if (pair) lean_epilogue_tile(p, tmem_base + (uint32_t)(acc * 2 * BLOCK_N + BLOCK_N), q, lane, 0, h0 + p.BH, n0, co0, relu);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty + 8 * acc) : "memory");
+            t += pair ? 2 : 1;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
 // ------------------------------------------------------------------ wgrad kernel
 struct WgradParams {
     int N, H, W, Cin, Cout;
@@ -1414,6 +1612,23 @@ static int launch_fprop_lean(const CUtensorMap& mx, const CUtensorMap& mw, const
     return 0;
 }
 
+static int launch_fprop_pair(const CUtensorMap& mx, const CUtensorMap& mx2, const CUtensorMap& mw, const FpropParams& p, cudaStream_t st) {
+    constexpr size_t smem = 2 * (40960 + 3 * 16384) + 1024 + (2 * 2 + 4) * 8 + 16;
+    static_assert(smem <= 227 * 1024, "pair fprop: shared memory budget");
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(conv_fprop_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return cuda_status(e, "fprop_tc_pair smem attribute");
+        attr_set = true;
+    }
+    const int m_tiles = p.tilesW * p.tilesH * p.tilesN;
+    const int n_tiles = m_tiles * (p.Cout / 128);
+    const int grid = n_tiles < sm_count() ? n_tiles : sm_count();
+    conv_fprop_tc_pair_kernel<<<grid, 192, smem, st>>>(mx, mx2, mw, p, m_tiles, n_tiles);
+    CTGAN_CHECK_LAUNCH("conv_fprop_tc_pair");
+    return 0;
+}
+
 }  // namespace tc
 }  // namespace ctgan
 
@@ -1421,7 +1636,7 @@ using namespace ctgan;
 using namespace ctgan::tc;
 
 static bool g_use_halo = true;
-static int g_fprop_variant = 3;   // 3 = persistent grouped-stage kernel, 2 = persistent per-k-block rings, 1 = one tile per CTA
+static int g_fprop_variant = 4;   // 4 = 256-pixel work items where possible (else 3), 3 = persistent grouped-stage kernel, 2 = persistent per-k-block rings, 1 = one tile per CTA
 /* test hook: selects the fprop_tc kernel family (both are compared in tests/) */
 extern "C" void ctgan_set_fprop_variant(int v) { g_fprop_variant = v; }
 static int g_wgrad_variant = 2;   // 2 = filter-column CTAs sharing one x halo box (3x3), 1 = one (x, dY) box pair per tap
@@ -1454,7 +1669,13 @@ extern "C" int ctgan_conv_fprop_tc(const ctgan_conv_desc* d, const void* x, cons
     if (int r = make_act_map(&mx, x, d->N, d->H, d->W, d->Cin, p.BW, halo ? p.BH + d->kh - 1 : p.BH, p.BN)) return r;
     if (int r = make_filter_map(&mw, wp, d->kh * d->kw, d->Cout, d->Cin, block_n)) return r;
     cudaStream_t st = as_stream(stream);
-    if (g_fprop_variant == 3 && block_n == 128) {                    // persistent, grouped stages, lean issue loop (default)
+    if (g_fprop_variant == 4 && block_n == 128 && halo && d->kh == 3 && p.tilesW == 1 && p.BN == 1 && p.tilesH >= 2 &&
+        (uint32_t)(2 * p.BH + 2) * p.BW * 128u <= 40960u && p.tilesH * p.tilesN * (d->Cout / 128) >= 2 * sm_count()) {
+        CUtensorMap mx2;                                             // 256-pixel work items (two row blocks per halo box)
+        if (int r = make_act_map(&mx2, x, d->N, d->H, d->W, d->Cin, p.BW, 2 * p.BH + 2, 1)) return r;
+        return launch_fprop_pair(mx, mx2, mw, p, st);
+    }
+    if (g_fprop_variant >= 3 && block_n == 128) {                    // persistent, grouped stages, lean issue loop
         if (halo && d->kh == 3) return launch_fprop_lean<1>(mx, mw, p, st);
         if (!halo) return launch_fprop_lean<0>(mx, mw, p, st);
     }

@@ -111,7 +111,8 @@ def test_conv_mixed_dtype_heads(K):
 
 
 @pytest.mark.parametrize('shape', [(24, 32, 32, 3), (80, 16, 16, 3), (20, 32, 32, 5), (300, 8, 8, 3), (3, 16, 16, 1),
-                                   (200, 4, 4, 3), (37, 32, 32, 3)])
+                                   (200, 4, 4, 3), (37, 32, 32, 3), (64, 32, 32, 3), (200, 16, 16, 3), (60, 20, 32, 3),
+                                   (41, 28, 16, 3)])
 def test_tc_fprop_variants_match(K, shape):
     """The fprop_tc kernel family -- persistent (default) vs one-tile-per-CTA, each with and without the halo-reuse
     A pipeline -- all compute the same convolution (up to the bf16 rounding of a different accumulation order)
@@ -125,7 +126,7 @@ def test_tc_fprop_variants_match(K, shape):
     ref_f, ref_d = FB().conv_fprop(x, wq, b, g), FB().conv_dgrad(dy, wq, g)
     ref_r = FB().conv_fprop(x, wq, b, g, relu=True, residual=r)
     try:
-        for variant in (3, 2, 1):
+        for variant in (4, 3, 2, 1):
             for halo in (1, 0):
                 _lib.lib.ctgan_set_fprop_variant(variant)
                 _lib.lib.ctgan_set_fprop_halo(halo)
@@ -134,7 +135,7 @@ def test_tc_fprop_variants_match(K, shape):
                 yr = K.conv_fprop(to_dev(x), w.cuda(), b.cuda(), g, relu=True, residual=to_dev(r))
                 assert rel(yf, ref_f) < 1e-2 and rel(yd, ref_d) < 1e-2 and rel(yr, ref_r) < 1e-2, (variant, halo)
     finally:
-        _lib.lib.ctgan_set_fprop_variant(3)
+        _lib.lib.ctgan_set_fprop_variant(4)
         _lib.lib.ctgan_set_fprop_halo(1)
 
 
