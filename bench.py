@@ -213,7 +213,7 @@ def run_ours(args):
     if args.no_graph:
         gt = None
     else:
-        gt = GraphedTrainer(tr, (dev_x[0], dev_y[0]))
+        gt = GraphedTrainer(tr, (dev_x[0], dev_y[0]), pregen_steps=0 if args.no_pregen else N_CRITIC)
     state = {'it': 0, 'b': 0}
 
     def iteration(e2e):
@@ -225,6 +225,9 @@ def run_ours(args):
                 g = gt.gen_step()
                 if e2e:
                     host_out[N_CRITIC, 0:1].copy_(g.reshape(-1)[:1], non_blocking=True)
+            if gt.pregen_steps:                # fakes of the 5 critic steps in one generator forward (their labels first)
+                idx = [(state['b'] + 1 + i) % pool for i in range(N_CRITIC)]
+                gt.begin_iteration(src_y[idx])
             for i in range(N_CRITIC):
                 b = state['b'] = (state['b'] + 1) % pool
                 out = gt.critic_step(src_x[b], src_y[b])
@@ -284,7 +287,7 @@ def run_ours(args):
     it_s = world * args.steps / (ms * 1e-3)
     it_s_e2e = world * args.steps / (ms_e2e * 1e-3)
     if gt is not None:
-        launches = args.steps * (gt.gen_kernels + N_CRITIC * gt.critic_kernels)
+        launches = args.steps * (gt.gen_kernels + N_CRITIC * gt.critic_kernels + gt.pregen_kernels)
     else:
         launches = eager_launches
     roof = roofline_dominant_kernel(torch, peaks)
@@ -303,7 +306,8 @@ def run_ours(args):
         },
         'clocks': clocks,
         'e2e': {'value': it_s_e2e, 'unit': UNIT, 'ms_per_step': ms_e2e / args.steps,
-                'h2d_bytes_per_step': N_CRITIC * (BATCH * 3072 * 4 + BATCH * 4 + 4) + 4,
+                'h2d_bytes_per_step': N_CRITIC * (BATCH * 3072 * 4 + BATCH * 4 + 4) + 4 +
+                                      (N_CRITIC * BATCH * 4 if (gt is not None and gt.pregen_steps) else 0),
                 'd2h_bytes_per_step': N_CRITIC * 32 + 4},
         'gpu_launches': int(launches),
         'roofline': roof,
@@ -325,6 +329,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-graph', action='store_true', help='launch every kernel eagerly (debug / profiling)')
+    ap.add_argument('--no-pregen', action='store_true', help='one generator forward per critic step instead of one per iteration')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     if args.impl == 'reference':

@@ -223,14 +223,25 @@ class Trainer:
         finally:
             BN_GROUPS = 1
 
-    def critic_forward_backward(self, all_real_data_int, all_real_labels, with_metrics=False):
+    def generate_fakes(self, labels_steps):
+        """Fake batches for S consecutive critic steps in ONE generator forward (the generator does not change
+        between the CRITIC_ITERS critic steps of an iteration, :384-394): labels_steps = the S*B real labels,
+        step-major.  Batch-norm statistics stay per 32-sample device split (S*N_DEVICES groups), so every step's
+        fakes are what its own Generator call (:196-199) would produce from the same noise."""
+        S, h = labels_steps.shape[0] // self.B, self.B // N_DEVICES
+        with torch.no_grad():
+            return self._generate([('z.%d.%d' % (k, i), h) for k in range(S) for i in range(N_DEVICES)], labels_steps,
+                                  S * self.B)
+
+    def critic_forward_backward(self, all_real_data_int, all_real_labels, with_metrics=False, fake_data=None):
         RNG = self.rng
         B = all_real_data_int.shape[0]
         h = B // N_DEVICES
-        with torch.no_grad():
-            RNG.begin_stack([h] * N_DEVICES)
-            fake_data = self._generate([('z.%d' % i, h) for i in range(N_DEVICES)], all_real_labels, B)
-            RNG.end_stack()
+        if fake_data is None:
+            with torch.no_grad():
+                RNG.begin_stack([h] * N_DEVICES)
+                fake_data = self._generate([('z.%d' % i, h) for i in range(N_DEVICES)], all_real_labels, B)
+                RNG.end_stack()
         if RNG.replay is not None:                                                              # golden-vector tests
             all_real_data = K.add(K.prep_real(all_real_data_int, 256., 0.), RNG.uniform('dequant', all_real_data_int.shape))
         else:
@@ -274,9 +285,10 @@ class Trainer:
         res.update(metrics)
         return res
 
-    def critic_step(self, all_real_data_int, all_real_labels, iteration=0, with_metrics=False, use_device_lr=False):
+    def critic_step(self, all_real_data_int, all_real_labels, iteration=0, with_metrics=False, use_device_lr=False,
+                    fake_data=None):
         self.disc_opt.zero_grad()
-        res = self.critic_forward_backward(all_real_data_int, all_real_labels, with_metrics)
+        res = self.critic_forward_backward(all_real_data_int, all_real_labels, with_metrics, fake_data=fake_data)
         world = self.disc_opt.all_reduce()
         self.disc_opt.step(self.lr(iteration), world, use_device_lr=use_device_lr)
         self.rng.end_step()

@@ -74,10 +74,15 @@ class _Step:
 
 
 class GraphedTrainer:
-    """Wraps a Trainer (gan_cifar_resnet / gan_cifar / gan_mnist) built with graph_safe_rng=True."""
+    """Wraps a Trainer (gan_cifar_resnet / gan_cifar / gan_mnist) built with graph_safe_rng=True.
 
-    def __init__(self, trainer, example_inputs, warmup=3):
+    pregen_steps = S > 0 (trainers with generate_fakes): the fake batches of the next S critic steps come from ONE
+    generator forward, replayed by begin_iteration(labels of those S steps) -- the generator is constant between two
+    generator steps, and one 5x64-sample forward costs far less than five 64-sample forwards of latency-bound kernels."""
+
+    def __init__(self, trainer, example_inputs, warmup=3, pregen_steps=0):
         self.tr = tr = trainer
+        self.pregen_steps = pregen_steps if hasattr(trainer, 'generate_fakes') else 0
         self.static_inputs = tuple(torch.empty_like(t) for t in example_inputs)
         for s, t in zip(self.static_inputs, example_inputs):
             s.copy_(t)
@@ -86,7 +91,16 @@ class GraphedTrainer:
             raise RuntimeError('GraphedTrainer needs a Trainer created with graph_safe_rng=True')
         tr.rng.record = False
 
+        S = self.pregen_steps
+        if S:
+            dev, B = example_inputs[0].device, example_inputs[0].shape[0]
+            self.labels_all = example_inputs[1].repeat(S).contiguous()
+            self.fake_cur = torch.zeros(B, example_inputs[0].shape[1], dtype=torch.float32, device=dev)
+            self._k = 0
+
         def critic_fb():
+            if S:
+                return tr.critic_forward_backward(*self.static_inputs, fake_data=self.fake_cur)['out']
             return tr.critic_forward_backward(*self.static_inputs)['out']
 
         def gen_fb():
@@ -107,15 +121,36 @@ class GraphedTrainer:
         self.critic = _Step(tr.disc_opt, critic_fb, tr.rng, None)
         self.gen = _Step(tr.gen_opt, gen_fb, tr.rng, self.critic.pool)
         self.critic_kernels, self.gen_kernels = self.critic.kernels, self.gen.kernels
+        self.pregen_kernels = 0
+        if S:
+            k0 = K._lib.lib.ctgan_kernel_launches()
+            self.pregen = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.pregen, pool=self.critic.pool):
+                self.fakes_all = tr.generate_fakes(self.labels_all)
+                tr.rng.end_step()
+            self.pregen_kernels = K._lib.lib.ctgan_kernel_launches() - k0
 
     def _lr(self):
         return self.tr.lr(self.iteration) if hasattr(self.tr, 'lr') else None
+
+    def begin_iteration(self, labels_all, non_blocking=True):
+        """pregen mode: labels_all = the real labels of the next pregen_steps critic batches (step-major, device or
+        pinned host); replays the batched generator forward."""
+        self.labels_all.copy_(labels_all.reshape(-1), non_blocking=non_blocking)
+        self.pregen.replay()
+        self._k = 0
 
     def critic_step(self, *inputs, non_blocking=True):
         """inputs: tensors (device or pinned host) copied into the static buffers, then one replay.
         Returns the static float[8] loss tensor {cost, wgan, ct, gp, acgan, ...} (device)."""
         for s, t in zip(self.static_inputs, inputs):
             s.copy_(t, non_blocking=non_blocking)
+        if self.pregen_steps:
+            if self._k >= self.pregen_steps:
+                raise RuntimeError('GraphedTrainer: begin_iteration() must precede every %d critic steps' % self.pregen_steps)
+            B = self.fake_cur.shape[0]
+            self.fake_cur.copy_(self.fakes_all[self._k * B:(self._k + 1) * B])
+            self._k += 1
         self.tr.disc_opt.set_device_lr(self._lr())
         return self.critic.replay()
 

@@ -218,7 +218,10 @@ class FlatAdam:
         self.flat_m = torch.zeros(total, dtype=torch.float32, device=dev)
         self.flat_v = torch.zeros(total, dtype=torch.float32, device=dev)
         self.lr_t_dev = torch.zeros(1, dtype=torch.float32, device=dev)
-        self._lr_t_pinned = torch.zeros(1, dtype=torch.float32).pin_memory() if dev.type == 'cuda' else None
+        # lr_t staging: a RING of pinned slots -- the host runs many replays ahead of the device, so a single slot
+        # would be overwritten before its asynchronous upload has executed
+        self._lr_ring = torch.zeros(64, dtype=torch.float32).pin_memory() if dev.type == 'cuda' else None
+        self._lr_ring_ev, self._lr_ring_i = [None] * 64, 0
         self.params = {}
         new = {}
         for n, p in named.items():
@@ -278,8 +281,15 @@ class FlatAdam:
         """Host side of a graph replay: bump t and upload lr_t (async, pinned)."""
         if advance:
             self.t += 1
-        self._lr_t_pinned[0] = self.lr_t(lr)
-        self.lr_t_dev.copy_(self._lr_t_pinned, non_blocking=True)
+        i = self._lr_ring_i % 64
+        self._lr_ring_i += 1
+        if self._lr_ring_ev[i] is not None:
+            self._lr_ring_ev[i].synchronize()           # the upload that last used this slot has executed
+        self._lr_ring[i] = self.lr_t(lr)
+        self.lr_t_dev.copy_(self._lr_ring[i:i + 1], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._lr_ring_ev[i] = ev
 
     def state_dict(self):
         return {'t': self.t, 'p': {n: q.detach().clone() for n, q in self.params.items()},

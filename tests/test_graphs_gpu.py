@@ -1,0 +1,115 @@
+"""GPU tests of the CUDA-graph / stream-branch execution of the training step (graphs.GraphedTrainer): replaying the
+captured graphs must train exactly like launching the same steps eagerly, with and without the batched pre-generation of
+the fake batches, and the stream branches must not change a step's result."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _trainer(seed=11, B=16, dtype=torch.bfloat16):
+    import ctgan_b200.gan_cifar_resnet as R
+    np.random.seed(1234)
+    return R.Trainer(device='cuda', seed=seed, act_dtype=dtype, batch_size=B, graph_safe_rng=True)
+
+
+def _batches(n, B, seed=5):
+    rs = np.random.RandomState(seed)
+    xs = torch.from_numpy(rs.randint(0, 256, (n, B, 3072)).astype('int32')).cuda()
+    ys = torch.from_numpy(rs.randint(0, 10, (n, B)).astype('int32')).cuda()
+    return xs, ys
+
+
+def _rel(a, b):
+    return ((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30)).item()
+
+
+def test_generate_fakes_matches_per_step_generation():
+    """Rows of step 0 of a batched S-step generator forward == the S=1 forward from the same noise (batch-norm
+    statistics are per 32-sample split), and a critic step fed those fakes == the step generating its own."""
+    B = 16
+    xs, ys = _batches(3, B)
+    # one model per process (tflib's module-level parameter dict): build, run and read each trainer in turn
+    a = _trainer(B=B); one = a.generate_fakes(ys[0]).clone()
+    b = _trainer(B=B); three = b.generate_fakes(ys.reshape(-1)).clone()
+    assert three.shape == (3 * B, 3072)
+    assert torch.equal(three[:B], one)
+    assert not torch.equal(three[B:2 * B], three[:B])
+    c = _trainer(B=B); c.disc_opt.zero_grad(); r1 = c.critic_forward_backward(xs[0], ys[0])
+    g1 = c.disc_opt.flat_g.clone()
+    d = _trainer(B=B); fake = d.generate_fakes(ys[0]); d.disc_opt.zero_grad()
+    r2 = d.critic_forward_backward(xs[0], ys[0], fake_data=fake)
+    g2 = d.disc_opt.flat_g.clone()
+    assert torch.equal(r1['fake_data'], fake)
+    assert _rel(r2['out'][:5], r1['out'][:5]) < 1e-5
+    assert _rel(g2, g1) < 1e-4
+
+
+@pytest.mark.parametrize('pregen', [0, 2])
+def test_graph_replay_trains_like_eager(pregen):
+    """3 warm-up steps + 2 iterations (1 generator step + 2 critic steps): GraphedTrainer replays vs the same sequence
+    launched eagerly from the same seeds (differences: atomic accumulation order only)."""
+    from ctgan_b200.graphs import GraphedTrainer
+    B, NC = 16, 2
+    xs, ys = _batches(1 + 2 * NC, B)
+    graphed = _trainer(B=B)
+    gt = GraphedTrainer(graphed, (xs[0], ys[0]), warmup=3, pregen_steps=pregen)
+    for it in range(2):
+        gt.iteration = it
+        gt.gen_step()
+        if pregen:
+            gt.begin_iteration(ys[1 + it * NC:1 + (it + 1) * NC])
+        for k in range(NC):
+            out_g = gt.critic_step(xs[1 + it * NC + k], ys[1 + it * NC + k]).clone()
+    torch.cuda.synchronize()
+    pd_g, pg_g = graphed.disc_opt.flat_p.clone(), graphed.gen_opt.flat_p.clone()
+
+    eager = _trainer(B=B)
+    pd0, pg0 = eager.disc_opt.flat_p.clone(), eager.gen_opt.flat_p.clone()
+    for _ in range(3):                                      # GraphedTrainer's warm-up steps
+        eager.disc_opt.set_device_lr(eager.lr(0)); eager.critic_step(xs[0], ys[0], use_device_lr=True)
+        eager.gen_opt.set_device_lr(eager.lr(0)); eager.gen_step(use_device_lr=True)
+    for it in range(2):
+        eager.gen_opt.set_device_lr(eager.lr(it)); eager.gen_step(use_device_lr=True)
+        fakes = None
+        if pregen:
+            fakes = eager.generate_fakes(ys[1 + it * NC:1 + (it + 1) * NC].reshape(-1)); eager.rng.end_step()
+        for k in range(NC):
+            eager.disc_opt.set_device_lr(eager.lr(it))
+            f = fakes[k * B:(k + 1) * B] if pregen else None
+            out_e = eager.critic_step(xs[1 + it * NC + k], ys[1 + it * NC + k], use_device_lr=True, fake_data=f)['out']
+    torch.cuda.synchronize()
+    pd_e, pg_e = eager.disc_opt.flat_p.clone(), eager.gen_opt.flat_p.clone()
+    print('update-relative differences: D %.3e  G %.3e' % (_rel(pd_g - pd0, pd_e - pd0), _rel(pg_g - pg0, pg_e - pg0)))
+    # GAN dynamics amplify the bf16 / atomic-order noise of two runs to a few percent after 7 critic updates (two eager
+    # runs differ by as much); a wrong learning rate, random stream or stale buffer shows up as tens of percent
+    print('last critic step, graph vs eager:', out_g[:5].tolist(), out_e[:5].tolist())
+    assert _rel(out_g[:5], out_e[:5]) < 0.1
+    # the accumulated UPDATES (7 critic / 5 generator Adam steps) agree; bf16 activation-pattern flips from a different
+    # atomic accumulation order move individual sign-like Adam updates, so this is a statistical bound
+    assert _rel(pd_g - pd0, pd_e - pd0) < 0.25
+    assert _rel(pg_g - pg0, pg_e - pg0) < 0.25
+
+
+def test_stream_branches_do_not_change_a_step():
+    """Side-stream wgrad + gradient-penalty branch vs everything on one stream: same losses and gradients."""
+    import ctgan_b200.kernels as K
+    B = 16
+    xs, ys = _batches(1, B)
+    res = {}
+    for on in (True, False):
+        K.config.side_stream = K.config.branch_streams = on
+        try:
+            tr = _trainer(B=B)
+            tr.disc_opt.zero_grad()
+            out = tr.critic_forward_backward(xs[0], ys[0])['out']
+            tr.gen_opt.zero_grad()
+            tr.gen_forward_backward()
+            torch.cuda.synchronize()
+            res[on] = (out.clone(), tr.disc_opt.flat_g.clone(), tr.gen_opt.flat_g.clone())
+        finally:
+            K.config.side_stream = K.config.branch_streams = True
+    assert _rel(res[True][0][:5], res[False][0][:5]) < 1e-5
+    assert _rel(res[True][1], res[False][1]) < 1e-4
+    assert _rel(res[True][2], res[False][2]) < 1e-4
