@@ -174,6 +174,99 @@ __global__ void bn_apply_kernel(const T* __restrict__ x, const float* __restrict
     }
 }
 
+// ---- BF16 fast paths (C/8 a power of two <= 256): 16-byte accesses, C/8 threads per row --------------------
+// Same workspace layout and finalize kernel as above.  Per thread plain sum / sum of squares over its <= ~64 rows
+// (converted to (mean, M2) before any merge, so the cancellation stays at the 1e-7 level), then Chan merges.
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { f[2 * e] = __bfloat162float(h[e].x); f[2 * e + 1] = __bfloat162float(h[e].y); }
+}
+__global__ void __launch_bounds__(256)
+bn_stats_bf16_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ ws, int64_t Rg, int C, int rows_per_block, int nbg) {
+    __shared__ float sh_mean[2048], sh_m2[2048], sh_cnt[256];
+    const int tpr = C >> 3;
+    const int cg = threadIdx.x % tpr, rl = threadIdx.x / tpr, rstep = 256 / tpr;
+    const int g = blockIdx.x / nbg, rb = blockIdx.x - g * nbg;
+    const int64_t r0 = (int64_t)g * Rg + (int64_t)rb * rows_per_block;
+    const int64_t r1 = min((int64_t)(g + 1) * Rg, r0 + rows_per_block);
+    float s[8], ss[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { s[e] = 0.f; ss[e] = 0.f; }
+    const __nv_bfloat16* base = x + cg * 8;
+    int64_t r = r0 + rl;
+    float cnt = 0.f;
+    for (; r + 3 * (int64_t)rstep < r1; r += 4 * (int64_t)rstep) {
+        uint4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = __ldg(reinterpret_cast<const uint4*>(base + (r + u * (int64_t)rstep) * C));
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            float f[8];
+            unpack8(v[u], f);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { s[e] += f[e]; ss[e] = fmaf(f[e], f[e], ss[e]); }
+        }
+        cnt += 4.f;
+    }
+    for (; r < r1; r += rstep) {
+        float f[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(base + r * C)), f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { s[e] += f[e]; ss[e] = fmaf(f[e], f[e], ss[e]); }
+        cnt += 1.f;
+    }
+    const float inv = cnt > 0.f ? 1.f / cnt : 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const float m = s[e] * inv;
+        sh_mean[rl * C + cg * 8 + e] = m;
+        sh_m2[rl * C + cg * 8 + e] = fmaxf(ss[e] - s[e] * m, 0.f);
+    }
+    if (cg == 0) sh_cnt[rl] = cnt;
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += 256) {
+        float n = 0.f, mean = 0.f, m2 = 0.f;
+        for (int k = 0; k < rstep; ++k) chan_merge(n, mean, m2, sh_cnt[k], sh_mean[k * C + c], sh_m2[k * C + c]);
+        ws[((int64_t)blockIdx.x * C + c) * 2 + 0] = mean;
+        ws[((int64_t)blockIdx.x * C + c) * 2 + 1] = m2;
+    }
+}
+
+// blockIdx.y = sample, blockIdx.x = chunk of its HW rows: the per-(sample, channel) scale / shift are computed once
+// per thread, then y = relu(x * scale + shift) with 16-byte loads and stores.
+__global__ void __launch_bounds__(256)
+bn_apply_bf16_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                     const int32_t* __restrict__ labels, const float* __restrict__ mean, const float* __restrict__ invstd,
+                     __nv_bfloat16* __restrict__ y, int HW, int C, int relu, int n_per_group, int rows_per_chunk) {
+    const int tpr = C >> 3;
+    const int cg = threadIdx.x % tpr, rl = threadIdx.x / tpr, rstep = 256 / tpr;
+    const int n = blockIdx.y;
+    const int l = labels ? labels[n] : 0;
+    const int64_t go = (int64_t)(n / n_per_group) * C + cg * 8, lo = (int64_t)l * C + cg * 8;
+    float sc[8], sf[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        sc[e] = gamma[lo + e] * invstd[go + e];
+        sf[e] = beta[lo + e] - mean[go + e] * sc[e];
+    }
+    const int h0 = blockIdx.x * rows_per_chunk, h1 = min(HW, h0 + rows_per_chunk);
+    const int64_t base = (int64_t)n * HW * C + cg * 8;
+    for (int h = h0 + rl; h < h1; h += rstep) {
+        float f[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(x + base + (int64_t)h * C)), f);
+        uint4 ov;
+        __nv_bfloat162* op = reinterpret_cast<__nv_bfloat162*>(&ov);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            float a = fmaf(f[2 * e], sc[2 * e], sf[2 * e]), b = fmaf(f[2 * e + 1], sc[2 * e + 1], sf[2 * e + 1]);
+            if (relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+            op[e] = __floats2bfloat162_rn(a, b);
+        }
+        *reinterpret_cast<uint4*>(y + base + (int64_t)h * C) = ov;
+    }
+}
+
 // ---- backward stage 1: per-(sample, hw split, channel) sums of dy and dy*xhat ---------
 // ws[((n*S + s)*C + c)*2 + {0,1}]
 template <typename T>
@@ -385,12 +478,25 @@ extern "C" int ctgan_bn_fwd(const void* x, const float* gamma, const float* beta
     int nbg = bn_fwd_rowblocks(Rg);
     int rpb = (int)((Rg + nbg - 1) / nbg);
     nbg = (int)((Rg + rpb - 1) / rpb);
+    const int tpr = C / 8;
+    const bool fast = dtype == CTGAN_BF16 && C % 8 == 0 && tpr <= 256 && (tpr & (tpr - 1)) == 0 &&
+                      ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
     dim3 blk(BN_LANES, BN_ROWS), grid(nbg * groups, ceil_div(C, BN_CCH));
-    if (dtype == CTGAN_F32) bn_stats_kernel<float><<<grid, blk, 0, st>>>((const float*)x, ws, Rg, C, rpb, nbg);
+    if (fast) bn_stats_bf16_kernel<<<nbg * groups, 256, 0, st>>>((const __nv_bfloat16*)x, ws, Rg, C, rpb, nbg);
+    else if (dtype == CTGAN_F32) bn_stats_kernel<float><<<grid, blk, 0, st>>>((const float*)x, ws, Rg, C, rpb, nbg);
     else bn_stats_kernel<__nv_bfloat16><<<grid, blk, 0, st>>>((const __nv_bfloat16*)x, ws, Rg, C, rpb, nbg);
     CTGAN_CHECK_LAUNCH("bn_stats");
     bn_finalize_kernel<<<dim3(ceil_div(C, 4), groups), 128, 0, st>>>(ws, save_mean, save_invstd, Rg, C, nbg, rpb, eps);
     CTGAN_CHECK_LAUNCH("bn_finalize");
+    if (fast && N <= 65535) {
+        const int rstep = 256 / tpr;
+        int rpc = 4 * rstep;                                   // >= 4 rows per thread, more when there are plenty of blocks
+        while ((int64_t)N * ceil_div(HW, rpc) > 16 * (int64_t)sm_count() && rpc < HW) rpc *= 2;
+        bn_apply_bf16_kernel<<<dim3(ceil_div(HW, rpc), N), 256, 0, st>>>((const __nv_bfloat16*)x, gamma, beta, labels, save_mean,
+                                                                        save_invstd, (__nv_bfloat16*)y, HW, C, relu, N / groups, rpc);
+        CTGAN_CHECK_LAUNCH("bn_apply");
+        return 0;
+    }
     int g2 = elementwise_grid(R * (C / 4), 256);
     if (dtype == CTGAN_F32)
         bn_apply_kernel<float><<<g2, 256, 0, st>>>((const float*)x, gamma, beta, labels, save_mean, save_invstd, (float*)y, R, HW, C, relu, N / groups);

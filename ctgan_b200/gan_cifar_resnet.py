@@ -73,7 +73,15 @@ def Normalize(name, inputs, labels=None, relu=False):
         return nonlinearity(inputs) if relu else inputs
 
 
+COMMUTE_1X1 = True   # evaluate 1x1 shortcut convs on the low-resolution side of their resampling (same function)
+
+
 def ConvMeanPool(name, input_dim, output_dim, filter_size, inputs, he_init=True, biases=True):
+    if filter_size == 1 and COMMUTE_1X1:
+        # a 1x1 conv commutes with the 2x2 mean (both linear, the bias is constant over the window): pool first,
+        # convolve a quarter of the pixels
+        return lib.ops.conv2d.Conv2D(name, input_dim, output_dim, filter_size, F.mean_pool_2x2(inputs), he_init=he_init,
+                                     biases=biases)
     output = lib.ops.conv2d.Conv2D(name, input_dim, output_dim, filter_size, inputs, he_init=he_init, biases=biases)
     return F.mean_pool_2x2(output)
 
@@ -84,6 +92,11 @@ def MeanPoolConv(name, input_dim, output_dim, filter_size, inputs, he_init=True,
 
 
 def UpsampleConv(name, input_dim, output_dim, filter_size, inputs, he_init=True, biases=True):
+    if filter_size == 1 and COMMUTE_1X1:
+        # a 1x1 conv of a nearest-neighbour upsampled map == the upsampled 1x1 conv (every output pixel sees the same
+        # input pixel): convolve at the low resolution, bit-identical result for a quarter of the work
+        output = lib.ops.conv2d.Conv2D(name, input_dim, output_dim, filter_size, inputs, he_init=he_init, biases=biases)
+        return F.upsample_2x(output)
     output = F.upsample_2x(inputs)
     return lib.ops.conv2d.Conv2D(name, input_dim, output_dim, filter_size, output, he_init=he_init, biases=biases)
 

@@ -1,0 +1,31 @@
+"""Replay time of each captured graph of the ResNet iteration (CUDA events, 20 replays each, inputs resident)."""
+import os, sys
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), '..'))
+import numpy as np, torch
+import ctgan_b200.gan_cifar_resnet as R
+from ctgan_b200.graphs import GraphedTrainer
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+np.random.seed(1234)
+tr = R.Trainer(device='cuda', seed=1234, act_dtype=torch.bfloat16, batch_size=B, graph_safe_rng=True)
+rs = np.random.RandomState(0)
+x = torch.from_numpy(rs.randint(0, 256, (B, 3072)).astype('int32')).cuda()
+y = torch.from_numpy(rs.randint(0, 10, (B,)).astype('int32')).cuda()
+gt = GraphedTrainer(tr, (x, y), pregen_steps=5)
+gt.begin_iteration(y.repeat(5))
+
+def t(fn, reps=20):
+    for _ in range(3): fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps): fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps * 1e3
+
+def critic():
+    gt._k = 0
+    gt.critic_step(x, y)
+print('critic graph  %8.1f us  (%d kernels)' % (t(critic), gt.critic_kernels))
+print('gen graph     %8.1f us  (%d kernels)' % (t(gt.gen_step), gt.gen_kernels))
+print('pregen graph  %8.1f us  (%d kernels)' % (t(lambda: gt.begin_iteration(y.repeat(5))), gt.pregen_kernels))

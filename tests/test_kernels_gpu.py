@@ -229,7 +229,7 @@ def test_prep_real_and_interpolate(K):
 
 @pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize('shape,cond', [((32, 128, 8, 8), True), ((6, 128, 32, 32), False), ((64, 8192), False),
-                                        ((5, 256, 8, 8), False)])
+                                        ((5, 256, 8, 8), False), ((64, 128, 32, 32), True), ((10, 128, 4, 4), True)])
 @pytest.mark.parametrize('groups', [1, 2])
 @pytest.mark.parametrize('relu', [False, True])
 def test_batch_norm(K, dtype, shape, cond, relu, groups):
