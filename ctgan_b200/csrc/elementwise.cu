@@ -144,16 +144,18 @@ __global__ void pool2x2_kernel(const T* __restrict__ x, T* __restrict__ y, int N
 template <typename T, int V>
 __global__ void upsample2x_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H, int W, int C, float scale) {
     using P = Pack<T, V>;
-    const int Ho = 2 * H, Wo = 2 * W, CV = C / V;
-    int64_t total = (int64_t)N * Ho * Wo * CV;
+    // one thread per INPUT vector: one load, four stores (the 2x2 replicas)
+    const int Wo = 2 * W, CV = C / V;
+    int64_t total = (int64_t)N * H * W * CV;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         int cv = i % CV; int64_t t = i / CV;
-        int wo = t % Wo; t /= Wo;
-        int ho = t % Ho; int n = t / Ho;
-        P a = reinterpret_cast<const P*>(x + (((int64_t)n * H + ho / 2) * W + wo / 2) * C)[cv], o;
+        int w = t % W; t /= W;                       // t = n * H + h
+        P a = reinterpret_cast<const P*>(x)[i], o;
 #pragma unroll
         for (int k = 0; k < V; ++k) o.v[k] = from_f<T>(to_f<T>(a.v[k]) * scale);
-        reinterpret_cast<P*>(y)[i] = o;
+        P* row0 = reinterpret_cast<P*>(y + ((2 * t) * Wo + 2 * w) * (int64_t)C) + cv;
+        P* row1 = reinterpret_cast<P*>(y + ((2 * t + 1) * Wo + 2 * w) * (int64_t)C) + cv;
+        row0[0] = o; row0[CV] = o; row1[0] = o; row1[CV] = o;
     }
 }
 template <typename T>
@@ -354,7 +356,7 @@ extern "C" int ctgan_bias_add(const void* x, const float* b, void* y, int64_t ro
 template <typename T>
 static int launch_resample(bool pool, const void* x, void* y, int N, int H, int W, int C, float scale, cudaStream_t st) {
     constexpr int V = vec_width<T>();
-    const int64_t out_elems = pool ? (int64_t)N * (H / 2) * (W / 2) * C : (int64_t)N * H * W * C * 4;
+    const int64_t out_elems = pool ? (int64_t)N * (H / 2) * (W / 2) * C : (int64_t)N * H * W * C;   // threads: pool = outputs, upsample = inputs
     const bool vec = C % V == 0 && aligned16(x) && aligned16(y);
     const int grid = elementwise_grid(vec ? out_elems / V : out_elems, 256);
     if (pool) {

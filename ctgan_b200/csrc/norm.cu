@@ -317,6 +317,92 @@ bn_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T*
     }
 }
 
+// BF16 fast path of stage 1 (same workspace layout): blockIdx.y = sample, blockIdx.x = hw split.
+__global__ void __launch_bounds__(256)
+bn_bwd_reduce_bf16_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
+                          const __nv_bfloat16* __restrict__ y, const float* __restrict__ mean,
+                          const float* __restrict__ invstd, float* __restrict__ ws, int HW, int C, int S, int relu,
+                          int n_per_group) {
+    __shared__ float sh1[2048], sh2[2048];
+    const int tpr = C >> 3;
+    const int cg = threadIdx.x % tpr, rl = threadIdx.x / tpr, rstep = 256 / tpr;
+    const int n = blockIdx.y, sp = blockIdx.x;
+    const int per = (HW + S - 1) / S;
+    const int h0 = sp * per, h1 = min(HW, h0 + per);
+    const int64_t go = (int64_t)(n / n_per_group) * C + cg * 8;
+    float mu[8], is[8], s1[8], s2[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { mu[e] = mean[go + e]; is[e] = invstd[go + e]; s1[e] = 0.f; s2[e] = 0.f; }
+    const int64_t base = (int64_t)n * HW * C + cg * 8;
+    for (int h = h0 + rl; h < h1; h += rstep) {
+        const int64_t off = base + (int64_t)h * C;
+        float g[8], v[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(dy + off)), g);
+        unpack8(__ldg(reinterpret_cast<const uint4*>(x + off)), v);
+        if (relu) {
+            float o[8];
+            unpack8(__ldg(reinterpret_cast<const uint4*>(y + off)), o);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) g[e] = o[e] > 0.f ? g[e] : 0.f;
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { s1[e] += g[e]; s2[e] = fmaf(g[e], (v[e] - mu[e]) * is[e], s2[e]); }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { sh1[rl * C + cg * 8 + e] = s1[e]; sh2[rl * C + cg * 8 + e] = s2[e]; }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += 256) {
+        float a = 0.f, b = 0.f;
+        for (int k = 0; k < rstep; ++k) { a += sh1[k * C + c]; b += sh2[k * C + c]; }
+        ws[(((int64_t)n * S + sp) * C + c) * 2 + 0] = a;
+        ws[(((int64_t)n * S + sp) * C + c) * 2 + 1] = b;
+    }
+}
+
+// BF16 fast path of stage 3: blockIdx.y = sample, blockIdx.x = chunk of its HW rows.
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_bf16_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
+                         const __nv_bfloat16* __restrict__ y, const float* __restrict__ gamma,
+                         const int32_t* __restrict__ labels, const float* __restrict__ mean,
+                         const float* __restrict__ invstd, const float* __restrict__ coef, __nv_bfloat16* __restrict__ dx,
+                         int HW, int C, int relu, int n_per_group, int groups, int rows_per_chunk) {
+    const int tpr = C >> 3;
+    const int cg = threadIdx.x % tpr, rl = threadIdx.x / tpr, rstep = 256 / tpr;
+    const int n = blockIdx.y;
+    const int l = labels ? labels[n] : 0;
+    const int64_t go = (int64_t)(n / n_per_group) * C + cg * 8, lo = (int64_t)l * C + cg * 8;
+    float mu[8], is[8], gm[8], c1[8], c2[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        mu[e] = mean[go + e]; is[e] = invstd[go + e]; gm[e] = gamma[lo + e];
+        c1[e] = coef[go + e]; c2[e] = coef[(int64_t)groups * C + go + e];
+    }
+    const int h0 = blockIdx.x * rows_per_chunk, h1 = min(HW, h0 + rows_per_chunk);
+    const int64_t base = (int64_t)n * HW * C + cg * 8;
+    for (int h = h0 + rl; h < h1; h += rstep) {
+        const int64_t off = base + (int64_t)h * C;
+        float g[8], v[8], o[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(dy + off)), g);
+        unpack8(__ldg(reinterpret_cast<const uint4*>(x + off)), v);
+        if (relu) {
+            float yo[8];
+            unpack8(__ldg(reinterpret_cast<const uint4*>(y + off)), yo);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) g[e] = yo[e] > 0.f ? g[e] : 0.f;
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const float xh = (v[e] - mu[e]) * is[e];
+            o[e] = is[e] * (gm[e] * g[e] - c1[e] - xh * c2[e]);
+        }
+        uint4 ov;
+        __nv_bfloat162* op = reinterpret_cast<__nv_bfloat162*>(&ov);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) op[e] = __floats2bfloat162_rn(o[2 * e], o[2 * e + 1]);
+        *reinterpret_cast<uint4*>(dx + off) = ov;
+    }
+}
+
 // ---- backward stage 2: per channel: table gradients + the two means BN needs ----------
 // coef[g*C + c] = mean_Rg(gamma_l * dy), coef[G*C + g*C + c] = mean_Rg(gamma_l * dy * xhat).
 // One warp per channel; the per-label table sums (shared by all groups) go through shared-memory atomics.
@@ -519,14 +605,31 @@ extern "C" int ctgan_bn_bwd(const void* dy, const void* x, const void* y, const 
     const int64_t R = (int64_t)N * HW, Rg = R / groups;
     int S = bn_bwd_splits(HW);
     float* coef = ws + (int64_t)N * S * C * 2;
+    const int tpr = C / 8;
+    const bool fast = dtype == CTGAN_BF16 && C % 8 == 0 && tpr <= 256 && (tpr & (tpr - 1)) == 0 && N <= 65535 &&
+                      ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx) |
+                        reinterpret_cast<uintptr_t>(y)) & 15) == 0;
     dim3 blk(BN_LANES, BN_ROWS), grid(N * S, ceil_div(C, BN_CCH));
-    if (dtype == CTGAN_F32)
+    if (fast)
+        bn_bwd_reduce_bf16_kernel<<<dim3(S, N), 256, 0, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (const __nv_bfloat16*)y,
+                                                             save_mean, save_invstd, ws, HW, C, S, relu, N / groups);
+    else if (dtype == CTGAN_F32)
         bn_bwd_reduce_kernel<float><<<grid, blk, 0, st>>>((const float*)dy, (const float*)x, (const float*)y, save_mean, save_invstd, ws, HW, C, S, relu, N / groups);
     else
         bn_bwd_reduce_kernel<__nv_bfloat16><<<grid, blk, 0, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (const __nv_bfloat16*)y, save_mean, save_invstd, ws, HW, C, S, relu, N / groups);
     CTGAN_CHECK_LAUNCH("bn_bwd_reduce");
     bn_bwd_finalize_kernel<<<ceil_div(C, 4), 128, sizeof(float) * 8 * n_labels, st>>>(ws, gamma, labels, dgamma, dbeta, coef, N, S, C, n_labels, 1.f / (float)Rg, groups);
     CTGAN_CHECK_LAUNCH("bn_bwd_finalize");
+    if (fast) {
+        const int rstep = 256 / tpr;
+        int rpc = 4 * rstep;
+        while ((int64_t)N * ceil_div(HW, rpc) > 16 * (int64_t)sm_count() && rpc < HW) rpc *= 2;
+        bn_bwd_apply_bf16_kernel<<<dim3(ceil_div(HW, rpc), N), 256, 0, st>>>(
+            (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (const __nv_bfloat16*)y, gamma, labels, save_mean, save_invstd, coef,
+            (__nv_bfloat16*)dx, HW, C, relu, N / groups, groups, rpc);
+        CTGAN_CHECK_LAUNCH("bn_bwd_apply");
+        return 0;
+    }
     int g2 = elementwise_grid(R * (C / 4), 256);
     if (dtype == CTGAN_F32)
         bn_bwd_apply_kernel<float><<<g2, 256, 0, st>>>((const float*)dy, (const float*)x, (const float*)y, gamma, labels, save_mean, save_invstd, coef, (float*)dx, R, HW, C, relu, N / groups, groups);
