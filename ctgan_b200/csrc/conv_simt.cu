@@ -19,6 +19,13 @@ int try_dgrad(const ctgan_conv_desc* d, const void* dy, const float* w, void* dx
 bool wgrad_ok(const ctgan_conv_desc* d, const void* x, const void* dy);
 int try_wgrad(const ctgan_conv_desc* d, const void* x, const void* dy, float* dw, cudaStream_t st, int* rc);
 }
+namespace head {   // conv_head.cu: Linear(K -> N <= 16) on 2-D activations (the critic heads)
+int try_fprop(const ctgan_conv_desc* d, const void* x, const float* w, const float* bias, void* y, int flags, cudaStream_t st, int* rc);
+int try_dgrad(const ctgan_conv_desc* d, const void* dy, const float* w, void* dx, cudaStream_t st, int* rc);
+int try_wgrad(const ctgan_conv_desc* d, const void* x, const void* dy, float* dw, cudaStream_t st, int* rc);
+bool ok(const ctgan_conv_desc* d);
+}
+
 
 enum { MODE_FPROP = 0, MODE_DGRAD = 1, MODE_WGRAD = 2 };
 
@@ -227,6 +234,7 @@ extern "C" int ctgan_conv_fprop(const ctgan_conv_desc* d, const void* x, const f
                                 const float* bias, void* y, int flags, void* stream) {
     if (int r = check_desc(d)) return r;
     CTGAN_REQUIRE(x && w && y, CTGAN_ERR_BAD_DESC, "conv_fprop: null pointer");
+    { int rc = 0; if (head::try_fprop(d, x, w, bias, y, flags, as_stream(stream), &rc)) return rc; }
     { int rc = 0; if (thin::try_fprop(d, x, w, bias, y, flags, as_stream(stream), &rc)) return rc; }
     Geom g = make_geom(d);
     int64_t M64 = (int64_t)d->N * d->Ho * d->Wo;
@@ -242,6 +250,7 @@ extern "C" int ctgan_conv_dgrad(const ctgan_conv_desc* d, const void* dy, const 
                                 void* dx, void* stream) {
     if (int r = check_desc(d)) return r;
     CTGAN_REQUIRE(dy && w && dx, CTGAN_ERR_BAD_DESC, "conv_dgrad: null pointer");
+    { int rc = 0; if (head::try_dgrad(d, dy, w, dx, as_stream(stream), &rc)) return rc; }
     { int rc = 0; if (thin::try_dgrad(d, dy, w, dx, as_stream(stream), &rc)) return rc; }
     Geom g = make_geom(d);
     int64_t M64 = (int64_t)d->N * d->H * d->W;
@@ -257,6 +266,15 @@ extern "C" int ctgan_conv_wgrad(const ctgan_conv_desc* d, const void* x, const v
                                 float* dw, int accumulate, void* stream) {
     if (int r = check_desc(d)) return r;
     CTGAN_REQUIRE(x && dy && dw, CTGAN_ERR_BAD_DESC, "conv_wgrad: null pointer");
+    if (head::ok(d)) {
+        cudaStream_t ts = as_stream(stream);
+        if (!accumulate) {
+            cudaError_t e = cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)d->Cin * d->Cout, ts);
+            if (e != cudaSuccess) return cuda_status(e, "conv_wgrad memset");
+        }
+        int rc = 0;
+        if (head::try_wgrad(d, x, dy, dw, ts, &rc)) return rc;
+    }
     if (thin::wgrad_ok(d, x, dy)) {
         cudaStream_t ts = as_stream(stream);
         if (!accumulate) {
