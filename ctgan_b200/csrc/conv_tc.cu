@@ -1716,7 +1716,7 @@ extern "C" int ctgan_conv_wgrad_tc(const ctgan_conv_desc* d, const void* x, cons
     // layers are bound by the latency of the per-CTA K loop, not by the 49 K reductions each CTA adds
     int splits = sm_count() / (tiles * tap_groups);
     if (splits < 1) splits = 1;
-    int max_splits = total_chunks / 4; if (max_splits < 1) max_splits = 1;
+    int max_splits = total_chunks / 4; if (max_splits < 1) max_splits = 1;     // (2..16 chunks per CTA measure the same)
     if (splits > max_splits) splits = max_splits;
     p.chunks_per_split = ceil_div(total_chunks, splits);
     splits = ceil_div(total_chunks, p.chunks_per_split);

@@ -25,7 +25,7 @@ def run(N, H, C, k, variant, reps=40):
     fl = 2.0 * N * H * H * C * C * k * k
     print('wgrad N=%4d %2dx%-2d k=%d variant=%d  %8.1f us  %7.1f TFLOP/s' % (N, H, H, k, variant, us, fl / us / 1e6), flush=True)
 
-for (N, H, k) in [(192, 32, 3), (128, 32, 3), (192, 16, 3), (192, 8, 3), (64, 8, 3), (192, 32, 1)]:
-    for variant in (1, 2):
+for (N, H, k) in [(192, 32, 3), (64, 32, 3), (192, 16, 3), (64, 16, 3), (128, 16, 3), (192, 8, 3), (64, 8, 3), (128, 8, 3)]:
+    for variant in (2,):
         run(N, H, 128, k, variant)
 _lib.lib.ctgan_set_wgrad_variant(2)
