@@ -22,6 +22,7 @@ class Config:
     use_thin_tc = True       # route 3-channel-side convs through the im2col tensor-core path
     side_stream = True       # run direct-accumulation wgrad / bias-grad launches on a second stream
     branch_streams = True    # run independent sub-graphs of a step (GP pass vs stacked pass) as stream branches
+    branch_priority = -1     # CUDA stream priority of the branch stream (lower = higher priority)
     tc_min_rows = 1          # (tunable) minimum GEMM rows to prefer the tensor-core path
 
 
@@ -131,7 +132,8 @@ def fork_branch(t):
         return None
     dev = t.device.index
     if dev not in _branch_streams:
-        _branch_streams[dev] = torch.cuda.Stream(device=dev)
+        # high priority: the branch is the longer chain of small kernels (3 traversals at batch B vs 2 at 3B)
+        _branch_streams[dev] = torch.cuda.Stream(device=dev, priority=config.branch_priority)
     ev = torch.cuda.Event()
     ev.record(torch.cuda.current_stream(dev))
     return (dev, ev)

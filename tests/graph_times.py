@@ -6,6 +6,11 @@ import ctgan_b200.gan_cifar_resnet as R
 from ctgan_b200.graphs import GraphedTrainer
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+import ctgan_b200.kernels as K
+if len(sys.argv) > 2:
+    K.config.branch_priority = int(sys.argv[2])
+if len(sys.argv) > 3:
+    K.config.side_stream = K.config.branch_streams = bool(int(sys.argv[3]))
 np.random.seed(1234)
 tr = R.Trainer(device='cuda', seed=1234, act_dtype=torch.bfloat16, batch_size=B, graph_safe_rng=True)
 rs = np.random.RandomState(0)
