@@ -65,13 +65,14 @@ def _dense_like(g, ref_dim4):
 # ------------------------------------------------------------------------- conv family
 class ConvF(Function):
     @staticmethod
-    def forward(ctx, x, w, b, g, out_dtype, col=None):
+    def forward(ctx, x, w, b, g, out_dtype, col=None, residual=None):
         ctx.g = g
         ctx.save_for_backward(x, w)
         ctx.has_bias = b is not None
         ctx.bias = b
         ctx.col = col if col is not None else K.thin_col(x, g, 'x')   # im2col of a 3-channel x: built once, reused by wgrad
-        return K.conv_fprop(x, w, b, g, out_dtype=out_dtype, w_is_param=_is_param(w), col=ctx.col)
+        # residual: y = conv(x) + b + residual in the conv epilogue (the block's skip connection); its gradient is gy
+        return K.conv_fprop(x, w, b, g, out_dtype=out_dtype, w_is_param=_is_param(w), col=ctx.col, residual=residual)
 
     @staticmethod
     def backward(ctx, gy):
@@ -93,7 +94,9 @@ class ConvF(Function):
                 K.on_side(lambda: K.bias_grad(gy.detach(), accumulate_into=b.grad), gy)
             else:
                 gb = K.bias_grad(gy.detach())
-        return gx, gw, gb, None, None, None
+        n_in = len(ctx.needs_input_grad)                 # apply() is called with 5, 6 or 7 arguments
+        g_res = gy if (n_in > 6 and ctx.needs_input_grad[6]) else None
+        return (gx, gw, gb, None, None, None, g_res)[:n_in]
 
 
 class ConvD(Function):
@@ -151,10 +154,15 @@ def ensure_nhwc(x):
     return x
 
 
-def conv2d(x, w, b, k, stride, out_dtype=None):
-    """tf.nn.conv2d(SAME) + bias_add on a logical-NCHW activation."""
+def conv2d(x, w, b, k, stride, out_dtype=None, residual=None):
+    """tf.nn.conv2d(SAME) + bias_add on a logical-NCHW activation (+ an optional residual added in the epilogue)."""
     N, H, W, Cin = K.nhwc_dims(x)
     g = K.same_geom(N, H, W, Cin, w.shape[-1], k, stride)
+    if residual is not None:
+        residual = ensure_nhwc(residual)
+        if residual.dtype != (out_dtype or x.dtype) or tuple(residual.shape) != (N, w.shape[-1], g.Ho, g.Wo):
+            raise RuntimeError('ctgan_b200: residual must have the shape and dtype of the conv output')
+        return ConvF.apply(x, w, b, g, out_dtype or x.dtype, None, residual)
     return ConvF.apply(x, w, b, g, out_dtype or x.dtype)
 
 

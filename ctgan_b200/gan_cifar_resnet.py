@@ -74,6 +74,7 @@ def Normalize(name, inputs, labels=None, relu=False):
 
 
 COMMUTE_1X1 = True   # evaluate 1x1 shortcut convs on the low-resolution side of their resampling (same function)
+FUSE_SKIP_ADD = True  # shortcut + conv_2(...) inside conv_2's epilogue where conv_2 is not followed by pooling
 
 
 def ConvMeanPool(name, input_dim, output_dim, filter_size, inputs, he_init=True, biases=True):
@@ -130,6 +131,9 @@ def ResidualBlock(name, input_dim, output_dim, filter_size, inputs, resample=Non
     output = Normalize(name + '.N1', output, labels=labels, relu=True)
     output = conv_1(name + '.Conv1', filter_size=filter_size, inputs=output)
     output = Normalize(name + '.N2', output, labels=labels, relu=True)
+    if resample != 'down' and FUSE_SKIP_ADD:
+        # conv_2 is a plain Conv2D at the shortcut's resolution: the skip connection is added in its epilogue
+        return conv_2(name + '.Conv2', filter_size=filter_size, inputs=output, residual=shortcut)
     output = conv_2(name + '.Conv2', filter_size=filter_size, inputs=output)
 
     return F.add(shortcut, output)
