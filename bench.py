@@ -138,11 +138,12 @@ class ClockSampler:
 
 # ----------------------------------------------------------------------------- our arm
 def roofline_dominant_kernel(torch, peaks):
-    """tcgen05 implicit-GEMM conv of Discriminator.1.Conv2's shape on the stacked real+fake pass:
-    128 images, 32x32, 3x3, 128->128 (55 % of the critic's forward FLOPs).  Timed alone with CUDA
-    events on the launching stream; 6 rotating buffer sets (6 x 67 MB) exceed the 126 MB L2."""
+    """tcgen05 implicit-GEMM conv of Discriminator.1.Conv2 as the critic step launches it: the stacked pass
+    (real', fake', real'' = 3 x 64 = 192 images), 32x32, 3x3, 128->128 -- the single most expensive launch of the
+    step, fprop and (same kernel, flipped filter pack) dgrad.  Timed alone with CUDA events on the launching
+    stream; 6 rotating buffer sets (6 x 101 MB) exceed the 126 MB L2."""
     import ctgan_b200.kernels as K
-    N, H, W, C = 128, 32, 32, 128
+    N, H, W, C = 3 * BATCH, 32, 32, 128
     g = K.same_geom(N, H, W, C, C, 3, 1)
     sets = []
     for i in range(6):
@@ -171,10 +172,10 @@ def roofline_dominant_kernel(torch, peaks):
     traffic = None
     try:
         with open(os.path.join(ROOT, 'profiles', 'roofline_traffic.json')) as f:
-            traffic = json.load(f).get('conv_fprop_tc_128x32x32x128_bytes')
+            traffic = json.load(f).get('conv_fprop_tc_192x32x32x128_bytes')
     except Exception:
         pass
-    return {'bound': 'tensor', 'kernel': 'conv_fprop_tc_pair_kernel (3x3, 128->128, 128x32x32)', 'achieved': achieved,
+    return {'bound': 'tensor', 'kernel': 'conv_fprop_tc_pair_kernel (3x3, 128->128, %dx32x32)' % N, 'achieved': achieved,
             'peak': peaks['burst'], 'peak_source': 'MEASURED_PEAKS.json bf16_tflops (burst; kernel timed alone)'
             if peaks['src'] == 'measured' else 'fallback 1590', 'unit': 'TFLOP/s', 'frac': achieved / peaks['burst'],
             'traffic': traffic, 'flops_per_launch': flops, 'us_per_launch': ms * 1e3}

@@ -1,4 +1,4 @@
-"""ncu target: the dominant tcgen05 kernels at Discriminator.1.Conv2's shape (128 images, 32x32, 3x3, 128->128).
+"""ncu target: the dominant tcgen05 kernels at Discriminator.1.Conv2's shape (the stacked critic pass: 192 images, 32x32, 3x3, 128->128).
   ncu --set full --clock-control none --import-source on -k regex:conv_ -o gpurun_out/prof python tests/ncu_target.py"""
 import os
 import sys
@@ -7,7 +7,7 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), '..'
 import torch
 import ctgan_b200.kernels as K
 
-N, H, C = 128, 32, 128
+N, H, C = 192, 32, 128
 g = K.same_geom(N, H, H, C, C, 3, 1)
 x = torch.randn(N, C, H, H, device='cuda').bfloat16().contiguous(memory_format=torch.channels_last)
 dy = torch.randn(N, C, H, H, device='cuda').bfloat16().contiguous(memory_format=torch.channels_last)
