@@ -582,6 +582,79 @@ conv_fprop_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, cons
 }
 
 // ------------------------------------------------------------------ fprop kernel, persistent, grouped stages
+// Epilogue of one 128-pixel x 128-channel accumulator (persistent kernels): thread = pixel row = TMEM lane; per 32 fp32
+// columns: + bias (+ residual) (ReLU), bf16 pack, and 32-BYTE global accesses (STG.256 / LDG.256) -- a row's 16 channels per
+// instruction are one full sector, half the store instructions of 16-byte accesses.
+__device__ __forceinline__ void lean_epilogue_tile(const FpropParams& p, uint32_t tmem_addr, int q, int lane,
+                                                   int w0, int h0, int n0, int co0, bool relu) {
+    int t = q * 32 + lane;
+    const int bw = t % p.BW; t /= p.BW;
+    const int bh = t % p.BH; const int bn = t / p.BH;
+    const int n = n0 + bn, h = h0 + bh, w = w0 + bw;
+    const bool valid = (n < p.N) && (h < p.H) && (w < p.W);
+    const int64_t pix = ((int64_t)n * p.H + h) * p.W + w;
+    __nv_bfloat16* yrow = p.y + pix * p.Cout + co0;
+    const __nv_bfloat16* rrow = p.residual ? p.residual + pix * p.Cout + co0 : nullptr;
+    const bool wide = ((reinterpret_cast<uintptr_t>(p.y) | reinterpret_cast<uintptr_t>(p.residual)) & 31) == 0;
+#pragma unroll 1
+    for (int c0 = 0; c0 < 128; c0 += 32) {
+        uint32_t v32[32];
+        tmem_ld32(tmem_addr + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v32);
+        if (valid) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 16) {
+                float v[16];
+                if (p.bias) {
+#pragma unroll
+                    for (int e = 0; e < 16; e += 4) {
+                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + co0 + c0 + j + e));
+                        v[e] = b4.x; v[e + 1] = b4.y; v[e + 2] = b4.z; v[e + 3] = b4.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) v[e] = 0.f;
+                }
+#pragma unroll
+                for (int e = 0; e < 16; ++e) v[e] += __uint_as_float(v32[j + e]);
+                if (rrow) {
+                    uint32_t rw[8];
+                    if (wide) {
+                        asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                                     : "=r"(rw[0]), "=r"(rw[1]), "=r"(rw[2]), "=r"(rw[3]), "=r"(rw[4]), "=r"(rw[5]), "=r"(rw[6]), "=r"(rw[7])
+                                     : "l"(rrow + c0 + j));
+                    } else {
+                        const uint4 r0 = *reinterpret_cast<const uint4*>(rrow + c0 + j), r1 = *reinterpret_cast<const uint4*>(rrow + c0 + j + 8);
+                        rw[0] = r0.x; rw[1] = r0.y; rw[2] = r0.z; rw[3] = r0.w; rw[4] = r1.x; rw[5] = r1.y; rw[6] = r1.z; rw[7] = r1.w;
+                    }
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const __nv_bfloat162 r2 = *reinterpret_cast<const __nv_bfloat162*>(&rw[e]);
+                        v[2 * e] += __bfloat162float(r2.x); v[2 * e + 1] += __bfloat162float(r2.y);
+                    }
+                }
+                if (relu) {
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) v[e] = fmaxf(v[e], 0.f);
+                }
+                uint32_t ow[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const __nv_bfloat162 o2 = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+                    ow[e] = *reinterpret_cast<const uint32_t*>(&o2);
+                }
+                if (wide) {
+                    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                                 ::"l"(yrow + c0 + j), "r"(ow[0]), "r"(ow[1]), "r"(ow[2]), "r"(ow[3]), "r"(ow[4]), "r"(ow[5]), "r"(ow[6]), "r"(ow[7])
+                                 : "memory");
+                } else {
+                    *reinterpret_cast<uint4*>(yrow + c0 + j) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+                    *reinterpret_cast<uint4*>(yrow + c0 + j + 8) = make_uint4(ow[4], ow[5], ow[6], ow[7]);
+                }
+            }
+        }
+    }
+}
+
 // Same roles as the persistent kernel above, but the MMA-issuing thread is kept as lean as possible: with N = 128 one
 // tcgen05.mma occupies the tensor pipe for only 64 cycles, so every scalar instruction of the issuing thread between two
 // MMAs shows up as idle tensor time (tests/micro/mma_rate.cu: 75 cycles per MMA with a bare loop, 163 with a barrier
@@ -724,52 +797,9 @@ conv_fprop_tc_lean_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
             const int tw = mt % p.tilesW; mt /= p.tilesW;
             const int th = mt % p.tilesH; const int tn = mt / p.tilesH;
             const int co0 = nb * BLOCK_N;
-            int t = q * 32 + lane;
-            const int bw = t % p.BW; t /= p.BW;
-            const int bh = t % p.BH; const int bn = t / p.BH;
-            const int n = tn * p.BN + bn, h = th * p.BH + bh, w = tw * p.BW + bw;
-            const bool valid = (n < p.N) && (h < p.H) && (w < p.W);
-            const int64_t pix = ((int64_t)n * p.H + h) * p.W + w;
-            __nv_bfloat16* yrow = p.y + pix * p.Cout + co0;
-            const __nv_bfloat16* rrow = p.residual ? p.residual + pix * p.Cout + co0 : nullptr;
             mbar_wait(tfull + 8 * acc, (uint32_t)(it >> 1) & 1u);
             tc_fence_after();
-#pragma unroll 1
-            for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-                uint32_t v32[32];
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + c0), v32);
-                if (valid) {
-#pragma unroll
-                    for (int j = 0; j < 32; j += 8) {
-                        float v[8];
-                        if (p.bias) {
-                            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + co0 + c0 + j));
-                            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + co0 + c0 + j + 4));
-                            v[0] = b0.x; v[1] = b0.y; v[2] = b0.z; v[3] = b0.w; v[4] = b1.x; v[5] = b1.y; v[6] = b1.z; v[7] = b1.w;
-                        } else {
-#pragma unroll
-                            for (int e = 0; e < 8; ++e) v[e] = 0.f;
-                        }
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) v[e] += __uint_as_float(v32[j + e]);
-                        if (rrow) {
-                            uint4 rv = *reinterpret_cast<const uint4*>(rrow + c0 + j);
-                            const __nv_bfloat162* rp = reinterpret_cast<const __nv_bfloat162*>(&rv);
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) { v[2 * e] += __bfloat162float(rp[e].x); v[2 * e + 1] += __bfloat162float(rp[e].y); }
-                        }
-                        if (relu) {
-#pragma unroll
-                            for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
-                        }
-                        uint4 ov;
-                        __nv_bfloat162* op = reinterpret_cast<__nv_bfloat162*>(&ov);
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) op[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
-                        *reinterpret_cast<uint4*>(yrow + c0 + j) = ov;
-                    }
-                }
-            }
+            lean_epilogue_tile(p, tmem_base + (uint32_t)(acc * BLOCK_N), q, lane, tw * p.BW, th * p.BH, tn * p.BN, co0, relu);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty + 8 * acc) : "memory");
@@ -787,54 +817,6 @@ conv_fprop_tc_lean_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
 // accumulators -- 44 KB per 12 MMAs instead of 72 KB.  Two stages of 88 KB; TMEM 2 x (2 x 128) columns double-buffered.
 // Tiles are enumerated n-block-major (tile = nb * m_tiles + mt) and split into contiguous per-CTA ranges, so every warp
 // role derives the same item sequence (pair if the next tile is the next row block of the same image, else single).
-__device__ __forceinline__ void lean_epilogue_tile(const FpropParams& p, uint32_t tmem_addr, int q, int lane,
-                                                   int w0, int h0, int n0, int co0, bool relu) {
-    int t = q * 32 + lane;
-    const int bw = t % p.BW; t /= p.BW;
-    const int bh = t % p.BH; const int bn = t / p.BH;
-    const int n = n0 + bn, h = h0 + bh, w = w0 + bw;
-    const bool valid = (n < p.N) && (h < p.H) && (w < p.W);
-    const int64_t pix = ((int64_t)n * p.H + h) * p.W + w;
-    __nv_bfloat16* yrow = p.y + pix * p.Cout + co0;
-    const __nv_bfloat16* rrow = p.residual ? p.residual + pix * p.Cout + co0 : nullptr;
-#pragma unroll 1
-    for (int c0 = 0; c0 < 128; c0 += 32) {
-        uint32_t v32[32];
-        tmem_ld32(tmem_addr + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v32);
-        if (valid) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-                float v[8];
-                if (p.bias) {
-                    const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + co0 + c0 + j));
-                    const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + co0 + c0 + j + 4));
-                    v[0] = b0.x; v[1] = b0.y; v[2] = b0.z; v[3] = b0.w; v[4] = b1.x; v[5] = b1.y; v[6] = b1.z; v[7] = b1.w;
-                } else {
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) v[e] = 0.f;
-                }
-#pragma unroll
-                for (int e = 0; e < 8; ++e) v[e] += __uint_as_float(v32[j + e]);
-                if (rrow) {
-                    uint4 rv = *reinterpret_cast<const uint4*>(rrow + c0 + j);
-                    const __nv_bfloat162* rp = reinterpret_cast<const __nv_bfloat162*>(&rv);
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) { v[2 * e] += __bfloat162float(rp[e].x); v[2 * e + 1] += __bfloat162float(rp[e].y); }
-                }
-                if (relu) {
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
-                }
-                uint4 ov;
-                __nv_bfloat162* op = reinterpret_cast<__nv_bfloat162*>(&ov);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) op[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
-                *reinterpret_cast<uint4*>(yrow + c0 + j) = ov;
-            }
-        }
-    }
-}
-
 __global__ void __launch_bounds__(192, 1)
 conv_fprop_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_x2,
                           const __grid_constant__ CUtensorMap tmap_w, const FpropParams p, const int m_tiles, const int n_tiles)
