@@ -161,7 +161,7 @@ struct FpropParams {
 };
 
 // Epilogue shared by the fprop kernels: thread = tile row = TMEM lane; 32 fp32 columns per tcgen05.ld,
-// + bias (+ residual) (ReLU), bf16 pack, 16-byte stores.
+// + bias (+ residual) (ReLU), bf16 pack, 32-byte stores.
 template <int BLOCK_N>
 __device__ __forceinline__ void fprop_epilogue(const FpropParams& p, uint32_t tmem_base, const float* s_bias,
                                                int warp, int lane, int w0, int h0, int n0, int co0) {
@@ -175,31 +175,51 @@ __device__ __forceinline__ void fprop_epilogue(const FpropParams& p, uint32_t tm
     __nv_bfloat16* yrow = p.y + pix * p.Cout + co0;
     const __nv_bfloat16* rrow = p.residual ? p.residual + pix * p.Cout + co0 : nullptr;
     const bool relu = (p.flags & CTGAN_EPI_RELU) != 0;
+    const bool wide = ((reinterpret_cast<uintptr_t>(p.y) | reinterpret_cast<uintptr_t>(p.residual)) & 31) == 0;   // 32-byte accesses
 #pragma unroll 1
     for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
         uint32_t acc[32];
         tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, acc);   // warp-collective
         if (valid) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-                float v[8];
+            for (int j = 0; j < 32; j += 16) {
+                float v[16];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(acc[j + e]) + s_bias[c0 + j + e];
+                for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(acc[j + e]) + s_bias[c0 + j + e];
                 if (rrow) {
-                    uint4 rv = *reinterpret_cast<const uint4*>(rrow + c0 + j);
-                    const __nv_bfloat162* rp = reinterpret_cast<const __nv_bfloat162*>(&rv);
+                    uint32_t rw[8];
+                    if (wide) {
+                        asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                                     : "=r"(rw[0]), "=r"(rw[1]), "=r"(rw[2]), "=r"(rw[3]), "=r"(rw[4]), "=r"(rw[5]), "=r"(rw[6]), "=r"(rw[7])
+                                     : "l"(rrow + c0 + j));
+                    } else {
+                        const uint4 r0 = *reinterpret_cast<const uint4*>(rrow + c0 + j), r1 = *reinterpret_cast<const uint4*>(rrow + c0 + j + 8);
+                        rw[0] = r0.x; rw[1] = r0.y; rw[2] = r0.z; rw[3] = r0.w; rw[4] = r1.x; rw[5] = r1.y; rw[6] = r1.z; rw[7] = r1.w;
+                    }
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) { v[2 * e] += __bfloat162float(rp[e].x); v[2 * e + 1] += __bfloat162float(rp[e].y); }
+                    for (int e = 0; e < 8; ++e) {
+                        const __nv_bfloat162 r2 = *reinterpret_cast<const __nv_bfloat162*>(&rw[e]);
+                        v[2 * e] += __bfloat162float(r2.x); v[2 * e + 1] += __bfloat162float(r2.y);
+                    }
                 }
                 if (relu) {
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
+                    for (int e = 0; e < 16; ++e) v[e] = fmaxf(v[e], 0.f);
                 }
-                uint4 ov;
-                __nv_bfloat162* op = reinterpret_cast<__nv_bfloat162*>(&ov);
+                uint32_t ow[8];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) op[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
-                *reinterpret_cast<uint4*>(yrow + c0 + j) = ov;
+                for (int e = 0; e < 8; ++e) {
+                    const __nv_bfloat162 o2 = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+                    ow[e] = *reinterpret_cast<const uint32_t*>(&o2);
+                }
+                if (wide) {
+                    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                                 ::"l"(yrow + c0 + j), "r"(ow[0]), "r"(ow[1]), "r"(ow[2]), "r"(ow[3]), "r"(ow[4]), "r"(ow[5]), "r"(ow[6]), "r"(ow[7])
+                                 : "memory");
+                } else {
+                    *reinterpret_cast<uint4*>(yrow + c0 + j) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+                    *reinterpret_cast<uint4*>(yrow + c0 + j + 8) = make_uint4(ow[4], ow[5], ow[6], ow[7]);
+                }
             }
         }
     }
