@@ -64,6 +64,7 @@ static int launch_map2(const void* a, const void* b, void* out, int64_t n, F f, 
 
 struct AddOp  { __device__ float operator()(float a, float b) const { return a + b; } };
 struct MulOp  { __device__ float operator()(float a, float b) const { return a * b; } };
+struct ReluMaskOp { __device__ float operator()(float g, float y) const { return y > 0.f ? g : 0.f; } };   // g * [relu output > 0]
 struct ScaleOp { float s; __device__ float operator()(float a) const { return a * s; } };
 struct TanhOp { __device__ float operator()(float a) const { return tanhf(a); } };
 struct SigmOp { __device__ float operator()(float a) const { return 1.f / (1.f + __expf(-a)); } };
@@ -113,6 +114,78 @@ __global__ void act_dropout_kernel(const T* __restrict__ x, const float* __restr
         }
         reinterpret_cast<P*>(y)[i] = py;
         if (m) reinterpret_cast<P*>(m)[i] = pm;
+    }
+}
+
+// ---- fused dropout -> (skip connection, ReLU) fork and the mask algebra of its backward ---------------------
+// A residual block input after dropout feeds the block's shortcut (d) AND the block's first ReLU (r = relu(d)):
+//   d = x * md,  r = x * mdr,   md = floor(keep+u)/keep,  mdr = md * [x > 0]        (one kernel instead of two)
+// backward:        gx = gd * md + gr * mdr                                           (mask_sum2: one instead of three)
+// double backward: c -> (c * md, c * mdr)                                            (mask_fork2: one instead of two)
+// `ma == nullptr` means an identity mask on that branch (a fork without dropout).
+template <typename T, int V>
+__global__ void fork_dropout_relu_kernel(const T* __restrict__ x, const float* __restrict__ u, T* __restrict__ d,
+                                         T* __restrict__ r, T* __restrict__ md, T* __restrict__ mdr, int64_t nvec,
+                                         float keep, uint64_t seed, uint64_t offset, const uint64_t* __restrict__ dyn) {
+    using P = Pack<T, V>;
+    if (dyn) offset += dyn[0];
+    const float inv_keep = 1.f / keep;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+        P px = reinterpret_cast<const P*>(x)[i], pd, pr, pmd, pmdr;
+        uint32_t rb[4];
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            const float xv = to_f<T>(px.v[j]);
+            const int64_t e = i * V + j;
+            float uu;
+            if (u) {
+                uu = u[e];
+            } else {
+                const uint64_t se = offset + (uint64_t)e;
+                if (V == 1 || (j & 3) == 0) Philox::block(seed, se >> 2, rb);
+                uu = Philox::to_uniform(rb[se & 3]);
+            }
+            pmd.v[j] = from_f<T>(floorf(keep + uu) * inv_keep);
+            const float mdf = to_f<T>(pmd.v[j]);                       // the ROUNDED multiplier: d == x * md exactly
+            pmdr.v[j] = from_f<T>(xv > 0.f ? mdf : 0.f);
+            pd.v[j] = from_f<T>(xv * mdf);
+            pr.v[j] = from_f<T>(xv > 0.f ? xv * mdf : 0.f);
+        }
+        reinterpret_cast<P*>(d)[i] = pd;
+        reinterpret_cast<P*>(r)[i] = pr;
+        reinterpret_cast<P*>(md)[i] = pmd;
+        reinterpret_cast<P*>(mdr)[i] = pmdr;
+    }
+}
+template <typename T, int V>
+__global__ void mask_sum2_kernel(const T* __restrict__ a, const T* __restrict__ ma, const T* __restrict__ b,
+                                 const T* __restrict__ mb, T* __restrict__ out, int64_t nvec) {
+    using P = Pack<T, V>;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+        P pa = reinterpret_cast<const P*>(a)[i], pb = reinterpret_cast<const P*>(b)[i], pmb = reinterpret_cast<const P*>(mb)[i], po, pma;
+        if (ma) pma = reinterpret_cast<const P*>(ma)[i];
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            const float av = ma ? to_f<T>(pa.v[j]) * to_f<T>(pma.v[j]) : to_f<T>(pa.v[j]);
+            po.v[j] = from_f<T>(fmaf(to_f<T>(pb.v[j]), to_f<T>(pmb.v[j]), av));
+        }
+        reinterpret_cast<P*>(out)[i] = po;
+    }
+}
+template <typename T, int V>
+__global__ void mask_fork2_kernel(const T* __restrict__ c, const T* __restrict__ ma, const T* __restrict__ mb,
+                                  T* __restrict__ o1, T* __restrict__ o2, int64_t nvec) {
+    using P = Pack<T, V>;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+        P pc = reinterpret_cast<const P*>(c)[i], pma = reinterpret_cast<const P*>(ma)[i], pmb = reinterpret_cast<const P*>(mb)[i], p1, p2;
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            const float cv = to_f<T>(pc.v[j]);
+            p1.v[j] = from_f<T>(cv * to_f<T>(pma.v[j]));
+            p2.v[j] = from_f<T>(cv * to_f<T>(pmb.v[j]));
+        }
+        reinterpret_cast<P*>(o1)[i] = p1;
+        reinterpret_cast<P*>(o2)[i] = p2;
     }
 }
 
@@ -341,6 +414,58 @@ extern "C" int ctgan_act_dropout_fwd(const void* x, const float* u, void* y, voi
     if (n <= 0) return 0;
     DISPATCH_T(dtype, return launch_act_dropout<float>(x, u, y, m, n, slope, keep, seed, offset, dyn_offset, as_stream(stream)),
                       return launch_act_dropout<__nv_bfloat16>(x, u, y, m, n, slope, keep, seed, offset, dyn_offset, as_stream(stream)));
+}
+
+template <typename T>
+static int launch_fork(const void* x, const float* u, void* d, void* r, void* md, void* mdr, int64_t n, float keep,
+                       uint64_t seed, uint64_t offset, const uint64_t* dyn, cudaStream_t st) {
+    constexpr int V = vec_width<T>();
+    const bool vec = aligned16(x) && aligned16(d) && aligned16(r) && aligned16(md) && aligned16(mdr) && n % V == 0 && (offset & 3) == 0;
+    if (vec) fork_dropout_relu_kernel<T, V><<<elementwise_grid(n / V, 256), 256, 0, st>>>((const T*)x, u, (T*)d, (T*)r, (T*)md, (T*)mdr, n / V, keep, seed, offset, dyn);
+    else     fork_dropout_relu_kernel<T, 1><<<elementwise_grid(n, 256), 256, 0, st>>>((const T*)x, u, (T*)d, (T*)r, (T*)md, (T*)mdr, n, keep, seed, offset, dyn);
+    CTGAN_CHECK_LAUNCH("fork_dropout_relu");
+    return 0;
+}
+extern "C" int ctgan_fork_dropout_relu(const void* x, const float* u, void* d, void* r, void* md, void* mdr, int64_t n, int dtype,
+                                       float keep, uint64_t seed, uint64_t offset, const uint64_t* dyn_offset, void* stream) {
+    CTGAN_REQUIRE(keep > 0.f && keep <= 1.f && x && d && r && md && mdr, CTGAN_ERR_BAD_DESC, "fork_dropout_relu: bad args");
+    if (n <= 0) return 0;
+    DISPATCH_T(dtype, return launch_fork<float>(x, u, d, r, md, mdr, n, keep, seed, offset, dyn_offset, as_stream(stream)),
+                      return launch_fork<__nv_bfloat16>(x, u, d, r, md, mdr, n, keep, seed, offset, dyn_offset, as_stream(stream)));
+}
+template <typename T>
+static int launch_mask_sum2(const void* a, const void* ma, const void* b, const void* mb, void* out, int64_t n, cudaStream_t st) {
+    constexpr int V = vec_width<T>();
+    const bool vec = aligned16(a) && (!ma || aligned16(ma)) && aligned16(b) && aligned16(mb) && aligned16(out) && n % V == 0;
+    if (vec) mask_sum2_kernel<T, V><<<elementwise_grid(n / V, 256), 256, 0, st>>>((const T*)a, (const T*)ma, (const T*)b, (const T*)mb, (T*)out, n / V);
+    else     mask_sum2_kernel<T, 1><<<elementwise_grid(n, 256), 256, 0, st>>>((const T*)a, (const T*)ma, (const T*)b, (const T*)mb, (T*)out, n);
+    CTGAN_CHECK_LAUNCH("mask_sum2");
+    return 0;
+}
+extern "C" int ctgan_mask_sum2(const void* a, const void* ma, const void* b, const void* mb, void* out, int64_t n, int dtype, void* stream) {
+    CTGAN_REQUIRE(a && b && mb && out, CTGAN_ERR_BAD_DESC, "mask_sum2: null pointer");
+    if (n <= 0) return 0;
+    DISPATCH_T(dtype, return launch_mask_sum2<float>(a, ma, b, mb, out, n, as_stream(stream)),
+                      return launch_mask_sum2<__nv_bfloat16>(a, ma, b, mb, out, n, as_stream(stream)));
+}
+template <typename T>
+static int launch_mask_fork2(const void* c, const void* ma, const void* mb, void* o1, void* o2, int64_t n, cudaStream_t st) {
+    constexpr int V = vec_width<T>();
+    const bool vec = aligned16(c) && aligned16(ma) && aligned16(mb) && aligned16(o1) && aligned16(o2) && n % V == 0;
+    if (vec) mask_fork2_kernel<T, V><<<elementwise_grid(n / V, 256), 256, 0, st>>>((const T*)c, (const T*)ma, (const T*)mb, (T*)o1, (T*)o2, n / V);
+    else     mask_fork2_kernel<T, 1><<<elementwise_grid(n, 256), 256, 0, st>>>((const T*)c, (const T*)ma, (const T*)mb, (T*)o1, (T*)o2, n);
+    CTGAN_CHECK_LAUNCH("mask_fork2");
+    return 0;
+}
+extern "C" int ctgan_mask_fork2(const void* c, const void* ma, const void* mb, void* o1, void* o2, int64_t n, int dtype, void* stream) {
+    CTGAN_REQUIRE(c && ma && mb && o1 && o2, CTGAN_ERR_BAD_DESC, "mask_fork2: null pointer");
+    if (n <= 0) return 0;
+    DISPATCH_T(dtype, return launch_mask_fork2<float>(c, ma, mb, o1, o2, n, as_stream(stream)),
+                      return launch_mask_fork2<__nv_bfloat16>(c, ma, mb, o1, o2, n, as_stream(stream)));
+}
+extern "C" int ctgan_mul_relu_mask(const void* g, const void* y, void* out, int64_t n, int dtype, void* stream) {
+    DISPATCH_T(dtype, return launch_map2<float>(g, y, out, n, ReluMaskOp{}, as_stream(stream), "mul_relu_mask"),
+                      return launch_map2<__nv_bfloat16>(g, y, out, n, ReluMaskOp{}, as_stream(stream), "mul_relu_mask"));
 }
 
 extern "C" int ctgan_bias_add(const void* x, const float* b, void* y, int64_t rows, int C, int dtype, void* stream) {

@@ -65,19 +65,26 @@ def _dense_like(g, ref_dim4):
 # ------------------------------------------------------------------------- conv family
 class ConvF(Function):
     @staticmethod
-    def forward(ctx, x, w, b, g, out_dtype, col=None, residual=None):
+    def forward(ctx, x, w, b, g, out_dtype, col=None, residual=None, relu=False):
         ctx.g = g
         ctx.save_for_backward(x, w)
         ctx.has_bias = b is not None
         ctx.bias = b
         ctx.col = col if col is not None else K.thin_col(x, g, 'x')   # im2col of a 3-channel x: built once, reused by wgrad
         # residual: y = conv(x) + b + residual in the conv epilogue (the block's skip connection); its gradient is gy
-        return K.conv_fprop(x, w, b, g, out_dtype=out_dtype, w_is_param=_is_param(w), col=ctx.col, residual=residual)
+        # relu: the nonlinearity that follows the conv, in the epilogue; its multiplier is [y > 0]
+        y = K.conv_fprop(x, w, b, g, out_dtype=out_dtype, w_is_param=_is_param(w), col=ctx.col, residual=residual, relu=relu)
+        ctx.relu_out = y.detach() if relu else None      # detached: a constant for MulReluMask, never an autograd edge
+        if relu and pattern_recorder is not None:
+            pattern_recorder(y.detach() > 0)
+        return y
 
     @staticmethod
     def backward(ctx, gy):
         x, w = ctx.saved_tensors
         gy = _dense_like(gy, True)
+        if ctx.relu_out is not None:
+            gy = MulReluMask.apply(gy, ctx.relu_out)
         gx = gw = gb = None
         dycol = K.thin_col(gy, ctx.g, 'dy')          # im2col of a 3-channel gy: shared by dgrad and wgrad
         if ctx.needs_input_grad[0]:
@@ -96,7 +103,7 @@ class ConvF(Function):
                 gb = K.bias_grad(gy.detach())
         n_in = len(ctx.needs_input_grad)                 # apply() is called with 5, 6 or 7 arguments
         g_res = gy if (n_in > 6 and ctx.needs_input_grad[6]) else None
-        return (gx, gw, gb, None, None, None, g_res)[:n_in]
+        return (gx, gw, gb, None, None, None, g_res, None)[:n_in]
 
 
 class ConvD(Function):
@@ -154,7 +161,7 @@ def ensure_nhwc(x):
     return x
 
 
-def conv2d(x, w, b, k, stride, out_dtype=None, residual=None):
+def conv2d(x, w, b, k, stride, out_dtype=None, residual=None, relu=False):
     """tf.nn.conv2d(SAME) + bias_add on a logical-NCHW activation (+ an optional residual added in the epilogue)."""
     N, H, W, Cin = K.nhwc_dims(x)
     g = K.same_geom(N, H, W, Cin, w.shape[-1], k, stride)
@@ -162,7 +169,9 @@ def conv2d(x, w, b, k, stride, out_dtype=None, residual=None):
         residual = ensure_nhwc(residual)
         if residual.dtype != (out_dtype or x.dtype) or tuple(residual.shape) != (N, w.shape[-1], g.Ho, g.Wo):
             raise RuntimeError('ctgan_b200: residual must have the shape and dtype of the conv output')
-        return ConvF.apply(x, w, b, g, out_dtype or x.dtype, None, residual)
+        return ConvF.apply(x, w, b, g, out_dtype or x.dtype, None, residual, relu)
+    if relu:
+        return ConvF.apply(x, w, b, g, out_dtype or x.dtype, None, None, True)
     return ConvF.apply(x, w, b, g, out_dtype or x.dtype)
 
 
@@ -249,6 +258,106 @@ def dropout(x, keep, u=None, seed=0, offset=0, dyn=None):
     if keep == 1.0:
         return x
     return ActDropout.apply(x, 1.0, keep, u, seed, offset, dyn)
+
+
+class MaskSum2(Function):
+    """a*ma + b*mb with constant multipliers (ma None = identity): the backward of a fork."""
+
+    @staticmethod
+    def forward(ctx, a, b, ma, mb):
+        ctx.ma, ctx.mb = ma, mb
+        return K.mask_sum2(a, ma, b, mb)
+
+    @staticmethod
+    def backward(ctx, c):
+        c = _dense_like(c, True)
+        if ctx.ma is None:
+            return c, MulConst.apply(c, ctx.mb), None, None
+        ca, cb = MaskFork2.apply(c, ctx.ma, ctx.mb)
+        return ca, cb, None, None
+
+
+class MaskFork2(Function):
+    """c -> (c*ma, c*mb) with constant multipliers: the backward of MaskSum2."""
+
+    @staticmethod
+    def forward(ctx, c, ma, mb):
+        ctx.ma, ctx.mb = ma, mb
+        return K.mask_fork2(c, ma, mb)
+
+    @staticmethod
+    def backward(ctx, ga, gb):
+        return _mask_sum(ga, gb, ctx.ma, ctx.mb), None, None
+
+
+def _mask_sum(ga, gb, ma, mb):
+    """ga*ma + gb*mb where either incoming gradient may be absent."""
+    if ga is None and gb is None:
+        return None
+    if gb is None:
+        ga = _dense_like(ga, True)
+        return MulConst.apply(ga, ma) if ma is not None else ga
+    if ga is None:
+        return MulConst.apply(_dense_like(gb, True), mb)
+    return MaskSum2.apply(_dense_like(ga, True), _dense_like(gb, True), ma, mb)
+
+
+class ForkDropoutRelu(Function):
+    """(d, r) = (dropout(x), relu(dropout(x))) in one kernel: the input of a residual block whose skip connection
+    takes d and whose first nonlinearity takes r.  backward: gx = gd*md + gr*mdr in one kernel."""
+
+    @staticmethod
+    def forward(ctx, x, keep, u, seed, offset, dyn=None):
+        d, r, md, mdr = K.fork_dropout_relu(x, keep, u=u, seed=seed, offset=offset, dyn=dyn)
+        if pattern_recorder is not None:
+            pattern_recorder(x.detach() > 0)
+        ctx.md, ctx.mdr = md, mdr
+        return d, r
+
+    @staticmethod
+    def backward(ctx, gd, gr):
+        return _mask_sum(gd, gr, ctx.md, ctx.mdr), None, None, None, None, None
+
+
+class ForkRelu(Function):
+    """(x, relu(x)) for a block input without dropout: backward gx = gd + gr*m in one kernel."""
+
+    @staticmethod
+    def forward(ctx, x):
+        r, m = K.act_dropout(x, 0.0, 1.0)
+        if pattern_recorder is not None:
+            pattern_recorder(x.detach() > 0)
+        ctx.m = m
+        return x.view_as(x), r
+
+    @staticmethod
+    def backward(ctx, gd, gr):
+        return _mask_sum(gd, gr, None, ctx.m)
+
+
+def fork_dropout_relu(x, keep, u=None, seed=0, offset=0, dyn=None):
+    """-> (dropout(x), relu(dropout(x)))."""
+    if keep == 1.0:
+        return ForkRelu.apply(x)
+    return ForkDropoutRelu.apply(x, keep, u, seed, offset, dyn)
+
+
+def fork_relu(x):
+    """-> (x, relu(x))."""
+    return ForkRelu.apply(x)
+
+
+class MulReluMask(Function):
+    """g * [y > 0], y = the output of a ReLU fused into a conv epilogue (a constant here)."""
+
+    @staticmethod
+    def forward(ctx, g, y):
+        ctx.y = y
+        return K.mul_relu_mask(g, y)
+
+    @staticmethod
+    def backward(ctx, c):
+        return MulReluMask.apply(_dense_like(c, True), ctx.y), None
 
 
 class Add(Function):

@@ -75,6 +75,7 @@ def Normalize(name, inputs, labels=None, relu=False):
 
 COMMUTE_1X1 = True   # evaluate 1x1 shortcut convs on the low-resolution side of their resampling (same function)
 FUSE_SKIP_ADD = True  # shortcut + conv_2(...) inside conv_2's epilogue where conv_2 is not followed by pooling
+FUSE_D_ACT = True     # critic: relu in conv_1's epilogue, dropout -> (skip, relu) forks as one node (see functional.Fork*)
 
 
 def ConvMeanPool(name, input_dim, output_dim, filter_size, inputs, he_init=True, biases=True):
@@ -102,9 +103,16 @@ def UpsampleConv(name, input_dim, output_dim, filter_size, inputs, he_init=True,
     return lib.ops.conv2d.Conv2D(name, input_dim, output_dim, filter_size, output, he_init=he_init, biases=biases)
 
 
-def ResidualBlock(name, input_dim, output_dim, filter_size, inputs, resample=None, no_dropout=False, labels=None):
+def _plain_relu_block(name):
+    """True for blocks whose Normalize() is just the nonlinearity (the critic: NORMALIZATION_D is False)."""
+    return FUSE_D_ACT and ('Discriminator' in name) and not NORMALIZATION_D
+
+
+def ResidualBlock(name, input_dim, output_dim, filter_size, inputs, resample=None, no_dropout=False, labels=None,
+                  pre_act=None):
     """
     resample: None, 'down', or 'up'
+    pre_act (extension): relu(inputs) when the caller already computed it together with `inputs` (F.fork_dropout_relu)
     """
     if resample == 'down':
         conv_1 = functools.partial(lib.ops.conv2d.Conv2D, input_dim=input_dim, output_dim=input_dim)
@@ -121,16 +129,25 @@ def ResidualBlock(name, input_dim, output_dim, filter_size, inputs, resample=Non
     else:
         raise Exception('invalid resample value')
 
+    fused_act = _plain_relu_block(name) and resample != 'up'
+    if fused_act and pre_act is None:
+        # N1 = relu(inputs) and the skip connection both read `inputs`: one node, so that backward is one kernel
+        inputs, pre_act = F.fork_relu(inputs)
+
     if output_dim == input_dim and resample is None:
         shortcut = inputs  # Identity skip-connection
     else:
         shortcut = conv_shortcut(name + '.Shortcut', input_dim=input_dim, output_dim=output_dim, filter_size=1,
                                  he_init=False, biases=True, inputs=inputs)
 
-    output = inputs
-    output = Normalize(name + '.N1', output, labels=labels, relu=True)
-    output = conv_1(name + '.Conv1', filter_size=filter_size, inputs=output)
-    output = Normalize(name + '.N2', output, labels=labels, relu=True)
+    if fused_act:
+        # N2 = relu(conv_1(.)) in conv_1's epilogue
+        output = conv_1(name + '.Conv1', filter_size=filter_size, inputs=pre_act, relu=True)
+    else:
+        output = inputs
+        output = Normalize(name + '.N1', output, labels=labels, relu=True)
+        output = conv_1(name + '.Conv1', filter_size=filter_size, inputs=output)
+        output = Normalize(name + '.N2', output, labels=labels, relu=True)
     if resample != 'down' and FUSE_SKIP_ADD:
         # conv_2 is a plain Conv2D at the shortcut's resolution: the skip connection is added in its epilogue
         return conv_2(name + '.Conv2', filter_size=filter_size, inputs=output, residual=shortcut)
@@ -147,8 +164,11 @@ def OptimizedResBlockDisc1(inputs):
                              biases=True, inputs=inputs)
 
     output = inputs
-    output = conv_1('Discriminator.1.Conv1', filter_size=3, inputs=output)
-    output = nonlinearity(output)
+    if FUSE_D_ACT:
+        output = conv_1('Discriminator.1.Conv1', filter_size=3, inputs=output, relu=True)   # nonlinearity in the epilogue
+    else:
+        output = conv_1('Discriminator.1.Conv1', filter_size=3, inputs=output)
+        output = nonlinearity(output)
     output = conv_2('Discriminator.1.Conv2', filter_size=3, inputs=output)
     return F.add(shortcut, output)
 
@@ -174,16 +194,32 @@ def _dropout(output, keep):
     return F.dropout(output, keep, **RNG.dropout_args(output))
 
 
+def _dropout_relu(output, keep):
+    """(dropout(x), relu(dropout(x)))"""
+    if keep == 1.0:
+        return F.fork_relu(output)
+    return F.fork_dropout_relu(output, keep, **RNG.dropout_args(output))
+
+
 def Discriminator(inputs, labels, kp1, kp2, kp3):  # three more parameters of keep rate
     output = F.to_nhwc(inputs, 3, 32, 32, ACT_DTYPE)              # tf.reshape(inputs, [-1, 3, 32, 32])
     output = OptimizedResBlockDisc1(output)
     output = ResidualBlock('Discriminator.2', DIM_D, DIM_D, 3, output, resample='down', labels=labels)
-    output = _dropout(output, kp1)  # dropout after activator
-    output = ResidualBlock('Discriminator.3', DIM_D, DIM_D, 3, output, resample=None, labels=labels)
-    output = _dropout(output, kp2)  # dropout after activator
-    output = ResidualBlock('Discriminator.4', DIM_D, DIM_D, 3, output, resample=None, labels=labels)
-    output = _dropout(output, kp3)  # dropout after activator
-    output = nonlinearity(output)
+    if FUSE_D_ACT and not NORMALIZATION_D:
+        # dropout -> (skip connection, first relu of the next block) as one node; the last dropout + relu as one kernel
+        # (relu and dropout commute: both multiply by a non-negative constant)
+        output, act = _dropout_relu(output, kp1)
+        output = ResidualBlock('Discriminator.3', DIM_D, DIM_D, 3, output, resample=None, labels=labels, pre_act=act)
+        output, act = _dropout_relu(output, kp2)
+        output = ResidualBlock('Discriminator.4', DIM_D, DIM_D, 3, output, resample=None, labels=labels, pre_act=act)
+        output = F.relu(output) if kp3 == 1.0 else F.leaky_relu_dropout(output, 0.0, kp3, **RNG.dropout_args(output))
+    else:
+        output = _dropout(output, kp1)  # dropout after activator
+        output = ResidualBlock('Discriminator.3', DIM_D, DIM_D, 3, output, resample=None, labels=labels)
+        output = _dropout(output, kp2)  # dropout after activator
+        output = ResidualBlock('Discriminator.4', DIM_D, DIM_D, 3, output, resample=None, labels=labels)
+        output = _dropout(output, kp3)  # dropout after activator
+        output = nonlinearity(output)
     output2 = F.spatial_mean(output)  # corresponding to D_
     output_wgan = lib.ops.linear.Linear('Discriminator.Output', DIM_D, 1, output2, out_dtype=torch.float32)
     output_wgan = output_wgan.reshape(-1)  # conrresponding to D

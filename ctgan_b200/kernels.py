@@ -503,6 +503,45 @@ def act_dropout(x, slope, keep, u=None, seed=0, offset=0, want_mask=True, dyn=No
     return y, m
 
 
+def fork_dropout_relu(x, keep, u=None, seed=0, offset=0, dyn=None):
+    """d = dropout(x), r = relu(d) and their multipliers (md, mdr) in one kernel; same Philox slice as act_dropout."""
+    _dense(x)
+    d, r, md, mdr = (torch.empty_like(x) for _ in range(4))
+    if u is not None:
+        _dense(u)
+        if u.dtype != torch.float32 or u.shape != x.shape or u.stride() != x.stride():
+            raise RuntimeError('ctgan_b200: explicit dropout noise must be float32 with the layout of x')
+    call('ctgan_fork_dropout_relu', _p(x), _p(u), _p(d), _p(r), _p(md), _p(mdr), x.numel(), _dt(x), float(keep),
+         int(seed), int(offset), _p(dyn), _stream())
+    return d, r, md, mdr
+
+
+def mask_sum2(a, ma, b, mb):
+    """a*ma + b*mb (ma None: a + b*mb)."""
+    _dense(a); _dense(b); _dense(mb); _same_layout(a, b); _same_layout(b, mb)
+    if ma is not None:
+        _dense(ma); _same_layout(a, ma)
+    out = torch.empty_like(a)
+    call('ctgan_mask_sum2', _p(a), _p(ma), _p(b), _p(mb), _p(out), a.numel(), _dt(a), _stream())
+    return out
+
+
+def mask_fork2(c, ma, mb):
+    """(c*ma, c*mb)."""
+    _dense(c); _dense(ma); _dense(mb); _same_layout(c, ma); _same_layout(c, mb)
+    o1, o2 = torch.empty_like(c), torch.empty_like(c)
+    call('ctgan_mask_fork2', _p(c), _p(ma), _p(mb), _p(o1), _p(o2), c.numel(), _dt(c), _stream())
+    return o1, o2
+
+
+def mul_relu_mask(g, y):
+    """g * [y > 0]: the backward of a ReLU whose output is y."""
+    _dense(g); _dense(y); _same_layout(g, y)
+    out = torch.empty_like(g)
+    call('ctgan_mul_relu_mask', _p(g), _p(y), _p(out), g.numel(), _dt(g), _stream())
+    return out
+
+
 def unary_fwd(x, kind):
     _dense(x)
     y = torch.empty_like(x)

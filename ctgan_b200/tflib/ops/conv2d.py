@@ -35,7 +35,7 @@ def _uniform(stdev, size):
 
 
 def Conv2D(name, input_dim, output_dim, filter_size, inputs, he_init=True, mask_type=None, stride=1,
-           weightnorm=None, biases=True, gain=1., residual=None):
+           weightnorm=None, biases=True, gain=1., residual=None, relu=False):
     """
     inputs: tensor of shape (batch size, num channels, height, width)
     mask_type: one of None, 'a', 'b'  (PixelCNN masks: unused by the CT-GAN scripts -> unsupported)
@@ -68,4 +68,5 @@ def Conv2D(name, input_dim, output_dim, filter_size, inputs, he_init=True, mask_
     if inputs.shape[1] != input_dim:
         raise Exception('Conv2D %s: expected %d input channels, got %d' % (name, input_dim, inputs.shape[1]))
     # residual (extension): a tensor of the output's shape added in the conv epilogue (skip connections)
-    return F.conv2d(inputs, filters, _biases, filter_size, stride, residual=residual)
+    # relu (extension): the nonlinearity that follows this conv, applied in the epilogue
+    return F.conv2d(inputs, filters, _biases, filter_size, stride, residual=residual, relu=relu)

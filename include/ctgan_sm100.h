@@ -143,6 +143,18 @@ int ctgan_scale(const void* a, float s, void* out, int64_t n, int dtype, void* s
 int ctgan_act_dropout_fwd(const void* x, const float* u, void* y, void* m, int64_t n, int dtype,
                           float slope, float keep, uint64_t seed, uint64_t offset,
                           const uint64_t* dyn_offset /*nullable*/, void* stream);
+/* Fused forms of the same masks where a block input forks into the skip connection and the block's first ReLU
+ * (Discriminator: tf.nn.dropout after ResidualBlock 2/3 followed by ResidualBlock's shortcut + nonlinearity,
+ * TG/CT_gan_cifar_resnet.py:113-139,183-190):
+ *   fork_dropout_relu: d = x*md, r = x*mdr, md = floor(keep+u)/keep, mdr = md*[x>0]  (same Philox slice as act_dropout_fwd)
+ *   mask_sum2:         out = a*ma + b*mb        (ma == NULL: out = a + b*mb)           backward of a fork
+ *   mask_fork2:        o1 = c*ma, o2 = c*mb                                            backward of mask_sum2
+ *   mul_relu_mask:     out = g*[y>0]            backward of a ReLU fused into a conv epilogue (y = its output) */
+int ctgan_fork_dropout_relu(const void* x, const float* u, void* d, void* r, void* md, void* mdr, int64_t n, int dtype,
+                            float keep, uint64_t seed, uint64_t offset, const uint64_t* dyn_offset, void* stream);
+int ctgan_mask_sum2(const void* a, const void* ma, const void* b, const void* mb, void* out, int64_t n, int dtype, void* stream);
+int ctgan_mask_fork2(const void* c, const void* ma, const void* mb, void* o1, void* o2, int64_t n, int dtype, void* stream);
+int ctgan_mul_relu_mask(const void* g, const void* y, void* out, int64_t n, int dtype, void* stream);
 
 /* unary: kind 0 = tanh, 1 = sigmoid (TG/CT_gan_cifar.py:77, TG/CT_gan_mnist.py:85) */
 int ctgan_unary_fwd(const void* x, void* y, int64_t n, int dtype, int kind, void* stream);

@@ -144,6 +144,27 @@ def act_dropout(x, slope, keep, u=None, seed=0, offset=0, want_mask=True, dyn=No
     return y, (m if want_mask else None)
 
 
+def fork_dropout_relu(x, keep, u=None, seed=0, offset=0, dyn=None):
+    xf = _f(x)
+    uu = _f(u) if u is not None else _uniform_like(x, seed, offset, dyn)
+    md = _out(torch.floor(torch.tensor(keep, dtype=torch.float32) + uu) * float(np.float32(1.0) / np.float32(keep)), x.dtype)
+    mdr = _out(torch.where(xf > 0, _f(md), torch.zeros_like(xf)), x.dtype)
+    return _out(xf * _f(md), x.dtype), _out(xf * _f(mdr), x.dtype), md, mdr
+
+
+def mask_sum2(a, ma, b, mb):
+    av = _f(a) * _f(ma) if ma is not None else _f(a)
+    return _out(av + _f(b) * _f(mb), a.dtype)
+
+
+def mask_fork2(c, ma, mb):
+    return _out(_f(c) * _f(ma), c.dtype), _out(_f(c) * _f(mb), c.dtype)
+
+
+def mul_relu_mask(g, y):
+    return _out(torch.where(_f(y) > 0, _f(g), torch.zeros_like(_f(g))), g.dtype)
+
+
 def unary_fwd(x, kind):
     return _out(torch.tanh(_f(x)) if kind == 0 else torch.sigmoid(_f(x)), x.dtype)
 
@@ -362,7 +383,7 @@ def invalidate_weight_cache(ptrs=None):
 
 
 _NAMES = ['conv_fprop', 'conv_dgrad', 'conv_wgrad', 'bias_grad', 'bias_add', 'add', 'mul', 'scale', 'cast',
-          'act_dropout', 'unary_fwd', 'unary_bwd', 'pool2x2', 'upsample2x', 'spatial_sum', 'spatial_bcast',
+          'act_dropout', 'fork_dropout_relu', 'mask_sum2', 'mask_fork2', 'mul_relu_mask', 'unary_fwd', 'unary_bwd', 'pool2x2', 'upsample2x', 'spatial_sum', 'spatial_bcast',
           'nchw_to_nhwc', 'nhwc_to_nchw', 'crop', 'crop_bwd', 'prep_real', 'interpolate', 'bn_fwd', 'bn_bwd',
           'ct_gp_loss_fwd', 'ct_gp_loss_bwd', 'mean_fwd', 'mean_bwd', 'softmax_ce_fwd', 'softmax_ce_bwd',
           'adam_step', 'philox_uniform', 'philox_normal', 'philox_labels', 'counter_add', 'invalidate_weight_cache']

@@ -382,3 +382,50 @@ def test_thin_tc_conv_family(K, geom):
         assert rel(acc - 0.25, fb.conv_wgrad(x, dy, g, tuple(w.shape))) < 2e-3, thin
     for a, b_ in zip(res[True], res[False]):
         assert rel(a, b_.float().cpu()) < 2e-2
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_fused_mask_kernels(K, dtype):
+    """fork_dropout_relu == act_dropout(slope 1) followed by relu (same Philox slice); mask_sum2 / mask_fork2 /
+    mul_relu_mask against their definitions."""
+    fb = FB()
+    x = act((6, 128, 8, 8), dtype, 1)
+    d, r, md, mdr = K.fork_dropout_relu(to_dev(x), 0.5, seed=9, offset=64)
+    d0, m0 = K.act_dropout(to_dev(x), 1.0, 0.5, seed=9, offset=64)
+    r0, m1 = K.act_dropout(d0, 0.0, 1.0)
+    assert torch.equal(d, d0) and torch.equal(md, m0) and torch.equal(r, r0)
+    assert torch.equal(mdr.float(), (m0.float() * m1.float()))
+    dr, rr, mdr_, mdrr = fb.fork_dropout_relu(x, 0.5, seed=9, offset=64)
+    assert torch.equal(d.cpu(), dr) and torch.equal(r.cpu(), rr) and torch.equal(md.cpu(), mdr_) and torch.equal(mdr.cpu(), mdrr)
+    a, b = act((6, 128, 8, 8), dtype, 2), act((6, 128, 8, 8), dtype, 3)
+    tol = 1e-6 if dtype == torch.float32 else 8e-3
+    assert rel(K.mask_sum2(to_dev(a), md, to_dev(b), mdr), fb.mask_sum2(a, md.cpu(), b, mdr.cpu())) < tol
+    assert rel(K.mask_sum2(to_dev(a), None, to_dev(b), mdr), fb.mask_sum2(a, None, b, mdr.cpu())) < tol
+    o1, o2 = K.mask_fork2(to_dev(a), md, mdr)
+    assert torch.equal(o1, K.mul(to_dev(a), md)) and torch.equal(o2, K.mul(to_dev(a), mdr))
+    assert torch.equal(K.mul_relu_mask(to_dev(a), r), K.mul(to_dev(a), m1))
+
+
+def test_fused_activation_graph_matches_unfused():
+    """The critic with fused activation nodes (relu in conv epilogues, dropout/relu forks, skip add in the epilogue) vs
+    the literal op sequence of the reference: same losses and gradients for the critic and the generator step."""
+    import numpy as np
+    import ctgan_b200.gan_cifar_resnet as R
+    rs = np.random.RandomState(3)
+    x = torch.from_numpy(rs.randint(0, 256, (8, 3072)).astype('int32')).cuda()
+    y = torch.from_numpy(rs.randint(0, 10, (8,)).astype('int32')).cuda()
+    res = {}
+    for fused in (True, False):
+        R.FUSE_D_ACT = R.FUSE_SKIP_ADD = R.COMMUTE_1X1 = fused
+        try:
+            np.random.seed(1234)
+            tr = R.Trainer(device='cuda', seed=5, act_dtype=torch.float32, batch_size=8)
+            tr.disc_opt.zero_grad()
+            out = tr.critic_forward_backward(x, y)
+            tr.gen_opt.zero_grad()
+            gc = tr.gen_forward_backward()['cost']
+            res[fused] = (out['out'].clone(), out['gradients'].clone(), tr.disc_opt.flat_g.clone(), gc.clone(), tr.gen_opt.flat_g.clone())
+        finally:
+            R.FUSE_D_ACT = R.FUSE_SKIP_ADD = R.COMMUTE_1X1 = True
+    for a, b in zip(res[True], res[False]):
+        assert rel(a, b) < 2e-3
