@@ -9,7 +9,7 @@ import os
 from ctypes import c_int, c_int32, c_int64, c_uint64, c_float, c_void_p, c_char_p, POINTER, Structure
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libctgan_sm100.so')
+LIB_PATH = os.environ.get('CTGAN_SM100_LIB') or os.path.join(_HERE, 'libctgan_sm100.so')   # override: A/B builds
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(
@@ -46,6 +46,7 @@ _PROTOS = {
     'ctgan_set_fprop_variant': (None, [c_int]),
     'ctgan_set_wgrad_variant': (None, [c_int]),
     'ctgan_conv_fprop_tc': (c_int, [POINTER(ConvDesc), P, P, P, P, P, c_int, P]),
+    'ctgan_conv_fprop_tc_masked': (c_int, [POINTER(ConvDesc), P, P, P, P, P, P, c_int, P]),
     'ctgan_conv_wgrad_tc': (c_int, [POINTER(ConvDesc), P, P, P, P]),
     'ctgan_pack_filter_bf16': (c_int, [P, P, c_int, c_int, c_int, c_int, P]),
     'ctgan_pack_filters_multi': (c_int, [P, P, P, c_int, P]),

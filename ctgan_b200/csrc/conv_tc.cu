@@ -158,15 +158,48 @@ struct FpropParams {
     __nv_bfloat16* y;
     const float* bias;
     const __nv_bfloat16* residual;
+    const __nv_bfloat16* relu_mask;    // output is zeroed where this tensor (shape of y) is <= 0: dgrad into a ReLU output
 };
 
-// Epilogue shared by the fprop kernels: thread = tile row = TMEM lane; 32 fp32 columns per tcgen05.ld,
-// + bias (+ residual) (ReLU), bf16 pack, 32-byte stores.
-template <int BLOCK_N>
-__device__ __forceinline__ void fprop_epilogue(const FpropParams& p, uint32_t tmem_base, const float* s_bias,
-                                               int warp, int lane, int w0, int h0, int n0, int co0) {
-    const int row = warp * 32 + lane;
-    int t = row;
+// 32-byte global accesses (LDG.256 / STG.256): 16 bf16 channels of one pixel row per instruction = one full sector.
+__device__ __forceinline__ void ld16_bf16(const __nv_bfloat16* p, bool wide, float (&f)[16]) {
+    uint32_t rw[8];
+    if (wide) {
+        asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(rw[0]), "=r"(rw[1]), "=r"(rw[2]), "=r"(rw[3]), "=r"(rw[4]), "=r"(rw[5]), "=r"(rw[6]), "=r"(rw[7]) : "l"(p));
+    } else {
+        const uint4 r0 = *reinterpret_cast<const uint4*>(p), r1 = *reinterpret_cast<const uint4*>(p + 8);
+        rw[0] = r0.x; rw[1] = r0.y; rw[2] = r0.z; rw[3] = r0.w; rw[4] = r1.x; rw[5] = r1.y; rw[6] = r1.z; rw[7] = r1.w;
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const __nv_bfloat162 r2 = *reinterpret_cast<const __nv_bfloat162*>(&rw[e]);
+        f[2 * e] = __bfloat162float(r2.x); f[2 * e + 1] = __bfloat162float(r2.y);
+    }
+}
+__device__ __forceinline__ void st16_bf16(__nv_bfloat16* p, bool wide, const float (&v)[16]) {
+    uint32_t ow[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const __nv_bfloat162 o2 = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+        ow[e] = *reinterpret_cast<const uint32_t*>(&o2);
+    }
+    if (wide) {
+        asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                     ::"l"(p), "r"(ow[0]), "r"(ow[1]), "r"(ow[2]), "r"(ow[3]), "r"(ow[4]), "r"(ow[5]), "r"(ow[6]), "r"(ow[7]) : "memory");
+    } else {
+        *reinterpret_cast<uint4*>(p) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+        *reinterpret_cast<uint4*>(p + 8) = make_uint4(ow[4], ow[5], ow[6], ow[7]);
+    }
+}
+
+// Epilogue of one accumulator tile of NCOLS channels (all fprop kernels): thread = pixel row = TMEM lane; per 32 fp32
+// columns from tcgen05.ld: + bias (+ residual) (ReLU) (zero where relu_mask <= 0), bf16 pack, 32-byte stores.
+// `bias` points at the tile's first channel (shared or global memory) or is null.
+template <int NCOLS, bool BIAS_GLOBAL>
+__device__ __forceinline__ void tile_epilogue(const FpropParams& p, uint32_t tmem_addr, const float* bias, int q, int lane,
+                                              int w0, int h0, int n0, int co0) {
+    int t = q * 32 + lane;
     const int bw = t % p.BW; t /= p.BW;
     const int bh = t % p.BH; const int bn = t / p.BH;
     const int n = n0 + bn, h = h0 + bh, w = w0 + bw;
@@ -174,55 +207,57 @@ __device__ __forceinline__ void fprop_epilogue(const FpropParams& p, uint32_t tm
     const int64_t pix = ((int64_t)n * p.H + h) * p.W + w;
     __nv_bfloat16* yrow = p.y + pix * p.Cout + co0;
     const __nv_bfloat16* rrow = p.residual ? p.residual + pix * p.Cout + co0 : nullptr;
+    const __nv_bfloat16* mrow = p.relu_mask ? p.relu_mask + pix * p.Cout + co0 : nullptr;
     const bool relu = (p.flags & CTGAN_EPI_RELU) != 0;
-    const bool wide = ((reinterpret_cast<uintptr_t>(p.y) | reinterpret_cast<uintptr_t>(p.residual)) & 31) == 0;   // 32-byte accesses
+    const bool wide = ((reinterpret_cast<uintptr_t>(p.y) | reinterpret_cast<uintptr_t>(p.residual) |
+                        reinterpret_cast<uintptr_t>(p.relu_mask)) & 31) == 0;
+    const bool bias_vec = bias != nullptr && (reinterpret_cast<uintptr_t>(bias) & 15) == 0;
 #pragma unroll 1
-    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-        uint32_t acc[32];
-        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, acc);   // warp-collective
+    for (int c0 = 0; c0 < NCOLS; c0 += 32) {
+        uint32_t v32[32];
+        tmem_ld32(tmem_addr + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v32);     // warp-collective
         if (valid) {
 #pragma unroll
             for (int j = 0; j < 32; j += 16) {
                 float v[16];
+                if (bias_vec) {
 #pragma unroll
-                for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(acc[j + e]) + s_bias[c0 + j + e];
+                    for (int e = 0; e < 16; e += 4) {
+                        const float4 b4 = BIAS_GLOBAL ? __ldg(reinterpret_cast<const float4*>(bias + c0 + j + e))
+                                                      : *reinterpret_cast<const float4*>(bias + c0 + j + e);
+                        v[e] = b4.x; v[e + 1] = b4.y; v[e + 2] = b4.z; v[e + 3] = b4.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) v[e] = bias ? bias[c0 + j + e] : 0.f;
+                }
+#pragma unroll
+                for (int e = 0; e < 16; ++e) v[e] += __uint_as_float(v32[j + e]);
                 if (rrow) {
-                    uint32_t rw[8];
-                    if (wide) {
-                        asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                                     : "=r"(rw[0]), "=r"(rw[1]), "=r"(rw[2]), "=r"(rw[3]), "=r"(rw[4]), "=r"(rw[5]), "=r"(rw[6]), "=r"(rw[7])
-                                     : "l"(rrow + c0 + j));
-                    } else {
-                        const uint4 r0 = *reinterpret_cast<const uint4*>(rrow + c0 + j), r1 = *reinterpret_cast<const uint4*>(rrow + c0 + j + 8);
-                        rw[0] = r0.x; rw[1] = r0.y; rw[2] = r0.z; rw[3] = r0.w; rw[4] = r1.x; rw[5] = r1.y; rw[6] = r1.z; rw[7] = r1.w;
-                    }
+                    float r[16];
+                    ld16_bf16(rrow + c0 + j, wide, r);
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        const __nv_bfloat162 r2 = *reinterpret_cast<const __nv_bfloat162*>(&rw[e]);
-                        v[2 * e] += __bfloat162float(r2.x); v[2 * e + 1] += __bfloat162float(r2.y);
-                    }
+                    for (int e = 0; e < 16; ++e) v[e] += r[e];
                 }
                 if (relu) {
 #pragma unroll
                     for (int e = 0; e < 16; ++e) v[e] = fmaxf(v[e], 0.f);
                 }
-                uint32_t ow[8];
+                if (mrow) {
+                    float m[16];
+                    ld16_bf16(mrow + c0 + j, wide, m);
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    const __nv_bfloat162 o2 = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
-                    ow[e] = *reinterpret_cast<const uint32_t*>(&o2);
+                    for (int e = 0; e < 16; ++e) v[e] = m[e] > 0.f ? v[e] : 0.f;
                 }
-                if (wide) {
-                    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
-                                 ::"l"(yrow + c0 + j), "r"(ow[0]), "r"(ow[1]), "r"(ow[2]), "r"(ow[3]), "r"(ow[4]), "r"(ow[5]), "r"(ow[6]), "r"(ow[7])
-                                 : "memory");
-                } else {
-                    *reinterpret_cast<uint4*>(yrow + c0 + j) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
-                    *reinterpret_cast<uint4*>(yrow + c0 + j + 8) = make_uint4(ow[4], ow[5], ow[6], ow[7]);
-                }
+                st16_bf16(yrow + c0 + j, wide, v);
             }
         }
     }
+}
+template <int BLOCK_N>
+__device__ __forceinline__ void fprop_epilogue(const FpropParams& p, uint32_t tmem_base, const float* s_bias,
+                                               int warp, int lane, int w0, int h0, int n0, int co0) {
+    tile_epilogue<BLOCK_N, false>(p, tmem_base, s_bias, warp, lane, w0, h0, n0, co0);
 }
 
 // ------------------------------------------------------------------ fprop kernel
@@ -543,52 +578,10 @@ conv_fprop_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, cons
             const int tw = mt % p.tilesW; mt /= p.tilesW;
             const int th = mt % p.tilesH; const int tn = mt / p.tilesH;
             const int co0 = nb * BLOCK_N;
-            int t = q * 32 + lane;
-            const int bw = t % p.BW; t /= p.BW;
-            const int bh = t % p.BH; const int bn = t / p.BH;
-            const int n = tn * p.BN + bn, h = th * p.BH + bh, w = tw * p.BW + bw;
-            const bool valid = (n < p.N) && (h < p.H) && (w < p.W);
-            const int64_t pix = ((int64_t)n * p.H + h) * p.W + w;
-            __nv_bfloat16* yrow = p.y + pix * p.Cout + co0;
-            const __nv_bfloat16* rrow = p.residual ? p.residual + pix * p.Cout + co0 : nullptr;
             mbar_wait(tfull + 8 * acc, acc_phase);
             tc_fence_after();
-#pragma unroll 1
-            for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-                uint32_t v32[32];
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + c0), v32);
-                if (valid) {
-#pragma unroll
-                    for (int j = 0; j < 32; j += 8) {
-                        float v[8];
-                        if (p.bias) {
-                            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + co0 + c0 + j));
-                            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + co0 + c0 + j + 4));
-                            v[0] = b0.x; v[1] = b0.y; v[2] = b0.z; v[3] = b0.w; v[4] = b1.x; v[5] = b1.y; v[6] = b1.z; v[7] = b1.w;
-                        } else {
-#pragma unroll
-                            for (int e = 0; e < 8; ++e) v[e] = 0.f;
-                        }
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) v[e] += __uint_as_float(v32[j + e]);
-                        if (rrow) {
-                            uint4 rv = *reinterpret_cast<const uint4*>(rrow + c0 + j);
-                            const __nv_bfloat162* rp = reinterpret_cast<const __nv_bfloat162*>(&rv);
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) { v[2 * e] += __bfloat162float(rp[e].x); v[2 * e + 1] += __bfloat162float(rp[e].y); }
-                        }
-                        if (relu) {
-#pragma unroll
-                            for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
-                        }
-                        uint4 ov;
-                        __nv_bfloat162* op = reinterpret_cast<__nv_bfloat162*>(&ov);
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) op[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
-                        *reinterpret_cast<uint4*>(yrow + c0 + j) = ov;
-                    }
-                }
-            }
+            tile_epilogue<BLOCK_N, true>(p, tmem_base + (uint32_t)(acc * BLOCK_N), p.bias ? p.bias + co0 : nullptr, q, lane,
+                                   tw * p.BW, th * p.BH, tn * p.BN, co0);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {                                        // this warp has finished reading the accumulator
@@ -602,9 +595,9 @@ conv_fprop_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, cons
 }
 
 // ------------------------------------------------------------------ fprop kernel, persistent, grouped stages
-// Epilogue of one 128-pixel x 128-channel accumulator (persistent kernels): thread = pixel row = TMEM lane; per 32 fp32
-// columns: + bias (+ residual) (ReLU), bf16 pack, and 32-BYTE global accesses (STG.256 / LDG.256) -- a row's 16 channels per
-// instruction are one full sector, half the store instructions of 16-byte accesses.
+// Epilogue of one 128-pixel x 128-channel accumulator of the lean / pair kernels: hand-scheduled version of
+// tile_epilogue<128, true> without the relu_mask operand (the generic template, and even an untaken mask branch here,
+// measured 3-4 % slower on the whole step; masked launches take the per-k-block persistent kernel instead).
 __device__ __forceinline__ void lean_epilogue_tile(const FpropParams& p, uint32_t tmem_addr, int q, int lane,
                                                    int w0, int h0, int n0, int co0, bool relu) {
     int t = q * 32 + lane;
@@ -1648,7 +1641,13 @@ extern "C" void ctgan_set_fprop_halo(int on) { g_use_halo = on != 0; }
 
 extern "C" int ctgan_conv_fprop_tc(const ctgan_conv_desc* d, const void* x, const void* wp,
                                    const float* bias, const void* residual, void* y, int flags, void* stream) {
+    return ctgan_conv_fprop_tc_masked(d, x, wp, bias, residual, nullptr, y, flags, stream);
+}
+
+extern "C" int ctgan_conv_fprop_tc_masked(const ctgan_conv_desc* d, const void* x, const void* wp, const float* bias,
+                                          const void* residual, const void* relu_mask, void* y, int flags, void* stream) {
     if (int r = check_tc_desc(d, "conv_fprop_tc")) return r;
+    CTGAN_REQUIRE((reinterpret_cast<uintptr_t>(relu_mask) & 15) == 0, CTGAN_ERR_BAD_DESC, "conv_fprop_tc: relu_mask must be 16-byte aligned");
     CTGAN_REQUIRE(x && wp && y, CTGAN_ERR_BAD_DESC, "conv_fprop_tc: null pointer");
     CTGAN_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(wp) & 15) == 0 &&
                   (reinterpret_cast<uintptr_t>(y) & 15) == 0 && (reinterpret_cast<uintptr_t>(residual) & 15) == 0,
@@ -1662,6 +1661,7 @@ extern "C" int ctgan_conv_fprop_tc(const ctgan_conv_desc* d, const void* x, cons
     p.y = reinterpret_cast<__nv_bfloat16*>(y);
     p.bias = bias;
     p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
+    p.relu_mask = reinterpret_cast<const __nv_bfloat16*>(relu_mask);
     const int block_n = (d->Cout % 128 == 0) ? 128 : 64;
     const int ctas = p.tilesW * p.tilesH * p.tilesN * (d->Cout / block_n);
     // halo-reuse variant: k x k filters (k > 1) on tiles that are whole rows of one image, more than one wave of CTAs
@@ -1671,17 +1671,18 @@ extern "C" int ctgan_conv_fprop_tc(const ctgan_conv_desc* d, const void* x, cons
     if (int r = make_act_map(&mx, x, d->N, d->H, d->W, d->Cin, p.BW, halo ? p.BH + d->kh - 1 : p.BH, p.BN)) return r;
     if (int r = make_filter_map(&mw, wp, d->kh * d->kw, d->Cout, d->Cin, block_n)) return r;
     cudaStream_t st = as_stream(stream);
-    if (g_fprop_variant == 4 && block_n == 128 && halo && d->kh == 3 && p.tilesW == 1 && p.BN == 1 && p.tilesH >= 2 &&
+    const int variant = relu_mask ? (g_fprop_variant < 2 ? g_fprop_variant : 2) : g_fprop_variant;   // lean / pair kernels: no mask operand
+    if (variant == 4 && block_n == 128 && halo && d->kh == 3 && p.tilesW == 1 && p.BN == 1 && p.tilesH >= 2 &&
         (uint32_t)(2 * p.BH + 2) * p.BW * 128u <= 40960u && p.tilesH * p.tilesN * (d->Cout / 128) >= 2 * sm_count()) {
         CUtensorMap mx2;                                             // 256-pixel work items (two row blocks per halo box)
         if (int r = make_act_map(&mx2, x, d->N, d->H, d->W, d->Cin, p.BW, 2 * p.BH + 2, 1)) return r;
         return launch_fprop_pair(mx, mx2, mw, p, st);
     }
-    if (g_fprop_variant >= 3 && block_n == 128) {                    // persistent, grouped stages, lean issue loop
+    if (variant >= 3 && block_n == 128) {                            // persistent, grouped stages, lean issue loop
         if (halo && d->kh == 3) return launch_fprop_lean<1>(mx, mw, p, st);
         if (!halo) return launch_fprop_lean<0>(mx, mw, p, st);
     }
-    if (g_fprop_variant >= 2 && block_n == 128) {                    // persistent, per-k-block rings
+    if (variant >= 2 && block_n == 128) {                            // persistent, per-k-block rings
         if (halo) return launch_fprop_persistent<3, 8, 24576, 1>(mx, mw, p, st);
         return launch_fprop_persistent<6, 6, 16384, 0>(mx, mw, p, st);
     }

@@ -65,7 +65,10 @@ def _dense_like(g, ref_dim4):
 # ------------------------------------------------------------------------- conv family
 class ConvF(Function):
     @staticmethod
-    def forward(ctx, x, w, b, g, out_dtype, col=None, residual=None, relu=False):
+    def forward(ctx, x, w, b, g, out_dtype, col=None, residual=None, relu=False, in_relu=False, relu_bwd_fused=False):
+        # in_relu: x is the output of a ReLU whose backward this conv applies in its dgrad epilogue (dx zeroed where
+        #          x <= 0); the producer is then built with relu_bwd_fused=True and skips its own mask multiply
+        ctx.in_relu, ctx.relu_bwd_fused = in_relu, relu_bwd_fused
         ctx.g = g
         ctx.save_for_backward(x, w)
         ctx.has_bias = b is not None
@@ -83,12 +86,12 @@ class ConvF(Function):
     def backward(ctx, gy):
         x, w = ctx.saved_tensors
         gy = _dense_like(gy, True)
-        if ctx.relu_out is not None:
+        if ctx.relu_out is not None and not ctx.relu_bwd_fused:
             gy = MulReluMask.apply(gy, ctx.relu_out)
         gx = gw = gb = None
         dycol = K.thin_col(gy, ctx.g, 'dy')          # im2col of a 3-channel gy: shared by dgrad and wgrad
         if ctx.needs_input_grad[0]:
-            gx = ConvD.apply(gy, w, ctx.g, x.dtype, dycol)
+            gx = ConvD.apply(gy, w, ctx.g, x.dtype, dycol, x.detach() if ctx.in_relu else None)
         if ctx.needs_input_grad[1]:
             if _direct(w):
                 col, g = (ctx.col if ctx.col is not None else dycol), ctx.g
@@ -103,22 +106,25 @@ class ConvF(Function):
                 gb = K.bias_grad(gy.detach())
         n_in = len(ctx.needs_input_grad)                 # apply() is called with 5, 6 or 7 arguments
         g_res = gy if (n_in > 6 and ctx.needs_input_grad[6]) else None
-        return (gx, gw, gb, None, None, None, g_res, None)[:n_in]
+        return (gx, gw, gb, None, None, None, g_res, None, None, None)[:n_in]
 
 
 class ConvD(Function):
     """dx = conv^T(gy, w) for the forward geometry g (== Deconv2D forward)."""
 
     @staticmethod
-    def forward(ctx, gy, w, g, out_dtype, col=None):
+    def forward(ctx, gy, w, g, out_dtype, col=None, relu_mask=None):
         ctx.g = g
         ctx.save_for_backward(gy, w)
-        return K.conv_dgrad(gy, w, g, out_dtype=out_dtype, w_is_param=_is_param(w), col=col)
+        ctx.relu_mask = relu_mask                     # constant: dx = conv^T(gy, w) * [relu_mask > 0]
+        return K.conv_dgrad(gy, w, g, out_dtype=out_dtype, w_is_param=_is_param(w), col=col, relu_mask=relu_mask)
 
     @staticmethod
     def backward(ctx, c):
         gy, w = ctx.saved_tensors
         c = _dense_like(c, True)
+        if ctx.relu_mask is not None:
+            c = MulReluMask.apply(c, ctx.relu_mask)
         ggy = gw = None
         ccol = K.thin_col(c, ctx.g, 'x')             # im2col of a 3-channel c: shared by fprop and wgrad
         if ctx.needs_input_grad[0]:
@@ -129,7 +135,7 @@ class ConvD(Function):
                 K.on_side(lambda: K.conv_wgrad(c, gy, g, tuple(w.shape), accumulate_into=w.grad, col=ccol), c, gy, ccol)
             else:
                 gw = ConvG.apply(c, gy, ctx.g, tuple(w.shape))
-        return ggy, gw, None, None, None
+        return (ggy, gw, None, None, None, None)[:len(ctx.needs_input_grad)]
 
 
 class ConvG(Function):
@@ -161,7 +167,7 @@ def ensure_nhwc(x):
     return x
 
 
-def conv2d(x, w, b, k, stride, out_dtype=None, residual=None, relu=False):
+def conv2d(x, w, b, k, stride, out_dtype=None, residual=None, relu=False, in_relu=False, relu_bwd_fused=False):
     """tf.nn.conv2d(SAME) + bias_add on a logical-NCHW activation (+ an optional residual added in the epilogue)."""
     N, H, W, Cin = K.nhwc_dims(x)
     g = K.same_geom(N, H, W, Cin, w.shape[-1], k, stride)
@@ -169,9 +175,9 @@ def conv2d(x, w, b, k, stride, out_dtype=None, residual=None, relu=False):
         residual = ensure_nhwc(residual)
         if residual.dtype != (out_dtype or x.dtype) or tuple(residual.shape) != (N, w.shape[-1], g.Ho, g.Wo):
             raise RuntimeError('ctgan_b200: residual must have the shape and dtype of the conv output')
-        return ConvF.apply(x, w, b, g, out_dtype or x.dtype, None, residual, relu)
-    if relu:
-        return ConvF.apply(x, w, b, g, out_dtype or x.dtype, None, None, True)
+        return ConvF.apply(x, w, b, g, out_dtype or x.dtype, None, residual, relu, in_relu, relu_bwd_fused)
+    if relu or in_relu:
+        return ConvF.apply(x, w, b, g, out_dtype or x.dtype, None, None, relu, in_relu, relu_bwd_fused)
     return ConvF.apply(x, w, b, g, out_dtype or x.dtype)
 
 

@@ -76,9 +76,16 @@ def Normalize(name, inputs, labels=None, relu=False):
 COMMUTE_1X1 = True   # evaluate 1x1 shortcut convs on the low-resolution side of their resampling (same function)
 FUSE_SKIP_ADD = True  # shortcut + conv_2(...) inside conv_2's epilogue where conv_2 is not followed by pooling
 FUSE_D_ACT = True     # critic: relu in conv_1's epilogue, dropout -> (skip, relu) forks as one node (see functional.Fork*)
+# the ReLU backward inside conv_2's dgrad epilogue (ConvF in_relu / relu_bwd_fused): implemented and tested, but the
+# extra strided mask loads in the (exposed) epilogue of the small layers cost what the saved multiply kernels gain
+FUSE_RELU_BWD = False
 
 
-def ConvMeanPool(name, input_dim, output_dim, filter_size, inputs, he_init=True, biases=True):
+def ConvMeanPool(name, input_dim, output_dim, filter_size, inputs, he_init=True, biases=True, in_relu=False):
+    if in_relu:
+        output = lib.ops.conv2d.Conv2D(name, input_dim, output_dim, filter_size, inputs, he_init=he_init, biases=biases,
+                                       in_relu=True)
+        return F.mean_pool_2x2(output)
     if filter_size == 1 and COMMUTE_1X1:
         # a 1x1 conv commutes with the 2x2 mean (both linear, the bias is constant over the window): pool first,
         # convolve a quarter of the pixels
@@ -141,8 +148,12 @@ def ResidualBlock(name, input_dim, output_dim, filter_size, inputs, resample=Non
                                  he_init=False, biases=True, inputs=inputs)
 
     if fused_act:
-        # N2 = relu(conv_1(.)) in conv_1's epilogue
-        output = conv_1(name + '.Conv1', filter_size=filter_size, inputs=pre_act, relu=True)
+        # N2 = relu(conv_1(.)) in conv_1's epilogue; its backward ([output > 0]) in conv_2's dgrad epilogue
+        output = conv_1(name + '.Conv1', filter_size=filter_size, inputs=pre_act, relu=True, relu_bwd_fused=FUSE_RELU_BWD)
+        if resample != 'down' and FUSE_SKIP_ADD:
+            return conv_2(name + '.Conv2', filter_size=filter_size, inputs=output, residual=shortcut, in_relu=FUSE_RELU_BWD)
+        output = conv_2(name + '.Conv2', filter_size=filter_size, inputs=output, in_relu=FUSE_RELU_BWD)
+        return F.add(shortcut, output)
     else:
         output = inputs
         output = Normalize(name + '.N1', output, labels=labels, relu=True)
@@ -165,11 +176,13 @@ def OptimizedResBlockDisc1(inputs):
 
     output = inputs
     if FUSE_D_ACT:
-        output = conv_1('Discriminator.1.Conv1', filter_size=3, inputs=output, relu=True)   # nonlinearity in the epilogue
+        # nonlinearity in conv_1's epilogue, its backward in conv_2's dgrad epilogue
+        output = conv_1('Discriminator.1.Conv1', filter_size=3, inputs=output, relu=True, relu_bwd_fused=FUSE_RELU_BWD)
+        output = conv_2('Discriminator.1.Conv2', filter_size=3, inputs=output, in_relu=FUSE_RELU_BWD)
     else:
         output = conv_1('Discriminator.1.Conv1', filter_size=3, inputs=output)
         output = nonlinearity(output)
-    output = conv_2('Discriminator.1.Conv2', filter_size=3, inputs=output)
+        output = conv_2('Discriminator.1.Conv2', filter_size=3, inputs=output)
     return F.add(shortcut, output)
 
 

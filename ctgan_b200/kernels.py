@@ -371,9 +371,12 @@ def conv_fprop(x, w, bias, g, relu=False, residual=None, out_dtype=None, w_is_pa
     return y
 
 
-def conv_dgrad(dy, w, g, out_dtype=None, w_is_param=False, col=None):
-    """dx = conv^T(dy, w) with the geometry of the FORWARD conv g.  Also Deconv2D forward."""
+def conv_dgrad(dy, w, g, out_dtype=None, w_is_param=False, col=None, relu_mask=None):
+    """dx = conv^T(dy, w) with the geometry of the FORWARD conv g.  Also Deconv2D forward.
+    relu_mask: a tensor of dx's shape (the conv's input, itself a ReLU output): dx is zeroed where it is <= 0."""
     require_nhwc(dy, 'dy')
+    if relu_mask is not None:
+        require_nhwc(relu_mask, 'relu_mask')
     _check_filter(w, g)
     two_d = dy.dim() == 2
     out_dtype = out_dtype or dy.dtype
@@ -384,8 +387,10 @@ def conv_dgrad(dy, w, g, out_dtype=None, w_is_param=False, col=None):
         gt = ConvGeom(g.N, g.H, g.W, g.Cout, g.H, g.W, g.Cin, g.kh, g.kw, 1, g.kh - 1 - g.pad_t, g.kw - 1 - g.pad_l)
         wp = pack_filter(w, 1, cacheable=w_is_param)
         d = _desc(gt, BF16, BF16)
-        call('ctgan_conv_fprop_tc', ctypes.byref(d), _p(dy), _p(wp), None, None, _p(dx), 0, _stream())
+        call('ctgan_conv_fprop_tc_masked', ctypes.byref(d), _p(dy), _p(wp), None, None, _p(relu_mask), _p(dx), 0, _stream())
         return dx
+    if relu_mask is not None:                       # other paths: the mask as a separate kernel
+        return mul_relu_mask(conv_dgrad(dy, w, g, out_dtype=out_dtype, w_is_param=w_is_param, col=col), relu_mask)
     side = _thin_side(g, dy) if (xdt == BF16 and ydt == BF16) else None
     if side == 'in':                                  # dxcol[(t,ci)] = dy x w^T, dx = col2im(dxcol, -1)
         dxcol = _gemm1x1_tc(dy, pack_filter_thin(w, 3, cacheable=w_is_param), None, g, g.Cout, 64)

@@ -35,7 +35,8 @@ def _uniform(stdev, size):
 
 
 def Conv2D(name, input_dim, output_dim, filter_size, inputs, he_init=True, mask_type=None, stride=1,
-           weightnorm=None, biases=True, gain=1., residual=None, relu=False):
+           weightnorm=None, biases=True, gain=1., residual=None, relu=False, in_relu=False,
+           relu_bwd_fused=False):
     """
     inputs: tensor of shape (batch size, num channels, height, width)
     mask_type: one of None, 'a', 'b'  (PixelCNN masks: unused by the CT-GAN scripts -> unsupported)
@@ -69,4 +70,7 @@ def Conv2D(name, input_dim, output_dim, filter_size, inputs, he_init=True, mask_
         raise Exception('Conv2D %s: expected %d input channels, got %d' % (name, input_dim, inputs.shape[1]))
     # residual (extension): a tensor of the output's shape added in the conv epilogue (skip connections)
     # relu (extension): the nonlinearity that follows this conv, applied in the epilogue
-    return F.conv2d(inputs, filters, _biases, filter_size, stride, residual=residual, relu=relu)
+    # in_relu / relu_bwd_fused (extension): see functional.ConvF -- the ReLU between two convs differentiated inside
+    # the second conv's dgrad epilogue
+    return F.conv2d(inputs, filters, _biases, filter_size, stride, residual=residual, relu=relu, in_relu=in_relu,
+                    relu_bwd_fused=relu_bwd_fused)

@@ -94,6 +94,11 @@ void ctgan_set_wgrad_variant(int v);
 int ctgan_conv_fprop_tc(const ctgan_conv_desc* d, const void* x, const void* wp,
                         const float* bias /*nullable*/, const void* residual /*nullable*/,
                         void* y, int flags, void* stream);
+/* same, and the output is zeroed wherever relu_mask (bf16, the shape of y; nullable) is <= 0: the dgrad into a tensor
+ * that is the output of a ReLU (Conv2DBackpropInput followed by ReluGrad, one kernel) */
+int ctgan_conv_fprop_tc_masked(const ctgan_conv_desc* d, const void* x, const void* wp, const float* bias /*nullable*/,
+                               const void* residual /*nullable*/, const void* relu_mask /*nullable*/, void* y, int flags,
+                               void* stream);
 /* dw[r,s,c,o] (float HWIO) = sum_pixels x[.., c] * dy[.., o]; split over pixels with
  * fp32 atomics, so dw must hold the value to accumulate onto (zeros for a plain wgrad). */
 int ctgan_conv_wgrad_tc(const ctgan_conv_desc* d, const void* x, const void* dy,

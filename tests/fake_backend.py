@@ -58,7 +58,9 @@ def conv_fprop(x, w, bias, g, relu=False, residual=None, out_dtype=None, w_is_pa
     return _out(y, out_dtype or x.dtype)
 
 
-def conv_dgrad(dy, w, g, out_dtype=None, w_is_param=False, col=None):
+def conv_dgrad(dy, w, g, out_dtype=None, w_is_param=False, col=None, relu_mask=None):
+    if relu_mask is not None:
+        return mul_relu_mask(conv_dgrad(dy, w, g, out_dtype=out_dtype), relu_mask)
     two_d = dy.dim() == 2
     x = torch.zeros(g.N, g.Cin, g.H, g.W, requires_grad=True)
     with torch.enable_grad():

@@ -416,7 +416,7 @@ def test_fused_activation_graph_matches_unfused():
     y = torch.from_numpy(rs.randint(0, 10, (8,)).astype('int32')).cuda()
     res = {}
     for fused in (True, False):
-        R.FUSE_D_ACT = R.FUSE_SKIP_ADD = R.COMMUTE_1X1 = fused
+        R.FUSE_D_ACT = R.FUSE_SKIP_ADD = R.COMMUTE_1X1 = R.FUSE_RELU_BWD = fused
         try:
             np.random.seed(1234)
             tr = R.Trainer(device='cuda', seed=5, act_dtype=torch.float32, batch_size=8)
@@ -427,5 +427,25 @@ def test_fused_activation_graph_matches_unfused():
             res[fused] = (out['out'].clone(), out['gradients'].clone(), tr.disc_opt.flat_g.clone(), gc.clone(), tr.gen_opt.flat_g.clone())
         finally:
             R.FUSE_D_ACT = R.FUSE_SKIP_ADD = R.COMMUTE_1X1 = True
+            R.FUSE_RELU_BWD = False
     for a, b in zip(res[True], res[False]):
         assert rel(a, b) < 2e-3
+
+
+@pytest.mark.parametrize('shape', [(64, 32, 32, 3), (24, 16, 16, 3), (10, 8, 8, 3), (6, 16, 16, 1)])
+def test_dgrad_relu_mask_epilogue(K, shape):
+    """conv_dgrad(..., relu_mask=x) == conv_dgrad(...) * [x > 0] on every tensor-core kernel family (pair, lean<1>, lean<0>)
+    and on the SIMT path."""
+    N, H, W, k = shape
+    g = K.same_geom(N, H, W, 128, 128, k, 1)
+    dy, xm = act((N, 128, H, W), torch.bfloat16, 2), act((N, 128, H, W), torch.bfloat16, 7)
+    w = filt((k, k, 128, 128), 3)
+    for use_tc in (True, False):
+        K.config.use_tc = use_tc
+        try:
+            plain = K.conv_dgrad(to_dev(dy), w.cuda(), g)
+            masked = K.conv_dgrad(to_dev(dy), w.cuda(), g, relu_mask=to_dev(xm))
+        finally:
+            K.config.use_tc = True
+        want = torch.where(to_dev(xm) > 0, plain, torch.zeros_like(plain))
+        assert torch.equal(masked == 0, want == 0) and rel(masked, want) < 4e-3, use_tc     # (a different kernel accumulates)
