@@ -20,6 +20,7 @@ lib = ctypes.CDLL(LIB_PATH)
 
 F32, BF16 = 0, 1
 EPI_RELU = 1
+EPI_RES_UP2 = 2
 
 
 class ConvDesc(Structure):

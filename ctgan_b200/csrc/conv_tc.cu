@@ -206,7 +206,8 @@ __device__ __forceinline__ void tile_epilogue(const FpropParams& p, uint32_t tme
     const bool valid = (n < p.N) && (h < p.H) && (w < p.W);
     const int64_t pix = ((int64_t)n * p.H + h) * p.W + w;
     __nv_bfloat16* yrow = p.y + pix * p.Cout + co0;
-    const __nv_bfloat16* rrow = p.residual ? p.residual + pix * p.Cout + co0 : nullptr;
+    const int64_t rpix = (p.flags & CTGAN_EPI_RES_UP2) ? ((int64_t)n * (p.H >> 1) + (h >> 1)) * (p.W >> 1) + (w >> 1) : pix;
+    const __nv_bfloat16* rrow = p.residual ? p.residual + rpix * p.Cout + co0 : nullptr;
     const __nv_bfloat16* mrow = p.relu_mask ? p.relu_mask + pix * p.Cout + co0 : nullptr;
     const bool relu = (p.flags & CTGAN_EPI_RELU) != 0;
     const bool wide = ((reinterpret_cast<uintptr_t>(p.y) | reinterpret_cast<uintptr_t>(p.residual) |
@@ -607,7 +608,8 @@ __device__ __forceinline__ void lean_epilogue_tile(const FpropParams& p, uint32_
     const bool valid = (n < p.N) && (h < p.H) && (w < p.W);
     const int64_t pix = ((int64_t)n * p.H + h) * p.W + w;
     __nv_bfloat16* yrow = p.y + pix * p.Cout + co0;
-    const __nv_bfloat16* rrow = p.residual ? p.residual + pix * p.Cout + co0 : nullptr;
+    const int64_t rpix = (p.flags & CTGAN_EPI_RES_UP2) ? ((int64_t)n * (p.H >> 1) + (h >> 1)) * (p.W >> 1) + (w >> 1) : pix;
+    const __nv_bfloat16* rrow = p.residual ? p.residual + rpix * p.Cout + co0 : nullptr;
     const bool wide = ((reinterpret_cast<uintptr_t>(p.y) | reinterpret_cast<uintptr_t>(p.residual)) & 31) == 0;
 #pragma unroll 1
     for (int c0 = 0; c0 < 128; c0 += 32) {
@@ -1648,6 +1650,8 @@ extern "C" int ctgan_conv_fprop_tc_masked(const ctgan_conv_desc* d, const void* 
                                           const void* residual, const void* relu_mask, void* y, int flags, void* stream) {
     if (int r = check_tc_desc(d, "conv_fprop_tc")) return r;
     CTGAN_REQUIRE((reinterpret_cast<uintptr_t>(relu_mask) & 15) == 0, CTGAN_ERR_BAD_DESC, "conv_fprop_tc: relu_mask must be 16-byte aligned");
+    CTGAN_REQUIRE(!(flags & CTGAN_EPI_RES_UP2) || (residual && d->H % 2 == 0 && d->W % 2 == 0), CTGAN_ERR_BAD_DESC,
+                  "conv_fprop_tc: RES_UP2 needs a residual and even H, W");
     CTGAN_REQUIRE(x && wp && y, CTGAN_ERR_BAD_DESC, "conv_fprop_tc: null pointer");
     CTGAN_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(wp) & 15) == 0 &&
                   (reinterpret_cast<uintptr_t>(y) & 15) == 0 && (reinterpret_cast<uintptr_t>(residual) & 15) == 0,

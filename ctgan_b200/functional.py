@@ -65,7 +65,10 @@ def _dense_like(g, ref_dim4):
 # ------------------------------------------------------------------------- conv family
 class ConvF(Function):
     @staticmethod
-    def forward(ctx, x, w, b, g, out_dtype, col=None, residual=None, relu=False, in_relu=False, relu_bwd_fused=False):
+    def forward(ctx, x, w, b, g, out_dtype, col=None, residual=None, relu=False, in_relu=False, relu_bwd_fused=False,
+                res_up2=False):
+        # res_up2: residual has half the output resolution and is added nearest-neighbour upsampled
+        ctx.res_up2 = res_up2
         # in_relu: x is the output of a ReLU whose backward this conv applies in its dgrad epilogue (dx zeroed where
         #          x <= 0); the producer is then built with relu_bwd_fused=True and skips its own mask multiply
         ctx.in_relu, ctx.relu_bwd_fused = in_relu, relu_bwd_fused
@@ -76,7 +79,8 @@ class ConvF(Function):
         ctx.col = col if col is not None else K.thin_col(x, g, 'x')   # im2col of a 3-channel x: built once, reused by wgrad
         # residual: y = conv(x) + b + residual in the conv epilogue (the block's skip connection); its gradient is gy
         # relu: the nonlinearity that follows the conv, in the epilogue; its multiplier is [y > 0]
-        y = K.conv_fprop(x, w, b, g, out_dtype=out_dtype, w_is_param=_is_param(w), col=ctx.col, residual=residual, relu=relu)
+        y = K.conv_fprop(x, w, b, g, out_dtype=out_dtype, w_is_param=_is_param(w), col=ctx.col, residual=residual, relu=relu,
+                         res_up2=res_up2)
         ctx.relu_out = y.detach() if relu else None      # detached: a constant for MulReluMask, never an autograd edge
         if relu and pattern_recorder is not None:
             pattern_recorder(y.detach() > 0)
@@ -105,8 +109,10 @@ class ConvF(Function):
             else:
                 gb = K.bias_grad(gy.detach())
         n_in = len(ctx.needs_input_grad)                 # apply() is called with 5, 6 or 7 arguments
-        g_res = gy if (n_in > 6 and ctx.needs_input_grad[6]) else None
-        return (gx, gw, gb, None, None, None, g_res, None, None, None)[:n_in]
+        g_res = None
+        if n_in > 6 and ctx.needs_input_grad[6]:
+            g_res = Pool.apply(gy, 1.0) if ctx.res_up2 else gy       # adjoint of the 2x nearest upsample: 2x2 sums
+        return (gx, gw, gb, None, None, None, g_res, None, None, None, None)[:n_in]
 
 
 class ConvD(Function):
@@ -167,15 +173,17 @@ def ensure_nhwc(x):
     return x
 
 
-def conv2d(x, w, b, k, stride, out_dtype=None, residual=None, relu=False, in_relu=False, relu_bwd_fused=False):
+def conv2d(x, w, b, k, stride, out_dtype=None, residual=None, relu=False, in_relu=False, relu_bwd_fused=False,
+           res_up2=False):
     """tf.nn.conv2d(SAME) + bias_add on a logical-NCHW activation (+ an optional residual added in the epilogue)."""
     N, H, W, Cin = K.nhwc_dims(x)
     g = K.same_geom(N, H, W, Cin, w.shape[-1], k, stride)
     if residual is not None:
         residual = ensure_nhwc(residual)
-        if residual.dtype != (out_dtype or x.dtype) or tuple(residual.shape) != (N, w.shape[-1], g.Ho, g.Wo):
+        want = (N, w.shape[-1], g.Ho // 2, g.Wo // 2) if res_up2 else (N, w.shape[-1], g.Ho, g.Wo)
+        if residual.dtype != (out_dtype or x.dtype) or tuple(residual.shape) != want:
             raise RuntimeError('ctgan_b200: residual must have the shape and dtype of the conv output')
-        return ConvF.apply(x, w, b, g, out_dtype or x.dtype, None, residual, relu, in_relu, relu_bwd_fused)
+        return ConvF.apply(x, w, b, g, out_dtype or x.dtype, None, residual, relu, in_relu, relu_bwd_fused, res_up2)
     if relu or in_relu:
         return ConvF.apply(x, w, b, g, out_dtype or x.dtype, None, None, relu, in_relu, relu_bwd_fused)
     return ConvF.apply(x, w, b, g, out_dtype or x.dtype)

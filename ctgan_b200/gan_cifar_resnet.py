@@ -141,8 +141,14 @@ def ResidualBlock(name, input_dim, output_dim, filter_size, inputs, resample=Non
         # N1 = relu(inputs) and the skip connection both read `inputs`: one node, so that backward is one kernel
         inputs, pre_act = F.fork_relu(inputs)
 
+    shortcut_up2 = False
     if output_dim == input_dim and resample is None:
         shortcut = inputs  # Identity skip-connection
+    elif resample == 'up' and FUSE_SKIP_ADD and COMMUTE_1X1:
+        # UpsampleConv shortcut: the 1x1 conv at the low resolution; its nearest-neighbour upsample is never materialised,
+        # conv_2's epilogue adds shortcut[h/2, w/2]
+        shortcut = lib.ops.conv2d.Conv2D(name + '.Shortcut', input_dim, output_dim, 1, inputs, he_init=False, biases=True)
+        shortcut_up2 = True
     else:
         shortcut = conv_shortcut(name + '.Shortcut', input_dim=input_dim, output_dim=output_dim, filter_size=1,
                                  he_init=False, biases=True, inputs=inputs)
@@ -161,7 +167,7 @@ def ResidualBlock(name, input_dim, output_dim, filter_size, inputs, resample=Non
         output = Normalize(name + '.N2', output, labels=labels, relu=True)
     if resample != 'down' and FUSE_SKIP_ADD:
         # conv_2 is a plain Conv2D at the shortcut's resolution: the skip connection is added in its epilogue
-        return conv_2(name + '.Conv2', filter_size=filter_size, inputs=output, residual=shortcut)
+        return conv_2(name + '.Conv2', filter_size=filter_size, inputs=output, residual=shortcut, residual_up2=shortcut_up2)
     output = conv_2(name + '.Conv2', filter_size=filter_size, inputs=output)
 
     return F.add(shortcut, output)

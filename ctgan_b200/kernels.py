@@ -337,15 +337,18 @@ class FilterPacker:
             _pack_cache[(p.data_ptr(), tuple(p.shape), flip)] = self.packs[dst:dst + numel]
 
 
-def conv_fprop(x, w, bias, g, relu=False, residual=None, out_dtype=None, w_is_param=False, col=None):
-    """y = conv(x, w) [+ bias] [+ residual] [relu].  x NHWC/2-D act, w float HWIO."""
+def conv_fprop(x, w, bias, g, relu=False, residual=None, out_dtype=None, w_is_param=False, col=None, res_up2=False):
+    """y = conv(x, w) [+ bias] [+ residual] [relu].  x NHWC/2-D act, w float HWIO.
+    res_up2: residual is [N, Cout, Ho/2, Wo/2] and is added nearest-neighbour upsampled (in the tensor-core epilogue)."""
+    if res_up2 and residual is not None and not (_dt(x) == BF16 and (out_dtype or x.dtype) == torch.bfloat16 and _tc_geom_ok(g)):
+        residual, res_up2 = upsample2x(residual, 1.0), False        # other paths: materialise the upsampled residual
     require_nhwc(x, 'x')
     _check_filter(w, g)
     two_d = x.dim() == 2
     out_dtype = out_dtype or x.dtype
     y = empty_act(_y_shape(g, two_d), out_dtype, x.device)
     xdt, ydt = _dt(x), _dt(y)
-    flags = _lib.EPI_RELU if relu else 0
+    flags = (_lib.EPI_RELU if relu else 0) | (_lib.EPI_RES_UP2 if (res_up2 and residual is not None) else 0)
     if xdt == BF16 and ydt == BF16 and _tc_geom_ok(g):
         wp = pack_filter(w, 0, cacheable=w_is_param)
         if residual is not None:

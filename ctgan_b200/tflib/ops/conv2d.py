@@ -36,7 +36,7 @@ def _uniform(stdev, size):
 
 def Conv2D(name, input_dim, output_dim, filter_size, inputs, he_init=True, mask_type=None, stride=1,
            weightnorm=None, biases=True, gain=1., residual=None, relu=False, in_relu=False,
-           relu_bwd_fused=False):
+           relu_bwd_fused=False, residual_up2=False):
     """
     inputs: tensor of shape (batch size, num channels, height, width)
     mask_type: one of None, 'a', 'b'  (PixelCNN masks: unused by the CT-GAN scripts -> unsupported)
@@ -72,5 +72,6 @@ def Conv2D(name, input_dim, output_dim, filter_size, inputs, he_init=True, mask_
     # relu (extension): the nonlinearity that follows this conv, applied in the epilogue
     # in_relu / relu_bwd_fused (extension): see functional.ConvF -- the ReLU between two convs differentiated inside
     # the second conv's dgrad epilogue
+    # residual_up2 (extension): residual at half resolution, added nearest-neighbour upsampled
     return F.conv2d(inputs, filters, _biases, filter_size, stride, residual=residual, relu=relu, in_relu=in_relu,
-                    relu_bwd_fused=relu_bwd_fused)
+                    relu_bwd_fused=relu_bwd_fused, res_up2=residual_up2)

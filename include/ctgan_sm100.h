@@ -69,6 +69,8 @@ typedef struct {
 } ctgan_conv_desc;
 
 #define CTGAN_EPI_RELU 1           /* y = max(y, 0) after bias (+residual) */
+#define CTGAN_EPI_RES_UP2 2        /* tensor-core path: residual is [N, H/2, W/2, Cout]; pixel (h, w) adds residual (h/2, w/2)
+                                      (nearest-neighbour 2x upsample of a ResidualBlock('up') shortcut, never materialised) */
 
 /* generic SIMT implicit-GEMM kernels: any shape, fp32 FMA, float accumulate */
 int ctgan_conv_fprop(const ctgan_conv_desc* d, const void* x, const float* w_hwio,

@@ -45,7 +45,9 @@ def _conv(x4, w, g):
     return y[:, :, :g.Ho, :g.Wo]
 
 
-def conv_fprop(x, w, bias, g, relu=False, residual=None, out_dtype=None, w_is_param=False, col=None):
+def conv_fprop(x, w, bias, g, relu=False, residual=None, out_dtype=None, w_is_param=False, col=None, res_up2=False):
+    if res_up2 and residual is not None:
+        residual = upsample2x(residual, 1.0)
     two_d = x.dim() == 2
     y = _conv(_as4(x, g, 'x'), w.detach(), g)
     if bias is not None:

@@ -449,3 +449,15 @@ def test_dgrad_relu_mask_epilogue(K, shape):
             K.config.use_tc = True
         want = torch.where(to_dev(xm) > 0, plain, torch.zeros_like(plain))
         assert torch.equal(masked == 0, want == 0) and rel(masked, want) < 4e-3, use_tc     # (a different kernel accumulates)
+
+
+@pytest.mark.parametrize('shape', [(64, 32, 32), (40, 16, 16), (12, 8, 8)])
+def test_residual_upsampled_in_epilogue(K, shape):
+    """conv_fprop(..., residual=low_res, res_up2=True) == conv_fprop(..., residual=upsample2x(low_res)), bit for bit."""
+    N, H, W = shape
+    g = K.same_geom(N, H, W, 128, 128, 3, 1)
+    x, r = act((N, 128, H, W), torch.bfloat16, 1), act((N, 128, H // 2, W // 2), torch.bfloat16, 5)
+    w, b = filt((3, 3, 128, 128), 3), act((128,), torch.float32, 4)
+    full = K.conv_fprop(to_dev(x), w.cuda(), b.cuda(), g, residual=K.upsample2x(to_dev(r), 1.0))
+    fused = K.conv_fprop(to_dev(x), w.cuda(), b.cuda(), g, residual=to_dev(r), res_up2=True)
+    assert torch.equal(full, fused)
