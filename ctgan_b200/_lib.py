@@ -66,6 +66,8 @@ _PROTOS = {
     'ctgan_mask_sum2': (c_int, [P, P, P, P, P, c_int64, c_int, P]),
     'ctgan_mask_fork2': (c_int, [P, P, P, P, P, c_int64, c_int, P]),
     'ctgan_mul_relu_mask': (c_int, [P, P, P, c_int64, c_int, P]),
+    'ctgan_pool_add_fork': (c_int, [c_int, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_float, c_uint64, c_uint64, P, P]),
+    'ctgan_mask_sum2_up': (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, P]),
     'ctgan_unary_fwd': (c_int, [P, P, c_int64, c_int, c_int, P]),
     'ctgan_unary_bwd': (c_int, [P, P, P, c_int64, c_int, c_int, P]),
     'ctgan_pool2x2': (c_int, [P, P, c_int, c_int, c_int, c_int, c_float, c_int, P]),

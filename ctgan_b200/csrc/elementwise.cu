@@ -189,6 +189,93 @@ __global__ void mask_fork2_kernel(const T* __restrict__ c, const T* __restrict__
     }
 }
 
+// ---- 2x2 mean pool + skip add + fork, and its adjoint -----------------------------------------------------
+// End of a down-sampling critic block: x = meanpool2x2(y) + s, then the next block's input fork (see above).
+//   pool_add_fork (COMPUTE = 1): masks from the data: m1 = dropout multiplier (keep < 1; else identity, m1 not written),
+//                                m2 = m1 * [x > 0];  o1 = x * m1, o2 = x * m2           (replaces pool, add, dropout, relu)
+//   pool_add_fork (COMPUTE = 0): the same linear map with GIVEN masks (m1 may be null = identity)
+//   mask_sum2_up: gx = a*m1 + b*m2 (low resolution) and gy = 0.25 * gx replicated 2x2      (the adjoint of the above)
+template <typename T, int V, int COMPUTE>
+__global__ void pool_add_fork_kernel(const T* __restrict__ y, const T* __restrict__ s, const float* __restrict__ u,
+                                     T* __restrict__ m1, T* __restrict__ m2, T* __restrict__ o1, T* __restrict__ o2,
+                                     int N, int H, int W, int C, float keep, uint64_t seed, uint64_t offset,
+                                     const uint64_t* __restrict__ dyn) {
+    using P = Pack<T, V>;
+    const int Ho = H / 2, Wo = W / 2, CV = C / V;
+    if (COMPUTE && dyn) offset += dyn[0];
+    const bool drop = COMPUTE && keep < 1.f;
+    const float inv_keep = 1.f / keep;
+    const int64_t total = (int64_t)N * Ho * Wo * CV;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int cv = i % CV; int64_t t = i / CV;
+        const int wo = t % Wo; t /= Wo;                                 // t = n * Ho + ho
+        const P* r0 = reinterpret_cast<const P*>(y + ((2 * t) * W + 2 * wo) * (int64_t)C) + cv;
+        const P* r1 = reinterpret_cast<const P*>(y + ((2 * t + 1) * W + 2 * wo) * (int64_t)C) + cv;
+        const P a = r0[0], b = r0[CV], c = r1[0], d = r1[CV], ps = reinterpret_cast<const P*>(s)[i];
+        P pm1, pm2, p1, p2;
+        if (!COMPUTE) { pm2 = reinterpret_cast<const P*>(m2)[i]; if (m1) pm1 = reinterpret_cast<const P*>(m1)[i]; }
+        uint32_t rb[4];
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            const float xf = 0.25f * (to_f<T>(a.v[j]) + to_f<T>(b.v[j]) + to_f<T>(c.v[j]) + to_f<T>(d.v[j])) + to_f<T>(ps.v[j]);
+            const float x = to_f<T>(from_f<T>(xf));                     // the block output as it would be stored
+            float f1 = 1.f, f2;
+            if (COMPUTE) {
+                if (drop) {
+                    const int64_t e = i * V + j;
+                    float uu;
+                    if (u) uu = u[e];
+                    else {
+                        const uint64_t se = offset + (uint64_t)e;
+                        if (V == 1 || (j & 3) == 0) Philox::block(seed, se >> 2, rb);
+                        uu = Philox::to_uniform(rb[se & 3]);
+                    }
+                    pm1.v[j] = from_f<T>(floorf(keep + uu) * inv_keep);
+                    f1 = to_f<T>(pm1.v[j]);
+                }
+                f2 = x > 0.f ? f1 : 0.f;
+                pm2.v[j] = from_f<T>(f2);
+            } else {
+                if (m1) f1 = to_f<T>(pm1.v[j]);
+                f2 = to_f<T>(pm2.v[j]);
+            }
+            p1.v[j] = from_f<T>(x * f1);
+            p2.v[j] = from_f<T>(x * f2);
+        }
+        reinterpret_cast<P*>(o1)[i] = p1;
+        reinterpret_cast<P*>(o2)[i] = p2;
+        if (COMPUTE) {
+            reinterpret_cast<P*>(m2)[i] = pm2;
+            if (drop) reinterpret_cast<P*>(m1)[i] = pm1;
+        }
+    }
+}
+template <typename T, int V>
+__global__ void mask_sum2_up_kernel(const T* __restrict__ a, const T* __restrict__ m1, const T* __restrict__ b,
+                                    const T* __restrict__ m2, T* __restrict__ gx, T* __restrict__ gy,
+                                    int N, int Ho, int Wo, int C) {
+    using P = Pack<T, V>;
+    const int W = 2 * Wo, CV = C / V;
+    const int64_t total = (int64_t)N * Ho * Wo * CV;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int cv = i % CV; int64_t t = i / CV;
+        const int wo = t % Wo; t /= Wo;
+        const P pa = reinterpret_cast<const P*>(a)[i], pb = reinterpret_cast<const P*>(b)[i], pm2 = reinterpret_cast<const P*>(m2)[i];
+        P pm1, px, py;
+        if (m1) pm1 = reinterpret_cast<const P*>(m1)[i];
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            const float av = m1 ? to_f<T>(pa.v[j]) * to_f<T>(pm1.v[j]) : to_f<T>(pa.v[j]);
+            px.v[j] = from_f<T>(fmaf(to_f<T>(pb.v[j]), to_f<T>(pm2.v[j]), av));
+            py.v[j] = from_f<T>(0.25f * to_f<T>(px.v[j]));
+        }
+        reinterpret_cast<P*>(gx)[i] = px;
+        P* r0 = reinterpret_cast<P*>(gy + ((2 * t) * W + 2 * wo) * (int64_t)C) + cv;
+        P* r1 = reinterpret_cast<P*>(gy + ((2 * t + 1) * W + 2 * wo) * (int64_t)C) + cv;
+        r0[0] = py; r0[CV] = py; r1[0] = py; r1[CV] = py;
+    }
+}
+
 template <typename T>
 __global__ void bias_add_kernel(const T* __restrict__ x, const float* __restrict__ b, T* __restrict__ y, int64_t total, int C) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
@@ -466,6 +553,49 @@ extern "C" int ctgan_mask_fork2(const void* c, const void* ma, const void* mb, v
 extern "C" int ctgan_mul_relu_mask(const void* g, const void* y, void* out, int64_t n, int dtype, void* stream) {
     DISPATCH_T(dtype, return launch_map2<float>(g, y, out, n, ReluMaskOp{}, as_stream(stream), "mul_relu_mask"),
                       return launch_map2<__nv_bfloat16>(g, y, out, n, ReluMaskOp{}, as_stream(stream), "mul_relu_mask"));
+}
+
+template <typename T>
+static int launch_pool_add_fork(int compute, const void* y, const void* s, const float* u, void* m1, void* m2, void* o1, void* o2,
+                                int N, int H, int W, int C, float keep, uint64_t seed, uint64_t offset, const uint64_t* dyn,
+                                cudaStream_t st) {
+    constexpr int V = vec_width<T>();
+    const bool vec = C % V == 0 && aligned16(y) && aligned16(s) && (!m1 || aligned16(m1)) && aligned16(m2) && aligned16(o1) &&
+                     aligned16(o2) && (offset & 3) == 0;
+    const int64_t n = (int64_t)N * (H / 2) * (W / 2) * C;
+#define CTGAN_PAF(VV, CC) pool_add_fork_kernel<T, VV, CC><<<elementwise_grid(n / VV, 256), 256, 0, st>>>( \
+        (const T*)y, (const T*)s, u, (T*)m1, (T*)m2, (T*)o1, (T*)o2, N, H, W, C, keep, seed, offset, dyn)
+    if (compute) { if (vec) CTGAN_PAF(V, 1); else CTGAN_PAF(1, 1); }
+    else         { if (vec) CTGAN_PAF(V, 0); else CTGAN_PAF(1, 0); }
+#undef CTGAN_PAF
+    CTGAN_CHECK_LAUNCH("pool_add_fork");
+    return 0;
+}
+extern "C" int ctgan_pool_add_fork(int compute_masks, const void* y, const void* s, const float* u, void* m1, void* m2, void* o1,
+                                   void* o2, int N, int H, int W, int C, int dtype, float keep, uint64_t seed, uint64_t offset,
+                                   const uint64_t* dyn_offset, void* stream) {
+    CTGAN_REQUIRE(y && s && m2 && o1 && o2 && N > 0 && H > 0 && W > 0 && C > 0 && H % 2 == 0 && W % 2 == 0 && keep > 0.f && keep <= 1.f,
+                  CTGAN_ERR_BAD_DESC, "pool_add_fork: bad args");
+    CTGAN_REQUIRE(!(compute_masks && keep < 1.f) || m1, CTGAN_ERR_BAD_DESC, "pool_add_fork: dropout needs the m1 output");
+    DISPATCH_T(dtype, return launch_pool_add_fork<float>(compute_masks, y, s, u, m1, m2, o1, o2, N, H, W, C, keep, seed, offset, dyn_offset, as_stream(stream)),
+                      return launch_pool_add_fork<__nv_bfloat16>(compute_masks, y, s, u, m1, m2, o1, o2, N, H, W, C, keep, seed, offset, dyn_offset, as_stream(stream)));
+}
+template <typename T>
+static int launch_mask_sum2_up(const void* a, const void* m1, const void* b, const void* m2, void* gx, void* gy, int N, int Ho, int Wo,
+                               int C, cudaStream_t st) {
+    constexpr int V = vec_width<T>();
+    const bool vec = C % V == 0 && aligned16(a) && (!m1 || aligned16(m1)) && aligned16(b) && aligned16(m2) && aligned16(gx) && aligned16(gy);
+    const int64_t n = (int64_t)N * Ho * Wo * C;
+    if (vec) mask_sum2_up_kernel<T, V><<<elementwise_grid(n / V, 256), 256, 0, st>>>((const T*)a, (const T*)m1, (const T*)b, (const T*)m2, (T*)gx, (T*)gy, N, Ho, Wo, C);
+    else     mask_sum2_up_kernel<T, 1><<<elementwise_grid(n, 256), 256, 0, st>>>((const T*)a, (const T*)m1, (const T*)b, (const T*)m2, (T*)gx, (T*)gy, N, Ho, Wo, C);
+    CTGAN_CHECK_LAUNCH("mask_sum2_up");
+    return 0;
+}
+extern "C" int ctgan_mask_sum2_up(const void* a, const void* m1, const void* b, const void* m2, void* gx, void* gy, int N, int Ho, int Wo,
+                                  int C, int dtype, void* stream) {
+    CTGAN_REQUIRE(a && b && m2 && gx && gy && N > 0 && Ho > 0 && Wo > 0 && C > 0, CTGAN_ERR_BAD_DESC, "mask_sum2_up: bad args");
+    DISPATCH_T(dtype, return launch_mask_sum2_up<float>(a, m1, b, m2, gx, gy, N, Ho, Wo, C, as_stream(stream)),
+                      return launch_mask_sum2_up<__nv_bfloat16>(a, m1, b, m2, gx, gy, N, Ho, Wo, C, as_stream(stream)));
 }
 
 extern "C" int ctgan_bias_add(const void* x, const float* b, void* y, int64_t rows, int C, int dtype, void* stream) {

@@ -361,6 +361,64 @@ def fork_relu(x):
     return ForkRelu.apply(x)
 
 
+class PoolAddFork(Function):
+    """(o1, o2) = (x*m1, x*m2), x = meanpool2x2(y) + s: the end of a down-sampling critic block (ConvMeanPool + skip add)
+    fused with the next block's input fork; masks computed from the data (forward pass) or given (its re-use as the
+    adjoint of MaskSumUp)."""
+
+    @staticmethod
+    def forward(ctx, y, s, keep, u, seed, offset, dyn, m1, m2):
+        if m2 is None:
+            o1, o2, m1, m2 = K.pool_add_fork(y, s, keep, u=u, seed=seed, offset=offset, dyn=dyn)
+            if pattern_recorder is not None:
+                # [x > 0] wherever it matters: a dropped element (m1 == 0) is zero on both sides whatever its pattern
+                pattern_recorder((m2.detach() > 0) if m1 is None else ((m2.detach() > 0) | (m1.detach() == 0)))
+        else:
+            o1, o2, _, _ = K.pool_add_fork(y, s, masks=(m1, m2))
+        ctx.m1, ctx.m2 = m1, m2
+        return o1, o2
+
+    @staticmethod
+    def backward(ctx, g1, g2):
+        gy, gs = _mask_sum_up(g1, g2, ctx.m1, ctx.m2)
+        return gy, gs, None, None, None, None, None, None, None
+
+
+class MaskSumUp(Function):
+    """(gy, gx): gx = a*m1 + b*m2, gy = 0.25*gx replicated 2x2 -- the adjoint of PoolAddFork with fixed masks."""
+
+    @staticmethod
+    def forward(ctx, a, b, m1, m2):
+        ctx.m1, ctx.m2 = m1, m2
+        return K.mask_sum2_up(a, m1, b, m2)
+
+    @staticmethod
+    def backward(ctx, cy, cx):
+        if cy is None and cx is None:
+            return None, None, None, None
+        if cy is None or cx is None:                  # one output unused: c = cx + meanpool(cy) from the unfused pieces
+            c = _dense_like(cx, True) if cy is None else Pool.apply(_dense_like(cy, True), 0.25)
+            ca = MulConst.apply(c, ctx.m1) if ctx.m1 is not None else c
+            return ca, MulConst.apply(c, ctx.m2), None, None
+        ca, cb = PoolAddFork.apply(_dense_like(cy, True), _dense_like(cx, True), 1.0, None, 0, 0, None, ctx.m1, ctx.m2)
+        return ca, cb, None, None
+
+
+def _mask_sum_up(g1, g2, m1, m2):
+    """-> (gy, gs) for incoming gradients of the two fork outputs (either may be absent)."""
+    if g1 is not None and g2 is not None:
+        return MaskSumUp.apply(_dense_like(g1, True), _dense_like(g2, True), m1, m2)
+    gx = _mask_sum(g1, g2, m1, m2)
+    if gx is None:
+        return None, None
+    return Upsample.apply(gx, 0.25), gx
+
+
+def pool_add_fork(y, s, keep=1.0, u=None, seed=0, offset=0, dyn=None):
+    """-> (d, r): d = dropout(meanpool2x2(y) + s) (no dropout for keep == 1), r = relu(d)."""
+    return PoolAddFork.apply(y, s, keep, u, seed, offset, dyn, None, None)
+
+
 class MulReluMask(Function):
     """g * [y > 0], y = the output of a ReLU fused into a conv epilogue (a constant here)."""
 

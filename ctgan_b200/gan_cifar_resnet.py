@@ -79,6 +79,7 @@ FUSE_D_ACT = True     # critic: relu in conv_1's epilogue, dropout -> (skip, rel
 # the ReLU backward inside conv_2's dgrad epilogue (ConvF in_relu / relu_bwd_fused): implemented and tested, but the
 # extra strided mask loads in the (exposed) epilogue of the small layers cost what the saved multiply kernels gain
 FUSE_RELU_BWD = False
+FUSE_POOL_FORK = True   # critic blocks 1, 2: mean pool + skip add + (dropout) + next relu as one kernel (functional.PoolAddFork)
 
 
 def ConvMeanPool(name, input_dim, output_dim, filter_size, inputs, he_init=True, biases=True, in_relu=False):
@@ -116,10 +117,12 @@ def _plain_relu_block(name):
 
 
 def ResidualBlock(name, input_dim, output_dim, filter_size, inputs, resample=None, no_dropout=False, labels=None,
-                  pre_act=None):
+                  pre_act=None, fork_keep=None):
     """
     resample: None, 'down', or 'up'
     pre_act (extension): relu(inputs) when the caller already computed it together with `inputs` (F.fork_dropout_relu)
+    fork_keep (extension, 'down' critic blocks): return (d, relu(d)) with d = dropout(block output, keep=fork_keep) -- the
+        mean pool, the skip add, the dropout that follows the block and the next block's first relu as ONE kernel
     """
     if resample == 'down':
         conv_1 = functools.partial(lib.ops.conv2d.Conv2D, input_dim=input_dim, output_dim=input_dim)
@@ -156,6 +159,9 @@ def ResidualBlock(name, input_dim, output_dim, filter_size, inputs, resample=Non
     if fused_act:
         # N2 = relu(conv_1(.)) in conv_1's epilogue; its backward ([output > 0]) in conv_2's dgrad epilogue
         output = conv_1(name + '.Conv1', filter_size=filter_size, inputs=pre_act, relu=True, relu_bwd_fused=FUSE_RELU_BWD)
+        if resample == 'down' and fork_keep is not None:
+            full = lib.ops.conv2d.Conv2D(name + '.Conv2', input_dim, output_dim, filter_size, output, in_relu=FUSE_RELU_BWD)
+            return _pool_add_fork(full, shortcut, fork_keep)
         if resample != 'down' and FUSE_SKIP_ADD:
             return conv_2(name + '.Conv2', filter_size=filter_size, inputs=output, residual=shortcut, in_relu=FUSE_RELU_BWD)
         output = conv_2(name + '.Conv2', filter_size=filter_size, inputs=output, in_relu=FUSE_RELU_BWD)
@@ -173,7 +179,14 @@ def ResidualBlock(name, input_dim, output_dim, filter_size, inputs, resample=Non
     return F.add(shortcut, output)
 
 
-def OptimizedResBlockDisc1(inputs):
+def _pool_add_fork(full, shortcut, keep):
+    """(d, relu(d)), d = dropout(meanpool(full) + shortcut)"""
+    if keep == 1.0:
+        return F.pool_add_fork(full, shortcut)
+    return F.pool_add_fork(full, shortcut, keep, **RNG.dropout_args(shortcut))
+
+
+def OptimizedResBlockDisc1(inputs, fork=False):
     conv_1 = functools.partial(lib.ops.conv2d.Conv2D, input_dim=3, output_dim=DIM_D)
     conv_2 = functools.partial(ConvMeanPool, input_dim=DIM_D, output_dim=DIM_D)
     conv_shortcut = MeanPoolConv
@@ -184,6 +197,9 @@ def OptimizedResBlockDisc1(inputs):
     if FUSE_D_ACT:
         # nonlinearity in conv_1's epilogue, its backward in conv_2's dgrad epilogue
         output = conv_1('Discriminator.1.Conv1', filter_size=3, inputs=output, relu=True, relu_bwd_fused=FUSE_RELU_BWD)
+        if fork:      # -> (block output, relu(block output)): pool + skip add + the next block's first relu in one kernel
+            full = lib.ops.conv2d.Conv2D('Discriminator.1.Conv2', DIM_D, DIM_D, 3, output, in_relu=FUSE_RELU_BWD)
+            return F.pool_add_fork(full, shortcut)
         output = conv_2('Discriminator.1.Conv2', filter_size=3, inputs=output, in_relu=FUSE_RELU_BWD)
     else:
         output = conv_1('Discriminator.1.Conv1', filter_size=3, inputs=output)
@@ -222,12 +238,19 @@ def _dropout_relu(output, keep):
 
 def Discriminator(inputs, labels, kp1, kp2, kp3):  # three more parameters of keep rate
     output = F.to_nhwc(inputs, 3, 32, 32, ACT_DTYPE)              # tf.reshape(inputs, [-1, 3, 32, 32])
-    output = OptimizedResBlockDisc1(output)
-    output = ResidualBlock('Discriminator.2', DIM_D, DIM_D, 3, output, resample='down', labels=labels)
+    if FUSE_D_ACT and FUSE_POOL_FORK and not NORMALIZATION_D:
+        output, act = OptimizedResBlockDisc1(output, fork=True)
+        output, act = ResidualBlock('Discriminator.2', DIM_D, DIM_D, 3, output, resample='down', labels=labels, pre_act=act,
+                                    fork_keep=kp1)
+    else:
+        output = OptimizedResBlockDisc1(output)
+        output = ResidualBlock('Discriminator.2', DIM_D, DIM_D, 3, output, resample='down', labels=labels)
+        act = None
     if FUSE_D_ACT and not NORMALIZATION_D:
         # dropout -> (skip connection, first relu of the next block) as one node; the last dropout + relu as one kernel
         # (relu and dropout commute: both multiply by a non-negative constant)
-        output, act = _dropout_relu(output, kp1)
+        if act is None:
+            output, act = _dropout_relu(output, kp1)
         output = ResidualBlock('Discriminator.3', DIM_D, DIM_D, 3, output, resample=None, labels=labels, pre_act=act)
         output, act = _dropout_relu(output, kp2)
         output = ResidualBlock('Discriminator.4', DIM_D, DIM_D, 3, output, resample=None, labels=labels, pre_act=act)

@@ -550,6 +550,40 @@ def mul_relu_mask(g, y):
     return out
 
 
+def pool_add_fork(y, s, keep=1.0, u=None, seed=0, offset=0, dyn=None, masks=None):
+    """x = meanpool2x2(y) + s; returns (o1, o2, m1, m2) with o1 = x*m1, o2 = x*m2.
+    masks=None: m1 = dropout multiplier (None when keep == 1), m2 = m1*[x>0] are computed; masks=(m1, m2): given."""
+    require_nhwc(y); require_nhwc(s)
+    N, C, H, W = y.shape
+    if tuple(s.shape) != (N, C, H // 2, W // 2) or s.dtype != y.dtype:
+        raise RuntimeError('ctgan_b200: pool_add_fork operands do not match')
+    o1, o2 = torch.empty_like(s), torch.empty_like(s)
+    if masks is None:
+        m1 = torch.empty_like(s) if keep < 1.0 else None
+        m2 = torch.empty_like(s)
+        if u is not None:
+            _dense(u)
+            if u.dtype != torch.float32 or u.shape != s.shape or u.stride() != s.stride():
+                raise RuntimeError('ctgan_b200: explicit dropout noise must be float32 with the layout of the output')
+        compute = 1
+    else:
+        m1, m2 = masks
+        compute = 0
+    call('ctgan_pool_add_fork', compute, _p(y), _p(s), _p(u), _p(m1), _p(m2), _p(o1), _p(o2), N, H, W, C, _dt(y), float(keep),
+         int(seed), int(offset), _p(dyn), _stream())
+    return o1, o2, m1, m2
+
+
+def mask_sum2_up(a, m1, b, m2):
+    """gx = a*m1 + b*m2 (m1 None: a + b*m2) and gy = 0.25*gx replicated 2x2; returns (gy, gx)."""
+    require_nhwc(a); _same_layout(a, b); _same_layout(b, m2)
+    N, C, Ho, Wo = a.shape
+    gx = torch.empty_like(a)
+    gy = empty_act((N, C, 2 * Ho, 2 * Wo), a.dtype, a.device)
+    call('ctgan_mask_sum2_up', _p(a), _p(m1), _p(b), _p(m2), _p(gx), _p(gy), N, Ho, Wo, C, _dt(a), _stream())
+    return gy, gx
+
+
 def unary_fwd(x, kind):
     _dense(x)
     y = torch.empty_like(x)

@@ -162,6 +162,16 @@ int ctgan_fork_dropout_relu(const void* x, const float* u, void* d, void* r, voi
 int ctgan_mask_sum2(const void* a, const void* ma, const void* b, const void* mb, void* out, int64_t n, int dtype, void* stream);
 int ctgan_mask_fork2(const void* c, const void* ma, const void* mb, void* o1, void* o2, int64_t n, int dtype, void* stream);
 int ctgan_mul_relu_mask(const void* g, const void* y, void* out, int64_t n, int dtype, void* stream);
+/* End of a down-sampling critic block fused with the next block's input fork (ConvMeanPool + shortcut add,
+ * TG/CT_gan_cifar_resnet.py:89-92,139, then :183-190): x = meanpool2x2(y) + s  (y [N,H,W,C], s [N,H/2,W/2,C]),
+ *   compute_masks = 1: m1 = floor(keep+u)/keep (written only if keep < 1), m2 = m1*[x>0]; o1 = x*m1, o2 = x*m2
+ *   compute_masks = 0: the same linear map with the given masks (m1 nullable = identity)
+ * mask_sum2_up is its adjoint: gx = a*m1 + b*m2 (low resolution), gy = 0.25*gx replicated 2x2. */
+int ctgan_pool_add_fork(int compute_masks, const void* y, const void* s, const float* u, void* m1, void* m2, void* o1, void* o2,
+                        int N, int H, int W, int C, int dtype, float keep, uint64_t seed, uint64_t offset,
+                        const uint64_t* dyn_offset, void* stream);
+int ctgan_mask_sum2_up(const void* a, const void* m1, const void* b, const void* m2, void* gx, void* gy, int N, int Ho, int Wo, int C,
+                       int dtype, void* stream);
 
 /* unary: kind 0 = tanh, 1 = sigmoid (TG/CT_gan_cifar.py:77, TG/CT_gan_mnist.py:85) */
 int ctgan_unary_fwd(const void* x, void* y, int64_t n, int dtype, int kind, void* stream);

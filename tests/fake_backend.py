@@ -169,6 +169,28 @@ def mul_relu_mask(g, y):
     return _out(torch.where(_f(y) > 0, _f(g), torch.zeros_like(_f(g))), g.dtype)
 
 
+def pool_add_fork(y, s, keep=1.0, u=None, seed=0, offset=0, dyn=None, masks=None):
+    yf = _f(y)
+    xf = (yf[:, :, ::2, ::2] + yf[:, :, 1::2, ::2] + yf[:, :, ::2, 1::2] + yf[:, :, 1::2, 1::2]) * 0.25 + _f(s)
+    x = _out(xf, s.dtype)
+    if masks is None:
+        m1 = None
+        if keep < 1.0:
+            uu = _f(u) if u is not None else _uniform_like(x, seed, offset, dyn)
+            m1 = _out(torch.floor(torch.tensor(keep, dtype=torch.float32) + uu) * float(np.float32(1.0) / np.float32(keep)), s.dtype)
+        f1 = _f(m1) if m1 is not None else torch.ones_like(_f(x))
+        m2 = _out(torch.where(_f(x) > 0, f1, torch.zeros_like(f1)), s.dtype)
+    else:
+        m1, m2 = masks
+        f1 = _f(m1) if m1 is not None else torch.ones_like(_f(x))
+    return _out(_f(x) * f1, s.dtype), _out(_f(x) * _f(m2), s.dtype), m1, m2
+
+
+def mask_sum2_up(a, m1, b, m2):
+    gx = mask_sum2(a, m1, b, m2)
+    return upsample2x(gx, 0.25), gx
+
+
 def unary_fwd(x, kind):
     return _out(torch.tanh(_f(x)) if kind == 0 else torch.sigmoid(_f(x)), x.dtype)
 
@@ -387,7 +409,7 @@ def invalidate_weight_cache(ptrs=None):
 
 
 _NAMES = ['conv_fprop', 'conv_dgrad', 'conv_wgrad', 'bias_grad', 'bias_add', 'add', 'mul', 'scale', 'cast',
-          'act_dropout', 'fork_dropout_relu', 'mask_sum2', 'mask_fork2', 'mul_relu_mask', 'unary_fwd', 'unary_bwd', 'pool2x2', 'upsample2x', 'spatial_sum', 'spatial_bcast',
+          'act_dropout', 'fork_dropout_relu', 'mask_sum2', 'mask_fork2', 'mul_relu_mask', 'pool_add_fork', 'mask_sum2_up', 'unary_fwd', 'unary_bwd', 'pool2x2', 'upsample2x', 'spatial_sum', 'spatial_bcast',
           'nchw_to_nhwc', 'nhwc_to_nchw', 'crop', 'crop_bwd', 'prep_real', 'interpolate', 'bn_fwd', 'bn_bwd',
           'ct_gp_loss_fwd', 'ct_gp_loss_bwd', 'mean_fwd', 'mean_bwd', 'softmax_ce_fwd', 'softmax_ce_bwd',
           'adam_step', 'philox_uniform', 'philox_normal', 'philox_labels', 'counter_add', 'invalidate_weight_cache']

@@ -416,7 +416,7 @@ def test_fused_activation_graph_matches_unfused():
     y = torch.from_numpy(rs.randint(0, 10, (8,)).astype('int32')).cuda()
     res = {}
     for fused in (True, False):
-        R.FUSE_D_ACT = R.FUSE_SKIP_ADD = R.COMMUTE_1X1 = R.FUSE_RELU_BWD = fused
+        R.FUSE_D_ACT = R.FUSE_SKIP_ADD = R.COMMUTE_1X1 = R.FUSE_RELU_BWD = R.FUSE_POOL_FORK = fused
         try:
             np.random.seed(1234)
             tr = R.Trainer(device='cuda', seed=5, act_dtype=torch.float32, batch_size=8)
@@ -426,7 +426,7 @@ def test_fused_activation_graph_matches_unfused():
             gc = tr.gen_forward_backward()['cost']
             res[fused] = (out['out'].clone(), out['gradients'].clone(), tr.disc_opt.flat_g.clone(), gc.clone(), tr.gen_opt.flat_g.clone())
         finally:
-            R.FUSE_D_ACT = R.FUSE_SKIP_ADD = R.COMMUTE_1X1 = True
+            R.FUSE_D_ACT = R.FUSE_SKIP_ADD = R.COMMUTE_1X1 = R.FUSE_POOL_FORK = True
             R.FUSE_RELU_BWD = False
     for a, b in zip(res[True], res[False]):
         assert rel(a, b) < 2e-3
@@ -461,3 +461,26 @@ def test_residual_upsampled_in_epilogue(K, shape):
     full = K.conv_fprop(to_dev(x), w.cuda(), b.cuda(), g, residual=K.upsample2x(to_dev(r), 1.0))
     fused = K.conv_fprop(to_dev(x), w.cuda(), b.cuda(), g, residual=to_dev(r), res_up2=True)
     assert torch.equal(full, fused)
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('keep', [1.0, 0.5])
+def test_pool_add_fork_kernels(K, dtype, keep):
+    """pool_add_fork / mask_sum2_up against the CPU stand-ins (and so against pool -> add -> dropout -> relu)."""
+    fb = FB()
+    y, s = act((6, 128, 16, 16), dtype, 1), act((6, 128, 8, 8), dtype, 2)
+    o1, o2, m1, m2 = K.pool_add_fork(to_dev(y), to_dev(s), keep, seed=7, offset=128)
+    r1, r2, q1, q2 = fb.pool_add_fork(y, s, keep, seed=7, offset=128)
+    tol = 1e-6 if dtype == torch.float32 else 8e-3
+    assert (m1 is None) == (keep == 1.0)
+    if m1 is not None:
+        assert torch.equal(m1.cpu(), q1)
+    # a pooled value within rounding of zero may land on the other side of the ReLU: compare away from it
+    far = (r1.float().abs() > 1e-2)
+    assert torch.equal(m2.cpu()[far], q2[far]) and rel(o1, r1) < tol and rel(o2.cpu() * far, r2 * far) < tol
+    p1, p2, _, _ = K.pool_add_fork(to_dev(y), to_dev(s), masks=(m1, m2))
+    assert torch.equal(p1, o1) and torch.equal(p2, o2)
+    a, b = act((6, 128, 8, 8), dtype, 3), act((6, 128, 8, 8), dtype, 4)
+    gy, gx = K.mask_sum2_up(to_dev(a), m1, to_dev(b), m2)
+    hy, hx = fb.mask_sum2_up(a, None if m1 is None else m1.cpu(), b, m2.cpu())
+    assert rel(gx, hx) < tol and rel(gy, hy) < tol
