@@ -7,6 +7,7 @@ namespace ctgan {
 
 static thread_local char g_err[512] = "";
 unsigned long long g_kernel_launches = 0;
+int g_pdl = 1;
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -47,6 +48,7 @@ int elementwise_grid(int64_t work_items, int threads) {
 extern "C" int ctgan_version(void) { return 100; }
 
 extern "C" unsigned long long ctgan_kernel_launches(void) { return ctgan::g_kernel_launches; }
+extern "C" void ctgan_set_pdl(int on) { ctgan::g_pdl = on != 0; }
 
 extern "C" const char* ctgan_last_error(void) { return ctgan::g_err; }
 

@@ -21,6 +21,32 @@ extern unsigned long long g_kernel_launches;   // kernels launched by this libra
         if (_e != cudaSuccess) return ::ctgan::cuda_status(_e, what); \
     } while (0)
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// A step is a chain of ~200 short kernels; with plain stream order every boundary costs a full drain + launch.  All
+// kernels of the library are launched with the programmatic-stream-serialization attribute and begin with
+//     griddepcontrol.launch_dependents;   (the next kernel's CTAs may become resident once all of ours have started)
+//     griddepcontrol.wait;                (block until every prerequisite grid has completed and its writes are visible)
+// so the dependent kernel's launch latency, CTA scheduling and (for the tcgen05 kernels) barrier / TMEM / tensor-map
+// set-up overlap the tail of its predecessor.  No global memory is touched before the wait: ordering semantics are
+// exactly those of the stream.  CUDA-graph capture turns the attribute into programmatic dependency edges.
+extern int g_pdl;                                   // ctgan_set_pdl(): 0 = plain launches (api.cu)
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_entry() { pdl_launch_dependents(); pdl_wait(); }
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = g_pdl ? 1 : 0;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#define CTGAN_LAUNCH(kernel, grid, block, smem, stream, ...) \
+    (void)::ctgan::launch_pdl(kernel, grid, block, smem, stream, __VA_ARGS__)
+
 #define CTGAN_REQUIRE(cond, code, ...)                             \
     do {                                                           \
         if (!(cond)) { ::ctgan::set_error(__VA_ARGS__); return (code); } \

@@ -15,6 +15,7 @@ constexpr int MAX_N = 16;
 __global__ void __launch_bounds__(256)
 head_fprop_kernel(const void* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, void* __restrict__ y,
                   int M, int K, int N, int xdt, int ydt, int relu) {
+    ctgan::pdl_entry();
     const int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (m >= M) return;
     float acc[MAX_N];
@@ -42,6 +43,7 @@ head_fprop_kernel(const void* __restrict__ x, const float* __restrict__ w, const
 
 __global__ void __launch_bounds__(256)
 head_dgrad_kernel(const void* __restrict__ dy, const float* __restrict__ w, void* __restrict__ dx, int M, int K, int N, int xdt, int ydt) {
+    ctgan::pdl_entry();
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= (int64_t)M * K) return;
     const int k = (int)(i % K), m = (int)(i / K);
@@ -54,6 +56,7 @@ head_dgrad_kernel(const void* __restrict__ dy, const float* __restrict__ w, void
 __global__ void __launch_bounds__(256)
 head_wgrad_kernel(const void* __restrict__ x, const void* __restrict__ dy, float* __restrict__ dw, int M, int K, int N, int xdt, int ydt,
                   int rows_per_split) {
+    ctgan::pdl_entry();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;                 // i = n * K + k: consecutive threads read consecutive x
     if (i >= K * N) return;
     const int k = i % K, n = i / K;
@@ -72,7 +75,7 @@ static bool is_head(const ctgan_conv_desc* d) {
 int try_fprop(const ctgan_conv_desc* d, const void* x, const float* w, const float* bias, void* y, int flags, cudaStream_t st, int* rc) {
     if (!is_head(d)) return 0;
     const int64_t threads = (int64_t)d->N * 32;
-    head_fprop_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(x, w, bias, y, d->N, d->Cin, d->Cout, d->x_dtype, d->y_dtype,
+    CTGAN_LAUNCH((head_fprop_kernel), (unsigned)((threads + 255) / 256), 256, 0, st, x, w, bias, y, d->N, d->Cin, d->Cout, d->x_dtype, d->y_dtype,
                                                                         (flags & CTGAN_EPI_RELU) ? 1 : 0);
     *rc = 0;
     cudaError_t e = cudaGetLastError();
@@ -83,7 +86,7 @@ int try_fprop(const ctgan_conv_desc* d, const void* x, const float* w, const flo
 int try_dgrad(const ctgan_conv_desc* d, const void* dy, const float* w, void* dx, cudaStream_t st, int* rc) {
     if (!is_head(d)) return 0;
     const int64_t threads = (int64_t)d->N * d->Cin;
-    head_dgrad_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(dy, w, dx, d->N, d->Cin, d->Cout, d->x_dtype, d->y_dtype);
+    CTGAN_LAUNCH((head_dgrad_kernel), (unsigned)((threads + 255) / 256), 256, 0, st, dy, w, dx, d->N, d->Cin, d->Cout, d->x_dtype, d->y_dtype);
     *rc = 0;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) *rc = cuda_status(e, "head_dgrad"); else ++g_kernel_launches;
@@ -97,7 +100,7 @@ int try_wgrad(const ctgan_conv_desc* d, const void* x, const void* dy, float* dw
     int splits = d->N / 32; if (splits < 1) splits = 1; if (splits > 16) splits = 16;
     const int rps = (d->N + splits - 1) / splits;
     splits = (d->N + rps - 1) / rps;
-    head_wgrad_kernel<<<dim3((threads + 255) / 256, splits), 256, 0, st>>>(x, dy, dw, d->N, d->Cin, d->Cout, d->x_dtype, d->y_dtype, rps);
+    CTGAN_LAUNCH((head_wgrad_kernel), dim3((threads + 255) / 256, splits), 256, 0, st, x, dy, dw, d->N, d->Cin, d->Cout, d->x_dtype, d->y_dtype, rps);
     *rc = 0;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) *rc = cuda_status(e, "head_wgrad"); else ++g_kernel_launches;

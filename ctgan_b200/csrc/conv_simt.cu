@@ -42,6 +42,7 @@ igemm_simt_kernel(Geom g, const void* __restrict__ Asrc, const void* __restrict_
                   void* __restrict__ out, const float* __restrict__ bias, int flags,
                   int M, int Ncol, int K, int k_per_split, int use_atomic)
 {
+    ctgan::pdl_entry();
     __shared__ float As[BK][BM + 4];
     __shared__ float Bs[BK][BN + 4];
 
@@ -241,7 +242,7 @@ extern "C" int ctgan_conv_fprop(const ctgan_conv_desc* d, const void* x, const f
     CTGAN_REQUIRE(M64 < (1ll << 31), CTGAN_ERR_UNSUPPORTED, "conv_fprop: too many output pixels");
     int M = (int)M64, Ncol = d->Cout, K = d->kh * d->kw * d->Cin;
     dim3 grid(ceil_div(M, BM), ceil_div(Ncol, BN), 1);
-    igemm_simt_kernel<MODE_FPROP><<<grid, NT, 0, as_stream(stream)>>>(g, x, w, y, bias, flags, M, Ncol, K, K, 0);
+    CTGAN_LAUNCH((igemm_simt_kernel<MODE_FPROP>), grid, NT, 0, as_stream(stream), g, x, w, y, bias, flags, M, Ncol, K, K, 0);
     CTGAN_CHECK_LAUNCH("conv_fprop");
     return 0;
 }
@@ -257,7 +258,7 @@ extern "C" int ctgan_conv_dgrad(const ctgan_conv_desc* d, const void* dy, const 
     CTGAN_REQUIRE(M64 < (1ll << 31), CTGAN_ERR_UNSUPPORTED, "conv_dgrad: too many input pixels");
     int M = (int)M64, Ncol = d->Cin, K = d->kh * d->kw * d->Cout;
     dim3 grid(ceil_div(M, BM), ceil_div(Ncol, BN), 1);
-    igemm_simt_kernel<MODE_DGRAD><<<grid, NT, 0, as_stream(stream)>>>(g, dy, w, dx, nullptr, 0, M, Ncol, K, K, 0);
+    CTGAN_LAUNCH((igemm_simt_kernel<MODE_DGRAD>), grid, NT, 0, as_stream(stream), g, dy, w, dx, nullptr, 0, M, Ncol, K, K, 0);
     CTGAN_CHECK_LAUNCH("conv_dgrad");
     return 0;
 }
@@ -303,7 +304,7 @@ extern "C" int ctgan_conv_wgrad(const ctgan_conv_desc* d, const void* x, const v
         if (e != cudaSuccess) return cuda_status(e, "conv_wgrad memset");
     }
     dim3 grid(ceil_div(M, BM), ceil_div(Ncol, BN), split);
-    igemm_simt_kernel<MODE_WGRAD><<<grid, NT, 0, st>>>(g, x, dy, dw, nullptr, 0, M, Ncol, K, k_per_split, use_atomic);
+    CTGAN_LAUNCH((igemm_simt_kernel<MODE_WGRAD>), grid, NT, 0, st, g, x, dy, dw, nullptr, 0, M, Ncol, K, k_per_split, use_atomic);
     CTGAN_CHECK_LAUNCH("conv_wgrad");
     return 0;
 }

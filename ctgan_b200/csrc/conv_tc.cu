@@ -267,6 +267,7 @@ __global__ void __launch_bounds__(128)
 conv_fprop_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                      const FpropParams p)
 {
+    ctgan::pdl_launch_dependents();
     constexpr uint32_t A_BYTES = BLOCK_M * BLOCK_K * 2;       // 16 KB
     constexpr uint32_t B_BYTES = BLOCK_N * BLOCK_K * 2;
     constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
@@ -306,6 +307,7 @@ conv_fprop_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    ctgan::pdl_wait();          // nothing above touches global memory written by earlier kernels
 
     if (warp == 0 && lane == 0) {
         // ================= TMA producer =================
@@ -363,6 +365,7 @@ __global__ void __launch_bounds__(128)
 conv_fprop_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                           const FpropParams p, const uint32_t a_slot_bytes)
 {
+    ctgan::pdl_launch_dependents();
     constexpr uint32_t B_BYTES = BLOCK_N * BLOCK_K * 2;
     constexpr int TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
 
@@ -401,6 +404,7 @@ conv_fprop_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    ctgan::pdl_wait();          // nothing above touches global memory written by earlier kernels
 
     if (warp == 0 && lane == 0) {
         // ================= TMA producer =================
@@ -473,6 +477,7 @@ __global__ void __launch_bounds__(192, 1)
 conv_fprop_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                                 const FpropParams p, const int n_tiles)
 {
+    ctgan::pdl_launch_dependents();
     constexpr int BLOCK_N = 128;
     constexpr uint32_t B_BYTES = BLOCK_N * BLOCK_K * 2;
     constexpr int TMEM_COLS = 256;
@@ -508,6 +513,7 @@ conv_fprop_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, cons
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    ctgan::pdl_wait();          // nothing above touches global memory written by earlier kernels
 
     if (warp == 0 && lane == 0) {
         // ================= TMA producer =================
@@ -694,6 +700,7 @@ __global__ void __launch_bounds__(192, 1)
 conv_fprop_tc_lean_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                           const FpropParams p, const int n_tiles)
 {
+    ctgan::pdl_launch_dependents();
     constexpr int BLOCK_N = 128;
     constexpr int STAGES = 3;
     constexpr int NB = HALO ? 3 : 2;                                  // filter boxes (k-blocks) per stage
@@ -731,6 +738,7 @@ conv_fprop_tc_lean_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    ctgan::pdl_wait();          // nothing above touches global memory written by earlier kernels
 
     if (warp == 0 && lane == 0) {
         // ================= TMA producer =================
@@ -836,6 +844,7 @@ __global__ void __launch_bounds__(192, 1)
 conv_fprop_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_x2,
                           const __grid_constant__ CUtensorMap tmap_w, const FpropParams p, const int m_tiles, const int n_tiles)
 {
+    ctgan::pdl_launch_dependents();
     constexpr int BLOCK_N = 128;
     constexpr int STAGES = 2;
     constexpr uint32_t A_REGION = 40960u;                             // (2*BH+2) rows x BW pixels x 128 B <= 40 KB
@@ -879,6 +888,7 @@ conv_fprop_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    ctgan::pdl_wait();          // nothing above touches global memory written by earlier kernels
 
     if (warp == 0 && lane == 0) {
         // ================= TMA producer =================
@@ -991,6 +1001,7 @@ __global__ void __launch_bounds__(128)
 conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_dy,
                      const WgradParams p)
 {
+    ctgan::pdl_launch_dependents();
     constexpr int BLOCK_N = 128;
     constexpr uint32_t HALF_BYTES = 64 * 64 * 2;              // [64 px][64 ch] bf16 = 8 KB
     constexpr uint32_t A_BYTES = 2 * HALF_BYTES, B_BYTES = 2 * HALF_BYTES;
@@ -1028,6 +1039,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    ctgan::pdl_wait();          // nothing above touches global memory written by earlier kernels
 
     if (warp == 0 && lane == 0) {
         // ================= TMA producer =================
@@ -1112,6 +1124,7 @@ __global__ void __launch_bounds__(128, 1)
 conv_wgrad_tc_lean_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_dy,
                           const WgradParams p)
 {
+    ctgan::pdl_launch_dependents();
     constexpr int BLOCK_N = 128;
     constexpr uint32_t A_SLOT = 16384, B_HALF = 8192;
     constexpr uint32_t STAGE_BYTES = 2 * A_SLOT + 2 * B_HALF;             // 48 KB
@@ -1146,6 +1159,7 @@ conv_wgrad_tc_lean_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    ctgan::pdl_wait();          // nothing above touches global memory written by earlier kernels
 
     if (warp == 0) {
         if (lane == 0) {
@@ -1224,6 +1238,7 @@ conv_wgrad_tc_lean_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
 // transpose_flip == 0: wp[t][o][c] = w[t][c][o];  == 1: wp[t][c][o] = w[taps-1-t][c][o]
 __global__ void pack_filter_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wp,
                                    int taps, int Cin, int Cout, int transpose_flip) {
+    ctgan::pdl_entry();
     int64_t total = (int64_t)taps * Cin * Cout;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         if (transpose_flip) {
@@ -1259,6 +1274,7 @@ __device__ __forceinline__ void pack_thin_body(const float* __restrict__ w, __nv
     }
 }
 __global__ void pack_thin_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wp, int taps, int C, int Cw, int kind) {
+    ctgan::pdl_entry();
     pack_thin_body(w, wp, taps, C, Cw, kind, blockIdx.x * (int64_t)blockDim.x + threadIdx.x, (int64_t)gridDim.x * blockDim.x);
 }
 
@@ -1267,6 +1283,7 @@ __global__ void pack_thin_kernel(const float* __restrict__ w, __nv_bfloat16* __r
 struct PackEntry { long long src, dst; int taps, cin, cout, flip; };
 __global__ void pack_filters_multi_kernel(const float* __restrict__ flat, __nv_bfloat16* __restrict__ packs,
                                           const PackEntry* __restrict__ table) {
+    ctgan::pdl_entry();
     const PackEntry e = table[blockIdx.y];
     const float* w = flat + e.src;
     __nv_bfloat16* wp = packs + e.dst;
@@ -1298,6 +1315,7 @@ __global__ void pack_filters_multi_kernel(const float* __restrict__ flat, __nv_b
 __global__ void __launch_bounds__(256)
 im2col_thin_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ col,
                    int N, int H, int W, int C, int kh, int kw, int pad_t, int pad_l, int sign) {
+    ctgan::pdl_entry();
     // per column k: (dh, dw, c) packed as bytes (dh+8, dw+8, c, valid); built once per block
     __shared__ uint32_t tab[64];
     if (threadIdx.x < 64) {
@@ -1334,6 +1352,7 @@ im2col_thin_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restr
 __global__ void col2im_thin_kernel(const __nv_bfloat16* __restrict__ col, const float* __restrict__ bias,
                                    __nv_bfloat16* __restrict__ dst, int N, int H, int W, int C, int kh, int kw,
                                    int pad_t, int pad_l, int sign) {
+    ctgan::pdl_entry();
     const int64_t total = (int64_t)N * H * W;
     for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < total; p += (int64_t)gridDim.x * blockDim.x) {
         const int w = (int)(p % W); const int64_t q = p / W;
@@ -1372,6 +1391,7 @@ __global__ void __launch_bounds__(128, 1)
 wgrad_thin_tc_kernel(const __grid_constant__ CUtensorMap tmap_wide, const __grid_constant__ CUtensorMap tmap_col,
                      const WgradThinParams p)
 {
+    ctgan::pdl_launch_dependents();
     constexpr uint32_t A_BYTES = 16384, A_HALF = 8192, B_BYTES = 8192;
     constexpr uint32_t STAGE_BYTES = 2 * (A_BYTES + B_BYTES);             // 48 KB
     constexpr int TMEM_COLS = 64;
@@ -1402,6 +1422,7 @@ wgrad_thin_tc_kernel(const __grid_constant__ CUtensorMap tmap_wide, const __grid
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    ctgan::pdl_wait();          // nothing above touches global memory written by earlier kernels
 
     if (warp == 0) {
         if (lane == 0) {
@@ -1551,7 +1572,7 @@ static int launch_fprop(const CUtensorMap& mx, const CUtensorMap& mw, const Fpro
         attr_set = true;
     }
     dim3 grid(p.tilesW * p.tilesH * p.tilesN, p.Cout / BLOCK_N);
-    conv_fprop_tc_kernel<BLOCK_N, STAGES><<<grid, 128, smem, st>>>(mx, mw, p);
+    CTGAN_LAUNCH((conv_fprop_tc_kernel<BLOCK_N, STAGES>), grid, 128, smem, st, mx, mw, p);
     CTGAN_CHECK_LAUNCH("conv_fprop_tc");
     return 0;
 }
@@ -1568,7 +1589,7 @@ static int launch_fprop_halo(const CUtensorMap& mx, const CUtensorMap& mw, const
         attr_set = true;
     }
     dim3 grid(p.tilesW * p.tilesH * p.tilesN, p.Cout / BLOCK_N);
-    conv_fprop_tc_halo_kernel<BLOCK_N, SA, SB><<<grid, 128, smem, st>>>(mx, mw, p, a_slot);
+    CTGAN_LAUNCH((conv_fprop_tc_halo_kernel<BLOCK_N, SA, SB>), grid, 128, smem, st, mx, mw, p, a_slot);
     CTGAN_CHECK_LAUNCH("conv_fprop_tc_halo");
     return 0;
 }
@@ -1586,7 +1607,7 @@ static int launch_fprop_persistent(const CUtensorMap& mx, const CUtensorMap& mw,
     }
     const int n_tiles = p.tilesW * p.tilesH * p.tilesN * (p.Cout / 128);
     const int grid = n_tiles < sm_count() ? n_tiles : sm_count();
-    conv_fprop_tc_persistent_kernel<SA, SB, A_SLOT, HALO><<<grid, 192, smem, st>>>(mx, mw, p, n_tiles);
+    CTGAN_LAUNCH((conv_fprop_tc_persistent_kernel<SA, SB, A_SLOT, HALO>), grid, 192, smem, st, mx, mw, p, n_tiles);
     CTGAN_CHECK_LAUNCH("conv_fprop_tc_persistent");
     return 0;
 }
@@ -1604,7 +1625,7 @@ static int launch_fprop_lean(const CUtensorMap& mx, const CUtensorMap& mw, const
     }
     const int n_tiles = p.tilesW * p.tilesH * p.tilesN * (p.Cout / 128);
     const int grid = n_tiles < sm_count() ? n_tiles : sm_count();
-    conv_fprop_tc_lean_kernel<HALO><<<grid, 192, smem, st>>>(mx, mw, p, n_tiles);
+    CTGAN_LAUNCH((conv_fprop_tc_lean_kernel<HALO>), grid, 192, smem, st, mx, mw, p, n_tiles);
     CTGAN_CHECK_LAUNCH("conv_fprop_tc_lean");
     return 0;
 }
@@ -1621,7 +1642,7 @@ static int launch_fprop_pair(const CUtensorMap& mx, const CUtensorMap& mx2, cons
     const int m_tiles = p.tilesW * p.tilesH * p.tilesN;
     const int n_tiles = m_tiles * (p.Cout / 128);
     const int grid = n_tiles < sm_count() ? n_tiles : sm_count();
-    conv_fprop_tc_pair_kernel<<<grid, 192, smem, st>>>(mx, mx2, mw, p, m_tiles, n_tiles);
+    CTGAN_LAUNCH((conv_fprop_tc_pair_kernel), grid, 192, smem, st, mx, mx2, mw, p, m_tiles, n_tiles);
     CTGAN_CHECK_LAUNCH("conv_fprop_tc_pair");
     return 0;
 }
@@ -1739,7 +1760,7 @@ extern "C" int ctgan_conv_wgrad_tc(const ctgan_conv_desc* d, const void* x, cons
             if (e != cudaSuccess) return cuda_status(e, "wgrad_tc_lean smem attribute");
             lean_attr_set = true;
         }
-        conv_wgrad_tc_lean_kernel<STAGES><<<dim3(tiles, tap_groups, splits), 128, smem_lean, as_stream(stream)>>>(mx, mdy, p);
+        CTGAN_LAUNCH((conv_wgrad_tc_lean_kernel<STAGES>), dim3(tiles, tap_groups, splits), 128, smem_lean, as_stream(stream), mx, mdy, p);
         CTGAN_CHECK_LAUNCH("conv_wgrad_tc_lean");
         return 0;
     }
@@ -1751,14 +1772,14 @@ extern "C" int ctgan_conv_wgrad_tc(const ctgan_conv_desc* d, const void* x, cons
         attr_set = true;
     }
     dim3 grid(tiles, tap_groups, splits);
-    conv_wgrad_tc_kernel<STAGES><<<grid, 128, smem, as_stream(stream)>>>(mx, mdy, p);
+    CTGAN_LAUNCH((conv_wgrad_tc_kernel<STAGES>), grid, 128, smem, as_stream(stream), mx, mdy, p);
     CTGAN_CHECK_LAUNCH("conv_wgrad_tc");
     return 0;
 }
 
 extern "C" int ctgan_pack_filters_multi(const float* flat, void* packs, const void* table, int n_entries, void* stream) {
     CTGAN_REQUIRE(flat && packs && table && n_entries > 0 && n_entries <= 65535, CTGAN_ERR_BAD_DESC, "pack_filters_multi: bad args");
-    pack_filters_multi_kernel<<<dim3(64, n_entries), 256, 0, as_stream(stream)>>>(flat, reinterpret_cast<__nv_bfloat16*>(packs),
+    CTGAN_LAUNCH((pack_filters_multi_kernel), dim3(64, n_entries), 256, 0, as_stream(stream), flat, reinterpret_cast<__nv_bfloat16*>(packs),
                                                                                 reinterpret_cast<const PackEntry*>(table));
     CTGAN_CHECK_LAUNCH("pack_filters_multi");
     return 0;
@@ -1767,7 +1788,7 @@ extern "C" int ctgan_pack_filters_multi(const float* flat, void* packs, const vo
 extern "C" int ctgan_pack_filter_bf16(const float* w, void* wp, int taps, int Cin, int Cout, int transpose_flip, void* stream) {
     CTGAN_REQUIRE(w && wp && taps > 0 && Cin > 0 && Cout > 0, CTGAN_ERR_BAD_DESC, "pack_filter_bf16: bad args");
     int64_t total = (int64_t)taps * Cin * Cout;
-    pack_filter_kernel<<<elementwise_grid(total, 256), 256, 0, as_stream(stream)>>>(w, reinterpret_cast<__nv_bfloat16*>(wp), taps, Cin, Cout, transpose_flip);
+    CTGAN_LAUNCH((pack_filter_kernel), elementwise_grid(total, 256), 256, 0, as_stream(stream), w, reinterpret_cast<__nv_bfloat16*>(wp), taps, Cin, Cout, transpose_flip);
     CTGAN_CHECK_LAUNCH("pack_filter_bf16");
     return 0;
 }
@@ -1785,7 +1806,7 @@ extern "C" int ctgan_im2col_thin(const ctgan_conv_desc* d, int C, int sign, cons
     if (int r = check_thin(d, C, "im2col_thin")) return r;
     CTGAN_REQUIRE(src && col && (sign == 1 || sign == -1) && (reinterpret_cast<uintptr_t>(col) & 15) == 0, CTGAN_ERR_BAD_DESC, "im2col_thin: bad args");
     const int64_t total = (int64_t)d->N * d->H * d->W * 8;
-    im2col_thin_kernel<<<elementwise_grid(total, 256), 256, 0, as_stream(stream)>>>(
+    CTGAN_LAUNCH((im2col_thin_kernel), elementwise_grid(total, 256), 256, 0, as_stream(stream), 
         reinterpret_cast<const __nv_bfloat16*>(src), reinterpret_cast<__nv_bfloat16*>(col), d->N, d->H, d->W, C, d->kh, d->kw,
         d->pad_t, d->pad_l, sign);
     CTGAN_CHECK_LAUNCH("im2col_thin");
@@ -1796,7 +1817,7 @@ extern "C" int ctgan_col2im_thin(const ctgan_conv_desc* d, int C, int sign, cons
     if (int r = check_thin(d, C, "col2im_thin")) return r;
     CTGAN_REQUIRE(col && dst && (sign == 1 || sign == -1), CTGAN_ERR_BAD_DESC, "col2im_thin: bad args");
     const int64_t total = (int64_t)d->N * d->H * d->W;
-    col2im_thin_kernel<<<elementwise_grid(total, 128), 128, 0, as_stream(stream)>>>(
+    CTGAN_LAUNCH((col2im_thin_kernel), elementwise_grid(total, 128), 128, 0, as_stream(stream), 
         reinterpret_cast<const __nv_bfloat16*>(col), bias, reinterpret_cast<__nv_bfloat16*>(dst), d->N, d->H, d->W, C, d->kh, d->kw,
         d->pad_t, d->pad_l, sign);
     CTGAN_CHECK_LAUNCH("col2im_thin");
@@ -1805,7 +1826,7 @@ extern "C" int ctgan_col2im_thin(const ctgan_conv_desc* d, int C, int sign, cons
 
 extern "C" int ctgan_pack_filter_thin(const float* w, void* wp, int taps, int C, int Cw, int kind, void* stream) {
     CTGAN_REQUIRE(w && wp && taps > 0 && C > 0 && taps * C <= 64 && Cw > 0 && kind >= 0 && kind <= 3, CTGAN_ERR_BAD_DESC, "pack_filter_thin: bad args");
-    pack_thin_kernel<<<elementwise_grid((int64_t)64 * Cw, 256), 256, 0, as_stream(stream)>>>(w, reinterpret_cast<__nv_bfloat16*>(wp), taps, C, Cw, kind);
+    CTGAN_LAUNCH((pack_thin_kernel), elementwise_grid((int64_t)64 * Cw, 256), 256, 0, as_stream(stream), w, reinterpret_cast<__nv_bfloat16*>(wp), taps, C, Cw, kind);
     CTGAN_CHECK_LAUNCH("pack_filter_thin");
     return 0;
 }
@@ -1839,7 +1860,7 @@ extern "C" int ctgan_wgrad_thin_tc(const void* wide, const void* col, long long 
         if (e != cudaSuccess) return cuda_status(e, "wgrad_thin_tc smem attribute");
         attr_set = true;
     }
-    wgrad_thin_tc_kernel<STAGES><<<dim3(tiles, 1, (unsigned)splits), 128, smem, as_stream(stream)>>>(mw, mc, p);
+    CTGAN_LAUNCH((wgrad_thin_tc_kernel<STAGES>), dim3(tiles, 1, (unsigned)splits), 128, smem, as_stream(stream), mw, mc, p);
     CTGAN_CHECK_LAUNCH("wgrad_thin_tc");
     return 0;
 }

@@ -46,6 +46,7 @@ __global__ void __launch_bounds__(256)
 thin_contract_kernel(Geom g, const TA* __restrict__ src, const float* __restrict__ w, const float* __restrict__ bias,
                      TA* __restrict__ out, int relu)
 {
+    ctgan::pdl_entry();
     constexpr int TAPS = KS * KS;
     extern __shared__ float4 ws4[];
     const int wide = DG ? g.Cout : g.Cin;
@@ -122,6 +123,7 @@ template <typename TA, int KS>
 __global__ void __launch_bounds__(256)
 thin_wgrad_wide_x_kernel(Geom g, const TA* __restrict__ x, const TA* __restrict__ dy, float* __restrict__ dw)
 {
+    ctgan::pdl_entry();
     constexpr int TAPS = KS * KS;
     extern __shared__ float sdw[];                  // [TAPS][Cin][4]
     const int T = g.Cout, wide = g.Cin, wg = wide / 4, S = g.stride;
@@ -180,6 +182,7 @@ template <typename TA>
 __global__ void __launch_bounds__(256)
 thin_wgrad_wide_dy_kernel(Geom g, const TA* __restrict__ x, const TA* __restrict__ dy, float* __restrict__ dw)
 {
+    ctgan::pdl_entry();
     constexpr int ROWS = 32;
     extern __shared__ float sdw[];                  // [ROWS][Cout]
     const int T = g.Cin, wide = g.Cout, wg = wide / 4, S = g.stride;
@@ -265,7 +268,7 @@ static int launch_contract_t(const Geom& g, int wide, int64_t npix, const void* 
         if (e != cudaSuccess) return cuda_status(e, "thin_contract smem attribute");
         set = true;
     }
-    thin_contract_kernel<TA, DG, KS, S><<<pixel_grid(npix, KS == 5 ? 2 : 4), 256, smem, st>>>(g, (const TA*)src, w, bias, (TA*)out, relu);
+    CTGAN_LAUNCH((thin_contract_kernel<TA, DG, KS, S>), pixel_grid(npix, KS == 5 ? 2 : 4), 256, smem, st, g, (const TA*)src, w, bias, (TA*)out, relu);
     CTGAN_CHECK_LAUNCH("thin_contract");
     return 0;
 }
@@ -311,7 +314,7 @@ static int launch_wgrad_wide_x_t(const ctgan_conv_desc* d, const void* x, const 
         if (e != cudaSuccess) return cuda_status(e, "thin_wgrad_wide_x smem attribute");
         set = true;
     }
-    thin_wgrad_wide_x_kernel<TA, KS><<<pixel_grid((int64_t)d->N * d->Ho * d->Wo, 1), 256, smem, st>>>(g, (const TA*)x, (const TA*)dy, dw);
+    CTGAN_LAUNCH((thin_wgrad_wide_x_kernel<TA, KS>), pixel_grid((int64_t)d->N * d->Ho * d->Wo, 1), 256, smem, st, g, (const TA*)x, (const TA*)dy, dw);
     CTGAN_CHECK_LAUNCH("thin_wgrad_wide_x");
     return 0;
 }
@@ -328,7 +331,7 @@ static int launch_wgrad_wide_dy(const ctgan_conv_desc* d, const void* x, const v
         if (e != cudaSuccess) return cuda_status(e, "thin_wgrad_wide_dy smem attribute");
         set = true;
     }
-    thin_wgrad_wide_dy_kernel<TA><<<grid, 256, smem, st>>>(g, (const TA*)x, (const TA*)dy, dw);
+    CTGAN_LAUNCH((thin_wgrad_wide_dy_kernel<TA>), grid, 256, smem, st, g, (const TA*)x, (const TA*)dy, dw);
     CTGAN_CHECK_LAUNCH("thin_wgrad_wide_dy");
     return 0;
 }

@@ -16,6 +16,7 @@ static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t
 // ---- generic map kernels: out[i] = f(a[i]) / f(a[i], b[i]) -----------------
 template <typename T, int V, typename F>
 __global__ void map1_kernel(const T* __restrict__ a, T* __restrict__ out, int64_t nvec, F f) {
+    ctgan::pdl_entry();
     using P = Pack<T, V>;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
         P pa = reinterpret_cast<const P*>(a)[i], po;
@@ -26,6 +27,7 @@ __global__ void map1_kernel(const T* __restrict__ a, T* __restrict__ out, int64_
 }
 template <typename T, int V, typename F>
 __global__ void map2_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ out, int64_t nvec, F f) {
+    ctgan::pdl_entry();
     using P = Pack<T, V>;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
         P pa = reinterpret_cast<const P*>(a)[i], pb = reinterpret_cast<const P*>(b)[i], po;
@@ -41,9 +43,9 @@ static int launch_map1(const void* a, void* out, int64_t n, F f, cudaStream_t st
     constexpr int V = vec_width<T>();
     if (aligned16(a) && aligned16(out) && n % V == 0) {
         int64_t nv = n / V;
-        map1_kernel<T, V, F><<<elementwise_grid(nv, 256), 256, 0, st>>>((const T*)a, (T*)out, nv, f);
+        CTGAN_LAUNCH((map1_kernel<T, V, F>), elementwise_grid(nv, 256), 256, 0, st, (const T*)a, (T*)out, nv, f);
     } else {
-        map1_kernel<T, 1, F><<<elementwise_grid(n, 256), 256, 0, st>>>((const T*)a, (T*)out, n, f);
+        CTGAN_LAUNCH((map1_kernel<T, 1, F>), elementwise_grid(n, 256), 256, 0, st, (const T*)a, (T*)out, n, f);
     }
     CTGAN_CHECK_LAUNCH(what);
     return 0;
@@ -54,9 +56,9 @@ static int launch_map2(const void* a, const void* b, void* out, int64_t n, F f, 
     constexpr int V = vec_width<T>();
     if (aligned16(a) && aligned16(b) && aligned16(out) && n % V == 0) {
         int64_t nv = n / V;
-        map2_kernel<T, V, F><<<elementwise_grid(nv, 256), 256, 0, st>>>((const T*)a, (const T*)b, (T*)out, nv, f);
+        CTGAN_LAUNCH((map2_kernel<T, V, F>), elementwise_grid(nv, 256), 256, 0, st, (const T*)a, (const T*)b, (T*)out, nv, f);
     } else {
-        map2_kernel<T, 1, F><<<elementwise_grid(n, 256), 256, 0, st>>>((const T*)a, (const T*)b, (T*)out, n, f);
+        CTGAN_LAUNCH((map2_kernel<T, 1, F>), elementwise_grid(n, 256), 256, 0, st, (const T*)a, (const T*)b, (T*)out, n, f);
     }
     CTGAN_CHECK_LAUNCH(what);
     return 0;
@@ -75,6 +77,7 @@ struct SigmBwd { __device__ float operator()(float y, float dy) const { return d
 // ---- cast --------------------------------------------------------------------
 template <typename TI, typename TO>
 __global__ void cast_kernel(const TI* __restrict__ x, TO* __restrict__ y, int64_t n) {
+    ctgan::pdl_entry();
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         y[i] = from_f<TO>(to_f<TI>(x[i]));
 }
@@ -84,6 +87,7 @@ template <typename T, int V>
 __global__ void act_dropout_kernel(const T* __restrict__ x, const float* __restrict__ u, T* __restrict__ y,
                                    T* __restrict__ m, int64_t nvec, float slope, float keep,
                                    uint64_t seed, uint64_t offset, const uint64_t* __restrict__ dyn) {
+    ctgan::pdl_entry();
     using P = Pack<T, V>;
     if (dyn) offset += dyn[0];
     const bool drop = keep < 1.f;
@@ -127,6 +131,7 @@ template <typename T, int V>
 __global__ void fork_dropout_relu_kernel(const T* __restrict__ x, const float* __restrict__ u, T* __restrict__ d,
                                          T* __restrict__ r, T* __restrict__ md, T* __restrict__ mdr, int64_t nvec,
                                          float keep, uint64_t seed, uint64_t offset, const uint64_t* __restrict__ dyn) {
+    ctgan::pdl_entry();
     using P = Pack<T, V>;
     if (dyn) offset += dyn[0];
     const float inv_keep = 1.f / keep;
@@ -160,6 +165,7 @@ __global__ void fork_dropout_relu_kernel(const T* __restrict__ x, const float* _
 template <typename T, int V>
 __global__ void mask_sum2_kernel(const T* __restrict__ a, const T* __restrict__ ma, const T* __restrict__ b,
                                  const T* __restrict__ mb, T* __restrict__ out, int64_t nvec) {
+    ctgan::pdl_entry();
     using P = Pack<T, V>;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
         P pa = reinterpret_cast<const P*>(a)[i], pb = reinterpret_cast<const P*>(b)[i], pmb = reinterpret_cast<const P*>(mb)[i], po, pma;
@@ -175,6 +181,7 @@ __global__ void mask_sum2_kernel(const T* __restrict__ a, const T* __restrict__ 
 template <typename T, int V>
 __global__ void mask_fork2_kernel(const T* __restrict__ c, const T* __restrict__ ma, const T* __restrict__ mb,
                                   T* __restrict__ o1, T* __restrict__ o2, int64_t nvec) {
+    ctgan::pdl_entry();
     using P = Pack<T, V>;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
         P pc = reinterpret_cast<const P*>(c)[i], pma = reinterpret_cast<const P*>(ma)[i], pmb = reinterpret_cast<const P*>(mb)[i], p1, p2;
@@ -200,6 +207,7 @@ __global__ void pool_add_fork_kernel(const T* __restrict__ y, const T* __restric
                                      T* __restrict__ m1, T* __restrict__ m2, T* __restrict__ o1, T* __restrict__ o2,
                                      int N, int H, int W, int C, float keep, uint64_t seed, uint64_t offset,
                                      const uint64_t* __restrict__ dyn) {
+    ctgan::pdl_entry();
     using P = Pack<T, V>;
     const int Ho = H / 2, Wo = W / 2, CV = C / V;
     if (COMPUTE && dyn) offset += dyn[0];
@@ -254,6 +262,7 @@ template <typename T, int V>
 __global__ void mask_sum2_up_kernel(const T* __restrict__ a, const T* __restrict__ m1, const T* __restrict__ b,
                                     const T* __restrict__ m2, T* __restrict__ gx, T* __restrict__ gy,
                                     int N, int Ho, int Wo, int C) {
+    ctgan::pdl_entry();
     using P = Pack<T, V>;
     const int W = 2 * Wo, CV = C / V;
     const int64_t total = (int64_t)N * Ho * Wo * CV;
@@ -278,6 +287,7 @@ __global__ void mask_sum2_up_kernel(const T* __restrict__ a, const T* __restrict
 
 template <typename T>
 __global__ void bias_add_kernel(const T* __restrict__ x, const float* __restrict__ b, T* __restrict__ y, int64_t total, int C) {
+    ctgan::pdl_entry();
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
         y[i] = from_f<T>(to_f<T>(x[i]) + b[i % C]);
 }
@@ -286,6 +296,7 @@ __global__ void bias_add_kernel(const T* __restrict__ x, const float* __restrict
 // V channels (16 bytes when the channel count allows) per thread; index math once per vector.
 template <typename T, int V>
 __global__ void pool2x2_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H, int W, int C, float scale) {
+    ctgan::pdl_entry();
     using P = Pack<T, V>;
     const int Ho = H / 2, Wo = W / 2, CV = C / V;
     int64_t total = (int64_t)N * Ho * Wo * CV;
@@ -303,6 +314,7 @@ __global__ void pool2x2_kernel(const T* __restrict__ x, T* __restrict__ y, int N
 }
 template <typename T, int V>
 __global__ void upsample2x_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H, int W, int C, float scale) {
+    ctgan::pdl_entry();
     using P = Pack<T, V>;
     // one thread per INPUT vector: one load, four stores (the 2x2 replicas)
     const int Wo = 2 * W, CV = C / V;
@@ -320,6 +332,7 @@ __global__ void upsample2x_kernel(const T* __restrict__ x, T* __restrict__ y, in
 }
 template <typename T>
 __global__ void spatial_sum_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int HW, int C, float scale) {
+    ctgan::pdl_entry();
     int64_t total = (int64_t)N * C;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         int c = i % C; int n = i / C;
@@ -331,6 +344,7 @@ __global__ void spatial_sum_kernel(const T* __restrict__ x, T* __restrict__ y, i
 }
 template <typename T>
 __global__ void spatial_bcast_kernel(const T* __restrict__ y, T* __restrict__ x, int N, int HW, int C, float scale) {
+    ctgan::pdl_entry();
     int64_t total = (int64_t)N * HW * C;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         int c = i % C; int n = i / ((int64_t)HW * C);
@@ -343,6 +357,7 @@ __global__ void spatial_bcast_kernel(const T* __restrict__ y, T* __restrict__ x,
 // used on are tiny, so no smem transpose.
 __global__ void nchw_to_nhwc_kernel(const void* __restrict__ x, int xdt, void* __restrict__ y, int ydt,
                                     int N, int C, int H, int W) {
+    ctgan::pdl_entry();
     int64_t total = (int64_t)N * C * H * W;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         int c = i % C; int64_t t = i / C;
@@ -353,6 +368,7 @@ __global__ void nchw_to_nhwc_kernel(const void* __restrict__ x, int xdt, void* _
 }
 __global__ void nhwc_to_nchw_kernel(const void* __restrict__ x, int xdt, void* __restrict__ y, int ydt,
                                     int N, int C, int H, int W) {
+    ctgan::pdl_entry();
     int64_t total = (int64_t)N * C * H * W;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         int w = i % W; int64_t t = i / W;
@@ -363,6 +379,7 @@ __global__ void nhwc_to_nchw_kernel(const void* __restrict__ x, int xdt, void* _
 }
 template <typename T>
 __global__ void crop_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H, int W, int C, int h, int w, int fwd) {
+    ctgan::pdl_entry();
     // fwd: y[N,h,w,C] = x[N,:h,:w,C];  !fwd: y is [N,H,W,C] zero-padded copy of x[N,h,w,C]
     int64_t total = fwd ? (int64_t)N * h * w * C : (int64_t)N * H * W * C;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -381,6 +398,7 @@ __global__ void crop_kernel(const T* __restrict__ x, T* __restrict__ y, int N, i
 
 __global__ void prep_real_div_kernel(const int32_t* __restrict__ x, float* __restrict__ y, int64_t n, float denom,
                                      float noise_hi, uint64_t seed, uint64_t offset, const uint64_t* __restrict__ dyn) {
+    ctgan::pdl_entry();
     if (dyn) offset += dyn[0];
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         float v = 2.f * (__fdiv_rn((float)x[i], denom) - 0.5f);       // true division: /255 is not exact as a multiply
@@ -390,6 +408,7 @@ __global__ void prep_real_div_kernel(const int32_t* __restrict__ x, float* __res
 }
 __global__ void interpolate_kernel(const float* __restrict__ real, const float* __restrict__ fake,
                                    const float* __restrict__ alpha, float* __restrict__ out, int B, int P) {
+    ctgan::pdl_entry();
     int64_t total = (int64_t)B * P;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         int b = i / P;
@@ -401,12 +420,14 @@ __global__ void interpolate_kernel(const float* __restrict__ real, const float* 
 // ---- RNG ---------------------------------------------------------------------
 __global__ void philox_uniform_kernel(float* __restrict__ out, int64_t n, float lo, float hi, uint64_t seed, uint64_t offset,
                                       const uint64_t* __restrict__ dyn) {
+    ctgan::pdl_entry();
     if (dyn) offset += dyn[0];
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         out[i] = lo + (hi - lo) * Philox::uniform_at(seed, offset + (uint64_t)i);
 }
 __global__ void philox_normal_kernel(float* __restrict__ out, int64_t n, uint64_t seed, uint64_t offset,
                                      const uint64_t* __restrict__ dyn) {
+    ctgan::pdl_entry();
     if (dyn) offset += dyn[0];
     // element i uses stream elements (2i, 2i+1): Box-Muller, cosine branch only
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -418,12 +439,14 @@ __global__ void philox_normal_kernel(float* __restrict__ out, int64_t n, uint64_
 }
 __global__ void philox_labels_kernel(int32_t* __restrict__ out, int64_t n, int n_labels, uint64_t seed, uint64_t offset,
                                      const uint64_t* __restrict__ dyn) {
+    ctgan::pdl_entry();
     if (dyn) offset += dyn[0];
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         out[i] = (int32_t)(Philox::uniform_at(seed, offset + (uint64_t)i) * (float)n_labels);
 }
 
-__global__ void counter_add_kernel(uint64_t* ctr, uint64_t delta) { ctr[0] += delta; }
+__global__ void counter_add_kernel(uint64_t* ctr, uint64_t delta) {
+    ctgan::pdl_entry(); ctr[0] += delta; }
 
 }  // namespace ctgan
 
@@ -472,10 +495,10 @@ extern "C" int ctgan_cast(const void* x, int xdt, void* y, int ydt, int64_t n, v
     if (n <= 0) return 0;
     cudaStream_t st = as_stream(stream);
     int grid = elementwise_grid(n, 256);
-    if (xdt == CTGAN_F32 && ydt == CTGAN_BF16) cast_kernel<float, __nv_bfloat16><<<grid, 256, 0, st>>>((const float*)x, (__nv_bfloat16*)y, n);
-    else if (xdt == CTGAN_BF16 && ydt == CTGAN_F32) cast_kernel<__nv_bfloat16, float><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, (float*)y, n);
-    else if (xdt == CTGAN_F32) cast_kernel<float, float><<<grid, 256, 0, st>>>((const float*)x, (float*)y, n);
-    else cast_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, n);
+    if (xdt == CTGAN_F32 && ydt == CTGAN_BF16) CTGAN_LAUNCH((cast_kernel<float, __nv_bfloat16>), grid, 256, 0, st, (const float*)x, (__nv_bfloat16*)y, n);
+    else if (xdt == CTGAN_BF16 && ydt == CTGAN_F32) CTGAN_LAUNCH((cast_kernel<__nv_bfloat16, float>), grid, 256, 0, st, (const __nv_bfloat16*)x, (float*)y, n);
+    else if (xdt == CTGAN_F32) CTGAN_LAUNCH((cast_kernel<float, float>), grid, 256, 0, st, (const float*)x, (float*)y, n);
+    else CTGAN_LAUNCH((cast_kernel<__nv_bfloat16, __nv_bfloat16>), grid, 256, 0, st, (const __nv_bfloat16*)x, (__nv_bfloat16*)y, n);
     CTGAN_CHECK_LAUNCH("cast");
     return 0;
 }
@@ -487,9 +510,9 @@ static int launch_act_dropout(const void* x, const float* u, void* y, void* m, i
     bool vec = aligned16(x) && aligned16(y) && (m == nullptr || aligned16(m)) && n % V == 0 && (offset & 3) == 0;
     if (vec) {
         int64_t nv = n / V;
-        act_dropout_kernel<T, V><<<elementwise_grid(nv, 256), 256, 0, st>>>((const T*)x, u, (T*)y, (T*)m, nv, slope, keep, seed, offset, dyn);
+        CTGAN_LAUNCH((act_dropout_kernel<T, V>), elementwise_grid(nv, 256), 256, 0, st, (const T*)x, u, (T*)y, (T*)m, nv, slope, keep, seed, offset, dyn);
     } else {
-        act_dropout_kernel<T, 1><<<elementwise_grid(n, 256), 256, 0, st>>>((const T*)x, u, (T*)y, (T*)m, n, slope, keep, seed, offset, dyn);
+        CTGAN_LAUNCH((act_dropout_kernel<T, 1>), elementwise_grid(n, 256), 256, 0, st, (const T*)x, u, (T*)y, (T*)m, n, slope, keep, seed, offset, dyn);
     }
     CTGAN_CHECK_LAUNCH("act_dropout_fwd");
     return 0;
@@ -508,8 +531,8 @@ static int launch_fork(const void* x, const float* u, void* d, void* r, void* md
                        uint64_t seed, uint64_t offset, const uint64_t* dyn, cudaStream_t st) {
     constexpr int V = vec_width<T>();
     const bool vec = aligned16(x) && aligned16(d) && aligned16(r) && aligned16(md) && aligned16(mdr) && n % V == 0 && (offset & 3) == 0;
-    if (vec) fork_dropout_relu_kernel<T, V><<<elementwise_grid(n / V, 256), 256, 0, st>>>((const T*)x, u, (T*)d, (T*)r, (T*)md, (T*)mdr, n / V, keep, seed, offset, dyn);
-    else     fork_dropout_relu_kernel<T, 1><<<elementwise_grid(n, 256), 256, 0, st>>>((const T*)x, u, (T*)d, (T*)r, (T*)md, (T*)mdr, n, keep, seed, offset, dyn);
+    if (vec) CTGAN_LAUNCH((fork_dropout_relu_kernel<T, V>), elementwise_grid(n / V, 256), 256, 0, st, (const T*)x, u, (T*)d, (T*)r, (T*)md, (T*)mdr, n / V, keep, seed, offset, dyn);
+    else     CTGAN_LAUNCH((fork_dropout_relu_kernel<T, 1>), elementwise_grid(n, 256), 256, 0, st, (const T*)x, u, (T*)d, (T*)r, (T*)md, (T*)mdr, n, keep, seed, offset, dyn);
     CTGAN_CHECK_LAUNCH("fork_dropout_relu");
     return 0;
 }
@@ -524,8 +547,8 @@ template <typename T>
 static int launch_mask_sum2(const void* a, const void* ma, const void* b, const void* mb, void* out, int64_t n, cudaStream_t st) {
     constexpr int V = vec_width<T>();
     const bool vec = aligned16(a) && (!ma || aligned16(ma)) && aligned16(b) && aligned16(mb) && aligned16(out) && n % V == 0;
-    if (vec) mask_sum2_kernel<T, V><<<elementwise_grid(n / V, 256), 256, 0, st>>>((const T*)a, (const T*)ma, (const T*)b, (const T*)mb, (T*)out, n / V);
-    else     mask_sum2_kernel<T, 1><<<elementwise_grid(n, 256), 256, 0, st>>>((const T*)a, (const T*)ma, (const T*)b, (const T*)mb, (T*)out, n);
+    if (vec) CTGAN_LAUNCH((mask_sum2_kernel<T, V>), elementwise_grid(n / V, 256), 256, 0, st, (const T*)a, (const T*)ma, (const T*)b, (const T*)mb, (T*)out, n / V);
+    else     CTGAN_LAUNCH((mask_sum2_kernel<T, 1>), elementwise_grid(n, 256), 256, 0, st, (const T*)a, (const T*)ma, (const T*)b, (const T*)mb, (T*)out, n);
     CTGAN_CHECK_LAUNCH("mask_sum2");
     return 0;
 }
@@ -539,8 +562,8 @@ template <typename T>
 static int launch_mask_fork2(const void* c, const void* ma, const void* mb, void* o1, void* o2, int64_t n, cudaStream_t st) {
     constexpr int V = vec_width<T>();
     const bool vec = aligned16(c) && aligned16(ma) && aligned16(mb) && aligned16(o1) && aligned16(o2) && n % V == 0;
-    if (vec) mask_fork2_kernel<T, V><<<elementwise_grid(n / V, 256), 256, 0, st>>>((const T*)c, (const T*)ma, (const T*)mb, (T*)o1, (T*)o2, n / V);
-    else     mask_fork2_kernel<T, 1><<<elementwise_grid(n, 256), 256, 0, st>>>((const T*)c, (const T*)ma, (const T*)mb, (T*)o1, (T*)o2, n);
+    if (vec) CTGAN_LAUNCH((mask_fork2_kernel<T, V>), elementwise_grid(n / V, 256), 256, 0, st, (const T*)c, (const T*)ma, (const T*)mb, (T*)o1, (T*)o2, n / V);
+    else     CTGAN_LAUNCH((mask_fork2_kernel<T, 1>), elementwise_grid(n, 256), 256, 0, st, (const T*)c, (const T*)ma, (const T*)mb, (T*)o1, (T*)o2, n);
     CTGAN_CHECK_LAUNCH("mask_fork2");
     return 0;
 }
@@ -563,7 +586,7 @@ static int launch_pool_add_fork(int compute, const void* y, const void* s, const
     const bool vec = C % V == 0 && aligned16(y) && aligned16(s) && (!m1 || aligned16(m1)) && aligned16(m2) && aligned16(o1) &&
                      aligned16(o2) && (offset & 3) == 0;
     const int64_t n = (int64_t)N * (H / 2) * (W / 2) * C;
-#define CTGAN_PAF(VV, CC) pool_add_fork_kernel<T, VV, CC><<<elementwise_grid(n / VV, 256), 256, 0, st>>>( \
+#define CTGAN_PAF(VV, CC) CTGAN_LAUNCH((pool_add_fork_kernel<T, VV, CC>), elementwise_grid(n / VV, 256), 256, 0, st,  \
         (const T*)y, (const T*)s, u, (T*)m1, (T*)m2, (T*)o1, (T*)o2, N, H, W, C, keep, seed, offset, dyn)
     if (compute) { if (vec) CTGAN_PAF(V, 1); else CTGAN_PAF(1, 1); }
     else         { if (vec) CTGAN_PAF(V, 0); else CTGAN_PAF(1, 0); }
@@ -586,8 +609,8 @@ static int launch_mask_sum2_up(const void* a, const void* m1, const void* b, con
     constexpr int V = vec_width<T>();
     const bool vec = C % V == 0 && aligned16(a) && (!m1 || aligned16(m1)) && aligned16(b) && aligned16(m2) && aligned16(gx) && aligned16(gy);
     const int64_t n = (int64_t)N * Ho * Wo * C;
-    if (vec) mask_sum2_up_kernel<T, V><<<elementwise_grid(n / V, 256), 256, 0, st>>>((const T*)a, (const T*)m1, (const T*)b, (const T*)m2, (T*)gx, (T*)gy, N, Ho, Wo, C);
-    else     mask_sum2_up_kernel<T, 1><<<elementwise_grid(n, 256), 256, 0, st>>>((const T*)a, (const T*)m1, (const T*)b, (const T*)m2, (T*)gx, (T*)gy, N, Ho, Wo, C);
+    if (vec) CTGAN_LAUNCH((mask_sum2_up_kernel<T, V>), elementwise_grid(n / V, 256), 256, 0, st, (const T*)a, (const T*)m1, (const T*)b, (const T*)m2, (T*)gx, (T*)gy, N, Ho, Wo, C);
+    else     CTGAN_LAUNCH((mask_sum2_up_kernel<T, 1>), elementwise_grid(n, 256), 256, 0, st, (const T*)a, (const T*)m1, (const T*)b, (const T*)m2, (T*)gx, (T*)gy, N, Ho, Wo, C);
     CTGAN_CHECK_LAUNCH("mask_sum2_up");
     return 0;
 }
@@ -603,8 +626,8 @@ extern "C" int ctgan_bias_add(const void* x, const float* b, void* y, int64_t ro
     int64_t total = rows * C;
     int grid = elementwise_grid(total, 256);
     cudaStream_t st = as_stream(stream);
-    DISPATCH_T(dtype, (bias_add_kernel<float><<<grid, 256, 0, st>>>((const float*)x, b, (float*)y, total, C)),
-                      (bias_add_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, b, (__nv_bfloat16*)y, total, C)));
+    DISPATCH_T(dtype, (CTGAN_LAUNCH((bias_add_kernel<float>), grid, 256, 0, st, (const float*)x, b, (float*)y, total, C)),
+                      (CTGAN_LAUNCH((bias_add_kernel<__nv_bfloat16>), grid, 256, 0, st, (const __nv_bfloat16*)x, b, (__nv_bfloat16*)y, total, C)));
     CTGAN_CHECK_LAUNCH("bias_add");
     return 0;
 }
@@ -615,11 +638,11 @@ static int launch_resample(bool pool, const void* x, void* y, int N, int H, int 
     const bool vec = C % V == 0 && aligned16(x) && aligned16(y);
     const int grid = elementwise_grid(vec ? out_elems / V : out_elems, 256);
     if (pool) {
-        if (vec) pool2x2_kernel<T, V><<<grid, 256, 0, st>>>((const T*)x, (T*)y, N, H, W, C, scale);
-        else     pool2x2_kernel<T, 1><<<grid, 256, 0, st>>>((const T*)x, (T*)y, N, H, W, C, scale);
+        if (vec) CTGAN_LAUNCH((pool2x2_kernel<T, V>), grid, 256, 0, st, (const T*)x, (T*)y, N, H, W, C, scale);
+        else     CTGAN_LAUNCH((pool2x2_kernel<T, 1>), grid, 256, 0, st, (const T*)x, (T*)y, N, H, W, C, scale);
     } else {
-        if (vec) upsample2x_kernel<T, V><<<grid, 256, 0, st>>>((const T*)x, (T*)y, N, H, W, C, scale);
-        else     upsample2x_kernel<T, 1><<<grid, 256, 0, st>>>((const T*)x, (T*)y, N, H, W, C, scale);
+        if (vec) CTGAN_LAUNCH((upsample2x_kernel<T, V>), grid, 256, 0, st, (const T*)x, (T*)y, N, H, W, C, scale);
+        else     CTGAN_LAUNCH((upsample2x_kernel<T, 1>), grid, 256, 0, st, (const T*)x, (T*)y, N, H, W, C, scale);
     }
     CTGAN_CHECK_LAUNCH(pool ? "pool2x2" : "upsample2x");
     return 0;
@@ -638,8 +661,8 @@ extern "C" int ctgan_spatial_sum(const void* x, void* y, int N, int HW, int C, f
     CTGAN_REQUIRE(N > 0 && HW > 0 && C > 0, CTGAN_ERR_BAD_DESC, "spatial_sum: bad shape");
     int grid = elementwise_grid((int64_t)N * C, 128);
     cudaStream_t st = as_stream(stream);
-    DISPATCH_T(dtype, (spatial_sum_kernel<float><<<grid, 128, 0, st>>>((const float*)x, (float*)y, N, HW, C, scale)),
-                      (spatial_sum_kernel<__nv_bfloat16><<<grid, 128, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, N, HW, C, scale)));
+    DISPATCH_T(dtype, (CTGAN_LAUNCH((spatial_sum_kernel<float>), grid, 128, 0, st, (const float*)x, (float*)y, N, HW, C, scale)),
+                      (CTGAN_LAUNCH((spatial_sum_kernel<__nv_bfloat16>), grid, 128, 0, st, (const __nv_bfloat16*)x, (__nv_bfloat16*)y, N, HW, C, scale)));
     CTGAN_CHECK_LAUNCH("spatial_sum");
     return 0;
 }
@@ -647,21 +670,21 @@ extern "C" int ctgan_spatial_bcast(const void* y, void* x, int N, int HW, int C,
     CTGAN_REQUIRE(N > 0 && HW > 0 && C > 0, CTGAN_ERR_BAD_DESC, "spatial_bcast: bad shape");
     int grid = elementwise_grid((int64_t)N * HW * C, 256);
     cudaStream_t st = as_stream(stream);
-    DISPATCH_T(dtype, (spatial_bcast_kernel<float><<<grid, 256, 0, st>>>((const float*)y, (float*)x, N, HW, C, scale)),
-                      (spatial_bcast_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)y, (__nv_bfloat16*)x, N, HW, C, scale)));
+    DISPATCH_T(dtype, (CTGAN_LAUNCH((spatial_bcast_kernel<float>), grid, 256, 0, st, (const float*)y, (float*)x, N, HW, C, scale)),
+                      (CTGAN_LAUNCH((spatial_bcast_kernel<__nv_bfloat16>), grid, 256, 0, st, (const __nv_bfloat16*)y, (__nv_bfloat16*)x, N, HW, C, scale)));
     CTGAN_CHECK_LAUNCH("spatial_bcast");
     return 0;
 }
 
 extern "C" int ctgan_nchw_to_nhwc(const void* x, int xdt, void* y, int ydt, int N, int C, int H, int W, void* stream) {
     CTGAN_REQUIRE(dtype_ok(xdt) && dtype_ok(ydt) && N > 0 && C > 0 && H > 0 && W > 0, CTGAN_ERR_BAD_DESC, "nchw_to_nhwc: bad args");
-    nchw_to_nhwc_kernel<<<elementwise_grid((int64_t)N * C * H * W, 256), 256, 0, as_stream(stream)>>>(x, xdt, y, ydt, N, C, H, W);
+    CTGAN_LAUNCH((nchw_to_nhwc_kernel), elementwise_grid((int64_t)N * C * H * W, 256), 256, 0, as_stream(stream), x, xdt, y, ydt, N, C, H, W);
     CTGAN_CHECK_LAUNCH("nchw_to_nhwc");
     return 0;
 }
 extern "C" int ctgan_nhwc_to_nchw(const void* x, int xdt, void* y, int ydt, int N, int C, int H, int W, void* stream) {
     CTGAN_REQUIRE(dtype_ok(xdt) && dtype_ok(ydt) && N > 0 && C > 0 && H > 0 && W > 0, CTGAN_ERR_BAD_DESC, "nhwc_to_nchw: bad args");
-    nhwc_to_nchw_kernel<<<elementwise_grid((int64_t)N * C * H * W, 256), 256, 0, as_stream(stream)>>>(x, xdt, y, ydt, N, C, H, W);
+    CTGAN_LAUNCH((nhwc_to_nchw_kernel), elementwise_grid((int64_t)N * C * H * W, 256), 256, 0, as_stream(stream), x, xdt, y, ydt, N, C, H, W);
     CTGAN_CHECK_LAUNCH("nhwc_to_nchw");
     return 0;
 }
@@ -670,8 +693,8 @@ static int crop_impl(const void* x, void* y, int N, int H, int W, int C, int h, 
     int64_t total = fwd ? (int64_t)N * h * w * C : (int64_t)N * H * W * C;
     int grid = elementwise_grid(total, 256);
     cudaStream_t st = as_stream(stream);
-    DISPATCH_T(dtype, (crop_kernel<float><<<grid, 256, 0, st>>>((const float*)x, (float*)y, N, H, W, C, h, w, fwd)),
-                      (crop_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, N, H, W, C, h, w, fwd)));
+    DISPATCH_T(dtype, (CTGAN_LAUNCH((crop_kernel<float>), grid, 256, 0, st, (const float*)x, (float*)y, N, H, W, C, h, w, fwd)),
+                      (CTGAN_LAUNCH((crop_kernel<__nv_bfloat16>), grid, 256, 0, st, (const __nv_bfloat16*)x, (__nv_bfloat16*)y, N, H, W, C, h, w, fwd)));
     CTGAN_CHECK_LAUNCH("crop");
     return 0;
 }
@@ -686,34 +709,34 @@ extern "C" int ctgan_prep_real(const int32_t* x, float* y, int64_t n, float deno
                                uint64_t seed, uint64_t offset, const uint64_t* dyn_offset, void* stream) {
     CTGAN_REQUIRE(denom > 0.f, CTGAN_ERR_BAD_DESC, "prep_real: denom must be positive");
     if (n <= 0) return 0;
-    prep_real_div_kernel<<<elementwise_grid(n, 256), 256, 0, as_stream(stream)>>>(x, y, n, denom, noise_hi, seed, offset, dyn_offset);
+    CTGAN_LAUNCH((prep_real_div_kernel), elementwise_grid(n, 256), 256, 0, as_stream(stream), x, y, n, denom, noise_hi, seed, offset, dyn_offset);
     CTGAN_CHECK_LAUNCH("prep_real");
     return 0;
 }
 extern "C" int ctgan_interpolate(const float* real, const float* fake, const float* alpha, float* out,
                                  int B, int P, void* stream) {
     CTGAN_REQUIRE(B > 0 && P > 0, CTGAN_ERR_BAD_DESC, "interpolate: bad shape");
-    interpolate_kernel<<<elementwise_grid((int64_t)B * P, 256), 256, 0, as_stream(stream)>>>(real, fake, alpha, out, B, P);
+    CTGAN_LAUNCH((interpolate_kernel), elementwise_grid((int64_t)B * P, 256), 256, 0, as_stream(stream), real, fake, alpha, out, B, P);
     CTGAN_CHECK_LAUNCH("interpolate");
     return 0;
 }
 
 extern "C" int ctgan_counter_add(uint64_t* counter, uint64_t delta, void* stream) {
     CTGAN_REQUIRE(counter != nullptr, CTGAN_ERR_BAD_DESC, "counter_add: null pointer");
-    counter_add_kernel<<<1, 1, 0, as_stream(stream)>>>(counter, delta);
+    CTGAN_LAUNCH((counter_add_kernel), 1, 1, 0, as_stream(stream), counter, delta);
     CTGAN_CHECK_LAUNCH("counter_add");
     return 0;
 }
 extern "C" int ctgan_philox_uniform(float* out, int64_t n, float lo, float hi, uint64_t seed, uint64_t offset,
                                     const uint64_t* dyn_offset, void* stream) {
     if (n <= 0) return 0;
-    philox_uniform_kernel<<<elementwise_grid(n, 256), 256, 0, as_stream(stream)>>>(out, n, lo, hi, seed, offset, dyn_offset);
+    CTGAN_LAUNCH((philox_uniform_kernel), elementwise_grid(n, 256), 256, 0, as_stream(stream), out, n, lo, hi, seed, offset, dyn_offset);
     CTGAN_CHECK_LAUNCH("philox_uniform");
     return 0;
 }
 extern "C" int ctgan_philox_normal(float* out, int64_t n, uint64_t seed, uint64_t offset, const uint64_t* dyn_offset, void* stream) {
     if (n <= 0) return 0;
-    philox_normal_kernel<<<elementwise_grid(n, 256), 256, 0, as_stream(stream)>>>(out, n, seed, offset, dyn_offset);
+    CTGAN_LAUNCH((philox_normal_kernel), elementwise_grid(n, 256), 256, 0, as_stream(stream), out, n, seed, offset, dyn_offset);
     CTGAN_CHECK_LAUNCH("philox_normal");
     return 0;
 }
@@ -721,7 +744,7 @@ extern "C" int ctgan_philox_labels(int32_t* out, int64_t n, int n_labels, uint64
                                    const uint64_t* dyn_offset, void* stream) {
     CTGAN_REQUIRE(n_labels > 0, CTGAN_ERR_BAD_DESC, "philox_labels: n_labels must be positive");
     if (n <= 0) return 0;
-    philox_labels_kernel<<<elementwise_grid(n, 256), 256, 0, as_stream(stream)>>>(out, n, n_labels, seed, offset, dyn_offset);
+    CTGAN_LAUNCH((philox_labels_kernel), elementwise_grid(n, 256), 256, 0, as_stream(stream), out, n, n_labels, seed, offset, dyn_offset);
     CTGAN_CHECK_LAUNCH("philox_labels");
     return 0;
 }

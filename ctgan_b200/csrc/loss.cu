@@ -36,6 +36,7 @@ ct_gp_per_sample_kernel(ctgan_loss_desc d, const float* __restrict__ d_real, con
                         const void* __restrict__ f1, const void* __restrict__ f2, const float* __restrict__ grad,
                         const float* __restrict__ logits, const int32_t* __restrict__ labels,
                         float* __restrict__ per_sample) {
+    ctgan::pdl_entry();
     __shared__ float sh[32];
     const int i = blockIdx.x;
     float sq = 0.f;
@@ -72,6 +73,7 @@ ct_gp_per_sample_kernel(ctgan_loss_desc d, const float* __restrict__ d_real, con
 __global__ void __launch_bounds__(LOSS_T)
 ct_gp_tail_kernel(ctgan_loss_desc d, const float* __restrict__ d_real, const float* __restrict__ d_fake,
                   const float* __restrict__ per_sample, int has_logits, float* __restrict__ out) {
+    ctgan::pdl_entry();
     __shared__ float sh[32];
     float sr = 0.f, sf = 0.f, sct = 0.f, sgp = 0.f, sce = 0.f;
     for (int i = threadIdx.x; i < d.B; i += LOSS_T) {
@@ -104,6 +106,7 @@ ct_gp_bwd_kernel(ctgan_loss_desc d, const float* __restrict__ gcost,
                  float* __restrict__ g_d_real, float* __restrict__ g_d_real2, float* __restrict__ g_d_fake,
                  void* __restrict__ g_f1, void* __restrict__ g_f2, float* __restrict__ g_grad,
                  float* __restrict__ g_logits) {
+    ctgan::pdl_entry();
     const int i = blockIdx.x;
     const float g = gcost[0];
     const float invB = 1.f / (float)d.B;
@@ -147,6 +150,7 @@ ct_gp_bwd_kernel(ctgan_loss_desc d, const float* __restrict__ gcost,
 
 __global__ void __launch_bounds__(LOSS_T)
 mean_kernel(const float* __restrict__ x, float* __restrict__ out, int n, float sign) {
+    ctgan::pdl_entry();
     __shared__ float sh[32];
     float s = 0.f;
     for (int i = threadIdx.x; i < n; i += LOSS_T) s += x[i];
@@ -155,6 +159,7 @@ mean_kernel(const float* __restrict__ x, float* __restrict__ out, int n, float s
 }
 
 __global__ void mean_bwd_kernel(const float* __restrict__ gcost, float* __restrict__ g, int n, float sign) {
+    ctgan::pdl_entry();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) g[i] = sign * gcost[0] / (float)n;
 }
@@ -162,6 +167,7 @@ __global__ void mean_bwd_kernel(const float* __restrict__ gcost, float* __restri
 __global__ void __launch_bounds__(LOSS_T)
 softmax_ce_fwd_kernel(const float* __restrict__ logits, const int32_t* __restrict__ labels, float* __restrict__ out,
                       int B, int K) {
+    ctgan::pdl_entry();
     __shared__ float sh[32];
     float s = 0.f;
     for (int i = threadIdx.x; i < B; i += LOSS_T) {
@@ -178,6 +184,7 @@ softmax_ce_fwd_kernel(const float* __restrict__ logits, const int32_t* __restric
 __global__ void softmax_ce_bwd_kernel(const float* __restrict__ logits, const int32_t* __restrict__ labels,
                                       const float* __restrict__ gcost, float scale, float* __restrict__ g_logits,
                                       int B, int K) {
+    ctgan::pdl_entry();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B) return;
     const float* lg = logits + (int64_t)i * K;
@@ -210,9 +217,9 @@ extern "C" int ctgan_ct_gp_loss_fwd(const ctgan_loss_desc* d, const float* d_rea
     CTGAN_REQUIRE(d_real && d_real2 && d_fake && f1 && f2 && grad && out && per_sample, CTGAN_ERR_BAD_DESC, "loss_fwd: null pointer");
     CTGAN_REQUIRE(!logits || (labels && d->n_classes > 0), CTGAN_ERR_BAD_DESC, "loss_fwd: logits need labels and n_classes");
     cudaStream_t st = as_stream(stream);
-    ct_gp_per_sample_kernel<<<d->B, LOSS_T, 0, st>>>(*d, d_real, d_real2, f1, f2, grad, logits, labels, per_sample);
+    CTGAN_LAUNCH((ct_gp_per_sample_kernel), d->B, LOSS_T, 0, st, *d, d_real, d_real2, f1, f2, grad, logits, labels, per_sample);
     CTGAN_CHECK_LAUNCH("ct_gp_per_sample");
-    ct_gp_tail_kernel<<<1, LOSS_T, 0, st>>>(*d, d_real, d_fake, per_sample, logits != nullptr, out);
+    CTGAN_LAUNCH((ct_gp_tail_kernel), 1, LOSS_T, 0, st, *d, d_real, d_fake, per_sample, logits != nullptr, out);
     CTGAN_CHECK_LAUNCH("ct_gp_tail");
     return 0;
 }
@@ -227,7 +234,7 @@ extern "C" int ctgan_ct_gp_loss_bwd(const ctgan_loss_desc* d, const float* gcost
     CTGAN_REQUIRE(gcost && d_real && d_real2 && f1 && f2 && grad && per_sample && g_d_real && g_d_real2 && g_d_fake &&
                   g_f1 && g_f2 && g_grad, CTGAN_ERR_BAD_DESC, "loss_bwd: null pointer");
     CTGAN_REQUIRE(!logits || (labels && g_logits && d->n_classes > 0), CTGAN_ERR_BAD_DESC, "loss_bwd: logits need labels/g_logits");
-    ct_gp_bwd_kernel<<<d->B, LOSS_T, 0, as_stream(stream)>>>(*d, gcost, d_real, d_real2, f1, f2, grad, logits, labels,
+    CTGAN_LAUNCH((ct_gp_bwd_kernel), d->B, LOSS_T, 0, as_stream(stream), *d, gcost, d_real, d_real2, f1, f2, grad, logits, labels,
                                                             per_sample, g_d_real, g_d_real2, g_d_fake, g_f1, g_f2,
                                                             g_grad, g_logits);
     CTGAN_CHECK_LAUNCH("ct_gp_bwd");
@@ -236,26 +243,26 @@ extern "C" int ctgan_ct_gp_loss_bwd(const ctgan_loss_desc* d, const float* gcost
 
 extern "C" int ctgan_mean_fwd(const float* x, float* out, int n, float sign, void* stream) {
     CTGAN_REQUIRE(x && out && n > 0, CTGAN_ERR_BAD_DESC, "mean_fwd: bad args");
-    mean_kernel<<<1, LOSS_T, 0, as_stream(stream)>>>(x, out, n, sign);
+    CTGAN_LAUNCH((mean_kernel), 1, LOSS_T, 0, as_stream(stream), x, out, n, sign);
     CTGAN_CHECK_LAUNCH("mean_fwd");
     return 0;
 }
 extern "C" int ctgan_mean_bwd(const float* gcost, float* g, int n, float sign, void* stream) {
     CTGAN_REQUIRE(gcost && g && n > 0, CTGAN_ERR_BAD_DESC, "mean_bwd: bad args");
-    mean_bwd_kernel<<<ceil_div(n, 128), 128, 0, as_stream(stream)>>>(gcost, g, n, sign);
+    CTGAN_LAUNCH((mean_bwd_kernel), ceil_div(n, 128), 128, 0, as_stream(stream), gcost, g, n, sign);
     CTGAN_CHECK_LAUNCH("mean_bwd");
     return 0;
 }
 extern "C" int ctgan_softmax_ce_fwd(const float* logits, const int32_t* labels, float* out, int B, int K, void* stream) {
     CTGAN_REQUIRE(logits && labels && out && B > 0 && K > 0, CTGAN_ERR_BAD_DESC, "softmax_ce_fwd: bad args");
-    softmax_ce_fwd_kernel<<<1, LOSS_T, 0, as_stream(stream)>>>(logits, labels, out, B, K);
+    CTGAN_LAUNCH((softmax_ce_fwd_kernel), 1, LOSS_T, 0, as_stream(stream), logits, labels, out, B, K);
     CTGAN_CHECK_LAUNCH("softmax_ce_fwd");
     return 0;
 }
 extern "C" int ctgan_softmax_ce_bwd(const float* logits, const int32_t* labels, const float* gcost, float scale,
                                     float* g_logits, int B, int K, void* stream) {
     CTGAN_REQUIRE(logits && labels && gcost && g_logits && B > 0 && K > 0, CTGAN_ERR_BAD_DESC, "softmax_ce_bwd: bad args");
-    softmax_ce_bwd_kernel<<<ceil_div(B, 128), 128, 0, as_stream(stream)>>>(logits, labels, gcost, scale, g_logits, B, K);
+    CTGAN_LAUNCH((softmax_ce_bwd_kernel), ceil_div(B, 128), 128, 0, as_stream(stream), logits, labels, gcost, scale, g_logits, B, K);
     CTGAN_CHECK_LAUNCH("softmax_ce_bwd");
     return 0;
 }

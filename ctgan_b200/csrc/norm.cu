@@ -59,6 +59,7 @@ template <> __device__ __forceinline__ void store4<__nv_bfloat16>(__nv_bfloat16*
 template <typename T>
 __global__ void __launch_bounds__(BN_LANES * BN_ROWS)
 bn_stats_kernel(const T* __restrict__ x, float* __restrict__ ws, int64_t Rg, int C, int rows_per_block, int nbg) {
+    ctgan::pdl_entry();
     const int lane = threadIdx.x, ry = threadIdx.y;
     const int c = blockIdx.y * BN_CCH + lane * 4;
     const int g = blockIdx.x / nbg, rb = blockIdx.x - g * nbg;
@@ -123,6 +124,7 @@ __global__ void __launch_bounds__(128)
 bn_finalize_kernel(const float* __restrict__ ws, float* __restrict__ save_mean,
                    float* __restrict__ save_invstd, int64_t Rg, int C, int nbg,
                    int rows_per_block, float eps) {
+    ctgan::pdl_entry();
     const int lane = threadIdx.x & 31;
     const int c = blockIdx.x * 4 + (threadIdx.x >> 5);
     const int g = blockIdx.y;
@@ -153,6 +155,7 @@ __global__ void bn_apply_kernel(const T* __restrict__ x, const float* __restrict
                                 const int32_t* __restrict__ labels, const float* __restrict__ mean,
                                 const float* __restrict__ invstd, T* __restrict__ y,
                                 int64_t R, int HW, int C, int relu, int n_per_group) {
+    ctgan::pdl_entry();
     const int C4 = C / 4;
     int64_t total = R * C4;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -184,6 +187,7 @@ __device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
 }
 __global__ void __launch_bounds__(256)
 bn_stats_bf16_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ ws, int64_t Rg, int C, int rows_per_block, int nbg) {
+    ctgan::pdl_entry();
     __shared__ float sh_mean[2048], sh_m2[2048], sh_cnt[256];
     const int tpr = C >> 3;
     const int cg = threadIdx.x % tpr, rl = threadIdx.x / tpr, rstep = 256 / tpr;
@@ -239,6 +243,7 @@ __global__ void __launch_bounds__(256)
 bn_apply_bf16_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                      const int32_t* __restrict__ labels, const float* __restrict__ mean, const float* __restrict__ invstd,
                      __nv_bfloat16* __restrict__ y, int HW, int C, int relu, int n_per_group, int rows_per_chunk) {
+    ctgan::pdl_entry();
     const int tpr = C >> 3;
     const int cg = threadIdx.x % tpr, rl = threadIdx.x / tpr, rstep = 256 / tpr;
     const int n = blockIdx.y;
@@ -274,6 +279,7 @@ __global__ void __launch_bounds__(BN_LANES * BN_ROWS)
 bn_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ y,
                      const float* __restrict__ mean, const float* __restrict__ invstd, float* __restrict__ ws,
                      int HW, int C, int S, int relu, int n_per_group) {
+    ctgan::pdl_entry();
     const int lane = threadIdx.x, ry = threadIdx.y;
     const int c = blockIdx.y * BN_CCH + lane * 4;
     const int n = blockIdx.x / S, s = blockIdx.x % S;
@@ -323,6 +329,7 @@ bn_bwd_reduce_bf16_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloa
                           const __nv_bfloat16* __restrict__ y, const float* __restrict__ mean,
                           const float* __restrict__ invstd, float* __restrict__ ws, int HW, int C, int S, int relu,
                           int n_per_group) {
+    ctgan::pdl_entry();
     __shared__ float sh1[2048], sh2[2048];
     const int tpr = C >> 3;
     const int cg = threadIdx.x % tpr, rl = threadIdx.x / tpr, rstep = 256 / tpr;
@@ -366,6 +373,7 @@ bn_bwd_apply_bf16_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat
                          const int32_t* __restrict__ labels, const float* __restrict__ mean,
                          const float* __restrict__ invstd, const float* __restrict__ coef, __nv_bfloat16* __restrict__ dx,
                          int HW, int C, int relu, int n_per_group, int groups, int rows_per_chunk) {
+    ctgan::pdl_entry();
     const int tpr = C >> 3;
     const int cg = threadIdx.x % tpr, rl = threadIdx.x / tpr, rstep = 256 / tpr;
     const int n = blockIdx.y;
@@ -411,6 +419,7 @@ bn_bwd_finalize_kernel(const float* __restrict__ ws, const float* __restrict__ g
                        const int32_t* __restrict__ labels, float* __restrict__ dgamma,
                        float* __restrict__ dbeta, float* __restrict__ coef,
                        int N, int S, int C, int n_labels, float inv_Rg, int groups) {
+    ctgan::pdl_entry();
     extern __shared__ float tab[];                    // [4 warps][2][n_labels]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int c = blockIdx.x * 4 + warp;
@@ -455,6 +464,7 @@ __global__ void bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restric
                                     const float* __restrict__ mean, const float* __restrict__ invstd,
                                     const float* __restrict__ coef, T* __restrict__ dx,
                                     int64_t R, int HW, int C, int relu, int n_per_group, int groups) {
+    ctgan::pdl_entry();
     const int C4 = C / 4;
     int64_t total = R * C4;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -485,6 +495,7 @@ __global__ void bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restric
 // ---- bias gradient: column sums -------------------------------------------------
 __global__ void __launch_bounds__(256)
 bias_grad_kernel(const void* __restrict__ dy, float* __restrict__ db, int64_t rows, int C, int dt, int rows_per_block) {
+    ctgan::pdl_entry();
     // blockDim = (32 channel lanes, 8 row lanes); one channel per lane
     const int lane = threadIdx.x, ry = threadIdx.y;
     const int c = blockIdx.y * 32 + lane;
@@ -504,6 +515,7 @@ bias_grad_kernel(const void* __restrict__ dy, float* __restrict__ db, int64_t ro
 // BF16, C/8 a power of two <= 256: 16-byte loads, C/8 threads per row, 4 rows in flight per thread
 __global__ void __launch_bounds__(256)
 bias_grad_bf16_kernel(const __nv_bfloat16* __restrict__ dy, float* __restrict__ db, int64_t rows, int C, int rows_per_block) {
+    ctgan::pdl_entry();
     __shared__ float sh[256 * 8];
     const int tpr = C >> 3;                                  // threads per row
     const int cg = threadIdx.x % tpr, rl = threadIdx.x / tpr, rstep = 256 / tpr;
@@ -568,26 +580,26 @@ extern "C" int ctgan_bn_fwd(const void* x, const float* gamma, const float* beta
     const bool fast = dtype == CTGAN_BF16 && C % 8 == 0 && tpr <= 256 && (tpr & (tpr - 1)) == 0 &&
                       ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
     dim3 blk(BN_LANES, BN_ROWS), grid(nbg * groups, ceil_div(C, BN_CCH));
-    if (fast) bn_stats_bf16_kernel<<<nbg * groups, 256, 0, st>>>((const __nv_bfloat16*)x, ws, Rg, C, rpb, nbg);
-    else if (dtype == CTGAN_F32) bn_stats_kernel<float><<<grid, blk, 0, st>>>((const float*)x, ws, Rg, C, rpb, nbg);
-    else bn_stats_kernel<__nv_bfloat16><<<grid, blk, 0, st>>>((const __nv_bfloat16*)x, ws, Rg, C, rpb, nbg);
+    if (fast) CTGAN_LAUNCH((bn_stats_bf16_kernel), nbg * groups, 256, 0, st, (const __nv_bfloat16*)x, ws, Rg, C, rpb, nbg);
+    else if (dtype == CTGAN_F32) CTGAN_LAUNCH((bn_stats_kernel<float>), grid, blk, 0, st, (const float*)x, ws, Rg, C, rpb, nbg);
+    else CTGAN_LAUNCH((bn_stats_kernel<__nv_bfloat16>), grid, blk, 0, st, (const __nv_bfloat16*)x, ws, Rg, C, rpb, nbg);
     CTGAN_CHECK_LAUNCH("bn_stats");
-    bn_finalize_kernel<<<dim3(ceil_div(C, 4), groups), 128, 0, st>>>(ws, save_mean, save_invstd, Rg, C, nbg, rpb, eps);
+    CTGAN_LAUNCH((bn_finalize_kernel), dim3(ceil_div(C, 4), groups), 128, 0, st, ws, save_mean, save_invstd, Rg, C, nbg, rpb, eps);
     CTGAN_CHECK_LAUNCH("bn_finalize");
     if (fast && N <= 65535) {
         const int rstep = 256 / tpr;
         int rpc = 4 * rstep;                                   // >= 4 rows per thread, more when there are plenty of blocks
         while ((int64_t)N * ceil_div(HW, rpc) > 16 * (int64_t)sm_count() && rpc < HW) rpc *= 2;
-        bn_apply_bf16_kernel<<<dim3(ceil_div(HW, rpc), N), 256, 0, st>>>((const __nv_bfloat16*)x, gamma, beta, labels, save_mean,
+        CTGAN_LAUNCH((bn_apply_bf16_kernel), dim3(ceil_div(HW, rpc), N), 256, 0, st, (const __nv_bfloat16*)x, gamma, beta, labels, save_mean,
                                                                         save_invstd, (__nv_bfloat16*)y, HW, C, relu, N / groups, rpc);
         CTGAN_CHECK_LAUNCH("bn_apply");
         return 0;
     }
     int g2 = elementwise_grid(R * (C / 4), 256);
     if (dtype == CTGAN_F32)
-        bn_apply_kernel<float><<<g2, 256, 0, st>>>((const float*)x, gamma, beta, labels, save_mean, save_invstd, (float*)y, R, HW, C, relu, N / groups);
+        CTGAN_LAUNCH((bn_apply_kernel<float>), g2, 256, 0, st, (const float*)x, gamma, beta, labels, save_mean, save_invstd, (float*)y, R, HW, C, relu, N / groups);
     else
-        bn_apply_kernel<__nv_bfloat16><<<g2, 256, 0, st>>>((const __nv_bfloat16*)x, gamma, beta, labels, save_mean, save_invstd, (__nv_bfloat16*)y, R, HW, C, relu, N / groups);
+        CTGAN_LAUNCH((bn_apply_kernel<__nv_bfloat16>), g2, 256, 0, st, (const __nv_bfloat16*)x, gamma, beta, labels, save_mean, save_invstd, (__nv_bfloat16*)y, R, HW, C, relu, N / groups);
     CTGAN_CHECK_LAUNCH("bn_apply");
     return 0;
 }
@@ -611,20 +623,20 @@ extern "C" int ctgan_bn_bwd(const void* dy, const void* x, const void* y, const 
                         reinterpret_cast<uintptr_t>(y)) & 15) == 0;
     dim3 blk(BN_LANES, BN_ROWS), grid(N * S, ceil_div(C, BN_CCH));
     if (fast)
-        bn_bwd_reduce_bf16_kernel<<<dim3(S, N), 256, 0, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (const __nv_bfloat16*)y,
+        CTGAN_LAUNCH((bn_bwd_reduce_bf16_kernel), dim3(S, N), 256, 0, st, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (const __nv_bfloat16*)y,
                                                              save_mean, save_invstd, ws, HW, C, S, relu, N / groups);
     else if (dtype == CTGAN_F32)
-        bn_bwd_reduce_kernel<float><<<grid, blk, 0, st>>>((const float*)dy, (const float*)x, (const float*)y, save_mean, save_invstd, ws, HW, C, S, relu, N / groups);
+        CTGAN_LAUNCH((bn_bwd_reduce_kernel<float>), grid, blk, 0, st, (const float*)dy, (const float*)x, (const float*)y, save_mean, save_invstd, ws, HW, C, S, relu, N / groups);
     else
-        bn_bwd_reduce_kernel<__nv_bfloat16><<<grid, blk, 0, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (const __nv_bfloat16*)y, save_mean, save_invstd, ws, HW, C, S, relu, N / groups);
+        CTGAN_LAUNCH((bn_bwd_reduce_kernel<__nv_bfloat16>), grid, blk, 0, st, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (const __nv_bfloat16*)y, save_mean, save_invstd, ws, HW, C, S, relu, N / groups);
     CTGAN_CHECK_LAUNCH("bn_bwd_reduce");
-    bn_bwd_finalize_kernel<<<ceil_div(C, 4), 128, sizeof(float) * 8 * n_labels, st>>>(ws, gamma, labels, dgamma, dbeta, coef, N, S, C, n_labels, 1.f / (float)Rg, groups);
+    CTGAN_LAUNCH((bn_bwd_finalize_kernel), ceil_div(C, 4), 128, sizeof(float) * 8 * n_labels, st, ws, gamma, labels, dgamma, dbeta, coef, N, S, C, n_labels, 1.f / (float)Rg, groups);
     CTGAN_CHECK_LAUNCH("bn_bwd_finalize");
     if (fast) {
         const int rstep = 256 / tpr;
         int rpc = 4 * rstep;
         while ((int64_t)N * ceil_div(HW, rpc) > 16 * (int64_t)sm_count() && rpc < HW) rpc *= 2;
-        bn_bwd_apply_bf16_kernel<<<dim3(ceil_div(HW, rpc), N), 256, 0, st>>>(
+        CTGAN_LAUNCH((bn_bwd_apply_bf16_kernel), dim3(ceil_div(HW, rpc), N), 256, 0, st, 
             (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (const __nv_bfloat16*)y, gamma, labels, save_mean, save_invstd, coef,
             (__nv_bfloat16*)dx, HW, C, relu, N / groups, groups, rpc);
         CTGAN_CHECK_LAUNCH("bn_bwd_apply");
@@ -632,9 +644,9 @@ extern "C" int ctgan_bn_bwd(const void* dy, const void* x, const void* y, const 
     }
     int g2 = elementwise_grid(R * (C / 4), 256);
     if (dtype == CTGAN_F32)
-        bn_bwd_apply_kernel<float><<<g2, 256, 0, st>>>((const float*)dy, (const float*)x, (const float*)y, gamma, labels, save_mean, save_invstd, coef, (float*)dx, R, HW, C, relu, N / groups, groups);
+        CTGAN_LAUNCH((bn_bwd_apply_kernel<float>), g2, 256, 0, st, (const float*)dy, (const float*)x, (const float*)y, gamma, labels, save_mean, save_invstd, coef, (float*)dx, R, HW, C, relu, N / groups, groups);
     else
-        bn_bwd_apply_kernel<__nv_bfloat16><<<g2, 256, 0, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (const __nv_bfloat16*)y, gamma, labels, save_mean, save_invstd, coef, (__nv_bfloat16*)dx, R, HW, C, relu, N / groups, groups);
+        CTGAN_LAUNCH((bn_bwd_apply_kernel<__nv_bfloat16>), g2, 256, 0, st, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (const __nv_bfloat16*)y, gamma, labels, save_mean, save_invstd, coef, (__nv_bfloat16*)dx, R, HW, C, relu, N / groups, groups);
     CTGAN_CHECK_LAUNCH("bn_bwd_apply");
     return 0;
 }
@@ -654,7 +666,7 @@ extern "C" int ctgan_bias_grad(const void* dy, float* db, int64_t rows, int C, i
         if (nb > cap) nb = cap;
         int rpb = (int)((rows + nb - 1) / nb);
         nb = (rows + rpb - 1) / rpb;
-        bias_grad_bf16_kernel<<<(unsigned)nb, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(dy), db, rows, C, rpb);
+        CTGAN_LAUNCH((bias_grad_bf16_kernel), (unsigned)nb, 256, 0, st, reinterpret_cast<const __nv_bfloat16*>(dy), db, rows, C, rpb);
         CTGAN_CHECK_LAUNCH("bias_grad");
         return 0;
     }
@@ -666,7 +678,7 @@ extern "C" int ctgan_bias_grad(const void* dy, float* db, int64_t rows, int C, i
     int rpb = (int)((rows + nb - 1) / nb);
     nb = (rows + rpb - 1) / rpb;
     dim3 blk(32, 8), grid((unsigned)nb, cblocks);
-    bias_grad_kernel<<<grid, blk, 0, st>>>(dy, db, rows, C, dtype, rpb);
+    CTGAN_LAUNCH((bias_grad_kernel), grid, blk, 0, st, dy, db, rows, C, dtype, rpb);
     CTGAN_CHECK_LAUNCH("bias_grad");
     return 0;
 }

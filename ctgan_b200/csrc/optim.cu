@@ -12,6 +12,7 @@ template <int V>
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, int64_t nvec, float lr_t, float b1, float b2, float eps,
                             float gscale, const float* __restrict__ lr_t_dev) {
+    ctgan::pdl_entry();
     if (lr_t_dev) lr_t = lr_t_dev[0];
     struct alignas(4 * V) F { float a[V]; };
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
@@ -43,9 +44,9 @@ extern "C" int ctgan_adam_step(float* p, const float* g, float* m, float* v, int
     auto al = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
     if (n % 4 == 0 && al(p) && al(g) && al(m) && al(v)) {
         int64_t nv = n / 4;
-        adam_kernel<4><<<elementwise_grid(nv, 256), 256, 0, st>>>(p, g, m, v, nv, lr_t, beta1, beta2, eps, grad_scale, lr_t_dev);
+        CTGAN_LAUNCH((adam_kernel<4>), elementwise_grid(nv, 256), 256, 0, st, p, g, m, v, nv, lr_t, beta1, beta2, eps, grad_scale, lr_t_dev);
     } else {
-        adam_kernel<1><<<elementwise_grid(n, 256), 256, 0, st>>>(p, g, m, v, n, lr_t, beta1, beta2, eps, grad_scale, lr_t_dev);
+        CTGAN_LAUNCH((adam_kernel<1>), elementwise_grid(n, 256), 256, 0, st, p, g, m, v, n, lr_t, beta1, beta2, eps, grad_scale, lr_t_dev);
     }
     CTGAN_CHECK_LAUNCH("adam_step");
     return 0;

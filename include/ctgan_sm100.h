@@ -89,6 +89,9 @@ int ctgan_conv_wgrad(const ctgan_conv_desc* d, const void* x, const void* dy,
  * residual (nullable, BF16, same shape as y) is added before the optional ReLU. */
 /* test hook: on == 0 disables the halo-reuse variant of fprop_tc (default on) */
 void ctgan_set_fprop_halo(int on);
+/* 1 (default): kernels are launched with programmatic stream serialization (each begins with griddepcontrol.launch_dependents +
+ * griddepcontrol.wait, so launch latency and set-up overlap the predecessor's tail; ordering semantics unchanged); 0: plain launches */
+void ctgan_set_pdl(int on);
 /* test hook: 3 = persistent grouped-stage fprop_tc kernel (default), 2 = persistent per-k-block rings, 1 = one tile per CTA */
 void ctgan_set_fprop_variant(int v);
 /* test/benchmark hook: 2 (default) = 3x3 wgrad CTAs own one filter column and share the x halo box; 1 = per-tap boxes */

@@ -11,6 +11,9 @@ if len(sys.argv) > 2:
     K.config.branch_priority = int(sys.argv[2])
 if len(sys.argv) > 3:
     K.config.side_stream = K.config.branch_streams = bool(int(sys.argv[3]))
+if len(sys.argv) > 4:
+    from ctgan_b200 import _lib
+    _lib.lib.ctgan_set_pdl(int(sys.argv[4]))
 np.random.seed(1234)
 tr = R.Trainer(device='cuda', seed=1234, act_dtype=torch.bfloat16, batch_size=B, graph_safe_rng=True)
 rs = np.random.RandomState(0)
