@@ -661,6 +661,46 @@ class CTGPLoss(Function):
         return g_real, g_real2, g_fake, g_f1, g_f2, g_grad, g_logits, None, None
 
 
+class CTGPLossStacked(Function):
+    """CTGPLoss on the outputs of ONE stacked critic call: d_all [R] / f_all [R, F] / logits_all [R, L] hold the reference's
+    separate critic calls as row ranges; rows = dict(real=(a, b), real2=(a, b), fake=(a, b)).  The backward kernel
+    writes straight into row ranges of the full-size gradients (no slice-backward zero-fills, copies and adds)."""
+
+    @staticmethod
+    def forward(ctx, d_all, f_all, grad, logits_all, labels, hp, rows):
+        (r0, r1), (s0, s1), (k0, k1) = rows['real'], rows['real2'], rows['fake']
+        d_all, f_all = d_all.contiguous(), f_all.contiguous()
+        la = logits_all.contiguous() if logits_all is not None else None
+        d_real, d_real2, d_fake = d_all[r0:r1], d_all[s0:s1], d_all[k0:k1]
+        f1, f2 = f_all[r0:r1], f_all[s0:s1]
+        lg = la[r0:r1] if la is not None else None
+        B, F_ = f1.shape
+        desc = LossDesc(B, d_fake.shape[0], F_, grad.shape[1], 0 if lg is None else lg.shape[1],
+                        BF16 if f1.dtype == torch.bfloat16 else F32,
+                        hp['lambda_gp'], hp['lambda2'], hp['factor_m'], hp.get('acgan_scale', 0.0))
+        grad = grad.contiguous()
+        out, per_sample = K.ct_gp_loss_fwd(desc, d_real, d_real2, d_fake, f1, f2, grad, lg, labels)
+        ctx.desc, ctx.labels, ctx.rows = desc, labels, rows
+        ctx.save_for_backward(d_all, f_all, grad, per_sample, *([la] if la is not None else []))
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gout):
+        saved = ctx.saved_tensors
+        d_all, f_all, grad, per_sample = saved[:4]
+        la = saved[4] if len(saved) > 4 else None
+        (r0, r1), (s0, s1), (k0, k1) = ctx.rows['real'], ctx.rows['real2'], ctx.rows['fake']
+        covered = (r1 - r0) + (s1 - s0) + (k1 - k0) == d_all.shape[0]
+        g_d = torch.empty_like(d_all) if covered else torch.zeros_like(d_all)
+        g_f = torch.zeros_like(f_all)                              # the fake rows carry no feature gradient
+        g_l = torch.zeros_like(la) if la is not None else None
+        outs = (g_d[r0:r1], g_d[s0:s1], g_d[k0:k1], g_f[r0:r1], g_f[s0:s1], g_l[r0:r1] if g_l is not None else None)
+        g = K.ct_gp_loss_bwd(ctx.desc, gout[0:1].contiguous(), d_all[r0:r1], d_all[s0:s1], f_all[r0:r1], f_all[s0:s1], grad,
+                             la[r0:r1] if la is not None else None, ctx.labels, per_sample, outs=outs)
+        return g_d, g_f, g[5], g_l, None, None, None
+
+
 class MeanLoss(Function):
     @staticmethod
     def forward(ctx, d, sign):

@@ -117,8 +117,6 @@ class Trainer:
         RNG.begin_stack([B, B, B])
         d_all, f_all = m.Discriminator(stacked)
         RNG.end_stack()
-        disc_real, disc_real_, disc_fake = d_all[:B], d_all[B:2 * B], d_all[2 * B:]
-        disc_real_2, disc_real_2_ = f_all[:B], f_all[B:2 * B]
         with K.branch(fork):                          # second stream / CUDA-graph branch (see gan_cifar_resnet.py)
             alpha = RNG.uniform('alpha', (B, 1))
             interpolates = K.interpolate(real_data, fake_data, alpha).requires_grad_(True)
@@ -127,8 +125,8 @@ class Trainer:
             gradients = torch.autograd.grad(d_interp, interpolates, grad_outputs=torch.ones_like(d_interp),
                                             create_graph=True)[0]
         K.join_branch(fork)
-        out = F.CTGPLoss.apply(disc_real, disc_real_, disc_fake, disc_real_2, disc_real_2_, gradients, None, None,
-                               self.hp)
+        out = F.CTGPLossStacked.apply(d_all, f_all, gradients, None, None, self.hp,
+                                      dict(real=(0, B), real2=(B, 2 * B), fake=(2 * B, 3 * B)))
         out[0].backward(inputs=self.disc_opt.param_list())
         K.join_branch(fork)
         K.join_side()

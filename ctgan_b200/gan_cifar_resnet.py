@@ -358,8 +358,6 @@ class Trainer:
                 pred = clean.argmax(dim=1).to(torch.int32)
                 metrics['acgan_acc'] = (pred[:B] == all_real_labels).float().mean()
                 metrics['acgan_fake_acc'] = (pred[B:] == all_real_labels).float().mean()
-        disc_real, disc_fake, disc_real_ = disc_all[:B], disc_all[B:2 * B], disc_all[2 * B:]
-        disc_real_2, disc_real_2_ = disc_all_2[:B], disc_all_2[2 * B:]
         # gradient-penalty pass: independent of the stacked pass until the loss, so it runs as a second branch
         # (stream / CUDA-graph branch); autograd replays each branch's backward on the stream of its forward
         with K.branch(fork):
@@ -370,9 +368,11 @@ class Trainer:
             gradients = torch.autograd.grad(d_interp, interpolates, grad_outputs=torch.ones_like(d_interp),
                                             create_graph=True)[0]                                   # :284
         K.join_branch(fork)
-        logits = disc_all_acgan[:B] if (CONDITIONAL and ACGAN) else None
-        out = F.CTGPLoss.apply(disc_real, disc_real_, disc_fake, disc_real_2, disc_real_2_, gradients, logits,
-                               all_real_labels if logits is not None else None, self.hp)
+        use_logits = CONDITIONAL and ACGAN
+        # WGAN term and CE use pass ' (rows [0, 2B)), the CT term the real halves of ' and '' (:244-300)
+        out = F.CTGPLossStacked.apply(disc_all, disc_all_2, gradients, disc_all_acgan if use_logits else None,
+                                      all_real_labels if use_logits else None, self.hp,
+                                      dict(real=(0, B), fake=(B, 2 * B), real2=(2 * B, 3 * B)))
         out[0].backward(inputs=self.disc_opt.param_list())
         K.join_branch(fork)
         K.join_side()

@@ -727,15 +727,23 @@ def ct_gp_loss_fwd(desc, d_real, d_real2, d_fake, f1, f2, grad, logits, labels):
     return out, per_sample
 
 
-def ct_gp_loss_bwd(desc, gcost, d_real, d_real2, f1, f2, grad, logits, labels, per_sample):
+def ct_gp_loss_bwd(desc, gcost, d_real, d_real2, f1, f2, grad, logits, labels, per_sample, outs=None):
+    """outs: optional (g_real, g_real2, g_fake, g_f1, g_f2, g_logits) contiguous destination views (row ranges of the
+    gradients of stacked critic outputs), so that no slice-backward / accumulation kernels are needed."""
     dev = d_real.device
-    g_real = torch.empty(desc.B, dtype=torch.float32, device=dev)
-    g_real2 = torch.empty(desc.B, dtype=torch.float32, device=dev)
-    g_fake = torch.empty(desc.NF, dtype=torch.float32, device=dev)
-    g_f1 = torch.empty_like(f1)
-    g_f2 = torch.empty_like(f2)
+    if outs is not None:
+        g_real, g_real2, g_fake, g_f1, g_f2, g_logits = outs
+        for t in outs:
+            if t is not None and not t.is_contiguous():
+                raise RuntimeError('ctgan_b200: loss gradient destinations must be contiguous')
+    else:
+        g_real = torch.empty(desc.B, dtype=torch.float32, device=dev)
+        g_real2 = torch.empty(desc.B, dtype=torch.float32, device=dev)
+        g_fake = torch.empty(desc.NF, dtype=torch.float32, device=dev)
+        g_f1 = torch.empty_like(f1)
+        g_f2 = torch.empty_like(f2)
+        g_logits = torch.empty_like(logits) if logits is not None else None
     g_grad = torch.empty_like(grad)
-    g_logits = torch.empty_like(logits) if logits is not None else None
     call('ctgan_ct_gp_loss_bwd', ctypes.byref(desc), _p(gcost), _p(d_real), _p(d_real2), _p(f1), _p(f2), _p(grad),
          _p(logits), _p(labels), _p(per_sample), _p(g_real), _p(g_real2), _p(g_fake), _p(g_f1), _p(g_f2),
          _p(g_grad), _p(g_logits), _stream())

@@ -328,7 +328,13 @@ def ct_gp_loss_fwd(desc, d_real, d_real2, d_fake, f1, f2, grad, logits, labels):
     return out, per.reshape(-1)
 
 
-def ct_gp_loss_bwd(desc, gcost, d_real, d_real2, f1, f2, grad, logits, labels, per_sample):
+def ct_gp_loss_bwd(desc, gcost, d_real, d_real2, f1, f2, grad, logits, labels, per_sample, outs=None):
+    if outs is not None:
+        r = ct_gp_loss_bwd(desc, gcost, d_real, d_real2, f1, f2, grad, logits, labels, per_sample)
+        for dst, src in zip(outs, (r[0], r[1], r[2], r[3], r[4], r[6])):
+            if dst is not None:
+                dst.copy_(src)
+        return r
     per = per_sample.reshape(-1, 4)
     g, B = gcost[0], desc.B
     active = (per[:, 0] >= 0).float()
