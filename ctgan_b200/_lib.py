@@ -56,6 +56,10 @@ _PROTOS = {
     'ctgan_col2im_thin': (c_int, [POINTER(ConvDesc), c_int, c_int, P, P, P, P]),
     'ctgan_pack_filter_thin': (c_int, [P, P, c_int, c_int, c_int, c_int, P]),
     'ctgan_wgrad_thin_tc': (c_int, [P, P, c_int64, c_int, c_int, c_int, c_int, P, P]),
+    'ctgan_space_to_depth': (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P]),
+    'ctgan_depth_to_space': (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P]),
+    'ctgan_pack_filter_s2d': (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, P]),
+    'ctgan_s2d_filter_grad': (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     'ctgan_bias_grad': (c_int, [P, P, c_int64, c_int, c_int, c_int, P]),
     'ctgan_bias_add': (c_int, [P, P, P, c_int64, c_int, c_int, P]),
     'ctgan_cast': (c_int, [P, c_int, P, c_int, c_int64, P]),

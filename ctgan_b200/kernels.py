@@ -20,6 +20,8 @@ CL = torch.channels_last
 class Config:
     use_tc = True            # use the tcgen05 kernels when a call is eligible
     use_thin_tc = True       # route 3-channel-side convs through the im2col tensor-core path
+    use_s2d = False          # stride-2 5x5 convs (DCGAN critics / Deconv2D) as 3x3 tensor-core convs over the space-to-depth image
+    s2d_min_extent = 1       # (tunable) smallest space-to-depth image side that takes the tensor-core route
     side_stream = True       # run direct-accumulation wgrad / bias-grad launches on a second stream
     branch_streams = True    # run independent sub-graphs of a step (GP pass vs stacked pass) as stream branches
     branch_priority = -1     # CUDA stream priority of the branch stream (lower = higher priority)
@@ -202,6 +204,7 @@ def invalidate_weight_cache(ptrs=None):
     """Called by an optimizer after ITS parameters changed in place (ptrs = their data pointers; None = all)."""
     if ptrs is None:
         _pack_cache.clear()
+        _s2d_packs.clear()
         return
     for k in [k for k in _pack_cache if k[0] in ptrs]:
         del _pack_cache[k]
@@ -262,6 +265,8 @@ def pack_filter_thin(w, kind, cacheable=False):
 def thin_col(t, g, role):
     """The im2col matrix conv_fprop/conv_wgrad (role 'x') or conv_dgrad/conv_wgrad (role 'dy') would build from t, or
     None when the call does not take the thin path -- lets a caller build it once and pass it to both."""
+    if role == 'x' and s2d_geom(g, t) is not None:
+        return space_to_depth(t, g)                     # shared by fprop and wgrad of a stride-2 conv
     side = _thin_side(g, t)
     if side == 'in' and role == 'x':
         return im2col_thin(t, g, g.Cin, 1)
@@ -300,6 +305,7 @@ class FilterPacker:
     def __init__(self, flat_p, params, offsets):
         import numpy as np
         self.flat_p = flat_p
+        self.param_ptrs = [p.data_ptr() for p in params.values() if p.dim() == 4]
         rows, self.views, dst = [], [], 0
         for name, p in params.items():
             if p.dim() == 4:
@@ -330,11 +336,108 @@ class FilterPacker:
 
     def refresh(self):
         """Re-pack everything (one launch) and publish the views in the pack cache of the current epoch."""
-        if not self.n or not (config.use_tc and tc_available()):
+        if not (config.use_tc and tc_available()):
             return
-        call('ctgan_pack_filters_multi', _p(self.flat_p), _p(self.packs), _p(self.table), self.n, _stream())
-        for p, flip, dst, numel in self.views:
-            _pack_cache[(p.data_ptr(), tuple(p.shape), flip)] = self.packs[dst:dst + numel]
+        if self.n:
+            call('ctgan_pack_filters_multi', _p(self.flat_p), _p(self.packs), _p(self.table), self.n, _stream())
+            for p, flip, dst, numel in self.views:
+                _pack_cache[(p.data_ptr(), tuple(p.shape), flip)] = self.packs[dst:dst + numel]
+        refresh_s2d_packs(self.param_ptrs)
+
+
+# ---- raw tensor-core launches (operands already in kernel layout)
+def _fprop_tc_packed(x, wp, bias, residual, relu_mask, y, g, flags):
+    """y = conv(x, packed filter) on the stride-1 tcgen05 kernels; g is the stride-1 geometry the kernel sees."""
+    d = _desc(g, BF16, BF16)
+    if relu_mask is None:
+        call('ctgan_conv_fprop_tc', ctypes.byref(d), _p(x), _p(wp), _p(bias), _p(residual), _p(y), flags, _stream())
+    else:
+        call('ctgan_conv_fprop_tc_masked', ctypes.byref(d), _p(x), _p(wp), _p(bias), _p(residual), _p(relu_mask), _p(y), flags, _stream())
+    return y
+
+
+def _wgrad_tc_raw(x, dy, g, dw):
+    """dw (float HWIO of g, pre-initialised) += wgrad(x, dy) on the tcgen05 kernels."""
+    d = _desc(g, BF16, BF16)
+    call('ctgan_conv_wgrad_tc', ctypes.byref(d), _p(x), _p(dy), _p(dw), _stream())
+    return dw
+
+
+# ---- stride-2 5x5 'SAME' convs as 3x3 stride-1 tensor-core convs over the space-to-depth image (csrc/conv_s2d.cu)
+def s2d_geom(g, t=None):
+    """The 3x3 / stride-1 geometry (over [N, 4*Cin, ceil(H/2), ceil(W/2)]) equivalent to the stride-2 conv g, or None
+    when the call does not take that route.  t: an activation of the call (dtype check)."""
+    if not (config.use_tc and config.use_s2d and tc_available()):
+        return None
+    if t is not None and (t.dim() != 4 or t.dtype != torch.bfloat16):
+        return None
+    if g.stride != 2 or g.kh != g.kw or not (0 <= g.pad_t <= 2 and 0 <= g.pad_l <= 2):
+        return None
+    if g.kh - 1 - g.pad_t > 3 or g.kw - 1 - g.pad_l > 3 or g.kh < 3:      # block offsets of the taps must be {-1, 0, +1}
+        return None
+    Hs, Ws = (g.H + 1) // 2, (g.W + 1) // 2
+    if Hs != g.Ho or Ws != g.Wo or min(Hs, Ws) < config.s2d_min_extent:
+        return None
+    if (4 * g.Cin) % 64 or g.Cout % 64:
+        return None
+    return ConvGeom(g.N, Hs, Ws, 4 * g.Cin, Hs, Ws, g.Cout, 3, 3, 1, 1, 1)
+
+
+def space_to_depth(x, g):
+    """x [N,Cin,H,W] -> xs [N,4*Cin,ceil(H/2),ceil(W/2)], channel (dy*2+dx)*Cin + c <- x[.., 2i+dy, 2j+dx] (zero outside)."""
+    require_nhwc(x, 'x')
+    xs = empty_act((g.N, 4 * g.Cin, (g.H + 1) // 2, (g.W + 1) // 2), x.dtype, x.device)
+    call('ctgan_space_to_depth', _p(x), _p(xs), g.N, g.H, g.W, g.Cin, _dt(x), _stream())
+    return xs
+
+
+def depth_to_space(xs, g):
+    """Inverse of space_to_depth, cropped to the [N,Cin,H,W] of g."""
+    require_nhwc(xs, 'xs')
+    x = empty_act((g.N, g.Cin, g.H, g.W), xs.dtype, xs.device)
+    call('ctgan_depth_to_space', _p(xs), _p(x), g.N, g.H, g.W, g.Cin, _dt(xs), _stream())
+    return x
+
+
+def _pack_filter_s2d_launch(w, wp_f, wp_d, g):
+    call('ctgan_pack_filter_s2d', _p(w), _p(wp_f), _p(wp_d), g.kh, g.Cin, g.Cout, g.pad_t, g.pad_l, _stream())
+
+
+def _s2d_filter_grad_launch(dw3, dw, g, accumulate):
+    call('ctgan_s2d_filter_grad', _p(dw3), _p(dw), g.kh, g.Cin, g.Cout, g.pad_t, g.pad_l, int(accumulate), _stream())
+
+
+# persistent (fprop, dgrad) operand pairs of PARAMETER filters on the space-to-depth route: {param ptr: {key: (w, wp_f, wp_d, g)}}.
+# They are created at a filter's first use (the pads depend on the input extent, which only the call knows) and
+# re-packed in place after every optimizer step by FilterPacker.refresh(), so a captured CUDA graph always reads
+# current weights from the same addresses.
+_s2d_packs = {}
+
+
+def pack_filter_s2d(w, g, flip, cacheable=False):
+    """bf16 operands of the embedded 3x3 filter: flip 0 -> [9][Cout][4Cin] (fprop), 1 -> tap-flipped [9][4Cin][Cout] (dgrad)."""
+    key = (w.data_ptr(), tuple(w.shape), 's2d', g.pad_t, g.pad_l)
+    if cacheable and key in _pack_cache:
+        return _pack_cache[key][flip]
+    if cacheable and key in _s2d_packs.get(w.data_ptr(), {}):
+        _, wp_f, wp_d, _ = _s2d_packs[w.data_ptr()][key]           # invalidated by an update: re-pack in place
+    else:
+        n = 36 * g.Cin * g.Cout
+        wp_f = torch.empty(n, dtype=torch.bfloat16, device=w.device)
+        wp_d = torch.empty(n, dtype=torch.bfloat16, device=w.device)
+    _pack_filter_s2d_launch(w, wp_f, wp_d, g)
+    if cacheable:
+        _pack_cache[key] = (wp_f, wp_d)
+        _s2d_packs.setdefault(w.data_ptr(), {})[key] = (w.detach(), wp_f, wp_d, g)
+    return (wp_f, wp_d)[flip]
+
+
+def refresh_s2d_packs(ptrs):
+    """Re-pack (in place) every registered space-to-depth operand of the parameters at `ptrs`; publish them in the cache."""
+    for ptr in ptrs:
+        for key, (w, wp_f, wp_d, g) in _s2d_packs.get(ptr, {}).items():
+            _pack_filter_s2d_launch(w, wp_f, wp_d, g)
+            _pack_cache[key] = (wp_f, wp_d)
 
 
 def conv_fprop(x, w, bias, g, relu=False, residual=None, out_dtype=None, w_is_param=False, col=None, res_up2=False):
@@ -353,9 +456,13 @@ def conv_fprop(x, w, bias, g, relu=False, residual=None, out_dtype=None, w_is_pa
         wp = pack_filter(w, 0, cacheable=w_is_param)
         if residual is not None:
             require_nhwc(residual, 'residual')
-        d = _desc(g, xdt, ydt)
-        call('ctgan_conv_fprop_tc', ctypes.byref(d), _p(x), _p(wp), _p(bias), _p(residual), _p(y), flags, _stream())
-        return y
+        return _fprop_tc_packed(x, wp, bias, residual, None, y, g, flags)
+    g3 = s2d_geom(g, x) if (xdt == BF16 and ydt == BF16) else None
+    if g3 is not None:                                # stride 2: 3x3 conv over the space-to-depth image
+        if residual is not None:
+            require_nhwc(residual, 'residual')
+        xs = col if (col is not None and tuple(col.shape) == (g3.N, g3.Cin, g3.H, g3.W)) else space_to_depth(x, g)
+        return _fprop_tc_packed(xs, pack_filter_s2d(w, g, 0, cacheable=w_is_param), bias, residual, None, y, g3, flags)
     side = _thin_side(g, x) if (xdt == BF16 and ydt == BF16) else None
     if side == 'in':                                  # y = im2col(x) x w[(t,c)][Cout]
         if residual is not None:
@@ -389,11 +496,15 @@ def conv_dgrad(dy, w, g, out_dtype=None, w_is_param=False, col=None, relu_mask=N
         # stride-1 dgrad == fprop of dy with the tap-flipped filter, Cin<->Cout, pad -> k-1-pad
         gt = ConvGeom(g.N, g.H, g.W, g.Cout, g.H, g.W, g.Cin, g.kh, g.kw, 1, g.kh - 1 - g.pad_t, g.kw - 1 - g.pad_l)
         wp = pack_filter(w, 1, cacheable=w_is_param)
-        d = _desc(gt, BF16, BF16)
-        call('ctgan_conv_fprop_tc_masked', ctypes.byref(d), _p(dy), _p(wp), None, None, _p(relu_mask), _p(dx), 0, _stream())
-        return dx
+        return _fprop_tc_packed(dy, wp, None, None, relu_mask, dx, gt, 0)
     if relu_mask is not None:                       # other paths: the mask as a separate kernel
         return mul_relu_mask(conv_dgrad(dy, w, g, out_dtype=out_dtype, w_is_param=w_is_param, col=col), relu_mask)
+    g3 = s2d_geom(g, dy) if (xdt == BF16 and ydt == BF16) else None
+    if g3 is not None:                                # dxs = dgrad of the 3x3 conv (fprop with the flipped pack), dx = depth_to_space
+        gt = ConvGeom(g3.N, g3.H, g3.W, g3.Cout, g3.H, g3.W, g3.Cin, 3, 3, 1, 1, 1)
+        dxs = empty_act((g3.N, g3.Cin, g3.H, g3.W), torch.bfloat16, dy.device)
+        _fprop_tc_packed(dy, pack_filter_s2d(w, g, 1, cacheable=w_is_param), None, None, None, dxs, gt, 0)
+        return depth_to_space(dxs, g)
     side = _thin_side(g, dy) if (xdt == BF16 and ydt == BF16) else None
     if side == 'in':                                  # dxcol[(t,ci)] = dy x w^T, dx = col2im(dxcol, -1)
         dxcol = _gemm1x1_tc(dy, pack_filter_thin(w, 3, cacheable=w_is_param), None, g, g.Cout, 64)
@@ -419,7 +530,13 @@ def conv_wgrad(x, dy, g, w_shape, accumulate_into=None, col=None):
         raise RuntimeError('ctgan_b200: accumulate_into must be a contiguous float32 tensor of the filter shape')
     if xdt == BF16 and ydt == BF16 and _tc_geom_ok(g) and g.Cin % 128 == 0 and g.Cout % 128 == 0:
         dw = acc if acc is not None else torch.zeros(w_shape, dtype=torch.float32, device=x.device)
-        call('ctgan_conv_wgrad_tc', ctypes.byref(d), _p(x), _p(dy), _p(dw), _stream())
+        return _wgrad_tc_raw(x, dy, g, dw)
+    g3 = s2d_geom(g, x) if (xdt == BF16 and ydt == BF16) else None
+    if g3 is not None and g3.Cin % 128 == 0 and g3.Cout % 128 == 0:
+        xs = col if (col is not None and tuple(col.shape) == (g3.N, g3.Cin, g3.H, g3.W)) else space_to_depth(x, g)
+        dw3 = _wgrad_tc_raw(xs, dy, g3, torch.zeros((3, 3, g3.Cin, g3.Cout), dtype=torch.float32, device=x.device))
+        dw = acc if acc is not None else torch.empty(w_shape, dtype=torch.float32, device=x.device)
+        _s2d_filter_grad_launch(dw3, dw, g, acc is not None)
         return dw
     side = _thin_side(g, x) if (xdt == BF16 and ydt == BF16) else None
     if side is not None:

@@ -131,6 +131,23 @@ int ctgan_pack_filter_thin(const float* w, void* wp_bf16, int taps, int C, int C
 int ctgan_wgrad_thin_tc(const void* wide, const void* col, long long P, int Cw, int C, int taps, int mode, float* dw, void* stream);
 int ctgan_pack_filters_multi(const float* flat_params, void* packs_bf16, const void* table, int n_entries, void* stream);
 
+/* ---- stride-2 5x5 convolutions on the tensor cores (the DCGAN critics' tf.nn.conv2d(stride 2),
+ * TG/tflib/ops/conv2d.py:106-112 called from TG/CT_gan_cifar.py:84-94 and TG/CT_gan_mnist.py:92-102, and -- as their
+ * dgrad -- the generators' tf.nn.conv2d_transpose, TG/tflib/ops/deconv2d.py:97-103).  A stride-2 'SAME' correlation
+ * over x [N,H,W,C] is a stride-1 3x3 pad-1 correlation over the space-to-depth image
+ *   xs [N,Hs,Ws,4C],  xs[n,i,j,(dy*2+dx)*C+c] = x[n,2i+dy,2j+dx,c]  (zero outside x),  Hs = ceil(H/2), Ws = ceil(W/2)
+ * with the embedded filter W3[R,S,(dy*2+dx)*C+c,o] = w[2(R-1)+dy+pad_t, 2(S-1)+dx+pad_l, c, o] (zero outside k x k),
+ * valid when pad <= 2 and k-1-pad <= 3 (k = 5 with TF-SAME pads 1 or 2).  fprop = ctgan_conv_fprop_tc(xs, wp_f),
+ * dgrad = depth_to_space(ctgan_conv_fprop_tc(dy, wp_d)), wgrad = s2d_filter_grad(ctgan_conv_wgrad_tc(xs, dy)).
+ *   space_to_depth / depth_to_space: H, W, C are those of the full-resolution tensor x; depth_to_space crops to H x W.
+ *   pack_filter_s2d: w float HWIO [k][k][Cin][Cout] -> wp_f [9][Cout][4Cin] and the tap-flipped wp_d [9][4Cin][Cout]
+ *                    (bf16; either may be null).
+ *   s2d_filter_grad: dw [k][k][Cin][Cout] (+)= the tap entries of dw3 [3][3][4Cin][Cout] (both float HWIO). */
+int ctgan_space_to_depth(const void* x, void* xs, int N, int H, int W, int C, int dtype, void* stream);
+int ctgan_depth_to_space(const void* xs, void* x, int N, int H, int W, int C, int dtype, void* stream);
+int ctgan_pack_filter_s2d(const float* w, void* wp_f, void* wp_d, int k, int Cin, int Cout, int pad_t, int pad_l, void* stream);
+int ctgan_s2d_filter_grad(const float* dw3, float* dw, int k, int Cin, int Cout, int pad_t, int pad_l, int accumulate, void* stream);
+
 /* db[c] (float) = sum over rows of dy[rows][C]   (gradient of tf.nn.bias_add) */
 int ctgan_bias_grad(const void* dy, float* db, int64_t rows, int C, int dtype,
                     int accumulate, void* stream);

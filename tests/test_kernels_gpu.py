@@ -484,3 +484,81 @@ def test_pool_add_fork_kernels(K, dtype, keep):
     gy, gx = K.mask_sum2_up(to_dev(a), m1, to_dev(b), m2)
     hy, hx = fb.mask_sum2_up(a, None if m1 is None else m1.cpu(), b, m2.cpu())
     assert rel(gx, hx) < tol and rel(gy, hy) < tol
+
+
+# ---------------------------------------------------------------- stride-2 5x5 convs on the tensor cores (csrc/conv_s2d.cu)
+S2D_GEOMS = [
+    # N, H, W, Cin, Cout  (5x5, stride 2, TF SAME)
+    (64, 16, 16, 128, 256),    # CIFAR Discriminator.2 / (as dgrad) Generator.3
+    (64, 8, 8, 256, 512),      # CIFAR Discriminator.3 / Generator.2
+    (192, 16, 16, 128, 256),   # ... on the stacked critic pass
+    (5, 8, 8, 128, 256),       # MNIST Generator.2 (as dgrad), ragged batch
+    (50, 14, 14, 64, 128),     # MNIST Discriminator.2 / Generator.3: 7x7 space-to-depth image
+    (50, 7, 7, 128, 256),      # MNIST Discriminator.3: odd extent, pads (2, 2)
+    (3, 12, 20, 32, 128),      # non-square, 4*Cin = 128
+]
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('shape', [(3, 16, 16, 128), (2, 7, 7, 64), (4, 9, 6, 3), (1, 32, 32, 8)])
+def test_s2d_layout_kernels(K, shape, dtype):
+    """space_to_depth / depth_to_space against the test-side restatement (exact: pure data movement)."""
+    from tests import test_s2d_host as H
+    N, Hh, W, C = shape
+    g = K.same_geom(N, Hh, W, C, 64, 5, 2)
+    x = act((N, C, Hh, W), dtype, 1)
+    xs = K.space_to_depth(to_dev(x), g)
+    ref = H._s2d(x, g)
+    assert xs.shape == ref.shape and xs.is_contiguous(memory_format=CL) and torch.equal(xs.cpu(), ref)
+    back = K.depth_to_space(xs, g)
+    assert back.shape == x.shape and torch.equal(back.cpu(), x)
+
+
+@pytest.mark.parametrize('geom', [(5, 8, 16, 1), (5, 32, 64, 2), (5, 3, 5, 1), (3, 16, 32, 0)])
+def test_s2d_filter_kernels(K, geom):
+    """pack_filter_s2d (both operand layouts) and its adjoint s2d_filter_grad against the restatement."""
+    from tests import test_s2d_host as H
+    k, Cin, Cout, pad = geom
+    g = K.ConvGeom(1, 8, 8, Cin, 4, 4, Cout, k, k, 2, pad, pad)
+    w = filt((k, k, Cin, Cout), 3, 1.0)
+    n = 36 * Cin * Cout
+    wp_f = torch.empty(n, dtype=torch.bfloat16, device='cuda')
+    wp_d = torch.empty(n, dtype=torch.bfloat16, device='cuda')
+    K._pack_filter_s2d_launch(w.cuda(), wp_f, wp_d, g)
+    rf, rd = torch.empty(n, dtype=torch.bfloat16), torch.empty(n, dtype=torch.bfloat16)
+    H._pack_launch(w, rf, rd, g)
+    assert torch.equal(wp_f.cpu(), rf) and torch.equal(wp_d.cpu(), rd)
+    dw3 = filt((3, 3, 4 * Cin, Cout), 5, 1.0)
+    for accumulate in (0, 1):
+        dw = torch.ones(k, k, Cin, Cout, device='cuda')
+        K._s2d_filter_grad_launch(dw3.cuda(), dw, g, accumulate)
+        ref = torch.ones(k, k, Cin, Cout)
+        H._filter_grad_launch(dw3, ref, g, accumulate)
+        assert torch.equal(dw.cpu(), ref)
+
+
+@pytest.mark.parametrize('geom', S2D_GEOMS)
+def test_s2d_conv_family(K, geom):
+    """Stride-2 5x5 SAME conv family on the space-to-depth tensor-core route vs the direct CPU evaluation, and vs the
+    SIMT kernels the same call takes with the route off."""
+    N, H, W, Cin, Cout = geom
+    g = K.same_geom(N, H, W, Cin, Cout, 5, 2)
+    x, dy = act((N, Cin, H, W), torch.bfloat16, 1), act((N, Cout, g.Ho, g.Wo), torch.bfloat16, 2)
+    w, b = filt((5, 5, Cin, Cout), 3), act((Cout,), torch.float32, 4)
+    K.config.use_s2d = True
+    try:
+        assert K.s2d_geom(g, to_dev(x)) is not None
+        y = K.conv_fprop(to_dev(x), w.cuda(), b.cuda(), g)
+        dx = K.conv_dgrad(to_dev(dy), w.cuda(), g)
+        dw = K.conv_wgrad(to_dev(x), to_dev(dy), g, tuple(w.shape))
+        acc = torch.ones(5, 5, Cin, Cout, device='cuda')
+        K.conv_wgrad(to_dev(x), to_dev(dy), g, tuple(w.shape), accumulate_into=acc, col=K.thin_col(to_dev(x), g, 'x'))
+    finally:
+        K.config.use_s2d = False
+    ys = K.conv_fprop(to_dev(x), w.cuda(), b.cuda(), g)               # SIMT route
+    wq = w.to(torch.bfloat16).float()
+    fb = FB()
+    assert rel(y, fb.conv_fprop(x, wq, b, g)) < 1e-2 and rel(y, ys) < 1.5e-2
+    assert rel(dx, fb.conv_dgrad(dy, wq, g)) < 1e-2
+    ref_w = fb.conv_wgrad(x, dy, g, tuple(w.shape))
+    assert rel(dw, ref_w) < 2e-3 and rel(acc - 1, ref_w) < 2e-3

@@ -68,6 +68,27 @@ def test_step_parity(script, B, path, conditioned):
     _check(rep, path, 'gen', conditioned)
 
 
+@pytest.mark.parametrize('script,B', [('mnist', 50), ('cifar', 64)])
+def test_step_parity_s2d_route(script, B):
+    """The DCGAN scripts with their stride-2 5x5 convs / Deconv2D layers on the tensor cores (space-to-depth route,
+    kernels.config.use_s2d): same parity bars as the BF16 path of test_step_parity."""
+    _need_gpu()
+    import ctgan_b200.kernels as K
+    K.config.use_s2d = True
+    try:
+        tr, om = parity.build_pair(script, 'cuda', torch.bfloat16, B)
+        parity.perturb_params(tr, om)
+        ff = TOL['bf16']['floor']
+        rep = parity.critic_parity(script, tr, om, parity.make_inputs(script, B, 11), conditioned=True, floor_frac=ff)
+        _check(rep, 'bf16', 'critic', True)
+        rep = parity.gen_parity(script, tr, om, conditioned=True, floor_frac=ff)
+        _check(rep, 'bf16', 'gen', True)
+        assert K._s2d_packs, 'the space-to-depth route was not taken'
+    finally:
+        K.config.use_s2d = False
+        K.invalidate_weight_cache()
+
+
 def test_full_size_resnet_bf16_critic():
     """BASELINE configs[2]: CT_gan_cifar_resnet.py, batch 64, DIM 128, BF16 tensor-core path
     (oracle in float32 to keep the CPU side at a few seconds)."""
