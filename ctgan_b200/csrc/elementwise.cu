@@ -396,7 +396,8 @@ __global__ void crop_kernel(const T* __restrict__ x, T* __restrict__ y, int N, i
     }
 }
 
-__global__ void prep_real_div_kernel(const int32_t* __restrict__ x, float* __restrict__ y, int64_t n, float denom,
+template <typename TIn>
+__global__ void prep_real_div_kernel(const TIn* __restrict__ x, float* __restrict__ y, int64_t n, float denom,
                                      float noise_hi, uint64_t seed, uint64_t offset, const uint64_t* __restrict__ dyn) {
     ctgan::pdl_entry();
     if (dyn) offset += dyn[0];
@@ -709,8 +710,16 @@ extern "C" int ctgan_prep_real(const int32_t* x, float* y, int64_t n, float deno
                                uint64_t seed, uint64_t offset, const uint64_t* dyn_offset, void* stream) {
     CTGAN_REQUIRE(denom > 0.f, CTGAN_ERR_BAD_DESC, "prep_real: denom must be positive");
     if (n <= 0) return 0;
-    CTGAN_LAUNCH((prep_real_div_kernel), elementwise_grid(n, 256), 256, 0, as_stream(stream), x, y, n, denom, noise_hi, seed, offset, dyn_offset);
+    CTGAN_LAUNCH((prep_real_div_kernel<int32_t>), elementwise_grid(n, 256), 256, 0, as_stream(stream), x, y, n, denom, noise_hi, seed, offset, dyn_offset);
     CTGAN_CHECK_LAUNCH("prep_real");
+    return 0;
+}
+extern "C" int ctgan_prep_real_u8(const uint8_t* x, float* y, int64_t n, float denom, float noise_hi,
+                                  uint64_t seed, uint64_t offset, const uint64_t* dyn_offset, void* stream) {
+    CTGAN_REQUIRE(denom > 0.f, CTGAN_ERR_BAD_DESC, "prep_real_u8: denom must be positive");
+    if (n <= 0) return 0;
+    CTGAN_LAUNCH((prep_real_div_kernel<uint8_t>), elementwise_grid(n, 256), 256, 0, as_stream(stream), x, y, n, denom, noise_hi, seed, offset, dyn_offset);
+    CTGAN_CHECK_LAUNCH("prep_real_u8");
     return 0;
 }
 extern "C" int ctgan_interpolate(const float* real, const float* fake, const float* alpha, float* out,

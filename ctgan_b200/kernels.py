@@ -20,7 +20,7 @@ CL = torch.channels_last
 class Config:
     use_tc = True            # use the tcgen05 kernels when a call is eligible
     use_thin_tc = True       # route 3-channel-side convs through the im2col tensor-core path
-    use_s2d = False          # stride-2 5x5 convs (DCGAN critics / Deconv2D) as 3x3 tensor-core convs over the space-to-depth image
+    use_s2d = True           # stride-2 5x5 convs (DCGAN critics / Deconv2D) as 3x3 tensor-core convs over the space-to-depth image
     s2d_min_extent = 1       # (tunable) smallest space-to-depth image side that takes the tensor-core route
     side_stream = True       # run direct-accumulation wgrad / bias-grad launches on a second stream
     branch_streams = True    # run independent sub-graphs of a step (GP pass vs stacked pass) as stream branches
@@ -784,10 +784,10 @@ def crop_bwd(dy, H, W):
 
 def prep_real(x_int, denom, noise_hi=0., seed=0, offset=0, dyn=None):
     _chk(x_int)
-    if x_int.dtype != torch.int32 or not x_int.is_contiguous():
-        raise RuntimeError('ctgan_b200: real data must be contiguous int32')
+    if x_int.dtype not in (torch.int32, torch.uint8) or not x_int.is_contiguous():
+        raise RuntimeError('ctgan_b200: real data must be contiguous int32 or uint8')
     y = torch.empty(x_int.shape, dtype=torch.float32, device=x_int.device)
-    call('ctgan_prep_real', _p(x_int), _p(y), x_int.numel(), float(denom), float(noise_hi), int(seed), int(offset), _p(dyn), _stream())
+    call('ctgan_prep_real' if x_int.dtype == torch.int32 else 'ctgan_prep_real_u8', _p(x_int), _p(y), x_int.numel(), float(denom), float(noise_hi), int(seed), int(offset), _p(dyn), _stream())
     return y
 
 

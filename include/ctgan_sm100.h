@@ -220,6 +220,10 @@ int ctgan_crop_bwd(const void* dy, void* dx, int N, int H, int W, int C, int h, 
  * when noise_hi > 0.  y is float [n]. */
 int ctgan_prep_real(const int32_t* x_int, float* y, int64_t n, float denom, float noise_hi,
                     uint64_t seed, uint64_t offset, const uint64_t* dyn_offset /*nullable*/, void* stream);
+/* the same on the uint8 pixels the reference's loaders yield (TG/tflib/cifar10.py:17-19 `images` is uint8; the
+ * feed converts to the int32 placeholder TG/CT_gan_cifar_resnet.py:191): 1 byte/pixel over PCIe instead of 4 */
+int ctgan_prep_real_u8(const uint8_t* x_u8, float* y, int64_t n, float denom, float noise_hi,
+                       uint64_t seed, uint64_t offset, const uint64_t* dyn_offset /*nullable*/, void* stream);
 /* out[b,p] = real[b,p] + alpha[b] * (fake[b,p] - real[b,p])   (TG/CT_gan_cifar.py:142-143) */
 int ctgan_interpolate(const float* real, const float* fake, const float* alpha, float* out,
                       int B, int P, void* stream);

@@ -113,3 +113,49 @@ def test_stream_branches_do_not_change_a_step():
     assert _rel(res[True][0][:5], res[False][0][:5]) < 1e-5
     assert _rel(res[True][1], res[False][1]) < 1e-4
     assert _rel(res[True][2], res[False][2]) < 1e-4
+
+
+def test_dcgan_graph_replay_trains_like_eager():
+    """CT_gan_cifar.py with its stride-2 layers on the space-to-depth tensor-core route: the operand packs of those
+    filters are created at first use and re-packed in place after every optimizer step (kernels._s2d_packs), so a
+    captured graph must keep reading current weights.  3 warm-up steps + 2 x (generator step + 2 critic steps),
+    graph replay vs the same sequence launched eagerly from the same seeds."""
+    import ctgan_b200.gan_cifar as C
+    import ctgan_b200.kernels as K
+    from ctgan_b200.graphs import GraphedTrainer
+    B, NC = 16, 2
+    rs = np.random.RandomState(5)
+    xs = torch.from_numpy(rs.randint(0, 256, (1 + 2 * NC, B, 3072)).astype('int32')).cuda()
+
+    def trainer():
+        np.random.seed(1234)
+        return C.Trainer(device='cuda', seed=11, act_dtype=torch.bfloat16, batch_size=B, graph_safe_rng=True)
+
+    graphed = trainer()
+    pd0, pg0 = graphed.disc_opt.flat_p.clone(), graphed.gen_opt.flat_p.clone()
+    gt = GraphedTrainer(graphed, (xs[0],), warmup=3)
+    assert K._s2d_packs, 'the space-to-depth route was not taken'
+    for it in range(2):
+        gt.gen_step()
+        for k in range(NC):
+            out_g = gt.critic_step(xs[1 + it * NC + k]).clone()
+    torch.cuda.synchronize()
+    pd_g, pg_g = graphed.disc_opt.flat_p.clone(), graphed.gen_opt.flat_p.clone()
+
+    eager = trainer()
+    for _ in range(3):
+        eager.disc_opt.set_device_lr(None); eager.critic_step(xs[0], use_device_lr=True)
+        eager.gen_opt.set_device_lr(None); eager.gen_step(use_device_lr=True)
+    for it in range(2):
+        eager.gen_opt.set_device_lr(None); eager.gen_step(use_device_lr=True)
+        for k in range(NC):
+            eager.disc_opt.set_device_lr(None)
+            out_e = eager.critic_step(xs[1 + it * NC + k], use_device_lr=True)['out']
+    torch.cuda.synchronize()
+    pd_e, pg_e = eager.disc_opt.flat_p.clone(), eager.gen_opt.flat_p.clone()
+    print('update-relative differences: D %.3e  G %.3e' % (_rel(pd_g - pd0, pd_e - pd0), _rel(pg_g - pg0, pg_e - pg0)))
+    print('last critic step, graph vs eager:', out_g[:4].tolist(), out_e[:4].tolist())
+    assert _rel(out_g[:4], out_e[:4]) < 0.1
+    # stale operand packs would freeze the critic at its initial weights inside the graph: tens of percent here
+    assert _rel(pd_g - pd0, pd_e - pd0) < 0.25
+    assert _rel(pg_g - pg0, pg_e - pg0) < 0.25

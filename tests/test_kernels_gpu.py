@@ -86,7 +86,8 @@ def test_conv_family(K, geom, dtype, use_tc):
         db = K.bias_grad(to_dev(dy))
     finally:
         K.config.use_tc = True
-    wq = w.to(torch.bfloat16).float() if (use_tc and K._tc_geom_ok(g)) else w     # TC path rounds the filter to bf16
+    on_tc = use_tc and dtype == torch.bfloat16 and (K._tc_geom_ok(g) or K.s2d_geom(g) is not None)
+    wq = w.to(torch.bfloat16).float() if on_tc else w     # the tensor-core routes round the filter to bf16
     fb = FB()
     tol = 1e-4 if dtype == torch.float32 else 1e-2
     assert y.shape == ((N, Cout) if two_d else (N, Cout, g.Ho, g.Wo)) and y.dtype == dtype
@@ -222,6 +223,8 @@ def test_prep_real_and_interpolate(K):
     ref = fb.prep_real(xi, 256., 1. / 128, seed=5, offset=16)
     np.testing.assert_allclose(got.numpy(), ref.numpy(), atol=1e-7)
     assert float(got.min()) >= -1.0 and float(got.max()) < 1.0
+    got8 = K.prep_real(xi.to(torch.uint8).cuda(), 256., 1. / 128, seed=5, offset=16).cpu()       # the loaders' uint8 pixels
+    assert torch.equal(got8, got)
     r, f, a = torch.randn(5, 64), torch.randn(5, 64), torch.rand(5, 1)
     np.testing.assert_allclose(K.interpolate(r.cuda(), f.cuda(), a.cuda()).cpu().numpy(),
                                fb.interpolate(r, f, a).numpy(), atol=1e-6)
@@ -553,9 +556,10 @@ def test_s2d_conv_family(K, geom):
         dw = K.conv_wgrad(to_dev(x), to_dev(dy), g, tuple(w.shape))
         acc = torch.ones(5, 5, Cin, Cout, device='cuda')
         K.conv_wgrad(to_dev(x), to_dev(dy), g, tuple(w.shape), accumulate_into=acc, col=K.thin_col(to_dev(x), g, 'x'))
-    finally:
         K.config.use_s2d = False
-    ys = K.conv_fprop(to_dev(x), w.cuda(), b.cuda(), g)               # SIMT route
+        ys = K.conv_fprop(to_dev(x), w.cuda(), b.cuda(), g)           # SIMT route
+    finally:
+        K.config.use_s2d = True
     wq = w.to(torch.bfloat16).float()
     fb = FB()
     assert rel(y, fb.conv_fprop(x, wq, b, g)) < 1e-2 and rel(y, ys) < 1.5e-2

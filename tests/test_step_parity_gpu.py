@@ -85,7 +85,7 @@ def test_step_parity_s2d_route(script, B):
         _check(rep, 'bf16', 'gen', True)
         assert K._s2d_packs, 'the space-to-depth route was not taken'
     finally:
-        K.config.use_s2d = False
+        K.config.use_s2d = True
         K.invalidate_weight_cache()
 
 
