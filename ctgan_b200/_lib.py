@@ -60,6 +60,10 @@ _PROTOS = {
     'ctgan_depth_to_space': (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P]),
     'ctgan_pack_filter_s2d': (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, P]),
     'ctgan_s2d_filter_grad': (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
+    'ctgan_im2col_strided': (c_int, [POINTER(ConvDesc), c_int, P, P, P]),
+    'ctgan_col2im_strided': (c_int, [POINTER(ConvDesc), c_int, P, P, P, P]),
+    'ctgan_pack_filter_padk': (c_int, [P, P, P, c_int, c_int, P]),
+    'ctgan_add_prefix': (c_int, [P, P, c_int64, c_int, P]),
     'ctgan_bias_grad': (c_int, [P, P, c_int64, c_int, c_int, c_int, P]),
     'ctgan_bias_add': (c_int, [P, P, P, c_int64, c_int, c_int, P]),
     'ctgan_cast': (c_int, [P, c_int, P, c_int, c_int64, P]),

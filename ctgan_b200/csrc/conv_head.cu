@@ -41,6 +41,35 @@ head_fprop_kernel(const void* __restrict__ x, const float* __restrict__ w, const
     }
 }
 
+// N == 1 with a long K (the DCGAN critics' 'Discriminator.Output' Linear(4*4*4*DIM -> 1) on the flattened features,
+// TG/CT_gan_cifar.py:98, TG/CT_gan_mnist.py:106): one 128-thread CTA per row, 16-byte loads of x, float4 loads of w,
+// 4 independent loads in flight per lane -- the warp-per-row kernel above spends one DRAM latency per 32 elements.
+__global__ void __launch_bounds__(128)
+head_fprop_n1_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                     void* __restrict__ y, int M, int K, int ydt, int relu) {
+    ctgan::pdl_entry();
+    __shared__ float part[4];
+    const int m = blockIdx.x;
+    const __nv_bfloat16* xr = x + (int64_t)m * K;
+    float acc = 0.f;
+    for (int k = threadIdx.x * 8; k < K; k += 128 * 8) {
+        const uint4 raw = *reinterpret_cast<const uint4*>(xr + k);
+        const float4 w0 = *reinterpret_cast<const float4*>(w + k), w1 = *reinterpret_cast<const float4*>(w + k + 4);
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+        const float2 a = __bfloat1622float2(h[0]), b = __bfloat1622float2(h[1]), c = __bfloat1622float2(h[2]), d = __bfloat1622float2(h[3]);
+        acc = fmaf(a.x, w0.x, acc); acc = fmaf(a.y, w0.y, acc); acc = fmaf(b.x, w0.z, acc); acc = fmaf(b.y, w0.w, acc);
+        acc = fmaf(c.x, w1.x, acc); acc = fmaf(c.y, w1.y, acc); acc = fmaf(d.x, w1.z, acc); acc = fmaf(d.y, w1.w, acc);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float v = part[0] + part[1] + part[2] + part[3] + (bias ? bias[0] : 0.f);
+        st_act(y, m, ydt, relu ? fmaxf(v, 0.f) : v);
+    }
+}
+
 __global__ void __launch_bounds__(256)
 head_dgrad_kernel(const void* __restrict__ dy, const float* __restrict__ w, void* __restrict__ dx, int M, int K, int N, int xdt, int ydt) {
     ctgan::pdl_entry();
@@ -74,6 +103,15 @@ static bool is_head(const ctgan_conv_desc* d) {
 
 int try_fprop(const ctgan_conv_desc* d, const void* x, const float* w, const float* bias, void* y, int flags, cudaStream_t st, int* rc) {
     if (!is_head(d)) return 0;
+    if (d->Cout == 1 && d->x_dtype == CTGAN_BF16 && d->Cin % 8 == 0 && d->Cin >= 1024 &&
+        ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w)) & 15) == 0) {
+        CTGAN_LAUNCH((head_fprop_n1_kernel), (unsigned)d->N, 128, 0, st, reinterpret_cast<const __nv_bfloat16*>(x), w, bias, y, d->N, d->Cin,
+                                                                  d->y_dtype, (flags & CTGAN_EPI_RELU) ? 1 : 0);
+        *rc = 0;
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) *rc = cuda_status(e, "head_fprop_n1"); else ++g_kernel_launches;
+        return 1;
+    }
     const int64_t threads = (int64_t)d->N * 32;
     CTGAN_LAUNCH((head_fprop_kernel), (unsigned)((threads + 255) / 256), 256, 0, st, x, w, bias, y, d->N, d->Cin, d->Cout, d->x_dtype, d->y_dtype,
                                                                         (flags & CTGAN_EPI_RELU) ? 1 : 0);

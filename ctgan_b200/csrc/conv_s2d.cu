@@ -61,22 +61,37 @@ __device__ __forceinline__ int s2d_src_tap(int R, int d, int pad) { return 2 * (
 // w HWIO [k][k][C][O] float -> bf16 operands of the 3x3 conv with 4C input channels:
 //   wp_f [T][O][4C]           (fprop: rows = output channels, K = input channels)         T = R*3 + S
 //   wp_d [8-T][4C][O]         (dgrad: tap-flipped, rows = input channels, K = output channels)
-__global__ void pack_filter_s2d_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wp_f,
-                                       __nv_bfloat16* __restrict__ wp_d, int k, int C, int O, int pad_t, int pad_l) {
+// One CTA = one 32 (kc) x 32 (o) tile of one embedded tap: w is read and wp_d written along o, wp_f written along kc
+// through a shared-memory transpose, so that all three streams are coalesced.
+__global__ void __launch_bounds__(256)
+pack_filter_s2d_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wp_f,
+                       __nv_bfloat16* __restrict__ wp_d, int k, int C, int O, int pad_t, int pad_l) {
     pdl_entry();
+    __shared__ __nv_bfloat16 tile[32][33];
     const int C4 = 4 * C;
-    const int64_t total = (int64_t)9 * O * C4;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        int kc = (int)(i % C4); int64_t t = i / C4;
-        int o = (int)(t % O); int T = (int)(t / O);
-        const int R = T / 3, S = T - 3 * R;
-        const int q = kc / C, c = kc - q * C;
-        const int r = s2d_src_tap(R, q >> 1, pad_t), s = s2d_src_tap(S, q & 1, pad_l);
+    const int T = blockIdx.z, R = T / 3, S = T - 3 * R;
+    const int kc0 = blockIdx.y * 32, o0 = blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;           // 32 x 8
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int kc = kc0 + ty + 8 * j, o = o0 + tx;
         float v = 0.f;
-        if (r >= 0 && r < k && s >= 0 && s < k) v = w[(((int64_t)r * k + s) * C + c) * O + o];
+        if (kc < C4 && o < O) {
+            const int q = kc / C, c = kc - q * C;
+            const int r = s2d_src_tap(R, q >> 1, pad_t), s = s2d_src_tap(S, q & 1, pad_l);
+            if (r >= 0 && r < k && s >= 0 && s < k) v = w[(((int64_t)r * k + s) * C + c) * O + o];
+        }
         const __nv_bfloat16 b = __float2bfloat16_rn(v);
-        if (wp_f) wp_f[i] = b;
-        if (wp_d) wp_d[((int64_t)(8 - T) * C4 + kc) * O + o] = b;
+        tile[ty + 8 * j][tx] = b;
+        if (wp_d && kc < C4 && o < O) wp_d[((int64_t)(8 - T) * C4 + kc) * O + o] = b;
+    }
+    __syncthreads();
+    if (wp_f) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int o = o0 + ty + 8 * j, kc = kc0 + tx;
+            if (kc < C4 && o < O) wp_f[((int64_t)T * O + o) * C4 + kc] = tile[tx][ty + 8 * j];
+        }
     }
 }
 
@@ -95,6 +110,122 @@ __global__ void s2d_filter_grad_kernel(const float* __restrict__ dw3, float* __r
         const float v = dw3[(((int64_t)(R * 3 + S) * 4 + (dy * 2 + dx)) * C + c) * O + o];
         if (accumulate) atomicAdd(dw + i, v); else dw[i] = v;
     }
+}
+
+
+// ------------------------------------------------------------------ stride-2 convs with a thin (<= 8 channel) input
+// Discriminator.1 (3 -> DIM, 5x5/2: TG/CT_gan_cifar.py:84, 1 -> DIM: TG/CT_gan_mnist.py:92) and -- as the dgrad of that
+// geometry -- the generators' last Deconv2D (DIM -> 3 / 1: TG/CT_gan_cifar.py:75, TG/CT_gan_mnist.py:83).  K = taps*C =
+// 75 (25) fits one 128-column im2col row per OUTPUT pixel, so the family becomes 1x1 tensor-core GEMMs:
+//   fprop: y    = col x W128,           col[p][(r*kw+s)*C + c] = x[n, st*ho + r - pad_t, st*wo + s - pad_l, c]   (zero outside / k >= taps*C)
+//   dgrad: dx   = col2im(dy x W128^T)   dx[n,h,w,c] = sum over taps with (h + pad_t - r) = st*ho of dcol[(n,ho,wo)][(r*kw+s)*C + c]
+//   wgrad: dW   = first taps*C rows of col^T x dy  (HWIO order == the column order)
+__global__ void __launch_bounds__(256)
+im2col_strided_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ col,
+                      int N, int H, int W, int C, int Ho, int Wo, int kh, int kw, int stride, int pad_t, int pad_l) {
+    pdl_entry();
+    __shared__ uint32_t tab[128];                 // per column k: (r, s, c, valid) as bytes
+    if (threadIdx.x < 128) {
+        const int k = threadIdx.x;
+        uint32_t e = 0;
+        if (k < kh * kw * C) {
+            const int t = k / C, c = k - t * C;
+            const int r = t / kw, s = t - r * kw;
+            e = (uint32_t)r | ((uint32_t)s << 8) | ((uint32_t)c << 16) | (1u << 24);
+        }
+        tab[k] = e;
+    }
+    __syncthreads();
+    const int64_t total = (int64_t)N * Ho * Wo * 16;         // 16 threads per output pixel, one 16-byte store each
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t p = i >> 4;
+        const int g = (int)(i & 15);
+        const int wo = (int)(p % Wo); const int64_t q = p / Wo;
+        const int ho = (int)(q % Ho); const int64_t n = q / Ho;
+        const int h0 = ho * stride - pad_t, w0 = wo * stride - pad_l;
+        const __nv_bfloat16* img = src + n * (int64_t)H * W * C;
+        __align__(16) __nv_bfloat16 v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const uint32_t te = tab[g * 8 + e];
+            const int hh = h0 + (int)(te & 0xff), ww = w0 + (int)((te >> 8) & 0xff), c = (int)((te >> 16) & 0xff);
+            const bool ok = (te >> 24) && hh >= 0 && hh < H && ww >= 0 && ww < W;
+            v[e] = ok ? img[((int64_t)hh * W + ww) * C + c] : __float2bfloat16_rn(0.f);
+        }
+        *reinterpret_cast<uint4*>(col + p * 128 + g * 8) = *reinterpret_cast<const uint4*>(v);
+    }
+}
+
+__global__ void __launch_bounds__(128)
+col2im_strided_kernel(const __nv_bfloat16* __restrict__ col, const float* __restrict__ bias, __nv_bfloat16* __restrict__ dst,
+                      int N, int H, int W, int C, int Ho, int Wo, int kh, int kw, int stride, int pad_t, int pad_l) {
+    pdl_entry();
+    const int64_t total = (int64_t)N * H * W;
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < total; p += (int64_t)gridDim.x * blockDim.x) {
+        const int w = (int)(p % W); const int64_t q = p / W;
+        const int h = (int)(q % H); const int64_t n = q / H;
+        float acc[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[c] = (bias && c < C) ? bias[c] : 0.f;
+        for (int r = 0; r < kh; ++r) {
+            const int th = h + pad_t - r;
+            if (th < 0 || th % stride) continue;
+            const int ho = th / stride;
+            if (ho >= Ho) continue;
+            for (int s = 0; s < kw; ++s) {
+                const int tw = w + pad_l - s;
+                if (tw < 0 || tw % stride) continue;
+                const int wo = tw / stride;
+                if (wo >= Wo) continue;
+                const __nv_bfloat16* row = col + ((n * Ho + ho) * Wo + wo) * 128 + (r * kw + s) * C;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) if (c < C) acc[c] += __bfloat162float(row[c]);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 8; ++c) if (c < C) dst[p * C + c] = __float2bfloat16_rn(acc[c]);
+    }
+}
+
+// w [Kreal][O] float (HWIO flattened) -> wp_f [O][128] and wp_d [128][O] bf16, rows/columns k >= Kreal zero
+__global__ void __launch_bounds__(256)
+pack_filter_padk_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wp_f, __nv_bfloat16* __restrict__ wp_d,
+                        int Kreal, int O) {
+    pdl_entry();
+    __shared__ __nv_bfloat16 tile[32][33];
+    const int k0 = blockIdx.y * 32, o0 = blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int k = k0 + ty + 8 * j, o = o0 + tx;
+        const float v = (k < Kreal && o < O) ? w[(int64_t)k * O + o] : 0.f;
+        const __nv_bfloat16 b = __float2bfloat16_rn(v);
+        tile[ty + 8 * j][tx] = b;
+        if (wp_d && o < O) wp_d[(int64_t)k * O + o] = b;
+    }
+    __syncthreads();
+    if (wp_f) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int o = o0 + ty + 8 * j, k = k0 + tx;
+            if (o < O) wp_f[(int64_t)o * 128 + k] = tile[tx][ty + 8 * j];
+        }
+    }
+}
+
+__global__ void add_prefix_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t n, int accumulate) {
+    pdl_entry();
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        if (accumulate) atomicAdd(dst + i, src[i]); else dst[i] = src[i];
+    }
+}
+
+static int check_strided_thin(const ctgan_conv_desc* d, int C, const char* who) {
+    CTGAN_REQUIRE(d != nullptr, CTGAN_ERR_BAD_DESC, "%s: null descriptor", who);
+    CTGAN_REQUIRE(d->N > 0 && d->H > 0 && d->W > 0 && d->Ho > 0 && d->Wo > 0 && d->kh > 0 && d->kw > 0 && d->stride >= 1 &&
+                  d->pad_t >= 0 && d->pad_l >= 0 && d->kh < 256 && d->kw < 256, CTGAN_ERR_BAD_DESC, "%s: bad geometry", who);
+    CTGAN_REQUIRE(C > 0 && C <= 8 && d->kh * d->kw * C <= 128, CTGAN_ERR_UNSUPPORTED, "%s: needs C <= 8 and taps*C <= 128", who);
+    return 0;
 }
 
 static int check_s2d_filter(int k, int C, int O, int pad_t, int pad_l, const char* who) {
@@ -149,8 +280,8 @@ extern "C" int ctgan_pack_filter_s2d(const float* w, void* wp_f, void* wp_d, int
                                      void* stream) {
     if (int r = check_s2d_filter(k, Cin, Cout, pad_t, pad_l, "pack_filter_s2d")) return r;
     CTGAN_REQUIRE(w && (wp_f || wp_d), CTGAN_ERR_BAD_DESC, "pack_filter_s2d: null pointer");
-    const int64_t total = (int64_t)36 * Cin * Cout;
-    CTGAN_LAUNCH((pack_filter_s2d_kernel), elementwise_grid(total, 256), 256, 0, as_stream(stream), w,
+    CTGAN_REQUIRE((4 * Cin + 31) / 32 <= 65535, CTGAN_ERR_UNSUPPORTED, "pack_filter_s2d: Cin too large");
+    CTGAN_LAUNCH((pack_filter_s2d_kernel), dim3((Cout + 31) / 32, (4 * Cin + 31) / 32, 9), 256, 0, as_stream(stream), w,
                  reinterpret_cast<__nv_bfloat16*>(wp_f), reinterpret_cast<__nv_bfloat16*>(wp_d), k, Cin, Cout, pad_t, pad_l);
     CTGAN_CHECK_LAUNCH("pack_filter_s2d");
     return 0;
@@ -164,5 +295,43 @@ extern "C" int ctgan_s2d_filter_grad(const float* dw3, float* dw, int k, int Cin
     CTGAN_LAUNCH((s2d_filter_grad_kernel), elementwise_grid(total, 256), 256, 0, as_stream(stream), dw3, dw, k, Cin, Cout,
                  pad_t, pad_l, accumulate);
     CTGAN_CHECK_LAUNCH("s2d_filter_grad");
+    return 0;
+}
+
+extern "C" int ctgan_im2col_strided(const ctgan_conv_desc* d, int C, const void* src, void* col, void* stream) {
+    if (int r = check_strided_thin(d, C, "im2col_strided")) return r;
+    CTGAN_REQUIRE(src && col && (reinterpret_cast<uintptr_t>(col) & 15) == 0, CTGAN_ERR_BAD_DESC, "im2col_strided: bad pointers");
+    const int64_t total = (int64_t)d->N * d->Ho * d->Wo * 16;
+    CTGAN_LAUNCH((im2col_strided_kernel), elementwise_grid(total, 256), 256, 0, as_stream(stream),
+                 reinterpret_cast<const __nv_bfloat16*>(src), reinterpret_cast<__nv_bfloat16*>(col), d->N, d->H, d->W, C, d->Ho, d->Wo,
+                 d->kh, d->kw, d->stride, d->pad_t, d->pad_l);
+    CTGAN_CHECK_LAUNCH("im2col_strided");
+    return 0;
+}
+
+extern "C" int ctgan_col2im_strided(const ctgan_conv_desc* d, int C, const void* col, const float* bias, void* dst, void* stream) {
+    if (int r = check_strided_thin(d, C, "col2im_strided")) return r;
+    CTGAN_REQUIRE(col && dst, CTGAN_ERR_BAD_DESC, "col2im_strided: null pointer");
+    const int64_t total = (int64_t)d->N * d->H * d->W;
+    CTGAN_LAUNCH((col2im_strided_kernel), elementwise_grid(total, 128), 128, 0, as_stream(stream),
+                 reinterpret_cast<const __nv_bfloat16*>(col), bias, reinterpret_cast<__nv_bfloat16*>(dst), d->N, d->H, d->W, C, d->Ho, d->Wo,
+                 d->kh, d->kw, d->stride, d->pad_t, d->pad_l);
+    CTGAN_CHECK_LAUNCH("col2im_strided");
+    return 0;
+}
+
+extern "C" int ctgan_pack_filter_padk(const float* w, void* wp_f, void* wp_d, int Kreal, int Cout, void* stream) {
+    CTGAN_REQUIRE(w && (wp_f || wp_d) && Kreal > 0 && Kreal <= 128 && Cout > 0, CTGAN_ERR_BAD_DESC, "pack_filter_padk: bad args");
+    CTGAN_LAUNCH((pack_filter_padk_kernel), dim3((Cout + 31) / 32, 4), 256, 0, as_stream(stream), w,
+                 reinterpret_cast<__nv_bfloat16*>(wp_f), reinterpret_cast<__nv_bfloat16*>(wp_d), Kreal, Cout);
+    CTGAN_CHECK_LAUNCH("pack_filter_padk");
+    return 0;
+}
+
+extern "C" int ctgan_add_prefix(const float* src, float* dst, int64_t n, int accumulate, void* stream) {
+    CTGAN_REQUIRE(src && dst && n >= 0, CTGAN_ERR_BAD_DESC, "add_prefix: bad args");
+    if (n == 0) return 0;
+    CTGAN_LAUNCH((add_prefix_kernel), elementwise_grid(n, 256), 256, 0, as_stream(stream), src, dst, n, accumulate);
+    CTGAN_CHECK_LAUNCH("add_prefix");
     return 0;
 }

@@ -21,6 +21,7 @@ class Config:
     use_tc = True            # use the tcgen05 kernels when a call is eligible
     use_thin_tc = True       # route 3-channel-side convs through the im2col tensor-core path
     use_s2d = True           # stride-2 5x5 convs (DCGAN critics / Deconv2D) as 3x3 tensor-core convs over the space-to-depth image
+    use_thin_s2 = True       # stride-2 convs with a <= 8 channel input (Discriminator.1, the last Deconv2D) as im2col + 1x1 tensor-core GEMMs
     s2d_min_extent = 1       # (tunable) smallest space-to-depth image side that takes the tensor-core route
     side_stream = True       # run direct-accumulation wgrad / bias-grad launches on a second stream
     branch_streams = True    # run independent sub-graphs of a step (GP pass vs stacked pass) as stream branches
@@ -204,7 +205,7 @@ def invalidate_weight_cache(ptrs=None):
     """Called by an optimizer after ITS parameters changed in place (ptrs = their data pointers; None = all)."""
     if ptrs is None:
         _pack_cache.clear()
-        _s2d_packs.clear()
+        _lazy_packs.clear()
         return
     for k in [k for k in _pack_cache if k[0] in ptrs]:
         del _pack_cache[k]
@@ -212,20 +213,17 @@ def invalidate_weight_cache(ptrs=None):
 
 def pack_filter(w, transpose_flip, cacheable=False):
     """float HWIO [kh,kw,Cin,Cout] (or [in,out]) -> bf16 operand of the tcgen05 kernels."""
-    key = (w.data_ptr(), tuple(w.shape), transpose_flip) if cacheable else None
-    if key is not None and key in _pack_cache:
-        return _pack_cache[key]
     if w.dim() == 4:
         taps, cin, cout = w.shape[0] * w.shape[1], w.shape[2], w.shape[3]
     else:
         taps, cin, cout = 1, w.shape[0], w.shape[1]
     if w.dtype != torch.float32 or not w.is_contiguous():
         raise RuntimeError('ctgan_b200: filters must be contiguous float32 HWIO')
-    wp = torch.empty(taps * cin * cout, dtype=torch.bfloat16, device=w.device)
-    call('ctgan_pack_filter_bf16', _p(w), _p(wp), taps, cin, cout, int(transpose_flip), _stream())
-    if key is not None:
-        _pack_cache[key] = wp
-    return wp
+    wd = w.detach()
+    return _lazy_pack(w, (w.data_ptr(), tuple(w.shape), transpose_flip),
+                      lambda: torch.empty(taps * cin * cout, dtype=torch.bfloat16, device=w.device),
+                      lambda wp: call('ctgan_pack_filter_bf16', _p(wd), _p(wp), taps, cin, cout, int(transpose_flip), _stream()),
+                      cacheable)
 
 
 def _check_filter(w, g):
@@ -267,6 +265,8 @@ def thin_col(t, g, role):
     None when the call does not take the thin path -- lets a caller build it once and pass it to both."""
     if role == 'x' and s2d_geom(g, t) is not None:
         return space_to_depth(t, g)                     # shared by fprop and wgrad of a stride-2 conv
+    if role == 'x' and thin_s2_ok(g, t):
+        return im2col_strided(t, g)
     side = _thin_side(g, t)
     if side == 'in' and role == 'x':
         return im2col_thin(t, g, g.Cin, 1)
@@ -320,7 +320,7 @@ class FilterPacker:
                     self.views.append((p, 2 + kind, dst, 64 * max(cin, cout)))
                     dst += 64 * max(cin, cout)
                 continue
-            if cin % 64 or cout % 64:
+            if cin % 64 or cout % 64 or taps > 9:       # k > 3: stride-2 layers, packed lazily in the layout their route needs
                 continue
             for flip in (0, 1):
                 rows.append((offsets[name], dst, taps, cin, cout, flip))
@@ -342,7 +342,7 @@ class FilterPacker:
             call('ctgan_pack_filters_multi', _p(self.flat_p), _p(self.packs), _p(self.table), self.n, _stream())
             for p, flip, dst, numel in self.views:
                 _pack_cache[(p.data_ptr(), tuple(p.shape), flip)] = self.packs[dst:dst + numel]
-        refresh_s2d_packs(self.param_ptrs)
+        refresh_lazy_packs(self.param_ptrs)
 
 
 # ---- raw tensor-core launches (operands already in kernel layout)
@@ -407,37 +407,86 @@ def _s2d_filter_grad_launch(dw3, dw, g, accumulate):
     call('ctgan_s2d_filter_grad', _p(dw3), _p(dw), g.kh, g.Cin, g.Cout, g.pad_t, g.pad_l, int(accumulate), _stream())
 
 
-# persistent (fprop, dgrad) operand pairs of PARAMETER filters on the space-to-depth route: {param ptr: {key: (w, wp_f, wp_d, g)}}.
-# They are created at a filter's first use (the pads depend on the input extent, which only the call knows) and
-# re-packed in place after every optimizer step by FilterPacker.refresh(), so a captured CUDA graph always reads
-# current weights from the same addresses.
-_s2d_packs = {}
+# Persistent operand packs of PARAMETER filters that the one-launch FilterPacker does not cover: {param ptr: {key: (launch, bufs)}}.
+# They are created at a filter's first use (the layout can depend on the call: the space-to-depth pads follow the
+# input extent) and re-packed IN PLACE after every optimizer step by FilterPacker.refresh(), so a captured CUDA
+# graph always reads current weights from the same addresses.
+_lazy_packs = {}
+
+
+def _lazy_pack(w, key, make_bufs, launch, cacheable):
+    if cacheable and key in _pack_cache:
+        return _pack_cache[key]
+    reg = _lazy_packs.get(w.data_ptr(), {}) if cacheable else {}
+    bufs = reg[key][1] if key in reg else make_bufs()     # registered but invalidated by an update: re-pack in place
+    launch(bufs)
+    if cacheable:
+        _pack_cache[key] = bufs
+        _lazy_packs.setdefault(w.data_ptr(), {})[key] = (launch, bufs)
+    return bufs
+
+
+def refresh_lazy_packs(ptrs):
+    """Re-pack (in place) every registered operand of the parameters at `ptrs`; publish them in the cache."""
+    for ptr in ptrs:
+        for key, (launch, bufs) in _lazy_packs.get(ptr, {}).items():
+            launch(bufs)
+            _pack_cache[key] = bufs
 
 
 def pack_filter_s2d(w, g, flip, cacheable=False):
     """bf16 operands of the embedded 3x3 filter: flip 0 -> [9][Cout][4Cin] (fprop), 1 -> tap-flipped [9][4Cin][Cout] (dgrad)."""
-    key = (w.data_ptr(), tuple(w.shape), 's2d', g.pad_t, g.pad_l)
-    if cacheable and key in _pack_cache:
-        return _pack_cache[key][flip]
-    if cacheable and key in _s2d_packs.get(w.data_ptr(), {}):
-        _, wp_f, wp_d, _ = _s2d_packs[w.data_ptr()][key]           # invalidated by an update: re-pack in place
-    else:
-        n = 36 * g.Cin * g.Cout
-        wp_f = torch.empty(n, dtype=torch.bfloat16, device=w.device)
-        wp_d = torch.empty(n, dtype=torch.bfloat16, device=w.device)
-    _pack_filter_s2d_launch(w, wp_f, wp_d, g)
-    if cacheable:
-        _pack_cache[key] = (wp_f, wp_d)
-        _s2d_packs.setdefault(w.data_ptr(), {})[key] = (w.detach(), wp_f, wp_d, g)
-    return (wp_f, wp_d)[flip]
+    wd, n = w.detach(), 36 * g.Cin * g.Cout
+    return _lazy_pack(w, (w.data_ptr(), tuple(w.shape), 's2d', g.pad_t, g.pad_l),
+                      lambda: tuple(torch.empty(n, dtype=torch.bfloat16, device=w.device) for _ in range(2)),
+                      lambda bufs: _pack_filter_s2d_launch(wd, bufs[0], bufs[1], g), cacheable)[flip]
 
 
-def refresh_s2d_packs(ptrs):
-    """Re-pack (in place) every registered space-to-depth operand of the parameters at `ptrs`; publish them in the cache."""
-    for ptr in ptrs:
-        for key, (w, wp_f, wp_d, g) in _s2d_packs.get(ptr, {}).items():
-            _pack_filter_s2d_launch(w, wp_f, wp_d, g)
-            _pack_cache[key] = (wp_f, wp_d)
+# ---- stride-2 convs with a thin (<= 8 channel) input as im2col + 1x1 tensor-core GEMMs (csrc/conv_s2d.cu)
+def thin_s2_ok(g, t=None):
+    if not (config.use_tc and config.use_thin_s2 and tc_available()):
+        return False
+    if t is not None and (t.dim() != 4 or t.dtype != torch.bfloat16):
+        return False
+    return (g.stride == 2 and g.Cin <= 8 and g.kh * g.kw * g.Cin <= 128 and g.Cout % 64 == 0 and g.kh < 256 and g.kw < 256
+            and g.Ho * g.Wo >= 16)
+
+
+def _out_pixels_geom(g, cin, cout):
+    """1x1 geometry over the OUTPUT pixels of g."""
+    return ConvGeom(g.N, g.Ho, g.Wo, cin, g.Ho, g.Wo, cout, 1, 1, 1, 0, 0)
+
+
+def im2col_strided(x, g):
+    """col [N, 128, Ho, Wo] (NHWC: one 128-column row per output pixel), column (r*kw+s)*Cin + c."""
+    require_nhwc(x, 'x')
+    col = empty_act((g.N, 128, g.Ho, g.Wo), torch.bfloat16, x.device)
+    d = _desc(g, BF16, BF16)
+    call('ctgan_im2col_strided', ctypes.byref(d), g.Cin, _p(x), _p(col), _stream())
+    return col
+
+
+def col2im_strided(col, bias, g):
+    dx = empty_act((g.N, g.Cin, g.H, g.W), torch.bfloat16, col.device)
+    d = _desc(g, BF16, BF16)
+    call('ctgan_col2im_strided', ctypes.byref(d), g.Cin, _p(col), _p(bias), _p(dx), _stream())
+    return dx
+
+
+def _pack_filter_padk_launch(w, wp_f, wp_d, g):
+    call('ctgan_pack_filter_padk', _p(w), _p(wp_f), _p(wp_d), g.kh * g.kw * g.Cin, g.Cout, _stream())
+
+
+def _add_prefix_launch(src, dst, n, accumulate):
+    call('ctgan_add_prefix', _p(src), _p(dst), int(n), int(accumulate), _stream())
+
+
+def pack_filter_padk(w, g, flip, cacheable=False):
+    """bf16 operands of the filter as a [128 -> Cout] matrix (rows >= taps*Cin zero): flip 0 -> [Cout][128], 1 -> [128][Cout]."""
+    wd, n = w.detach(), 128 * g.Cout
+    return _lazy_pack(w, (w.data_ptr(), tuple(w.shape), 'padk'),
+                      lambda: tuple(torch.empty(n, dtype=torch.bfloat16, device=w.device) for _ in range(2)),
+                      lambda bufs: _pack_filter_padk_launch(wd, bufs[0], bufs[1], g), cacheable)[flip]
 
 
 def conv_fprop(x, w, bias, g, relu=False, residual=None, out_dtype=None, w_is_param=False, col=None, res_up2=False):
@@ -463,6 +512,12 @@ def conv_fprop(x, w, bias, g, relu=False, residual=None, out_dtype=None, w_is_pa
             require_nhwc(residual, 'residual')
         xs = col if (col is not None and tuple(col.shape) == (g3.N, g3.Cin, g3.H, g3.W)) else space_to_depth(x, g)
         return _fprop_tc_packed(xs, pack_filter_s2d(w, g, 0, cacheable=w_is_param), bias, residual, None, y, g3, flags)
+    if xdt == BF16 and ydt == BF16 and thin_s2_ok(g, x):      # y = im2col_strided(x) x W128
+        if residual is not None:
+            require_nhwc(residual, 'residual')
+        col = col if (col is not None and tuple(col.shape) == (g.N, 128, g.Ho, g.Wo)) else im2col_strided(x, g)
+        return _fprop_tc_packed(col, pack_filter_padk(w, g, 0, cacheable=w_is_param), bias, residual, None, y,
+                                _out_pixels_geom(g, 128, g.Cout), flags)
     side = _thin_side(g, x) if (xdt == BF16 and ydt == BF16) else None
     if side == 'in':                                  # y = im2col(x) x w[(t,c)][Cout]
         if residual is not None:
@@ -505,6 +560,11 @@ def conv_dgrad(dy, w, g, out_dtype=None, w_is_param=False, col=None, relu_mask=N
         dxs = empty_act((g3.N, g3.Cin, g3.H, g3.W), torch.bfloat16, dy.device)
         _fprop_tc_packed(dy, pack_filter_s2d(w, g, 1, cacheable=w_is_param), None, None, None, dxs, gt, 0)
         return depth_to_space(dxs, g)
+    if xdt == BF16 and ydt == BF16 and thin_s2_ok(g, dy):     # dcol = dy x W128^T, dx = col2im_strided(dcol)
+        dcol = empty_act((g.N, 128, g.Ho, g.Wo), torch.bfloat16, dy.device)
+        _fprop_tc_packed(dy, pack_filter_padk(w, g, 1, cacheable=w_is_param), None, None, None, dcol,
+                         _out_pixels_geom(g, g.Cout, 128), 0)
+        return col2im_strided(dcol, None, g)
     side = _thin_side(g, dy) if (xdt == BF16 and ydt == BF16) else None
     if side == 'in':                                  # dxcol[(t,ci)] = dy x w^T, dx = col2im(dxcol, -1)
         dxcol = _gemm1x1_tc(dy, pack_filter_thin(w, 3, cacheable=w_is_param), None, g, g.Cout, 64)
@@ -537,6 +597,13 @@ def conv_wgrad(x, dy, g, w_shape, accumulate_into=None, col=None):
         dw3 = _wgrad_tc_raw(xs, dy, g3, torch.zeros((3, 3, g3.Cin, g3.Cout), dtype=torch.float32, device=x.device))
         dw = acc if acc is not None else torch.empty(w_shape, dtype=torch.float32, device=x.device)
         _s2d_filter_grad_launch(dw3, dw, g, acc is not None)
+        return dw
+    if xdt == BF16 and ydt == BF16 and thin_s2_ok(g, x) and g.Cout % 128 == 0:
+        col = col if (col is not None and tuple(col.shape) == (g.N, 128, g.Ho, g.Wo)) else im2col_strided(x, g)
+        dw128 = _wgrad_tc_raw(col, dy, _out_pixels_geom(g, 128, g.Cout),
+                              torch.zeros((1, 1, 128, g.Cout), dtype=torch.float32, device=x.device))
+        dw = acc if acc is not None else torch.empty(w_shape, dtype=torch.float32, device=x.device)
+        _add_prefix_launch(dw128, dw, g.kh * g.kw * g.Cin * g.Cout, acc is not None)     # HWIO order == column order
         return dw
     side = _thin_side(g, x) if (xdt == BF16 and ydt == BF16) else None
     if side is not None:

@@ -148,6 +148,21 @@ int ctgan_depth_to_space(const void* xs, void* x, int N, int H, int W, int C, in
 int ctgan_pack_filter_s2d(const float* w, void* wp_f, void* wp_d, int k, int Cin, int Cout, int pad_t, int pad_l, void* stream);
 int ctgan_s2d_filter_grad(const float* dw3, float* dw, int k, int Cin, int Cout, int pad_t, int pad_l, int accumulate, void* stream);
 
+/* ---- strided convolutions with a thin (C <= 8 channel, taps*C <= 128) input on the tensor cores: 'Discriminator.1'
+ * (3 -> DIM 5x5/2, TG/CT_gan_cifar.py:84; 1 -> DIM, TG/CT_gan_mnist.py:92) and, as the dgrad of that geometry, the
+ * generators' last Deconv2D (TG/CT_gan_cifar.py:75, TG/CT_gan_mnist.py:83; op = TG/tflib/ops/deconv2d.py:97-103).
+ * One 128-column im2col row per OUTPUT pixel p = (n, ho, wo), column k = (r*kw + s)*C + c (HWIO order):
+ *   im2col_strided: col[p][k] = x[n, stride*ho + r - pad_t, stride*wo + s - pad_l, c]     (zero outside x / k >= taps*C)
+ *   col2im_strided: dx[n,h,w,c] = bias[c] + sum over taps with h + pad_t - r = stride*ho (same for w) of col[(n,ho,wo)][k]
+ * so fprop = ctgan_conv_fprop_tc(1x1, col, wp_f), dgrad = col2im_strided(ctgan_conv_fprop_tc(1x1, dy, wp_d)) and
+ * wgrad = the first taps*C rows of ctgan_conv_wgrad_tc(1x1, col, dy), added with ctgan_add_prefix.
+ *   pack_filter_padk: w float [Kreal][Cout] (HWIO flattened) -> wp_f [Cout][128], wp_d [128][Cout] bf16, zero for k >= Kreal.
+ *   add_prefix: dst[i] (+)= src[i], i < n  (atomic when accumulating: several streams add into one gradient bucket). */
+int ctgan_im2col_strided(const ctgan_conv_desc* d, int C, const void* x, void* col, void* stream);
+int ctgan_col2im_strided(const ctgan_conv_desc* d, int C, const void* col, const float* bias /*nullable*/, void* dx, void* stream);
+int ctgan_pack_filter_padk(const float* w, void* wp_f, void* wp_d, int Kreal, int Cout, void* stream);
+int ctgan_add_prefix(const float* src, float* dst, int64_t n, int accumulate, void* stream);
+
 /* db[c] (float) = sum over rows of dy[rows][C]   (gradient of tf.nn.bias_add) */
 int ctgan_bias_grad(const void* dy, float* db, int64_t rows, int C, int dtype,
                     int accumulate, void* stream);

@@ -16,6 +16,7 @@ The reference is Python 2 + TensorFlow 1.2.1 and cannot be imported here.  This 
 naming/layout, init formulas, loss formulas.  What it cannot pin: TensorFlow's internal kernels (absent).
 """
 import importlib
+import importlib.util
 import os
 import re
 import sys
@@ -76,6 +77,46 @@ def _load_ref_tflib(shim):
         else:
             sys.modules['tensorflow'] = saved_tf
     return lib
+
+
+def py2to3_host(src):
+    """Additional py2 idioms of the host-side utility modules (tflib/cifar10.py, mnist.py, plot.py, save_images.py):
+    integer `/` on python ints and list-returning dict views."""
+    src = py2to3(src)
+    for old, new in [('len(images) / batch_size', 'len(images) // batch_size'),            # cifar10.py:33,60
+                     ('np.mean(vals.values())', 'np.mean(list(vals.values()))'),            # plot.py:25
+                     ('np.sort(_since_beginning[name].keys())', 'np.sort(list(_since_beginning[name].keys()))'),   # plot.py:28
+                     ('n_samples/rows', 'n_samples//rows'),                                 # save_images.py:19
+                     ('j = n/nw', 'j = n//nw')]:                                            # save_images.py:34
+        src = src.replace(old, new)
+    return src
+
+
+def load_ref_host_module(name, stubs=None):
+    """Import ONE host-side utility module of the reference's tflib (translated), e.g. 'cifar10', 'mnist', 'plot',
+    'save_images', as a stand-alone module.  stubs: {module name: module object} bound in sys.modules during the import
+    (matplotlib / scipy.misc are not installed here)."""
+    os.makedirs(OUT_DIR, exist_ok=True)
+    with open(os.path.join(REF_ROOT, 'tflib', name + '.py')) as f:
+        src = py2to3_host(f.read())
+    path = os.path.join(OUT_DIR, 'ref_host_%s.py' % name)
+    with open(path, 'w') as f:
+        f.write(src)
+    saved = {}
+    for k, v in (stubs or {}).items():
+        saved[k] = sys.modules.get(k)
+        sys.modules[k] = v
+    try:
+        spec = importlib.util.spec_from_file_location('ref_host_' + name, path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                del sys.modules[k]
+            else:
+                sys.modules[k] = v
+    return mod
 
 
 def _section(path, first, last, dedent=False):

@@ -134,7 +134,7 @@ def test_dcgan_graph_replay_trains_like_eager():
     graphed = trainer()
     pd0, pg0 = graphed.disc_opt.flat_p.clone(), graphed.gen_opt.flat_p.clone()
     gt = GraphedTrainer(graphed, (xs[0],), warmup=3)
-    assert K._s2d_packs, 'the space-to-depth route was not taken'
+    assert K._lazy_packs, 'the space-to-depth route was not taken'
     for it in range(2):
         gt.gen_step()
         for k in range(NC):

@@ -566,3 +566,58 @@ def test_s2d_conv_family(K, geom):
     assert rel(dx, fb.conv_dgrad(dy, wq, g)) < 1e-2
     ref_w = fb.conv_wgrad(x, dy, g, tuple(w.shape))
     assert rel(dw, ref_w) < 2e-3 and rel(acc - 1, ref_w) < 2e-3
+
+
+THIN_S2_GEOMS = [
+    # N, H, W, Cin, Cout, k  (stride 2, TF SAME)
+    (192, 32, 32, 3, 128, 5),   # CIFAR Discriminator.1 on the stacked critic pass / (as dgrad) Generator.5
+    (64, 32, 32, 3, 128, 5),
+    (50, 28, 28, 1, 64, 5),     # MNIST Discriminator.1 / Generator.5 (Cout = 64: wgrad on the SIMT kernel)
+    (3, 14, 10, 3, 128, 5),     # non-square, ragged pixel count
+    (2, 9, 9, 2, 256, 3),       # odd extent, 3x3
+]
+
+
+@pytest.mark.parametrize('geom', THIN_S2_GEOMS)
+def test_thin_strided_conv_family(K, geom):
+    """Stride-2 convs with a <= 8-channel input (im2col_strided / col2im_strided / pack_filter_padk / add_prefix + the
+    1x1 tcgen05 GEMMs): the layout kernels exactly against the test-side restatement, the family against the direct
+    CPU evaluation."""
+    from tests import test_s2d_host as H
+    N, Hh, W, Cin, Cout, k = geom
+    g = K.same_geom(N, Hh, W, Cin, Cout, k, 2)
+    x, dy = act((N, Cin, Hh, W), torch.bfloat16, 1), act((N, Cout, g.Ho, g.Wo), torch.bfloat16, 2)
+    w, b = filt((k, k, Cin, Cout), 3, 0.1), act((Cout,), torch.float32, 4)
+    assert K.thin_s2_ok(g, to_dev(x))
+    col = K.im2col_strided(to_dev(x), g)
+    assert torch.equal(col.cpu(), H._im2col_strided(x, g))
+    dcol = act((N, 128, g.Ho, g.Wo), torch.bfloat16, 6)
+    got, ref = K.col2im_strided(to_dev(dcol), b.cuda(), g), H._col2im_strided(dcol, b, g)
+    assert rel(got, ref) < 4e-3                       # fp32 sums of <= 9 bf16 terms, one bf16 rounding
+    n = 128 * Cout
+    wp = [torch.empty(n, dtype=torch.bfloat16, device='cuda') for _ in range(2)]
+    K._pack_filter_padk_launch(w.cuda(), wp[0], wp[1], g)
+    rp = [torch.empty(n, dtype=torch.bfloat16) for _ in range(2)]
+    H._padk_launch(w, rp[0], rp[1], g)
+    assert torch.equal(wp[0].cpu(), rp[0]) and torch.equal(wp[1].cpu(), rp[1])
+
+    y = K.conv_fprop(to_dev(x), w.cuda(), b.cuda(), g, col=col)
+    dx = K.conv_dgrad(to_dev(dy), w.cuda(), g)
+    dw = K.conv_wgrad(to_dev(x), to_dev(dy), g, tuple(w.shape))
+    acc = torch.ones(k, k, Cin, Cout, device='cuda')
+    K.conv_wgrad(to_dev(x), to_dev(dy), g, tuple(w.shape), accumulate_into=acc, col=col)
+    wq = w.to(torch.bfloat16).float()
+    fb = FB()
+    assert rel(y, fb.conv_fprop(x, wq, b, g)) < 1e-2
+    assert rel(dx, fb.conv_dgrad(dy, wq, g)) < 1.5e-2
+    ref_w = fb.conv_wgrad(x, dy, g, tuple(w.shape))
+    assert rel(dw, ref_w) < 2e-3 and rel(acc - 1, ref_w) < 2e-3
+
+
+def test_head_fprop_long_k(K):
+    """Discriminator.Output of the DCGAN critics: Linear(8192 -> 1) on BF16 features, float logits."""
+    for M, Kd in ((192, 8192), (50, 4096), (7, 1024)):
+        g = K.ConvGeom(M, 1, 1, Kd, 1, 1, 1, 1, 1, 1, 0, 0)
+        x, w, b = act((M, Kd), torch.bfloat16, 1), filt((1, 1, Kd, 1), 2, 0.05), act((1,), torch.float32, 3)
+        y = K.conv_fprop(x.cuda(), w.cuda(), b.cuda(), g, out_dtype=torch.float32)
+        assert rel(y, FB().conv_fprop(x, w, b, g, out_dtype=torch.float32)) < 1e-5

@@ -79,6 +79,51 @@ def _filter_grad_launch(dw3, dw, g, accumulate):
         dw.copy_(out)
 
 
+def _im2col_strided(x, g):
+    """col[p][(r*kw+s)*C + c] = x[n, st*ho + r - pad_t, st*wo + s - pad_l, c], 128 columns per output pixel."""
+    import torch.nn.functional as TF
+    st, C = g.stride, g.Cin
+    need_h, need_w = (g.Ho - 1) * st + g.kh, (g.Wo - 1) * st + g.kw
+    xp = TF.pad(x.float(), (g.pad_l, max(need_w - g.W - g.pad_l, 0), g.pad_t, max(need_h - g.H - g.pad_t, 0)))
+    col = torch.zeros(g.N, 128, g.Ho, g.Wo)
+    for r in range(g.kh):
+        for s_ in range(g.kw):
+            k0 = (r * g.kw + s_) * C
+            col[:, k0:k0 + C] = xp[:, :, r:r + st * g.Ho:st, s_:s_ + st * g.Wo:st]
+    return col.to(torch.bfloat16).contiguous(memory_format=CL)
+
+
+def _col2im_strided(col, bias, g):
+    st, C = g.stride, g.Cin
+    need_h, need_w = (g.Ho - 1) * st + g.kh, (g.Wo - 1) * st + g.kw
+    Hp, Wp = max(need_h, g.H + g.pad_t), max(need_w, g.W + g.pad_l)
+    dxp = torch.zeros(g.N, C, Hp, Wp)
+    for r in range(g.kh):
+        for s_ in range(g.kw):
+            k0 = (r * g.kw + s_) * C
+            dxp[:, :, r:r + st * g.Ho:st, s_:s_ + st * g.Wo:st] += col[:, k0:k0 + C].float()
+    dx = dxp[:, :, g.pad_t:g.pad_t + g.H, g.pad_l:g.pad_l + g.W]
+    if bias is not None:
+        dx = dx + bias.view(1, -1, 1, 1)
+    return dx.to(torch.bfloat16).contiguous(memory_format=CL)
+
+
+def _padk_launch(w, wp_f, wp_d, g):
+    kreal = g.kh * g.kw * g.Cin
+    w2 = w.detach().reshape(kreal, g.Cout).to(torch.bfloat16)
+    f = torch.zeros(g.Cout, 128, dtype=torch.bfloat16); f[:, :kreal] = w2.t()
+    d = torch.zeros(128, g.Cout, dtype=torch.bfloat16); d[:kreal] = w2
+    wp_f.copy_(f.reshape(-1)); wp_d.copy_(d.reshape(-1))
+
+
+def _add_prefix(src, dst, n, accumulate):
+    flat = dst.view(-1)
+    if accumulate:
+        flat[:n] += src.reshape(-1)[:n]
+    else:
+        flat[:n] = src.reshape(-1)[:n]
+
+
 @pytest.fixture
 def K(monkeypatch):
     import ctgan_b200.kernels as K
@@ -91,6 +136,10 @@ def K(monkeypatch):
     monkeypatch.setattr(K, '_fprop_tc_packed', _fprop_packed)
     monkeypatch.setattr(K, '_wgrad_tc_raw', _wgrad_raw)
     monkeypatch.setattr(K, '_s2d_filter_grad_launch', _filter_grad_launch)
+    monkeypatch.setattr(K, 'im2col_strided', _im2col_strided)
+    monkeypatch.setattr(K, 'col2im_strided', _col2im_strided)
+    monkeypatch.setattr(K, '_pack_filter_padk_launch', _padk_launch)
+    monkeypatch.setattr(K, '_add_prefix_launch', _add_prefix)
     monkeypatch.setattr(K.config, 'use_s2d', True)
     K.invalidate_weight_cache()
     yield K
@@ -151,6 +200,43 @@ def test_s2d_route_equals_stride2_conv(K, geom, monkeypatch):
         assert simt == ['ctgan_conv_wgrad']
 
 
+THIN_GEOMS = [
+    # N, H, W, Cin, Cout, k  (stride 2, TF SAME)
+    (2, 32, 32, 3, 128, 5),    # CIFAR Discriminator.1 / (as dgrad) Generator.5
+    (3, 28, 28, 1, 64, 5),     # MNIST Discriminator.1 / Generator.5: Cout = 64 -> wgrad falls through
+    (2, 14, 10, 3, 128, 5),    # non-square
+    (2, 9, 9, 2, 128, 3),      # odd extent, 3x3
+]
+
+
+@pytest.mark.parametrize('geom', THIN_GEOMS)
+def test_thin_strided_route_equals_stride2_conv(K, geom, monkeypatch):
+    """Stride-2 convs with a thin input as im2col (128 columns per output pixel) + 1x1 tensor-core GEMMs."""
+    N, H, W, Cin, Cout, k = geom
+    g = K.same_geom(N, H, W, Cin, Cout, k, 2)
+    assert K.thin_s2_ok(g) and K.s2d_geom(g) is None
+    x, dy = act((N, Cin, H, W), 1), act((N, Cout, g.Ho, g.Wo), 2)
+    w = (torch.randn(k, k, Cin, Cout, generator=torch.Generator().manual_seed(3)) * 0.1).contiguous()
+    b = torch.randn(Cout, generator=torch.Generator().manual_seed(4))
+    wq = w.to(torch.bfloat16).float()
+    simt = []
+    monkeypatch.setattr(K, 'call', lambda name, *a: simt.append(name))
+    y = K.conv_fprop(x, w, b, g, col=K.thin_col(x, g, 'x'))
+    assert rel(y, fb.conv_fprop(x, wq, b, g)) < 1e-2
+    dx = K.conv_dgrad(dy, w, g)
+    assert tuple(dx.shape) == (N, Cin, H, W) and rel(dx, fb.conv_dgrad(dy, wq, g)) < 1.5e-2
+    assert not simt
+    ref = fb.conv_wgrad(x, dy, g, tuple(w.shape))
+    if Cout % 128 == 0:
+        assert rel(K.conv_wgrad(x, dy, g, tuple(w.shape)), ref) < 1e-5
+        acc = torch.ones_like(w)
+        K.conv_wgrad(x, dy, g, tuple(w.shape), accumulate_into=acc, col=K.thin_col(x, g, 'x'))
+        assert rel(acc - 1, ref) < 1e-4 and not simt
+    else:
+        K.conv_wgrad(x, dy, g, tuple(w.shape))
+        assert simt == ['ctgan_conv_wgrad']
+
+
 def test_s2d_param_packs_are_persistent_and_refreshed(K):
     """Parameter filters: the operand pair is packed once, republished in place after an optimizer step."""
     g = K.same_geom(2, 8, 8, 32, 128, 5, 2)
@@ -161,7 +247,7 @@ def test_s2d_param_packs_are_persistent_and_refreshed(K):
     before = p0.clone()
     w.mul_(2.0)
     K.invalidate_weight_cache({w.data_ptr()})
-    K.refresh_s2d_packs([w.data_ptr()])
+    K.refresh_lazy_packs([w.data_ptr()])
     assert K.pack_filter_s2d(w, g, 0, cacheable=True) is p0 and K.pack_filter_s2d(w, g, 1, cacheable=True) is d0
     assert torch.equal(p0.float(), (before.float() * 2).to(torch.bfloat16).float())
 
@@ -199,6 +285,11 @@ def test_tensor_core_branches_bind_their_entry_points(K, monkeypatch):
     KK.conv_fprop(x2, w2, b, g2)
     KK.conv_dgrad(dy2, w2, g2)
     KK.conv_wgrad(x2, dy2, g2, tuple(w2.shape))
+    g3 = KK.same_geom(2, 32, 32, 3, 128, 5, 2)
+    x3, dy3, w3 = act((2, 3, 32, 32), 1), act((2, 128, 16, 16), 2), torch.randn(5, 5, 3, 128)
+    KK.conv_fprop(x3, w3, b, g3)
+    KK.conv_dgrad(dy3, w3, g3)
+    KK.conv_wgrad(x3, dy3, g3, tuple(w3.shape))
     names = [n for n, _ in calls]
     assert names == ['ctgan_pack_filter_bf16', 'ctgan_conv_fprop_tc',
                      'ctgan_pack_filter_bf16', 'ctgan_conv_fprop_tc',
@@ -206,7 +297,10 @@ def test_tensor_core_branches_bind_their_entry_points(K, monkeypatch):
                      'ctgan_conv_wgrad_tc',
                      'ctgan_space_to_depth', 'ctgan_pack_filter_s2d', 'ctgan_conv_fprop_tc',
                      'ctgan_pack_filter_s2d', 'ctgan_conv_fprop_tc', 'ctgan_depth_to_space',
-                     'ctgan_space_to_depth', 'ctgan_conv_wgrad_tc', 'ctgan_s2d_filter_grad'], names
+                     'ctgan_space_to_depth', 'ctgan_conv_wgrad_tc', 'ctgan_s2d_filter_grad',
+                     'ctgan_im2col_strided', 'ctgan_pack_filter_padk', 'ctgan_conv_fprop_tc',
+                     'ctgan_pack_filter_padk', 'ctgan_conv_fprop_tc', 'ctgan_col2im_strided',
+                     'ctgan_im2col_strided', 'ctgan_conv_wgrad_tc', 'ctgan_add_prefix'], names
     for name, nargs in calls:
         assert nargs == len(_lib._PROTOS[name][1]), name
     KK.invalidate_weight_cache()

@@ -83,7 +83,7 @@ def test_step_parity_s2d_route(script, B):
         _check(rep, 'bf16', 'critic', True)
         rep = parity.gen_parity(script, tr, om, conditioned=True, floor_frac=ff)
         _check(rep, 'bf16', 'gen', True)
-        assert K._s2d_packs, 'the space-to-depth route was not taken'
+        assert K._lazy_packs, 'the space-to-depth route was not taken'
     finally:
         K.config.use_s2d = True
         K.invalidate_weight_cache()
