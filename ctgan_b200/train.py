@@ -1,0 +1,173 @@
+"""The training loops of the three scripts (TG/CT_gan_mnist.py:226-271, TG/CT_gan_cifar.py:186-236,
+TG/CT_gan_cifar_resnet.py:391-434) around the B200 training step.
+
+Per iteration, exactly as the reference schedules it: one generator step (skipped at iteration 0), then CRITIC_ITERS
+critic steps each on a fresh real batch; `lib.plot` metrics with the reference's names; every `dev_every` iterations
+the critic cost over the dev set and a sample grid from fixed noise; `lib.plot.flush()` / `tick()` at the reference's
+cadence.  What differs is how it executes: both steps are CUDA-graph replays (graphs.GraphedTrainer), real batches
+arrive through data.DeviceFeeder (pinned, asynchronous, uint8), metrics are fetched asynchronously (tflib.plot), so
+the host never waits for the device inside an iteration.  Inception score (TG/tflib/inception_score.py: a frozen TF
+graph downloaded at run time) is out of scope.
+
+    python -m ctgan_b200.train cifar_resnet --data-dir /path/to/cifar-10-batches-py --iters 1000
+"""
+import argparse
+import importlib
+import os
+import time
+
+import numpy as np
+import torch
+
+from . import tflib as lib
+from . import checkpoint
+from .data import DeviceFeeder, inf_train_gen
+from .graphs import GraphedTrainer
+from .tflib import plot as _plot, save_images as _save_images, cifar10 as _cifar10, mnist as _mnist
+
+SCRIPTS = {'mnist': 'gan_mnist', 'cifar': 'gan_cifar', 'cifar_resnet': 'gan_cifar_resnet'}
+
+
+def _loaders(script, mod, batch_size, data_dir, n_examples):
+    if script == 'mnist':
+        train, dev, _ = _mnist.load(batch_size, batch_size, n_examples, filepath=data_dir)
+    else:
+        train, dev = _cifar10.load(batch_size, data_dir, n_examples)
+    return train, dev
+
+
+class Session:
+    """One training run: model, graphs, feeder, fixed sample noise."""
+
+    def __init__(self, script, data_dir, batch_size=None, n_examples=None, device='cuda', seed=1234, out_dir='.',
+                 act_dtype=torch.bfloat16, use_graphs=True, init_seed=1234):
+        self.script, self.out_dir = script, out_dir
+        self.mod = mod = importlib.import_module('ctgan_b200.' + SCRIPTS[script])
+        self.B = batch_size or mod.BATCH_SIZE
+        self.n_critic = getattr(mod, 'N_CRITIC', None) or mod.CRITIC_ITERS
+        self.resnet = script == 'cifar_resnet'
+        np.random.seed(init_seed)                               # initial weights: the reference's numpy-global init
+        self.tr = mod.Trainer(device=device, seed=seed, act_dtype=act_dtype, batch_size=self.B, graph_safe_rng=use_graphs)
+        self.train_epoch, self.dev_epoch = _loaders(script, mod, self.B, data_dir, n_examples or mod.n_examples)
+        take = 2 if self.resnet else 1
+        self.feeder = DeviceFeeder(inf_train_gen(self.train_epoch), device, depth=2, take=take, hold=self.n_critic)
+        # fixed noise for the sample grids (:341-343 / TG/CT_gan_cifar.py:157-158 / TG/CT_gan_mnist.py:206-207)
+        n_fixed = 100 if self.resnet else 128
+        self.fixed_noise = torch.from_numpy(np.random.normal(size=(n_fixed, 128)).astype('float32')).to(device)
+        self.fixed_labels = torch.tensor([0, 1, 2, 3, 4, 5, 6, 7, 8, 9] * 10, dtype=torch.int32, device=device) if self.resnet else None
+        self.gt = None
+        if use_graphs:
+            first = next(self.feeder)
+            self._pending = first
+            self.gt = GraphedTrainer(self.tr, tuple(first), pregen_steps=self.n_critic if self.resnet else 0)
+        else:
+            self._pending = None
+        self.iteration = 0
+
+    # -- one reference iteration ----------------------------------------------------------------------------------
+    def _next_batch(self):
+        if self._pending is not None:
+            b, self._pending = self._pending, None
+            return b
+        return next(self.feeder)
+
+    def run_iteration(self):
+        it, tr, gt = self.iteration, self.tr, self.gt
+        start = time.time()
+        if gt is not None:
+            gt.iteration = it
+        if it > 0:
+            gt.gen_step() if gt is not None else tr.gen_step(iteration=it)
+        batches = [self._next_batch() for _ in range(self.n_critic)]      # all stay valid: feeder hold = n_critic
+        if gt is not None and gt.pregen_steps:
+            gt.begin_iteration(torch.cat([b[1] for b in batches]))
+        out = None
+        for b in batches:
+            out = gt.critic_step(*b) if gt is not None else tr.critic_step(*b, iteration=it)['out']
+        if self.resnet:
+            _plot.plot('cost', out[0])
+            if self.mod.CONDITIONAL and self.mod.ACGAN:
+                _plot.plot('wgan', out[1])
+                _plot.plot('acgan', out[4])
+        else:
+            _plot.plot('train disc cost', out[0])
+        _plot.plot('time', time.time() - start)
+        self.iteration = it + 1
+        return out
+
+    # -- the every-100-iterations block -----------------------------------------------------------------------------
+    def dev_cost(self, max_batches=None):
+        """Mean critic cost over one dev epoch (fresh dropout / interpolation draws, no parameter update)."""
+        tr, costs = self.tr, []
+        for k, batch in enumerate(self.dev_epoch()):
+            if max_batches is not None and k >= max_batches:
+                break
+            arrays = [torch.from_numpy(np.ascontiguousarray(a if a.dtype == np.uint8 else
+                                                           (a.astype('int32') if a.dtype.kind in 'iu' else a.astype('float32'))))
+                      .to(tr.device) for a in (batch[:2] if self.resnet else batch[:1])]
+            tr.disc_opt.zero_grad()
+            costs.append(tr.critic_forward_backward(*arrays)['out'][0:1].clone())
+            tr.rng.end_step()
+        tr.disc_opt.zero_grad()
+        return float(torch.cat(costs).mean().item()) if costs else float('nan')
+
+    def generate_image(self, frame):
+        mod = self.mod
+        with torch.no_grad():
+            if self.resnet:
+                samples = mod.Generator(self.fixed_noise.shape[0], self.fixed_labels, noise=self.fixed_noise)
+            else:
+                samples = mod.Generator(self.fixed_noise.shape[0], noise=self.fixed_noise)
+        samples = samples.float().cpu().numpy()
+        if self.script == 'mnist':
+            path = os.path.join(self.out_dir, 'samples_{}.png'.format(frame))
+            _save_images.save_images(samples.reshape((-1, 28, 28)), path)
+        else:
+            samples = ((samples + 1.) * (255. / 2)).astype('int32')
+            ext = 'png' if self.resnet else 'jpg'
+            path = os.path.join(self.out_dir, 'samples_{}.{}'.format(frame, ext))
+            _save_images.save_images(samples.reshape((-1, 3, 32, 32)), path)
+        return path
+
+
+def train(script, data_dir, iters=None, dev_every=100, out_dir='.', checkpoint_every=None, dev_batches=None, **kw):
+    """Run `iters` iterations (default: the script's ITERS).  Returns the Session."""
+    os.makedirs(out_dir, exist_ok=True)
+    s = Session(script, data_dir, out_dir=out_dir, **kw)
+    _plot.reset()
+    _plot.output_dir = out_dir
+    iters = iters if iters is not None else s.mod.ITERS
+    flush_early = 500 if s.resnet else 5                     # :431 `iteration < 500`; DCGAN scripts: `iteration < 5`
+    flush_every = 1000 if s.resnet else 100
+    for iteration in range(iters):
+        s.run_iteration()
+        if iteration % dev_every == dev_every - 1:
+            _plot.plot('dev_cost' if s.resnet else 'dev disc cost', s.dev_cost(dev_batches))
+            s.generate_image(iteration)
+            if script == 'cifar':
+                checkpoint.save_disc_params_pyn(os.path.join(out_dir, 'param.pyn'))       # TG/CT_gan_cifar.py:216-222
+        if checkpoint_every and iteration % checkpoint_every == checkpoint_every - 1:
+            checkpoint.save(os.path.join(out_dir, 'checkpoint.npz'), s.tr)
+        if iteration < flush_early or iteration % flush_every == flush_every - 1:
+            _plot.flush()
+        _plot.tick()
+    return s
+
+
+def main():
+    ap = argparse.ArgumentParser(description=__doc__.split('\n')[0])
+    ap.add_argument('script', choices=sorted(SCRIPTS))
+    ap.add_argument('--data-dir', required=True, help='cifar-10-batches-py directory, or the mnist.pkl.gz path')
+    ap.add_argument('--iters', type=int, default=None)
+    ap.add_argument('--out-dir', default='.')
+    ap.add_argument('--batch-size', type=int, default=None)
+    ap.add_argument('--n-examples', type=int, default=None)
+    ap.add_argument('--checkpoint-every', type=int, default=None)
+    ap.add_argument('--no-graphs', action='store_true')
+    a = ap.parse_args()
+    train(a.script, a.data_dir, iters=a.iters, out_dir=a.out_dir, batch_size=a.batch_size, n_examples=a.n_examples,
+          checkpoint_every=a.checkpoint_every, use_graphs=not a.no_graphs)
+
+
+if __name__ == '__main__':
+    main()

@@ -592,7 +592,8 @@ def test_thin_strided_conv_family(K, geom):
     col = K.im2col_strided(to_dev(x), g)
     assert torch.equal(col.cpu(), H._im2col_strided(x, g))
     dcol = act((N, 128, g.Ho, g.Wo), torch.bfloat16, 6)
-    got, ref = K.col2im_strided(to_dev(dcol), b.cuda(), g), H._col2im_strided(dcol, b, g)
+    bc = act((Cin,), torch.float32, 7)
+    got, ref = K.col2im_strided(to_dev(dcol), bc.cuda(), g), H._col2im_strided(dcol, bc, g)
     assert rel(got, ref) < 4e-3                       # fp32 sums of <= 9 bf16 terms, one bf16 rounding
     n = 128 * Cout
     wp = [torch.empty(n, dtype=torch.bfloat16, device='cuda') for _ in range(2)]

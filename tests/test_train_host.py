@@ -1,0 +1,102 @@
+"""Host logic of the training loop, the input feeder and the checkpoints (`-m "not gpu"`, kernels replaced by the
+TEST-ONLY stand-ins of tests/fake_backend.py): the reference's iteration schedule (TG/CT_gan_cifar_resnet.py:393-434),
+metric names, files written, and an exact save / load round trip."""
+import gzip
+import os
+import pickle
+
+import numpy as np
+import pytest
+import torch
+
+from tests.test_host_utils import write_cifar_dir, mnist_sets
+
+
+def test_device_feeder_ring_keeps_the_last_batches_valid():
+    from ctgan_b200.data import DeviceFeeder, inf_train_gen
+
+    def epoch():
+        for i in range(7):
+            yield np.full((4, 8), i, dtype='uint8'), np.full((4,), i, dtype='int64'), 'ignored'
+
+    f = DeviceFeeder(inf_train_gen(epoch), 'cpu', depth=2, hold=3, take=2)
+    held = []
+    for k in range(20):
+        x, y = next(f)
+        assert x.dtype == torch.uint8 and y.dtype == torch.int32          # pixels stay bytes, labels become int32
+        held = (held + [(k % 7, x, y)])[-3:]
+        for v, a, b in held:
+            assert int(a[0, 0]) == v and int(b[0]) == v
+    assert f.bytes_per_batch == 4 * 8 + 4 * 4
+    g = DeviceFeeder(inf_train_gen(epoch), 'cpu', keep_uint8=False, take=1)
+    assert next(g)[0].dtype == torch.int32
+
+
+@pytest.mark.parametrize('script', ['cifar', 'cifar_resnet', 'mnist'])
+def test_train_loop_schedule_and_outputs(fake_kernels, tmp_path, script, capsys):
+    from ctgan_b200 import train as T
+    import ctgan_b200.tflib.plot as plot
+    if script == 'mnist':
+        data = str(tmp_path / 'mnist.pkl.gz')
+        with gzip.open(data, 'wb') as f:
+            pickle.dump(tuple(mnist_sets(n=(40, 8, 8))), f, protocol=2)
+    else:
+        data = write_cifar_dir(str(tmp_path / 'data'), n_per_file=8)
+    out = str(tmp_path / 'out')
+    sess = T.train(script, data, iters=3, dev_every=2, out_dir=out, dev_batches=1, batch_size=4, n_examples=40,
+                   device='cpu', use_graphs=False, act_dtype=torch.float32, checkpoint_every=3)
+    try:
+        # iteration 0 has no generator step (:396); every iteration runs N_CRITIC critic steps on fresh batches
+        n_critic = sess.n_critic
+        assert n_critic == 5
+        assert sess.tr.disc_opt.t == 3 * n_critic and sess.tr.gen_opt.t == 2
+        assert sess.feeder.batches == 3 * n_critic
+        log = pickle.load(open(os.path.join(out, 'log.pkl'), 'rb'))
+        cost_name = 'cost' if script == 'cifar_resnet' else 'train disc cost'
+        dev_name = 'dev_cost' if script == 'cifar_resnet' else 'dev disc cost'
+        assert sorted(log[cost_name]) == [0, 1, 2] and sorted(log['time']) == [0, 1, 2] and sorted(log[dev_name]) == [1]
+        if script == 'cifar_resnet':
+            assert sorted(log['wgan']) == [0, 1, 2] and sorted(log['acgan']) == [0, 1, 2]
+        assert all(np.isfinite(v) for v in log[cost_name].values())
+        ext = {'cifar': 'jpg', 'cifar_resnet': 'png', 'mnist': 'png'}[script]
+        assert os.path.getsize(os.path.join(out, 'samples_1.%s' % ext)) > 0
+        assert os.path.exists(os.path.join(out, 'checkpoint.npz'))
+        if script == 'cifar':
+            para = np.load(os.path.join(out, 'param.pyn.npy'), allow_pickle=True)
+            assert len(para) == 8 and para[0].shape == (5, 5, 3, 128)        # 3 convs + Output: Filters/W + Biases/b
+        assert 'iter 0\t' in capsys.readouterr().out
+    finally:
+        plot.output_dir = '.'
+        plot.reset()
+
+
+def test_checkpoint_round_trip_resumes_exactly(fake_kernels, tmp_path):
+    import ctgan_b200.gan_cifar as C
+    import ctgan_b200.tflib as lib
+    from ctgan_b200 import checkpoint
+    x = torch.from_numpy(np.random.RandomState(0).randint(0, 256, (3, 4, 3072)).astype('int32'))
+
+    def fresh():
+        np.random.seed(5)
+        return C.Trainer(device='cpu', seed=9, act_dtype=torch.float32, batch_size=4)
+
+    a = fresh()
+    a.critic_step(x[0]); a.gen_step()
+    path = str(tmp_path / 'ck.npz')
+    checkpoint.save(path, a)
+    blob = np.load(path)
+    assert blob['param/Discriminator.2.Filters'].shape == (5, 5, 128, 256)            # reference name, HWIO
+    assert blob['param/Generator.Input.W'].shape == (128, 8192)
+    a.rng.offset = 1000
+    a.critic_step(x[1])
+    want = a.disc_opt.flat_p.clone()
+
+    b = fresh()
+    checkpoint.load(path, b)
+    assert b.disc_opt.t == 1 and b.gen_opt.t == 1
+    b.rng.offset = 1000
+    b.critic_step(x[1])
+    assert torch.equal(b.disc_opt.flat_p, want)
+    with pytest.raises(KeyError):
+        lib.param('Discriminator.Extra', np.zeros(2, dtype='float32'))
+        checkpoint.load(path, None)
