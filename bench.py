@@ -329,6 +329,184 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+# ----------------------------------------------------------------------------- DCGAN workloads (BASELINE configs[0], [1])
+DCGAN = {
+    # script: (module, oracle module, batch, critic GFLOP, generator GFLOP, input row, config name)
+    'cifar': ('ctgan_b200.gan_cifar', 'oracle.ct_gan_cifar', 64, 191.51, 68.95, 3072,
+              'CT_gan_cifar.py DCGAN critic/generator, 32x32x3 synthetic batch 64, critic_iters=5 (BASELINE configs[1])'),
+    'mnist': ('ctgan_b200.gan_mnist', 'oracle.ct_gan_mnist', 50, 32.80, 11.83, 784,
+              'CT_gan_mnist.py DCGAN-style critic/generator, 28x28x1 synthetic batch 50, dropout CT term + GP (BASELINE configs[0])'),
+}
+
+
+def _dcgan_batches(np, script, pool, B, seed):
+    rs = np.random.RandomState(seed)
+    if script == 'cifar':
+        return rs.randint(0, 256, (pool, B, 3072)).astype('int32')
+    return rs.random_sample((pool, B, 784)).astype('float32')
+
+
+def time_cpu_dcgan(script, max_seconds=25.0):
+    import importlib
+    import numpy as np
+    import torch
+    from oracle.rand import SeededRandom
+    _, ora, B = DCGAN[script][:3]
+    torch.set_num_threads(os.cpu_count() or 1)
+    np.random.seed(1234)
+    m = importlib.import_module(ora).Model(dtype=torch.float32, batch_size=B).build()
+    x = torch.from_numpy(_dcgan_batches(np, script, 1, B, 1234)[0])
+    t0 = time.time(); m.critic_step(SeededRandom(1), x, iteration=0); t_warm = time.time() - t0
+    n = max(1, min(5, int(max_seconds / max(2.2 * t_warm, 1e-3))))
+    tc = tg = 0.0
+    for i in range(n):
+        t0 = time.time(); m.critic_step(SeededRandom(10 + i), x, iteration=i); tc += time.time() - t0
+        t0 = time.time(); m.gen_step(SeededRandom(100 + i), iteration=i); tg += time.time() - t0
+    tc, tg = tc / n, tg / n
+    return dict(value=1.0 / (N_CRITIC * tc + tg), unit='iterations/s', cores=torch.get_num_threads(), kind='port',
+                sample='%d critic + %d generator steps at batch %d (fp32 oracle, PyTorch-CPU); iteration = 5*critic + 1*gen = %.2f s'
+                       % (n, n, B, N_CRITIC * tc + tg))
+
+
+def roofline_dcgan_kernel(torch, peaks, script, B):
+    """The dominant launch of the DCGAN critic step: the second stride-2 5x5 conv on the stacked pass (3B images), run as a 3x3
+    tcgen05 conv over the space-to-depth image.  ALGORITHMIC FLOPs = the 5x5/2 conv's (25 taps); the kernel executes 36/25 of them."""
+    import ctypes
+    import ctgan_b200.kernels as K
+    from ctgan_b200 import _lib
+    N, H, Cin, Cout = (3 * B, 16, 128, 256) if script == 'cifar' else (3 * B, 14, 64, 128)
+    g = K.same_geom(N, H, H, Cin, Cout, 5, 2)
+    g3 = K.s2d_geom(g)
+    sets = [K.space_to_depth(torch.randn(N, Cin, H, H, device='cuda').to(torch.bfloat16).contiguous(memory_format=torch.channels_last), g)
+            for _ in range(8)]
+    w = (torch.randn(5, 5, Cin, Cout, device='cuda') * 0.03).contiguous()
+    wp = K.pack_filter_s2d(w, g, 0)
+    b = torch.zeros(Cout, device='cuda')
+    ys = [torch.empty((N, Cout, g.Ho, g.Wo), dtype=torch.bfloat16, device='cuda').contiguous(memory_format=torch.channels_last) for _ in range(8)]
+    d = K._desc(g3, _lib.BF16, _lib.BF16)
+    def launch(i):
+        _lib.call('ctgan_conv_fprop_tc', ctypes.byref(d), K._p(sets[i % 8]), K._p(wp), K._p(b), None, K._p(ys[i % 8]), 0, K._stream())
+    for i in range(8):
+        launch(i)
+    torch.cuda.synchronize()
+    reps = 40
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(reps):
+        launch(i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    flops = 2.0 * N * g.Ho * g.Wo * Cin * Cout * 25
+    achieved = flops / (ms * 1e-3) / 1e12
+    return {'bound': 'tensor', 'kernel': 'conv_fprop_tc_lean_kernel<0> as the 5x5/2 conv %d->%d on %dx%dx%d (3x3 over the space-to-depth image)'
+                                         % (Cin, Cout, N, H, H),
+            'achieved': achieved, 'peak': peaks['burst'], 'peak_source': 'MEASURED_PEAKS.json bf16_tflops (burst; kernel timed alone)'
+            if peaks['src'] == 'measured' else 'fallback 1590', 'unit': 'TFLOP/s', 'frac': achieved / peaks['burst'], 'traffic': None,
+            'flops_per_launch': flops, 'executed_flops_per_launch': flops * 36 / 25, 'us_per_launch': ms * 1e3}
+
+
+def run_dcgan(args):
+    """`--workload cifar|mnist`: the same measurement for the DCGAN scripts (parity-test configurations; not the default line)."""
+    import importlib
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    script = args.workload
+    modname, _, B, gf_c, gf_g, row, cfg = DCGAN[script]
+    rank, local_rank, world = (int(os.environ.get(k, d)) for k, d in (('RANK', '0'), ('LOCAL_RANK', '0'), ('WORLD_SIZE', '1')))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device (the product has no CPU path)')
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    dev = torch.device('cuda', local_rank)
+    from ctgan_b200 import _lib
+    from ctgan_b200.graphs import GraphedTrainer
+    mod = importlib.import_module(modname)
+    np.random.seed(1234)
+    tr = mod.Trainer(device=dev, seed=1234 + rank, act_dtype=torch.bfloat16, batch_size=B, graph_safe_rng=True)
+    pool = 8
+    host_x = torch.from_numpy(_dcgan_batches(np, script, pool, B, 1234 + rank)).pin_memory()
+    dev_x = host_x.to(dev)
+    host_out = torch.zeros(N_CRITIC + 1, 8, dtype=torch.float32).pin_memory()
+    gt = GraphedTrainer(tr, (dev_x[0],))
+    state = {'b': 0}
+
+    def iteration(e2e):
+        src = host_x if e2e else dev_x
+        g = gt.gen_step()
+        if e2e:
+            host_out[N_CRITIC, 0:1].copy_(g.reshape(-1)[:1], non_blocking=True)
+        for i in range(N_CRITIC):
+            b = state['b'] = (state['b'] + 1) % pool
+            out = gt.critic_step(src[b])
+            if e2e:
+                host_out[i].copy_(out, non_blocking=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(e2e, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            iteration(e2e)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    for _ in range(max(3, args.warmup)):
+        iteration(False)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ms = timed(False, args.steps)
+    clocks = sampler.stop() if sampler else None
+    for _ in range(2):
+        iteration(True)
+    ms_e2e = timed(True, args.steps)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = load_peaks()
+    unit = 'iterations/s (1 gen + 5 critic steps of batch %d per GPU; aggregate over GPUs)' % B
+    it_s, it_s_e2e = world * args.steps / (ms * 1e-3), world * args.steps / (ms_e2e * 1e-3)
+    gflop = N_CRITIC * gf_c + gf_g
+    step_tflops = gflop * 1e-3 * (args.steps / (ms * 1e-3))
+    line = {
+        'metric': 'CT-GAN train iters/sec (%s)' % ('CIFAR DCGAN' if script == 'cifar' else 'MNIST DCGAN'), 'value': it_s, 'unit': unit,
+        'n_gpus': world, 'steps': args.steps, 'warmup': max(3, args.warmup), 'ms_per_step': ms / args.steps, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
+        'config': {'workload': cfg, 'per_gpu_batch': B, 'critic_iters': N_CRITIC, 'cuda_graphs': True,
+                   'l2_policy': '8 rotating input batches; activations of the stacked critic pass exceed L2 only for cifar; no explicit flush',
+                   'precision': 'BF16 operands / fp32 accumulate (tcgen05; stride-2 5x5 layers as 3x3 convs over the space-to-depth image), '
+                                'fp32 master weights and optimizer'},
+        'clocks': clocks,
+        'e2e': {'value': it_s_e2e, 'unit': unit, 'ms_per_step': ms_e2e / args.steps,
+                'h2d_bytes_per_step': N_CRITIC * (B * row * 4 + 4) + 4, 'd2h_bytes_per_step': N_CRITIC * 32 + 4},
+        'gpu_launches': int(args.steps * (gt.gen_kernels + N_CRITIC * gt.critic_kernels)),
+        'roofline': roofline_dcgan_kernel(torch, peaks, script, B),
+        'step_tensor_utilisation': {'algorithmic_gflop_per_iteration': gflop, 'achieved_tflops_per_gpu': step_tflops,
+                                    'frac_of_sustained_peak': step_tflops / peaks['sustained'], 'peak': peaks['sustained']},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line['cpu_baseline'] = time_cpu_dcgan(script)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -338,9 +516,13 @@ def main():
     ap.add_argument('--no-graph', action='store_true', help='launch every kernel eagerly (debug / profiling)')
     ap.add_argument('--no-pregen', action='store_true', help='one generator forward per critic step instead of one per iteration')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--workload', default='resnet', choices=['resnet', 'cifar', 'mnist'],
+                    help="resnet = BASELINE.json's metric (default); cifar / mnist = the DCGAN parity configurations (our arm only)")
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)
+    elif args.workload != 'resnet':
+        run_dcgan(args)
     else:
         run_ours(args)
 
