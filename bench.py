@@ -16,6 +16,9 @@ path, synthetic CIFAR-shaped data, random-init weights.  One JSON line is printe
   cpu_baseline / --impl reference
             the CPU transcription of the reference graph (oracle/, PyTorch-CPU fp32, all host
             threads) -- TF 1.2.1 cannot be installed here
+  --workload cifar|mnist
+            the same line for the DCGAN scripts CT_gan_cifar.py / CT_gan_mnist.py (BASELINE configs[1] / [0]: parity
+            configurations, not the headline); default = resnet, BASELINE.json's metric
 """
 import argparse
 import json
@@ -83,6 +86,19 @@ def time_cpu_reference(max_seconds=150.0, want_steps=1):
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
+        return
+    if getattr(args, 'workload', 'resnet') != 'resnet':
+        script = args.workload
+        cb = time_cpu_dcgan(script, max_seconds=60.0)
+        unit = 'iterations/s (1 gen + 5 critic steps of batch %d per GPU; aggregate over GPUs)' % DCGAN[script][2]
+        cb['unit'] = unit
+        print(json.dumps({
+            'impl': 'reference', 'metric': 'CT-GAN train iters/sec (%s)' % ('CIFAR DCGAN' if script == 'cifar' else 'MNIST DCGAN'),
+            'value': cb['value'], 'unit': unit, 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': 1e3 / cb['value'], 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+            'data': 'synthetic', 'config': {'workload': DCGAN[script][6] + '; CPU transcription of the reference graph on host cores'},
+            'cpu_baseline': cb, 'e2e': {'value': cb['value'], 'unit': unit, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0}), flush=True)
         return
     cb, sec = time_cpu_reference(max_seconds=150.0, want_steps=max(1, args.steps))
     line = {

@@ -19,7 +19,6 @@ import time
 import numpy as np
 import torch
 
-from . import tflib as lib
 from . import checkpoint
 from .data import DeviceFeeder, inf_train_gen
 from .graphs import GraphedTrainer
