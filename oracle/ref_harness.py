@@ -54,7 +54,7 @@ def _load_ref_tflib(shim):
     pkg_dir = os.path.join(OUT_DIR, 'tflib')
     os.makedirs(os.path.join(pkg_dir, 'ops'), exist_ok=True)
     for rel in ['__init__.py', 'ops/__init__.py', 'ops/conv2d.py', 'ops/deconv2d.py', 'ops/linear.py',
-                'ops/batchnorm.py', 'ops/cond_batchnorm.py']:
+                'ops/batchnorm.py', 'ops/cond_batchnorm.py', 'ops/layernorm.py']:
         with open(os.path.join(REF_ROOT, 'tflib', rel)) as f:
             src = py2to3(f.read())
         if rel == '__init__.py':
@@ -68,7 +68,7 @@ def _load_ref_tflib(shim):
     sys.path.insert(0, OUT_DIR)
     try:
         lib = importlib.import_module('tflib')
-        for m in ('conv2d', 'deconv2d', 'linear', 'batchnorm', 'cond_batchnorm'):
+        for m in ('conv2d', 'deconv2d', 'linear', 'batchnorm', 'cond_batchnorm', 'layernorm'):
             importlib.import_module('tflib.ops.' + m)
     finally:
         sys.path.remove(OUT_DIR)
@@ -133,6 +133,9 @@ SECTIONS = {
     'mnist': dict(file='CT_gan_mnist.py', consts=(26, 35), funcs=(39, 108), graph=(110, 167), dedent=False),
     'cifar': dict(file='CT_gan_cifar.py', consts=(34, 43), funcs=(47, 100), graph=(102, 151), dedent=False),
     'resnet': dict(file='CT_gan_cifar_resnet.py', consts=(37, 56), funcs=(67, 186), graph=(190, 330), dedent=True),
+    # hyper-parameters, EVERY architecture function of the file (only GoodGenerator / GoodDiscriminator
+    # are called), `Generator, Discriminator = GeneratorAndDiscriminator()`, then the two-tower loss graph
+    '64x64': dict(file='CT_gan_64x64.py', consts=(28, 37), funcs=(41, 469), graph=(473, 546), dedent=True),
 }
 
 # random draws of the reference graph, in graph-construction order, mapped onto the oracle's tags
@@ -149,6 +152,12 @@ def _draw_tags(script):
         tags += ['alpha'] + D3('drop.gp')
         if script == 'cifar':
             tags += [None] * 3                         # Discriminator(real_data) for `gradients2` (:145, dev metric)
+        return tags
+    if script == '64x64':                              # per tower: G, D(real) x2, D(fake), alpha, D(interpolates)
+        tags = []
+        for i in range(2):
+            tags += ['z.%d' % i] + D3('drop.%d.real1' % i) + D3('drop.%d.real2' % i) + D3('drop.%d.fake' % i)
+            tags += ['alpha.%d' % i] + D3('drop.%d.gp' % i)
         return tags
     tags = ['z.0', 'z.1', 'dequant'] + D3('drop.p1') + D3('drop.p2')     # clean pass: keep_prob 1 -> no draw
     tags += ['alpha'] + D3('drop.gp')
@@ -197,10 +206,12 @@ def run_reference(script, batch_size, seed, inputs, dim=None):
             tape_gen[tag[:-1] if tag.endswith('g') else tag] = t2
         else:
             tape_disc[tag] = t
-    if script != 'resnet':
+    if script == '64x64':
+        tape_gen = {k: v for k, v in tape_disc.items() if k.startswith('z.') or k.endswith(('.fake.1', '.fake.2', '.fake.3'))}
+    elif script != 'resnet':
         tape_gen = {k: v for k, v in tape_disc.items() if k == 'z' or k.startswith('drop.fake')}
     params = {n: p for n, p in lib._params.items()}
-    disc_sel = 'Discriminator.' if script == 'resnet' else 'Discriminator'
+    disc_sel = 'Discriminator.' if script in ('resnet', '64x64') else 'Discriminator'
     dnames = [n for n, p in params.items() if disc_sel in n and p.requires_grad]
     gnames = [n for n, p in params.items() if 'Generator' in n and p.requires_grad]
     dgr = torch.autograd.grad(ns['disc_cost'], [params[n] for n in dnames], retain_graph=True, allow_unused=True)

@@ -17,6 +17,7 @@ import torch
 from .. import tf_ops
 
 DT = torch.float64
+__version__ = '1.2.1'
 float32 = 'float32'
 int32 = 'int32'
 

@@ -143,6 +143,16 @@ class TFLib:
         scale = self.param(name + '.scale', np.ones(shape, dtype='float32'))
         return tf_ops.batch_normalization(inputs, mean, var, offset, scale, 1e-5)
 
+    def Layernorm(self, name, norm_axes, inputs):
+        """TG/tflib/ops/layernorm.py:6-21: per-sample moments over `norm_axes` (keep_dims), scale / offset per
+        'neuron' = the first of norm_axes (channels for BCHW), eps 1e-5."""
+        mean, var = tf_ops.moments(inputs, norm_axes)
+        n_neurons = inputs.shape[norm_axes[0]]
+        offset = self.param(name + '.offset', np.zeros(n_neurons, dtype='float32'))
+        scale = self.param(name + '.scale', np.ones(n_neurons, dtype='float32'))
+        bshape = [-1] + [1 for _ in range(len(norm_axes) - 1)]
+        return tf_ops.batch_normalization(inputs, mean, var, offset.reshape(bshape), scale.reshape(bshape), 1e-5)
+
     def CondBatchnorm(self, name, axes, inputs, labels=None, n_labels=None):
         """TG/tflib/ops/cond_batchnorm.py:6-17."""
         if axes != [0, 2, 3]:

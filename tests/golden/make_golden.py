@@ -17,7 +17,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, ROOT)
 from oracle import ref_harness as RH   # noqa: E402
 
-CASES = {'mnist': dict(B=6, dim=8, seed=101), 'cifar': dict(B=4, dim=8, seed=202), 'resnet': dict(B=4, dim=16, seed=303)}
+CASES = {'mnist': dict(B=6, dim=8, seed=101), 'cifar': dict(B=4, dim=8, seed=202), 'resnet': dict(B=4, dim=16, seed=303),
+         '64x64': dict(B=4, dim=4, seed=404)}
 
 
 def inputs_for(script, B, seed):
@@ -26,12 +27,16 @@ def inputs_for(script, B, seed):
         return (rs.random_sample((B, 784)).astype('float32'),)
     if script == 'cifar':
         return (rs.randint(0, 256, (B, 3072)).astype('int32'),)
+    if script == '64x64':
+        return (rs.randint(0, 256, (B, 3, 64, 64)).astype('int32'),)
     return (rs.randint(0, 256, (B, 3072)).astype('int32'), rs.randint(0, 10, (B,)).astype('int32'))
 
 
-def main():
+def main(only=None):
     out_dir = os.path.dirname(os.path.abspath(__file__))
     for script, c in CASES.items():
+        if only and script not in only:
+            continue
         inputs = inputs_for(script, c['B'], c['seed'])
         r = RH.run_reference(script, c['B'], c['seed'], inputs, dim=c['dim'])
         blob = {'meta.B': np.int64(c['B']), 'meta.dim': np.int64(c['dim']), 'meta.seed': np.int64(c['seed'])}
@@ -56,4 +61,4 @@ def main():
 
 
 if __name__ == '__main__':
-    main()
+    main(sys.argv[1:])

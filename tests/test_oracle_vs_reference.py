@@ -18,11 +18,11 @@ import numpy as np
 import pytest
 import torch
 
-from oracle import ct_gan_mnist, ct_gan_cifar, ct_gan_cifar_resnet, ref_harness
+from oracle import ct_gan_mnist, ct_gan_cifar, ct_gan_cifar_resnet, ct_gan_64x64, ref_harness
 from oracle.rand import ReplayRandom
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
-MODS = {'mnist': ct_gan_mnist, 'cifar': ct_gan_cifar, 'resnet': ct_gan_cifar_resnet}
+MODS = {'mnist': ct_gan_mnist, 'cifar': ct_gan_cifar, 'resnet': ct_gan_cifar_resnet, '64x64': ct_gan_64x64}
 
 
 def _model(script, B, dim):
@@ -50,7 +50,8 @@ def _compare(script, m, params, inputs, tape_disc, tape_gen, ref, tol):
     named = m.lib.named_params_with_name(m.disc_name)
     grads = m._grads(out['cost'], named)
     assert abs(float(out['cost']) - float(ref['disc_cost'])) <= tol * max(1.0, abs(float(ref['disc_cost'])))
-    assert _rel(out['gradients'], ref['gp_gradients']) < tol
+    gp_rows = len(ref['gp_gradients'])          # 64x64: the reference's `gradients` is the LAST tower's (TG/CT_gan_64x64.py:505)
+    assert _rel(out['gradients'][-gp_rows:], ref['gp_gradients']) < tol
     floor = 1e-6 * max(float(torch.as_tensor(g).double().norm()) for g in ref['disc_grads'].values())
     for n, g in ref['disc_grads'].items():
         err = float((grads[n].double() - torch.as_tensor(g).double()).norm()) / max(float(torch.as_tensor(g).double().norm()), floor)
@@ -76,7 +77,7 @@ def load_golden(script):
                 inputs=inputs, tape_disc=pick('tape_disc.'), tape_gen=pick('tape_gen.'), ref=ref)
 
 
-@pytest.mark.parametrize('script', ['mnist', 'cifar', 'resnet'])
+@pytest.mark.parametrize('script', ['mnist', 'cifar', 'resnet', '64x64'])
 def test_oracle_matches_golden(script):
     g = load_golden(script)
     m = _model(script, g['B'], g['dim'])
@@ -84,20 +85,23 @@ def test_oracle_matches_golden(script):
 
 
 @pytest.mark.skipif(not ref_harness.available(), reason='/root/reference not present (GPU box)')
-@pytest.mark.parametrize('script,B', [('mnist', 5), ('cifar', 3), ('resnet', 2)])
+@pytest.mark.parametrize('script,B', [('mnist', 5), ('cifar', 3), ('resnet', 2), ('64x64', 2)])
 def test_oracle_matches_live_reference(script, B):
     from tests.golden.make_golden import inputs_for
     inputs = inputs_for(script, B, 77)
     r = ref_harness.run_reference(script, B, 77, inputs)                  # the scripts' real widths
-    dim = {'mnist': 64, 'cifar': 128, 'resnet': 128}[script]
+    dim = {'mnist': 64, 'cifar': 128, 'resnet': 128, '64x64': 64}[script]
     m = _model(script, B, dim)
     ref = dict(disc_cost=r['disc_cost'], gen_cost=r['gen_cost'], gp_gradients=r['gp_gradients'],
                disc_grads=r['disc_grads'], gen_grads={k: v for k, v in r['gen_grads'].items() if v is not None})
     _compare(script, m, r['params'], inputs, r['tape_disc'], r['tape_gen'], ref, tol=1e-9)
     # parameter counts the survey derived from the reference
     count = lambda sel: sum(int(np.prod(p.shape)) for n, p in r['params'].items() if sel in n and r['trainable'][n])
-    expect = {'mnist': (1030145, 1554177), 'cifar': (4114689, 5179907), 'resnet': (1055115, 1218307)}[script]
-    assert (count('Discriminator'), count('Generator')) == expect
+    expect = {'mnist': (1030145, 1554177), 'cifar': (4114689, 5179907), 'resnet': (1055115, 1218307), '64x64': None}[script]
+    if expect is not None:
+        assert (count('Discriminator'), count('Generator')) == expect
+    else:
+        print('64x64 parameter counts: D %d, G %d' % (count('Discriminator'), count('Generator')))
 
 
 @pytest.mark.skipif(not ref_harness.available(), reason='/root/reference not present (GPU box)')
