@@ -16,11 +16,16 @@ import numpy as np
 import torch
 
 
-def inf_train_gen(epoch_fn):
-    """TG/CT_gan_cifar_resnet.py:363-366 / TG/CT_gan_mnist.py:220-223."""
+def inf_train_gen(epoch_fn, rank=0, world=1):
+    """TG/CT_gan_cifar_resnet.py:363-366 / TG/CT_gan_mnist.py:220-223.  Data parallel (world > 1): every rank runs the
+    SAME generator (same numpy seed => same shuffles) and keeps batches rank, rank + world, ... -- disjoint shards of one
+    epoch order, the batch-sharding the reference's tower loop does inside one process (TG/CT_gan_64x64.py:475-480)."""
+    k = 0
     while True:
         for batch in epoch_fn():
-            yield batch
+            if k % world == rank:
+                yield batch
+            k += 1
 
 
 def _host_dtype(a, keep_uint8):

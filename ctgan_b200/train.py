@@ -35,6 +35,13 @@ def _loaders(script, mod, batch_size, data_dir, n_examples):
     return train, dev
 
 
+def _rank_world():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
 class Session:
     """One training run: model, graphs, feeder, fixed sample noise."""
 
@@ -46,10 +53,13 @@ class Session:
         self.n_critic = getattr(mod, 'N_CRITIC', None) or mod.CRITIC_ITERS
         self.resnet = script == 'cifar_resnet'
         np.random.seed(init_seed)                               # initial weights: the reference's numpy-global init
-        self.tr = mod.Trainer(device=device, seed=seed, act_dtype=act_dtype, batch_size=self.B, graph_safe_rng=use_graphs)
+        # data parallel: identical initial weights and data order on every rank, rank-dependent random streams / shards
+        self.tr = mod.Trainer(device=device, seed=seed + _rank_world()[0], act_dtype=act_dtype, batch_size=self.B,
+                              graph_safe_rng=use_graphs)
         self.train_epoch, self.dev_epoch = _loaders(script, mod, self.B, data_dir, n_examples or mod.n_examples)
         take = 2 if self.resnet else 1
-        self.feeder = DeviceFeeder(inf_train_gen(self.train_epoch), device, depth=2, take=take, hold=self.n_critic)
+        rank, world = _rank_world()
+        self.feeder = DeviceFeeder(inf_train_gen(self.train_epoch, rank, world), device, depth=2, take=take, hold=self.n_critic)
         # fixed noise for the sample grids (:341-343 / TG/CT_gan_cifar.py:157-158 / TG/CT_gan_mnist.py:206-207)
         n_fixed = 100 if self.resnet else 128
         self.fixed_noise = torch.from_numpy(np.random.normal(size=(n_fixed, 128)).astype('float32')).to(device)
@@ -138,17 +148,22 @@ def train(script, data_dir, iters=None, dev_every=100, out_dir='.', checkpoint_e
     iters = iters if iters is not None else s.mod.ITERS
     flush_early = 500 if s.resnet else 5                     # :431 `iteration < 500`; DCGAN scripts: `iteration < 5`
     flush_every = 1000 if s.resnet else 100
+    writer = _rank_world()[0] == 0                           # replicas are identical: rank 0 writes the files
     for iteration in range(iters):
         s.run_iteration()
         if iteration % dev_every == dev_every - 1:
             _plot.plot('dev_cost' if s.resnet else 'dev disc cost', s.dev_cost(dev_batches))
-            s.generate_image(iteration)
-            if script == 'cifar':
-                checkpoint.save_disc_params_pyn(os.path.join(out_dir, 'param.pyn'))       # TG/CT_gan_cifar.py:216-222
-        if checkpoint_every and iteration % checkpoint_every == checkpoint_every - 1:
+            if writer:
+                s.generate_image(iteration)
+                if script == 'cifar':
+                    checkpoint.save_disc_params_pyn(os.path.join(out_dir, 'param.pyn'))   # TG/CT_gan_cifar.py:216-222
+        if writer and checkpoint_every and iteration % checkpoint_every == checkpoint_every - 1:
             checkpoint.save(os.path.join(out_dir, 'checkpoint.npz'), s.tr)
         if iteration < flush_early or iteration % flush_every == flush_every - 1:
-            _plot.flush()
+            if writer:
+                _plot.flush()
+            else:
+                _plot._since_last_flush.clear()
         _plot.tick()
     return s
 

@@ -66,3 +66,43 @@ def test_two_rank_gloo_data_parallel(tmp_path, script):
     r0, r1 = torch.load(tmp_path / 'rank0.pt'), torch.load(tmp_path / 'rank1.pt')
     assert torch.equal(r0['p'], r1['p'])                        # replicas stay bit-identical
     assert not torch.equal(r0['local'], r1['local'])            # shards / random streams differ per rank
+
+
+def _train_worker(rank, world, port, data_dir, out_dir):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.set_num_threads(2)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from tests import fake_backend
+    fake_backend.install(_MP())
+    from ctgan_b200 import train as T
+    seen = []
+    import ctgan_b200.data as D
+    orig = D.DeviceFeeder.__next__
+
+    def spy(self):
+        out = orig(self)
+        seen.append(out[0].clone())
+        return out
+    D.DeviceFeeder.__next__ = spy
+    sess = T.train('cifar', data_dir, iters=2, dev_every=100, out_dir=os.path.join(out_dir, 'run'), batch_size=4, n_examples=80,
+                   device='cpu', use_graphs=False, act_dtype=torch.float32)
+    torch.save(dict(pd=sess.tr.disc_opt.flat_p, pg=sess.tr.gen_opt.flat_p, seen=torch.stack(seen)),
+               os.path.join(out_dir, 'train_rank%d.pt' % rank))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_training_loop_shards_the_epoch(tmp_path):
+    """ctgan_b200.train under world_size 2: both ranks walk the same epoch order and take alternating batches
+    (disjoint shards), gradients are all-reduced every step, replicas stay bit-identical, rank 0 writes the logs."""
+    from tests.test_host_utils import write_cifar_dir
+    data = write_cifar_dir(str(tmp_path / 'data'), n_per_file=16)
+    port = _free_port()
+    mp.spawn(_train_worker, args=(2, port, data, str(tmp_path)), nprocs=2, join=True)
+    r0, r1 = torch.load(tmp_path / 'train_rank0.pt'), torch.load(tmp_path / 'train_rank1.pt')
+    assert torch.equal(r0['pd'], r1['pd']) and torch.equal(r0['pg'], r1['pg'])
+    assert r0['seen'].shape == r1['seen'].shape == (10, 4, 3072)
+    rows0 = {bytes(r.numpy().tobytes()) for b in r0['seen'] for r in b}
+    rows1 = {bytes(r.numpy().tobytes()) for b in r1['seen'] for r in b}
+    assert not (rows0 & rows1)                                  # no image is seen by both ranks within the epoch
+    assert os.path.exists(tmp_path / 'run' / 'log.pkl')
