@@ -45,6 +45,50 @@ def _is_param(w):
 direct_param_grads = True
 
 
+# Which parameter gradients the RUNNING backward pass is asked for.  `ctx.needs_input_grad` only says that a parameter
+# requires grad, not that this particular backward wants its gradient: the gradient penalty's first backward
+# (tf.gradients(D(x^), [x^]), TG/CT_gan_cifar.py:144) wants d/dx^ only, and the generator step differentiates through the
+# critic without updating it (var_list=gen_params, TG/CT_gan_cifar.py:153).  Without these switches every critic layer ran a
+# filter-gradient and a bias-gradient kernel in both cases and threw the result away (11 + 11 launches per ResNet critic
+# step, 12 + 12 per generator step).
+_skip_param_grads = False
+_frozen_ptrs = set()
+
+
+class no_param_grads:
+    """with no_param_grads(): the backward passes run inside produce input gradients only."""
+
+    def __enter__(self):
+        global _skip_param_grads
+        self.prev, _skip_param_grads = _skip_param_grads, True
+        return self
+
+    def __exit__(self, *exc):
+        global _skip_param_grads
+        _skip_param_grads = self.prev
+        return False
+
+
+class frozen:
+    """with frozen(params): backward passes run inside skip the gradients of these parameters."""
+
+    def __init__(self, params):
+        self.ptrs = {p.data_ptr() for p in params}
+
+    def __enter__(self):
+        self.added = self.ptrs - _frozen_ptrs
+        _frozen_ptrs.update(self.added)
+        return self
+
+    def __exit__(self, *exc):
+        _frozen_ptrs.difference_update(self.added)
+        return False
+
+
+def _wants(p):
+    return not _skip_param_grads and p.data_ptr() not in _frozen_ptrs
+
+
 def _direct(p):
     return (direct_param_grads and not torch.is_grad_enabled() and p.is_leaf and p.grad is not None
             and p.grad.is_contiguous() and _is_param(p))
@@ -96,13 +140,13 @@ class ConvF(Function):
         dycol = K.thin_col(gy, ctx.g, 'dy')          # im2col of a 3-channel gy: shared by dgrad and wgrad
         if ctx.needs_input_grad[0]:
             gx = ConvD.apply(gy, w, ctx.g, x.dtype, dycol, x.detach() if ctx.in_relu else None)
-        if ctx.needs_input_grad[1]:
+        if ctx.needs_input_grad[1] and _wants(w):
             if _direct(w):
                 col, g = (ctx.col if ctx.col is not None else dycol), ctx.g
                 K.on_side(lambda: K.conv_wgrad(x, gy, g, tuple(w.shape), accumulate_into=w.grad, col=col), x, gy, col)
             else:
                 gw = ConvG.apply(x, gy, ctx.g, tuple(w.shape))
-        if ctx.has_bias and ctx.needs_input_grad[2]:
+        if ctx.has_bias and ctx.needs_input_grad[2] and _wants(ctx.bias):
             b = ctx.bias
             if _direct(b):
                 K.on_side(lambda: K.bias_grad(gy.detach(), accumulate_into=b.grad), gy)
@@ -135,7 +179,7 @@ class ConvD(Function):
         ccol = K.thin_col(c, ctx.g, 'x')             # im2col of a 3-channel c: shared by fprop and wgrad
         if ctx.needs_input_grad[0]:
             ggy = ConvF.apply(c, w, None, ctx.g, gy.dtype, ccol)
-        if ctx.needs_input_grad[1]:
+        if ctx.needs_input_grad[1] and _wants(w):
             if _direct(w):
                 g = ctx.g
                 K.on_side(lambda: K.conv_wgrad(c, gy, g, tuple(w.shape), accumulate_into=w.grad, col=ccol), c, gy, ccol)
@@ -219,7 +263,7 @@ class BiasAdd(Function):
     def backward(ctx, gy):
         gy = _dense_like(gy, True)
         gb = None
-        if ctx.needs_input_grad[1]:
+        if ctx.needs_input_grad[1] and _wants(ctx.bias):
             if _direct(ctx.bias):
                 b = ctx.bias
                 K.on_side(lambda: K.bias_grad(gy.detach(), accumulate_into=b.grad), gy)

@@ -122,8 +122,9 @@ class Trainer:
             interpolates = K.interpolate(real_data, fake_data, alpha).requires_grad_(True)
             RNG.scope('drop.gp')
             d_interp = m.Discriminator(interpolates)[0]
-            gradients = torch.autograd.grad(d_interp, interpolates, grad_outputs=torch.ones_like(d_interp),
-                                            create_graph=True)[0]
+            with F.no_param_grads():                  # tf.gradients(..., [interpolates]): d/dx^ only (:144)
+                gradients = torch.autograd.grad(d_interp, interpolates, grad_outputs=torch.ones_like(d_interp),
+                                                create_graph=True)[0]
         K.join_branch(fork)
         out = F.CTGPLossStacked.apply(d_all, f_all, gradients, None, None, self.hp,
                                       dict(real=(0, B), real2=(B, 2 * B), fake=(2 * B, 3 * B)))
@@ -146,7 +147,8 @@ class Trainer:
         RNG.scope('drop.fake')
         disc_fake, _ = m.Discriminator(fake_data)
         gen_cost = F.MeanLoss.apply(disc_fake, -1.0)
-        gen_cost.backward(inputs=self.gen_opt.param_list())
+        with F.frozen(self.disc_opt.param_list()):    # var_list=gen_params (:153): the critic is differentiated through, not updated
+            gen_cost.backward(inputs=self.gen_opt.param_list())
         K.join_side()
         return dict(cost=gen_cost.detach())
 

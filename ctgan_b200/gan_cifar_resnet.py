@@ -365,8 +365,9 @@ class Trainer:
             interpolates = K.interpolate(all_real_data, fake_data, alpha).requires_grad_(True)     # :277-283
             RNG.scope('drop.gp')
             d_interp = Discriminator(interpolates, all_real_labels, 0.8, 0.5, 0.5)[0]
-            gradients = torch.autograd.grad(d_interp, interpolates, grad_outputs=torch.ones_like(d_interp),
-                                            create_graph=True)[0]                                   # :284
+            with F.no_param_grads():                  # tf.gradients(..., [interpolates]): d/dx^ only
+                gradients = torch.autograd.grad(d_interp, interpolates, grad_outputs=torch.ones_like(d_interp),
+                                                create_graph=True)[0]                               # :284
         K.join_branch(fork)
         use_logits = CONDITIONAL and ACGAN
         # WGAN term and CE use pass ' (rows [0, 2B)), the CT term the real halves of ' and '' (:244-300)
@@ -403,7 +404,8 @@ class Trainer:
         gen_cost = F.MeanLoss.apply(disc_fake, -1.0)
         if CONDITIONAL and ACGAN:
             gen_cost = gen_cost + ACGAN_SCALE_G * F.SoftmaxCE.apply(disc_fake_acgan, fake_labels)
-        gen_cost.backward(inputs=self.gen_opt.param_list())
+        with F.frozen(self.disc_opt.param_list()):    # var_list = gen_params (:336): the critic is not updated here
+            gen_cost.backward(inputs=self.gen_opt.param_list())
         K.join_side()
         return dict(cost=gen_cost.detach())
 

@@ -100,3 +100,35 @@ def test_init_formulas_match_reference_statistics(fake_kernels):
     for got, exp in [(bound('A.Filters'), exp_a), (bound('B.Filters'), exp_b), (bound('C.Filters'), exp_c), (bound('D.W'), exp_d)]:
         assert 0.9 * exp < got <= exp * (1 + 1e-6)
     assert float(lib._params['A.Biases'].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize('script,critic,gen', [('resnet', (23, 12), (11, 11)), ('cifar', (8, 4), (4, 4)), ('mnist', (8, 4), (4, 4))])
+def test_no_discarded_parameter_gradient_launches(fake_kernels, script, critic, gen):
+    """A step launches exactly the filter- / bias-gradient kernels whose results are applied: per critic step one per
+    critic layer for the stacked pass + one filter gradient per layer for the gradient penalty's double backward (none in
+    its FIRST backward, which only wants d/dx^); per generator step the generator's own (the critic is differentiated
+    through, not updated).  (ResNet: 12 critic layers, 11 of them under the GP; 11 generator layers.)"""
+    import collections
+    import importlib
+    import ctgan_b200.kernels as K
+    counts = collections.Counter()
+    for name in ('conv_wgrad', 'bias_grad'):
+        def wrap(f=getattr(K, name), name=name):
+            def g(*a, **k):
+                counts[name] += 1
+                return f(*a, **k)
+            return g
+        setattr(K, name, wrap())
+    try:
+        mod = importlib.import_module(parity.SCRIPTS[script][0])
+        np.random.seed(0)
+        tr = mod.Trainer(device='cpu', seed=1, act_dtype=torch.float32, batch_size=4)
+        counts.clear()
+        tr.critic_step(*parity.make_inputs(script, 4, 3))
+        assert (counts['conv_wgrad'], counts['bias_grad']) == critic
+        counts.clear()
+        tr.gen_step()
+        assert (counts['conv_wgrad'], counts['bias_grad']) == gen
+    finally:
+        from tests import fake_backend
+        K.conv_wgrad, K.bias_grad = fake_backend.conv_wgrad, fake_backend.bias_grad     # the fixture restores the real ones
