@@ -93,6 +93,11 @@ _PROTOS = {
     'ctgan_bn_workspace_floats': (c_int64, [c_int, c_int, c_int, c_int]),
     'ctgan_bn_fwd': (c_int, [P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_float, c_int, c_int, c_int, P]),
     'ctgan_bn_bwd': (c_int, [P, P, P, P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
+    'ctgan_ln_workspace_floats': (c_int64, [c_int, c_int64]),
+    'ctgan_ln_fwd': (c_int, [P, P, P, P, P, P, P, c_int, c_int64, c_int, c_float, c_int, P]),
+    'ctgan_ln_core': (c_int, [P, P, P, P, P, P, P, c_int, c_int64, c_int, c_int, c_int, c_int, P]),
+    'ctgan_ln_param_grad': (c_int, [P, P, P, P, P, P, c_int, c_int64, c_int, c_int, P]),
+    'ctgan_ln_bwd2_x': (c_int, [P, P, P, P, P, P, P, P, c_int, c_int64, c_int, c_int, P]),
     'ctgan_ct_gp_loss_fwd': (c_int, [POINTER(LossDesc), P, P, P, P, P, P, P, P, P, P, P]),
     'ctgan_ct_gp_loss_bwd': (c_int, [POINTER(LossDesc), P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P]),
     'ctgan_mean_fwd': (c_int, [P, P, c_int, c_float, P]),

@@ -652,6 +652,71 @@ def batch_norm(x, gamma, beta, labels=None, eps=1e-5, relu=False, groups=1):
     return BatchNormReLU.apply(x, gamma, beta, labels, eps, relu, groups)
 
 
+class LayerNorm(Function):
+    """Layer normalisation over each sample's (C,H,W) with per-channel gamma / beta (TG/tflib/ops/layernorm.py:6-21) -- the
+    critic's Normalize in TG/CT_gan_64x64.py:87-93.  STAGED.  Twice differentiable: layer norm is not
+    piecewise linear, so the gradient penalty needs the second-order terms of LayerNormBwd below."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps):
+        y, mean, rstd = K.ln_fwd(x, gamma, beta, eps)
+        ctx.save_for_backward(x, gamma, mean, rstd)
+        ctx.beta = beta
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, gamma, mean, rstd = ctx.saved_tensors
+        beta = ctx.beta
+        gy = _dense_like(gy, True)
+        dx = dgamma = dbeta = None
+        if ctx.needs_input_grad[0]:
+            # under create_graph (the penalty's first backward) this node is differentiated again
+            dx = LayerNormBwd.apply(gy, x, gamma, mean, rstd)
+        if ctx.needs_input_grad[1] and _wants(gamma):
+            # parameter gradients are never differentiated further: plain kernels, detached
+            if _direct(gamma) and _direct(beta):
+                g, b = gamma.grad, beta.grad
+                K.on_side(lambda: K.ln_param_grad(gy.detach(), x.detach(), mean, rstd, g, b), gy, x)
+            else:
+                dgamma, dbeta = torch.zeros_like(gamma), torch.zeros_like(gamma)
+                K.ln_param_grad(gy.detach(), x.detach(), mean, rstd, dgamma, dbeta)
+        return dx, dgamma, dbeta, None
+
+
+class LayerNormBwd(Function):
+    """dx = core(gamma * gy) with core(u) = rstd * (u - mean_s(u) - xh * mean_s(u * xh)); mean / rstd are functions of x.
+    Its backward (cotangent c of dx):  ggy = gamma * core(c),  ggamma_c = sum gy * core(c),  gx = K.ln_bwd2_x(...)."""
+
+    @staticmethod
+    def forward(ctx, gy, x, gamma, mean, rstd):
+        ctx.save_for_backward(gy, x, gamma, mean, rstd)
+        return K.ln_core(gy, x, gamma, mean, rstd, 1, 0)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, c):
+        gy, x, gamma, mean, rstd = ctx.saved_tensors
+        c = _dense_like(c, True)
+        ggy = gx = ggamma = None
+        if ctx.needs_input_grad[0]:
+            ggy = K.ln_core(c, x, gamma, mean, rstd, 0, 1)
+        if ctx.needs_input_grad[1]:
+            gx = K.ln_bwd2_x(c, gy, x, gamma, mean, rstd)
+        if ctx.needs_input_grad[2] and _wants(gamma):
+            t = K.mul(gy, K.ln_core(c, x, gamma, mean, rstd, 0, 0))
+            if _direct(gamma):
+                g = gamma.grad
+                K.on_side(lambda: K.bias_grad(t, accumulate_into=g), t)
+            else:
+                ggamma = K.bias_grad(t)
+        return ggy, gx, ggamma, None, None
+
+
+def layer_norm(x, gamma, beta, eps=1e-5):
+    return LayerNorm.apply(x, gamma, beta, eps)
+
+
 class Unary(Function):
     @staticmethod
     def forward(ctx, x, kind):

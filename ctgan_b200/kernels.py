@@ -895,6 +895,57 @@ def bn_bwd(dy, x, y, gamma, labels, mean, invstd, relu, groups=1):
     return dx, dgamma, dbeta
 
 
+# --------------------------------------------------------------------------- layer norm (STAGED: csrc/layernorm.cu)
+def _ln_dims(x):
+    require_nhwc(x)
+    if x.dim() != 4:
+        raise RuntimeError('ctgan_b200: layer norm expects a 4-D activation')
+    N, C = x.shape[0], x.shape[1]
+    return N, x.numel() // N, C
+
+
+def _ln_ws(N, M, device):
+    return torch.empty(_lib.lib.ctgan_ln_workspace_floats(N, M), dtype=torch.float32, device=device)
+
+
+def ln_fwd(x, gamma, beta, eps):
+    """y = (x - mean_s) * rstd_s * gamma_c + beta_c over each sample's (C,H,W); returns (y, mean [N], rstd [N])."""
+    N, M, C = _ln_dims(x)
+    y = torch.empty_like(x)
+    mean = torch.empty(N, dtype=torch.float32, device=x.device)
+    rstd = torch.empty(N, dtype=torch.float32, device=x.device)
+    call('ctgan_ln_fwd', _p(x), _p(gamma), _p(beta), _p(y), _p(mean), _p(rstd), _p(_ln_ws(N, M, x.device)), N, M, C, float(eps),
+         _dt(x), _stream())
+    return y, mean, rstd
+
+
+def ln_core(v, x, gamma, mean, rstd, pre_scale, post_scale):
+    """[gamma *] rstd * (u - mean_s(u) - xh * mean_s(u * xh)),  u = [gamma *] v."""
+    N, M, C = _ln_dims(x)
+    require_nhwc(v); _same_layout(v, x)
+    out = torch.empty_like(x)
+    call('ctgan_ln_core', _p(v), _p(x), _p(gamma), _p(mean), _p(rstd), _p(out), _p(_ln_ws(N, M, x.device)), N, M, C,
+         int(pre_scale), int(post_scale), _dt(x), _stream())
+    return out
+
+
+def ln_param_grad(v, x, mean, rstd, dgamma, dbeta):
+    """dgamma[c] += sum v * xh, dbeta[c] += sum v (float accumulators, e.g. slices of the flat gradient bucket)."""
+    N, M, C = _ln_dims(x)
+    require_nhwc(v); _same_layout(v, x)
+    call('ctgan_ln_param_grad', _p(v), _p(x), _p(mean), _p(rstd), _p(dgamma), _p(dbeta), N, M, C, _dt(x), _stream())
+
+
+def ln_bwd2_x(c, gy, x, gamma, mean, rstd):
+    """The x-derivative of <c, core(gamma * gy)>."""
+    N, M, C = _ln_dims(x)
+    require_nhwc(c); require_nhwc(gy); _same_layout(c, x); _same_layout(gy, x)
+    gx = torch.empty_like(x)
+    call('ctgan_ln_bwd2_x', _p(c), _p(gy), _p(x), _p(gamma), _p(mean), _p(rstd), _p(gx), _p(_ln_ws(N, M, x.device)), N, M, C,
+         _dt(x), _stream())
+    return gx
+
+
 # --------------------------------------------------------------------------- losses
 def _f32c(t, name):
     _chk(t, name)

@@ -264,6 +264,26 @@ int ctgan_bn_bwd(const void* dy, const void* x, const void* y, const float* gamm
                  void* dx, float* dgamma, float* dbeta, float* ws,
                  int N, int HW, int C, int n_labels, int relu, int groups, int dtype, void* stream);
 
+/* ---- layer normalisation over (C,H,W) per sample, per-channel scale / offset (STAGED, SURVEY.md 8(f) N4: the critic's
+ * Normalize of TG/CT_gan_64x64.py:87-93; op TG/tflib/ops/layernorm.py:6-21, eps 1e-5).  x, y, v, out: NHWC activations
+ * [N][M], M = H*W*C; mean, rstd: float [N]; gamma, beta, dgamma, dbeta: float [C]; ws: ctgan_ln_workspace_floats() floats.
+ * With xh = (x - mean) * rstd and core(u) = rstd * (u - mean_s(u) - xh * mean_s(u * xh)) over each sample:
+ *   ln_fwd         y = xh * gamma + beta (also writes mean, rstd)
+ *   ln_core        out = [gamma *] core([gamma *] v)      pre_scale / post_scale select the two products:
+ *                  backward dx = core(gamma * gy);  backward-of-backward ggy = gamma * core(c)
+ *   ln_param_grad  dgamma[c] += sum v * xh,  dbeta[c] += sum v   (dbeta nullable)
+ *   ln_bwd2_x      the x-derivative of <c, dx>:  gx = -rstd^2 * [xh*Q + B*(a - mean a) + A*(b - mean b) - 2*xh*A*B],
+ *                  a = c, b = gamma * gy, A = mean_s(a*xh), B = mean_s(b*xh), Q = mean_s(a*b) - mean a * mean b - A*B */
+int64_t ctgan_ln_workspace_floats(int N, int64_t M);
+int ctgan_ln_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd, float* ws,
+                 int N, int64_t M, int C, float eps, int dtype, void* stream);
+int ctgan_ln_core(const void* v, const void* x, const float* gamma, const float* mean, const float* rstd, void* out, float* ws,
+                  int N, int64_t M, int C, int pre_scale, int post_scale, int dtype, void* stream);
+int ctgan_ln_param_grad(const void* v, const void* x, const float* mean, const float* rstd, float* dgamma, float* dbeta,
+                        int N, int64_t M, int C, int dtype, void* stream);
+int ctgan_ln_bwd2_x(const void* c, const void* gy, const void* x, const float* gamma, const float* mean, const float* rstd,
+                    void* gx, float* ws, int N, int64_t M, int C, int dtype, void* stream);
+
 /* ---- fused CT + GP + WGAN (+ACGAN) loss -----------------------------------
  * TG/CT_gan_cifar.py:123-151, TG/CT_gan_mnist.py:146-167, TG/CT_gan_cifar_resnet.py:244-300.
  *   wgan  = mean(d_fake[0..NF)) - mean(d_real[0..B))

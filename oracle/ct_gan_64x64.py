@@ -152,7 +152,8 @@ class Model(StepMixin):
             costs.append(wgan + ct + LAMBDA * gp)
             parts.append(dict(wgan=wgan, ct=ct, gp=gp, gradients=gradients, fake_data=fake_data, real_data=real_data))
         cost = sum(costs) / self.N_DEVICES                 # :546
-        return dict(cost=cost, wgan_term=sum(p['wgan'] for p in parts) / self.N_DEVICES,
+        wgan = sum(p['wgan'] for p in parts) / self.N_DEVICES
+        return dict(cost=cost, wgan_term=wgan, wgan=wgan,
                     ct=sum(p['ct'] for p in parts) / self.N_DEVICES, gp=sum(p['gp'] for p in parts) / self.N_DEVICES,
                     gradients=torch.cat([p['gradients'] for p in parts], 0),
                     fake_data=torch.cat([p['fake_data'] for p in parts], 0),

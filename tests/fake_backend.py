@@ -306,6 +306,45 @@ def _bn_bwd1(dy, x, y, gamma, labels, mean, invstd, relu):
     return dx, dgamma.reshape(gamma.shape), dbeta.reshape(gamma.shape)
 
 
+def _ln_parts(x, mean, rstd):
+    N = x.shape[0]
+    xh = (_f(x) - mean.view(N, 1, 1, 1)) * rstd.view(N, 1, 1, 1)
+    smean = lambda t: t.mean(dim=(1, 2, 3), keepdim=True)
+    return xh, smean, rstd.view(N, 1, 1, 1)
+
+
+def ln_fwd(x, gamma, beta, eps):
+    xf = _f(x)
+    mean = xf.mean(dim=(1, 2, 3))
+    var = ((xf - mean.view(-1, 1, 1, 1)) ** 2).mean(dim=(1, 2, 3))
+    rstd = torch.rsqrt(var + eps)
+    xh, _, _ = _ln_parts(x, mean, rstd)
+    return _out(xh * _f(gamma).view(1, -1, 1, 1) + _f(beta).view(1, -1, 1, 1), x.dtype), mean, rstd
+
+
+def ln_core(v, x, gamma, mean, rstd, pre_scale, post_scale):
+    xh, smean, r = _ln_parts(x, mean, rstd)
+    g = _f(gamma).view(1, -1, 1, 1)
+    u = _f(v) * g if pre_scale else _f(v)
+    out = r * (u - smean(u) - xh * smean(u * xh))
+    return _out(out * g if post_scale else out, x.dtype)
+
+
+def ln_param_grad(v, x, mean, rstd, dgamma, dbeta):
+    xh, _, _ = _ln_parts(x, mean, rstd)
+    dgamma.add_((_f(v) * xh).sum(dim=(0, 2, 3)))
+    if dbeta is not None:
+        dbeta.add_(_f(v).sum(dim=(0, 2, 3)))
+
+
+def ln_bwd2_x(c, gy, x, gamma, mean, rstd):
+    xh, smean, r = _ln_parts(x, mean, rstd)
+    a, b = _f(c), _f(gy) * _f(gamma).view(1, -1, 1, 1)
+    abar, bbar, A, B = smean(a), smean(b), smean(a * xh), smean(b * xh)
+    Q = smean(a * b) - abar * bbar - A * B
+    return _out(-r * r * (xh * Q + B * (a - abar) + A * (b - bbar) - 2 * xh * A * B), x.dtype)
+
+
 def _loss_terms(desc, d_real, d_real2, d_fake, f1, f2, grad, logits, labels):
     diff = d_real - d_real2
     ct_i = desc.lambda2 * diff ** 2 + desc.lambda2 * 0.1 * ((_f(f1) - _f(f2)) ** 2).mean(dim=1) - desc.factor_m
@@ -418,6 +457,7 @@ _NAMES = ['conv_fprop', 'conv_dgrad', 'conv_wgrad', 'bias_grad', 'bias_add', 'ad
           'act_dropout', 'fork_dropout_relu', 'mask_sum2', 'mask_fork2', 'mul_relu_mask', 'pool_add_fork', 'mask_sum2_up', 'unary_fwd', 'unary_bwd', 'pool2x2', 'upsample2x', 'spatial_sum', 'spatial_bcast',
           'nchw_to_nhwc', 'nhwc_to_nchw', 'crop', 'crop_bwd', 'prep_real', 'interpolate', 'bn_fwd', 'bn_bwd',
           'ct_gp_loss_fwd', 'ct_gp_loss_bwd', 'mean_fwd', 'mean_bwd', 'softmax_ce_fwd', 'softmax_ce_bwd',
+          'ln_fwd', 'ln_core', 'ln_param_grad', 'ln_bwd2_x',
           'adam_step', 'philox_uniform', 'philox_normal', 'philox_labels', 'counter_add', 'invalidate_weight_cache']
 
 

@@ -13,6 +13,7 @@ SCRIPTS = {
     'mnist': ('ctgan_b200.gan_mnist', 'oracle.ct_gan_mnist'),
     'cifar': ('ctgan_b200.gan_cifar', 'oracle.ct_gan_cifar'),
     'resnet': ('ctgan_b200.gan_cifar_resnet', 'oracle.ct_gan_cifar_resnet'),
+    '64x64': ('ctgan_b200.gan_64x64', 'oracle.ct_gan_64x64'),          # STAGED
 }
 
 
@@ -35,19 +36,21 @@ def make_inputs(script, B, seed):
         return (torch.from_numpy(rs.random_sample((B, 784)).astype('float32')),)
     if script == 'cifar':
         return (torch.from_numpy(rs.randint(0, 256, (B, 3072)).astype('int32')),)
+    if script == '64x64':
+        return (torch.from_numpy(rs.randint(0, 256, (B, 3, 64, 64)).astype('int32')),)
     return (torch.from_numpy(rs.randint(0, 256, (B, 3072)).astype('int32')),
             torch.from_numpy(rs.randint(0, 10, (B,)).astype('int32')))
 
 
-def build_pair(script, device, act_dtype, B, seed=7, oracle_dtype=torch.float64):
+def build_pair(script, device, act_dtype, B, seed=7, oracle_dtype=torch.float64, **model_kw):
     prod_name, ora_name = SCRIPTS[script]
     prod = importlib.import_module(prod_name)
     ora = importlib.import_module(ora_name)
     np.random.seed(seed)
-    tr = prod.Trainer(device=device, seed=seed + 100, act_dtype=act_dtype, batch_size=B, record=True)
+    tr = prod.Trainer(device=device, seed=seed + 100, act_dtype=act_dtype, batch_size=B, record=True, **model_kw)
     import ctgan_b200.tflib as lib
     np.random.seed(seed)
-    om = ora.Model(dtype=oracle_dtype, batch_size=B).build()
+    om = ora.Model(dtype=oracle_dtype, batch_size=B, **model_kw).build()
     # identical weights: copy product -> oracle by reference name
     assert set(om.lib._params) == set(lib._params), (sorted(set(om.lib._params) ^ set(lib._params)))
     for n, p in lib._params.items():
@@ -99,7 +102,10 @@ def critic_parity(script, tr, om, inputs, iteration=0, conditioned=False, floor_
     tr.rng.stop_recording()
     tape = _fix_tape(script, tr.rng.tape, inputs[0].shape[0])
     kw = dict(with_clean=False) if script == 'resnet' else {}
-    ref = om.disc_cost(ReplayRandom(tape, tr.rng.patterns if conditioned else None), *inputs, **kw)
+    pats = tr.rng.patterns if conditioned else None
+    if pats is not None and hasattr(tr, 'oracle_pattern_order'):
+        pats = tr.oracle_pattern_order(pats, 'critic')
+    ref = om.disc_cost(ReplayRandom(tape, pats), *inputs, **kw)
     named = om.lib.named_params_with_name(om.disc_name)
     ref_grads = om._grads(ref['cost'], named)
     out = res['out'].cpu()
@@ -136,7 +142,10 @@ def gen_parity(script, tr, om, iteration=1, conditioned=False, floor_frac=1e-4):
     res = tr.gen_forward_backward()
     tr.rng.stop_recording()
     tape = dict(tr.rng.tape)
-    ref = om.gen_cost(ReplayRandom(tape, tr.rng.patterns if conditioned else None))
+    pats = tr.rng.patterns if conditioned else None
+    if pats is not None and hasattr(tr, 'oracle_pattern_order'):
+        pats = tr.oracle_pattern_order(pats, 'gen')
+    ref = om.gen_cost(ReplayRandom(tape, pats))
     named = om.lib.named_params_with_name(om.gen_name)
     ref_grads = om._grads(ref['cost'], named)
     report = {'loss.gen_cost': abs(float(res['cost']) - float(ref['cost'])) / max(abs(float(ref['cost'])), 0.05)}
