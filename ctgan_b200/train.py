@@ -22,14 +22,18 @@ import torch
 from . import checkpoint
 from .data import DeviceFeeder, inf_train_gen
 from .graphs import GraphedTrainer
-from .tflib import plot as _plot, save_images as _save_images, cifar10 as _cifar10, mnist as _mnist
+from .tflib import plot as _plot, save_images as _save_images, cifar10 as _cifar10, mnist as _mnist, small_imagenet as _imagenet
 
-SCRIPTS = {'mnist': 'gan_mnist', 'cifar': 'gan_cifar', 'cifar_resnet': 'gan_cifar_resnet'}
+SCRIPTS = {'mnist': 'gan_mnist', 'cifar': 'gan_cifar', 'cifar_resnet': 'gan_cifar_resnet',
+           '64x64': 'gan_64x64'}        # 64x64: STAGED, see gan_64x64.py
 
 
 def _loaders(script, mod, batch_size, data_dir, n_examples):
     if script == 'mnist':
         train, dev, _ = _mnist.load(batch_size, batch_size, n_examples, filepath=data_dir)
+    elif script == '64x64':                                  # TG/CT_gan_64x64.py:613; n_examples = (n_train, n_valid) files
+        n_train, n_valid = n_examples if isinstance(n_examples, (tuple, list)) else (1281149, 49999)
+        train, dev = _imagenet.load(batch_size, data_dir, n_train, n_valid)
     else:
         train, dev = _cifar10.load(batch_size, data_dir, n_examples)
     return train, dev
@@ -46,7 +50,7 @@ class Session:
     """One training run: model, graphs, feeder, fixed sample noise."""
 
     def __init__(self, script, data_dir, batch_size=None, n_examples=None, device='cuda', seed=1234, out_dir='.',
-                 act_dtype=torch.bfloat16, use_graphs=True, init_seed=1234):
+                 act_dtype=torch.bfloat16, use_graphs=True, init_seed=1234, model_kw=None):
         self.script, self.out_dir = script, out_dir
         self.mod = mod = importlib.import_module('ctgan_b200.' + SCRIPTS[script])
         self.B = batch_size or mod.BATCH_SIZE
@@ -55,13 +59,13 @@ class Session:
         np.random.seed(init_seed)                               # initial weights: the reference's numpy-global init
         # data parallel: identical initial weights and data order on every rank, rank-dependent random streams / shards
         self.tr = mod.Trainer(device=device, seed=seed + _rank_world()[0], act_dtype=act_dtype, batch_size=self.B,
-                              graph_safe_rng=use_graphs)
-        self.train_epoch, self.dev_epoch = _loaders(script, mod, self.B, data_dir, n_examples or mod.n_examples)
+                              graph_safe_rng=use_graphs, **(model_kw or {}))
+        self.train_epoch, self.dev_epoch = _loaders(script, mod, self.B, data_dir, n_examples or getattr(mod, 'n_examples', None))
         take = 2 if self.resnet else 1
         rank, world = _rank_world()
         self.feeder = DeviceFeeder(inf_train_gen(self.train_epoch, rank, world), device, depth=2, take=take, hold=self.n_critic)
         # fixed noise for the sample grids (:341-343 / TG/CT_gan_cifar.py:157-158 / TG/CT_gan_mnist.py:206-207)
-        n_fixed = 100 if self.resnet else 128
+        n_fixed = 100 if self.resnet else (self.B if script == '64x64' else 128)        # TG/CT_gan_64x64.py:582
         self.fixed_noise = torch.from_numpy(np.random.normal(size=(n_fixed, 128)).astype('float32')).to(device)
         self.fixed_labels = torch.tensor([0, 1, 2, 3, 4, 5, 6, 7, 8, 9] * 10, dtype=torch.int32, device=device) if self.resnet else None
         self.gt = None
@@ -125,12 +129,22 @@ class Session:
         with torch.no_grad():
             if self.resnet:
                 samples = mod.Generator(self.fixed_noise.shape[0], self.fixed_labels, noise=self.fixed_noise)
+            elif self.script == '64x64':                     # one Generator call per tower (:584-586): per-tower BN statistics
+                mod.BN_GROUPS = mod.N_GPUS
+                try:
+                    samples = mod.Generator(self.fixed_noise.shape[0], noise=self.fixed_noise)
+                finally:
+                    mod.BN_GROUPS = 1
             else:
                 samples = mod.Generator(self.fixed_noise.shape[0], noise=self.fixed_noise)
         samples = samples.float().cpu().numpy()
         if self.script == 'mnist':
             path = os.path.join(self.out_dir, 'samples_{}.png'.format(frame))
             _save_images.save_images(samples.reshape((-1, 28, 28)), path)
+        elif self.script == '64x64':
+            samples = ((samples + 1.) * (255.99 / 2)).astype('int32')               # :593
+            path = os.path.join(self.out_dir, 'samples_{}.png'.format(frame))
+            _save_images.save_images(samples.reshape((-1, 3, 64, 64)), path)
         else:
             samples = ((samples + 1.) * (255. / 2)).astype('int32')
             ext = 'png' if self.resnet else 'jpg'
@@ -139,15 +153,16 @@ class Session:
         return path
 
 
-def train(script, data_dir, iters=None, dev_every=100, out_dir='.', checkpoint_every=None, dev_batches=None, **kw):
+def train(script, data_dir, iters=None, dev_every=None, out_dir='.', checkpoint_every=None, dev_batches=None, **kw):
     """Run `iters` iterations (default: the script's ITERS).  Returns the Session."""
     os.makedirs(out_dir, exist_ok=True)
     s = Session(script, data_dir, out_dir=out_dir, **kw)
+    dev_every = dev_every or (200 if script == '64x64' else 100)          # TG/CT_gan_64x64.py:656
     _plot.reset()
     _plot.output_dir = out_dir
     iters = iters if iters is not None else s.mod.ITERS
     flush_early = 500 if s.resnet else 5                     # :431 `iteration < 500`; DCGAN scripts: `iteration < 5`
-    flush_every = 1000 if s.resnet else 100
+    flush_every = 1000 if s.resnet else (200 if script == '64x64' else 100)
     writer = _rank_world()[0] == 0                           # replicas are identical: rank 0 writes the files
     for iteration in range(iters):
         s.run_iteration()

@@ -87,7 +87,8 @@ def py2to3_host(src):
                      ('np.mean(vals.values())', 'np.mean(list(vals.values()))'),            # plot.py:25
                      ('np.sort(_since_beginning[name].keys())', 'np.sort(list(_since_beginning[name].keys()))'),   # plot.py:28
                      ('n_samples/rows', 'n_samples//rows'),                                 # save_images.py:19
-                     ('j = n/nw', 'j = n//nw')]:                                            # save_images.py:34
+                     ('j = n/nw', 'j = n//nw'),                                             # save_images.py:34
+                     ('files = range(n_files)', 'files = list(range(n_files))')]:           # small_imagenet.py:9 (py2 range is a list)
         src = src.replace(old, new)
     return src
 

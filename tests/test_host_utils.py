@@ -198,3 +198,30 @@ def test_save_images_fixture():
     grid = mine.tile_images(X)
     assert grid.shape == (320, 320, 3)
     np.testing.assert_array_equal(grid.sum(axis=(1, 2)), gold['grid_row_sums'])
+
+
+@needs_ref
+def test_small_imagenet_generator_matches_reference_module(tmp_path):
+    """TG/tflib/small_imagenet.py, including its round-robin buffer quirk (a batch is yielded right after slot 0 was
+    overwritten by the next batch's first file)."""
+    from PIL import Image
+    import ctgan_b200.tflib.small_imagenet as mine
+    d = tmp_path / 'train_64x64'
+    d.mkdir()
+    n_files, bs = 23, 4
+    rs = np.random.RandomState(9)
+    for i in range(1, n_files + 1):
+        Image.fromarray(rs.randint(0, 256, (64, 64, 3)).astype('uint8'), 'RGB').save(str(d / ('%s.png' % str(i).zfill(2))))
+    misc = types.ModuleType('scipy.misc')
+    misc.imread = lambda p: np.asarray(Image.open(p).convert('RGB'))
+    sp = types.ModuleType('scipy')
+    sp.misc = misc
+    ref = RH.load_ref_host_module('small_imagenet', stubs={'scipy': sp, 'scipy.misc': misc})
+    # the reference shuffles a py2 `range` list in place: under py3 the translated module needs a list
+    def run(mod):
+        gen = mod.make_generator(str(d), n_files, bs)
+        return [b[0].copy() for _ in range(2) for b in gen()]
+    got, want = run(mine), run(ref)
+    assert len(got) == len(want) == 2 * ((n_files - 1) // bs)
+    for a, b in zip(got, want):
+        assert a.dtype == b.dtype == np.int32 and a.shape == (bs, 3, 64, 64) and np.array_equal(a, b)

@@ -100,3 +100,30 @@ def test_checkpoint_round_trip_resumes_exactly(fake_kernels, tmp_path):
     with pytest.raises(KeyError):
         lib.param('Discriminator.Extra', np.zeros(2, dtype='float32'))
         checkpoint.load(path, None)
+
+
+def test_train_loop_64x64_staged(fake_kernels, tmp_path, capsys):
+    """The CT_gan_64x64.py loop (STAGED row N4) over tflib.small_imagenet PNG folders: schedule, metric names, files."""
+    from PIL import Image
+    from ctgan_b200 import train as T
+    import ctgan_b200.tflib.plot as plot
+    import ctgan_b200.gan_64x64 as G
+    rs = np.random.RandomState(0)
+    for sub, n in (('train_64x64', 45), ('valid_64x64', 9)):
+        d = tmp_path / 'data' / sub
+        d.mkdir(parents=True)
+        for i in range(1, n + 1):
+            Image.fromarray(rs.randint(0, 256, (64, 64, 3)).astype('uint8'), 'RGB').save(str(d / ('%s.png' % str(i).zfill(len(str(n))))))
+    out = str(tmp_path / 'out')
+    try:
+        sess = T.train('64x64', str(tmp_path / 'data'), iters=2, dev_every=2, out_dir=out, dev_batches=1, batch_size=4,
+                       n_examples=(45, 9), device='cpu', use_graphs=False, act_dtype=torch.float32, model_kw=dict(dim=4))
+        assert sess.tr.disc_opt.t == 2 * 5 and sess.tr.gen_opt.t == 1
+        log = pickle.load(open(os.path.join(out, 'log.pkl'), 'rb'))
+        assert sorted(log['train disc cost']) == [0, 1] and sorted(log['dev disc cost']) == [1]
+        assert all(np.isfinite(v) for v in log['train disc cost'].values())
+        assert os.path.getsize(os.path.join(out, 'samples_1.png')) > 0
+    finally:
+        plot.output_dir = '.'
+        plot.reset()
+        G.DIM = 64
