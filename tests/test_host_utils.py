@@ -225,3 +225,22 @@ def test_small_imagenet_generator_matches_reference_module(tmp_path):
     assert len(got) == len(want) == 2 * ((n_files - 1) // bs)
     for a, b in zip(got, want):
         assert a.dtype == b.dtype == np.int32 and a.shape == (bs, 3, 64, 64) and np.array_equal(a, b)
+
+
+@needs_ref
+@pytest.mark.parametrize('script,ref_file', [('mnist', 'CT_gan_mnist.py'), ('cifar', 'CT_gan_cifar.py'),
+                                             ('cifar_resnet', 'CT_gan_cifar_resnet.py'), ('64x64', 'CT_gan_64x64.py')])
+def test_training_loop_metric_names_are_the_reference_scripts(script, ref_file):
+    """Every metric name ctgan_b200.train logs for a script is one the reference script logs with lib.plot.plot(...)."""
+    import inspect
+    import re
+    from ctgan_b200 import train as T
+    with open(os.path.join(RH.REF_ROOT, ref_file)) as f:
+        ref_names = set(re.findall(r"lib\.plot\.plot\('([^']+)'", f.read()))
+    src = inspect.getsource(T)
+    ours = set(re.findall(r"_plot\.plot\('([^']+)'", src))
+    for m in re.findall(r"_plot\.plot\('([^']+)' if s\.resnet else '([^']+)'", src):
+        ours.update(m)
+    resnet_only = {'cost', 'wgan', 'acgan', 'dev_cost'}
+    mine = {n for n in ours if (n in resnet_only) == (script == 'cifar_resnet') or n == 'time'}
+    assert mine and mine <= ref_names, (sorted(mine - ref_names), sorted(ref_names))
