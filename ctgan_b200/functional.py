@@ -677,7 +677,9 @@ class LayerNorm(Function):
             # parameter gradients are never differentiated further: plain kernels, detached
             if _direct(gamma) and _direct(beta):
                 g, b = gamma.grad, beta.grad
-                K.on_side(lambda: K.ln_param_grad(gy.detach(), x.detach(), mean, rstd, g, b), gy, x)
+                # mean / rstd are 4*N-byte blocks: once this node is released the allocator hands them to the next small
+                # allocation of the main stream while the side stream may not have run yet -- keep them until the join
+                K.on_side(lambda: K.ln_param_grad(gy.detach(), x.detach(), mean, rstd, g, b), gy, x, mean, rstd)
             else:
                 dgamma, dbeta = torch.zeros_like(gamma), torch.zeros_like(gamma)
                 K.ln_param_grad(gy.detach(), x.detach(), mean, rstd, dgamma, dbeta)
