@@ -1,0 +1,265 @@
+// conv_wgrad_multi.cu -- the filter gradients of MANY layers in ONE persistent tcgen05 launch.
+//
+// At batch 64 a filter gradient (Conv2DBackpropFilter, autodiff of TG/tflib/ops/conv2d.py:106) is a short GEMM: K = pixels
+// is 4 096 .. 196 608, the output 9 x 128 x 128 floats.  Launched one layer at a time (conv_wgrad_tc_lean_kernel) every
+// launch has to split its pixel range ~49 ways to fill 148 SMs, so each CTA runs a few hundred cycles of MMAs and then adds a
+// full 196 KB accumulator into the same 590 KB of dW with red.global -- the round-1 timeline shows 14 such launches per
+// ResNet critic step at 25-50 us each (ideal 1-13 us), serialised behind each other because every CTA owns its SM's whole
+// TMEM: ~45 % of the step's span.  Nothing reads a filter gradient before the optimizer step, so the launches are deferred
+// (kernels.defer_wgrad) and executed HERE as one work list:
+//   job   = one layer's (x, dY, dW) with its own geometry and tensor maps (a table in the kernel's parameter space),
+//   item  = (job, 128x128 accumulator tile, filter column s, pixel-chunk range); every CTA walks items blockIdx.x,
+//           blockIdx.x + gridDim.x, ... -- ~2-3 items per SM over ALL layers, so an item is long (>= ~50 chunks) whatever
+//           the layer's size, the red.global volume drops ~5x and barrier / TMEM / tensor-map set-up is paid once per step.
+// Per item the pipeline is conv_wgrad_tc_lean_kernel's: one CTA owns the kh row taps (r, s) of filter column s, which
+// read ONE (BH+kh-1)-row halo box of x (shifted by r rows through the descriptor start address) and one dY chunk, both as
+// MN-major operands (no transposed copy of an activation exists); kh x 128 TMEM columns; 4-stage TMA ring of 48 KB.
+// Warp roles: 0 = TMA producer, 1 = MMA issuer (+ TMEM allocator), 2..5 = epilogue (TMEM -> red.global.add.v4.f32).
+#include "tc_common.cuh"
+
+namespace ctgan {
+namespace tc {
+
+constexpr int WG_MAX_JOBS = 24;
+
+struct alignas(64) WgradJob {
+    CUtensorMap mx, mdy;            // x: box (64 ch, BW, BH + kh - 1, BN);  dY: box (64 ch, BW, BH, BN)
+    float* dw;                      // [kh][kw][Cin][Cout] float, accumulated into
+    int Cin, Cout, kh, kw, pad_t, pad_l;
+    int BW, BH, BN, chunksW, chunksH;
+    int co_blocks;                  // Cout / 128
+    int splits, chunks_per_split, total_chunks;
+    int item0;                      // index of this job's first work item
+    uint32_t a_bytes;               // bytes of one 64-channel half of the x box
+};
+struct WgradJobTable {
+    WgradJob job[WG_MAX_JOBS];
+    int n_jobs, n_items;
+};
+
+struct WgItem { int j, ci0, co0, s_tap, chunk0, nchunks; };
+
+__device__ __forceinline__ WgItem wg_decode(const WgradJobTable& tab, int item) {
+    int j = 0;
+#pragma unroll 1
+    while (j + 1 < tab.n_jobs && item >= tab.job[j + 1].item0) ++j;
+    const WgradJob& J = tab.job[j];
+    int local = item - J.item0;
+    const int z = local % J.splits; local /= J.splits;
+    const int s = local % J.kw; const int tile = local / J.kw;
+    WgItem it;
+    it.j = j;
+    it.ci0 = (tile / J.co_blocks) * 128; it.co0 = (tile % J.co_blocks) * 128;
+    it.s_tap = s;
+    it.chunk0 = z * J.chunks_per_split;
+    it.nchunks = min(J.chunks_per_split, J.total_chunks - it.chunk0);
+    return it;
+}
+
+template <int STAGES>
+__global__ void __launch_bounds__(192, 1)
+conv_wgrad_tc_multi_kernel(const __grid_constant__ WgradJobTable tab)
+{
+    ctgan::pdl_launch_dependents();
+    constexpr uint32_t A_SLOT = 16384, B_HALF = 8192;
+    constexpr uint32_t STAGE_BYTES = 2 * A_SLOT + 2 * B_HALF;             // 48 KB
+    constexpr int TMEM_COLS = 512;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2);
+
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform
+    const uint32_t s_base = smem_u32(smem);
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES);
+    const uint32_t tfull = smem_u32(bars + 2 * STAGES), tempty = smem_u32(bars + 2 * STAGES + 1);
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        mbar_init(tfull, 1); mbar_init(tempty, 4);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<TMEM_COLS>(smem_u32(tmem_slot));
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    ctgan::pdl_wait();          // nothing above touches global memory written by earlier kernels
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ================= TMA producer =================
+            int st = 0; uint32_t ph = 0;
+            for (int item = blockIdx.x; item < tab.n_items; item += gridDim.x) {
+                const WgItem it = wg_decode(tab, item);
+                const WgradJob& J = tab.job[it.j];
+                const CUtensorMap* mx = &J.mx; const CUtensorMap* mdy = &J.mdy;
+                const int dx = it.s_tap - J.pad_l;
+                for (int c = 0; c < it.nchunks; ++c) {
+                    int ch = it.chunk0 + c;
+                    const int cw = ch % J.chunksW; ch /= J.chunksW;
+                    const int chh = ch % J.chunksH; const int cn = ch / J.chunksH;
+                    const int w0 = cw * J.BW, h0 = chh * J.BH, n0 = cn * J.BN;
+                    const uint32_t sb = s_base + st * STAGE_BYTES, fb = full0 + 8 * st;
+                    mbar_wait(empty0 + 8 * st, ph ^ 1);
+                    mbar_expect_tx(fb, 2 * J.a_bytes + 2 * B_HALF);
+                    tma_load_4d(sb,                       mx,  fb, it.ci0,      w0 + dx, h0 - J.pad_t, n0);
+                    tma_load_4d(sb + A_SLOT,              mx,  fb, it.ci0 + 64, w0 + dx, h0 - J.pad_t, n0);
+                    tma_load_4d(sb + 2 * A_SLOT,          mdy, fb, it.co0,      w0, h0, n0);
+                    tma_load_4d(sb + 2 * A_SLOT + B_HALF, mdy, fb, it.co0 + 64, w0, h0, n0);
+                    if (++st == STAGES) { st = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer (whole warp runs the loop; one elected lane issues) =================
+        // both operands MN-major: smem rows are K (pixels); LBO = distance between the two 64-channel halves
+        constexpr uint32_t idesc = make_idesc(BLOCK_M, 128, 1, 1);
+        const uint32_t a_lo0 = ((s_base & 0x3FFFFu) >> 4) | ((A_SLOT >> 4) << 16);
+        const uint32_t b_lo0 = (((s_base + 2 * A_SLOT) & 0x3FFFFu) >> 4) | ((B_HALF >> 4) << 16);
+        int st = 0; uint32_t ph = 0;
+        uint32_t n = 0;
+        for (int item = blockIdx.x; item < tab.n_items; item += gridDim.x, ++n) {
+            const WgItem it = wg_decode(tab, item);
+            const WgradJob& J = tab.job[it.j];
+            const int kh = J.kh;
+            const uint32_t row_step = ((uint32_t)J.BW * 128u) >> 4;      // one image row down = filter row r + 1
+            mbar_wait(tempty, (n & 1u) ^ 1u);                            // the epilogue has drained the accumulators
+            tc_fence_after();
+            for (int c = 0; c < it.nchunks; ++c) {
+                mbar_wait(full0 + 8 * st, ph);
+                tc_fence_after();
+                const uint32_t a_lo = a_lo0 + st * (STAGE_BYTES >> 4), b_lo = b_lo0 + st * (STAGE_BYTES >> 4);
+                if (elect_one()) {
+#pragma unroll
+                    for (int r = 0; r < 3; ++r) {
+                        if (r < kh) {
+#pragma unroll
+                            for (int k = 0; k < 64 / UMMA_K; ++k)     // 16 pixel rows = 2048 bytes along K
+                                umma_bf16_lo(tmem_base + (uint32_t)(r * 128), a_lo + r * row_step + 128 * k, b_lo + 128 * k, idesc,
+                                             k ? 1u : (c > 0 ? 1u : 0u));
+                        }
+                    }
+                    umma_commit(empty0 + 8 * st);
+                    if (c == it.nchunks - 1) umma_commit(tfull);
+                }
+                __syncwarp();
+                if (++st == STAGES) { st = 0; ph ^= 1; }
+            }
+        }
+    } else {
+        // ================= epilogue warps: TMEM -> vector reductions into dW (float, HWIO) =================
+        const int q = warp & 3;                                          // TMEM lane quadrant this warp may access
+        uint32_t n = 0;
+        for (int item = blockIdx.x; item < tab.n_items; item += gridDim.x, ++n) {
+            const WgItem it = wg_decode(tab, item);
+            const WgradJob& J = tab.job[it.j];
+            mbar_wait(tfull, n & 1u);
+            tc_fence_after();
+            const int ci = it.ci0 + q * 32 + lane;
+            for (int r = 0; r < J.kh; ++r) {
+                float* dst = J.dw + ((int64_t)(r * J.kw + it.s_tap) * J.Cin + ci) * J.Cout + it.co0;
+#pragma unroll 1
+                for (int c0 = 0; c0 < 128; c0 += 32) {
+                    uint32_t acc[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(r * 128 + c0), acc);
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};"
+                                     ::"l"(dst + c0 + j), "f"(__uint_as_float(acc[j])), "f"(__uint_as_float(acc[j + 1])),
+                                       "f"(__uint_as_float(acc[j + 2])), "f"(__uint_as_float(acc[j + 3])) : "memory");
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty) : "memory");
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
+}  // namespace tc
+}  // namespace ctgan
+
+using namespace ctgan;
+using namespace ctgan::tc;
+
+static int g_wgrad_multi_items_per_sm = 2;
+/* tuning hook: work items per SM the deferred filter-gradient launch aims for */
+extern "C" void ctgan_set_wgrad_multi_items_per_sm(int v) { g_wgrad_multi_items_per_sm = v < 1 ? 1 : v; }
+
+/* 1 when (d) can be a job of ctgan_conv_wgrad_tc_multi */
+extern "C" int ctgan_conv_wgrad_tc_multi_ok(const ctgan_conv_desc* d) {
+    if (!d || !ctgan_tc_available()) return 0;
+    if (d->x_dtype != CTGAN_BF16 || d->y_dtype != CTGAN_BF16 || d->stride != 1 || d->Ho != d->H || d->Wo != d->W) return 0;
+    if (d->N <= 0 || d->H <= 0 || d->W <= 0 || d->Cin <= 0 || d->Cout <= 0 || d->Cin % 128 || d->Cout % 128) return 0;
+    if (!((d->kh == 3 && d->kw == 3) || (d->kh == 1 && d->kw == 1))) return 0;
+    if (d->pad_t < 0 || d->pad_l < 0 || d->pad_t >= d->kh || d->pad_l >= d->kw) return 0;
+    int BW, BH, BN;
+    pixel_box(d->H, d->W, 64, &BW, &BH, &BN);
+    if (d->kh == 1) return 1;
+    return BN == 1 && BW % 8 == 0 && (uint32_t)(BH + 2) * BW * 128u <= 16384u;
+}
+
+extern "C" int ctgan_conv_wgrad_tc_multi(int n, const ctgan_conv_desc* descs, const void* const* xs, const void* const* dys,
+                                         float* const* dws, void* stream) {
+    CTGAN_REQUIRE(n > 0 && descs && xs && dys && dws, CTGAN_ERR_BAD_DESC, "conv_wgrad_tc_multi: bad args");
+    constexpr int STAGES = 4;
+    constexpr size_t smem = (size_t)STAGES * 49152 + 1024 + (2 * STAGES + 2) * 8 + 16;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(conv_wgrad_tc_multi_kernel<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return cuda_status(e, "wgrad_tc_multi smem attribute");
+        attr_set = true;
+    }
+    for (int base = 0; base < n; base += WG_MAX_JOBS) {
+        const int nj = (n - base) < WG_MAX_JOBS ? (n - base) : WG_MAX_JOBS;
+        static thread_local WgradJobTable tab;
+        // MMA groups (4 instructions) per (accumulator tile, filter column) and in total
+        long long total = 0;
+        long long col_work[WG_MAX_JOBS];
+        for (int i = 0; i < nj; ++i) {
+            const ctgan_conv_desc* d = descs + base + i;
+            CTGAN_REQUIRE(ctgan_conv_wgrad_tc_multi_ok(d), CTGAN_ERR_UNSUPPORTED, "conv_wgrad_tc_multi: job %d is not eligible", base + i);
+            CTGAN_REQUIRE(xs[base + i] && dys[base + i] && dws[base + i] &&
+                          ((reinterpret_cast<uintptr_t>(xs[base + i]) | reinterpret_cast<uintptr_t>(dys[base + i]) |
+                            reinterpret_cast<uintptr_t>(dws[base + i])) & 15) == 0,
+                          CTGAN_ERR_BAD_DESC, "conv_wgrad_tc_multi: job %d: null or misaligned pointer", base + i);
+            WgradJob& J = tab.job[i];
+            J.dw = dws[base + i];
+            J.Cin = d->Cin; J.Cout = d->Cout; J.kh = d->kh; J.kw = d->kw; J.pad_t = d->pad_t; J.pad_l = d->pad_l;
+            pixel_box(d->H, d->W, 64, &J.BW, &J.BH, &J.BN);
+            J.chunksW = ceil_div(d->W, J.BW); J.chunksH = ceil_div(d->H, J.BH);
+            J.total_chunks = J.chunksW * J.chunksH * ceil_div(d->N, J.BN);
+            J.co_blocks = d->Cout / 128;
+            J.a_bytes = (uint32_t)(J.BH + d->kh - 1) * J.BW * J.BN * 128u;
+            if (int r = make_act_map(&J.mx, xs[base + i], d->N, d->H, d->W, d->Cin, J.BW, J.BH + d->kh - 1, J.BN)) return r;
+            if (int r = make_act_map(&J.mdy, dys[base + i], d->N, d->H, d->W, d->Cout, J.BW, J.BH, J.BN)) return r;
+            col_work[i] = (long long)J.total_chunks * d->kh;
+            total += col_work[i] * (d->Cin / 128) * J.co_blocks * d->kw;
+        }
+        // one item ~ total / (items_per_sm * SMs) MMA groups, never below 24 (8 chunks of a 3x3 column)
+        long long target = (total + (long long)g_wgrad_multi_items_per_sm * sm_count() - 1) / ((long long)g_wgrad_multi_items_per_sm * sm_count());
+        if (target < 24) target = 24;
+        int items = 0;
+        for (int i = 0; i < nj; ++i) {
+            WgradJob& J = tab.job[i];
+            long long s = (col_work[i] + target / 2) / target;
+            if (s < 1) s = 1;
+            if (s > J.total_chunks) s = J.total_chunks;
+            J.chunks_per_split = ceil_div(J.total_chunks, s);
+            J.splits = ceil_div(J.total_chunks, J.chunks_per_split);
+            J.item0 = items;
+            items += (J.Cin / 128) * J.co_blocks * J.kw * J.splits;
+        }
+        tab.n_jobs = nj; tab.n_items = items;
+        const int grid = items < sm_count() ? items : sm_count();
+        CTGAN_LAUNCH((conv_wgrad_tc_multi_kernel<STAGES>), grid, 192, smem, as_stream(stream), tab);
+        CTGAN_CHECK_LAUNCH("conv_wgrad_tc_multi");
+    }
+    return 0;
+}

@@ -94,6 +94,15 @@ def _direct(p):
             and p.grad.is_contiguous() and _is_param(p))
 
 
+def _direct_wgrad(x, gy, g, w, col):
+    """w.grad += wgrad(x, gy) in the final backward: tensor-core jobs are queued and run as ONE launch over all layers at the
+    step's join (K.flush_wgrads); the other routes launch now on the side stream."""
+    if K.wgrad_deferrable(x, gy, g):
+        K.conv_wgrad(x, gy, g, tuple(w.shape), accumulate_into=w.grad, col=col, defer=True)
+    else:
+        K.on_side(lambda: K.conv_wgrad(x, gy, g, tuple(w.shape), accumulate_into=w.grad, col=col), x, gy, col)
+
+
 def _dense_like(g, ref_dim4):
     """Make an incoming gradient dense in the layout the kernels use."""
     if g is None:
@@ -143,7 +152,7 @@ class ConvF(Function):
         if ctx.needs_input_grad[1] and _wants(w):
             if _direct(w):
                 col, g = (ctx.col if ctx.col is not None else dycol), ctx.g
-                K.on_side(lambda: K.conv_wgrad(x, gy, g, tuple(w.shape), accumulate_into=w.grad, col=col), x, gy, col)
+                _direct_wgrad(x, gy, g, w, col)
             else:
                 gw = ConvG.apply(x, gy, ctx.g, tuple(w.shape))
         if ctx.has_bias and ctx.needs_input_grad[2] and _wants(ctx.bias):
@@ -181,8 +190,7 @@ class ConvD(Function):
             ggy = ConvF.apply(c, w, None, ctx.g, gy.dtype, ccol)
         if ctx.needs_input_grad[1] and _wants(w):
             if _direct(w):
-                g = ctx.g
-                K.on_side(lambda: K.conv_wgrad(c, gy, g, tuple(w.shape), accumulate_into=w.grad, col=ccol), c, gy, ccol)
+                _direct_wgrad(c, gy, ctx.g, w, ccol)
             else:
                 gw = ConvG.apply(c, gy, ctx.g, tuple(w.shape))
         return (ggy, gw, None, None, None, None)[:len(ctx.needs_input_grad)]

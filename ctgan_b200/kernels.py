@@ -27,6 +27,7 @@ class Config:
     branch_streams = True    # run independent sub-graphs of a step (GP pass vs stacked pass) as stream branches
     branch_priority = -1     # CUDA stream priority of the branch stream (lower = higher priority)
     tc_min_rows = 1          # (tunable) minimum GEMM rows to prefer the tensor-core path
+    defer_wgrad = True       # queue the final backward's tensor-core filter gradients and run them as ONE launch at the join
 
 
 config = Config()
@@ -118,7 +119,9 @@ def on_side(fn, *keep):
 
 
 def join_side():
-    """Make the current stream wait for the side stream's work; release the kept tensors."""
+    """Make the current stream wait for the side stream's work; release the kept tensors.  Deferred filter gradients
+    (defer_wgrad) are launched here, on the current stream."""
+    flush_wgrads()
     if _side_pending:
         for dev in {d for d, _ in _side_pending}:
             torch.cuda.current_stream(dev).wait_stream(_side_streams[dev])
@@ -577,10 +580,75 @@ def conv_dgrad(dy, w, g, out_dtype=None, w_is_param=False, col=None, relu_mask=N
     return dx
 
 
-def conv_wgrad(x, dy, g, w_shape, accumulate_into=None, col=None):
+# ---- deferred filter gradients: every tensor-core wgrad of a backward pass as ONE launch (csrc/conv_wgrad_multi.cu)
+_wgrad_queue = []        # (x, dy, geometry, dw) jobs; the tensors stay alive until the flush
+_wgrad_post = []         # launches that consume a job's scratch result (space-to-depth gather, im2col prefix add)
+
+
+def _wgrad_multi_ok(g):
+    d = _desc(g, BF16, BF16)
+    return bool(_lib.lib.ctgan_conv_wgrad_tc_multi_ok(ctypes.byref(d)))
+
+
+def flush_wgrads():
+    """Launch the queued filter gradients (one kernel per 24 jobs) and their post-processing on the current stream."""
+    if not _wgrad_queue:
+        return
+    jobs, post = list(_wgrad_queue), list(_wgrad_post)
+    _wgrad_queue.clear()
+    _wgrad_post.clear()
+    n = len(jobs)
+    descs = (ConvDesc * n)(*[_desc(g, BF16, BF16) for _, _, g, _ in jobs])
+    xs = (ctypes.c_void_p * n)(*[x.data_ptr() for x, _, _, _ in jobs])
+    dys = (ctypes.c_void_p * n)(*[dy.data_ptr() for _, dy, _, _ in jobs])
+    dws = (ctypes.c_void_p * n)(*[dw.data_ptr() for _, _, _, dw in jobs])
+    call('ctgan_conv_wgrad_tc_multi', n, descs, xs, dys, dws, _stream())
+    for fn in post:
+        fn()
+
+
+def _wgrad_tc(x, dy, g, dw, defer, post=None):
+    """dw += wgrad(x, dy) on the tensor cores, now or (defer) at the next join_side(); post() consumes dw afterwards."""
+    if defer and config.defer_wgrad and _wgrad_multi_ok(g):
+        _wgrad_queue.append((x, dy, g, dw))
+        if post is not None:
+            _wgrad_post.append(post)
+        return
+    _wgrad_tc_raw(x, dy, g, dw)
+    if post is not None:
+        post()
+
+
+def _wgrad_route(x, dy, g):
+    """Which kernel family conv_wgrad takes: ('tc', g) | ('s2d', g3) | ('padk', g1) | ('thin', side) | ('simt', None)."""
+    xdt, ydt = _dt(x), _dt(dy)
+    bf = xdt == BF16 and ydt == BF16
+    if bf and _tc_geom_ok(g) and g.Cin % 128 == 0 and g.Cout % 128 == 0:
+        return 'tc', g
+    g3 = s2d_geom(g, x) if bf else None
+    if g3 is not None and g3.Cin % 128 == 0 and g3.Cout % 128 == 0:
+        return 's2d', g3
+    if bf and thin_s2_ok(g, x) and g.Cout % 128 == 0:
+        return 'padk', _out_pixels_geom(g, 128, g.Cout)
+    side = _thin_side(g, x) if bf else None
+    if side is not None:
+        return 'thin', side
+    return 'simt', None
+
+
+def wgrad_deferrable(x, dy, g):
+    """True when conv_wgrad(x, dy, g, ..., defer=True) only queues work (no launch on the calling stream)."""
+    if not (config.defer_wgrad and x.is_cuda):
+        return False
+    route, gj = _wgrad_route(x, dy, g)
+    return route in ('tc', 's2d', 'padk') and _wgrad_multi_ok(gj)
+
+
+def conv_wgrad(x, dy, g, w_shape, accumulate_into=None, col=None, defer=False):
     """dw (float HWIO, shape w_shape) = sum over pixels of x (shifted) * dy.
     accumulate_into: a float tensor of that shape (e.g. the parameter's slice of the flat gradient
-    bucket) to ADD the result to instead of allocating one; returns it."""
+    bucket) to ADD the result to instead of allocating one; returns it.
+    defer (with accumulate_into): the tensor-core routes only queue the job; K.join_side() launches the queue."""
     require_nhwc(x, 'x')
     require_nhwc(dy, 'dy')
     xdt, ydt = _dt(x), _dt(dy)
@@ -588,25 +656,28 @@ def conv_wgrad(x, dy, g, w_shape, accumulate_into=None, col=None):
     acc = accumulate_into
     if acc is not None and (acc.dtype != torch.float32 or not acc.is_contiguous() or tuple(acc.shape) != tuple(w_shape)):
         raise RuntimeError('ctgan_b200: accumulate_into must be a contiguous float32 tensor of the filter shape')
-    if xdt == BF16 and ydt == BF16 and _tc_geom_ok(g) and g.Cin % 128 == 0 and g.Cout % 128 == 0:
+    defer = defer and acc is not None
+    route, gj = _wgrad_route(x, dy, g)
+    if route == 'tc':
         dw = acc if acc is not None else torch.zeros(w_shape, dtype=torch.float32, device=x.device)
-        return _wgrad_tc_raw(x, dy, g, dw)
-    g3 = s2d_geom(g, x) if (xdt == BF16 and ydt == BF16) else None
-    if g3 is not None and g3.Cin % 128 == 0 and g3.Cout % 128 == 0:
+        _wgrad_tc(x, dy, g, dw, defer)
+        return dw
+    if route == 's2d':
+        g3 = gj
         xs = col if (col is not None and tuple(col.shape) == (g3.N, g3.Cin, g3.H, g3.W)) else space_to_depth(x, g)
-        dw3 = _wgrad_tc_raw(xs, dy, g3, torch.zeros((3, 3, g3.Cin, g3.Cout), dtype=torch.float32, device=x.device))
+        dw3 = torch.zeros((3, 3, g3.Cin, g3.Cout), dtype=torch.float32, device=x.device)
         dw = acc if acc is not None else torch.empty(w_shape, dtype=torch.float32, device=x.device)
-        _s2d_filter_grad_launch(dw3, dw, g, acc is not None)
+        _wgrad_tc(xs, dy, g3, dw3, defer, post=lambda: _s2d_filter_grad_launch(dw3, dw, g, acc is not None))
         return dw
-    if xdt == BF16 and ydt == BF16 and thin_s2_ok(g, x) and g.Cout % 128 == 0:
+    if route == 'padk':
         col = col if (col is not None and tuple(col.shape) == (g.N, 128, g.Ho, g.Wo)) else im2col_strided(x, g)
-        dw128 = _wgrad_tc_raw(col, dy, _out_pixels_geom(g, 128, g.Cout),
-                              torch.zeros((1, 1, 128, g.Cout), dtype=torch.float32, device=x.device))
+        dw128 = torch.zeros((1, 1, 128, g.Cout), dtype=torch.float32, device=x.device)
         dw = acc if acc is not None else torch.empty(w_shape, dtype=torch.float32, device=x.device)
-        _add_prefix_launch(dw128, dw, g.kh * g.kw * g.Cin * g.Cout, acc is not None)     # HWIO order == column order
+        n_real = g.kh * g.kw * g.Cin * g.Cout                                   # HWIO order == column order
+        _wgrad_tc(col, dy, gj, dw128, defer, post=lambda: _add_prefix_launch(dw128, dw, n_real, acc is not None))
         return dw
-    side = _thin_side(g, x) if (xdt == BF16 and ydt == BF16) else None
-    if side is not None:
+    if route == 'thin':
+        side = gj
         dw = acc if acc is not None else torch.zeros(w_shape, dtype=torch.float32, device=x.device)
         P, taps = g.N * g.H * g.W, g.kh * g.kw
         if side == 'in':

@@ -236,6 +236,10 @@ class FlatAdam:
         self._ptrs = set(q.data_ptr() for q in self.params.values())
         K.invalidate_weight_cache()
         self.packer = K.FilterPacker(self.flat_p, self.params, offs) if dev.type == 'cuda' else None
+        # publish the one-launch operand packs NOW: a filter first used before the first optimizer step would otherwise
+        # get its own lazily created pack, re-packed by one extra launch per filter and layout after every step
+        # (16 + 18 tail launches per ResNet critic / generator step in the round-1 timelines)
+        self.refresh_packs()
 
     def param_list(self):
         return list(self.params.values())

@@ -108,6 +108,17 @@ int ctgan_conv_fprop_tc_masked(const ctgan_conv_desc* d, const void* x, const vo
  * fp32 atomics, so dw must hold the value to accumulate onto (zeros for a plain wgrad). */
 int ctgan_conv_wgrad_tc(const ctgan_conv_desc* d, const void* x, const void* dy,
                         float* dw, void* stream);
+/* The filter gradients of n layers in ONE persistent launch (csrc/conv_wgrad_multi.cu): job i adds wgrad(xs[i], dys[i]) of
+ * geometry descs[i] into dws[i] (float HWIO, pre-initialised) exactly like n calls of ctgan_conv_wgrad_tc, but the work of
+ * all jobs is cut into ~2 items per SM, so small layers neither under-fill the GPU nor pay a 49-way split of their pixel
+ * range.  descs / xs / dys / dws are HOST arrays (read during the call).  Eligible jobs (ctgan_conv_wgrad_tc_multi_ok):
+ * BF16, stride 1, Cin and Cout multiples of 128, 1x1, or 3x3 on images of >= 64 pixels with a power-of-two width >= 8.
+ * Replaces Conv2DBackpropFilter of every Conv2D of a backward pass (autodiff of TG/tflib/ops/conv2d.py:106). */
+int ctgan_conv_wgrad_tc_multi_ok(const ctgan_conv_desc* d);
+int ctgan_conv_wgrad_tc_multi(int n, const ctgan_conv_desc* descs, const void* const* xs, const void* const* dys,
+                              float* const* dws, void* stream);
+/* tuning hook: work items per SM that launch aims for (default 2) */
+void ctgan_set_wgrad_multi_items_per_sm(int v);
 /* w_hwio float [taps][Cin][Cout] ->
  *   transpose_flip==0: wp[t][o][c] = w[t][c][o]                (fprop operand)
  *   transpose_flip==1: wp[t][c][o] = w[taps-1-t][c][o]         (dgrad operand)  */

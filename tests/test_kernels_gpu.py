@@ -354,6 +354,53 @@ def test_tc_wgrad_variants_match(K, shape):
         _lib.lib.ctgan_set_wgrad_variant(2)
 
 
+@pytest.mark.parametrize('items_per_sm', [2, 1, 5])
+def test_tc_wgrad_multi_job_launch(K, items_per_sm):
+    """Deferred filter gradients (csrc/conv_wgrad_multi.cu): a mix of layers -- 3x3 at 32x32 / 16x16 / 8x8, 1x1, a Linear,
+    ragged batch sizes, wide Cin / Cout, two jobs adding into the SAME gradient -- queued and run as one launch, against
+    the CPU reference of each job; the queue is empty afterwards and ineligible jobs launch immediately."""
+    from ctgan_b200 import _lib
+    shapes = [(64, 8, 8, 3, 128, 128), (37, 8, 8, 3, 128, 128), (20, 16, 16, 3, 128, 256), (7, 32, 32, 3, 256, 128),
+              (50, 8, 8, 1, 128, 128), (130, 1, 1, 1, 128, 384), (64, 8, 8, 3, 128, 128)]
+    _lib.lib.ctgan_set_wgrad_multi_items_per_sm(items_per_sm)
+    try:
+        refs, accs, keep = [], [], []
+        for i, (N, H, W, k, Cin, Cout) in enumerate(shapes):
+            g = K.same_geom(N, H, W, Cin, Cout, k, 1)
+            two_d = H == 1
+            x = act((N, Cin) if two_d else (N, Cin, H, W), torch.bfloat16, 10 + i)
+            dy = act((N, Cout) if two_d else (N, Cout, H, W), torch.bfloat16, 30 + i)
+            ref = FB().conv_wgrad(x, dy, g, (k, k, Cin, Cout))
+            if i == len(shapes) - 1:                       # second contribution to job 0's gradient
+                acc, ref = accs[0], None
+                refs[0] = refs[0] + FB().conv_wgrad(x, dy, g, (k, k, Cin, Cout))
+            else:
+                acc = torch.full((k, k, Cin, Cout), 0.25, device='cuda')
+            xd, dyd = to_dev(x), to_dev(dy)
+            assert K.wgrad_deferrable(xd, dyd, g)
+            K.conv_wgrad(xd, dyd, g, (k, k, Cin, Cout), accumulate_into=acc, defer=True)
+            keep.append((xd, dyd))
+            if ref is not None:
+                refs.append(ref); accs.append(acc)
+        assert len(K._wgrad_queue) == len(shapes)
+        for acc in accs:
+            assert float((acc - 0.25).abs().max()) == 0.0        # nothing has run yet
+        K.join_side()
+        assert not K._wgrad_queue
+        for i, (acc, ref) in enumerate(zip(accs, refs)):
+            assert rel(acc - 0.25, ref) < 2e-3, (i, shapes[i])
+        # 4x4 images: several images per 64-pixel chunk cannot use the halo box -> not deferrable, runs at once
+        g = K.same_geom(40, 4, 4, 128, 128, 3, 1)
+        x, dy = act((40, 128, 4, 4), torch.bfloat16, 1), act((40, 128, 4, 4), torch.bfloat16, 2)
+        assert not K.wgrad_deferrable(to_dev(x), to_dev(dy), g)
+        acc = torch.zeros((3, 3, 128, 128), device='cuda')
+        K.conv_wgrad(to_dev(x), to_dev(dy), g, (3, 3, 128, 128), accumulate_into=acc, defer=True)
+        assert not K._wgrad_queue
+        assert rel(acc, FB().conv_wgrad(x, dy, g, (3, 3, 128, 128))) < 2e-3
+    finally:
+        _lib.lib.ctgan_set_wgrad_multi_items_per_sm(2)
+
+
 @pytest.mark.parametrize('geom', [(5, 32, 32, 3, 128, 3), (3, 16, 16, 3, 128, 1), (4, 32, 32, 128, 3, 3), (70, 8, 8, 3, 256, 3),
                                   (2, 16, 16, 256, 4, 3), (3, 12, 20, 3, 128, 3)])
 def test_thin_tc_conv_family(K, geom):
