@@ -21,6 +21,7 @@ lib = ctypes.CDLL(LIB_PATH)
 F32, BF16 = 0, 1
 EPI_RELU = 1
 EPI_RES_UP2 = 2
+BN_RELU, BN_UP2, BN_ACCUM = 1, 2, 4
 
 
 class ConvDesc(Structure):
@@ -46,9 +47,11 @@ _PROTOS = {
     'ctgan_set_fprop_halo': (None, [c_int]),
     'ctgan_set_fprop_variant': (None, [c_int]),
     'ctgan_set_pdl': (None, [c_int]),
+    'ctgan_set_sm_limit': (None, [c_int]),
     'ctgan_set_wgrad_variant': (None, [c_int]),
     'ctgan_conv_fprop_tc': (c_int, [POINTER(ConvDesc), P, P, P, P, P, c_int, P]),
     'ctgan_conv_fprop_tc_masked': (c_int, [POINTER(ConvDesc), P, P, P, P, P, P, c_int, P]),
+    'ctgan_conv_fprop_tc_actdrop': (c_int, [POINTER(ConvDesc), P, P, P, P, P, c_float, c_float, c_uint64, c_uint64, P, c_int, P]),
     'ctgan_conv_wgrad_tc': (c_int, [POINTER(ConvDesc), P, P, P, P]),
     'ctgan_conv_wgrad_tc_multi_ok': (c_int, [POINTER(ConvDesc)]),
     'ctgan_conv_wgrad_tc_multi': (c_int, [c_int, POINTER(ConvDesc), POINTER(P), POINTER(P), POINTER(P), P]),
@@ -61,6 +64,8 @@ _PROTOS = {
     'ctgan_wgrad_thin_tc': (c_int, [P, P, c_int64, c_int, c_int, c_int, c_int, P, P]),
     'ctgan_space_to_depth': (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P]),
     'ctgan_depth_to_space': (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P]),
+    'ctgan_space_to_depth_mul': (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, P]),
+    'ctgan_depth_to_space_mul': (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, P]),
     'ctgan_pack_filter_s2d': (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, P]),
     'ctgan_s2d_filter_grad': (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     'ctgan_im2col_strided': (c_int, [POINTER(ConvDesc), c_int, P, P, P]),
@@ -96,6 +101,9 @@ _PROTOS = {
     'ctgan_bn_workspace_floats': (c_int64, [c_int, c_int, c_int, c_int]),
     'ctgan_bn_fwd': (c_int, [P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_float, c_int, c_int, c_int, P]),
     'ctgan_bn_bwd': (c_int, [P, P, P, P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
+    'ctgan_bn_fused_ok': (c_int, [c_int, c_int, c_int, c_int, c_int, c_int]),
+    'ctgan_bn_fwd_fused': (c_int, [P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_float, c_int, c_int, P]),
+    'ctgan_bn_bwd_fused': (c_int, [P, P, P, P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     'ctgan_ln_workspace_floats': (c_int64, [c_int, c_int64]),
     'ctgan_ln_fwd': (c_int, [P, P, P, P, P, P, P, c_int, c_int64, c_int, c_float, c_int, P]),
     'ctgan_ln_core': (c_int, [P, P, P, P, P, P, P, c_int, c_int64, c_int, c_int, c_int, c_int, P]),

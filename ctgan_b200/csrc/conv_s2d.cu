@@ -18,8 +18,11 @@ namespace ctgan {
 namespace {
 
 // x [N,H,W,C] -> xs [N,Hs,Ws,4C]; VEC elements of T per thread (C % VEC == 0)
+// mul (nullable): a multiplier in the SPACE-TO-DEPTH layout applied to every element moved (the dropout / LeakyReLU
+// multiplier a fused conv epilogue stored in that layout: backward = depth_to_space(g * m), its adjoint = space_to_depth(c) * m)
 template <typename T, int VEC, bool FWD>
-__global__ void s2d_kernel(const T* __restrict__ src, T* __restrict__ dst, int N, int H, int W, int C, int Hs, int Ws) {
+__global__ void s2d_kernel(const T* __restrict__ src, const T* __restrict__ mul, T* __restrict__ dst, int N, int H, int W, int C,
+                           int Hs, int Ws) {
     pdl_entry();
     struct alignas(sizeof(T) * VEC) Vec { T v[VEC]; };
     const int cv = C / VEC;
@@ -39,6 +42,11 @@ __global__ void s2d_kernel(const T* __restrict__ src, T* __restrict__ dst, int N
 #pragma unroll
                 for (int e = 0; e < VEC; ++e) val.v[e] = from_f<T>(0.f);
             }
+            if (mul) {
+                const Vec m = reinterpret_cast<const Vec*>(mul)[idx];
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) val.v[e] = from_f<T>(to_f<T>(val.v[e]) * to_f<T>(m.v[e]));
+            }
             reinterpret_cast<Vec*>(dst)[idx] = val;
         }
     } else {
@@ -49,8 +57,14 @@ __global__ void s2d_kernel(const T* __restrict__ src, T* __restrict__ dst, int N
             int w = (int)(t % W); t /= W;
             int h = (int)(t % H); int n = (int)(t / H);
             const int q = ((h & 1) << 1) | (w & 1);
-            reinterpret_cast<Vec*>(dst)[idx] =
-                reinterpret_cast<const Vec*>(src)[((((int64_t)n * Hs + (h >> 1)) * Ws + (w >> 1)) * 4 + q) * cv + c];
+            const int64_t sidx = ((((int64_t)n * Hs + (h >> 1)) * Ws + (w >> 1)) * 4 + q) * cv + c;
+            Vec val = reinterpret_cast<const Vec*>(src)[sidx];
+            if (mul) {
+                const Vec m = reinterpret_cast<const Vec*>(mul)[sidx];
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) val.v[e] = from_f<T>(to_f<T>(val.v[e]) * to_f<T>(m.v[e]));
+            }
+            reinterpret_cast<Vec*>(dst)[idx] = val;
         }
     }
 }
@@ -237,27 +251,27 @@ static int check_s2d_filter(int k, int C, int O, int pad_t, int pad_l, const cha
 }
 
 template <bool FWD>
-static int s2d_impl(const void* src, void* dst, int N, int H, int W, int C, int dtype, void* stream, const char* who) {
+static int s2d_impl(const void* src, const void* mul, void* dst, int N, int H, int W, int C, int dtype, void* stream, const char* who) {
     CTGAN_REQUIRE(src && dst && N > 0 && H > 0 && W > 0 && C > 0 && dtype_ok(dtype), CTGAN_ERR_BAD_DESC, "%s: bad args", who);
     const int Hs = (H + 1) / 2, Ws = (W + 1) / 2;
     cudaStream_t st = as_stream(stream);
-    const bool aligned = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(mul)) & 15) == 0;
     if (dtype == CTGAN_BF16 && C % 8 == 0 && aligned) {
         const int64_t total = FWD ? (int64_t)N * Hs * Ws * 4 * (C / 8) : (int64_t)N * H * W * (C / 8);
         CTGAN_LAUNCH((s2d_kernel<__nv_bfloat16, 8, FWD>), elementwise_grid(total, 256), 256, 0, st,
-                     (const __nv_bfloat16*)src, (__nv_bfloat16*)dst, N, H, W, C, Hs, Ws);
+                     (const __nv_bfloat16*)src, (const __nv_bfloat16*)mul, (__nv_bfloat16*)dst, N, H, W, C, Hs, Ws);
     } else if (dtype == CTGAN_BF16) {
         const int64_t total = FWD ? (int64_t)N * Hs * Ws * 4 * C : (int64_t)N * H * W * C;
         CTGAN_LAUNCH((s2d_kernel<__nv_bfloat16, 1, FWD>), elementwise_grid(total, 256), 256, 0, st,
-                     (const __nv_bfloat16*)src, (__nv_bfloat16*)dst, N, H, W, C, Hs, Ws);
+                     (const __nv_bfloat16*)src, (const __nv_bfloat16*)mul, (__nv_bfloat16*)dst, N, H, W, C, Hs, Ws);
     } else if (C % 4 == 0 && aligned) {
         const int64_t total = FWD ? (int64_t)N * Hs * Ws * 4 * (C / 4) : (int64_t)N * H * W * (C / 4);
         CTGAN_LAUNCH((s2d_kernel<float, 4, FWD>), elementwise_grid(total, 256), 256, 0, st,
-                     (const float*)src, (float*)dst, N, H, W, C, Hs, Ws);
+                     (const float*)src, (const float*)mul, (float*)dst, N, H, W, C, Hs, Ws);
     } else {
         const int64_t total = FWD ? (int64_t)N * Hs * Ws * 4 * C : (int64_t)N * H * W * C;
         CTGAN_LAUNCH((s2d_kernel<float, 1, FWD>), elementwise_grid(total, 256), 256, 0, st,
-                     (const float*)src, (float*)dst, N, H, W, C, Hs, Ws);
+                     (const float*)src, (const float*)mul, (float*)dst, N, H, W, C, Hs, Ws);
     }
     CTGAN_CHECK_LAUNCH(who);
     return 0;
@@ -269,11 +283,21 @@ static int s2d_impl(const void* src, void* dst, int N, int H, int W, int C, int 
 using namespace ctgan;
 
 extern "C" int ctgan_space_to_depth(const void* x, void* xs, int N, int H, int W, int C, int dtype, void* stream) {
-    return s2d_impl<true>(x, xs, N, H, W, C, dtype, stream, "space_to_depth");
+    return s2d_impl<true>(x, nullptr, xs, N, H, W, C, dtype, stream, "space_to_depth");
 }
 
 extern "C" int ctgan_depth_to_space(const void* xs, void* x, int N, int H, int W, int C, int dtype, void* stream) {
-    return s2d_impl<false>(xs, x, N, H, W, C, dtype, stream, "depth_to_space");
+    return s2d_impl<false>(xs, nullptr, x, N, H, W, C, dtype, stream, "depth_to_space");
+}
+
+extern "C" int ctgan_space_to_depth_mul(const void* x, const void* ms, void* xs, int N, int H, int W, int C, int dtype, void* stream) {
+    CTGAN_REQUIRE(ms != nullptr, CTGAN_ERR_BAD_DESC, "space_to_depth_mul: null multiplier");
+    return s2d_impl<true>(x, ms, xs, N, H, W, C, dtype, stream, "space_to_depth_mul");
+}
+
+extern "C" int ctgan_depth_to_space_mul(const void* xs, const void* ms, void* x, int N, int H, int W, int C, int dtype, void* stream) {
+    CTGAN_REQUIRE(ms != nullptr, CTGAN_ERR_BAD_DESC, "depth_to_space_mul: null multiplier");
+    return s2d_impl<false>(xs, ms, x, N, H, W, C, dtype, stream, "depth_to_space_mul");
 }
 
 extern "C" int ctgan_pack_filter_s2d(const float* w, void* wp_f, void* wp_d, int k, int Cin, int Cout, int pad_t, int pad_l,

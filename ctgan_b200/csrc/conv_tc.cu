@@ -41,6 +41,14 @@ struct FpropParams {
     const float* bias;
     const __nv_bfloat16* residual;
     const __nv_bfloat16* relu_mask;    // output is zeroed where this tensor (shape of y) is <= 0: dgrad into a ReLU output
+    // EPI_ACTDROP epilogue (lean kernels): y = v * m, m = (v > 0 ? 1 : slope) * (keep < 1 ? floor(keep + u) / keep : 1), v = conv + bias,
+    // u = Philox(seed, offset + dyn[0] + NHWC element index); m is stored next to y; out_s2d: y and m are written in the
+    // space-to-depth layout [N, H/2, W/2, 4*Cout] the next stride-2 layer consumes (H, W even)
+    __nv_bfloat16* mult;
+    float slope, keep;
+    unsigned long long seed, offset;
+    const unsigned long long* dyn;
+    int out_s2d;
 };
 
 // 32-byte global accesses (LDG.256 / STG.256): 16 bf16 channels of one pixel row per instruction = one full sector.
@@ -236,257 +244,40 @@ conv_fprop_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
     if (warp == 2) tmem_dealloc<TMEM_COLS>(tmem_base);
 }
 
-// ------------------------------------------------------------------ fprop kernel, halo reuse (k x k, k > 1)
-// Tiles that cover BH full-width rows of ONE image (BN == 1, BW*128 B a multiple of the 1 KB swizzle atom).
-// For every (cin block, column shift s) ONE box of BH+kh-1 rows is loaded; the kh row taps read it through
-// descriptors advanced by r*BW rows (r*BW*128 bytes: whole swizzle atoms, so the layout stays canonical).
-// L2->SM traffic of the A operand drops by kh/(1+(kh-1)/BH) (2x for 3x3 on 4-row tiles); the filter (B operand)
-// streams through its own, deeper ring.
-template <int BLOCK_N, int SA, int SB>
-__global__ void __launch_bounds__(128)
-conv_fprop_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
-                          const FpropParams p, const uint32_t a_slot_bytes)
-{
-    ctgan::pdl_launch_dependents();
-    constexpr uint32_t B_BYTES = BLOCK_N * BLOCK_K * 2;
-    constexpr int TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
-
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const uint32_t a_base = smem_u32(smem);
-    const uint32_t b_base = a_base + SA * a_slot_bytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SA * a_slot_bytes + SB * B_BYTES);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * SA + 2 * SB + 1);
-    float* s_bias = reinterpret_cast<float*>(tmem_slot + 2);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t fullA = smem_u32(bars), emptyA = smem_u32(bars + SA);
-    const uint32_t fullB = smem_u32(bars + 2 * SA), emptyB = smem_u32(bars + 2 * SA + SB);
-    const uint32_t accum_bar = smem_u32(bars + 2 * SA + 2 * SB);
-
-    int mt = blockIdx.x;
-    const int tw = mt % p.tilesW; mt /= p.tilesW;
-    const int th = mt % p.tilesH; const int tn = mt / p.tilesH;
-    const int w0 = tw * p.BW, h0 = th * p.BH, n0 = tn;          // BN == 1
-    const int co0 = blockIdx.y * BLOCK_N;
-    const int cin_blocks = p.Cin / BLOCK_K;
-    const uint32_t a_bytes = (uint32_t)(p.BH + p.kh - 1) * p.BW * 128u;
-
-    if (warp == 0 && lane == 0) {
-        prefetch_tmap(&tmap_x);
-        prefetch_tmap(&tmap_w);
-        for (int s = 0; s < SA; ++s) { mbar_init(fullA + 8 * s, 1); mbar_init(emptyA + 8 * s, 1); }
-        for (int s = 0; s < SB; ++s) { mbar_init(fullB + 8 * s, 1); mbar_init(emptyB + 8 * s, 1); }
-        mbar_init(accum_bar, 1);
-        fence_barrier_init();
-    }
-    if (warp == 2) tmem_alloc<TMEM_COLS>(smem_u32(tmem_slot));
-    if (threadIdx.x < BLOCK_N) s_bias[threadIdx.x] = p.bias ? p.bias[co0 + threadIdx.x] : 0.f;
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-    ctgan::pdl_wait();          // nothing above touches global memory written by earlier kernels
-
-    if (warp == 0 && lane == 0) {
-        // ================= TMA producer =================
-        int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
-        for (int cb = 0; cb < cin_blocks; ++cb) {
-            for (int s = 0; s < p.kw; ++s) {
-                mbar_wait(emptyA + 8 * sa, pa ^ 1);
-                mbar_expect_tx(fullA + 8 * sa, a_bytes);
-                tma_load_4d(a_base + sa * a_slot_bytes, &tmap_x, fullA + 8 * sa, cb * BLOCK_K, w0 + s - p.pad_l, h0 - p.pad_t, n0);
-                if (++sa == SA) { sa = 0; pa ^= 1; }
-                for (int r = 0; r < p.kh; ++r) {
-                    mbar_wait(emptyB + 8 * sb, pb ^ 1);
-                    mbar_expect_tx(fullB + 8 * sb, B_BYTES);
-                    tma_load_3d(b_base + sb * B_BYTES, &tmap_w, fullB + 8 * sb, cb * BLOCK_K, co0, r * p.kw + s);
-                    if (++sb == SB) { sb = 0; pb ^= 1; }
-                }
-            }
-        }
-    } else if (warp == 1 && lane == 0) {
-        // ================= MMA issuer =================
-        constexpr uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N, 0, 0);
-        int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
-        uint32_t first = 1;
-        const int last_cb = cin_blocks - 1, last_s = p.kw - 1, last_r = p.kh - 1;
-        for (int cb = 0; cb < cin_blocks; ++cb) {
-            for (int s = 0; s < p.kw; ++s) {
-                mbar_wait(fullA + 8 * sa, pa);
-                tc_fence_after();
-                const uint32_t a_src = a_base + sa * a_slot_bytes;
-                for (int r = 0; r < p.kh; ++r) {
-                    mbar_wait(fullB + 8 * sb, pb);
-                    tc_fence_after();
-                    // row tap r: skip r image rows = r*BW pixel rows of 128 B each
-                    const uint64_t a_desc = make_smem_desc(a_src + (uint32_t)(r * p.BW) * 128u, 16, 1024);
-                    const uint64_t b_desc = make_smem_desc(b_base + sb * B_BYTES, 16, 1024);
-#pragma unroll
-                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                        umma_bf16(tmem_base, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, first ? 0u : 1u);
-                        first = 0;
-                    }
-                    umma_commit(emptyB + 8 * sb);
-                    if (r == last_r) umma_commit(emptyA + 8 * sa);
-                    if (cb == last_cb && s == last_s && r == last_r) umma_commit(accum_bar);
-                    if (++sb == SB) { sb = 0; pb ^= 1; }
-                }
-                if (++sa == SA) { sa = 0; pa ^= 1; }
-            }
-        }
-    }
-    __syncwarp();
-
-    mbar_wait(accum_bar, 0);
-    tc_fence_after();
-    fprop_epilogue<BLOCK_N>(p, tmem_base, s_bias, warp, lane, w0, h0, n0, co0);
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 2) tmem_dealloc<TMEM_COLS>(tmem_base);
-}
-
-// ------------------------------------------------------------------ fprop kernel, persistent
-// One CTA per SM loops over output tiles (static round-robin).  Six warps: warp 0 = TMA producer, warp 1 = MMA
-// issuer (+ TMEM allocator), warps 2-5 = epilogue.  Two 128-column TMEM accumulators: the epilogue of tile i
-// overlaps the main loop of tile i+1.  Operands flow through two independent mbarrier rings, SA slots for the
-// activation boxes and SB slots for the 16 KB filter boxes (200 KB of shared memory in flight per SM), deep
-// enough to cover the L2 round trip that bounds the 3-stage kernels above (ncu: 36-38 % tensor-active, far from
-// both the L2 and the tensor ceiling).  HALO = 1: one (BH+kh-1)-row box per (cin block, column shift), row taps
-// through shifted descriptors (see the halo kernel); HALO = 0: one box per (cin block, tap).
-template <int SA, int SB, int A_SLOT, int HALO>
-__global__ void __launch_bounds__(192, 1)
-conv_fprop_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
-                                const FpropParams p, const int n_tiles)
-{
-    ctgan::pdl_launch_dependents();
-    constexpr int BLOCK_N = 128;
-    constexpr uint32_t B_BYTES = BLOCK_N * BLOCK_K * 2;
-    constexpr int TMEM_COLS = 256;
-
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const uint32_t a_base = smem_u32(smem);
-    const uint32_t b_base = a_base + SA * A_SLOT;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SA * A_SLOT + SB * B_BYTES);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * SA + 2 * SB + 4);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t fullA = smem_u32(bars), emptyA = smem_u32(bars + SA);
-    const uint32_t fullB = smem_u32(bars + 2 * SA), emptyB = smem_u32(bars + 2 * SA + SB);
-    const uint32_t tfull = smem_u32(bars + 2 * SA + 2 * SB), tempty = smem_u32(bars + 2 * SA + 2 * SB + 2);
-
-    const int cin_blocks = p.Cin / BLOCK_K;
-    const int n_blocks = p.Cout / BLOCK_N;
-    const int rtaps = HALO ? p.kh : 1;                              // row taps served by one activation box
-    const int groups = cin_blocks * (HALO ? p.kw : p.kh * p.kw);    // activation boxes per tile
-    const uint32_t a_bytes = (uint32_t)(HALO ? p.BH + p.kh - 1 : p.BH) * p.BW * p.BN * 128u;
-
-    if (warp == 0 && lane == 0) {
-        prefetch_tmap(&tmap_x);
-        prefetch_tmap(&tmap_w);
-        for (int s = 0; s < SA; ++s) { mbar_init(fullA + 8 * s, 1); mbar_init(emptyA + 8 * s, 1); }
-        for (int s = 0; s < SB; ++s) { mbar_init(fullB + 8 * s, 1); mbar_init(emptyB + 8 * s, 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(tfull + 8 * s, 1); mbar_init(tempty + 8 * s, 4); }
-        fence_barrier_init();
-    }
-    if (warp == 1) tmem_alloc<TMEM_COLS>(smem_u32(tmem_slot));
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-    ctgan::pdl_wait();          // nothing above touches global memory written by earlier kernels
-
-    if (warp == 0 && lane == 0) {
-        // ================= TMA producer =================
-        int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            const int nb = tile % n_blocks; int mt = tile / n_blocks;
-            const int tw = mt % p.tilesW; mt /= p.tilesW;
-            const int th = mt % p.tilesH; const int tn = mt / p.tilesH;
-            const int w0 = tw * p.BW, h0 = th * p.BH, n0 = tn * p.BN, co0 = nb * BLOCK_N;
-            for (int gi = 0; gi < groups; ++gi) {
-                int cb, s, r0;
-                if (HALO) { cb = gi / p.kw; s = gi - cb * p.kw; r0 = 0; }
-                else { cb = gi / (p.kh * p.kw); const int tap = gi - cb * p.kh * p.kw; r0 = tap / p.kw; s = tap - r0 * p.kw; }
-                mbar_wait(emptyA + 8 * sa, pa ^ 1);
-                mbar_expect_tx(fullA + 8 * sa, a_bytes);
-                tma_load_4d(a_base + sa * A_SLOT, &tmap_x, fullA + 8 * sa, cb * BLOCK_K, w0 + s - p.pad_l, h0 + r0 - p.pad_t, n0);
-                if (++sa == SA) { sa = 0; pa ^= 1; }
-                for (int r = 0; r < rtaps; ++r) {
-                    mbar_wait(emptyB + 8 * sb, pb ^ 1);
-                    mbar_expect_tx(fullB + 8 * sb, B_BYTES);
-                    tma_load_3d(b_base + sb * B_BYTES, &tmap_w, fullB + 8 * sb, cb * BLOCK_K, co0, (r0 + r) * p.kw + s);
-                    if (++sb == SB) { sb = 0; pb ^= 1; }
-                }
-            }
-        }
-    } else if (warp == 1 && lane == 0) {
-        // ================= MMA issuer =================
-        constexpr uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N, 0, 0);
-        int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
-        int it = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-            const int acc = it & 1;
-            const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
-            mbar_wait(tempty + 8 * acc, acc_phase ^ 1);            // epilogue has drained this accumulator
-            tc_fence_after();
-            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
-            uint32_t first = 1;
-            for (int gi = 0; gi < groups; ++gi) {
-                mbar_wait(fullA + 8 * sa, pa);
-                tc_fence_after();
-                const uint32_t a_src = a_base + sa * A_SLOT;
-                for (int r = 0; r < rtaps; ++r) {
-                    mbar_wait(fullB + 8 * sb, pb);
-                    tc_fence_after();
-                    const uint64_t a_desc = make_smem_desc(a_src + (HALO ? (uint32_t)(r * p.BW) * 128u : 0u), 16, 1024);
-                    const uint64_t b_desc = make_smem_desc(b_base + sb * B_BYTES, 16, 1024);
-#pragma unroll
-                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                        umma_bf16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, first ? 0u : 1u);
-                        first = 0;
-                    }
-                    umma_commit(emptyB + 8 * sb);
-                    if (++sb == SB) { sb = 0; pb ^= 1; }
-                }
-                umma_commit(emptyA + 8 * sa);
-                if (++sa == SA) { sa = 0; pa ^= 1; }
-            }
-            umma_commit(tfull + 8 * acc);
-        }
-    } else if (warp >= 2) {
-        // ================= epilogue warps: TMEM -> registers -> global =================
-        const int q = warp & 3;                                    // TMEM lane quadrant this warp may access
-        const bool relu = (p.flags & CTGAN_EPI_RELU) != 0;
-        int it = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-            const int acc = it & 1;
-            const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
-            const int nb = tile % n_blocks; int mt = tile / n_blocks;
-            const int tw = mt % p.tilesW; mt /= p.tilesW;
-            const int th = mt % p.tilesH; const int tn = mt / p.tilesH;
-            const int co0 = nb * BLOCK_N;
-            mbar_wait(tfull + 8 * acc, acc_phase);
-            tc_fence_after();
-            tile_epilogue<BLOCK_N, true>(p, tmem_base + (uint32_t)(acc * BLOCK_N), p.bias ? p.bias + co0 : nullptr, q, lane,
-                                   tw * p.BW, th * p.BH, tn * p.BN, co0);
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) {                                        // this warp has finished reading the accumulator
-                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty + 8 * acc) : "memory");
-            }
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem_base);
-}
-
 // ------------------------------------------------------------------ fprop kernel, persistent, grouped stages
-// Epilogue of one 128-pixel x 128-channel accumulator of the lean / pair kernels: hand-scheduled version of
-// tile_epilogue<128, true> without the relu_mask operand (the generic template, and even an untaken mask branch here,
-// measured 3-4 % slower on the whole step; masked launches take the per-k-block persistent kernel instead).
+// Epilogue of one 128-pixel x 128-channel accumulator of the lean / pair kernels (thread = pixel row = TMEM lane, 32-byte
+// global accesses).  The variant is a TEMPLATE parameter: an untaken runtime branch for an extra operand measured 3-4 %
+// slower on the whole step (registers of the four epilogue warps).
+//   EPI_PLAIN    y = [relu](conv + bias [+ residual | residual upsampled 2x])
+//   EPI_MASK     ... and y = 0 where relu_mask <= 0  (Conv2DBackpropInput followed by ReluGrad: the dgrad into a tensor
+//                that is a ReLU output -- no separate mask-multiply kernel in the backward chains)
+//   EPI_ACTDROP  v = conv + bias;  m = (v > 0 ? 1 : slope) * floor(keep + u) / keep;  y = v * m, m stored beside y:
+//                Conv2D -> LeakyReLU -> tf.nn.dropout of the DCGAN critics (TG/CT_gan_cifar.py:84-96, CT_gan_mnist.py:92-104,
+//                bias at TG/tflib/ops/conv2d.py:114-120) in the conv epilogue.  u comes from Philox4x32-10 in registers at
+//                the element's NHWC index (the stream act_dropout_kernel draws from), optionally written in the
+//                space-to-depth layout of the next stride-2 layer.
+enum { EPI_PLAIN = 0, EPI_MASK = 1, EPI_ACTDROP = 2 };
+
+__device__ __forceinline__ void ldg16_bf16(const __nv_bfloat16* p, bool wide, uint32_t (&rw)[8]) {
+    if (wide) {
+        asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(rw[0]), "=r"(rw[1]), "=r"(rw[2]), "=r"(rw[3]), "=r"(rw[4]), "=r"(rw[5]), "=r"(rw[6]), "=r"(rw[7]) : "l"(p));
+    } else {
+        const uint4 r0 = *reinterpret_cast<const uint4*>(p), r1 = *reinterpret_cast<const uint4*>(p + 8);
+        rw[0] = r0.x; rw[1] = r0.y; rw[2] = r0.z; rw[3] = r0.w; rw[4] = r1.x; rw[5] = r1.y; rw[6] = r1.z; rw[7] = r1.w;
+    }
+}
+__device__ __forceinline__ void stg16_bf16(__nv_bfloat16* p, bool wide, const uint32_t (&ow)[8]) {
+    if (wide) {
+        asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                     ::"l"(p), "r"(ow[0]), "r"(ow[1]), "r"(ow[2]), "r"(ow[3]), "r"(ow[4]), "r"(ow[5]), "r"(ow[6]), "r"(ow[7]) : "memory");
+    } else {
+        *reinterpret_cast<uint4*>(p) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+        *reinterpret_cast<uint4*>(p + 8) = make_uint4(ow[4], ow[5], ow[6], ow[7]);
+    }
+}
+
+template <int EPI>
 __device__ __forceinline__ void lean_epilogue_tile(const FpropParams& p, uint32_t tmem_addr, int q, int lane,
                                                    int w0, int h0, int n0, int co0, bool relu) {
     int t = q * 32 + lane;
@@ -495,10 +286,26 @@ __device__ __forceinline__ void lean_epilogue_tile(const FpropParams& p, uint32_
     const int n = n0 + bn, h = h0 + bh, w = w0 + bw;
     const bool valid = (n < p.N) && (h < p.H) && (w < p.W);
     const int64_t pix = ((int64_t)n * p.H + h) * p.W + w;
-    __nv_bfloat16* yrow = p.y + pix * p.Cout + co0;
+    int64_t orow = pix * p.Cout;                                     // element offset of this pixel's row in y (and m)
+    if (EPI == EPI_ACTDROP && p.out_s2d)
+        orow = ((((int64_t)n * (p.H >> 1) + (h >> 1)) * (p.W >> 1) + (w >> 1)) * 4 + ((h & 1) * 2 + (w & 1))) * p.Cout;
+    __nv_bfloat16* yrow = p.y + orow + co0;
     const int64_t rpix = (p.flags & CTGAN_EPI_RES_UP2) ? ((int64_t)n * (p.H >> 1) + (h >> 1)) * (p.W >> 1) + (w >> 1) : pix;
-    const __nv_bfloat16* rrow = p.residual ? p.residual + rpix * p.Cout + co0 : nullptr;
-    const bool wide = ((reinterpret_cast<uintptr_t>(p.y) | reinterpret_cast<uintptr_t>(p.residual)) & 31) == 0;
+    const __nv_bfloat16* rrow = (EPI != EPI_ACTDROP && p.residual) ? p.residual + rpix * p.Cout + co0 : nullptr;
+    const __nv_bfloat16* mrow = (EPI == EPI_MASK) ? p.relu_mask + pix * p.Cout + co0 : nullptr;
+    __nv_bfloat16* mult_row = (EPI == EPI_ACTDROP) ? p.mult + orow + co0 : nullptr;
+    const bool wide = ((reinterpret_cast<uintptr_t>(p.y) | reinterpret_cast<uintptr_t>(p.residual) |
+                        (EPI == EPI_MASK ? reinterpret_cast<uintptr_t>(p.relu_mask) : 0) |
+                        (EPI == EPI_ACTDROP ? reinterpret_cast<uintptr_t>(p.mult) : 0)) & 31) == 0;
+    // EPI_ACTDROP: absolute Philox stream index of channel co0 of this pixel (a multiple of 4: offsets are 4-aligned)
+    unsigned long long se0 = 0;
+    bool drop = false;
+    float inv_keep = 1.f;
+    if (EPI == EPI_ACTDROP) {
+        drop = p.keep < 1.f;
+        inv_keep = 1.f / p.keep;
+        se0 = p.offset + (p.dyn ? *p.dyn : 0ull) + (unsigned long long)(pix * p.Cout + co0);
+    }
 #pragma unroll 1
     for (int c0 = 0; c0 < 128; c0 += 32) {
         uint32_t v32[32];
@@ -521,14 +328,7 @@ __device__ __forceinline__ void lean_epilogue_tile(const FpropParams& p, uint32_
                 for (int e = 0; e < 16; ++e) v[e] += __uint_as_float(v32[j + e]);
                 if (rrow) {
                     uint32_t rw[8];
-                    if (wide) {
-                        asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                                     : "=r"(rw[0]), "=r"(rw[1]), "=r"(rw[2]), "=r"(rw[3]), "=r"(rw[4]), "=r"(rw[5]), "=r"(rw[6]), "=r"(rw[7])
-                                     : "l"(rrow + c0 + j));
-                    } else {
-                        const uint4 r0 = *reinterpret_cast<const uint4*>(rrow + c0 + j), r1 = *reinterpret_cast<const uint4*>(rrow + c0 + j + 8);
-                        rw[0] = r0.x; rw[1] = r0.y; rw[2] = r0.z; rw[3] = r0.w; rw[4] = r1.x; rw[5] = r1.y; rw[6] = r1.z; rw[7] = r1.w;
-                    }
+                    ldg16_bf16(rrow + c0 + j, wide, rw);
 #pragma unroll
                     for (int e = 0; e < 8; ++e) {
                         const __nv_bfloat162 r2 = *reinterpret_cast<const __nv_bfloat162*>(&rw[e]);
@@ -539,20 +339,46 @@ __device__ __forceinline__ void lean_epilogue_tile(const FpropParams& p, uint32_
 #pragma unroll
                     for (int e = 0; e < 16; ++e) v[e] = fmaxf(v[e], 0.f);
                 }
-                uint32_t ow[8];
+                if (EPI == EPI_MASK) {
+                    uint32_t mw[8];
+                    ldg16_bf16(mrow + c0 + j, wide, mw);
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    const __nv_bfloat162 o2 = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
-                    ow[e] = *reinterpret_cast<const uint32_t*>(&o2);
+                    for (int e = 0; e < 8; ++e) {
+                        const __nv_bfloat162 m2 = *reinterpret_cast<const __nv_bfloat162*>(&mw[e]);
+                        v[2 * e] = __bfloat162float(m2.x) > 0.f ? v[2 * e] : 0.f;
+                        v[2 * e + 1] = __bfloat162float(m2.y) > 0.f ? v[2 * e + 1] : 0.f;
+                    }
                 }
-                if (wide) {
-                    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
-                                 ::"l"(yrow + c0 + j), "r"(ow[0]), "r"(ow[1]), "r"(ow[2]), "r"(ow[3]), "r"(ow[4]), "r"(ow[5]), "r"(ow[6]), "r"(ow[7])
-                                 : "memory");
+                uint32_t ow[8];
+                if (EPI == EPI_ACTDROP) {
+                    uint32_t mo[8];
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        uint32_t r[4] = {0u, 0u, 0u, 0u};
+                        if (drop) Philox::block(p.seed, (se0 + (unsigned long long)(c0 + j + 4 * b)) >> 2, r);
+                        float mm[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            float mult = v[4 * b + e] > 0.f ? 1.f : p.slope;
+                            if (drop) mult *= floorf(p.keep + Philox::to_uniform(r[e])) * inv_keep;
+                            mm[e] = mult;
+                        }
+                        // y = v * (the ROUNDED multiplier): y == v * m holds exactly for the stored m (as act_dropout_kernel)
+                        const __nv_bfloat162 ma = __floats2bfloat162_rn(mm[0], mm[1]), mb = __floats2bfloat162_rn(mm[2], mm[3]);
+                        mo[2 * b] = *reinterpret_cast<const uint32_t*>(&ma); mo[2 * b + 1] = *reinterpret_cast<const uint32_t*>(&mb);
+                        const __nv_bfloat162 ya = __floats2bfloat162_rn(v[4 * b] * __bfloat162float(ma.x), v[4 * b + 1] * __bfloat162float(ma.y));
+                        const __nv_bfloat162 yb = __floats2bfloat162_rn(v[4 * b + 2] * __bfloat162float(mb.x), v[4 * b + 3] * __bfloat162float(mb.y));
+                        ow[2 * b] = *reinterpret_cast<const uint32_t*>(&ya); ow[2 * b + 1] = *reinterpret_cast<const uint32_t*>(&yb);
+                    }
+                    stg16_bf16(mult_row + c0 + j, wide, mo);
                 } else {
-                    *reinterpret_cast<uint4*>(yrow + c0 + j) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
-                    *reinterpret_cast<uint4*>(yrow + c0 + j + 8) = make_uint4(ow[4], ow[5], ow[6], ow[7]);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const __nv_bfloat162 o2 = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+                        ow[e] = *reinterpret_cast<const uint32_t*>(&o2);
+                    }
                 }
+                stg16_bf16(yrow + c0 + j, wide, ow);
             }
         }
     }
@@ -567,7 +393,7 @@ __device__ __forceinline__ void lean_epilogue_tile(const FpropParams& p, uint32_
 //   HALO = 0 (1x1, 8x8 / 4x4 tiles, linear): stage = 2 consecutive (activation, filter) box pairs   ->  8 MMAs, 64 KB
 // Three stages in flight; descriptors are pre-built 32-bit words plus immediate offsets.
 
-template <int HALO>
+template <int HALO, int EPI>
 __global__ void __launch_bounds__(192, 1)
 conv_fprop_tc_lean_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                           const FpropParams p, const int n_tiles)
@@ -694,7 +520,7 @@ conv_fprop_tc_lean_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
             const int co0 = nb * BLOCK_N;
             mbar_wait(tfull + 8 * acc, (uint32_t)(it >> 1) & 1u);
             tc_fence_after();
-            lean_epilogue_tile(p, tmem_base + (uint32_t)(acc * BLOCK_N), q, lane, tw * p.BW, th * p.BH, tn * p.BN, co0, relu);
+            lean_epilogue_tile<EPI>(p, tmem_base + (uint32_t)(acc * BLOCK_N), q, lane, tw * p.BW, th * p.BH, tn * p.BN, co0, relu);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty + 8 * acc) : "memory");
@@ -712,6 +538,7 @@ conv_fprop_tc_lean_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
 // accumulators -- 44 KB per 12 MMAs instead of 72 KB.  Two stages of 88 KB; TMEM 2 x (2 x 128) columns double-buffered.
 // Tiles are enumerated n-block-major (tile = nb * m_tiles + mt) and split into contiguous per-CTA ranges, so every warp
 // role derives the same item sequence (pair if the next tile is the next row block of the same image, else single).
+template <int EPI>
 __global__ void __launch_bounds__(192, 1)
 conv_fprop_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_x2,
                           const __grid_constant__ CUtensorMap tmap_w, const FpropParams p, const int m_tiles, const int n_tiles)
@@ -844,8 +671,8 @@ conv_fprop_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
             const int h0 = th * p.BH, n0 = tn * p.BN, co0 = nb * BLOCK_N;
             mbar_wait(tfull + 8 * acc, (uint32_t)(it >> 1) & 1u);
             tc_fence_after();
-            lean_epilogue_tile(p, tmem_base + (uint32_t)(acc * 2 * BLOCK_N), q, lane, 0, h0, n0, co0, relu);
-            if (pair) lean_epilogue_tile(p, tmem_base + (uint32_t)(acc * 2 * BLOCK_N + BLOCK_N), q, lane, 0, h0 + p.BH, n0, co0, relu);
+            lean_epilogue_tile<EPI>(p, tmem_base + (uint32_t)(acc * 2 * BLOCK_N), q, lane, 0, h0, n0, co0, relu);
+            if (pair) lean_epilogue_tile<EPI>(p, tmem_base + (uint32_t)(acc * 2 * BLOCK_N + BLOCK_N), q, lane, 0, h0 + p.BH, n0, co0, relu);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty + 8 * acc) : "memory");
@@ -1394,72 +1221,38 @@ static int launch_fprop(const CUtensorMap& mx, const CUtensorMap& mw, const Fpro
     return 0;
 }
 
-template <int BLOCK_N, int SA, int SB>
-static int launch_fprop_halo(const CUtensorMap& mx, const CUtensorMap& mw, const FpropParams& p, cudaStream_t st) {
-    const uint32_t a_bytes = (uint32_t)(p.BH + p.kh - 1) * p.BW * 128u;
-    const uint32_t a_slot = (a_bytes + 1023u) & ~1023u;
-    const size_t smem = (size_t)SA * a_slot + (size_t)SB * BLOCK_N * BLOCK_K * 2 + 1024 + (2 * SA + 2 * SB + 1) * 8 + 16 + BLOCK_N * 4;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv_fprop_tc_halo_kernel<BLOCK_N, SA, SB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        if (e != cudaSuccess) return cuda_status(e, "fprop_tc_halo smem attribute");
-        attr_set = true;
-    }
-    dim3 grid(p.tilesW * p.tilesH * p.tilesN, p.Cout / BLOCK_N);
-    CTGAN_LAUNCH((conv_fprop_tc_halo_kernel<BLOCK_N, SA, SB>), grid, 128, smem, st, mx, mw, p, a_slot);
-    CTGAN_CHECK_LAUNCH("conv_fprop_tc_halo");
-    return 0;
-}
-
-template <int SA, int SB, int A_SLOT, int HALO>
-static int launch_fprop_persistent(const CUtensorMap& mx, const CUtensorMap& mw, const FpropParams& p, cudaStream_t st) {
-    constexpr size_t smem = (size_t)SA * A_SLOT + (size_t)SB * 16384 + 1024 + (2 * SA + 2 * SB + 4) * 8 + 16;
-    static_assert(smem <= 227 * 1024, "persistent fprop: shared memory budget");
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv_fprop_tc_persistent_kernel<SA, SB, A_SLOT, HALO>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return cuda_status(e, "fprop_tc_persistent smem attribute");
-        attr_set = true;
-    }
-    const int n_tiles = p.tilesW * p.tilesH * p.tilesN * (p.Cout / 128);
-    const int grid = n_tiles < sm_count() ? n_tiles : sm_count();
-    CTGAN_LAUNCH((conv_fprop_tc_persistent_kernel<SA, SB, A_SLOT, HALO>), grid, 192, smem, st, mx, mw, p, n_tiles);
-    CTGAN_CHECK_LAUNCH("conv_fprop_tc_persistent");
-    return 0;
-}
-
-template <int HALO>
+template <int HALO, int EPI>
 static int launch_fprop_lean(const CUtensorMap& mx, const CUtensorMap& mw, const FpropParams& p, cudaStream_t st) {
     constexpr size_t stage = HALO ? (24576 + 3 * 16384) : (32768 + 2 * 16384);
     constexpr size_t smem = 3 * stage + 1024 + (2 * 3 + 4) * 8 + 16;
     static_assert(smem <= 227 * 1024, "lean fprop: shared memory budget");
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv_fprop_tc_lean_kernel<HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(conv_fprop_tc_lean_kernel<HALO, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return cuda_status(e, "fprop_tc_lean smem attribute");
         attr_set = true;
     }
     const int n_tiles = p.tilesW * p.tilesH * p.tilesN * (p.Cout / 128);
-    const int grid = n_tiles < sm_count() ? n_tiles : sm_count();
-    CTGAN_LAUNCH((conv_fprop_tc_lean_kernel<HALO>), grid, 192, smem, st, mx, mw, p, n_tiles);
+    const int grid = n_tiles < tc_grid_cap() ? n_tiles : tc_grid_cap();
+    CTGAN_LAUNCH((conv_fprop_tc_lean_kernel<HALO, EPI>), grid, 192, smem, st, mx, mw, p, n_tiles);
     CTGAN_CHECK_LAUNCH("conv_fprop_tc_lean");
     return 0;
 }
 
+template <int EPI>
 static int launch_fprop_pair(const CUtensorMap& mx, const CUtensorMap& mx2, const CUtensorMap& mw, const FpropParams& p, cudaStream_t st) {
     constexpr size_t smem = 2 * (40960 + 3 * 16384) + 1024 + (2 * 2 + 4) * 8 + 16;
     static_assert(smem <= 227 * 1024, "pair fprop: shared memory budget");
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv_fprop_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(conv_fprop_tc_pair_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return cuda_status(e, "fprop_tc_pair smem attribute");
         attr_set = true;
     }
     const int m_tiles = p.tilesW * p.tilesH * p.tilesN;
     const int n_tiles = m_tiles * (p.Cout / 128);
-    const int grid = n_tiles < sm_count() ? n_tiles : sm_count();
-    CTGAN_LAUNCH((conv_fprop_tc_pair_kernel), grid, 192, smem, st, mx, mx2, mw, p, m_tiles, n_tiles);
+    const int grid = n_tiles < tc_grid_cap() ? n_tiles : tc_grid_cap();
+    CTGAN_LAUNCH((conv_fprop_tc_pair_kernel<EPI>), grid, 192, smem, st, mx, mx2, mw, p, m_tiles, n_tiles);
     CTGAN_CHECK_LAUNCH("conv_fprop_tc_pair");
     return 0;
 }
@@ -1471,13 +1264,55 @@ using namespace ctgan;
 using namespace ctgan::tc;
 
 static bool g_use_halo = true;
-static int g_fprop_variant = 4;   // 4 = 256-pixel work items where possible (else 3), 3 = persistent grouped-stage kernel, 2 = persistent per-k-block rings, 1 = one tile per CTA
-/* test hook: selects the fprop_tc kernel family (both are compared in tests/) */
+static int g_fprop_variant = 4;   // 4 = 256-pixel work items where possible (else 3), 3 = persistent grouped-stage (lean) kernel, 1 = one tile per CTA
+/* test hook: selects the fprop_tc kernel family (the families are compared in tests/) */
 extern "C" void ctgan_set_fprop_variant(int v) { g_fprop_variant = v; }
 static int g_wgrad_variant = 2;   // 2 = filter-column CTAs sharing one x halo box (3x3), 1 = one (x, dY) box pair per tap
 extern "C" void ctgan_set_wgrad_variant(int v) { g_wgrad_variant = v; }
-/* test hook: 0 disables the halo-reuse fprop variant (both variants are compared in tests/) */
+/* test hook: 0 disables the halo-reuse A pipeline (both are compared in tests/) */
 extern "C" void ctgan_set_fprop_halo(int on) { g_use_halo = on != 0; }
+
+// common launcher of the stride-1 tcgen05 forward family; epi selects the epilogue of the lean / pair kernels
+static int fprop_tc_launch(const ctgan_conv_desc* d, const void* x, const void* wp, FpropParams& p, int epi, void* stream) {
+    p.N = d->N; p.H = d->H; p.W = d->W; p.Cin = d->Cin; p.Cout = d->Cout;
+    p.kh = d->kh; p.kw = d->kw; p.pad_t = d->pad_t; p.pad_l = d->pad_l;
+    pixel_box(d->H, d->W, BLOCK_M, &p.BW, &p.BH, &p.BN);
+    p.tilesW = ceil_div(d->W, p.BW); p.tilesH = ceil_div(d->H, p.BH); p.tilesN = ceil_div(d->N, p.BN);
+    const int block_n = (d->Cout % 128 == 0) ? 128 : 64;
+    CTGAN_REQUIRE(epi != EPI_ACTDROP || block_n == 128, CTGAN_ERR_UNSUPPORTED, "conv_fprop_tc_actdrop: Cout must be a multiple of 128");
+    // halo-reuse A pipeline: k x k filters (k > 1) on tiles that are whole rows of one image
+    const bool halo = g_use_halo && block_n == 128 && d->kh == 3 && p.BN == 1 && (p.BW % 8) == 0 &&
+                      (uint32_t)(p.BH + d->kh - 1) * p.BW * 128u <= 24576u && g_fprop_variant >= 3;
+    CUtensorMap mx, mw;
+    if (int r = make_act_map(&mx, x, d->N, d->H, d->W, d->Cin, p.BW, halo ? p.BH + d->kh - 1 : p.BH, p.BN)) return r;
+    if (int r = make_filter_map(&mw, wp, d->kh * d->kw, d->Cout, d->Cin, block_n)) return r;
+    cudaStream_t st = as_stream(stream);
+    const int variant = (epi == EPI_ACTDROP && g_fprop_variant < 3) ? 3 : g_fprop_variant;   // only the lean kernels have that epilogue
+    if (variant == 4 && epi != EPI_ACTDROP && halo && p.tilesW == 1 && p.tilesH >= 2 &&
+        (uint32_t)(2 * p.BH + 2) * p.BW * 128u <= 40960u && p.tilesH * p.tilesN * (d->Cout / 128) >= 2 * sm_count()) {
+        CUtensorMap mx2;                                             // 256-pixel work items (two row blocks per halo box)
+        if (int r = make_act_map(&mx2, x, d->N, d->H, d->W, d->Cin, p.BW, 2 * p.BH + 2, 1)) return r;
+        return epi == EPI_MASK ? launch_fprop_pair<EPI_MASK>(mx, mx2, mw, p, st) : launch_fprop_pair<EPI_PLAIN>(mx, mx2, mw, p, st);
+    }
+    if (variant >= 3 && block_n == 128) {                            // persistent, grouped stages, lean issue loop
+        if (halo) {
+            if (epi == EPI_MASK) return launch_fprop_lean<1, EPI_MASK>(mx, mw, p, st);
+            if (epi == EPI_ACTDROP) return launch_fprop_lean<1, EPI_ACTDROP>(mx, mw, p, st);
+            return launch_fprop_lean<1, EPI_PLAIN>(mx, mw, p, st);
+        }
+        if (epi == EPI_MASK) return launch_fprop_lean<0, EPI_MASK>(mx, mw, p, st);
+        if (epi == EPI_ACTDROP) return launch_fprop_lean<0, EPI_ACTDROP>(mx, mw, p, st);
+        return launch_fprop_lean<0, EPI_PLAIN>(mx, mw, p, st);
+    }
+    if (block_n == 128) {
+        // one tile per CTA (cross-check family).  Few tiles: the K loop is latency-bound, 6-deep TMA ring; many tiles:
+        // 3 stages x 2 co-resident CTAs per SM.
+        const int ctas = p.tilesW * p.tilesH * p.tilesN * (d->Cout / block_n);
+        if (ctas <= sm_count()) return launch_fprop<128, 6>(mx, mw, p, st);
+        return launch_fprop<128, 3>(mx, mw, p, st);
+    }
+    return launch_fprop<64, 4>(mx, mw, p, st);
+}
 
 extern "C" int ctgan_conv_fprop_tc(const ctgan_conv_desc* d, const void* x, const void* wp,
                                    const float* bias, const void* residual, void* y, int flags, void* stream) {
@@ -1494,48 +1329,32 @@ extern "C" int ctgan_conv_fprop_tc_masked(const ctgan_conv_desc* d, const void* 
     CTGAN_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(wp) & 15) == 0 &&
                   (reinterpret_cast<uintptr_t>(y) & 15) == 0 && (reinterpret_cast<uintptr_t>(residual) & 15) == 0,
                   CTGAN_ERR_BAD_DESC, "conv_fprop_tc: pointers must be 16-byte aligned");
-    FpropParams p;
-    p.N = d->N; p.H = d->H; p.W = d->W; p.Cin = d->Cin; p.Cout = d->Cout;
-    p.kh = d->kh; p.kw = d->kw; p.pad_t = d->pad_t; p.pad_l = d->pad_l;
-    pixel_box(d->H, d->W, BLOCK_M, &p.BW, &p.BH, &p.BN);
-    p.tilesW = ceil_div(d->W, p.BW); p.tilesH = ceil_div(d->H, p.BH); p.tilesN = ceil_div(d->N, p.BN);
+    FpropParams p = {};
     p.flags = flags;
     p.y = reinterpret_cast<__nv_bfloat16*>(y);
     p.bias = bias;
     p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
     p.relu_mask = reinterpret_cast<const __nv_bfloat16*>(relu_mask);
-    const int block_n = (d->Cout % 128 == 0) ? 128 : 64;
-    const int ctas = p.tilesW * p.tilesH * p.tilesN * (d->Cout / block_n);
-    // halo-reuse variant: k x k filters (k > 1) on tiles that are whole rows of one image, more than one wave of CTAs
-    const bool halo = g_use_halo && block_n == 128 && d->kh > 1 && d->kh <= 5 && p.BN == 1 && (p.BW % 8) == 0 &&
-                      (uint32_t)(p.BH + d->kh - 1) * p.BW * 128u <= 24576u && (g_fprop_variant >= 2 || ctas > sm_count());
-    CUtensorMap mx, mw;
-    if (int r = make_act_map(&mx, x, d->N, d->H, d->W, d->Cin, p.BW, halo ? p.BH + d->kh - 1 : p.BH, p.BN)) return r;
-    if (int r = make_filter_map(&mw, wp, d->kh * d->kw, d->Cout, d->Cin, block_n)) return r;
-    cudaStream_t st = as_stream(stream);
-    const int variant = relu_mask ? (g_fprop_variant < 2 ? g_fprop_variant : 2) : g_fprop_variant;   // lean / pair kernels: no mask operand
-    if (variant == 4 && block_n == 128 && halo && d->kh == 3 && p.tilesW == 1 && p.BN == 1 && p.tilesH >= 2 &&
-        (uint32_t)(2 * p.BH + 2) * p.BW * 128u <= 40960u && p.tilesH * p.tilesN * (d->Cout / 128) >= 2 * sm_count()) {
-        CUtensorMap mx2;                                             // 256-pixel work items (two row blocks per halo box)
-        if (int r = make_act_map(&mx2, x, d->N, d->H, d->W, d->Cin, p.BW, 2 * p.BH + 2, 1)) return r;
-        return launch_fprop_pair(mx, mx2, mw, p, st);
-    }
-    if (variant >= 3 && block_n == 128) {                            // persistent, grouped stages, lean issue loop
-        if (halo && d->kh == 3) return launch_fprop_lean<1>(mx, mw, p, st);
-        if (!halo) return launch_fprop_lean<0>(mx, mw, p, st);
-    }
-    if (variant >= 2 && block_n == 128) {                            // persistent, per-k-block rings
-        if (halo) return launch_fprop_persistent<3, 8, 24576, 1>(mx, mw, p, st);
-        return launch_fprop_persistent<6, 6, 16384, 0>(mx, mw, p, st);
-    }
-    if (halo) return launch_fprop_halo<128, 2, 3>(mx, mw, p, st);
-    if (block_n == 128) {
-        // Few tiles (8x8 / 4x4 layers at batch 64): one CTA per SM at most, so the K loop is latency-bound --
-        // use a 6-deep TMA ring.  Many tiles: 3 stages x 2 co-resident CTAs per SM.
-        if (ctas <= sm_count()) return launch_fprop<128, 6>(mx, mw, p, st);
-        return launch_fprop<128, 3>(mx, mw, p, st);
-    }
-    return launch_fprop<64, 4>(mx, mw, p, st);
+    return fprop_tc_launch(d, x, wp, p, relu_mask ? EPI_MASK : EPI_PLAIN, stream);
+}
+
+extern "C" int ctgan_conv_fprop_tc_actdrop(const ctgan_conv_desc* d, const void* x, const void* wp, const float* bias, void* y,
+                                           void* mult, float slope, float keep, uint64_t seed, uint64_t offset,
+                                           const uint64_t* dyn_offset, int out_s2d, void* stream) {
+    if (int r = check_tc_desc(d, "conv_fprop_tc_actdrop")) return r;
+    CTGAN_REQUIRE(x && wp && y && mult, CTGAN_ERR_BAD_DESC, "conv_fprop_tc_actdrop: null pointer");
+    CTGAN_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(wp) | reinterpret_cast<uintptr_t>(y) |
+                    reinterpret_cast<uintptr_t>(mult)) & 15) == 0, CTGAN_ERR_BAD_DESC, "conv_fprop_tc_actdrop: pointers must be 16-byte aligned");
+    CTGAN_REQUIRE(keep > 0.f && keep <= 1.f && (offset & 3) == 0, CTGAN_ERR_BAD_DESC, "conv_fprop_tc_actdrop: keep in (0,1], offset a multiple of 4");
+    CTGAN_REQUIRE(!out_s2d || (d->H % 2 == 0 && d->W % 2 == 0), CTGAN_ERR_UNSUPPORTED, "conv_fprop_tc_actdrop: space-to-depth output needs even H, W");
+    FpropParams p = {};
+    p.y = reinterpret_cast<__nv_bfloat16*>(y);
+    p.bias = bias;
+    p.mult = reinterpret_cast<__nv_bfloat16*>(mult);
+    p.slope = slope; p.keep = keep; p.seed = seed; p.offset = offset;
+    p.dyn = reinterpret_cast<const unsigned long long*>(dyn_offset);
+    p.out_s2d = out_s2d ? 1 : 0;
+    return fprop_tc_launch(d, x, wp, p, EPI_ACTDROP, stream);
 }
 
 extern "C" int ctgan_conv_wgrad_tc(const ctgan_conv_desc* d, const void* x, const void* dy, float* dw, void* stream) {

@@ -492,6 +492,270 @@ __global__ void bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restric
     }
 }
 
+// ---- BF16 "fused" path (ctgan_bn_fwd_fused / ctgan_bn_bwd_fused): two kernels per direction instead of three --------
+// The generator step of the round-1 timeline spent 36 % of its kernel time in batch norm: stats / finalize / apply (and
+// reduce / finalize / apply backward) are three dependent launches, the finalize kernels are latency chains of
+// uncoalesced loads on 32 blocks, and one 16-byte load is in flight per thread.  Here
+//   * the statistics kernel adds per-block sums with red.global into a [G][C][2] accumulator (zeroed by a memset node);
+//     the sums are of d = x - shift, shift = the group's first row, so that E[d^2] - E[d]^2 does not cancel;
+//   * the apply kernel derives mean / invstd from the accumulator itself (no finalize launch), keeps 4 rows in flight
+//     per thread and can write its output nearest-neighbour upsampled 2x (CTGAN_BN_UP2: the tf.concat x4 +
+//     depth_to_space of UpsampleConv, TG/CT_gan_cifar_resnet.py:100-107, fused into the normalisation that precedes it);
+//   * backward: the ReLU pattern is recomputed from x ( y > 0  <=>  fma(x, scale, shift) > 0, the very expression the
+//     forward evaluated ), so y is neither saved nor read; per-(sample, split) sums go straight into the per-label
+//     dgamma / dbeta tables (CTGAN_BN_ACCUM: the flat gradient bucket) and the two per-group means with red.global;
+//     with CTGAN_BN_UP2 the incoming gradient has the upsampled shape and is summed 2x2 on load (the adjoint).
+__device__ __forceinline__ void bn_load8(const __nv_bfloat16* p, float (&f)[8]) {
+    unpack8(__ldg(reinterpret_cast<const uint4*>(p)), f);
+}
+
+__global__ void __launch_bounds__(256)
+bn_sums_bf16_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ acc, int64_t Rg, int C, int rows_per_block, int nbg) {
+    ctgan::pdl_entry();
+    __shared__ float sh1[2048], sh2[2048];
+    const int tpr = C >> 3;
+    const int cg = threadIdx.x % tpr, rl = threadIdx.x / tpr, rstep = 256 / tpr;
+    const int g = blockIdx.x / nbg, rb = blockIdx.x - g * nbg;
+    const int64_t r0 = (int64_t)g * Rg + (int64_t)rb * rows_per_block;
+    const int64_t r1 = min((int64_t)(g + 1) * Rg, r0 + rows_per_block);
+    const __nv_bfloat16* base = x + cg * 8;
+    float shift[8], s[8], ss[8];
+    bn_load8(base + (int64_t)g * Rg * C, shift);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { s[e] = 0.f; ss[e] = 0.f; }
+    int64_t r = r0 + rl;
+    for (; r + 7 * (int64_t)rstep < r1; r += 8 * (int64_t)rstep) {
+        uint4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = __ldg(reinterpret_cast<const uint4*>(base + (r + u * (int64_t)rstep) * C));
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            float f[8];
+            unpack8(v[u], f);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { const float d = f[e] - shift[e]; s[e] += d; ss[e] = fmaf(d, d, ss[e]); }
+        }
+    }
+    for (; r < r1; r += rstep) {
+        float f[8];
+        bn_load8(base + r * C, f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { const float d = f[e] - shift[e]; s[e] += d; ss[e] = fmaf(d, d, ss[e]); }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { sh1[rl * C + cg * 8 + e] = s[e]; sh2[rl * C + cg * 8 + e] = ss[e]; }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += 256) {
+        float a = 0.f, b = 0.f;
+        for (int k = 0; k < rstep; ++k) { a += sh1[k * C + c]; b += sh2[k * C + c]; }
+        atomicAdd(acc + ((int64_t)g * C + c) * 2 + 0, a);
+        atomicAdd(acc + ((int64_t)g * C + c) * 2 + 1, b);
+    }
+}
+
+// blockIdx.y = sample, blockIdx.x = chunk of its H*W pixels.
+template <int UP2>
+__global__ void __launch_bounds__(256)
+bn_apply_fused_bf16_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                           const int32_t* __restrict__ labels, const float* __restrict__ acc, float* __restrict__ save_mean,
+                           float* __restrict__ save_invstd, __nv_bfloat16* __restrict__ y, int H, int W, int C, int relu,
+                           int n_per_group, int rows_per_chunk, float inv_Rg, float eps) {
+    ctgan::pdl_entry();
+    const int tpr = C >> 3, HW = H * W;
+    const int cg = threadIdx.x % tpr, rl = threadIdx.x / tpr, rstep = 256 / tpr;
+    const int n = blockIdx.y, g = n / n_per_group;
+    const int l = labels ? labels[n] : 0;
+    const int64_t go = (int64_t)g * C + cg * 8, lo = (int64_t)l * C + cg * 8;
+    float sc[8], sf[8];
+    {
+        float shift[8];
+        bn_load8(x + (int64_t)g * n_per_group * HW * C + cg * 8, shift);
+        const bool writer = blockIdx.x == 0 && n == g * n_per_group && rl == 0;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const float m1 = acc[(go + e) * 2] * inv_Rg, m2 = acc[(go + e) * 2 + 1] * inv_Rg;
+            const float mean = shift[e] + m1;
+            const float is = rsqrtf(fmaxf(m2 - m1 * m1, 0.f) + eps);
+            if (writer) { save_mean[go + e] = mean; save_invstd[go + e] = is; }
+            sc[e] = gamma[lo + e] * is;
+            sf[e] = beta[lo + e] - mean * sc[e];
+        }
+    }
+    const int h0 = blockIdx.x * rows_per_chunk, h1 = min(HW, h0 + rows_per_chunk);
+    const int64_t base = (int64_t)n * HW * C + cg * 8;
+    const int64_t obase = (UP2 ? 4 : 1) * (int64_t)n * HW * C + cg * 8;
+    for (int h = h0 + rl; h < h1; h += 4 * rstep) {
+        uint4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (h + u * rstep < h1) v[u] = __ldg(reinterpret_cast<const uint4*>(x + base + (int64_t)(h + u * rstep) * C));
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int hh = h + u * rstep;
+            if (hh < h1) {
+                float f[8];
+                unpack8(v[u], f);
+                uint4 ov;
+                __nv_bfloat162* op = reinterpret_cast<__nv_bfloat162*>(&ov);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    float a = fmaf(f[2 * e], sc[2 * e], sf[2 * e]), b = fmaf(f[2 * e + 1], sc[2 * e + 1], sf[2 * e + 1]);
+                    if (relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+                    op[e] = __floats2bfloat162_rn(a, b);
+                }
+                if (UP2) {
+                    const int ph = hh / W, pw = hh - ph * W;
+                    __nv_bfloat16* o = y + obase + ((int64_t)(2 * ph) * (2 * W) + 2 * pw) * C;
+                    *reinterpret_cast<uint4*>(o) = ov;
+                    *reinterpret_cast<uint4*>(o + C) = ov;
+                    *reinterpret_cast<uint4*>(o + (int64_t)2 * W * C) = ov;
+                    *reinterpret_cast<uint4*>(o + (int64_t)2 * W * C + C) = ov;
+                } else {
+                    *reinterpret_cast<uint4*>(y + obase + (int64_t)hh * C) = ov;
+                }
+            }
+        }
+    }
+}
+
+// the gradient that reaches the normalisation output at pixel hh of sample n: dy itself, or (UP2) the sum over the 2x2
+// block of the upsampled gradient; masked by the recomputed ReLU pattern.
+template <int UP2>
+__device__ __forceinline__ void bn_load_grad(const __nv_bfloat16* __restrict__ dy, int64_t n, int hh, int H, int W, int C, int cg,
+                                             float (&g)[8]) {
+    if (UP2) {
+        const int ph = hh / W, pw = hh - ph * W;
+        const __nv_bfloat16* p = dy + 4 * n * H * W * C + ((int64_t)(2 * ph) * (2 * W) + 2 * pw) * C + cg * 8;
+        float a[8], b[8], c[8], d[8];
+        bn_load8(p, a); bn_load8(p + C, b); bn_load8(p + (int64_t)2 * W * C, c); bn_load8(p + (int64_t)2 * W * C + C, d);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) g[e] = (a[e] + b[e]) + (c[e] + d[e]);
+    } else {
+        bn_load8(dy + (n * H * W + hh) * C + cg * 8, g);
+    }
+}
+
+// blockIdx.y = sample, blockIdx.x = split of its H*W pixels
+template <int UP2>
+__global__ void __launch_bounds__(256)
+bn_bwd_sums_bf16_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
+                        const float* __restrict__ beta, const int32_t* __restrict__ labels, const float* __restrict__ mean,
+                        const float* __restrict__ invstd, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                        float* __restrict__ coef, int H, int W, int C, int S, int relu, int n_per_group) {
+    ctgan::pdl_entry();
+    __shared__ float sh1[2048], sh2[2048];
+    const int tpr = C >> 3, HW = H * W;
+    const int cg = threadIdx.x % tpr, rl = threadIdx.x / tpr, rstep = 256 / tpr;
+    const int n = blockIdx.y, sp = blockIdx.x, g = n / n_per_group;
+    const int l = labels ? labels[n] : 0;
+    const int per = (HW + S - 1) / S;
+    const int h0 = sp * per, h1 = min(HW, h0 + per);
+    const int64_t go = (int64_t)g * C + cg * 8, lo = (int64_t)l * C + cg * 8;
+    float mu[8], is[8], sc[8], sf[8], s1[8], s2[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        mu[e] = mean[go + e]; is[e] = invstd[go + e];
+        sc[e] = gamma[lo + e] * is[e];
+        sf[e] = beta[lo + e] - mu[e] * sc[e];
+        s1[e] = 0.f; s2[e] = 0.f;
+    }
+    const int64_t base = (int64_t)n * HW * C + cg * 8;
+    for (int h = h0 + rl; h < h1; h += 2 * rstep) {
+        float gq[2][8], vq[2][8];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int hh = h + u * rstep;
+            if (hh < h1) {
+                bn_load_grad<UP2>(dy, n, hh, H, W, C, cg, gq[u]);
+                bn_load8(x + base + (int64_t)hh * C, vq[u]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            if (h + u * rstep < h1) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    float gg = gq[u][e];
+                    if (relu) gg = fmaf(vq[u][e], sc[e], sf[e]) > 0.f ? gg : 0.f;
+                    s1[e] += gg;
+                    s2[e] = fmaf(gg, (vq[u][e] - mu[e]) * is[e], s2[e]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { sh1[rl * C + cg * 8 + e] = s1[e]; sh2[rl * C + cg * 8 + e] = s2[e]; }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += 256) {
+        float a = 0.f, b = 0.f;
+        for (int k = 0; k < rstep; ++k) { a += sh1[k * C + c]; b += sh2[k * C + c]; }
+        const float gm = gamma[(int64_t)l * C + c];
+        atomicAdd(dbeta + (int64_t)l * C + c, a);
+        atomicAdd(dgamma + (int64_t)l * C + c, b);
+        atomicAdd(coef + ((int64_t)g * C + c) * 2 + 0, gm * a);
+        atomicAdd(coef + ((int64_t)g * C + c) * 2 + 1, gm * b);
+    }
+}
+
+// blockIdx.y = sample (walked in REVERSE order of the sums kernel: its last reads are the hottest lines of the L2),
+// blockIdx.x = chunk of its H*W pixels.
+template <int UP2>
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_fused_bf16_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
+                               const float* __restrict__ gamma, const float* __restrict__ beta,
+                               const int32_t* __restrict__ labels, const float* __restrict__ mean,
+                               const float* __restrict__ invstd, const float* __restrict__ coef,
+                               __nv_bfloat16* __restrict__ dx, int H, int W, int C, int relu, int n_per_group,
+                               int rows_per_chunk, float inv_Rg) {
+    ctgan::pdl_entry();
+    const int tpr = C >> 3, HW = H * W;
+    const int cg = threadIdx.x % tpr, rl = threadIdx.x / tpr, rstep = 256 / tpr;
+    const int n = gridDim.y - 1 - blockIdx.y, g = n / n_per_group;
+    const int l = labels ? labels[n] : 0;
+    const int64_t go = (int64_t)g * C + cg * 8, lo = (int64_t)l * C + cg * 8;
+    float mu[8], is[8], gm[8], sc[8], sf[8], c1[8], c2[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        mu[e] = mean[go + e]; is[e] = invstd[go + e]; gm[e] = gamma[lo + e];
+        sc[e] = gm[e] * is[e];
+        sf[e] = beta[lo + e] - mu[e] * sc[e];
+        c1[e] = coef[(go + e) * 2] * inv_Rg; c2[e] = coef[(go + e) * 2 + 1] * inv_Rg;
+    }
+    const int chunk = gridDim.x - 1 - blockIdx.x;
+    const int h0 = chunk * rows_per_chunk, h1 = min(HW, h0 + rows_per_chunk);
+    const int64_t base = (int64_t)n * HW * C + cg * 8;
+    for (int h = h0 + rl; h < h1; h += 2 * rstep) {
+        float gq[2][8], vq[2][8];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int hh = h + u * rstep;
+            if (hh < h1) {
+                bn_load_grad<UP2>(dy, n, hh, H, W, C, cg, gq[u]);
+                bn_load8(x + base + (int64_t)hh * C, vq[u]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int hh = h + u * rstep;
+            if (hh < h1) {
+                float o[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    float gg = gq[u][e];
+                    if (relu) gg = fmaf(vq[u][e], sc[e], sf[e]) > 0.f ? gg : 0.f;
+                    const float xh = (vq[u][e] - mu[e]) * is[e];
+                    o[e] = is[e] * (gm[e] * gg - c1[e] - xh * c2[e]);
+                }
+                uint4 ov;
+                __nv_bfloat162* op = reinterpret_cast<__nv_bfloat162*>(&ov);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) op[e] = __floats2bfloat162_rn(o[2 * e], o[2 * e + 1]);
+                *reinterpret_cast<uint4*>(dx + base + (int64_t)hh * C) = ov;
+            }
+        }
+    }
+}
+
 // ---- bias gradient: column sums -------------------------------------------------
 __global__ void __launch_bounds__(256)
 bias_grad_kernel(const void* __restrict__ dy, float* __restrict__ db, int64_t rows, int C, int dt, int rows_per_block) {
@@ -648,6 +912,93 @@ extern "C" int ctgan_bn_bwd(const void* dy, const void* x, const void* y, const 
     else
         CTGAN_LAUNCH((bn_bwd_apply_kernel<__nv_bfloat16>), g2, 256, 0, st, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (const __nv_bfloat16*)y, gamma, labels, save_mean, save_invstd, coef, (__nv_bfloat16*)dx, R, HW, C, relu, N / groups, groups);
     CTGAN_CHECK_LAUNCH("bn_bwd_apply");
+    return 0;
+}
+
+static bool bn_fused_ok(int N, int H, int W, int C, int groups, int dtype) {
+    const int tpr = C / 8;
+    return dtype == CTGAN_BF16 && N > 0 && N <= 65535 && H > 0 && W > 0 && C > 0 && C % 8 == 0 && tpr <= 256 &&
+           (tpr & (tpr - 1)) == 0 && groups >= 1 && N % groups == 0;
+}
+static int bn_rows_per_chunk(int N, int HW, int tpr, int rows_in_flight) {
+    const int rstep = 256 / tpr;
+    int rpc = rows_in_flight * rstep;
+    while ((int64_t)N * ceil_div(HW, rpc) > 16 * (int64_t)sm_count() && rpc < HW) rpc *= 2;
+    return rpc;
+}
+
+extern "C" int ctgan_bn_fused_ok(int N, int H, int W, int C, int groups, int dtype) { return bn_fused_ok(N, H, W, C, groups, dtype) ? 1 : 0; }
+
+extern "C" int ctgan_bn_fwd_fused(const void* x, const float* gamma, const float* beta, const int32_t* labels, void* y,
+                                  float* save_mean, float* save_invstd, float* ws, int N, int H, int W, int C, float eps,
+                                  int flags, int groups, void* stream) {
+    CTGAN_REQUIRE(bn_fused_ok(N, H, W, C, groups, CTGAN_BF16), CTGAN_ERR_UNSUPPORTED, "bn_fwd_fused: needs BF16, C/8 a power of two <= 256, groups | N");
+    CTGAN_REQUIRE(x && gamma && beta && y && save_mean && save_invstd && ws, CTGAN_ERR_BAD_DESC, "bn_fwd_fused: null pointer");
+    CTGAN_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0, CTGAN_ERR_BAD_DESC, "bn_fwd_fused: x, y must be 16-byte aligned");
+    cudaStream_t st = as_stream(stream);
+    const int HW = H * W, tpr = C / 8, rstep = 256 / tpr;
+    const int64_t Rg = (int64_t)(N / groups) * HW;
+    cudaError_t e = cudaMemsetAsync(ws, 0, sizeof(float) * 2 * (size_t)groups * C, st);
+    if (e != cudaSuccess) return cuda_status(e, "bn_fwd_fused memset");
+    // ~4 blocks per SM, at least 8 row steps each (8 loads in flight per thread)
+    int64_t nbg = (4 * (int64_t)sm_count() + groups - 1) / groups;
+    const int64_t max_nbg = (Rg + 8 * rstep - 1) / (8 * rstep);
+    if (nbg > max_nbg) nbg = max_nbg;
+    if (nbg < 1) nbg = 1;
+    const int rpb = (int)((Rg + nbg - 1) / nbg);
+    nbg = (Rg + rpb - 1) / rpb;
+    CTGAN_LAUNCH((bn_sums_bf16_kernel), (unsigned)(nbg * groups), 256, 0, st, (const __nv_bfloat16*)x, ws, Rg, C, rpb, (int)nbg);
+    CTGAN_CHECK_LAUNCH("bn_sums");
+    const int rpc = bn_rows_per_chunk(N, HW, tpr, 4);
+    const int relu = (flags & CTGAN_BN_RELU) ? 1 : 0;
+    if (flags & CTGAN_BN_UP2)
+        CTGAN_LAUNCH((bn_apply_fused_bf16_kernel<1>), dim3(ceil_div(HW, rpc), N), 256, 0, st, (const __nv_bfloat16*)x, gamma, beta, labels,
+                     (const float*)ws, save_mean, save_invstd, (__nv_bfloat16*)y, H, W, C, relu, N / groups, rpc, 1.f / (float)Rg, eps);
+    else
+        CTGAN_LAUNCH((bn_apply_fused_bf16_kernel<0>), dim3(ceil_div(HW, rpc), N), 256, 0, st, (const __nv_bfloat16*)x, gamma, beta, labels,
+                     (const float*)ws, save_mean, save_invstd, (__nv_bfloat16*)y, H, W, C, relu, N / groups, rpc, 1.f / (float)Rg, eps);
+    CTGAN_CHECK_LAUNCH("bn_apply_fused");
+    return 0;
+}
+
+extern "C" int ctgan_bn_bwd_fused(const void* dy, const void* x, const float* gamma, const float* beta, const int32_t* labels,
+                                  const float* save_mean, const float* save_invstd, void* dx, float* dgamma, float* dbeta,
+                                  float* ws, int N, int H, int W, int C, int n_labels, int flags, int groups, void* stream) {
+    CTGAN_REQUIRE(bn_fused_ok(N, H, W, C, groups, CTGAN_BF16) && n_labels > 0, CTGAN_ERR_UNSUPPORTED, "bn_bwd_fused: needs BF16, C/8 a power of two <= 256, groups | N");
+    CTGAN_REQUIRE(dy && x && gamma && beta && save_mean && save_invstd && dx && dgamma && dbeta && ws, CTGAN_ERR_BAD_DESC, "bn_bwd_fused: null pointer");
+    CTGAN_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx)) & 15) == 0,
+                  CTGAN_ERR_BAD_DESC, "bn_bwd_fused: dy, x, dx must be 16-byte aligned");
+    cudaStream_t st = as_stream(stream);
+    const int HW = H * W, tpr = C / 8, rstep = 256 / tpr;
+    const int64_t Rg = (int64_t)(N / groups) * HW;
+    cudaError_t e = cudaMemsetAsync(ws, 0, sizeof(float) * 2 * (size_t)groups * C, st);
+    if (e == cudaSuccess && !(flags & CTGAN_BN_ACCUM)) {
+        e = cudaMemsetAsync(dgamma, 0, sizeof(float) * (size_t)n_labels * C, st);
+        if (e == cudaSuccess) e = cudaMemsetAsync(dbeta, 0, sizeof(float) * (size_t)n_labels * C, st);
+    }
+    if (e != cudaSuccess) return cuda_status(e, "bn_bwd_fused memset");
+    // splits of a sample's pixels: ~4 blocks per SM, at least 4 row steps per block
+    int S = (int)((4 * (int64_t)sm_count() + N - 1) / N);
+    const int maxS = ceil_div(HW, 4 * rstep);
+    if (S > maxS) S = maxS;
+    if (S < 1) S = 1;
+    const int relu = (flags & CTGAN_BN_RELU) ? 1 : 0;
+    const int rpc = bn_rows_per_chunk(N, HW, tpr, 4);
+    const float inv_Rg = 1.f / (float)Rg;
+    if (flags & CTGAN_BN_UP2) {
+        CTGAN_LAUNCH((bn_bwd_sums_bf16_kernel<1>), dim3(S, N), 256, 0, st, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, gamma, beta, labels,
+                     save_mean, save_invstd, dgamma, dbeta, ws, H, W, C, S, relu, N / groups);
+        CTGAN_CHECK_LAUNCH("bn_bwd_sums");
+        CTGAN_LAUNCH((bn_bwd_apply_fused_bf16_kernel<1>), dim3(ceil_div(HW, rpc), N), 256, 0, st, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x,
+                     gamma, beta, labels, save_mean, save_invstd, (const float*)ws, (__nv_bfloat16*)dx, H, W, C, relu, N / groups, rpc, inv_Rg);
+    } else {
+        CTGAN_LAUNCH((bn_bwd_sums_bf16_kernel<0>), dim3(S, N), 256, 0, st, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, gamma, beta, labels,
+                     save_mean, save_invstd, dgamma, dbeta, ws, H, W, C, S, relu, N / groups);
+        CTGAN_CHECK_LAUNCH("bn_bwd_sums");
+        CTGAN_LAUNCH((bn_bwd_apply_fused_bf16_kernel<0>), dim3(ceil_div(HW, rpc), N), 256, 0, st, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x,
+                     gamma, beta, labels, save_mean, save_invstd, (const float*)ws, (__nv_bfloat16*)dx, H, W, C, relu, N / groups, rpc, inv_Rg);
+    }
+    CTGAN_CHECK_LAUNCH("bn_bwd_apply_fused");
     return 0;
 }
 

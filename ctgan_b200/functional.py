@@ -116,20 +116,91 @@ def _dense_like(g, ref_dim4):
 
 
 # ------------------------------------------------------------------------- conv family
+class S2DAct:
+    """An activation [N, C, H, W] (H, W even) held in the SPACE-TO-DEPTH layout [N, 4C, H/2, W/2] of the stride-2 layer
+    that consumes it: written that way by the producing conv's fused epilogue (ConvF act=..., out_s2d), read directly as
+    the 3x3 tensor-core conv's input -- no layout kernel in between."""
+
+    def __init__(self, t, C, H, W):
+        self.t, self.C, self.H, self.W = t, C, H, W
+
+    @property
+    def shape(self):
+        return (self.t.shape[0], self.C, self.H, self.W)
+
+    def dim(self):
+        return 4
+
+    @property
+    def dtype(self):
+        return self.t.dtype
+
+
+def _plain_geom(N, H, W, C):
+    """Geometry record for the layout kernels (space_to_depth / depth_to_space read N, H, W, Cin)."""
+    return K.ConvGeom(N, H, W, C, H, W, C, 1, 1, 1, 0, 0)
+
+
+class D2SMul(Function):
+    """x = depth_to_space(xs * m), m a constant multiplier stored in the space-to-depth layout: the backward of an
+    activation + dropout whose result a fused conv epilogue wrote in that layout (one kernel)."""
+
+    @staticmethod
+    def forward(ctx, xs, m, geom):
+        ctx.m, ctx.geom = m, geom
+        return K.depth_to_space(xs, geom, mul=m)
+
+    @staticmethod
+    def backward(ctx, c):
+        return S2DMul.apply(_dense_like(c, True), ctx.m, ctx.geom), None, None
+
+
+class S2DMul(Function):
+    """xs = space_to_depth(x) * m: the adjoint of D2SMul (the gradient penalty's double backward)."""
+
+    @staticmethod
+    def forward(ctx, x, m, geom):
+        ctx.m, ctx.geom = m, geom
+        return K.space_to_depth(x, geom, mul=m)
+
+    @staticmethod
+    def backward(ctx, c):
+        return D2SMul.apply(_dense_like(c, True), ctx.m, ctx.geom), None, None
+
+
 class ConvF(Function):
     @staticmethod
     def forward(ctx, x, w, b, g, out_dtype, col=None, residual=None, relu=False, in_relu=False, relu_bwd_fused=False,
-                res_up2=False):
+                res_up2=False, act=None, x_s2d=False):
         # res_up2: residual has half the output resolution and is added nearest-neighbour upsampled
         ctx.res_up2 = res_up2
         # in_relu: x is the output of a ReLU whose backward this conv applies in its dgrad epilogue (dx zeroed where
         #          x <= 0); the producer is then built with relu_bwd_fused=True and skips its own mask multiply
         ctx.in_relu, ctx.relu_bwd_fused = in_relu, relu_bwd_fused
         ctx.g = g
+        ctx.sm_limit = K.get_sm_limit()
         ctx.save_for_backward(x, w)
         ctx.has_bias = b is not None
         ctx.bias = b
-        ctx.col = col if col is not None else K.thin_col(x, g, 'x')   # im2col of a 3-channel x: built once, reused by wgrad
+        # x_s2d: x IS the space-to-depth image of the conv's input (S2DAct); its gradient is returned in that layout
+        ctx.x_s2d = x_s2d
+        ctx.col = x if x_s2d else (col if col is not None else K.thin_col(x, g, 'x'))   # im2col / s2d of x: built once, reused by wgrad
+        ctx.mult = ctx.out_geom = None
+        if act is not None:
+            # act = (slope, keep, seed, offset, dyn, out_s2d): bias + LeakyReLU + dropout in the conv epilogue; the
+            # multiplier m it stores makes backward and double backward plain products (MulConst / D2SMul)
+            slope, keep, seed, offset, dyn, out_s2d = act
+            y, m = K.conv_fprop_actdrop(x, w, b, g, slope, keep, seed, offset, dyn, out_s2d=out_s2d, w_is_param=_is_param(w),
+                                        col=ctx.col)
+            ctx.mult = m
+            ctx.out_geom = _plain_geom(g.N, g.Ho, g.Wo, g.Cout) if out_s2d else None
+            ctx.relu_out = None
+            if pattern_recorder is not None and slope != 1.0:
+                md = m.detach().float()
+                if out_s2d:
+                    md = K.depth_to_space(m.detach(), ctx.out_geom).float()
+                pattern_recorder(md > 0.5 * (1.0 + slope) / keep)      # m in {0, slope/keep, 1/keep}: kept and v > 0
+            return y
         # residual: y = conv(x) + b + residual in the conv epilogue (the block's skip connection); its gradient is gy
         # relu: the nonlinearity that follows the conv, in the epilogue; its multiplier is [y > 0]
         y = K.conv_fprop(x, w, b, g, out_dtype=out_dtype, w_is_param=_is_param(w), col=ctx.col, residual=residual, relu=relu,
@@ -143,17 +214,22 @@ class ConvF(Function):
     def backward(ctx, gy):
         x, w = ctx.saved_tensors
         gy = _dense_like(gy, True)
+        if ctx.mult is not None:
+            gy = D2SMul.apply(gy, ctx.mult, ctx.out_geom) if ctx.out_geom is not None else MulConst.apply(gy, ctx.mult)
         if ctx.relu_out is not None and not ctx.relu_bwd_fused:
             gy = MulReluMask.apply(gy, ctx.relu_out)
         gx = gw = gb = None
         dycol = K.thin_col(gy, ctx.g, 'dy')          # im2col of a 3-channel gy: shared by dgrad and wgrad
         if ctx.needs_input_grad[0]:
-            gx = ConvD.apply(gy, w, ctx.g, x.dtype, dycol, x.detach() if ctx.in_relu else None)
+            with K.sm_limit(ctx.sm_limit):
+                gx = ConvD.apply(gy, w, ctx.g, x.dtype, dycol, x.detach() if ctx.in_relu else None, ctx.x_s2d)
         if ctx.needs_input_grad[1] and _wants(w):
             if _direct(w):
                 col, g = (ctx.col if ctx.col is not None else dycol), ctx.g
                 _direct_wgrad(x, gy, g, w, col)
             else:
+                if ctx.x_s2d:
+                    raise RuntimeError('ctgan_b200: a conv fed in space-to-depth layout supports in-place filter gradients only')
                 gw = ConvG.apply(x, gy, ctx.g, tuple(w.shape))
         if ctx.has_bias and ctx.needs_input_grad[2] and _wants(ctx.bias):
             b = ctx.bias
@@ -161,22 +237,26 @@ class ConvF(Function):
                 K.on_side(lambda: K.bias_grad(gy.detach(), accumulate_into=b.grad), gy)
             else:
                 gb = K.bias_grad(gy.detach())
-        n_in = len(ctx.needs_input_grad)                 # apply() is called with 5, 6 or 7 arguments
+        n_in = len(ctx.needs_input_grad)                 # apply() is called with 5 .. 13 arguments
         g_res = None
         if n_in > 6 and ctx.needs_input_grad[6]:
             g_res = Pool.apply(gy, 1.0) if ctx.res_up2 else gy       # adjoint of the 2x nearest upsample: 2x2 sums
-        return (gx, gw, gb, None, None, None, g_res, None, None, None, None)[:n_in]
+        return (gx, gw, gb, None, None, None, g_res, None, None, None, None, None, None)[:n_in]
 
 
 class ConvD(Function):
-    """dx = conv^T(gy, w) for the forward geometry g (== Deconv2D forward)."""
+    """dx = conv^T(gy, w) for the forward geometry g (== Deconv2D forward).  out_s2d: dx is produced (and its cotangent
+    arrives) in the space-to-depth layout the conv's input was handed over in."""
 
     @staticmethod
-    def forward(ctx, gy, w, g, out_dtype, col=None, relu_mask=None):
+    def forward(ctx, gy, w, g, out_dtype, col=None, relu_mask=None, out_s2d=False):
         ctx.g = g
+        ctx.sm_limit = K.get_sm_limit()
+        ctx.out_s2d = out_s2d
         ctx.save_for_backward(gy, w)
         ctx.relu_mask = relu_mask                     # constant: dx = conv^T(gy, w) * [relu_mask > 0]
-        return K.conv_dgrad(gy, w, g, out_dtype=out_dtype, w_is_param=_is_param(w), col=col, relu_mask=relu_mask)
+        return K.conv_dgrad(gy, w, g, out_dtype=out_dtype, w_is_param=_is_param(w), col=col, relu_mask=relu_mask,
+                            out_s2d=out_s2d)
 
     @staticmethod
     def backward(ctx, c):
@@ -185,15 +265,21 @@ class ConvD(Function):
         if ctx.relu_mask is not None:
             c = MulReluMask.apply(c, ctx.relu_mask)
         ggy = gw = None
-        ccol = K.thin_col(c, ctx.g, 'x')             # im2col of a 3-channel c: shared by fprop and wgrad
+        ccol = c if ctx.out_s2d else K.thin_col(c, ctx.g, 'x')   # im2col / s2d of c: shared by fprop and wgrad
         if ctx.needs_input_grad[0]:
-            ggy = ConvF.apply(c, w, None, ctx.g, gy.dtype, ccol)
+            with K.sm_limit(ctx.sm_limit):
+                if ctx.out_s2d:
+                    ggy = ConvF.apply(c, w, None, ctx.g, gy.dtype, None, None, False, False, False, False, None, True)
+                else:
+                    ggy = ConvF.apply(c, w, None, ctx.g, gy.dtype, ccol)
         if ctx.needs_input_grad[1] and _wants(w):
             if _direct(w):
                 _direct_wgrad(c, gy, ctx.g, w, ccol)
             else:
+                if ctx.out_s2d:
+                    raise RuntimeError('ctgan_b200: a conv fed in space-to-depth layout supports in-place filter gradients only')
                 gw = ConvG.apply(c, gy, ctx.g, tuple(w.shape))
-        return (ggy, gw, None, None, None, None)[:len(ctx.needs_input_grad)]
+        return (ggy, gw, None, None, None, None, None)[:len(ctx.needs_input_grad)]
 
 
 class ConvG(Function):
@@ -228,6 +314,12 @@ def ensure_nhwc(x):
 def conv2d(x, w, b, k, stride, out_dtype=None, residual=None, relu=False, in_relu=False, relu_bwd_fused=False,
            res_up2=False):
     """tf.nn.conv2d(SAME) + bias_add on a logical-NCHW activation (+ an optional residual added in the epilogue)."""
+    if isinstance(x, S2DAct):
+        N, Cin, H, W = x.shape
+        g = K.same_geom(N, H, W, Cin, w.shape[-1], k, stride)
+        if residual is not None or relu or in_relu:
+            raise RuntimeError('ctgan_b200: a space-to-depth input supports the plain conv only')
+        return ConvF.apply(x.t, w, b, g, out_dtype or x.dtype, None, None, False, False, False, False, None, True)
     N, H, W, Cin = K.nhwc_dims(x)
     g = K.same_geom(N, H, W, Cin, w.shape[-1], k, stride)
     if residual is not None:
@@ -239,6 +331,33 @@ def conv2d(x, w, b, k, stride, out_dtype=None, residual=None, relu=False, in_rel
     if relu or in_relu:
         return ConvF.apply(x, w, b, g, out_dtype or x.dtype, None, None, relu, in_relu, relu_bwd_fused)
     return ConvF.apply(x, w, b, g, out_dtype or x.dtype)
+
+
+def conv2d_act_dropout(x, w, b, k, stride, slope, keep, rng, next_cout=None, next_k=None):
+    """Conv2D -> LeakyReLU(slope) -> tf.nn.dropout(keep) (TG/CT_gan_cifar.py:84-96): in the conv epilogue when the conv
+    takes a tensor-core route, else as conv + one activation kernel.  rng: the DeviceRandom whose next dropout site this
+    is.  next_cout / next_k: the stride-2 conv that consumes the result -- when that conv takes the space-to-depth route
+    the result is returned as an S2DAct (written by the epilogue in that layout)."""
+    x_s2d = isinstance(x, S2DAct)
+    xt = x.t if x_s2d else x
+    if x_s2d:
+        N, Cin, H, W = x.shape
+    else:
+        N, H, W, Cin = K.nhwc_dims(x)
+    Cout = w.shape[-1]
+    g = K.same_geom(N, H, W, Cin, Cout, k, stride)
+    like = torch.empty((N, Cout, g.Ho, g.Wo), dtype=xt.dtype, device='meta').contiguous(memory_format=CL)
+    args = rng.dropout_args(like) if keep < 1.0 else dict(seed=0, offset=0, dyn=None)
+    if 'u' not in args and K.conv_actdrop_route(xt, g) is not None:
+        out_s2d = False
+        if next_cout is not None and g.Ho % 2 == 0 and g.Wo % 2 == 0:
+            gn = K.same_geom(N, g.Ho, g.Wo, Cout, next_cout, next_k, 2)
+            out_s2d = K.s2d_geom(gn, xt) is not None
+        act = (slope, keep, args['seed'], args['offset'], args['dyn'], out_s2d)
+        y = ConvF.apply(xt, w, b, g, xt.dtype, None, None, False, False, False, False, act, x_s2d)
+        return S2DAct(y, Cout, g.Ho, g.Wo) if out_s2d else y
+    y = conv2d(x, w, b, k, stride)
+    return ActDropout.apply(y, slope, keep, args.get('u'), args.get('seed', 0), args.get('offset', 0), args.get('dyn'))
 
 
 def conv2d_transpose2(x, w, b):
@@ -633,31 +752,43 @@ def cast(x, dtype):
 
 # ------------------------------------------------------------------------- generator-only ops
 class BatchNormReLU(Function):
-    """Training-mode BN (biased var, eps) with optional per-label gamma/beta and fused ReLU."""
+    """Training-mode BN (biased var, eps) with optional per-label gamma/beta, fused ReLU and (up2) the nearest-neighbour
+    2x upsampling of the UpsampleConv that follows it written directly by the normalisation kernel."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, labels, eps, relu, groups=1):
-        y, mean, invstd = K.bn_fwd(x, gamma, beta, labels, eps, relu, groups)
-        ctx.groups = groups
+    def forward(ctx, x, gamma, beta, labels, eps, relu, groups=1, up2=False):
+        y, mean, invstd = K.bn_fwd(x, gamma, beta, labels, eps, relu, groups, up2)
+        ctx.groups, ctx.up2 = groups, up2
         if pattern_recorder is not None and relu:
-            pattern_recorder(y.detach() > 0)
+            yd = y.detach()
+            pattern_recorder((yd[:, :, ::2, ::2] if up2 else yd) > 0)
         ctx.relu = relu
         ctx.labels = labels
-        ctx.save_for_backward(x, y, gamma, mean, invstd)
+        ctx.params = (gamma, beta)
+        # the two-kernel path recomputes the ReLU pattern from x: y need not be kept alive for the backward
+        keep_y = y if (relu and not K.bn_fused_ok(x, groups)) else None
+        ctx.save_for_backward(x, keep_y, gamma, beta, mean, invstd)
         return y
 
     @staticmethod
     @once_differentiable
     def backward(ctx, gy):
-        x, y, gamma, mean, invstd = ctx.saved_tensors
+        x, y, gamma, beta, mean, invstd = ctx.saved_tensors
         gy = _dense_like(gy, True)
-        dx, dgamma, dbeta = K.bn_bwd(gy, x, y, gamma, ctx.labels, mean, invstd, ctx.relu, ctx.groups)
-        return dx, dgamma, dbeta, None, None, None, None
+        pg, pb = ctx.params
+        if ctx.needs_input_grad[1] and ctx.needs_input_grad[2] and _direct(pg) and _direct(pb):
+            # table gradients are added into the flat gradient bucket by the reduction kernel itself
+            dx, _, _ = K.bn_bwd(gy, x, y, gamma, beta, ctx.labels, mean, invstd, ctx.relu, ctx.groups, ctx.up2,
+                                accumulate_into=(pg.grad, pb.grad))
+            return dx, None, None, None, None, None, None, None
+        dx, dgamma, dbeta = K.bn_bwd(gy, x, y, gamma, beta, ctx.labels, mean, invstd, ctx.relu, ctx.groups, ctx.up2)
+        return dx, dgamma, dbeta, None, None, None, None, None
 
 
-def batch_norm(x, gamma, beta, labels=None, eps=1e-5, relu=False, groups=1):
-    """groups > 1: statistics per block of N/groups consecutive samples (one block per reference device split)."""
-    return BatchNormReLU.apply(x, gamma, beta, labels, eps, relu, groups)
+def batch_norm(x, gamma, beta, labels=None, eps=1e-5, relu=False, groups=1, up2=False):
+    """groups > 1: statistics per block of N/groups consecutive samples (one block per reference device split).
+    up2: returns the result nearest-neighbour upsampled 2x."""
+    return BatchNormReLU.apply(x, gamma, beta, labels, eps, relu, groups, up2)
 
 
 class LayerNorm(Function):

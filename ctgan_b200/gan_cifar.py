@@ -38,6 +38,12 @@ def _lrelu_dropout(output, keep):
     return F.leaky_relu_dropout(output, 0.2, keep, **RNG.dropout_args(output))
 
 
+def _conv_lrelu_dropout(name, input_dim, output_dim, inputs, keep, next_cout=None):
+    """lib.ops.conv2d.Conv2D(name, ., ., 5, ., stride=2) -> LeakyReLU -> tf.nn.dropout(keep_prob=keep)"""
+    return lib.ops.conv2d.Conv2D(name, input_dim, output_dim, 5, inputs, stride=2,
+                                 act_dropout=dict(slope=0.2, keep=keep, rng=RNG, next_cout=next_cout, next_k=5))
+
+
 def Generator(n_samples, noise=None):
     if noise is None:
         noise = RNG.normal('z', (n_samples, 128))
@@ -60,12 +66,11 @@ def Generator(n_samples, noise=None):
 def Discriminator(inputs):
     output = F.to_nhwc(inputs, 3, 32, 32, ACT_DTYPE)
 
-    output = lib.ops.conv2d.Conv2D('Discriminator.1', 3, DIM, 5, output, stride=2)
-    output = _lrelu_dropout(output, 0.50)
-    output = lib.ops.conv2d.Conv2D('Discriminator.2', DIM, 2 * DIM, 5, output, stride=2)
-    output = _lrelu_dropout(output, 0.50)
-    output = lib.ops.conv2d.Conv2D('Discriminator.3', 2 * DIM, 4 * DIM, 5, output, stride=2)
-    output = _lrelu_dropout(output, 0.50)
+    # Conv2D -> LeakyReLU -> dropout (:84-96) as ONE kernel per layer: bias + LeakyReLU + Philox dropout in the conv
+    # epilogue, the result written directly in the space-to-depth layout the next stride-2 layer reads
+    output = _conv_lrelu_dropout('Discriminator.1', 3, DIM, output, 0.50, next_cout=2 * DIM)
+    output = _conv_lrelu_dropout('Discriminator.2', DIM, 2 * DIM, output, 0.50, next_cout=4 * DIM)
+    output = _conv_lrelu_dropout('Discriminator.3', 2 * DIM, 4 * DIM, output, 0.50)
     output2 = F.to_flat_nchw(output)  # corresponding to D_  (tf.reshape(output, [-1, 4*4*4*DIM]))
     output = lib.ops.linear.Linear('Discriminator.Output', 4 * 4 * 4 * DIM, 1, output2, out_dtype=torch.float32)
     return output.reshape(-1), output2

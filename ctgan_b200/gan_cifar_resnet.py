@@ -55,8 +55,9 @@ def nonlinearity(x):
     return F.relu(x)
 
 
-def Normalize(name, inputs, labels=None, relu=False):
-    """:70-87.  `relu=True` fuses the nonlinearity() that follows every Normalize call."""
+def Normalize(name, inputs, labels=None, relu=False, up2=False):
+    """:70-87.  `relu=True` fuses the nonlinearity() that follows every Normalize call; `up2=True` also the nearest-neighbour
+    2x upsampling of the UpsampleConv that consumes it (generator blocks, :132-137 with :100-107)."""
     if not CONDITIONAL:
         labels = None
     if CONDITIONAL and ACGAN and ('Discriminator' in name):
@@ -66,11 +67,12 @@ def Normalize(name, inputs, labels=None, relu=False):
     elif ('Generator' in name) and NORMALIZATION_G:
         if labels is not None:
             return lib.ops.cond_batchnorm.Batchnorm(name, [0, 2, 3], inputs, labels=labels, n_labels=10, relu=relu,
-                                                    groups=BN_GROUPS)
+                                                    groups=BN_GROUPS, up2=up2)
         else:
-            return lib.ops.batchnorm.Batchnorm(name, [0, 2, 3], inputs, fused=True, relu=relu, groups=BN_GROUPS)
+            return lib.ops.batchnorm.Batchnorm(name, [0, 2, 3], inputs, fused=True, relu=relu, groups=BN_GROUPS, up2=up2)
     else:
-        return nonlinearity(inputs) if relu else inputs
+        output = nonlinearity(inputs) if relu else inputs
+        return F.upsample_2x(output) if up2 else output
 
 
 COMMUTE_1X1 = True   # evaluate 1x1 shortcut convs on the low-resolution side of their resampling (same function)
@@ -80,6 +82,7 @@ FUSE_D_ACT = True     # critic: relu in conv_1's epilogue, dropout -> (skip, rel
 # extra strided mask loads in the (exposed) epilogue of the small layers cost what the saved multiply kernels gain
 FUSE_RELU_BWD = False
 FUSE_POOL_FORK = True   # critic blocks 1, 2: mean pool + skip add + (dropout) + next relu as one kernel (functional.PoolAddFork)
+FUSE_BN_UP = True       # generator blocks: Normalize + relu writes its output already upsampled (the UpsampleConv input)
 
 
 def ConvMeanPool(name, input_dim, output_dim, filter_size, inputs, he_init=True, biases=True, in_relu=False):
@@ -168,8 +171,13 @@ def ResidualBlock(name, input_dim, output_dim, filter_size, inputs, resample=Non
         return F.add(shortcut, output)
     else:
         output = inputs
-        output = Normalize(name + '.N1', output, labels=labels, relu=True)
-        output = conv_1(name + '.Conv1', filter_size=filter_size, inputs=output)
+        if resample == 'up' and FUSE_BN_UP:
+            # UpsampleConv(N1(x)): the normalisation kernel writes the 2x nearest-neighbour upsampled activation itself
+            output = Normalize(name + '.N1', output, labels=labels, relu=True, up2=True)
+            output = lib.ops.conv2d.Conv2D(name + '.Conv1', input_dim, output_dim, filter_size, output)
+        else:
+            output = Normalize(name + '.N1', output, labels=labels, relu=True)
+            output = conv_1(name + '.Conv1', filter_size=filter_size, inputs=output)
         output = Normalize(name + '.N2', output, labels=labels, relu=True)
     if resample != 'down' and FUSE_SKIP_ADD:
         # conv_2 is a plain Conv2D at the shortcut's resolution: the skip connection is added in its epilogue
@@ -349,7 +357,8 @@ class Trainer:
         stacked_labels = torch.cat([all_real_labels, all_real_labels, all_real_labels], dim=0)
         RNG.scope_parts([('drop.p1', 2 * B), ('drop.p2', B)])
         RNG.begin_stack([2 * B, B])
-        disc_all, disc_all_2, disc_all_acgan = Discriminator(stacked, stacked_labels, 0.8, 0.5, 0.5)
+        with K.sm_limit(K.config.stacked_sm_limit if fork is not None else 0):
+            disc_all, disc_all_2, disc_all_acgan = Discriminator(stacked, stacked_labels, 0.8, 0.5, 0.5)
         RNG.end_stack()
         metrics = {}
         if with_metrics and CONDITIONAL and ACGAN:

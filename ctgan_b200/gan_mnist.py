@@ -35,6 +35,12 @@ def _lrelu_dropout(output, keep):
     return F.leaky_relu_dropout(output, 0.2, keep, **RNG.dropout_args(output))
 
 
+def _conv_lrelu_dropout(name, input_dim, output_dim, inputs, keep, next_cout=None):
+    """lib.ops.conv2d.Conv2D(name, ., ., 5, ., stride=2) -> LeakyReLU -> tf.nn.dropout(keep_prob=keep)"""
+    return lib.ops.conv2d.Conv2D(name, input_dim, output_dim, 5, inputs, stride=2,
+                                 act_dropout=dict(slope=0.2, keep=keep, rng=RNG, next_cout=next_cout, next_k=5))
+
+
 def Generator(n_samples, noise=None):
     if noise is None:
         noise = RNG.normal('z', (n_samples, 128))
@@ -58,12 +64,10 @@ def Generator(n_samples, noise=None):
 
 def Discriminator(inputs):
     output = F.to_nhwc(inputs, 1, 28, 28, ACT_DTYPE)
-    output = lib.ops.conv2d.Conv2D('Discriminator.1', 1, DIM, 5, output, stride=2)
-    output = _lrelu_dropout(output, 0.50)  # adding dropout after activators
-    output = lib.ops.conv2d.Conv2D('Discriminator.2', DIM, 2 * DIM, 5, output, stride=2)
-    output = _lrelu_dropout(output, 0.50)
-    output = lib.ops.conv2d.Conv2D('Discriminator.3', 2 * DIM, 4 * DIM, 5, output, stride=2)
-    output = _lrelu_dropout(output, 0.50)
+    # Conv2D -> LeakyReLU -> dropout (:92-104), fused into the conv epilogue where the conv runs on the tensor cores
+    output = _conv_lrelu_dropout('Discriminator.1', 1, DIM, output, 0.50, next_cout=2 * DIM)  # adding dropout after activators
+    output = _conv_lrelu_dropout('Discriminator.2', DIM, 2 * DIM, output, 0.50, next_cout=4 * DIM)
+    output = _conv_lrelu_dropout('Discriminator.3', 2 * DIM, 4 * DIM, output, 0.50)
     output2 = F.to_flat_nchw(output)  # D_
     output = lib.ops.linear.Linear('Discriminator.Output', 4 * 4 * 4 * DIM, 1, output2, out_dtype=torch.float32)  # D
     return output.reshape(-1), output2

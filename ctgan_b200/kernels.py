@@ -27,6 +27,9 @@ class Config:
     branch_streams = True    # run independent sub-graphs of a step (GP pass vs stacked pass) as stream branches
     branch_priority = -1     # CUDA stream priority of the branch stream (lower = higher priority)
     tc_min_rows = 1          # (tunable) minimum GEMM rows to prefer the tensor-core path
+    use_bn_fused = True      # BF16 batch norm as two kernels per direction (sums with red.global + apply)
+    stacked_sm_limit = 0     # SM budget of the stacked critic pass while the gradient-penalty branch runs beside it (0 = all)
+    fuse_act_dropout = True  # Conv2D -> LeakyReLU -> dropout of the DCGAN critics in the tcgen05 conv epilogue (Philox in registers)
     defer_wgrad = True       # queue the final backward's tensor-core filter gradients and run them as ONE launch at the join
 
 
@@ -126,6 +129,34 @@ def join_side():
         for dev in {d for d, _ in _side_pending}:
             torch.cuda.current_stream(dev).wait_stream(_side_streams[dev])
         _side_pending.clear()
+
+
+# SM budget of the persistent tensor-core launches issued inside a `with sm_limit(n)` block (0 = all SMs).  Autograd
+# nodes remember the budget of their forward (functional.ConvF / ConvD) and re-apply it in their backward.
+_sm_limit = 0
+
+
+def get_sm_limit():
+    return _sm_limit
+
+
+class sm_limit:
+    def __init__(self, n):
+        self.n = int(n or 0)
+
+    def __enter__(self):
+        global _sm_limit
+        self.prev, _sm_limit = _sm_limit, self.n
+        if self.n != self.prev:
+            _lib.lib.ctgan_set_sm_limit(self.n)
+        return self
+
+    def __exit__(self, *exc):
+        global _sm_limit
+        if self.prev != _sm_limit:
+            _lib.lib.ctgan_set_sm_limit(self.prev)
+        _sm_limit = self.prev
+        return False
 
 
 # Independent sub-graphs of one step (the gradient-penalty pass vs the stacked critic pass) as two stream branches.
@@ -386,19 +417,28 @@ def s2d_geom(g, t=None):
     return ConvGeom(g.N, Hs, Ws, 4 * g.Cin, Hs, Ws, g.Cout, 3, 3, 1, 1, 1)
 
 
-def space_to_depth(x, g):
-    """x [N,Cin,H,W] -> xs [N,4*Cin,ceil(H/2),ceil(W/2)], channel (dy*2+dx)*Cin + c <- x[.., 2i+dy, 2j+dx] (zero outside)."""
+def space_to_depth(x, g, mul=None):
+    """x [N,Cin,H,W] -> xs [N,4*Cin,ceil(H/2),ceil(W/2)], channel (dy*2+dx)*Cin + c <- x[.., 2i+dy, 2j+dx] (zero outside).
+    mul: a multiplier in the layout of xs applied on the way (xs = space_to_depth(x) * mul)."""
     require_nhwc(x, 'x')
     xs = empty_act((g.N, 4 * g.Cin, (g.H + 1) // 2, (g.W + 1) // 2), x.dtype, x.device)
-    call('ctgan_space_to_depth', _p(x), _p(xs), g.N, g.H, g.W, g.Cin, _dt(x), _stream())
+    if mul is None:
+        call('ctgan_space_to_depth', _p(x), _p(xs), g.N, g.H, g.W, g.Cin, _dt(x), _stream())
+    else:
+        require_nhwc(mul, 'mul'); _same_layout(mul, xs)
+        call('ctgan_space_to_depth_mul', _p(x), _p(mul), _p(xs), g.N, g.H, g.W, g.Cin, _dt(x), _stream())
     return xs
 
 
-def depth_to_space(xs, g):
-    """Inverse of space_to_depth, cropped to the [N,Cin,H,W] of g."""
+def depth_to_space(xs, g, mul=None):
+    """Inverse of space_to_depth, cropped to the [N,Cin,H,W] of g.  mul (layout of xs): x = depth_to_space(xs * mul)."""
     require_nhwc(xs, 'xs')
     x = empty_act((g.N, g.Cin, g.H, g.W), xs.dtype, xs.device)
-    call('ctgan_depth_to_space', _p(xs), _p(x), g.N, g.H, g.W, g.Cin, _dt(xs), _stream())
+    if mul is None:
+        call('ctgan_depth_to_space', _p(xs), _p(x), g.N, g.H, g.W, g.Cin, _dt(xs), _stream())
+    else:
+        require_nhwc(mul, 'mul'); _same_layout(mul, xs)
+        call('ctgan_depth_to_space_mul', _p(xs), _p(mul), _p(x), g.N, g.H, g.W, g.Cin, _dt(xs), _stream())
     return x
 
 
@@ -539,9 +579,55 @@ def conv_fprop(x, w, bias, g, relu=False, residual=None, out_dtype=None, w_is_pa
     return y
 
 
-def conv_dgrad(dy, w, g, out_dtype=None, w_is_param=False, col=None, relu_mask=None):
+def conv_actdrop_route(x, g):
+    """The tensor-core route whose epilogue can apply bias + LeakyReLU + dropout for the conv g on activation x
+    ('tc' | 's2d' | 'padk'), or None (then conv_fprop + act_dropout run as two kernels)."""
+    if not (config.use_tc and config.fuse_act_dropout and tc_available() and x.is_cuda and x.dtype == torch.bfloat16):
+        return None
+    if g.Cout % 128 or x.dim() != 4:
+        return None
+    if _tc_geom_ok(g):
+        return 'tc'
+    if s2d_geom(g, x) is not None:
+        return 's2d'
+    if thin_s2_ok(g, x):
+        return 'padk'
+    return None
+
+
+def conv_fprop_actdrop(x, w, bias, g, slope, keep, seed, offset, dyn=None, out_s2d=False, w_is_param=False, col=None):
+    """(y, m): y = v * m with v = conv(x, w) + bias and m = (v > 0 ? 1 : slope) * floor(keep + u) / keep, both from the
+    conv epilogue (ctgan_conv_fprop_tc_actdrop).  out_s2d: y and m come in the space-to-depth layout
+    [N, 4*Cout, Ho/2, Wo/2] of a following stride-2 layer.  Call only when conv_actdrop_route(x, g) is not None."""
+    require_nhwc(x, 'x')
+    _check_filter(w, g)
+    route = conv_actdrop_route(x, g)
+    if route is None:
+        raise RuntimeError('ctgan_b200: conv_fprop_actdrop needs a tensor-core route (see conv_actdrop_route)')
+    shape = (g.N, 4 * g.Cout, g.Ho // 2, g.Wo // 2) if out_s2d else (g.N, g.Cout, g.Ho, g.Wo)
+    if out_s2d and (g.Ho % 2 or g.Wo % 2):
+        raise RuntimeError('ctgan_b200: space-to-depth output needs even Ho, Wo')
+    y, m = empty_act(shape, torch.bfloat16, x.device), empty_act(shape, torch.bfloat16, x.device)
+    if route == 'tc':
+        src, wp, gk = x, pack_filter(w, 0, cacheable=w_is_param), g
+    elif route == 's2d':
+        g3 = s2d_geom(g, x)
+        src = col if (col is not None and tuple(col.shape) == (g3.N, g3.Cin, g3.H, g3.W)) else space_to_depth(x, g)
+        wp, gk = pack_filter_s2d(w, g, 0, cacheable=w_is_param), g3
+    else:
+        src = col if (col is not None and tuple(col.shape) == (g.N, 128, g.Ho, g.Wo)) else im2col_strided(x, g)
+        wp, gk = pack_filter_padk(w, g, 0, cacheable=w_is_param), _out_pixels_geom(g, 128, g.Cout)
+    d = _desc(gk, BF16, BF16)
+    call('ctgan_conv_fprop_tc_actdrop', ctypes.byref(d), _p(src), _p(wp), _p(bias), _p(y), _p(m), float(slope), float(keep),
+         int(seed), int(offset), _p(dyn), int(bool(out_s2d)), _stream())
+    return y, m
+
+
+def conv_dgrad(dy, w, g, out_dtype=None, w_is_param=False, col=None, relu_mask=None, out_s2d=False):
     """dx = conv^T(dy, w) with the geometry of the FORWARD conv g.  Also Deconv2D forward.
-    relu_mask: a tensor of dx's shape (the conv's input, itself a ReLU output): dx is zeroed where it is <= 0."""
+    relu_mask: a tensor of dx's shape (the conv's input, itself a ReLU output): dx is zeroed where it is <= 0.
+    out_s2d (space-to-depth route only): return dx in the space-to-depth layout [N, 4*Cin, H/2, W/2] -- the layout the
+    conv's input was handed over in -- instead of converting it back."""
     require_nhwc(dy, 'dy')
     if relu_mask is not None:
         require_nhwc(relu_mask, 'relu_mask')
@@ -562,7 +648,9 @@ def conv_dgrad(dy, w, g, out_dtype=None, w_is_param=False, col=None, relu_mask=N
         gt = ConvGeom(g3.N, g3.H, g3.W, g3.Cout, g3.H, g3.W, g3.Cin, 3, 3, 1, 1, 1)
         dxs = empty_act((g3.N, g3.Cin, g3.H, g3.W), torch.bfloat16, dy.device)
         _fprop_tc_packed(dy, pack_filter_s2d(w, g, 1, cacheable=w_is_param), None, None, None, dxs, gt, 0)
-        return depth_to_space(dxs, g)
+        return dxs if out_s2d else depth_to_space(dxs, g)
+    if out_s2d:
+        raise RuntimeError('ctgan_b200: conv_dgrad(out_s2d=True) needs the space-to-depth route')
     if xdt == BF16 and ydt == BF16 and thin_s2_ok(g, dy):     # dcol = dy x W128^T, dx = col2im_strided(dcol)
         dcol = empty_act((g.N, 128, g.Ho, g.Wo), torch.bfloat16, dy.device)
         _fprop_tc_packed(dy, pack_filter_padk(w, g, 1, cacheable=w_is_param), None, None, None, dcol,
@@ -941,28 +1029,66 @@ def interpolate(real, fake, alpha):
 
 
 # --------------------------------------------------------------------------- batch norm
-def bn_fwd(x, gamma, beta, labels, eps, relu, groups=1):
+def bn_fused_ok(x, groups=1):
+    """True when the two-kernel BF16 batch-norm path (ctgan_bn_fwd_fused / ctgan_bn_bwd_fused) takes this activation."""
+    if not (x.is_cuda and x.dtype == torch.bfloat16 and config.use_bn_fused):
+        return False
+    N, H, W, C = nhwc_dims(x)
+    return bool(_lib.lib.ctgan_bn_fused_ok(N, H, W, C, groups, BF16)) and x.data_ptr() % 16 == 0
+
+
+def bn_fwd(x, gamma, beta, labels, eps, relu, groups=1, up2=False):
+    """Training-mode batch norm (+ per-label gamma/beta rows, + ReLU).  up2: the output is written nearest-neighbour
+    upsampled 2x ([N, C, 2H, 2W]) -- the UpsampleConv that follows Normalize + relu in the generator blocks."""
     require_nhwc(x)
     N, H, W, C = nhwc_dims(x)
-    y = torch.empty_like(x)
     mean = torch.empty((groups, C), dtype=torch.float32, device=x.device)
     invstd = torch.empty((groups, C), dtype=torch.float32, device=x.device)
+    if bn_fused_ok(x, groups):
+        y = empty_act((N, C, 2 * H, 2 * W), x.dtype, x.device) if up2 else torch.empty_like(x)
+        ws = torch.empty(2 * groups * C, dtype=torch.float32, device=x.device)
+        flags = (_lib.BN_RELU if relu else 0) | (_lib.BN_UP2 if up2 else 0)
+        call('ctgan_bn_fwd_fused', _p(x), _p(gamma), _p(beta), _p(labels), _p(y), _p(mean), _p(invstd), _p(ws),
+             N, H, W, C, float(eps), flags, int(groups), _stream())
+        return y, mean, invstd
+    y = torch.empty_like(x)
     ws = torch.empty(_lib.lib.ctgan_bn_workspace_floats(N, H * W, C, groups), dtype=torch.float32, device=x.device)
     call('ctgan_bn_fwd', _p(x), _p(gamma), _p(beta), _p(labels), _p(y), _p(mean), _p(invstd), _p(ws),
          N, H * W, C, float(eps), int(relu), int(groups), _dt(x), _stream())
+    if up2:
+        y = upsample2x(y, 1.0)
     return y, mean, invstd
 
 
-def bn_bwd(dy, x, y, gamma, labels, mean, invstd, relu, groups=1):
+def bn_bwd(dy, x, y, gamma, beta, labels, mean, invstd, relu, groups=1, up2=False, accumulate_into=None):
+    """Returns (dx, dgamma, dbeta).  y: the forward output (only the three-kernel path reads it: the ReLU pattern; with
+    up2 it is the upsampled output).  up2: dy has the upsampled shape.  accumulate_into=(dgamma, dbeta): float
+    accumulators (slices of the flat gradient bucket) the table gradients are ADDED to; they are returned."""
     require_nhwc(dy); require_nhwc(x)
     N, H, W, C = nhwc_dims(x)
     n_labels = gamma.numel() // C
     dx = torch.empty_like(x)
+    if bn_fused_ok(x, groups) and dy.data_ptr() % 16 == 0:
+        if accumulate_into is not None:
+            dgamma, dbeta = accumulate_into
+        else:
+            dgamma, dbeta = torch.empty_like(gamma), torch.empty_like(gamma)
+        ws = torch.empty(2 * groups * C, dtype=torch.float32, device=x.device)
+        flags = (_lib.BN_RELU if relu else 0) | (_lib.BN_UP2 if up2 else 0) | (_lib.BN_ACCUM if accumulate_into is not None else 0)
+        call('ctgan_bn_bwd_fused', _p(dy), _p(x), _p(gamma), _p(beta), _p(labels), _p(mean), _p(invstd), _p(dx), _p(dgamma),
+             _p(dbeta), _p(ws), N, H, W, C, n_labels, flags, int(groups), _stream())
+        return dx, dgamma, dbeta
+    if up2:
+        dy = pool2x2(dy, 1.0)                       # adjoint of the nearest-neighbour upsample: 2x2 sums
+        y = y[:, :, ::2, ::2].contiguous(memory_format=CL) if (relu and y is not None) else y
     dgamma = torch.empty_like(gamma)
     dbeta = torch.empty_like(gamma)
     ws = torch.empty(_lib.lib.ctgan_bn_workspace_floats(N, H * W, C, groups), dtype=torch.float32, device=x.device)
     call('ctgan_bn_bwd', _p(dy), _p(x), _p(y), _p(gamma), _p(labels), _p(mean), _p(invstd), _p(dx), _p(dgamma),
          _p(dbeta), _p(ws), N, H * W, C, n_labels, int(relu), int(groups), _dt(x), _stream())
+    if accumulate_into is not None:
+        accumulate_into[0].add_(dgamma); accumulate_into[1].add_(dbeta)
+        return dx, accumulate_into[0], accumulate_into[1]
     return dx, dgamma, dbeta
 
 

@@ -10,7 +10,7 @@ from ... import functional as F
 
 
 def Batchnorm(name, axes, inputs, is_training=None, stats_iter=None, update_moving_stats=True, fused=True,
-              labels=None, n_labels=None, relu=False, groups=1):
+              labels=None, n_labels=None, relu=False, groups=1, up2=False):
     """conditional batchnorm (dumoulin et al 2016) for BCHW conv filtermaps"""
     if axes != [0, 2, 3]:
         raise Exception('unsupported')
@@ -18,4 +18,4 @@ def Batchnorm(name, axes, inputs, is_training=None, stats_iter=None, update_movi
     C = inputs.shape[1]
     offset_m = lib.param(name + '.offset', np.zeros([n_labels, C], dtype='float32'))
     scale_m = lib.param(name + '.scale', np.ones([n_labels, C], dtype='float32'))
-    return F.batch_norm(inputs, scale_m, offset_m, labels, 1e-5, relu, groups)
+    return F.batch_norm(inputs, scale_m, offset_m, labels, 1e-5, relu, groups, up2)

@@ -36,7 +36,7 @@ def _uniform(stdev, size):
 
 def Conv2D(name, input_dim, output_dim, filter_size, inputs, he_init=True, mask_type=None, stride=1,
            weightnorm=None, biases=True, gain=1., residual=None, relu=False, in_relu=False,
-           relu_bwd_fused=False, residual_up2=False):
+           relu_bwd_fused=False, residual_up2=False, act_dropout=None):
     """
     inputs: tensor of shape (batch size, num channels, height, width)
     mask_type: one of None, 'a', 'b'  (PixelCNN masks: unused by the CT-GAN scripts -> unsupported)
@@ -65,7 +65,8 @@ def Conv2D(name, input_dim, output_dim, filter_size, inputs, he_init=True, mask_
     filters = lib.param(name + '.Filters', filter_values)
     _biases = lib.param(name + '.Biases', np.zeros(output_dim, dtype='float32')) if biases else None
 
-    inputs = F.ensure_nhwc(inputs)
+    if not isinstance(inputs, F.S2DAct):
+        inputs = F.ensure_nhwc(inputs)
     if inputs.shape[1] != input_dim:
         raise Exception('Conv2D %s: expected %d input channels, got %d' % (name, input_dim, inputs.shape[1]))
     # residual (extension): a tensor of the output's shape added in the conv epilogue (skip connections)
@@ -73,5 +74,9 @@ def Conv2D(name, input_dim, output_dim, filter_size, inputs, he_init=True, mask_
     # in_relu / relu_bwd_fused (extension): see functional.ConvF -- the ReLU between two convs differentiated inside
     # the second conv's dgrad epilogue
     # residual_up2 (extension): residual at half resolution, added nearest-neighbour upsampled
+    # act_dropout (extension) = dict(slope, keep, rng[, next_cout, next_k]): the LeakyReLU + tf.nn.dropout that follow this
+    # conv in the DCGAN critics (TG/CT_gan_cifar.py:84-96), applied in the conv epilogue (functional.conv2d_act_dropout)
+    if act_dropout is not None:
+        return F.conv2d_act_dropout(inputs, filters, _biases, filter_size, stride, **act_dropout)
     return F.conv2d(inputs, filters, _biases, filter_size, stride, residual=residual, relu=relu, in_relu=in_relu,
                     relu_bwd_fused=relu_bwd_fused, res_up2=residual_up2)

@@ -92,7 +92,9 @@ void ctgan_set_fprop_halo(int on);
 /* 1 (default): kernels are launched with programmatic stream serialization (each begins with griddepcontrol.launch_dependents +
  * griddepcontrol.wait, so launch latency and set-up overlap the predecessor's tail; ordering semantics unchanged); 0: plain launches */
 void ctgan_set_pdl(int on);
-/* test hook: 3 = persistent grouped-stage fprop_tc kernel (default), 2 = persistent per-k-block rings, 1 = one tile per CTA */
+/* scheduling hook: persistent tcgen05 fprop launches use at most n SMs (0 = all): leaves SMs to a concurrent stream branch */
+void ctgan_set_sm_limit(int n);
+/* test hook: 4 = 256-pixel work items where eligible, else 3 (default); 3 = persistent grouped-stage kernel; 1 = one tile per CTA */
 void ctgan_set_fprop_variant(int v);
 /* test/benchmark hook: 2 (default) = 3x3 wgrad CTAs own one filter column and share the x halo box; 1 = per-tap boxes */
 void ctgan_set_wgrad_variant(int v);
@@ -104,6 +106,17 @@ int ctgan_conv_fprop_tc(const ctgan_conv_desc* d, const void* x, const void* wp,
 int ctgan_conv_fprop_tc_masked(const ctgan_conv_desc* d, const void* x, const void* wp, const float* bias /*nullable*/,
                                const void* residual /*nullable*/, const void* relu_mask /*nullable*/, void* y, int flags,
                                void* stream);
+/* Conv2D -> (+bias) -> LeakyReLU(slope) -> tf.nn.dropout(keep) in the conv EPILOGUE (TG/CT_gan_cifar.py:84-96,
+ * TG/CT_gan_mnist.py:92-104; bias_add at TG/tflib/ops/conv2d.py:114-120):
+ *   v = conv(x, wp) + bias;  m = (v > 0 ? 1 : slope) * (keep < 1 ? floor(keep + u) / keep : 1);  y = v * m
+ * u = Philox4x32-10(seed) uniform number offset + *dyn_offset + (NHWC element index of y): the stream ctgan_act_dropout_fwd
+ * draws from, generated in registers.  mult (bf16, layout of y) receives m: the backward and the double backward are
+ * products with m.  out_s2d != 0 (H, W even): y and mult are written in the space-to-depth layout [N, H/2, W/2, 4*Cout],
+ * channel (dy*2+dx)*Cout + c <- pixel (2i+dy, 2j+dx), i.e. directly as the input of the next stride-2 layer's 3x3 conv
+ * (ctgan_space_to_depth not needed).  Cout must be a multiple of 128; slope = 1 gives plain dropout, keep = 1 plain LeakyReLU. */
+int ctgan_conv_fprop_tc_actdrop(const ctgan_conv_desc* d, const void* x, const void* wp, const float* bias /*nullable*/,
+                                void* y, void* mult, float slope, float keep, uint64_t seed, uint64_t offset,
+                                const uint64_t* dyn_offset /*nullable*/, int out_s2d, void* stream);
 /* dw[r,s,c,o] (float HWIO) = sum_pixels x[.., c] * dy[.., o]; split over pixels with
  * fp32 atomics, so dw must hold the value to accumulate onto (zeros for a plain wgrad). */
 int ctgan_conv_wgrad_tc(const ctgan_conv_desc* d, const void* x, const void* dy,
@@ -156,6 +169,11 @@ int ctgan_pack_filters_multi(const float* flat_params, void* packs_bf16, const v
  *   s2d_filter_grad: dw [k][k][Cin][Cout] (+)= the tap entries of dw3 [3][3][4Cin][Cout] (both float HWIO). */
 int ctgan_space_to_depth(const void* x, void* xs, int N, int H, int W, int C, int dtype, void* stream);
 int ctgan_depth_to_space(const void* xs, void* x, int N, int H, int W, int C, int dtype, void* stream);
+/* the same moves with an element-wise multiplier ms stored in the SPACE-TO-DEPTH layout (the multiplier written by
+ * ctgan_conv_fprop_tc_actdrop with out_s2d): x = depth_to_space(xs * ms) is the backward of that fused activation, and
+ * xs = space_to_depth(x) * ms its adjoint (the gradient penalty's double backward) */
+int ctgan_space_to_depth_mul(const void* x, const void* ms, void* xs, int N, int H, int W, int C, int dtype, void* stream);
+int ctgan_depth_to_space_mul(const void* xs, const void* ms, void* x, int N, int H, int W, int C, int dtype, void* stream);
 int ctgan_pack_filter_s2d(const float* w, void* wp_f, void* wp_d, int k, int Cin, int Cout, int pad_t, int pad_l, void* stream);
 int ctgan_s2d_filter_grad(const float* dw3, float* dw, int k, int Cin, int Cout, int pad_t, int pad_l, int accumulate, void* stream);
 
@@ -274,6 +292,24 @@ int ctgan_bn_bwd(const void* dy, const void* x, const void* y, const float* gamm
                  const int32_t* labels, const float* save_mean, const float* save_invstd,
                  void* dx, float* dgamma, float* dbeta, float* ws,
                  int N, int HW, int C, int n_labels, int relu, int groups, int dtype, void* stream);
+
+/* BF16 fast path of the two calls above: TWO kernels per direction (statistics with red.global into ws + apply; the finalize
+ * launches are gone), optional 2x nearest-neighbour upsampling of the output fused in (the tf.concat x4 + depth_to_space of
+ * UpsampleConv, TG/CT_gan_cifar_resnet.py:100-107, which follows Normalize + relu in every generator block :132-137), the
+ * ReLU pattern recomputed from x in the backward (y is not an input), and parameter gradients optionally accumulated in place.
+ * x: [N,H,W,C] bf16.  flags: CTGAN_BN_RELU; CTGAN_BN_UP2 (fwd: y is [N,2H,2W,C]; bwd: dy has that shape and is summed 2x2 on
+ * load); CTGAN_BN_ACCUM (bwd: dgamma / dbeta [n_labels][C] are added to instead of overwritten, e.g. slices of the flat
+ * gradient bucket).  ws: >= 2*groups*C floats.  Eligible (ctgan_bn_fused_ok): BF16, C/8 a power of two <= 256, groups | N. */
+#define CTGAN_BN_RELU  1
+#define CTGAN_BN_UP2   2
+#define CTGAN_BN_ACCUM 4
+int ctgan_bn_fused_ok(int N, int H, int W, int C, int groups, int dtype);
+int ctgan_bn_fwd_fused(const void* x, const float* gamma, const float* beta, const int32_t* labels, void* y,
+                       float* save_mean, float* save_invstd, float* ws, int N, int H, int W, int C, float eps,
+                       int flags, int groups, void* stream);
+int ctgan_bn_bwd_fused(const void* dy, const void* x, const float* gamma, const float* beta, const int32_t* labels,
+                       const float* save_mean, const float* save_invstd, void* dx, float* dgamma, float* dbeta,
+                       float* ws, int N, int H, int W, int C, int n_labels, int flags, int groups, void* stream);
 
 /* ---- layer normalisation over (C,H,W) per sample, per-channel scale / offset (STAGED, SURVEY.md 8(f) N4: the critic's
  * Normalize of TG/CT_gan_64x64.py:87-93; op TG/tflib/ops/layernorm.py:6-21, eps 1e-5).  x, y, v, out: NHWC activations

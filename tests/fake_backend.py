@@ -60,7 +60,7 @@ def conv_fprop(x, w, bias, g, relu=False, residual=None, out_dtype=None, w_is_pa
     return _out(y, out_dtype or x.dtype)
 
 
-def conv_dgrad(dy, w, g, out_dtype=None, w_is_param=False, col=None, relu_mask=None):
+def conv_dgrad(dy, w, g, out_dtype=None, w_is_param=False, col=None, relu_mask=None, out_s2d=False):
     if relu_mask is not None:
         return mul_relu_mask(conv_dgrad(dy, w, g, out_dtype=out_dtype), relu_mask)
     two_d = dy.dim() == 2
@@ -266,7 +266,14 @@ def _bn_fwd1(x, gamma, beta, labels, eps, relu):
     return y, mean, invstd
 
 
-def bn_fwd(x, gamma, beta, labels, eps, relu, groups=1):
+def bn_fused_ok(x, groups=1):
+    return False
+
+
+def bn_fwd(x, gamma, beta, labels, eps, relu, groups=1, up2=False):
+    if up2:
+        y, m, i = bn_fwd(x, gamma, beta, labels, eps, relu, groups)
+        return upsample2x(y, 1.0), m, i
     n = x.shape[0] // groups
     parts = [_bn_fwd1(x[g * n:(g + 1) * n], gamma, beta, None if labels is None else labels[g * n:(g + 1) * n], eps, relu)
              for g in range(groups)]
@@ -274,9 +281,16 @@ def bn_fwd(x, gamma, beta, labels, eps, relu, groups=1):
     return _out(y, x.dtype), torch.stack([p[1] for p in parts]), torch.stack([p[2] for p in parts])
 
 
-def bn_bwd(dy, x, y, gamma, labels, mean, invstd, relu, groups=1):
+def bn_bwd(dy, x, y, gamma, beta, labels, mean, invstd, relu, groups=1, up2=False, accumulate_into=None):
+    if up2:
+        dy = pool2x2(dy, 1.0)
+        y = y[:, :, ::2, ::2] if y is not None else None
+    if accumulate_into is not None:
+        dx, dg, db = bn_bwd(dy, x, y, gamma, beta, labels, mean, invstd, relu, groups)
+        accumulate_into[0].add_(dg); accumulate_into[1].add_(db)
+        return dx, accumulate_into[0], accumulate_into[1]
     n = x.shape[0] // groups
-    outs = [_bn_bwd1(dy[g * n:(g + 1) * n], x[g * n:(g + 1) * n], y[g * n:(g + 1) * n], gamma,
+    outs = [_bn_bwd1(dy[g * n:(g + 1) * n], x[g * n:(g + 1) * n], None if y is None else y[g * n:(g + 1) * n], gamma,
                      None if labels is None else labels[g * n:(g + 1) * n], mean.reshape(groups, -1)[g],
                      invstd.reshape(groups, -1)[g], relu) for g in range(groups)]
     dx = torch.cat([o[0] for o in outs], 0)
@@ -455,7 +469,7 @@ def invalidate_weight_cache(ptrs=None):
 
 _NAMES = ['conv_fprop', 'conv_dgrad', 'conv_wgrad', 'bias_grad', 'bias_add', 'add', 'mul', 'scale', 'cast',
           'act_dropout', 'fork_dropout_relu', 'mask_sum2', 'mask_fork2', 'mul_relu_mask', 'pool_add_fork', 'mask_sum2_up', 'unary_fwd', 'unary_bwd', 'pool2x2', 'upsample2x', 'spatial_sum', 'spatial_bcast',
-          'nchw_to_nhwc', 'nhwc_to_nchw', 'crop', 'crop_bwd', 'prep_real', 'interpolate', 'bn_fwd', 'bn_bwd',
+          'nchw_to_nhwc', 'nhwc_to_nchw', 'crop', 'crop_bwd', 'prep_real', 'interpolate', 'bn_fwd', 'bn_bwd', 'bn_fused_ok',
           'ct_gp_loss_fwd', 'ct_gp_loss_bwd', 'mean_fwd', 'mean_bwd', 'softmax_ce_fwd', 'softmax_ce_bwd',
           'ln_fwd', 'ln_core', 'ln_param_grad', 'ln_bwd2_x',
           'adam_step', 'philox_uniform', 'philox_normal', 'philox_labels', 'counter_add', 'invalidate_weight_cache']

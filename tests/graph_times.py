@@ -14,6 +14,12 @@ if len(sys.argv) > 3:
 if len(sys.argv) > 4:
     from ctgan_b200 import _lib
     _lib.lib.ctgan_set_pdl(int(sys.argv[4]))
+import os
+if os.environ.get('CTGAN_STACKED_SM_LIMIT'):
+    K.config.stacked_sm_limit = int(os.environ['CTGAN_STACKED_SM_LIMIT'])
+if os.environ.get('CTGAN_WGRAD_ITEMS'):
+    from ctgan_b200 import _lib as _L
+    _L.lib.ctgan_set_wgrad_multi_items_per_sm(int(os.environ['CTGAN_WGRAD_ITEMS']))
 np.random.seed(1234)
 tr = R.Trainer(device='cuda', seed=1234, act_dtype=torch.bfloat16, batch_size=B, graph_safe_rng=True)
 rs = np.random.RandomState(0)

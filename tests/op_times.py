@@ -75,7 +75,7 @@ gam, bet = torch.ones(10, 128, device=dev), torch.zeros(10, 128, device=dev)
 lab = torch.randint(0, 10, (128,), device=dev, dtype=torch.int32)
 y, m, i = K.bn_fwd(a, gam, bet, lab, 1e-5, True)
 timeit('bn_fwd cond+relu', lambda: K.bn_fwd(a, gam, bet, lab, 1e-5, True), bytes_=3 * nb)
-timeit('bn_bwd cond+relu', lambda: K.bn_bwd(b, a, y, gam, lab, m, i, True), bytes_=6 * nb)
+timeit('bn_bwd cond+relu', lambda: K.bn_bwd(b, a, y, gam, bet, lab, m, i, True), bytes_=6 * nb)
 print('--- element-wise at [128,128,8,8] bf16 (2 MB)')
 a8, b8 = act(128, 128, 8, 8), act(128, 128, 8, 8)
 timeit('add 8x8', lambda: K.add(a8, b8))

@@ -115,8 +115,8 @@ def test_conv_mixed_dtype_heads(K):
                                    (200, 4, 4, 3), (37, 32, 32, 3), (64, 32, 32, 3), (200, 16, 16, 3), (60, 20, 32, 3),
                                    (41, 28, 16, 3)])
 def test_tc_fprop_variants_match(K, shape):
-    """The fprop_tc kernel family -- persistent (default) vs one-tile-per-CTA, each with and without the halo-reuse
-    A pipeline -- all compute the same convolution (up to the bf16 rounding of a different accumulation order)
+    """The fprop_tc kernel family -- 256-pixel work items / persistent grouped stages (default) vs one-tile-per-CTA, with
+    and without the halo-reuse A pipeline -- all compute the same convolution (up to the bf16 rounding of a different accumulation order)
     and match the CPU reference; also as dgrad (flipped filter pack) and with the residual/ReLU epilogue."""
     from ctgan_b200 import _lib
     N, H, W, k = shape
@@ -127,7 +127,7 @@ def test_tc_fprop_variants_match(K, shape):
     ref_f, ref_d = FB().conv_fprop(x, wq, b, g), FB().conv_dgrad(dy, wq, g)
     ref_r = FB().conv_fprop(x, wq, b, g, relu=True, residual=r)
     try:
-        for variant in (4, 3, 2, 1):
+        for variant in (4, 3, 1):
             for halo in (1, 0):
                 _lib.lib.ctgan_set_fprop_variant(variant)
                 _lib.lib.ctgan_set_fprop_halo(halo)
@@ -199,6 +199,48 @@ def test_act_dropout_matches_philox_reference(K, dtype, slope, keep):
     assert torch.equal(y3, y)
 
 
+@pytest.mark.parametrize('geom', [(6, 16, 16, 128, 128, 3, 1), (70, 8, 8, 128, 256, 3, 1), (5, 32, 32, 3, 128, 5, 2),
+                                  (9, 16, 16, 128, 256, 5, 2), (7, 14, 14, 64, 128, 5, 2), (11, 8, 8, 256, 512, 5, 2)])
+@pytest.mark.parametrize('slope,keep', [(0.2, 0.5), (0.2, 1.0), (1.0, 0.8)])
+def test_conv_actdrop_epilogue(K, geom, slope, keep):
+    """Conv2D -> LeakyReLU -> dropout in the tcgen05 conv epilogue (stride-1, space-to-depth and strided-im2col routes):
+    the multiplier is (v > 0 ? 1 : slope) * floor(keep + u) / keep with u = numpy Philox at the element's NHWC index
+    (offset + device counter), y = v * m, also when written in the space-to-depth layout of the next stride-2 layer."""
+    from tests import philox_ref
+    N, H, W, Cin, Cout, k, stride = geom
+    g = K.same_geom(N, H, W, Cin, Cout, k, stride)
+    x, w, b = act((N, Cin, H, W), torch.bfloat16, 1), filt((k, k, Cin, Cout), 3), act((Cout,), torch.float32, 4)
+    xd = to_dev(x)
+    assert K.conv_actdrop_route(xd, g) == ('tc' if stride == 1 else ('padk' if Cin == 3 else 's2d'))
+    v = FB().conv_fprop(x, w.to(torch.bfloat16).float(), b, g, out_dtype=torch.float32)      # [N, Cout, Ho, Wo]
+    seed, off, dynv = 0xABCDEF0123, 8192, 1028
+    n_el = N * g.Ho * g.Wo * Cout
+    u = torch.from_numpy(philox_ref.uniform(seed, off + dynv, n_el)).reshape(N, g.Ho, g.Wo, Cout).permute(0, 3, 1, 2)
+    mult = torch.where(v > 0, torch.ones_like(v), torch.full_like(v, slope))
+    if keep < 1.0:
+        mult = mult * torch.floor(keep + u) / keep
+    mr = mult.to(torch.bfloat16).float()
+    dyn = torch.tensor([dynv], dtype=torch.int64, device='cuda')
+    y, m = K.conv_fprop_actdrop(xd, w.cuda(), b.cuda(), g, slope, keep, seed, off, dyn=dyn)
+    sure = v.abs() > 2e-2 * v.abs().mean()                    # away from the sign boundary the multiplier is exact
+    assert torch.equal(m.cpu().float()[sure], mr[sure])
+    assert float((m.cpu().float() != mr).float().mean()) < 2e-2
+    assert rel(y.cpu().float()[sure], (v * mr)[sure]) < 1e-2
+    assert rel(y.float(), v.cuda() * m.float()) < 1e-2        # y == v * m for the stored multiplier
+    if g.Ho % 2 == 0 and g.Wo % 2 == 0:
+        ys, ms = K.conv_fprop_actdrop(xd, w.cuda(), b.cuda(), g, slope, keep, seed, off, dyn=dyn, out_s2d=True)
+        og = K.ConvGeom(N, g.Ho, g.Wo, Cout, g.Ho, g.Wo, Cout, 1, 1, 1, 0, 0)
+        assert tuple(ys.shape) == (N, 4 * Cout, g.Ho // 2, g.Wo // 2)
+        assert torch.equal(K.depth_to_space(ys, og), y) and torch.equal(K.depth_to_space(ms, og), m)
+        # layout kernels with the multiplier: the backward / double backward of the fused activation
+        gq = to_dev(act((N, 4 * Cout, g.Ho // 2, g.Wo // 2), torch.bfloat16, 9))
+        d = K.depth_to_space(gq, og, mul=ms)
+        assert rel(d, K.depth_to_space(gq, og).float() * m.float()) < 1e-2
+        c = to_dev(act((N, Cout, g.Ho, g.Wo), torch.bfloat16, 10))
+        sq = K.space_to_depth(c, og, mul=ms)
+        assert rel(sq, K.space_to_depth(c, og).float() * ms.float()) < 1e-2
+
+
 def test_philox_streams_match_reference(K):
     from tests import philox_ref
     seed = 987654321987
@@ -235,25 +277,54 @@ def test_prep_real_and_interpolate(K):
                                         ((5, 256, 8, 8), False), ((64, 128, 32, 32), True), ((10, 128, 4, 4), True)])
 @pytest.mark.parametrize('groups', [1, 2])
 @pytest.mark.parametrize('relu', [False, True])
-def test_batch_norm(K, dtype, shape, cond, relu, groups):
+@pytest.mark.parametrize('fused', [True, False])
+def test_batch_norm(K, dtype, shape, cond, relu, groups, fused):
+    """Both batch-norm paths (two-kernel BF16 'fused' path with red.global sums; generic three-kernel Welford path)
+    against the PyTorch-CPU definition; mean offset 0.5 with std 2 exercises the shifted sums."""
     fb = FB()
     if shape[0] % groups:
         pytest.skip('batch not divisible by groups')
-    C = shape[1]
-    x = act(shape, dtype, 1, 2.0) + 0.5
-    x = x.contiguous(memory_format=CL) if len(shape) == 4 else x
-    nl = 10 if cond else 1
-    gamma, beta = act((nl, C), torch.float32, 2) + 1.0, act((nl, C), torch.float32, 3)
-    labels = torch.randint(0, 10, (shape[0],), dtype=torch.int32) if cond else None
-    dy = act(shape, dtype, 4)
-    y, mean, invstd = K.bn_fwd(to_dev(x), gamma.cuda(), beta.cuda(), labels.cuda() if cond else None, 1e-5, relu, groups)
-    yr, mr, ir = fb.bn_fwd(x, gamma, beta, labels, 1e-5, relu, groups)
-    tol = 2e-5 if dtype == torch.float32 else 1e-2
-    assert rel(mean, mr) < 1e-5 and rel(invstd, ir) < 1e-5 and rel(y, yr) < tol
-    dx, dg, db = K.bn_bwd(to_dev(dy), to_dev(x), y, gamma.cuda(), labels.cuda() if cond else None, mean, invstd, relu, groups)
-    dxr, dgr, dbr = fb.bn_bwd(dy, x, y.cpu(), gamma, labels, mean.cpu(), invstd.cpu(), relu, groups)
-    assert rel(dx, dxr) < (1e-4 if dtype == torch.float32 else 2e-2)
-    assert rel(dg, dgr) < 1e-4 and rel(db, dbr) < 1e-4
+    if fused and dtype != torch.bfloat16:
+        pytest.skip('the fused path is BF16 only')
+    K.config.use_bn_fused = fused
+    try:
+        C = shape[1]
+        x = act(shape, dtype, 1, 2.0) + 0.5
+        x = x.contiguous(memory_format=CL) if len(shape) == 4 else x
+        nl = 10 if cond else 1
+        gamma, beta = act((nl, C), torch.float32, 2) + 1.0, act((nl, C), torch.float32, 3)
+        labels = torch.randint(0, 10, (shape[0],), dtype=torch.int32) if cond else None
+        dy = act(shape, dtype, 4)
+        lab = labels.cuda() if cond else None
+        if fused and not K.bn_fused_ok(to_dev(x), groups):
+            pytest.skip('shape not eligible for the fused path')
+        assert K.bn_fused_ok(to_dev(x), groups) == fused
+        y, mean, invstd = K.bn_fwd(to_dev(x), gamma.cuda(), beta.cuda(), lab, 1e-5, relu, groups)
+        yr, mr, ir = fb.bn_fwd(x, gamma, beta, labels, 1e-5, relu, groups)
+        tol = 2e-5 if dtype == torch.float32 else 1e-2
+        assert rel(mean, mr) < 1e-5 and rel(invstd, ir) < 1e-5 and rel(y, yr) < tol
+        dx, dg, db = K.bn_bwd(to_dev(dy), to_dev(x), y, gamma.cuda(), beta.cuda(), lab, mean, invstd, relu, groups)
+        dxr, dgr, dbr = fb.bn_bwd(dy, x, y.cpu(), gamma, beta, labels, mean.cpu(), invstd.cpu(), relu, groups)
+        assert rel(dx, dxr) < (1e-4 if dtype == torch.float32 else 2e-2)
+        assert rel(dg, dgr) < 1e-4 and rel(db, dbr) < 1e-4
+        # parameter gradients accumulated in place (the flat gradient bucket)
+        ag, ab = torch.full_like(dg, 0.5), torch.full_like(db, -0.25)
+        dx2, _, _ = K.bn_bwd(to_dev(dy), to_dev(x), y, gamma.cuda(), beta.cuda(), lab, mean, invstd, relu, groups, accumulate_into=(ag, ab))
+        assert rel(dx2, dxr) < (1e-4 if dtype == torch.float32 else 2e-2)
+        assert rel(ag - 0.5, dgr) < 1e-4 and rel(ab + 0.25, dbr) < 1e-4
+        if len(shape) == 4:
+            # output written 2x nearest-neighbour upsampled; the gradient arrives with that shape
+            N, _, H, W = shape
+            yu, mean_u, invstd_u = K.bn_fwd(to_dev(x), gamma.cuda(), beta.cuda(), lab, 1e-5, relu, groups, up2=True)
+            assert tuple(yu.shape) == (N, C, 2 * H, 2 * W) and yu.is_contiguous(memory_format=CL)
+            assert rel(yu, fb.upsample2x(yr.to(dtype), 1.0)) < tol
+            dyu = act((N, C, 2 * H, 2 * W), dtype, 5)
+            dxu, dgu, dbu = K.bn_bwd(to_dev(dyu), to_dev(x), yu, gamma.cuda(), beta.cuda(), lab, mean_u, invstd_u, relu, groups, up2=True)
+            dxr, dgr, dbr = fb.bn_bwd(dyu, x, fb.upsample2x(y.cpu(), 1.0), gamma, beta, labels, mean.cpu(), invstd.cpu(), relu, groups, up2=True)
+            assert rel(dxu, dxr) < (1e-4 if dtype == torch.float32 else 2e-2)
+            assert rel(dgu, dgr) < (1e-4 if dtype == torch.float32 else 3e-3) and rel(dbu, dbr) < (1e-4 if dtype == torch.float32 else 3e-3)
+    finally:
+        K.config.use_bn_fused = True
 
 
 @pytest.mark.parametrize('feat_dtype', [torch.float32, torch.bfloat16])
