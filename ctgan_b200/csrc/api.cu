@@ -35,15 +35,6 @@ int sm_count() {
     return cached;
 }
 
-// SMs a persistent tcgen05 launch may occupy (ctgan_set_sm_limit): two stream branches of one step (the 64-image
-// gradient-penalty chain and the 192-image stacked pass) each own one SM per CTA (~200 KB of shared memory), so a
-// persistent kernel that fills all 148 SMs stalls the other branch's short kernels for its whole duration.
-static int g_sm_limit = 0;
-int tc_grid_cap() {
-    const int n = sm_count();
-    return (g_sm_limit > 0 && g_sm_limit < n) ? g_sm_limit : n;
-}
-
 int elementwise_grid(int64_t work_items, int threads) {
     int64_t blocks = (work_items + threads - 1) / threads;
     int64_t cap = (int64_t)sm_count() * 8;
@@ -58,7 +49,6 @@ extern "C" int ctgan_version(void) { return 100; }
 
 extern "C" unsigned long long ctgan_kernel_launches(void) { return ctgan::g_kernel_launches; }
 extern "C" void ctgan_set_pdl(int on) { ctgan::g_pdl = on != 0; }
-extern "C" void ctgan_set_sm_limit(int n) { ctgan::g_sm_limit = n; }
 
 extern "C" const char* ctgan_last_error(void) { return ctgan::g_err; }
 

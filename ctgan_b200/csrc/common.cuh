@@ -60,7 +60,6 @@ static inline bool dtype_ok(int dt) { return dt == CTGAN_F32 || dt == CTGAN_BF16
 // grid size for a grid-stride element-wise kernel: enough CTAs for ~8 waves max, multiple of SMs
 int elementwise_grid(int64_t work_items, int threads);
 int sm_count();
-int tc_grid_cap();        // SMs a persistent tcgen05 launch may occupy: sm_count() or the ctgan_set_sm_limit() value
 
 // ---------------------------------------------------------------- dtype access
 // Runtime-dtype loads/stores (uniform branch) for the generic kernels.

@@ -1233,7 +1233,7 @@ static int launch_fprop_lean(const CUtensorMap& mx, const CUtensorMap& mw, const
         attr_set = true;
     }
     const int n_tiles = p.tilesW * p.tilesH * p.tilesN * (p.Cout / 128);
-    const int grid = n_tiles < tc_grid_cap() ? n_tiles : tc_grid_cap();
+    const int grid = n_tiles < sm_count() ? n_tiles : sm_count();
     CTGAN_LAUNCH((conv_fprop_tc_lean_kernel<HALO, EPI>), grid, 192, smem, st, mx, mw, p, n_tiles);
     CTGAN_CHECK_LAUNCH("conv_fprop_tc_lean");
     return 0;
@@ -1251,7 +1251,7 @@ static int launch_fprop_pair(const CUtensorMap& mx, const CUtensorMap& mx2, cons
     }
     const int m_tiles = p.tilesW * p.tilesH * p.tilesN;
     const int n_tiles = m_tiles * (p.Cout / 128);
-    const int grid = n_tiles < tc_grid_cap() ? n_tiles : tc_grid_cap();
+    const int grid = n_tiles < sm_count() ? n_tiles : sm_count();
     CTGAN_LAUNCH((conv_fprop_tc_pair_kernel<EPI>), grid, 192, smem, st, mx, mx2, mw, p, m_tiles, n_tiles);
     CTGAN_CHECK_LAUNCH("conv_fprop_tc_pair");
     return 0;

@@ -178,7 +178,6 @@ class ConvF(Function):
         #          x <= 0); the producer is then built with relu_bwd_fused=True and skips its own mask multiply
         ctx.in_relu, ctx.relu_bwd_fused = in_relu, relu_bwd_fused
         ctx.g = g
-        ctx.sm_limit = K.get_sm_limit()
         ctx.save_for_backward(x, w)
         ctx.has_bias = b is not None
         ctx.bias = b
@@ -221,8 +220,7 @@ class ConvF(Function):
         gx = gw = gb = None
         dycol = K.thin_col(gy, ctx.g, 'dy')          # im2col of a 3-channel gy: shared by dgrad and wgrad
         if ctx.needs_input_grad[0]:
-            with K.sm_limit(ctx.sm_limit):
-                gx = ConvD.apply(gy, w, ctx.g, x.dtype, dycol, x.detach() if ctx.in_relu else None, ctx.x_s2d)
+            gx = ConvD.apply(gy, w, ctx.g, x.dtype, dycol, x.detach() if ctx.in_relu else None, ctx.x_s2d)
         if ctx.needs_input_grad[1] and _wants(w):
             if _direct(w):
                 col, g = (ctx.col if ctx.col is not None else dycol), ctx.g
@@ -251,7 +249,6 @@ class ConvD(Function):
     @staticmethod
     def forward(ctx, gy, w, g, out_dtype, col=None, relu_mask=None, out_s2d=False):
         ctx.g = g
-        ctx.sm_limit = K.get_sm_limit()
         ctx.out_s2d = out_s2d
         ctx.save_for_backward(gy, w)
         ctx.relu_mask = relu_mask                     # constant: dx = conv^T(gy, w) * [relu_mask > 0]
@@ -267,11 +264,10 @@ class ConvD(Function):
         ggy = gw = None
         ccol = c if ctx.out_s2d else K.thin_col(c, ctx.g, 'x')   # im2col / s2d of c: shared by fprop and wgrad
         if ctx.needs_input_grad[0]:
-            with K.sm_limit(ctx.sm_limit):
-                if ctx.out_s2d:
-                    ggy = ConvF.apply(c, w, None, ctx.g, gy.dtype, None, None, False, False, False, False, None, True)
-                else:
-                    ggy = ConvF.apply(c, w, None, ctx.g, gy.dtype, ccol)
+            if ctx.out_s2d:
+                ggy = ConvF.apply(c, w, None, ctx.g, gy.dtype, None, None, False, False, False, False, None, True)
+            else:
+                ggy = ConvF.apply(c, w, None, ctx.g, gy.dtype, ccol)
         if ctx.needs_input_grad[1] and _wants(w):
             if _direct(w):
                 _direct_wgrad(c, gy, ctx.g, w, ccol)

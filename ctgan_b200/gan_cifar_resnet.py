@@ -78,9 +78,9 @@ def Normalize(name, inputs, labels=None, relu=False, up2=False):
 COMMUTE_1X1 = True   # evaluate 1x1 shortcut convs on the low-resolution side of their resampling (same function)
 FUSE_SKIP_ADD = True  # shortcut + conv_2(...) inside conv_2's epilogue where conv_2 is not followed by pooling
 FUSE_D_ACT = True     # critic: relu in conv_1's epilogue, dropout -> (skip, relu) forks as one node (see functional.Fork*)
-# the ReLU backward inside conv_2's dgrad epilogue (ConvF in_relu / relu_bwd_fused): implemented and tested, but the
-# extra strided mask loads in the (exposed) epilogue of the small layers cost what the saved multiply kernels gain
-FUSE_RELU_BWD = False
+# the ReLU backward inside conv_2's dgrad epilogue (ConvF in_relu / relu_bwd_fused; EPI_MASK variant of the lean / pair
+# kernels): 8 fewer mask-multiply launches per critic step (993 -> 979 us)
+FUSE_RELU_BWD = True
 FUSE_POOL_FORK = True   # critic blocks 1, 2: mean pool + skip add + (dropout) + next relu as one kernel (functional.PoolAddFork)
 FUSE_BN_UP = True       # generator blocks: Normalize + relu writes its output already upsampled (the UpsampleConv input)
 
@@ -357,8 +357,7 @@ class Trainer:
         stacked_labels = torch.cat([all_real_labels, all_real_labels, all_real_labels], dim=0)
         RNG.scope_parts([('drop.p1', 2 * B), ('drop.p2', B)])
         RNG.begin_stack([2 * B, B])
-        with K.sm_limit(K.config.stacked_sm_limit if fork is not None else 0):
-            disc_all, disc_all_2, disc_all_acgan = Discriminator(stacked, stacked_labels, 0.8, 0.5, 0.5)
+        disc_all, disc_all_2, disc_all_acgan = Discriminator(stacked, stacked_labels, 0.8, 0.5, 0.5)
         RNG.end_stack()
         metrics = {}
         if with_metrics and CONDITIONAL and ACGAN:

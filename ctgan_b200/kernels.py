@@ -28,7 +28,6 @@ class Config:
     branch_priority = -1     # CUDA stream priority of the branch stream (lower = higher priority)
     tc_min_rows = 1          # (tunable) minimum GEMM rows to prefer the tensor-core path
     use_bn_fused = True      # BF16 batch norm as two kernels per direction (sums with red.global + apply)
-    stacked_sm_limit = 0     # SM budget of the stacked critic pass while the gradient-penalty branch runs beside it (0 = all)
     fuse_act_dropout = True  # Conv2D -> LeakyReLU -> dropout of the DCGAN critics in the tcgen05 conv epilogue (Philox in registers)
     defer_wgrad = True       # queue the final backward's tensor-core filter gradients and run them as ONE launch at the join
 
@@ -129,34 +128,6 @@ def join_side():
         for dev in {d for d, _ in _side_pending}:
             torch.cuda.current_stream(dev).wait_stream(_side_streams[dev])
         _side_pending.clear()
-
-
-# SM budget of the persistent tensor-core launches issued inside a `with sm_limit(n)` block (0 = all SMs).  Autograd
-# nodes remember the budget of their forward (functional.ConvF / ConvD) and re-apply it in their backward.
-_sm_limit = 0
-
-
-def get_sm_limit():
-    return _sm_limit
-
-
-class sm_limit:
-    def __init__(self, n):
-        self.n = int(n or 0)
-
-    def __enter__(self):
-        global _sm_limit
-        self.prev, _sm_limit = _sm_limit, self.n
-        if self.n != self.prev:
-            _lib.lib.ctgan_set_sm_limit(self.n)
-        return self
-
-    def __exit__(self, *exc):
-        global _sm_limit
-        if self.prev != _sm_limit:
-            _lib.lib.ctgan_set_sm_limit(self.prev)
-        _sm_limit = self.prev
-        return False
 
 
 # Independent sub-graphs of one step (the gradient-penalty pass vs the stacked critic pass) as two stream branches.

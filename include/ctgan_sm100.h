@@ -92,8 +92,6 @@ void ctgan_set_fprop_halo(int on);
 /* 1 (default): kernels are launched with programmatic stream serialization (each begins with griddepcontrol.launch_dependents +
  * griddepcontrol.wait, so launch latency and set-up overlap the predecessor's tail; ordering semantics unchanged); 0: plain launches */
 void ctgan_set_pdl(int on);
-/* scheduling hook: persistent tcgen05 fprop launches use at most n SMs (0 = all): leaves SMs to a concurrent stream branch */
-void ctgan_set_sm_limit(int n);
 /* test hook: 4 = 256-pixel work items where eligible, else 3 (default); 3 = persistent grouped-stage kernel; 1 = one tile per CTA */
 void ctgan_set_fprop_variant(int v);
 /* test/benchmark hook: 2 (default) = 3x3 wgrad CTAs own one filter column and share the x halo box; 1 = per-tap boxes */

@@ -15,8 +15,8 @@ if len(sys.argv) > 4:
     from ctgan_b200 import _lib
     _lib.lib.ctgan_set_pdl(int(sys.argv[4]))
 import os
-if os.environ.get('CTGAN_STACKED_SM_LIMIT'):
-    K.config.stacked_sm_limit = int(os.environ['CTGAN_STACKED_SM_LIMIT'])
+if os.environ.get('CTGAN_FUSE_RELU_BWD'):
+    R.FUSE_RELU_BWD = bool(int(os.environ['CTGAN_FUSE_RELU_BWD']))
 if os.environ.get('CTGAN_WGRAD_ITEMS'):
     from ctgan_b200 import _lib as _L
     _L.lib.ctgan_set_wgrad_multi_items_per_sm(int(os.environ['CTGAN_WGRAD_ITEMS']))
