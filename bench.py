@@ -3,16 +3,21 @@
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--no-graph]
   torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
 
-A "step" is ONE training iteration of CT_gan_cifar_resnet.py -- 1 generator step + 5 critic
+The metric counts training ITERATIONS of CT_gan_cifar_resnet.py -- 1 generator step + 5 critic
 steps (TG/CT_gan_cifar_resnet.py:393-404) -- at batch 64 per GPU, DIM 128, BF16 tensor-core
-path, synthetic CIFAR-shaped data, random-init weights.  One JSON line is printed by rank 0.
+path, synthetic CIFAR-shaped data, random-init weights.  One bench "step" (--steps K) is a block of
+ITERS_PER_STEP = 16 such iterations, so that the driver's K = 20 gives a timed region of ~2 s (320
+iterations) instead of 0.14 s -- long enough for sustained clocks and a few dozen nvidia-smi samples.
+`value` is iterations/s whatever the block size.  One JSON line is printed by rank 0.
 
   value     iterations/s with the real batches already resident in HBM
   e2e       the same loop through the public API with HOST batches: every critic step copies
             its int32 [64,3072] batch + labels from pinned host memory and reads the 8 loss
             scalars back; every generator step reads its loss back
-  roofline  the dominant kernel (tcgen05 implicit-GEMM conv, 3x3 128->128 @32x32, 128 images),
-            timed alone with CUDA events over buffers that exceed L2
+  roofline  the kernel family with the largest share of the step, timed alone with CUDA events over buffers
+            that exceed L2; roofline_top3 = the three largest families (shares: profiles/r02_kernel_shares.json)
+  other_workloads
+            the same measurement (value + e2e) for CT_gan_cifar.py and CT_gan_mnist.py at the same N
   cpu_baseline / --impl reference
             the CPU transcription of the reference graph (oracle/, PyTorch-CPU fp32, all host
             threads) -- TF 1.2.1 cannot be installed here
@@ -36,6 +41,7 @@ METRIC = 'CT-GAN train iters/sec (CIFAR ResNet)'
 UNIT = 'iterations/s (1 gen + 5 critic steps of batch 64 per GPU; aggregate over GPUs)'
 BATCH = 64
 N_CRITIC = 5
+ITERS_PER_STEP = 16           # training iterations per bench step (see the module docstring)
 ITER_GFLOP = 2990.34          # algorithmic FLOPs of one iteration of the REFERENCE graph
 # executed: the 1x1 shortcut convs run on the low-resolution side of their resampling (gan_cifar_resnet.COMMUTE_1X1, exact):
 # -0.75 * 2*256*128*128 FLOP per critic pass-image (Discriminator.2.Shortcut) over 5*(3*192 + 4*64) + 2*128 image-traversals,
@@ -54,13 +60,15 @@ def load_peaks():
 
 
 # ----------------------------------------------------------------------------- CPU reference arm
-def time_cpu_reference(max_seconds=150.0, want_steps=1):
-    """Times the oracle (CPU transcription of CT_gan_cifar_resnet.py, fp32, all host threads) on a
-    bounded sample: n critic steps + n generator steps at batch 64; an iteration = 5 critic + 1 gen."""
+REF_DEAD_WORK = ('executes the reference graph as written, including the metrics-only clean critic pass and the fake half of '
+                 'the second stochastic pass (TG/CT_gan_cifar_resnet.py:228,238-242: +173.66 GFLOP per critic step) that the GPU '
+                 'arm does not execute because nothing consumes them')
+
+
+def _cpu_model():
     import numpy as np
     import torch
     from oracle import ct_gan_cifar_resnet as R
-    from oracle.rand import SeededRandom
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     np.random.seed(1234)
@@ -68,6 +76,14 @@ def time_cpu_reference(max_seconds=150.0, want_steps=1):
     rs = np.random.RandomState(1234)
     x = torch.from_numpy(rs.randint(0, 256, (BATCH, 3072)).astype('int32'))
     y = torch.from_numpy(rs.randint(0, 10, (BATCH,)).astype('int32'))
+    return m, x, y, torch.get_num_threads()
+
+
+def time_cpu_reference(max_seconds=150.0, want_steps=1):
+    """cpu_baseline of the default line: the oracle (CPU transcription of CT_gan_cifar_resnet.py, fp32, all host threads)
+    on a bounded sample: n critic steps + n generator steps at batch 64; an iteration = 5 critic + 1 gen."""
+    from oracle.rand import SeededRandom
+    m, x, y, cores = _cpu_model()
     t0 = time.time()
     m.critic_step(SeededRandom(1), x, y, iteration=0)            # warm-up (also sizes the sample)
     t_warm = time.time() - t0
@@ -78,12 +94,16 @@ def time_cpu_reference(max_seconds=150.0, want_steps=1):
         t0 = time.time(); m.gen_step(SeededRandom(100 + i), iteration=i); tg += time.time() - t0
     tc, tg = tc / n, tg / n
     it_s = 1.0 / (N_CRITIC * tc + tg)
-    return dict(value=it_s, unit=UNIT, cores=torch.get_num_threads(), kind='port',
+    return dict(value=it_s, unit=UNIT, cores=cores, kind='port',
                 sample='%d critic + %d generator steps at batch 64 (fp32 oracle, PyTorch-CPU); iteration = 5*critic + 1*gen '
-                       '= %.2f s' % (n, n, N_CRITIC * tc + tg)), (N_CRITIC * tc + tg)
+                       '= %.2f s; %s' % (n, n, N_CRITIC * tc + tg, REF_DEAD_WORK)), (N_CRITIC * tc + tg)
 
 
 def run_reference(args):
+    """`--impl reference`: the reference's own CPU path (TF 1.2.1 is not installable -> its PyTorch-CPU transcription, oracle/)
+    on all host threads.  W warm-up + EXACTLY K timed steps; a step is one full training iteration (1 generator + 5 critic
+    steps) when W + K of them fit in ~4 minutes, else a bounded sample of it (1 generator + 1 critic step; the line says so
+    and extrapolates value = 1 / (5 * critic + generator))."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
@@ -100,15 +120,47 @@ def run_reference(args):
             'cpu_baseline': cb, 'e2e': {'value': cb['value'], 'unit': unit, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}), flush=True)
         return
-    cb, sec = time_cpu_reference(max_seconds=150.0, want_steps=max(1, args.steps))
+    from oracle.rand import SeededRandom
+    m, x, y, cores = _cpu_model()
+    K_, W_ = max(1, args.steps), max(0, args.warmup)
+    t0 = time.time(); m.critic_step(SeededRandom(1), x, y, iteration=0); tc0 = time.time() - t0
+    t0 = time.time(); m.gen_step(SeededRandom(2), iteration=0); tg0 = time.time() - t0
+    full = (K_ + W_) * (N_CRITIC * tc0 + tg0) <= 240.0
+    n_c = N_CRITIC if full else 1
+
+    def step(i):
+        tc = tg = 0.0
+        t0 = time.time(); m.gen_step(SeededRandom(100 + i), iteration=i); tg = time.time() - t0
+        for k in range(n_c):
+            t0 = time.time(); m.critic_step(SeededRandom(1000 + 10 * i + k), x, y, iteration=i); tc += time.time() - t0
+        return tc / n_c, tg
+    for i in range(W_ if full else min(W_, 1)):
+        step(i)
+    t_begin = time.time()
+    tcs, tgs = [], []
+    for i in range(K_):
+        tc, tg = step(W_ + i)
+        tcs.append(tc); tgs.append(tg)
+    wall = time.time() - t_begin
+    tc, tg = sum(tcs) / K_, sum(tgs) / K_
+    sec_iter = N_CRITIC * tc + tg
+    value = 1.0 / sec_iter
+    sample = ('%d timed steps, each %s at batch 64 (fp32 PyTorch-CPU transcription of the reference graph, %d threads); '
+              'critic step %.3f s, generator step %.3f s, iteration = 5*critic + 1*gen = %.2f s; %s'
+              % (K_, 'one full iteration (1 generator + 5 critic steps)' if full else
+                 'a bounded sample of one iteration (1 generator + 1 critic step; value extrapolates to 1 + 5)', cores, tc, tg,
+                 sec_iter, REF_DEAD_WORK))
+    cb = dict(value=value, unit=UNIT, cores=cores, kind='port', sample=sample)
     line = {
-        'impl': 'reference', 'metric': METRIC, 'value': cb['value'], 'unit': UNIT, 'n_gpus': args.gpus,
-        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': sec * 1e3, 'higher_is_better': True,
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
+        'steps': K_, 'warmup': W_, 'ms_per_step': wall / K_ * 1e3, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': {'workload': 'CT_gan_cifar_resnet.py critic+generator iteration, batch 64, DIM 128 (BASELINE configs[2]); '
-                               'CPU transcription of the reference graph on host cores'},
+                               'CPU transcription of the reference graph on host cores',
+                   'step': 'one full training iteration' if full else 'bounded sample: 1 generator + 1 critic step',
+                   'dead_work': REF_DEAD_WORK},
         'cpu_baseline': cb,
-        'e2e': {'value': cb['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
     print(json.dumps(line), flush=True)
@@ -158,48 +210,106 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- our arm
-def roofline_dominant_kernel(torch, peaks):
-    """tcgen05 implicit-GEMM conv of Discriminator.1.Conv2 as the critic step launches it: the stacked pass
-    (real', fake', real'' = 3 x 64 = 192 images), 32x32, 3x3, 128->128 -- the single most expensive launch of the
-    step, fprop and (same kernel, flipped filter pack) dgrad.  Timed alone with CUDA events on the launching
-    stream; 6 rotating buffer sets (6 x 101 MB) exceed the 126 MB L2."""
-    import ctgan_b200.kernels as K
-    N, H, W, C = 3 * BATCH, 32, 32, 128
-    g = K.same_geom(N, H, W, C, C, 3, 1)
-    sets = []
-    for i in range(6):
-        x = torch.randn(N, C, H, W, device='cuda').to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
-        sets.append(x)
-    w = (torch.randn(3, 3, C, C, device='cuda') * 0.03).contiguous()
-    b = torch.zeros(C, device='cuda')
-    for i in range(6):
-        K.conv_fprop(sets[i], w, b, g, w_is_param=False)
+def _time_launches(torch, launch, n_sets, reps):
+    for i in range(n_sets):
+        launch(i)
     torch.cuda.synchronize()
-    reps = 30
-    wp = K.pack_filter(w, 0)
-    import ctypes
-    from ctgan_b200 import _lib
-    d = K._desc(g, _lib.BF16, _lib.BF16)
-    ys = [torch.empty_like(sets[0]) for _ in range(6)]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(reps):
-        _lib.call('ctgan_conv_fprop_tc', ctypes.byref(d), K._p(sets[i % 6]), K._p(wp), K._p(b), None, K._p(ys[i % 6]), 0, K._stream())
+        launch(i)
     e1.record()
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / reps
-    flops = 2.0 * N * H * W * C * C * 9
-    achieved = flops / (ms * 1e-3) / 1e12
+    return e0.elapsed_time(e1) / reps            # ms per launch
+
+
+def _bf16_act(torch, shape):
+    return torch.randn(*shape, device='cuda').to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+
+
+def roofline_kernels(torch, peaks):
+    """The three kernel families with the largest share of the ResNet iteration (shares: profiles/r02_kernel_shares.json, from
+    the ncu launch list of the same build), each timed alone with CUDA events on the launching stream, rotating over buffer
+    sets that exceed the 126 MB L2:
+      * conv_fprop_tc_lean_kernel<0>: the 8x8 3x3 128->128 layers (Discriminator.3/.4, fprop / dgrad / double-backward fprop)
+        as the 64-image gradient-penalty pass launches them -- 32 tiles on 148 SMs, the latency-bound small-layer family;
+      * conv_wgrad_tc_multi_kernel: every tensor-core filter gradient of one critic step (stacked pass 192 images +
+        gradient-penalty pass 64 images; 3x3 at 32x32, 16x16 x2, 8x8 x4 and the 1x1 shortcut, each) as ONE launch;
+      * conv_fprop_tc_pair_kernel: Discriminator.1.Conv2 on the stacked 192-image pass (32x32, 3x3, 128->128), the single
+        largest GEMM of the step (fprop and, same kernel with the flipped filter pack, dgrad)."""
+    import ctypes
+    import ctgan_b200.kernels as K
+    from ctgan_b200 import _lib
+    C = 128
+    peak_src = ('MEASURED_PEAKS.json bf16_tflops (burst; kernel timed alone)' if peaks['src'] == 'measured' else 'fallback 1590')
+    shares = {}
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'r02_kernel_shares.json')) as f:
+            shares = json.load(f)
+    except Exception:
+        pass
+    w = (torch.randn(3, 3, C, C, device='cuda') * 0.03).contiguous()
+    b = torch.zeros(C, device='cuda')
+    wp = K.pack_filter(w, 0)
+    out = []
+
+    def entry(key, kernel, flops, ms, traffic=None, extra=None):
+        ach = flops / (ms * 1e-3) / 1e12
+        e = {'bound': 'tensor', 'kernel': kernel, 'share_of_step': shares.get(key), 'achieved': ach, 'peak': peaks['burst'],
+             'peak_source': peak_src, 'unit': 'TFLOP/s', 'frac': ach / peaks['burst'], 'traffic': traffic,
+             'flops_per_launch': flops, 'us_per_launch': ms * 1e3}
+        if extra:
+            e.update(extra)
+        out.append(e)
+
+    # (1) pair kernel, 192 x 32 x 32
+    N, H = 3 * BATCH, 32
+    g = K.same_geom(N, H, H, C, C, 3, 1)
+    xs = [_bf16_act(torch, (N, C, H, H)) for _ in range(6)]
+    ys = [torch.empty_like(xs[0]) for _ in range(6)]
+    d = K._desc(g, _lib.BF16, _lib.BF16)
+    ms = _time_launches(torch, lambda i: _lib.call('ctgan_conv_fprop_tc', ctypes.byref(d), K._p(xs[i % 6]), K._p(wp), K._p(b), None,
+                                                  K._p(ys[i % 6]), 0, K._stream()), 6, 30)
     traffic = None
     try:
         with open(os.path.join(ROOT, 'profiles', 'roofline_traffic.json')) as f:
             traffic = json.load(f).get('conv_fprop_tc_192x32x32x128_bytes')
     except Exception:
         pass
-    return {'bound': 'tensor', 'kernel': 'conv_fprop_tc_pair_kernel (3x3, 128->128, %dx32x32)' % N, 'achieved': achieved,
-            'peak': peaks['burst'], 'peak_source': 'MEASURED_PEAKS.json bf16_tflops (burst; kernel timed alone)'
-            if peaks['src'] == 'measured' else 'fallback 1590', 'unit': 'TFLOP/s', 'frac': achieved / peaks['burst'],
-            'traffic': traffic, 'flops_per_launch': flops, 'us_per_launch': ms * 1e3}
+    entry('conv_fprop_tc_pair_kernel', 'conv_fprop_tc_pair_kernel (3x3, 128->128, %dx32x32)' % N, 2.0 * N * H * H * C * C * 9, ms, traffic)
+    del xs, ys
+
+    # (2) lean<0> kernel, 64 x 8 x 8 (80 buffer sets of 1 MB in + 1 MB out)
+    N, H = BATCH, 8
+    g = K.same_geom(N, H, H, C, C, 3, 1)
+    xs = [_bf16_act(torch, (N, C, H, H)) for _ in range(80)]
+    ys = [torch.empty_like(xs[0]) for _ in range(80)]
+    d8 = K._desc(g, _lib.BF16, _lib.BF16)
+    ms = _time_launches(torch, lambda i: _lib.call('ctgan_conv_fprop_tc', ctypes.byref(d8), K._p(xs[i % 80]), K._p(wp), K._p(b), None,
+                                                  K._p(ys[i % 80]), 0, K._stream()), 80, 160)
+    entry('conv_fprop_tc_lean_kernel<0>', 'conv_fprop_tc_lean_kernel<0> (3x3, 128->128, %dx8x8: 32 tiles on 148 SMs)' % N,
+          2.0 * N * H * H * C * C * 9, ms)
+    del xs, ys
+
+    # (3) all filter gradients of one critic step in one launch
+    jobs, flops = [], 0.0
+    for n in (3 * BATCH, BATCH):
+        for (h, k, reps) in ((32, 3, 1), (16, 3, 2), (8, 3, 4), (8, 1, 1)):
+            for _ in range(reps):
+                gj = K.same_geom(n, h, h, C, C, k, 1)
+                jobs.append((_bf16_act(torch, (n, C, h, h)), _bf16_act(torch, (n, C, h, h)), gj,
+                             torch.zeros(k, k, C, C, device='cuda')))
+                flops += 2.0 * n * h * h * C * C * k * k
+
+    def launch_multi(i):
+        for xj, dyj, gj, dwj in jobs:
+            K.conv_wgrad(xj, dyj, gj, tuple(dwj.shape), accumulate_into=dwj, defer=True)
+        K.flush_wgrads()
+    ms = _time_launches(torch, launch_multi, 2, 20)
+    entry('conv_wgrad_tc_multi_kernel', 'conv_wgrad_tc_multi_kernel (the %d filter gradients of one critic step: 192 + 64 images)' % len(jobs),
+          flops, ms, None, {'operand_bytes': int(sum(2 * xj.numel() * 2 for xj, _, _, _ in jobs))})
+    out.sort(key=lambda e: -(e['share_of_step'] or 0.0))
+    return out
 
 
 def run_ours(args):
@@ -273,11 +383,13 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    IPS = ITERS_PER_STEP
+
     def timed(e2e, steps):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(steps):
+        for _ in range(steps * IPS):
             iteration(e2e)
         e1.record()
         barrier()
@@ -288,7 +400,7 @@ def run_ours(args):
             ms = float(t.item())
         return ms
 
-    for _ in range(max(3, args.warmup)):
+    for _ in range(max(3, args.warmup) * IPS):
         iteration(False)
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
@@ -300,20 +412,36 @@ def run_ours(args):
     for _ in range(2):
         iteration(True)
     ms_e2e = timed(True, args.steps)
+    n_iters = args.steps * IPS
+    if gt is not None:
+        launches = n_iters * (gt.gen_kernels + N_CRITIC * gt.critic_kernels + gt.pregen_kernels)
+    else:
+        launches = eager_launches
+    pregen_on = gt is not None and bool(gt.pregen_steps)
+
+    # the DCGAN scripts at the same N (north_star: MNIST and CIFAR throughput at 1 / 2 / 4 / 8 GPUs): free the ResNet model
+    # first -- tflib keeps ONE model per process (module-level parameter dict, like the reference)
+    others = {}
+    if not args.no_other_workloads and not args.no_graph:
+        del gt, tr
+        torch.cuda.empty_cache()
+        for script in ('cifar', 'mnist'):
+            o = measure_dcgan(args, script, rank, local_rank, world, dev, with_roofline=False)
+            if rank == 0:
+                others[o['metric']] = {k: o[k] for k in ('value', 'unit', 'ms_per_step', 'e2e', 'gpu_launches', 'step_tensor_utilisation')}
+                others[o['metric']]['config'] = o['config']['workload']
+            torch.cuda.empty_cache()
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
     peaks = load_peaks()
-    it_s = world * args.steps / (ms * 1e-3)
-    it_s_e2e = world * args.steps / (ms_e2e * 1e-3)
-    if gt is not None:
-        launches = args.steps * (gt.gen_kernels + N_CRITIC * gt.critic_kernels + gt.pregen_kernels)
-    else:
-        launches = eager_launches
-    roof = roofline_dominant_kernel(torch, peaks)
-    step_tflops = ITER_GFLOP_EXECUTED * 1e-3 * (args.steps / (ms * 1e-3))   # per GPU, FLOPs actually required by the executed math
+    it_s = world * n_iters / (ms * 1e-3)
+    it_s_e2e = world * n_iters / (ms_e2e * 1e-3)
+    top3 = roofline_kernels(torch, peaks)
+    roof = top3[0]
+    step_tflops = ITER_GFLOP_EXECUTED * 1e-3 * (n_iters / (ms * 1e-3))   # per GPU, FLOPs actually required by the executed math
     line = {
         'metric': METRIC, 'value': it_s, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': max(3, args.warmup),
         'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
@@ -322,17 +450,20 @@ def run_ours(args):
             'workload': 'CT_gan_cifar_resnet.py iteration = 1 generator step (2x64 fakes) + 5 critic steps (64 real + 64 fake, '
                         '2 stochastic passes + GP double-backward), batch 64 per GPU, DIM_G=DIM_D=128, conditional+ACGAN '
                         '(BASELINE configs[2]; configs[3] when n_gpus>1: batch-sharded data parallel, NCCL all-reduce of flat grads)',
-            'per_gpu_batch': BATCH, 'critic_iters': N_CRITIC, 'cuda_graphs': gt is not None,
+            'step': '%d training iterations (so that --steps 20 times %d iterations, ~2 s)' % (IPS, 20 * IPS),
+            'per_gpu_batch': BATCH, 'critic_iters': N_CRITIC, 'cuda_graphs': not args.no_graph,
             'l2_policy': 'working set per iteration (~1.5 GB of activations, 8 rotating input batches) exceeds the 126 MB L2; no explicit flush',
             'precision': 'BF16 operands / fp32 accumulate (tcgen05), fp32 master weights and optimizer',
         },
         'clocks': clocks,
         'e2e': {'value': it_s_e2e, 'unit': UNIT, 'ms_per_step': ms_e2e / args.steps,
-                'h2d_bytes_per_step': N_CRITIC * (BATCH * 3072 * 4 + BATCH * 4 + 4) + 4 +
-                                      (N_CRITIC * BATCH * 4 if (gt is not None and gt.pregen_steps) else 0),
-                'd2h_bytes_per_step': N_CRITIC * 32 + 4},
+                'h2d_bytes_per_step': IPS * (N_CRITIC * (BATCH * 3072 * 4 + BATCH * 4 + 4) + 4 +
+                                             (N_CRITIC * BATCH * 4 if pregen_on else 0)),
+                'd2h_bytes_per_step': IPS * (N_CRITIC * 32 + 4)},
         'gpu_launches': int(launches),
         'roofline': roof,
+        'roofline_top3': top3,
+        'other_workloads': others,
         'step_tensor_utilisation': {'algorithmic_gflop_per_iteration': ITER_GFLOP, 'executed_gflop_per_iteration': ITER_GFLOP_EXECUTED,
                                     'achieved_tflops_per_gpu': step_tflops,
                                     'frac_of_sustained_peak': step_tflops / peaks['sustained'], 'peak': peaks['sustained']},
@@ -422,23 +553,14 @@ def roofline_dcgan_kernel(torch, peaks, script, B):
             'flops_per_launch': flops, 'executed_flops_per_launch': flops * 36 / 25, 'us_per_launch': ms * 1e3}
 
 
-def run_dcgan(args):
-    """`--workload cifar|mnist`: the same measurement for the DCGAN scripts (parity-test configurations; not the default line)."""
+def measure_dcgan(args, script, rank, local_rank, world, dev, with_roofline=True):
+    """One DCGAN workload (CT_gan_cifar.py / CT_gan_mnist.py) measured like the headline: W warm-up + K timed steps of
+    ITERS_PER_STEP iterations, device-resident (`value`) and through host batches (`e2e`); returns the JSON line (rank 0)."""
     import importlib
     import numpy as np
     import torch
     import torch.distributed as dist
-    script = args.workload
     modname, _, B, gf_c, gf_g, row, cfg = DCGAN[script]
-    rank, local_rank, world = (int(os.environ.get(k, d)) for k, d in (('RANK', '0'), ('LOCAL_RANK', '0'), ('WORLD_SIZE', '1')))
-    if not torch.cuda.is_available():
-        raise SystemExit('bench.py: no CUDA device (the product has no CPU path)')
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
-    dev = torch.device('cuda', local_rank)
-    from ctgan_b200 import _lib
     from ctgan_b200.graphs import GraphedTrainer
     mod = importlib.import_module(modname)
     np.random.seed(1234)
@@ -449,6 +571,7 @@ def run_dcgan(args):
     host_out = torch.zeros(N_CRITIC + 1, 8, dtype=torch.float32).pin_memory()
     gt = GraphedTrainer(tr, (dev_x[0],))
     state = {'b': 0}
+    IPS = ITERS_PER_STEP
 
     def iteration(e2e):
         src = host_x if e2e else dev_x
@@ -470,7 +593,7 @@ def run_dcgan(args):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(steps):
+        for _ in range(steps * IPS):
             iteration(e2e)
         e1.record()
         barrier()
@@ -481,7 +604,7 @@ def run_dcgan(args):
             ms = float(t.item())
         return ms
 
-    for _ in range(max(3, args.warmup)):
+    for _ in range(max(3, args.warmup) * IPS):
         iteration(False)
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
@@ -491,34 +614,54 @@ def run_dcgan(args):
     for _ in range(2):
         iteration(True)
     ms_e2e = timed(True, args.steps)
+    n_iters = args.steps * IPS
+    launches = int(n_iters * (gt.gen_kernels + N_CRITIC * gt.critic_kernels))
+    del gt, tr
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        return None
     peaks = load_peaks()
     unit = 'iterations/s (1 gen + 5 critic steps of batch %d per GPU; aggregate over GPUs)' % B
-    it_s, it_s_e2e = world * args.steps / (ms * 1e-3), world * args.steps / (ms_e2e * 1e-3)
+    it_s, it_s_e2e = world * n_iters / (ms * 1e-3), world * n_iters / (ms_e2e * 1e-3)
     gflop = N_CRITIC * gf_c + gf_g
-    step_tflops = gflop * 1e-3 * (args.steps / (ms * 1e-3))
+    step_tflops = gflop * 1e-3 * (n_iters / (ms * 1e-3))
     line = {
         'metric': 'CT-GAN train iters/sec (%s)' % ('CIFAR DCGAN' if script == 'cifar' else 'MNIST DCGAN'), 'value': it_s, 'unit': unit,
         'n_gpus': world, 'steps': args.steps, 'warmup': max(3, args.warmup), 'ms_per_step': ms / args.steps, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
-        'config': {'workload': cfg, 'per_gpu_batch': B, 'critic_iters': N_CRITIC, 'cuda_graphs': True,
+        'config': {'workload': cfg, 'step': '%d training iterations' % IPS, 'per_gpu_batch': B, 'critic_iters': N_CRITIC, 'cuda_graphs': True,
                    'l2_policy': '8 rotating input batches; activations of the stacked critic pass exceed L2 only for cifar; no explicit flush',
-                   'precision': 'BF16 operands / fp32 accumulate (tcgen05; stride-2 5x5 layers as 3x3 convs over the space-to-depth image), '
-                                'fp32 master weights and optimizer'},
+                   'precision': 'BF16 operands / fp32 accumulate (tcgen05; stride-2 5x5 layers as 3x3 convs over the space-to-depth image, '
+                                'bias + LeakyReLU + Philox dropout in the conv epilogue), fp32 master weights and optimizer'},
         'clocks': clocks,
         'e2e': {'value': it_s_e2e, 'unit': unit, 'ms_per_step': ms_e2e / args.steps,
-                'h2d_bytes_per_step': N_CRITIC * (B * row * 4 + 4) + 4, 'd2h_bytes_per_step': N_CRITIC * 32 + 4},
-        'gpu_launches': int(args.steps * (gt.gen_kernels + N_CRITIC * gt.critic_kernels)),
-        'roofline': roofline_dcgan_kernel(torch, peaks, script, B),
+                'h2d_bytes_per_step': IPS * (N_CRITIC * (B * row * 4 + 4) + 4), 'd2h_bytes_per_step': IPS * (N_CRITIC * 32 + 4)},
+        'gpu_launches': launches,
         'step_tensor_utilisation': {'algorithmic_gflop_per_iteration': gflop, 'achieved_tflops_per_gpu': step_tflops,
                                     'frac_of_sustained_peak': step_tflops / peaks['sustained'], 'peak': peaks['sustained']},
     }
-    if world == 1 and not args.no_cpu_baseline:
-        line['cpu_baseline'] = time_cpu_dcgan(script)
-    print(json.dumps(line), flush=True)
+    if with_roofline:
+        line['roofline'] = roofline_dcgan_kernel(torch, peaks, script, B)
+    return line
+
+
+def run_dcgan(args):
+    """`--workload cifar|mnist`: the DCGAN scripts as the bench line (BASELINE configs[1] / [0])."""
+    import torch
+    import torch.distributed as dist
+    script = args.workload
+    rank, local_rank, world = (int(os.environ.get(k, d)) for k, d in (('RANK', '0'), ('LOCAL_RANK', '0'), ('WORLD_SIZE', '1')))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device (the product has no CPU path)')
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    dev = torch.device('cuda', local_rank)
+    line = measure_dcgan(args, script, rank, local_rank, world, dev)
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            line['cpu_baseline'] = time_cpu_dcgan(script)
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -532,6 +675,7 @@ def main():
     ap.add_argument('--no-graph', action='store_true', help='launch every kernel eagerly (debug / profiling)')
     ap.add_argument('--no-pregen', action='store_true', help='one generator forward per critic step instead of one per iteration')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-other-workloads', action='store_true', help='skip the CIFAR-DCGAN / MNIST lines of the default run')
     ap.add_argument('--workload', default='resnet', choices=['resnet', 'cifar', 'mnist'],
                     help="resnet = BASELINE.json's metric (default); cifar / mnist = the DCGAN parity configurations (our arm only)")
     args = ap.parse_args()

@@ -5,7 +5,9 @@ The reference keeps its weights in TF variables named `<op name>.Filters` (HWIO)
 (TG/CT_gan_cifar.py:216-222; the LSUN script uses tf.train.Saver, LS/wgan_LSUN_Bedrooms128.py:367,395).  The
 parameters of this package live under the SAME names and layouts (float32 masters inside FlatAdam's flat buffers), so
 a checkpoint is simply {name: float32 array} -- loadable into a TF graph of the reference by name, and vice versa --
-plus, optionally, the Adam moments and step counts of both optimizers for an exact resume.
+plus, optionally, what an exact resume needs: the Adam moments and step counts of both optimizers, the Philox state (seed,
+device counter, host offset), the iteration (the ResNet script's learning-rate decay depends on it) and numpy's global
+RandomState (the loaders' epoch shuffles).
 """
 import numpy as np
 import torch
@@ -16,8 +18,8 @@ from . import kernels as K
 _OPT_KEYS = ('gen_opt', 'disc_opt')
 
 
-def state_dict(trainer=None):
-    """{reference name: float32 numpy array} of every registered parameter (+ optimizer state of `trainer`)."""
+def state_dict(trainer=None, iteration=None):
+    """{reference name: float32 numpy array} of every registered parameter (+ optimizer / random state of `trainer`)."""
     blob = {'param/' + n: p.detach().cpu().numpy().astype('float32') for n, p in lib._params.items()}
     if trainer is not None:
         for key in _OPT_KEYS:
@@ -28,12 +30,20 @@ def state_dict(trainer=None):
                 shape = tuple(opt.params[n].shape)
                 blob['opt/%s/m/%s' % (key, n)] = opt.flat_m[o:o + sz].reshape(shape).cpu().numpy()
                 blob['opt/%s/v/%s' % (key, n)] = opt.flat_v[o:o + sz].reshape(shape).cpu().numpy()
-        blob['rng/seed'] = np.uint64(trainer.rng.seed)
+        rng = trainer.rng
+        blob['rng/seed'] = np.uint64(rng.seed)
+        blob['rng/offset'] = np.int64(rng.offset)
+        blob['rng/dyn'] = np.int64(int(rng.dyn.item()) if rng.dyn is not None else -1)
+        st = np.random.get_state()
+        blob['np_rng/keys'], blob['np_rng/pos'] = st[1], np.int64(st[2])
+        blob['np_rng/gauss'] = np.array([st[3], st[4]], dtype='float64')
+    if iteration is not None:
+        blob['iteration'] = np.int64(iteration)
     return blob
 
 
-def save(path, trainer=None):
-    np.savez(path, **state_dict(trainer))
+def save(path, trainer=None, iteration=None):
+    np.savez(path, **state_dict(trainer, iteration))
 
 
 def load(path_or_blob, trainer=None, strict=True):
@@ -60,10 +70,21 @@ def load(path_or_blob, trainer=None, strict=True):
                     for which, flat in (('m', opt.flat_m), ('v', opt.flat_v)):
                         a = np.ascontiguousarray(blob['opt/%s/%s/%s' % (key, which, n)], dtype='float32').reshape(-1)
                         flat[o:o + sz].copy_(torch.from_numpy(a).to(flat.device))
+        if trainer is not None and 'rng/offset' in blob:
+            rng = trainer.rng
+            rng.seed = int(blob['rng/seed'])
+            rng.offset = int(blob['rng/offset'])
+            if rng.dyn is not None and int(blob['rng/dyn']) >= 0:
+                rng.dyn.fill_(int(blob['rng/dyn']))
+            elif rng.dyn is None and int(blob['rng/dyn']) > 0:
+                rng.offset += int(blob['rng/dyn'])        # saved in graph mode, resumed eagerly: one counter
+            np.random.set_state(('MT19937', np.asarray(blob['np_rng/keys'], dtype='uint32'), int(blob['np_rng/pos']),
+                                 int(blob['np_rng/gauss'][0]), float(blob['np_rng/gauss'][1])))
     K.invalidate_weight_cache(None if trainer is None else (trainer.gen_opt._ptrs | trainer.disc_opt._ptrs))
     if trainer is not None:
         trainer.gen_opt.refresh_packs()
         trainer.disc_opt.refresh_packs()
+    return {'iteration': int(blob['iteration'])} if 'iteration' in blob else {}
 
 
 def save_disc_params_pyn(path='param.pyn', selector='Discriminator'):

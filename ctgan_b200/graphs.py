@@ -106,6 +106,14 @@ class GraphedTrainer:
         def gen_fb():
             return tr.gen_forward_backward()['cost']
 
+        # The warm-up below runs REAL steps (allocator warm-up, lazy operand packs, NCCL buffers): snapshot everything they
+        # change -- parameters, Adam moments and step counts, the Philox counters -- and restore it after the capture, so
+        # that iteration 0 starts from the initial model exactly like the eager / reference loop (TG/CT_gan_cifar_resnet.py
+        # :393-404 runs no generator step and no update before the first critic step)
+        opts = (tr.disc_opt, tr.gen_opt)
+        snap = [(o.flat_p.clone(), o.flat_m.clone(), o.flat_v.clone(), o.t) for o in opts]
+        rng_snap = (tr.rng.dyn.clone(), tr.rng.offset)
+
         # warm-up on a side stream (allocator + lazy init), eager, including the all-reduce
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -129,6 +137,17 @@ class GraphedTrainer:
                 self.fakes_all = tr.generate_fakes(self.labels_all)
                 tr.rng.end_step()
             self.pregen_kernels = K._lib.lib.ctgan_kernel_launches() - k0
+
+        # undo the warm-up steps (captures execute nothing): initial weights, zero moments, t = 0, Philox counters
+        torch.cuda.synchronize()
+        for o, (p0, m0, v0, t0) in zip(opts, snap):
+            o.flat_p.copy_(p0); o.flat_m.copy_(m0); o.flat_v.copy_(v0)
+            o.t = t0
+            K.invalidate_weight_cache(o._ptrs)
+            o.refresh_packs()                       # bf16 operand copies, re-packed in place at the captured addresses
+        tr.rng.dyn.copy_(rng_snap[0])
+        tr.rng.offset = rng_snap[1]
+        torch.cuda.synchronize()
 
     def _lr(self):
         return self.tr.lr(self.iteration) if hasattr(self.tr, 'lr') else None

@@ -69,7 +69,10 @@ def named_params_with_name(name, trainable_only=True):
 
 
 def delete_all_params():
+    """TG/tflib/__init__.py:39-40.  Also drops the aliases (the reference keeps them: a stale alias would redirect a
+    name of the next model built in this process to a parameter of the deleted one)."""
     _params.clear()
+    _param_aliases.clear()
     _F._param_ptrs.clear()
 
 

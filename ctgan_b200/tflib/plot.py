@@ -41,7 +41,8 @@ class _Pending:
 
 
 def _resolve(v):
-    return v.value() if isinstance(v, _Pending) else v
+    """Lazy metrics (device scalars copied asynchronously, device-timed durations) resolve when the log is flushed."""
+    return v.value() if callable(getattr(v, 'value', None)) else v
 
 
 def tick():

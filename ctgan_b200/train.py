@@ -46,6 +46,17 @@ def _rank_world():
     return 0, 1
 
 
+class _EventSeconds:
+    """A device-timed duration that resolves when lib.plot flushes (value()): the iteration time without a sync."""
+
+    def __init__(self, ev0, ev1):
+        self.ev0, self.ev1 = ev0, ev1
+
+    def value(self):
+        self.ev1.synchronize()
+        return self.ev0.elapsed_time(self.ev1) * 1e-3
+
+
 class Session:
     """One training run: model, graphs, feeder, fixed sample noise."""
 
@@ -89,6 +100,8 @@ class Session:
         start = time.time()
         if gt is not None:
             gt.iteration = it
+            ev0 = torch.cuda.Event(enable_timing=True)
+            ev0.record()
         if it > 0:
             gt.gen_step() if gt is not None else tr.gen_step(iteration=it)
         batches = [self._next_batch() for _ in range(self.n_critic)]      # all stay valid: feeder hold = n_critic
@@ -98,13 +111,23 @@ class Session:
         for b in batches:
             out = gt.critic_step(*b) if gt is not None else tr.critic_step(*b, iteration=it)['out']
         if self.resnet:
+            # names and contents of TG/CT_gan_cifar_resnet.py:406-412: 'wgan' is disc_wgan = Wasserstein term + CT + 10*GP
+            # (:295), i.e. the cost without its ACGAN part; out = {cost, wgan term, ct, gp, acgan, ...}.  The two clean-pass
+            # accuracies ('acc_real', 'acc_fake') are not plotted: that metrics-only critic pass is not executed here.
             _plot.plot('cost', out[0])
             if self.mod.CONDITIONAL and self.mod.ACGAN:
-                _plot.plot('wgan', out[1])
+                _plot.plot('wgan', out[0] - self.mod.ACGAN_SCALE * out[4])
                 _plot.plot('acgan', out[4])
         else:
             _plot.plot('train disc cost', out[0])
-        _plot.plot('time', time.time() - start)
+        # graph mode: replays are asynchronous, so host wall time would only measure the enqueue; time the iteration on the
+        # device instead (events resolved lazily in flush(), like the other metrics)
+        if gt is not None:
+            ev1 = torch.cuda.Event(enable_timing=True)
+            ev1.record()
+            _plot.plot('time', _EventSeconds(ev0, ev1))
+        else:
+            _plot.plot('time', time.time() - start)
         self.iteration = it + 1
         return out
 
@@ -153,10 +176,13 @@ class Session:
         return path
 
 
-def train(script, data_dir, iters=None, dev_every=None, out_dir='.', checkpoint_every=None, dev_batches=None, **kw):
-    """Run `iters` iterations (default: the script's ITERS).  Returns the Session."""
+def train(script, data_dir, iters=None, dev_every=None, out_dir='.', checkpoint_every=None, dev_batches=None, resume=None, **kw):
+    """Run up to iteration `iters` (default: the script's ITERS).  resume: a checkpoint written by checkpoint.save() -- weights,
+    Adam state, the Philox counters and the iteration (learning-rate decay) continue from it.  Returns the Session."""
     os.makedirs(out_dir, exist_ok=True)
     s = Session(script, data_dir, out_dir=out_dir, **kw)
+    if resume:
+        s.iteration = checkpoint.load(resume, s.tr).get('iteration', 0)
     dev_every = dev_every or (200 if script == '64x64' else 100)          # TG/CT_gan_64x64.py:656
     _plot.reset()
     _plot.output_dir = out_dir
@@ -164,7 +190,7 @@ def train(script, data_dir, iters=None, dev_every=None, out_dir='.', checkpoint_
     flush_early = 500 if s.resnet else 5                     # :431 `iteration < 500`; DCGAN scripts: `iteration < 5`
     flush_every = 1000 if s.resnet else (200 if script == '64x64' else 100)
     writer = _rank_world()[0] == 0                           # replicas are identical: rank 0 writes the files
-    for iteration in range(iters):
+    for iteration in range(s.iteration, iters):
         s.run_iteration()
         if iteration % dev_every == dev_every - 1:
             _plot.plot('dev_cost' if s.resnet else 'dev disc cost', s.dev_cost(dev_batches))
@@ -173,7 +199,7 @@ def train(script, data_dir, iters=None, dev_every=None, out_dir='.', checkpoint_
                 if script == 'cifar':
                     checkpoint.save_disc_params_pyn(os.path.join(out_dir, 'param.pyn'))   # TG/CT_gan_cifar.py:216-222
         if writer and checkpoint_every and iteration % checkpoint_every == checkpoint_every - 1:
-            checkpoint.save(os.path.join(out_dir, 'checkpoint.npz'), s.tr)
+            checkpoint.save(os.path.join(out_dir, 'checkpoint.npz'), s.tr, iteration=iteration + 1)
         if iteration < flush_early or iteration % flush_every == flush_every - 1:
             if writer:
                 _plot.flush()
@@ -193,9 +219,10 @@ def main():
     ap.add_argument('--n-examples', type=int, default=None)
     ap.add_argument('--checkpoint-every', type=int, default=None)
     ap.add_argument('--no-graphs', action='store_true')
+    ap.add_argument('--resume', default=None, help='checkpoint.npz of an earlier run to continue from')
     a = ap.parse_args()
     train(a.script, a.data_dir, iters=a.iters, out_dir=a.out_dir, batch_size=a.batch_size, n_examples=a.n_examples,
-          checkpoint_every=a.checkpoint_every, use_graphs=not a.no_graphs)
+          checkpoint_every=a.checkpoint_every, use_graphs=not a.no_graphs, resume=a.resume)
 
 
 if __name__ == '__main__':

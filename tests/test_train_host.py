@@ -57,6 +57,8 @@ def test_train_loop_schedule_and_outputs(fake_kernels, tmp_path, script, capsys)
         assert sorted(log[cost_name]) == [0, 1, 2] and sorted(log['time']) == [0, 1, 2] and sorted(log[dev_name]) == [1]
         if script == 'cifar_resnet':
             assert sorted(log['wgan']) == [0, 1, 2] and sorted(log['acgan']) == [0, 1, 2]
+            # 'wgan' = disc_wgan (TG/CT_gan_cifar_resnet.py:295) = cost - ACGAN_SCALE * acgan (:300)
+            assert all(abs(log['wgan'][i] - (log['cost'][i] - log['acgan'][i])) < 1e-4 * max(1., abs(log['cost'][i])) for i in range(3))
         assert all(np.isfinite(v) for v in log[cost_name].values())
         ext = {'cifar': 'jpg', 'cifar_resnet': 'png', 'mnist': 'png'}[script]
         assert os.path.getsize(os.path.join(out, 'samples_1.%s' % ext)) > 0
@@ -65,6 +67,12 @@ def test_train_loop_schedule_and_outputs(fake_kernels, tmp_path, script, capsys)
             para = np.load(os.path.join(out, 'param.pyn.npy'), allow_pickle=True)
             assert len(para) == 8 and para[0].shape == (5, 5, 3, 128)        # 3 convs + Output: Filters/W + Biases/b
         assert 'iter 0\t' in capsys.readouterr().out
+        # --resume: the loop continues at the saved iteration (here 3) with the saved optimizer / random state
+        blob = np.load(os.path.join(out, 'checkpoint.npz'))
+        assert int(blob['iteration']) == 3
+        sess2 = T.train(script, data, iters=4, dev_every=2, out_dir=out, dev_batches=1, batch_size=4, n_examples=40,
+                        device='cpu', use_graphs=False, act_dtype=torch.float32, resume=os.path.join(out, 'checkpoint.npz'))
+        assert sess2.iteration == 4 and sess2.tr.disc_opt.t == 4 * n_critic and sess2.tr.gen_opt.t == 3
     finally:
         plot.output_dir = '.'
         plot.reset()
@@ -83,18 +91,22 @@ def test_checkpoint_round_trip_resumes_exactly(fake_kernels, tmp_path):
     a = fresh()
     a.critic_step(x[0]); a.gen_step()
     path = str(tmp_path / 'ck.npz')
-    checkpoint.save(path, a)
+    checkpoint.save(path, a, iteration=7)
     blob = np.load(path)
     assert blob['param/Discriminator.2.Filters'].shape == (5, 5, 128, 256)            # reference name, HWIO
     assert blob['param/Generator.Input.W'].shape == (128, 8192)
-    a.rng.offset = 1000
+    assert a.rng.offset > 0 and int(blob['rng/offset']) == a.rng.offset          # the Philox position is part of the state
+    np_next = np.random.RandomState()
+    np_next.set_state(np.random.get_state())
     a.critic_step(x[1])
     want = a.disc_opt.flat_p.clone()
 
     b = fresh()
-    checkpoint.load(path, b)
+    np.random.seed(123)                                      # a resumed process starts with some other numpy state
+    assert checkpoint.load(path, b) == {'iteration': 7}
     assert b.disc_opt.t == 1 and b.gen_opt.t == 1
-    b.rng.offset = 1000
+    assert b.rng.offset == int(blob['rng/offset'])           # same noise / dropout stream position, no manual fix-up
+    assert np.random.randint(1 << 30) == np_next.randint(1 << 30)                 # loaders' shuffles continue too
     b.critic_step(x[1])
     assert torch.equal(b.disc_opt.flat_p, want)
     with pytest.raises(KeyError):
