@@ -206,14 +206,18 @@ def _tc_geom_ok(g):
 _pack_cache = {}
 
 
-def invalidate_weight_cache(ptrs=None):
-    """Called by an optimizer after ITS parameters changed in place (ptrs = their data pointers; None = all)."""
+def invalidate_weight_cache(ptrs=None, forget=False):
+    """Called by an optimizer after ITS parameters changed in place (ptrs = their data pointers; None = all).
+    forget: the tensors at `ptrs` no longer exist (moved into a flat buffer): also drop their registered lazy packs."""
     if ptrs is None:
         _pack_cache.clear()
         _lazy_packs.clear()
         return
     for k in [k for k in _pack_cache if k[0] in ptrs]:
         del _pack_cache[k]
+    if forget:
+        for ptr in ptrs:
+            _lazy_packs.pop(ptr, None)
 
 
 def pack_filter(w, transpose_flip, cacheable=False):

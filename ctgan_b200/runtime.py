@@ -224,6 +224,7 @@ class FlatAdam:
         self._lr_ring_ev, self._lr_ring_i = [None] * 64, 0
         self.params = {}
         new = {}
+        old_ptrs = {p.data_ptr() for p in named.values()}
         for n, p in named.items():
             o, sz = offs[n], sizes[n]
             self.flat_p[o:o + sz].copy_(p.detach().reshape(-1))
@@ -234,7 +235,9 @@ class FlatAdam:
         lib.rebind_params(new)
         self.offsets, self.sizes = offs, sizes
         self._ptrs = set(q.data_ptr() for q in self.params.values())
-        K.invalidate_weight_cache()
+        # only THIS optimizer's tensors moved: a blanket invalidation would also drop the packs another optimizer of the
+        # same model published a moment ago (the generator's, when the critic's optimizer is built second)
+        K.invalidate_weight_cache(old_ptrs, forget=True)
         self.packer = K.FilterPacker(self.flat_p, self.params, offs) if dev.type == 'cuda' else None
         # publish the one-launch operand packs NOW: a filter first used before the first optimizer step would otherwise
         # get its own lazily created pack, re-packed by one extra launch per filter and layout after every step

