@@ -47,6 +47,7 @@ _PROTOS = {
     'ctgan_set_fprop_halo': (None, [c_int]),
     'ctgan_set_fprop_variant': (None, [c_int]),
     'ctgan_set_pdl': (None, [c_int]),
+    'ctgan_set_splitk': (None, [c_int]),
     'ctgan_set_wgrad_variant': (None, [c_int]),
     'ctgan_conv_fprop_tc': (c_int, [POINTER(ConvDesc), P, P, P, P, P, c_int, P]),
     'ctgan_conv_fprop_tc_masked': (c_int, [POINTER(ConvDesc), P, P, P, P, P, P, c_int, P]),

@@ -31,26 +31,6 @@ namespace ctgan {
 namespace tc {
 
 
-struct FpropParams {
-    int N, H, W, Cin, Cout;
-    int kh, kw, pad_t, pad_l;
-    int BW, BH, BN;                // pixel box of one M tile: BN*BH*BW == 128
-    int tilesW, tilesH, tilesN;
-    int flags;
-    __nv_bfloat16* y;
-    const float* bias;
-    const __nv_bfloat16* residual;
-    const __nv_bfloat16* relu_mask;    // output is zeroed where this tensor (shape of y) is <= 0: dgrad into a ReLU output
-    // EPI_ACTDROP epilogue (lean kernels): y = v * m, m = (v > 0 ? 1 : slope) * (keep < 1 ? floor(keep + u) / keep : 1), v = conv + bias,
-    // u = Philox(seed, offset + dyn[0] + NHWC element index); m is stored next to y; out_s2d: y and m are written in the
-    // space-to-depth layout [N, H/2, W/2, 4*Cout] the next stride-2 layer consumes (H, W even)
-    __nv_bfloat16* mult;
-    float slope, keep;
-    unsigned long long seed, offset;
-    const unsigned long long* dyn;
-    int out_s2d;
-};
-
 // 32-byte global accesses (LDG.256 / STG.256): 16 bf16 channels of one pixel row per instruction = one full sector.
 __device__ __forceinline__ void ld16_bf16(const __nv_bfloat16* p, bool wide, float (&f)[16]) {
     uint32_t rw[8];
@@ -256,27 +236,6 @@ conv_fprop_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
 //                bias at TG/tflib/ops/conv2d.py:114-120) in the conv epilogue.  u comes from Philox4x32-10 in registers at
 //                the element's NHWC index (the stream act_dropout_kernel draws from), optionally written in the
 //                space-to-depth layout of the next stride-2 layer.
-enum { EPI_PLAIN = 0, EPI_MASK = 1, EPI_ACTDROP = 2 };
-
-__device__ __forceinline__ void ldg16_bf16(const __nv_bfloat16* p, bool wide, uint32_t (&rw)[8]) {
-    if (wide) {
-        asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                     : "=r"(rw[0]), "=r"(rw[1]), "=r"(rw[2]), "=r"(rw[3]), "=r"(rw[4]), "=r"(rw[5]), "=r"(rw[6]), "=r"(rw[7]) : "l"(p));
-    } else {
-        const uint4 r0 = *reinterpret_cast<const uint4*>(p), r1 = *reinterpret_cast<const uint4*>(p + 8);
-        rw[0] = r0.x; rw[1] = r0.y; rw[2] = r0.z; rw[3] = r0.w; rw[4] = r1.x; rw[5] = r1.y; rw[6] = r1.z; rw[7] = r1.w;
-    }
-}
-__device__ __forceinline__ void stg16_bf16(__nv_bfloat16* p, bool wide, const uint32_t (&ow)[8]) {
-    if (wide) {
-        asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
-                     ::"l"(p), "r"(ow[0]), "r"(ow[1]), "r"(ow[2]), "r"(ow[3]), "r"(ow[4]), "r"(ow[5]), "r"(ow[6]), "r"(ow[7]) : "memory");
-    } else {
-        *reinterpret_cast<uint4*>(p) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
-        *reinterpret_cast<uint4*>(p + 8) = make_uint4(ow[4], ow[5], ow[6], ow[7]);
-    }
-}
-
 template <int EPI>
 __device__ __forceinline__ void lean_epilogue_tile(const FpropParams& p, uint32_t tmem_addr, int q, int lane,
                                                    int w0, int h0, int n0, int co0, bool relu) {
@@ -1263,6 +1222,14 @@ static int launch_fprop_pair(const CUtensorMap& mx, const CUtensorMap& mx2, cons
 using namespace ctgan;
 using namespace ctgan::tc;
 
+namespace ctgan { namespace tc {
+int splitk_factor(int n_tiles, int groups);                              // conv_splitk.cu
+int launch_fprop_splitk(int split, int epi, const CUtensorMap& mx, const CUtensorMap& mw, const FpropParams& p, int n_tiles,
+                        cudaStream_t st);
+} }
+static bool g_use_splitk = true;
+/* test / A-B hook: 0 = sub-wave layers run on conv_fprop_tc_lean_kernel<0> instead of the cluster split-K kernel */
+extern "C" void ctgan_set_splitk(int on) { g_use_splitk = on != 0; }
 static bool g_use_halo = true;
 static int g_fprop_variant = 4;   // 4 = 256-pixel work items where possible (else 3), 3 = persistent grouped-stage (lean) kernel, 1 = one tile per CTA
 /* test hook: selects the fprop_tc kernel family (the families are compared in tests/) */
@@ -1300,8 +1267,12 @@ static int fprop_tc_launch(const ctgan_conv_desc* d, const void* x, const void* 
             if (epi == EPI_ACTDROP) return launch_fprop_lean<1, EPI_ACTDROP>(mx, mw, p, st);
             return launch_fprop_lean<1, EPI_PLAIN>(mx, mw, p, st);
         }
-        if (epi == EPI_MASK) return launch_fprop_lean<0, EPI_MASK>(mx, mw, p, st);
         if (epi == EPI_ACTDROP) return launch_fprop_lean<0, EPI_ACTDROP>(mx, mw, p, st);
+        // fewer tiles than half the SMs: split K over a cluster of 2 / 4 CTAs (conv_splitk.cu)
+        const int n_tiles = p.tilesW * p.tilesH * p.tilesN * (d->Cout / 128);
+        const int split = g_use_splitk ? splitk_factor(n_tiles, (d->kh * d->kw * (d->Cin / 64) + 1) / 2) : 0;
+        if (split) return launch_fprop_splitk(split, epi, mx, mw, p, n_tiles, st);
+        if (epi == EPI_MASK) return launch_fprop_lean<0, EPI_MASK>(mx, mw, p, st);
         return launch_fprop_lean<0, EPI_PLAIN>(mx, mw, p, st);
     }
     if (block_n == 128) {

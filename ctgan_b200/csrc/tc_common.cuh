@@ -137,6 +137,50 @@ constexpr int BLOCK_M = 128;       // tile rows = TMEM lanes
 constexpr int BLOCK_K = 64;        // bf16 elements per 128-byte swizzle row
 constexpr int UMMA_K  = 16;
 
+// ------------------------------------------------------------------ forward-family parameters and epilogue helpers
+struct FpropParams {
+    int N, H, W, Cin, Cout;
+    int kh, kw, pad_t, pad_l;
+    int BW, BH, BN;                // pixel box of one M tile: BN*BH*BW == 128
+    int tilesW, tilesH, tilesN;
+    int flags;
+    __nv_bfloat16* y;
+    const float* bias;
+    const __nv_bfloat16* residual;
+    const __nv_bfloat16* relu_mask;    // output is zeroed where this tensor (shape of y) is <= 0: dgrad into a ReLU output
+    // EPI_ACTDROP epilogue (lean kernels): y = v * m, m = (v > 0 ? 1 : slope) * (keep < 1 ? floor(keep + u) / keep : 1), v = conv + bias,
+    // u = Philox(seed, offset + dyn[0] + NHWC element index); m is stored next to y; out_s2d: y and m are written in the
+    // space-to-depth layout [N, H/2, W/2, 4*Cout] the next stride-2 layer consumes (H, W even)
+    __nv_bfloat16* mult;
+    float slope, keep;
+    unsigned long long seed, offset;
+    const unsigned long long* dyn;
+    int out_s2d;
+};
+
+
+enum { EPI_PLAIN = 0, EPI_MASK = 1, EPI_ACTDROP = 2 };
+
+__device__ __forceinline__ void ldg16_bf16(const __nv_bfloat16* p, bool wide, uint32_t (&rw)[8]) {
+    if (wide) {
+        asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(rw[0]), "=r"(rw[1]), "=r"(rw[2]), "=r"(rw[3]), "=r"(rw[4]), "=r"(rw[5]), "=r"(rw[6]), "=r"(rw[7]) : "l"(p));
+    } else {
+        const uint4 r0 = *reinterpret_cast<const uint4*>(p), r1 = *reinterpret_cast<const uint4*>(p + 8);
+        rw[0] = r0.x; rw[1] = r0.y; rw[2] = r0.z; rw[3] = r0.w; rw[4] = r1.x; rw[5] = r1.y; rw[6] = r1.z; rw[7] = r1.w;
+    }
+}
+__device__ __forceinline__ void stg16_bf16(__nv_bfloat16* p, bool wide, const uint32_t (&ow)[8]) {
+    if (wide) {
+        asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                     ::"l"(p), "r"(ow[0]), "r"(ow[1]), "r"(ow[2]), "r"(ow[3]), "r"(ow[4]), "r"(ow[5]), "r"(ow[6]), "r"(ow[7]) : "memory");
+    } else {
+        *reinterpret_cast<uint4*>(p) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+        *reinterpret_cast<uint4*>(p + 8) = make_uint4(ow[4], ow[5], ow[6], ow[7]);
+    }
+}
+
+
 // ------------------------------------------------------------------ host side: tensor maps
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,

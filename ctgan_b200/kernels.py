@@ -130,6 +130,29 @@ def join_side():
         _side_pending.clear()
 
 
+class splitk:
+    """with splitk(False): the tcgen05 forward launches issued inside keep one CTA per tile.  The cluster split-K kernel
+    (csrc/conv_splitk.cu) shortens a sub-wave layer's latency by occupying up to 4x the SMs; that pays when the layer runs
+    alone (generator step, DCGAN steps: -25 us / step) and costs when a second stream branch competes for the SMs (the
+    ResNet critic step with its gradient-penalty branch: +30 us) -- measured, profiles/README.md."""
+    _on = True
+
+    def __init__(self, on):
+        self.on = bool(on)
+
+    def __enter__(self):
+        self.prev, splitk._on = splitk._on, self.on
+        if self.on != self.prev:
+            _lib.lib.ctgan_set_splitk(int(self.on))
+        return self
+
+    def __exit__(self, *exc):
+        if self.prev != splitk._on:
+            _lib.lib.ctgan_set_splitk(int(self.prev))
+        splitk._on = self.prev
+        return False
+
+
 # Independent sub-graphs of one step (the gradient-penalty pass vs the stacked critic pass) as two stream branches.
 _branch_streams = {}
 

@@ -94,6 +94,9 @@ void ctgan_set_fprop_halo(int on);
 void ctgan_set_pdl(int on);
 /* test hook: 4 = 256-pixel work items where eligible, else 3 (default); 3 = persistent grouped-stage kernel; 1 = one tile per CTA */
 void ctgan_set_fprop_variant(int v);
+/* test / A-B hook: 1 (default) = layers with fewer output tiles than half the SMs split K over a cluster of 2 / 4 CTAs and
+ * reduce the partial accumulators through distributed shared memory (csrc/conv_splitk.cu); 0 = one CTA per tile */
+void ctgan_set_splitk(int on);
 /* test/benchmark hook: 2 (default) = 3x3 wgrad CTAs own one filter column and share the x halo box; 1 = per-tap boxes */
 void ctgan_set_wgrad_variant(int v);
 int ctgan_conv_fprop_tc(const ctgan_conv_desc* d, const void* x, const void* wp,

@@ -17,6 +17,9 @@ if len(sys.argv) > 4:
 import os
 if os.environ.get('CTGAN_FUSE_RELU_BWD'):
     R.FUSE_RELU_BWD = bool(int(os.environ['CTGAN_FUSE_RELU_BWD']))
+if os.environ.get('CTGAN_SPLITK'):
+    from ctgan_b200 import _lib as _L2
+    _L2.lib.ctgan_set_splitk(int(os.environ['CTGAN_SPLITK']))
 if os.environ.get('CTGAN_WGRAD_ITEMS'):
     from ctgan_b200 import _lib as _L
     _L.lib.ctgan_set_wgrad_multi_items_per_sm(int(os.environ['CTGAN_WGRAD_ITEMS']))

@@ -140,6 +140,42 @@ def test_tc_fprop_variants_match(K, shape):
         _lib.lib.ctgan_set_fprop_halo(1)
 
 
+@pytest.mark.parametrize('shape', [(64, 8, 8, 3, 128, 128), (128, 8, 8, 3, 128, 128), (40, 8, 8, 3, 128, 128), (30, 4, 4, 3, 128, 128),
+                                   (32, 8, 8, 3, 128, 256), (9, 8, 8, 3, 256, 128), (60, 8, 8, 1, 512, 128), (24, 4, 4, 3, 1024, 512)])
+def test_tc_splitk_cluster_kernel(K, shape):
+    """Layers with fewer output tiles than half the SMs: K split over a cluster of 2 / 4 CTAs, partial accumulators
+    reduce-scattered through distributed shared memory (csrc/conv_splitk.cu) -- against the CPU reference and the
+    one-CTA-per-tile kernel, as fprop (+bias), dgrad, with the residual + ReLU epilogue and with the ReLU-backward mask."""
+    from ctgan_b200 import _lib
+    N, H, W, k, Cin, Cout = shape
+    g = K.same_geom(N, H, W, Cin, Cout, k, 1)
+    x, dy = act((N, Cin, H, W), torch.bfloat16, 1), act((N, Cout, H, W), torch.bfloat16, 2)
+    r, mk = act((N, Cout, H, W), torch.bfloat16, 5), act((N, Cin, H, W), torch.bfloat16, 6)
+    w, b = filt((k, k, Cin, Cout), 3), act((Cout,), torch.float32, 4)
+    wq = w.to(torch.bfloat16).float()
+    ref_f, ref_d = FB().conv_fprop(x, wq, b, g), FB().conv_dgrad(dy, wq, g)
+    ref_r = FB().conv_fprop(x, wq, b, g, relu=True, residual=r)
+    ref_m = FB().conv_dgrad(dy, wq, g, relu_mask=mk)
+    outs = {}
+    try:
+        for on in (1, 0):
+            _lib.lib.ctgan_set_splitk(on)
+            yf = K.conv_fprop(to_dev(x), w.cuda(), b.cuda(), g)
+            yd = K.conv_dgrad(to_dev(dy), w.cuda(), g)
+            yr = K.conv_fprop(to_dev(x), w.cuda(), b.cuda(), g, relu=True, residual=to_dev(r))
+            ym = K.conv_dgrad(to_dev(dy), w.cuda(), g, relu_mask=to_dev(mk))
+            assert rel(yf, ref_f) < 1e-2 and rel(yd, ref_d) < 1e-2 and rel(yr, ref_r) < 1e-2 and rel(ym, ref_m) < 1e-2, on
+            outs[on] = (yf, yd, yr, ym)
+        for a, c in zip(outs[1], outs[0]):
+            assert rel(a, c) < 4e-3              # same products, different summation order, one bf16 rounding
+        # deterministic: no atomics anywhere on this path
+        assert torch.equal(K.conv_fprop(to_dev(x), w.cuda(), b.cuda(), g), outs[0][0])
+        _lib.lib.ctgan_set_splitk(1)
+        assert torch.equal(K.conv_fprop(to_dev(x), w.cuda(), b.cuda(), g), outs[1][0])
+    finally:
+        _lib.lib.ctgan_set_splitk(1)
+
+
 def test_tc_residual_relu_epilogue(K):
     g = K.same_geom(3, 8, 8, 128, 128, 3, 1)
     x, r = act((3, 128, 8, 8), torch.bfloat16, 1), act((3, 128, 8, 8), torch.bfloat16, 2)
