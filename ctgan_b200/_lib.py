@@ -116,6 +116,13 @@ _PROTOS = {
     'ctgan_softmax_ce_fwd': (c_int, [P, P, P, c_int, c_int, P]),
     'ctgan_softmax_ce_bwd': (c_int, [P, P, P, c_float, P, c_int, c_int, P]),
     'ctgan_adam_step': (c_int, [P, P, P, P, c_int64, c_float, c_float, c_float, c_float, c_float, P, P]),
+    'ctgan_peer_alloc': (c_int, [POINTER(P), c_int64]),
+    'ctgan_peer_free': (c_int, [P]),
+    'ctgan_ipc_get_handle': (c_int, [P, P]),
+    'ctgan_ipc_open_handle': (c_int, [P, POINTER(P)]),
+    'ctgan_ipc_close_handle': (c_int, [P]),
+    'ctgan_peer_flag_bytes': (c_int, []),
+    'ctgan_peer_reduce_adam': (c_int, [c_int, c_int, POINTER(P), POINTER(P), POINTER(P), P, P, c_int64, c_float, c_float, c_float, c_float, c_float, P, P]),
     'ctgan_philox_uniform': (c_int, [P, c_int64, c_float, c_float, c_uint64, c_uint64, P, P]),
     'ctgan_counter_add': (c_int, [P, c_uint64, P]),
     'ctgan_philox_normal': (c_int, [P, c_int64, c_uint64, c_uint64, P, P]),

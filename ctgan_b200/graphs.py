@@ -8,11 +8,10 @@ replayed; everything that changes between replays lives in device memory:
   * random numbers               -> Philox streams offset by a device counter (runtime.DeviceRandom),
   * the learning rate lr_t       -> FlatAdam.lr_t_dev, uploaded from pinned memory per replay.
 
-Data parallel (world_size > 1): each step is captured as TWO graphs -- (zero_grad, forward,
-backward) and (Adam, RNG advance) -- with the NCCL all-reduce of the flat gradient bucket
-issued eagerly between them on the same stream.  The collective is one launch per step
-(4.2 MB / 4.9 MB), so keeping it out of the capture costs ~one host launch and avoids
-depending on NCCL-inside-capture behaviour.
+Data parallel (world_size > 1): with peer buffers (runtime.PeerBuffers, the default) the gradient exchange is part of
+the update kernel (csrc/peer.cu: reduce-scatter + Adam + all-gather over NVLink peer memory), so a step is ONE graph
+exactly like on a single GPU.  NCCL fallback: each step is captured as TWO graphs -- (zero_grad, forward, backward) and
+(Adam, RNG advance) -- with the all-reduce of the flat gradient bucket issued eagerly between them on the same stream.
 """
 import torch
 
@@ -29,6 +28,7 @@ class _Step:
 
     def __init__(self, opt, fwd_bwd, rng, pool):
         self.opt, self.rng, self.world = opt, rng, _world()
+        self.one_graph = self.world == 1 or getattr(opt, 'peer', None) is not None
         self.kernels = 0
 
         def whole():
@@ -47,7 +47,7 @@ class _Step:
             rng.end_step()
 
         k0 = K._lib.lib.ctgan_kernel_launches()
-        if self.world == 1:
+        if self.one_graph:
             self.g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.g, pool=pool):
                 self.out = whole()
@@ -64,7 +64,7 @@ class _Step:
         self.kernels = K._lib.lib.ctgan_kernel_launches() - k0
 
     def replay(self):
-        if self.world == 1:
+        if self.one_graph:
             self.g.replay()
         else:
             self.ga.replay()

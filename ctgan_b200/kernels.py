@@ -29,6 +29,7 @@ class Config:
     tc_min_rows = 1          # (tunable) minimum GEMM rows to prefer the tensor-core path
     use_bn_fused = True      # BF16 batch norm as two kernels per direction (sums with red.global + apply)
     fuse_act_dropout = True  # Conv2D -> LeakyReLU -> dropout of the DCGAN critics in the tcgen05 conv epilogue (Philox in registers)
+    peer_update = True       # data parallel: reduce-scatter + Adam + all-gather as one kernel over NVLink peer memory (else NCCL all-reduce)
     defer_wgrad = True       # queue the final backward's tensor-core filter gradients and run them as ONE launch at the join
 
 
@@ -1236,3 +1237,38 @@ def philox_labels(n, device, n_labels, seed, offset, dyn=None):
 
 def counter_add(counter, delta):
     call('ctgan_counter_add', _p(counter), int(delta), _stream())
+
+
+# --------------------------------------------------------------------------- data parallel over peer memory (csrc/peer.cu)
+class _RawFloats:
+    """float32 view of a raw device allocation for torch.as_tensor (CUDA array interface)."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {'shape': (int(n),), 'typestr': '<f4', 'data': (int(ptr), False), 'version': 2}
+
+
+def peer_alloc_floats(n, device):
+    """(tensor, ptr): n zeroed floats in cudaMalloc memory that can be exported over CUDA IPC."""
+    out = ctypes.c_void_p()
+    with torch.cuda.device(device):
+        call('ctgan_peer_alloc', ctypes.byref(out), int(n) * 4)
+        t = torch.as_tensor(_RawFloats(out.value, n), device=device)
+    return t, out.value
+
+
+def ipc_handle(ptr):
+    buf = ctypes.create_string_buffer(64)
+    call('ctgan_ipc_get_handle', ctypes.c_void_p(ptr), buf)
+    return buf.raw
+
+
+def ipc_open(handle):
+    out = ctypes.c_void_p()
+    call('ctgan_ipc_open_handle', ctypes.create_string_buffer(handle, 64), ctypes.byref(out))
+    return out.value
+
+
+def peer_reduce_adam(world, rank, g_ptrs, p_ptrs, flag_ptrs, m, v, n, lr_t, beta1, beta2, eps, grad_scale, lr_t_dev=None):
+    arr = lambda ps: (ctypes.c_void_p * world)(*ps)
+    call('ctgan_peer_reduce_adam', world, rank, arr(g_ptrs), arr(p_ptrs), arr(flag_ptrs), _p(m), _p(v), int(n), float(lr_t),
+         float(beta1), float(beta2), float(eps), float(grad_scale), _p(lr_t_dev), _stream())

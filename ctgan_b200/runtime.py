@@ -9,8 +9,11 @@ data-parallel gradient exchange.
   * `FlatAdam` replaces tf.train.AdamOptimizer(...).minimize(cost, var_list=...)
     (TG/CT_gan_cifar.py:153-154, TG/CT_gan_cifar_resnet.py:333-338): parameters, gradients
     and both moments live in four flat float buffers, one fused kernel per update.
-  * Data parallel: one process per GPU, gradients of the flat buffer are
-    summed with one NCCL all-reduce and the 1/world factor is folded into the Adam kernel.
+  * Data parallel: one process per GPU.  Default: the flat gradient bucket and the flat parameter
+    buffer live in peer-visible memory (CUDA IPC over NVLink / NVSwitch) and ONE kernel per rank does reduce-scatter +
+    Adam on the owned slice + all-gather of the new parameters (csrc/peer.cu) -- no NCCL call inside a step, so a
+    data-parallel step is one CUDA graph.  Fallback (kernels.config.peer_update = False, or IPC unavailable): one NCCL
+    all-reduce of the bucket, the 1/world factor folded into the Adam kernel.
 """
 import math
 
@@ -191,6 +194,55 @@ class DeviceRandom:
         return '%s.%d' % (self._scope, self._site)
 
 
+def _dist_world():
+    import torch.distributed as dist
+    return dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+
+
+class PeerBuffers:
+    """Flat parameter and gradient buffers of one optimizer in peer-visible memory, plus the mappings of every other
+    rank's buffers and flag blocks (CUDA IPC, one node): the operands of K.peer_reduce_adam."""
+
+    @classmethod
+    def create(cls, n, dev):
+        import torch.distributed as dist
+        import warnings
+        self = cls()
+        self.world, self.rank = dist.get_world_size(), dist.get_rank()
+        ok = torch.ones(1, device=dev)
+        try:
+            self.p, p_ptr = K.peer_alloc_floats(n, dev)
+            self.g, g_ptr = K.peer_alloc_floats(n, dev)
+            self.flags, f_ptr = K.peer_alloc_floats(K._lib.lib.ctgan_peer_flag_bytes() // 4, dev)
+            mine = (K.ipc_handle(p_ptr), K.ipc_handle(g_ptr), K.ipc_handle(f_ptr))
+        except Exception as e:                                  # e.g. IPC not permitted in this container
+            warnings.warn('ctgan_b200: peer buffers unavailable (%s); falling back to NCCL all-reduce' % e)
+            ok.zero_()
+            mine = None
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)               # all ranks take the same path
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, mine)
+        if ok.item() == 0:
+            return None
+        self.p_ptrs, self.g_ptrs, self.flag_ptrs = [], [], []
+        try:
+            for r, h in enumerate(everyone):
+                if r == self.rank:
+                    ptrs = (p_ptr, g_ptr, f_ptr)
+                else:
+                    with torch.cuda.device(dev):
+                        ptrs = tuple(K.ipc_open(x) for x in h)
+                self.p_ptrs.append(ptrs[0]); self.g_ptrs.append(ptrs[1]); self.flag_ptrs.append(ptrs[2])
+        except Exception as e:
+            warnings.warn('ctgan_b200: could not map the peers\' buffers (%s); falling back to NCCL all-reduce' % e)
+            ok.zero_()
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if ok.item() == 0:
+            return None
+        dist.barrier()
+        return self
+
+
 class FlatAdam:
     """TF-semantics Adam over the parameters selected by name (substring), held flat.
 
@@ -213,8 +265,14 @@ class FlatAdam:
             offs[n] = total
             total += (sizes[n] + self.PAD - 1) // self.PAD * self.PAD
         self.n = total
-        self.flat_p = torch.zeros(total, dtype=torch.float32, device=dev)
-        self.flat_g = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.peer = None
+        if dev.type == 'cuda' and K.config.peer_update and _dist_world() > 1:
+            self.peer = PeerBuffers.create(total, dev)
+        if self.peer is not None:
+            self.flat_p, self.flat_g = self.peer.p, self.peer.g
+        else:
+            self.flat_p = torch.zeros(total, dtype=torch.float32, device=dev)
+            self.flat_g = torch.zeros(total, dtype=torch.float32, device=dev)
         self.flat_m = torch.zeros(total, dtype=torch.float32, device=dev)
         self.flat_v = torch.zeros(total, dtype=torch.float32, device=dev)
         self.lr_t_dev = torch.zeros(1, dtype=torch.float32, device=dev)
@@ -259,9 +317,12 @@ class FlatAdam:
         return lr * math.sqrt(1. - self.beta2 ** t) / (1. - self.beta1 ** t)
 
     def all_reduce(self):
-        """Sum the flat gradient bucket over ranks (NCCL); the 1/world scale is applied in step()."""
+        """Sum the flat gradient bucket over ranks (NCCL); the 1/world scale is applied in step().  With peer buffers the
+        exchange happens inside step() (one kernel: reduce-scatter + Adam + all-gather): nothing to do here."""
         import torch.distributed as dist
         K.join_side()
+        if self.peer is not None:
+            return self.peer.world
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             dist.all_reduce(self.flat_g)
             return dist.get_world_size()
@@ -273,9 +334,15 @@ class FlatAdam:
         K.join_side()                        # filter / bias gradients accumulated on the side stream
         if not use_device_lr:
             self.t += 1                      # graph mode: t advances in set_device_lr() at replay time
-        K.adam_step(self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.lr_t(lr) if not use_device_lr else 0.0,
-                    self.beta1, self.beta2, self.eps, grad_scale=1.0 / world,
-                    lr_t_dev=self.lr_t_dev if use_device_lr else None)
+        if self.peer is not None:
+            pb = self.peer
+            K.peer_reduce_adam(pb.world, pb.rank, pb.g_ptrs, pb.p_ptrs, pb.flag_ptrs, self.flat_m, self.flat_v, self.n,
+                               self.lr_t(lr) if not use_device_lr else 0.0, self.beta1, self.beta2, self.eps,
+                               grad_scale=1.0 / pb.world, lr_t_dev=self.lr_t_dev if use_device_lr else None)
+        else:
+            K.adam_step(self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.lr_t(lr) if not use_device_lr else 0.0,
+                        self.beta1, self.beta2, self.eps, grad_scale=1.0 / world,
+                        lr_t_dev=self.lr_t_dev if use_device_lr else None)
         K.invalidate_weight_cache(self._ptrs)
         self.refresh_packs()
 

@@ -375,6 +375,26 @@ int ctgan_adam_step(float* p, const float* g, float* m, float* v, int64_t n,
                     float lr_t, float beta1, float beta2, float eps, float grad_scale,
                     const float* lr_t_dev /*nullable: overrides lr_t, for graph replay*/, void* stream);
 
+/* ---- data parallel: the optimizer update as ONE kernel over NVLink peer memory (csrc/peer.cu) --------
+ * reduce-scatter of the ranks' flat gradient buckets + Adam on the owned slice + all-gather of the new parameters, with
+ * in-kernel barriers over peer flag words: replaces NCCL all-reduce + ctgan_adam_step, needs no host call between two CUDA
+ * graphs, and keeps replicas bit-identical (each element is summed and updated by exactly one rank).
+ *   ctgan_peer_alloc / _free          cudaMalloc'ed (zeroed) device memory that can be exported over CUDA IPC
+ *   ctgan_ipc_get_handle / _open / _close   64-byte cudaIpcMemHandle_t of such an allocation <-> its mapping in another process
+ *   ctgan_peer_flag_bytes             size of one rank's flag block (allocate with ctgan_peer_alloc)
+ *   ctgan_peer_reduce_adam            g, p, flags: HOST arrays of `world` device pointers (entry `rank` = own buffers, the others
+ *                                     the peers' buffers opened over IPC); m, v: own moments; n floats (multiple of 4);
+ *                                     update rule and lr_t_dev as ctgan_adam_step.  Every rank must launch it once per step. */
+int ctgan_peer_alloc(void** out, int64_t bytes);
+int ctgan_peer_free(void* ptr);
+int ctgan_ipc_get_handle(const void* ptr, void* handle64);
+int ctgan_ipc_open_handle(const void* handle64, void** out);
+int ctgan_ipc_close_handle(void* ptr);
+int ctgan_peer_flag_bytes(void);
+int ctgan_peer_reduce_adam(int world, int rank, float* const* g, float* const* p, void* const* flags, float* m, float* v,
+                           int64_t n, float lr_t, float beta1, float beta2, float eps, float grad_scale,
+                           const float* lr_t_dev /*nullable*/, void* stream);
+
 /* ---- Philox4x32-10 random numbers -------------------------------------------
  * Element i of a stream (seed, offset) is lane (offset+i)&3 of
  * philox4x32_10(counter = (offset+i)>>2, key = seed); u = (bits >> 8) * 2^-24 in [0,1).
