@@ -34,6 +34,10 @@ class Config:
 
 
 config = Config()
+# A/B switches from the environment (benchmarks): CTGAN_PEER_UPDATE=0 -> NCCL all-reduce + Adam instead of the peer-memory kernel
+import os as _os
+if _os.environ.get('CTGAN_PEER_UPDATE') is not None:
+    config.peer_update = bool(int(_os.environ['CTGAN_PEER_UPDATE']))
 
 _tc_avail = None
 
