@@ -56,6 +56,12 @@ _PROTOS = {
     'ctgan_conv_wgrad_tc_multi_ok': (c_int, [POINTER(ConvDesc)]),
     'ctgan_conv_wgrad_tc_multi': (c_int, [c_int, POINTER(ConvDesc), POINTER(P), POINTER(P), POINTER(P), P]),
     'ctgan_set_wgrad_multi_items_per_sm': (None, [c_int]),
+    'ctgan_conv_tf32_ok': (c_int, [POINTER(ConvDesc)]),
+    'ctgan_conv_fprop_tf32': (c_int, [POINTER(ConvDesc), P, P, P, P, P, P, c_int, P]),
+    'ctgan_conv_wgrad_tf32_multi_ok': (c_int, [POINTER(ConvDesc)]),
+    'ctgan_conv_wgrad_tf32_multi': (c_int, [c_int, POINTER(ConvDesc), POINTER(P), POINTER(P), POINTER(P), P]),
+    'ctgan_pack_filter_f32': (c_int, [P, P, c_int, c_int, c_int, c_int, P]),
+    'ctgan_pack_filters_multi_f32': (c_int, [P, P, P, c_int, P]),
     'ctgan_pack_filter_bf16': (c_int, [P, P, c_int, c_int, c_int, c_int, P]),
     'ctgan_pack_filters_multi': (c_int, [P, P, P, c_int, P]),
     'ctgan_im2col_thin': (c_int, [POINTER(ConvDesc), c_int, c_int, P, P, P]),

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 OBJ = os.path.join(CSRC, 'build')
 LIB = os.path.join(HERE, 'libctgan_sm100.so')
-SOURCES = ['api.cu', 'conv_simt.cu', 'conv_thin.cu', 'conv_head.cu', 'conv_tc.cu', 'conv_wgrad_multi.cu', 'conv_splitk.cu', 'conv_s2d.cu', 'elementwise.cu', 'norm.cu', 'layernorm.cu', 'loss.cu', 'optim.cu', 'peer.cu']
+SOURCES = ['api.cu', 'conv_simt.cu', 'conv_thin.cu', 'conv_head.cu', 'conv_tc.cu', 'conv_wgrad_multi.cu', 'conv_splitk.cu', 'conv_tf32.cu', 'conv_s2d.cu', 'elementwise.cu', 'norm.cu', 'layernorm.cu', 'loss.cu', 'optim.cu', 'peer.cu']
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
          '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr']

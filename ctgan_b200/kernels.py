@@ -30,6 +30,7 @@ class Config:
     use_bn_fused = True      # BF16 batch norm as two kernels per direction (sums with red.global + apply)
     fuse_act_dropout = True  # Conv2D -> LeakyReLU -> dropout of the DCGAN critics in the tcgen05 conv epilogue (Philox in registers)
     peer_update = True       # data parallel: reduce-scatter + Adam + all-gather as one kernel over NVLink peer memory (else NCCL all-reduce)
+    tf32 = False             # fp32 activations: stride-1 convs / linears on tcgen05 kind::tf32 instead of the FP32-FMA SIMT kernels
     defer_wgrad = True       # queue the final backward's tensor-core filter gradients and run them as ONE launch at the join
 
 
@@ -230,6 +231,12 @@ def _tc_geom_ok(g):
             and g.Cin % 64 == 0 and g.Cout % 64 == 0 and 0 <= g.pad_t < g.kh and 0 <= g.pad_l < g.kw)
 
 
+def _tf32_geom_ok(g, cin_mult=32):
+    """float activations on the tensor cores (kind::tf32): opt-in, stride 1, Cin % cin_mult == 0, Cout % 128 == 0."""
+    return (config.tf32 and config.use_tc and tc_available() and g.stride == 1 and g.Ho == g.H and g.Wo == g.W
+            and g.Cin % cin_mult == 0 and g.Cout % 128 == 0 and 0 <= g.pad_t < g.kh and 0 <= g.pad_l < g.kw)
+
+
 # packed-filter cache for PARAMETERS only (keyed by storage address, shape, layout)
 _pack_cache = {}
 
@@ -261,6 +268,27 @@ def pack_filter(w, transpose_flip, cacheable=False):
                       lambda: torch.empty(taps * cin * cout, dtype=torch.bfloat16, device=w.device),
                       lambda wp: call('ctgan_pack_filter_bf16', _p(wd), _p(wp), taps, cin, cout, int(transpose_flip), _stream()),
                       cacheable)
+
+
+def pack_filter_f32(w, transpose_flip, cacheable=False):
+    """float HWIO [kh,kw,Cin,Cout] (or [in,out]) -> float operand of the kind::tf32 kernels (same layouts as pack_filter)."""
+    if w.dim() == 4:
+        taps, cin, cout = w.shape[0] * w.shape[1], w.shape[2], w.shape[3]
+    else:
+        taps, cin, cout = 1, w.shape[0], w.shape[1]
+    if w.dtype != torch.float32 or not w.is_contiguous():
+        raise RuntimeError('ctgan_b200: filters must be contiguous float32 HWIO')
+    wd = w.detach()
+    return _lazy_pack(w, (w.data_ptr(), tuple(w.shape), 'f32', transpose_flip),
+                      lambda: torch.empty(taps * cin * cout, dtype=torch.float32, device=w.device),
+                      lambda wp: call('ctgan_pack_filter_f32', _p(wd), _p(wp), taps, cin, cout, int(transpose_flip), _stream()),
+                      cacheable)
+
+
+def _fprop_tf32(x, wp, bias, residual, relu_mask, y, g, flags):
+    d = _desc(g, F32, F32)
+    call('ctgan_conv_fprop_tf32', ctypes.byref(d), _p(x), _p(wp), _p(bias), _p(residual), _p(relu_mask), _p(y), flags, _stream())
+    return y
 
 
 def _check_filter(w, g):
@@ -342,7 +370,7 @@ class FilterPacker:
     def __init__(self, flat_p, params, offsets):
         import numpy as np
         self.flat_p = flat_p
-        self.param_ptrs = [p.data_ptr() for p in params.values() if p.dim() == 4]
+        self.param_ptrs = [p.data_ptr() for p in params.values() if p.dim() in (2, 4)]
         rows, self.views, dst = [], [], 0
         for name, p in params.items():
             if p.dim() == 4:
@@ -363,6 +391,29 @@ class FilterPacker:
                 rows.append((offsets[name], dst, taps, cin, cout, flip))
                 self.views.append((p, flip, dst, taps * cin * cout))
                 dst += (taps * cin * cout + 63) // 64 * 64
+        # float operand packs of the same filters for the kind::tf32 path (kernels.config.tf32)
+        rows32, self.views32, dst32 = [], [], 0
+        if config.tf32:
+            for name, p in params.items():
+                if p.dim() == 4:
+                    taps, cin, cout = p.shape[0] * p.shape[1], p.shape[2], p.shape[3]
+                elif p.dim() == 2 and name.endswith('.W'):
+                    taps, cin, cout = 1, p.shape[0], p.shape[1]
+                else:
+                    continue
+                if cin % 32 or cout % 32 or taps > 9 or (cin % 128 and cout % 128):
+                    continue
+                for flip in (0, 1):
+                    rows32.append((offsets[name], dst32, taps, cin, cout, flip))
+                    self.views32.append((p, flip, dst32, taps * cin * cout))
+                    dst32 += (taps * cin * cout + 63) // 64 * 64
+        self.n32 = len(rows32)
+        if self.n32:
+            tab = np.zeros(self.n32, dtype=[('src', '<i8'), ('dst', '<i8'), ('taps', '<i4'), ('cin', '<i4'), ('cout', '<i4'), ('flip', '<i4')])
+            for i, r in enumerate(rows32):
+                tab[i] = r
+            self.table32 = torch.from_numpy(tab.view(np.uint8).copy()).to(flat_p.device)
+            self.packs32 = torch.empty(dst32, dtype=torch.float32, device=flat_p.device)
         self.n = len(rows)
         if self.n:
             tab = np.zeros(self.n, dtype=[('src', '<i8'), ('dst', '<i8'), ('taps', '<i4'), ('cin', '<i4'), ('cout', '<i4'), ('flip', '<i4')])
@@ -379,6 +430,10 @@ class FilterPacker:
             call('ctgan_pack_filters_multi', _p(self.flat_p), _p(self.packs), _p(self.table), self.n, _stream())
             for p, flip, dst, numel in self.views:
                 _pack_cache[(p.data_ptr(), tuple(p.shape), flip)] = self.packs[dst:dst + numel]
+        if self.n32:
+            call('ctgan_pack_filters_multi_f32', _p(self.flat_p), _p(self.packs32), _p(self.table32), self.n32, _stream())
+            for p, flip, dst, numel in self.views32:
+                _pack_cache[(p.data_ptr(), tuple(p.shape), 'f32', flip)] = self.packs32[dst:dst + numel]
         refresh_lazy_packs(self.param_ptrs)
 
 
@@ -552,6 +607,10 @@ def conv_fprop(x, w, bias, g, relu=False, residual=None, out_dtype=None, w_is_pa
         if residual is not None:
             require_nhwc(residual, 'residual')
         return _fprop_tc_packed(x, wp, bias, residual, None, y, g, flags)
+    if xdt == F32 and ydt == F32 and _tf32_geom_ok(g):
+        if residual is not None:
+            require_nhwc(residual, 'residual')
+        return _fprop_tf32(x, pack_filter_f32(w, 0, cacheable=w_is_param), bias, residual, None, y, g, flags)
     g3 = s2d_geom(g, x) if (xdt == BF16 and ydt == BF16) else None
     if g3 is not None:                                # stride 2: 3x3 conv over the space-to-depth image
         if residual is not None:
@@ -644,6 +703,10 @@ def conv_dgrad(dy, w, g, out_dtype=None, w_is_param=False, col=None, relu_mask=N
         gt = ConvGeom(g.N, g.H, g.W, g.Cout, g.H, g.W, g.Cin, g.kh, g.kw, 1, g.kh - 1 - g.pad_t, g.kw - 1 - g.pad_l)
         wp = pack_filter(w, 1, cacheable=w_is_param)
         return _fprop_tc_packed(dy, wp, None, None, relu_mask, dx, gt, 0)
+    if xdt == F32 and ydt == F32:
+        gt = ConvGeom(g.N, g.H, g.W, g.Cout, g.H, g.W, g.Cin, g.kh, g.kw, 1, g.kh - 1 - g.pad_t, g.kw - 1 - g.pad_l)
+        if g.stride == 1 and g.Ho == g.H and g.Wo == g.W and _tf32_geom_ok(gt):
+            return _fprop_tf32(dy, pack_filter_f32(w, 1, cacheable=w_is_param), None, None, relu_mask, dx, gt, 0)
     if relu_mask is not None:                       # other paths: the mask as a separate kernel
         return mul_relu_mask(conv_dgrad(dy, w, g, out_dtype=out_dtype, w_is_param=w_is_param, col=col), relu_mask)
     g3 = s2d_geom(g, dy) if (xdt == BF16 and ydt == BF16) else None
@@ -673,6 +736,7 @@ def conv_dgrad(dy, w, g, out_dtype=None, w_is_param=False, col=None, relu_mask=N
 
 # ---- deferred filter gradients: every tensor-core wgrad of a backward pass as ONE launch (csrc/conv_wgrad_multi.cu)
 _wgrad_queue = []        # (x, dy, geometry, dw) jobs; the tensors stay alive until the flush
+_wgrad_queue32 = []      # the same for float operands (kind::tf32)
 _wgrad_post = []         # launches that consume a job's scratch result (space-to-depth gather, im2col prefix add)
 
 
@@ -681,21 +745,34 @@ def _wgrad_multi_ok(g):
     return bool(_lib.lib.ctgan_conv_wgrad_tc_multi_ok(ctypes.byref(d)))
 
 
+def _launch_wgrad_jobs(jobs, dt, entry):
+    n = len(jobs)
+    descs = (ConvDesc * n)(*[_desc(g, dt, dt) for _, _, g, _ in jobs])
+    xs = (ctypes.c_void_p * n)(*[x.data_ptr() for x, _, _, _ in jobs])
+    dys = (ctypes.c_void_p * n)(*[dy.data_ptr() for _, dy, _, _ in jobs])
+    dws = (ctypes.c_void_p * n)(*[dw.data_ptr() for _, _, _, dw in jobs])
+    call(entry, n, descs, xs, dys, dws, _stream())
+
+
 def flush_wgrads():
     """Launch the queued filter gradients (one kernel per 24 jobs) and their post-processing on the current stream."""
+    if _wgrad_queue32:
+        jobs = list(_wgrad_queue32)
+        _wgrad_queue32.clear()
+        _launch_wgrad_jobs(jobs, F32, 'ctgan_conv_wgrad_tf32_multi')
     if not _wgrad_queue:
         return
     jobs, post = list(_wgrad_queue), list(_wgrad_post)
     _wgrad_queue.clear()
     _wgrad_post.clear()
-    n = len(jobs)
-    descs = (ConvDesc * n)(*[_desc(g, BF16, BF16) for _, _, g, _ in jobs])
-    xs = (ctypes.c_void_p * n)(*[x.data_ptr() for x, _, _, _ in jobs])
-    dys = (ctypes.c_void_p * n)(*[dy.data_ptr() for _, dy, _, _ in jobs])
-    dws = (ctypes.c_void_p * n)(*[dw.data_ptr() for _, _, _, dw in jobs])
-    call('ctgan_conv_wgrad_tc_multi', n, descs, xs, dys, dws, _stream())
+    _launch_wgrad_jobs(jobs, BF16, 'ctgan_conv_wgrad_tc_multi')
     for fn in post:
         fn()
+
+
+def _wgrad_tf32_ok(g):
+    d = _desc(g, F32, F32)
+    return _tf32_geom_ok(g, 128) and bool(_lib.lib.ctgan_conv_wgrad_tf32_multi_ok(ctypes.byref(d)))
 
 
 def _wgrad_tc(x, dy, g, dw, defer, post=None):
@@ -714,6 +791,8 @@ def _wgrad_route(x, dy, g):
     """Which kernel family conv_wgrad takes: ('tc', g) | ('s2d', g3) | ('padk', g1) | ('thin', side) | ('simt', None)."""
     xdt, ydt = _dt(x), _dt(dy)
     bf = xdt == BF16 and ydt == BF16
+    if xdt == F32 and ydt == F32 and _wgrad_tf32_ok(g):
+        return 'tf32', g
     if bf and _tc_geom_ok(g) and g.Cin % 128 == 0 and g.Cout % 128 == 0:
         return 'tc', g
     g3 = s2d_geom(g, x) if bf else None
@@ -732,6 +811,8 @@ def wgrad_deferrable(x, dy, g):
     if not (config.defer_wgrad and x.is_cuda):
         return False
     route, gj = _wgrad_route(x, dy, g)
+    if route == 'tf32':
+        return True
     return route in ('tc', 's2d', 'padk') and _wgrad_multi_ok(gj)
 
 
@@ -749,6 +830,13 @@ def conv_wgrad(x, dy, g, w_shape, accumulate_into=None, col=None, defer=False):
         raise RuntimeError('ctgan_b200: accumulate_into must be a contiguous float32 tensor of the filter shape')
     defer = defer and acc is not None
     route, gj = _wgrad_route(x, dy, g)
+    if route == 'tf32':
+        dw = acc if acc is not None else torch.zeros(w_shape, dtype=torch.float32, device=x.device)
+        if defer and config.defer_wgrad:
+            _wgrad_queue32.append((x, dy, g, dw))
+        else:
+            _launch_wgrad_jobs([(x, dy, g, dw)], F32, 'ctgan_conv_wgrad_tf32_multi')
+        return dw
     if route == 'tc':
         dw = acc if acc is not None else torch.zeros(w_shape, dtype=torch.float32, device=x.device)
         _wgrad_tc(x, dy, g, dw, defer)

@@ -133,6 +133,22 @@ int ctgan_conv_wgrad_tc_multi(int n, const ctgan_conv_desc* descs, const void* c
                               float* const* dws, void* stream);
 /* tuning hook: work items per SM that launch aims for (default 2) */
 void ctgan_set_wgrad_multi_items_per_sm(int v);
+/* ---- the fp32-storage path on the tensor cores: tcgen05.mma kind::tf32 (csrc/conv_tf32.cu) -------------------------
+ * x, y, residual, relu_mask: FLOAT NHWC tensors; wp: float operand pack from ctgan_pack_filter_f32 / _multi_f32
+ * ([taps][Cout][Cin] for fprop, tap-flipped [taps][Cin][Cout] for dgrad).  Products are formed with TF32 operand precision
+ * (10-bit mantissa), accumulated in fp32.  Stride 1, Cin a multiple of 32, Cout of 128 (ctgan_conv_tf32_ok).  Epilogue as
+ * ctgan_conv_fprop_tc_masked.  The wgrad entry is the float twin of ctgan_conv_wgrad_tc_multi (Cin, Cout multiples of 128).
+ * Replaces tf.nn.conv2d / Conv2DBackpropInput / Conv2DBackpropFilter / tf.matmul on float tensors
+ * (TG/tflib/ops/conv2d.py:106-112, linear.py:132-136) -- north_star: "TF32/BF16 inputs and fp32 accumulation". */
+int ctgan_conv_tf32_ok(const ctgan_conv_desc* d);
+int ctgan_conv_fprop_tf32(const ctgan_conv_desc* d, const void* x, const void* wp, const float* bias /*nullable*/,
+                          const void* residual /*nullable*/, const void* relu_mask /*nullable*/, void* y, int flags, void* stream);
+int ctgan_conv_wgrad_tf32_multi_ok(const ctgan_conv_desc* d);
+int ctgan_conv_wgrad_tf32_multi(int n, const ctgan_conv_desc* descs, const void* const* xs, const void* const* dys,
+                                float* const* dws, void* stream);
+int ctgan_pack_filter_f32(const float* w_hwio, float* wp, int taps, int Cin, int Cout, int transpose_flip, void* stream);
+/* table: as ctgan_pack_filters_multi, dst offsets in floats */
+int ctgan_pack_filters_multi_f32(const float* flat, float* packs, const void* table, int n_entries, void* stream);
 /* w_hwio float [taps][Cin][Cout] ->
  *   transpose_flip==0: wp[t][o][c] = w[t][c][o]                (fprop operand)
  *   transpose_flip==1: wp[t][c][o] = w[taps-1-t][c][o]         (dgrad operand)  */

@@ -176,6 +176,50 @@ def test_tc_splitk_cluster_kernel(K, shape):
         _lib.lib.ctgan_set_splitk(1)
 
 
+@pytest.mark.parametrize('shape', [(6, 32, 32, 3, 128, 128), (20, 16, 16, 3, 128, 256), (70, 8, 8, 3, 256, 128), (9, 16, 16, 1, 128, 128),
+                                   (130, 1, 1, 1, 128, 384), (37, 8, 8, 3, 128, 128), (33, 4, 4, 3, 128, 128)])
+def test_tf32_conv_family(K, shape):
+    """The fp32-storage path on the tensor cores (tcgen05 kind::tf32, csrc/conv_tf32.cu): fprop (+bias, +residual, ReLU),
+    dgrad (+ReLU-backward mask) and the multi-job wgrad against the PyTorch-CPU fp32 reference.  Tolerance 3e-3: every
+    product is formed from operands rounded to TF32 (2^-11), accumulation is fp32."""
+    N, H, W, k, Cin, Cout = shape
+    g = K.same_geom(N, H, W, Cin, Cout, k, 1)
+    two_d = H == 1
+    xs, ys = ((N, Cin), (N, Cout)) if two_d else ((N, Cin, H, W), (N, Cout, H, W))
+    x, dy, r, mk = act(xs, torch.float32, 1), act(ys, torch.float32, 2), act(ys, torch.float32, 5), act(xs, torch.float32, 6)
+    w, b = filt((k, k, Cin, Cout), 3), act((Cout,), torch.float32, 4)
+    K.config.tf32 = True
+    try:
+        assert K._tf32_geom_ok(g)
+        yf = K.conv_fprop(to_dev(x), w.cuda(), b.cuda(), g)
+        assert yf.dtype == torch.float32 and rel(yf, FB().conv_fprop(x, w, b, g)) < 3e-3
+        if not two_d:
+            yr = K.conv_fprop(to_dev(x), w.cuda(), b.cuda(), g, relu=True, residual=to_dev(r))
+            assert rel(yr, FB().conv_fprop(x, w, b, g, relu=True, residual=r)) < 3e-3
+            ym = K.conv_dgrad(to_dev(dy), w.cuda(), g, relu_mask=to_dev(mk))
+            assert rel(ym, FB().conv_dgrad(dy, w, g, relu_mask=mk)) < 3e-3
+        yd = K.conv_dgrad(to_dev(dy), w.cuda(), g)
+        assert rel(yd, FB().conv_dgrad(dy, w, g)) < 3e-3
+        ref_w = FB().conv_wgrad(x, dy, g, (k, k, Cin, Cout))
+        if K._wgrad_tf32_ok(g):
+            dw = K.conv_wgrad(to_dev(x), to_dev(dy), g, (k, k, Cin, Cout))
+            assert rel(dw, ref_w) < 3e-3
+            acc = torch.full((k, k, Cin, Cout), 0.5, device='cuda')
+            xd, dyd = to_dev(x), to_dev(dy)
+            K.conv_wgrad(xd, dyd, g, (k, k, Cin, Cout), accumulate_into=acc, defer=True)
+            assert len(K._wgrad_queue32) == 1 and float((acc - 0.5).abs().max()) == 0.0
+            K.join_side()
+            assert not K._wgrad_queue32 and rel(acc - 0.5, ref_w) < 3e-3
+        else:
+            assert H == 4                                    # several images per 64-pixel chunk: SIMT fallback
+            assert rel(K.conv_wgrad(to_dev(x), to_dev(dy), g, (k, k, Cin, Cout)), ref_w) < 1e-4
+        # the SIMT fp32 kernels (config.tf32 off) agree to tf32 rounding
+        K.config.tf32 = False
+        assert rel(K.conv_fprop(to_dev(x), w.cuda(), b.cuda(), g), yf) < 3e-3
+    finally:
+        K.config.tf32 = False
+
+
 def test_tc_residual_relu_epilogue(K):
     g = K.same_geom(3, 8, 8, 128, 128, 3, 1)
     x, r = act((3, 128, 8, 8), torch.bfloat16, 1), act((3, 128, 8, 8), torch.bfloat16, 2)
