@@ -315,7 +315,8 @@ conv_wgrad_tf32_multi_kernel(const __grid_constant__ Wgrad32Table tab)
             }
         }
     } else if (warp == 1) {
-        // both operands MN-major: smem rows are K (pixels), 32 channels = 128 B per row; LBO = distance between 32-channel groups
+        // both operands MN-major: smem rows are K (pixels), 32 channels = 128 B per row; LBO = distance between 32-channel
+        // groups.  TF32 MN-major operands use the 32-byte-atom swizzle (tc_common.cuh: umma_tf32_mn_lo).
         constexpr uint32_t idesc = make_idesc_tf32(BLOCK_M, 128, 1, 1);
         const uint32_t a_lo0 = ((s_base & 0x3FFFFu) >> 4) | ((A_SLOT >> 4) << 16);
         const uint32_t b_lo0 = (((s_base + 4 * A_SLOT) & 0x3FFFFu) >> 4) | ((B_SLOT >> 4) << 16);
@@ -338,8 +339,8 @@ conv_wgrad_tf32_multi_kernel(const __grid_constant__ Wgrad32Table tab)
                         if (r < kh) {
 #pragma unroll
                             for (int k = 0; k < 8; ++k)               // 8 pixel rows = 1024 bytes along K per instruction
-                                umma_tf32_lo(tmem_base + (uint32_t)(r * 128), a_lo + r * row_step + 64 * k, b_lo + 64 * k, idesc,
-                                             k ? 1u : (c > 0 ? 1u : 0u));
+                                umma_tf32_mn_lo(tmem_base + (uint32_t)(r * 128), a_lo + r * row_step + 64 * k, b_lo + 64 * k, idesc,
+                                                k ? 1u : (c > 0 ? 1u : 0u));
                         }
                     }
                     umma_commit(empty0 + 8 * st);
@@ -526,8 +527,8 @@ extern "C" int ctgan_conv_wgrad_tf32_multi(int n, const ctgan_conv_desc* descs, 
             J.total_chunks = J.chunksW * J.chunksH * ceil_div(d->N, J.BN);
             J.co_blocks = d->Cout / 128;
             J.a_bytes = (uint32_t)(J.BH + d->kh - 1) * J.BW * J.BN * 128u;
-            if (int r = make_act_map_f32(&J.mx, xs[base + i], d->N, d->H, d->W, d->Cin, J.BW, J.BH + d->kh - 1, J.BN)) return r;
-            if (int r = make_act_map_f32(&J.mdy, dys[base + i], d->N, d->H, d->W, d->Cout, J.BW, J.BH, J.BN)) return r;
+            if (int r = make_act_map_f32(&J.mx, xs[base + i], d->N, d->H, d->W, d->Cin, J.BW, J.BH + d->kh - 1, J.BN, true)) return r;
+            if (int r = make_act_map_f32(&J.mdy, dys[base + i], d->N, d->H, d->W, d->Cout, J.BW, J.BH, J.BN, true)) return r;
             col_work[i] = (long long)J.total_chunks * d->kh;
             total += col_work[i] * (d->Cin / 128) * J.co_blocks * d->kw;
         }

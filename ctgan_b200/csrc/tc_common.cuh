@@ -148,6 +148,20 @@ __device__ __forceinline__ void umma_tf32_lo(uint32_t d_tmem, uint32_t a_lo, uin
         ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(0x40004040u) : "memory");
 }
 
+// MN-major TF32 operands exist in ONE shared-memory layout only (CUTLASS: "for mn-major tf32 operands, SW128_32B is the only
+// available smem layout"): 128-byte rows whose 32-byte chunks are swizzled by (row mod 4) -- TMA mode SWIZZLE_128B_ATOM_32B,
+// descriptor layout type 1 (SWIZZLE_128B_BASE32B), K atoms of 4 rows: SBO = 512 B.
+__device__ __forceinline__ void umma_tf32_mn_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+    // hi word: SBO (512 B >> 4 = 0x20) | version 1 (bit 46) | layout type 1 (bits 61..63)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %5};\n\t"
+        "mov.b64 db, {%2, %5};\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(0x20004020u) : "memory");
+}
+
 constexpr int BLOCK_M = 128;       // tile rows = TMEM lanes
 constexpr int BLOCK_K = 64;        // bf16 elements per 128-byte swizzle row
 constexpr int UMMA_K  = 16;
@@ -233,7 +247,8 @@ static inline int make_act_map(CUtensorMap* map, const void* base, int N, int H,
     return 0;
 }
 // the same maps over FLOAT tensors: a 128-byte swizzle row holds 32 channels
-static inline int make_act_map_f32(CUtensorMap* map, const void* base, int N, int H, int W, int C, int BW, int BH, int BN) {
+static inline int make_act_map_f32(CUtensorMap* map, const void* base, int N, int H, int W, int C, int BW, int BH, int BN,
+                                   bool mn_major = false) {
     CTGAN_REQUIRE(BW <= 256 && BH <= 256 && BN <= 256, CTGAN_ERR_UNSUPPORTED, "activation box dimension exceeds 256");
     EncodeTiledFn enc = get_encode_fn();
     CTGAN_REQUIRE(enc != nullptr, CTGAN_ERR_DRIVER, "cuTensorMapEncodeTiled entry point not available");
@@ -241,9 +256,10 @@ static inline int make_act_map_f32(CUtensorMap* map, const void* base, int N, in
     cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
     cuuint32_t box[4] = {32, (cuuint32_t)BW, (cuuint32_t)BH, (cuuint32_t)BN};
     cuuint32_t estr[4] = {1, 1, 1, 1};
+    // mn_major: the operand is consumed MN-major by kind::tf32 (wgrad) -> 32-byte swizzle atoms (see umma_tf32_mn_lo)
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(base), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     CTGAN_REQUIRE(r == CUDA_SUCCESS, CTGAN_ERR_DRIVER, "cuTensorMapEncodeTiled(float activation) failed: CUresult %d", (int)r);
     return 0;
 }
