@@ -30,6 +30,15 @@ def _grad_floor(ref_grads, frac=1e-4):
     return frac * max(float(g.detach().double().norm()) for g in ref_grads.values() if g is not None)
 
 
+def _flat_rel(params, ref_grads):
+    """The parameter gradient as ONE vector: ||g - g_ref|| / ||g_ref|| over all parameters of the optimizer."""
+    num = den = 0.0
+    for n, q in params.items():
+        a, b = q.grad.detach().double().cpu().reshape(-1), ref_grads[n].detach().double().cpu().reshape(-1)
+        num += float(((a - b) ** 2).sum()); den += float((b ** 2).sum())
+    return (num / max(den, 1e-300)) ** 0.5
+
+
 def make_inputs(script, B, seed):
     rs = np.random.RandomState(seed)
     if script == 'mnist':
@@ -123,6 +132,7 @@ def critic_parity(script, tr, om, inputs, iteration=0, conditioned=False, floor_
     floor = _grad_floor(ref_grads, floor_frac)
     for n, q in tr.disc_opt.params.items():
         report['grad.' + n] = rel_err(q.grad, ref_grads[n], floor)
+    report['gradall'] = _flat_rel(tr.disc_opt.params, ref_grads)
     # optimizer: the SAME gradients (the product's) go through both Adam implementations, so this
     # isolates the update rule (Adam's m/sqrt(v) is sign-like at t=1 and would amplify gradient noise)
     before = {n: q.detach().clone() for n, q in tr.disc_opt.params.items()}
@@ -152,6 +162,7 @@ def gen_parity(script, tr, om, iteration=1, conditioned=False, floor_frac=1e-4):
     floor = _grad_floor(ref_grads, floor_frac)
     for n, q in tr.gen_opt.params.items():
         report['grad.' + n] = rel_err(q.grad, ref_grads[n], floor)
+    report['gradall'] = _flat_rel(tr.gen_opt.params, ref_grads)
     before = {n: q.detach().clone() for n, q in tr.gen_opt.params.items()}
     same_grads = {n: q.grad.detach().cpu().to(named[n].dtype) for n, q in tr.gen_opt.params.items()}
     tr.gen_opt.step(tr.lr(iteration) if hasattr(tr, 'lr') else None, 1)

@@ -2,23 +2,30 @@
 executed by the CUDA kernels through the C ABI, against the CPU oracle replaying the SAME
 weights, dropout masks, interpolation alphas, noise and labels (exported from the device
 Philox streams).  Compared: loss terms (wgan, CT, GP, ACGAN, total), the GP gradient,
-every parameter gradient (norm-relative per tensor) and the Adam update.
+the parameter gradient as one vector ('gradall'), every parameter gradient tensor
+(norm-relative per tensor, 'grad.<name>') and the Adam update.
 
-Tolerances follow BASELINE.json north_star -- 1e-3 relative on the fp32 path, 1e-2 on the
-BF16 path -- for the LOSS TERMS in every mode, and for GRADIENTS in the pattern-conditioned
-mode.  Why two modes (measured table: profiles/r01_parity_report.txt):
-  * the critic/generator are piecewise linear (ReLU, LeakyReLU, dropout).  A pre-activation
-    that is ~0 gets its 0/1 pattern from rounding noise; ONE flipped element out of N moves a
-    norm-relative gradient error to ~1/sqrt(N).  fp32-vs-fp64 flips a handful of elements
-    (errors up to ~2e-3); BF16 pre-activations carry ~3e-3 noise, flip ~0.25 % of the
-    patterns per layer and so move gradients by 3-15 % although every loss term still
-    agrees to <5e-3.  That is a property of comparing two precisions of a ReLU network,
-    not of a kernel.
-  * "conditioned" mode hands the device's activation patterns to the oracle (exactly like
-    the exported dropout masks), so both sides differentiate the SAME linear region and the
-    comparison isolates arithmetic: fp32 gradients agree to <1e-3 (measured <2e-4), BF16
-    critic gradients to ~1e-2 (measured 4e-3..1.5e-2, generator median ~1e-2).
-  * "independent" mode (oracle decides its own patterns) is kept as an honest upper bound.
+THE BAR (BASELINE.json north_star, as written): loss terms and parameter gradients within
+1e-3 relative error on the fp32 path, 1e-2 on the reduced-precision tensor-core paths
+(BF16 storage + kind::f16; fp32 storage + kind::tf32).  It is asserted on
+    * every loss term,
+    * the GP gradient,
+    * the parameter gradient of the step ('gradall': ||g - g_ref|| / ||g_ref|| over all
+      parameters of the optimizer),
+for the critic AND the generator step, with the device's activation patterns handed to the
+oracle together with the dropout masks ("conditioned": both sides differentiate the same
+linear region of the piecewise-linear network, so the comparison measures arithmetic).
+Reported and bounded as DIAGNOSTICS, not as the bar:
+    * the worst single parameter tensor ('grad.<name>', floor = a fraction of the largest
+      gradient norm): BF16 storage rounds every activation and cotangent to 2^-9, ~20 layers
+      deep, so individual small tensors sit at 1-3e-2 while the whole gradient is within 1e-2;
+    * "independent" mode (the oracle decides its own ReLU / LeakyReLU patterns): a
+      pre-activation that is ~0 takes its pattern from rounding noise, ONE flipped element out
+      of N moves a norm-relative gradient error to ~1/sqrt(N).  fp32-vs-fp64 flips a handful of
+      elements (<= 2e-3); BF16 operand rounding flips ~0.25 % of the patterns per layer and
+      moves gradients by 3-15 % with unchanged losses; TF32 ~4x fewer.  That is a property of
+      comparing two precisions of a ReLU network, not of a kernel
+      (measured table: profiles/r02_parity_report.txt).
 'adam.*' feeds the device's gradients to both Adam implementations and compares the update
 recovered from fp32 parameters of size O(1) (carries ~6e-4 of subtraction rounding: 2e-3 bound).
 """
@@ -30,10 +37,30 @@ from tests import parity
 pytestmark = pytest.mark.gpu
 
 TOL = {
-    # path: (loss, grad conditioned critic, grad conditioned gen, grad independent, floor_frac)
-    'fp32': dict(loss=1e-3, cond_c=1e-3, cond_g=1e-3, indep=1e-2, gp_cond=1e-3, gp_indep=1e-2, floor=1e-4),
-    'bf16': dict(loss=1e-2, cond_c=2e-2, cond_g=3e-2, indep=0.25, gp_cond=1e-2, gp_indep=0.25, floor=1e-2),
+    # bar: loss terms, GP gradient, whole parameter gradient (conditioned).  diag_*: per-tensor worst case, independent mode.
+    'fp32': dict(bar=1e-3, diag_c=1e-3, diag_g=1e-3, indep_all=5e-3, indep=1e-2, floor=1e-4),
+    'bf16': dict(bar=1e-2, diag_c=2e-2, diag_g=3e-2, indep_all=0.2, indep=0.25, floor=1e-2),
+    'tf32': dict(bar=1e-2, diag_c=1e-2, diag_g=1e-2, indep_all=5e-2, indep=0.1, floor=1e-3),
 }
+
+
+class _path:
+    """Selects the arithmetic path of the product: (activation dtype, kernels.config.tf32)."""
+
+    def __init__(self, path):
+        self.path = path
+        self.dtype = torch.bfloat16 if path == 'bf16' else torch.float32
+
+    def __enter__(self):
+        import ctgan_b200.kernels as K
+        self.K, self.prev = K, K.config.tf32
+        K.config.tf32 = self.path == 'tf32'
+        return self.dtype
+
+    def __exit__(self, *exc):
+        self.K.config.tf32 = self.prev
+        self.K.invalidate_weight_cache()
+        return False
 
 
 def _need_gpu():
@@ -43,29 +70,52 @@ def _need_gpu():
 
 def _check(rep, path, what, conditioned):
     t = TOL[path]
-    msg = '%s/%s/%s: %s' % (what, path, 'cond' if conditioned else 'indep', parity.format_report(rep, 8))
+    msg = '%s/%s/%s: gradall=%.2e %s' % (what, path, 'cond' if conditioned else 'indep', rep['gradall'], parity.format_report(rep, 8))
     print(msg)
-    assert parity.worst(rep, 'loss.')[0] < t['loss'], msg
-    gtol = (t['cond_c'] if what == 'critic' else t['cond_g']) if conditioned else t['indep']
-    assert parity.worst(rep, 'grad.')[0] < gtol, msg
-    if 'gp_gradient' in rep:
-        assert rep['gp_gradient'] < (t['gp_cond'] if conditioned else t['gp_indep']), msg
+    assert parity.worst(rep, 'loss.')[0] < t['bar'], msg                       # losses: the bar in BOTH modes
+    if conditioned:
+        assert rep['gradall'] < t['bar'], msg                                  # the parameter gradient of the step
+        if 'gp_gradient' in rep:
+            assert rep['gp_gradient'] < t['bar'], msg
+        assert parity.worst(rep, 'grad.')[0] < (t['diag_c'] if what == 'critic' else t['diag_g']), msg
+    else:
+        assert rep['gradall'] < t['indep_all'], msg
+        assert parity.worst(rep, 'grad.')[0] < t['indep'], msg
+        if 'gp_gradient' in rep:
+            assert rep['gp_gradient'] < t['indep'], msg
     assert parity.worst(rep, 'adam.')[0] < 2e-3, msg
 
 
 @pytest.mark.parametrize('conditioned', [True, False])
-@pytest.mark.parametrize('path', ['fp32', 'bf16'])
+@pytest.mark.parametrize('path', ['fp32', 'bf16', 'tf32'])
 @pytest.mark.parametrize('script,B', [('mnist', 50), ('cifar', 64), ('resnet', 16)])
 def test_step_parity(script, B, path, conditioned):
     _need_gpu()
-    dtype = torch.float32 if path == 'fp32' else torch.bfloat16
-    tr, om = parity.build_pair(script, 'cuda', dtype, B)
-    parity.perturb_params(tr, om)
-    ff = TOL[path]['floor']
-    rep = parity.critic_parity(script, tr, om, parity.make_inputs(script, B, 11), conditioned=conditioned, floor_frac=ff)
-    _check(rep, path, 'critic', conditioned)
-    rep = parity.gen_parity(script, tr, om, conditioned=conditioned, floor_frac=ff)
-    _check(rep, path, 'gen', conditioned)
+    if path == 'tf32' and script != 'resnet':
+        pytest.skip('the kind::tf32 kernels cover the stride-1 layers (ResNet); the DCGAN fp32 path is SIMT')
+    with _path(path) as dtype:
+        tr, om = parity.build_pair(script, 'cuda', dtype, B)
+        parity.perturb_params(tr, om)
+        ff = TOL[path]['floor']
+        rep = parity.critic_parity(script, tr, om, parity.make_inputs(script, B, 11), conditioned=conditioned, floor_frac=ff)
+        _check(rep, path, 'critic', conditioned)
+        rep = parity.gen_parity(script, tr, om, conditioned=conditioned, floor_frac=ff)
+        _check(rep, path, 'gen', conditioned)
+
+
+@pytest.mark.parametrize('path', ['bf16', 'tf32', 'fp32'])
+def test_full_size_resnet_step(path):
+    """BASELINE configs[2] as benchmarked: CT_gan_cifar_resnet.py, batch 64, DIM 128 -- critic step AND generator step, on the
+    BF16 tensor-core path (what bench.py times), the TF32 tensor-core path and the fp32 path (oracle in float32 to keep the
+    CPU side at a few seconds per step; its own rounding is ~1e-6)."""
+    _need_gpu()
+    with _path(path) as dtype:
+        tr, om = parity.build_pair('resnet', 'cuda', dtype, 64, oracle_dtype=torch.float32)
+        ff = TOL[path]['floor']
+        rep = parity.critic_parity('resnet', tr, om, parity.make_inputs('resnet', 64, 5), conditioned=True, floor_frac=ff)
+        _check(rep, path, 'critic', True)
+        rep = parity.gen_parity('resnet', tr, om, conditioned=True, floor_frac=ff)
+        _check(rep, path, 'gen', True)
 
 
 @pytest.mark.parametrize('script,B', [('mnist', 50), ('cifar', 64)])
@@ -87,15 +137,6 @@ def test_step_parity_s2d_route(script, B):
     finally:
         K.config.use_s2d = True
         K.invalidate_weight_cache()
-
-
-def test_full_size_resnet_bf16_critic():
-    """BASELINE configs[2]: CT_gan_cifar_resnet.py, batch 64, DIM 128, BF16 tensor-core path
-    (oracle in float32 to keep the CPU side at a few seconds)."""
-    _need_gpu()
-    tr, om = parity.build_pair('resnet', 'cuda', torch.bfloat16, 64, oracle_dtype=torch.float32)
-    rep = parity.critic_parity('resnet', tr, om, parity.make_inputs('resnet', 64, 5), conditioned=True, floor_frac=1e-2)
-    _check(rep, 'bf16', 'critic', True)
 
 
 def test_two_consecutive_iterations_stay_in_parity():
