@@ -386,6 +386,13 @@ conv_wgrad_tf32_multi_kernel(const __grid_constant__ Wgrad32Table tab)
 // ------------------------------------------------------------------ filter packs (float -> float, re-laid out)
 // entry e (blockIdx.y) = {src offset in the flat parameter buffer, dst offset in the pack buffer (floats), taps, Cin, Cout, flip}
 //   flip == 0: wp[t][o][c] = w[t][c][o]          flip == 1: wp[t][c][o] = w[taps-1-t][c][o]
+// The tensor core TRUNCATES fp32 operands to TF32; the filter operand is rounded to nearest here (cvt.rna.tf32), which
+// removes the systematic shrink of that side of every product.
+__device__ __forceinline__ float round_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
 struct Pack32Entry { long long src, dst; int taps, cin, cout, flip; };
 __global__ void pack_filters_f32_kernel(const float* __restrict__ flat, float* __restrict__ packs, const Pack32Entry* __restrict__ table) {
     ctgan::pdl_entry();
@@ -396,11 +403,11 @@ __global__ void pack_filters_f32_kernel(const float* __restrict__ flat, float* _
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         if (e.flip) {
             const int64_t t = i / ((int64_t)e.cin * e.cout), rem = i - t * (int64_t)e.cin * e.cout;
-            wp[i] = w[(int64_t)(e.taps - 1 - t) * e.cin * e.cout + rem];
+            wp[i] = round_tf32(w[(int64_t)(e.taps - 1 - t) * e.cin * e.cout + rem]);
         } else {
             const int c = (int)(i % e.cin); const int64_t q = i / e.cin;
             const int o = (int)(q % e.cout); const int t = (int)(q / e.cout);
-            wp[i] = w[((int64_t)t * e.cin + c) * e.cout + o];
+            wp[i] = round_tf32(w[((int64_t)t * e.cin + c) * e.cout + o]);
         }
     }
 }
@@ -410,11 +417,11 @@ __global__ void pack_filter_f32_kernel(const float* __restrict__ w, float* __res
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         if (flip) {
             const int64_t t = i / ((int64_t)Cin * Cout), rem = i - t * (int64_t)Cin * Cout;
-            wp[i] = w[(int64_t)(taps - 1 - t) * Cin * Cout + rem];
+            wp[i] = round_tf32(w[(int64_t)(taps - 1 - t) * Cin * Cout + rem]);
         } else {
             const int c = (int)(i % Cin); const int64_t q = i / Cin;
             const int o = (int)(q % Cout); const int t = (int)(q / Cout);
-            wp[i] = w[((int64_t)t * Cin + c) * Cout + o];
+            wp[i] = round_tf32(w[((int64_t)t * Cin + c) * Cout + o]);
         }
     }
 }

@@ -48,7 +48,9 @@ def Generator(n_samples, noise=None):
     if noise is None:
         noise = RNG.normal('z', (n_samples, 128))
     noise = F.cast(noise, ACT_DTYPE)
-    output = lib.ops.linear.Linear('Generator.Input', 128, 4 * 4 * 4 * DIM, noise)
+    # the Linear output stays float until it is normalised: rounding it to bf16 BEFORE the mean subtraction of BN1 would be
+    # amplified by |mean| / std (64 samples per feature); the [64, 8192] tensor is tiny
+    output = lib.ops.linear.Linear('Generator.Input', 128, 4 * 4 * 4 * DIM, noise, out_dtype=torch.float32)
     output = lib.ops.batchnorm.Batchnorm('Generator.BN1', [0], output, relu=True)
     output = F.to_nhwc(output, 4 * DIM, 4, 4, ACT_DTYPE)
 
