@@ -61,8 +61,9 @@ def Generator(n_samples, noise=None):
     output = lib.ops.batchnorm.Batchnorm('Generator.BN3', [0, 2, 3], output, relu=True)
 
     output = lib.ops.deconv2d.Deconv2D('Generator.5', DIM, 3, 5, output)
-    output = F.tanh(output)
-    return F.to_flat_nchw(output, torch.float32)
+    # the image leaves the bf16 domain BEFORE the tanh: one rounding less on the generator's output (a tiny tensor)
+    output = F.to_flat_nchw(output, torch.float32)
+    return F.tanh(output)
 
 
 def Discriminator(inputs):

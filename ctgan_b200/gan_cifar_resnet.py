@@ -227,8 +227,10 @@ def Generator(n_samples, labels, noise=None):
     output = ResidualBlock('Generator.3', DIM_G, DIM_G, 3, output, resample='up', labels=labels)
     output = Normalize('Generator.OutputN', output, relu=True)
     output = lib.ops.conv2d.Conv2D('Generator.Output', DIM_G, 3, 3, output, he_init=False)
-    output = F.tanh(output)
-    return F.to_flat_nchw(output, torch.float32)                  # tf.reshape(output, [-1, OUTPUT_DIM])
+    # the 3-channel image leaves the bf16 domain BEFORE the tanh: the generator's output (the critic's input, and what
+    # the parity tests compare) carries one rounding less; the [B, 3072] tensor is tiny
+    output = F.to_flat_nchw(output, torch.float32)                # tf.reshape(output, [-1, OUTPUT_DIM])
+    return F.tanh(output)
 
 
 def _dropout(output, keep):

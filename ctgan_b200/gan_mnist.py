@@ -58,8 +58,9 @@ def Generator(n_samples, noise=None):
     output = F.relu(output)
 
     output = lib.ops.deconv2d.Deconv2D('Generator.5', DIM, 1, 5, output)
-    output = F.sigmoid(output)
-    return F.to_flat_nchw(output, torch.float32)
+    # the image leaves the bf16 domain BEFORE the sigmoid: one rounding less on the generator's output (a tiny tensor)
+    output = F.to_flat_nchw(output, torch.float32)
+    return F.sigmoid(output)
 
 
 def Discriminator(inputs):

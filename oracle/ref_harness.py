@@ -166,15 +166,25 @@ def _draw_tags(script):
     return tags
 
 
-def run_reference(script, batch_size, seed, inputs, dim=None):
+def run_reference(script, batch_size, seed, inputs, dim=None, param_init=None):
     """Execute the reference's own code for one evaluation of disc_cost / gen_cost.
     inputs: tuple of numpy arrays fed to the script's placeholders (real data[, labels]).
+    param_init(name, value) -> value: optional replacement of every parameter's initial value at the moment the
+    reference's lib.param() creates it (full-width fixtures regenerate their weights from a formula instead of storing them).
     Returns dict(params, disc, gen, tape_disc, tape_gen, disc_grads, gen_grads, gp_gradients)."""
     from . import tf_shim as shim
     sec = SECTIONS[script]
     path = os.path.join(REF_ROOT, sec['file'])
     lib = _load_ref_tflib(shim)
     lib.delete_all_params()
+    if param_init is not None:
+        ref_param = lib.param
+
+        def param(name, *args, **kwargs):
+            if name not in lib._params and args:
+                args = (param_init(name, np.asarray(args[0])),) + tuple(args[1:])
+            return ref_param(name, *args, **kwargs)
+        lib.param = param
     ns = {'tf': shim, 'lib': lib, 'np': np, 'functools': importlib.import_module('functools'), '__name__': 'ref_section'}
     exec(compile(_section(path, *sec['consts']), sec['file'] + ':consts', 'exec'), ns)
     ns['BATCH_SIZE'] = batch_size

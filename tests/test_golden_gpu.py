@@ -58,3 +58,92 @@ def test_product_matches_reference_golden(script):
     finally:
         for k, v in saved.items():
             setattr(prod, k, v)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Full width (DIM 128: the shapes the tcgen05 kernels run), every arithmetic path of the product, against vectors the
+# REFERENCE'S OWN CODE produced in float64 (tests/golden/resnet128.npz, script tests/golden/make_golden_full.py).
+# The comparison is direct -- no oracle, no activation patterns handed over -- so gradient bounds are those of two
+# precisions of a ReLU network deciding their own patterns (tests/test_step_parity_gpu.py, "independent" mode);
+# the loss terms carry north_star's bar.
+FULL_TOL = {   # path: (loss terms, GP gradient / whole parameter gradient, worst single parameter tensor)
+    'fp32': (1e-3, 5e-3, 1e-2),
+    'tf32': (1e-2, 5e-2, 0.1),
+    'bf16': (1e-2, 0.2, 0.25),
+}
+
+
+def _load_full():
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'resnet128.npz'))
+    tapes = {'disc': {}, 'gen': {}}
+    for k in z.files:
+        for kind in ('disc', 'gen'):
+            if k.startswith('tape_%s.' % kind):
+                tapes[kind][k[len('tape_%s.' % kind):]] = torch.from_numpy(z[k])
+            elif k.startswith('keepbits_%s.' % kind):
+                tag = k[len('keepbits_%s.' % kind):]
+                shape = tuple(int(v) for v in z['keepshape_%s.%s' % (kind, tag)])
+                bits = np.unpackbits(z[k])[:int(np.prod(shape))].reshape(shape).astype(bool)
+                tapes[kind][tag] = torch.from_numpy(np.where(bits, np.float32(0.999), np.float32(0.0)))   # floor(keep + u)
+    return z, tapes
+
+
+@pytest.mark.parametrize('path', ['bf16', 'tf32', 'fp32'])
+def test_full_width_product_matches_reference_golden(path):
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    from tests.golden.det_params import det_param
+    from tests.test_step_parity_gpu import _path
+    import ctgan_b200.gan_cifar_resnet as R
+    import ctgan_b200.tflib as lib
+    import ctgan_b200.kernels as K
+    z, tapes = _load_full()
+    B, seed, stride = int(z['meta.B']), int(z['meta.seed']), int(z['meta.stride'])
+    assert R.DIM_G == int(z['meta.dim']) == R.DIM_D
+    tol_loss, tol_all, tol_one = FULL_TOL[path]
+    with _path(path) as dtype:
+        np.random.seed(0)
+        tr = R.Trainer(device='cuda', seed=1, act_dtype=dtype, batch_size=B)
+        with torch.no_grad():
+            for n, p in lib._params.items():
+                p.copy_(torch.from_numpy(det_param(n, p.detach().cpu().numpy(), seed)).to(p.device))
+        K.invalidate_weight_cache(tr.gen_opt._ptrs | tr.disc_opt._ptrs)
+        tr.gen_opt.refresh_packs(); tr.disc_opt.refresh_packs()
+        inputs = (torch.from_numpy(z['input.0']).cuda(), torch.from_numpy(z['input.1']).cuda())
+
+        def compare(opt, kind, cost, ref_cost):
+            assert abs(cost - ref_cost) <= tol_loss * max(1.0, abs(ref_cost)), (kind, cost, ref_cost)
+            num = den = 0.0
+            worst = (0.0, '')
+            floor = 1e-2 * max(float(z['gnorm_%s.%s' % (kind, n)]) for n in opt.params if 'gnorm_%s.%s' % (kind, n) in z.files)
+            for n, q in opt.params.items():
+                if 'gsample_%s.%s' % (kind, n) not in z.files:
+                    continue
+                got = q.grad.detach().double().cpu().reshape(-1)
+                want = torch.from_numpy(z['gsample_%s.%s' % (kind, n)]).double()
+                d2, w2 = float(((got[::stride] - want) ** 2).sum()), float((want ** 2).sum())
+                num += d2; den += w2
+                # one tensor: sampled elements, scaled to the full tensor's norm (floor: 1 % of the largest gradient)
+                gn = float(z['gnorm_%s.%s' % (kind, n)])
+                e = (d2 / max(w2, 1e-300)) ** 0.5 * gn / max(gn, floor)
+                worst = max(worst, (e, n))
+                assert abs(float(got.norm()) - gn) <= tol_one * max(gn, floor), (kind, n, float(got.norm()), gn)
+            print('%s/%s: cost %.6f (ref %.6f)  sampled gradient %.2e  worst tensor %.2e %s' % (kind, path, cost, ref_cost,
+                                                                                        (num / den) ** 0.5, worst[0], worst[1]))
+            assert (num / den) ** 0.5 < tol_all, (kind, (num / den) ** 0.5)
+            assert worst[0] < tol_one, (kind, worst)
+
+        tr.rng.replay = tapes['disc']
+        tr.disc_opt.zero_grad()
+        res = tr.critic_forward_backward(*inputs)
+        out = res['out'].cpu()
+        # out = {cost, wgan term, ct, gp, acgan}: the reference's CT_ and gradient_penalty (= 10 * gp, :286) are separate fetches
+        assert abs(float(out[2]) - float(z['CT_'])) <= tol_loss * max(1.0, abs(float(z['CT_'])))
+        assert abs(10.0 * float(out[3]) - float(z['gradient_penalty'])) <= tol_loss * max(1.0, abs(float(z['gradient_penalty'])))
+        assert parity.rel_err(res['gradients'], torch.from_numpy(z['gp_gradients'])) < tol_all
+        compare(tr.disc_opt, 'disc', float(out[0]), float(z['disc_cost']))
+        tr.rng.replay = tapes['gen']
+        tr.gen_opt.zero_grad()
+        res = tr.gen_forward_backward()
+        compare(tr.gen_opt, 'gen', float(res['cost']), float(z['gen_cost']))
