@@ -134,9 +134,14 @@ class GraphedTrainer:
             k0 = K._lib.lib.ctgan_kernel_launches()
             self.pregen = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.pregen, pool=self.critic.pool):
-                self.fakes_all = tr.generate_fakes(self.labels_all)
+                fakes = tr.generate_fakes(self.labels_all)
                 tr.rng.end_step()
             self.pregen_kernels = K._lib.lib.ctgan_kernel_launches() - k0
+            # The three graphs share one memory pool: a tensor produced by one graph may be overwritten by the NEXT replay of
+            # another (its block is free while that graph is captured).  The fakes are read across S critic replays, so they
+            # are copied out of the pool right after the generator replay (one 4 MB copy per iteration).
+            self._fakes_pool = fakes
+            self.fakes_all = torch.empty_like(fakes)
 
         # undo the warm-up steps (captures execute nothing): initial weights, zero moments, t = 0, Philox counters
         torch.cuda.synchronize()
@@ -157,6 +162,7 @@ class GraphedTrainer:
         pinned host); replays the batched generator forward."""
         self.labels_all.copy_(labels_all.reshape(-1), non_blocking=non_blocking)
         self.pregen.replay()
+        self.fakes_all.copy_(self._fakes_pool)
         self._k = 0
 
     def critic_step(self, *inputs, non_blocking=True):

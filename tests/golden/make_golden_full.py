@@ -4,7 +4,7 @@ container (needs /root/reference):      python tests/golden/make_golden_full.py
 
 Kept small (~350 KB): parameters come from tests/golden/det_params.py (regenerated on both sides), dropout draws are
 stored as their keep decisions (1 bit each; the test replays u = 0.999 / 0.0), parameter gradients as their norm plus
-every 61st element."""
+every 61st element (tensors of <= 4096 elements in full)."""
 import os
 import sys
 
@@ -41,7 +41,7 @@ def main():
             if g is not None:
                 f = g.numpy().astype('float64').reshape(-1)
                 blob['gnorm_%s.%s' % (kind, n)] = np.float64(np.linalg.norm(f))
-                blob['gsample_%s.%s' % (kind, n)] = f[::STRIDE].astype('float32')
+                blob['gsample_%s.%s' % (kind, n)] = (f if f.size <= 4096 else f[::STRIDE]).astype('float32')   # small tensors in full
     for k in ('disc_cost', 'gen_cost', 'gradient_penalty', 'CT_', 'disc_wgan', 'disc_acgan'):
         blob[k] = r[k].numpy().astype('float64')
     blob['gp_gradients'] = r['gp_gradients'].numpy().astype('float32')
