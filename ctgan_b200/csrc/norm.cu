@@ -523,24 +523,21 @@ bn_sums_bf16_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ acc
     bn_load8(base + (int64_t)g * Rg * C, shift);
 #pragma unroll
     for (int e = 0; e < 8; ++e) { s[e] = 0.f; ss[e] = 0.f; }
-    int64_t r = r0 + rl;
-    for (; r + 7 * (int64_t)rstep < r1; r += 8 * (int64_t)rstep) {
+    // 8 rows in flight per thread in EVERY iteration (predicated tail: no single-load remainder loop)
+    for (int64_t r = r0 + rl; r < r1; r += 8 * (int64_t)rstep) {
         uint4 v[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) v[u] = __ldg(reinterpret_cast<const uint4*>(base + (r + u * (int64_t)rstep) * C));
+        for (int u = 0; u < 8; ++u)
+            if (r + u * (int64_t)rstep < r1) v[u] = __ldg(reinterpret_cast<const uint4*>(base + (r + u * (int64_t)rstep) * C));
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-            float f[8];
-            unpack8(v[u], f);
+            if (r + u * (int64_t)rstep < r1) {
+                float f[8];
+                unpack8(v[u], f);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) { const float d = f[e] - shift[e]; s[e] += d; ss[e] = fmaf(d, d, ss[e]); }
+                for (int e = 0; e < 8; ++e) { const float d = f[e] - shift[e]; s[e] += d; ss[e] = fmaf(d, d, ss[e]); }
+            }
         }
-    }
-    for (; r < r1; r += rstep) {
-        float f[8];
-        bn_load8(base + r * C, f);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) { const float d = f[e] - shift[e]; s[e] += d; ss[e] = fmaf(d, d, ss[e]); }
     }
 #pragma unroll
     for (int e = 0; e < 8; ++e) { sh1[rl * C + cg * 8 + e] = s[e]; sh2[rl * C + cg * 8 + e] = ss[e]; }
@@ -619,21 +616,30 @@ bn_apply_fused_bf16_kernel(const __nv_bfloat16* __restrict__ x, const float* __r
 }
 
 // the gradient that reaches the normalisation output at pixel hh of sample n: dy itself, or (UP2) the sum over the 2x2
-// block of the upsampled gradient; masked by the recomputed ReLU pattern.
-template <int UP2>
-__device__ __forceinline__ void bn_load_grad(const __nv_bfloat16* __restrict__ dy, int64_t n, int hh, int H, int W, int C, int cg,
-                                             float (&g)[8]) {
-    if (UP2) {
+// block of the upsampled gradient.  Held as raw 16-byte loads so that several rows are in flight before the first use.
+template <int UP2> struct BnGradRaw;
+template <> struct BnGradRaw<0> {
+    uint4 a;
+    __device__ __forceinline__ void load(const __nv_bfloat16* __restrict__ dy, int64_t n, int hh, int H, int W, int C, int cg) {
+        a = __ldg(reinterpret_cast<const uint4*>(dy + (n * H * W + hh) * C + cg * 8));
+    }
+    __device__ __forceinline__ void get(float (&g)[8]) const { unpack8(a, g); }
+};
+template <> struct BnGradRaw<1> {
+    uint4 a, b, c, d;
+    __device__ __forceinline__ void load(const __nv_bfloat16* __restrict__ dy, int64_t n, int hh, int H, int W, int C, int cg) {
         const int ph = hh / W, pw = hh - ph * W;
         const __nv_bfloat16* p = dy + 4 * n * H * W * C + ((int64_t)(2 * ph) * (2 * W) + 2 * pw) * C + cg * 8;
-        float a[8], b[8], c[8], d[8];
-        bn_load8(p, a); bn_load8(p + C, b); bn_load8(p + (int64_t)2 * W * C, c); bn_load8(p + (int64_t)2 * W * C + C, d);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) g[e] = (a[e] + b[e]) + (c[e] + d[e]);
-    } else {
-        bn_load8(dy + (n * H * W + hh) * C + cg * 8, g);
+        a = __ldg(reinterpret_cast<const uint4*>(p)); b = __ldg(reinterpret_cast<const uint4*>(p + C));
+        c = __ldg(reinterpret_cast<const uint4*>(p + (int64_t)2 * W * C)); d = __ldg(reinterpret_cast<const uint4*>(p + (int64_t)2 * W * C + C));
     }
-}
+    __device__ __forceinline__ void get(float (&g)[8]) const {
+        float fa[8], fb[8], fc[8], fd[8];
+        unpack8(a, fa); unpack8(b, fb); unpack8(c, fc); unpack8(d, fd);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) g[e] = (fa[e] + fb[e]) + (fc[e] + fd[e]);
+    }
+};
 
 // blockIdx.y = sample, blockIdx.x = split of its H*W pixels
 template <int UP2>
@@ -660,25 +666,30 @@ bn_bwd_sums_bf16_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat1
         s1[e] = 0.f; s2[e] = 0.f;
     }
     const int64_t base = (int64_t)n * HW * C + cg * 8;
-    for (int h = h0 + rl; h < h1; h += 2 * rstep) {
-        float gq[2][8], vq[2][8];
+    constexpr int ROWS = UP2 ? 2 : 4;                    // rows in flight per thread (UP2: four gradient loads per row)
+    for (int h = h0 + rl; h < h1; h += ROWS * rstep) {
+        BnGradRaw<UP2> graw[ROWS];
+        uint4 vraw[ROWS];
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
+        for (int u = 0; u < ROWS; ++u) {
             const int hh = h + u * rstep;
             if (hh < h1) {
-                bn_load_grad<UP2>(dy, n, hh, H, W, C, cg, gq[u]);
-                bn_load8(x + base + (int64_t)hh * C, vq[u]);
+                graw[u].load(dy, n, hh, H, W, C, cg);
+                vraw[u] = __ldg(reinterpret_cast<const uint4*>(x + base + (int64_t)hh * C));
             }
         }
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
+        for (int u = 0; u < ROWS; ++u) {
             if (h + u * rstep < h1) {
+                float gq[8], vq[8];
+                graw[u].get(gq);
+                unpack8(vraw[u], vq);
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
-                    float gg = gq[u][e];
-                    if (relu) gg = fmaf(vq[u][e], sc[e], sf[e]) > 0.f ? gg : 0.f;
+                    float gg = gq[e];
+                    if (relu) gg = fmaf(vq[e], sc[e], sf[e]) > 0.f ? gg : 0.f;
                     s1[e] += gg;
-                    s2[e] = fmaf(gg, (vq[u][e] - mu[e]) * is[e], s2[e]);
+                    s2[e] = fmaf(gg, (vq[e] - mu[e]) * is[e], s2[e]);
                 }
             }
         }
@@ -724,26 +735,30 @@ bn_bwd_apply_fused_bf16_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_
     const int chunk = gridDim.x - 1 - blockIdx.x;
     const int h0 = chunk * rows_per_chunk, h1 = min(HW, h0 + rows_per_chunk);
     const int64_t base = (int64_t)n * HW * C + cg * 8;
-    for (int h = h0 + rl; h < h1; h += 2 * rstep) {
-        float gq[2][8], vq[2][8];
+    constexpr int ROWS = UP2 ? 2 : 4;
+    for (int h = h0 + rl; h < h1; h += ROWS * rstep) {
+        BnGradRaw<UP2> graw[ROWS];
+        uint4 vraw[ROWS];
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
+        for (int u = 0; u < ROWS; ++u) {
             const int hh = h + u * rstep;
             if (hh < h1) {
-                bn_load_grad<UP2>(dy, n, hh, H, W, C, cg, gq[u]);
-                bn_load8(x + base + (int64_t)hh * C, vq[u]);
+                graw[u].load(dy, n, hh, H, W, C, cg);
+                vraw[u] = __ldg(reinterpret_cast<const uint4*>(x + base + (int64_t)hh * C));
             }
         }
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
+        for (int u = 0; u < ROWS; ++u) {
             const int hh = h + u * rstep;
             if (hh < h1) {
-                float o[8];
+                float gq[8], vq[8], o[8];
+                graw[u].get(gq);
+                unpack8(vraw[u], vq);
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
-                    float gg = gq[u][e];
-                    if (relu) gg = fmaf(vq[u][e], sc[e], sf[e]) > 0.f ? gg : 0.f;
-                    const float xh = (vq[u][e] - mu[e]) * is[e];
+                    float gg = gq[e];
+                    if (relu) gg = fmaf(vq[e], sc[e], sf[e]) > 0.f ? gg : 0.f;
+                    const float xh = (vq[e] - mu[e]) * is[e];
                     o[e] = is[e] * (gm[e] * gg - c1[e] - xh * c2[e]);
                 }
                 uint4 ov;
@@ -921,9 +936,11 @@ static bool bn_fused_ok(int N, int H, int W, int C, int groups, int dtype) {
            (tpr & (tpr - 1)) == 0 && groups >= 1 && N % groups == 0;
 }
 static int bn_rows_per_chunk(int N, int HW, int tpr, int rows_in_flight) {
+    // ~4 blocks per SM: every block first derives its 8 channels' scale / shift from the accumulators (a chain of dependent
+    // loads); with one 4-row batch per block (the first version: 2048 blocks for 128x32x32) that prologue was the kernel
     const int rstep = 256 / tpr;
     int rpc = rows_in_flight * rstep;
-    while ((int64_t)N * ceil_div(HW, rpc) > 16 * (int64_t)sm_count() && rpc < HW) rpc *= 2;
+    while ((int64_t)N * ceil_div(HW, rpc) > 4 * (int64_t)sm_count() && rpc < HW) rpc *= 2;
     return rpc;
 }
 
