@@ -12,6 +12,7 @@ Deliberate, result-preserving departures from the reference graph (SURVEY.md 8(d
     pass feeds nothing (`disc_fake_`, `disc_fake_2_` are never used, :238-242);
   * the metrics-only clean pass (:228) runs only when `with_metrics=True`.
 """
+import contextlib
 import functools
 
 import torch
@@ -364,7 +365,8 @@ class Trainer:
         stacked_labels = torch.cat([all_real_labels, all_real_labels, all_real_labels], dim=0)
         RNG.scope_parts([('drop.p1', 2 * B), ('drop.p2', B)])
         RNG.begin_stack([2 * B, B])
-        disc_all, disc_all_2, disc_all_acgan = Discriminator(stacked, stacked_labels, 0.8, 0.5, 0.5)
+        with (K.branch(fork) if K.config.branch_stacked else contextlib.nullcontext()):
+            disc_all, disc_all_2, disc_all_acgan = Discriminator(stacked, stacked_labels, 0.8, 0.5, 0.5)
         RNG.end_stack()
         metrics = {}
         if with_metrics and CONDITIONAL and ACGAN:
@@ -375,7 +377,7 @@ class Trainer:
                 metrics['acgan_fake_acc'] = (pred[B:] == all_real_labels).float().mean()
         # gradient-penalty pass: independent of the stacked pass until the loss, so it runs as a second branch
         # (stream / CUDA-graph branch); autograd replays each branch's backward on the stream of its forward
-        with K.branch(fork):
+        with (contextlib.nullcontext() if K.config.branch_stacked else K.branch(fork)):
             alpha = RNG.uniform('alpha', (B, 1))
             interpolates = K.interpolate(all_real_data, fake_data, alpha).requires_grad_(True)     # :277-283
             RNG.scope('drop.gp')

@@ -26,6 +26,7 @@ class Config:
     side_stream = True       # run direct-accumulation wgrad / bias-grad launches on a second stream
     branch_streams = True    # run independent sub-graphs of a step (GP pass vs stacked pass) as stream branches
     branch_priority = -1     # CUDA stream priority of the branch stream (lower = higher priority)
+    branch_stacked = False   # which sub-graph runs on the branch stream: False = the gradient-penalty pass, True = the stacked pass
     tc_min_rows = 1          # (tunable) minimum GEMM rows to prefer the tensor-core path
     use_bn_fused = True      # BF16 batch norm as two kernels per direction (sums with red.global + apply)
     fuse_act_dropout = True  # Conv2D -> LeakyReLU -> dropout of the DCGAN critics in the tcgen05 conv epilogue (Philox in registers)
