@@ -341,7 +341,7 @@ class Trainer:
 
     def critic_forward_backward(self, all_real_data_int, all_real_labels, with_metrics=False, fake_data=None):
         # two stream branches share the SMs in this step: sub-wave layers keep one CTA per tile (see kernels.splitk)
-        with K.splitk(not K.config.branch_streams):
+        with K.splitk(K.config.critic_splitk or not K.config.branch_streams):
             return self._critic_forward_backward(all_real_data_int, all_real_labels, with_metrics, fake_data)
 
     def _critic_forward_backward(self, all_real_data_int, all_real_labels, with_metrics=False, fake_data=None):

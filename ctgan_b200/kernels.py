@@ -25,7 +25,8 @@ class Config:
     s2d_min_extent = 1       # (tunable) smallest space-to-depth image side that takes the tensor-core route
     side_stream = True       # run direct-accumulation wgrad / bias-grad launches on a second stream
     branch_streams = True    # run independent sub-graphs of a step (GP pass vs stacked pass) as stream branches
-    branch_priority = -1     # CUDA stream priority of the branch stream (lower = higher priority)
+    branch_priority = 0      # CUDA stream priority of the branch stream (lower = higher priority): equal priorities measure best
+    critic_splitk = False    # cluster split-K inside the two-branch ResNet critic step (see kernels.splitk)
     branch_stacked = False   # which sub-graph runs on the branch stream: False = the gradient-penalty pass, True = the stacked pass
     tc_min_rows = 1          # (tunable) minimum GEMM rows to prefer the tensor-core path
     use_bn_fused = True      # BF16 batch norm as two kernels per direction (sums with red.global + apply)

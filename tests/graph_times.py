@@ -17,6 +17,8 @@ if len(sys.argv) > 4:
 import os
 if os.environ.get('CTGAN_FUSE_RELU_BWD'):
     R.FUSE_RELU_BWD = bool(int(os.environ['CTGAN_FUSE_RELU_BWD']))
+if os.environ.get('CTGAN_CRITIC_SPLITK'):
+    K.config.critic_splitk = bool(int(os.environ['CTGAN_CRITIC_SPLITK']))
 if os.environ.get('CTGAN_BRANCH_STACKED'):
     K.config.branch_stacked = bool(int(os.environ['CTGAN_BRANCH_STACKED']))
 if os.environ.get('CTGAN_SPLITK'):
