@@ -1,6 +1,6 @@
 // layernorm.cu -- layer normalisation over (C,H,W) per sample with per-channel scale / offset: the critic's Normalize
-// of TG/CT_gan_64x64.py:87-93 (op: TG/tflib/ops/layernorm.py:6-21, eps 1e-5).  STAGED for SURVEY.md 8(f) row N4: written
-// and exercised against the CPU restatement through the stand-in backend, not yet validated on a B200.
+// of TG/CT_gan_64x64.py:87-93 (op: TG/tflib/ops/layernorm.py:6-21, eps 1e-5).  SURVEY.md 8(f) row N4; validated on a B200 by
+// tests/test_64x64_gpu.py (kernel family against the PyTorch-CPU definitions, and the CT_gan_64x64.py step against the oracle).
 //
 // Unlike every other critic op, layer norm is not piecewise linear, so the gradient penalty (a derivative of a derivative)
 // needs its genuine second-order terms.  With, per sample, M = C*H*W, xh = (x - mean) * r, r = rsqrt(var + eps),

@@ -789,7 +789,7 @@ def batch_norm(x, gamma, beta, labels=None, eps=1e-5, relu=False, groups=1, up2=
 
 class LayerNorm(Function):
     """Layer normalisation over each sample's (C,H,W) with per-channel gamma / beta (TG/tflib/ops/layernorm.py:6-21) -- the
-    critic's Normalize in TG/CT_gan_64x64.py:87-93.  STAGED.  Twice differentiable: layer norm is not
+    critic's Normalize in TG/CT_gan_64x64.py:87-93.  Twice differentiable: layer norm is not
     piecewise linear, so the gradient penalty needs the second-order terms of LayerNormBwd below."""
 
     @staticmethod

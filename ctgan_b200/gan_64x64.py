@@ -1,8 +1,8 @@
 """CT-GAN for 64x64 images: the training step of TG/CT_gan_64x64.py (MODE='wgan-ct', GoodGenerator / GoodDiscriminator).
 
-STAGED: host logic and parity against the oracle are verified on the stand-in backend
-(tests/test_gan_64x64_host.py); the layer-norm kernels it needs (csrc/layernorm.cu) have not run on a B200 yet, so the GPU
-tests for this file are opt-in (CTGAN_STAGED=1) and bench.py does not use it.
+SURVEY.md 8(f) row N4: host logic and parity against the oracle on the stand-in backend (tests/test_gan_64x64_host.py), the
+layer-norm kernels (csrc/layernorm.cu) and one critic + generator step against the oracle on a B200 (tests/test_64x64_gpu.py,
+fp32 and BF16 paths).  bench.py does not time it (not in BASELINE.json's configs).
 
 Hyper-parameters :28-37, Normalize :87-93, ConvMeanPool / MeanPoolConv / UpsampleConv :106-124, ResidualBlock :166-200,
 GoodGenerator :204-221, GoodDiscriminator :357-373, loss graph :480-546 (wgan-ct :494-519), Adam(1e-4, 0, .9) :560-564.

@@ -1185,7 +1185,7 @@ def bn_bwd(dy, x, y, gamma, beta, labels, mean, invstd, relu, groups=1, up2=Fals
     return dx, dgamma, dbeta
 
 
-# --------------------------------------------------------------------------- layer norm (STAGED: csrc/layernorm.cu)
+# --------------------------------------------------------------------------- layer norm (csrc/layernorm.cu)
 def _ln_dims(x):
     require_nhwc(x)
     if x.dim() != 4:

@@ -1,4 +1,4 @@
-"""lib.ops.layernorm.Layernorm -- drop-in for TG/tflib/ops/layernorm.py:6-21 (STAGED: SURVEY.md 8(f) N4).
+"""lib.ops.layernorm.Layernorm -- drop-in for TG/tflib/ops/layernorm.py:6-21.
 
 Per-sample moments over `norm_axes` (the CT scripts only use [1,2,3] on BCHW data: TG/CT_gan_64x64.py:91), biased variance,
 eps 1e-5, `<name>.offset` / `<name>.scale` of length n_neurons = the size of the first normalised axis (channels)."""

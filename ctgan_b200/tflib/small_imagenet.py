@@ -1,5 +1,5 @@
 """64x64 ImageNet batch generators with the reference's semantics (TG/tflib/small_imagenet.py:5-24), for CT_gan_64x64.py
-(staged with the rest of that row).
+(SURVEY.md 8(f) N4).
 
 `load(batch_size, data_dir)` -> `(train_epoch, valid_epoch)` over `<data_dir>/train_64x64/<i>.png` (1,281,149 files) and
 `<data_dir>/valid_64x64/<i>.png` (49,999 files), file names zero-padded to the width of the file count.  One epoch =

@@ -25,7 +25,7 @@ from .graphs import GraphedTrainer
 from .tflib import plot as _plot, save_images as _save_images, cifar10 as _cifar10, mnist as _mnist, small_imagenet as _imagenet
 
 SCRIPTS = {'mnist': 'gan_mnist', 'cifar': 'gan_cifar', 'cifar_resnet': 'gan_cifar_resnet',
-           '64x64': 'gan_64x64'}        # 64x64: STAGED, see gan_64x64.py
+           '64x64': 'gan_64x64'}        # 64x64: SURVEY.md 8(f) N4, see gan_64x64.py
 
 
 def _loaders(script, mod, batch_size, data_dir, n_examples):

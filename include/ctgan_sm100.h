@@ -328,7 +328,7 @@ int ctgan_bn_bwd_fused(const void* dy, const void* x, const float* gamma, const 
                        const float* save_mean, const float* save_invstd, void* dx, float* dgamma, float* dbeta,
                        float* ws, int N, int H, int W, int C, int n_labels, int flags, int groups, void* stream);
 
-/* ---- layer normalisation over (C,H,W) per sample, per-channel scale / offset (STAGED, SURVEY.md 8(f) N4: the critic's
+/* ---- layer normalisation over (C,H,W) per sample, per-channel scale / offset (the critic's
  * Normalize of TG/CT_gan_64x64.py:87-93; op TG/tflib/ops/layernorm.py:6-21, eps 1e-5).  x, y, v, out: NHWC activations
  * [N][M], M = H*W*C; mean, rstd: float [N]; gamma, beta, dgamma, dbeta: float [C]; ws: ctgan_ln_workspace_floats() floats.
  * With xh = (x - mean) * rstd and core(u) = rstd * (u - mean_s(u) - xh * mean_s(u * xh)) over each sample:

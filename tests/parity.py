@@ -13,7 +13,7 @@ SCRIPTS = {
     'mnist': ('ctgan_b200.gan_mnist', 'oracle.ct_gan_mnist'),
     'cifar': ('ctgan_b200.gan_cifar', 'oracle.ct_gan_cifar'),
     'resnet': ('ctgan_b200.gan_cifar_resnet', 'oracle.ct_gan_cifar_resnet'),
-    '64x64': ('ctgan_b200.gan_64x64', 'oracle.ct_gan_64x64'),          # STAGED
+    '64x64': ('ctgan_b200.gan_64x64', 'oracle.ct_gan_64x64'),
 }
 
 

@@ -1,4 +1,4 @@
-"""CT_gan_64x64.py (STAGED) on the stand-in backend: one critic step and one generator step of
+"""CT_gan_64x64.py on the stand-in backend: one critic step and one generator step of
 ctgan_b200/gan_64x64.py against the oracle restatement (itself pinned to the reference's code: tests/test_oracle_vs_reference.py)
 with the same weights and replayed random draws -- loss terms, the GP gradient, every parameter gradient (the critic's
 include the second-order layer-norm terms) and the Adam update."""

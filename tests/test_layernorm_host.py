@@ -1,4 +1,4 @@
-"""Layer norm (STAGED) on the stand-in backend: the twice-differentiable composition in
+"""Layer norm on the stand-in backend: the twice-differentiable composition in
 ctgan_b200/functional.py (LayerNorm / LayerNormBwd) against PyTorch autograd of the plain formula -- first order (dx, dgamma,
 dbeta) and the second-order terms the gradient penalty needs (d<c, dx>/d{gy, x, gamma}), including the closed form of the
 x-derivative documented in csrc/layernorm.cu."""

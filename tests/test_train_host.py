@@ -114,8 +114,8 @@ def test_checkpoint_round_trip_resumes_exactly(fake_kernels, tmp_path):
         checkpoint.load(path, None)
 
 
-def test_train_loop_64x64_staged(fake_kernels, tmp_path, capsys):
-    """The CT_gan_64x64.py loop (STAGED row N4) over tflib.small_imagenet PNG folders: schedule, metric names, files."""
+def test_train_loop_64x64(fake_kernels, tmp_path, capsys):
+    """The CT_gan_64x64.py loop (row N4) over tflib.small_imagenet PNG folders: schedule, metric names, files."""
     from PIL import Image
     from ctgan_b200 import train as T
     import ctgan_b200.tflib.plot as plot
