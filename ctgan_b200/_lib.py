@@ -103,6 +103,8 @@ _PROTOS = {
     'ctgan_crop_bwd': (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     'ctgan_prep_real': (c_int, [P, P, c_int64, c_float, c_float, c_uint64, c_uint64, P, P]),
     'ctgan_prep_real_u8': (c_int, [P, P, c_int64, c_float, c_float, c_uint64, c_uint64, P, P]),
+    'ctgan_prep_real_dup': (c_int, [P, c_int, P, P, c_int64, c_float, c_float, c_uint64, c_uint64, P, P]),
+    'ctgan_memset_zero': (c_int, [P, c_int64, P]),
     'ctgan_interpolate': (c_int, [P, P, P, P, c_int, c_int, P]),
     'ctgan_bn_workspace_floats': (c_int64, [c_int, c_int, c_int, c_int]),
     'ctgan_bn_fwd': (c_int, [P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_float, c_int, c_int, c_int, P]),

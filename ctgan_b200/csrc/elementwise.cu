@@ -396,8 +396,10 @@ __global__ void crop_kernel(const T* __restrict__ x, T* __restrict__ y, int N, i
     }
 }
 
+// y2 (nullable): a second destination for the same values -- the real batch occupies two row ranges of the stacked critic
+// input (passes ' and ''), written here instead of by a concatenation kernel
 template <typename TIn>
-__global__ void prep_real_div_kernel(const TIn* __restrict__ x, float* __restrict__ y, int64_t n, float denom,
+__global__ void prep_real_div_kernel(const TIn* __restrict__ x, float* __restrict__ y, float* __restrict__ y2, int64_t n, float denom,
                                      float noise_hi, uint64_t seed, uint64_t offset, const uint64_t* __restrict__ dyn) {
     ctgan::pdl_entry();
     if (dyn) offset += dyn[0];
@@ -405,6 +407,7 @@ __global__ void prep_real_div_kernel(const TIn* __restrict__ x, float* __restric
         float v = 2.f * (__fdiv_rn((float)x[i], denom) - 0.5f);       // true division: /255 is not exact as a multiply
         if (noise_hi > 0.f) v += noise_hi * Philox::uniform_at(seed, offset + (uint64_t)i);
         y[i] = v;
+        if (y2) y2[i] = v;
     }
 }
 __global__ void interpolate_kernel(const float* __restrict__ real, const float* __restrict__ fake,
@@ -708,19 +711,26 @@ extern "C" int ctgan_crop_bwd(const void* dy, void* dx, int N, int H, int W, int
 
 extern "C" int ctgan_prep_real(const int32_t* x, float* y, int64_t n, float denom, float noise_hi,
                                uint64_t seed, uint64_t offset, const uint64_t* dyn_offset, void* stream) {
-    CTGAN_REQUIRE(denom > 0.f, CTGAN_ERR_BAD_DESC, "prep_real: denom must be positive");
-    if (n <= 0) return 0;
-    CTGAN_LAUNCH((prep_real_div_kernel<int32_t>), elementwise_grid(n, 256), 256, 0, as_stream(stream), x, y, n, denom, noise_hi, seed, offset, dyn_offset);
-    CTGAN_CHECK_LAUNCH("prep_real");
-    return 0;
+    return ctgan_prep_real_dup(x, CTGAN_F32 /* int32 */, y, nullptr, n, denom, noise_hi, seed, offset, dyn_offset, stream);
 }
 extern "C" int ctgan_prep_real_u8(const uint8_t* x, float* y, int64_t n, float denom, float noise_hi,
                                   uint64_t seed, uint64_t offset, const uint64_t* dyn_offset, void* stream) {
-    CTGAN_REQUIRE(denom > 0.f, CTGAN_ERR_BAD_DESC, "prep_real_u8: denom must be positive");
+    return ctgan_prep_real_dup(x, 1 /* uint8 */, y, nullptr, n, denom, noise_hi, seed, offset, dyn_offset, stream);
+}
+extern "C" int ctgan_prep_real_dup(const void* x, int x_is_u8, float* y, float* y2, int64_t n, float denom, float noise_hi,
+                                   uint64_t seed, uint64_t offset, const uint64_t* dyn_offset, void* stream) {
+    CTGAN_REQUIRE(denom > 0.f && x && y, CTGAN_ERR_BAD_DESC, "prep_real: denom must be positive, x / y non-null");
     if (n <= 0) return 0;
-    CTGAN_LAUNCH((prep_real_div_kernel<uint8_t>), elementwise_grid(n, 256), 256, 0, as_stream(stream), x, y, n, denom, noise_hi, seed, offset, dyn_offset);
-    CTGAN_CHECK_LAUNCH("prep_real_u8");
+    if (x_is_u8)
+        CTGAN_LAUNCH((prep_real_div_kernel<uint8_t>), elementwise_grid(n, 256), 256, 0, as_stream(stream), (const uint8_t*)x, y, y2, n, denom, noise_hi, seed, offset, dyn_offset);
+    else
+        CTGAN_LAUNCH((prep_real_div_kernel<int32_t>), elementwise_grid(n, 256), 256, 0, as_stream(stream), (const int32_t*)x, y, y2, n, denom, noise_hi, seed, offset, dyn_offset);
+    CTGAN_CHECK_LAUNCH("prep_real");
     return 0;
+}
+extern "C" int ctgan_memset_zero(void* p, int64_t bytes, void* stream) {
+    CTGAN_REQUIRE(p && bytes >= 0, CTGAN_ERR_BAD_DESC, "memset_zero: bad args");
+    return cuda_status(cudaMemsetAsync(p, 0, (size_t)bytes, as_stream(stream)), "memset_zero");
 }
 extern "C" int ctgan_interpolate(const float* real, const float* fake, const float* alpha, float* out,
                                  int B, int P, void* stream) {

@@ -613,6 +613,41 @@ def add(a, b):
     return Add.apply(a, b)
 
 
+class Fork2(Function):
+    """(x, x): a tensor consumed by two sub-graphs (a block's shortcut and its first layer).  The engine would sum the two
+    gradients with an ATen add; here the adjoint is the library's own add kernel (and, being an Add node, differentiable
+    again for the gradient penalty)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.view_as(x), x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g1, g2):
+        if g1 is None or g2 is None:
+            return g1 if g2 is None else g2
+        return Add.apply(_dense_like(g1, True), _dense_like(g2, True))
+
+
+def fork2(x):
+    return Fork2.apply(x) if x.requires_grad else (x, x)
+
+
+class AddScaled(Function):
+    """a + s * b on tensors of one shape (the generator cost: -mean D(G(z)) + 0.1 * CE, TG/CT_gan_cifar_resnet.py:326-330)."""
+
+    @staticmethod
+    def forward(ctx, a, b, s):
+        ctx.s = s
+        return K.add(a, K.scale(b, s))
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        g = g.contiguous()
+        return g, K.scale(g, ctx.s), None
+
+
 class Pool(Function):
     @staticmethod
     def forward(ctx, x, scale):

@@ -148,6 +148,10 @@ def ResidualBlock(name, input_dim, output_dim, filter_size, inputs, resample=Non
         # N1 = relu(inputs) and the skip connection both read `inputs`: one node, so that backward is one kernel
         inputs, pre_act = F.fork_relu(inputs)
 
+    if not fused_act and resample == 'up':
+        inputs, inputs_main = F.fork2(inputs)            # block input -> (shortcut, N1): explicit fork, adjoint = K.add
+    else:
+        inputs_main = inputs
     shortcut_up2 = False
     if output_dim == input_dim and resample is None:
         shortcut = inputs  # Identity skip-connection
@@ -171,7 +175,7 @@ def ResidualBlock(name, input_dim, output_dim, filter_size, inputs, resample=Non
         output = conv_2(name + '.Conv2', filter_size=filter_size, inputs=output, in_relu=FUSE_RELU_BWD)
         return F.add(shortcut, output)
     else:
-        output = inputs
+        output = inputs_main
         if resample == 'up' and FUSE_BN_UP:
             # UpsampleConv(N1(x)): the normalisation kernel writes the 2x nearest-neighbour upsampled activation itself
             output = Normalize(name + '.N1', output, labels=labels, relu=True, up2=True)
@@ -199,10 +203,11 @@ def OptimizedResBlockDisc1(inputs, fork=False):
     conv_1 = functools.partial(lib.ops.conv2d.Conv2D, input_dim=3, output_dim=DIM_D)
     conv_2 = functools.partial(ConvMeanPool, input_dim=DIM_D, output_dim=DIM_D)
     conv_shortcut = MeanPoolConv
+    inputs, inputs_main = F.fork2(inputs)                # image -> (shortcut, conv_1): explicit fork (x^ and fakes carry gradients)
     shortcut = conv_shortcut('Discriminator.1.Shortcut', input_dim=3, output_dim=DIM_D, filter_size=1, he_init=False,
                              biases=True, inputs=inputs)
 
-    output = inputs
+    output = inputs_main
     if FUSE_D_ACT:
         # nonlinearity in conv_1's epilogue, its backward in conv_2's dgrad epilogue
         output = conv_1('Discriminator.1.Conv1', filter_size=3, inputs=output, relu=True, relu_bwd_fused=FUSE_RELU_BWD)
@@ -311,6 +316,14 @@ class Trainer:
         global ACT_DTYPE, RNG
         RNG = self.rng
 
+    def _ones_like(self, t):
+        """A constant tensor of ones shaped like t, created once (tf.gradients' implicit grad_ys; no fill kernel per step)."""
+        key = (tuple(t.shape), t.dtype)
+        cache = self.__dict__.setdefault('_ones', {})
+        if key not in cache:
+            cache[key] = torch.ones_like(t)
+        return cache[key]
+
     @staticmethod
     def lr(iteration):
         decay = max(0., 1. - (float(iteration) / ITERS)) if DECAY else 1.
@@ -353,16 +366,21 @@ class Trainer:
                 RNG.begin_stack([h] * N_DEVICES)
                 fake_data = self._generate([('z.%d' % i, h) for i in range(N_DEVICES)], all_real_labels, B)
                 RNG.end_stack()
+        # stochastic pass ' on real+fake (2B rows) and pass '' on the real half (B rows) as ONE critic call: same weights,
+        # independent dropout draws per row -- the reference's two calls at :226-227.  The stacked input [real, fake, real] is
+        # written in place: the input-scaling kernel stores the real batch into both of its row ranges, the fakes are copied
+        # into theirs (no concatenation kernel).
+        stacked = torch.empty((3 * B, all_real_data_int.shape[1]), dtype=torch.float32, device=all_real_data_int.device)
+        all_real_data = stacked[:B]
         if RNG.replay is not None:                                                              # golden-vector tests
-            all_real_data = K.add(K.prep_real(all_real_data_int, 256., 0.), RNG.uniform('dequant', all_real_data_int.shape))
+            all_real_data.copy_(K.add(K.prep_real(all_real_data_int, 256., 0.), RNG.uniform('dequant', all_real_data_int.shape)))
+            stacked[2 * B:].copy_(all_real_data)
         else:
             seed, off, dyn = RNG.stream('dequant', all_real_data_int)
-            all_real_data = K.prep_real(all_real_data_int, 256., 1. / 128, seed, off, dyn=dyn)  # :201-202
-        # stochastic pass ' on real+fake (2B rows) and pass '' on the real half (B rows) as ONE critic call:
-        # same weights, independent dropout draws per row -- the reference's two calls at :226-227
+            K.prep_real(all_real_data_int, 256., 1. / 128, seed, off, dyn=dyn, out=all_real_data, out2=stacked[2 * B:])  # :201-202
+        stacked[B:2 * B].copy_(fake_data)
         fork = K.fork_branch(all_real_data)          # the gradient-penalty pass below depends on nothing after this point
-        stacked = torch.cat([all_real_data, fake_data, all_real_data], dim=0)
-        stacked_labels = torch.cat([all_real_labels, all_real_labels, all_real_labels], dim=0)
+        stacked_labels = None     # the critic never reads labels (NORMALIZATION_D is False; ACGAN conditions through its loss)
         RNG.scope_parts([('drop.p1', 2 * B), ('drop.p2', B)])
         RNG.begin_stack([2 * B, B])
         with (K.branch(fork) if K.config.branch_stacked else contextlib.nullcontext()):
@@ -371,7 +389,7 @@ class Trainer:
         metrics = {}
         if with_metrics and CONDITIONAL and ACGAN:
             with torch.no_grad():
-                _, _, clean = Discriminator(stacked[:2 * B], stacked_labels[:2 * B], 1.0, 1.0, 1.0)
+                _, _, clean = Discriminator(stacked[:2 * B], None, 1.0, 1.0, 1.0)
                 pred = clean.argmax(dim=1).to(torch.int32)
                 metrics['acgan_acc'] = (pred[:B] == all_real_labels).float().mean()
                 metrics['acgan_fake_acc'] = (pred[B:] == all_real_labels).float().mean()
@@ -383,7 +401,7 @@ class Trainer:
             RNG.scope('drop.gp')
             d_interp = Discriminator(interpolates, all_real_labels, 0.8, 0.5, 0.5)[0]
             with F.no_param_grads():                  # tf.gradients(..., [interpolates]): d/dx^ only
-                gradients = torch.autograd.grad(d_interp, interpolates, grad_outputs=torch.ones_like(d_interp),
+                gradients = torch.autograd.grad(d_interp, interpolates, grad_outputs=self._ones_like(d_interp),
                                                 create_graph=True)[0]                               # :284
         K.join_branch(fork)
         use_logits = CONDITIONAL and ACGAN
@@ -420,7 +438,7 @@ class Trainer:
         # mean over the stacked batch == (cost_dev0 + cost_dev1) / len(DEVICES)  (equal split sizes)
         gen_cost = F.MeanLoss.apply(disc_fake, -1.0)
         if CONDITIONAL and ACGAN:
-            gen_cost = gen_cost + ACGAN_SCALE_G * F.SoftmaxCE.apply(disc_fake_acgan, fake_labels)
+            gen_cost = F.AddScaled.apply(gen_cost, F.SoftmaxCE.apply(disc_fake_acgan, fake_labels), ACGAN_SCALE_G)
         with F.frozen(self.disc_opt.param_list()):    # var_list = gen_params (:336): the critic is not updated here
             gen_cost.backward(inputs=self.gen_opt.param_list())
         K.join_side()

@@ -1101,13 +1101,28 @@ def crop_bwd(dy, H, W):
     return dx
 
 
-def prep_real(x_int, denom, noise_hi=0., seed=0, offset=0, dyn=None):
+def prep_real(x_int, denom, noise_hi=0., seed=0, offset=0, dyn=None, out=None, out2=None):
+    """2 * (x / denom - .5) [+ U[0, noise_hi)].  out / out2: contiguous float destinations of x's shape (e.g. two row ranges of
+    a stacked critic input) written instead of a fresh tensor."""
     _chk(x_int)
     if x_int.dtype not in (torch.int32, torch.uint8) or not x_int.is_contiguous():
         raise RuntimeError('ctgan_b200: real data must be contiguous int32 or uint8')
-    y = torch.empty(x_int.shape, dtype=torch.float32, device=x_int.device)
-    call('ctgan_prep_real' if x_int.dtype == torch.int32 else 'ctgan_prep_real_u8', _p(x_int), _p(y), x_int.numel(), float(denom), float(noise_hi), int(seed), int(offset), _p(dyn), _stream())
+    y = out if out is not None else torch.empty(x_int.shape, dtype=torch.float32, device=x_int.device)
+    for t in (y, out2):
+        if t is not None and (t.dtype != torch.float32 or not t.is_contiguous() or t.numel() != x_int.numel()):
+            raise RuntimeError('ctgan_b200: prep_real destinations must be contiguous float32 of the input size')
+    call('ctgan_prep_real_dup', _p(x_int), int(x_int.dtype == torch.uint8), _p(y), _p(out2), x_int.numel(), float(denom), float(noise_hi),
+         int(seed), int(offset), _p(dyn), _stream())
     return y
+
+
+def zero_(t):
+    """In-place zero fill as a memset node (no fill kernel)."""
+    _chk(t)
+    if not t.is_contiguous():
+        raise RuntimeError('ctgan_b200: zero_ needs a contiguous tensor')
+    call('ctgan_memset_zero', _p(t), t.numel() * t.element_size(), _stream())
+    return t
 
 
 def interpolate(real, fake, alpha):

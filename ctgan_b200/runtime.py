@@ -306,7 +306,7 @@ class FlatAdam:
         return list(self.params.values())
 
     def zero_grad(self):
-        self.flat_g.zero_()
+        K.zero_(self.flat_g) if self.flat_g.is_cuda else self.flat_g.zero_()
         for q in self.params.values():       # keep .grad bound to the flat views
             if q.grad is None or q.grad.data_ptr() != self.flat_g.data_ptr() + 4 * self.offsets[q.ctgan_name]:
                 q.grad = self.flat_g[self.offsets[q.ctgan_name]:self.offsets[q.ctgan_name] + q.numel()].view(q.shape)

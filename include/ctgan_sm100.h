@@ -285,6 +285,12 @@ int ctgan_prep_real(const int32_t* x_int, float* y, int64_t n, float denom, floa
  * feed converts to the int32 placeholder TG/CT_gan_cifar_resnet.py:191): 1 byte/pixel over PCIe instead of 4 */
 int ctgan_prep_real_u8(const uint8_t* x_u8, float* y, int64_t n, float denom, float noise_hi,
                        uint64_t seed, uint64_t offset, const uint64_t* dyn_offset /*nullable*/, void* stream);
+/* the same with a second destination y2 (nullable) receiving identical values -- the real batch occupies two row ranges of the
+ * stacked critic input -- and the input type as a flag (0 = int32, 1 = uint8) */
+int ctgan_prep_real_dup(const void* x, int x_is_u8, float* y, float* y2, int64_t n, float denom, float noise_hi,
+                        uint64_t seed, uint64_t offset, const uint64_t* dyn_offset, void* stream);
+/* cudaMemsetAsync(p, 0, bytes): the zero-fill of the flat gradient bucket as a memset node instead of a fill kernel */
+int ctgan_memset_zero(void* p, int64_t bytes, void* stream);
 /* out[b,p] = real[b,p] + alpha[b] * (fake[b,p] - real[b,p])   (TG/CT_gan_cifar.py:142-143) */
 int ctgan_interpolate(const float* real, const float* fake, const float* alpha, float* out,
                       int B, int P, void* stream);

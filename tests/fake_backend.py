@@ -238,10 +238,15 @@ def crop_bwd(dy, H, W):
     return _out(out, dy.dtype)
 
 
-def prep_real(x_int, denom, noise_hi=0., seed=0, offset=0, dyn=None):
+def prep_real(x_int, denom, noise_hi=0., seed=0, offset=0, dyn=None, out=None, out2=None):
     y = 2 * ((x_int.to(torch.float32) / np.float32(denom)) - 0.5)
     if noise_hi > 0:
         y = y + np.float32(noise_hi) * _uniform_like(x_int, seed, offset, dyn)
+    if out2 is not None:
+        out2.copy_(y.reshape(out2.shape))
+    if out is not None:
+        out.copy_(y.reshape(out.shape))
+        return out
     return y
 
 
