@@ -217,6 +217,10 @@ class ConvF(Function):
             gy = D2SMul.apply(gy, ctx.mult, ctx.out_geom) if ctx.out_geom is not None else MulConst.apply(gy, ctx.mult)
         if ctx.relu_out is not None and not ctx.relu_bwd_fused:
             gy = MulReluMask.apply(gy, ctx.relu_out)
+        n_in = len(ctx.needs_input_grad)                 # apply() is called with 5 .. 13 arguments
+        gy_res = None
+        if n_in > 6 and ctx.needs_input_grad[6] and ctx.needs_input_grad[0] and gy.requires_grad:
+            gy, gy_res = Fork2.apply(gy)                 # (dgrad operand, residual gradient): explicit fork for the double backward
         gx = gw = gb = None
         dycol = K.thin_col(gy, ctx.g, 'dy')          # im2col of a 3-channel gy: shared by dgrad and wgrad
         if ctx.needs_input_grad[0]:
@@ -235,10 +239,10 @@ class ConvF(Function):
                 K.on_side(lambda: K.bias_grad(gy.detach(), accumulate_into=b.grad), gy)
             else:
                 gb = K.bias_grad(gy.detach())
-        n_in = len(ctx.needs_input_grad)                 # apply() is called with 5 .. 13 arguments
         g_res = None
         if n_in > 6 and ctx.needs_input_grad[6]:
-            g_res = Pool.apply(gy, 1.0) if ctx.res_up2 else gy       # adjoint of the 2x nearest upsample: 2x2 sums
+            gr = gy_res if gy_res is not None else gy
+            g_res = Pool.apply(gr, 1.0) if ctx.res_up2 else gr       # adjoint of the 2x nearest upsample: 2x2 sums
         return (gx, gw, gb, None, None, None, g_res, None, None, None, None, None, None)[:n_in]
 
 
@@ -973,9 +977,9 @@ class CTGPLossStacked(Function):
         la = saved[4] if len(saved) > 4 else None
         (r0, r1), (s0, s1), (k0, k1) = ctx.rows['real'], ctx.rows['real2'], ctx.rows['fake']
         covered = (r1 - r0) + (s1 - s0) + (k1 - k0) == d_all.shape[0]
-        g_d = torch.empty_like(d_all) if covered else torch.zeros_like(d_all)
-        g_f = torch.zeros_like(f_all)                              # the fake rows carry no feature gradient
-        g_l = torch.zeros_like(la) if la is not None else None
+        g_d = torch.empty_like(d_all) if covered else K.zeros_like(d_all)
+        g_f = K.zeros_like(f_all)                                  # the fake rows carry no feature gradient
+        g_l = K.zeros_like(la) if la is not None else None
         outs = (g_d[r0:r1], g_d[s0:s1], g_d[k0:k1], g_f[r0:r1], g_f[s0:s1], g_l[r0:r1] if g_l is not None else None)
         g = K.ct_gp_loss_bwd(ctx.desc, gout[0:1].contiguous(), d_all[r0:r1], d_all[s0:s1], f_all[r0:r1], f_all[s0:s1], grad,
                              la[r0:r1] if la is not None else None, ctx.labels, per_sample, outs=outs)

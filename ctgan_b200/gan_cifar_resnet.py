@@ -279,10 +279,15 @@ def Discriminator(inputs, labels, kp1, kp2, kp3):  # three more parameters of ke
         output = _dropout(output, kp3)  # dropout after activator
         output = nonlinearity(output)
     output2 = F.spatial_mean(output)  # corresponding to D_
-    output_wgan = lib.ops.linear.Linear('Discriminator.Output', DIM_D, 1, output2, out_dtype=torch.float32)
+    # D_ feeds the critic head, the ACGAN head and (returned) the consistency term: explicit forks, so that the three
+    # gradients are summed by the library's add kernel
+    output2, feat = F.fork2(output2)
+    if CONDITIONAL and ACGAN:
+        feat, feat_ac = F.fork2(feat)
+    output_wgan = lib.ops.linear.Linear('Discriminator.Output', DIM_D, 1, feat, out_dtype=torch.float32)
     output_wgan = output_wgan.reshape(-1)  # conrresponding to D
     if CONDITIONAL and ACGAN:
-        output_acgan = lib.ops.linear.Linear('Discriminator.ACGANOutput', DIM_D, 10, output2, out_dtype=torch.float32)
+        output_acgan = lib.ops.linear.Linear('Discriminator.ACGANOutput', DIM_D, 10, feat_ac, out_dtype=torch.float32)
         return output_wgan, output2, output_acgan
     else:
         return output_wgan, output2, None  # two layers' of output
@@ -409,7 +414,7 @@ class Trainer:
         out = F.CTGPLossStacked.apply(disc_all, disc_all_2, gradients, disc_all_acgan if use_logits else None,
                                       all_real_labels if use_logits else None, self.hp,
                                       dict(real=(0, B), fake=(B, 2 * B), real2=(2 * B, 3 * B)))
-        out[0].backward(inputs=self.disc_opt.param_list())
+        out[0].backward(gradient=self._ones_like(out[0]), inputs=self.disc_opt.param_list())
         K.join_branch(fork)
         K.join_side()
         res = dict(out=out.detach(), gradients=gradients.detach(), fake_data=fake_data, real_data=all_real_data)
@@ -440,7 +445,7 @@ class Trainer:
         if CONDITIONAL and ACGAN:
             gen_cost = F.AddScaled.apply(gen_cost, F.SoftmaxCE.apply(disc_fake_acgan, fake_labels), ACGAN_SCALE_G)
         with F.frozen(self.disc_opt.param_list()):    # var_list = gen_params (:336): the critic is not updated here
-            gen_cost.backward(inputs=self.gen_opt.param_list())
+            gen_cost.backward(gradient=self._ones_like(gen_cost), inputs=self.gen_opt.param_list())
         K.join_side()
         return dict(cost=gen_cost.detach())
 

@@ -833,33 +833,33 @@ def conv_wgrad(x, dy, g, w_shape, accumulate_into=None, col=None, defer=False):
     defer = defer and acc is not None
     route, gj = _wgrad_route(x, dy, g)
     if route == 'tf32':
-        dw = acc if acc is not None else torch.zeros(w_shape, dtype=torch.float32, device=x.device)
+        dw = acc if acc is not None else zeros(w_shape, torch.float32, x.device)
         if defer and config.defer_wgrad:
             _wgrad_queue32.append((x, dy, g, dw))
         else:
             _launch_wgrad_jobs([(x, dy, g, dw)], F32, 'ctgan_conv_wgrad_tf32_multi')
         return dw
     if route == 'tc':
-        dw = acc if acc is not None else torch.zeros(w_shape, dtype=torch.float32, device=x.device)
+        dw = acc if acc is not None else zeros(w_shape, torch.float32, x.device)
         _wgrad_tc(x, dy, g, dw, defer)
         return dw
     if route == 's2d':
         g3 = gj
         xs = col if (col is not None and tuple(col.shape) == (g3.N, g3.Cin, g3.H, g3.W)) else space_to_depth(x, g)
-        dw3 = torch.zeros((3, 3, g3.Cin, g3.Cout), dtype=torch.float32, device=x.device)
+        dw3 = zeros((3, 3, g3.Cin, g3.Cout), torch.float32, x.device)
         dw = acc if acc is not None else torch.empty(w_shape, dtype=torch.float32, device=x.device)
         _wgrad_tc(xs, dy, g3, dw3, defer, post=lambda: _s2d_filter_grad_launch(dw3, dw, g, acc is not None))
         return dw
     if route == 'padk':
         col = col if (col is not None and tuple(col.shape) == (g.N, 128, g.Ho, g.Wo)) else im2col_strided(x, g)
-        dw128 = torch.zeros((1, 1, 128, g.Cout), dtype=torch.float32, device=x.device)
+        dw128 = zeros((1, 1, 128, g.Cout), torch.float32, x.device)
         dw = acc if acc is not None else torch.empty(w_shape, dtype=torch.float32, device=x.device)
         n_real = g.kh * g.kw * g.Cin * g.Cout                                   # HWIO order == column order
         _wgrad_tc(col, dy, gj, dw128, defer, post=lambda: _add_prefix_launch(dw128, dw, n_real, acc is not None))
         return dw
     if route == 'thin':
         side = gj
-        dw = acc if acc is not None else torch.zeros(w_shape, dtype=torch.float32, device=x.device)
+        dw = acc if acc is not None else zeros(w_shape, torch.float32, x.device)
         P, taps = g.N * g.H * g.W, g.kh * g.kw
         if side == 'in':
             col = col if col is not None else im2col_thin(x, g, g.Cin, 1)
@@ -1114,6 +1114,17 @@ def prep_real(x_int, denom, noise_hi=0., seed=0, offset=0, dyn=None, out=None, o
     call('ctgan_prep_real_dup', _p(x_int), int(x_int.dtype == torch.uint8), _p(y), _p(out2), x_int.numel(), float(denom), float(noise_hi),
          int(seed), int(offset), _p(dyn), _stream())
     return y
+
+
+def zeros_like(t):
+    """torch.zeros_like through a memset node (no fill kernel inside the captured steps)."""
+    out = torch.empty_like(t)
+    return zero_(out) if (out.is_cuda and out.is_contiguous()) else out.zero_()
+
+
+def zeros(shape, dtype, device):
+    out = torch.empty(shape, dtype=dtype, device=device)
+    return zero_(out) if out.is_cuda else out.zero_()
 
 
 def zero_(t):
