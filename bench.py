@@ -285,10 +285,15 @@ def roofline_kernels(torch, peaks):
     xs = [_bf16_act(torch, (N, C, H, H)) for _ in range(80)]
     ys = [torch.empty_like(xs[0]) for _ in range(80)]
     d8 = K._desc(g, _lib.BF16, _lib.BF16)
-    ms = _time_launches(torch, lambda i: _lib.call('ctgan_conv_fprop_tc', ctypes.byref(d8), K._p(xs[i % 80]), K._p(wp), K._p(b), None,
-                                                  K._p(ys[i % 80]), 0, K._stream()), 80, 160)
-    entry('conv_fprop_tc_lean_kernel<0>', 'conv_fprop_tc_lean_kernel<0> (3x3, 128->128, %dx8x8: 32 tiles on 148 SMs)' % N,
-          2.0 * N * H * H * C * C * 9, ms)
+    launch8 = lambda i: _lib.call('ctgan_conv_fprop_tc', ctypes.byref(d8), K._p(xs[i % 80]), K._p(wp), K._p(b), None,
+                                  K._p(ys[i % 80]), 0, K._stream())
+    with K.splitk(False):                     # one CTA per tile: what the two-branch critic step launches
+        ms = _time_launches(torch, launch8, 80, 160)
+    entry('conv_fprop_tc_lean_kernel<0>', 'conv_fprop_tc_lean_kernel<0> (3x3, 128->128, %dx8x8: 32 tiles on 148 SMs, one CTA per tile; '
+          'latency-bound: 1.2 GFLOP per launch)' % N, 2.0 * N * H * H * C * C * 9, ms)
+    with K.splitk(True):                      # cluster split-K (4 CTAs per tile): what the generator / DCGAN steps launch
+        ms_sk = _time_launches(torch, launch8, 80, 160)
+    out[-1]['split_k_cluster_us_per_launch'] = ms_sk * 1e3
     del xs, ys
 
     # (3) all filter gradients of one critic step in one launch

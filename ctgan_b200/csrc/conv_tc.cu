@@ -951,14 +951,34 @@ __global__ void pack_filters_multi_kernel(const float* __restrict__ flat, __nv_b
         return;
     }
     const int64_t total = (int64_t)e.taps * e.cin * e.cout;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        if (e.flip) {
+    if (e.flip) {                                        // same element order inside a tap: coalesced reads and writes
+        for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
             int64_t t = i / ((int64_t)e.cin * e.cout), rem = i - t * (int64_t)e.cin * e.cout;
             wp[i] = __float2bfloat16_rn(w[(int64_t)(e.taps - 1 - t) * e.cin * e.cout + rem]);
-        } else {
-            int c = i % e.cin; int64_t q = i / e.cin;
-            int o = q % e.cout; int t = q / e.cout;
-            wp[i] = __float2bfloat16_rn(w[((int64_t)t * e.cin + c) * e.cout + o]);
+        }
+        return;
+    }
+    // flip == 0 is a [Cin][Cout] -> [Cout][Cin] transpose per tap: 32 x 32 tiles through shared memory, so that the float
+    // reads run along Cout and the bf16 writes along Cin (the element-wise version read with a stride of Cout floats and
+    // made this launch -- the tail of every optimizer step -- 16 us)
+    __shared__ float tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;           // 32 x 8
+    const int ct = (e.cin + 31) / 32, ot = (e.cout + 31) / 32;
+    const int ntiles = e.taps * ct * ot;
+    for (int tl = blockIdx.x; tl < ntiles; tl += gridDim.x) {
+        const int t = tl / (ct * ot), r = tl - t * ct * ot;
+        const int c0 = (r / ot) * 32, o0 = (r % ot) * 32;
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c = c0 + ty + 8 * j, o = o0 + tx;
+            tile[ty + 8 * j][tx] = (c < e.cin && o < e.cout) ? w[((int64_t)t * e.cin + c) * e.cout + o] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int o = o0 + ty + 8 * j, c = c0 + tx;
+            if (c < e.cin && o < e.cout) wp[((int64_t)t * e.cout + o) * e.cin + c] = __float2bfloat16_rn(tile[tx][ty + 8 * j]);
         }
     }
 }
