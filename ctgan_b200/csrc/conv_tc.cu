@@ -241,7 +241,9 @@ __device__ __forceinline__ void lean_epilogue_tile(const FpropParams& p, uint32_
                                                    int w0, int h0, int n0, int co0, bool relu) {
     int t = q * 32 + lane;
     const int bw = t % p.BW; t /= p.BW;
-    const int bh = t % p.BH; const int bn = t / p.BH;
+    int bh, bn;
+    if (p.hn) { bn = t % p.BN; bh = t / p.BN; }          // [h][n][w] pixel order (several small images per tile)
+    else { bh = t % p.BH; bn = t / p.BH; }
     const int n = n0 + bn, h = h0 + bh, w = w0 + bw;
     const bool valid = (n < p.N) && (h < p.H) && (w < p.W);
     const int64_t pix = ((int64_t)n * p.H + h) * p.W + w;
@@ -411,7 +413,8 @@ conv_fprop_tc_lean_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
                 if (HALO) {
                     const int cb = gi / p.kw, s = gi - cb * p.kw;
                     mbar_expect_tx(fb, a_bytes + NB * B_BYTES);
-                    tma_load_4d(sb, &tmap_x, fb, cb * BLOCK_K, w0 + s - p.pad_l, h0 - p.pad_t, n0);
+                    if (p.hn) tma_load_4d(sb, &tmap_x, fb, cb * BLOCK_K, w0 + s - p.pad_l, n0, h0 - p.pad_t);   // dims (C, W, N, H)
+                    else      tma_load_4d(sb, &tmap_x, fb, cb * BLOCK_K, w0 + s - p.pad_l, h0 - p.pad_t, n0);
 #pragma unroll
                     for (int r = 0; r < NB; ++r)
                         tma_load_3d(sb + A_REGION + r * B_BYTES, &tmap_w, fb, cb * BLOCK_K, co0, r * p.kw + s);
@@ -435,7 +438,8 @@ conv_fprop_tc_lean_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
         uint32_t lo[STAGES];
 #pragma unroll
         for (int s = 0; s < STAGES; ++s) lo[s] = (((s_base + s * STAGE_BYTES) & 0x3FFFFu) >> 4) | (1u << 16);
-        const uint32_t row_step = HALO ? ((uint32_t)p.BW * 128u) >> 4 : (16384u >> 4);   // A offset between the NB k-blocks
+        // A offset between the NB k-blocks: one image row (HALO; BN images side by side in [h][n][w] order) | one 16 KB box
+        const uint32_t row_step = HALO ? ((uint32_t)p.BW * (p.hn ? p.BN : 1) * 128u) >> 4 : (16384u >> 4);
         int st = 0; uint32_t ph = 0;
         int it = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
@@ -1251,13 +1255,15 @@ static bool g_use_splitk = true;
 /* test / A-B hook: 0 = sub-wave layers run on conv_fprop_tc_lean_kernel<0> instead of the cluster split-K kernel */
 extern "C" void ctgan_set_splitk(int on) { g_use_splitk = on != 0; }
 static bool g_use_halo = true;
+static bool g_use_halo_hn = true;
 static int g_fprop_variant = 4;   // 4 = 256-pixel work items where possible (else 3), 3 = persistent grouped-stage (lean) kernel, 1 = one tile per CTA
 /* test hook: selects the fprop_tc kernel family (the families are compared in tests/) */
 extern "C" void ctgan_set_fprop_variant(int v) { g_fprop_variant = v; }
 static int g_wgrad_variant = 2;   // 2 = filter-column CTAs sharing one x halo box (3x3), 1 = one (x, dY) box pair per tap
 extern "C" void ctgan_set_wgrad_variant(int v) { g_wgrad_variant = v; }
 /* test hook: 0 disables the halo-reuse A pipeline (both are compared in tests/) */
-extern "C" void ctgan_set_fprop_halo(int on) { g_use_halo = on != 0; }
+// 0: per-tap boxes only; 1: halo boxes wherever eligible; 2: halo boxes for one-image tiles only (not the [h][n][w] ones)
+extern "C" void ctgan_set_fprop_halo(int on) { g_use_halo = on != 0; g_use_halo_hn = on == 1; }
 
 // common launcher of the stride-1 tcgen05 forward family; epi selects the epilogue of the lean / pair kernels
 static int fprop_tc_launch(const ctgan_conv_desc* d, const void* x, const void* wp, FpropParams& p, int epi, void* stream) {
@@ -1268,10 +1274,22 @@ static int fprop_tc_launch(const ctgan_conv_desc* d, const void* x, const void* 
     const int block_n = (d->Cout % 128 == 0) ? 128 : 64;
     CTGAN_REQUIRE(epi != EPI_ACTDROP || block_n == 128, CTGAN_ERR_UNSUPPORTED, "conv_fprop_tc_actdrop: Cout must be a multiple of 128");
     // halo-reuse A pipeline: k x k filters (k > 1) on tiles that are whole rows of one image
-    const bool halo = g_use_halo && block_n == 128 && d->kh == 3 && p.BN == 1 && (p.BW % 8) == 0 &&
-                      (uint32_t)(p.BH + d->kh - 1) * p.BW * 128u <= 24576u && g_fprop_variant >= 3;
+    bool halo = g_use_halo && block_n == 128 && d->kh == 3 && p.BN == 1 && (p.BW % 8) == 0 &&
+                (uint32_t)(p.BH + d->kh - 1) * p.BW * 128u <= 24576u && g_fprop_variant >= 3;
+    // several small images per tile (8x8, 4x4): the halo pipeline on a box laid out [h][n][w] (make_act_map_hn) -- one
+    // (BH+2)-row box per (cin block, column shift) instead of one box per tap: 2.4x less activation traffic per tile
+    // (a sub-wave layer that cluster split-K takes keeps the per-tap boxes that kernel expects)
+    const int n_tiles_all = p.tilesW * p.tilesH * p.tilesN * (d->Cout / 128);
+    const int split_all = (g_use_splitk && block_n == 128) ? splitk_factor(n_tiles_all, (d->kh * d->kw * (d->Cin / 64) + 1) / 2) : 0;
+    const bool halo_hn = !halo && g_use_halo_hn && block_n == 128 && d->kh == 3 && p.BN > 1 && p.tilesW == 1 && p.tilesH == 1 &&
+                         (p.BN * p.BW) % 8 == 0 && (uint32_t)(p.BH + 2) * p.BN * p.BW * 128u <= 24576u && g_fprop_variant >= 3 &&
+                         epi != EPI_ACTDROP && !split_all;
+    p.hn = halo_hn ? 1 : 0;
     CUtensorMap mx, mw;
-    if (int r = make_act_map(&mx, x, d->N, d->H, d->W, d->Cin, p.BW, halo ? p.BH + d->kh - 1 : p.BH, p.BN)) return r;
+    if (halo_hn) {
+        if (int r = make_act_map_hn(&mx, x, d->N, d->H, d->W, d->Cin, p.BW, p.BH + 2, p.BN)) return r;
+        halo = true;
+    } else if (int r = make_act_map(&mx, x, d->N, d->H, d->W, d->Cin, p.BW, halo ? p.BH + d->kh - 1 : p.BH, p.BN)) return r;
     if (int r = make_filter_map(&mw, wp, d->kh * d->kw, d->Cout, d->Cin, block_n)) return r;
     cudaStream_t st = as_stream(stream);
     const int variant = (epi == EPI_ACTDROP && g_fprop_variant < 3) ? 3 : g_fprop_variant;   // only the lean kernels have that epilogue

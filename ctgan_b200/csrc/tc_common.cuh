@@ -172,6 +172,7 @@ struct FpropParams {
     int kh, kw, pad_t, pad_l;
     int BW, BH, BN;                // pixel box of one M tile: BN*BH*BW == 128
     int tilesW, tilesH, tilesN;
+    int hn;                        // 1: the pixels of a tile are ordered [h][n][w] (several small images per tile, halo pipeline)
     int flags;
     __nv_bfloat16* y;
     const float* bias;
@@ -274,6 +275,23 @@ static inline int make_filter_map_f32(CUtensorMap* map, const void* base, int ta
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     CTGAN_REQUIRE(r == CUDA_SUCCESS, CTGAN_ERR_DRIVER, "cuTensorMapEncodeTiled(float filter) failed: CUresult %d", (int)r);
+    return 0;
+}
+// The same NHWC bf16 tensor with the two outer dimensions exchanged, dims (C, W, N, H), box (64, BW, BN, BH): a box that
+// holds SEVERAL small images lands in shared memory as [h][n][w] pixels, so that a filter-row shift is a uniform offset of
+// BN*BW pixel rows (a whole number of swizzle atoms when BN*BW % 8 == 0) -- the halo pipeline for 8x8 / 4x4 images.
+static inline int make_act_map_hn(CUtensorMap* map, const void* base, int N, int H, int W, int C, int BW, int BH, int BN) {
+    CTGAN_REQUIRE(BW <= 256 && BH <= 256 && BN <= 256, CTGAN_ERR_UNSUPPORTED, "activation box dimension exceeds 256");
+    EncodeTiledFn enc = get_encode_fn();
+    CTGAN_REQUIRE(enc != nullptr, CTGAN_ERR_DRIVER, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)N, (cuuint64_t)H};
+    cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)H * W * C * 2, (cuuint64_t)W * C * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)BW, (cuuint32_t)BN, (cuuint32_t)BH};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CTGAN_REQUIRE(r == CUDA_SUCCESS, CTGAN_ERR_DRIVER, "cuTensorMapEncodeTiled(activation, [h][n][w]) failed: CUresult %d", (int)r);
     return 0;
 }
 // 3-D map over a packed filter [taps][rows][K] bf16: dims (K, rows, taps), box (64, box_rows, 1)

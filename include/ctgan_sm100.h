@@ -87,7 +87,8 @@ int ctgan_conv_wgrad(const ctgan_conv_desc* d, const void* x, const void* dy,
  * fprop_tc also serves dgrad of a stride-1 conv: pack with transpose_flip=1 and
  * swap Cin/Cout, pad = k-1-pad in the descriptor.
  * residual (nullable, BF16, same shape as y) is added before the optional ReLU. */
-/* test hook: on == 0 disables the halo-reuse variant of fprop_tc (default on) */
+/* test hook: 0 disables the halo-reuse variants of fprop_tc; 1 (default) = wherever eligible, including tiles of several
+ * small images ([h][n][w] boxes through a tensor map with N and H exchanged); 2 = one-image tiles only */
 void ctgan_set_fprop_halo(int on);
 /* 1 (default): kernels are launched with programmatic stream serialization (each begins with griddepcontrol.launch_dependents +
  * griddepcontrol.wait, so launch latency and set-up overlap the predecessor's tail; ordering semantics unchanged); 0: plain launches */

@@ -24,6 +24,9 @@ if os.environ.get('CTGAN_BRANCH_STACKED'):
 if os.environ.get('CTGAN_SPLITK'):
     from ctgan_b200 import _lib as _L2
     _L2.lib.ctgan_set_splitk(int(os.environ['CTGAN_SPLITK']))
+if os.environ.get('CTGAN_HALO'):
+    from ctgan_b200 import _lib as _L3
+    _L3.lib.ctgan_set_fprop_halo(int(os.environ['CTGAN_HALO']))
 if os.environ.get('CTGAN_WGRAD_ITEMS'):
     from ctgan_b200 import _lib as _L
     _L.lib.ctgan_set_wgrad_multi_items_per_sm(int(os.environ['CTGAN_WGRAD_ITEMS']))

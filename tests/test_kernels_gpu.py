@@ -113,7 +113,7 @@ def test_conv_mixed_dtype_heads(K):
 
 @pytest.mark.parametrize('shape', [(24, 32, 32, 3), (80, 16, 16, 3), (20, 32, 32, 5), (300, 8, 8, 3), (3, 16, 16, 1),
                                    (200, 4, 4, 3), (37, 32, 32, 3), (64, 32, 32, 3), (200, 16, 16, 3), (60, 20, 32, 3),
-                                   (41, 28, 16, 3)])
+                                   (41, 28, 16, 3), (301, 8, 8, 3), (1190, 4, 4, 3)])
 def test_tc_fprop_variants_match(K, shape):
     """The fprop_tc kernel family -- 256-pixel work items / persistent grouped stages (default) vs one-tile-per-CTA, with
     and without the halo-reuse A pipeline -- all compute the same convolution (up to the bf16 rounding of a different accumulation order)
