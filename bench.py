@@ -230,13 +230,14 @@ def _bf16_act(torch, shape):
 def roofline_kernels(torch, peaks):
     """The three kernel families with the largest share of the ResNet iteration (shares: profiles/r02_kernel_shares.json, from
     the ncu launch list of the same build), each timed alone with CUDA events on the launching stream, rotating over buffer
-    sets that exceed the 126 MB L2:
-      * conv_fprop_tc_lean_kernel<0>: the 8x8 3x3 128->128 layers (Discriminator.3/.4, fprop / dgrad / double-backward fprop)
-        as the 64-image gradient-penalty pass launches them -- 32 tiles on 148 SMs, the latency-bound small-layer family;
-      * conv_wgrad_tc_multi_kernel: every tensor-core filter gradient of one critic step (stacked pass 192 images +
-        gradient-penalty pass 64 images; 3x3 at 32x32, 16x16 x2, 8x8 x4 and the 1x1 shortcut, each) as ONE launch;
+    sets that exceed the 126 MB L2.  `roofline` is the family with the LARGEST share:
       * conv_fprop_tc_pair_kernel: Discriminator.1.Conv2 on the stacked 192-image pass (32x32, 3x3, 128->128), the single
-        largest GEMM of the step (fprop and, same kernel with the flipped filter pack, dgrad)."""
+        largest GEMM of the step (fprop and, same kernel with the flipped filter pack, dgrad);
+      * the sub-wave 3x3 family: the 8x8 layers (Discriminator.3/.4, fprop / dgrad / double-backward fprop) as the 64-image
+        gradient-penalty pass launches them -- 32 tiles on 148 SMs, latency-bound (conv_fprop_tc_lean_kernel<1> with [h][n][w]
+        halo boxes inside the two-branch critic step, the cluster split-K kernel elsewhere);
+      * conv_wgrad_tc_multi_kernel: every tensor-core filter gradient of one critic step (stacked pass 192 images +
+        gradient-penalty pass 64 images; 3x3 at 32x32, 16x16 x2, 8x8 x4 and the 1x1 shortcut, each) as ONE launch."""
     import ctypes
     import ctgan_b200.kernels as K
     from ctgan_b200 import _lib
@@ -279,7 +280,7 @@ def roofline_kernels(torch, peaks):
     entry('conv_fprop_tc_pair_kernel', 'conv_fprop_tc_pair_kernel (3x3, 128->128, %dx32x32)' % N, 2.0 * N * H * H * C * C * 9, ms, traffic)
     del xs, ys
 
-    # (2) lean<0> kernel, 64 x 8 x 8 (80 buffer sets of 1 MB in + 1 MB out)
+    # (2) sub-wave 3x3 conv, 64 x 8 x 8 (80 buffer sets of 1 MB in + 1 MB out)
     N, H = BATCH, 8
     g = K.same_geom(N, H, H, C, C, 3, 1)
     xs = [_bf16_act(torch, (N, C, H, H)) for _ in range(80)]
@@ -289,7 +290,7 @@ def roofline_kernels(torch, peaks):
                                   K._p(ys[i % 80]), 0, K._stream())
     with K.splitk(False):                     # one CTA per tile: what the two-branch critic step launches
         ms = _time_launches(torch, launch8, 80, 160)
-    entry('conv_fprop_tc_lean_kernel<0>', 'conv_fprop_tc_lean_kernel<0> (3x3, 128->128, %dx8x8: 32 tiles on 148 SMs, one CTA per tile; '
+    entry('sub_wave_3x3', 'conv_fprop_tc_lean_kernel<1> (3x3, 128->128, %dx8x8: 32 tiles on 148 SMs, one CTA per tile of two images; '
           'latency-bound: 1.2 GFLOP per launch)' % N, 2.0 * N * H * H * C * C * 9, ms)
     with K.splitk(True):                      # cluster split-K (4 CTAs per tile): what the generator / DCGAN steps launch
         ms_sk = _time_launches(torch, launch8, 80, 160)

@@ -1,0 +1,8 @@
+set -x
+P=gpurun_out/r2p
+timeout 1500 python -m pytest tests -m gpu -q > ${P}_tests.log 2>&1; tail -3 ${P}_tests.log
+timeout 900 python tests/parity_report.py > ${P}_parity_report.txt 2>${P}_parity.err; tail -2 ${P}_parity.err
+timeout 600 python bench.py --steps 20 --warmup 5 > ${P}_bench.json 2>${P}_bench.err; cut -c1-400 ${P}_bench.json
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file ${P}_launches.csv python tests/profile_step.py 64 > /dev/null 2>&1; grep -c tc:: ${P}_launches.csv
+timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -f -o ${P}_top python tests/profile_kernels.py > ${P}_ncu.log 2>&1; tail -2 ${P}_ncu.log
+ls -la gpurun_out | tail -8
