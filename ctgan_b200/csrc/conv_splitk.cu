@@ -176,13 +176,27 @@ conv_fprop_tc_splitk_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
         const bool valid = (n < p.N) && (h < p.H) && (w < p.W);
         const int64_t pix = ((int64_t)n * p.H + h) * p.W + w;
         const int cbase = co0 + (int)rank * CW;
-        __nv_bfloat16* yrow = p.y + pix * p.Cout + cbase;
+        int64_t orow = pix * p.Cout;                                 // element offset of this pixel's row in y (and m)
+        if (EPI == EPI_ACTDROP && p.out_s2d)
+            orow = ((((int64_t)n * (p.H >> 1) + (h >> 1)) * (p.W >> 1) + (w >> 1)) * 4 + ((h & 1) * 2 + (w & 1))) * p.Cout;
+        __nv_bfloat16* yrow = p.y + orow + cbase;
+        __nv_bfloat16* mult_row = (EPI == EPI_ACTDROP) ? p.mult + orow + cbase : nullptr;
+        // EPI_ACTDROP (see lean_epilogue_tile): absolute Philox stream index of channel cbase of this pixel
+        unsigned long long se0 = 0;
+        bool drop = false;
+        float inv_keep = 1.f;
+        if (EPI == EPI_ACTDROP) {
+            drop = p.keep < 1.f;
+            inv_keep = 1.f / p.keep;
+            se0 = p.offset + (p.dyn ? *p.dyn : 0ull) + (unsigned long long)(pix * p.Cout + cbase);
+        }
         const int64_t rpix = (p.flags & CTGAN_EPI_RES_UP2) ? ((int64_t)n * (p.H >> 1) + (h >> 1)) * (p.W >> 1) + (w >> 1) : pix;
-        const __nv_bfloat16* rrow = p.residual ? p.residual + rpix * p.Cout + cbase : nullptr;
+        const __nv_bfloat16* rrow = (EPI != EPI_ACTDROP && p.residual) ? p.residual + rpix * p.Cout + cbase : nullptr;
         const __nv_bfloat16* mrow = (EPI == EPI_MASK) ? p.relu_mask + pix * p.Cout + cbase : nullptr;
         const bool relu = (p.flags & CTGAN_EPI_RELU) != 0;
         const bool wide = ((reinterpret_cast<uintptr_t>(p.y) | reinterpret_cast<uintptr_t>(p.residual) |
-                            (EPI == EPI_MASK ? reinterpret_cast<uintptr_t>(p.relu_mask) : 0)) & 31) == 0;
+                            (EPI == EPI_MASK ? reinterpret_cast<uintptr_t>(p.relu_mask) : 0) |
+                            (EPI == EPI_ACTDROP ? reinterpret_cast<uintptr_t>(p.mult) : 0)) & 31) == 0;
         const float4* red = reinterpret_cast<const float4*>(smem + STAGES * STAGE_BYTES);
 #pragma unroll
         for (int u = 0; u < UNITS; ++u) {
@@ -234,10 +248,32 @@ conv_fprop_tc_splitk_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
                         }
                     }
                     uint32_t ow[8];
+                    if (EPI == EPI_ACTDROP) {
+                        uint32_t mo[8];
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        const __nv_bfloat162 o2 = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
-                        ow[e] = *reinterpret_cast<const uint32_t*>(&o2);
+                        for (int b = 0; b < 4; ++b) {
+                            uint32_t r[4] = {0u, 0u, 0u, 0u};
+                            if (drop) Philox::block(p.seed, (se0 + (unsigned long long)(c + 4 * b)) >> 2, r);
+                            float mm[4];
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                float mult = v[4 * b + e] > 0.f ? 1.f : p.slope;
+                                if (drop) mult *= floorf(p.keep + Philox::to_uniform(r[e])) * inv_keep;
+                                mm[e] = mult;
+                            }
+                            const __nv_bfloat162 ma = __floats2bfloat162_rn(mm[0], mm[1]), mb = __floats2bfloat162_rn(mm[2], mm[3]);
+                            mo[2 * b] = *reinterpret_cast<const uint32_t*>(&ma); mo[2 * b + 1] = *reinterpret_cast<const uint32_t*>(&mb);
+                            const __nv_bfloat162 ya = __floats2bfloat162_rn(v[4 * b] * __bfloat162float(ma.x), v[4 * b + 1] * __bfloat162float(ma.y));
+                            const __nv_bfloat162 yb = __floats2bfloat162_rn(v[4 * b + 2] * __bfloat162float(mb.x), v[4 * b + 3] * __bfloat162float(mb.y));
+                            ow[2 * b] = *reinterpret_cast<const uint32_t*>(&ya); ow[2 * b + 1] = *reinterpret_cast<const uint32_t*>(&yb);
+                        }
+                        stg16_bf16(mult_row + c, wide, mo);
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const __nv_bfloat162 o2 = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+                            ow[e] = *reinterpret_cast<const uint32_t*>(&o2);
+                        }
                     }
                     stg16_bf16(yrow + c, wide, ow);
                 }
@@ -283,7 +319,11 @@ int splitk_factor(int n_tiles, int groups) {
 
 int launch_fprop_splitk(int split, int epi, const CUtensorMap& mx, const CUtensorMap& mw, const FpropParams& p, int n_tiles,
                         cudaStream_t st) {
-    if (split == 4) return epi == EPI_MASK ? launch_splitk<4, EPI_MASK>(mx, mw, p, n_tiles, st) : launch_splitk<4, EPI_PLAIN>(mx, mw, p, n_tiles, st);
+    if (split == 4) {
+        if (epi == EPI_ACTDROP) return launch_splitk<4, EPI_ACTDROP>(mx, mw, p, n_tiles, st);
+        return epi == EPI_MASK ? launch_splitk<4, EPI_MASK>(mx, mw, p, n_tiles, st) : launch_splitk<4, EPI_PLAIN>(mx, mw, p, n_tiles, st);
+    }
+    if (epi == EPI_ACTDROP) return launch_splitk<2, EPI_ACTDROP>(mx, mw, p, n_tiles, st);
     return epi == EPI_MASK ? launch_splitk<2, EPI_MASK>(mx, mw, p, n_tiles, st) : launch_splitk<2, EPI_PLAIN>(mx, mw, p, n_tiles, st);
 }
 

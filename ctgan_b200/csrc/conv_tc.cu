@@ -1283,7 +1283,7 @@ static int fprop_tc_launch(const ctgan_conv_desc* d, const void* x, const void* 
     const int split_all = (g_use_splitk && block_n == 128) ? splitk_factor(n_tiles_all, (d->kh * d->kw * (d->Cin / 64) + 1) / 2) : 0;
     const bool halo_hn = !halo && g_use_halo_hn && block_n == 128 && d->kh == 3 && p.BN > 1 && p.tilesW == 1 && p.tilesH == 1 &&
                          (p.BN * p.BW) % 8 == 0 && (uint32_t)(p.BH + 2) * p.BN * p.BW * 128u <= 24576u && g_fprop_variant >= 3 &&
-                         epi != EPI_ACTDROP && !split_all;
+                         !split_all;
     p.hn = halo_hn ? 1 : 0;
     CUtensorMap mx, mw;
     if (halo_hn) {
@@ -1305,11 +1305,11 @@ static int fprop_tc_launch(const ctgan_conv_desc* d, const void* x, const void* 
             if (epi == EPI_ACTDROP) return launch_fprop_lean<1, EPI_ACTDROP>(mx, mw, p, st);
             return launch_fprop_lean<1, EPI_PLAIN>(mx, mw, p, st);
         }
-        if (epi == EPI_ACTDROP) return launch_fprop_lean<0, EPI_ACTDROP>(mx, mw, p, st);
         // fewer tiles than half the SMs: split K over a cluster of 2 / 4 CTAs (conv_splitk.cu)
         const int n_tiles = p.tilesW * p.tilesH * p.tilesN * (d->Cout / 128);
         const int split = g_use_splitk ? splitk_factor(n_tiles, (d->kh * d->kw * (d->Cin / 64) + 1) / 2) : 0;
         if (split) return launch_fprop_splitk(split, epi, mx, mw, p, n_tiles, st);
+        if (epi == EPI_ACTDROP) return launch_fprop_lean<0, EPI_ACTDROP>(mx, mw, p, st);
         if (epi == EPI_MASK) return launch_fprop_lean<0, EPI_MASK>(mx, mw, p, st);
         return launch_fprop_lean<0, EPI_PLAIN>(mx, mw, p, st);
     }

@@ -432,6 +432,9 @@ class Trainer:
 
     # ---------------------------------------------------------------- generator (gen_train_op, :314-330,335,337)
     def gen_forward_backward(self):
+        if K.config.gen_towers and K.config.branch_streams and self.device.type == 'cuda' and N_DEVICES > 1:
+            with K.splitk(K.config.gen_splitk):
+                return self._gen_towers()
         RNG = self.rng
         n = GEN_BS_MULTIPLE * self.B // N_DEVICES
         fake_labels = RNG.labels_parts([('labels.%d' % i, n) for i in range(N_DEVICES)])
@@ -446,6 +449,38 @@ class Trainer:
             gen_cost = F.AddScaled.apply(gen_cost, F.SoftmaxCE.apply(disc_fake_acgan, fake_labels), ACGAN_SCALE_G)
         with F.frozen(self.disc_opt.param_list()):    # var_list = gen_params (:336): the critic is not updated here
             gen_cost.backward(gradient=self._ones_like(gen_cost), inputs=self.gen_opt.param_list())
+        K.join_side()
+        return dict(cost=gen_cost.detach())
+
+    def _gen_towers(self):
+        """The generator step as the reference builds it (:314-330): one tower per device split -- Generator(n) -> Discriminator
+        -> cost -- here on alternating stream branches.  The step is a single dependent chain of mostly sub-wave kernels
+        (8x8 / 16x16 layers at 64-128 samples), so two independent towers fill the SMs the way the gradient-penalty branch
+        does in the critic step; the filter gradients of both towers are queued and run as one multi-job launch at the end."""
+        RNG = self.rng
+        n = GEN_BS_MULTIPLE * self.B // N_DEVICES
+        # labels, noise and every dropout site draw the numbers the stacked batch would (DeviceRandom.scope_tower)
+        all_labels = RNG.labels_parts([('labels.%d' % i, n) for i in range(N_DEVICES)])
+        all_noise = RNG.normal_parts([('z.%d' % i, n) for i in range(N_DEVICES)], 128)
+        fork = K.fork_branch(all_noise)
+        costs, part = [], 1.0 / N_DEVICES
+        for i in range(N_DEVICES):
+            with (K.branch(fork) if i % 2 else contextlib.nullcontext()):
+                labels = all_labels[i * n:(i + 1) * n]
+                fake = Generator(n, labels, noise=all_noise[i * n:(i + 1) * n])
+                RNG.scope_tower('drop', i, N_DEVICES)
+                disc_fake, _, disc_fake_acgan = Discriminator(fake, labels, 0.8, 0.5, 0.5)
+                cost = F.MeanLoss.apply(disc_fake, -part)
+                if CONDITIONAL and ACGAN:
+                    cost = F.AddScaled.apply(cost, F.SoftmaxCE.apply(disc_fake_acgan, labels), ACGAN_SCALE_G * part)
+                costs.append(cost)
+        K.join_branch(fork)
+        gen_cost = costs[0]                            # (cost_dev0 + cost_dev1) / len(DEVICES)  (:330)
+        for cost in costs[1:]:
+            gen_cost = F.AddScaled.apply(gen_cost, cost, 1.0)
+        with F.frozen(self.disc_opt.param_list()):    # var_list = gen_params (:336): the critic is not updated here
+            gen_cost.backward(gradient=self._ones_like(gen_cost), inputs=self.gen_opt.param_list())
+        K.join_branch(fork)
         K.join_side()
         return dict(cost=gen_cost.detach())
 

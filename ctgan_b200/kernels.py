@@ -27,6 +27,9 @@ class Config:
     branch_streams = True    # run independent sub-graphs of a step (GP pass vs stacked pass) as stream branches
     branch_priority = 0      # CUDA stream priority of the branch stream (lower = higher priority): equal priorities measure best
     critic_splitk = False    # cluster split-K inside the two-branch ResNet critic step (see kernels.splitk)
+    gen_towers = False       # ResNet generator step: the reference's per-device towers as two stream branches instead of one stacked
+                             # batch (measured: 1303 us vs 1226 us stacked -- twice the launches, no shorter chain; kept as a checked option)
+    gen_splitk = False       # cluster split-K inside the two-tower generator step
     branch_stacked = False   # which sub-graph runs on the branch stream: False = the gradient-penalty pass, True = the stacked pass
     tc_min_rows = 1          # (tunable) minimum GEMM rows to prefer the tensor-core path
     use_bn_fused = True      # BF16 batch norm as two kernels per direction (sums with red.global + apply)

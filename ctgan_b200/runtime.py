@@ -34,6 +34,7 @@ class DeviceRandom:
         self.tape = {}
         self._scope = ''
         self._parts = None           # [(tag prefix, rows)] when several reference passes run as one stacked batch
+        self._tower = None           # (i, towers) while the passes run one after the other on their own rows (scope_tower)
         self._site = 0
         self.patterns = []
         self._stack = None
@@ -69,13 +70,22 @@ class DeviceRandom:
         F.pattern_recorder = None
 
     def scope(self, name):
-        self._scope, self._parts, self._site = name, None, 0
+        self._scope, self._parts, self._site, self._tower = name, None, 0, None
+
+    def scope_tower(self, prefix, i, towers):
+        """Dropout sites of tower i of `towers` equal passes that run one after the other (each on its own rows): site k of
+        every tower draws from ONE Philox slice, tower i taking the i-th part of it -- exactly the numbers a single pass over
+        the towers' batches stacked along dim 0 (scope_parts) draws, so the two execution orders are interchangeable.
+        Tower 0 must run first; tags are '<prefix>.<i>.<site>' as for separate passes."""
+        self._scope, self._parts, self._site, self._tower = '%s.%d' % (prefix, i), None, 0, (i, towers)
+        if i == 0:
+            self._tower_offs = []
 
     def scope_parts(self, parts):
         """The next dropout sites act on a batch that stacks several reference passes along dim 0:
         parts = [(tag prefix, rows), ...].  One Philox slice per site; when recording, each part's rows are
         exported under '<prefix>.<site>' exactly as if the passes had run separately."""
-        self._scope, self._parts, self._site = parts[0][0], list(parts), 0
+        self._scope, self._parts, self._site, self._tower = parts[0][0], list(parts), 0, None
 
     def begin_stack(self, rows):
         """Activation patterns recorded until end_stack() belong to a stacked batch with these row counts."""
@@ -134,6 +144,17 @@ class DeviceRandom:
     def dropout_stream(self, like):
         """Philox slice for the next dropout site of the current scope; returns (seed, offset, dyn)."""
         self._site += 1
+        if self._tower is not None:
+            i, towers = self._tower
+            n = like.numel()
+            if i == 0:
+                self._tower_offs.append(self._take(towers * n))
+            off = self._tower_offs[self._site - 1] + i * n
+            if self.record:
+                mf = CL if (like.dim() == 4 and like.is_contiguous(memory_format=CL)) else None
+                self._keep('%s.%d' % (self._scope, self._site),
+                           K.philox_uniform(tuple(like.shape), self.device, self.seed, off, memory_format=mf, dyn=self.dyn))
+            return self.seed, off, self.dyn
         if self._parts is None:
             return self.stream('%s.%d' % (self._scope, self._site), like)
         off = self._take(like.numel())

@@ -14,7 +14,7 @@ def t(fn, reps=40):
     for i in range(reps): fn(i)
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / reps * 1e3
-for (N, C, H, groups) in ((128, 128, 32, 2), (320, 128, 32, 10), (128, 128, 16, 2), (128, 128, 8, 2)):
+for (N, C, H, groups) in ((128, 128, 32, 2), (320, 128, 32, 10), (128, 128, 16, 2), (128, 128, 8, 2), (1024, 128, 32, 2), (4096, 128, 32, 2)):
     S = max(2, int(300e6 // (N * C * H * H * 2)) + 1)
     xs = [act(N, C, H) for _ in range(S)]; dys = [act(N, C, H) for _ in range(S)]
     gam, bet = torch.ones(10, C, device='cuda'), torch.zeros(10, C, device='cuda')

@@ -119,6 +119,29 @@ def test_stream_branches_do_not_change_a_step():
     assert _rel(res[True][2], res[False][2]) < 6e-2
 
 
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_generator_towers_match_the_stacked_batch(dtype):
+    """kernels.config.gen_towers: the generator step as two stream-branch towers (the reference's per-device graph) draws the
+    same random numbers (DeviceRandom.scope_tower) and computes the same cost and gradients as the one stacked batch."""
+    import ctgan_b200.kernels as K
+    res = {}
+    for towers in (True, False):
+        K.config.gen_towers = towers
+        try:
+            tr = _trainer(B=16, dtype=dtype)
+            tr.gen_opt.zero_grad()
+            cost = tr.gen_forward_backward()['cost']
+            torch.cuda.synchronize()
+            res[towers] = (cost.clone(), tr.gen_opt.flat_g.clone(), tr.rng.offset)
+        finally:
+            K.config.gen_towers = False
+    assert res[True][2] == res[False][2]                      # same Philox slices consumed
+    assert _rel(res[True][0], res[False][0]) < 1e-3
+    # fp32: the same arithmetic in another order.  bf16: batch-norm statistics rounded differently flip a few ReLU patterns at
+    # B=16 (the bound test_stream_branches_do_not_change_a_step uses for two runs of the SAME schedule)
+    assert _rel(res[True][1], res[False][1]) < (1e-3 if dtype == torch.float32 else 6e-2)
+
+
 def test_dcgan_graph_replay_trains_like_eager():
     """CT_gan_cifar.py with its stride-2 layers on the space-to-depth tensor-core route: the operand packs of those
     filters are created at first use and re-packed in place after every optimizer step (kernels._s2d_packs), so a

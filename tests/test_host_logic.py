@@ -132,3 +132,24 @@ def test_no_discarded_parameter_gradient_launches(fake_kernels, script, critic, 
     finally:
         from tests import fake_backend
         K.conv_wgrad, K.bias_grad = fake_backend.conv_wgrad, fake_backend.bias_grad     # the fixture restores the real ones
+
+
+def test_tower_scopes_draw_the_slices_of_the_stacked_batch(fake_kernels):
+    """DeviceRandom.scope_tower: site k of tower i reads part i of the Philox slice that the stacked pass (scope_parts) reserves
+    for site k -- the two-branch generator step draws the same numbers as the one-batch generator step."""
+    from ctgan_b200.runtime import DeviceRandom
+    like_tower = [torch.empty(4, 8, 2, 2), torch.empty(4, 6)]
+    like_stack = [torch.empty(8, 8, 2, 2), torch.empty(8, 6)]
+    a = DeviceRandom(3, 'cpu')
+    a.scope_parts([('drop.0', 4), ('drop.1', 4)])
+    stacked = [a.dropout_stream(t)[1] for t in like_stack]
+    b = DeviceRandom(3, 'cpu')
+    got = []
+    for i in range(2):
+        b.scope_tower('drop', i, 2)
+        got.append([b.dropout_stream(t)[1] for t in like_tower])
+    assert got[0] == stacked
+    assert got[1] == [o + t.numel() for o, t in zip(stacked, like_tower)]
+    assert a.offset == b.offset
+    b.scope('x')
+    assert b._tower is None

@@ -280,7 +280,8 @@ def test_act_dropout_matches_philox_reference(K, dtype, slope, keep):
 
 
 @pytest.mark.parametrize('geom', [(6, 16, 16, 128, 128, 3, 1), (70, 8, 8, 128, 256, 3, 1), (5, 32, 32, 3, 128, 5, 2),
-                                  (9, 16, 16, 128, 256, 5, 2), (7, 14, 14, 64, 128, 5, 2), (11, 8, 8, 256, 512, 5, 2)])
+                                  (9, 16, 16, 128, 256, 5, 2), (7, 14, 14, 64, 128, 5, 2), (11, 8, 8, 256, 512, 5, 2),
+                                  (300, 8, 8, 128, 128, 3, 1), (200, 8, 8, 256, 512, 5, 2)])   # last two: [h][n][w] halo boxes (no split-K)
 @pytest.mark.parametrize('slope,keep', [(0.2, 0.5), (0.2, 1.0), (1.0, 0.8)])
 def test_conv_actdrop_epilogue(K, geom, slope, keep):
     """Conv2D -> LeakyReLU -> dropout in the tcgen05 conv epilogue (stride-1, space-to-depth and strided-im2col routes):
