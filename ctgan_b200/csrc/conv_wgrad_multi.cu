@@ -28,6 +28,7 @@ struct alignas(64) WgradJob {
     int Cin, Cout, kh, kw, pad_t, pad_l;
     int BW, BH, BN, chunksW, chunksH;
     int co_blocks;                  // Cout / 128
+    int hn;                         // 1: chunks of several small images, boxes laid out [h][n][w] (tensor maps with N and H exchanged)
     int splits, chunks_per_split, total_chunks;
     int item0;                      // index of this job's first work item
     uint32_t a_bytes;               // bytes of one 64-channel half of the x box
@@ -104,10 +105,17 @@ conv_wgrad_tc_multi_kernel(const __grid_constant__ WgradJobTable tab)
                     const uint32_t sb = s_base + st * STAGE_BYTES, fb = full0 + 8 * st;
                     mbar_wait(empty0 + 8 * st, ph ^ 1);
                     mbar_expect_tx(fb, 2 * J.a_bytes + 2 * B_HALF);
-                    tma_load_4d(sb,                       mx,  fb, it.ci0,      w0 + dx, h0 - J.pad_t, n0);
-                    tma_load_4d(sb + A_SLOT,              mx,  fb, it.ci0 + 64, w0 + dx, h0 - J.pad_t, n0);
-                    tma_load_4d(sb + 2 * A_SLOT,          mdy, fb, it.co0,      w0, h0, n0);
-                    tma_load_4d(sb + 2 * A_SLOT + B_HALF, mdy, fb, it.co0 + 64, w0, h0, n0);
+                    if (J.hn) {                            // dims (C, W, N, H)
+                        tma_load_4d(sb,                       mx,  fb, it.ci0,      w0 + dx, n0, h0 - J.pad_t);
+                        tma_load_4d(sb + A_SLOT,              mx,  fb, it.ci0 + 64, w0 + dx, n0, h0 - J.pad_t);
+                        tma_load_4d(sb + 2 * A_SLOT,          mdy, fb, it.co0,      w0, n0, h0);
+                        tma_load_4d(sb + 2 * A_SLOT + B_HALF, mdy, fb, it.co0 + 64, w0, n0, h0);
+                    } else {
+                        tma_load_4d(sb,                       mx,  fb, it.ci0,      w0 + dx, h0 - J.pad_t, n0);
+                        tma_load_4d(sb + A_SLOT,              mx,  fb, it.ci0 + 64, w0 + dx, h0 - J.pad_t, n0);
+                        tma_load_4d(sb + 2 * A_SLOT,          mdy, fb, it.co0,      w0, h0, n0);
+                        tma_load_4d(sb + 2 * A_SLOT + B_HALF, mdy, fb, it.co0 + 64, w0, h0, n0);
+                    }
                     if (++st == STAGES) { st = 0; ph ^= 1; }
                 }
             }
@@ -124,7 +132,7 @@ conv_wgrad_tc_multi_kernel(const __grid_constant__ WgradJobTable tab)
             const WgItem it = wg_decode(tab, item);
             const WgradJob& J = tab.job[it.j];
             const int kh = J.kh;
-            const uint32_t row_step = ((uint32_t)J.BW * 128u) >> 4;      // one image row down = filter row r + 1
+            const uint32_t row_step = ((uint32_t)J.BW * (J.hn ? J.BN : 1) * 128u) >> 4;   // one image row down = filter row r + 1
             mbar_wait(tempty, (n & 1u) ^ 1u);                            // the epilogue has drained the accumulators
             tc_fence_after();
             for (int c = 0; c < it.nchunks; ++c) {
@@ -202,7 +210,9 @@ extern "C" int ctgan_conv_wgrad_tc_multi_ok(const ctgan_conv_desc* d) {
     int BW, BH, BN;
     pixel_box(d->H, d->W, 64, &BW, &BH, &BN);
     if (d->kh == 1) return 1;
-    return BN == 1 && BW % 8 == 0 && (uint32_t)(BH + 2) * BW * 128u <= 16384u;
+    if (BN == 1) return BW % 8 == 0 && (uint32_t)(BH + 2) * BW * 128u <= 16384u;
+    // several whole small images per 64-pixel chunk (4x4): [h][n][w] boxes, filter row shift = BN * BW pixel rows
+    return BW == d->W && BH == d->H && (BN * BW) % 8 == 0 && (uint32_t)(BH + 2) * BN * BW * 128u <= 16384u;
 }
 
 extern "C" int ctgan_conv_wgrad_tc_multi(int n, const ctgan_conv_desc* descs, const void* const* xs, const void* const* dys,
@@ -237,8 +247,14 @@ extern "C" int ctgan_conv_wgrad_tc_multi(int n, const ctgan_conv_desc* descs, co
             J.total_chunks = J.chunksW * J.chunksH * ceil_div(d->N, J.BN);
             J.co_blocks = d->Cout / 128;
             J.a_bytes = (uint32_t)(J.BH + d->kh - 1) * J.BW * J.BN * 128u;
-            if (int r = make_act_map(&J.mx, xs[base + i], d->N, d->H, d->W, d->Cin, J.BW, J.BH + d->kh - 1, J.BN)) return r;
-            if (int r = make_act_map(&J.mdy, dys[base + i], d->N, d->H, d->W, d->Cout, J.BW, J.BH, J.BN)) return r;
+            J.hn = (d->kh == 3 && J.BN > 1) ? 1 : 0;
+            if (J.hn) {
+                if (int r = make_act_map_hn(&J.mx, xs[base + i], d->N, d->H, d->W, d->Cin, J.BW, J.BH + d->kh - 1, J.BN)) return r;
+                if (int r = make_act_map_hn(&J.mdy, dys[base + i], d->N, d->H, d->W, d->Cout, J.BW, J.BH, J.BN)) return r;
+            } else {
+                if (int r = make_act_map(&J.mx, xs[base + i], d->N, d->H, d->W, d->Cin, J.BW, J.BH + d->kh - 1, J.BN)) return r;
+                if (int r = make_act_map(&J.mdy, dys[base + i], d->N, d->H, d->W, d->Cout, J.BW, J.BH, J.BN)) return r;
+            }
             col_work[i] = (long long)J.total_chunks * d->kh;
             total += col_work[i] * (d->Cin / 128) * J.co_blocks * d->kw;
         }

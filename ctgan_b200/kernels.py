@@ -431,6 +431,10 @@ class FilterPacker:
         """Re-pack everything (one launch) and publish the views in the pack cache of the current epoch."""
         if not (config.use_tc and tc_available()):
             return
+        # the per-filter packs (space-to-depth / thin-channel operands) run on the side stream next to the one-launch pack
+        lazy = [ptr for ptr in self.param_ptrs if _lazy_packs.get(ptr)]
+        if lazy:
+            on_side(lambda: refresh_lazy_packs(lazy), self.flat_p)
         if self.n:
             call('ctgan_pack_filters_multi', _p(self.flat_p), _p(self.packs), _p(self.table), self.n, _stream())
             for p, flip, dst, numel in self.views:
@@ -439,7 +443,8 @@ class FilterPacker:
             call('ctgan_pack_filters_multi_f32', _p(self.flat_p), _p(self.packs32), _p(self.table32), self.n32, _stream())
             for p, flip, dst, numel in self.views32:
                 _pack_cache[(p.data_ptr(), tuple(p.shape), 'f32', flip)] = self.packs32[dst:dst + numel]
-        refresh_lazy_packs(self.param_ptrs)
+        if lazy:
+            join_side()
 
 
 # ---- raw tensor-core launches (operands already in kernel layout)

@@ -509,12 +509,13 @@ def test_tc_wgrad_variants_match(K, shape):
 
 @pytest.mark.parametrize('items_per_sm', [2, 1, 5])
 def test_tc_wgrad_multi_job_launch(K, items_per_sm):
-    """Deferred filter gradients (csrc/conv_wgrad_multi.cu): a mix of layers -- 3x3 at 32x32 / 16x16 / 8x8, 1x1, a Linear,
+    """Deferred filter gradients (csrc/conv_wgrad_multi.cu): a mix of layers -- 3x3 at 32x32 / 16x16 / 8x8 / 4x4, 1x1, a Linear,
     ragged batch sizes, wide Cin / Cout, two jobs adding into the SAME gradient -- queued and run as one launch, against
     the CPU reference of each job; the queue is empty afterwards and ineligible jobs launch immediately."""
     from ctgan_b200 import _lib
     shapes = [(64, 8, 8, 3, 128, 128), (37, 8, 8, 3, 128, 128), (20, 16, 16, 3, 128, 256), (7, 32, 32, 3, 256, 128),
-              (50, 8, 8, 1, 128, 128), (130, 1, 1, 1, 128, 384), (64, 8, 8, 3, 128, 128)]
+              (50, 8, 8, 1, 128, 128), (130, 1, 1, 1, 128, 384), (40, 4, 4, 3, 128, 128), (33, 4, 4, 3, 256, 128),
+              (64, 8, 8, 3, 128, 128)]       # 4x4: four images per 64-pixel chunk, [h][n][w] halo boxes
     _lib.lib.ctgan_set_wgrad_multi_items_per_sm(items_per_sm)
     try:
         refs, accs, keep = [], [], []
@@ -542,14 +543,14 @@ def test_tc_wgrad_multi_job_launch(K, items_per_sm):
         assert not K._wgrad_queue
         for i, (acc, ref) in enumerate(zip(accs, refs)):
             assert rel(acc - 0.25, ref) < 2e-3, (i, shapes[i])
-        # 4x4 images: several images per 64-pixel chunk cannot use the halo box -> not deferrable, runs at once
-        g = K.same_geom(40, 4, 4, 128, 128, 3, 1)
-        x, dy = act((40, 128, 4, 4), torch.bfloat16, 1), act((40, 128, 4, 4), torch.bfloat16, 2)
+        # a 5x5 stride-1 filter is not a job of the multi-launch kernel (3x3 / 1x1 only) -> not deferrable, runs at once
+        g = K.same_geom(40, 8, 8, 128, 128, 5, 1)
+        x, dy = act((40, 128, 8, 8), torch.bfloat16, 1), act((40, 128, 8, 8), torch.bfloat16, 2)
         assert not K.wgrad_deferrable(to_dev(x), to_dev(dy), g)
-        acc = torch.zeros((3, 3, 128, 128), device='cuda')
-        K.conv_wgrad(to_dev(x), to_dev(dy), g, (3, 3, 128, 128), accumulate_into=acc, defer=True)
+        acc = torch.zeros((5, 5, 128, 128), device='cuda')
+        K.conv_wgrad(to_dev(x), to_dev(dy), g, (5, 5, 128, 128), accumulate_into=acc, defer=True)
         assert not K._wgrad_queue
-        assert rel(acc, FB().conv_wgrad(x, dy, g, (3, 3, 128, 128))) < 2e-3
+        assert rel(acc, FB().conv_wgrad(x, dy, g, (5, 5, 128, 128))) < 2e-3
     finally:
         _lib.lib.ctgan_set_wgrad_multi_items_per_sm(2)
 
