@@ -55,6 +55,7 @@ _PROTOS = {
     'ctgan_conv_wgrad_tc': (c_int, [POINTER(ConvDesc), P, P, P, P]),
     'ctgan_conv_wgrad_tc_multi_ok': (c_int, [POINTER(ConvDesc)]),
     'ctgan_conv_wgrad_tc_multi': (c_int, [c_int, POINTER(ConvDesc), POINTER(P), POINTER(P), POINTER(P), P]),
+    'ctgan_conv_wgrad_tc_multi_embed': (c_int, [c_int, POINTER(ConvDesc), POINTER(P), POINTER(P), POINTER(P), POINTER(c_int), P]),
     'ctgan_set_wgrad_multi_items_per_sm': (None, [c_int]),
     'ctgan_conv_tf32_ok': (c_int, [POINTER(ConvDesc)]),
     'ctgan_conv_fprop_tf32': (c_int, [POINTER(ConvDesc), P, P, P, P, P, P, c_int, P]),

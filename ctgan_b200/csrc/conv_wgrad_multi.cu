@@ -29,6 +29,11 @@ struct alignas(64) WgradJob {
     int BW, BH, BN, chunksW, chunksH;
     int co_blocks;                  // Cout / 128
     int hn;                         // 1: chunks of several small images, boxes laid out [h][n][w] (tensor maps with N and H exchanged)
+    // space-to-depth embedding (emb_k > 0): the job is the 3x3 correlation over the 4C-channel image that stands for a
+    // stride-2 emb_k x emb_k filter (conv_s2d.cu); dw is THAT filter's gradient [emb_k][emb_k][emb_C][Cout], and tap (R, S),
+    // channel block (dy, dx) of the embedded filter is tap (2R + dy - 2 + pad_t, 2S + dx - 2 + pad_l) of it -- or nothing
+    // (11 of the 36 combinations for 5x5), which is then neither multiplied nor stored
+    int emb_k, emb_C, emb_pad_t, emb_pad_l;
     int splits, chunks_per_split, total_chunks;
     int item0;                      // index of this job's first work item
     uint32_t a_bytes;               // bytes of one 64-channel half of the x box
@@ -38,7 +43,7 @@ struct WgradJobTable {
     int n_jobs, n_items;
 };
 
-struct WgItem { int j, ci0, co0, s_tap, chunk0, nchunks; };
+struct WgItem { int j, ci0, co0, s_tap, chunk0, nchunks, rmask, s5, dyv, c0; };
 
 __device__ __forceinline__ WgItem wg_decode(const WgradJobTable& tab, int item) {
     int j = 0;
@@ -47,13 +52,31 @@ __device__ __forceinline__ WgItem wg_decode(const WgradJobTable& tab, int item) 
     const WgradJob& J = tab.job[j];
     int local = item - J.item0;
     const int z = local % J.splits; local /= J.splits;
-    const int s = local % J.kw; const int tile = local / J.kw;
     WgItem it;
     it.j = j;
-    it.ci0 = (tile / J.co_blocks) * 128; it.co0 = (tile % J.co_blocks) * 128;
-    it.s_tap = s;
     it.chunk0 = z * J.chunks_per_split;
     it.nchunks = min(J.chunks_per_split, J.total_chunks - it.chunk0);
+    if (J.emb_k > 0) {
+        // items enumerate the REAL filter's columns s5 and the row parity dy: every item has 2-3 live row taps
+        const int s5 = local % J.emb_k; local /= J.emb_k;
+        const int dyv = local & 1; const int tile = local >> 1;
+        const int as = s5 - J.emb_pad_l + 2;
+        it.s_tap = as >> 1;
+        it.c0 = (tile / J.co_blocks) * 128; it.co0 = (tile % J.co_blocks) * 128;
+        it.ci0 = (dyv * 2 + (as & 1)) * J.emb_C + it.c0;
+        it.s5 = s5; it.dyv = dyv;
+        it.rmask = 0;
+#pragma unroll
+        for (int R = 0; R < 3; ++R) {
+            const int r5 = 2 * R + dyv - 2 + J.emb_pad_t;
+            if (r5 >= 0 && r5 < J.emb_k) it.rmask |= 1 << R;
+        }
+        return it;
+    }
+    const int s = local % J.kw; const int tile = local / J.kw;
+    it.ci0 = (tile / J.co_blocks) * 128; it.co0 = (tile % J.co_blocks) * 128;
+    it.s_tap = s;
+    it.rmask = (1 << J.kh) - 1; it.s5 = 0; it.dyv = 0; it.c0 = it.ci0;
     return it;
 }
 
@@ -131,7 +154,7 @@ conv_wgrad_tc_multi_kernel(const __grid_constant__ WgradJobTable tab)
         for (int item = blockIdx.x; item < tab.n_items; item += gridDim.x, ++n) {
             const WgItem it = wg_decode(tab, item);
             const WgradJob& J = tab.job[it.j];
-            const int kh = J.kh;
+            const int rmask = it.rmask;
             const uint32_t row_step = ((uint32_t)J.BW * (J.hn ? J.BN : 1) * 128u) >> 4;   // one image row down = filter row r + 1
             mbar_wait(tempty, (n & 1u) ^ 1u);                            // the epilogue has drained the accumulators
             tc_fence_after();
@@ -142,7 +165,7 @@ conv_wgrad_tc_multi_kernel(const __grid_constant__ WgradJobTable tab)
                 if (elect_one()) {
 #pragma unroll
                     for (int r = 0; r < 3; ++r) {
-                        if (r < kh) {
+                        if ((rmask >> r) & 1) {
 #pragma unroll
                             for (int k = 0; k < 64 / UMMA_K; ++k)     // 16 pixel rows = 2048 bytes along K
                                 umma_bf16_lo(tmem_base + (uint32_t)(r * 128), a_lo + r * row_step + 128 * k, b_lo + 128 * k, idesc,
@@ -165,9 +188,12 @@ conv_wgrad_tc_multi_kernel(const __grid_constant__ WgradJobTable tab)
             const WgradJob& J = tab.job[it.j];
             mbar_wait(tfull, n & 1u);
             tc_fence_after();
-            const int ci = it.ci0 + q * 32 + lane;
-            for (int r = 0; r < J.kh; ++r) {
-                float* dst = J.dw + ((int64_t)(r * J.kw + it.s_tap) * J.Cin + ci) * J.Cout + it.co0;
+            const int ci = it.c0 + q * 32 + lane;
+            for (int r = 0; r < 3; ++r) {
+                if (!((it.rmask >> r) & 1)) continue;
+                float* dst = J.emb_k > 0
+                    ? J.dw + ((int64_t)((2 * r + it.dyv - 2 + J.emb_pad_t) * J.emb_k + it.s5) * J.emb_C + ci) * J.Cout + it.co0
+                    : J.dw + ((int64_t)(r * J.kw + it.s_tap) * J.Cin + ci) * J.Cout + it.co0;
 #pragma unroll 1
                 for (int c0 = 0; c0 < 128; c0 += 32) {
                     uint32_t acc[32];
@@ -217,6 +243,11 @@ extern "C" int ctgan_conv_wgrad_tc_multi_ok(const ctgan_conv_desc* d) {
 
 extern "C" int ctgan_conv_wgrad_tc_multi(int n, const ctgan_conv_desc* descs, const void* const* xs, const void* const* dys,
                                          float* const* dws, void* stream) {
+    return ctgan_conv_wgrad_tc_multi_embed(n, descs, xs, dys, dws, nullptr, stream);
+}
+
+extern "C" int ctgan_conv_wgrad_tc_multi_embed(int n, const ctgan_conv_desc* descs, const void* const* xs, const void* const* dys,
+                                               float* const* dws, const int* embed, void* stream) {
     CTGAN_REQUIRE(n > 0 && descs && xs && dys && dws, CTGAN_ERR_BAD_DESC, "conv_wgrad_tc_multi: bad args");
     constexpr int STAGES = 4;
     constexpr size_t smem = (size_t)STAGES * 49152 + 1024 + (2 * STAGES + 2) * 8 + 16;
@@ -247,6 +278,14 @@ extern "C" int ctgan_conv_wgrad_tc_multi(int n, const ctgan_conv_desc* descs, co
             J.total_chunks = J.chunksW * J.chunksH * ceil_div(d->N, J.BN);
             J.co_blocks = d->Cout / 128;
             J.a_bytes = (uint32_t)(J.BH + d->kh - 1) * J.BW * J.BN * 128u;
+            J.emb_k = J.emb_C = J.emb_pad_t = J.emb_pad_l = 0;
+            if (embed && embed[4 * (base + i)] > 0) {
+                const int* e = embed + 4 * (base + i);
+                CTGAN_REQUIRE(d->kh == 3 && d->kw == 3 && d->pad_t == 1 && d->pad_l == 1 && e[0] <= 5 && e[1] > 0 && e[1] % 128 == 0 &&
+                              4 * e[1] == d->Cin && e[2] >= 0 && e[2] <= 2 && e[3] >= 0 && e[3] <= 2,
+                              CTGAN_ERR_UNSUPPORTED, "conv_wgrad_tc_multi: job %d: bad space-to-depth embedding", base + i);
+                J.emb_k = e[0]; J.emb_C = e[1]; J.emb_pad_t = e[2]; J.emb_pad_l = e[3];
+            }
             J.hn = (d->kh == 3 && J.BN > 1) ? 1 : 0;
             if (J.hn) {
                 if (int r = make_act_map_hn(&J.mx, xs[base + i], d->N, d->H, d->W, d->Cin, J.BW, J.BH + d->kh - 1, J.BN)) return r;
@@ -256,7 +295,8 @@ extern "C" int ctgan_conv_wgrad_tc_multi(int n, const ctgan_conv_desc* descs, co
                 if (int r = make_act_map(&J.mdy, dys[base + i], d->N, d->H, d->W, d->Cout, J.BW, J.BH, J.BN)) return r;
             }
             col_work[i] = (long long)J.total_chunks * d->kh;
-            total += col_work[i] * (d->Cin / 128) * J.co_blocks * d->kw;
+            total += J.emb_k > 0 ? col_work[i] * (J.emb_C / 128) * J.co_blocks * 2 * J.emb_k
+                                 : col_work[i] * (d->Cin / 128) * J.co_blocks * d->kw;
         }
         // one item ~ total / (items_per_sm * SMs) MMA groups, never below 24 (8 chunks of a 3x3 column)
         long long target = (total + (long long)g_wgrad_multi_items_per_sm * sm_count() - 1) / ((long long)g_wgrad_multi_items_per_sm * sm_count());
@@ -270,7 +310,7 @@ extern "C" int ctgan_conv_wgrad_tc_multi(int n, const ctgan_conv_desc* descs, co
             J.chunks_per_split = ceil_div(J.total_chunks, s);
             J.splits = ceil_div(J.total_chunks, J.chunks_per_split);
             J.item0 = items;
-            items += (J.Cin / 128) * J.co_blocks * J.kw * J.splits;
+            items += (J.emb_k > 0 ? (J.emb_C / 128) * 2 * J.emb_k : (J.Cin / 128) * J.kw) * J.co_blocks * J.splits;
         }
         tab.n_jobs = nj; tab.n_items = items;
         const int grid = items < sm_count() ? items : sm_count();

@@ -27,6 +27,7 @@ class Config:
     branch_streams = True    # run independent sub-graphs of a step (GP pass vs stacked pass) as stream branches
     branch_priority = 0      # CUDA stream priority of the branch stream (lower = higher priority): equal priorities measure best
     critic_splitk = False    # cluster split-K inside the two-branch ResNet critic step (see kernels.splitk)
+    s2d_embed_wgrad = True   # stride-2 filter gradients: the embedded 3x3 job writes the k x k gradient itself (no scratch + gather)
     gen_towers = False       # ResNet generator step: the reference's per-device towers as two stream branches instead of one stacked
                              # batch (measured: 1303 us vs 1226 us stacked -- twice the launches, no shorter chain; kept as a checked option)
     gen_splitk = False       # cluster split-K inside the two-tower generator step
@@ -756,12 +757,17 @@ def _wgrad_multi_ok(g):
 
 
 def _launch_wgrad_jobs(jobs, dt, entry):
+    """jobs: (x, dy, geometry, dw[, embed]) -- embed = (k, C, pad_t, pad_l) of the stride-2 filter a space-to-depth job stands for."""
     n = len(jobs)
-    descs = (ConvDesc * n)(*[_desc(g, dt, dt) for _, _, g, _ in jobs])
-    xs = (ctypes.c_void_p * n)(*[x.data_ptr() for x, _, _, _ in jobs])
-    dys = (ctypes.c_void_p * n)(*[dy.data_ptr() for _, dy, _, _ in jobs])
-    dws = (ctypes.c_void_p * n)(*[dw.data_ptr() for _, _, _, dw in jobs])
-    call(entry, n, descs, xs, dys, dws, _stream())
+    descs = (ConvDesc * n)(*[_desc(j[2], dt, dt) for j in jobs])
+    xs = (ctypes.c_void_p * n)(*[j[0].data_ptr() for j in jobs])
+    dys = (ctypes.c_void_p * n)(*[j[1].data_ptr() for j in jobs])
+    dws = (ctypes.c_void_p * n)(*[j[3].data_ptr() for j in jobs])
+    if any(len(j) > 4 and j[4] is not None for j in jobs):
+        emb = (ctypes.c_int * (4 * n))(*[v for j in jobs for v in (j[4] if len(j) > 4 and j[4] is not None else (0, 0, 0, 0))])
+        call(entry + '_embed', n, descs, xs, dys, dws, emb, _stream())
+    else:
+        call(entry, n, descs, xs, dys, dws, _stream())
 
 
 def flush_wgrads():
@@ -785,12 +791,16 @@ def _wgrad_tf32_ok(g):
     return _tf32_geom_ok(g, 128) and bool(_lib.lib.ctgan_conv_wgrad_tf32_multi_ok(ctypes.byref(d)))
 
 
-def _wgrad_tc(x, dy, g, dw, defer, post=None):
-    """dw += wgrad(x, dy) on the tensor cores, now or (defer) at the next join_side(); post() consumes dw afterwards."""
+def _wgrad_tc(x, dy, g, dw, defer, post=None, embed=None):
+    """dw += wgrad(x, dy) on the tensor cores, now or (defer) at the next join_side(); post() consumes dw afterwards.
+    embed: see _launch_wgrad_jobs (the job reduces straight into the stride-2 filter's gradient)."""
     if defer and config.defer_wgrad and _wgrad_multi_ok(g):
-        _wgrad_queue.append((x, dy, g, dw))
+        _wgrad_queue.append((x, dy, g, dw, embed))
         if post is not None:
             _wgrad_post.append(post)
+        return
+    if embed is not None:
+        _launch_wgrad_jobs([(x, dy, g, dw, embed)], BF16, 'ctgan_conv_wgrad_tc_multi')
         return
     _wgrad_tc_raw(x, dy, g, dw)
     if post is not None:
@@ -854,6 +864,11 @@ def conv_wgrad(x, dy, g, w_shape, accumulate_into=None, col=None, defer=False):
     if route == 's2d':
         g3 = gj
         xs = col if (col is not None and tuple(col.shape) == (g3.N, g3.Cin, g3.H, g3.W)) else space_to_depth(x, g)
+        if config.s2d_embed_wgrad and g.Cin % 128 == 0 and g.kh == g.kw and g.kh <= 5 and _wgrad_multi_ok(g3):
+            # only the taps of the embedded filter that carry an element of w, reduced straight into its gradient
+            dw = acc if acc is not None else zeros(w_shape, torch.float32, x.device)
+            _wgrad_tc(xs, dy, g3, dw, defer, embed=(g.kh, g.Cin, g.pad_t, g.pad_l))
+            return dw
         dw3 = zeros((3, 3, g3.Cin, g3.Cout), torch.float32, x.device)
         dw = acc if acc is not None else torch.empty(w_shape, dtype=torch.float32, device=x.device)
         _wgrad_tc(xs, dy, g3, dw3, defer, post=lambda: _s2d_filter_grad_launch(dw3, dw, g, acc is not None))

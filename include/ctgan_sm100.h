@@ -130,6 +130,13 @@ int ctgan_conv_wgrad_tc(const ctgan_conv_desc* d, const void* x, const void* dy,
  * BF16, stride 1, Cin and Cout multiples of 128, 1x1, or 3x3 on images of >= 64 pixels with a power-of-two width >= 8.
  * Replaces Conv2DBackpropFilter of every Conv2D of a backward pass (autodiff of TG/tflib/ops/conv2d.py:106). */
 int ctgan_conv_wgrad_tc_multi_ok(const ctgan_conv_desc* d);
+/* ..._embed: the same launch with an optional space-to-depth embedding per job (embed = n x 4 ints {k, C, pad_t, pad_l}, k = 0 or
+ * embed == NULL: plain job).  An embedded job is the 3x3 pad-1 correlation over the 4C-channel space-to-depth image that stands for a
+ * stride-2 k x k (k <= 5) convolution with C input channels (C % 128 == 0) and TF-SAME pads (pad_t, pad_l): descs[i] describes the
+ * 3x3 geometry (Cin = 4C), dws[i] is the k x k filter gradient [k][k][C][Cout] itself -- only the row/column taps that carry a filter
+ * element are multiplied, and they are reduced straight into it (no 3x3x4C scratch, zero-fill or gather: ctgan_s2d_filter_grad). */
+int ctgan_conv_wgrad_tc_multi_embed(int n, const ctgan_conv_desc* descs, const void* const* xs, const void* const* dys,
+                                    float* const* dws, const int* embed, void* stream);
 int ctgan_conv_wgrad_tc_multi(int n, const ctgan_conv_desc* descs, const void* const* xs, const void* const* dys,
                               float* const* dws, void* stream);
 /* tuning hook: work items per SM that launch aims for (default 2) */
