@@ -21,7 +21,7 @@ iterations) instead of 0.14 s -- long enough for sustained clocks and a few doze
   cpu_baseline / --impl reference
             the CPU transcription of the reference graph (oracle/, PyTorch-CPU fp32, all host
             threads) -- TF 1.2.1 cannot be installed here
-  --workload cifar|mnist
+  --workload cifar|mnist|64x64
             the same line for the DCGAN scripts CT_gan_cifar.py / CT_gan_mnist.py (BASELINE configs[1] / [0]: parity
             configurations, not the headline); default = resnet, BASELINE.json's metric
 """
@@ -489,13 +489,20 @@ DCGAN = {
               'CT_gan_cifar.py DCGAN critic/generator, 32x32x3 synthetic batch 64, critic_iters=5 (BASELINE configs[1])'),
     'mnist': ('ctgan_b200.gan_mnist', 'oracle.ct_gan_mnist', 50, 32.80, 11.83, 784,
               'CT_gan_mnist.py DCGAN-style critic/generator, 28x28x1 synthetic batch 50, dropout CT term + GP (BASELINE configs[0])'),
+    # SURVEY 8(f) row N4; GFLOP = executed conv / linear GEMM work counted per launcher call (2 FLOP / MAC), not a SURVEY figure
+    '64x64': ('ctgan_b200.gan_64x64', 'oracle.ct_gan_64x64', 64, 3445.21, 1120.42, 12288,
+              'CT_gan_64x64.py GoodGenerator / GoodDiscriminator (ResNet, layer norm in the critic), MODE wgan-ct, 64x64x3 synthetic batch 64, '
+              'DIM 64, critic_iters=5 (SURVEY 8(f) row N4)'),
 }
+DCGAN_ITERS_PER_STEP = {'64x64': 2}         # ~36 ms per iteration: 20 steps x 2 iterations = 1.5 s timed
 
 
 def _dcgan_batches(np, script, pool, B, seed):
     rs = np.random.RandomState(seed)
     if script == 'cifar':
         return rs.randint(0, 256, (pool, B, 3072)).astype('int32')
+    if script == '64x64':
+        return rs.randint(0, 256, (pool, B, 3, 64, 64)).astype('int32')
     return rs.random_sample((pool, B, 784)).astype('float32')
 
 
@@ -577,7 +584,7 @@ def measure_dcgan(args, script, rank, local_rank, world, dev, with_roofline=True
     host_out = torch.zeros(N_CRITIC + 1, 8, dtype=torch.float32).pin_memory()
     gt = GraphedTrainer(tr, (dev_x[0],))
     state = {'b': 0}
-    IPS = ITERS_PER_STEP
+    IPS = DCGAN_ITERS_PER_STEP.get(script, ITERS_PER_STEP)
 
     def iteration(e2e):
         src = host_x if e2e else dev_x
@@ -631,13 +638,16 @@ def measure_dcgan(args, script, rank, local_rank, world, dev, with_roofline=True
     gflop = N_CRITIC * gf_c + gf_g
     step_tflops = gflop * 1e-3 * (n_iters / (ms * 1e-3))
     line = {
-        'metric': 'CT-GAN train iters/sec (%s)' % ('CIFAR DCGAN' if script == 'cifar' else 'MNIST DCGAN'), 'value': it_s, 'unit': unit,
+        'metric': 'CT-GAN train iters/sec (%s)' % {'cifar': 'CIFAR DCGAN', 'mnist': 'MNIST DCGAN', '64x64': 'ImageNet 64x64 ResNet'}[script],
+        'value': it_s, 'unit': unit,
         'n_gpus': world, 'steps': args.steps, 'warmup': max(3, args.warmup), 'ms_per_step': ms / args.steps, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
         'config': {'workload': cfg, 'step': '%d training iterations' % IPS, 'per_gpu_batch': B, 'critic_iters': N_CRITIC, 'cuda_graphs': True,
                    'l2_policy': '8 rotating input batches; activations of the stacked critic pass exceed L2 only for cifar; no explicit flush',
-                   'precision': 'BF16 operands / fp32 accumulate (tcgen05; stride-2 5x5 layers as 3x3 convs over the space-to-depth image, '
-                                'bias + LeakyReLU + Philox dropout in the conv epilogue), fp32 master weights and optimizer'},
+                   'precision': ('BF16 operands / fp32 accumulate (tcgen05), layer-norm statistics in fp32, fp32 master weights and optimizer'
+                                 if script == '64x64' else
+                                 'BF16 operands / fp32 accumulate (tcgen05; stride-2 5x5 layers as 3x3 convs over the space-to-depth image, '
+                                 'bias + LeakyReLU + Philox dropout in the conv epilogue), fp32 master weights and optimizer')},
         'clocks': clocks,
         'e2e': {'value': it_s_e2e, 'unit': unit, 'ms_per_step': ms_e2e / args.steps,
                 'h2d_bytes_per_step': IPS * (N_CRITIC * (B * row * 4 + 4) + 4), 'd2h_bytes_per_step': IPS * (N_CRITIC * 32 + 4)},
@@ -645,7 +655,7 @@ def measure_dcgan(args, script, rank, local_rank, world, dev, with_roofline=True
         'step_tensor_utilisation': {'algorithmic_gflop_per_iteration': gflop, 'achieved_tflops_per_gpu': step_tflops,
                                     'frac_of_sustained_peak': step_tflops / peaks['sustained'], 'peak': peaks['sustained']},
     }
-    if with_roofline:
+    if with_roofline and script in ('cifar', 'mnist'):
         line['roofline'] = roofline_dcgan_kernel(torch, peaks, script, B)
     return line
 
@@ -682,7 +692,7 @@ def main():
     ap.add_argument('--no-pregen', action='store_true', help='one generator forward per critic step instead of one per iteration')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-other-workloads', action='store_true', help='skip the CIFAR-DCGAN / MNIST lines of the default run')
-    ap.add_argument('--workload', default='resnet', choices=['resnet', 'cifar', 'mnist'],
+    ap.add_argument('--workload', default='resnet', choices=['resnet', 'cifar', 'mnist', '64x64'],
                     help="resnet = BASELINE.json's metric (default); cifar / mnist = the DCGAN parity configurations (our arm only)")
     args = ap.parse_args()
     if args.impl == 'reference':

@@ -1064,6 +1064,7 @@ __global__ void col2im_thin_kernel(const __nv_bfloat16* __restrict__ col, const 
 struct WgradThinParams {
     long long total_chunks;
     int chunks_per_split, C, kreal;
+    int Cw;                        // channels of the wide tensor (a multiple of 64; rows >= Cw of the last tile are zero-filled, not stored)
     long long sA, sB, sC;
     float* dw;
 };
@@ -1155,6 +1156,7 @@ wgrad_thin_tc_kernel(const __grid_constant__ CUtensorMap tmap_wide, const __grid
     if (nchunks > 0) {
         mbar_wait(accum_bar, 0);
         tc_fence_after();
+        const bool row_ok = cw0 + warp * 32 + lane < p.Cw;
         float* dst = p.dw + (long long)(cw0 + warp * 32 + lane) * p.sC;
         int t = 0, c = 0;
 #pragma unroll 1
@@ -1164,7 +1166,7 @@ wgrad_thin_tc_kernel(const __grid_constant__ CUtensorMap tmap_wide, const __grid
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
                 if (c0 + j < p.kreal) {
-                    atomicAdd(dst + t * p.sA + c * p.sB, __uint_as_float(acc[j]));
+                    if (row_ok) atomicAdd(dst + t * p.sA + c * p.sB, __uint_as_float(acc[j]));
                     if (++c == p.C) { c = 0; ++t; }
                 }
             }
@@ -1478,7 +1480,7 @@ extern "C" int ctgan_pack_filter_thin(const float* w, void* wp, int taps, int C,
 
 extern "C" int ctgan_wgrad_thin_tc(const void* wide, const void* col, long long P, int Cw, int C, int taps, int mode,
                                    float* dw, void* stream) {
-    CTGAN_REQUIRE(wide && col && dw && P > 0 && P < (1ll << 31) && Cw > 0 && Cw % 128 == 0 && C > 0 && taps > 0 && taps * C <= 64 &&
+    CTGAN_REQUIRE(wide && col && dw && P > 0 && P < (1ll << 31) && Cw > 0 && Cw % 64 == 0 && C > 0 && taps > 0 && taps * C <= 64 &&
                   (mode == 0 || mode == 1), CTGAN_ERR_BAD_DESC, "wgrad_thin_tc: bad args");
     CTGAN_REQUIRE((reinterpret_cast<uintptr_t>(wide) & 15) == 0 && (reinterpret_cast<uintptr_t>(col) & 15) == 0, CTGAN_ERR_BAD_DESC,
                   "wgrad_thin_tc: pointers must be 16-byte aligned");
@@ -1486,10 +1488,10 @@ extern "C" int ctgan_wgrad_thin_tc(const void* wide, const void* col, long long 
     constexpr int STAGES = 4;
     WgradThinParams p;
     p.total_chunks = (P + 63) / 64;
-    p.C = C; p.kreal = taps * C; p.dw = dw;
+    p.C = C; p.kreal = taps * C; p.dw = dw; p.Cw = Cw;
     if (mode == 0) { p.sA = (long long)C * Cw; p.sB = Cw; p.sC = 1; }          // dw [taps][C][Cw]
     else           { p.sA = (long long)Cw * C; p.sB = 1;  p.sC = C; }          // dw [taps][Cw][C]
-    const int tiles = Cw / 128;
+    const int tiles = (Cw + 127) / 128;
     long long splits = sm_count() / tiles; if (splits < 1) splits = 1;
     long long max_splits = p.total_chunks / 8; if (max_splits < 1) max_splits = 1;
     if (splits > max_splits) splits = max_splits;

@@ -80,13 +80,14 @@ __device__ __forceinline__ WgItem wg_decode(const WgradJobTable& tab, int item) 
     return it;
 }
 
-template <int STAGES>
+// <4 stages, 16 KB x-halves> by default; <3, 24 KB> when a job's halo box is larger (64-pixel-wide images: 3 rows x 64 pixels)
+template <int STAGES, uint32_t A_SLOT = 16384>
 __global__ void __launch_bounds__(192, 1)
 conv_wgrad_tc_multi_kernel(const __grid_constant__ WgradJobTable tab)
 {
     ctgan::pdl_launch_dependents();
-    constexpr uint32_t A_SLOT = 16384, B_HALF = 8192;
-    constexpr uint32_t STAGE_BYTES = 2 * A_SLOT + 2 * B_HALF;             // 48 KB
+    constexpr uint32_t B_HALF = 8192;
+    constexpr uint32_t STAGE_BYTES = 2 * A_SLOT + 2 * B_HALF;             // 48 KB (64 KB)
     constexpr int TMEM_COLS = 512;
 
     extern __shared__ uint8_t smem_raw[];
@@ -189,6 +190,9 @@ conv_wgrad_tc_multi_kernel(const __grid_constant__ WgradJobTable tab)
             mbar_wait(tfull, n & 1u);
             tc_fence_after();
             const int ci = it.c0 + q * 32 + lane;
+            // Cin / Cout = 64 (mod 128): the upper 64-channel operand half is out of bounds (TMA zero fill); those rows /
+            // columns of the accumulator are not stored
+            const bool row_ok = ci < (J.emb_k > 0 ? J.emb_C : J.Cin);
             for (int r = 0; r < 3; ++r) {
                 if (!((it.rmask >> r) & 1)) continue;
                 float* dst = J.emb_k > 0
@@ -198,6 +202,7 @@ conv_wgrad_tc_multi_kernel(const __grid_constant__ WgradJobTable tab)
                 for (int c0 = 0; c0 < 128; c0 += 32) {
                     uint32_t acc[32];
                     tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(r * 128 + c0), acc);
+                    if (!row_ok || it.co0 + c0 >= J.Cout) continue;
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
                         asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};"
@@ -230,13 +235,13 @@ extern "C" void ctgan_set_wgrad_multi_items_per_sm(int v) { g_wgrad_multi_items_
 extern "C" int ctgan_conv_wgrad_tc_multi_ok(const ctgan_conv_desc* d) {
     if (!d || !ctgan_tc_available()) return 0;
     if (d->x_dtype != CTGAN_BF16 || d->y_dtype != CTGAN_BF16 || d->stride != 1 || d->Ho != d->H || d->Wo != d->W) return 0;
-    if (d->N <= 0 || d->H <= 0 || d->W <= 0 || d->Cin <= 0 || d->Cout <= 0 || d->Cin % 128 || d->Cout % 128) return 0;
+    if (d->N <= 0 || d->H <= 0 || d->W <= 0 || d->Cin <= 0 || d->Cout <= 0 || d->Cin % 64 || d->Cout % 64) return 0;
     if (!((d->kh == 3 && d->kw == 3) || (d->kh == 1 && d->kw == 1))) return 0;
     if (d->pad_t < 0 || d->pad_l < 0 || d->pad_t >= d->kh || d->pad_l >= d->kw) return 0;
     int BW, BH, BN;
     pixel_box(d->H, d->W, 64, &BW, &BH, &BN);
     if (d->kh == 1) return 1;
-    if (BN == 1) return BW % 8 == 0 && (uint32_t)(BH + 2) * BW * 128u <= 16384u;
+    if (BN == 1) return BW % 8 == 0 && (uint32_t)(BH + 2) * BW * 128u <= 24576u;
     // several whole small images per 64-pixel chunk (4x4): [h][n][w] boxes, filter row shift = BN * BW pixel rows
     return BW == d->W && BH == d->H && (BN * BW) % 8 == 0 && (uint32_t)(BH + 2) * BN * BW * 128u <= 16384u;
 }
@@ -251,9 +256,12 @@ extern "C" int ctgan_conv_wgrad_tc_multi_embed(int n, const ctgan_conv_desc* des
     CTGAN_REQUIRE(n > 0 && descs && xs && dys && dws, CTGAN_ERR_BAD_DESC, "conv_wgrad_tc_multi: bad args");
     constexpr int STAGES = 4;
     constexpr size_t smem = (size_t)STAGES * 49152 + 1024 + (2 * STAGES + 2) * 8 + 16;
+    constexpr size_t smem_big = (size_t)3 * 65536 + 1024 + (2 * 3 + 2) * 8 + 16;
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(conv_wgrad_tc_multi_kernel<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(conv_wgrad_tc_multi_kernel<3, 24576>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_big);
         if (e != cudaSuccess) return cuda_status(e, "wgrad_tc_multi smem attribute");
         attr_set = true;
     }
@@ -263,6 +271,7 @@ extern "C" int ctgan_conv_wgrad_tc_multi_embed(int n, const ctgan_conv_desc* des
         // MMA groups (4 instructions) per (accumulator tile, filter column) and in total
         long long total = 0;
         long long col_work[WG_MAX_JOBS];
+        bool big = false;                      // some x halo box exceeds 16 KB per 64-channel half
         for (int i = 0; i < nj; ++i) {
             const ctgan_conv_desc* d = descs + base + i;
             CTGAN_REQUIRE(ctgan_conv_wgrad_tc_multi_ok(d), CTGAN_ERR_UNSUPPORTED, "conv_wgrad_tc_multi: job %d is not eligible", base + i);
@@ -276,8 +285,9 @@ extern "C" int ctgan_conv_wgrad_tc_multi_embed(int n, const ctgan_conv_desc* des
             pixel_box(d->H, d->W, 64, &J.BW, &J.BH, &J.BN);
             J.chunksW = ceil_div(d->W, J.BW); J.chunksH = ceil_div(d->H, J.BH);
             J.total_chunks = J.chunksW * J.chunksH * ceil_div(d->N, J.BN);
-            J.co_blocks = d->Cout / 128;
+            J.co_blocks = ceil_div(d->Cout, 128);
             J.a_bytes = (uint32_t)(J.BH + d->kh - 1) * J.BW * J.BN * 128u;
+            big = big || J.a_bytes > 16384u;
             J.emb_k = J.emb_C = J.emb_pad_t = J.emb_pad_l = 0;
             if (embed && embed[4 * (base + i)] > 0) {
                 const int* e = embed + 4 * (base + i);
@@ -296,7 +306,7 @@ extern "C" int ctgan_conv_wgrad_tc_multi_embed(int n, const ctgan_conv_desc* des
             }
             col_work[i] = (long long)J.total_chunks * d->kh;
             total += J.emb_k > 0 ? col_work[i] * (J.emb_C / 128) * J.co_blocks * 2 * J.emb_k
-                                 : col_work[i] * (d->Cin / 128) * J.co_blocks * d->kw;
+                                 : col_work[i] * ceil_div(d->Cin, 128) * J.co_blocks * d->kw;
         }
         // one item ~ total / (items_per_sm * SMs) MMA groups, never below 24 (8 chunks of a 3x3 column)
         long long target = (total + (long long)g_wgrad_multi_items_per_sm * sm_count() - 1) / ((long long)g_wgrad_multi_items_per_sm * sm_count());
@@ -310,11 +320,12 @@ extern "C" int ctgan_conv_wgrad_tc_multi_embed(int n, const ctgan_conv_desc* des
             J.chunks_per_split = ceil_div(J.total_chunks, s);
             J.splits = ceil_div(J.total_chunks, J.chunks_per_split);
             J.item0 = items;
-            items += (J.emb_k > 0 ? (J.emb_C / 128) * 2 * J.emb_k : (J.Cin / 128) * J.kw) * J.co_blocks * J.splits;
+            items += (J.emb_k > 0 ? (J.emb_C / 128) * 2 * J.emb_k : ceil_div(J.Cin, 128) * J.kw) * J.co_blocks * J.splits;
         }
         tab.n_jobs = nj; tab.n_items = items;
         const int grid = items < sm_count() ? items : sm_count();
-        CTGAN_LAUNCH((conv_wgrad_tc_multi_kernel<STAGES>), grid, 192, smem, as_stream(stream), tab);
+        if (big) CTGAN_LAUNCH((conv_wgrad_tc_multi_kernel<3, 24576>), grid, 192, smem_big, as_stream(stream), tab);
+        else     CTGAN_LAUNCH((conv_wgrad_tc_multi_kernel<STAGES>), grid, 192, smem, as_stream(stream), tab);
         CTGAN_CHECK_LAUNCH("conv_wgrad_tc_multi");
     }
     return 0;

@@ -311,9 +311,9 @@ def _thin_side(g, t):
     if not (g.stride == 1 and g.Ho == g.H and g.Wo == g.W and 0 <= g.pad_t < g.kh and 0 <= g.pad_l < g.kw and g.H * g.W >= 64):
         return None
     taps = g.kh * g.kw
-    if g.Cin <= 8 and taps * g.Cin <= 64 and g.Cout % 128 == 0:
+    if g.Cin <= 8 and taps * g.Cin <= 64 and g.Cout % 64 == 0:
         return 'in'
-    if g.Cout <= 8 and taps * g.Cout <= 64 and g.Cin % 128 == 0:
+    if g.Cout <= 8 and taps * g.Cout <= 64 and g.Cin % 64 == 0:
         return 'out'
     return None
 
@@ -385,7 +385,7 @@ class FilterPacker:
                 taps, cin, cout = 1, p.shape[0], p.shape[1]
             else:
                 continue
-            if p.dim() == 4 and taps * min(cin, cout) <= 64 and min(cin, cout) <= 8 and max(cin, cout) % 128 == 0:
+            if p.dim() == 4 and taps * min(cin, cout) <= 64 and min(cin, cout) <= 8 and max(cin, cout) % 64 == 0:
                 for kind in ((0, 3) if cin < cout else (2, 1)):       # thin operands: 64 x Cw each
                     rows.append((offsets[name], dst, taps, cin, cout, 2 + kind))
                     self.views.append((p, 2 + kind, dst, 64 * max(cin, cout)))
@@ -799,8 +799,10 @@ def _wgrad_tc(x, dy, g, dw, defer, post=None, embed=None):
         if post is not None:
             _wgrad_post.append(post)
         return
-    if embed is not None:
+    if embed is not None or g.Cin % 128 or g.Cout % 128:
         _launch_wgrad_jobs([(x, dy, g, dw, embed)], BF16, 'ctgan_conv_wgrad_tc_multi')
+        if post is not None:
+            post()
         return
     _wgrad_tc_raw(x, dy, g, dw)
     if post is not None:
@@ -813,8 +815,9 @@ def _wgrad_route(x, dy, g):
     bf = xdt == BF16 and ydt == BF16
     if xdt == F32 and ydt == F32 and _wgrad_tf32_ok(g):
         return 'tf32', g
-    if bf and _tc_geom_ok(g) and g.Cin % 128 == 0 and g.Cout % 128 == 0:
-        return 'tc', g
+    if bf and _tc_geom_ok(g) and ((g.Cin % 128 == 0 and g.Cout % 128 == 0) or
+                                  (g.Cin % 64 == 0 and g.Cout % 64 == 0 and _wgrad_multi_ok(g))):
+        return 'tc', g        # 64 (mod 128) channels: only the multi-job kernel (zero-filled upper operand half)
     g3 = s2d_geom(g, x) if bf else None
     if g3 is not None and g3.Cin % 128 == 0 and g3.Cout % 128 == 0:
         return 's2d', g3

@@ -127,7 +127,9 @@ int ctgan_conv_wgrad_tc(const ctgan_conv_desc* d, const void* x, const void* dy,
  * geometry descs[i] into dws[i] (float HWIO, pre-initialised) exactly like n calls of ctgan_conv_wgrad_tc, but the work of
  * all jobs is cut into ~2 items per SM, so small layers neither under-fill the GPU nor pay a 49-way split of their pixel
  * range.  descs / xs / dys / dws are HOST arrays (read during the call).  Eligible jobs (ctgan_conv_wgrad_tc_multi_ok):
- * BF16, stride 1, Cin and Cout multiples of 128, 1x1, or 3x3 on images of >= 64 pixels with a power-of-two width >= 8.
+ * BF16, stride 1, Cin and Cout multiples of 64 (a count that is 64 mod 128 leaves the upper half of one 128-channel operand
+ * zero-filled by TMA; those accumulator rows / columns are not stored), 1x1, or 3x3 on images of >= 64 pixels with a power-of-two
+ * width >= 8, or 3x3 on 4x4 images (several images per pixel chunk).
  * Replaces Conv2DBackpropFilter of every Conv2D of a backward pass (autodiff of TG/tflib/ops/conv2d.py:106). */
 int ctgan_conv_wgrad_tc_multi_ok(const ctgan_conv_desc* d);
 /* ..._embed: the same launch with an optional space-to-depth embedding per job (embed = n x 4 ints {k, C, pad_t, pad_l}, k = 0 or

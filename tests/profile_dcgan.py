@@ -1,7 +1,7 @@
 """Profiling driver: one eager critic step + one eager generator step of a DCGAN script (CT_gan_cifar.py / CT_gan_mnist.py,
 BF16 path) between cudaProfilerStart/Stop, for
   ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv ...
-Not a benchmark (numbers under ncu are never bench values).     python tests/profile_dcgan.py cifar|mnist [batch]"""
+Not a benchmark (numbers under ncu are never bench values).     python tests/profile_dcgan.py cifar|mnist|64x64 [batch]"""
 import importlib
 import os
 import sys
@@ -19,6 +19,8 @@ tr = mod.Trainer(device='cuda', seed=1234, act_dtype=torch.bfloat16, batch_size=
 rs = np.random.RandomState(0)
 if script == 'cifar':
     x = torch.from_numpy(rs.randint(0, 256, (B, 3072)).astype('int32')).cuda()
+elif script == '64x64':
+    x = torch.from_numpy(rs.randint(0, 256, (B, 3, 64, 64)).astype('int32')).cuda()
 else:
     x = torch.from_numpy(rs.random_sample((B, 784)).astype('float32')).cuda()
 for _ in range(2):

@@ -515,6 +515,8 @@ def test_tc_wgrad_multi_job_launch(K, items_per_sm):
     from ctgan_b200 import _lib
     shapes = [(64, 8, 8, 3, 128, 128), (37, 8, 8, 3, 128, 128), (20, 16, 16, 3, 128, 256), (7, 32, 32, 3, 256, 128),
               (50, 8, 8, 1, 128, 128), (130, 1, 1, 1, 128, 384), (40, 4, 4, 3, 128, 128), (33, 4, 4, 3, 256, 128),
+              (20, 16, 16, 3, 64, 64), (9, 8, 8, 3, 64, 128), (12, 8, 8, 1, 192, 64),      # 64 (mod 128) channels
+              (3, 64, 64, 3, 64, 128),                                                  # 64-pixel-wide image: 24 KB halo boxes
               (64, 8, 8, 3, 128, 128)]       # 4x4: four images per 64-pixel chunk, [h][n][w] halo boxes
     _lib.lib.ctgan_set_wgrad_multi_items_per_sm(items_per_sm)
     try:
@@ -556,6 +558,7 @@ def test_tc_wgrad_multi_job_launch(K, items_per_sm):
 
 
 @pytest.mark.parametrize('geom', [(5, 32, 32, 3, 128, 3), (3, 16, 16, 3, 128, 1), (4, 32, 32, 128, 3, 3), (70, 8, 8, 3, 256, 3),
+                                  (3, 64, 64, 3, 64, 3), (2, 64, 64, 64, 3, 3), (5, 16, 16, 3, 192, 3),      # wide side 64 (mod 128)
                                   (2, 16, 16, 256, 4, 3), (3, 12, 20, 3, 128, 3)])
 def test_thin_tc_conv_family(K, geom):
     """3-channel-side convs (Discriminator.1.*, Generator.Output) through the im2col tensor-core path: fprop, dgrad,
