@@ -21,6 +21,18 @@ _params = {}
 _param_aliases = {}
 _device = None
 
+# Parameter-name suffixes.  The LSUN fork of the package (LS/tflib/ops/conv2d.py:117, batchnorm.py:24, layernorm.py:15, with
+# LS = TG/LSUN_bedrooms) names conv biases and normalisation offsets `<name>.b`; the CT scripts' package uses
+# `<name>.Biases` / `<name>.offset`.  `set_name_style('lsun')` before building a model selects the fork's names.
+CONV_BIAS, NORM_OFFSET = '.Biases', '.offset'
+
+
+def set_name_style(style):
+    global CONV_BIAS, NORM_OFFSET
+    if style not in ('ct', 'lsun'):
+        raise Exception('unknown name style %r' % (style,))
+    CONV_BIAS, NORM_OFFSET = ('.b', '.b') if style == 'lsun' else ('.Biases', '.offset')
+
 
 def set_device(device):
     """Device new parameters are created on (default: current CUDA device)."""
@@ -71,9 +83,11 @@ def named_params_with_name(name, trainable_only=True):
 def delete_all_params():
     """TG/tflib/__init__.py:39-40.  Also drops the aliases (the reference keeps them: a stale alias would redirect a
     name of the next model built in this process to a parameter of the deleted one)."""
+    global CONV_BIAS, NORM_OFFSET
     _params.clear()
     _param_aliases.clear()
     _F._param_ptrs.clear()
+    CONV_BIAS, NORM_OFFSET = '.Biases', '.offset'          # the next model states its own name style
 
 
 def alias_params(replace_dict):

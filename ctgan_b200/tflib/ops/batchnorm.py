@@ -23,20 +23,20 @@ def Batchnorm(name, axes, inputs, is_training=None, stats_iter=None, update_movi
             raise Exception('Unsupported configuration')
         inputs = F.ensure_nhwc(inputs)
         C = inputs.shape[1]
-        offset = lib.param(name + '.offset', np.zeros(C, dtype='float32'))
+        offset = lib.param(name + lib.NORM_OFFSET, np.zeros(C, dtype='float32'))
         scale = lib.param(name + '.scale', np.ones(C, dtype='float32'))
         lib.param(name + '.moving_mean', np.zeros(C, dtype='float32'), trainable=False)
         lib.param(name + '.moving_variance', np.ones(C, dtype='float32'), trainable=False)
         return F.batch_norm(inputs, scale, offset, None, 1e-5, relu, groups, up2)
     if axes == [0] and inputs.dim() == 2:
         shape = [1, inputs.shape[1]]
-        offset = lib.param(name + '.offset', np.zeros(shape, dtype='float32'))
+        offset = lib.param(name + lib.NORM_OFFSET, np.zeros(shape, dtype='float32'))
         scale = lib.param(name + '.scale', np.ones(shape, dtype='float32'))
         return F.batch_norm(inputs, scale, offset, None, 1e-5, relu, groups, up2)
     if axes == [0, 2, 3]:          # unfused spelling of the same statistics (params shaped [1,C,1,1])
         inputs = F.ensure_nhwc(inputs)
         shape = [1, inputs.shape[1], 1, 1]
-        offset = lib.param(name + '.offset', np.zeros(shape, dtype='float32'))
+        offset = lib.param(name + lib.NORM_OFFSET, np.zeros(shape, dtype='float32'))
         scale = lib.param(name + '.scale', np.ones(shape, dtype='float32'))
         return F.batch_norm(inputs, scale, offset, None, 1e-5, relu, 1, up2)
     raise Exception('Unsupported configuration')

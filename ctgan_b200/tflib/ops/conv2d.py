@@ -63,7 +63,7 @@ def Conv2D(name, input_dim, output_dim, filter_size, inputs, he_init=True, mask_
     else:
         filter_values = None
     filters = lib.param(name + '.Filters', filter_values)
-    _biases = lib.param(name + '.Biases', np.zeros(output_dim, dtype='float32')) if biases else None
+    _biases = lib.param(name + lib.CONV_BIAS, np.zeros(output_dim, dtype='float32')) if biases else None
 
     if not isinstance(inputs, F.S2DAct):
         inputs = F.ensure_nhwc(inputs)

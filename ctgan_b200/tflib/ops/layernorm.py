@@ -13,6 +13,6 @@ def Layernorm(name, norm_axes, inputs):
         raise Exception('Layernorm over non-standard axes is unsupported')
     inputs = F.ensure_nhwc(inputs)
     n_neurons = inputs.shape[norm_axes[0]]
-    offset = lib.param(name + '.offset', np.zeros(n_neurons, dtype='float32'))
+    offset = lib.param(name + lib.NORM_OFFSET, np.zeros(n_neurons, dtype='float32'))
     scale = lib.param(name + '.scale', np.ones(n_neurons, dtype='float32'))
     return F.layer_norm(inputs, scale, offset, 1e-5)

@@ -49,14 +49,29 @@ def py2to3(src):
     return '\n'.join(out) + '\n'
 
 
-def _load_ref_tflib(shim):
-    """Import the reference's tflib package (translated) with `tensorflow` -> shim.  Returns the module."""
+def _load_ref_tflib(shim, fork=None):
+    """Import the reference's tflib package (translated) with `tensorflow` -> shim.  Returns the module.
+    fork='LSUN_bedrooms': the copy of the package that ships next to LS/wgan_LSUN_Bedrooms128.py (other parameter names)."""
     pkg_dir = os.path.join(OUT_DIR, 'tflib')
     os.makedirs(os.path.join(pkg_dir, 'ops'), exist_ok=True)
-    for rel in ['__init__.py', 'ops/__init__.py', 'ops/conv2d.py', 'ops/deconv2d.py', 'ops/linear.py',
-                'ops/batchnorm.py', 'ops/cond_batchnorm.py', 'ops/layernorm.py']:
-        with open(os.path.join(REF_ROOT, 'tflib', rel)) as f:
-            src = py2to3(f.read())
+    src_root = os.path.join(REF_ROOT, fork, 'tflib') if fork else os.path.join(REF_ROOT, 'tflib')
+    rels = ['__init__.py', 'ops/__init__.py', 'ops/conv2d.py', 'ops/deconv2d.py', 'ops/linear.py',
+            'ops/batchnorm.py', 'ops/cond_batchnorm.py', 'ops/layernorm.py']
+    stale = os.path.join(pkg_dir, 'debug.py')
+    if os.path.exists(stale):
+        os.remove(stale)
+    if fork:
+        rels.append('debug.py')                        # imported by the fork's conv2d.py / batchnorm.py
+    for rel in rels:
+        path = os.path.join(src_root, rel)
+        if rel == 'ops/__init__.py' and not os.path.exists(path):
+            src = ''                                   # the fork ships only the compiled ops/__init__.pyc
+        else:
+            with open(path) as f:
+                src = f.read()
+            if rel == 'debug.py':                      # only imported; its print_all_stats (a multi-line py2 print) is dropped
+                src = src[:src.index('def print_all_stats')]
+            src = py2to3(src)
         if rel == '__init__.py':
             src = src.replace("locale.setlocale(locale.LC_ALL, '')", "pass")
         with open(os.path.join(pkg_dir, rel), 'w') as f:
@@ -137,6 +152,11 @@ SECTIONS = {
     # hyper-parameters, EVERY architecture function of the file (only GoodGenerator / GoodDiscriminator
     # are called), `Generator, Discriminator = GeneratorAndDiscriminator()`, then the two-tower loss graph
     '64x64': dict(file='CT_gan_64x64.py', consts=(28, 37), funcs=(41, 469), graph=(473, 546), dedent=True),
+    # N4, second half: LS/wgan_LSUN_Bedrooms128.py with the fork of tflib next to it.  consts = hyper-parameters +
+    # GeneratorAndDiscriminator (:31-60) and OUTPUT_DIM / DEVICES (:64-65); graph = placeholders .. disc_cost + decay (:211-288)
+    # and the generator cost (:291-295) -- the two AdamOptimizer(...).minimize lines (:289, :296) are not executed
+    'lsun128': dict(file='LSUN_bedrooms/wgan_LSUN_Bedrooms128.py', fork='LSUN_bedrooms', consts=[(31, 60), (64, 65)], funcs=(67, 205),
+                    graph=[(211, 288), (291, 295)], dedent=True),
 }
 
 # random draws of the reference graph, in graph-construction order, mapped onto the oracle's tags
@@ -154,6 +174,10 @@ def _draw_tags(script):
         if script == 'cifar':
             tags += [None] * 3                         # Discriminator(real_data) for `gradients2` (:145, dev metric)
         return tags
+    if script == 'lsun128':                            # G x2, D(real+fake) x2, alpha, D(interpolates); then per device G, D
+        tags = ['z.0', 'z.1'] + D3('drop.p1') + D3('drop.p2') + ['alpha'] + D3('drop.gp')
+        tags += ['z.0g', 'drop.0.1', 'drop.0.2', 'drop.0.3', 'z.1g', 'drop.1.1', 'drop.1.2', 'drop.1.3']
+        return tags
     if script == '64x64':                              # per tower: G, D(real) x2, D(fake), alpha, D(interpolates)
         tags = []
         for i in range(2):
@@ -166,7 +190,11 @@ def _draw_tags(script):
     return tags
 
 
-def run_reference(script, batch_size, seed, inputs, dim=None, param_init=None):
+def _ranges(r):
+    return [r] if isinstance(r[0], int) else list(r)
+
+
+def run_reference(script, batch_size, seed, inputs, dim=None, param_init=None, width=None):
     """Execute the reference's own code for one evaluation of disc_cost / gen_cost.
     inputs: tuple of numpy arrays fed to the script's placeholders (real data[, labels]).
     param_init(name, value) -> value: optional replacement of every parameter's initial value at the moment the
@@ -175,7 +203,8 @@ def run_reference(script, batch_size, seed, inputs, dim=None, param_init=None):
     from . import tf_shim as shim
     sec = SECTIONS[script]
     path = os.path.join(REF_ROOT, sec['file'])
-    lib = _load_ref_tflib(shim)
+    shim.reset_variables()
+    lib = _load_ref_tflib(shim, sec.get('fork'))
     lib.delete_all_params()
     if param_init is not None:
         ref_param = lib.param
@@ -186,8 +215,15 @@ def run_reference(script, batch_size, seed, inputs, dim=None, param_init=None):
             return ref_param(name, *args, **kwargs)
         lib.param = param
     ns = {'tf': shim, 'lib': lib, 'np': np, 'functools': importlib.import_module('functools'), '__name__': 'ref_section'}
-    exec(compile(_section(path, *sec['consts']), sec['file'] + ':consts', 'exec'), ns)
+    if script == 'lsun128':
+        ns['N_GPUS'] = 2                               # :6
+    for rng_ in _ranges(sec['consts']):
+        exec(compile(_section(path, *rng_), sec['file'] + ':consts', 'exec'), ns)
     ns['BATCH_SIZE'] = batch_size
+    if width is not None:                              # narrower model (LSUN script: every DIM_G_* / DIM_D_* constant)
+        for k in list(ns):
+            if k.startswith(('DIM_G_', 'DIM_D_')):
+                ns[k] = max(1, int(ns[k] * width))
     if dim is not None:                                # smaller model for the committed golden fixtures
         for k in ('DIM', 'DIM_G', 'DIM_D'):
             if k in ns:
@@ -198,11 +234,14 @@ def run_reference(script, batch_size, seed, inputs, dim=None, param_init=None):
     exec(compile(_section(path, *sec['funcs']), sec['file'] + ':funcs', 'exec'), ns)
     np.random.seed(seed)                               # the reference draws initial weights from numpy's global RNG
     feeds = [torch.from_numpy(np.asarray(a)) for a in inputs]
-    if script == 'resnet':
-        feeds = [torch.tensor(0, dtype=torch.int32)] + feeds          # _iteration placeholder (:190)
+    if script in ('resnet', 'lsun128'):
+        feeds = [torch.tensor(0, dtype=torch.int32)] + feeds          # _iteration placeholder (:190 / LS :211)
+    if script == 'lsun128':
+        ns['Generator'], ns['Discriminator'] = ns['GeneratorAndDiscriminator']()      # LS :209
     shim.reset(seed + 1, feeds)
-    graph_src = _section(path, *sec['graph'], dedent=sec['dedent'])
-    exec(compile(graph_src, sec['file'] + ':graph', 'exec'), ns)
+    for rng_ in _ranges(sec['graph']):
+        graph_src = _section(path, *rng_, dedent=sec['dedent'])
+        exec(compile(graph_src, sec['file'] + ':graph', 'exec'), ns)
     draws = list(shim.draws)
     tags = _draw_tags(script)
     assert len(draws) == len(tags), (len(draws), len(tags), [k for k, _ in draws])
@@ -210,7 +249,7 @@ def run_reference(script, batch_size, seed, inputs, dim=None, param_init=None):
     for tag, (kind, t) in zip(tags, draws):
         if tag is None:
             continue
-        if script == 'resnet' and (tag.endswith('g') or tag.startswith('labels.') or tag.startswith('drop.0') or tag.startswith('drop.1')):
+        if script in ('resnet', 'lsun128') and (tag.endswith('g') or tag.startswith('labels.') or tag.startswith('drop.0') or tag.startswith('drop.1')):
             t2 = t
             if tag.startswith('labels.'):
                 t2 = torch.floor(t * np.float32(10)).to(torch.int32)
@@ -219,10 +258,10 @@ def run_reference(script, batch_size, seed, inputs, dim=None, param_init=None):
             tape_disc[tag] = t
     if script == '64x64':
         tape_gen = {k: v for k, v in tape_disc.items() if k.startswith('z.') or k.endswith(('.fake.1', '.fake.2', '.fake.3'))}
-    elif script != 'resnet':
+    elif script not in ('resnet', 'lsun128'):
         tape_gen = {k: v for k, v in tape_disc.items() if k == 'z' or k.startswith('drop.fake')}
     params = {n: p for n, p in lib._params.items()}
-    disc_sel = 'Discriminator.' if script in ('resnet', '64x64') else 'Discriminator'
+    disc_sel = 'Discriminator.' if script in ('resnet', '64x64', 'lsun128') else 'Discriminator'
     dnames = [n for n, p in params.items() if disc_sel in n and p.requires_grad]
     gnames = [n for n, p in params.items() if 'Generator' in n and p.requires_grad]
     dgr = torch.autograd.grad(ns['disc_cost'], [params[n] for n in dnames], retain_graph=True, allow_unused=True)

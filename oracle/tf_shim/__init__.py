@@ -26,11 +26,29 @@ draws = []            # [(kind, tensor)] in call order
 feeds = []            # values handed out by tf.placeholder, in call order
 
 
+_variables = []       # every tf.Variable created since the last reset_variables()
+
+
 def reset(seed, placeholder_values):
     global rng
     rng = np.random.RandomState(seed)
     draws.clear()
     feeds[:] = list(placeholder_values)
+
+
+def reset_variables():
+    _variables.clear()
+
+
+class _IdentityList(list):
+    """`p in tf.trainable_variables()` (LS/tflib/__init__.py:38-39) must compare variables by identity, not by value."""
+
+    def __contains__(self, item):
+        return any(item is v for v in self)
+
+
+def trainable_variables():
+    return _IdentityList(v for v in _variables if v.requires_grad)
 
 
 class _Shape(tuple):
@@ -55,6 +73,7 @@ def _t(x):
 def Variable(initial_value, name=None, trainable=True, **kw):
     v = torch.tensor(np.asarray(initial_value), dtype=DT, requires_grad=bool(trainable))
     v.tf_name = name
+    _variables.append(v)
     return v
 
 

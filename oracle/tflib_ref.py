@@ -16,7 +16,10 @@ from . import tf_ops
 class TFLib:
     """One instance == one `tflib` module state (its `_params` dict)."""
 
-    def __init__(self, dtype=torch.float64):
+    def __init__(self, dtype=torch.float64, style='ct'):
+        # style 'lsun': the LSUN fork's names -- conv biases and normalisation offsets are `<name>.b`
+        # (LS/tflib/ops/conv2d.py:117, batchnorm.py:24, layernorm.py:15 with LS = TG/LSUN_bedrooms)
+        self.conv_bias, self.norm_offset = ('.b', '.b') if style == 'lsun' else ('.Biases', '.offset')
         self.dtype = dtype
         self._params = {}          # TG/tflib/__init__.py:8
         self._trainable = {}
@@ -62,7 +65,7 @@ class TFLib:
         filters = self.param(name + '.Filters', filter_values)
         result = tf_ops.conv2d_same(inputs, filters, stride)
         if biases:
-            b = self.param(name + '.Biases', np.zeros(output_dim, dtype='float32'))
+            b = self.param(name + self.conv_bias, np.zeros(output_dim, dtype='float32'))
             result = tf_ops.bias_add_nchw(result, b)
         return result
 
@@ -130,7 +133,7 @@ class TFLib:
             raise Exception('Unsupported configuration')
         if (axes == [0, 2, 3]) and fused:
             C = inputs.shape[1]
-            offset = self.param(name + '.offset', np.zeros(C, dtype='float32'))
+            offset = self.param(name + self.norm_offset, np.zeros(C, dtype='float32'))
             scale = self.param(name + '.scale', np.ones(C, dtype='float32'))
             self.param(name + '.moving_mean', np.zeros(C, dtype='float32'), trainable=False)
             self.param(name + '.moving_variance', np.ones(C, dtype='float32'), trainable=False)
@@ -139,7 +142,7 @@ class TFLib:
         shape = list(mean.shape)
         if 0 not in axes:
             shape[0] = 1
-        offset = self.param(name + '.offset', np.zeros(shape, dtype='float32'))
+        offset = self.param(name + self.norm_offset, np.zeros(shape, dtype='float32'))
         scale = self.param(name + '.scale', np.ones(shape, dtype='float32'))
         return tf_ops.batch_normalization(inputs, mean, var, offset, scale, 1e-5)
 
@@ -148,7 +151,7 @@ class TFLib:
         'neuron' = the first of norm_axes (channels for BCHW), eps 1e-5."""
         mean, var = tf_ops.moments(inputs, norm_axes)
         n_neurons = inputs.shape[norm_axes[0]]
-        offset = self.param(name + '.offset', np.zeros(n_neurons, dtype='float32'))
+        offset = self.param(name + self.norm_offset, np.zeros(n_neurons, dtype='float32'))
         scale = self.param(name + '.scale', np.ones(n_neurons, dtype='float32'))
         bshape = [-1] + [1 for _ in range(len(norm_axes) - 1)]
         return tf_ops.batch_normalization(inputs, mean, var, offset.reshape(bshape), scale.reshape(bshape), 1e-5)

@@ -18,7 +18,8 @@ sys.path.insert(0, ROOT)
 from oracle import ref_harness as RH   # noqa: E402
 
 CASES = {'mnist': dict(B=6, dim=8, seed=101), 'cifar': dict(B=4, dim=8, seed=202), 'resnet': dict(B=4, dim=16, seed=303),
-         '64x64': dict(B=4, dim=4, seed=404)}
+         '64x64': dict(B=4, dim=4, seed=404),
+         'lsun128': dict(B=2, dim=32, seed=505)}          # LS/wgan_LSUN_Bedrooms128.py at 1/32 of its widths (meta.dim = the divisor)
 
 
 def inputs_for(script, B, seed):
@@ -29,6 +30,8 @@ def inputs_for(script, B, seed):
         return (rs.randint(0, 256, (B, 3072)).astype('int32'),)
     if script == '64x64':
         return (rs.randint(0, 256, (B, 3, 64, 64)).astype('int32'),)
+    if script == 'lsun128':
+        return (rs.randint(0, 256, (B, 3, 128, 128)).astype('int32'),)
     return (rs.randint(0, 256, (B, 3072)).astype('int32'), rs.randint(0, 10, (B,)).astype('int32'))
 
 
@@ -38,7 +41,10 @@ def main(only=None):
         if only and script not in only:
             continue
         inputs = inputs_for(script, c['B'], c['seed'])
-        r = RH.run_reference(script, c['B'], c['seed'], inputs, dim=c['dim'])
+        if script == 'lsun128':
+            r = RH.run_reference(script, c['B'], c['seed'], inputs, width=1.0 / c['dim'])
+        else:
+            r = RH.run_reference(script, c['B'], c['seed'], inputs, dim=c['dim'])
         blob = {'meta.B': np.int64(c['B']), 'meta.dim': np.int64(c['dim']), 'meta.seed': np.int64(c['seed'])}
         for i, a in enumerate(inputs):
             blob['input.%d' % i] = a

@@ -14,6 +14,7 @@ SCRIPTS = {
     'cifar': ('ctgan_b200.gan_cifar', 'oracle.ct_gan_cifar'),
     'resnet': ('ctgan_b200.gan_cifar_resnet', 'oracle.ct_gan_cifar_resnet'),
     '64x64': ('ctgan_b200.gan_64x64', 'oracle.ct_gan_64x64'),
+    'lsun128': ('ctgan_b200.gan_lsun128', 'oracle.wgan_lsun128'),      # N4, second half (LS/wgan_LSUN_Bedrooms128.py)
 }
 
 
@@ -47,6 +48,8 @@ def make_inputs(script, B, seed):
         return (torch.from_numpy(rs.randint(0, 256, (B, 3072)).astype('int32')),)
     if script == '64x64':
         return (torch.from_numpy(rs.randint(0, 256, (B, 3, 64, 64)).astype('int32')),)
+    if script == 'lsun128':
+        return (torch.from_numpy(rs.randint(0, 256, (B, 3, 128, 128)).astype('int32')),)
     return (torch.from_numpy(rs.randint(0, 256, (B, 3072)).astype('int32')),
             torch.from_numpy(rs.randint(0, 10, (B,)).astype('int32')))
 
@@ -89,7 +92,7 @@ def perturb_params(tr, om, seed=3, scale=0.05):
 
 def _fix_tape(script, tape, B):
     tape = dict(tape)
-    if script == 'resnet':
+    if script in ('resnet', 'lsun128'):
         if 'dequant' in tape:
             tape['dequant'] = tape['dequant'].cpu() * (1.0 / 128)     # kernel applies noise_hi * u
         for k in list(tape):

@@ -14,10 +14,12 @@ from tests import parity
 from tests.test_oracle_vs_reference import load_golden
 
 pytestmark = pytest.mark.gpu
-DIM_NAMES = {'mnist': ['DIM'], 'cifar': ['DIM'], 'resnet': ['DIM_G', 'DIM_D']}
+DIM_NAMES = {'mnist': ['DIM'], 'cifar': ['DIM'], 'resnet': ['DIM_G', 'DIM_D'], '64x64': ['DIM']}
+# (LS/wgan_LSUN_Bedrooms128.py: tests/test_lsun128_gpu.py against tests/golden/lsun128q.npz -- the small lsun128.npz fixture that pins
+# the oracle has 2-channel layers, below the kernels' 4-channel granularity)
 
 
-@pytest.mark.parametrize('script', ['mnist', 'cifar', 'resnet'])
+@pytest.mark.parametrize('script', ['mnist', 'cifar', 'resnet', '64x64'])
 def test_product_matches_reference_golden(script):
     if not torch.cuda.is_available():
         pytest.skip('no CUDA device')
@@ -42,7 +44,8 @@ def test_product_matches_reference_golden(script):
         res = tr.critic_forward_backward(*inputs)
         cost = float(res['out'][0])
         assert abs(cost - float(ref['disc_cost'])) <= 1e-3 * max(1.0, abs(float(ref['disc_cost']))), (cost, float(ref['disc_cost']))
-        assert parity.rel_err(res['gradients'], torch.from_numpy(ref['gp_gradients'])) < 1e-3
+        gp_rows = len(ref['gp_gradients'])       # 64x64: the reference's `gradients` is the LAST tower's (TG/CT_gan_64x64.py:505)
+        assert parity.rel_err(res['gradients'][-gp_rows:], torch.from_numpy(ref['gp_gradients'])) < 1e-3
         floor = 1e-4 * max(float(np.linalg.norm(v)) for v in ref['disc_grads'].values())
         for n, q in tr.disc_opt.params.items():
             assert parity.rel_err(q.grad, torch.from_numpy(ref['disc_grads'][n]), floor) < 1e-3, n
@@ -54,7 +57,8 @@ def test_product_matches_reference_golden(script):
         floor = 1e-4 * max(float(np.linalg.norm(v)) for v in ref['gen_grads'].values())
         for n, q in tr.gen_opt.params.items():
             if n in ref['gen_grads']:
-                assert parity.rel_err(q.grad, torch.from_numpy(ref['gen_grads'][n]), floor) < 2e-3, n
+                # 64x64 at DIM 4: 4-element tensors, one ReLU tie flip moves them by a few 1e-3
+                assert parity.rel_err(q.grad, torch.from_numpy(ref['gen_grads'][n]), floor) < (5e-3 if script == '64x64' else 2e-3), n
     finally:
         for k, v in saved.items():
             setattr(prod, k, v)

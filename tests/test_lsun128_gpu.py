@@ -1,0 +1,147 @@
+"""GPU (`-m gpu`) tests of SURVEY.md 8(f) row N4, second half: LS/wgan_LSUN_Bedrooms128.py (ctgan_b200/gan_lsun128.py).
+One critic step and one generator step through the C ABI against the oracle (pinned to the reference's own code,
+tests/test_oracle_vs_reference.py) at a quarter of the reference's widths, on the fp32 and BF16 paths, and the full-width model
+(128..1024 channels: the tcgen05 routes incl. the stride-2 3x3 convs through space-to-depth) cross-checked between the two paths."""
+import numpy as np
+import pytest
+import torch
+
+from tests import parity
+
+pytestmark = pytest.mark.gpu
+
+
+def _need_gpu():
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+
+
+@pytest.mark.parametrize('path', ['fp32', 'bf16'])
+def test_lsun128_step_parity(path):
+    _need_gpu()
+    dtype = torch.float32 if path == 'fp32' else torch.bfloat16
+    B = 4 if path == 'fp32' else 8         # BF16: 4 samples per device for the generator's batch-norm statistics (2 amplify the rounding)
+    tr, om = parity.build_pair('lsun128', 'cuda', dtype, B, width=0.25, oracle_dtype=torch.float32 if path == 'bf16' else torch.float64)
+    try:
+        parity.perturb_params(tr, om)
+        floor = 1e-4 if path == 'fp32' else 1e-2
+        rep = parity.critic_parity('lsun128', tr, om, parity.make_inputs('lsun128', B, 11), iteration=1000, conditioned=True, floor_frac=floor)
+        print('critic', parity.format_report(rep, 8))
+        # bar: 1e-3 on the fp32 path.  BF16 (a "next" row, like CT_gan_64x64.py): loss terms 1e-2, the step's gradient and every
+        # tensor 3e-2 -- measured 1.3e-2 / 2.1e-2 at this width and batch (the fakes of a 5-batch-norm BF16 generator with 4
+        # samples per device differ from the oracle's by 2.5e-2, which the critic's gradients inherit)
+        assert parity.worst(rep, 'loss.')[0] < (1e-3 if path == 'fp32' else 1e-2)
+        assert rep['gradall'] < (1e-3 if path == 'fp32' else 3e-2) and rep['gp_gradient'] < (1e-3 if path == 'fp32' else 3e-2)
+        assert parity.worst(rep, 'grad.')[0] < (1e-3 if path == 'fp32' else 3e-2)
+        assert parity.worst(rep, 'adam.')[0] < 2e-3
+        rep = parity.gen_parity('lsun128', tr, om, iteration=1000, conditioned=True, floor_frac=floor)
+        print('gen', parity.format_report(rep, 8))
+        assert parity.worst(rep, 'loss.')[0] < (1e-3 if path == 'fp32' else 1e-2)
+        assert rep['gradall'] < (1e-3 if path == 'fp32' else 3e-2)
+        assert parity.worst(rep, 'grad.')[0] < (1e-3 if path == 'fp32' else 3e-2)
+    finally:
+        import ctgan_b200.gan_lsun128 as G
+        G.WIDTH = 1.0
+
+
+def test_lsun128_full_width_paths_agree():
+    """The reference's widths (critic 128 -> 1024 channels, generator 512 -> 64): the BF16 tensor-core path against the fp32 path
+    from the same weights, noise and dropout draws -- loss terms within 1e-2, the step's parameter gradient within the bound two
+    precisions of a ReLU network allow (tests/test_step_parity_gpu.py, independent mode)."""
+    _need_gpu()
+    import ctgan_b200.gan_lsun128 as G
+    B = 4          # 2 samples per device for the generator's batch-norm statistics
+    x = parity.make_inputs('lsun128', B, 3)[0].cuda()
+    res = {}
+    for dtype in (torch.float32, torch.bfloat16):
+        np.random.seed(5)
+        tr = G.Trainer(device='cuda', seed=9, act_dtype=dtype, batch_size=B)
+        tr.disc_opt.zero_grad()
+        out = tr.critic_forward_backward(x)['out']
+        tr.gen_opt.zero_grad()
+        cost = tr.gen_forward_backward()['cost']
+        torch.cuda.synchronize()
+        res[dtype] = (out[:4].clone(), tr.disc_opt.flat_g.clone(), cost.clone(), tr.gen_opt.flat_g.clone())
+        assert torch.isfinite(res[dtype][1]).all() and torch.isfinite(res[dtype][3]).all()
+    a, b = res[torch.bfloat16], res[torch.float32]
+    rel = lambda p, q: float((p.double() - q.double()).norm() / q.double().norm().clamp_min(1e-30))
+    scale = max(1.0, float(b[0][0].abs()))
+    assert float((a[0] - b[0]).abs().max()) < 2e-2 * scale, (a[0].tolist(), b[0].tolist())
+    assert abs(float(a[2]) - float(b[2])) < 2e-2 * max(1.0, abs(float(b[2])))
+    # generator: batch-norm statistics over 2 samples x 16 pixels at the first block amplify the BF16 rounding
+    assert rel(a[1], b[1]) < 0.2 and rel(a[3], b[3]) < 0.5, (rel(a[1], b[1]), rel(a[3], b[3]))
+
+
+GOLD_TOL = {'fp32': (1e-3, 5e-3, 1e-2), 'bf16': (1e-2, 0.2, 0.3)}    # loss terms, sampled gradient / GP gradient, one tensor's norm
+
+
+@pytest.mark.parametrize('path', ['fp32', 'bf16'])
+def test_lsun128_product_matches_reference_golden(path):
+    """tests/golden/lsun128q.npz (tests/golden/make_golden_full.py lsun128q): one critic and one generator step of
+    LS/wgan_LSUN_Bedrooms128.py at a quarter of its widths (critic 32 -> 256 channels: tensor-core routes from 64 up), batch 4,
+    evaluated by THE REFERENCE'S OWN CODE in float64 -- compared directly, no oracle and no activation patterns handed over, so
+    the gradient bounds are those of two precisions of a ReLU network (tests/test_golden_gpu.py, FULL_TOL)."""
+    _need_gpu()
+    import os
+    from tests.golden.det_params import det_param
+    import ctgan_b200.gan_lsun128 as G
+    import ctgan_b200.tflib as lib
+    import ctgan_b200.kernels as K
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'lsun128q.npz'))
+    tapes = {'disc': {}, 'gen': {}}
+    for k in z.files:
+        for kind in ('disc', 'gen'):
+            if k.startswith('tape_%s.' % kind):
+                tapes[kind][k[len('tape_%s.' % kind):]] = torch.from_numpy(z[k])
+            elif k.startswith('keepbits_%s.' % kind):
+                tag = k[len('keepbits_%s.' % kind):]
+                shape = tuple(int(v) for v in z['keepshape_%s.%s' % (kind, tag)])
+                bits = np.unpackbits(z[k])[:int(np.prod(shape))].reshape(shape).astype(bool)
+                tapes[kind][tag] = torch.from_numpy(np.where(bits, np.float32(0.999), np.float32(0.0)))   # floor(keep + u)
+    B, seed, stride = int(z['meta.B']), int(z['meta.seed']), int(z['meta.stride'])
+    tol_loss, tol_all, tol_one = GOLD_TOL[path]
+    dtype = torch.float32 if path == 'fp32' else torch.bfloat16
+    try:
+        np.random.seed(0)
+        tr = G.Trainer(device='cuda', seed=1, act_dtype=dtype, batch_size=B, width=1.0 / int(z['meta.dim']))
+        with torch.no_grad():
+            for n, p in lib._params.items():
+                p.copy_(torch.from_numpy(det_param(n, p.detach().cpu().numpy(), seed)).to(p.device))
+        K.invalidate_weight_cache(tr.gen_opt._ptrs | tr.disc_opt._ptrs)
+        tr.gen_opt.refresh_packs(); tr.disc_opt.refresh_packs()
+        x = torch.from_numpy(z['input.0'].astype('int32')).cuda()
+
+        def compare(opt, kind, cost, ref_cost):
+            assert abs(cost - ref_cost) <= tol_loss * max(1.0, abs(ref_cost)), (kind, cost, ref_cost)
+            num = den = 0.0
+            floor = 1e-2 * max(float(z['gnorm_%s.%s' % (kind, n)]) for n in opt.params if 'gnorm_%s.%s' % (kind, n) in z.files)
+            for n, q in opt.params.items():
+                if 'gsample_%s.%s' % (kind, n) not in z.files:
+                    continue
+                got = q.grad.detach().double().cpu().reshape(-1)
+                want = torch.from_numpy(z['gsample_%s.%s' % (kind, n)]).double()
+                sel = got if want.numel() == got.numel() else got[::stride]
+                num += float(((sel - want) ** 2).sum()); den += float((want ** 2).sum())
+                gn = float(z['gnorm_%s.%s' % (kind, n)])
+                assert abs(float(got.norm()) - gn) <= tol_one * max(gn, floor), (kind, n, float(got.norm()), gn)
+            print('%s/%s: cost %.6f (ref %.6f)  sampled gradient %.2e' % (kind, path, cost, ref_cost, (num / den) ** 0.5))
+            # BF16 generator: batch-norm statistics over 2 samples per device amplify the rounding (measured 0.25; critic 0.10)
+            assert (num / den) ** 0.5 < (2 * tol_all if (kind == 'gen' and path == 'bf16') else tol_all), (kind, (num / den) ** 0.5)
+
+        tr.rng.replay = tapes['disc']
+        tr.disc_opt.zero_grad()
+        res = tr.critic_forward_backward(x)
+        out = res['out'].cpu()
+        assert abs(float(out[2]) - float(z['CT_'])) <= tol_loss * max(1.0, abs(float(z['CT_'])))
+        assert abs(10.0 * float(out[3]) - float(z['gradient_penalty'])) <= tol_loss * max(1.0, abs(float(z['gradient_penalty'])))
+        gp = res['gradients'].detach().double().cpu().reshape(-1)
+        want = torch.from_numpy(z['gp_gradients_sample']).double()
+        assert float((gp[::stride] - want).norm() / want.norm()) < tol_all
+        assert abs(float(gp.norm()) - float(z['gp_gradients_norm'])) < tol_all * float(z['gp_gradients_norm'])
+        compare(tr.disc_opt, 'disc', float(out[0]), float(z['disc_cost']))
+        tr.rng.replay = tapes['gen']
+        tr.gen_opt.zero_grad()
+        res = tr.gen_forward_backward()
+        compare(tr.gen_opt, 'gen', float(res['cost']), float(z['gen_cost']))
+    finally:
+        G.WIDTH = 1.0

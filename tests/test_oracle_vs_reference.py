@@ -18,15 +18,17 @@ import numpy as np
 import pytest
 import torch
 
-from oracle import ct_gan_mnist, ct_gan_cifar, ct_gan_cifar_resnet, ct_gan_64x64, ref_harness
+from oracle import ct_gan_mnist, ct_gan_cifar, ct_gan_cifar_resnet, ct_gan_64x64, wgan_lsun128, ref_harness
 from oracle.rand import ReplayRandom
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
-MODS = {'mnist': ct_gan_mnist, 'cifar': ct_gan_cifar, 'resnet': ct_gan_cifar_resnet, '64x64': ct_gan_64x64}
+MODS = {'mnist': ct_gan_mnist, 'cifar': ct_gan_cifar, 'resnet': ct_gan_cifar_resnet, '64x64': ct_gan_64x64, 'lsun128': wgan_lsun128}
 
 
 def _model(script, B, dim):
-    if script == 'resnet':
+    if script == 'lsun128':                      # dim = the divisor of the reference's widths
+        m = MODS[script].Model(dtype=torch.float64, batch_size=B, width=1.0 / dim)
+    elif script == 'resnet':
         m = MODS[script].Model(dtype=torch.float64, batch_size=B, dim_g=dim, dim_d=dim)
     else:
         m = MODS[script].Model(dtype=torch.float64, batch_size=B, dim=dim)
@@ -77,7 +79,7 @@ def load_golden(script):
                 inputs=inputs, tape_disc=pick('tape_disc.'), tape_gen=pick('tape_gen.'), ref=ref)
 
 
-@pytest.mark.parametrize('script', ['mnist', 'cifar', 'resnet', '64x64'])
+@pytest.mark.parametrize('script', ['mnist', 'cifar', 'resnet', '64x64', 'lsun128'])
 def test_oracle_matches_golden(script):
     g = load_golden(script)
     m = _model(script, g['B'], g['dim'])
@@ -85,23 +87,24 @@ def test_oracle_matches_golden(script):
 
 
 @pytest.mark.skipif(not ref_harness.available(), reason='/root/reference not present (GPU box)')
-@pytest.mark.parametrize('script,B', [('mnist', 5), ('cifar', 3), ('resnet', 2), ('64x64', 2)])
+@pytest.mark.parametrize('script,B', [('mnist', 5), ('cifar', 3), ('resnet', 2), ('64x64', 2), ('lsun128', 2)])
 def test_oracle_matches_live_reference(script, B):
     from tests.golden.make_golden import inputs_for
     inputs = inputs_for(script, B, 77)
-    r = ref_harness.run_reference(script, B, 77, inputs)                  # the scripts' real widths
-    dim = {'mnist': 64, 'cifar': 128, 'resnet': 128, '64x64': 64}[script]
+    # the scripts' real widths (the 128x128 LSUN model at 1/4 of them: fp64 on CPU)
+    r = ref_harness.run_reference(script, B, 77, inputs, **(dict(width=0.25) if script == 'lsun128' else {}))
+    dim = {'mnist': 64, 'cifar': 128, 'resnet': 128, '64x64': 64, 'lsun128': 4}[script]
     m = _model(script, B, dim)
     ref = dict(disc_cost=r['disc_cost'], gen_cost=r['gen_cost'], gp_gradients=r['gp_gradients'],
                disc_grads=r['disc_grads'], gen_grads={k: v for k, v in r['gen_grads'].items() if v is not None})
     _compare(script, m, r['params'], inputs, r['tape_disc'], r['tape_gen'], ref, tol=1e-9)
     # parameter counts the survey derived from the reference
     count = lambda sel: sum(int(np.prod(p.shape)) for n, p in r['params'].items() if sel in n and r['trainable'][n])
-    expect = {'mnist': (1030145, 1554177), 'cifar': (4114689, 5179907), 'resnet': (1055115, 1218307), '64x64': None}[script]
+    expect = {'mnist': (1030145, 1554177), 'cifar': (4114689, 5179907), 'resnet': (1055115, 1218307), '64x64': None, 'lsun128': None}[script]
     if expect is not None:
         assert (count('Discriminator'), count('Generator')) == expect
     else:
-        print('64x64 parameter counts: D %d, G %d' % (count('Discriminator'), count('Generator')))
+        print('%s parameter counts: D %d, G %d' % (script, count('Discriminator'), count('Generator')))
 
 
 @pytest.mark.skipif(not ref_harness.available(), reason='/root/reference not present (GPU box)')
