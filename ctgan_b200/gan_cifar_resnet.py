@@ -425,9 +425,10 @@ class Trainer:
                     fake_data=None):
         self.disc_opt.zero_grad()
         res = self.critic_forward_backward(all_real_data_int, all_real_labels, with_metrics, fake_data=fake_data)
+        self.rng.end_step(side=True)                  # the Philox counter advances next to the optimizer kernels
         world = self.disc_opt.all_reduce()
         self.disc_opt.step(self.lr(iteration), world, use_device_lr=use_device_lr)
-        self.rng.end_step()
+        K.join_side()
         return res
 
     # ---------------------------------------------------------------- generator (gen_train_op, :314-330,335,337)
@@ -487,7 +488,8 @@ class Trainer:
     def gen_step(self, iteration=0, use_device_lr=False):
         self.gen_opt.zero_grad()
         res = self.gen_forward_backward()
+        self.rng.end_step(side=True)
         world = self.gen_opt.all_reduce()
         self.gen_opt.step(self.lr(iteration), world, use_device_lr=use_device_lr)
-        self.rng.end_step()
+        K.join_side()
         return res

@@ -34,8 +34,9 @@ class _Step:
         def whole():
             opt.zero_grad()
             out = fwd_bwd()
+            rng.end_step(side=True)               # the Philox counter advances on the side stream, next to the optimizer kernels
             opt.step(None, 1, use_device_lr=True)
-            rng.end_step()
+            K.join_side()
             return out
 
         def part_a():

@@ -50,10 +50,16 @@ class DeviceRandom:
         self.offset += (int(n) + 3) // 4 * 4        # keep every slice 4-aligned (vectorised Philox)
         return off
 
-    def end_step(self):
-        """Graph-safe mode: fold the offsets consumed by this step into the device counter."""
+    def end_step(self, side=False):
+        """Graph-safe mode: fold the offsets consumed by this step into the device counter.
+        side: launch the counter update on the side stream (the caller joins it: K.join_side()) -- nothing of the current
+        step reads the counter any more once its backward pass is queued, so it overlaps the optimizer kernels."""
         if self.dyn is not None and self.offset:
-            K.counter_add(self.dyn, self.offset)
+            n, dyn = self.offset, self.dyn
+            if side:
+                K.on_side(lambda: K.counter_add(dyn, n), dyn)
+            else:
+                K.counter_add(dyn, n)
             self.offset = 0
 
     def begin_recording(self):
