@@ -85,8 +85,16 @@ class frozen:
         return False
 
 
-def _wants(p):
-    return not _skip_param_grads and p.data_ptr() not in _frozen_ptrs
+def _wants(p, ptr=None):
+    """ptr: the parameter a derived operand stands for (derived_from), recorded by the forward pass."""
+    return not _skip_param_grads and (ptr if ptr is not None else p.data_ptr()) not in _frozen_ptrs
+
+
+def derived_from(t, param):
+    """Mark t (a differentiable re-ordering of `param`, e.g. the critic head's rows in NHWC order) so that frozen(params)
+    also skips the gradient of t in the layer that consumes it."""
+    t._ctgan_src_ptr = param.data_ptr()
+    return t
 
 
 def _direct(p):
@@ -178,6 +186,7 @@ class ConvF(Function):
         #          x <= 0); the producer is then built with relu_bwd_fused=True and skips its own mask multiply
         ctx.in_relu, ctx.relu_bwd_fused = in_relu, relu_bwd_fused
         ctx.g = g
+        ctx.w_ptr = getattr(w, '_ctgan_src_ptr', None)
         ctx.save_for_backward(x, w)
         ctx.has_bias = b is not None
         ctx.bias = b
@@ -225,7 +234,7 @@ class ConvF(Function):
         dycol = K.thin_col(gy, ctx.g, 'dy')          # im2col of a 3-channel gy: shared by dgrad and wgrad
         if ctx.needs_input_grad[0]:
             gx = ConvD.apply(gy, w, ctx.g, x.dtype, dycol, x.detach() if ctx.in_relu else None, ctx.x_s2d)
-        if ctx.needs_input_grad[1] and _wants(w):
+        if ctx.needs_input_grad[1] and _wants(w, ctx.w_ptr):
             if _direct(w):
                 col, g = (ctx.col if ctx.col is not None else dycol), ctx.g
                 _direct_wgrad(x, gy, g, w, col)
@@ -737,6 +746,13 @@ class ToNCHW(Function):
 
 def to_nhwc(x_flat, C, H, W, dtype):
     return ToNHWC.apply(x_flat, C, H, W, dtype)
+
+
+def flat_nhwc(x):
+    """logical [N,C,H,W] NHWC activation -> [N, H*W*C] in its OWN element order: a view, no kernel (cf. to_flat_nchw)."""
+    x = ensure_nhwc(x)
+    N, C, H, W = x.shape
+    return x.permute(0, 2, 3, 1).reshape(N, H * W * C)
 
 
 def to_flat_nchw(x, dtype=None):

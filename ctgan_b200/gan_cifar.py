@@ -27,6 +27,7 @@ IMG_C, IMG_HW = 3, 32
 
 ACT_DTYPE = torch.bfloat16
 RNG = None
+HEAD_NHWC = True     # the critic head reads the last feature map in its own (h, w, c) order (Discriminator below)
 
 
 def LeakyReLU(x, alpha=0.2):
@@ -74,6 +75,14 @@ def Discriminator(inputs):
     output = _conv_lrelu_dropout('Discriminator.1', 3, DIM, output, 0.50, next_cout=2 * DIM)
     output = _conv_lrelu_dropout('Discriminator.2', DIM, 2 * DIM, output, 0.50, next_cout=4 * DIM)
     output = _conv_lrelu_dropout('Discriminator.3', 2 * DIM, 4 * DIM, output, 0.50)
+    if HEAD_NHWC:
+        # D_ (the features of the consistency term, a mean over them: :133) and the head's input stay in the activation's own
+        # (h, w, c) order; the head re-orders its 4*4*4*DIM weights instead (lib.ops.linear.Linear(input_nhwc=...)) -- no
+        # transposition of the activations / their gradients in any of the step's passes
+        output2 = F.flat_nhwc(output)
+        output = lib.ops.linear.Linear('Discriminator.Output', 4 * 4 * 4 * DIM, 1, output2, out_dtype=torch.float32,
+                                       input_nhwc=(4 * DIM, 4, 4))
+        return output.reshape(-1), output2
     output2 = F.to_flat_nchw(output)  # corresponding to D_  (tf.reshape(output, [-1, 4*4*4*DIM]))
     output = lib.ops.linear.Linear('Discriminator.Output', 4 * 4 * 4 * DIM, 1, output2, out_dtype=torch.float32)
     return output.reshape(-1), output2

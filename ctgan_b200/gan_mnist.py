@@ -25,6 +25,7 @@ OUTPUT_DIM = 784  # Number of pixels in MNIST (28*28)
 
 ACT_DTYPE = torch.bfloat16
 RNG = None
+HEAD_NHWC = True     # see gan_cifar.HEAD_NHWC
 
 
 def LeakyReLU(x, alpha=0.2):
@@ -69,6 +70,11 @@ def Discriminator(inputs):
     output = _conv_lrelu_dropout('Discriminator.1', 1, DIM, output, 0.50, next_cout=2 * DIM)  # adding dropout after activators
     output = _conv_lrelu_dropout('Discriminator.2', DIM, 2 * DIM, output, 0.50, next_cout=4 * DIM)
     output = _conv_lrelu_dropout('Discriminator.3', 2 * DIM, 4 * DIM, output, 0.50)
+    if HEAD_NHWC:                       # see gan_cifar.Discriminator
+        output2 = F.flat_nhwc(output)
+        output = lib.ops.linear.Linear('Discriminator.Output', 4 * 4 * 4 * DIM, 1, output2, out_dtype=torch.float32,
+                                       input_nhwc=(4 * DIM, 4, 4))
+        return output.reshape(-1), output2
     output2 = F.to_flat_nchw(output)  # D_
     output = lib.ops.linear.Linear('Discriminator.Output', 4 * 4 * 4 * DIM, 1, output2, out_dtype=torch.float32)  # D
     return output.reshape(-1), output2

@@ -35,10 +35,14 @@ def unset_weights_stdev():
 
 
 def Linear(name, input_dim, output_dim, inputs, biases=True, initialization=None, weightnorm=None, gain=1.,
-           out_dtype=None):
+           out_dtype=None, input_nhwc=None):
     """
     initialization: None, `lecun`, 'glorot', `he`, 'glorot_he', `orthogonal`, `("uniform", range)`
     out_dtype (extension): dtype of the result; the critic heads keep float32 outputs.
+    input_nhwc (extension) = (C, H, W): `inputs` is functional.flat_nhwc(activation) -- the features of a [N, C, H, W] map in
+        (h, w, c) order instead of the (c, h, w) order of tf.reshape(output, [-1, C*H*W]) (TG/CT_gan_cifar.py:97).  The parameter
+        keeps the reference's row order; its K rows are re-ordered on the fly (one layout kernel over K floats, twice
+        differentiable) instead of transposing the batch of activations and, in the backward passes, their gradients.
     """
     def uniform(stdev, size):
         if _weights_stdev is not None:
@@ -80,6 +84,13 @@ def Linear(name, input_dim, output_dim, inputs, biases=True, initialization=None
     weight = lib.param(name + '.W', weight_values)
     b = lib.param(name + '.b', np.zeros((output_dim,), dtype='float32')) if biases else None
 
+    if input_nhwc is not None:
+        C, H, W = input_nhwc
+        if output_dim != 1 or inputs.dim() != 2 or C * H * W != input_dim:
+            raise Exception('Unsupported configuration')
+        import torch
+        weight = F.derived_from(
+            F.to_nhwc(weight.reshape(1, input_dim), C, H, W, torch.float32).permute(0, 2, 3, 1).reshape(input_dim, 1), weight)
     if inputs.dim() == 2:
         return F.linear(inputs, weight, b, out_dtype=out_dtype)
     lead = inputs.shape[:-1]
