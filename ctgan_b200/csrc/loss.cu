@@ -38,24 +38,33 @@ ct_gp_per_sample_kernel(ctgan_loss_desc d, const float* __restrict__ d_real, con
                         float* __restrict__ per_sample) {
     ctgan::pdl_entry();
     __shared__ float sh[32];
+    // The two halves of the loss can be evaluated separately (the gradient-penalty term shares nothing with the critic
+    // outputs of the stacked pass): grad == nullptr -> no penalty term (slope recorded as 1), d_real == nullptr -> penalty only.
     const int i = blockIdx.x;
     float sq = 0.f;
-    for (int f = threadIdx.x; f < d.F; f += LOSS_T) {
-        float a = ld_act(f1, (int64_t)i * d.F + f, d.feat_dtype) - ld_act(f2, (int64_t)i * d.F + f, d.feat_dtype);
-        sq += a * a;
+    if (d_real) {
+        for (int f = threadIdx.x; f < d.F; f += LOSS_T) {
+            float a = ld_act(f1, (int64_t)i * d.F + f, d.feat_dtype) - ld_act(f2, (int64_t)i * d.F + f, d.feat_dtype);
+            sq += a * a;
+        }
     }
     sq = block_sum(sq, sh);
     float g2 = 0.f;
-    for (int p = threadIdx.x; p < d.P; p += LOSS_T) {
-        float a = grad[(int64_t)i * d.P + p];
-        g2 += a * a;
+    if (grad) {
+        for (int p = threadIdx.x; p < d.P; p += LOSS_T) {
+            float a = grad[(int64_t)i * d.P + p];
+            g2 += a * a;
+        }
     }
     g2 = block_sum(g2, sh);
     if (threadIdx.x == 0) {
-        float diff = d_real[i] - d_real2[i];
-        float ct = d.lambda2 * diff * diff + d.lambda2 * 0.1f * (sq / (float)d.F);
-        per_sample[i * 4 + 0] = ct - d.factor_m;
-        per_sample[i * 4 + 1] = sqrtf(g2);
+        float ct = -1.f;                                   // inactive under max(CT - M, 0)
+        if (d_real) {
+            float diff = d_real[i] - d_real2[i];
+            ct = d.lambda2 * diff * diff + d.lambda2 * 0.1f * (sq / (float)d.F) - d.factor_m;
+        }
+        per_sample[i * 4 + 0] = ct;
+        per_sample[i * 4 + 1] = grad ? sqrtf(g2) : 1.f;
         float ce = 0.f;
         if (logits) {
             const float* lg = logits + (int64_t)i * d.n_classes;
@@ -77,14 +86,14 @@ ct_gp_tail_kernel(ctgan_loss_desc d, const float* __restrict__ d_real, const flo
     __shared__ float sh[32];
     float sr = 0.f, sf = 0.f, sct = 0.f, sgp = 0.f, sce = 0.f;
     for (int i = threadIdx.x; i < d.B; i += LOSS_T) {
-        sr += d_real[i];
+        if (d_real) sr += d_real[i];
         float c = per_sample[i * 4 + 0];
         sct += fmaxf(c, 0.f);
         float s = per_sample[i * 4 + 1] - 1.f;
         sgp += s * s;
         sce += per_sample[i * 4 + 2];
     }
-    for (int i = threadIdx.x; i < d.NF; i += LOSS_T) sf += d_fake[i];
+    if (d_fake) for (int i = threadIdx.x; i < d.NF; i += LOSS_T) sf += d_fake[i];
     sr = block_sum(sr, sh); sf = block_sum(sf, sh); sct = block_sum(sct, sh);
     sgp = block_sum(sgp, sh); sce = block_sum(sce, sh);
     if (threadIdx.x == 0) {
@@ -113,28 +122,32 @@ ct_gp_bwd_kernel(ctgan_loss_desc d, const float* __restrict__ gcost,
     // tf.maximum(CT-M, 0*(CT-M)): the gradient flows to the first argument where it is >= the second
     const float active = per_sample[i * 4 + 0] >= 0.f ? 1.f : 0.f;
     const float gct = g * active * invB;
-    if (threadIdx.x == 0) {
-        float diff = d_real[i] - d_real2[i];
-        float t = gct * 2.f * d.lambda2 * diff;
-        g_d_real[i] = -g * invB + t;
-        g_d_real2[i] = -t;
-    }
-    for (int j = i * LOSS_T + threadIdx.x; j < d.NF; j += gridDim.x * LOSS_T) g_d_fake[j] = g / (float)d.NF;
-    const float cf = gct * 0.1f * d.lambda2 * 2.f / (float)d.F;
-    for (int f = threadIdx.x; f < d.F; f += LOSS_T) {
-        int64_t o = (int64_t)i * d.F + f;
-        float a = ld_act(f1, o, d.feat_dtype) - ld_act(f2, o, d.feat_dtype);
-        st_act(g_f1, o, d.feat_dtype, cf * a);
-        st_act(g_f2, o, d.feat_dtype, -cf * a);
+    if (d_real) {
+        if (threadIdx.x == 0) {
+            float diff = d_real[i] - d_real2[i];
+            float t = gct * 2.f * d.lambda2 * diff;
+            g_d_real[i] = -g * invB + t;
+            g_d_real2[i] = -t;
+        }
+        for (int j = i * LOSS_T + threadIdx.x; j < d.NF; j += gridDim.x * LOSS_T) g_d_fake[j] = g / (float)d.NF;
+        const float cf = gct * 0.1f * d.lambda2 * 2.f / (float)d.F;
+        for (int f = threadIdx.x; f < d.F; f += LOSS_T) {
+            int64_t o = (int64_t)i * d.F + f;
+            float a = ld_act(f1, o, d.feat_dtype) - ld_act(f2, o, d.feat_dtype);
+            st_act(g_f1, o, d.feat_dtype, cf * a);
+            st_act(g_f2, o, d.feat_dtype, -cf * a);
+        }
     }
     // d/dgrad of lambda * mean((s-1)^2), s = ||grad||: lambda * 2 (s-1)/s * grad / B.
     // The reference has no epsilon under the sqrt (TG/CT_gan_cifar.py:148), so s == 0 is NaN there;
     // here a zero slope yields a zero cotangent instead of poisoning the step.
     const float s = per_sample[i * 4 + 1];
     const float cg = s > 0.f ? g * d.lambda_gp * invB * 2.f * (s - 1.f) / s : 0.f;
-    for (int p = threadIdx.x; p < d.P; p += LOSS_T) {
-        int64_t o = (int64_t)i * d.P + p;
-        g_grad[o] = cg * grad[o];
+    if (grad) {
+        for (int p = threadIdx.x; p < d.P; p += LOSS_T) {
+            int64_t o = (int64_t)i * d.P + p;
+            g_grad[o] = cg * grad[o];
+        }
     }
     if (logits && threadIdx.x < d.n_classes) {
         const float* lg = logits + (int64_t)i * d.n_classes;
@@ -214,7 +227,9 @@ extern "C" int ctgan_ct_gp_loss_fwd(const ctgan_loss_desc* d, const float* d_rea
                                     const float* logits, const int32_t* labels,
                                     float* out, float* per_sample, void* stream) {
     if (int r = check_loss_desc(d)) return r;
-    CTGAN_REQUIRE(d_real && d_real2 && d_fake && f1 && f2 && grad && out && per_sample, CTGAN_ERR_BAD_DESC, "loss_fwd: null pointer");
+    CTGAN_REQUIRE(out && per_sample && (grad || d_real) && (!d_real || (d_real2 && d_fake && f1 && f2)), CTGAN_ERR_BAD_DESC,
+                  "loss_fwd: null pointer (grad may be null: no penalty term; d_real.. may be null together: penalty only)");
+    CTGAN_REQUIRE(d_real || !logits, CTGAN_ERR_BAD_DESC, "loss_fwd: the penalty-only form takes no logits");
     CTGAN_REQUIRE(!logits || (labels && d->n_classes > 0), CTGAN_ERR_BAD_DESC, "loss_fwd: logits need labels and n_classes");
     cudaStream_t st = as_stream(stream);
     CTGAN_LAUNCH((ct_gp_per_sample_kernel), d->B, LOSS_T, 0, st, *d, d_real, d_real2, f1, f2, grad, logits, labels, per_sample);
@@ -231,8 +246,10 @@ extern "C" int ctgan_ct_gp_loss_bwd(const ctgan_loss_desc* d, const float* gcost
                                     float* g_d_real, float* g_d_real2, float* g_d_fake, void* g_f1, void* g_f2,
                                     float* g_grad, float* g_logits, void* stream) {
     if (int r = check_loss_desc(d)) return r;
-    CTGAN_REQUIRE(gcost && d_real && d_real2 && f1 && f2 && grad && per_sample && g_d_real && g_d_real2 && g_d_fake &&
-                  g_f1 && g_f2 && g_grad, CTGAN_ERR_BAD_DESC, "loss_bwd: null pointer");
+    CTGAN_REQUIRE(gcost && per_sample && (grad || d_real) && (!grad || g_grad) &&
+                  (!d_real || (d_real2 && f1 && f2 && g_d_real && g_d_real2 && g_d_fake && g_f1 && g_f2)),
+                  CTGAN_ERR_BAD_DESC, "loss_bwd: null pointer");
+    CTGAN_REQUIRE(d_real || !logits, CTGAN_ERR_BAD_DESC, "loss_bwd: the penalty-only form takes no logits");
     CTGAN_REQUIRE(!logits || (labels && g_logits && d->n_classes > 0), CTGAN_ERR_BAD_DESC, "loss_bwd: logits need labels/g_logits");
     CTGAN_LAUNCH((ct_gp_bwd_kernel), d->B, LOSS_T, 0, as_stream(stream), *d, gcost, d_real, d_real2, f1, f2, grad, logits, labels,
                                                             per_sample, g_d_real, g_d_real2, g_d_fake, g_f1, g_f2,

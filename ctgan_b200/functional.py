@@ -976,13 +976,14 @@ class CTGPLossStacked(Function):
         f1, f2 = f_all[r0:r1], f_all[s0:s1]
         lg = la[r0:r1] if la is not None else None
         B, F_ = f1.shape
-        desc = LossDesc(B, d_fake.shape[0], F_, grad.shape[1], 0 if lg is None else lg.shape[1],
+        # grad None: the loss without its gradient-penalty term (GPLoss evaluates that one on its own stream branch)
+        desc = LossDesc(B, d_fake.shape[0], F_, grad.shape[1] if grad is not None else 1, 0 if lg is None else lg.shape[1],
                         BF16 if f1.dtype == torch.bfloat16 else F32,
                         hp['lambda_gp'], hp['lambda2'], hp['factor_m'], hp.get('acgan_scale', 0.0))
-        grad = grad.contiguous()
+        grad = grad.contiguous() if grad is not None else None
         out, per_sample = K.ct_gp_loss_fwd(desc, d_real, d_real2, d_fake, f1, f2, grad, lg, labels)
-        ctx.desc, ctx.labels, ctx.rows = desc, labels, rows
-        ctx.save_for_backward(d_all, f_all, grad, per_sample, *([la] if la is not None else []))
+        ctx.desc, ctx.labels, ctx.rows, ctx.has_grad = desc, labels, rows, grad is not None
+        ctx.save_for_backward(d_all, f_all, grad if grad is not None else per_sample, per_sample, *([la] if la is not None else []))
         return out
 
     @staticmethod
@@ -990,6 +991,8 @@ class CTGPLossStacked(Function):
     def backward(ctx, gout):
         saved = ctx.saved_tensors
         d_all, f_all, grad, per_sample = saved[:4]
+        if not ctx.has_grad:
+            grad = None
         la = saved[4] if len(saved) > 4 else None
         (r0, r1), (s0, s1), (k0, k1) = ctx.rows['real'], ctx.rows['real2'], ctx.rows['fake']
         covered = (r1 - r0) + (s1 - s0) + (k1 - k0) == d_all.shape[0]
@@ -1000,6 +1003,28 @@ class CTGPLossStacked(Function):
         g = K.ct_gp_loss_bwd(ctx.desc, gout[0:1].contiguous(), d_all[r0:r1], d_all[s0:s1], f_all[r0:r1], f_all[s0:s1], grad,
                              la[r0:r1] if la is not None else None, ctx.labels, per_sample, outs=outs)
         return g_d, g_f, g[5], g_l, None, None, None
+
+
+class GPLoss(Function):
+    """lambda * mean((||grad_i||_2 - 1)^2): the gradient-penalty term on its own (TG/CT_gan_cifar_resnet.py:284-286), for the
+    schedule that differentiates it on the penalty's stream branch while the stacked pass runs its own backward.
+    Returns float[8] {lambda*gp, 0, 0, gp, 0, ...}; only element 0 is differentiable."""
+
+    @staticmethod
+    def forward(ctx, grad, hp):
+        grad = grad.contiguous()
+        desc = LossDesc(grad.shape[0], 1, 1, grad.shape[1], 0, F32, hp['lambda_gp'], hp['lambda2'], hp['factor_m'], 0.0)
+        out, per_sample = K.ct_gp_loss_fwd(desc, None, None, None, None, None, grad, None, None)
+        ctx.desc = desc
+        ctx.save_for_backward(grad, per_sample)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gout):
+        grad, per_sample = ctx.saved_tensors
+        g = K.ct_gp_loss_bwd(ctx.desc, gout[0:1].contiguous(), None, None, None, None, grad, None, None, per_sample)
+        return g[5], None
 
 
 class MeanLoss(Function):

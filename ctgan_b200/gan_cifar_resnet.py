@@ -391,6 +391,15 @@ class Trainer:
         with (K.branch(fork) if K.config.branch_stacked else contextlib.nullcontext()):
             disc_all, disc_all_2, disc_all_acgan = Discriminator(stacked, stacked_labels, 0.8, 0.5, 0.5)
         RNG.end_stack()
+        use_logits = CONDITIONAL and ACGAN
+        rows = dict(real=(0, B), fake=(B, 2 * B), real2=(2 * B, 3 * B))
+        decoupled = K.config.decouple_gp and not K.config.branch_stacked
+        if decoupled:
+            # the WGAN, CT and ACGAN terms depend on the stacked pass only: its backward starts now, on this stream, while the
+            # penalty branch is still in its forward / first backward (the two halves of the loss: functional.GPLoss)
+            out_a = F.CTGPLossStacked.apply(disc_all, disc_all_2, None, disc_all_acgan if use_logits else None,
+                                            all_real_labels if use_logits else None, self.hp, rows)
+            out_a[0].backward(gradient=self._ones_like(out_a[0]), inputs=self.disc_opt.param_list())
         metrics = {}
         if with_metrics and CONDITIONAL and ACGAN:
             with torch.no_grad():
@@ -408,14 +417,18 @@ class Trainer:
             with F.no_param_grads():                  # tf.gradients(..., [interpolates]): d/dx^ only
                 gradients = torch.autograd.grad(d_interp, interpolates, grad_outputs=self._ones_like(d_interp),
                                                 create_graph=True)[0]                               # :284
+            if decoupled:
+                out_b = F.GPLoss.apply(gradients, self.hp)
+                out_b[0].backward(gradient=self._ones_like(out_b[0]), inputs=self.disc_opt.param_list())
         K.join_branch(fork)
-        use_logits = CONDITIONAL and ACGAN
-        # WGAN term and CE use pass ' (rows [0, 2B)), the CT term the real halves of ' and '' (:244-300)
-        out = F.CTGPLossStacked.apply(disc_all, disc_all_2, gradients, disc_all_acgan if use_logits else None,
-                                      all_real_labels if use_logits else None, self.hp,
-                                      dict(real=(0, B), fake=(B, 2 * B), real2=(2 * B, 3 * B)))
-        out[0].backward(gradient=self._ones_like(out[0]), inputs=self.disc_opt.param_list())
-        K.join_branch(fork)
+        if decoupled:
+            out = K.add(out_a.detach(), out_b.detach())        # {cost, wgan, ct, gp, acgan}: the halves fill disjoint terms
+        else:
+            # WGAN term and CE use pass ' (rows [0, 2B)), the CT term the real halves of ' and '' (:244-300)
+            out = F.CTGPLossStacked.apply(disc_all, disc_all_2, gradients, disc_all_acgan if use_logits else None,
+                                          all_real_labels if use_logits else None, self.hp, rows)
+            out[0].backward(gradient=self._ones_like(out[0]), inputs=self.disc_opt.param_list())
+            K.join_branch(fork)
         K.join_side()
         res = dict(out=out.detach(), gradients=gradients.detach(), fake_data=fake_data, real_data=all_real_data)
         res.update(metrics)

@@ -28,6 +28,10 @@ class Config:
     branch_priority = 0      # CUDA stream priority of the branch stream (lower = higher priority): equal priorities measure best
     critic_splitk = False    # cluster split-K inside the two-branch ResNet critic step (see kernels.splitk)
     s2d_embed_wgrad = True   # stride-2 filter gradients: the embedded 3x3 job writes the k x k gradient itself (no scratch + gather)
+    decouple_gp = False      # ResNet critic step: the stacked pass runs its own backward as soon as its half of the loss is known,
+                             # the gradient penalty is differentiated on its stream branch (two backward calls, gan_cifar_resnet.py).
+                             # Measured equal (922-928 vs 919-923 us): the penalty branch's three traversals at batch 64 are the
+                             # critical path either way (profiles/r02_experiments.md); kept as a checked option
     gen_towers = False       # ResNet generator step: the reference's per-device towers as two stream branches instead of one stacked
                              # batch (measured: 1303 us vs 1226 us stacked -- twice the launches, no shorter chain; kept as a checked option)
     gen_splitk = False       # cluster split-K inside the two-tower generator step
@@ -1297,8 +1301,10 @@ def _f32c(t, name):
 
 
 def ct_gp_loss_fwd(desc, d_real, d_real2, d_fake, f1, f2, grad, logits, labels):
-    out = torch.empty(8, dtype=torch.float32, device=d_real.device)
-    per_sample = torch.empty(4 * desc.B, dtype=torch.float32, device=d_real.device)
+    """grad None: no penalty term; d_real .. f2 None: the penalty term only (include/ctgan_sm100.h)."""
+    dev = (d_real if d_real is not None else grad).device
+    out = torch.empty(8, dtype=torch.float32, device=dev)
+    per_sample = torch.empty(4 * desc.B, dtype=torch.float32, device=dev)
     call('ctgan_ct_gp_loss_fwd', ctypes.byref(desc), _p(d_real), _p(d_real2), _p(d_fake), _p(f1), _p(f2), _p(grad),
          _p(logits), _p(labels), _p(out), _p(per_sample), _stream())
     return out, per_sample
@@ -1307,7 +1313,12 @@ def ct_gp_loss_fwd(desc, d_real, d_real2, d_fake, f1, f2, grad, logits, labels):
 def ct_gp_loss_bwd(desc, gcost, d_real, d_real2, f1, f2, grad, logits, labels, per_sample, outs=None):
     """outs: optional (g_real, g_real2, g_fake, g_f1, g_f2, g_logits) contiguous destination views (row ranges of the
     gradients of stacked critic outputs), so that no slice-backward / accumulation kernels are needed."""
-    dev = d_real.device
+    dev = (d_real if d_real is not None else grad).device
+    if d_real is None:                                   # penalty only
+        g_grad = torch.empty_like(grad)
+        call('ctgan_ct_gp_loss_bwd', ctypes.byref(desc), _p(gcost), None, None, None, None, _p(grad), None, None, _p(per_sample),
+             None, None, None, None, None, _p(g_grad), None, _stream())
+        return None, None, None, None, None, g_grad, None
     if outs is not None:
         g_real, g_real2, g_fake, g_f1, g_f2, g_logits = outs
         for t in outs:
@@ -1320,7 +1331,7 @@ def ct_gp_loss_bwd(desc, gcost, d_real, d_real2, f1, f2, grad, logits, labels, p
         g_f1 = torch.empty_like(f1)
         g_f2 = torch.empty_like(f2)
         g_logits = torch.empty_like(logits) if logits is not None else None
-    g_grad = torch.empty_like(grad)
+    g_grad = torch.empty_like(grad) if grad is not None else None
     call('ctgan_ct_gp_loss_bwd', ctypes.byref(desc), _p(gcost), _p(d_real), _p(d_real2), _p(f1), _p(f2), _p(grad),
          _p(logits), _p(labels), _p(per_sample), _p(g_real), _p(g_real2), _p(g_fake), _p(g_f1), _p(g_f2),
          _p(g_grad), _p(g_logits), _stream())

@@ -373,7 +373,10 @@ int ctgan_ln_bwd2_x(const void* c, const void* gy, const void* x, const float* g
  *   cost  = wgan + ct + lambda*gp + acgan_scale*acgan
  * d_* are float; f1,f2 [B,F] have `feat_dtype`; grad [B,P] float; logits [B,10] float.
  * out (float[8]) = {cost, wgan, ct, gp, acgan, 0,0,0}.  per_sample (float [4*B]) keeps
- * {CT_i - M, s_i, 0, 0} for the backward.  One warp-shuffle reduction kernel. */
+ * {CT_i - M, s_i, 0, 0} for the backward.  One warp-shuffle reduction kernel.
+ * The two halves can be evaluated separately (the penalty shares nothing with the critic outputs of the stacked pass, so its
+ * branch of the step need not wait for them): grad == NULL -> no penalty term (gp = 0, g_grad untouched);
+ * d_real == d_real2 == d_fake == f1 == f2 == NULL (and logits NULL) -> cost = lambda*gp only. */
 typedef struct {
     int32_t B, NF, F, P, n_classes, feat_dtype;
     float lambda_gp, lambda2, factor_m, acgan_scale;

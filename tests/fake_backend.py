@@ -374,6 +374,22 @@ def _loss_terms(desc, d_real, d_real2, d_fake, f1, f2, grad, logits, labels):
 
 
 def ct_gp_loss_fwd(desc, d_real, d_real2, d_fake, f1, f2, grad, logits, labels):
+    if d_real is None:                                    # the penalty term only
+        s = torch.sqrt((grad ** 2).sum(1))
+        gp = ((s - 1) ** 2).mean()
+        out = torch.zeros(8)
+        out[0], out[3] = desc.lambda_gp * gp, gp
+        per = torch.zeros(desc.B, 4)
+        per[:, 0], per[:, 1] = -1.0, s
+        return out, per.reshape(-1)
+    if grad is None:                                      # no penalty term: slopes recorded as 1
+        out, per = ct_gp_loss_fwd(desc, d_real, d_real2, d_fake, f1, f2, torch.zeros(desc.B, 1), logits, labels)
+        per = per.reshape(-1, 4).clone()
+        out = out.clone()
+        out[0] = out[0] - desc.lambda_gp * out[3]
+        out[3] = 0.0
+        per[:, 1] = 1.0
+        return out, per.reshape(-1)
     ct_i, s, ce = _loss_terms(desc, d_real, d_real2, d_fake, f1, f2, grad, logits, labels)
     wgan = d_fake.mean() - d_real.mean()
     ct, gp = torch.clamp(ct_i, min=0).mean(), ((s - 1) ** 2).mean()
@@ -395,6 +411,10 @@ def ct_gp_loss_bwd(desc, gcost, d_real, d_real2, f1, f2, grad, logits, labels, p
         return r
     per = per_sample.reshape(-1, 4)
     g, B = gcost[0], desc.B
+    if d_real is None:                                    # the penalty term only
+        s = per[:, 1]
+        cg = torch.where(s > 0, g * desc.lambda_gp / B * 2 * (s - 1) / s, torch.zeros_like(s))
+        return None, None, None, None, None, cg.view(-1, 1) * grad, None
     active = (per[:, 0] >= 0).float()
     gct = g * active / B
     diff = d_real - d_real2
@@ -405,7 +425,7 @@ def ct_gp_loss_bwd(desc, gcost, d_real, d_real2, f1, f2, grad, logits, labels, p
     gf1 = (gct * 0.1 * desc.lambda2 * 2 / desc.F).view(-1, 1) * a
     s = per[:, 1]
     cg = torch.where(s > 0, g * desc.lambda_gp / B * 2 * (s - 1) / s, torch.zeros_like(s))
-    g_grad = cg.view(-1, 1) * grad
+    g_grad = cg.view(-1, 1) * grad if grad is not None else None
     g_logits = None
     if logits is not None:
         p = torch.softmax(logits, 1)

@@ -153,3 +153,23 @@ def test_tower_scopes_draw_the_slices_of_the_stacked_batch(fake_kernels):
     assert a.offset == b.offset
     b.scope('x')
     assert b._tower is None
+
+
+def test_decoupled_penalty_schedule_matches_the_fused_loss(fake_kernels):
+    """kernels.config.decouple_gp: the stacked pass differentiates its half of the critic loss (WGAN + CT + ACGAN) before the
+    gradient-penalty pass has run, the penalty is differentiated by a second backward call -- same loss terms and the same
+    accumulated parameter gradient as one backward pass over the fused loss."""
+    import ctgan_b200.kernels as K
+    from tests import parity
+    res = {}
+    for on in (False, True):
+        K.config.decouple_gp = on
+        try:
+            tr, om = parity.build_pair('resnet', 'cpu', torch.float32, 4)
+            parity.perturb_params(tr, om)
+            rep = parity.critic_parity('resnet', tr, om, parity.make_inputs('resnet', 4, 11), conditioned=True)
+            res[on] = rep
+            assert parity.worst({k: v for k, v in rep.items() if not k.startswith('adam.')})[0] < 5e-4, parity.format_report(rep)
+        finally:
+            K.config.decouple_gp = False
+    assert abs(res[True]['gradall'] - res[False]['gradall']) < 1e-5
