@@ -434,6 +434,20 @@ class Trainer:
         res.update(metrics)
         return res
 
+    def acgan_accuracy(self, all_real_data_int, all_real_labels, fake_data):
+        """disc_acgan_acc / disc_acgan_fake_acc (:297-298, plotted as 'acc_real' / 'acc_fake' :410-411): the critic WITHOUT
+        dropout (keep probabilities 1: no random draws) on the real batch and on `fake_data` (the fakes of a critic step,
+        conditioned on the same labels).  Metrics only -- nothing of the training step depends on it; the loop runs it every
+        `acc_every` iterations instead of inside every critic step as the reference graph does."""
+        B = all_real_data_int.shape[0]
+        with torch.no_grad():
+            both = torch.empty((2 * B, all_real_data_int.shape[1]), dtype=torch.float32, device=all_real_data_int.device)
+            K.prep_real(all_real_data_int, 256., 0., out=both[:B])
+            both[B:].copy_(fake_data)
+            _, _, clean = Discriminator(both, None, 1.0, 1.0, 1.0)
+            pred = clean.argmax(dim=1).to(torch.int32)
+            return (pred[:B] == all_real_labels).float().mean(), (pred[B:] == all_real_labels).float().mean()
+
     def critic_step(self, all_real_data_int, all_real_labels, iteration=0, with_metrics=False, use_device_lr=False,
                     fake_data=None):
         self.disc_opt.zero_grad()

@@ -61,7 +61,7 @@ class Session:
     """One training run: model, graphs, feeder, fixed sample noise."""
 
     def __init__(self, script, data_dir, batch_size=None, n_examples=None, device='cuda', seed=1234, out_dir='.',
-                 act_dtype=torch.bfloat16, use_graphs=True, init_seed=1234, model_kw=None):
+                 act_dtype=torch.bfloat16, use_graphs=True, init_seed=1234, model_kw=None, acc_every=0):
         self.script, self.out_dir = script, out_dir
         self.mod = mod = importlib.import_module('ctgan_b200.' + SCRIPTS[script])
         self.B = batch_size or mod.BATCH_SIZE
@@ -87,6 +87,7 @@ class Session:
         else:
             self._pending = None
         self.iteration = 0
+        self.acc_every, self._last_fakes = acc_every, None
 
     # -- one reference iteration ----------------------------------------------------------------------------------
     def _next_batch(self):
@@ -109,15 +110,26 @@ class Session:
             gt.begin_iteration(torch.cat([b[1] for b in batches]))
         out = None
         for b in batches:
-            out = gt.critic_step(*b) if gt is not None else tr.critic_step(*b, iteration=it)['out']
+            if gt is not None:
+                out = gt.critic_step(*b)
+            else:
+                res = tr.critic_step(*b, iteration=it)
+                out, self._last_fakes = res['out'], res.get('fake_data')
         if self.resnet:
             # names and contents of TG/CT_gan_cifar_resnet.py:406-412: 'wgan' is disc_wgan = Wasserstein term + CT + 10*GP
             # (:295), i.e. the cost without its ACGAN part; out = {cost, wgan term, ct, gp, acgan, ...}.  The two clean-pass
-            # accuracies ('acc_real', 'acc_fake') are not plotted: that metrics-only critic pass is not executed here.
+            # accuracies ('acc_real', 'acc_fake', :410-411) come from a metrics-only critic pass that the training step does not
+            # execute: it runs here every `acc_every` iterations (0 = never) on the last critic batch and its fakes.
             _plot.plot('cost', out[0])
             if self.mod.CONDITIONAL and self.mod.ACGAN:
                 _plot.plot('wgan', out[0] - self.mod.ACGAN_SCALE * out[4])
                 _plot.plot('acgan', out[4])
+                if self.acc_every and it % self.acc_every == 0:
+                    fakes = gt.fake_cur if (gt is not None and gt.pregen_steps) else self._last_fakes
+                    if fakes is not None:
+                        acc_real, acc_fake = tr.acgan_accuracy(batches[-1][0], batches[-1][1], fakes)
+                        _plot.plot('acc_real', acc_real)
+                        _plot.plot('acc_fake', acc_fake)
         else:
             _plot.plot('train disc cost', out[0])
         # graph mode: replays are asynchronous, so host wall time would only measure the enqueue; time the iteration on the
@@ -220,9 +232,11 @@ def main():
     ap.add_argument('--checkpoint-every', type=int, default=None)
     ap.add_argument('--no-graphs', action='store_true')
     ap.add_argument('--resume', default=None, help='checkpoint.npz of an earlier run to continue from')
+    ap.add_argument('--acc-every', type=int, default=0,
+                    help="cifar_resnet: plot 'acc_real' / 'acc_fake' (the reference's metrics-only critic pass) every N iterations; 0 = never")
     a = ap.parse_args()
     train(a.script, a.data_dir, iters=a.iters, out_dir=a.out_dir, batch_size=a.batch_size, n_examples=a.n_examples,
-          checkpoint_every=a.checkpoint_every, use_graphs=not a.no_graphs, resume=a.resume)
+          checkpoint_every=a.checkpoint_every, use_graphs=not a.no_graphs, resume=a.resume, acc_every=a.acc_every)
 
 
 if __name__ == '__main__':

@@ -56,12 +56,14 @@ def test_training_loop_in_graph_mode(tmp_path, script, capsys):
     out = str(tmp_path / 'out')
     try:
         sess = T.train(script, d, iters=3, dev_every=2, out_dir=out, dev_batches=1, batch_size=16, n_examples=160,
-                       checkpoint_every=3)
+                       checkpoint_every=3, acc_every=2)
         torch.cuda.synchronize()
         assert sess.gt is not None and sess.tr.disc_opt.t == 15 and sess.tr.gen_opt.t == 2     # the capture's warm-up steps are undone
         log = pickle.load(open(os.path.join(out, 'log.pkl'), 'rb'))
         name = 'cost' if script == 'cifar_resnet' else 'train disc cost'
         assert sorted(log[name]) == [0, 1, 2] and all(np.isfinite(v) for v in log[name].values())
+        if script == 'cifar_resnet':           # the metrics-only clean pass between graph replays (fakes of the last critic step)
+            assert sorted(log['acc_real']) == [0, 2] and all(0.0 <= v <= 1.0 for v in log['acc_fake'].values())
         dev = log['dev_cost' if script == 'cifar_resnet' else 'dev disc cost']
         assert sorted(dev) == [1] and np.isfinite(dev[1])
         assert os.path.getsize(os.path.join(out, 'samples_1.%s' % ('png' if script == 'cifar_resnet' else 'jpg'))) > 0

@@ -44,7 +44,7 @@ def test_train_loop_schedule_and_outputs(fake_kernels, tmp_path, script, capsys)
         data = write_cifar_dir(str(tmp_path / 'data'), n_per_file=8)
     out = str(tmp_path / 'out')
     sess = T.train(script, data, iters=3, dev_every=2, out_dir=out, dev_batches=1, batch_size=4, n_examples=40,
-                   device='cpu', use_graphs=False, act_dtype=torch.float32, checkpoint_every=3)
+                   device='cpu', use_graphs=False, act_dtype=torch.float32, checkpoint_every=3, acc_every=2)
     try:
         # iteration 0 has no generator step (:396); every iteration runs N_CRITIC critic steps on fresh batches
         n_critic = sess.n_critic
@@ -57,6 +57,9 @@ def test_train_loop_schedule_and_outputs(fake_kernels, tmp_path, script, capsys)
         assert sorted(log[cost_name]) == [0, 1, 2] and sorted(log['time']) == [0, 1, 2] and sorted(log[dev_name]) == [1]
         if script == 'cifar_resnet':
             assert sorted(log['wgan']) == [0, 1, 2] and sorted(log['acgan']) == [0, 1, 2]
+            # 'acc_real' / 'acc_fake' (TG/CT_gan_cifar_resnet.py:410-411): the metrics-only clean pass, every acc_every iterations
+            assert sorted(log['acc_real']) == [0, 2] and sorted(log['acc_fake']) == [0, 2]
+            assert all(0.0 <= v <= 1.0 for v in list(log['acc_real'].values()) + list(log['acc_fake'].values()))
             # 'wgan' = disc_wgan (TG/CT_gan_cifar_resnet.py:295) = cost - ACGAN_SCALE * acgan (:300)
             assert all(abs(log['wgan'][i] - (log['cost'][i] - log['acgan'][i])) < 1e-4 * max(1., abs(log['cost'][i])) for i in range(3))
         assert all(np.isfinite(v) for v in log[cost_name].values())
