@@ -241,6 +241,6 @@ def test_training_loop_metric_names_are_the_reference_scripts(script, ref_file):
     ours = set(re.findall(r"_plot\.plot\('([^']+)'", src))
     for m in re.findall(r"_plot\.plot\('([^']+)' if s\.resnet else '([^']+)'", src):
         ours.update(m)
-    resnet_only = {'cost', 'wgan', 'acgan', 'dev_cost'}
+    resnet_only = {'cost', 'wgan', 'acgan', 'dev_cost', 'acc_real', 'acc_fake'}
     mine = {n for n in ours if (n in resnet_only) == (script == 'cifar_resnet') or n == 'time'}
     assert mine and mine <= ref_names, (sorted(mine - ref_names), sorted(ref_names))
