@@ -21,7 +21,7 @@ iterations) instead of 0.14 s -- long enough for sustained clocks and a few doze
   cpu_baseline / --impl reference
             the CPU transcription of the reference graph (oracle/, PyTorch-CPU fp32, all host
             threads) -- TF 1.2.1 cannot be installed here
-  --workload cifar|mnist|64x64
+  --workload cifar|mnist|64x64|lsun128
             the same line for the DCGAN scripts CT_gan_cifar.py / CT_gan_mnist.py (BASELINE configs[1] / [0]: parity
             configurations, not the headline); default = resnet, BASELINE.json's metric
 """
@@ -493,8 +493,12 @@ DCGAN = {
     '64x64': ('ctgan_b200.gan_64x64', 'oracle.ct_gan_64x64', 64, 3445.21, 1120.42, 12288,
               'CT_gan_64x64.py GoodGenerator / GoodDiscriminator (ResNet, layer norm in the critic), MODE wgan-ct, 64x64x3 synthetic batch 64, '
               'DIM 64, critic_iters=5 (SURVEY 8(f) row N4)'),
+    # the same row's second script; GFLOP None = counted at run time (_count_gemm_gflop) from the launcher calls of one eager iteration
+    'lsun128': ('ctgan_b200.gan_lsun128', 'oracle.wgan_lsun128', 64, None, None, 49152,
+                'LSUN_bedrooms/wgan_LSUN_Bedrooms128.py ResnetGenerator / ResnetDiscriminator (layer norm in the critic), 128x128x3 synthetic '
+                'batch 64, critic 128..1024 channels, critic_iters=5 (SURVEY 8(f) row N4)'),
 }
-DCGAN_ITERS_PER_STEP = {'64x64': 2}         # ~36 ms per iteration: 20 steps x 2 iterations = 1.5 s timed
+DCGAN_ITERS_PER_STEP = {'64x64': 2, 'lsun128': 1}         # 64x64: ~46 ms per iteration; lsun128: ~0.4 s
 
 
 def _dcgan_batches(np, script, pool, B, seed):
@@ -503,6 +507,8 @@ def _dcgan_batches(np, script, pool, B, seed):
         return rs.randint(0, 256, (pool, B, 3072)).astype('int32')
     if script == '64x64':
         return rs.randint(0, 256, (pool, B, 3, 64, 64)).astype('int32')
+    if script == 'lsun128':
+        return rs.randint(0, 256, (pool, B, 3, 128, 128)).astype('int32')
     return rs.random_sample((pool, B, 784)).astype('float32')
 
 
@@ -566,6 +572,31 @@ def roofline_dcgan_kernel(torch, peaks, script, B):
             'flops_per_launch': flops, 'executed_flops_per_launch': flops * 36 / 25, 'us_per_launch': ms * 1e3}
 
 
+def _count_gemm_gflop(tr, x):
+    """Executed conv / linear GEMM work (2 FLOP per MAC, from the geometry of every launcher call) of one eager critic step and
+    one eager generator step: (critic GFLOP, generator GFLOP).  For workloads SURVEY.md gives no figure for."""
+    import ctgan_b200.kernels as K
+    tot = {'f': 0.0}
+    names = ('conv_fprop', 'conv_dgrad', 'conv_wgrad', 'conv_fprop_actdrop')
+    saved = {n: getattr(K, n) for n in names}
+
+    def wrap(fn):
+        def w(*a, **k):
+            g = next(v for v in a if isinstance(v, K.ConvGeom))
+            tot['f'] += 2.0 * g.N * g.Ho * g.Wo * g.Cin * g.Cout * g.kh * g.kw
+            return fn(*a, **k)
+        return w
+    for n in names:
+        setattr(K, n, wrap(saved[n]))
+    try:
+        tot['f'] = 0.0; tr.critic_step(x); c = tot['f']
+        tot['f'] = 0.0; tr.gen_step(); g = tot['f']
+    finally:
+        for n in names:
+            setattr(K, n, saved[n])
+    return c / 1e9, g / 1e9
+
+
 def measure_dcgan(args, script, rank, local_rank, world, dev, with_roofline=True):
     """One DCGAN workload (CT_gan_cifar.py / CT_gan_mnist.py) measured like the headline: W warm-up + K timed steps of
     ITERS_PER_STEP iterations, device-resident (`value`) and through host batches (`e2e`); returns the JSON line (rank 0)."""
@@ -582,6 +613,8 @@ def measure_dcgan(args, script, rank, local_rank, world, dev, with_roofline=True
     host_x = torch.from_numpy(_dcgan_batches(np, script, pool, B, 1234 + rank)).pin_memory()
     dev_x = host_x.to(dev)
     host_out = torch.zeros(N_CRITIC + 1, 8, dtype=torch.float32).pin_memory()
+    if gf_c is None:
+        gf_c, gf_g = _count_gemm_gflop(tr, dev_x[0])
     gt = GraphedTrainer(tr, (dev_x[0],))
     state = {'b': 0}
     IPS = DCGAN_ITERS_PER_STEP.get(script, ITERS_PER_STEP)
@@ -638,14 +671,14 @@ def measure_dcgan(args, script, rank, local_rank, world, dev, with_roofline=True
     gflop = N_CRITIC * gf_c + gf_g
     step_tflops = gflop * 1e-3 * (n_iters / (ms * 1e-3))
     line = {
-        'metric': 'CT-GAN train iters/sec (%s)' % {'cifar': 'CIFAR DCGAN', 'mnist': 'MNIST DCGAN', '64x64': 'ImageNet 64x64 ResNet'}[script],
+        'metric': 'CT-GAN train iters/sec (%s)' % {'cifar': 'CIFAR DCGAN', 'mnist': 'MNIST DCGAN', '64x64': 'ImageNet 64x64 ResNet', 'lsun128': 'LSUN 128x128 ResNet'}[script],
         'value': it_s, 'unit': unit,
         'n_gpus': world, 'steps': args.steps, 'warmup': max(3, args.warmup), 'ms_per_step': ms / args.steps, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
         'config': {'workload': cfg, 'step': '%d training iterations' % IPS, 'per_gpu_batch': B, 'critic_iters': N_CRITIC, 'cuda_graphs': True,
                    'l2_policy': '8 rotating input batches; activations of the stacked critic pass exceed L2 only for cifar; no explicit flush',
                    'precision': ('BF16 operands / fp32 accumulate (tcgen05), layer-norm statistics in fp32, fp32 master weights and optimizer'
-                                 if script == '64x64' else
+                                 if script in ('64x64', 'lsun128') else
                                  'BF16 operands / fp32 accumulate (tcgen05; stride-2 5x5 layers as 3x3 convs over the space-to-depth image, '
                                  'bias + LeakyReLU + Philox dropout in the conv epilogue), fp32 master weights and optimizer')},
         'clocks': clocks,
@@ -692,7 +725,7 @@ def main():
     ap.add_argument('--no-pregen', action='store_true', help='one generator forward per critic step instead of one per iteration')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-other-workloads', action='store_true', help='skip the CIFAR-DCGAN / MNIST lines of the default run')
-    ap.add_argument('--workload', default='resnet', choices=['resnet', 'cifar', 'mnist', '64x64'],
+    ap.add_argument('--workload', default='resnet', choices=['resnet', 'cifar', 'mnist', '64x64', 'lsun128'],
                     help="resnet = BASELINE.json's metric (default); cifar / mnist = the DCGAN parity configurations (our arm only)")
     args = ap.parse_args()
     if args.impl == 'reference':

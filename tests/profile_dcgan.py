@@ -21,6 +21,8 @@ if script == 'cifar':
     x = torch.from_numpy(rs.randint(0, 256, (B, 3072)).astype('int32')).cuda()
 elif script == '64x64':
     x = torch.from_numpy(rs.randint(0, 256, (B, 3, 64, 64)).astype('int32')).cuda()
+elif script == 'lsun128':
+    x = torch.from_numpy(rs.randint(0, 256, (B, 3, 128, 128)).astype('int32')).cuda()
 else:
     x = torch.from_numpy(rs.random_sample((B, 784)).astype('float32')).cuda()
 for _ in range(2):

@@ -1,5 +1,5 @@
 """Diagnostic: which conv geometries of a script's step reach the SIMT kernels (ctgan_conv_fprop / _dgrad / _wgrad).
-    python tests/which_simt.py cifar|mnist|64x64|cifar_resnet"""
+    python tests/which_simt.py cifar|mnist|64x64|lsun128|cifar_resnet"""
 import collections
 import importlib
 import os
@@ -32,6 +32,8 @@ tr = mod.Trainer(device='cuda', seed=1, act_dtype=torch.bfloat16, batch_size=B)
 rs = np.random.RandomState(0)
 if script == '64x64':
     args = (torch.from_numpy(rs.randint(0, 256, (B, 3, 64, 64)).astype('int32')).cuda(),)
+elif script == 'lsun128':
+    args = (torch.from_numpy(rs.randint(0, 256, (B, 3, 128, 128)).astype('int32')).cuda(),)
 elif script == 'mnist':
     args = (torch.from_numpy(rs.random_sample((B, 784)).astype('float32')).cuda(),)
 elif script == 'cifar':
