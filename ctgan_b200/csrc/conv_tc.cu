@@ -1444,7 +1444,8 @@ extern "C" int ctgan_pack_filter_bf16(const float* w, void* wp, int taps, int Ci
 static int check_thin(const ctgan_conv_desc* d, int C, const char* who) {
     CTGAN_REQUIRE(d != nullptr, CTGAN_ERR_BAD_DESC, "%s: null descriptor", who);
     CTGAN_REQUIRE(d->N > 0 && d->H > 0 && d->W > 0 && d->kh > 0 && d->kw > 0 && d->stride == 1 && d->Ho == d->H && d->Wo == d->W &&
-                  d->pad_t >= 0 && d->pad_l >= 0 && d->pad_t < d->kh && d->pad_l < d->kw, CTGAN_ERR_BAD_DESC, "%s: bad geometry", who);
+                  d->pad_t > -8 && d->pad_t < 8 && d->pad_l >= 0 && d->pad_l < d->kw, CTGAN_ERR_BAD_DESC, "%s: bad geometry", who);
+    // (pad_t outside [0, kh): a group of filter rows of a larger filter, see kernels._thin_split; offsets are stored in bytes +-8)
     CTGAN_REQUIRE(C > 0 && C <= 8 && d->kh * d->kw * C <= 64, CTGAN_ERR_UNSUPPORTED, "%s: needs C <= 8 and taps*C <= 64", who);
     return 0;
 }

@@ -312,7 +312,8 @@ def _thin_side(g, t):
     """'in' / 'out' when the conv has a thin (<= 8 channel) input / output side the im2col GEMM path handles."""
     if not (config.use_tc and config.use_thin_tc and tc_available()) or t.dim() != 4 or t.dtype != torch.bfloat16:
         return None
-    if not (g.stride == 1 and g.Ho == g.H and g.Wo == g.W and 0 <= g.pad_t < g.kh and 0 <= g.pad_l < g.kw and g.H * g.W >= 64):
+    # (pad_t may fall outside [0, kh): the row groups of a filter split by _thin_split keep the whole filter's offsets)
+    if not (g.stride == 1 and g.Ho == g.H and g.Wo == g.W and -8 < g.pad_t < 8 and 0 <= g.pad_l < g.kw and g.H * g.W >= 64):
         return None
     taps = g.kh * g.kw
     if g.Cin <= 8 and taps * g.Cin <= 64 and g.Cout % 64 == 0:
@@ -320,6 +321,26 @@ def _thin_side(g, t):
     if g.Cout <= 8 and taps * g.Cout <= 64 and g.Cin % 64 == 0:
         return 'out'
     return None
+
+
+def _thin_split(g, t):
+    """[(r0, r1), ...]: filter-row groups for a stride-1 conv with a thin (<= 8 channel) side whose taps * C exceed the 64
+    im2col columns of the thin tensor-core route (LSUN Generator.Output: 5x5, 64 -> 3: 75 columns) -- each group is a conv
+    of its own (kh = r1 - r0, pad_t shifted) that fits; the family is linear in the filter, so fprop / dgrad are sums over
+    the groups and wgrad fills the groups' row blocks of dw.  None when the call needs no split (or cannot use the route)."""
+    if not (config.use_tc and config.use_thin_tc and tc_available()) or t.dim() != 4 or t.dtype != torch.bfloat16:
+        return None
+    if not (g.stride == 1 and g.Ho == g.H and g.Wo == g.W and 0 <= g.pad_t < g.kh and 0 <= g.pad_l < g.kw and g.H * g.W >= 64):
+        return None
+    C, Cw = min(g.Cin, g.Cout), max(g.Cin, g.Cout)
+    if C > 8 or Cw % 64 or g.kh * g.kw * C <= 64 or g.kw * C > 64 or g.kh > 8:
+        return None
+    rows = 64 // (g.kw * C)
+    return [(r, min(r + rows, g.kh)) for r in range(0, g.kh, rows)]
+
+
+def _sub_geom(g, r0, r1):
+    return g._replace(kh=r1 - r0, pad_t=g.pad_t - r0)
 
 
 def pack_filter_thin(w, kind, cacheable=False):
@@ -612,6 +633,13 @@ def conv_fprop(x, w, bias, g, relu=False, residual=None, out_dtype=None, w_is_pa
         residual, res_up2 = upsample2x(residual, 1.0), False        # other paths: materialise the upsampled residual
     require_nhwc(x, 'x')
     _check_filter(w, g)
+    parts = _thin_split(g, x) if (not relu and residual is None and (out_dtype or x.dtype) == torch.bfloat16) else None
+    if parts:                                         # thin side with > 64 im2col columns: the sum over filter-row groups
+        y = None
+        for i, (r0, r1) in enumerate(parts):
+            yi = conv_fprop(x, w[r0:r1], bias if i == 0 else None, _sub_geom(g, r0, r1))
+            y = yi if y is None else add(y, yi)
+        return y
     two_d = x.dim() == 2
     out_dtype = out_dtype or x.dtype
     y = empty_act(_y_shape(g, two_d), out_dtype, x.device)
@@ -709,6 +737,13 @@ def conv_dgrad(dy, w, g, out_dtype=None, w_is_param=False, col=None, relu_mask=N
     if relu_mask is not None:
         require_nhwc(relu_mask, 'relu_mask')
     _check_filter(w, g)
+    parts = _thin_split(g, dy) if (not out_s2d and (out_dtype or dy.dtype) == torch.bfloat16) else None
+    if parts:                                         # see conv_fprop
+        dx = None
+        for r0, r1 in parts:
+            di = conv_dgrad(dy, w[r0:r1], _sub_geom(g, r0, r1))
+            dx = di if dx is None else add(dx, di)
+        return mul_relu_mask(dx, relu_mask) if relu_mask is not None else dx
     two_d = dy.dim() == 2
     out_dtype = out_dtype or dy.dtype
     dx = empty_act(_x_shape(g, two_d), out_dtype, dy.device)
@@ -856,6 +891,12 @@ def conv_wgrad(x, dy, g, w_shape, accumulate_into=None, col=None, defer=False):
     if acc is not None and (acc.dtype != torch.float32 or not acc.is_contiguous() or tuple(acc.shape) != tuple(w_shape)):
         raise RuntimeError('ctgan_b200: accumulate_into must be a contiguous float32 tensor of the filter shape')
     defer = defer and acc is not None
+    parts = _thin_split(g, x) if (xdt == BF16 and ydt == BF16) else None
+    if parts:                                         # see conv_fprop: every row group fills its own block of dw
+        dw = acc if acc is not None else zeros(w_shape, torch.float32, x.device)
+        for r0, r1 in parts:
+            conv_wgrad(x, dy, _sub_geom(g, r0, r1), (r1 - r0,) + tuple(w_shape[1:]), accumulate_into=dw[r0:r1])
+        return dw
     route, gj = _wgrad_route(x, dy, g)
     if route == 'tf32':
         dw = acc if acc is not None else zeros(w_shape, torch.float32, x.device)
