@@ -23,12 +23,16 @@ from . import checkpoint
 from .data import DeviceFeeder, inf_train_gen
 from .graphs import GraphedTrainer
 from .tflib import plot as _plot, save_images as _save_images, cifar10 as _cifar10, mnist as _mnist, small_imagenet as _imagenet
+from .tflib import imagenet as _lsun
 
 SCRIPTS = {'mnist': 'gan_mnist', 'cifar': 'gan_cifar', 'cifar_resnet': 'gan_cifar_resnet',
-           '64x64': 'gan_64x64'}        # 64x64: SURVEY.md 8(f) N4, see gan_64x64.py
+           '64x64': 'gan_64x64',        # 64x64: SURVEY.md 8(f) N4, see gan_64x64.py
+           'lsun128': 'gan_lsun128'}    # LS/wgan_LSUN_Bedrooms128.py (same row): its own schedule, see run_iteration / train
 
 
 def _loaders(script, mod, batch_size, data_dir, n_examples):
+    if script == 'lsun128':                                  # LS/wgan_LSUN_Bedrooms128.py:351-352: one image folder, no dev set
+        return _lsun.load(batch_size, data_dir), None
     if script == 'mnist':
         train, dev, _ = _mnist.load(batch_size, batch_size, n_examples, filepath=data_dir)
     elif script == '64x64':                                  # TG/CT_gan_64x64.py:613; n_examples = (n_train, n_valid) files
@@ -76,7 +80,7 @@ class Session:
         rank, world = _rank_world()
         self.feeder = DeviceFeeder(inf_train_gen(self.train_epoch, rank, world), device, depth=2, take=take, hold=self.n_critic)
         # fixed noise for the sample grids (:341-343 / TG/CT_gan_cifar.py:157-158 / TG/CT_gan_mnist.py:206-207)
-        n_fixed = 100 if self.resnet else (self.B if script == '64x64' else 128)        # TG/CT_gan_64x64.py:582
+        n_fixed = 100 if self.resnet else (self.B if script == '64x64' else (64 if script == 'lsun128' else 128))   # TG/CT_gan_64x64.py:582, LS :341
         self.fixed_noise = torch.from_numpy(np.random.normal(size=(n_fixed, 128)).astype('float32')).to(device)
         self.fixed_labels = torch.tensor([0, 1, 2, 3, 4, 5, 6, 7, 8, 9] * 10, dtype=torch.int32, device=device) if self.resnet else None
         self.gt = None
@@ -103,7 +107,8 @@ class Session:
             gt.iteration = it
             ev0 = torch.cuda.Event(enable_timing=True)
             ev0.record()
-        if it > 0:
+        lsun = self.script == 'lsun128'          # LS/wgan_LSUN_Bedrooms128.py:373-389: the critic steps FIRST, then a generator step in
+        if it > 0 and not lsun:                  # every iteration (also iteration 0)
             gt.gen_step() if gt is not None else tr.gen_step(iteration=it)
         batches = [self._next_batch() for _ in range(self.n_critic)]      # all stay valid: feeder hold = n_critic
         if gt is not None and gt.pregen_steps:
@@ -115,7 +120,10 @@ class Session:
             else:
                 res = tr.critic_step(*b, iteration=it)
                 out, self._last_fakes = res['out'], res.get('fake_data')
-        if self.resnet:
+        if lsun:
+            gt.gen_step() if gt is not None else tr.gen_step(iteration=it)
+            _plot.plot('cost', out[0])                                    # LS :391
+        elif self.resnet:
             # names and contents of TG/CT_gan_cifar_resnet.py:406-412: 'wgan' is disc_wgan = Wasserstein term + CT + 10*GP
             # (:295), i.e. the cost without its ACGAN part; out = {cost, wgan term, ct, gp, acgan, ...}.  The two clean-pass
             # accuracies ('acc_real', 'acc_fake', :410-411) come from a metrics-only critic pass that the training step does not
@@ -176,10 +184,11 @@ class Session:
         if self.script == 'mnist':
             path = os.path.join(self.out_dir, 'samples_{}.png'.format(frame))
             _save_images.save_images(samples.reshape((-1, 28, 28)), path)
-        elif self.script == '64x64':
-            samples = ((samples + 1.) * (255.99 / 2)).astype('int32')               # :593
+        elif self.script in ('64x64', 'lsun128'):
+            samples = ((samples + 1.) * (255.99 / 2)).astype('int32')               # :593 / LS :345
             path = os.path.join(self.out_dir, 'samples_{}.png'.format(frame))
-            _save_images.save_images(samples.reshape((-1, 3, 64, 64)), path)
+            side = 64 if self.script == '64x64' else 128
+            _save_images.save_images(samples.reshape((-1, 3, side, side)), path)
         else:
             samples = ((samples + 1.) * (255. / 2)).astype('int32')
             ext = 'png' if self.resnet else 'jpg'
@@ -202,6 +211,25 @@ def train(script, data_dir, iters=None, dev_every=None, out_dir='.', checkpoint_
     flush_early = 500 if s.resnet else 5                     # :431 `iteration < 500`; DCGAN scripts: `iteration < 5`
     flush_every = 1000 if s.resnet else (200 if script == '64x64' else 100)
     writer = _rank_world()[0] == 0                           # replicas are identical: rank 0 writes the files
+    if script == 'lsun128':
+        # LS/wgan_LSUN_Bedrooms128.py:365,373-400: samples before the loop and every 100 iterations (at iteration % 100 == 0),
+        # params.ckpt every 1000, flush every 5 (its fork of plot.flush also prints standard deviations: not reproduced), no dev set
+        if writer and s.iteration == 0:
+            s.generate_image(0)
+        for iteration in range(s.iteration, iters):
+            s.run_iteration()
+            if writer and iteration % 100 == 0:
+                s.generate_image(iteration)
+            every = checkpoint_every or 1000
+            if writer and iteration % every == 0:
+                checkpoint.save(os.path.join(out_dir, 'checkpoint.npz'), s.tr, iteration=iteration + 1)
+            if iteration % 5 == 0:
+                if writer:
+                    _plot.flush()
+                else:
+                    _plot._since_last_flush.clear()
+            _plot.tick()
+        return s
     for iteration in range(s.iteration, iters):
         s.run_iteration()
         if iteration % dev_every == dev_every - 1:

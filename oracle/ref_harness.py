@@ -108,14 +108,16 @@ def py2to3_host(src):
     return src
 
 
-def load_ref_host_module(name, stubs=None):
+def load_ref_host_module(name, stubs=None, fork=None):
     """Import ONE host-side utility module of the reference's tflib (translated), e.g. 'cifar10', 'mnist', 'plot',
     'save_images', as a stand-alone module.  stubs: {module name: module object} bound in sys.modules during the import
-    (matplotlib / scipy.misc are not installed here)."""
+    (matplotlib / scipy.misc are not installed here).  fork='LSUN_bedrooms': the copy of tflib next to the LSUN script."""
     os.makedirs(OUT_DIR, exist_ok=True)
-    with open(os.path.join(REF_ROOT, 'tflib', name + '.py')) as f:
+    with open(os.path.join(REF_ROOT, fork, 'tflib', name + '.py') if fork else os.path.join(REF_ROOT, 'tflib', name + '.py')) as f:
         src = py2to3_host(f.read())
-    path = os.path.join(OUT_DIR, 'ref_host_%s.py' % name)
+    if fork:
+        src = src.replace('shell=True).split("\\n")', 'shell=True).decode().split("\\n")')     # py3: check_output returns bytes
+    path = os.path.join(OUT_DIR, 'ref_host_%s%s.py' % (name, '_' + fork if fork else ''))
     with open(path, 'w') as f:
         f.write(src)
     saved = {}

@@ -228,6 +228,42 @@ def test_small_imagenet_generator_matches_reference_module(tmp_path):
 
 
 @needs_ref
+def test_lsun_folder_generator_matches_reference_module(tmp_path):
+    """LS/tflib/imagenet.py (the loader of LS/wgan_LSUN_Bedrooms128.py): compounding in-place shuffles of the file list,
+    the round-robin buffer yielded right after slot 0 was overwritten, greyscale broadcast, wrong-size images skipped with
+    their slot left stale, and the horizontal flips that compound because the reference re-binds its buffer to a reversed view."""
+    from PIL import Image
+    import ctgan_b200.tflib.imagenet as mine
+    d = tmp_path / 'lsun'
+    d.mkdir()
+    rs = np.random.RandomState(4)
+    for i in range(19):
+        if i == 5:
+            img = Image.fromarray(rs.randint(0, 256, (128, 128)).astype('uint8'), 'L')            # greyscale
+        elif i == 11:
+            img = Image.fromarray(rs.randint(0, 256, (64, 128, 3)).astype('uint8'), 'RGB')        # wrong size: skipped
+        else:
+            img = Image.fromarray(rs.randint(0, 256, (128, 128, 3)).astype('uint8'), 'RGB')
+        img.save(str(d / ('img_%02d.png' % i)))
+    misc = types.ModuleType('scipy.misc')
+    sp = types.ModuleType('scipy')
+    sp.misc = misc
+    pil = types.ModuleType('Image')
+    pil.open = Image.open
+    ref = RH.load_ref_host_module('imagenet', stubs={'scipy': sp, 'scipy.misc': misc, 'Image': pil}, fork='LSUN_bedrooms')
+
+    def run(mod):
+        np.random.seed(77)                                   # the flips use numpy's global RandomState
+        gen = mod.make_generator(str(d), 4)
+        return [np.array(b[0]) for _ in range(3) for b in gen()]
+    got, want = run(mine), run(ref)
+    assert len(got) == len(want) == 3 * 4
+    for a, b in zip(got, want):
+        assert a.dtype == b.dtype == np.int32 and a.shape == (4, 3, 128, 128) and np.array_equal(a, b)
+    assert any(not np.array_equal(x, y) for x, y in zip(got[:4], got[4:8]))                       # epochs differ
+
+
+@needs_ref
 @pytest.mark.parametrize('script,ref_file', [('mnist', 'CT_gan_mnist.py'), ('cifar', 'CT_gan_cifar.py'),
                                              ('cifar_resnet', 'CT_gan_cifar_resnet.py'), ('64x64', 'CT_gan_64x64.py')])
 def test_training_loop_metric_names_are_the_reference_scripts(script, ref_file):

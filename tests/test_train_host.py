@@ -142,3 +142,32 @@ def test_train_loop_64x64(fake_kernels, tmp_path, capsys):
         plot.output_dir = '.'
         plot.reset()
         G.DIM = 64
+
+
+def test_train_loop_lsun128(fake_kernels, tmp_path, capsys):
+    """The LS/wgan_LSUN_Bedrooms128.py loop (row N4): critic steps first, a generator step in EVERY iteration, 'cost' / 'time'
+    metrics, samples before the loop and at iteration % 100 == 0, batches from the image-folder loader (incl. its mirrored views)."""
+    from PIL import Image
+    from ctgan_b200 import train as T
+    import ctgan_b200.tflib.plot as plot
+    import ctgan_b200.gan_lsun128 as G
+    rs = np.random.RandomState(0)
+    d = tmp_path / 'lsun'
+    d.mkdir()
+    for i in range(60):
+        Image.fromarray(rs.randint(0, 256, (128, 128, 3)).astype('uint8'), 'RGB').save(str(d / ('%03d.png' % i)))
+    out = str(tmp_path / 'out')
+    try:
+        np.random.seed(3)
+        sess = T.train('lsun128', str(d), iters=2, out_dir=out, batch_size=4, device='cpu', use_graphs=False,
+                       act_dtype=torch.float32, model_kw=dict(width=1.0 / 32))
+        assert sess.tr.disc_opt.t == 2 * 5 and sess.tr.gen_opt.t == 2            # LS :373-389: no skipped generator step
+        log = pickle.load(open(os.path.join(out, 'log.pkl'), 'rb'))
+        assert sorted(log['cost']) == [0] and sorted(log['time']) == [0] and sess.iteration == 2   # flushed at iteration % 5 == 0 (LS :398)
+        assert all(np.isfinite(v) for v in log['cost'].values())
+        assert os.path.getsize(os.path.join(out, 'samples_0.png')) > 0
+        assert os.path.exists(os.path.join(out, 'checkpoint.npz'))
+    finally:
+        plot.output_dir = '.'
+        plot.reset()
+        G.WIDTH = 1.0
