@@ -26,7 +26,7 @@ e1.record()
 torch.cuda.synchronize()
 log = pickle.load(open(os.path.join(out, 'log.pkl'), 'rb'))
 cost = [log['cost'][k] for k in sorted(log['cost'])]
-print('iterations logged: %d; cost first/last: %.3f / %.3f; all finite: %s; wall incl. capture, dev cost and samples: %.1f s'
+print('logged iterations: %d; cost first/last: %.3f / %.3f; all finite: %s; wall incl. capture, dev cost and samples: %.1f s'
       % (len(cost), cost[0], cost[-1], bool(np.all(np.isfinite(cost))), e0.elapsed_time(e1) * 1e-3))
 for name in ('wgan', 'acgan', 'acc_real', 'acc_fake', 'dev_cost', 'time'):
     v = [log[name][k] for k in sorted(log[name])]
