@@ -80,14 +80,18 @@ __device__ __forceinline__ WgItem wg_decode(const WgradJobTable& tab, int item) 
     return it;
 }
 
-// <4 stages, 16 KB x-halves> by default; <3, 24 KB> when a job's halo box is larger (64-pixel-wide images: 3 rows x 64 pixels)
-template <int STAGES, uint32_t A_SLOT = 16384>
+// CHUNK = pixels per pipeline stage (the K extent of one stage's MMAs).  <4 stages, 16 KB x-halves, 64 pixels>: the original
+// geometry; <3, 24 KB, 64> when a 64-pixel job's halo box is larger (64-pixel-wide images).  <2, 32 KB, 128> (default,
+// ctgan_set_wgrad_multi_chunk): 128-pixel chunks -- the halo rows are shared by twice as many image rows (32x32 image:
+// 6 rows loaded per 4 used instead of 4 per 2; 64-pixel-wide: 4 per 2 instead of 3 per 1), so a stage moves 80 KB per 24 MMAs
+// instead of 48 KB per 12: the kernel is bound by its L2 -> shared-memory fill.
+template <int STAGES, uint32_t A_SLOT = 16384, int CHUNK = 64>
 __global__ void __launch_bounds__(192, 1)
 conv_wgrad_tc_multi_kernel(const __grid_constant__ WgradJobTable tab)
 {
     ctgan::pdl_launch_dependents();
-    constexpr uint32_t B_HALF = 8192;
-    constexpr uint32_t STAGE_BYTES = 2 * A_SLOT + 2 * B_HALF;             // 48 KB (64 KB)
+    constexpr uint32_t B_HALF = CHUNK * 128;                              // [CHUNK px][64 ch] bf16
+    constexpr uint32_t STAGE_BYTES = 2 * A_SLOT + 2 * B_HALF;             // 48 KB (64 KB; 96 KB)
     constexpr int TMEM_COLS = 512;
 
     extern __shared__ uint8_t smem_raw[];
@@ -168,7 +172,7 @@ conv_wgrad_tc_multi_kernel(const __grid_constant__ WgradJobTable tab)
                     for (int r = 0; r < 3; ++r) {
                         if ((rmask >> r) & 1) {
 #pragma unroll
-                            for (int k = 0; k < 64 / UMMA_K; ++k)     // 16 pixel rows = 2048 bytes along K
+                            for (int k = 0; k < CHUNK / UMMA_K; ++k)  // 16 pixel rows = 2048 bytes along K
                                 umma_bf16_lo(tmem_base + (uint32_t)(r * 128), a_lo + r * row_step + 128 * k, b_lo + 128 * k, idesc,
                                              k ? 1u : (c > 0 ? 1u : 0u));
                         }
@@ -227,9 +231,26 @@ conv_wgrad_tc_multi_kernel(const __grid_constant__ WgradJobTable tab)
 using namespace ctgan;
 using namespace ctgan::tc;
 
+static int g_wgrad_multi_chunk = 0;
+/* tuning / test hook: pixels per pipeline stage of the multi-job filter-gradient kernel: 64, 128, or 0 (default) = 128 for a
+ * launch with a job on images at least 64 pixels wide (measured: CT_gan_64x64.py +0.9 %, LSUN 128x128 +1.6 %; the CIFAR ResNet
+ * step, 32 pixels wide at most, is 0.5 % faster with 64: two 96 KB stages pipeline less deeply than four of 48 KB) */
+extern "C" void ctgan_set_wgrad_multi_chunk(int px) { g_wgrad_multi_chunk = (px == 64 || px == 128) ? px : 0; }
 static int g_wgrad_multi_items_per_sm = 2;
 /* tuning hook: work items per SM the deferred filter-gradient launch aims for */
 extern "C" void ctgan_set_wgrad_multi_items_per_sm(int v) { g_wgrad_multi_items_per_sm = v < 1 ? 1 : v; }
+
+// can (d) be cut into `chunk`-pixel K chunks whose x halo box fits one operand slot?
+static bool wgrad_chunk_ok(const ctgan_conv_desc* d, int chunk) {
+    const uint32_t slot = chunk == 128 ? 32768u : 24576u;
+    int BW, BH, BN;
+    pixel_box(d->H, d->W, chunk, &BW, &BH, &BN);
+    if (BW > 256 || BH > 256 || BN > 256) return false;
+    if (d->kh == 1) return true;
+    if (BN == 1) return BW % 8 == 0 && (uint32_t)(BH + 2) * BW * 128u <= slot;
+    // several whole small images per chunk (8x8 / 4x4): [h][n][w] boxes, filter row shift = BN * BW pixel rows
+    return BW == d->W && BH == d->H && (BN * BW) % 8 == 0 && (uint32_t)(BH + 2) * BN * BW * 128u <= (chunk == 128 ? 32768u : 16384u);
+}
 
 /* 1 when (d) can be a job of ctgan_conv_wgrad_tc_multi */
 extern "C" int ctgan_conv_wgrad_tc_multi_ok(const ctgan_conv_desc* d) {
@@ -238,12 +259,7 @@ extern "C" int ctgan_conv_wgrad_tc_multi_ok(const ctgan_conv_desc* d) {
     if (d->N <= 0 || d->H <= 0 || d->W <= 0 || d->Cin <= 0 || d->Cout <= 0 || d->Cin % 64 || d->Cout % 64) return 0;
     if (!((d->kh == 3 && d->kw == 3) || (d->kh == 1 && d->kw == 1))) return 0;
     if (d->pad_t < 0 || d->pad_l < 0 || d->pad_t >= d->kh || d->pad_l >= d->kw) return 0;
-    int BW, BH, BN;
-    pixel_box(d->H, d->W, 64, &BW, &BH, &BN);
-    if (d->kh == 1) return 1;
-    if (BN == 1) return BW % 8 == 0 && (uint32_t)(BH + 2) * BW * 128u <= 24576u;
-    // several whole small images per 64-pixel chunk (4x4): [h][n][w] boxes, filter row shift = BN * BW pixel rows
-    return BW == d->W && BH == d->H && (BN * BW) % 8 == 0 && (uint32_t)(BH + 2) * BN * BW * 128u <= 16384u;
+    return wgrad_chunk_ok(d, 64) || (g_wgrad_multi_chunk != 64 && wgrad_chunk_ok(d, 128));
 }
 
 extern "C" int ctgan_conv_wgrad_tc_multi(int n, const ctgan_conv_desc* descs, const void* const* xs, const void* const* dys,
@@ -257,11 +273,14 @@ extern "C" int ctgan_conv_wgrad_tc_multi_embed(int n, const ctgan_conv_desc* des
     constexpr int STAGES = 4;
     constexpr size_t smem = (size_t)STAGES * 49152 + 1024 + (2 * STAGES + 2) * 8 + 16;
     constexpr size_t smem_big = (size_t)3 * 65536 + 1024 + (2 * 3 + 2) * 8 + 16;
+    constexpr size_t smem_128 = (size_t)2 * 98304 + 1024 + (2 * 2 + 2) * 8 + 16;
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(conv_wgrad_tc_multi_kernel<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e == cudaSuccess)
             e = cudaFuncSetAttribute(conv_wgrad_tc_multi_kernel<3, 24576>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_big);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(conv_wgrad_tc_multi_kernel<2, 32768, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_128);
         if (e != cudaSuccess) return cuda_status(e, "wgrad_tc_multi smem attribute");
         attr_set = true;
     }
@@ -272,6 +291,14 @@ extern "C" int ctgan_conv_wgrad_tc_multi_embed(int n, const ctgan_conv_desc* des
         long long total = 0;
         long long col_work[WG_MAX_JOBS];
         bool big = false;                      // some x halo box exceeds 16 KB per 64-channel half
+        // 128-pixel chunks when every job of this launch can be cut that way, else 64
+        int chunk = g_wgrad_multi_chunk;
+        if (chunk == 0) {
+            chunk = 64;
+            for (int i = 0; i < nj; ++i) if (descs[base + i].W >= 64) chunk = 128;
+        }
+        for (int i = 0; i < nj && chunk == 128; ++i)
+            if (!wgrad_chunk_ok(descs + base + i, 128)) chunk = 64;
         for (int i = 0; i < nj; ++i) {
             const ctgan_conv_desc* d = descs + base + i;
             CTGAN_REQUIRE(ctgan_conv_wgrad_tc_multi_ok(d), CTGAN_ERR_UNSUPPORTED, "conv_wgrad_tc_multi: job %d is not eligible", base + i);
@@ -282,7 +309,8 @@ extern "C" int ctgan_conv_wgrad_tc_multi_embed(int n, const ctgan_conv_desc* des
             WgradJob& J = tab.job[i];
             J.dw = dws[base + i];
             J.Cin = d->Cin; J.Cout = d->Cout; J.kh = d->kh; J.kw = d->kw; J.pad_t = d->pad_t; J.pad_l = d->pad_l;
-            pixel_box(d->H, d->W, 64, &J.BW, &J.BH, &J.BN);
+            CTGAN_REQUIRE(wgrad_chunk_ok(d, chunk), CTGAN_ERR_UNSUPPORTED, "conv_wgrad_tc_multi: job %d does not fit %d-pixel chunks", base + i, chunk);
+            pixel_box(d->H, d->W, chunk, &J.BW, &J.BH, &J.BN);
             J.chunksW = ceil_div(d->W, J.BW); J.chunksH = ceil_div(d->H, J.BH);
             J.total_chunks = J.chunksW * J.chunksH * ceil_div(d->N, J.BN);
             J.co_blocks = ceil_div(d->Cout, 128);
@@ -304,7 +332,7 @@ extern "C" int ctgan_conv_wgrad_tc_multi_embed(int n, const ctgan_conv_desc* des
                 if (int r = make_act_map(&J.mx, xs[base + i], d->N, d->H, d->W, d->Cin, J.BW, J.BH + d->kh - 1, J.BN)) return r;
                 if (int r = make_act_map(&J.mdy, dys[base + i], d->N, d->H, d->W, d->Cout, J.BW, J.BH, J.BN)) return r;
             }
-            col_work[i] = (long long)J.total_chunks * d->kh;
+            col_work[i] = (long long)J.total_chunks * d->kh * (chunk / 64);
             total += J.emb_k > 0 ? col_work[i] * (J.emb_C / 128) * J.co_blocks * 2 * J.emb_k
                                  : col_work[i] * ceil_div(d->Cin, 128) * J.co_blocks * d->kw;
         }
@@ -324,7 +352,8 @@ extern "C" int ctgan_conv_wgrad_tc_multi_embed(int n, const ctgan_conv_desc* des
         }
         tab.n_jobs = nj; tab.n_items = items;
         const int grid = items < sm_count() ? items : sm_count();
-        if (big) CTGAN_LAUNCH((conv_wgrad_tc_multi_kernel<3, 24576>), grid, 192, smem_big, as_stream(stream), tab);
+        if (chunk == 128) CTGAN_LAUNCH((conv_wgrad_tc_multi_kernel<2, 32768, 128>), grid, 192, smem_128, as_stream(stream), tab);
+        else if (big) CTGAN_LAUNCH((conv_wgrad_tc_multi_kernel<3, 24576>), grid, 192, smem_big, as_stream(stream), tab);
         else     CTGAN_LAUNCH((conv_wgrad_tc_multi_kernel<STAGES>), grid, 192, smem, as_stream(stream), tab);
         CTGAN_CHECK_LAUNCH("conv_wgrad_tc_multi");
     }

@@ -137,6 +137,9 @@ int ctgan_conv_wgrad_tc_multi_ok(const ctgan_conv_desc* d);
  * stride-2 k x k (k <= 5) convolution with C input channels (C % 128 == 0) and TF-SAME pads (pad_t, pad_l): descs[i] describes the
  * 3x3 geometry (Cin = 4C), dws[i] is the k x k filter gradient [k][k][C][Cout] itself -- only the row/column taps that carry a filter
  * element are multiplied, and they are reduced straight into it (no 3x3x4C scratch, zero-fill or gather: ctgan_s2d_filter_grad). */
+/* tuning / test hook: pixels per pipeline stage of the multi-job kernel: 64, 128, or 0 (default) = 128 when a job's images are
+ * at least 64 pixels wide (their halo rows are then shared by twice as many image rows), else 64 */
+void ctgan_set_wgrad_multi_chunk(int px);
 int ctgan_conv_wgrad_tc_multi_embed(int n, const ctgan_conv_desc* descs, const void* const* xs, const void* const* dys,
                                     float* const* dws, const int* embed, void* stream);
 int ctgan_conv_wgrad_tc_multi(int n, const ctgan_conv_desc* descs, const void* const* xs, const void* const* dys,

@@ -30,6 +30,9 @@ if os.environ.get('CTGAN_GEN_SPLITK'):
     K.config.gen_splitk = bool(int(os.environ['CTGAN_GEN_SPLITK']))
 if os.environ.get('CTGAN_DECOUPLE_GP'):
     K.config.decouple_gp = bool(int(os.environ['CTGAN_DECOUPLE_GP']))
+if os.environ.get('CTGAN_WGRAD_CHUNK'):
+    from ctgan_b200 import _lib as _L4
+    _L4.lib.ctgan_set_wgrad_multi_chunk(int(os.environ['CTGAN_WGRAD_CHUNK']))
 if os.environ.get('CTGAN_HALO'):
     from ctgan_b200 import _lib as _L3
     _L3.lib.ctgan_set_fprop_halo(int(os.environ['CTGAN_HALO']))
