@@ -48,6 +48,11 @@ ITER_GFLOP = 2990.34          # algorithmic FLOPs of one iteration of the REFERE
 # -0.75 * 2*(64+256+1024)*128*128 per generator pass-image (Generator.{1,2,3}.Shortcut) over 320 + 3*128 image-traversals
 ITER_GFLOP_EXECUTED = ITER_GFLOP - (0.75 * 2 * 256 * 128 * 128 * (5 * (3 * 192 + 4 * 64) + 2 * 128)
                                     + 0.75 * 2 * (64 + 256 + 1024) * 128 * 128 * (320 + 3 * 128)) * 1e-9
+# ... and ConvMeanPool(3x3) as one stride-2 4x4 conv (kernels.config.pool_conv_s2d, exact in real arithmetic): 16 taps at a
+# quarter of the positions instead of 9 at all of them = -5/9 of 2*1024*1152*128 FLOP per image-traversal of
+# Discriminator.1.Conv2 (every pass: same traversal count as above) and of 2*256*1152*128 for Discriminator.2.Conv2 where the
+# route's size policy takes it (the 192-image stacked pass: forward, dgrad, wgrad of 5 critic steps)
+POOL_CONV_GFLOP_SAVED = 5.0 / 9.0 * 2 * 1152 * 128 * (1024 * (5 * (3 * 192 + 4 * 64) + 2 * 128) + 256 * (5 * 3 * 192)) * 1e-9
 
 
 def load_peaks():
@@ -447,7 +452,11 @@ def run_ours(args):
     it_s_e2e = world * n_iters / (ms_e2e * 1e-3)
     top3 = roofline_kernels(torch, peaks)
     roof = top3[0]
-    step_tflops = ITER_GFLOP_EXECUTED * 1e-3 * (n_iters / (ms * 1e-3))   # per GPU, FLOPs actually required by the executed math
+    import ctgan_b200.kernels as _K
+    executed = ITER_GFLOP_EXECUTED - (POOL_CONV_GFLOP_SAVED if _K.config.pool_conv_s2d else 0.0)
+    step_tflops = executed * 1e-3 * (n_iters / (ms * 1e-3))              # per GPU, FLOPs actually required by the executed math
+    ref_tflops = ITER_GFLOP * 1e-3 * (n_iters / (ms * 1e-3))             # ... the reference graph's FLOPs per second (what a
+    #                                                                      non-restructured implementation would have to sustain)
     line = {
         'metric': METRIC, 'value': it_s, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': max(3, args.warmup),
         'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
@@ -470,9 +479,13 @@ def run_ours(args):
         'roofline': roof,
         'roofline_top3': top3,
         'other_workloads': others,
-        'step_tensor_utilisation': {'algorithmic_gflop_per_iteration': ITER_GFLOP, 'executed_gflop_per_iteration': ITER_GFLOP_EXECUTED,
+        'step_tensor_utilisation': {'algorithmic_gflop_per_iteration': ITER_GFLOP, 'executed_gflop_per_iteration': executed,
                                     'achieved_tflops_per_gpu': step_tflops,
-                                    'frac_of_sustained_peak': step_tflops / peaks['sustained'], 'peak': peaks['sustained']},
+                                    'frac_of_sustained_peak': step_tflops / peaks['sustained'], 'peak': peaks['sustained'],
+                                    'reference_graph_tflops_per_gpu': ref_tflops,
+                                    'reference_graph_frac_of_sustained_peak': ref_tflops / peaks['sustained'],
+                                    'note': 'executed = reference graph minus the exact algebraic restructurings (1x1 shortcut convs on '
+                                            'the low-resolution side; ConvMeanPool(3x3) as one 4x4 / stride-2 conv)'},
     }
     if world == 1 and not args.no_cpu_baseline:
         cb, _ = time_cpu_reference(max_seconds=25.0, want_steps=1)

@@ -21,6 +21,9 @@ lib = ctypes.CDLL(LIB_PATH)
 F32, BF16 = 0, 1
 EPI_RELU = 1
 EPI_RES_UP2 = 2
+EPI_OUT_S2D = 4
+EPI_OUT_D2S = 8
+EPI_S2D_SKIP = 256
 BN_RELU, BN_UP2, BN_ACCUM = 1, 2, 4
 
 
@@ -74,6 +77,9 @@ _PROTOS = {
     'ctgan_depth_to_space': (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P]),
     'ctgan_space_to_depth_mul': (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, P]),
     'ctgan_depth_to_space_mul': (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, P]),
+    'ctgan_space_to_depth_mask': (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, P]),
+    'ctgan_box_filter': (c_int, [P, P, c_int, c_int, P]),
+    'ctgan_box_filter_grad': (c_int, [P, P, c_int, c_int, P]),
     'ctgan_pack_filter_s2d': (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, P]),
     'ctgan_s2d_filter_grad': (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     'ctgan_im2col_strided': (c_int, [POINTER(ConvDesc), c_int, P, P, P]),

@@ -248,9 +248,15 @@ __device__ __forceinline__ void lean_epilogue_tile(const FpropParams& p, uint32_
     const bool valid = (n < p.N) && (h < p.H) && (w < p.W);
     const int64_t pix = ((int64_t)n * p.H + h) * p.W + w;
     int64_t orow = pix * p.Cout;                                     // element offset of this pixel's row in y (and m)
-    if (EPI == EPI_ACTDROP && p.out_s2d)
+    if (p.out_s2d)
         orow = ((((int64_t)n * (p.H >> 1) + (h >> 1)) * (p.W >> 1) + (w >> 1)) * 4 + ((h & 1) * 2 + (w & 1))) * p.Cout;
     __nv_bfloat16* yrow = p.y + orow + co0;
+    if (p.out_d2s) {
+        // this conv's output is the space-to-depth image [N, H, W, 4C] of a [N, 2H, 2W, C] tensor (the dgrad of a stride-2
+        // conv on the 3x3 route): channel block co0 is phase (dy, dx) = co0 / C; write that tensor in its plain layout
+        const int C = p.Cout >> 2, ph = co0 / C;
+        yrow = p.y + ((((int64_t)n * (2 * p.H) + 2 * h + (ph >> 1)) * (2 * p.W) + 2 * w + (ph & 1))) * C + (co0 - ph * C);
+    }
     const int64_t rpix = (p.flags & CTGAN_EPI_RES_UP2) ? ((int64_t)n * (p.H >> 1) + (h >> 1)) * (p.W >> 1) + (w >> 1) : pix;
     const __nv_bfloat16* rrow = (EPI != EPI_ACTDROP && p.residual) ? p.residual + rpix * p.Cout + co0 : nullptr;
     const __nv_bfloat16* mrow = (EPI == EPI_MASK) ? p.relu_mask + pix * p.Cout + co0 : nullptr;
@@ -408,16 +414,21 @@ conv_fprop_tc_lean_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
             const int th = mt % p.tilesH; const int tn = mt / p.tilesH;
             const int w0 = tw * p.BW, h0 = th * p.BH, n0 = tn * p.BN, co0 = nb * BLOCK_N;
             for (int gi = 0; gi < groups; ++gi) {
+                uint32_t rmask = 7u, cmask = 7u;
+                if (HALO) {
+                    s2d_live_masks(p, gi / p.kw, co0, rmask, cmask);
+                    if (!((cmask >> (gi % p.kw)) & 1u)) continue;      // an all-zero filter column of this phase: no stage
+                }
                 const uint32_t sb = s_base + st * STAGE_BYTES, fb = full0 + 8 * st;
                 mbar_wait(empty0 + 8 * st, ph ^ 1);
                 if (HALO) {
                     const int cb = gi / p.kw, s = gi - cb * p.kw;
-                    mbar_expect_tx(fb, a_bytes + NB * B_BYTES);
+                    mbar_expect_tx(fb, a_bytes + (uint32_t)__popc(rmask) * B_BYTES);
                     if (p.hn) tma_load_4d(sb, &tmap_x, fb, cb * BLOCK_K, w0 + s - p.pad_l, n0, h0 - p.pad_t);   // dims (C, W, N, H)
                     else      tma_load_4d(sb, &tmap_x, fb, cb * BLOCK_K, w0 + s - p.pad_l, h0 - p.pad_t, n0);
 #pragma unroll
                     for (int r = 0; r < NB; ++r)
-                        tma_load_3d(sb + A_REGION + r * B_BYTES, &tmap_w, fb, cb * BLOCK_K, co0, r * p.kw + s);
+                        if ((rmask >> r) & 1u) tma_load_3d(sb + A_REGION + r * B_BYTES, &tmap_w, fb, cb * BLOCK_K, co0, r * p.kw + s);
                 } else {
                     const int kb0 = gi * 2, nk = min(2, kblocks - kb0);
                     mbar_expect_tx(fb, (uint32_t)nk * (a_bytes + B_BYTES));
@@ -447,7 +458,22 @@ conv_fprop_tc_lean_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
             mbar_wait(tempty + 8 * acc, ((uint32_t)(it >> 1) & 1u) ^ 1u);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
+            const int co0 = (tile % n_blocks) * BLOCK_N;
+            int last_gi = groups - 1;                               // the last group that is not skipped (see the producer)
+            if (HALO && p.skip_k > 0) {
+                for (; last_gi > 0; --last_gi) {
+                    uint32_t rm, cm;
+                    s2d_live_masks(p, last_gi / p.kw, co0, rm, cm);
+                    if ((cm >> (last_gi % p.kw)) & 1u) break;
+                }
+            }
+            uint32_t accf = 0u;                                     // 0: the first MMA of the tile overwrites the accumulator
             for (int gi = 0; gi < groups; ++gi) {
+                uint32_t rmask = 7u, cmask = 7u;
+                if (HALO) {
+                    s2d_live_masks(p, gi / p.kw, co0, rmask, cmask);
+                    if (!((cmask >> (gi % p.kw)) & 1u)) continue;
+                }
                 mbar_wait(full0 + 8 * st, ph);
                 tc_fence_after();
                 const uint32_t a_lo = st == 0 ? lo[0] : (st == 1 ? lo[1] : lo[2]);
@@ -456,16 +482,18 @@ conv_fprop_tc_lean_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
                 if (elect_one()) {
 #pragma unroll
                     for (int j = 0; j < NB; ++j) {
-                        if (j < nk) {
+                        if (j < nk && (!HALO || ((rmask >> j) & 1u))) {
 #pragma unroll
-                            for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-                                umma_bf16_lo(d_tmem, a_lo + j * row_step + 2 * k, b_lo + j * (B_BYTES >> 4) + 2 * k, idesc,
-                                             (j | k) ? 1u : (gi > 0 ? 1u : 0u));
+                            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                                umma_bf16_lo(d_tmem, a_lo + j * row_step + 2 * k, b_lo + j * (B_BYTES >> 4) + 2 * k, idesc, accf);
+                                accf = 1u;
+                            }
                         }
                     }
                     umma_commit(empty0 + 8 * st);
-                    if (gi == groups - 1) umma_commit(tfull + 8 * acc);
+                    if (gi == last_gi) umma_commit(tfull + 8 * acc);
                 }
+                accf = 1u;
                 __syncwarp();
                 if (++st == STAGES) { st = 0; ph ^= 1; }
             }
@@ -561,14 +589,17 @@ conv_fprop_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
             const int th = mt % p.tilesH, tn = mt / p.tilesH;
             const int h0 = th * p.BH, n0 = tn * p.BN, co0 = nb * BLOCK_N;
             for (int gi = 0; gi < groups; ++gi) {
-                const uint32_t sb = s_base + st * STAGE_BYTES, fb = full0 + 8 * st;
                 const int cb = gi / p.kw, s = gi - cb * p.kw;
+                uint32_t rmask, cmask;
+                s2d_live_masks(p, cb, co0, rmask, cmask);
+                if (!((cmask >> s) & 1u)) continue;                    // an all-zero filter column of this phase: no stage
+                const uint32_t sb = s_base + st * STAGE_BYTES, fb = full0 + 8 * st;
                 mbar_wait(empty0 + 8 * st, ph ^ 1);
-                mbar_expect_tx(fb, (pair ? a2_bytes : a1_bytes) + 3 * B_BYTES);
+                mbar_expect_tx(fb, (pair ? a2_bytes : a1_bytes) + (uint32_t)__popc(rmask) * B_BYTES);
                 tma_load_4d(sb, pair ? &tmap_x2 : &tmap_x, fb, cb * BLOCK_K, s - p.pad_l, h0 - p.pad_t, n0);
 #pragma unroll
                 for (int r = 0; r < 3; ++r)
-                    tma_load_3d(sb + A_REGION + r * B_BYTES, &tmap_w, fb, cb * BLOCK_K, co0, r * p.kw + s);
+                    if ((rmask >> r) & 1u) tma_load_3d(sb + A_REGION + r * B_BYTES, &tmap_w, fb, cb * BLOCK_K, co0, r * p.kw + s);
                 if (++st == STAGES) { st = 0; ph ^= 1; }
             }
             t += pair ? 2 : 1;
@@ -587,7 +618,20 @@ conv_fprop_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
             mbar_wait(tempty + 8 * acc, ((uint32_t)(it >> 1) & 1u) ^ 1u);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 2 * BLOCK_N);
+            const int co0 = (t / m_tiles) * BLOCK_N;
+            int last_gi = groups - 1;                               // the last group that is not skipped (see the producer)
+            if (p.skip_k > 0) {
+                for (; last_gi > 0; --last_gi) {
+                    uint32_t rm, cm;
+                    s2d_live_masks(p, last_gi / p.kw, co0, rm, cm);
+                    if ((cm >> (last_gi % p.kw)) & 1u) break;
+                }
+            }
+            uint32_t accf = 0u;                                     // 0: the first MMA of the item overwrites the accumulators
             for (int gi = 0; gi < groups; ++gi) {
+                uint32_t rmask, cmask;
+                s2d_live_masks(p, gi / p.kw, co0, rmask, cmask);
+                if (!((cmask >> (gi % p.kw)) & 1u)) continue;
                 mbar_wait(full0 + 8 * st, ph);
                 tc_fence_after();
                 const uint32_t a_lo = lo0 + st * (STAGE_BYTES >> 4);
@@ -596,26 +640,30 @@ conv_fprop_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
                     if (pair) {
 #pragma unroll
                         for (int r = 0; r < 3; ++r) {
+                            if (!((rmask >> r) & 1u)) continue;
 #pragma unroll
                             for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                                const uint32_t accf = (r | k) ? 1u : (gi > 0 ? 1u : 0u);
                                 umma_bf16_lo(d_tmem, a_lo + r * row_step + 2 * k, b_lo + r * (B_BYTES >> 4) + 2 * k, idesc, accf);
                                 umma_bf16_lo(d_tmem + BLOCK_N, a_lo + tile1_off + r * row_step + 2 * k, b_lo + r * (B_BYTES >> 4) + 2 * k,
                                              idesc, accf);
+                                accf = 1u;
                             }
                         }
                     } else {
 #pragma unroll
                         for (int r = 0; r < 3; ++r) {
+                            if (!((rmask >> r) & 1u)) continue;
 #pragma unroll
-                            for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-                                umma_bf16_lo(d_tmem, a_lo + r * row_step + 2 * k, b_lo + r * (B_BYTES >> 4) + 2 * k, idesc,
-                                             (r | k) ? 1u : (gi > 0 ? 1u : 0u));
+                            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                                umma_bf16_lo(d_tmem, a_lo + r * row_step + 2 * k, b_lo + r * (B_BYTES >> 4) + 2 * k, idesc, accf);
+                                accf = 1u;
+                            }
                         }
                     }
                     umma_commit(empty0 + 8 * st);
-                    if (gi == groups - 1) umma_commit(tfull + 8 * acc);
+                    if (gi == last_gi) umma_commit(tfull + 8 * acc);
                 }
+                accf = 1u;
                 __syncwarp();
                 if (++st == STAGES) { st = 0; ph ^= 1; }
             }
@@ -1282,7 +1330,12 @@ static int fprop_tc_launch(const ctgan_conv_desc* d, const void* x, const void* 
     // (BH+2)-row box per (cin block, column shift) instead of one box per tap: 2.4x less activation traffic per tile
     // (a sub-wave layer that cluster split-K takes keeps the per-tap boxes that kernel expects)
     const int n_tiles_all = p.tilesW * p.tilesH * p.tilesN * (d->Cout / 128);
-    const int split_all = (g_use_splitk && block_n == 128) ? splitk_factor(n_tiles_all, (d->kh * d->kw * (d->Cin / 64) + 1) / 2) : 0;
+    // launches with a layout-changing epilogue stay on the lean / pair kernels; zero-block skipping (an optimisation only)
+    // applies where those kernels run anyway: a sub-wave layer keeps the cluster split-K kernel and multiplies the zeros
+    const bool special = (epi != EPI_ACTDROP && p.out_s2d) || p.out_d2s;
+    CTGAN_REQUIRE(!(special || p.skip_k > 0) || (block_n == 128 && g_fprop_variant >= 3), CTGAN_ERR_UNSUPPORTED,
+                  "conv_fprop_tc: OUT_S2D / OUT_D2S / S2D_SKIP need Cout %% 128 == 0 and the lean kernel family");
+    const int split_all = (g_use_splitk && block_n == 128 && !special) ? splitk_factor(n_tiles_all, (d->kh * d->kw * (d->Cin / 64) + 1) / 2) : 0;
     const bool halo_hn = !halo && g_use_halo_hn && block_n == 128 && d->kh == 3 && p.BN > 1 && p.tilesW == 1 && p.tilesH == 1 &&
                          (p.BN * p.BW) % 8 == 0 && (uint32_t)(p.BH + 2) * p.BN * p.BW * 128u <= 24576u && g_fprop_variant >= 3 &&
                          !split_all;
@@ -1309,7 +1362,7 @@ static int fprop_tc_launch(const ctgan_conv_desc* d, const void* x, const void* 
         }
         // fewer tiles than half the SMs: split K over a cluster of 2 / 4 CTAs (conv_splitk.cu)
         const int n_tiles = p.tilesW * p.tilesH * p.tilesN * (d->Cout / 128);
-        const int split = g_use_splitk ? splitk_factor(n_tiles, (d->kh * d->kw * (d->Cin / 64) + 1) / 2) : 0;
+        const int split = (g_use_splitk && !special) ? splitk_factor(n_tiles, (d->kh * d->kw * (d->Cin / 64) + 1) / 2) : 0;
         if (split) return launch_fprop_splitk(split, epi, mx, mw, p, n_tiles, st);
         if (epi == EPI_ACTDROP) return launch_fprop_lean<0, EPI_ACTDROP>(mx, mw, p, st);
         if (epi == EPI_MASK) return launch_fprop_lean<0, EPI_MASK>(mx, mw, p, st);
@@ -1346,6 +1399,18 @@ extern "C" int ctgan_conv_fprop_tc_masked(const ctgan_conv_desc* d, const void* 
     p.bias = bias;
     p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
     p.relu_mask = reinterpret_cast<const __nv_bfloat16*>(relu_mask);
+    p.out_s2d = (flags & CTGAN_EPI_OUT_S2D) ? 1 : 0;
+    p.out_d2s = (flags & CTGAN_EPI_OUT_D2S) ? 1 : 0;
+    CTGAN_REQUIRE(!p.out_s2d || (d->H % 2 == 0 && d->W % 2 == 0 && !p.out_d2s), CTGAN_ERR_UNSUPPORTED,
+                  "conv_fprop_tc: OUT_S2D needs even H, W (and excludes OUT_D2S)");
+    CTGAN_REQUIRE(!p.out_d2s || (d->Cout % 512 == 0 && !residual), CTGAN_ERR_UNSUPPORTED,
+                  "conv_fprop_tc: OUT_D2S needs Cout = 4C with C %% 128 == 0 and no residual");
+    if (flags & CTGAN_EPI_S2D_SKIP) {
+        p.skip_mode = (flags >> 9) & 1; p.skip_k = (flags >> 10) & 15; p.skip_pad_t = (flags >> 14) & 3; p.skip_pad_l = (flags >> 16) & 3;
+        CTGAN_REQUIRE(d->kh == 3 && d->kw == 3 && p.skip_k >= 3 && p.skip_k <= 7 &&
+                      (p.skip_mode ? d->Cout % 512 == 0 : d->Cin % 256 == 0), CTGAN_ERR_UNSUPPORTED,
+                      "conv_fprop_tc: S2D_SKIP needs a 3x3 filter over 4C channels, C %% 64 == 0 (input phases) / C %% 128 == 0 (output phases)");
+    }
     return fprop_tc_launch(d, x, wp, p, relu_mask ? EPI_MASK : EPI_PLAIN, stream);
 }
 

@@ -185,8 +185,33 @@ struct FpropParams {
     float slope, keep;
     unsigned long long seed, offset;
     const unsigned long long* dyn;
-    int out_s2d;
+    int out_s2d;                   // any epilogue (CTGAN_EPI_OUT_S2D / the actdrop entry): y (and m) in the space-to-depth layout
+    int out_d2s;                   // CTGAN_EPI_OUT_D2S: y is a space-to-depth image, written as the plain tensor it stands for
+    // CTGAN_EPI_S2D_SKIP: the 3x3 filter embeds a stride-2 skip_k x skip_k one (conv_s2d.cu): (tap, phase) blocks that hold no
+    // filter element are all-zero and are neither loaded nor multiplied.  skip_mode 0: phases = 64-channel blocks of the
+    // INPUT (fprop over the space-to-depth image), 1: phases = 128-channel blocks of the OUTPUT, taps flipped (its dgrad)
+    int skip_k, skip_mode, skip_pad_t, skip_pad_l;
 };
+
+// live embedded taps (bit R of the result) of phase coordinate d: source tap 2(R-1) + d + pad inside [0, k)
+__device__ __forceinline__ uint32_t s2d_live3(int k, int pad, int d, bool flip) {
+    uint32_t m = 0;
+#pragma unroll
+    for (int R = 0; R < 3; ++R) {
+        const int r = 2 * (R - 1) + d + pad;
+        if (r >= 0 && r < k) m |= 1u << (flip ? 2 - R : R);
+    }
+    return m;
+}
+// (row mask, column mask) of the live taps for input-channel block cb / output-channel block co0 of a launch; 7, 7 = all
+__device__ __forceinline__ void s2d_live_masks(const FpropParams& p, int cb, int co0, uint32_t& rmask, uint32_t& cmask) {
+    rmask = cmask = 7u;
+    if (p.skip_k > 0) {
+        const int ph = p.skip_mode ? co0 / (p.Cout >> 2) : (cb * 64) / (p.Cin >> 2);
+        rmask = s2d_live3(p.skip_k, p.skip_pad_t, ph >> 1, p.skip_mode != 0);
+        cmask = s2d_live3(p.skip_k, p.skip_pad_l, ph & 1, p.skip_mode != 0);
+    }
+}
 
 
 enum { EPI_PLAIN = 0, EPI_MASK = 1, EPI_ACTDROP = 2 };

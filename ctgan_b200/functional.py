@@ -105,6 +105,9 @@ def _direct(p):
 def _direct_wgrad(x, gy, g, w, col):
     """w.grad += wgrad(x, gy) in the final backward: tensor-core jobs are queued and run as ONE launch over all layers at the
     step's join (K.flush_wgrads); the other routes launch now on the side stream."""
+    ent = _box_by_w4.get(w.data_ptr())
+    if ent is not None:
+        _box_dirty[w.data_ptr()] = ent           # its scratch gradient is folded into the 3x3 parameter's at the next join
     if K.wgrad_deferrable(x, gy, g):
         K.conv_wgrad(x, gy, g, tuple(w.shape), accumulate_into=w.grad, col=col, defer=True)
     else:
@@ -129,8 +132,11 @@ class S2DAct:
     that consumes it: written that way by the producing conv's fused epilogue (ConvF act=..., out_s2d), read directly as
     the 3x3 tensor-core conv's input -- no layout kernel in between."""
 
-    def __init__(self, t, C, H, W):
+    def __init__(self, t, C, H, W, plain_grad=False):
         self.t, self.C, self.H, self.W = t, C, H, W
+        # plain_grad: the producer (ConvF out_s2d) expects the gradient of t with the PLAIN [N, C, H, W] layout inside t's
+        # shape -- what the consuming conv's dgrad epilogue writes (OUT_D2S), see conv_mean_pool_s2d
+        self.plain_grad = plain_grad
 
     @property
     def shape(self):
@@ -142,6 +148,66 @@ class S2DAct:
     @property
     def dtype(self):
         return self.t.dtype
+
+
+def _plain_in_s2d_shape(x):
+    """The plain NHWC tensor x [N, C, H, W] re-viewed (no copy) with the shape [N, 4C, H/2, W/2] of its space-to-depth image."""
+    N, C, H, W = x.shape
+    return x.permute(0, 2, 3, 1).reshape(N, H // 2, W // 2, 4 * C).permute(0, 3, 1, 2)
+
+
+def _s2d_shape_as_plain(t):
+    """Inverse of _plain_in_s2d_shape: t [N, 4C, Hs, Ws] holding plain-layout content -> [N, C, 2Hs, 2Ws]."""
+    N, C4, Hs, Ws = t.shape
+    return t.permute(0, 2, 3, 1).reshape(N, 2 * Hs, 2 * Ws, C4 // 4).permute(0, 3, 1, 2)
+
+
+# ConvMeanPool(3x3) filters as derived 4x4 / stride-2 filters (csrc/conv_s2d.cu: box_filter_kernel)
+_box_filters = {}        # 3x3 parameter ptr -> (w3, w4)
+_box_by_w4 = {}          # w4 ptr -> (w3, w4)
+_box_dirty = {}          # w4 ptr -> (w3, w4) whose scratch gradient holds contributions of the running backward pass
+
+
+def box_filter(w3):
+    """The 'SAME' 4x4 / stride-2 filter W4 = boxsum(w3) / 4 that makes mean_pool_2x2(conv3x3(x, w3)) ONE conv (2.25x fewer
+    multiply-adds, TG/CT_gan_cifar_resnet.py:89-92): a leaf kept current by FilterPacker.refresh() after every optimizer
+    step; the filter-gradient kernels accumulate into its scratch .grad, folded into w3.grad at the step's join."""
+    ent = _box_filters.get(w3.data_ptr())
+    if ent is not None and ent[0] is w3:
+        return ent[1]
+    w3d = w3.detach()
+    w4 = torch.empty((4, 4) + tuple(w3.shape[2:]), dtype=torch.float32, device=w3.device).requires_grad_(True)
+    w4.grad = K.zeros(tuple(w4.shape), torch.float32, w3.device)
+    w4d = w4.detach()
+    K.box_filter(w3d, w4d)
+    register_param(w4)
+    derived_from(w4, w3)
+    K.register_derived_filter(w3, w4, lambda: K.box_filter(w3d, w4d))
+    _box_filters[w3.data_ptr()] = _box_by_w4[w4.data_ptr()] = (w3, w4)
+    return w4
+
+
+def _fold_box_grads():
+    for w3, w4 in _box_dirty.values():
+        if w3.grad is not None:
+            K.box_filter_grad(w4.grad, w3.grad)
+    _box_dirty.clear()
+
+
+K._join_hooks.append(_fold_box_grads)
+
+
+class S2DMask(Function):
+    """xs = space_to_depth(x) * [pattern > 0], pattern a ReLU output in the space-to-depth layout: the adjoint of a dgrad
+    epilogue that applied that ReLU's backward and wrote the plain layout (the gradient penalty's double backward)."""
+
+    @staticmethod
+    def forward(ctx, x, pattern, geom):
+        return K.space_to_depth_mask(x, pattern, geom)
+
+    @staticmethod
+    def backward(ctx, c):
+        raise RuntimeError('ctgan_b200: S2DMask is differentiated once (third-order gradients are not needed)')
 
 
 def _plain_geom(N, H, W, C):
@@ -179,7 +245,7 @@ class S2DMul(Function):
 class ConvF(Function):
     @staticmethod
     def forward(ctx, x, w, b, g, out_dtype, col=None, residual=None, relu=False, in_relu=False, relu_bwd_fused=False,
-                res_up2=False, act=None, x_s2d=False):
+                res_up2=False, act=None, x_s2d=False, out_s2d=False):
         # res_up2: residual has half the output resolution and is added nearest-neighbour upsampled
         ctx.res_up2 = res_up2
         # in_relu: x is the output of a ReLU whose backward this conv applies in its dgrad epilogue (dx zeroed where
@@ -194,6 +260,18 @@ class ConvF(Function):
         ctx.x_s2d = x_s2d
         ctx.col = x if x_s2d else (col if col is not None else K.thin_col(x, g, 'x'))   # im2col / s2d of x: built once, reused by wgrad
         ctx.mult = ctx.out_geom = None
+        # out_s2d (no act): y = [relu](conv + b) written by the epilogue in the space-to-depth layout of the stride-2 conv that
+        # consumes it (conv_mean_pool_s2d); that conv's dgrad applies the ReLU's backward and returns the PLAIN layout
+        ctx.out_plain_grad = False
+        if out_s2d and act is None:
+            if not (relu and relu_bwd_fused) or residual is not None or x_s2d:
+                raise RuntimeError('ctgan_b200: ConvF(out_s2d) is the relu-fused producer of a conv_mean_pool_s2d only')
+            y = K.conv_fprop(x, w, b, g, out_dtype=out_dtype, w_is_param=_is_param(w), col=ctx.col, relu=True, out_s2d=True)
+            ctx.relu_out = y.detach()
+            ctx.out_plain_grad = True
+            if pattern_recorder is not None:
+                pattern_recorder(K.depth_to_space(y.detach(), _plain_geom(g.N, g.Ho, g.Wo, g.Cout)) > 0)
+            return y
         if act is not None:
             # act = (slope, keep, seed, offset, dyn, out_s2d): bias + LeakyReLU + dropout in the conv epilogue; the
             # multiplier m it stores makes backward and double backward plain products (MulConst / D2SMul)
@@ -222,6 +300,8 @@ class ConvF(Function):
     def backward(ctx, gy):
         x, w = ctx.saved_tensors
         gy = _dense_like(gy, True)
+        if ctx.out_plain_grad:
+            gy = _s2d_shape_as_plain(gy)
         if ctx.mult is not None:
             gy = D2SMul.apply(gy, ctx.mult, ctx.out_geom) if ctx.out_geom is not None else MulConst.apply(gy, ctx.mult)
         if ctx.relu_out is not None and not ctx.relu_bwd_fused:
@@ -252,7 +332,7 @@ class ConvF(Function):
         if n_in > 6 and ctx.needs_input_grad[6]:
             gr = gy_res if gy_res is not None else gy
             g_res = Pool.apply(gr, 1.0) if ctx.res_up2 else gr       # adjoint of the 2x nearest upsample: 2x2 sums
-        return (gx, gw, gb, None, None, None, g_res, None, None, None, None, None, None)[:n_in]
+        return (gx, gw, gb, None, None, None, g_res, None, None, None, None, None, None, None)[:n_in]
 
 
 class ConvD(Function):
@@ -265,6 +345,12 @@ class ConvD(Function):
         ctx.out_s2d = out_s2d
         ctx.save_for_backward(gy, w)
         ctx.relu_mask = relu_mask                     # constant: dx = conv^T(gy, w) * [relu_mask > 0]
+        # an s2d-fed conv behind a fused ReLU (conv_mean_pool_s2d): relu_mask has the space-to-depth layout, dx is masked
+        # and written in the PLAIN layout by the dgrad epilogue, handed back inside the shape of the layer's input
+        ctx.plain_grad = bool(out_s2d and relu_mask is not None)
+        if ctx.plain_grad:
+            dx = K.conv_dgrad(gy, w, g, out_dtype=out_dtype, w_is_param=_is_param(w), col=col, relu_mask=relu_mask)
+            return _plain_in_s2d_shape(dx)
         return K.conv_dgrad(gy, w, g, out_dtype=out_dtype, w_is_param=_is_param(w), col=col, relu_mask=relu_mask,
                             out_s2d=out_s2d)
 
@@ -272,7 +358,10 @@ class ConvD(Function):
     def backward(ctx, c):
         gy, w = ctx.saved_tensors
         c = _dense_like(c, True)
-        if ctx.relu_mask is not None:
+        if ctx.plain_grad:
+            g_ = ctx.g
+            c = S2DMask.apply(_dense_like(_s2d_shape_as_plain(c), True), ctx.relu_mask, _plain_geom(g_.N, g_.H, g_.W, g_.Cin))
+        elif ctx.relu_mask is not None:
             c = MulReluMask.apply(c, ctx.relu_mask)
         ggy = gw = None
         ccol = c if ctx.out_s2d else K.thin_col(c, ctx.g, 'x')   # im2col / s2d of c: shared by fprop and wgrad
@@ -320,9 +409,49 @@ def ensure_nhwc(x):
     return x
 
 
+def conv2d_s2d_out_ok(x, cout, k):
+    """True when conv2d(x, ., ., k, 1, relu=True, relu_bwd_fused=True, out_s2d=True) has a route."""
+    if isinstance(x, S2DAct) or x.dim() != 4:
+        return False
+    N, H, W, Cin = K.nhwc_dims(x)
+    return K.conv_fprop_s2d_out_ok(x, K.same_geom(N, H, W, Cin, cout, k, 1))
+
+
+def conv_mean_pool_s2d_ok(x, cin, cout):
+    """True when mean_pool_2x2(conv3x3(x)) of a bf16 [N, cin, H, W] activation can run as ONE stride-2 4x4 conv on the
+    space-to-depth route (all three of its kernels on the tensor cores, zero blocks skipped)."""
+    if not (K.config.pool_conv_s2d and K.config.s2d_embed_wgrad and direct_param_grads) or x.dim() != 4 or not x.is_cuda:
+        return False
+    N, H, W, _ = K.nhwc_dims(x)
+    if H % 2 or W % 2 or cin % 128 or cout % 128 or x.dtype != torch.bfloat16:
+        return False
+    if N * H * W // 512 < K.config.pool_conv_min_tiles:
+        # a quarter of the tiles, each with 16/9 of the k-blocks: a layer that is already below one wave of 128-pixel tiles
+        # is latency-bound and only gets slower (Discriminator.2.Conv2 at batch 64: 128 -> 32 tiles)
+        return False
+    g = K.same_geom(N, H, W, cin, cout, 4, 2)
+    g3 = K.s2d_geom(g, x)
+    return g3 is not None and K._wgrad_multi_ok(g3)
+
+
+def conv_mean_pool_s2d(xs, w3, b, residual=None):
+    """mean_pool_2x2(conv2d(x, w3, 'SAME') + b) [+ residual] for x = relu(.) handed over as an S2DAct by its producer
+    (conv2d(..., relu=True, relu_bwd_fused=True, out_s2d=True)): ONE 'SAME' 4x4 / stride-2 conv with the box-summed filter
+    (functional.box_filter), 16 taps at a quarter of the positions.  Its dgrad applies the producer's ReLU backward."""
+    if not (isinstance(xs, S2DAct) and xs.plain_grad):
+        raise RuntimeError('ctgan_b200: conv_mean_pool_s2d needs the S2DAct of a conv2d(out_s2d=True) producer')
+    w4 = box_filter(w3)
+    N, Cin, H, W = xs.shape
+    g = K.same_geom(N, H, W, Cin, w4.shape[-1], 4, 2)
+    if residual is not None:
+        residual = ensure_nhwc(residual)
+    return ConvF.apply(xs.t, w4, b, g, xs.dtype, None, residual, False, True, False, False, None, True)
+
+
 def conv2d(x, w, b, k, stride, out_dtype=None, residual=None, relu=False, in_relu=False, relu_bwd_fused=False,
-           res_up2=False):
-    """tf.nn.conv2d(SAME) + bias_add on a logical-NCHW activation (+ an optional residual added in the epilogue)."""
+           res_up2=False, out_s2d=False):
+    """tf.nn.conv2d(SAME) + bias_add on a logical-NCHW activation (+ an optional residual added in the epilogue).
+    out_s2d: return the result as an S2DAct for conv_mean_pool_s2d (see conv2d_s2d_out_ok)."""
     if isinstance(x, S2DAct):
         N, Cin, H, W = x.shape
         g = K.same_geom(N, H, W, Cin, w.shape[-1], k, stride)
@@ -331,6 +460,9 @@ def conv2d(x, w, b, k, stride, out_dtype=None, residual=None, relu=False, in_rel
         return ConvF.apply(x.t, w, b, g, out_dtype or x.dtype, None, None, False, False, False, False, None, True)
     N, H, W, Cin = K.nhwc_dims(x)
     g = K.same_geom(N, H, W, Cin, w.shape[-1], k, stride)
+    if out_s2d:
+        y = ConvF.apply(x, w, b, g, out_dtype or x.dtype, None, None, relu, in_relu, relu_bwd_fused, False, None, False, True)
+        return S2DAct(y, w.shape[-1], g.Ho, g.Wo, plain_grad=True)
     if residual is not None:
         residual = ensure_nhwc(residual)
         want = (N, w.shape[-1], g.Ho // 2, g.Wo // 2) if res_up2 else (N, w.shape[-1], g.Ho, g.Wo)

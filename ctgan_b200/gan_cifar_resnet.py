@@ -166,6 +166,12 @@ def ResidualBlock(name, input_dim, output_dim, filter_size, inputs, resample=Non
 
     if fused_act:
         # N2 = relu(conv_1(.)) in conv_1's epilogue; its backward ([output > 0]) in conv_2's dgrad epilogue
+        if resample == 'down' and _pool_conv_fused(pre_act, input_dim, input_dim, output_dim, filter_size):
+            # conv_1 hands relu(conv_1) over in the space-to-depth layout; conv_2 + mean pool + skip add are ONE stride-2 conv
+            output = conv_1(name + '.Conv1', filter_size=filter_size, inputs=pre_act, relu=True, relu_bwd_fused=True, out_s2d=True)
+            output = lib.ops.conv2d.Conv2D(name + '.Conv2', input_dim, output_dim, filter_size, output, mean_pool=True,
+                                           residual=shortcut)
+            return _dropout_relu(output, fork_keep) if fork_keep is not None else output
         output = conv_1(name + '.Conv1', filter_size=filter_size, inputs=pre_act, relu=True, relu_bwd_fused=FUSE_RELU_BWD)
         if resample == 'down' and fork_keep is not None:
             full = lib.ops.conv2d.Conv2D(name + '.Conv2', input_dim, output_dim, filter_size, output, in_relu=FUSE_RELU_BWD)
@@ -192,6 +198,13 @@ def ResidualBlock(name, input_dim, output_dim, filter_size, inputs, resample=Non
     return F.add(shortcut, output)
 
 
+def _pool_conv_fused(x, cin, cmid, cout, filter_size):
+    """True when [3x3 conv cin -> cmid, relu, ConvMeanPool(3x3) cmid -> cout] on activation x takes the fused route: the
+    first conv writes the space-to-depth layout, the second and its mean pool run as one stride-2 4x4 conv."""
+    return (FUSE_D_ACT and FUSE_RELU_BWD and FUSE_SKIP_ADD and filter_size == 3 and not isinstance(x, F.S2DAct)
+            and F.conv2d_s2d_out_ok(x, cmid, 3) and F.conv_mean_pool_s2d_ok(x, cmid, cout))
+
+
 def _pool_add_fork(full, shortcut, keep):
     """(d, relu(d)), d = dropout(meanpool(full) + shortcut)"""
     if keep == 1.0:
@@ -208,6 +221,10 @@ def OptimizedResBlockDisc1(inputs, fork=False):
                              biases=True, inputs=inputs)
 
     output = inputs_main
+    if FUSE_D_ACT and _pool_conv_fused(output, 3, DIM_D, DIM_D, 3):
+        output = conv_1('Discriminator.1.Conv1', filter_size=3, inputs=output, relu=True, relu_bwd_fused=True, out_s2d=True)
+        output = lib.ops.conv2d.Conv2D('Discriminator.1.Conv2', DIM_D, DIM_D, 3, output, mean_pool=True, residual=shortcut)
+        return F.fork_relu(output) if fork else output
     if FUSE_D_ACT:
         # nonlinearity in conv_1's epilogue, its backward in conv_2's dgrad epilogue
         output = conv_1('Discriminator.1.Conv1', filter_size=3, inputs=output, relu=True, relu_bwd_fused=FUSE_RELU_BWD)

@@ -27,6 +27,11 @@ class Config:
     branch_streams = True    # run independent sub-graphs of a step (GP pass vs stacked pass) as stream branches
     branch_priority = 0      # CUDA stream priority of the branch stream (lower = higher priority): equal priorities measure best
     critic_splitk = False    # cluster split-K inside the two-branch ResNet critic step (see kernels.splitk)
+    s2d_skip = True          # space-to-depth route: skip the (tap, phase) blocks of the embedded 3x3 filter that hold no filter element
+    s2d_skip_max_k = 4       # ... for stride-2 filters up to this size: 16 of 36 blocks live for k = 4; with k = 5 (25 of 36) the
+                             # shorter MMA stream does not pay for the issue loop's mask arithmetic (CIFAR-DCGAN 248 -> 243 it/s)
+    pool_conv_min_tiles = 96 # ... for layers with at least this many 128-pixel output tiles (measured, profiles/r02_experiments.md)
+    pool_conv_s2d = True     # ConvMeanPool(3x3) as ONE stride-2 4x4 conv on the space-to-depth route (gan_cifar_resnet.ConvMeanPool)
     s2d_embed_wgrad = True   # stride-2 filter gradients: the embedded 3x3 job writes the k x k gradient itself (no scratch + gather)
     decouple_gp = False      # ResNet critic step: the stacked pass runs its own backward as soon as its half of the loss is known,
                              # the gradient penalty is differentiated on its stream branch (two backward calls, gan_cifar_resnet.py).
@@ -45,6 +50,13 @@ class Config:
 
 
 config = Config()
+import os as _os
+# A/B hook for the benches and tests/graph_times.py: CTGAN_CONFIG="pool_conv_s2d=0,s2d_skip=0" overrides switches at import
+for _kv in filter(None, _os.environ.get('CTGAN_CONFIG', '').split(',')):
+    _k, _v = _kv.split('=')
+    if not hasattr(Config, _k.strip()):
+        raise RuntimeError('ctgan_b200: CTGAN_CONFIG names an unknown switch %r' % _k)
+    setattr(config, _k.strip(), type(getattr(Config, _k.strip()))(int(_v)))
 # A/B switches from the environment (benchmarks): CTGAN_PEER_UPDATE=0 -> NCCL all-reduce + Adam instead of the peer-memory kernel
 import os as _os
 if _os.environ.get('CTGAN_PEER_UPDATE') is not None:
@@ -144,6 +156,8 @@ def join_side():
         for dev in {d for d, _ in _side_pending}:
             torch.cuda.current_stream(dev).wait_stream(_side_streams[dev])
         _side_pending.clear()
+    for hook in _join_hooks:
+        hook()
 
 
 class splitk:
@@ -257,12 +271,37 @@ def invalidate_weight_cache(ptrs=None, forget=False):
     if ptrs is None:
         _pack_cache.clear()
         _lazy_packs.clear()
+        _derived_filters.clear()
         return
     for k in [k for k in _pack_cache if k[0] in ptrs]:
         del _pack_cache[k]
     if forget:
         for ptr in ptrs:
             _lazy_packs.pop(ptr, None)
+            for d, _ in _derived_filters.pop(ptr, ()):
+                _lazy_packs.pop(d.data_ptr(), None)
+
+
+# Filters COMPUTED from a parameter by a kernel of their own (ConvMeanPool's box-summed 4x4 filter, functional.box_filter):
+# {parameter ptr: [(derived tensor, launch that recomputes it in place)]}.  FilterPacker.refresh() re-runs the launches and
+# re-packs the derived tensors' operands after every optimizer step; _join_hooks fold their scratch gradients back.
+_derived_filters = {}
+_join_hooks = []
+
+
+def register_derived_filter(src, derived, refresh):
+    _derived_filters.setdefault(src.data_ptr(), []).append((derived, refresh))
+
+
+def box_filter(w3, w4):
+    """w4 [4,4,Cin,Cout] = the 'SAME' 4x4 / stride-2 filter equal to mean-pooling the 'SAME' 3x3 conv with w3 over 2x2 windows."""
+    call('ctgan_box_filter', _p(w3), _p(w4), w3.shape[2], w3.shape[3], _stream())
+    return w4
+
+
+def box_filter_grad(dw4, dw3):
+    """dw3 += the adjoint of box_filter applied to dw4; dw4 is cleared."""
+    call('ctgan_box_filter_grad', _p(dw4), _p(dw3), dw3.shape[2], dw3.shape[3], _stream())
 
 
 def pack_filter(w, transpose_flip, cacheable=False):
@@ -381,7 +420,8 @@ def im2col_thin(src, g, C, sign):
 def _gemm1x1_tc(x, wp, bias, g, cin, cout, residual=None, flags=0):
     """1x1 tensor-core conv over the pixels of g: [P x cin] x packed filter -> [P x cout]."""
     g1 = ConvGeom(g.N, g.H, g.W, cin, g.H, g.W, cout, 1, 1, 1, 0, 0)
-    y = empty_act((g.N, cout, g.H, g.W), torch.bfloat16, x.device)
+    s2d = bool(flags & _lib.EPI_OUT_S2D)
+    y = empty_act((g.N, 4 * cout, g.H // 2, g.W // 2) if s2d else (g.N, cout, g.H, g.W), torch.bfloat16, x.device)
     d = _desc(g1, BF16, BF16)
     call('ctgan_conv_fprop_tc', ctypes.byref(d), _p(x), _p(wp), _p(bias), _p(residual), _p(y), flags, _stream())
     return y
@@ -458,7 +498,10 @@ class FilterPacker:
         if not (config.use_tc and tc_available()):
             return
         # the per-filter packs (space-to-depth / thin-channel operands) run on the side stream next to the one-launch pack
-        lazy = [ptr for ptr in self.param_ptrs if _lazy_packs.get(ptr)]
+        derived = [e for ptr in self.param_ptrs for e in _derived_filters.get(ptr, ())]
+        for _, recompute in derived:
+            recompute()
+        lazy = [ptr for ptr in self.param_ptrs + [d.data_ptr() for d, _ in derived] if _lazy_packs.get(ptr)]
         if lazy:
             on_side(lambda: refresh_lazy_packs(lazy), self.flat_p)
         if self.n:
@@ -509,6 +552,22 @@ def s2d_geom(g, t=None):
     if (4 * g.Cin) % 64 or g.Cout % 64:
         return None
     return ConvGeom(g.N, Hs, Ws, 4 * g.Cin, Hs, Ws, g.Cout, 3, 3, 1, 1, 1)
+
+
+def _s2d_skip_flags(g, mode):
+    """CTGAN_EPI_S2D_SKIP flags for the 3x3 launch that stands for the stride-2 conv g (mode 0: its fprop, 1: its dgrad)."""
+    if not config.s2d_skip or g.Cin % (128 if mode else 64) or not (3 <= g.kh <= config.s2d_skip_max_k):
+        return 0
+    return _lib.EPI_S2D_SKIP | (mode << 9) | (g.kh << 10) | (g.pad_t << 14) | (g.pad_l << 16)
+
+
+def space_to_depth_mask(x, pattern, g):
+    """xs = space_to_depth(x) where `pattern` (a ReLU output in the space-to-depth layout) is positive, else 0."""
+    require_nhwc(x, 'x'); require_nhwc(pattern, 'pattern')
+    xs = empty_act((g.N, 4 * g.Cin, (g.H + 1) // 2, (g.W + 1) // 2), x.dtype, x.device)
+    _same_layout(pattern, xs)
+    call('ctgan_space_to_depth_mask', _p(x), _p(pattern), _p(xs), g.N, g.H, g.W, g.Cin, _dt(x), _stream())
+    return xs
 
 
 def space_to_depth(x, g, mul=None):
@@ -626,9 +685,32 @@ def pack_filter_padk(w, g, flip, cacheable=False):
                       lambda bufs: _pack_filter_padk_launch(wd, bufs[0], bufs[1], g), cacheable)[flip]
 
 
-def conv_fprop(x, w, bias, g, relu=False, residual=None, out_dtype=None, w_is_param=False, col=None, res_up2=False):
+def conv_fprop_s2d_out_ok(x, g):
+    """True when conv_fprop(x, ., ., g, out_s2d=True) has a route (the tcgen05 epilogue writes the space-to-depth layout)."""
+    if not (config.use_tc and tc_available() and x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 4):
+        return False
+    if g.stride != 1 or g.Ho % 2 or g.Wo % 2 or g.Cout % 128:
+        return False
+    return _tc_geom_ok(g) or (_thin_split(g, x) is None and _thin_side(g, x) == 'in')
+
+
+def conv_fprop(x, w, bias, g, relu=False, residual=None, out_dtype=None, w_is_param=False, col=None, res_up2=False,
+               out_s2d=False):
     """y = conv(x, w) [+ bias] [+ residual] [relu].  x NHWC/2-D act, w float HWIO.
-    res_up2: residual is [N, Cout, Ho/2, Wo/2] and is added nearest-neighbour upsampled (in the tensor-core epilogue)."""
+    res_up2: residual is [N, Cout, Ho/2, Wo/2] and is added nearest-neighbour upsampled (in the tensor-core epilogue).
+    out_s2d (see conv_fprop_s2d_out_ok): y is returned in the space-to-depth layout [N, 4*Cout, Ho/2, Wo/2] of the stride-2
+    conv that consumes it."""
+    if out_s2d:
+        if not conv_fprop_s2d_out_ok(x, g) or residual is not None:
+            raise RuntimeError('ctgan_b200: conv_fprop(out_s2d=True) needs a tensor-core route and no residual')
+        require_nhwc(x, 'x')
+        _check_filter(w, g)
+        flags = (_lib.EPI_RELU if relu else 0) | _lib.EPI_OUT_S2D
+        if _tc_geom_ok(g):
+            y = empty_act((g.N, 4 * g.Cout, g.Ho // 2, g.Wo // 2), torch.bfloat16, x.device)
+            return _fprop_tc_packed(x, pack_filter(w, 0, cacheable=w_is_param), bias, None, None, y, g, flags)
+        col = col if col is not None else im2col_thin(x, g, g.Cin, 1)
+        return _gemm1x1_tc(col, pack_filter_thin(w, 0, cacheable=w_is_param), bias, g, 64, g.Cout, None, flags)
     if res_up2 and residual is not None and not (_dt(x) == BF16 and (out_dtype or x.dtype) == torch.bfloat16 and _tc_geom_ok(g)):
         residual, res_up2 = upsample2x(residual, 1.0), False        # other paths: materialise the upsampled residual
     require_nhwc(x, 'x')
@@ -659,7 +741,8 @@ def conv_fprop(x, w, bias, g, relu=False, residual=None, out_dtype=None, w_is_pa
         if residual is not None:
             require_nhwc(residual, 'residual')
         xs = col if (col is not None and tuple(col.shape) == (g3.N, g3.Cin, g3.H, g3.W)) else space_to_depth(x, g)
-        return _fprop_tc_packed(xs, pack_filter_s2d(w, g, 0, cacheable=w_is_param), bias, residual, None, y, g3, flags)
+        return _fprop_tc_packed(xs, pack_filter_s2d(w, g, 0, cacheable=w_is_param), bias, residual, None, y, g3,
+                                flags | _s2d_skip_flags(g, 0))
     if xdt == BF16 and ydt == BF16 and thin_s2_ok(g, x):      # y = im2col_strided(x) x W128
         if residual is not None:
             require_nhwc(residual, 'residual')
@@ -757,13 +840,24 @@ def conv_dgrad(dy, w, g, out_dtype=None, w_is_param=False, col=None, relu_mask=N
         gt = ConvGeom(g.N, g.H, g.W, g.Cout, g.H, g.W, g.Cin, g.kh, g.kw, 1, g.kh - 1 - g.pad_t, g.kw - 1 - g.pad_l)
         if g.stride == 1 and g.Ho == g.H and g.Wo == g.W and _tf32_geom_ok(gt):
             return _fprop_tf32(dy, pack_filter_f32(w, 1, cacheable=w_is_param), None, None, relu_mask, dx, gt, 0)
+    g3 = s2d_geom(g, dy) if (xdt == BF16 and ydt == BF16) else None
+    if relu_mask is not None and g3 is not None and tuple(relu_mask.shape) == (g3.N, g3.Cin, g3.H, g3.W):
+        # the mask is the conv's input in the SPACE-TO-DEPTH layout (a ReLU output written that way by its producer)
+        gt = ConvGeom(g3.N, g3.H, g3.W, g3.Cout, g3.H, g3.W, g3.Cin, 3, 3, 1, 1, 1)
+        wp = pack_filter_s2d(w, g, 1, cacheable=w_is_param)
+        if out_s2d or g.Cin % 128 or g.H % 2 or g.W % 2:
+            dxs = empty_act((g3.N, g3.Cin, g3.H, g3.W), torch.bfloat16, dy.device)
+            _fprop_tc_packed(dy, wp, None, None, relu_mask, dxs, gt, _s2d_skip_flags(g, 1))
+            return dxs if out_s2d else depth_to_space(dxs, g)
+        # masked in the epilogue (mask read in its own layout), written as the plain [N, Cin, H, W] tensor
+        return _fprop_tc_packed(dy, wp, None, None, relu_mask, dx, gt, _s2d_skip_flags(g, 1) | _lib.EPI_OUT_D2S)
     if relu_mask is not None:                       # other paths: the mask as a separate kernel
         return mul_relu_mask(conv_dgrad(dy, w, g, out_dtype=out_dtype, w_is_param=w_is_param, col=col), relu_mask)
-    g3 = s2d_geom(g, dy) if (xdt == BF16 and ydt == BF16) else None
     if g3 is not None:                                # dxs = dgrad of the 3x3 conv (fprop with the flipped pack), dx = depth_to_space
         gt = ConvGeom(g3.N, g3.H, g3.W, g3.Cout, g3.H, g3.W, g3.Cin, 3, 3, 1, 1, 1)
+        wp = pack_filter_s2d(w, g, 1, cacheable=w_is_param)
         dxs = empty_act((g3.N, g3.Cin, g3.H, g3.W), torch.bfloat16, dy.device)
-        _fprop_tc_packed(dy, pack_filter_s2d(w, g, 1, cacheable=w_is_param), None, None, None, dxs, gt, 0)
+        _fprop_tc_packed(dy, wp, None, None, None, dxs, gt, _s2d_skip_flags(g, 1))
         return dxs if out_s2d else depth_to_space(dxs, g)
     if out_s2d:
         raise RuntimeError('ctgan_b200: conv_dgrad(out_s2d=True) needs the space-to-depth route')

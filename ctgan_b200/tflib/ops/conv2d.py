@@ -36,7 +36,7 @@ def _uniform(stdev, size):
 
 def Conv2D(name, input_dim, output_dim, filter_size, inputs, he_init=True, mask_type=None, stride=1,
            weightnorm=None, biases=True, gain=1., residual=None, relu=False, in_relu=False,
-           relu_bwd_fused=False, residual_up2=False, act_dropout=None):
+           relu_bwd_fused=False, residual_up2=False, act_dropout=None, out_s2d=False, mean_pool=False):
     """
     inputs: tensor of shape (batch size, num channels, height, width)
     mask_type: one of None, 'a', 'b'  (PixelCNN masks: unused by the CT-GAN scripts -> unsupported)
@@ -76,7 +76,14 @@ def Conv2D(name, input_dim, output_dim, filter_size, inputs, he_init=True, mask_
     # residual_up2 (extension): residual at half resolution, added nearest-neighbour upsampled
     # act_dropout (extension) = dict(slope, keep, rng[, next_cout, next_k]): the LeakyReLU + tf.nn.dropout that follow this
     # conv in the DCGAN critics (TG/CT_gan_cifar.py:84-96), applied in the conv epilogue (functional.conv2d_act_dropout)
+    # out_s2d (extension): the result (relu fused) is handed to the next layer as a functional.S2DAct -- the producer of
+    # mean_pool (extension): this 3x3 conv FOLLOWED BY the 2x2 mean pool of ConvMeanPool (TG/CT_gan_cifar_resnet.py:89-92) as
+    # one stride-2 conv over that S2DAct (functional.conv_mean_pool_s2d)
+    if mean_pool:
+        if filter_size != 3 or stride != 1:
+            raise Exception('Conv2D %s: mean_pool fuses a 3x3 / stride-1 conv only' % name)
+        return F.conv_mean_pool_s2d(inputs, filters, _biases, residual=residual)
     if act_dropout is not None:
         return F.conv2d_act_dropout(inputs, filters, _biases, filter_size, stride, **act_dropout)
     return F.conv2d(inputs, filters, _biases, filter_size, stride, residual=residual, relu=relu, in_relu=in_relu,
-                    relu_bwd_fused=relu_bwd_fused, res_up2=residual_up2)
+                    relu_bwd_fused=relu_bwd_fused, res_up2=residual_up2, out_s2d=out_s2d)

@@ -72,6 +72,20 @@ typedef struct {
 #define CTGAN_EPI_RES_UP2 2        /* tensor-core path: residual is [N, H/2, W/2, Cout]; pixel (h, w) adds residual (h/2, w/2)
                                       (nearest-neighbour 2x upsample of a ResidualBlock('up') shortcut, never materialised) */
 
+/* tensor-core path (lean / pair kernels), the space-to-depth route of stride-2 convs (ctgan_pack_filter_s2d):
+ * OUT_S2D: y [N,H,W,Cout] (H, W even) is written in the space-to-depth layout [N,H/2,W/2,4*Cout] of the stride-2 conv that
+ *          consumes it (residual / relu_mask keep the plain layout);
+ * OUT_D2S: the conv's output is the space-to-depth image [N,H,W,4C] of a plain [N,2H,2W,C] tensor (the dgrad of a stride-2
+ *          conv); y is written as THAT tensor; relu_mask (if any) has the space-to-depth layout;
+ * S2D_SKIP(mode,k,pad_t,pad_l): the packed 3x3 filter embeds a stride-2 k x k filter with those pads; the (tap, phase) blocks
+ *          that hold no filter element are skipped (25 of 36 live for k = 5, 16 of 36 for k = 4).  mode 0: the launch is
+ *          the fprop over the space-to-depth image (phases = input channel blocks); 1: its dgrad (flipped pack, phases =
+ *          output channel blocks).  Same result as without the flag. */
+#define CTGAN_EPI_OUT_S2D 4
+#define CTGAN_EPI_OUT_D2S 8
+#define CTGAN_EPI_S2D_SKIP 256
+#define CTGAN_EPI_S2D_SKIP_FLAGS(mode, k, pad_t, pad_l) (256 | ((mode) << 9) | ((k) << 10) | ((pad_t) << 14) | ((pad_l) << 16))
+
 /* generic SIMT implicit-GEMM kernels: any shape, fp32 FMA, float accumulate */
 int ctgan_conv_fprop(const ctgan_conv_desc* d, const void* x, const float* w_hwio,
                      const float* bias /*nullable*/, void* y, int flags, void* stream);
@@ -204,6 +218,14 @@ int ctgan_depth_to_space(const void* xs, void* x, int N, int H, int W, int C, in
  * xs = space_to_depth(x) * ms its adjoint (the gradient penalty's double backward) */
 int ctgan_space_to_depth_mul(const void* x, const void* ms, void* xs, int N, int H, int W, int C, int dtype, void* stream);
 int ctgan_depth_to_space_mul(const void* xs, const void* ms, void* x, int N, int H, int W, int C, int dtype, void* stream);
+/* xs = space_to_depth(x) where `pattern` (space-to-depth layout; a ReLU output) is positive, else 0: the adjoint of a dgrad
+ * epilogue that applied that ReLU's backward and wrote the plain layout (OUT_D2S + relu_mask), for the double backward */
+int ctgan_space_to_depth_mask(const void* x, const void* pattern, void* xs, int N, int H, int W, int C, int dtype, void* stream);
+/* ConvMeanPool(3x3) (TG/CT_gan_cifar_resnet.py:89-92) == one 'SAME' 4x4 / stride-2 conv with the box-summed filter
+ * w4[u][v] = 1/4 sum_{a,b in {0,1}} w3[u-a][v-b] (HWIO, float): 2.25x fewer multiply-adds.  box_filter_grad is the adjoint:
+ * dw3 += fold(dw4), and clears dw4 (the scratch gradient of the derived filter) for the next step. */
+int ctgan_box_filter(const float* w3, float* w4, int Cin, int Cout, void* stream);
+int ctgan_box_filter_grad(float* dw4, float* dw3, int Cin, int Cout, void* stream);
 int ctgan_pack_filter_s2d(const float* w, void* wp_f, void* wp_d, int k, int Cin, int Cout, int pad_t, int pad_l, void* stream);
 int ctgan_s2d_filter_grad(const float* dw3, float* dw, int k, int Cin, int Cout, int pad_t, int pad_l, int accumulate, void* stream);
 

@@ -17,6 +17,11 @@ from torch.profiler import profile, ProfilerActivity
 import ctgan_b200.gan_cifar_resnet as R
 from ctgan_b200.graphs import GraphedTrainer
 
+import ctgan_b200.kernels as K_
+if os.environ.get('CTGAN_POOL_CONV_TILES'):
+    K_.config.pool_conv_min_tiles = int(os.environ['CTGAN_POOL_CONV_TILES'])
+if os.environ.get('CTGAN_POOL_CONV'):
+    K_.config.pool_conv_s2d = bool(int(os.environ['CTGAN_POOL_CONV']))
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 prefix = sys.argv[2] if len(sys.argv) > 2 else 'gpurun_out/timeline'
 np.random.seed(1234)

@@ -30,6 +30,12 @@ if os.environ.get('CTGAN_GEN_SPLITK'):
     K.config.gen_splitk = bool(int(os.environ['CTGAN_GEN_SPLITK']))
 if os.environ.get('CTGAN_DECOUPLE_GP'):
     K.config.decouple_gp = bool(int(os.environ['CTGAN_DECOUPLE_GP']))
+if os.environ.get('CTGAN_POOL_CONV_TILES'):
+    K.config.pool_conv_min_tiles = int(os.environ['CTGAN_POOL_CONV_TILES'])
+if os.environ.get('CTGAN_POOL_CONV'):
+    K.config.pool_conv_s2d = bool(int(os.environ['CTGAN_POOL_CONV']))
+if os.environ.get('CTGAN_S2D_SKIP'):
+    K.config.s2d_skip = bool(int(os.environ['CTGAN_S2D_SKIP']))
 if os.environ.get('CTGAN_WGRAD_CHUNK'):
     from ctgan_b200 import _lib as _L4
     _L4.lib.ctgan_set_wgrad_multi_chunk(int(os.environ['CTGAN_WGRAD_CHUNK']))

@@ -833,3 +833,162 @@ def test_head_fprop_long_k(K):
         x, w, b = act((M, Kd), torch.bfloat16, 1), filt((1, 1, Kd, 1), 2, 0.05), act((1,), torch.float32, 3)
         y = K.conv_fprop(x.cuda(), w.cuda(), b.cuda(), g, out_dtype=torch.float32)
         assert rel(y, FB().conv_fprop(x, w, b, g, out_dtype=torch.float32)) < 1e-5
+
+
+# ---- ConvMeanPool(3x3) as one stride-2 4x4 conv: zero-block skipping, layout-changing epilogues, the box filter
+POOLCONV_GEOMS = [
+    # N, H, W, C (Cin = Cout = C)
+    (192, 32, 32, 128),     # ResNet Discriminator.1.Conv2 on the stacked pass: pair kernel (one 16x16 image per item)
+    (64, 32, 32, 128),      # ... on the gradient-penalty pass: lean kernel, halo boxes
+    (64, 16, 16, 128),      # Discriminator.2.Conv2: 8x8 space-to-depth images, [h][n][w] halo boxes
+    (3, 32, 32, 256),       # two channel blocks per phase, ragged tile count
+]
+
+
+@pytest.mark.parametrize('k', [4, 5])
+@pytest.mark.parametrize('geom', POOLCONV_GEOMS)
+def test_s2d_zero_block_skipping(K, geom, k):
+    """CTGAN_EPI_S2D_SKIP: the (tap, phase) blocks of the embedded 3x3 filter without a filter element are neither loaded
+    nor multiplied -- fprop and dgrad are BIT-IDENTICAL to the launches that multiply the zeros."""
+    N, H, W, C = geom
+    g = K.same_geom(N, H, W, C, C, k, 2)
+    x, dy = to_dev(act((N, C, H, W), torch.bfloat16, 1)), to_dev(act((N, C, g.Ho, g.Wo), torch.bfloat16, 2))
+    w, b = filt((k, k, C, C), 3).cuda(), act((C,), torch.float32, 4).cuda()
+    from ctgan_b200 import _lib
+    outs = {}
+    max_k, K.config.s2d_skip_max_k = K.config.s2d_skip_max_k, 7       # the policy (k <= 4 by default) is not under test
+    _lib.lib.ctgan_set_splitk(0)        # sub-wave layers keep the split-K kernel, which ignores the flag: compare lean with lean
+    try:
+        assert K.s2d_geom(g, x) is not None and K._s2d_skip_flags(g, 0) and K._s2d_skip_flags(g, 1)
+        for skip in (True, False):
+            K.config.s2d_skip = skip
+            outs[skip] = (K.conv_fprop(x, w, b, g), K.conv_dgrad(dy, w, g), K.conv_dgrad(dy, w, g, out_s2d=True))
+    finally:
+        K.config.s2d_skip, K.config.s2d_skip_max_k = True, max_k
+        _lib.lib.ctgan_set_splitk(1)
+    for a, c in zip(outs[True], outs[False]):
+        assert torch.equal(a, c)
+    wq = w.cpu().to(torch.bfloat16).float()
+    if N <= 64:
+        fb = FB()
+        assert rel(outs[True][0], fb.conv_fprop(x.cpu(), wq, b.cpu(), g)) < 1e-2
+        assert rel(outs[True][1], fb.conv_dgrad(dy.cpu(), wq, g)) < 1e-2
+
+
+@pytest.mark.parametrize('geom', [(64, 32, 32, 3, 128), (6, 16, 16, 128, 128), (192, 16, 16, 128, 128), (2, 8, 8, 128, 256)])
+def test_conv_epilogue_space_to_depth_output(K, geom):
+    """CTGAN_EPI_OUT_S2D: relu(conv + b) written by the epilogue in the space-to-depth layout == the layout kernel applied to
+    the plain result, bit for bit (thin-input GEMM route, lean and pair kernels)."""
+    N, H, W, Cin, Cout = geom
+    g = K.same_geom(N, H, W, Cin, Cout, 3, 1)
+    x = to_dev(act((N, Cin, H, W), torch.bfloat16, 1))
+    w, b = filt((3, 3, Cin, Cout), 3).cuda(), act((Cout,), torch.float32, 4).cuda()
+    assert K.conv_fprop_s2d_out_ok(x, g)
+    from ctgan_b200 import _lib
+    ys = K.conv_fprop(x, w, b, g, relu=True, out_s2d=True)
+    _lib.lib.ctgan_set_splitk(0)        # the layout-changing launch stays on the lean / pair kernels: same kernel for the reference
+    try:
+        y = K.conv_fprop(x, w, b, g, relu=True)
+    finally:
+        _lib.lib.ctgan_set_splitk(1)
+    assert tuple(ys.shape) == (N, 4 * Cout, H // 2, W // 2)
+    assert torch.equal(ys, K.space_to_depth(y, K.ConvGeom(N, H, W, Cout, H, W, Cout, 1, 1, 1, 0, 0)))
+
+
+@pytest.mark.parametrize('geom', POOLCONV_GEOMS)
+def test_s2d_dgrad_masked_plain_output(K, geom):
+    """CTGAN_EPI_OUT_D2S (+ relu_mask in the space-to-depth layout): the dgrad of the stride-2 conv, masked and written as
+    the plain tensor by the epilogue == mask multiply + depth_to_space of the space-to-depth result, bit for bit."""
+    N, H, W, C = geom
+    g = K.same_geom(N, H, W, C, C, 4, 2)
+    dy = to_dev(act((N, C, g.Ho, g.Wo), torch.bfloat16, 2))
+    w = filt((4, 4, C, C), 3).cuda()
+    hs = to_dev(act((N, 4 * C, H // 2, W // 2), torch.bfloat16, 5)).relu()       # the conv's input (a ReLU output), s2d layout
+    dx = K.conv_dgrad(dy, w, g, relu_mask=hs)
+    assert tuple(dx.shape) == (N, C, H, W)
+    dxs = K.conv_dgrad(dy, w, g, out_s2d=True)
+    ref = K.depth_to_space(K.mul_relu_mask(dxs, hs), g)
+    assert torch.equal(dx, ref)
+    # the adjoint used by the double backward: space_to_depth of a plain tensor, masked by the same pattern
+    c = to_dev(act((N, C, H, W), torch.bfloat16, 6))
+    pg = K.ConvGeom(N, H, W, C, H, W, C, 1, 1, 1, 0, 0)
+    assert torch.equal(K.space_to_depth_mask(c, hs, pg), K.mul_relu_mask(K.space_to_depth(c, pg), hs))
+
+
+def test_box_filter_is_conv_then_mean_pool(K):
+    """ctgan_box_filter: the stride-2 4x4 conv with the box-summed filter == mean_pool_2x2(conv3x3) (float, CPU reference);
+    ctgan_box_filter_grad is its adjoint and clears the scratch gradient."""
+    import torch.nn.functional as TF
+    C, O = 16, 24
+    w3 = filt((3, 3, C, O), 1, 1.0)
+    w4 = K.box_filter(w3.cuda(), torch.empty(4, 4, C, O, device='cuda')).cpu()
+    x = torch.randn(2, C, 12, 10, generator=torch.Generator().manual_seed(2))
+    ref = TF.avg_pool2d(TF.conv2d(x, w3.permute(3, 2, 0, 1), padding=1), 2)
+    got = TF.conv2d(x, w4.permute(3, 2, 0, 1), stride=2, padding=1)
+    assert rel(got, ref) < 1e-6
+    # adjoint: <box(w3), d4> == <w3, box^T(d4)>
+    d4 = filt((4, 4, C, O), 3, 1.0)
+    d3 = torch.ones(3, 3, C, O, device='cuda')
+    d4d = d4.cuda()
+    K.box_filter_grad(d4d, d3)
+    assert float(d4d.abs().max()) == 0.0
+    lhs = float((w4.double() * d4.double()).sum())
+    rhs = float((w3.double() * (d3.cpu().double() - 1)).sum())
+    assert abs(lhs - rhs) < 1e-6 * max(1.0, abs(lhs))
+
+
+@pytest.mark.parametrize('N', [64, 6])
+def test_conv_mean_pool_fused_block_matches_unfused(K, N):
+    """functional level: [conv3x3 + relu -> ConvMeanPool(3x3) + skip] through the fused route (space-to-depth hand-over, one
+    stride-2 conv, masked plain-layout dgrad, box-filter gradient fold) against the unfused ops: outputs, input gradient,
+    filter / bias gradients and the gradient-penalty style double backward."""
+    import ctgan_b200.functional as F
+    C, H, W = 128, 16, 16
+    gen = torch.Generator().manual_seed(0)
+
+    def leaf(shape, scale, dtype=torch.float32):
+        t = (torch.randn(shape, generator=gen) * scale).to(dtype).cuda()
+        if t.dim() == 4 and dtype == torch.bfloat16:
+            t = t.contiguous(memory_format=CL)
+        return t.requires_grad_(True)
+
+    w1, b1 = leaf((3, 3, C, C), 0.03), leaf((C,), 0.1)
+    w2, b2 = leaf((3, 3, C, C), 0.03), leaf((C,), 0.1)
+    x0 = leaf((N, C, H, W), 1.0, torch.bfloat16)
+    sc0 = leaf((N, C, H // 2, W // 2), 1.0, torch.bfloat16)
+    for p in (w1, b1, w2, b2):
+        F.register_param(p)
+
+    def block(x, sc, fused):
+        if fused:
+            hs = F.conv2d(x, w1, b1, 3, 1, relu=True, relu_bwd_fused=True, out_s2d=True)
+            return F.conv_mean_pool_s2d(hs, w2, b2, residual=sc)
+        h = F.conv2d(x, w1, b1, 3, 1, relu=True, relu_bwd_fused=True)
+        full = F.conv2d(h, w2, b2, 3, 1, in_relu=True)
+        return F.add(sc, F.mean_pool_2x2(full))
+
+    min_tiles, K.config.pool_conv_min_tiles = K.config.pool_conv_min_tiles, 1     # the route's size policy is not under test
+    try:
+        assert F.conv2d_s2d_out_ok(x0, C, 3) and F.conv_mean_pool_s2d_ok(x0, C, C)
+    finally:
+        K.config.pool_conv_min_tiles = min_tiles
+    res = {}
+    for fused in (True, False):
+        for p in (w1, b1, w2, b2):
+            p.grad = torch.zeros_like(p)
+        x = x0.detach().clone(memory_format=torch.preserve_format).requires_grad_(True)
+        sc = sc0.detach().clone(memory_format=torch.preserve_format).requires_grad_(True)
+        y = block(x, sc, fused)
+        # first derivative as the gradient penalty takes it: input gradient only, differentiable
+        with F.no_param_grads():
+            gx, = torch.autograd.grad(y.float().square().sum() * 1e-3, [x], create_graph=True)
+        loss = y.float().sum() * 1e-2 + gx.float().square().sum()
+        # the trainers' final backward: filter / bias gradients are accumulated in place by the kernels
+        loss.backward(inputs=[x, sc, w1, b1, w2, b2])
+        K.join_side()
+        torch.cuda.synchronize()
+        res[fused] = dict(y=y.detach().float(), gx=gx.detach().float(), dx=x.grad.float(), dsc=sc.grad.float(),
+                          w1=w1.grad.clone(), b1=b1.grad.clone(), w2=w2.grad.clone(), b2=b2.grad.clone())
+    tol = dict(y=1e-2, gx=1.5e-2, dx=2e-2, dsc=1e-2, w1=2e-2, b1=2e-2, w2=2e-2, b2=2e-2)
+    for k_, t in tol.items():
+        assert rel(res[True][k_], res[False][k_]) < t, (k_, rel(res[True][k_], res[False][k_]))

@@ -139,6 +139,33 @@ def test_step_parity_s2d_route(script, B):
         K.invalidate_weight_cache()
 
 
+@pytest.mark.parametrize('conditioned', [True, False])
+@pytest.mark.parametrize('route', ['fused_everywhere', 'off'])
+def test_resnet_parity_pool_conv_route(route, conditioned):
+    """ConvMeanPool(3x3) of the critic's two 'down' blocks as ONE stride-2 4x4 conv (functional.conv_mean_pool_s2d: producer
+    epilogue in the space-to-depth layout, zero-block skipping, masked plain-layout dgrad, box-filter gradient fold) in EVERY
+    pass of the step -- the size policy normally keeps the small passes on the unfused ops -- and with the route off: same
+    bars as the BF16 path of test_step_parity (TG/CT_gan_cifar_resnet.py:89-92,113-139)."""
+    _need_gpu()
+    import ctgan_b200.kernels as K
+    import ctgan_b200.functional as F
+    saved = (K.config.pool_conv_s2d, K.config.pool_conv_min_tiles)
+    K.config.pool_conv_s2d, K.config.pool_conv_min_tiles = (route != 'off'), 1
+    F._box_filters.clear()
+    try:
+        tr, om = parity.build_pair('resnet', 'cuda', torch.bfloat16, 16)
+        parity.perturb_params(tr, om)
+        ff = TOL['bf16']['floor']
+        rep = parity.critic_parity('resnet', tr, om, parity.make_inputs('resnet', 16, 11), conditioned=conditioned, floor_frac=ff)
+        _check(rep, 'bf16', 'critic', conditioned)
+        rep = parity.gen_parity('resnet', tr, om, conditioned=conditioned, floor_frac=ff)
+        _check(rep, 'bf16', 'gen', conditioned)
+        assert (len(F._box_filters) == 2) == (route != 'off'), 'Discriminator.{1,2}.Conv2 fused: %d' % len(F._box_filters)
+    finally:
+        K.config.pool_conv_s2d, K.config.pool_conv_min_tiles = saved
+        K.invalidate_weight_cache()
+
+
 def test_two_consecutive_iterations_stay_in_parity():
     """critic, critic, gen, critic on the fp32 path: optimizer state, weight-cache invalidation and
     the RNG stream bookkeeping across steps."""
