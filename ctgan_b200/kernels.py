@@ -30,8 +30,13 @@ class Config:
     s2d_skip = True          # space-to-depth route: skip the (tap, phase) blocks of the embedded 3x3 filter that hold no filter element
     s2d_skip_max_k = 4       # ... for stride-2 filters up to this size: 16 of 36 blocks live for k = 4; with k = 5 (25 of 36) the
                              # shorter MMA stream does not pay for the issue loop's mask arithmetic (CIFAR-DCGAN 248 -> 243 it/s)
-    pool_conv_min_tiles = 96 # ... for layers with at least this many 128-pixel output tiles (measured, profiles/r02_experiments.md)
-    pool_conv_s2d = True     # ConvMeanPool(3x3) as ONE stride-2 4x4 conv on the space-to-depth route (gan_cifar_resnet.ConvMeanPool)
+    # ConvMeanPool(3x3) as ONE stride-2 4x4 conv on the space-to-depth route (gan_cifar_resnet._pool_conv_fused, functional.
+    # conv_mean_pool_s2d): 2.25x fewer multiply-adds for Discriminator.{1,2}.Conv2.  OFF by default: measured
+    # +1.4 % it/s on the same box (151.0 -> 153.1; critic step -27 us, almost all of it in the filter-gradient launch) -- the
+    # forward / dgrad launches stay bound by the shared-memory fill (fewer live taps per halo box, the same filter bytes per MMA)
+    # and by one-image work items (192 items on 148 SMs), see profiles/r02_experiments.md.  Both settings are GPU-tested.
+    pool_conv_s2d = False
+    pool_conv_min_tiles = 96 # ... for layers with at least this many 128-pixel output tiles (smaller ones are latency-bound and lose)
     s2d_embed_wgrad = True   # stride-2 filter gradients: the embedded 3x3 job writes the k x k gradient itself (no scratch + gather)
     decouple_gp = False      # ResNet critic step: the stacked pass runs its own backward as soon as its half of the loss is known,
                              # the gradient penalty is differentiated on its stream branch (two backward calls, gan_cifar_resnet.py).

@@ -48,8 +48,20 @@ def test_generate_fakes_matches_per_step_generation():
     assert _rel(g2, g1) < 6e-2       # bf16 ReLU-pattern flips downstream of the few re-rounded fake pixels
 
 
+@pytest.fixture(params=[False, True], ids=['default', 'pool_conv'])
+def pool_conv(request):
+    """Second setting: ConvMeanPool(3x3) as one stride-2 conv in every pass (kernels.config.pool_conv_s2d) -- its derived 4x4
+    filters must be recomputed / re-packed in place by every replayed optimizer step and their scratch gradients folded."""
+    import ctgan_b200.kernels as K
+    saved = (K.config.pool_conv_s2d, K.config.pool_conv_min_tiles)
+    if request.param:
+        K.config.pool_conv_s2d, K.config.pool_conv_min_tiles = True, 1
+    yield request.param
+    K.config.pool_conv_s2d, K.config.pool_conv_min_tiles = saved
+
+
 @pytest.mark.parametrize('pregen', [0, 2])
-def test_graph_replay_trains_like_eager(pregen):
+def test_graph_replay_trains_like_eager(pregen, pool_conv):
     """2 iterations (1 generator step + 2 critic steps): GraphedTrainer replays vs the same sequence launched eagerly from
     the same seeds (differences: atomic accumulation order only).  The capture's warm-up steps leave no trace: weights,
     Adam state, step counts and the Philox counters are restored, so both start from the initial model."""

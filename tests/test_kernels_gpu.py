@@ -640,8 +640,7 @@ def test_fused_activation_graph_matches_unfused():
             gc = tr.gen_forward_backward()['cost']
             res[fused] = (out['out'].clone(), out['gradients'].clone(), tr.disc_opt.flat_g.clone(), gc.clone(), tr.gen_opt.flat_g.clone())
         finally:
-            R.FUSE_D_ACT = R.FUSE_SKIP_ADD = R.COMMUTE_1X1 = R.FUSE_POOL_FORK = True
-            R.FUSE_RELU_BWD = False
+            R.FUSE_D_ACT = R.FUSE_SKIP_ADD = R.COMMUTE_1X1 = R.FUSE_POOL_FORK = R.FUSE_RELU_BWD = True     # the module defaults
     for a, b in zip(res[True], res[False]):
         assert rel(a, b) < 2e-3
 
@@ -967,11 +966,12 @@ def test_conv_mean_pool_fused_block_matches_unfused(K, N):
         full = F.conv2d(h, w2, b2, 3, 1, in_relu=True)
         return F.add(sc, F.mean_pool_2x2(full))
 
-    min_tiles, K.config.pool_conv_min_tiles = K.config.pool_conv_min_tiles, 1     # the route's size policy is not under test
+    saved = (K.config.pool_conv_s2d, K.config.pool_conv_min_tiles)
+    K.config.pool_conv_s2d, K.config.pool_conv_min_tiles = True, 1               # the route's switch / size policy are not under test
     try:
         assert F.conv2d_s2d_out_ok(x0, C, 3) and F.conv_mean_pool_s2d_ok(x0, C, C)
     finally:
-        K.config.pool_conv_min_tiles = min_tiles
+        K.config.pool_conv_s2d, K.config.pool_conv_min_tiles = saved
     res = {}
     for fused in (True, False):
         for p in (w1, b1, w2, b2):
