@@ -236,7 +236,10 @@ conv_fprop_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
 //                bias at TG/tflib/ops/conv2d.py:114-120) in the conv epilogue.  u comes from Philox4x32-10 in registers at
 //                the element's NHWC index (the stream act_dropout_kernel draws from), optionally written in the
 //                space-to-depth layout of the next stride-2 layer.
-template <int EPI>
+//   S2D = true: the space-to-depth variants (CTGAN_EPI_OUT_S2D / OUT_D2S / S2D_SKIP).  A template parameter for the same reason:
+//                with the extra address arithmetic and mask tests as runtime branches the DEFAULT launches of the step ran
+//                3.5 % slower (critic graph 924 -> 957 us, same box).
+template <int EPI, bool S2D>
 __device__ __forceinline__ void lean_epilogue_tile(const FpropParams& p, uint32_t tmem_addr, int q, int lane,
                                                    int w0, int h0, int n0, int co0, bool relu) {
     int t = q * 32 + lane;
@@ -248,10 +251,10 @@ __device__ __forceinline__ void lean_epilogue_tile(const FpropParams& p, uint32_
     const bool valid = (n < p.N) && (h < p.H) && (w < p.W);
     const int64_t pix = ((int64_t)n * p.H + h) * p.W + w;
     int64_t orow = pix * p.Cout;                                     // element offset of this pixel's row in y (and m)
-    if (p.out_s2d)
+    if ((S2D || EPI == EPI_ACTDROP) && p.out_s2d)
         orow = ((((int64_t)n * (p.H >> 1) + (h >> 1)) * (p.W >> 1) + (w >> 1)) * 4 + ((h & 1) * 2 + (w & 1))) * p.Cout;
     __nv_bfloat16* yrow = p.y + orow + co0;
-    if (p.out_d2s) {
+    if (S2D && p.out_d2s) {
         // this conv's output is the space-to-depth image [N, H, W, 4C] of a [N, 2H, 2W, C] tensor (the dgrad of a stride-2
         // conv on the 3x3 route): channel block co0 is phase (dy, dx) = co0 / C; write that tensor in its plain layout
         const int C = p.Cout >> 2, ph = co0 / C;
@@ -360,7 +363,7 @@ __device__ __forceinline__ void lean_epilogue_tile(const FpropParams& p, uint32_
 //   HALO = 0 (1x1, 8x8 / 4x4 tiles, linear): stage = 2 consecutive (activation, filter) box pairs   ->  8 MMAs, 64 KB
 // Three stages in flight; descriptors are pre-built 32-bit words plus immediate offsets.
 
-template <int HALO, int EPI>
+template <int HALO, int EPI, bool S2D>
 __global__ void __launch_bounds__(192, 1)
 conv_fprop_tc_lean_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                           const FpropParams p, const int n_tiles)
@@ -415,7 +418,7 @@ conv_fprop_tc_lean_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
             const int w0 = tw * p.BW, h0 = th * p.BH, n0 = tn * p.BN, co0 = nb * BLOCK_N;
             for (int gi = 0; gi < groups; ++gi) {
                 uint32_t rmask = 7u, cmask = 7u;
-                if (HALO) {
+                if (HALO && S2D) {
                     s2d_live_masks(p, gi / p.kw, co0, rmask, cmask);
                     if (!((cmask >> (gi % p.kw)) & 1u)) continue;      // an all-zero filter column of this phase: no stage
                 }
@@ -423,12 +426,12 @@ conv_fprop_tc_lean_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
                 mbar_wait(empty0 + 8 * st, ph ^ 1);
                 if (HALO) {
                     const int cb = gi / p.kw, s = gi - cb * p.kw;
-                    mbar_expect_tx(fb, a_bytes + (uint32_t)__popc(rmask) * B_BYTES);
+                    mbar_expect_tx(fb, a_bytes + (S2D ? (uint32_t)__popc(rmask) : (uint32_t)NB) * B_BYTES);
                     if (p.hn) tma_load_4d(sb, &tmap_x, fb, cb * BLOCK_K, w0 + s - p.pad_l, n0, h0 - p.pad_t);   // dims (C, W, N, H)
                     else      tma_load_4d(sb, &tmap_x, fb, cb * BLOCK_K, w0 + s - p.pad_l, h0 - p.pad_t, n0);
 #pragma unroll
                     for (int r = 0; r < NB; ++r)
-                        if ((rmask >> r) & 1u) tma_load_3d(sb + A_REGION + r * B_BYTES, &tmap_w, fb, cb * BLOCK_K, co0, r * p.kw + s);
+                        if (!S2D || ((rmask >> r) & 1u)) tma_load_3d(sb + A_REGION + r * B_BYTES, &tmap_w, fb, cb * BLOCK_K, co0, r * p.kw + s);
                 } else {
                     const int kb0 = gi * 2, nk = min(2, kblocks - kb0);
                     mbar_expect_tx(fb, (uint32_t)nk * (a_bytes + B_BYTES));
@@ -458,9 +461,9 @@ conv_fprop_tc_lean_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
             mbar_wait(tempty + 8 * acc, ((uint32_t)(it >> 1) & 1u) ^ 1u);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
-            const int co0 = (tile % n_blocks) * BLOCK_N;
+            const int co0 = S2D ? (tile % n_blocks) * BLOCK_N : 0;
             int last_gi = groups - 1;                               // the last group that is not skipped (see the producer)
-            if (HALO && p.skip_k > 0) {
+            if (HALO && S2D && p.skip_k > 0) {
                 for (; last_gi > 0; --last_gi) {
                     uint32_t rm, cm;
                     s2d_live_masks(p, last_gi / p.kw, co0, rm, cm);
@@ -470,7 +473,7 @@ conv_fprop_tc_lean_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
             uint32_t accf = 0u;                                     // 0: the first MMA of the tile overwrites the accumulator
             for (int gi = 0; gi < groups; ++gi) {
                 uint32_t rmask = 7u, cmask = 7u;
-                if (HALO) {
+                if (HALO && S2D) {
                     s2d_live_masks(p, gi / p.kw, co0, rmask, cmask);
                     if (!((cmask >> (gi % p.kw)) & 1u)) continue;
                 }
@@ -482,18 +485,19 @@ conv_fprop_tc_lean_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
                 if (elect_one()) {
 #pragma unroll
                     for (int j = 0; j < NB; ++j) {
-                        if (j < nk && (!HALO || ((rmask >> j) & 1u))) {
+                        if (j < nk && (!(HALO && S2D) || ((rmask >> j) & 1u))) {
 #pragma unroll
                             for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                                umma_bf16_lo(d_tmem, a_lo + j * row_step + 2 * k, b_lo + j * (B_BYTES >> 4) + 2 * k, idesc, accf);
-                                accf = 1u;
+                                umma_bf16_lo(d_tmem, a_lo + j * row_step + 2 * k, b_lo + j * (B_BYTES >> 4) + 2 * k, idesc,
+                                             S2D ? accf : ((j | k) ? 1u : (gi > 0 ? 1u : 0u)));
+                                if (S2D) accf = 1u;
                             }
                         }
                     }
                     umma_commit(empty0 + 8 * st);
                     if (gi == last_gi) umma_commit(tfull + 8 * acc);
                 }
-                accf = 1u;
+                if (S2D) accf = 1u;
                 __syncwarp();
                 if (++st == STAGES) { st = 0; ph ^= 1; }
             }
@@ -511,7 +515,7 @@ conv_fprop_tc_lean_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
             const int co0 = nb * BLOCK_N;
             mbar_wait(tfull + 8 * acc, (uint32_t)(it >> 1) & 1u);
             tc_fence_after();
-            lean_epilogue_tile<EPI>(p, tmem_base + (uint32_t)(acc * BLOCK_N), q, lane, tw * p.BW, th * p.BH, tn * p.BN, co0, relu);
+            lean_epilogue_tile<EPI, S2D>(p, tmem_base + (uint32_t)(acc * BLOCK_N), q, lane, tw * p.BW, th * p.BH, tn * p.BN, co0, relu);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty + 8 * acc) : "memory");
@@ -529,7 +533,7 @@ conv_fprop_tc_lean_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
 // accumulators -- 44 KB per 12 MMAs instead of 72 KB.  Two stages of 88 KB; TMEM 2 x (2 x 128) columns double-buffered.
 // Tiles are enumerated n-block-major (tile = nb * m_tiles + mt) and split into contiguous per-CTA ranges, so every warp
 // role derives the same item sequence (pair if the next tile is the next row block of the same image, else single).
-template <int EPI>
+template <int EPI, bool S2D>
 __global__ void __launch_bounds__(192, 1)
 conv_fprop_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_x2,
                           const __grid_constant__ CUtensorMap tmap_w, const FpropParams p, const int m_tiles, const int n_tiles)
@@ -590,16 +594,18 @@ conv_fprop_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
             const int h0 = th * p.BH, n0 = tn * p.BN, co0 = nb * BLOCK_N;
             for (int gi = 0; gi < groups; ++gi) {
                 const int cb = gi / p.kw, s = gi - cb * p.kw;
-                uint32_t rmask, cmask;
-                s2d_live_masks(p, cb, co0, rmask, cmask);
-                if (!((cmask >> s) & 1u)) continue;                    // an all-zero filter column of this phase: no stage
+                uint32_t rmask = 7u, cmask = 7u;
+                if (S2D) {
+                    s2d_live_masks(p, cb, co0, rmask, cmask);
+                    if (!((cmask >> s) & 1u)) continue;                // an all-zero filter column of this phase: no stage
+                }
                 const uint32_t sb = s_base + st * STAGE_BYTES, fb = full0 + 8 * st;
                 mbar_wait(empty0 + 8 * st, ph ^ 1);
-                mbar_expect_tx(fb, (pair ? a2_bytes : a1_bytes) + (uint32_t)__popc(rmask) * B_BYTES);
+                mbar_expect_tx(fb, (pair ? a2_bytes : a1_bytes) + (S2D ? (uint32_t)__popc(rmask) : 3u) * B_BYTES);
                 tma_load_4d(sb, pair ? &tmap_x2 : &tmap_x, fb, cb * BLOCK_K, s - p.pad_l, h0 - p.pad_t, n0);
 #pragma unroll
                 for (int r = 0; r < 3; ++r)
-                    if ((rmask >> r) & 1u) tma_load_3d(sb + A_REGION + r * B_BYTES, &tmap_w, fb, cb * BLOCK_K, co0, r * p.kw + s);
+                    if (!S2D || ((rmask >> r) & 1u)) tma_load_3d(sb + A_REGION + r * B_BYTES, &tmap_w, fb, cb * BLOCK_K, co0, r * p.kw + s);
                 if (++st == STAGES) { st = 0; ph ^= 1; }
             }
             t += pair ? 2 : 1;
@@ -618,9 +624,9 @@ conv_fprop_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
             mbar_wait(tempty + 8 * acc, ((uint32_t)(it >> 1) & 1u) ^ 1u);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 2 * BLOCK_N);
-            const int co0 = (t / m_tiles) * BLOCK_N;
+            const int co0 = S2D ? (t / m_tiles) * BLOCK_N : 0;
             int last_gi = groups - 1;                               // the last group that is not skipped (see the producer)
-            if (p.skip_k > 0) {
+            if (S2D && p.skip_k > 0) {
                 for (; last_gi > 0; --last_gi) {
                     uint32_t rm, cm;
                     s2d_live_masks(p, last_gi / p.kw, co0, rm, cm);
@@ -629,9 +635,11 @@ conv_fprop_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
             }
             uint32_t accf = 0u;                                     // 0: the first MMA of the item overwrites the accumulators
             for (int gi = 0; gi < groups; ++gi) {
-                uint32_t rmask, cmask;
-                s2d_live_masks(p, gi / p.kw, co0, rmask, cmask);
-                if (!((cmask >> (gi % p.kw)) & 1u)) continue;
+                uint32_t rmask = 7u, cmask = 7u;
+                if (S2D) {
+                    s2d_live_masks(p, gi / p.kw, co0, rmask, cmask);
+                    if (!((cmask >> (gi % p.kw)) & 1u)) continue;
+                }
                 mbar_wait(full0 + 8 * st, ph);
                 tc_fence_after();
                 const uint32_t a_lo = lo0 + st * (STAGE_BYTES >> 4);
@@ -640,30 +648,32 @@ conv_fprop_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
                     if (pair) {
 #pragma unroll
                         for (int r = 0; r < 3; ++r) {
-                            if (!((rmask >> r) & 1u)) continue;
+                            if (S2D && !((rmask >> r) & 1u)) continue;
 #pragma unroll
                             for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                                umma_bf16_lo(d_tmem, a_lo + r * row_step + 2 * k, b_lo + r * (B_BYTES >> 4) + 2 * k, idesc, accf);
+                                const uint32_t af = S2D ? accf : ((r | k) ? 1u : (gi > 0 ? 1u : 0u));
+                                umma_bf16_lo(d_tmem, a_lo + r * row_step + 2 * k, b_lo + r * (B_BYTES >> 4) + 2 * k, idesc, af);
                                 umma_bf16_lo(d_tmem + BLOCK_N, a_lo + tile1_off + r * row_step + 2 * k, b_lo + r * (B_BYTES >> 4) + 2 * k,
-                                             idesc, accf);
-                                accf = 1u;
+                                             idesc, af);
+                                if (S2D) accf = 1u;
                             }
                         }
                     } else {
 #pragma unroll
                         for (int r = 0; r < 3; ++r) {
-                            if (!((rmask >> r) & 1u)) continue;
+                            if (S2D && !((rmask >> r) & 1u)) continue;
 #pragma unroll
                             for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                                umma_bf16_lo(d_tmem, a_lo + r * row_step + 2 * k, b_lo + r * (B_BYTES >> 4) + 2 * k, idesc, accf);
-                                accf = 1u;
+                                umma_bf16_lo(d_tmem, a_lo + r * row_step + 2 * k, b_lo + r * (B_BYTES >> 4) + 2 * k, idesc,
+                                             S2D ? accf : ((r | k) ? 1u : (gi > 0 ? 1u : 0u)));
+                                if (S2D) accf = 1u;
                             }
                         }
                     }
                     umma_commit(empty0 + 8 * st);
                     if (gi == last_gi) umma_commit(tfull + 8 * acc);
                 }
-                accf = 1u;
+                if (S2D) accf = 1u;
                 __syncwarp();
                 if (++st == STAGES) { st = 0; ph ^= 1; }
             }
@@ -682,8 +692,8 @@ conv_fprop_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
             const int h0 = th * p.BH, n0 = tn * p.BN, co0 = nb * BLOCK_N;
             mbar_wait(tfull + 8 * acc, (uint32_t)(it >> 1) & 1u);
             tc_fence_after();
-            lean_epilogue_tile<EPI>(p, tmem_base + (uint32_t)(acc * 2 * BLOCK_N), q, lane, 0, h0, n0, co0, relu);
-            if (pair) lean_epilogue_tile<EPI>(p, tmem_base + (uint32_t)(acc * 2 * BLOCK_N + BLOCK_N), q, lane, 0, h0 + p.BH, n0, co0, relu);
+            lean_epilogue_tile<EPI, S2D>(p, tmem_base + (uint32_t)(acc * 2 * BLOCK_N), q, lane, 0, h0, n0, co0, relu);
+            if (pair) lean_epilogue_tile<EPI, S2D>(p, tmem_base + (uint32_t)(acc * 2 * BLOCK_N + BLOCK_N), q, lane, 0, h0 + p.BH, n0, co0, relu);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty + 8 * acc) : "memory");
@@ -1254,38 +1264,38 @@ static int launch_fprop(const CUtensorMap& mx, const CUtensorMap& mw, const Fpro
     return 0;
 }
 
-template <int HALO, int EPI>
+template <int HALO, int EPI, bool S2D = false>
 static int launch_fprop_lean(const CUtensorMap& mx, const CUtensorMap& mw, const FpropParams& p, cudaStream_t st) {
     constexpr size_t stage = HALO ? (24576 + 3 * 16384) : (32768 + 2 * 16384);
     constexpr size_t smem = 3 * stage + 1024 + (2 * 3 + 4) * 8 + 16;
     static_assert(smem <= 227 * 1024, "lean fprop: shared memory budget");
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv_fprop_tc_lean_kernel<HALO, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(conv_fprop_tc_lean_kernel<HALO, EPI, S2D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return cuda_status(e, "fprop_tc_lean smem attribute");
         attr_set = true;
     }
     const int n_tiles = p.tilesW * p.tilesH * p.tilesN * (p.Cout / 128);
     const int grid = n_tiles < sm_count() ? n_tiles : sm_count();
-    CTGAN_LAUNCH((conv_fprop_tc_lean_kernel<HALO, EPI>), grid, 192, smem, st, mx, mw, p, n_tiles);
+    CTGAN_LAUNCH((conv_fprop_tc_lean_kernel<HALO, EPI, S2D>), grid, 192, smem, st, mx, mw, p, n_tiles);
     CTGAN_CHECK_LAUNCH("conv_fprop_tc_lean");
     return 0;
 }
 
-template <int EPI>
+template <int EPI, bool S2D = false>
 static int launch_fprop_pair(const CUtensorMap& mx, const CUtensorMap& mx2, const CUtensorMap& mw, const FpropParams& p, cudaStream_t st) {
     constexpr size_t smem = 2 * (40960 + 3 * 16384) + 1024 + (2 * 2 + 4) * 8 + 16;
     static_assert(smem <= 227 * 1024, "pair fprop: shared memory budget");
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv_fprop_tc_pair_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(conv_fprop_tc_pair_kernel<EPI, S2D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return cuda_status(e, "fprop_tc_pair smem attribute");
         attr_set = true;
     }
     const int m_tiles = p.tilesW * p.tilesH * p.tilesN;
     const int n_tiles = m_tiles * (p.Cout / 128);
     const int grid = n_tiles < sm_count() ? n_tiles : sm_count();
-    CTGAN_LAUNCH((conv_fprop_tc_pair_kernel<EPI>), grid, 192, smem, st, mx, mx2, mw, p, m_tiles, n_tiles);
+    CTGAN_LAUNCH((conv_fprop_tc_pair_kernel<EPI, S2D>), grid, 192, smem, st, mx, mx2, mw, p, m_tiles, n_tiles);
     CTGAN_CHECK_LAUNCH("conv_fprop_tc_pair");
     return 0;
 }
@@ -1333,6 +1343,7 @@ static int fprop_tc_launch(const ctgan_conv_desc* d, const void* x, const void* 
     // launches with a layout-changing epilogue stay on the lean / pair kernels; zero-block skipping (an optimisation only)
     // applies where those kernels run anyway: a sub-wave layer keeps the cluster split-K kernel and multiplies the zeros
     const bool special = (epi != EPI_ACTDROP && p.out_s2d) || p.out_d2s;
+    const bool s2d = special || (p.skip_k > 0 && epi != EPI_ACTDROP);    // -> the <.., S2D = true> instantiations
     CTGAN_REQUIRE(!(special || p.skip_k > 0) || (block_n == 128 && g_fprop_variant >= 3), CTGAN_ERR_UNSUPPORTED,
                   "conv_fprop_tc: OUT_S2D / OUT_D2S / S2D_SKIP need Cout %% 128 == 0 and the lean kernel family");
     const int split_all = (g_use_splitk && block_n == 128 && !special) ? splitk_factor(n_tiles_all, (d->kh * d->kw * (d->Cin / 64) + 1) / 2) : 0;
@@ -1352,9 +1363,14 @@ static int fprop_tc_launch(const ctgan_conv_desc* d, const void* x, const void* 
         (uint32_t)(2 * p.BH + 2) * p.BW * 128u <= 40960u && p.tilesH * p.tilesN * (d->Cout / 128) >= 2 * sm_count()) {
         CUtensorMap mx2;                                             // 256-pixel work items (two row blocks per halo box)
         if (int r = make_act_map(&mx2, x, d->N, d->H, d->W, d->Cin, p.BW, 2 * p.BH + 2, 1)) return r;
+        if (s2d) return epi == EPI_MASK ? launch_fprop_pair<EPI_MASK, true>(mx, mx2, mw, p, st) : launch_fprop_pair<EPI_PLAIN, true>(mx, mx2, mw, p, st);
         return epi == EPI_MASK ? launch_fprop_pair<EPI_MASK>(mx, mx2, mw, p, st) : launch_fprop_pair<EPI_PLAIN>(mx, mx2, mw, p, st);
     }
     if (variant >= 3 && block_n == 128) {                            // persistent, grouped stages, lean issue loop
+        if (halo && s2d) {
+            if (epi == EPI_MASK) return launch_fprop_lean<1, EPI_MASK, true>(mx, mw, p, st);
+            return launch_fprop_lean<1, EPI_PLAIN, true>(mx, mw, p, st);
+        }
         if (halo) {
             if (epi == EPI_MASK) return launch_fprop_lean<1, EPI_MASK>(mx, mw, p, st);
             if (epi == EPI_ACTDROP) return launch_fprop_lean<1, EPI_ACTDROP>(mx, mw, p, st);
@@ -1364,6 +1380,10 @@ static int fprop_tc_launch(const ctgan_conv_desc* d, const void* x, const void* 
         const int n_tiles = p.tilesW * p.tilesH * p.tilesN * (d->Cout / 128);
         const int split = (g_use_splitk && !special) ? splitk_factor(n_tiles, (d->kh * d->kw * (d->Cin / 64) + 1) / 2) : 0;
         if (split) return launch_fprop_splitk(split, epi, mx, mw, p, n_tiles, st);
+        if (special) {                                               // layout-changing epilogue on per-tap boxes (1x1 / non-halo tiles)
+            if (epi == EPI_MASK) return launch_fprop_lean<0, EPI_MASK, true>(mx, mw, p, st);
+            return launch_fprop_lean<0, EPI_PLAIN, true>(mx, mw, p, st);
+        }
         if (epi == EPI_ACTDROP) return launch_fprop_lean<0, EPI_ACTDROP>(mx, mw, p, st);
         if (epi == EPI_MASK) return launch_fprop_lean<0, EPI_MASK>(mx, mw, p, st);
         return launch_fprop_lean<0, EPI_PLAIN>(mx, mw, p, st);

@@ -32,8 +32,8 @@ class Config:
                              # shorter MMA stream does not pay for the issue loop's mask arithmetic (CIFAR-DCGAN 248 -> 243 it/s)
     # ConvMeanPool(3x3) as ONE stride-2 4x4 conv on the space-to-depth route (gan_cifar_resnet._pool_conv_fused, functional.
     # conv_mean_pool_s2d): 2.25x fewer multiply-adds for Discriminator.{1,2}.Conv2.  OFF by default: measured
-    # +1.4 % it/s on the same box (151.0 -> 153.1; critic step -27 us, almost all of it in the filter-gradient launch) -- the
-    # forward / dgrad launches stay bound by the shared-memory fill (fewer live taps per halo box, the same filter bytes per MMA)
+    # +0.9 % per iteration on the same box (critic graph 922.6 -> 913.3 us, generator 1235 -> 1227 us: the filter-gradient launch
+    # shrinks by 26 us) -- the forward / dgrad launches stay bound by the shared-memory fill (fewer live taps per halo box, the same filter bytes per MMA)
     # and by one-image work items (192 items on 148 SMs), see profiles/r02_experiments.md.  Both settings are GPU-tested.
     pool_conv_s2d = False
     pool_conv_min_tiles = 96 # ... for layers with at least this many 128-pixel output tiles (smaller ones are latency-bound and lose)
