@@ -239,7 +239,8 @@ conv_fprop_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
 //   S2D = true: the space-to-depth variants (CTGAN_EPI_OUT_S2D / OUT_D2S / S2D_SKIP).  A template parameter for the same reason:
 //                with the extra address arithmetic and mask tests as runtime branches the DEFAULT launches of the step ran
 //                3.5 % slower (critic graph 924 -> 957 us, same box).
-template <int EPI, bool S2D>
+//   NORES = true: launches without a residual operand (most of them): no residual pointer, loads or adds in the loop.
+template <int EPI, bool S2D, bool NORES>
 __device__ __forceinline__ void lean_epilogue_tile(const FpropParams& p, uint32_t tmem_addr, int q, int lane,
                                                    int w0, int h0, int n0, int co0, bool relu) {
     int t = q * 32 + lane;
@@ -261,10 +262,11 @@ __device__ __forceinline__ void lean_epilogue_tile(const FpropParams& p, uint32_
         yrow = p.y + ((((int64_t)n * (2 * p.H) + 2 * h + (ph >> 1)) * (2 * p.W) + 2 * w + (ph & 1))) * C + (co0 - ph * C);
     }
     const int64_t rpix = (p.flags & CTGAN_EPI_RES_UP2) ? ((int64_t)n * (p.H >> 1) + (h >> 1)) * (p.W >> 1) + (w >> 1) : pix;
-    const __nv_bfloat16* rrow = (EPI != EPI_ACTDROP && p.residual) ? p.residual + rpix * p.Cout + co0 : nullptr;
+    const __nv_bfloat16* rrow = (!NORES && EPI != EPI_ACTDROP && p.residual) ? p.residual + rpix * p.Cout + co0 : nullptr;
     const __nv_bfloat16* mrow = (EPI == EPI_MASK) ? p.relu_mask + pix * p.Cout + co0 : nullptr;
     __nv_bfloat16* mult_row = (EPI == EPI_ACTDROP) ? p.mult + orow + co0 : nullptr;
-    const bool wide = ((reinterpret_cast<uintptr_t>(p.y) | reinterpret_cast<uintptr_t>(p.residual) |
+    // NORES launches are dispatched only with 32-byte aligned y / relu_mask (every torch allocation): no 16-byte fallback code
+    const bool wide = NORES ? true : ((reinterpret_cast<uintptr_t>(p.y) | reinterpret_cast<uintptr_t>(p.residual) |
                         (EPI == EPI_MASK ? reinterpret_cast<uintptr_t>(p.relu_mask) : 0) |
                         (EPI == EPI_ACTDROP ? reinterpret_cast<uintptr_t>(p.mult) : 0)) & 31) == 0;
     // EPI_ACTDROP: absolute Philox stream index of channel co0 of this pixel (a multiple of 4: offsets are 4-aligned)
@@ -296,7 +298,7 @@ __device__ __forceinline__ void lean_epilogue_tile(const FpropParams& p, uint32_
                 }
 #pragma unroll
                 for (int e = 0; e < 16; ++e) v[e] += __uint_as_float(v32[j + e]);
-                if (rrow) {
+                if (!NORES && rrow) {
                     uint32_t rw[8];
                     ldg16_bf16(rrow + c0 + j, wide, rw);
 #pragma unroll
@@ -363,7 +365,7 @@ __device__ __forceinline__ void lean_epilogue_tile(const FpropParams& p, uint32_
 //   HALO = 0 (1x1, 8x8 / 4x4 tiles, linear): stage = 2 consecutive (activation, filter) box pairs   ->  8 MMAs, 64 KB
 // Three stages in flight; descriptors are pre-built 32-bit words plus immediate offsets.
 
-template <int HALO, int EPI, bool S2D>
+template <int HALO, int EPI, bool S2D, bool NORES>
 __global__ void __launch_bounds__(192, 1)
 conv_fprop_tc_lean_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                           const FpropParams p, const int n_tiles)
@@ -515,7 +517,7 @@ conv_fprop_tc_lean_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
             const int co0 = nb * BLOCK_N;
             mbar_wait(tfull + 8 * acc, (uint32_t)(it >> 1) & 1u);
             tc_fence_after();
-            lean_epilogue_tile<EPI, S2D>(p, tmem_base + (uint32_t)(acc * BLOCK_N), q, lane, tw * p.BW, th * p.BH, tn * p.BN, co0, relu);
+            lean_epilogue_tile<EPI, S2D, NORES>(p, tmem_base + (uint32_t)(acc * BLOCK_N), q, lane, tw * p.BW, th * p.BH, tn * p.BN, co0, relu);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty + 8 * acc) : "memory");
@@ -533,7 +535,7 @@ conv_fprop_tc_lean_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
 // accumulators -- 44 KB per 12 MMAs instead of 72 KB.  Two stages of 88 KB; TMEM 2 x (2 x 128) columns double-buffered.
 // Tiles are enumerated n-block-major (tile = nb * m_tiles + mt) and split into contiguous per-CTA ranges, so every warp
 // role derives the same item sequence (pair if the next tile is the next row block of the same image, else single).
-template <int EPI, bool S2D>
+template <int EPI, bool S2D, bool NORES>
 __global__ void __launch_bounds__(192, 1)
 conv_fprop_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_x2,
                           const __grid_constant__ CUtensorMap tmap_w, const FpropParams p, const int m_tiles, const int n_tiles)
@@ -692,8 +694,8 @@ conv_fprop_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
             const int h0 = th * p.BH, n0 = tn * p.BN, co0 = nb * BLOCK_N;
             mbar_wait(tfull + 8 * acc, (uint32_t)(it >> 1) & 1u);
             tc_fence_after();
-            lean_epilogue_tile<EPI, S2D>(p, tmem_base + (uint32_t)(acc * 2 * BLOCK_N), q, lane, 0, h0, n0, co0, relu);
-            if (pair) lean_epilogue_tile<EPI, S2D>(p, tmem_base + (uint32_t)(acc * 2 * BLOCK_N + BLOCK_N), q, lane, 0, h0 + p.BH, n0, co0, relu);
+            lean_epilogue_tile<EPI, S2D, NORES>(p, tmem_base + (uint32_t)(acc * 2 * BLOCK_N), q, lane, 0, h0, n0, co0, relu);
+            if (pair) lean_epilogue_tile<EPI, S2D, NORES>(p, tmem_base + (uint32_t)(acc * 2 * BLOCK_N + BLOCK_N), q, lane, 0, h0 + p.BH, n0, co0, relu);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty + 8 * acc) : "memory");
@@ -1264,38 +1266,38 @@ static int launch_fprop(const CUtensorMap& mx, const CUtensorMap& mw, const Fpro
     return 0;
 }
 
-template <int HALO, int EPI, bool S2D = false>
+template <int HALO, int EPI, bool S2D = false, bool NORES = false>
 static int launch_fprop_lean(const CUtensorMap& mx, const CUtensorMap& mw, const FpropParams& p, cudaStream_t st) {
     constexpr size_t stage = HALO ? (24576 + 3 * 16384) : (32768 + 2 * 16384);
     constexpr size_t smem = 3 * stage + 1024 + (2 * 3 + 4) * 8 + 16;
     static_assert(smem <= 227 * 1024, "lean fprop: shared memory budget");
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv_fprop_tc_lean_kernel<HALO, EPI, S2D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(conv_fprop_tc_lean_kernel<HALO, EPI, S2D, NORES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return cuda_status(e, "fprop_tc_lean smem attribute");
         attr_set = true;
     }
     const int n_tiles = p.tilesW * p.tilesH * p.tilesN * (p.Cout / 128);
     const int grid = n_tiles < sm_count() ? n_tiles : sm_count();
-    CTGAN_LAUNCH((conv_fprop_tc_lean_kernel<HALO, EPI, S2D>), grid, 192, smem, st, mx, mw, p, n_tiles);
+    CTGAN_LAUNCH((conv_fprop_tc_lean_kernel<HALO, EPI, S2D, NORES>), grid, 192, smem, st, mx, mw, p, n_tiles);
     CTGAN_CHECK_LAUNCH("conv_fprop_tc_lean");
     return 0;
 }
 
-template <int EPI, bool S2D = false>
+template <int EPI, bool S2D = false, bool NORES = false>
 static int launch_fprop_pair(const CUtensorMap& mx, const CUtensorMap& mx2, const CUtensorMap& mw, const FpropParams& p, cudaStream_t st) {
     constexpr size_t smem = 2 * (40960 + 3 * 16384) + 1024 + (2 * 2 + 4) * 8 + 16;
     static_assert(smem <= 227 * 1024, "pair fprop: shared memory budget");
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv_fprop_tc_pair_kernel<EPI, S2D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(conv_fprop_tc_pair_kernel<EPI, S2D, NORES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return cuda_status(e, "fprop_tc_pair smem attribute");
         attr_set = true;
     }
     const int m_tiles = p.tilesW * p.tilesH * p.tilesN;
     const int n_tiles = m_tiles * (p.Cout / 128);
     const int grid = n_tiles < sm_count() ? n_tiles : sm_count();
-    CTGAN_LAUNCH((conv_fprop_tc_pair_kernel<EPI, S2D>), grid, 192, smem, st, mx, mx2, mw, p, m_tiles, n_tiles);
+    CTGAN_LAUNCH((conv_fprop_tc_pair_kernel<EPI, S2D, NORES>), grid, 192, smem, st, mx, mx2, mw, p, m_tiles, n_tiles);
     CTGAN_CHECK_LAUNCH("conv_fprop_tc_pair");
     return 0;
 }
@@ -1319,6 +1321,9 @@ static bool g_use_halo_hn = true;
 static int g_fprop_variant = 4;   // 4 = 256-pixel work items where possible (else 3), 3 = persistent grouped-stage (lean) kernel, 1 = one tile per CTA
 /* test hook: selects the fprop_tc kernel family (the families are compared in tests/) */
 extern "C" void ctgan_set_fprop_variant(int v) { g_fprop_variant = v; }
+static bool g_fprop_nores = true;
+/* A/B hook: 0 = launches without a residual run the generic instantiations (residual pointer tested at run time) */
+extern "C" void ctgan_set_fprop_nores(int on) { g_fprop_nores = on != 0; }
 static int g_wgrad_variant = 2;   // 2 = filter-column CTAs sharing one x halo box (3x3), 1 = one (x, dY) box pair per tap
 extern "C" void ctgan_set_wgrad_variant(int v) { g_wgrad_variant = v; }
 /* test hook: 0 disables the halo-reuse A pipeline (both are compared in tests/) */
@@ -1344,6 +1349,8 @@ static int fprop_tc_launch(const ctgan_conv_desc* d, const void* x, const void* 
     // applies where those kernels run anyway: a sub-wave layer keeps the cluster split-K kernel and multiplies the zeros
     const bool special = (epi != EPI_ACTDROP && p.out_s2d) || p.out_d2s;
     const bool s2d = special || (p.skip_k > 0 && epi != EPI_ACTDROP);    // -> the <.., S2D = true> instantiations
+    const bool nores = g_fprop_nores && p.residual == nullptr &&         // -> the <.., NORES = true> instantiations
+                       ((reinterpret_cast<uintptr_t>(p.y) | reinterpret_cast<uintptr_t>(p.relu_mask)) & 31) == 0;
     CTGAN_REQUIRE(!(special || p.skip_k > 0) || (block_n == 128 && g_fprop_variant >= 3), CTGAN_ERR_UNSUPPORTED,
                   "conv_fprop_tc: OUT_S2D / OUT_D2S / S2D_SKIP need Cout %% 128 == 0 and the lean kernel family");
     const int split_all = (g_use_splitk && block_n == 128 && !special) ? splitk_factor(n_tiles_all, (d->kh * d->kw * (d->Cin / 64) + 1) / 2) : 0;
@@ -1364,6 +1371,8 @@ static int fprop_tc_launch(const ctgan_conv_desc* d, const void* x, const void* 
         CUtensorMap mx2;                                             // 256-pixel work items (two row blocks per halo box)
         if (int r = make_act_map(&mx2, x, d->N, d->H, d->W, d->Cin, p.BW, 2 * p.BH + 2, 1)) return r;
         if (s2d) return epi == EPI_MASK ? launch_fprop_pair<EPI_MASK, true>(mx, mx2, mw, p, st) : launch_fprop_pair<EPI_PLAIN, true>(mx, mx2, mw, p, st);
+        if (nores) return epi == EPI_MASK ? launch_fprop_pair<EPI_MASK, false, true>(mx, mx2, mw, p, st)
+                                          : launch_fprop_pair<EPI_PLAIN, false, true>(mx, mx2, mw, p, st);
         return epi == EPI_MASK ? launch_fprop_pair<EPI_MASK>(mx, mx2, mw, p, st) : launch_fprop_pair<EPI_PLAIN>(mx, mx2, mw, p, st);
     }
     if (variant >= 3 && block_n == 128) {                            // persistent, grouped stages, lean issue loop
@@ -1371,6 +1380,9 @@ static int fprop_tc_launch(const ctgan_conv_desc* d, const void* x, const void* 
             if (epi == EPI_MASK) return launch_fprop_lean<1, EPI_MASK, true>(mx, mw, p, st);
             return launch_fprop_lean<1, EPI_PLAIN, true>(mx, mw, p, st);
         }
+        if (halo && nores && epi != EPI_ACTDROP)
+            return epi == EPI_MASK ? launch_fprop_lean<1, EPI_MASK, false, true>(mx, mw, p, st)
+                                   : launch_fprop_lean<1, EPI_PLAIN, false, true>(mx, mw, p, st);
         if (halo) {
             if (epi == EPI_MASK) return launch_fprop_lean<1, EPI_MASK>(mx, mw, p, st);
             if (epi == EPI_ACTDROP) return launch_fprop_lean<1, EPI_ACTDROP>(mx, mw, p, st);
@@ -1385,6 +1397,8 @@ static int fprop_tc_launch(const ctgan_conv_desc* d, const void* x, const void* 
             return launch_fprop_lean<0, EPI_PLAIN, true>(mx, mw, p, st);
         }
         if (epi == EPI_ACTDROP) return launch_fprop_lean<0, EPI_ACTDROP>(mx, mw, p, st);
+        if (nores) return epi == EPI_MASK ? launch_fprop_lean<0, EPI_MASK, false, true>(mx, mw, p, st)
+                                          : launch_fprop_lean<0, EPI_PLAIN, false, true>(mx, mw, p, st);
         if (epi == EPI_MASK) return launch_fprop_lean<0, EPI_MASK>(mx, mw, p, st);
         return launch_fprop_lean<0, EPI_PLAIN>(mx, mw, p, st);
     }

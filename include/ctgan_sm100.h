@@ -154,6 +154,8 @@ int ctgan_conv_wgrad_tc_multi_ok(const ctgan_conv_desc* d);
 /* tuning / test hook: pixels per pipeline stage of the multi-job kernel: 64, 128, or 0 (default) = 128 when a job's images are
  * at least 64 pixels wide (their halo rows are then shared by twice as many image rows), else 64 */
 void ctgan_set_wgrad_multi_chunk(int px);
+/* A/B hook: 0 = tensor-core forward launches without a residual use the generic kernels (residual tested at run time) */
+void ctgan_set_fprop_nores(int on);
 int ctgan_conv_wgrad_tc_multi_embed(int n, const ctgan_conv_desc* descs, const void* const* xs, const void* const* dys,
                                     float* const* dws, const int* embed, void* stream);
 int ctgan_conv_wgrad_tc_multi(int n, const ctgan_conv_desc* descs, const void* const* xs, const void* const* dys,

@@ -36,6 +36,9 @@ if os.environ.get('CTGAN_POOL_CONV'):
     K.config.pool_conv_s2d = bool(int(os.environ['CTGAN_POOL_CONV']))
 if os.environ.get('CTGAN_S2D_SKIP'):
     K.config.s2d_skip = bool(int(os.environ['CTGAN_S2D_SKIP']))
+if os.environ.get('CTGAN_NORES'):
+    from ctgan_b200 import _lib as _L5
+    _L5.lib.ctgan_set_fprop_nores(int(os.environ['CTGAN_NORES']))
 if os.environ.get('CTGAN_WGRAD_CHUNK'):
     from ctgan_b200 import _lib as _L4
     _L4.lib.ctgan_set_wgrad_multi_chunk(int(os.environ['CTGAN_WGRAD_CHUNK']))
