@@ -58,6 +58,8 @@ _PROTOS = {
     'ctgan_conv_wgrad_tc': (c_int, [POINTER(ConvDesc), P, P, P, P]),
     'ctgan_conv_wgrad_tc_multi_ok': (c_int, [POINTER(ConvDesc)]),
     'ctgan_set_wgrad_multi_chunk': (None, [c_int]),
+    'ctgan_set_wgrad_multi_balance': (None, [c_int, c_int]),
+    'ctgan_wgrad_multi_last_gain_pct': (c_int, []),
     'ctgan_set_fprop_nores': (None, [c_int]),
     'ctgan_conv_wgrad_tc_multi': (c_int, [c_int, POINTER(ConvDesc), POINTER(P), POINTER(P), POINTER(P), P]),
     'ctgan_conv_wgrad_tc_multi_embed': (c_int, [c_int, POINTER(ConvDesc), POINTER(P), POINTER(P), POINTER(P), POINTER(c_int), P]),

@@ -15,6 +15,8 @@
 // read ONE (BH+kh-1)-row halo box of x (shifted by r rows through the descriptor start address) and one dY chunk, both as
 // MN-major operands (no transposed copy of an activation exists); kh x 128 TMEM columns; 4-stage TMA ring of 48 KB.
 // Warp roles: 0 = TMA producer, 1 = MMA issuer (+ TMEM allocator), 2..5 = epilogue (TMEM -> red.global.add.v4.f32).
+#include <algorithm>
+#include <utility>
 #include "tc_common.cuh"
 
 namespace ctgan {
@@ -38,9 +40,16 @@ struct alignas(64) WgradJob {
     int item0;                      // index of this job's first work item
     uint32_t a_bytes;               // bytes of one 64-channel half of the x box
 };
+constexpr int WG_MAX_SLOTS = 1024;
 struct WgradJobTable {
     WgradJob job[WG_MAX_JOBS];
     int n_jobs, n_items;
+    // Work items differ in size (a job's chunk range is cut into `splits` nearly equal parts, but jobs differ), and a CTA runs
+    // only ~2 of them: round-robin assignment left the SMs busy 68 % of the launch (ncu: tensor pipe 67 % of active, 46 % of
+    // elapsed cycles).  The host assigns items longest-first to the least-loaded CTA; CTA b runs order[b], order[b + grid],
+    // ... until a negative entry.  n_slots == 0: no table (more than WG_MAX_SLOTS slots), item = slot.
+    int n_slots;
+    short order[WG_MAX_SLOTS];
 };
 
 struct WgItem { int j, ci0, co0, s_tap, chunk0, nchunks, rmask, s5, dyv, c0; };
@@ -120,7 +129,9 @@ conv_wgrad_tc_multi_kernel(const __grid_constant__ WgradJobTable tab)
         if (lane == 0) {
             // ================= TMA producer =================
             int st = 0; uint32_t ph = 0;
-            for (int item = blockIdx.x; item < tab.n_items; item += gridDim.x) {
+            for (int slot = blockIdx.x; slot < (tab.n_slots ? tab.n_slots : tab.n_items); slot += gridDim.x) {
+                const int item = tab.n_slots ? (int)tab.order[slot] : slot;
+                if (item < 0) break;
                 const WgItem it = wg_decode(tab, item);
                 const WgradJob& J = tab.job[it.j];
                 const CUtensorMap* mx = &J.mx; const CUtensorMap* mdy = &J.mdy;
@@ -156,7 +167,9 @@ conv_wgrad_tc_multi_kernel(const __grid_constant__ WgradJobTable tab)
         const uint32_t b_lo0 = (((s_base + 2 * A_SLOT) & 0x3FFFFu) >> 4) | ((B_HALF >> 4) << 16);
         int st = 0; uint32_t ph = 0;
         uint32_t n = 0;
-        for (int item = blockIdx.x; item < tab.n_items; item += gridDim.x, ++n) {
+        for (int slot = blockIdx.x; slot < (tab.n_slots ? tab.n_slots : tab.n_items); slot += gridDim.x, ++n) {
+            const int item = tab.n_slots ? (int)tab.order[slot] : slot;
+            if (item < 0) break;
             const WgItem it = wg_decode(tab, item);
             const WgradJob& J = tab.job[it.j];
             const int rmask = it.rmask;
@@ -188,7 +201,9 @@ conv_wgrad_tc_multi_kernel(const __grid_constant__ WgradJobTable tab)
         // ================= epilogue warps: TMEM -> vector reductions into dW (float, HWIO) =================
         const int q = warp & 3;                                          // TMEM lane quadrant this warp may access
         uint32_t n = 0;
-        for (int item = blockIdx.x; item < tab.n_items; item += gridDim.x, ++n) {
+        for (int slot = blockIdx.x; slot < (tab.n_slots ? tab.n_slots : tab.n_items); slot += gridDim.x, ++n) {
+            const int item = tab.n_slots ? (int)tab.order[slot] : slot;
+            if (item < 0) break;
             const WgItem it = wg_decode(tab, item);
             const WgradJob& J = tab.job[it.j];
             mbar_wait(tfull, n & 1u);
@@ -236,6 +251,20 @@ static int g_wgrad_multi_chunk = 0;
  * launch with a job on images at least 64 pixels wide (measured: CT_gan_64x64.py +0.9 %, LSUN 128x128 +1.6 %; the CIFAR ResNet
  * step, 32 pixels wide at most, is 0.5 % faster with 64: two 96 KB stages pipeline less deeply than four of 48 KB) */
 extern "C" void ctgan_set_wgrad_multi_chunk(int px) { g_wgrad_multi_chunk = (px == 64 || px == 128) ? px : 0; }
+static int g_wgrad_multi_balance = 1;
+static int g_wgrad_multi_item_overhead = 5;
+static int g_wgrad_multi_rotate = 0;
+static int g_wgrad_multi_min_gain_pct = 10;      // predicted makespan gain (%) below which round robin is kept
+static int g_wgrad_multi_last_gain_pct = 0;
+/* diagnostic: predicted makespan gain (%) of the longest-first assignment for the most recent launch */
+extern "C" int ctgan_wgrad_multi_last_gain_pct(void) { return g_wgrad_multi_last_gain_pct; }
+/* tuning / A-B hook: on = 1 assigns the work items longest-first to the least-loaded CTA (default), 0 = round robin;
+ * overhead = the fixed cost of an item (accumulator drain) in 64-pixel chunks used by that assignment */
+extern "C" void ctgan_set_wgrad_multi_balance(int on, int overhead) {
+    g_wgrad_multi_balance = on & 1; g_wgrad_multi_rotate = (on & 2) ? 1 : 0;       // on = 3: balanced + per-CTA rotation of the order
+    if (overhead >= 0) g_wgrad_multi_item_overhead = overhead;
+    g_wgrad_multi_min_gain_pct = (on & 4) ? 0 : 10;                                // on = 5: use the table whenever it exists
+}
 static int g_wgrad_multi_items_per_sm = 2;
 /* tuning hook: work items per SM the deferred filter-gradient launch aims for */
 extern "C" void ctgan_set_wgrad_multi_items_per_sm(int v) { g_wgrad_multi_items_per_sm = v < 1 ? 1 : v; }
@@ -352,6 +381,64 @@ extern "C" int ctgan_conv_wgrad_tc_multi_embed(int n, const ctgan_conv_desc* des
         }
         tab.n_jobs = nj; tab.n_items = items;
         const int grid = items < sm_count() ? items : sm_count();
+        // longest-processing-time-first assignment of the items to the CTAs (see WgradJobTable::order)
+        tab.n_slots = 0;
+        if (g_wgrad_multi_balance && items > grid && items <= WG_MAX_SLOTS) {
+            static thread_local int cost[WG_MAX_SLOTS], idx[WG_MAX_SLOTS], cnt[WG_MAX_SLOTS];
+            static thread_local long long load[WG_MAX_SLOTS];
+            int k = 0;
+            for (int i = 0; i < nj; ++i) {
+                const WgradJob& J = tab.job[i];
+                const int n_local = (i + 1 < nj ? tab.job[i + 1].item0 : items) - J.item0;
+                for (int l = 0; l < n_local; ++l, ++k) {
+                    const int z = l % J.splits;
+                    const int rest = J.total_chunks - z * J.chunks_per_split;
+                    const int nch = rest < J.chunks_per_split ? rest : J.chunks_per_split;
+                    cost[k] = nch * (chunk / 64) + g_wgrad_multi_item_overhead;     // in 64-pixel chunks; + the accumulator drain
+                    idx[k] = k;
+                }
+            }
+            std::stable_sort(idx, idx + items, [&](int a, int b) { return cost[a] > cost[b]; });
+            for (int b = 0; b < grid; ++b) { load[b] = 0; cnt[b] = 0; }
+            int max_cnt = 0;
+            static thread_local short assign[WG_MAX_SLOTS];       // CTA of the i-th sorted item
+            // min-heap of (load, CTA): the eager path runs this on the host before every launch
+            static thread_local std::pair<long long, int> heap[WG_MAX_SLOTS];
+            for (int b = 0; b < grid; ++b) heap[b] = std::make_pair(0LL, b);
+            const auto gt = [](const std::pair<long long, int>& x, const std::pair<long long, int>& y) { return x > y; };
+            for (int i = 0; i < items; ++i) {
+                std::pop_heap(heap, heap + grid, gt);                  // the least-loaded CTA moves to the back
+                std::pair<long long, int>& top = heap[grid - 1];
+                const int best = top.second;
+                assign[i] = (short)best; top.first += cost[idx[i]]; load[best] = top.first; ++cnt[best];
+                if (cnt[best] > max_cnt) max_cnt = cnt[best];
+                std::push_heap(heap, heap + grid, gt);
+            }
+            // use the table only where round robin is clearly unbalanced under the same cost model (the generator step's 8
+            // jobs: -31 us; the critic step's 16 jobs mix well by themselves and measured 2-20 us SLOWER with the table)
+            long long lpt_max = 0, rr_max = 0;
+            for (int b = 0; b < grid; ++b) {
+                if (load[b] > lpt_max) lpt_max = load[b];
+                long long rr = 0;
+                for (int i = b; i < items; i += grid) rr += cost[i];
+                if (rr > rr_max) rr_max = rr;
+            }
+            g_wgrad_multi_last_gain_pct = rr_max > 0 ? (int)(100 - 100 * lpt_max / rr_max) : 0;
+            if ((long long)max_cnt * grid <= WG_MAX_SLOTS && 100 * lpt_max < (long long)(100 - g_wgrad_multi_min_gain_pct) * rr_max) {
+                tab.n_slots = max_cnt * grid;
+                for (int i = 0; i < tab.n_slots; ++i) tab.order[i] = -1;
+                // optional (ctgan_set_wgrad_multi_balance(3, .)): CTA b starts with its (b mod count)-th item, so that equal-cost
+                // items of ONE job do not finish on every SM at the same moment -- measured equal (critic graph 919-920 vs 917-918 us)
+                static thread_local int pos[WG_MAX_SLOTS];
+                for (int b = 0; b < grid; ++b) pos[b] = 0;
+                for (int i = 0; i < items; ++i) {
+                    const int b = assign[i];
+                    const int at = g_wgrad_multi_rotate ? (pos[b] + b) % cnt[b] : pos[b];
+                    tab.order[b + grid * at] = (short)idx[i];
+                    ++pos[b];
+                }
+            }
+        }
         if (chunk == 128) CTGAN_LAUNCH((conv_wgrad_tc_multi_kernel<2, 32768, 128>), grid, 192, smem_128, as_stream(stream), tab);
         else if (big) CTGAN_LAUNCH((conv_wgrad_tc_multi_kernel<3, 24576>), grid, 192, smem_big, as_stream(stream), tab);
         else     CTGAN_LAUNCH((conv_wgrad_tc_multi_kernel<STAGES>), grid, 192, smem, as_stream(stream), tab);

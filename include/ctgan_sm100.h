@@ -154,6 +154,12 @@ int ctgan_conv_wgrad_tc_multi_ok(const ctgan_conv_desc* d);
 /* tuning / test hook: pixels per pipeline stage of the multi-job kernel: 64, 128, or 0 (default) = 128 when a job's images are
  * at least 64 pixels wide (their halo rows are then shared by twice as many image rows), else 64 */
 void ctgan_set_wgrad_multi_chunk(int px);
+/* tuning / A-B hook: on = 1 (default) assigns the launch's work items longest-first to the least-loaded CTA, 0 = round robin,
+ * 3 = as 1 with each CTA's list rotated, 5 = as 1 even when the predicted gain over round robin is below 10 %;
+ * overhead >= 0 sets the fixed per-item cost (in 64-pixel chunks) that assignment assumes */
+void ctgan_set_wgrad_multi_balance(int on, int overhead);
+/* diagnostic: predicted makespan gain (%) of that assignment over round robin for the most recent launch */
+int ctgan_wgrad_multi_last_gain_pct(void);
 /* A/B hook: 0 = tensor-core forward launches without a residual use the generic kernels (residual tested at run time) */
 void ctgan_set_fprop_nores(int on);
 int ctgan_conv_wgrad_tc_multi_embed(int n, const ctgan_conv_desc* descs, const void* const* xs, const void* const* dys,

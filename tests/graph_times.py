@@ -39,6 +39,10 @@ if os.environ.get('CTGAN_S2D_SKIP'):
 if os.environ.get('CTGAN_NORES'):
     from ctgan_b200 import _lib as _L5
     _L5.lib.ctgan_set_fprop_nores(int(os.environ['CTGAN_NORES']))
+if os.environ.get('CTGAN_WGRAD_BALANCE'):
+    from ctgan_b200 import _lib as _L6
+    _b = [int(v) for v in os.environ['CTGAN_WGRAD_BALANCE'].split(',')]
+    _L6.lib.ctgan_set_wgrad_multi_balance(_b[0], _b[1] if len(_b) > 1 else -1)
 if os.environ.get('CTGAN_WGRAD_CHUNK'):
     from ctgan_b200 import _lib as _L4
     _L4.lib.ctgan_set_wgrad_multi_chunk(int(os.environ['CTGAN_WGRAD_CHUNK']))

@@ -507,9 +507,10 @@ def test_tc_wgrad_variants_match(K, shape):
         _lib.lib.ctgan_set_wgrad_variant(2)
 
 
+@pytest.mark.parametrize('balance', [5, 0, 3])
 @pytest.mark.parametrize('chunk', [0, 64, 128])
 @pytest.mark.parametrize('items_per_sm', [2, 1, 5])
-def test_tc_wgrad_multi_job_launch(K, items_per_sm, chunk):
+def test_tc_wgrad_multi_job_launch(K, items_per_sm, chunk, balance):
     """Deferred filter gradients (csrc/conv_wgrad_multi.cu): a mix of layers -- 3x3 at 32x32 / 16x16 / 8x8 / 4x4, 1x1, a Linear,
     ragged batch sizes, wide Cin / Cout, two jobs adding into the SAME gradient -- queued and run as one launch, against
     the CPU reference of each job; the queue is empty afterwards and ineligible jobs launch immediately."""
@@ -521,6 +522,7 @@ def test_tc_wgrad_multi_job_launch(K, items_per_sm, chunk):
               (64, 8, 8, 3, 128, 128)]       # 4x4: four images per 64-pixel chunk, [h][n][w] halo boxes
     _lib.lib.ctgan_set_wgrad_multi_items_per_sm(items_per_sm)
     _lib.lib.ctgan_set_wgrad_multi_chunk(chunk)            # pixels per pipeline stage: 64 / 128 / by image width
+    _lib.lib.ctgan_set_wgrad_multi_balance(balance, -1)    # item -> CTA assignment: longest-first / round robin / rotated
     try:
         refs, accs, keep = [], [], []
         for i, (N, H, W, k, Cin, Cout) in enumerate(shapes):
@@ -558,6 +560,7 @@ def test_tc_wgrad_multi_job_launch(K, items_per_sm, chunk):
     finally:
         _lib.lib.ctgan_set_wgrad_multi_items_per_sm(2)
         _lib.lib.ctgan_set_wgrad_multi_chunk(0)
+        _lib.lib.ctgan_set_wgrad_multi_balance(1, -1)
 
 
 @pytest.mark.parametrize('geom', [(5, 32, 32, 3, 128, 3), (3, 16, 16, 3, 128, 1), (4, 32, 32, 128, 3, 3), (70, 8, 8, 3, 256, 3),
