@@ -60,6 +60,7 @@ _PROTOS = {
     'ctgan_set_wgrad_multi_chunk': (None, [c_int]),
     'ctgan_set_wgrad_multi_balance': (None, [c_int, c_int]),
     'ctgan_wgrad_multi_last_gain_pct': (c_int, []),
+    'ctgan_wgrad_multi_assign': (c_int, [P, c_int, c_int, c_int, c_int, P, P]),
     'ctgan_set_fprop_nores': (None, [c_int]),
     'ctgan_conv_wgrad_tc_multi': (c_int, [c_int, POINTER(ConvDesc), POINTER(P), POINTER(P), POINTER(P), P]),
     'ctgan_conv_wgrad_tc_multi_embed': (c_int, [c_int, POINTER(ConvDesc), POINTER(P), POINTER(P), POINTER(P), POINTER(c_int), P]),

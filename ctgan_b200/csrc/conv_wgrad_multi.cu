@@ -246,6 +246,58 @@ conv_wgrad_tc_multi_kernel(const __grid_constant__ WgradJobTable tab)
 using namespace ctgan;
 using namespace ctgan::tc;
 
+// Longest-processing-time-first assignment of `items` work items (cost[i] > 0) to `grid` CTAs: order[b + grid * k] = the k-th
+// item CTA b runs, -1 = none.  Returns the number of slots (a multiple of grid), or 0 -- keep round robin (item = slot) -- when
+// the table would not fit WG_MAX_SLOTS or the predicted makespan is not at least min_gain_pct % shorter than round robin's.
+// rotate: CTA b starts with its (b mod count)-th item.  *gain_pct receives the predicted gain.  Host code, no CUDA calls.
+static int wg_assign_items(const int* cost, int items, int grid, int min_gain_pct, bool rotate, short* order, int* gain_pct) {
+    if (gain_pct) *gain_pct = 0;
+    if (items <= grid || items > WG_MAX_SLOTS || grid <= 0) return 0;
+    static thread_local int idx[WG_MAX_SLOTS], cnt[WG_MAX_SLOTS], pos[WG_MAX_SLOTS];
+    static thread_local long long load[WG_MAX_SLOTS];
+    static thread_local short assign[WG_MAX_SLOTS];                   // CTA of the i-th sorted item
+    static thread_local std::pair<long long, int> heap[WG_MAX_SLOTS]; // min-heap of (load, CTA)
+    for (int i = 0; i < items; ++i) idx[i] = i;
+    std::stable_sort(idx, idx + items, [&](int a, int b) { return cost[a] > cost[b]; });
+    for (int b = 0; b < grid; ++b) { load[b] = 0; cnt[b] = 0; pos[b] = 0; heap[b] = std::make_pair(0LL, b); }
+    const auto gt = [](const std::pair<long long, int>& x, const std::pair<long long, int>& y) { return x > y; };
+    int max_cnt = 0;
+    for (int i = 0; i < items; ++i) {
+        std::pop_heap(heap, heap + grid, gt);                          // the least-loaded CTA moves to the back
+        std::pair<long long, int>& top = heap[grid - 1];
+        const int best = top.second;
+        assign[i] = (short)best; top.first += cost[idx[i]]; load[best] = top.first; ++cnt[best];
+        if (cnt[best] > max_cnt) max_cnt = cnt[best];
+        std::push_heap(heap, heap + grid, gt);
+    }
+    // use the table only where round robin is clearly unbalanced under the same cost model (the generator step's 8 jobs:
+    // -31 us; the critic step's 16 jobs mix well by themselves and the launch is bound by its shared-memory fill)
+    long long lpt_max = 0, rr_max = 0;
+    for (int b = 0; b < grid; ++b) {
+        if (load[b] > lpt_max) lpt_max = load[b];
+        long long rr = 0;
+        for (int i = b; i < items; i += grid) rr += cost[i];
+        if (rr > rr_max) rr_max = rr;
+    }
+    if (gain_pct) *gain_pct = rr_max > 0 ? (int)(100 - 100 * lpt_max / rr_max) : 0;
+    if ((long long)max_cnt * grid > WG_MAX_SLOTS || 100 * lpt_max >= (long long)(100 - min_gain_pct) * rr_max) return 0;
+    const int n_slots = max_cnt * grid;
+    for (int i = 0; i < n_slots; ++i) order[i] = -1;
+    for (int i = 0; i < items; ++i) {
+        const int b = assign[i];
+        // rotate (ctgan_set_wgrad_multi_balance(3, .)): equal-cost items of ONE job then do not finish on every SM at the
+        // same moment -- measured equal (critic graph 919-920 vs 917-918 us)
+        const int at = rotate ? (pos[b] + b) % cnt[b] : pos[b];
+        order[b + grid * at] = (short)idx[i];
+        ++pos[b];
+    }
+    return n_slots;
+}
+/* the assignment alone, for tests (host code: callable without a GPU): order must hold 1024 entries; returns the slot count */
+extern "C" int ctgan_wgrad_multi_assign(const int* cost, int items, int grid, int min_gain_pct, int rotate, short* order, int* gain_pct) {
+    return wg_assign_items(cost, items, grid, min_gain_pct, rotate != 0, order, gain_pct);
+}
+
 static int g_wgrad_multi_chunk = 0;
 /* tuning / test hook: pixels per pipeline stage of the multi-job filter-gradient kernel: 64, 128, or 0 (default) = 128 for a
  * launch with a job on images at least 64 pixels wide (measured: CT_gan_64x64.py +0.9 %, LSUN 128x128 +1.6 %; the CIFAR ResNet
@@ -384,8 +436,7 @@ extern "C" int ctgan_conv_wgrad_tc_multi_embed(int n, const ctgan_conv_desc* des
         // longest-processing-time-first assignment of the items to the CTAs (see WgradJobTable::order)
         tab.n_slots = 0;
         if (g_wgrad_multi_balance && items > grid && items <= WG_MAX_SLOTS) {
-            static thread_local int cost[WG_MAX_SLOTS], idx[WG_MAX_SLOTS], cnt[WG_MAX_SLOTS];
-            static thread_local long long load[WG_MAX_SLOTS];
+            static thread_local int cost[WG_MAX_SLOTS];
             int k = 0;
             for (int i = 0; i < nj; ++i) {
                 const WgradJob& J = tab.job[i];
@@ -395,49 +446,10 @@ extern "C" int ctgan_conv_wgrad_tc_multi_embed(int n, const ctgan_conv_desc* des
                     const int rest = J.total_chunks - z * J.chunks_per_split;
                     const int nch = rest < J.chunks_per_split ? rest : J.chunks_per_split;
                     cost[k] = nch * (chunk / 64) + g_wgrad_multi_item_overhead;     // in 64-pixel chunks; + the accumulator drain
-                    idx[k] = k;
                 }
             }
-            std::stable_sort(idx, idx + items, [&](int a, int b) { return cost[a] > cost[b]; });
-            for (int b = 0; b < grid; ++b) { load[b] = 0; cnt[b] = 0; }
-            int max_cnt = 0;
-            static thread_local short assign[WG_MAX_SLOTS];       // CTA of the i-th sorted item
-            // min-heap of (load, CTA): the eager path runs this on the host before every launch
-            static thread_local std::pair<long long, int> heap[WG_MAX_SLOTS];
-            for (int b = 0; b < grid; ++b) heap[b] = std::make_pair(0LL, b);
-            const auto gt = [](const std::pair<long long, int>& x, const std::pair<long long, int>& y) { return x > y; };
-            for (int i = 0; i < items; ++i) {
-                std::pop_heap(heap, heap + grid, gt);                  // the least-loaded CTA moves to the back
-                std::pair<long long, int>& top = heap[grid - 1];
-                const int best = top.second;
-                assign[i] = (short)best; top.first += cost[idx[i]]; load[best] = top.first; ++cnt[best];
-                if (cnt[best] > max_cnt) max_cnt = cnt[best];
-                std::push_heap(heap, heap + grid, gt);
-            }
-            // use the table only where round robin is clearly unbalanced under the same cost model (the generator step's 8
-            // jobs: -31 us; the critic step's 16 jobs mix well by themselves and measured 2-20 us SLOWER with the table)
-            long long lpt_max = 0, rr_max = 0;
-            for (int b = 0; b < grid; ++b) {
-                if (load[b] > lpt_max) lpt_max = load[b];
-                long long rr = 0;
-                for (int i = b; i < items; i += grid) rr += cost[i];
-                if (rr > rr_max) rr_max = rr;
-            }
-            g_wgrad_multi_last_gain_pct = rr_max > 0 ? (int)(100 - 100 * lpt_max / rr_max) : 0;
-            if ((long long)max_cnt * grid <= WG_MAX_SLOTS && 100 * lpt_max < (long long)(100 - g_wgrad_multi_min_gain_pct) * rr_max) {
-                tab.n_slots = max_cnt * grid;
-                for (int i = 0; i < tab.n_slots; ++i) tab.order[i] = -1;
-                // optional (ctgan_set_wgrad_multi_balance(3, .)): CTA b starts with its (b mod count)-th item, so that equal-cost
-                // items of ONE job do not finish on every SM at the same moment -- measured equal (critic graph 919-920 vs 917-918 us)
-                static thread_local int pos[WG_MAX_SLOTS];
-                for (int b = 0; b < grid; ++b) pos[b] = 0;
-                for (int i = 0; i < items; ++i) {
-                    const int b = assign[i];
-                    const int at = g_wgrad_multi_rotate ? (pos[b] + b) % cnt[b] : pos[b];
-                    tab.order[b + grid * at] = (short)idx[i];
-                    ++pos[b];
-                }
-            }
+            tab.n_slots = wg_assign_items(cost, items, grid, g_wgrad_multi_min_gain_pct, g_wgrad_multi_rotate != 0, tab.order,
+                                          &g_wgrad_multi_last_gain_pct);
         }
         if (chunk == 128) CTGAN_LAUNCH((conv_wgrad_tc_multi_kernel<2, 32768, 128>), grid, 192, smem_128, as_stream(stream), tab);
         else if (big) CTGAN_LAUNCH((conv_wgrad_tc_multi_kernel<3, 24576>), grid, 192, smem_big, as_stream(stream), tab);

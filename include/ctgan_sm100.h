@@ -160,6 +160,11 @@ void ctgan_set_wgrad_multi_chunk(int px);
 void ctgan_set_wgrad_multi_balance(int on, int overhead);
 /* diagnostic: predicted makespan gain (%) of that assignment over round robin for the most recent launch */
 int ctgan_wgrad_multi_last_gain_pct(void);
+/* the item -> CTA assignment alone (host code, callable without a GPU; tests): cost[items] > 0 in arbitrary units; order must
+ * hold 1024 entries and receives order[b + grid * k] = the k-th item CTA b runs (-1 = none).  Returns the number of slots used
+ * (a multiple of grid) or 0 = keep round robin (items <= grid, more than 1024 slots, or a predicted makespan gain below
+ * min_gain_pct %); *gain_pct (nullable) receives the predicted gain. */
+int ctgan_wgrad_multi_assign(const int* cost, int items, int grid, int min_gain_pct, int rotate, short* order, int* gain_pct);
 /* A/B hook: 0 = tensor-core forward launches without a residual use the generic kernels (residual tested at run time) */
 void ctgan_set_fprop_nores(int on);
 int ctgan_conv_wgrad_tc_multi_embed(int n, const ctgan_conv_desc* descs, const void* const* xs, const void* const* dys,
