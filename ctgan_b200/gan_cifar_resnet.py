@@ -201,7 +201,7 @@ def ResidualBlock(name, input_dim, output_dim, filter_size, inputs, resample=Non
 def _pool_conv_fused(x, cin, cmid, cout, filter_size):
     """True when [3x3 conv cin -> cmid, relu, ConvMeanPool(3x3) cmid -> cout] on activation x takes the fused route: the
     first conv writes the space-to-depth layout, the second and its mean pool run as one stride-2 4x4 conv."""
-    return (FUSE_D_ACT and FUSE_RELU_BWD and FUSE_SKIP_ADD and filter_size == 3 and not isinstance(x, F.S2DAct)
+    return (K.config.pool_conv_s2d and FUSE_D_ACT and FUSE_RELU_BWD and FUSE_SKIP_ADD and filter_size == 3 and not isinstance(x, F.S2DAct)
             and F.conv2d_s2d_out_ok(x, cmid, 3) and F.conv_mean_pool_s2d_ok(x, cmid, cout))
 
 
