@@ -69,3 +69,35 @@ def test_rotation_keeps_each_cta_its_items():
         k = len([i for i in lb if i >= 0])
         assert all(i >= 0 for i in lb[:k]) and all(i < 0 for i in lb[k:])
     assert a != b
+
+
+def test_conv_mean_pool_equals_one_stride2_conv_with_the_box_filter():
+    """The identity behind kernels.config.pool_conv_s2d (csrc/conv_s2d.cu box_filter_kernel, checked against the kernel in
+    tests/test_kernels_gpu.py): mean_pool_2x2(conv3x3_SAME(x, w) + b) == conv4x4_stride2_pad1(x, W4) + b with
+    W4[u][v] = 1/4 sum_{a,b in {0,1}} w[u-a][v-b], in float64 on the CPU (TG/CT_gan_cifar_resnet.py:89-92: ConvMeanPool)."""
+    import torch
+    import torch.nn.functional as TF
+    g = torch.Generator().manual_seed(0)
+    C, O = 5, 7
+    w = torch.randn(3, 3, C, O, generator=g, dtype=torch.float64)          # HWIO, as tflib stores filters
+    b = torch.randn(O, generator=g, dtype=torch.float64)
+    x = torch.randn(3, C, 12, 10, generator=g, dtype=torch.float64)
+    w4 = torch.zeros(4, 4, C, O, dtype=torch.float64)
+    for u in range(4):
+        for v in range(4):
+            for a in (0, 1):
+                for c in (0, 1):
+                    if 0 <= u - a < 3 and 0 <= v - c < 3:
+                        w4[u, v] += 0.25 * w[u - a, v - c]
+    ref = TF.avg_pool2d(TF.conv2d(x, w.permute(3, 2, 0, 1), b, padding=1), 2)
+    got = TF.conv2d(x, w4.permute(3, 2, 0, 1), b, stride=2, padding=1)
+    assert torch.allclose(got, ref, rtol=1e-12, atol=1e-12)
+    # 'SAME' padding of a 4x4 / stride-2 conv on an even extent is exactly pad 1 (kernels.same_geom)
+    import ctgan_b200.kernels as K
+    geo = K.same_geom(3, 12, 10, C, O, 4, 2)
+    assert (geo.pad_t, geo.pad_l, geo.Ho, geo.Wo) == (1, 1, 6, 5)
+    # live (tap, phase) blocks of the embedded 3x3 filter: 16 of 36 for k = 4, 25 of 36 for k = 5 (CTGAN_EPI_S2D_SKIP)
+    for k, pad, live in ((4, 1, 16), (5, 1, 25), (5, 2, 25)):
+        n = sum(1 for R in range(3) for S in range(3) for dy in (0, 1) for dx in (0, 1)
+                if 0 <= 2 * (R - 1) + dy + pad < k and 0 <= 2 * (S - 1) + dx + pad < k)
+        assert n == live, (k, pad, n)
